@@ -1,0 +1,37 @@
+"""Generate the committed golden fixtures from the REFERENCE's own code (oracle/_ref, compiled from /root/reference).
+
+Run in the build container only (where /root/reference exists):  python tests/golden/make_golden.py
+"""
+import os, sys
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import oracle_py
+
+
+def knn():
+    oracle_py.build_ref()
+    cases = {}
+    for name, (seed, nt, nq, k, flips) in {
+        "a": (7, 2000, 64, 10, 40),     # the tracker's shape (k=10), many exact ties
+        "b": (8, 300, 33, 32, 8),       # k = max
+        "c": (9, 5, 20, 10, 3),         # fewer train rows than k: -1 / 0 padding
+        "d": (10, 1000, 50, 2, 0),      # duplicates: distance-0 ties
+        "e": (11, 777, 40, 1, 20),
+    }.items():
+        t, q = oracle_py.synth_descriptors(seed, nt, nq, flips)
+        if name == "d":
+            t[500:] = t[:500]  # every row appears twice
+        for order in (0, 1):
+            idx, dist = oracle_py.ref_xflann_knn(q, t, k, 0, -1, order)
+            cases["%s_idx%d" % (name, order)] = idx
+            cases["%s_dist%d" % (name, order)] = dist
+        cases[name + "_t"], cases[name + "_q"], cases[name + "_k"] = t, q, np.int32(k)
+    np.savez_compressed(os.path.join(HERE, "knn_xflann_linear.npz"), **cases)
+    print("knn golden written", {k: v.shape for k, v in cases.items() if k.endswith("idx0")})
+
+
+if __name__ == "__main__":
+    knn()

@@ -1,0 +1,64 @@
+"""Parity of the sm_100a Hamming k-NN kernel (through the C ABI) with the oracle: bit-exact indices and distances,
+in the reference's heap order and in its sorted order."""
+import os
+import numpy as np
+import pytest
+import oracle_py
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "knn_xflann_linear.npz")
+
+
+@pytest.mark.parametrize("case", list("abcde"))
+@pytest.mark.parametrize("order", [0, 1])
+def test_gpu_matches_reference_golden(ctx, case, order):
+    g = np.load(GOLD)
+    idx, dist = ctx.hamming_knn(g[case + "_q"], g[case + "_t"], int(g[case + "_k"]), order)
+    assert np.array_equal(idx, g["%s_idx%d" % (case, order)])
+    assert np.array_equal(dist, g["%s_dist%d" % (case, order)])
+
+
+@pytest.mark.parametrize("nq,nt,k", [(2000, 2000, 10), (1, 1, 1), (17, 255, 10), (16, 256, 10), (15, 257, 3),
+                                      (100, 1025, 32), (5, 3, 10), (2000, 4000, 10), (33, 5000, 7)])
+@pytest.mark.parametrize("order", [0, 1])
+def test_gpu_matches_oracle(ctx, nq, nt, k, order):
+    t, q = oracle_py.synth_descriptors(1000 + nq + nt + k, nt, nq)
+    a = ctx.hamming_knn(q, t, k, order)
+    b = oracle_py.hamming_knn(q, t, k, order)
+    assert np.array_equal(a[0], b[0])
+    assert np.array_equal(a[1], b[1])
+
+
+def test_gpu_strided_rows_and_empty(ctx):
+    t, q = oracle_py.synth_descriptors(3, 500, 70)
+    qs = np.zeros((70, 48), np.uint8); qs[:, :32] = q        # cv::Mat rows with step > cols
+    ts = np.zeros((500, 64), np.uint8); ts[:, :32] = t
+    a = ctx.hamming_knn(qs[:, :32], ts[:, :32], 10)
+    b = oracle_py.hamming_knn(q, t, 10)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    i, d = ctx.hamming_knn(q[:0], t, 10)
+    assert i.shape == (0, 10)
+    i, d = ctx.hamming_knn(q, t[:0], 4)                       # empty train set: all padding
+    assert (i == -1).all() and (d == 0).all()
+
+
+def test_gpu_bad_arguments(ctx):
+    import ucoslam_b200
+    t, q = oracle_py.synth_descriptors(3, 50, 7)
+    with pytest.raises(ucoslam_b200.UcoError):
+        ctx.hamming_knn(q, t, 0)
+    with pytest.raises(ucoslam_b200.UcoError):
+        ctx.hamming_knn(q, t, 33)
+
+
+def test_gpu_large_scan_properties(ctx):
+    """Full-size property check (config 4 shape scaled to what the oracle cannot do in seconds): distances sorted,
+    each (idx, dist) pair consistent, and the k-th distance equals the true k-th order statistic."""
+    t, q = oracle_py.synth_descriptors(77, 200000, 256)
+    idx, dist = ctx.hamming_knn(q, t, 10, 1)
+    assert (np.diff(dist, axis=1) >= 0).all()
+    d_chk = np.unpackbits(q[:, None, :] ^ t[idx], axis=2).sum(2)
+    assert np.array_equal(d_chk, dist)
+    for i in range(0, 256, 37):
+        full = np.unpackbits(q[i][None, :] ^ t, axis=1).sum(1)
+        assert np.array_equal(np.sort(full)[:10], dist[i])

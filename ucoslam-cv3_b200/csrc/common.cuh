@@ -1,0 +1,61 @@
+// common.cuh — context object, error plumbing and workspace helpers shared by all translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+#include <vector>
+#include "../../include/ucoslam_b200.h"
+
+struct uco_dev_buf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct uco_orb_state;   // orb.cu
+struct uco_ba_state;    // ba.cu
+
+struct uco_b200_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    // grow-only device / pinned workspaces, keyed by slot
+    std::vector<uco_dev_buf> dev;
+    std::vector<uco_dev_buf> pin;
+    uco_orb_state* orb = nullptr;
+    uco_ba_state* ba = nullptr;
+};
+
+enum {  // device workspace slots
+    WS_KNN_Q = 0, WS_KNN_T, WS_KNN_IDX, WS_KNN_DIST,
+    WS_BOW_DESC, WS_BOW_OUT,
+    WS_GENERIC0, WS_GENERIC1, WS_GENERIC2, WS_GENERIC3,
+    WS_COUNT
+};
+
+int uco_fail(uco_b200_ctx* ctx, int code, const char* fmt, ...);
+// returns device pointer with at least `bytes` capacity for the slot (grow-only), nullptr on failure (error set)
+void* uco_ws(uco_b200_ctx* ctx, int slot, size_t bytes);
+void* uco_pinned(uco_b200_ctx* ctx, int slot, size_t bytes);
+
+void uco_orb_state_free(uco_b200_ctx* ctx);
+void uco_ba_state_free(uco_b200_ctx* ctx);
+
+#define UCO_CUDA(ctx, call)                                                                           \
+    do {                                                                                              \
+        cudaError_t e__ = (call);                                                                     \
+        if (e__ != cudaSuccess)                                                                       \
+            return uco_fail(ctx, UCO_E_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,             \
+                            cudaGetErrorString(e__));                                                 \
+    } while (0)
+
+#define UCO_LAUNCH_CHECK(ctx)                                                                         \
+    do {                                                                                              \
+        (ctx)->launches++;                                                                            \
+        cudaError_t e__ = cudaGetLastError();                                                         \
+        if (e__ != cudaSuccess)                                                                       \
+            return uco_fail(ctx, UCO_E_CUDA, "%s:%d kernel launch -> %s", __FILE__, __LINE__,         \
+                            cudaGetErrorString(e__));                                                 \
+    } while (0)

@@ -1,0 +1,106 @@
+// ctx.cu — context lifetime, error text, workspaces.
+#include "common.cuh"
+#include <cstdarg>
+#include <cstdio>
+#include <new>
+
+int uco_fail(uco_b200_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+void* uco_ws(uco_b200_ctx* ctx, int slot, size_t bytes) {
+    if ((size_t)slot >= ctx->dev.size()) ctx->dev.resize(slot + 1);
+    uco_dev_buf& b = ctx->dev[slot];
+    if (bytes == 0) bytes = 16;
+    if (b.cap >= bytes) return b.p;
+    if (b.p) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        uco_fail(ctx, UCO_E_NOMEM, "cudaMalloc(%zu) -> %s", want, cudaGetErrorString(e));
+        b.p = nullptr;
+        return nullptr;
+    }
+    b.cap = want;
+    return b.p;
+}
+
+void* uco_pinned(uco_b200_ctx* ctx, int slot, size_t bytes) {
+    if ((size_t)slot >= ctx->pin.size()) ctx->pin.resize(slot + 1);
+    uco_dev_buf& b = ctx->pin[slot];
+    if (bytes == 0) bytes = 16;
+    if (b.cap >= bytes) return b.p;
+    if (b.p) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFreeHost(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMallocHost(&b.p, want);
+    if (e != cudaSuccess) {
+        uco_fail(ctx, UCO_E_NOMEM, "cudaMallocHost(%zu) -> %s", want, cudaGetErrorString(e));
+        b.p = nullptr;
+        return nullptr;
+    }
+    b.cap = want;
+    return b.p;
+}
+
+extern "C" {
+
+uco_b200_ctx* uco_b200_create(int device, int flags) {
+    (void)flags;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return nullptr;
+    if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+    uco_b200_ctx* ctx = new (std::nothrow) uco_b200_ctx();
+    if (!ctx) return nullptr;
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return nullptr;
+    }
+    ctx->dev.resize(WS_COUNT);
+    ctx->pin.resize(WS_COUNT);
+    return ctx;
+}
+
+void uco_b200_destroy(uco_b200_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    uco_orb_state_free(ctx);
+    uco_ba_state_free(ctx);
+    for (auto& b : ctx->dev)
+        if (b.p) cudaFree(b.p);
+    for (auto& b : ctx->pin)
+        if (b.p) cudaFreeHost(b.p);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* uco_b200_last_error(const uco_b200_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context (no usable CUDA device?)"; }
+void* uco_b200_stream(uco_b200_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int uco_b200_sync(uco_b200_ctx* ctx) {
+    if (!ctx) return UCO_E_INVALID;
+    UCO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return UCO_OK;
+}
+uint64_t uco_b200_launch_count(const uco_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int uco_b200_version(void) { return 100; }
+
+}  // extern "C"
