@@ -253,9 +253,14 @@ def run_b200(args, rank, world, local_rank):
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(desc)
         print(json.dumps(line))
-    ctx.close()
+        sys.stdout.flush()
+    barrier()
     if world > 1:
         dist.destroy_process_group()
+    # the context (and its stream) outlives every torch object that references the stream; skip interpreter teardown
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 def cpu_baseline(desc):

@@ -6,11 +6,11 @@
 //   3rdparty/xflann/xflann/impl/distances.h:279-283 4 x popcount64 distance
 //   3rdparty/xflann/xflann/index.h:119-133          optional exchange sort of each result row
 //
-// Layout: train descriptors are dense 32-byte rows in HBM.  A CTA of KNN_WARPS warps owns
-// KNN_WARPS*2 queries; the train set streams through a KNN_STAGES-deep ring of shared-memory tiles filled by
+// Layout: train descriptors are dense 32-byte rows in HBM.  A CTA of KNN_WARPS warps owns KNN_WARPS queries (one per
+// warp); the train set streams through a KNN_STAGES-deep ring of shared-memory tiles filled by
 // 1-D TMA bulk copies (cp.async.bulk, completion on an mbarrier), so every train byte is read from L2/HBM once per
 // CTA with fully coalesced 128-B lines.  Inside a warp each lane owns one train row of the current 32-row
-// chunk and computes two distances (two queries held in registers, 8 x __popc each).  The result heap of
+// chunk and computes its distance to the warp's query (held in registers, 8 x __popc).  The result heap of
 // the reference is replayed EXACTLY: candidates that can enter the heap (d < current worst) are found with a
 // warp ballot and inserted by lane 0 in train-index order, which is the order the reference's scalar loop
 // pushes them, so the final array order (the "heap order" the tracker consumes, framematcher.cpp:239-270)
@@ -19,8 +19,6 @@
 #include <climits>
 
 #define KNN_WARPS 8
-#define KNN_QPW 2                 // queries per warp
-#define KNN_QPB (KNN_WARPS * KNN_QPW)
 #define KNN_TILE_ROWS 256         // train rows per shared-memory tile (8 KB)
 #define KNN_STAGES 4
 
@@ -52,79 +50,58 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
                  : "memory");
 }
 
-// ---- exact replay of xflann::impl::ResultSet (resultset.h:64-140) on one row of packed (dist<<32 | idx) -----------
-struct Heap {
-    unsigned long long* a;  // shared memory, cap entries
-    int n;
-    int cap;
-};
-__device__ __forceinline__ int hdist(unsigned long long v) { return (int)(v >> 32); }
+// ---- exact replay of xflann::impl::ResultSet (resultset.h:64-140) -------------------------------------------------
+// The heap lives in REGISTERS, replicated in every lane of the warp (all lanes execute the same uniform updates, so
+// there is no broadcast and no shared-memory round trip on the serial path).  An entry is packed as
+// dist << 23 | idx  (dist <= 256 needs 9 bits, idx < 2^23); the reference compares distances only.
+// All indices are compile-time constants (template recursion), so the array never leaves the register file.
+#define HD(v) ((v) >> 23)
 
-__device__ __forceinline__ void heap_sift_to_root(Heap& h, int index) {  // reference name: down()
-    while (index > 0) {
-        int parent = (index - 1) >> 1;
-        unsigned long long vp = h.a[parent], vi = h.a[index];
-        if (hdist(vp) < hdist(vi)) {
-            h.a[parent] = vi;
-            h.a[index] = vp;
-            index = parent;
-        } else
-            break;
-    }
-}
-__device__ __forceinline__ void heap_sift_from_root(Heap& h) {  // reference name: up(0)
-    int index = 0;
-    for (;;) {
-        int l = 2 * index + 1, r = l + 1;
-        if (l >= h.n) return;
-        unsigned long long vi = h.a[index], vl = h.a[l];
-        if (r >= h.n) {
-            if (hdist(vi) < hdist(vl)) {
-                h.a[index] = vl;
-                h.a[l] = vi;
-            }
-            return;
-        }
-        unsigned long long vr = h.a[r];
-        if (hdist(vr) < hdist(vl)) {
-            if (hdist(vi) < hdist(vl)) {
-                h.a[index] = vl;
-                h.a[l] = vi;
-                index = l;
-            } else
-                return;
+template <int K, int I, int N>
+__device__ __forceinline__ void sift_from_root(uint32_t (&h)[K]) {  // reference name: up(); N = live size
+    constexpr int L = 2 * I + 1, R = 2 * I + 2;
+    if constexpr (L < N) {
+        if constexpr (R >= N) {
+            if (HD(h[I]) < HD(h[L])) { uint32_t t = h[I]; h[I] = h[L]; h[L] = t; }
         } else {
-            if (hdist(vi) < hdist(vr)) {
-                h.a[index] = vr;
-                h.a[r] = vi;
-                index = r;
-            } else
-                return;
+            if (HD(h[R]) < HD(h[L])) {
+                if (HD(h[I]) < HD(h[L])) { uint32_t t = h[I]; h[I] = h[L]; h[L] = t; sift_from_root<K, L, N>(h); }
+            } else {
+                if (HD(h[I]) < HD(h[R])) { uint32_t t = h[I]; h[I] = h[R]; h[R] = t; sift_from_root<K, R, N>(h); }
+            }
         }
     }
 }
-__device__ __forceinline__ void heap_push(Heap& h, int dist, int idx) {
-    if (h.n >= h.cap) {
-        if (dist < hdist(h.a[0])) {
-            unsigned long long t = h.a[0];
-            h.a[0] = h.a[h.n - 1];
-            h.a[h.n - 1] = t;
-            h.n--;
-            if (h.n > 1) heap_sift_from_root(h);
-        } else
-            return;
+template <int K, int I>
+__device__ __forceinline__ void sift_to_root(uint32_t (&h)[K]) {  // reference name: down()
+    if constexpr (I > 0) {
+        constexpr int P = (I - 1) / 2;
+        if (HD(h[P]) < HD(h[I])) { uint32_t t = h[I]; h[I] = h[P]; h[P] = t; sift_to_root<K, P>(h); }
     }
-    h.a[h.n] = ((unsigned long long)(unsigned)dist << 32) | (unsigned)idx;
-    if (h.n > 0) heap_sift_to_root(h, h.n);
-    h.n++;
+}
+// push while the set is not full: n in [0, K)
+template <int K, int N>
+__device__ __forceinline__ void push_fill(uint32_t (&h)[K], int n, uint32_t v) {
+    if constexpr (N < K) {
+        if (n == N) { h[N] = v; sift_to_root<K, N>(h); }
+        else push_fill<K, N + 1>(h, n, v);
+    }
+}
+// push on a full set, caller has checked dist < HD(h[0])
+template <int K>
+__device__ __forceinline__ void push_full(uint32_t (&h)[K], uint32_t v) {
+    uint32_t t = h[0]; h[0] = h[K - 1]; h[K - 1] = t;    // swap(0, size-1); size--
+    if constexpr (K - 1 > 1) sift_from_root<K, 0, K - 1>(h);
+    h[K - 1] = v;                                          // append at the freed slot
+    sift_to_root<K, K - 1>(h);
 }
 
+template <int K>
 __global__ void __launch_bounds__(KNN_WARPS * 32)
-hamming_knn_kernel(const uint4* __restrict__ q, int nq, const uint4* __restrict__ t, int nt, int k, int order,
+hamming_knn_kernel(const uint4* __restrict__ q, int nq, const uint4* __restrict__ t, int nt, int order,
                    int32_t* __restrict__ out_idx, int32_t* __restrict__ out_dist) {
     __shared__ __align__(128) uint4 tile[KNN_STAGES][KNN_TILE_ROWS * 2];
     __shared__ __align__(8) uint64_t full[KNN_STAGES];
-    __shared__ unsigned long long heaps[KNN_QPB][UCO_KNN_MAX_K];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ntiles = (nt + KNN_TILE_ROWS - 1) / KNN_TILE_ROWS;
@@ -142,57 +119,51 @@ hamming_knn_kernel(const uint4* __restrict__ q, int nq, const uint4* __restrict_
         }
     }
 
-    // the two queries of this warp; lanes with (lane>>2)&1 read the second 16-byte half of their train row first
+    // this warp's query; lanes with (lane>>2)&1 read the second 16-byte half of their train row first
     // (bank-conflict-free LDS.128 on 32-byte rows), so their query halves are swapped to match.
-    const int q0 = (blockIdx.x * KNN_WARPS + warp) * KNN_QPW;
+    const int qi = blockIdx.x * KNN_WARPS + warp;
     const int swap = (lane >> 2) & 1;
-    uint4 qa[KNN_QPW], qb[KNN_QPW];
-    Heap h[KNN_QPW];
-    int worst[KNN_QPW];
-#pragma unroll
-    for (int j = 0; j < KNN_QPW; j++) {
-        int qi = min(q0 + j, nq - 1);
-        uint4 lo = q[(size_t)qi * 2], hi = q[(size_t)qi * 2 + 1];
-        qa[j] = swap ? hi : lo;
-        qb[j] = swap ? lo : hi;
-        h[j].a = heaps[warp * KNN_QPW + j];
-        h[j].n = 0;
-        h[j].cap = k;
-        worst[j] = INT_MAX;  // heap not full: everything enters
+    uint4 qa, qb;
+    {
+        int qq = min(qi, nq - 1);
+        uint4 lo = q[(size_t)qq * 2], hi = q[(size_t)qq * 2 + 1];
+        qa = swap ? hi : lo;
+        qb = swap ? lo : hi;
     }
+    uint32_t h[K];
+#pragma unroll
+    for (int i = 0; i < K; i++) h[i] = 0;
+    int n = 0;
+    int worst = INT_MAX;  // set not full: everything enters
 
     for (int tl = 0; tl < ntiles; tl++) {
         const int s = tl % KNN_STAGES;
         mbar_wait(&full[s], (tl / KNN_STAGES) & 1);
         const int rows = min(KNN_TILE_ROWS, nt - tl * KNN_TILE_ROWS);
         const uint4* tp = tile[s];
+#pragma unroll 2
         for (int c = 0; c < rows; c += 32) {
             const int r = c + lane;
             const bool valid = r < rows;
             const int rr = valid ? r : 0;
             uint4 ta = tp[rr * 2 + swap], tb = tp[rr * 2 + (swap ^ 1)];
-            int d[KNN_QPW];
-#pragma unroll
-            for (int j = 0; j < KNN_QPW; j++) {
-                d[j] = __popc(ta.x ^ qa[j].x) + __popc(ta.y ^ qa[j].y) + __popc(ta.z ^ qa[j].z) + __popc(ta.w ^ qa[j].w) +
-                       __popc(tb.x ^ qb[j].x) + __popc(tb.y ^ qb[j].y) + __popc(tb.z ^ qb[j].z) + __popc(tb.w ^ qb[j].w);
-            }
+            int d = __popc(ta.x ^ qa.x) + __popc(ta.y ^ qa.y) + __popc(ta.z ^ qa.z) + __popc(ta.w ^ qa.w) +
+                    __popc(tb.x ^ qb.x) + __popc(tb.y ^ qb.y) + __popc(tb.z ^ qb.z) + __popc(tb.w ^ qb.w);
             const int base = tl * KNN_TILE_ROWS + c;
-#pragma unroll
-            for (int j = 0; j < KNN_QPW; j++) {
-                unsigned m = __ballot_sync(0xffffffffu, valid && d[j] < worst[j]);
-                while (m) {
-                    int b = __ffs(m) - 1;
-                    m &= m - 1;
-                    int db = __shfl_sync(0xffffffffu, d[j], b);
-                    if (db < worst[j]) {  // worst only shrinks: re-test against the current value (warp-uniform)
-                        if (lane == 0) {
-                            heap_push(h[j], db, base + b);
-                            // once full, the reference tests  val.dist < distances[0]
-                            worst[j] = (h[j].n >= h[j].cap) ? hdist(h[j].a[0]) : INT_MAX;
-                        }
-                        worst[j] = __shfl_sync(0xffffffffu, worst[j], 0);
+            unsigned m = __ballot_sync(0xffffffffu, valid && d < worst);
+            while (m) {  // candidates in train-index order, exactly the order of the reference's scalar loop
+                int b = __ffs(m) - 1;
+                m &= m - 1;
+                int db = __shfl_sync(0xffffffffu, d, b);
+                if (db < worst) {  // worst only shrinks: re-test against the current value (warp-uniform)
+                    uint32_t v = ((uint32_t)db << 23) | (uint32_t)(base + b);
+                    if (n < K) {
+                        push_fill<K, 0>(h, n, v);
+                        n++;
+                    } else {
+                        push_full<K>(h, v);
                     }
+                    if (n >= K) worst = (int)HD(h[0]);  // once full the reference tests val.dist < distances[0]
                 }
             }
         }
@@ -206,33 +177,48 @@ hamming_knn_kernel(const uint4* __restrict__ q, int nq, const uint4* __restrict_
     }
 
     // write back: heap array order, -1 / 0 padding (linear.h:82-85: int32 quiet_NaN() == 0), optional exchange sort
-    if (lane == 0) {
+    if (qi >= nq) return;
+    int od[K], oi[K];
 #pragma unroll
-        for (int j = 0; j < KNN_QPW; j++) {
-            const int qi = q0 + j;
-            if (qi >= nq) continue;
-            unsigned long long* a = h[j].a;
-            for (int i = h[j].n; i < k; i++) a[i] = 0x00000000ffffffffull;  // dist 0, idx -1
-            if (order == UCO_KNN_SORTED) {                                   // index.h:119-133
-                for (int i = 0; i < k - 1; i++) {
-                    if ((int)(unsigned)a[i] != -1) {
-                        for (int jj = i + 1; jj < k; jj++) {
-                            if (hdist(a[i]) > hdist(a[jj])) {
-                                unsigned long long tmp = a[i];
-                                a[i] = a[jj];
-                                a[jj] = tmp;
-                            }
-                        }
-                    }
+    for (int i = 0; i < K; i++) {
+        od[i] = i < n ? (int)HD(h[i]) : 0;
+        oi[i] = i < n ? (int)(h[i] & 0x7fffffu) : -1;
+    }
+    if (order == UCO_KNN_SORTED) {  // index.h:119-133
+#pragma unroll
+        for (int i = 0; i < K - 1; i++) {
+#pragma unroll
+            for (int j = i + 1; j < K; j++) {
+                if (oi[i] != -1 && od[i] > od[j]) {
+                    int tmp = od[i]; od[i] = od[j]; od[j] = tmp;
+                    tmp = oi[i]; oi[i] = oi[j]; oi[j] = tmp;
                 }
-            }
-            for (int i = 0; i < k; i++) {
-                out_idx[(size_t)qi * k + i] = (int)(unsigned)a[i];
-                out_dist[(size_t)qi * k + i] = hdist(a[i]);
             }
         }
     }
+    // every lane holds the row; lanes 0..K-1 each store one element (coalesced)
+    int vd = 0, vi = 0;
+#pragma unroll
+    for (int i = 0; i < K; i++)
+        if (lane == i) { vd = od[i]; vi = oi[i]; }
+    if (lane < K) {
+        out_idx[(size_t)qi * K + lane] = vi;
+        out_dist[(size_t)qi * K + lane] = vd;
+    }
 }
+
+typedef void (*knn_fn)(const uint4*, int, const uint4*, int, int, int32_t*, int32_t*);
+template <int K>
+struct KnnTable {
+    static void fill(knn_fn* f) {
+        f[K] = hamming_knn_kernel<K>;
+        KnnTable<K - 1>::fill(f);
+    }
+};
+template <>
+struct KnnTable<0> {
+    static void fill(knn_fn*) {}
+};
 
 }  // namespace
 
@@ -246,9 +232,17 @@ extern "C" int uco_b200_hamming_knn_dev(uco_b200_ctx* ctx, const uint8_t* q_dev,
         return uco_fail(ctx, UCO_E_INVALID, "hamming_knn: null pointer");
     if (((uintptr_t)q_dev | (uintptr_t)t_dev) & 15)
         return uco_fail(ctx, UCO_E_INVALID, "hamming_knn: descriptor buffers must be 16-byte aligned");
-    int grid = (nq + KNN_QPB - 1) / KNN_QPB;
-    hamming_knn_kernel<<<grid, KNN_WARPS * 32, 0, ctx->stream>>>((const uint4*)q_dev, nq, (const uint4*)t_dev, nt, k,
-                                                                order, idx_dev, dist_dev);
+    if (nt >= (1 << 23))
+        return uco_fail(ctx, UCO_E_INVALID, "hamming_knn: train set above %d rows, shard it", (1 << 23) - 1);
+    static knn_fn table[UCO_KNN_MAX_K + 1];
+    static bool init = false;
+    if (!init) {
+        KnnTable<UCO_KNN_MAX_K>::fill(table);
+        init = true;
+    }
+    int grid = (nq + KNN_WARPS - 1) / KNN_WARPS;
+    table[k]<<<grid, KNN_WARPS * 32, 0, ctx->stream>>>((const uint4*)q_dev, nq, (const uint4*)t_dev, nt, order, idx_dev,
+                                                       dist_dev);
     UCO_LAUNCH_CHECK(ctx);
     return UCO_OK;
 }
