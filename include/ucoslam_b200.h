@@ -77,6 +77,60 @@ int uco_b200_hamming_knn(uco_b200_ctx* ctx, const uint8_t* q, int nq, size_t q_s
 int uco_b200_hamming_knn_dev(uco_b200_ctx* ctx, const uint8_t* q_dev, int nq, const uint8_t* t_dev, int nt, int k,
                              int order, int32_t* idx_dev, int32_t* dist_dev);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * K1-K6  ORB pyramid extractor
+ *   replaces ucoslam::ORBextractor::detectAndCompute_impl -> compute()
+ *     src/featureextractors/ORBextractor.cpp:1139-1149, 1247-1351   (and everything it calls, see csrc/orb.cu)
+ *   behind the plugin interface ucoslam::Feature2DSerializable
+ *     src/featureextractors/feature2dserializable.h:30-95  (FeatParams :34-61 -> uco_orb_params)
+ *   Output is what the reference returns: keypoints in cv::KeyPoint memory layout (28 bytes), level-major, and
+ *   N x 32 descriptor bytes; bit-exact against the CPU path (OpenCV 4.13 without IPP, libstdc++ 13, glibc libm).
+ * ---------------------------------------------------------------------------------------------------------- */
+#define UCO_ORB_MAX_LEVELS 16
+
+typedef struct uco_keypoint { /* == cv::KeyPoint */
+    float x, y;     /* pt, level-0 coordinates */
+    float size;     /* (int)(31 * scale[octave]) */
+    float angle;    /* degrees, [0,360) */
+    float response; /* FAST score */
+    int32_t octave;
+    int32_t class_id; /* -1 */
+} uco_keypoint;
+
+typedef struct uco_orb_params {
+    int32_t max_features;  /* FeatParams::maxFeatures */
+    int32_t n_levels;      /* FeatParams::nOctaveLevels */
+    float scale_factor;    /* FeatParams::scaleFactor */
+    int32_t ini_th_fast;   /* 20, ORBextractor.cpp:478 */
+    int32_t min_th_fast;   /* 7,  ORBextractor.cpp:479 */
+    int32_t blur_first;    /* ORBextractor::_doGaussianBlurAtFirst (default true) */
+} uco_orb_params;
+
+void uco_b200_orb_default_params(uco_orb_params* p);
+
+/* one frame: img is a host CV_8UC1 image (rows `stride` bytes apart). kps/desc hold `capacity` >= max_features entries. */
+int uco_b200_orb_extract(uco_b200_ctx* ctx, const uint8_t* img, int w, int h, size_t stride, const uco_orb_params* prm,
+                         uco_keypoint* kps, uint8_t* desc, int capacity, int* n_out);
+/* n_imgs frames of identical size in one pass (the throughput path): frame i writes kps[i*capacity ..], desc[i*capacity*32 ..],
+ * n_out[i]. */
+int uco_b200_orb_extract_batch(uco_b200_ctx* ctx, const uint8_t* const* imgs, int n_imgs, int w, int h, size_t stride,
+                               const uco_orb_params* prm, uco_keypoint* kps, uint8_t* desc, int capacity, int* n_out);
+/* device-resident, asynchronous: frames at imgs_dev + i*frame_stride, rows `pitch` bytes apart; outputs are device buffers of
+ * n_imgs * max_features entries (kps, desc) and n_imgs ints. */
+int uco_b200_orb_extract_batch_dev(uco_b200_ctx* ctx, const uint8_t* imgs_dev, int n_imgs, int w, int h, size_t pitch,
+                                   size_t frame_stride, const uco_orb_params* prm, uco_keypoint* kps_dev,
+                                   uint8_t* desc_dev, int* n_out_dev);
+
+/* inspection hooks for the per-stage parity tests (state of the last extract call on this context) */
+int uco_b200_orb_debug_level_info(uco_b200_ctx* ctx, int level, int* w, int* h, int* pitch, int* n_desired, int* rows,
+                                  int* cols);
+int uco_b200_orb_debug_pyramid(uco_b200_ctx* ctx, int frame, int level, uint8_t* out);
+int uco_b200_orb_debug_selected(uco_b200_ctx* ctx, int frame, int level, uint32_t* out, int cap, int* n);
+/* host-compiled copies of the exact-arithmetic device helpers (no GPU needed): what = 0 fastAtan2(in0=y, in1=x) -> out0;
+ * what = 1 sinf/cosf(in0) -> out0 = sin, out1 = cos.  retain_best: packed score<<24|y<<12|x, returns new count. */
+int uco_b200_probe_math(int what, const float* in0, const float* in1, int n, float* out0, float* out1);
+int uco_b200_probe_retain_best(uint32_t* packed, int count, int n_points);
+
 #ifdef __cplusplus
 }
 #endif

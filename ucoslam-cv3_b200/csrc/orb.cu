@@ -1,3 +1,881 @@
-// orb.cu — ORB pyramid extractor kernels (K1-K6).  Filled in below.
+// orb.cu — K1..K6: the ORB pyramid extractor of the reference, device resident end to end.
+//
+// Replaces ORBextractor::compute and everything below it (reference, relative to /root/reference):
+//   src/featureextractors/ORBextractor.cpp:1247-1351  compute(): blur, pyramid, per-level keypoints + descriptors, concatenate
+//   :1355-1392  ComputePyramid   (cv::resize INTER_CUBIC chain + copyMakeBorder REFLECT_101, 19 px)
+//   :899-1076   ComputeKeyPoints_thread (grid cells, cv::FAST th 20 / fallback 7, quota redistribution, retainBest)
+//   :79-106     IC_Angle,  :113-153 computeOrbDescriptor,  :1120-1137 computeDescriptors,  :1229 coordinate rescale
+// and the OpenCV primitives those call (GaussianBlur 8U fixed point, resize INTER_CUBIC 8U, FAST-9/16 score + 3x3 NMS,
+// KeyPointsFilter::retainBest, fastAtan2, cvRound), restated bit-exactly (see DESIGN.md "ORB: arithmetic contracts").
+//
+// Data layout in HBM (per context, sized for a batch of frames):
+//   pyramid : per frame one block holding all levels; each level is a (h+38) x pitch u8 image with the 19-px reflected
+//             border already filled (pitch = w+38 rounded up to 64 B), so FAST / orientation / rBRIEF never branch on edges
+//   cand    : per frame, per grid cell a slot of packed candidates  score<<24 | y<<12 | x  in row-major scan order
+//   sel     : per frame, per level the selected keypoints in the reference's final order
+//   out     : per frame max_features x 28-B cv::KeyPoint + max_features x 32-B descriptors, level-major
+// Kernels (one launch each per batch, grid.z / grid.y = frame): blur7 -> 7 x resize_cubic -> fast_cells -> select ->
+// orient_describe.  No host round trip: the selection that the reference does with std::nth_element runs on the
+// device as an exact replay (select_exact.h).
 #include "common.cuh"
-void uco_orb_state_free(uco_b200_ctx*) {}
+#include "orb_math.h"
+#include "orb_pattern.h"
+#include "select_exact.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#define ORB_E 19            // EDGE_THRESHOLD
+#define ORB_MAXL UCO_ORB_MAX_LEVELS
+#define ORB_MAX_CELLS_PER_LEVEL 1024
+
+namespace {
+
+struct LevelDev {
+    int w, h, pitch;        // level image size, bordered-buffer pitch
+    unsigned off;           // byte offset of the bordered buffer inside a frame's pyramid block
+    int n_desired;
+    int rows, cols, nf_cell, n_cells, cell_begin;
+    int sel_off, sel_cap;   // offset (entries) / capacity of this level's selected list inside a frame's sel block
+    float scale;            // mvScaleFactor[level]
+    int patch;              // (int)(PATCH_SIZE * scale)
+    int vec_limit;          // x < vec_limit takes OpenCV's float SIMD path in the vertical resize pass
+    int tab_x, tab_y;       // offsets into the resize tables (level >= 1)
+};
+struct CellDev {
+    short level, valid;
+    short x0, y0, w, h;     // cv::FAST ROI in level coordinates (iniX, iniY, hX, hY)
+    int cand_off, cand_cap; // slot inside a frame's candidate block (entries)
+};
+struct PlanDev {
+    int n_levels, n_cells_total, max_features, ini_th, min_th;
+    unsigned frame_bytes;   // pyramid block per frame
+    int cand_per_frame, sel_per_frame;
+    LevelDev lv[ORB_MAXL];
+};
+
+__constant__ int8_t c_pattern[UCO_ORB_NPTS * 2];
+__constant__ int c_umax[16];
+
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect101(int p, int len) {  // cv::borderInterpolate(BORDER_REFLECT_101)
+    if ((unsigned)p < (unsigned)len) return p;
+    if (len == 1) return 0;
+    do {
+        if (p < 0) p = -p;
+        else p = 2 * (len - 1) - p;
+    } while ((unsigned)p >= (unsigned)len);
+    return p;
+}
+
+// store level pixel (x,y) and its reflections into the 19-px border (copyMakeBorder REFLECT_101 of the finished level)
+__device__ __forceinline__ void store_with_border(uint8_t* buf, int pitch, int w, int h, int x, int y, uint8_t v) {
+    int xs[3], ys[3], nx = 1, ny = 1;
+    xs[0] = x;
+    ys[0] = y;
+    if (x >= 1 && x <= ORB_E) xs[nx++] = -x;
+    if (x <= w - 2 && x >= w - 1 - ORB_E) xs[nx++] = 2 * (w - 1) - x;
+    if (y >= 1 && y <= ORB_E) ys[ny++] = -y;
+    if (y <= h - 2 && y >= h - 1 - ORB_E) ys[ny++] = 2 * (h - 1) - y;
+    for (int j = 0; j < ny; j++)
+        for (int i = 0; i < nx; i++) buf[(size_t)(ys[j] + ORB_E) * pitch + xs[i] + ORB_E] = v;
+}
+
+// ---- K1: 7x7 sigma=2 Gaussian blur, OpenCV 8U fixed-point path (kernel {18,34,48,56,48,34,18}/256 per axis, 8.8 after the
+// horizontal pass, 16.16 after the vertical pass, + 0.5 and truncate) -> level 0 with border ------------------------------
+#define BL_TW 64
+#define BL_TH 16
+__global__ void __launch_bounds__(256) blur7_kernel(const __grid_constant__ PlanDev c_plan, const uint8_t* __restrict__ in, size_t in_pitch, size_t in_frame,
+                                                    uint8_t* __restrict__ pyr, int do_blur) {
+    const LevelDev& L = c_plan.lv[0];
+    const int w = L.w, h = L.h;
+    const uint8_t* src = in + (size_t)blockIdx.z * in_frame;
+    uint8_t* dst = pyr + (size_t)blockIdx.z * c_plan.frame_bytes + L.off;
+    const int x0 = blockIdx.x * BL_TW, y0 = blockIdx.y * BL_TH;
+    __shared__ uint8_t tin[BL_TH + 6][BL_TW + 8];
+    __shared__ uint16_t hb[BL_TH + 6][BL_TW];
+    for (int i = threadIdx.x; i < (BL_TH + 6) * (BL_TW + 6); i += 256) {
+        int r = i / (BL_TW + 6), c = i % (BL_TW + 6);
+        int yy = reflect101(y0 + r - 3, h), xx = reflect101(x0 + c - 3, w);
+        tin[r][c] = src[(size_t)yy * in_pitch + xx];
+    }
+    __syncthreads();
+    if (!do_blur) {
+        for (int i = threadIdx.x; i < BL_TH * BL_TW; i += 256) {
+            int r = i / BL_TW, c = i % BL_TW;
+            if (x0 + c < w && y0 + r < h) store_with_border(dst, L.pitch, w, h, x0 + c, y0 + r, tin[r + 3][c + 3]);
+        }
+        return;
+    }
+    for (int i = threadIdx.x; i < (BL_TH + 6) * BL_TW; i += 256) {
+        int r = i / BL_TW, c = i % BL_TW;
+        const uint8_t* p = &tin[r][c];
+        hb[r][c] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < BL_TH * BL_TW; i += 256) {
+        int r = i / BL_TW, c = i % BL_TW;
+        if (x0 + c < w && y0 + r < h) {
+            unsigned v = 18u * (hb[r][c] + hb[r + 6][c]) + 34u * (hb[r + 1][c] + hb[r + 5][c]) +
+                         48u * (hb[r + 2][c] + hb[r + 4][c]) + 56u * hb[r + 3][c];
+            store_with_border(dst, L.pitch, w, h, x0 + c, y0 + r, (uint8_t)((v + 32768u) >> 16));
+        }
+    }
+}
+
+// ---- K2: cv::resize INTER_CUBIC, 8U: integer horizontal pass (11-bit coefficients), vertical pass in float for
+// x < vec_limit (OpenCV's SSE VResizeCubicVec_32s8u) and in 22-bit fixed point for the row tail ---------------------------
+__global__ void __launch_bounds__(256) resize_cubic_kernel(const __grid_constant__ PlanDev c_plan, uint8_t* __restrict__ pyr, int level,
+                                                           const int* __restrict__ tab_ofs,
+                                                           const short4* __restrict__ tab_coef) {
+    const LevelDev& D = c_plan.lv[level];
+    const LevelDev& S = c_plan.lv[level - 1];
+    const int dx = blockIdx.x * 32 + threadIdx.x, dy = blockIdx.y * 8 + threadIdx.y;
+    if (dx >= D.w || dy >= D.h) return;
+    uint8_t* frame = pyr + (size_t)blockIdx.z * c_plan.frame_bytes;
+    const uint8_t* src = frame + S.off + (size_t)ORB_E * S.pitch + ORB_E;
+    const int sx = tab_ofs[D.tab_x + dx], sy = tab_ofs[D.tab_y + dy];
+    const short4 a = tab_coef[D.tab_x + dx], b = tab_coef[D.tab_y + dy];
+    const int c0 = min(max(sx - 1, 0), S.w - 1), c1 = min(max(sx, 0), S.w - 1), c2 = min(max(sx + 1, 0), S.w - 1),
+              c3 = min(max(sx + 2, 0), S.w - 1);
+    int Sr[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint8_t* p = src + (size_t)min(max(sy - 1 + k, 0), S.h - 1) * S.pitch;
+        Sr[k] = p[c0] * a.x + p[c1] * a.y + p[c2] * a.z + p[c3] * a.w;
+    }
+    int v;
+    if (dx < D.vec_limit) {
+        const float scale = 1.f / (2048.f * 2048.f);
+        float b0 = __fmul_rn((float)b.x, scale), b1 = __fmul_rn((float)b.y, scale), b2 = __fmul_rn((float)b.z, scale),
+              b3 = __fmul_rn((float)b.w, scale);
+        float t = __fmul_rn((float)Sr[3], b3);
+        t = __fadd_rn(__fmul_rn((float)Sr[2], b2), t);
+        t = __fadd_rn(__fmul_rn((float)Sr[1], b1), t);
+        t = __fadd_rn(__fmul_rn((float)Sr[0], b0), t);
+        v = __float2int_rn(t);
+    } else {
+        int acc = Sr[0] * b.x + Sr[1] * b.y + Sr[2] * b.z + Sr[3] * b.w;
+        v = (acc + (1 << 21)) >> 22;
+    }
+    v = min(max(v, 0), 255);
+    store_with_border(frame + D.off, D.pitch, D.w, D.h, dx, dy, (uint8_t)v);
+}
+
+// ---- K3 + K4a: FAST-9/16 corner score on each grid cell's interior + 3x3 non-maximum suppression clipped to the cell
+// (cv::FAST is called per cell ROI, ORBextractor.cpp:976-986, so neighbours in the adjacent cell never suppress) + ordered
+// compaction (row-major, the order cv::FAST emits) --------------------------------------------------------------------------
+__device__ __forceinline__ int fast_score(const uint8_t* p, int pitch, int th) {
+    // ring offsets of the 16-pixel Bresenham circle, starting at (0,3) going clockwise as OpenCV's makeOffsets
+    const int v = p[0];
+    int d[16];
+    d[0] = v - p[3 * pitch];
+    d[1] = v - p[3 * pitch + 1];
+    d[2] = v - p[2 * pitch + 2];
+    d[3] = v - p[pitch + 3];
+    d[4] = v - p[3];
+    d[5] = v - p[-pitch + 3];
+    d[6] = v - p[-2 * pitch + 2];
+    d[7] = v - p[-3 * pitch + 1];
+    d[8] = v - p[-3 * pitch];
+    d[9] = v - p[-3 * pitch - 1];
+    d[10] = v - p[-2 * pitch - 2];
+    d[11] = v - p[-pitch - 3];
+    d[12] = v - p[-3];
+    d[13] = v - p[pitch - 3];
+    d[14] = v - p[2 * pitch - 2];
+    d[15] = v - p[3 * pitch - 1];
+    unsigned dark = 0, bright = 0;  // ring pixel darker than v - th  /  brighter than v + th
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        dark |= (unsigned)(d[k] > th) << k;
+        bright |= (unsigned)(d[k] < -th) << k;
+    }
+    // 9 contiguous (circular) set bits?
+    unsigned md = dark | (dark << 16), mb = bright | (bright << 16);
+    unsigned rd = md & (md >> 1);
+    rd &= rd >> 2;
+    rd &= rd >> 4;
+    rd &= md >> 8;
+    unsigned rb = mb & (mb >> 1);
+    rb &= rb >> 2;
+    rb &= rb >> 4;
+    rb &= mb >> 8;
+    if (((rd | rb) & 0xffffu) == 0) return 0;
+    // score = max over the 16 arcs of 9 of min(d) and of min(-d), minus 1 (cv cornerScore<16>)
+    int best = th;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        int mn = d[k], mx = d[k];
+#pragma unroll
+        for (int j = 1; j < 9; j++) {
+            int e = d[(k + j) & 15];
+            mn = min(mn, e);
+            mx = max(mx, e);
+        }
+        best = max(best, max(mn, -mx));
+    }
+    return best - 1;
+}
+
+__global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__ PlanDev c_plan, const uint8_t* __restrict__ pyr, const CellDev* __restrict__ cells,
+                                                         uint32_t* __restrict__ cand, int* __restrict__ cand_cnt) {
+    extern __shared__ uint8_t smem[];
+    const int ci = blockIdx.x, f = blockIdx.y;
+    const CellDev C = cells[ci];
+    int* cnt = cand_cnt + ((size_t)f * c_plan.n_cells_total + ci) * 2;
+    const int iw = C.w - 6, ih = C.h - 6;
+    if (!C.valid || iw <= 0 || ih <= 0) {
+        if (threadIdx.x == 0) cnt[0] = cnt[1] = 0;
+        return;
+    }
+    const LevelDev& L = c_plan.lv[C.level];
+    const uint8_t* src = pyr + (size_t)f * c_plan.frame_bytes + L.off + (size_t)(C.y0 + ORB_E) * L.pitch + C.x0 + ORB_E;
+    const int rp = (C.w + 3) & ~3;                 // ROI pitch in shared memory
+    uint8_t* roi = smem;                            // C.h x rp
+    uint8_t* sc = smem + (size_t)rp * C.h;          // ih x iw scores
+    for (int i = threadIdx.x; i < C.h * C.w; i += 256) {
+        int r = i / C.w, c = i - r * C.w;
+        roi[r * rp + c] = src[(size_t)r * L.pitch + c];
+    }
+    __syncthreads();
+    const int min_th = c_plan.min_th, ini_th = c_plan.ini_th;
+    for (int i = threadIdx.x; i < iw * ih; i += 256) {
+        int r = i / iw, c = i - r * iw;
+        sc[i] = (uint8_t)fast_score(roi + (r + 3) * rp + c + 3, rp, min_th);
+    }
+    __syncthreads();
+    __shared__ int wsum[8];
+    __shared__ int running, running_ini;
+    if (threadIdx.x == 0) running = running_ini = 0;
+    __syncthreads();
+    uint32_t* out = cand + (size_t)f * c_plan.cand_per_frame + C.cand_off;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < iw * ih; base += 256) {
+        int i = base + threadIdx.x;
+        int s = 0, r = 0, c = 0;
+        bool keep = false;
+        if (i < iw * ih) {
+            r = i / iw;
+            c = i - r * iw;
+            s = sc[i];
+            if (s >= min_th) {
+                keep = true;
+#pragma unroll
+                for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+                    for (int dx = -1; dx <= 1; dx++) {
+                        if (dx == 0 && dy == 0) continue;
+                        int rr = r + dy, cc = c + dx;
+                        int nb = (rr >= 0 && rr < ih && cc >= 0 && cc < iw) ? sc[rr * iw + cc] : 0;
+                        keep = keep && (s > nb);
+                    }
+            }
+        }
+        unsigned m = __ballot_sync(0xffffffffu, keep);
+        unsigned mi = __ballot_sync(0xffffffffu, keep && s >= ini_th);
+        if (lane == 0) wsum[warp] = __popc(m) | (__popc(mi) << 16);
+        __syncthreads();
+        int before = running, tot = 0, tot_ini = 0;
+        for (int k = 0; k < 8; k++) {
+            int ws = wsum[k];
+            if (k < warp) before += ws & 0xffff;
+            tot += ws & 0xffff;
+            tot_ini += ws >> 16;
+        }
+        if (keep) {
+            int pos = before + __popc(m & ((1u << lane) - 1));
+            if (pos < C.cand_cap) out[pos] = ((uint32_t)s << 24) | ((uint32_t)(C.y0 + 3 + r) << 12) | (uint32_t)(C.x0 + 3 + c);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            running += tot;
+            running_ini += tot_ini;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        cnt[0] = min(running, C.cand_cap);
+        cnt[1] = running_ini;
+    }
+}
+
+// ---- K4b: per (frame, level) keypoint selection: threshold fallback, quota redistribution, per-cell retainBest, level-wide
+// retainBest — ComputeKeyPoints_thread, ORBextractor.cpp:980-1073, replayed exactly ------------------------------------------
+__global__ void __launch_bounds__(256) select_kernel(const __grid_constant__ PlanDev c_plan, const CellDev* __restrict__ cells, uint32_t* __restrict__ cand,
+                                                     const int* __restrict__ cand_cnt, uint32_t* __restrict__ sel,
+                                                     int* __restrict__ sel_cnt, int* __restrict__ err_flag) {
+    const int level = blockIdx.x, f = blockIdx.y;
+    const LevelDev& L = c_plan.lv[level];
+    __shared__ int n_total[ORB_MAX_CELLS_PER_LEVEL];
+    __shared__ short n_retain[ORB_MAX_CELLS_PER_LEVEL];
+    __shared__ short th_used[ORB_MAX_CELLS_PER_LEVEL];
+    __shared__ int offs[ORB_MAX_CELLS_PER_LEVEL];
+    __shared__ int total_s;
+    const int nc = L.n_cells;
+    const int* cnt = cand_cnt + ((size_t)f * c_plan.n_cells_total + L.cell_begin) * 2;
+    for (int c = threadIdx.x; c < nc; c += blockDim.x) {
+        int n_all = cnt[c * 2], n_ini = cnt[c * 2 + 1];
+        bool use_min = n_ini <= 3;                       // :982-987 (second FAST call with minThFAST)
+        n_total[c] = use_min ? n_all : n_ini;
+        th_used[c] = (short)(use_min ? c_plan.min_th : c_plan.ini_th);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {                              // :988-1039, serial exactly as the reference
+        const int nf = L.nf_cell;
+        int n_no_more = 0, n_dist = 0;
+        // 0 = may take more, 1 = bNoMore.  Cells the reference skips with `continue` keep bNoMore=false, nTotal=0.
+        for (int c = 0; c < nc; c++) {
+            const CellDev& C = cells[L.cell_begin + c];
+            if (!C.valid) {
+                n_retain[c] = 0;
+                offs[c] = 0;
+                continue;
+            }
+            int nk = n_total[c];
+            if (nk > nf) {
+                n_retain[c] = (short)nf;
+                offs[c] = 0;
+            } else {
+                n_retain[c] = (short)nk;
+                n_dist += nf - nk;
+                offs[c] = 1;
+                n_no_more++;
+            }
+        }
+        while (n_dist > 0 && n_no_more < nc) {
+            int n_new = nf + (int)ceilf((float)n_dist / (float)(nc - n_no_more));
+            n_dist = 0;
+            for (int c = 0; c < nc; c++) {
+                if (!offs[c]) {
+                    if (n_total[c] > n_new) {
+                        n_retain[c] = (short)n_new;
+                    } else {
+                        n_retain[c] = (short)n_total[c];
+                        n_dist += n_new - n_total[c];
+                        offs[c] = 1;
+                        n_no_more++;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // per-cell: keep candidates with score >= the threshold in force (stable), then retainBest + truncate, in place
+    for (int c = threadIdx.x; c < nc; c += blockDim.x) {
+        const CellDev& C = cells[L.cell_begin + c];
+        uint32_t* lst = cand + (size_t)f * c_plan.cand_per_frame + C.cand_off;
+        int n_all = C.valid ? cnt[c * 2] : 0;
+        int n = 0;
+        const uint32_t th = (uint32_t)th_used[c];
+        if (th == (uint32_t)c_plan.min_th) n = n_all;
+        else
+            for (int i = 0; i < n_all; i++) {
+                uint32_t e = lst[i];
+                if ((e >> 24) >= th) lst[n++] = e;
+            }
+        n_total[c] = uco_sel::retain_best_truncate(lst, n, n_retain[c]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int c = 0; c < nc; c++) {
+            offs[c] = run;
+            run += n_total[c];
+        }
+        if (run > L.sel_cap) {
+            atomicExch(err_flag, 1);
+            run = L.sel_cap;
+        }
+        total_s = run;
+    }
+    __syncthreads();
+    uint32_t* out = sel + (size_t)f * c_plan.sel_per_frame + L.sel_off;
+    for (int c = 0; c < nc; c++) {                       // concatenation in cell (row-major) order, :1046-1066
+        const CellDev& C = cells[L.cell_begin + c];
+        const uint32_t* lst = cand + (size_t)f * c_plan.cand_per_frame + C.cand_off;
+        for (int i = threadIdx.x; i < n_total[c]; i += blockDim.x)
+            if (offs[c] + i < L.sel_cap) out[offs[c] + i] = lst[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {                              // :1069-1073
+        int n = total_s;
+        if (n > L.n_desired) n = uco_sel::retain_best_truncate(out, n, L.n_desired);
+        sel_cnt[f * ORB_MAXL + level] = n;
+    }
+}
+
+// ---- K5 + K6: intensity-centroid orientation + steered rBRIEF, one warp per keypoint ------------------------------------
+__global__ void __launch_bounds__(256) orient_describe_kernel(const __grid_constant__ PlanDev c_plan, const uint8_t* __restrict__ pyr,
+                                                              const uint32_t* __restrict__ sel,
+                                                              const int* __restrict__ sel_cnt, uco_keypoint* __restrict__ kps,
+                                                              uint8_t* __restrict__ desc, int* __restrict__ n_out,
+                                                              int capacity) {
+    __shared__ float pat[UCO_ORB_NPTS * 2];
+    for (int i = threadIdx.x; i < UCO_ORB_NPTS * 2; i += blockDim.x) pat[(i & 31) * 32 + (i >> 5)] = (float)c_pattern[i];
+    __syncthreads();
+    const int f = blockIdx.y, lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int* cnt = sel_cnt + f * ORB_MAXL;
+    int level = -1, first = 0, total = 0;
+    for (int l = 0; l < c_plan.n_levels; l++) {
+        int n = cnt[l];
+        if (level < 0 && slot < total + n) {
+            level = l;
+            first = total;
+        }
+        total += n;
+    }
+    if (slot == 0 && lane == 0) n_out[f] = min(total, capacity);
+    if (level < 0 || slot >= capacity) return;
+    const LevelDev& L = c_plan.lv[level];
+    const uint32_t e = sel[(size_t)f * c_plan.sel_per_frame + L.sel_off + (slot - first)];
+    const int x = e & 0xfff, y = (e >> 12) & 0xfff, score = e >> 24;
+    const uint8_t* center = pyr + (size_t)f * c_plan.frame_bytes + L.off + (size_t)(y + ORB_E) * L.pitch + x + ORB_E;
+    // IC_Angle: lane v+15 sums image row v of the radius-15 disc
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+        const int v = lane - 15;
+        const int d = c_umax[v < 0 ? -v : v];
+        const uint8_t* row = center + v * L.pitch;
+        int su = 0, s1 = 0;
+        for (int u = -d; u <= d; u++) {
+            int val = row[u];
+            su += u * val;
+            s1 += val;
+        }
+        m10 = su;
+        m01 = v * s1;
+    }
+    m10 = __reduce_add_sync(0xffffffffu, m10);
+    m01 = __reduce_add_sync(0xffffffffu, m01);
+    const float angle = uco_math::fast_atan2_deg((float)m01, (float)m10);
+    const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
+    float a, b;
+    uco_math::sincos_glibc(__fmul_rn(angle, factorPI), &b, &a);   // a = cos, b = sin
+    // lane computes descriptor byte `lane` (tests 8*lane .. 8*lane+7)
+    const float* pp = pat + lane;  // pat[j * 32 + lane] = coordinate j of this lane's 16 sample points
+    unsigned byte = 0;
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+        float x0 = pp[(t * 4) * 32], y0 = pp[(t * 4 + 1) * 32], x1 = pp[(t * 4 + 2) * 32], y1 = pp[(t * 4 + 3) * 32];
+        int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+        int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+        int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+        int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+        int t0 = center[r0 * L.pitch + c0], t1 = center[r1 * L.pitch + c1];
+        byte |= (unsigned)(t0 < t1) << t;
+    }
+    const size_t o = (size_t)f * capacity + slot;
+    desc[o * 32 + lane] = (uint8_t)byte;
+    if (lane == 0) {
+        uco_keypoint k;
+        float fx = (float)x, fy = (float)y;
+        if (level != 0) {  // :1229  kp.pt = (kp.pt + (0.5,0.5)) * scale
+            fx = __fmul_rn(__fadd_rn(fx, 0.5f), L.scale);
+            fy = __fmul_rn(__fadd_rn(fy, 0.5f), L.scale);
+        }
+        k.x = fx;
+        k.y = fy;
+        k.size = (float)L.patch;
+        k.angle = angle;
+        k.response = (float)score;
+        k.octave = level;
+        k.class_id = -1;
+        kps[o] = k;
+    }
+}
+
+}  // namespace
+
+// =====================================================================================================================
+// host side: plan (precalculateParams + grid geometry + resize tables), buffers, launches
+// =====================================================================================================================
+struct uco_orb_state {
+    uco_orb_params prm{};
+    int w = 0, h = 0, batch_cap = 0;
+    PlanDev plan{};
+    std::vector<CellDev> cells;
+    int max_cell_smem = 0;
+    uint8_t* d_pyr = nullptr;
+    uint8_t* d_in = nullptr;       // staging for host images
+    size_t in_pitch = 0;
+    CellDev* d_cells = nullptr;
+    int* d_tab_ofs = nullptr;
+    short4* d_tab_coef = nullptr;
+    uint32_t* d_cand = nullptr;
+    int* d_cand_cnt = nullptr;
+    uint32_t* d_sel = nullptr;
+    int* d_sel_cnt = nullptr;
+    int* d_err = nullptr;
+    uco_keypoint* d_kps = nullptr;
+    uint8_t* d_desc = nullptr;
+    int* d_nout = nullptr;
+    int* h_nout = nullptr;         // pinned
+    int* h_err = nullptr;          // pinned
+};
+
+static void orb_free_buffers(uco_orb_state* s) {
+    cudaFree(s->d_pyr); cudaFree(s->d_in); cudaFree(s->d_cells); cudaFree(s->d_tab_ofs); cudaFree(s->d_tab_coef);
+    cudaFree(s->d_cand); cudaFree(s->d_cand_cnt); cudaFree(s->d_sel); cudaFree(s->d_sel_cnt); cudaFree(s->d_err);
+    cudaFree(s->d_kps); cudaFree(s->d_desc); cudaFree(s->d_nout);
+    if (s->h_nout) cudaFreeHost(s->h_nout);
+    if (s->h_err) cudaFreeHost(s->h_err);
+    s->d_pyr = s->d_in = nullptr; s->d_cells = nullptr; s->d_tab_ofs = nullptr; s->d_tab_coef = nullptr;
+    s->d_cand = nullptr; s->d_cand_cnt = nullptr; s->d_sel = nullptr; s->d_sel_cnt = nullptr; s->d_err = nullptr;
+    s->d_kps = nullptr; s->d_desc = nullptr; s->d_nout = nullptr; s->h_nout = nullptr; s->h_err = nullptr;
+}
+
+void uco_orb_state_free(uco_b200_ctx* ctx) {
+    if (!ctx->orb) return;
+    orb_free_buffers(ctx->orb);
+    delete ctx->orb;
+    ctx->orb = nullptr;
+}
+
+static inline int cv_round_host(float v) { return (int)lrintf(v); }
+
+// cv::resize INTER_CUBIC coefficient table for one axis (OpenCV imgproc resize.cpp: interpolateCubic, A = -0.75,
+// INTER_RESIZE_COEF_SCALE = 2048, saturate_cast<short> = round half even)
+static void cubic_table(int dst, int src, std::vector<int>& ofs, std::vector<short4>& coef) {
+    const double inv_scale = (double)dst / src;
+    const double scale = 1. / inv_scale;
+    for (int d = 0; d < dst; d++) {
+        float fx = (float)((d + 0.5) * scale - 0.5);
+        int sx = (int)floorf(fx);
+        fx -= sx;
+        const float A = -0.75f;
+        float c[4];
+        c[0] = ((A * (fx + 1) - 5 * A) * (fx + 1) + 8 * A) * (fx + 1) - 4 * A;
+        c[1] = ((A + 2) * fx - (A + 3)) * fx * fx + 1;
+        c[2] = ((A + 2) * (1 - fx) - (A + 3)) * (1 - fx) * (1 - fx) + 1;
+        c[3] = 1.f - c[0] - c[1] - c[2];
+        short4 s;
+        short* sp = &s.x;
+        for (int k = 0; k < 4; k++) {
+            long r = lrintf(c[k] * 2048.f);
+            sp[k] = (short)std::min(32767L, std::max(-32768L, r));
+        }
+        ofs.push_back(sx);
+        coef.push_back(s);
+    }
+}
+
+static int orb_prepare(uco_b200_ctx* ctx, int w, int h, const uco_orb_params* prm, int batch) {
+    uco_orb_state* s = ctx->orb;
+    if (!s) s = ctx->orb = new uco_orb_state();
+    const bool same_plan = s->w == w && s->h == h && memcmp(&s->prm, prm, sizeof *prm) == 0;
+    if (same_plan && batch <= s->batch_cap) return UCO_OK;
+    if (w > 4096 || h > 4096 || w < 64 || h < 64) return uco_fail(ctx, UCO_E_INVALID, "orb: image size %dx%d unsupported", w, h);
+    if (prm->n_levels < 1 || prm->n_levels > ORB_MAXL || prm->max_features < 1 || !(prm->scale_factor > 1.f))
+        return uco_fail(ctx, UCO_E_INVALID, "orb: bad parameters");
+    UCO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    orb_free_buffers(s);
+    s->batch_cap = 0;
+    s->prm = *prm;
+    s->w = w;
+    s->h = h;
+    s->cells.clear();
+    s->max_cell_smem = 0;
+    PlanDev& P = s->plan;
+    memset(&P, 0, sizeof P);
+    const int NL = prm->n_levels;
+    P.n_levels = NL;
+    P.max_features = prm->max_features;
+    P.ini_th = prm->ini_th_fast;
+    P.min_th = prm->min_th_fast;
+    // precalculateParams, ORBextractor.cpp:466-514
+    float sf[ORB_MAXL], inv[ORB_MAXL];
+    sf[0] = 1.0f;
+    for (int i = 1; i < NL; i++) sf[i] = sf[i - 1] * prm->scale_factor;
+    for (int i = 0; i < NL; i++) inv[i] = 1.0f / sf[i];
+    {
+        float factor = 1.0f / prm->scale_factor;
+        float nd = prm->max_features * (1 - factor) / (1 - (float)pow((double)factor, (double)NL));
+        int sum = 0;
+        for (int l = 0; l < NL - 1; l++) {
+            P.lv[l].n_desired = cv_round_host(nd);
+            sum += P.lv[l].n_desired;
+            nd *= factor;
+        }
+        P.lv[NL - 1].n_desired = std::max(prm->max_features - sum, 0);
+    }
+    std::vector<int> tab_ofs;
+    std::vector<short4> tab_coef;
+    unsigned off = 0;
+    int cand_off = 0, sel_off = 0;
+    const float image_ratio = (float)w / h;
+    for (int l = 0; l < NL; l++) {
+        LevelDev& L = P.lv[l];
+        L.w = cv_round_host((float)w * inv[l]);   // ComputePyramid :1370
+        L.h = cv_round_host((float)h * inv[l]);
+        if (L.w < 2 * ORB_E + 8 || L.h < 2 * ORB_E + 8)
+            return uco_fail(ctx, UCO_E_INVALID, "orb: level %d is %dx%d, too small for the 19-px border", l, L.w, L.h);
+        L.pitch = (L.w + 2 * ORB_E + 63) & ~63;
+        L.off = off;
+        off += (unsigned)L.pitch * (L.h + 2 * ORB_E);
+        off = (off + 255u) & ~255u;
+        L.scale = sf[l];
+        L.patch = (int)(31 * sf[l]);              // const int scaledPatchSize = PATCH_SIZE*mvScaleFactor[level]
+        L.vec_limit = (L.w / 8) * 8;
+        if (l > 0) {
+            L.tab_x = (int)tab_ofs.size();
+            cubic_table(L.w, P.lv[l - 1].w, tab_ofs, tab_coef);
+            L.tab_y = (int)tab_ofs.size();
+            cubic_table(L.h, P.lv[l - 1].h, tab_ofs, tab_coef);
+        }
+        // grid geometry, ComputeKeyPoints_thread :900-976
+        const int nd = L.n_desired;
+        const int level_cols = (int)sqrtf((float)nd / (5 * image_ratio));
+        const int level_rows = (int)(image_ratio * level_cols);
+        if (level_cols <= 0 || level_rows <= 0)
+            return uco_fail(ctx, UCO_E_INVALID, "orb: level %d has an empty cell grid (max_features too small)", l);
+        if (level_cols * level_rows > ORB_MAX_CELLS_PER_LEVEL)
+            return uco_fail(ctx, UCO_E_INVALID, "orb: level %d has too many cells", l);
+        const int min_b = ORB_E, max_bx = L.w - ORB_E, max_by = L.h - ORB_E;
+        const int W = max_bx - min_b, H = max_by - min_b;
+        const int cell_w = (int)ceilf((float)W / level_cols), cell_h = (int)ceilf((float)H / level_rows);
+        L.rows = level_rows;
+        L.cols = level_cols;
+        L.n_cells = level_rows * level_cols;
+        L.nf_cell = (int)ceilf((float)nd / L.n_cells);
+        L.cell_begin = (int)s->cells.size();
+        float hY = cell_h + 6;
+        std::vector<int> ini_x(level_cols);
+        for (int i = 0; i < level_rows; i++) {
+            const float iniY = min_b + i * cell_h - 3;
+            bool row_valid = true;
+            if (i == level_rows - 1) {
+                hY = max_by + 3 - iniY;
+                if (hY <= 0) row_valid = false;
+            }
+            float hX = cell_w + 6;
+            for (int j = 0; j < level_cols; j++) {
+                CellDev C{};
+                C.level = (short)l;
+                float iniX;
+                if (i == 0) {
+                    iniX = min_b + j * cell_w - 3;
+                    ini_x[j] = (int)iniX;
+                } else
+                    iniX = ini_x[j];
+                bool valid = row_valid;
+                if (valid && j == level_cols - 1) {
+                    hX = max_bx + 3 - iniX;
+                    if (hX <= 0) valid = false;
+                }
+                if (valid && ((int)iniY + (int)hY > L.h || (int)iniX + (int)hX > L.w))
+                    return uco_fail(ctx, UCO_E_INVALID, "orb: level %d cell (%d,%d) leaves the image (the reference's "
+                                    "cv::Mat::rowRange would assert)", l, i, j);
+                C.valid = valid;
+                C.x0 = (short)iniX;
+                C.y0 = (short)iniY;
+                C.w = (short)(valid ? hX : 0);
+                C.h = (short)(valid ? hY : 0);
+                int iw = std::max(C.w - 6, 0), ih = std::max(C.h - 6, 0);
+                C.cand_off = cand_off;
+                C.cand_cap = ((iw + 1) / 2) * ((ih + 1) / 2) + 1;
+                cand_off += C.cand_cap;
+                int smem = ((C.w + 3) & ~3) * C.h + iw * ih;
+                s->max_cell_smem = std::max(s->max_cell_smem, smem);
+                s->cells.push_back(C);
+            }
+        }
+        L.sel_off = sel_off;
+        L.sel_cap = 2 * nd + 2 * L.n_cells + 64;
+        sel_off += L.sel_cap;
+    }
+    if (s->max_cell_smem > 200 * 1024)
+        return uco_fail(ctx, UCO_E_INVALID, "orb: a grid cell needs %d bytes of shared memory (max_features too small for "
+                        "this image size)", s->max_cell_smem);
+    P.frame_bytes = off;
+    P.n_cells_total = (int)s->cells.size();
+    P.cand_per_frame = cand_off;
+    P.sel_per_frame = sel_off;
+
+    const int B = std::max(batch, 1);
+    s->in_pitch = (size_t)((w + 255) & ~255);
+    UCO_CUDA(ctx, cudaMalloc(&s->d_pyr, (size_t)P.frame_bytes * B));
+    UCO_CUDA(ctx, cudaMalloc(&s->d_in, s->in_pitch * h * B));
+    UCO_CUDA(ctx, cudaMalloc(&s->d_cells, sizeof(CellDev) * s->cells.size()));
+    UCO_CUDA(ctx, cudaMalloc(&s->d_tab_ofs, sizeof(int) * std::max<size_t>(tab_ofs.size(), 1)));
+    UCO_CUDA(ctx, cudaMalloc(&s->d_tab_coef, sizeof(short4) * std::max<size_t>(tab_coef.size(), 1)));
+    UCO_CUDA(ctx, cudaMalloc(&s->d_cand, sizeof(uint32_t) * (size_t)cand_off * B));
+    UCO_CUDA(ctx, cudaMalloc(&s->d_cand_cnt, sizeof(int) * 2 * s->cells.size() * B));
+    UCO_CUDA(ctx, cudaMalloc(&s->d_sel, sizeof(uint32_t) * (size_t)sel_off * B));
+    UCO_CUDA(ctx, cudaMalloc(&s->d_sel_cnt, sizeof(int) * ORB_MAXL * B));
+    UCO_CUDA(ctx, cudaMalloc(&s->d_err, sizeof(int)));
+    UCO_CUDA(ctx, cudaMalloc(&s->d_kps, sizeof(uco_keypoint) * (size_t)prm->max_features * B));
+    UCO_CUDA(ctx, cudaMalloc(&s->d_desc, (size_t)32 * prm->max_features * B));
+    UCO_CUDA(ctx, cudaMalloc(&s->d_nout, sizeof(int) * B));
+    UCO_CUDA(ctx, cudaMallocHost(&s->h_nout, sizeof(int) * B));
+    UCO_CUDA(ctx, cudaMallocHost(&s->h_err, sizeof(int)));
+    UCO_CUDA(ctx, cudaMemsetAsync(s->d_err, 0, sizeof(int), ctx->stream));
+    UCO_CUDA(ctx, cudaMemcpyAsync(s->d_cells, s->cells.data(), sizeof(CellDev) * s->cells.size(), cudaMemcpyHostToDevice,
+                                  ctx->stream));
+    if (!tab_ofs.empty()) {
+        UCO_CUDA(ctx, cudaMemcpyAsync(s->d_tab_ofs, tab_ofs.data(), sizeof(int) * tab_ofs.size(), cudaMemcpyHostToDevice,
+                                      ctx->stream));
+        UCO_CUDA(ctx, cudaMemcpyAsync(s->d_tab_coef, tab_coef.data(), sizeof(short4) * tab_coef.size(),
+                                      cudaMemcpyHostToDevice, ctx->stream));
+    }
+    // umax table, ORBextractor.cpp:436-451
+    int umax[16];
+    {
+        const int HP = 15;
+        int v, v0, vmax = (int)floorf(HP * sqrtf(2.f) / 2 + 1);
+        int vmin = (int)ceilf(HP * sqrtf(2.f) / 2);
+        const double hp2 = HP * HP;
+        for (v = 0; v <= vmax; ++v) umax[v] = (int)lrint(sqrt(hp2 - v * v));
+        for (v = HP, v0 = 0; v >= vmin; --v) {
+            while (umax[v0] == umax[v0 + 1]) ++v0;
+            umax[v] = v0;
+            ++v0;
+        }
+    }
+    UCO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    UCO_CUDA(ctx, cudaMemcpyToSymbol(c_pattern, uco_orb_pattern_xy, sizeof uco_orb_pattern_xy));
+    UCO_CUDA(ctx, cudaMemcpyToSymbol(c_umax, umax, sizeof umax));
+    if (s->max_cell_smem > 40 * 1024)
+        UCO_CUDA(ctx, cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_cell_smem));
+    s->batch_cap = B;
+    return UCO_OK;
+}
+
+// images already on the device (d_in layout: n frames of h rows, pitch in_pitch); everything asynchronous on ctx->stream
+static int orb_run_dev(uco_b200_ctx* ctx, const uint8_t* in_dev, size_t in_pitch, size_t in_frame, int n,
+                       uco_keypoint* kps_dev, uint8_t* desc_dev, int* nout_dev) {
+    uco_orb_state* s = ctx->orb;
+    const PlanDev& P = s->plan;
+    cudaStream_t st = ctx->stream;
+    dim3 g0((P.lv[0].w + BL_TW - 1) / BL_TW, (P.lv[0].h + BL_TH - 1) / BL_TH, n);
+    blur7_kernel<<<g0, 256, 0, st>>>(P, in_dev, in_pitch, in_frame, s->d_pyr, s->prm.blur_first);
+    UCO_LAUNCH_CHECK(ctx);
+    for (int l = 1; l < P.n_levels; l++) {
+        dim3 g((P.lv[l].w + 31) / 32, (P.lv[l].h + 7) / 8, n);
+        resize_cubic_kernel<<<g, dim3(32, 8), 0, st>>>(P, s->d_pyr, l, s->d_tab_ofs, s->d_tab_coef);
+        UCO_LAUNCH_CHECK(ctx);
+    }
+    fast_cells_kernel<<<dim3(P.n_cells_total, n), 256, s->max_cell_smem, st>>>(P, s->d_pyr, s->d_cells, s->d_cand, s->d_cand_cnt);
+    UCO_LAUNCH_CHECK(ctx);
+    select_kernel<<<dim3(P.n_levels, n), 256, 0, st>>>(P, s->d_cells, s->d_cand, s->d_cand_cnt, s->d_sel, s->d_sel_cnt, s->d_err);
+    UCO_LAUNCH_CHECK(ctx);
+    orient_describe_kernel<<<dim3((P.max_features + 7) / 8, n), 256, 0, st>>>(P, s->d_pyr, s->d_sel, s->d_sel_cnt, kps_dev,
+                                                                            desc_dev, nout_dev, P.max_features);
+    UCO_LAUNCH_CHECK(ctx);
+    return UCO_OK;
+}
+
+extern "C" {
+
+void uco_b200_orb_default_params(uco_orb_params* p) {
+    p->max_features = 4000;   // ucoslamtypes.cpp:31-40 / FeatParams defaults, feature2dserializable.h:34-39
+    p->n_levels = 8;
+    p->scale_factor = 1.2f;
+    p->ini_th_fast = 20;      // ORBextractor.cpp:478-479
+    p->min_th_fast = 7;
+    p->blur_first = 1;        // ORBextractor.h: _doGaussianBlurAtFirst = true
+}
+
+int uco_b200_orb_extract_batch_dev(uco_b200_ctx* ctx, const uint8_t* imgs_dev, int n_imgs, int w, int h, size_t pitch,
+                                   size_t frame_stride, const uco_orb_params* prm, uco_keypoint* kps_dev,
+                                   uint8_t* desc_dev, int* n_out_dev) {
+    if (!ctx) return UCO_E_INVALID;
+    if (!prm || n_imgs < 0) return uco_fail(ctx, UCO_E_INVALID, "orb: bad arguments");
+    if (n_imgs == 0) return UCO_OK;
+    if (!imgs_dev || !kps_dev || !desc_dev || !n_out_dev) return uco_fail(ctx, UCO_E_INVALID, "orb: null pointer");
+    if (pitch < (size_t)w) return uco_fail(ctx, UCO_E_INVALID, "orb: pitch below width");
+    int rc = orb_prepare(ctx, w, h, prm, n_imgs);
+    if (rc != UCO_OK) return rc;
+    return orb_run_dev(ctx, imgs_dev, pitch, frame_stride, n_imgs, kps_dev, desc_dev, n_out_dev);
+}
+
+int uco_b200_orb_extract_batch(uco_b200_ctx* ctx, const uint8_t* const* imgs, int n_imgs, int w, int h, size_t stride,
+                               const uco_orb_params* prm, uco_keypoint* kps, uint8_t* desc, int capacity, int* n_out) {
+    if (!ctx) return UCO_E_INVALID;
+    if (!prm || n_imgs < 0) return uco_fail(ctx, UCO_E_INVALID, "orb: bad arguments");
+    if (n_imgs == 0) return UCO_OK;
+    if (!imgs || !kps || !desc || !n_out) return uco_fail(ctx, UCO_E_INVALID, "orb: null pointer");
+    if (stride < (size_t)w) return uco_fail(ctx, UCO_E_INVALID, "orb: stride below width");
+    if (capacity < prm->max_features)
+        return uco_fail(ctx, UCO_E_CAPACITY, "orb: output capacity %d below max_features %d", capacity, prm->max_features);
+    int rc = orb_prepare(ctx, w, h, prm, n_imgs);
+    if (rc != UCO_OK) return rc;
+    uco_orb_state* s = ctx->orb;
+    for (int i = 0; i < n_imgs; i++) {
+        if (!imgs[i]) return uco_fail(ctx, UCO_E_INVALID, "orb: null image %d", i);
+        UCO_CUDA(ctx, cudaMemcpy2DAsync(s->d_in + (size_t)i * s->in_pitch * h, s->in_pitch, imgs[i], stride, w, h,
+                                        cudaMemcpyHostToDevice, ctx->stream));
+    }
+    rc = orb_run_dev(ctx, s->d_in, s->in_pitch, s->in_pitch * h, n_imgs, s->d_kps, s->d_desc, s->d_nout);
+    if (rc != UCO_OK) return rc;
+    const int mf = prm->max_features;
+    UCO_CUDA(ctx, cudaMemcpyAsync(s->h_nout, s->d_nout, sizeof(int) * n_imgs, cudaMemcpyDeviceToHost, ctx->stream));
+    UCO_CUDA(ctx, cudaMemcpyAsync(s->h_err, s->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    UCO_CUDA(ctx, cudaMemcpy2DAsync(kps, sizeof(uco_keypoint) * (size_t)capacity, s->d_kps, sizeof(uco_keypoint) * (size_t)mf,
+                                    sizeof(uco_keypoint) * (size_t)mf, n_imgs, cudaMemcpyDeviceToHost, ctx->stream));
+    UCO_CUDA(ctx, cudaMemcpy2DAsync(desc, (size_t)32 * capacity, s->d_desc, (size_t)32 * mf, (size_t)32 * mf, n_imgs,
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+    UCO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (*s->h_err) return uco_fail(ctx, UCO_E_CAPACITY, "orb: internal selection list overflow");
+    for (int i = 0; i < n_imgs; i++) n_out[i] = s->h_nout[i];
+    return UCO_OK;
+}
+
+int uco_b200_orb_extract(uco_b200_ctx* ctx, const uint8_t* img, int w, int h, size_t stride, const uco_orb_params* prm,
+                         uco_keypoint* kps, uint8_t* desc, int capacity, int* n_out) {
+    const uint8_t* one[1] = {img};
+    return uco_b200_orb_extract_batch(ctx, one, 1, w, h, stride, prm, kps, desc, capacity, n_out);
+}
+
+// ---- test / inspection hooks (used by the per-stage parity tests) -----------------------------------------------------
+int uco_b200_orb_debug_level_info(uco_b200_ctx* ctx, int level, int* w, int* h, int* pitch, int* n_desired, int* rows, int* cols) {
+    if (!ctx || !ctx->orb || level < 0 || level >= ctx->orb->plan.n_levels) return UCO_E_INVALID;
+    const LevelDev& L = ctx->orb->plan.lv[level];
+    *w = L.w; *h = L.h; *pitch = L.pitch; *n_desired = L.n_desired; *rows = L.rows; *cols = L.cols;
+    return UCO_OK;
+}
+// copies the bordered buffer of (frame, level) of the LAST extract call: (h+38) rows of `pitch` bytes
+int uco_b200_orb_debug_pyramid(uco_b200_ctx* ctx, int frame, int level, uint8_t* out) {
+    if (!ctx || !ctx->orb || level < 0 || level >= ctx->orb->plan.n_levels || frame < 0 || frame >= ctx->orb->batch_cap)
+        return UCO_E_INVALID;
+    const PlanDev& P = ctx->orb->plan;
+    const LevelDev& L = P.lv[level];
+    UCO_CUDA(ctx, cudaMemcpyAsync(out, ctx->orb->d_pyr + (size_t)frame * P.frame_bytes + L.off,
+                                  (size_t)L.pitch * (L.h + 2 * ORB_E), cudaMemcpyDeviceToHost, ctx->stream));
+    UCO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return UCO_OK;
+}
+// selected keypoints of (frame, level) before orientation: packed score<<24 | y<<12 | x ; returns count in *n
+int uco_b200_orb_debug_selected(uco_b200_ctx* ctx, int frame, int level, uint32_t* out, int cap, int* n) {
+    if (!ctx || !ctx->orb || level < 0 || level >= ctx->orb->plan.n_levels || frame < 0 || frame >= ctx->orb->batch_cap)
+        return UCO_E_INVALID;
+    const PlanDev& P = ctx->orb->plan;
+    const LevelDev& L = P.lv[level];
+    int cnt = 0;
+    UCO_CUDA(ctx, cudaMemcpyAsync(&cnt, ctx->orb->d_sel_cnt + frame * ORB_MAXL + level, sizeof(int), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    UCO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *n = cnt;
+    if (cnt > cap) cnt = cap;
+    UCO_CUDA(ctx, cudaMemcpyAsync(out, ctx->orb->d_sel + (size_t)frame * P.sel_per_frame + L.sel_off, sizeof(uint32_t) * cnt,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    UCO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return UCO_OK;
+}
+
+// host-compiled copies of the exact-arithmetic helpers, so CPU-only tests can pin them to libm / OpenCV / libstdc++
+int uco_b200_probe_math(int what, const float* in0, const float* in1, int n, float* out0, float* out1) {
+    for (int i = 0; i < n; i++) {
+        if (what == 0) out0[i] = uco_math::fast_atan2_deg(in0[i], in1[i]);
+        else if (what == 1) uco_math::sincos_glibc(in0[i], &out0[i], &out1[i]);
+        else return UCO_E_INVALID;
+    }
+    return UCO_OK;
+}
+int uco_b200_probe_retain_best(uint32_t* packed, int count, int n_points) {
+    return uco_sel::retain_best_truncate(packed, count, n_points);
+}
+
+}  // extern "C"

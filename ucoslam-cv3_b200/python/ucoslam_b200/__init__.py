@@ -26,7 +26,48 @@ SIGNATURES = {
     "uco_b200_version": (_i, []),
     "uco_b200_hamming_knn": (_i, [_vp, _vp, _i, _sz, _vp, _i, _sz, _i, _i, _vp, _vp]),
     "uco_b200_hamming_knn_dev": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp]),
+    "uco_b200_orb_default_params": (None, [_vp]),
+    "uco_b200_orb_extract": (_i, [_vp, _vp, _i, _i, _sz, _vp, _vp, _vp, _i, _vp]),
+    "uco_b200_orb_extract_batch": (_i, [_vp, _vp, _i, _i, _i, _sz, _vp, _vp, _vp, _i, _vp]),
+    "uco_b200_orb_extract_batch_dev": (_i, [_vp, _vp, _i, _i, _i, _sz, _sz, _vp, _vp, _vp, _vp]),
+    "uco_b200_orb_debug_level_info": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "uco_b200_orb_debug_pyramid": (_i, [_vp, _i, _i, _vp]),
+    "uco_b200_orb_debug_selected": (_i, [_vp, _i, _i, _vp, _i, _vp]),
+    "uco_b200_probe_math": (_i, [_i, _vp, _vp, _i, _vp, _vp]),
+    "uco_b200_probe_retain_best": (_i, [_vp, _i, _i]),
 }
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])  # uco_keypoint == cv::KeyPoint
+
+
+class OrbParams(ctypes.Structure):
+    _fields_ = [("max_features", _c.c_int32), ("n_levels", _c.c_int32), ("scale_factor", _c.c_float),
+                ("ini_th_fast", _c.c_int32), ("min_th_fast", _c.c_int32), ("blur_first", _c.c_int32)]
+
+    def __init__(self, max_features=2000, n_levels=8, scale_factor=1.2, ini_th=20, min_th=7, blur_first=True):
+        super().__init__(max_features, n_levels, scale_factor, ini_th, min_th, int(blur_first))
+
+
+def probe_fast_atan2(y, x):
+    y = np.ascontiguousarray(y, np.float32); x = np.ascontiguousarray(x, np.float32)
+    out = np.empty_like(y)
+    assert load().uco_b200_probe_math(0, _p(y), _p(x), len(y), _p(out), None) == 0
+    return out
+
+
+def probe_sincos(a):
+    a = np.ascontiguousarray(a, np.float32)
+    s = np.empty_like(a); c = np.empty_like(a)
+    assert load().uco_b200_probe_math(1, _p(a), None, len(a), _p(s), _p(c)) == 0
+    return s, c
+
+
+def probe_retain_best(packed, n_points):
+    packed = np.ascontiguousarray(packed, np.uint32).copy()
+    n = load().uco_b200_probe_retain_best(_p(packed), len(packed), int(n_points))
+    return packed[:n]
+
 
 _lib = None
 
@@ -105,6 +146,50 @@ class Context:
         ts = t.strides[0] if nt > 0 else 32
         self._chk(self.lib.uco_b200_hamming_knn(self.h, _p(q), nq, qs, _p(t), nt, ts, k, order, _p(idx), _p(dist)))
         return idx, dist
+
+    # -- K1-K6 ---------------------------------------------------------------------------------------------------
+    def orb_extract(self, img, prm=None):
+        """img: (h,w) uint8 host image (rows may be strided). Returns (keypoints[KP_DTYPE], desc[N,32])."""
+        k, d, n = self.orb_extract_batch([img], prm)
+        return k[0][:n[0]], d[0][:n[0]]
+
+    def orb_extract_batch(self, imgs, prm=None):
+        prm = prm or OrbParams()
+        n = len(imgs)
+        h, w = imgs[0].shape
+        stride = imgs[0].strides[0]
+        for im in imgs:
+            assert im.dtype == np.uint8 and im.shape == (h, w) and im.strides == (stride, 1)
+        cap = prm.max_features
+        kps = np.zeros((n, cap), KP_DTYPE)
+        desc = np.zeros((n, cap, 32), np.uint8)
+        nout = np.zeros(n, np.int32)
+        ptrs = (ctypes.c_void_p * n)(*[im.ctypes.data for im in imgs])
+        self._chk(self.lib.uco_b200_orb_extract_batch(self.h, ctypes.cast(ptrs, _vp), n, w, h, stride,
+                                                      ctypes.addressof(prm), _p(kps), _p(desc), cap, _p(nout)))
+        return kps, desc, nout
+
+    def orb_extract_batch_dev(self, imgs_dev, n, w, h, pitch, frame_stride, prm, kps_dev, desc_dev, nout_dev):
+        self._chk(self.lib.uco_b200_orb_extract_batch_dev(self.h, imgs_dev, n, w, h, pitch, frame_stride,
+                                                          ctypes.addressof(prm), kps_dev, desc_dev, nout_dev))
+
+    def orb_level_info(self, level):
+        v = [ctypes.c_int() for _ in range(6)]
+        self._chk(self.lib.uco_b200_orb_debug_level_info(self.h, level, *[ctypes.addressof(x) for x in v]))
+        return dict(zip(["w", "h", "pitch", "n_desired", "rows", "cols"], [x.value for x in v]))
+
+    def orb_pyramid_level(self, frame, level):
+        """Bordered buffer (h+38, w+38) of a level after the last extract call."""
+        li = self.orb_level_info(level)
+        buf = np.empty((li["h"] + 38, li["pitch"]), np.uint8)
+        self._chk(self.lib.uco_b200_orb_debug_pyramid(self.h, frame, level, _p(buf)))
+        return buf[:, :li["w"] + 38]
+
+    def orb_selected(self, frame, level):
+        out = np.empty(65536, np.uint32)
+        n = ctypes.c_int()
+        self._chk(self.lib.uco_b200_orb_debug_selected(self.h, frame, level, _p(out), len(out), ctypes.addressof(n)))
+        return out[:n.value].copy()
 
     def hamming_knn_dev(self, q_dev, nq, t_dev, nt, k, order, idx_dev, dist_dev):
         """Device pointers (ints, e.g. torch.Tensor.data_ptr()); asynchronous on the context stream."""
