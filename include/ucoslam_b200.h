@@ -126,6 +126,7 @@ int uco_b200_orb_debug_level_info(uco_b200_ctx* ctx, int level, int* w, int* h, 
                                   int* cols);
 int uco_b200_orb_debug_pyramid(uco_b200_ctx* ctx, int frame, int level, uint8_t* out);
 int uco_b200_orb_debug_selected(uco_b200_ctx* ctx, int frame, int level, uint32_t* out, int cap, int* n);
+int uco_b200_orb_debug_candidates(uco_b200_ctx* ctx, int frame, int cell, uint32_t* out, int cap, int* counts, int* geom);
 /* host-compiled copies of the exact-arithmetic device helpers (no GPU needed): what = 0 fastAtan2(in0=y, in1=x) -> out0;
  * what = 1 sinf/cosf(in0) -> out0 = sin, out1 = cos.  retain_best: packed score<<24|y<<12|x, returns new count. */
 int uco_b200_probe_math(int what, const float* in0, const float* in1, int n, float* out0, float* out1);

@@ -47,7 +47,7 @@ def cv_round(x):
 
 def retain_best(kps, n_points):
     """cv::KeyPointsFilter::retainBest, executed by the real libstdc++ (stl_helper.cpp)."""
-    kps = np.ascontiguousarray(kps)
+    kps = np.array(kps, dtype=KP_DTYPE, copy=True)
     n = stl().stl_retain_best(kps.ctypes.data_as(ctypes.c_void_p), len(kps), int(n_points))
     return kps[:n].copy()
 

@@ -203,8 +203,10 @@ __device__ __forceinline__ int fast_score(const uint8_t* p, int pitch, int th) {
     rb &= rb >> 4;
     rb &= mb >> 8;
     if (((rd | rb) & 0xffffu) == 0) return 0;
-    // score = max over the 16 arcs of 9 of min(d) and of min(-d), minus 1 (cv cornerScore<16>)
-    int best = th;
+    // score = max(th, A, B) - 1 with A = max over the 16 arcs of 9 of min(d), B = max over arcs of min(-d) = -min over arcs of
+    // max(d)  (cv cornerScore<16>).  B - 1 is formed as ~x (= -x - 1): ptxas 12.9 for sm_100a was observed to fold
+    // max(a, -b) into VIMNMX3 and LOSE the negation, so no negated value is ever fed to min/max here.
+    int a_best = -256, b_worst = 256;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         int mn = d[k], mx = d[k];
@@ -214,9 +216,10 @@ __device__ __forceinline__ int fast_score(const uint8_t* p, int pitch, int th) {
             mn = min(mn, e);
             mx = max(mx, e);
         }
-        best = max(best, max(mn, -mx));
+        a_best = max(a_best, mn);
+        b_worst = min(b_worst, mx);
     }
-    return best - 1;
+    return max(max(th, a_best) - 1, ~b_worst);
 }
 
 __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__ PlanDev c_plan, const uint8_t* __restrict__ pyr, const CellDev* __restrict__ cells,
@@ -860,6 +863,24 @@ int uco_b200_orb_debug_selected(uco_b200_ctx* ctx, int frame, int level, uint32_
     *n = cnt;
     if (cnt > cap) cnt = cap;
     UCO_CUDA(ctx, cudaMemcpyAsync(out, ctx->orb->d_sel + (size_t)frame * P.sel_per_frame + L.sel_off, sizeof(uint32_t) * cnt,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    UCO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return UCO_OK;
+}
+
+// raw FAST candidates of grid cell `cell` (index over all levels, row-major inside a level) of frame `frame`, as left by the
+// LAST extract call (note: the selection stage permutes / filters these lists in place).  geom = {level,valid,x0,y0,w,h}.
+int uco_b200_orb_debug_candidates(uco_b200_ctx* ctx, int frame, int cell, uint32_t* out, int cap, int* counts, int* geom) {
+    if (!ctx || !ctx->orb || frame < 0 || frame >= ctx->orb->batch_cap || cell < 0 || cell >= ctx->orb->plan.n_cells_total)
+        return UCO_E_INVALID;
+    uco_orb_state* s = ctx->orb;
+    const CellDev& C = s->cells[cell];
+    geom[0] = C.level; geom[1] = C.valid; geom[2] = C.x0; geom[3] = C.y0; geom[4] = C.w; geom[5] = C.h;
+    UCO_CUDA(ctx, cudaMemcpyAsync(counts, s->d_cand_cnt + ((size_t)frame * s->plan.n_cells_total + cell) * 2, 2 * sizeof(int),
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    UCO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int n = std::min(std::min(counts[0], cap), C.cand_cap);
+    UCO_CUDA(ctx, cudaMemcpyAsync(out, s->d_cand + (size_t)frame * s->plan.cand_per_frame + C.cand_off, sizeof(uint32_t) * n,
                                   cudaMemcpyDeviceToHost, ctx->stream));
     UCO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return UCO_OK;

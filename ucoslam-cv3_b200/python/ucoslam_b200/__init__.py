@@ -33,6 +33,7 @@ SIGNATURES = {
     "uco_b200_orb_debug_level_info": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "uco_b200_orb_debug_pyramid": (_i, [_vp, _i, _i, _vp]),
     "uco_b200_orb_debug_selected": (_i, [_vp, _i, _i, _vp, _i, _vp]),
+    "uco_b200_orb_debug_candidates": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp]),
     "uco_b200_probe_math": (_i, [_i, _vp, _vp, _i, _vp, _vp]),
     "uco_b200_probe_retain_best": (_i, [_vp, _i, _i]),
 }
@@ -190,6 +191,13 @@ class Context:
         n = ctypes.c_int()
         self._chk(self.lib.uco_b200_orb_debug_selected(self.h, frame, level, _p(out), len(out), ctypes.addressof(n)))
         return out[:n.value].copy()
+
+    def orb_candidates(self, frame, cell):
+        out = np.empty(16384, np.uint32)
+        counts = np.zeros(2, np.int32)
+        geom = np.zeros(6, np.int32)
+        self._chk(self.lib.uco_b200_orb_debug_candidates(self.h, frame, cell, _p(out), len(out), _p(counts), _p(geom)))
+        return out[:counts[0]].copy(), counts, geom
 
     def hamming_knn_dev(self, q_dev, nq, t_dev, nt, k, order, idx_dev, dist_dev):
         """Device pointers (ints, e.g. torch.Tensor.data_ptr()); asynchronous on the context stream."""
