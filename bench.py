@@ -3,13 +3,16 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--frames F]
 
-A step is one pass of the hot path over one batch of F synthetic frames of BASELINE config 2
-(640x480 mono, 2000 ORB keypoints/frame, 8 levels, local-BA window 10 KF).  Stages implemented so far are listed in
-config.stages; every stage runs through the C ABI of libucoslam_b200.so (no CPU fallback).
-  value  : frames/s with the step's inputs already resident in HBM (device-timed with CUDA events on the context stream,
-           L2 flushed between steps, max over ranks)
-  e2e    : the same work driven through the host-buffer C-ABI calls (H2D + D2H copies inside the timed region)
-  roofline / cpu_baseline : see DESIGN.md "Measurement"
+A step is one pass of the hot path over one batch of F synthetic frames of BASELINE config 2 (640x480 mono, 2000 ORB
+keypoints/frame, 8 levels x1.2, local-BA window 10 KF): ORB extraction of every frame, Hamming k-NN (k=10) of every frame
+against its predecessor and the stages listed in config.stages.  Every stage runs through the C ABI of libucoslam_b200.so
+(no CPU fallback: the library refuses to create a context without a CUDA device).
+  value   : frames/s with the step's input frames already resident in HBM (CUDA events on the context stream, L2 flushed
+            between timed steps, max over ranks)
+  e2e     : the same work through the host-buffer C-ABI calls (pinned host frames in, keypoints/descriptors/matches out;
+            H2D and D2H copies inside the timed region)
+  roofline: the dominant kernel of the step, timed live with CUDA events on the launching stream
+  cpu_baseline / --impl reference : the CPU path on this box's host cores (see DESIGN.md "Measurement")
 Multi-GPU: frames shard across ranks (independent units, no data-path collective) -> weak scaling.
 """
 import argparse, json, os, subprocess, sys, threading, time
@@ -17,14 +20,16 @@ import argparse, json, os, subprocess, sys, threading, time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "ucoslam-cv3_b200", "python"))
 
-KPTS, K_NN = 2000, 10
+W, H, KPTS, K_NN = 640, 480, 2000, 10
+METRIC = "frames/sec (ORB+match+local-BA) 640x480 mono"
 WORKLOAD = "config2: 640x480 mono tracking, 2000 ORB kpts/frame, local-BA window=10 KF"
+STAGES = ["orb_extract", "hamming_knn_match"]
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=64, help="frames per step per GPU")
@@ -52,7 +57,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in ln.split(",")])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05)
 
     def summary(self):
         self.stop_flag = True
@@ -69,62 +74,79 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
-def synth_frames_descriptors(n_frames, seed):
-    """Seeded synthetic ORB descriptors of consecutive frames: frame f+1 re-observes frame f's features with a few
-    flipped bits."""
-    import numpy as np
+def synth_clip(n_frames, seed):
+    """Seeded synthetic clip: perspective views of a multi-octave block-noise texture along a smooth camera path
+    (SURVEY.md 8(d)); FAST-dense, so every frame yields the full 2000 keypoints."""
+    import numpy as np, cv2
     rng = np.random.default_rng(seed)
-    cur = rng.integers(0, 256, (KPTS, 32), dtype=np.uint8)
-    out = [cur]
-    for _ in range(n_frames):
-        nxt = cur[rng.permutation(KPTS)].copy()
-        flips = rng.integers(0, 256, (KPTS, 12))
-        mask = np.zeros((KPTS, 32), np.uint8)
-        for j in range(12):
-            np.bitwise_xor.at(mask, (np.arange(KPTS), flips[:, j] >> 3), (1 << (flips[:, j] & 7)).astype(np.uint8))
-        nxt ^= mask
-        out.append(nxt)
-        cur = nxt
-    return np.stack(out)  # (n_frames+1, KPTS, 32)
+    size = 2048
+    acc = np.zeros((size, size), np.float64)
+    amp = 1.0
+    for blk in (64, 32, 16, 8, 4):
+        n = size // blk
+        acc += amp * np.kron(rng.random((n, n)), np.ones((blk, blk)))
+        amp *= 0.5
+    acc -= acc.min()
+    tex = (acc / acc.max() * 255).astype(np.uint8)
+    out = np.empty((n_frames, H, W), np.uint8)
+    for i in range(n_frames):
+        t = i * 0.02
+        c, s = np.cos(0.15 * np.sin(t)), np.sin(0.15 * np.sin(t))
+        zoom = 1.6 + 0.2 * np.sin(0.7 * t)
+        Hm = np.array([[c * zoom, -s * zoom, 300 + 120 * t], [s * zoom, c * zoom, 400 + 40 * np.sin(t)],
+                       [1e-4 * np.sin(t), 5e-5, 1.0]])
+        out[i] = cv2.warpPerspective(tex, Hm, (W, H), flags=cv2.INTER_LINEAR | cv2.WARP_INVERSE_MAP,
+                                     borderMode=cv2.BORDER_REFLECT_101)
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def cpu_reference_step(frames, oracle_py, orb_oracle, have_xflann):
+    """The reference's CPU path for the same stages: ORB extraction of every frame (cv2-backed restatement of
+    ORBextractor.cpp: the reference itself cannot be linked without OpenCV C++ headers) + FrameMatcher_Flann's
+    xflann HKMeans(32,0) build + 16-check k-NN against the previous frame (the reference's own code)."""
+    prev = None
+    for f in frames:
+        k, d = orb_oracle.extract(f, KPTS)
+        if prev is not None and len(d) and len(prev):
+            if have_xflann:
+                oracle_py.ref_xflann_knn(d, prev, K_NN, 1, 16, 0)
+            else:
+                oracle_py.hamming_knn(d, prev, K_NN, 0)
+        prev = d
+
+
+def cpu_baseline_info(have_xflann, n):
+    return {"cores": 1, "kind": "port",
+            "sample": "%d frames: ORB = Python/cv2-4.13 restatement of ORBextractor.cpp (blur/resize/FAST native OpenCV, "
+                      "1 thread; interpreter overhead included), match = %s" % (
+                          n, "the reference's xflann HKMeans(32,0) build + 16-check search, 1 thread" if have_xflann
+                          else "exact linear port")}
+
+
 def run_reference(args, rank, world):
-    """The reference's own CPU implementation of the path on the host cores (rank 0 only)."""
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import numpy as np, oracle_py
-    frames = min(args.frames, 8)
-    desc = synth_frames_descriptors(frames, 1234)
-    have_ref = oracle_py.load_ref("libref_xflann.so") is not None
-
-    def one_step():
-        for f in range(frames):
-            if have_ref:   # what FrameMatcher_Flann does: build HKMeans(32,0) on the train frame, search k=10, 16 checks
-                oracle_py.ref_xflann_knn(desc[f + 1], desc[f], K_NN, 1, 16, 0)
-            else:
-                oracle_py.hamming_knn(desc[f + 1], desc[f], K_NN, 0)
-
+    import oracle_py, orb_oracle
+    n = min(args.frames, 8)
+    frames = synth_clip(n, 1234)
+    have = oracle_py.load_ref("libref_xflann.so") is not None
     for _ in range(args.warmup):
-        one_step()
+        cpu_reference_step(frames, oracle_py, orb_oracle, have)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        one_step()
+        cpu_reference_step(frames, oracle_py, orb_oracle, have)
     dt = time.perf_counter() - t0
-    fps = frames * args.steps / dt
-    kind = "reference" if have_ref else "port"
-    line = {"impl": "reference", "metric": "frames/sec (ORB+match+local-BA) 640x480 mono", "value": fps,
-            "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "stages": ["match"], "frames_per_step": frames},
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 1, "kind": kind,
-                             "sample": "%d frames/step: xflann %s k=10 per frame pair, 1 thread (the reference runs "
-                                       "xflann with threads=1)" % (frames, "HKMeans(32,0) build + 16-check search"
-                                                                   if have_ref else "exact linear port")},
-            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    fps = n * args.steps / dt
+    info = cpu_baseline_info(have, n)
+    info.update({"value": fps, "unit": "frames/s"})
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                      "config": {"workload": WORKLOAD, "stages": STAGES, "frames_per_step": n},
+                      "cpu_baseline": info,
+                      "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -139,27 +161,51 @@ def run_b200(args, rank, world, local_rank):
     ctx = ucoslam_b200.Context(local_rank)
     stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
     F = args.frames
-    desc = synth_frames_descriptors(F, 1234 + rank)
-    desc_pin = torch.from_numpy(desc).pin_memory()
+    prm = ucoslam_b200.OrbParams(KPTS)
+    clip = synth_clip(F, 1234 + rank)
+    clip_pin = torch.from_numpy(clip).pin_memory()
     with torch.cuda.stream(stream):
-        desc_dev = desc_pin.to("cuda", non_blocking=True)
+        clip_dev = clip_pin.to("cuda", non_blocking=True)
+        kps_dev = torch.zeros((F, KPTS, 28), dtype=torch.uint8, device="cuda")
+        desc_dev = torch.zeros((F, KPTS, 32), dtype=torch.uint8, device="cuda")
+        nout_dev = torch.zeros(F, dtype=torch.int32, device="cuda")
         idx_dev = torch.empty((F, KPTS, K_NN), dtype=torch.int32, device="cuda")
         dist_dev = torch.empty((F, KPTS, K_NN), dtype=torch.int32, device="cuda")
         flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    kps_host = np.zeros((F, KPTS), ucoslam_b200.KP_DTYPE)
+    desc_host = torch.zeros((F, KPTS, 32), dtype=torch.uint8).pin_memory()
+    nout_host = np.zeros(F, np.int32)
     idx_host = torch.empty((F, KPTS, K_NN), dtype=torch.int32).pin_memory()
     dist_host = torch.empty((F, KPTS, K_NN), dtype=torch.int32).pin_memory()
+    img_ptrs = (ctypes_voidp_array(F))(*[clip_pin[i].data_ptr() for i in range(F)])
     ctx.sync()
 
-    def step_device():
-        for f in range(F):
-            ctx.hamming_knn_dev(desc_dev[f + 1].data_ptr(), KPTS, desc_dev[f].data_ptr(), KPTS, K_NN,
-                                ucoslam_b200.UCO_KNN_HEAP, idx_dev[f].data_ptr(), dist_dev[f].data_ptr())
+    def orb_dev():
+        ctx.orb_extract_batch_dev(clip_dev.data_ptr(), F, W, H, W, W * H, prm, kps_dev.data_ptr(), desc_dev.data_ptr(),
+                                  nout_dev.data_ptr())
 
-    def step_host():  # the reference-facing call with HOST buffers: H2D + kernel + D2H per frame
-        lib, h = ctx.lib, ctx.h
+    def knn_dev(f):  # frame f against its predecessor (frame 0 against the last one of the batch)
+        ctx.hamming_knn_dev(desc_dev[f].data_ptr(), KPTS, desc_dev[f - 1].data_ptr(), KPTS, K_NN,
+                            ucoslam_b200.UCO_KNN_HEAP, idx_dev[f].data_ptr(), dist_dev[f].data_ptr())
+
+    def step_device():
+        orb_dev()
         for f in range(F):
-            rc = lib.uco_b200_hamming_knn(h, desc_pin[f + 1].data_ptr(), KPTS, 32, desc_pin[f].data_ptr(), KPTS, 32,
-                                          K_NN, 0, idx_host[f].data_ptr(), dist_host[f].data_ptr())
+            knn_dev(f)
+
+    lib, h = ctx.lib, ctx.h
+    import ctypes
+    prm_p = ctypes.addressof(prm)
+
+    def step_host():  # reference-facing calls with HOST buffers: H2D + kernels + D2H inside
+        rc = lib.uco_b200_orb_extract_batch(h, ctypes.cast(img_ptrs, ctypes.c_void_p), F, W, H, W, prm_p,
+                                            kps_host.ctypes.data, desc_host.data_ptr(), KPTS, nout_host.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(lib.uco_b200_last_error(h))
+        for f in range(F):
+            rc = lib.uco_b200_hamming_knn(h, desc_host[f].data_ptr(), int(nout_host[f]), 32, desc_host[f - 1].data_ptr(),
+                                          int(nout_host[f - 1]), 32, K_NN, 0, idx_host[f].data_ptr(),
+                                          dist_host[f].data_ptr())
             if rc != 0:
                 raise RuntimeError(lib.uco_b200_last_error(h))
 
@@ -169,34 +215,43 @@ def run_b200(args, rank, world, local_rank):
         if world > 1:
             dist.barrier()
 
-    def timed(fn, steps, warmup):
+    def reduce_max(v):
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed_events(fn, reps, flush_l2=True):
+        """sum of per-repetition device durations (CUDA events on the context stream), L2 flushed between repetitions"""
         with torch.cuda.stream(stream):
-            for _ in range(warmup):
-                fn()
-                flush.zero_()
-            barrier()
             evs = []
-            n0 = ctx.launch_count()
-            for _ in range(steps):
-                flush.zero_()  # L2 flush between timed iterations (outside the event pair)
+            for _ in range(reps):
+                if flush_l2:
+                    flush.zero_()
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record(stream)
                 fn()
                 b.record(stream)
                 evs.append((a, b))
             barrier()
-            ms = sum(a.elapsed_time(b) for a, b in evs)
-            launches = ctx.launch_count() - n0
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), launches
+            return sum(a.elapsed_time(b) for a, b in evs)
+
+    # warm-up (also builds the extractor plan and its buffers), sanity: every frame yields the full keypoint budget
+    with torch.cuda.stream(stream):
+        for _ in range(max(args.warmup, 3)):
+            step_device()
+            flush.zero_()
+    barrier()
+    n_kp = nout_dev.cpu().numpy()
+    assert (n_kp == KPTS).all(), "synthetic frames must give %d keypoints, got %s" % (KPTS, n_kp[:8])
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    ms_dev, launches = timed(step_device, args.steps, args.warmup)
-    # e2e: wall clock around host-API steps (the call synchronises internally), max over ranks
+    n0 = ctx.launch_count()
+    ms_dev = reduce_max(timed_events(step_device, args.steps))
+    launches = ctx.launch_count() - n0
+
     for _ in range(max(1, args.warmup)):
         step_host()
     barrier()
@@ -204,54 +259,64 @@ def run_b200(args, rank, world, local_rank):
     for _ in range(args.steps):
         step_host()
     barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
+    e2e_ms = reduce_max((time.perf_counter() - t0) * 1e3)
     clocks = sampler.summary() if sampler else None
 
-    # roofline of the dominant kernel, timed live with CUDA events on the launching stream (same inputs, L2 flushed)
-    with torch.cuda.stream(stream):
-        per = []
-        for f in range(min(F, 16)):
+    # per-kernel device times of the same step (events at the stage boundaries inside the library)
+    ctx.set_profiling(True)
+    reps = 5
+    acc = {}
+    for _ in range(reps):
+        with torch.cuda.stream(stream):
             flush.zero_()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream)
-            ctx.hamming_knn_dev(desc_dev[f + 1].data_ptr(), KPTS, desc_dev[f].data_ptr(), KPTS, K_NN, 0,
-                                idx_dev[f].data_ptr(), dist_dev[f].data_ptr())
-            b.record(stream)
-            per.append((a, b))
-        barrier()
-        k_ms = sum(a.elapsed_time(b) for a, b in per) / len(per)
-    alg_bytes = 2 * KPTS * 32 + KPTS * K_NN * 8
+            orb_dev()
+        for k, v in ctx.orb_last_stage_ms().items():
+            acc[k] = acc.get(k, 0.0) + v / reps
+    ctx.set_profiling(False)
+    knn_ms = timed_events(lambda: [knn_dev(f) for f in range(F)], reps) / reps
+    stage_ms = dict(acc)
+    stage_ms["hamming_knn"] = knn_ms
+    pb = ctx.orb_plan_bytes()
+    cand_bytes = 0  # candidate lists are small and L2 resident; not counted as algorithmic traffic
+    alg = {  # ALGORITHMIC bytes per frame of each kernel (DESIGN.md "Measurement")
+        "blur": 2 * W * H,                                                        # read frame, write level 0
+        "resize": 2 * pb["pyramid_px"] - W * H - 179 * 134,                       # read levels 0..6, write levels 1..7
+        "fast_cells": pb["pyramid_px"] + cand_bytes,                              # read every level once
+        "select": 0,
+        "orient_describe": KPTS * (28 + 32),                                      # write keypoints + descriptors
+        "hamming_knn": 2 * KPTS * 32 + KPTS * K_NN * 8,
+    }
+    top = max(stage_ms, key=stage_ms.get)
     peaks = {}
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
         peaks = json.load(open(pk))
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-
+    achieved = alg[top] * F / (stage_ms[top] * 1e-3) / 1e9
+    orb_total_ms = sum(acc.values())
+    orb_alg = W * H + 2 * pb["pyramid_px"] + KPTS * 60                          # 2 328 264 B/frame
     if rank == 0:
         total_frames = F * world * args.steps
-        line = {"metric": "frames/sec (ORB+match+local-BA) 640x480 mono", "value": total_frames / (ms_dev * 1e-3),
-                "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "u8", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "stages": ["match"], "frames_per_step_per_gpu": F,
+        line = {"metric": METRIC, "value": total_frames / (ms_dev * 1e-3), "unit": "frames/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "stages": STAGES, "frames_per_step_per_gpu": F,
                            "parallelism": "frames sharded over %d GPU(s), no collective" % world,
                            "l2": "flushed between timed steps (256 MB write)"},
                 "e2e": {"value": total_frames / (e2e_ms * 1e-3), "unit": "frames/s",
-                        "h2d_bytes_per_step": F * 2 * KPTS * 32, "d2h_bytes_per_step": F * KPTS * K_NN * 8},
-                "gpu_launches": launches,
-                "clocks": clocks,
-                "roofline": {"kernel": "hamming_knn_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
-                             "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                        "h2d_bytes_per_step": F * (W * H + 2 * KPTS * 32),
+                        "d2h_bytes_per_step": F * (KPTS * 60 + 4 + KPTS * K_NN * 8)},
+                "gpu_launches": launches, "clocks": clocks,
+                "roofline": {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": achieved / hbm_peak, "traffic": None,
                              "peak_source": "measured" if peaks else "fallback",
-                             "kernel_us": k_ms * 1e3,
-                             "note": "2000x2000 k-NN is L2-resident and popc/latency bound; see DESIGN.md"}}
+                             "kernel_ms_per_step": stage_ms[top], "algorithmic_bytes_per_frame": alg[top]},
+                "stage_ms_per_step": stage_ms,
+                "orb_pipeline": {"ms_per_step": orb_total_ms, "algorithmic_bytes_per_frame": orb_alg,
+                                 "achieved_gbs": orb_alg * F / (orb_total_ms * 1e-3) / 1e9,
+                                 "frac_of_hbm_peak": orb_alg * F / (orb_total_ms * 1e-3) / 1e9 / hbm_peak}}
         if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(desc)
+            line["cpu_baseline"] = cpu_baseline(clip)
         print(json.dumps(line))
         sys.stdout.flush()
     barrier()
@@ -263,22 +328,24 @@ def run_b200(args, rank, world, local_rank):
     os._exit(0)
 
 
-def cpu_baseline(desc):
+def ctypes_voidp_array(n):
+    import ctypes
+    return ctypes.c_void_p * n
+
+
+def cpu_baseline(clip):
     """Bounded CPU sample of the same workload on this box's host cores (rank 0, N=1)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle_py
-    have_ref = oracle_py.load_ref("libref_xflann.so") is not None
-    n = min(len(desc) - 1, 8)
+    import oracle_py, orb_oracle
+    have = oracle_py.load_ref("libref_xflann.so") is not None
+    n = min(len(clip), 16)
+    cpu_reference_step(clip[:2], oracle_py, orb_oracle, have)  # warm caches
     t0 = time.perf_counter()
-    for f in range(n):
-        if have_ref:
-            oracle_py.ref_xflann_knn(desc[f + 1], desc[f], K_NN, 1, 16, 0)
-        else:
-            oracle_py.hamming_knn(desc[f + 1], desc[f], K_NN, 0)
+    cpu_reference_step(clip[:n], oracle_py, orb_oracle, have)
     dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": "frames/s", "cores": 1, "kind": "reference" if have_ref else "port",
-            "sample": "%d frame pairs, xflann %s, k=10" % (n, "HKMeans(32,0) build + 16-check search (reference setting)"
-                                                            if have_ref else "exact linear port")}
+    info = cpu_baseline_info(have, n)
+    info.update({"value": n / dt, "unit": "frames/s"})
+    return info
 
 
 def main():

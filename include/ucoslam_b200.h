@@ -51,6 +51,8 @@ uint64_t uco_b200_launch_count(const uco_b200_ctx* ctx);
 /* milliseconds accumulated on the context stream by the kernel class `what` between timing_begin/end.
  * what: 0 = all ORB kernels, 1 = hamming scan, 2 = bow, 3 = BA.  Measured with CUDA events on the stream. */
 int uco_b200_version(void);
+/* when on, multi-kernel entry points record CUDA events at their stage boundaries (read back with *_last_stage_ms) */
+void uco_b200_set_profiling(uco_b200_ctx* ctx, int on);
 
 /* ------------------------------------------------------------------------------------------------------------
  * K7  brute-force 256-bit Hamming k-NN
@@ -120,6 +122,9 @@ int uco_b200_orb_extract_batch(uco_b200_ctx* ctx, const uint8_t* const* imgs, in
 int uco_b200_orb_extract_batch_dev(uco_b200_ctx* ctx, const uint8_t* imgs_dev, int n_imgs, int w, int h, size_t pitch,
                                    size_t frame_stride, const uco_orb_params* prm, uco_keypoint* kps_dev,
                                    uint8_t* desc_dev, int* n_out_dev);
+
+int uco_b200_orb_last_stage_ms(uco_b200_ctx* ctx, float* out5);
+int uco_b200_orb_plan_bytes(uco_b200_ctx* ctx, uint64_t* out3);
 
 /* inspection hooks for the per-stage parity tests (state of the last extract call on this context) */
 int uco_b200_orb_debug_level_info(uco_b200_ctx* ctx, int level, int* w, int* h, int* pitch, int* n_desired, int* rows,

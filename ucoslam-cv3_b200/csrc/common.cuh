@@ -21,6 +21,7 @@ struct uco_b200_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     uint64_t launches = 0;
+    int profiling = 0;  // record per-stage CUDA events
     // grow-only device / pinned workspaces, keyed by slot
     std::vector<uco_dev_buf> dev;
     std::vector<uco_dev_buf> pin;

@@ -102,5 +102,6 @@ int uco_b200_sync(uco_b200_ctx* ctx) {
 }
 uint64_t uco_b200_launch_count(const uco_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int uco_b200_version(void) { return 100; }
+void uco_b200_set_profiling(uco_b200_ctx* ctx, int on) { if (ctx) ctx->profiling = on; }
 
 }  // extern "C"

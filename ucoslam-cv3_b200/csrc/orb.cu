@@ -517,6 +517,8 @@ struct uco_orb_state {
     int* d_nout = nullptr;
     int* h_nout = nullptr;         // pinned
     int* h_err = nullptr;          // pinned
+    cudaEvent_t ev[6] = {};        // stage boundaries when ctx->profiling is set
+    bool ev_valid = false;
 };
 
 static void orb_free_buffers(uco_orb_state* s) {
@@ -525,6 +527,9 @@ static void orb_free_buffers(uco_orb_state* s) {
     cudaFree(s->d_kps); cudaFree(s->d_desc); cudaFree(s->d_nout);
     if (s->h_nout) cudaFreeHost(s->h_nout);
     if (s->h_err) cudaFreeHost(s->h_err);
+    for (auto& e : s->ev)
+        if (e) { cudaEventDestroy(e); e = nullptr; }
+    s->ev_valid = false;
     s->d_pyr = s->d_in = nullptr; s->d_cells = nullptr; s->d_tab_ofs = nullptr; s->d_tab_coef = nullptr;
     s->d_cand = nullptr; s->d_cand_cnt = nullptr; s->d_sel = nullptr; s->d_sel_cnt = nullptr; s->d_err = nullptr;
     s->d_kps = nullptr; s->d_desc = nullptr; s->d_nout = nullptr; s->h_nout = nullptr; s->h_err = nullptr;
@@ -752,21 +757,33 @@ static int orb_run_dev(uco_b200_ctx* ctx, const uint8_t* in_dev, size_t in_pitch
     uco_orb_state* s = ctx->orb;
     const PlanDev& P = s->plan;
     cudaStream_t st = ctx->stream;
+    const bool prof = ctx->profiling != 0;
+    if (prof && !s->ev[0])
+        for (auto& e : s->ev) UCO_CUDA(ctx, cudaEventCreate(&e));
+    if (prof) cudaEventRecord(s->ev[0], st);
     dim3 g0((P.lv[0].w + BL_TW - 1) / BL_TW, (P.lv[0].h + BL_TH - 1) / BL_TH, n);
     blur7_kernel<<<g0, 256, 0, st>>>(P, in_dev, in_pitch, in_frame, s->d_pyr, s->prm.blur_first);
     UCO_LAUNCH_CHECK(ctx);
+    if (prof) cudaEventRecord(s->ev[1], st);
     for (int l = 1; l < P.n_levels; l++) {
         dim3 g((P.lv[l].w + 31) / 32, (P.lv[l].h + 7) / 8, n);
         resize_cubic_kernel<<<g, dim3(32, 8), 0, st>>>(P, s->d_pyr, l, s->d_tab_ofs, s->d_tab_coef);
         UCO_LAUNCH_CHECK(ctx);
     }
+    if (prof) cudaEventRecord(s->ev[2], st);
     fast_cells_kernel<<<dim3(P.n_cells_total, n), 256, s->max_cell_smem, st>>>(P, s->d_pyr, s->d_cells, s->d_cand, s->d_cand_cnt);
     UCO_LAUNCH_CHECK(ctx);
+    if (prof) cudaEventRecord(s->ev[3], st);
     select_kernel<<<dim3(P.n_levels, n), 256, 0, st>>>(P, s->d_cells, s->d_cand, s->d_cand_cnt, s->d_sel, s->d_sel_cnt, s->d_err);
     UCO_LAUNCH_CHECK(ctx);
+    if (prof) cudaEventRecord(s->ev[4], st);
     orient_describe_kernel<<<dim3((P.max_features + 7) / 8, n), 256, 0, st>>>(P, s->d_pyr, s->d_sel, s->d_sel_cnt, kps_dev,
                                                                             desc_dev, nout_dev, P.max_features);
     UCO_LAUNCH_CHECK(ctx);
+    if (prof) {
+        cudaEventRecord(s->ev[5], st);
+        s->ev_valid = true;
+    }
     return UCO_OK;
 }
 
@@ -830,6 +847,28 @@ int uco_b200_orb_extract(uco_b200_ctx* ctx, const uint8_t* img, int w, int h, si
                          uco_keypoint* kps, uint8_t* desc, int capacity, int* n_out) {
     const uint8_t* one[1] = {img};
     return uco_b200_orb_extract_batch(ctx, one, 1, w, h, stride, prm, kps, desc, capacity, n_out);
+}
+
+// device time (ms) of the stages of the LAST extract call, measured with CUDA events on the context stream when profiling
+// is enabled: out[0..4] = blur, resize chain, fast_cells, select, orient_describe.  Synchronises the stream.
+int uco_b200_orb_last_stage_ms(uco_b200_ctx* ctx, float* out) {
+    if (!ctx || !ctx->orb || !ctx->orb->ev_valid) return UCO_E_INVALID;
+    UCO_CUDA(ctx, cudaEventSynchronize(ctx->orb->ev[5]));
+    for (int i = 0; i < 5; i++) UCO_CUDA(ctx, cudaEventElapsedTime(&out[i], ctx->orb->ev[i], ctx->orb->ev[i + 1]));
+    return UCO_OK;
+}
+// algorithmic bytes per frame of the current plan: out[0] = input image, out[1] = pyramid level pixels (sum w*h),
+// out[2] = pyramid bytes incl. the 19-px borders
+int uco_b200_orb_plan_bytes(uco_b200_ctx* ctx, uint64_t* out) {
+    if (!ctx || !ctx->orb || !ctx->orb->batch_cap) return UCO_E_INVALID;
+    const PlanDev& P = ctx->orb->plan;
+    out[0] = (uint64_t)ctx->orb->w * ctx->orb->h;
+    out[1] = out[2] = 0;
+    for (int l = 0; l < P.n_levels; l++) {
+        out[1] += (uint64_t)P.lv[l].w * P.lv[l].h;
+        out[2] += (uint64_t)(P.lv[l].w + 2 * ORB_E) * (P.lv[l].h + 2 * ORB_E);
+    }
+    return UCO_OK;
 }
 
 // ---- test / inspection hooks (used by the per-stage parity tests) -----------------------------------------------------

@@ -30,6 +30,9 @@ SIGNATURES = {
     "uco_b200_orb_extract": (_i, [_vp, _vp, _i, _i, _sz, _vp, _vp, _vp, _i, _vp]),
     "uco_b200_orb_extract_batch": (_i, [_vp, _vp, _i, _i, _i, _sz, _vp, _vp, _vp, _i, _vp]),
     "uco_b200_orb_extract_batch_dev": (_i, [_vp, _vp, _i, _i, _i, _sz, _sz, _vp, _vp, _vp, _vp]),
+    "uco_b200_set_profiling": (None, [_vp, _i]),
+    "uco_b200_orb_last_stage_ms": (_i, [_vp, _vp]),
+    "uco_b200_orb_plan_bytes": (_i, [_vp, _vp]),
     "uco_b200_orb_debug_level_info": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "uco_b200_orb_debug_pyramid": (_i, [_vp, _i, _i, _vp]),
     "uco_b200_orb_debug_selected": (_i, [_vp, _i, _i, _vp, _i, _vp]),
@@ -173,6 +176,19 @@ class Context:
     def orb_extract_batch_dev(self, imgs_dev, n, w, h, pitch, frame_stride, prm, kps_dev, desc_dev, nout_dev):
         self._chk(self.lib.uco_b200_orb_extract_batch_dev(self.h, imgs_dev, n, w, h, pitch, frame_stride,
                                                           ctypes.addressof(prm), kps_dev, desc_dev, nout_dev))
+
+    def set_profiling(self, on):
+        self.lib.uco_b200_set_profiling(self.h, int(on))
+
+    def orb_last_stage_ms(self):
+        out = np.zeros(5, np.float32)
+        self._chk(self.lib.uco_b200_orb_last_stage_ms(self.h, _p(out)))
+        return dict(zip(["blur", "resize", "fast_cells", "select", "orient_describe"], out.tolist()))
+
+    def orb_plan_bytes(self):
+        out = np.zeros(3, np.uint64)
+        self._chk(self.lib.uco_b200_orb_plan_bytes(self.h, _p(out)))
+        return dict(zip(["input", "pyramid_px", "pyramid_bordered"], [int(v) for v in out]))
 
     def orb_level_info(self, level):
         v = [ctypes.c_int() for _ in range(6)]
