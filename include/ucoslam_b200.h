@@ -79,6 +79,14 @@ int uco_b200_hamming_knn(uco_b200_ctx* ctx, const uint8_t* q, int nq, size_t q_s
 int uco_b200_hamming_knn_dev(uco_b200_ctx* ctx, const uint8_t* q_dev, int nq, const uint8_t* t_dev, int nt, int k,
                              int order, int32_t* idx_dev, int32_t* dist_dev);
 
+/* a batch of independent (query set, train set) pairs in ONE launch (a clip: frame i against frame i-1).  Pair p reads
+ * q_dev + p*q_pair_stride (nq_dev ? min(nq_max, nq_dev[p]) : nq_max rows) and t_dev + p*t_pair_stride, and writes
+ * idx_dev/dist_dev + p*nq_max*k.  The optional per-pair row counts are DEVICE arrays (e.g. n_out_dev of
+ * uco_b200_orb_extract_batch_dev), so no host round trip is needed; rows >= nq of a pair are left untouched. */
+int uco_b200_hamming_knn_batch_dev(uco_b200_ctx* ctx, int n_pairs, const uint8_t* q_dev, size_t q_pair_stride, int nq_max,
+                                   const int32_t* nq_dev, const uint8_t* t_dev, size_t t_pair_stride, int nt_max,
+                                   const int32_t* nt_dev, int k, int order, int32_t* idx_dev, int32_t* dist_dev);
+
 /* ------------------------------------------------------------------------------------------------------------
  * K1-K6  ORB pyramid extractor
  *   replaces ucoslam::ORBextractor::detectAndCompute_impl -> compute()

@@ -62,3 +62,27 @@ def test_gpu_large_scan_properties(ctx):
     for i in range(0, 256, 37):
         full = np.unpackbits(q[i][None, :] ^ t, axis=1).sum(1)
         assert np.array_equal(np.sort(full)[:10], dist[i])
+
+
+def test_gpu_batch_pairs_with_device_counts(ctx):
+    """One launch over a clip: pair p = (frame p+1 vs frame p), per-pair row counts read from device memory."""
+    import torch, ucoslam_b200
+    F, N, k = 5, 600, 10
+    rng = np.random.default_rng(9)
+    desc = rng.integers(0, 256, (F, N, 32), dtype=np.uint8)
+    counts = np.array([600, 512, 77, 600, 1], np.int32)
+    stream = torch.cuda.ExternalStream(ctx.stream)
+    with torch.cuda.stream(stream):
+        d = torch.from_numpy(desc).cuda()
+        c = torch.from_numpy(counts).cuda()
+        idx = torch.full((F - 1, N, k), -7, dtype=torch.int32, device="cuda")
+        dist = torch.full((F - 1, N, k), -7, dtype=torch.int32, device="cuda")
+        ctx.hamming_knn_batch_dev(F - 1, d[1].data_ptr(), N * 32, N, c[1:].data_ptr(), d[0].data_ptr(), N * 32, N,
+                                  c.data_ptr(), k, ucoslam_b200.UCO_KNN_HEAP, idx.data_ptr(), dist.data_ptr())
+        ctx.sync()
+    idx, dist = idx.cpu().numpy(), dist.cpu().numpy()
+    for p in range(F - 1):
+        nq, nt = counts[p + 1], counts[p]
+        oi, od = oracle_py.hamming_knn(desc[p + 1][:nq], desc[p][:nt], k, 0)
+        assert np.array_equal(idx[p][:nq], oi) and np.array_equal(dist[p][:nq], od)
+        assert (idx[p][nq:] == -7).all()

@@ -99,7 +99,20 @@ __device__ __forceinline__ void push_full(uint32_t (&h)[K], uint32_t v) {
 template <int K>
 __global__ void __launch_bounds__(KNN_WARPS * 32)
 hamming_knn_kernel(const uint4* __restrict__ q, int nq, const uint4* __restrict__ t, int nt, int order,
-                   int32_t* __restrict__ out_idx, int32_t* __restrict__ out_dist) {
+                   int32_t* __restrict__ out_idx, int32_t* __restrict__ out_dist, const int* __restrict__ nq_dev,
+                   const int* __restrict__ nt_dev, size_t q_stride16, size_t t_stride16, size_t out_stride) {
+    // blockIdx.y = (query set, train set) pair of a batch; per-pair row counts may live on the device (e.g. the
+    // extractor's n_out), so a whole clip is matched without a host round trip
+    {
+        const int pair = blockIdx.y;
+        q += pair * q_stride16;
+        t += pair * t_stride16;
+        out_idx += pair * out_stride;
+        out_dist += pair * out_stride;
+        if (nq_dev) nq = min(nq, nq_dev[pair]);
+        if (nt_dev) nt = min(nt, nt_dev[pair]);
+        if ((int)(blockIdx.x * KNN_WARPS) >= nq) return;
+    }
     __shared__ __align__(128) uint4 tile[KNN_STAGES][KNN_TILE_ROWS * 2];
     __shared__ __align__(8) uint64_t full[KNN_STAGES];
 
@@ -207,7 +220,8 @@ hamming_knn_kernel(const uint4* __restrict__ q, int nq, const uint4* __restrict_
     }
 }
 
-typedef void (*knn_fn)(const uint4*, int, const uint4*, int, int, int32_t*, int32_t*);
+typedef void (*knn_fn)(const uint4*, int, const uint4*, int, int, int32_t*, int32_t*, const int*, const int*, size_t, size_t,
+                       size_t);
 template <int K>
 struct KnnTable {
     static void fill(knn_fn* f) {
@@ -222,29 +236,45 @@ struct KnnTable<0> {
 
 }  // namespace
 
-extern "C" int uco_b200_hamming_knn_dev(uco_b200_ctx* ctx, const uint8_t* q_dev, int nq, const uint8_t* t_dev, int nt,
-                                        int k, int order, int32_t* idx_dev, int32_t* dist_dev) {
+static int knn_launch(uco_b200_ctx* ctx, const uint8_t* q_dev, int nq, const uint8_t* t_dev, int nt, int k, int order,
+                      int32_t* idx_dev, int32_t* dist_dev, int n_pairs, const int* nq_dev, const int* nt_dev, size_t q_stride,
+                      size_t t_stride) {
     if (!ctx) return UCO_E_INVALID;
-    if (nq < 0 || nt < 0 || k <= 0 || k > UCO_KNN_MAX_K || (order != UCO_KNN_HEAP && order != UCO_KNN_SORTED))
+    if (nq < 0 || nt < 0 || n_pairs < 0 || k <= 0 || k > UCO_KNN_MAX_K || (order != UCO_KNN_HEAP && order != UCO_KNN_SORTED))
         return uco_fail(ctx, UCO_E_INVALID, "hamming_knn: bad sizes nq=%d nt=%d k=%d order=%d", nq, nt, k, order);
-    if (nq == 0) return UCO_OK;
+    if (nq == 0 || n_pairs == 0) return UCO_OK;
     if (!q_dev || !idx_dev || !dist_dev || (nt > 0 && !t_dev))
         return uco_fail(ctx, UCO_E_INVALID, "hamming_knn: null pointer");
-    if (((uintptr_t)q_dev | (uintptr_t)t_dev) & 15)
+    if ((((uintptr_t)q_dev | (uintptr_t)t_dev) & 15) || (q_stride & 15) || (t_stride & 15))
         return uco_fail(ctx, UCO_E_INVALID, "hamming_knn: descriptor buffers must be 16-byte aligned");
     if (nt >= (1 << 23))
         return uco_fail(ctx, UCO_E_INVALID, "hamming_knn: train set above %d rows, shard it", (1 << 23) - 1);
+    if (n_pairs > 65535) return uco_fail(ctx, UCO_E_INVALID, "hamming_knn: more than 65535 pairs in one call");
     static knn_fn table[UCO_KNN_MAX_K + 1];
     static bool init = false;
     if (!init) {
         KnnTable<UCO_KNN_MAX_K>::fill(table);
         init = true;
     }
-    int grid = (nq + KNN_WARPS - 1) / KNN_WARPS;
+    dim3 grid((nq + KNN_WARPS - 1) / KNN_WARPS, n_pairs);
     table[k]<<<grid, KNN_WARPS * 32, 0, ctx->stream>>>((const uint4*)q_dev, nq, (const uint4*)t_dev, nt, order, idx_dev,
-                                                       dist_dev);
+                                                       dist_dev, nq_dev, nt_dev, q_stride / 16, t_stride / 16,
+                                                       (size_t)nq * k);
     UCO_LAUNCH_CHECK(ctx);
     return UCO_OK;
+}
+
+extern "C" int uco_b200_hamming_knn_dev(uco_b200_ctx* ctx, const uint8_t* q_dev, int nq, const uint8_t* t_dev, int nt,
+                                        int k, int order, int32_t* idx_dev, int32_t* dist_dev) {
+    return knn_launch(ctx, q_dev, nq, t_dev, nt, k, order, idx_dev, dist_dev, 1, nullptr, nullptr, 0, 0);
+}
+
+extern "C" int uco_b200_hamming_knn_batch_dev(uco_b200_ctx* ctx, int n_pairs, const uint8_t* q_dev, size_t q_pair_stride,
+                                              int nq_max, const int32_t* nq_dev, const uint8_t* t_dev,
+                                              size_t t_pair_stride, int nt_max, const int32_t* nt_dev, int k, int order,
+                                              int32_t* idx_dev, int32_t* dist_dev) {
+    return knn_launch(ctx, q_dev, nq_max, t_dev, nt_max, k, order, idx_dev, dist_dev, n_pairs, nq_dev, nt_dev,
+                      q_pair_stride, t_pair_stride);
 }
 
 extern "C" int uco_b200_hamming_knn(uco_b200_ctx* ctx, const uint8_t* q, int nq, size_t q_stride, const uint8_t* t,

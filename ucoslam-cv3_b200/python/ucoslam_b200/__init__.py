@@ -26,6 +26,7 @@ SIGNATURES = {
     "uco_b200_version": (_i, []),
     "uco_b200_hamming_knn": (_i, [_vp, _vp, _i, _sz, _vp, _i, _sz, _i, _i, _vp, _vp]),
     "uco_b200_hamming_knn_dev": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp]),
+    "uco_b200_hamming_knn_batch_dev": (_i, [_vp, _i, _vp, _sz, _i, _vp, _vp, _sz, _i, _vp, _i, _i, _vp, _vp]),
     "uco_b200_orb_default_params": (None, [_vp]),
     "uco_b200_orb_extract": (_i, [_vp, _vp, _i, _i, _sz, _vp, _vp, _vp, _i, _vp]),
     "uco_b200_orb_extract_batch": (_i, [_vp, _vp, _i, _i, _i, _sz, _vp, _vp, _vp, _i, _vp]),
@@ -150,6 +151,11 @@ class Context:
         ts = t.strides[0] if nt > 0 else 32
         self._chk(self.lib.uco_b200_hamming_knn(self.h, _p(q), nq, qs, _p(t), nt, ts, k, order, _p(idx), _p(dist)))
         return idx, dist
+
+    def hamming_knn_batch_dev(self, n_pairs, q_dev, q_stride, nq_max, nq_dev, t_dev, t_stride, nt_max, nt_dev, k, order,
+                              idx_dev, dist_dev):
+        self._chk(self.lib.uco_b200_hamming_knn_batch_dev(self.h, n_pairs, q_dev, q_stride, nq_max, nq_dev, t_dev, t_stride,
+                                                          nt_max, nt_dev, k, order, idx_dev, dist_dev))
 
     # -- K1-K6 ---------------------------------------------------------------------------------------------------
     def orb_extract(self, img, prm=None):
