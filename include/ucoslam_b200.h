@@ -145,6 +145,26 @@ int uco_b200_orb_debug_candidates(uco_b200_ctx* ctx, int frame, int cell, uint32
 int uco_b200_probe_math(int what, const float* in0, const float* in1, int n, float* out0, float* out1);
 int uco_b200_probe_retain_best(uint32_t* packed, int count, int n_points);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * K9  bag-of-words transform (fbow vocabulary tree)
+ *   replaces fbow::Vocabulary::fromStream / transform(features, level, fBow&, fBow2&)
+ *     3rdparty/fbow/fbow/fbow.cpp:180-190, 51-90 ; 3rdparty/fbow/fbow/fbow.h:402-448
+ *   as used by KPFrameDataBase::computeBow, src/map_types/keyframedatabase.cpp:310-321 (level 3).
+ *   bytes: a complete .fbow stream (e.g. 3rdparty/vocabularies/orb.fbow).  Only CV_8UC1 / 32-byte vocabularies.
+ *   transform emits, per descriptor i: word[i] (0xFFFFFFFF = none), weight[i], node[i] = id of the tree node reached at
+ *   `level` (0xFFFFFFFF = none).  The host folds them in descriptor order into fBow (word -> sum of weights) and
+ *   fBow2 (node -> descriptor indices) exactly as fbow.h:428-436 does (see ucoslam-cv3_b200/host/bow_b200.h).
+ *   Errors mirror the reference: n == 0 -> "Vocabulary::transform No input data", bad signature -> UCO_E_FORMAT.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct uco_b200_voc uco_b200_voc;
+int uco_b200_bow_load(uco_b200_ctx* ctx, const void* bytes, size_t n, uco_b200_voc** voc);
+void uco_b200_bow_free(uco_b200_ctx* ctx, uco_b200_voc* voc);
+int uco_b200_bow_info(const uco_b200_voc* voc, uint32_t* k, uint32_t* nblocks, uint32_t* desc_size);
+int uco_b200_bow_transform(uco_b200_ctx* ctx, const uco_b200_voc* voc, const uint8_t* desc, int n, size_t stride, int level,
+                           uint32_t* word, float* weight, uint32_t* node);
+int uco_b200_bow_transform_dev(uco_b200_ctx* ctx, const uco_b200_voc* voc, const uint8_t* desc_dev, int n, int level,
+                               uint32_t* word_dev, float* weight_dev, uint32_t* node_dev);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,3 +80,123 @@ def synth_descriptors(seed, nt, nq, max_flips=40):
         bits = rng.integers(0, 256, nflip[i])
         np.bitwise_xor.at(q[i], bits >> 3, (1 << (bits & 7)).astype(np.uint8))
     return t, q
+
+
+# ---- bag of words (fbow) -------------------------------------------------------------------------------------------
+REF_VOC_PATH = os.path.join(HERE, "_ref", "orb.fbow")   # the reference's shipped vocabulary (copied by `make ref`)
+
+
+def ref_voc_bytes():
+    if not os.path.exists(REF_VOC_PATH):
+        return None
+    return np.fromfile(REF_VOC_PATH, dtype=np.uint8)
+
+
+def synth_vocabulary(seed, k=10, depth=4, desc_size=32, leaf_prob=0.08, partial_prob=0.1):
+    """A seeded vocabulary file image in fbow's stream format (fbow.cpp:160-190, fbow.h:125-194): a k-ary tree of
+    `depth` levels of internal blocks, with some early leaves and some blocks holding fewer than k nodes."""
+    rng = np.random.default_rng(seed)
+    feature_off, desc_wp = 8, 32
+    child_off = feature_off + k * desc_wp
+    block_size = child_off + 8 * k
+    block_size = (block_size + 7) // 8 * 8
+    blocks = []   # list of dict(n, parent, feats, infos)
+    words = [0]
+
+    def make_block(level, parent):
+        b = len(blocks)
+        n = k if rng.random() > partial_prob else int(rng.integers(1, k + 1))
+        blk = dict(n=n, parent=parent, feats=rng.integers(0, 256, (k, desc_size), dtype=np.uint8), ids=[0] * k, w=[0.0] * k,
+                   leaf=0)
+        blocks.append(blk)
+        for c in range(n):
+            if level == depth - 1 or rng.random() < leaf_prob:
+                blk["ids"][c] = 0x80000000 | words[0]
+                blk["w"][c] = float(np.float32(rng.random() * 3 + 0.01))
+                words[0] += 1
+            else:
+                blk["ids"][c] = make_block(level + 1, b)
+        return b
+
+    make_block(0, 0)
+    nb = len(blocks)
+    data = np.zeros(nb * block_size, np.uint8)
+    for i, blk in enumerate(blocks):
+        o = i * block_size
+        data[o:o + 2] = np.frombuffer(np.uint16(blk["n"]).tobytes(), np.uint8)
+        data[o + 4:o + 8] = np.frombuffer(np.uint32(blk["parent"]).tobytes(), np.uint8)
+        data[o + feature_off:o + feature_off + k * desc_wp] = blk["feats"].reshape(-1)
+        info = np.zeros(k, dtype=[("id", "<u4"), ("w", "<f4")])
+        info["id"] = blk["ids"]
+        info["w"] = blk["w"]
+        data[o + child_off:o + child_off + 8 * k] = np.frombuffer(info.tobytes(), np.uint8)
+    import struct
+    hdr = bytearray(128)
+    struct.pack_into("<Q", hdr, 0, 55824124)
+    hdr[8:11] = b"orb"
+    struct.pack_into("<II", hdr, 8 + 52, 8, nb)
+    struct.pack_into("<5Q", hdr, 8 + 64, desc_wp, block_size, feature_off, child_off, len(data))
+    struct.pack_into("<iiI", hdr, 8 + 104, 0, desc_size, k)
+    return np.concatenate([np.frombuffer(bytes(hdr), np.uint8), data])
+
+
+def bow_transform(voc_bytes, desc, level):
+    """oracle/bow_oracle.c: per-descriptor (word, weight, node)."""
+    lib = load_oracle()
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    voc_bytes = np.ascontiguousarray(voc_bytes, np.uint8)
+    n = len(desc)
+    word = np.empty(n, np.uint32)
+    weight = np.empty(n, np.float32)
+    node = np.empty(n, np.uint32)
+    rc = lib.oracle_bow_transform(_p(voc_bytes), _sz(len(voc_bytes)), _p(desc), n, _sz(32), int(level), _p(word),
+                                  _p(weight), _p(node))
+    if rc != 0:
+        raise RuntimeError("oracle_bow_transform rc=%d" % rc)
+    return word, weight, node
+
+
+def fold_bow(word, weight, node):
+    """What the host adapter does: fBow = map word -> sum of weights (f32, descriptor order); fBow2 = map node -> indices."""
+    bow, bow2 = {}, {}
+    for i in range(len(word)):
+        if word[i] != 0xFFFFFFFF:
+            bow[int(word[i])] = np.float32(bow.get(int(word[i]), np.float32(0)) + np.float32(weight[i]))
+        if node[i] != 0xFFFFFFFF:
+            bow2.setdefault(int(node[i]), []).append(i)
+    ids = np.array(sorted(bow), np.uint32)
+    w = np.array([bow[int(i)] for i in ids], np.float32)
+    n2 = np.array([k for k in sorted(bow2) for _ in bow2[k]], np.uint32)
+    f2 = np.array([x for k in sorted(bow2) for x in bow2[k]], np.uint32)
+    return ids, w, n2, f2
+
+
+class RefVocabulary:
+    """The reference's fbow::Vocabulary (oracle/_ref/libref_fbow.so)."""
+
+    def __init__(self, voc_bytes):
+        self.lib = load_ref("libref_fbow.so")
+        if self.lib is None:
+            raise RuntimeError("oracle/_ref/libref_fbow.so not built")
+        self.lib.ref_fbow_load_bytes.restype = ctypes.c_void_p
+        self.lib.ref_fbow_score.restype = ctypes.c_double
+        voc_bytes = np.ascontiguousarray(voc_bytes, np.uint8)
+        self.h = self.lib.ref_fbow_load_bytes(_p(voc_bytes), _sz(len(voc_bytes)))
+        if not self.h:
+            raise RuntimeError("fbow rejected the vocabulary")
+
+    def transform(self, desc, level):
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(desc)
+        ids = np.empty(n, np.uint32); w = np.empty(n, np.float32); n2 = np.empty(n, np.uint32); f2 = np.empty(n, np.uint32)
+        nb, nb2 = ctypes.c_int(), ctypes.c_int()
+        rc = self.lib.ref_fbow_transform(ctypes.c_void_p(self.h), _p(desc), n, int(level), _p(ids), _p(w), ctypes.byref(nb),
+                                         _p(n2), _p(f2), ctypes.byref(nb2))
+        if rc != 0:
+            raise RuntimeError("fbow transform threw")
+        return ids[:nb.value], w[:nb.value], n2[:nb2.value], f2[:nb2.value]
+
+    def close(self):
+        if self.h:
+            self.lib.ref_fbow_free(ctypes.c_void_p(self.h))
+            self.h = None

@@ -1,0 +1,34 @@
+// TEST INFRASTRUCTURE ONLY — minimal stand-in for <opencv2/core/core.hpp>, just enough of cv::Mat for the reference's
+// 3rdparty/fbow/fbow/fbow.{h,cpp} to compile unchanged in a container without OpenCV C++ headers.
+#pragma once
+#include <cassert>
+#include <cstddef>
+#include <cmath>
+#include <math.h>
+#include <cstring>
+#include <limits>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#define CV_8UC1 0
+#define CV_32FC1 5
+namespace cv {
+class Mat {
+public:
+    int rows = 0, cols = 0;
+    Mat() {}
+    Mat(int r, int c, int type, void* data, size_t step = 0) : rows(r), cols(c), _type(type), _data((unsigned char*)data) {
+        _step = step ? step : (size_t)c * elemSize();
+    }
+    int type() const { return _type; }
+    size_t elemSize() const { return _type == CV_32FC1 ? 4 : 1; }
+    size_t elemSize1() const { return elemSize(); }
+    template <typename T> T* ptr(int r = 0) { return (T*)(_data + (size_t)r * _step); }
+    template <typename T> const T* ptr(int r = 0) const { return (const T*)(_data + (size_t)r * _step); }
+    bool empty() const { return rows == 0 || cols == 0; }
+private:
+    int _type = 0;
+    unsigned char* _data = nullptr;
+    size_t _step = 0;
+};
+}  // namespace cv

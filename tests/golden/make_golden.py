@@ -33,5 +33,26 @@ def knn():
     print("knn golden written", {k: v.shape for k, v in cases.items() if k.endswith("idx0")})
 
 
+def bow():
+    """fbow::Vocabulary::transform of the reference on (a) its shipped orb.fbow and (b) seeded synthetic vocabularies."""
+    oracle_py.build_ref()
+    out = {}
+    rng = np.random.default_rng(77)
+    desc = rng.integers(0, 256, (1500, 32), dtype=np.uint8)
+    out["desc"] = desc
+    vocs = {"orb": oracle_py.ref_voc_bytes(), "s1": oracle_py.synth_vocabulary(1), "s2": oracle_py.synth_vocabulary(2, k=7, depth=3),
+            "s5": oracle_py.synth_vocabulary(5, k=16, depth=3, leaf_prob=0.3)}
+    for name, voc in vocs.items():
+        R = oracle_py.RefVocabulary(voc)
+        for level in (0, 3, 7):
+            ids, w, n2, f2 = R.transform(desc, level)
+            for k, v in zip(("ids", "w", "n2", "f2"), (ids, w, n2, f2)):
+                out["%s_L%d_%s" % (name, level, k)] = v
+        R.close()
+    np.savez_compressed(os.path.join(HERE, "bow_fbow.npz"), **out)
+    print("bow golden written", len(out))
+
+
 if __name__ == "__main__":
     knn()
+    bow()

@@ -38,6 +38,11 @@ SIGNATURES = {
     "uco_b200_orb_debug_pyramid": (_i, [_vp, _i, _i, _vp]),
     "uco_b200_orb_debug_selected": (_i, [_vp, _i, _i, _vp, _i, _vp]),
     "uco_b200_orb_debug_candidates": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp]),
+    "uco_b200_bow_load": (_i, [_vp, _vp, _sz, _vp]),
+    "uco_b200_bow_free": (None, [_vp, _vp]),
+    "uco_b200_bow_info": (_i, [_vp, _vp, _vp, _vp]),
+    "uco_b200_bow_transform": (_i, [_vp, _vp, _vp, _i, _sz, _i, _vp, _vp, _vp]),
+    "uco_b200_bow_transform_dev": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "uco_b200_probe_math": (_i, [_i, _vp, _vp, _i, _vp, _vp]),
     "uco_b200_probe_retain_best": (_i, [_vp, _i, _i]),
 }
@@ -151,6 +156,28 @@ class Context:
         ts = t.strides[0] if nt > 0 else 32
         self._chk(self.lib.uco_b200_hamming_knn(self.h, _p(q), nq, qs, _p(t), nt, ts, k, order, _p(idx), _p(dist)))
         return idx, dist
+
+    # -- K9 ------------------------------------------------------------------------------------------------------
+    def bow_load(self, voc_bytes):
+        voc_bytes = np.ascontiguousarray(voc_bytes, np.uint8)
+        h = ctypes.c_void_p()
+        self._chk(self.lib.uco_b200_bow_load(self.h, _p(voc_bytes), len(voc_bytes), ctypes.addressof(h)))
+        return h
+
+    def bow_free(self, voc):
+        self.lib.uco_b200_bow_free(self.h, voc)
+
+    def bow_transform(self, voc, desc, level):
+        """desc: (n,32) uint8 host rows. Returns per-descriptor (word, weight, node)."""
+        desc = np.asarray(desc)
+        n = desc.shape[0]
+        word = np.empty(n, np.uint32); weight = np.empty(n, np.float32); node = np.empty(n, np.uint32)
+        stride = desc.strides[0] if n else 32
+        self._chk(self.lib.uco_b200_bow_transform(self.h, voc, _p(desc), n, stride, level, _p(word), _p(weight), _p(node)))
+        return word, weight, node
+
+    def bow_transform_dev(self, voc, desc_dev, n, level, word_dev, weight_dev, node_dev):
+        self._chk(self.lib.uco_b200_bow_transform_dev(self.h, voc, desc_dev, n, level, word_dev, weight_dev, node_dev))
 
     def hamming_knn_batch_dev(self, n_pairs, q_dev, q_stride, nq_max, nq_dev, t_dev, t_stride, nt_max, nt_dev, k, order,
                               idx_dev, dist_dev):
