@@ -12,11 +12,28 @@
 #include <vector>
 #define CV_8UC1 0
 #define CV_32FC1 5
+#define CV_32F 5
+#include <memory>
 namespace cv {
+struct Point3f {
+    float x, y, z;
+    Point3f(float a = 0, float b = 0, float c = 0) : x(a), y(b), z(c) {}
+};
 class Mat {
 public:
     int rows = 0, cols = 0;
     Mat() {}
+    Mat(int r, int c, int type) : rows(r), cols(c), _type(type) {   // owning (typesg2o.h: cv::Mat cvMat(4,4,CV_32F))
+        _step = (size_t)c * elemSize();
+        _own = std::shared_ptr<unsigned char>(new unsigned char[_step * r](), std::default_delete<unsigned char[]>());
+        _data = _own.get();
+    }
+    Mat clone() const {
+        Mat m(rows, cols, _type);
+        for (int r = 0; r < rows; r++) memcpy(m._data + r * m._step, _data + r * _step, (size_t)cols * elemSize());
+        return m;
+    }
+    template <typename T> T& at(int r, int c) { return *(T*)(_data + (size_t)r * _step + (size_t)c * sizeof(T)); }
     Mat(int r, int c, int type, void* data, size_t step = 0) : rows(r), cols(c), _type(type), _data((unsigned char*)data) {
         _step = step ? step : (size_t)c * elemSize();
     }
@@ -30,5 +47,6 @@ private:
     int _type = 0;
     unsigned char* _data = nullptr;
     size_t _step = 0;
+    std::shared_ptr<unsigned char> _own;
 };
 }  // namespace cv

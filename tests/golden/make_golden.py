@@ -53,6 +53,30 @@ def bow():
     print("bow golden written", len(out))
 
 
+BA_CASES = {  # name -> synth_ba_problem kwargs, n_iters   (also imported by the tests)
+    "mono": (dict(seed=3, n_poses=6, n_fixed=1, n_points=160), 5),
+    "stereo": (dict(seed=4, n_poses=5, n_fixed=2, n_points=120, stereo_frac=0.5), 5),
+    "outliers": (dict(seed=5, n_poses=8, n_fixed=2, n_points=200, outlier_frac=0.15, stereo_frac=0.2), 10),
+    "allfree": (dict(seed=6, n_poses=4, n_fixed=0, n_points=100, pose_noise=(0.03, 1.5), point_noise=0.1), 5),
+}
+
+
+def ba():
+    """GlobalOptimizerG2O's graph + two-stage LM run by the reference's own g2o / typesg2o.h (oracle/ref_g2o_wrap.cpp)."""
+    oracle_py.build_ref()
+    out = {}
+    for name, (kw, iters) in BA_CASES.items():
+        pb = oracle_py.synth_ba_problem(**kw)
+        r = oracle_py.ref_ba_optimize(pb, iters)
+        for k in oracle_py.BA_INPUT_KEYS:
+            out["%s_in_%s" % (name, k)] = np.asarray(pb[k])
+        for k, v in r.items():
+            out["%s_out_%s" % (name, k)] = v
+    np.savez_compressed(os.path.join(HERE, "ba_g2o.npz"), **out)
+    print("ba golden written", {n: int(out[n + "_out_iters"].sum()) for n in BA_CASES})
+
+
 if __name__ == "__main__":
-    knn()
-    bow()
+    which = sys.argv[1:] or ["knn", "bow", "ba"]
+    for w in which:
+        globals()[w]()

@@ -1,0 +1,53 @@
+"""Pins oracle/ba_oracle.c to the reference's bundle adjustment: golden vectors produced by the reference's own g2o +
+typesg2o.h (tests/golden/make_golden.py ba -> ba_g2o.npz), and a live comparison where oracle/_ref exists.
+Tolerances (f64 against f64; the reduced system is solved by Cholesky here, by sparse LDLT in g2o): poses 1e-8, points 1e-7
+absolute (scene scale ~5 m), chi2 1e-7, identical iteration counts, LM trial counts, outlier levels and bad-association flags."""
+import os, sys
+import numpy as np
+import pytest
+import oracle_py
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "ba_g2o.npz")
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+from make_golden import BA_CASES
+
+
+def check_ba(got, ref, tol_pose=1e-8, tol_pt=1e-7, tol_chi=1e-7):
+    assert np.array_equal(got["iters"], ref["iters"])
+    n = int(ref["iters"].sum())
+    assert np.array_equal(got["trace"][:n, 1], ref["trace"][:n, 1]), "LM trials per iteration"
+    assert np.allclose(got["trace"][:n, 0], ref["trace"][:n, 0], rtol=1e-9, atol=1e-7)
+    assert np.abs(got["pose7"] - ref["pose7"]).max() < tol_pose
+    assert np.abs(got["point3"] - ref["point3"]).max() < tol_pt
+    assert np.abs(got["pose44"] - ref["pose44"]).max() < 1e-6
+    near_gate = np.minimum(np.abs(ref["chi2"] - 5.99), np.abs(ref["chi2"] - 7.815)) < 1e-6
+    assert np.abs(got["chi2"] - ref["chi2"])[~near_gate].max() < tol_chi * max(1.0, ref["chi2"].max())
+    assert np.array_equal(got["level"][~near_gate], ref["level"][~near_gate])
+    assert np.array_equal(got["bad"][~near_gate], ref["bad"][~near_gate])
+
+
+@pytest.mark.parametrize("name", list(BA_CASES))
+def test_oracle_matches_reference_golden(name):
+    g = np.load(GOLD)
+    pb = oracle_py.ba_problem_from_golden(g, name)
+    got = oracle_py.ba_optimize(pb, BA_CASES[name][1])
+    ref = {k[len(name) + 5:]: g[k] for k in g.files if k.startswith(name + "_out_")}
+    check_ba(got, ref)
+    assert ref["level"].sum() > 0  # the outlier stage did something
+
+
+def test_golden_inputs_are_reproducible():
+    g = np.load(GOLD)
+    for name, (kw, _) in BA_CASES.items():
+        pb = oracle_py.synth_ba_problem(**kw)
+        for k in oracle_py.BA_INPUT_KEYS:
+            assert np.array_equal(np.asarray(pb[k]), g["%s_in_%s" % (name, k)]), (name, k)
+
+
+def test_oracle_matches_live_reference():
+    if oracle_py.load_ref("libref_g2o.so") is None:
+        pytest.skip("oracle/_ref not built")
+    for kw, iters in ((dict(seed=11, n_poses=10, n_fixed=2, n_points=600, stereo_frac=0.3), 5),
+                      (dict(seed=12, n_poses=7, n_fixed=1, n_points=300, outlier_frac=0.1, pose_noise=(0.05, 2.0)), 10)):
+        pb = oracle_py.synth_ba_problem(**kw)
+        check_ba(oracle_py.ba_optimize(pb, iters), oracle_py.ref_ba_optimize(pb, iters))
