@@ -165,6 +165,53 @@ int uco_b200_bow_transform(uco_b200_ctx* ctx, const uco_b200_voc* voc, const uin
 int uco_b200_bow_transform_dev(uco_b200_ctx* ctx, const uco_b200_voc* voc, const uint8_t* desc_dev, int n, int level,
                                uint32_t* word_dev, float* weight_dev, uint32_t* node_dev);
 
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K10-K13  bundle adjustment (local and global): two-stage Levenberg-Marquardt with Schur complement
+ *   replaces ucoslam::GlobalOptimizerG2O::{setParams, optimize, getResults}
+ *     src/optimization/globaloptimizer_g2o.cpp:77-401, 418-463, 466-538
+ *   behind the plugin interface ucoslam::GlobalOptimizer (src/optimization/globaloptimizer.h:28-68), i.e. what g2o does
+ *   for that graph:
+ *     src/optimization/typesg2o.h:249-325, 338-405                 EdgeSE3ProjectXYZ / EdgeStereoSE3ProjectXYZ residual + Jacobians
+ *     3rdparty/g2o/g2o/core/base_binary_edge.hpp:83-155            per-edge quadratic form with Huber rho' weighting
+ *     3rdparty/g2o/g2o/core/block_solver.hpp:315-443               Schur complement, reduced solve, landmark back-substitution
+ *     3rdparty/g2o/g2o/core/optimization_algorithm_levenberg.cpp:58-175  LM control;  sparse_optimizer.cpp:366-436 outer loop
+ *   The caller (the C++ adapter GlobalOptimizerB200, ucoslam-cv3_b200/host/) flattens the Map into this structure exactly
+ *   as setParams walks it: one row per keyframe vertex, per map point vertex and per (map point, keyframe) observation.
+ *   All arithmetic is f64 on the device; inputs are the reference's f32 containers (cv::Mat CV_32F pose, cv::Point3f,
+ *   cv::KeyPoint::pt, vector<float> _InvScaleFactors).  Marker edges (ArUco) are not handled yet.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct uco_ba_problem {
+    int32_t n_poses, n_points, n_obs;
+    const float* poses44;        /* n_poses x 16  Frame::pose_f2g, row-major 4x4 */
+    const uint8_t* fixed;        /* n_poses       != 0: vertex fixed (isFixedFrame) */
+    const float* points3;        /* n_points x 3  MapPoint::getCoordinates() */
+    const int32_t* obs_pose;     /* n_obs         index into poses */
+    const int32_t* obs_point;    /* n_obs         index into points */
+    const float* obs_uv;         /* n_obs x 2     und_kpts[].pt */
+    const float* obs_ur;         /* n_obs         right-image x (kp_ur) of stereo observations; may be NULL when no stereo */
+    const uint8_t* obs_stereo;   /* n_obs         != 0: EdgeStereoSE3ProjectXYZ; may be NULL (all monocular) */
+    const float* obs_inv_sigma2; /* n_obs         _InvScaleFactors[kp.octave] */
+    float fx, fy, cx, cy, bf;    /* ImageParams; bf = baseline * fx */
+    int32_t n_iters;             /* ParamSet::nIters: stage 1 runs n_iters LM iterations, stage 2 runs 2 * n_iters */
+} uco_ba_problem;
+
+typedef struct uco_ba_result {   /* every pointer may be NULL (not wanted) */
+    double* pose7;               /* n_poses x 7   qx qy qz qw tx ty tz of the optimised vertices (f64) */
+    float* poses44;              /* n_poses x 16  what getResults stores in Frame::pose_f2g (fixed poses: input copied) */
+    double* points3;             /* n_points x 3  optimised points (f64; getResults narrows to cv::Point3f) */
+    double* obs_chi2;            /* n_obs         chi2 held by each edge at the end */
+    uint8_t* obs_level;          /* n_obs         1: edge was excluded after stage 1 (level 1) */
+    uint8_t* obs_bad;            /* n_obs         getBadAssociations() predicate, globaloptimizer_g2o.cpp:506-521 */
+    double* trace;               /* 64 x 2        per LM iteration: robust chi2, number of LM trials (both stages, in order) */
+    int32_t iters[2];            /* iterations executed by stage 1 / stage 2 (SparseOptimizer::optimize return values) */
+    float device_ms;             /* device time of the solve between first and last kernel (CUDA events) */
+} uco_ba_result;
+
+/* stop: optional flag polled between LM trials (GlobalOptimizerG2O::optimize(bool* stopASAP), sparse_optimizer.h:189);
+ * when raised during stage 1 the solve returns the current estimate with UCO_OK and iters[1] = 0 like the reference. */
+int uco_b200_ba_solve(uco_b200_ctx* ctx, const uco_ba_problem* pb, const volatile int* stop, uco_ba_result* res);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,3 +1,867 @@
-// ba.cu — bundle-adjustment kernels (K10-K14).
+// ba.cu — K10-K13: bundle adjustment on the device (f64): residuals, per-observation Jacobians and quadratic forms,
+// block-sparse Schur complement, dense reduced-camera solve, landmark back-substitution, Levenberg-Marquardt control.
+//
+// What it replaces (see include/ucoslam_b200.h for the entry point): GlobalOptimizerG2O's graph + g2o's
+// OptimizationAlgorithmLevenberg / BlockSolver_6_3 / LinearSolverEigen for that graph.
+//
+// Layout in HBM (everything f64 unless noted; one arena per solve, carved from a grow-only context workspace):
+//   pose[P x 7] (qx qy qz qw tx ty tz) + backup        pt[N x 3] + backup
+//   observations SORTED BY LANDMARK: obs_pose[M] i32, obs_lm[M] i32, z[M x 3], info[M], stereo[M] u8, active[M] u8,
+//                lm_ptr[N+1]; per free pose the list of its observations (pose_ptr[Pf+1], pose_obs[])
+//   per observation: err[M x 3], chi2[M], rho0[M], Hpl[M x 18] (6x3 block W of the (pose, landmark) pair), Y[M x 18] = W D^-1
+//   per landmark: Hll[N x 6] (symmetric packed), bl[N x 3], Dinv[N x 6], db[N x 3] = D^-1 bl, xl[N x 3]
+//   per free pose: Hpp[Pf x 36], bp[Pf x 6];  reduced system S[n x n] (n = 6 Pf, dense), bs[n], xp[n]
+//   Schur gather lists (built on the host once per solve): for every non-zero 6x6 block (i <= j) of S the list of
+//   (obs_a, obs_b) pairs of landmarks seen by both poses, in landmark order -> every sum has a FIXED order: no atomics,
+//   results are bitwise reproducible run to run.
+// Kernels per LM trial: ba_prep (D^-1, Y, db) -> ba_schur_gather (S, bs) -> ba_chol_solve -> ba_update (back-substitution,
+// backup, oplus) -> ba_errors -> ba_decide (ordered chi2 / scale reductions, gain ratio, lambda schedule, accept / restore).
+// The LM state machine lives on the device (LmState); the host only reads two flags per trial to know what to enqueue next.
 #include "common.cuh"
-void uco_ba_state_free(uco_b200_ctx*) {}
+#include "ba_math.cuh"
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace {
+using namespace ba;
+
+struct LmState {
+    double lambda, ni, currentChi, tempChi, rho, scale;
+    float prevChi2, curChi2, chi2Diff;
+    int it;          // outer iterations finished in this stage
+    int qmax;        // LM trials of the current iteration
+    int ok;          // SolverResult == OK
+    int cont_trial;  // the do-while of OptimizationAlgorithmLevenberg::solve goes on
+    int cont_iter;   // the for loop of SparseOptimizer::optimize goes on (before the iteration-count test)
+    int chol_fail;
+    int ntrace;
+    double trace[128];
+};
+
+struct BaDev {
+    int P, N, M, Pf, n, nblk;
+    double *pose, *pose_bak, *pt, *pt_bak;
+    const int *free_idx, *free_list, *lm_ptr, *obs_pose, *obs_lm, *pose_ptr, *pose_obs;
+    const double *z, *info;
+    const uint8_t* stereo;
+    uint8_t* active;
+    double *err, *chi2, *rho0, *Hll, *bl, *Hpl, *Y, *Dinv, *db, *xl, *Hpp, *bp, *S, *bs, *xp, *scale_lm, *scale_pose;
+    const int* blk_ptr;
+    const int2 *blk_ij, *con;
+    LmState* st;
+    Cam cam;
+    double d2, d3;      // Huber deltas sqrt(5.99f), sqrt(7.815f) (globaloptimizer_g2o.h:112-117)
+    float chi2d, chi3d;
+};
+
+// ---- K10 residuals: computeActiveErrors + the per-edge terms of activeRobustChi2 (sparse_optimizer.cpp:102-116) -------------
+__global__ void __launch_bounds__(256) ba_errors_kernel(const __grid_constant__ BaDev B, int robust) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B.M) return;
+    if (!B.active[i]) {  // level-1 edges are not evaluated any more: they keep their last error (g2o) and add nothing
+        B.rho0[i] = 0;
+        return;
+    }
+    Pose T = load_pose(B.pose + 7 * B.obs_pose[i]);
+    const double* X = B.pt + 3 * B.obs_lm[i];
+    double x[3] = {X[0], X[1], X[2]}, p[3], e[3];
+    se3_map(T, x, p);
+    bool st = B.stereo[i];
+    double z[3] = {B.z[3 * i], B.z[3 * i + 1], B.z[3 * i + 2]};
+    residual(p, z, st, B.cam, e);
+    double c2 = st ? (e[0] * e[0] + e[1] * e[1] + e[2] * e[2]) * B.info[i] : (e[0] * e[0] + e[1] * e[1]) * B.info[i];
+    B.err[3 * i] = e[0]; B.err[3 * i + 1] = e[1]; B.err[3 * i + 2] = e[2];
+    B.chi2[i] = c2;
+    double r0 = c2, r1;
+    if (robust) huber(c2, st ? B.d3 : B.d2, 1.0, r0, r1);
+    B.rho0[i] = r0;
+}
+
+// weights of one observation's quadratic form (base_binary_edge.hpp:104-151): wo = rho1 * information, orr = -(information e) rho1
+__device__ __forceinline__ void obs_weights(const BaDev& B, int i, int robust, double& wo, double* orr) {
+    double w = B.info[i], r1 = 1, r0;
+    if (robust) huber(B.chi2[i], B.stereo[i] ? B.d3 : B.d2, 1.0, r0, r1);
+    wo = r1 * w;
+#pragma unroll
+    for (int d = 0; d < 3; d++) orr[d] = -(w * B.err[3 * i + d]) * r1;
+}
+
+// ---- K11a linearize, landmark side: one thread per landmark walks its observations: Hll, bl, and the W block of each ---------
+__global__ void __launch_bounds__(128) ba_linearize_lm_kernel(const __grid_constant__ BaDev B, int robust) {
+    int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= B.N) return;
+    double H[6] = {0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};
+    double x[3] = {B.pt[3 * l], B.pt[3 * l + 1], B.pt[3 * l + 2]};
+    for (int i = B.lm_ptr[l]; i < B.lm_ptr[l + 1]; i++) {
+        double* W = B.Hpl + 18 * (size_t)i;
+        if (!B.active[i]) {
+#pragma unroll
+            for (int k = 0; k < 18; k++) W[k] = 0;
+            continue;
+        }
+        int pi = B.obs_pose[i];
+        Pose T = load_pose(B.pose + 7 * pi);
+        double p[3], R[9], JX[9], JT[18], wo, orr[3];
+        se3_map(T, x, p);
+        quat_to_R(T.q, R);
+        bool st = B.stereo[i];
+        jac_point(p, R, st, B.cam, JX);
+        obs_weights(B, i, robust, wo, orr);
+        const int D = st ? 3 : 2;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            double s = 0;
+            for (int d = 0; d < D; d++) s += JX[3 * d + a] * orr[d];
+            b[a] += s;
+        }
+        {
+            int k = 0;
+#pragma unroll
+            for (int a = 0; a < 3; a++)
+#pragma unroll
+                for (int c = a; c < 3; c++, k++) {
+                    double h = 0;
+                    for (int d = 0; d < D; d++) h += JX[3 * d + a] * wo * JX[3 * d + c];
+                    H[k] += h;
+                }
+        }
+        if (B.free_idx[pi] >= 0) {
+            jac_pose(p, st, B.cam, JT);
+#pragma unroll
+            for (int a = 0; a < 6; a++)
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    double h = 0;
+                    for (int d = 0; d < D; d++) h += JT[6 * d + a] * wo * JX[3 * d + c];
+                    W[3 * a + c] = h;
+                }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 18; k++) W[k] = 0;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) B.Hll[6 * (size_t)l + k] = H[k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) B.bl[3 * (size_t)l + k] = b[k];
+}
+
+// ---- K11b linearize, pose side: one CTA per free pose; ordered (strided + tree) reduction of J^T w J and J^T w r ----------------
+constexpr int POSE_THREADS = 128;
+__global__ void __launch_bounds__(POSE_THREADS) ba_linearize_pose_kernel(const __grid_constant__ BaDev B, int robust) {
+    int f = blockIdx.x;
+    int pi = B.free_list[f];
+    Pose T = load_pose(B.pose + 7 * pi);
+    double acc[27];
+#pragma unroll
+    for (int k = 0; k < 27; k++) acc[k] = 0;
+    for (int j = B.pose_ptr[f] + threadIdx.x; j < B.pose_ptr[f + 1]; j += POSE_THREADS) {
+        int i = B.pose_obs[j];
+        if (!B.active[i]) continue;
+        const double* X = B.pt + 3 * B.obs_lm[i];
+        double x[3] = {X[0], X[1], X[2]}, p[3], JT[18], wo, orr[3];
+        se3_map(T, x, p);
+        bool st = B.stereo[i];
+        jac_pose(p, st, B.cam, JT);
+        obs_weights(B, i, robust, wo, orr);
+        const int D = st ? 3 : 2;
+        int k = 0;
+#pragma unroll
+        for (int a = 0; a < 6; a++)
+#pragma unroll
+            for (int c = a; c < 6; c++, k++) {
+                double h = 0;
+                for (int d = 0; d < D; d++) h += JT[6 * d + a] * wo * JT[6 * d + c];
+                acc[k] += h;
+            }
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+            double s = 0;
+            for (int d = 0; d < D; d++) s += JT[6 * d + a] * orr[d];
+            acc[21 + a] += s;
+        }
+    }
+    __shared__ double red[POSE_THREADS / 32][27];
+#pragma unroll
+    for (int k = 0; k < 27; k++) {
+        double v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 27) {
+        double v = 0;
+#pragma unroll
+        for (int w = 0; w < POSE_THREADS / 32; w++) v += red[w][threadIdx.x];
+        red[0][threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 36) {
+        int a = threadIdx.x / 6, c = threadIdx.x % 6;
+        int lo = a < c ? a : c, hi = a < c ? c : a;
+        int k = lo * 6 - lo * (lo - 1) / 2 + (hi - lo);
+        B.Hpp[36 * (size_t)f + threadIdx.x] = red[0][k];
+    }
+    if (threadIdx.x < 6) B.bp[6 * (size_t)f + threadIdx.x] = red[0][21 + threadIdx.x];
+}
+
+// block-wide ordered sum / max over a strided sequence (blockDim.x == 1024)
+template <bool MAX>
+__device__ double block_reduce_1024(double v, double* sm) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = MAX ? fmax(v, w) : v + w;
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        v = sm[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double w = __shfl_xor_sync(0xffffffffu, v, o);
+            v = MAX ? fmax(v, w) : v + w;
+        }
+        if (threadIdx.x == 0) sm[32] = v;
+    }
+    __syncthreads();
+    return sm[32];
+}
+
+// ---- LM control, start of a stage / of an outer iteration (sparse_optimizer.cpp:366-381, levenberg.cpp:58-96,152-166) ----------
+__global__ void __launch_bounds__(1024) ba_iter_begin_kernel(const __grid_constant__ BaDev B, int first_of_stage) {
+    __shared__ double sm[33];
+    LmState* st = B.st;
+    if (first_of_stage) {
+        double s = 0;
+        for (int i = threadIdx.x; i < B.M; i += 1024) s += B.rho0[i];
+        s = block_reduce_1024<false>(s, sm);
+        double md = 0;  // computeLambdaInit: tau * max |diagonal| over all active vertices
+        for (int k = threadIdx.x; k < 6 * B.Pf; k += 1024) md = fmax(md, fabs(B.Hpp[36 * (size_t)(k / 6) + 7 * (k % 6)]));
+        for (int k = threadIdx.x; k < 3 * B.N; k += 1024) {
+            int l = k / 3, j = k % 3;
+            md = fmax(md, fabs(B.Hll[6 * (size_t)l + (j == 0 ? 0 : (j == 1 ? 3 : 5))]));
+        }
+        md = block_reduce_1024<true>(md, sm);
+        if (threadIdx.x == 0) {
+            st->currentChi = s;
+            st->lambda = 1e-5 * md;
+            st->ni = 2;
+            st->prevChi2 = st->curChi2 = st->chi2Diff = FLT_MAX;
+            st->it = 0;
+            st->ok = 1;
+            st->cont_iter = 1;
+        }
+    }
+    if (threadIdx.x == 0) {
+        float t = st->prevChi2;
+        st->prevChi2 = st->curChi2;
+        st->curChi2 = t;
+        st->qmax = 0;
+        st->rho = 0;
+        st->cont_trial = 1;
+    }
+}
+
+// ---- K12a per landmark: D^-1 = (Hll + lambda I)^-1, db = D^-1 bl, Y = W D^-1 for each of its observations --------------------
+__global__ void __launch_bounds__(128) ba_prep_kernel(const __grid_constant__ BaDev B) {
+    int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= B.N) return;
+    const double lambda = B.st->lambda;
+    double D[6], I[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) D[k] = B.Hll[6 * (size_t)l + k];
+    D[0] += lambda; D[3] += lambda; D[5] += lambda;
+    inv3_sym(D, I);
+#pragma unroll
+    for (int k = 0; k < 6; k++) B.Dinv[6 * (size_t)l + k] = I[k];
+    const double Im[9] = {I[0], I[1], I[2], I[1], I[3], I[4], I[2], I[4], I[5]};
+    double b[3] = {B.bl[3 * (size_t)l], B.bl[3 * (size_t)l + 1], B.bl[3 * (size_t)l + 2]};
+#pragma unroll
+    for (int a = 0; a < 3; a++) B.db[3 * (size_t)l + a] = Im[3 * a] * b[0] + Im[3 * a + 1] * b[1] + Im[3 * a + 2] * b[2];
+    for (int i = B.lm_ptr[l]; i < B.lm_ptr[l + 1]; i++) {
+        const double* W = B.Hpl + 18 * (size_t)i;
+        double* Y = B.Y + 18 * (size_t)i;
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+            double w0 = W[3 * a], w1 = W[3 * a + 1], w2 = W[3 * a + 2];
+#pragma unroll
+            for (int c = 0; c < 3; c++) Y[3 * a + c] = w0 * Im[c] + w1 * Im[3 + c] + w2 * Im[6 + c];
+        }
+    }
+}
+
+// ---- K12b Schur complement by gather (block_solver.hpp:329-400): one CTA per non-zero 6x6 block (i <= j) of S ----------------
+//   S(i,j) = [i == j] (Hpp(i) + lambda I) - sum over shared landmarks of Y_a W_b^T ;  bs(i) = bp(i) - sum over its observations W_a db
+constexpr int GATHER_CHUNKS = 8;
+__global__ void __launch_bounds__(36 * GATHER_CHUNKS) ba_schur_gather_kernel(const __grid_constant__ BaDev B) {
+    const int blk = blockIdx.x;
+    const int2 ij = B.blk_ij[blk];
+    const int beg = B.blk_ptr[blk], end = B.blk_ptr[blk + 1];
+    const int e = threadIdx.x % 36, chunk = threadIdx.x / 36, r = e / 6, c = e % 6;
+    const int len = end - beg, per = (len + GATHER_CHUNKS - 1) / GATHER_CHUNKS;
+    const int c0 = beg + chunk * per, c1 = min(end, c0 + per);
+    const bool diag = ij.x == ij.y;
+    double s = 0, sb = 0;
+    for (int k = c0; k < c1; k++) {
+        const int2 ab = B.con[k];
+        const double* Y = B.Y + 18 * (size_t)ab.x + 3 * r;
+        const double* W = B.Hpl + 18 * (size_t)ab.y + 3 * c;
+        s += Y[0] * W[0] + Y[1] * W[1] + Y[2] * W[2];
+        if (diag && c == 0) {
+            const double* Wa = B.Hpl + 18 * (size_t)ab.x + 3 * r;
+            const double* db = B.db + 3 * (size_t)B.obs_lm[ab.x];
+            sb += Wa[0] * db[0] + Wa[1] * db[1] + Wa[2] * db[2];
+        }
+    }
+    __shared__ double red[GATHER_CHUNKS][36], redb[GATHER_CHUNKS][6];
+    red[chunk][e] = s;
+    if (c == 0) redb[chunk][r] = sb;
+    __syncthreads();
+    if (chunk == 0) {
+        double t = 0;
+#pragma unroll
+        for (int k = 0; k < GATHER_CHUNKS; k++) t += red[k][e];
+        double h = 0;
+        if (diag) {
+            h = B.Hpp[36 * (size_t)ij.x + e];
+            if (r == c) h += B.st->lambda;
+        }
+        h -= t;
+        const int n = B.n;
+        B.S[(size_t)(6 * ij.x + r) * n + 6 * ij.y + c] = h;
+        if (!diag) B.S[(size_t)(6 * ij.y + c) * n + 6 * ij.x + r] = h;
+        if (diag && c == 0) {
+            double tb = 0;
+#pragma unroll
+            for (int k = 0; k < GATHER_CHUNKS; k++) tb += redb[k][r];
+            B.bs[6 * ij.x + r] = B.bp[6 * ij.x + r] - tb;
+        }
+    }
+}
+
+// ---- K13 dense reduced-camera solve S xp = bs (replaces LinearSolverEigen / SimplicialLDLT, linear_solver_eigen.h:92-123) --------
+// One CTA; the lower triangle of S plus bs as an extra row is held packed (row i at i(i+1)/2) in shared memory when it fits
+// (n <= 238), else in a global workspace.  Right-looking L D L^T: after eliminating column j the extra row holds w = L^-1 bs,
+// then one warp back-substitutes L^T x = D^-1 w.  A non-positive pivot raises chol_fail (the trial is then rejected).
+constexpr int CHOL_THREADS = 1024;
+__global__ void __launch_bounds__(CHOL_THREADS) ba_chol_solve_kernel(const __grid_constant__ BaDev B, double* gws, int use_smem) {
+    extern __shared__ double sm_dyn[];
+    __shared__ double col[1024];  // current column (chunks of up to 1024 rows at a time are not needed: n <= 1023 for this kernel)
+    __shared__ int fail;
+    const int n = B.n, tid = threadIdx.x;
+    double* A = use_smem ? sm_dyn : gws;
+    if (tid == 0) fail = 0;
+    // load lower triangle (+ rhs row n)
+    for (int i = tid / 32; i <= n; i += CHOL_THREADS / 32) {
+        double* row = A + (size_t)i * (i + 1) / 2;
+        if (i < n)
+            for (int k = tid & 31; k <= i; k += 32) row[k] = B.S[(size_t)i * n + k];
+        else
+            for (int k = tid & 31; k < n; k += 32) row[k] = B.bs[k];
+    }
+    __syncthreads();
+    for (int j = 0; j < n; j++) {
+        const double p = A[(size_t)j * (j + 1) / 2 + j];
+        if (!(p > 0) || !isfinite(p)) {
+            if (tid == 0) fail = 1;
+            break;  // uniform: every thread reads the same p
+        }
+        const int m = n - j;  // rows j+1 .. n
+        for (int t = tid; t < m; t += CHOL_THREADS) col[t] = A[(size_t)(j + 1 + t) * (j + 2 + t) / 2 + j];
+        __syncthreads();
+        const double inv = 1.0 / p;
+        for (int i = j + 1 + tid / 32; i <= n; i += CHOL_THREADS / 32) {
+            double* row = A + (size_t)i * (i + 1) / 2;
+            const double li = col[i - j - 1] * inv;
+            const int kmax = i < n ? i : n - 1;
+            for (int k = j + 1 + (tid & 31); k <= kmax; k += 32) row[k] -= li * col[k - j - 1];
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (fail) {
+        if (tid == 0) B.st->chol_fail = 1;
+        for (int k = tid; k < n; k += CHOL_THREADS) B.xp[k] = 0;
+        return;
+    }
+    if (tid == 0) B.st->chol_fail = 0;
+    if (tid < 32) {  // back-substitution: x_j = (w_j - sum_{i>j} A[i][j] x_i) / d_j ; s (in col[]) carries w minus the known terms
+        double* wrow = A + (size_t)n * (n + 1) / 2;
+        for (int k = tid; k < n; k += 32) col[k] = wrow[k];
+        __syncwarp();
+        for (int j = n - 1; j >= 0; j--) {
+            const double* row = A + (size_t)j * (j + 1) / 2;
+            const double xj = col[j] / row[j];
+            __syncwarp();
+            if (tid == 0) col[j] = xj;
+            for (int k = tid; k < j; k += 32) col[k] -= row[k] * xj;
+            __syncwarp();
+        }
+        for (int k = tid; k < n; k += 32) B.xp[k] = col[k];
+    }
+}
+
+// ---- K12c update: landmark back-substitution xl = D^-1 (bl - W^T xp) (block_solver.hpp:413-443), backup (push), oplus ----------
+__global__ void __launch_bounds__(128) ba_update_kernel(const __grid_constant__ BaDev B) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const LmState* st = B.st;
+    const bool apply = !st->chol_fail;
+    const double lambda = st->lambda;
+    if (t < B.N) {
+        const int l = t;
+        double c[3] = {B.bl[3 * (size_t)l], B.bl[3 * (size_t)l + 1], B.bl[3 * (size_t)l + 2]};
+        for (int i = B.lm_ptr[l]; i < B.lm_ptr[l + 1]; i++) {
+            int f = B.free_idx[B.obs_pose[i]];
+            if (f < 0 || !B.active[i]) continue;
+            const double* W = B.Hpl + 18 * (size_t)i;
+            const double* x = B.xp + 6 * f;
+#pragma unroll
+            for (int b = 0; b < 3; b++) {
+                double s = 0;
+#pragma unroll
+                for (int a = 0; a < 6; a++) s += W[3 * a + b] * x[a];
+                c[b] -= s;
+            }
+        }
+        const double* I = B.Dinv + 6 * (size_t)l;
+        double xl[3] = {I[0] * c[0] + I[1] * c[1] + I[2] * c[2], I[1] * c[0] + I[3] * c[1] + I[4] * c[2],
+                        I[2] * c[0] + I[4] * c[1] + I[5] * c[2]};
+        double sc = 0;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            double v = B.pt[3 * (size_t)l + k];
+            B.pt_bak[3 * (size_t)l + k] = v;
+            if (apply) B.pt[3 * (size_t)l + k] = v + xl[k];
+            B.xl[3 * (size_t)l + k] = xl[k];
+            sc += xl[k] * (lambda * xl[k] + B.bl[3 * (size_t)l + k]);
+        }
+        B.scale_lm[l] = sc;  // computeScale terms (levenberg.cpp:168-175)
+    } else if (t < B.N + B.Pf) {
+        const int f = t - B.N, pi = B.free_list[f];
+        Pose T = load_pose(B.pose + 7 * pi);
+        store_pose(B.pose_bak + 7 * pi, T);
+        double u[6], sc = 0;
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            u[k] = B.xp[6 * f + k];
+            sc += u[k] * (lambda * u[k] + B.bp[6 * f + k]);
+        }
+        B.scale_pose[f] = sc;
+        if (apply) {
+            se3_oplus(T, u);
+            store_pose(B.pose + 7 * pi, T);
+        }
+    }
+}
+
+// ---- LM control, end of a trial (levenberg.cpp:96-150) and, when the trial loop ends, of the iteration (sparse_optimizer.cpp:403-436)
+__global__ void __launch_bounds__(1024) ba_decide_kernel(const __grid_constant__ BaDev B, int stop, int max_iters) {
+    __shared__ double sm[33];
+    __shared__ int reject;
+    LmState* st = B.st;
+    double s = 0;
+    for (int i = threadIdx.x; i < B.M; i += 1024) s += B.rho0[i];
+    const double chi_raw = block_reduce_1024<false>(s, sm);
+    double sc = 0;
+    for (int f = threadIdx.x; f < B.Pf; f += 1024) sc += B.scale_pose[f];
+    const double sc_p = block_reduce_1024<false>(sc, sm);
+    sc = 0;
+    for (int l = threadIdx.x; l < B.N; l += 1024) sc += B.scale_lm[l];
+    const double sc_l = block_reduce_1024<false>(sc, sm);
+    if (threadIdx.x == 0) {
+        double tempChi = st->chol_fail ? DBL_MAX : chi_raw;
+        double rho = st->currentChi - tempChi;
+        double scale = sc_p + sc_l + 1e-3;
+        rho /= scale;
+        int rej = 0, lam_bad = 0;
+        if (rho > 0 && isfinite(tempChi) && !st->chol_fail) {
+            double alpha = 1. - pow((2 * rho - 1), 3.0);
+            alpha = fmin(alpha, 2. / 3.);
+            double sf = fmax(1. / 3., alpha);
+            st->lambda *= sf;
+            st->ni = 2;
+            st->currentChi = tempChi;
+        } else {
+            st->lambda *= st->ni;
+            st->ni *= 2;
+            rej = 1;
+            if (!isfinite(st->lambda)) lam_bad = 1;
+        }
+        if (!lam_bad) st->qmax++;
+        st->rho = rho;
+        st->tempChi = tempChi;
+        st->scale = scale;
+        reject = rej;
+        int cont = !lam_bad && rho < 0 && st->qmax < 10 && !stop;
+        st->cont_trial = cont;
+        if (!cont) {
+            if (st->qmax == 10 || rho == 0 || !isfinite(st->lambda)) st->ok = 0;
+            st->curChi2 = (float)chi_raw;
+            st->chi2Diff = st->prevChi2 - st->curChi2;
+            if (st->ntrace < 64) {
+                st->trace[2 * st->ntrace] = chi_raw;
+                st->trace[2 * st->ntrace + 1] = st->qmax;
+                st->ntrace++;
+            }
+            st->it++;
+            st->cont_iter = st->it < max_iters && !stop && st->ok && st->chi2Diff > 1.0f;
+        }
+    }
+    __syncthreads();
+    if (reject) {  // pop: restore the estimates saved before the update
+        for (int k = threadIdx.x; k < 3 * B.N; k += 1024) B.pt[k] = B.pt_bak[k];
+        for (int k = threadIdx.x; k < 7 * B.Pf; k += 1024) {
+            int pi = B.free_list[k / 7];
+            B.pose[7 * pi + k % 7] = B.pose_bak[7 * pi + k % 7];
+        }
+    }
+}
+
+// ---- between the stages (globaloptimizer_g2o.cpp:432-449): edges with chi2 above the gate or non-positive depth leave (level 1)
+__global__ void __launch_bounds__(256) ba_flag_outliers_kernel(const __grid_constant__ BaDev B) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B.M) return;
+    Pose T = load_pose(B.pose + 7 * B.obs_pose[i]);
+    const double* X = B.pt + 3 * B.obs_lm[i];
+    double x[3] = {X[0], X[1], X[2]}, p[3];
+    se3_map(T, x, p);
+    if (B.chi2[i] > (double)(B.stereo[i] ? B.chi3d : B.chi2d) || !(p[2] > 0.0)) B.active[i] = 0;
+}
+
+// ---- getResults (globaloptimizer_g2o.cpp:466-521): poses as f32 4x4, bad associations ---------------------------------------------
+__global__ void __launch_bounds__(256) ba_results_kernel(const __grid_constant__ BaDev B, const float* poses44_in, float* poses44_out,
+                                                         uint8_t* bad) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < B.P) {
+        float* m = poses44_out + 16 * t;
+        if (B.free_idx[t] < 0) {
+            for (int k = 0; k < 16; k++) m[k] = poses44_in[16 * t + k];
+        } else {
+            Pose T = load_pose(B.pose + 7 * t);
+            double R[9];
+            quat_to_R(T.q, R);
+            for (int r = 0; r < 3; r++) {
+                for (int c = 0; c < 3; c++) m[4 * r + c] = (float)R[3 * r + c];
+                m[4 * r + 3] = (float)T.t[r];
+            }
+            m[12] = m[13] = m[14] = 0;
+            m[15] = 1;
+        }
+    }
+}
+__global__ void __launch_bounds__(256) ba_bad_kernel(const __grid_constant__ BaDev B, const float* poses44_out, uint8_t* bad) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B.M) return;
+    Pose T = load_pose(B.pose + 7 * B.obs_pose[i]);
+    const double* X = B.pt + 3 * B.obs_lm[i];
+    double x[3] = {X[0], X[1], X[2]}, p[3];
+    se3_map(T, x, p);
+    int b = 0;
+    if (B.stereo[i]) {
+        if (B.chi2[i] > (double)B.chi3d || !(p[2] > 0.0)) b = 1;
+    } else if (B.chi2[i] > (double)B.chi2d) b = 1;
+    if (!b) {  // pincam = pose_f2g (f32) * point (f32), z < 0
+        const float* m = poses44_out + 16 * B.obs_pose[i];
+        float px = (float)x[0], py = (float)x[1], pz = (float)x[2];
+        float zc = m[8] * px + m[9] * py + m[10] * pz + m[11];
+        if (zc < 0) b = 1;
+    }
+    bad[i] = b;
+}
+
+__global__ void __launch_bounds__(128) ba_init_poses_kernel(const __grid_constant__ BaDev B, const float* poses44) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B.P) return;
+    Pose T = pose_from_m44f(poses44 + 16 * t);
+    store_pose(B.pose + 7 * t, T);
+    store_pose(B.pose_bak + 7 * t, T);
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------------------------
+struct Arena {
+    size_t off = 0;
+    size_t take(size_t bytes) {
+        size_t o = off;
+        off += (bytes + 255) & ~(size_t)255;
+        return o;
+    }
+};
+
+}  // namespace
+
+struct uco_ba_state {
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int smem_optin = 0;
+};
+
+void uco_ba_state_free(uco_b200_ctx* ctx) {
+    if (!ctx->ba) return;
+    if (ctx->ba->ev0) cudaEventDestroy(ctx->ba->ev0);
+    if (ctx->ba->ev1) cudaEventDestroy(ctx->ba->ev1);
+    delete ctx->ba;
+    ctx->ba = nullptr;
+}
+
+extern "C" int uco_b200_ba_solve(uco_b200_ctx* ctx, const uco_ba_problem* pb, const volatile int* stop, uco_ba_result* res) {
+    if (!ctx) return UCO_E_INVALID;
+    if (!pb || !res) return uco_fail(ctx, UCO_E_INVALID, "ba_solve: null problem / result");
+    const int P = pb->n_poses, N = pb->n_points, M = pb->n_obs;
+    if (P <= 0 || N < 0 || M < 0 || pb->n_iters < 0) return uco_fail(ctx, UCO_E_INVALID, "ba_solve: bad sizes");
+    if (!pb->poses44 || !pb->fixed || (N && !pb->points3) || (M && (!pb->obs_pose || !pb->obs_point || !pb->obs_uv || !pb->obs_inv_sigma2)))
+        return uco_fail(ctx, UCO_E_INVALID, "ba_solve: null input array");
+    for (int i = 0; i < M; i++) {
+        if ((unsigned)pb->obs_pose[i] >= (unsigned)P || (unsigned)pb->obs_point[i] >= (unsigned)N)
+            return uco_fail(ctx, UCO_E_INVALID, "ba_solve: observation %d references pose %d / point %d out of range", i,
+                            pb->obs_pose[i], pb->obs_point[i]);
+        if (pb->obs_stereo && pb->obs_stereo[i] && !pb->obs_ur) return uco_fail(ctx, UCO_E_INVALID, "ba_solve: stereo observation without obs_ur");
+    }
+    if (!ctx->ba) {
+        ctx->ba = new uco_ba_state();
+        cudaEventCreate(&ctx->ba->ev0);
+        cudaEventCreate(&ctx->ba->ev1);
+        cudaDeviceGetAttribute(&ctx->ba->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
+    }
+    // ---- structure (host): free-pose numbering, observations sorted by landmark, per-pose lists, Schur gather lists
+    std::vector<int> free_idx(P), free_list;
+    for (int i = 0; i < P; i++) {
+        free_idx[i] = pb->fixed[i] ? -1 : (int)free_list.size();
+        if (!pb->fixed[i]) free_list.push_back(i);
+    }
+    const int Pf = (int)free_list.size(), n = 6 * Pf;
+    if (n > 1023) return uco_fail(ctx, UCO_E_INVALID, "ba_solve: %d free poses exceed the single-CTA reduced solver (170)", Pf);
+    std::vector<int> lm_ptr(N + 1, 0), order(M), fill(N, 0);
+    for (int i = 0; i < M; i++) lm_ptr[pb->obs_point[i] + 1]++;
+    for (int l = 0; l < N; l++) lm_ptr[l + 1] += lm_ptr[l];
+    for (int i = 0; i < M; i++) order[lm_ptr[pb->obs_point[i]] + fill[pb->obs_point[i]]++] = i;  // sorted position -> caller index
+    std::vector<int> s_pose(M), s_lm(M);
+    for (int k = 0; k < M; k++) { s_pose[k] = pb->obs_pose[order[k]]; s_lm[k] = pb->obs_point[order[k]]; }
+    std::vector<int> pose_ptr(Pf + 1, 0), pose_obs;
+    for (int k = 0; k < M; k++) if (free_idx[s_pose[k]] >= 0) pose_ptr[free_idx[s_pose[k]] + 1]++;
+    for (int f = 0; f < Pf; f++) pose_ptr[f + 1] += pose_ptr[f];
+    pose_obs.resize(pose_ptr[Pf]);
+    {
+        std::vector<int> pf(Pf, 0);
+        for (int k = 0; k < M; k++) { int f = free_idx[s_pose[k]]; if (f >= 0) pose_obs[pose_ptr[f] + pf[f]++] = k; }
+    }
+    // gather lists: key = i * Pf + j (i <= j), contributions in landmark order
+    std::vector<int> blk_cnt((size_t)Pf * Pf, 0);
+    for (int l = 0; l < N; l++)
+        for (int a = lm_ptr[l]; a < lm_ptr[l + 1]; a++) {
+            int fa = free_idx[s_pose[a]];
+            if (fa < 0) continue;
+            for (int b = lm_ptr[l]; b < lm_ptr[l + 1]; b++) {
+                int fb = free_idx[s_pose[b]];
+                if (fb < fa || (fb == fa && b != a)) continue;
+                blk_cnt[(size_t)fa * Pf + fb]++;
+            }
+        }
+    std::vector<int> blk_of((size_t)Pf * Pf, -1), blk_ptr(1, 0);
+    std::vector<int2> blk_ij;
+    for (int i = 0; i < Pf; i++)
+        for (int j = i; j < Pf; j++)
+            if (blk_cnt[(size_t)i * Pf + j] || i == j) {  // diagonal blocks always exist (Hpp + lambda I)
+                blk_of[(size_t)i * Pf + j] = (int)blk_ij.size();
+                blk_ij.push_back(make_int2(i, j));
+                blk_ptr.push_back(blk_ptr.back() + blk_cnt[(size_t)i * Pf + j]);
+            }
+    const int nblk = (int)blk_ij.size();
+    std::vector<int2> con(blk_ptr.back());
+    {
+        std::vector<int> bf(nblk, 0);
+        for (int l = 0; l < N; l++)
+            for (int a = lm_ptr[l]; a < lm_ptr[l + 1]; a++) {
+                int fa = free_idx[s_pose[a]];
+                if (fa < 0) continue;
+                for (int b = lm_ptr[l]; b < lm_ptr[l + 1]; b++) {
+                    int fb = free_idx[s_pose[b]];
+                    if (fb < fa || (fb == fa && b != a)) continue;
+                    int k = blk_of[(size_t)fa * Pf + fb];
+                    con[blk_ptr[k] + bf[k]++] = make_int2(a, b);
+                }
+            }
+    }
+    // ---- arena: [inputs copied from the host in one transfer][device-only work arrays]
+    Arena A;
+    const size_t o_free_idx = A.take(4 * (size_t)P), o_free_list = A.take(4 * (size_t)(Pf + 1)), o_lm_ptr = A.take(4 * (size_t)(N + 1)),
+                 o_obs_pose = A.take(4 * (size_t)(M + 1)), o_obs_lm = A.take(4 * (size_t)(M + 1)), o_pose_ptr = A.take(4 * (size_t)(Pf + 1)),
+                 o_pose_obs = A.take(4 * (pose_obs.size() + 1)), o_blk_ptr = A.take(4 * (size_t)(nblk + 1)),
+                 o_blk_ij = A.take(8 * (size_t)(nblk + 1)), o_con = A.take(8 * (con.size() + 1)), o_z = A.take(24 * (size_t)(M + 1)),
+                 o_info = A.take(8 * (size_t)(M + 1)), o_stereo = A.take((size_t)M + 1), o_active = A.take((size_t)M + 1),
+                 o_pt = A.take(24 * (size_t)(N + 1)), o_p44 = A.take(64 * (size_t)P);
+    const size_t in_bytes = A.off;
+    const size_t o_pose = A.take(56 * (size_t)P), o_pose_bak = A.take(56 * (size_t)P), o_pt_bak = A.take(24 * (size_t)(N + 1)),
+                 o_err = A.take(24 * (size_t)(M + 1)), o_chi2 = A.take(8 * (size_t)(M + 1)), o_rho0 = A.take(8 * (size_t)(M + 1)),
+                 o_Hll = A.take(48 * (size_t)(N + 1)), o_bl = A.take(24 * (size_t)(N + 1)), o_Hpl = A.take(144 * (size_t)(M + 1)),
+                 o_Y = A.take(144 * (size_t)(M + 1)), o_Dinv = A.take(48 * (size_t)(N + 1)), o_db = A.take(24 * (size_t)(N + 1)),
+                 o_xl = A.take(24 * (size_t)(N + 1)), o_Hpp = A.take(288 * (size_t)(Pf + 1)), o_bp = A.take(48 * (size_t)(Pf + 1)),
+                 o_S = A.take(8 * ((size_t)n * n + 1)), o_bs = A.take(8 * (size_t)(n + 1)), o_xp = A.take(8 * (size_t)(n + 1)),
+                 o_scl = A.take(8 * (size_t)(N + 1)), o_scp = A.take(8 * (size_t)(Pf + 1)), o_st = A.take(sizeof(LmState)),
+                 o_p44o = A.take(64 * (size_t)P), o_bad = A.take((size_t)M + 1),
+                 o_chol = A.take(8 * ((size_t)(n + 1) * (n + 2) / 2 + 1));
+    uint8_t* d = (uint8_t*)uco_ws(ctx, WS_BA, A.off);
+    uint8_t* h = (uint8_t*)uco_pinned(ctx, WS_BA, in_bytes + sizeof(LmState));
+    if (!d || !h) return UCO_E_NOMEM;
+    memcpy(h + o_free_idx, free_idx.data(), 4 * (size_t)P);
+    memcpy(h + o_free_list, free_list.data(), 4 * (size_t)Pf);
+    memcpy(h + o_lm_ptr, lm_ptr.data(), 4 * (size_t)(N + 1));
+    memcpy(h + o_obs_pose, s_pose.data(), 4 * (size_t)M);
+    memcpy(h + o_obs_lm, s_lm.data(), 4 * (size_t)M);
+    memcpy(h + o_pose_ptr, pose_ptr.data(), 4 * (size_t)(Pf + 1));
+    memcpy(h + o_pose_obs, pose_obs.data(), 4 * pose_obs.size());
+    memcpy(h + o_blk_ptr, blk_ptr.data(), 4 * (size_t)(nblk + 1));
+    memcpy(h + o_blk_ij, blk_ij.data(), 8 * (size_t)nblk);
+    memcpy(h + o_con, con.data(), 8 * con.size());
+    {
+        double* z = (double*)(h + o_z);
+        double* info = (double*)(h + o_info);
+        uint8_t* st = h + o_stereo;
+        for (int k = 0; k < M; k++) {
+            int i = order[k];
+            bool s = pb->obs_stereo && pb->obs_stereo[i];
+            z[3 * k] = pb->obs_uv[2 * i]; z[3 * k + 1] = pb->obs_uv[2 * i + 1]; z[3 * k + 2] = s ? pb->obs_ur[i] : 0.0;
+            info[k] = pb->obs_inv_sigma2[i];
+            st[k] = s;
+        }
+        memset(h + o_active, 1, (size_t)M);
+        double* pt = (double*)(h + o_pt);
+        for (int k = 0; k < 3 * N; k++) pt[k] = pb->points3[k];
+        memcpy(h + o_p44, pb->poses44, 64 * (size_t)P);
+    }
+    cudaStream_t s = ctx->stream;
+    UCO_CUDA(ctx, cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, s));
+    UCO_CUDA(ctx, cudaMemsetAsync(d + o_st, 0, sizeof(LmState), s));
+    UCO_CUDA(ctx, cudaMemsetAsync(d + o_err, 0, 24 * (size_t)(M + 1), s));
+    UCO_CUDA(ctx, cudaMemsetAsync(d + o_chi2, 0, 8 * (size_t)(M + 1), s));
+    UCO_CUDA(ctx, cudaMemsetAsync(d + o_S, 0, 8 * ((size_t)n * n + 1), s));  // blocks without shared landmarks are never written: they stay zero
+    BaDev B;
+    B.P = P; B.N = N; B.M = M; B.Pf = Pf; B.n = n; B.nblk = nblk;
+    B.pose = (double*)(d + o_pose); B.pose_bak = (double*)(d + o_pose_bak); B.pt = (double*)(d + o_pt); B.pt_bak = (double*)(d + o_pt_bak);
+    B.free_idx = (int*)(d + o_free_idx); B.free_list = (int*)(d + o_free_list); B.lm_ptr = (int*)(d + o_lm_ptr);
+    B.obs_pose = (int*)(d + o_obs_pose); B.obs_lm = (int*)(d + o_obs_lm); B.pose_ptr = (int*)(d + o_pose_ptr); B.pose_obs = (int*)(d + o_pose_obs);
+    B.z = (double*)(d + o_z); B.info = (double*)(d + o_info); B.stereo = d + o_stereo; B.active = d + o_active;
+    B.err = (double*)(d + o_err); B.chi2 = (double*)(d + o_chi2); B.rho0 = (double*)(d + o_rho0); B.Hll = (double*)(d + o_Hll);
+    B.bl = (double*)(d + o_bl); B.Hpl = (double*)(d + o_Hpl); B.Y = (double*)(d + o_Y); B.Dinv = (double*)(d + o_Dinv); B.db = (double*)(d + o_db);
+    B.xl = (double*)(d + o_xl); B.Hpp = (double*)(d + o_Hpp); B.bp = (double*)(d + o_bp); B.S = (double*)(d + o_S); B.bs = (double*)(d + o_bs);
+    B.xp = (double*)(d + o_xp); B.scale_lm = (double*)(d + o_scl); B.scale_pose = (double*)(d + o_scp);
+    B.blk_ptr = (int*)(d + o_blk_ptr); B.blk_ij = (int2*)(d + o_blk_ij); B.con = (int2*)(d + o_con);
+    B.st = (LmState*)(d + o_st);
+    B.cam.fx = pb->fx; B.cam.fy = pb->fy; B.cam.cx = pb->cx; B.cam.cy = pb->cy; B.cam.bf = pb->bf; B.cam.bf_f = pb->bf;
+    B.chi2d = 5.99f; B.chi3d = 7.815f;
+    B.d2 = (double)sqrtf(B.chi2d); B.d3 = (double)sqrtf(B.chi3d);  // const float thHuber2D = sqrt(Chi2D)
+    LmState* hst = (LmState*)(h + in_bytes);
+    const size_t chol_bytes = 8 * ((size_t)(n + 1) * (n + 2) / 2);
+    const int chol_smem = chol_bytes + 16 * 1024 <= (size_t)ctx->ba->smem_optin;
+    if (chol_smem) UCO_CUDA(ctx, cudaFuncSetAttribute(ba_chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_bytes));
+    if (n > 1023) return uco_fail(ctx, UCO_E_INVALID, "ba_solve: reduced system too large");
+    const int gM = (M + 255) / 256, gN = (N + 127) / 128, gU = (N + Pf + 127) / 128;
+
+    UCO_CUDA(ctx, cudaEventRecord(ctx->ba->ev0, s));
+    ba_init_poses_kernel<<<(P + 127) / 128, 128, 0, s>>>(B, (const float*)(d + o_p44));
+    UCO_LAUNCH_CHECK(ctx);
+    int iters[2] = {0, 0};
+    bool stopped = false;
+    for (int stage = 0; stage < 2 && !stopped; stage++) {
+        const int robust = stage == 0, max_iters = stage == 0 ? pb->n_iters : 2 * pb->n_iters;
+        if (stage == 1 && M) {
+            ba_flag_outliers_kernel<<<gM, 256, 0, s>>>(B);
+            UCO_LAUNCH_CHECK(ctx);
+        }
+        if (M) {
+            ba_errors_kernel<<<gM, 256, 0, s>>>(B, robust);
+            UCO_LAUNCH_CHECK(ctx);
+        }
+        bool cont_iter = max_iters > 0 && !(stop && *stop);
+        for (int it = 0; cont_iter; it++) {
+            if (N) {
+                ba_linearize_lm_kernel<<<gN, 128, 0, s>>>(B, robust);
+                UCO_LAUNCH_CHECK(ctx);
+            }
+            if (Pf) {
+                ba_linearize_pose_kernel<<<Pf, POSE_THREADS, 0, s>>>(B, robust);
+                UCO_LAUNCH_CHECK(ctx);
+            }
+            ba_iter_begin_kernel<<<1, 1024, 0, s>>>(B, it == 0);
+            UCO_LAUNCH_CHECK(ctx);
+            bool cont_trial = true;
+            while (cont_trial) {
+                if (N) {
+                    ba_prep_kernel<<<gN, 128, 0, s>>>(B);
+                    UCO_LAUNCH_CHECK(ctx);
+                }
+                if (Pf) {
+                    ba_schur_gather_kernel<<<nblk, 36 * GATHER_CHUNKS, 0, s>>>(B);
+                    UCO_LAUNCH_CHECK(ctx);
+                    ba_chol_solve_kernel<<<1, CHOL_THREADS, chol_smem ? chol_bytes : 0, s>>>(B, (double*)(d + o_chol), chol_smem);
+                    UCO_LAUNCH_CHECK(ctx);
+                }
+                ba_update_kernel<<<gU, 128, 0, s>>>(B);
+                UCO_LAUNCH_CHECK(ctx);
+                if (M) {
+                    ba_errors_kernel<<<gM, 256, 0, s>>>(B, robust);
+                    UCO_LAUNCH_CHECK(ctx);
+                }
+                ba_decide_kernel<<<1, 1024, 0, s>>>(B, stop && *stop ? 1 : 0, max_iters);
+                UCO_LAUNCH_CHECK(ctx);
+                UCO_CUDA(ctx, cudaMemcpyAsync(hst, B.st, offsetof(LmState, trace), cudaMemcpyDeviceToHost, s));
+                UCO_CUDA(ctx, cudaStreamSynchronize(s));
+                cont_trial = hst->cont_trial != 0;
+            }
+            cont_iter = hst->cont_iter != 0;
+            iters[stage] = hst->it;
+        }
+        if (stop && *stop) stopped = true;  // GlobalOptimizerG2O::optimize: no second stage once stopASAP is raised
+    }
+    // ---- results
+    float* p44o = (float*)(d + o_p44o);
+    uint8_t* bad = d + o_bad;
+    ba_results_kernel<<<(P + 255) / 256, 256, 0, s>>>(B, (const float*)(d + o_p44), p44o, bad);
+    UCO_LAUNCH_CHECK(ctx);
+    if (M) {
+        ba_bad_kernel<<<gM, 256, 0, s>>>(B, p44o, bad);
+        UCO_LAUNCH_CHECK(ctx);
+    }
+    UCO_CUDA(ctx, cudaEventRecord(ctx->ba->ev1, s));
+    // D2H through a pinned staging area (reuses the input staging buffer), then scatter back to the caller's observation order
+    const size_t o_h_pose = 0, o_h_p44 = o_h_pose + 56 * (size_t)P, o_h_pt = o_h_p44 + 64 * (size_t)P, o_h_chi = o_h_pt + 24 * (size_t)N,
+                 o_h_act = o_h_chi + 8 * (size_t)M, o_h_bad = o_h_act + (size_t)M, o_h_st = ((o_h_bad + (size_t)M + 7) & ~(size_t)7),
+                 out_bytes = o_h_st + sizeof(LmState);
+    uint8_t* ho = (uint8_t*)uco_pinned(ctx, WS_BA_OUT, out_bytes);
+    if (!ho) return UCO_E_NOMEM;
+    UCO_CUDA(ctx, cudaMemcpyAsync(ho + o_h_pose, B.pose, 56 * (size_t)P, cudaMemcpyDeviceToHost, s));
+    UCO_CUDA(ctx, cudaMemcpyAsync(ho + o_h_p44, p44o, 64 * (size_t)P, cudaMemcpyDeviceToHost, s));
+    if (N) UCO_CUDA(ctx, cudaMemcpyAsync(ho + o_h_pt, B.pt, 24 * (size_t)N, cudaMemcpyDeviceToHost, s));
+    if (M) {
+        UCO_CUDA(ctx, cudaMemcpyAsync(ho + o_h_chi, B.chi2, 8 * (size_t)M, cudaMemcpyDeviceToHost, s));
+        UCO_CUDA(ctx, cudaMemcpyAsync(ho + o_h_act, B.active, (size_t)M, cudaMemcpyDeviceToHost, s));
+        UCO_CUDA(ctx, cudaMemcpyAsync(ho + o_h_bad, bad, (size_t)M, cudaMemcpyDeviceToHost, s));
+    }
+    UCO_CUDA(ctx, cudaMemcpyAsync(ho + o_h_st, B.st, sizeof(LmState), cudaMemcpyDeviceToHost, s));
+    UCO_CUDA(ctx, cudaStreamSynchronize(s));
+    if (res->pose7) memcpy(res->pose7, ho + o_h_pose, 56 * (size_t)P);
+    if (res->poses44) memcpy(res->poses44, ho + o_h_p44, 64 * (size_t)P);
+    if (res->points3) memcpy(res->points3, ho + o_h_pt, 24 * (size_t)N);
+    const double* hchi = (const double*)(ho + o_h_chi);
+    for (int k = 0; k < M; k++) {
+        int i = order[k];
+        if (res->obs_chi2) res->obs_chi2[i] = hchi[k];
+        if (res->obs_level) res->obs_level[i] = !(ho + o_h_act)[k];
+        if (res->obs_bad) res->obs_bad[i] = (ho + o_h_bad)[k];
+    }
+    const LmState* fst = (const LmState*)(ho + o_h_st);
+    if (res->trace) {
+        memset(res->trace, 0, sizeof(double) * 128);
+        memcpy(res->trace, fst->trace, sizeof(double) * 2 * (size_t)std::min(fst->ntrace, 64));
+    }
+    res->iters[0] = iters[0];
+    res->iters[1] = iters[1];
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ba->ev0, ctx->ba->ev1);
+    res->device_ms = ms;
+    return UCO_OK;
+}

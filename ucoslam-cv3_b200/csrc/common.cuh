@@ -33,6 +33,7 @@ enum {  // device workspace slots
     WS_KNN_Q = 0, WS_KNN_T, WS_KNN_IDX, WS_KNN_DIST,
     WS_BOW_DESC, WS_BOW_OUT,
     WS_GENERIC0, WS_GENERIC1, WS_GENERIC2, WS_GENERIC3,
+    WS_BA, WS_BA_OUT,
     WS_COUNT
 };
 

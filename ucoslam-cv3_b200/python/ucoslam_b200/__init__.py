@@ -43,6 +43,7 @@ SIGNATURES = {
     "uco_b200_bow_info": (_i, [_vp, _vp, _vp, _vp]),
     "uco_b200_bow_transform": (_i, [_vp, _vp, _vp, _i, _sz, _i, _vp, _vp, _vp]),
     "uco_b200_bow_transform_dev": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "uco_b200_ba_solve": (_i, [_vp, _vp, _vp, _vp]),
     "uco_b200_probe_math": (_i, [_i, _vp, _vp, _i, _vp, _vp]),
     "uco_b200_probe_retain_best": (_i, [_vp, _i, _i]),
 }
@@ -93,6 +94,18 @@ def load():
             f.restype, f.argtypes = res, args
         _lib = lib
     return _lib
+
+
+class BaProblem(ctypes.Structure):  # uco_ba_problem
+    _fields_ = [("n_poses", _c.c_int32), ("n_points", _c.c_int32), ("n_obs", _c.c_int32), ("poses44", _vp), ("fixed", _vp),
+                ("points3", _vp), ("obs_pose", _vp), ("obs_point", _vp), ("obs_uv", _vp), ("obs_ur", _vp), ("obs_stereo", _vp),
+                ("obs_inv_sigma2", _vp), ("fx", _c.c_float), ("fy", _c.c_float), ("cx", _c.c_float), ("cy", _c.c_float),
+                ("bf", _c.c_float), ("n_iters", _c.c_int32)]
+
+
+class BaResult(ctypes.Structure):  # uco_ba_result
+    _fields_ = [("pose7", _vp), ("poses44", _vp), ("points3", _vp), ("obs_chi2", _vp), ("obs_level", _vp), ("obs_bad", _vp),
+                ("trace", _vp), ("iters", _c.c_int32 * 2), ("device_ms", _c.c_float)]
 
 
 class UcoError(RuntimeError):
@@ -156,6 +169,27 @@ class Context:
         ts = t.strides[0] if nt > 0 else 32
         self._chk(self.lib.uco_b200_hamming_knn(self.h, _p(q), nq, qs, _p(t), nt, ts, k, order, _p(idx), _p(dist)))
         return idx, dist
+
+    # -- K10-K13 -------------------------------------------------------------------------------------------------
+    def ba_solve(self, pb, n_iters, stop=None):
+        """pb: dict with the uco_ba_problem arrays (poses44 f32 (P,16), fixed u8, points3 f32 (N,3), obs_pose/obs_point i32,
+        obs_uv f32 (M,2), obs_ur f32, obs_stereo u8, obs_inv_sigma2 f32, fx fy cx cy bf).  Returns a dict like the oracle's."""
+        A = lambda k, dt: np.ascontiguousarray(pb[k], dtype=dt)
+        a = dict(poses44=A("poses44", np.float32), fixed=A("fixed", np.uint8), points3=A("points3", np.float32),
+                 obs_pose=A("obs_pose", np.int32), obs_point=A("obs_point", np.int32), obs_uv=A("obs_uv", np.float32),
+                 obs_ur=A("obs_ur", np.float32), obs_stereo=A("obs_stereo", np.uint8), obs_inv_sigma2=A("obs_inv_sigma2", np.float32))
+        P, N, M = len(a["fixed"]), len(a["points3"]), len(a["obs_pose"])
+        out = dict(pose7=np.zeros((P, 7)), pose44=np.zeros((P, 16), np.float32), point3=np.zeros((N, 3)), chi2=np.zeros(M),
+                   level=np.zeros(M, np.uint8), bad=np.zeros(M, np.uint8), trace=np.zeros((64, 2)))
+        cp = BaProblem(P, N, M, _p(a["poses44"]), _p(a["fixed"]), _p(a["points3"]), _p(a["obs_pose"]), _p(a["obs_point"]),
+                       _p(a["obs_uv"]), _p(a["obs_ur"]), _p(a["obs_stereo"]), _p(a["obs_inv_sigma2"]), pb["fx"], pb["fy"],
+                       pb["cx"], pb["cy"], pb["bf"], int(n_iters))
+        cr = BaResult(_p(out["pose7"]), _p(out["pose44"]), _p(out["point3"]), _p(out["chi2"]), _p(out["level"]), _p(out["bad"]),
+                      _p(out["trace"]))
+        self._chk(self.lib.uco_b200_ba_solve(self.h, ctypes.addressof(cp), _p(stop), ctypes.addressof(cr)))
+        out["iters"] = np.array(list(cr.iters), np.int32)
+        out["device_ms"] = float(cr.device_ms)
+        return out
 
     # -- K9 ------------------------------------------------------------------------------------------------------
     def bow_load(self, voc_bytes):
