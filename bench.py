@@ -5,7 +5,8 @@
 
 A step is one pass of the hot path over one batch of F synthetic frames of BASELINE config 2 (640x480 mono, 2000 ORB
 keypoints/frame, 8 levels x1.2, local-BA window 10 KF): ORB extraction of every frame, Hamming k-NN (k=10) of every frame
-against its predecessor and the stages listed in config.stages.  Every stage runs through the C ABI of libucoslam_b200.so
+against its predecessor, and one local bundle adjustment (10 free + 2 fixed keyframes, 2000 points, ~15k observations, the
+reference's two-stage 5 + 10 LM iterations) per KF_EVERY = 8 frames.  Every stage runs through the C ABI of libucoslam_b200.so
 (no CPU fallback: the library refuses to create a context without a CUDA device).
   value   : frames/s with the step's input frames already resident in HBM (CUDA events on the context stream, L2 flushed
             between timed steps, max over ranks)
@@ -23,7 +24,10 @@ sys.path.insert(0, os.path.join(ROOT, "ucoslam-cv3_b200", "python"))
 W, H, KPTS, K_NN = 640, 480, 2000, 10
 METRIC = "frames/sec (ORB+match+local-BA) 640x480 mono"
 WORKLOAD = "config2: 640x480 mono tracking, 2000 ORB kpts/frame, local-BA window=10 KF"
-STAGES = ["orb_extract", "hamming_knn_match"]
+STAGES = ["orb_extract", "hamming_knn_match", "local_ba"]
+KF_EVERY = 8          # one keyframe (= one local-BA call, mapmanager.cpp:4005) per KF_EVERY frames
+BA_WINDOW = dict(n_poses=12, n_fixed=2, n_points=2000)   # 10 free KFs + 2 fixed observers, ~15k observations, nIters = 5
+BA_ITERS = 5
 
 
 def parse():
@@ -101,7 +105,12 @@ def synth_clip(n_frames, seed):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_reference_step(frames, oracle_py, orb_oracle, have_xflann):
+def ba_windows(n, seed):
+    from ucoslam_b200.synth import synth_ba_problem
+    return [synth_ba_problem(seed + i, **BA_WINDOW) for i in range(n)]
+
+
+def cpu_reference_step(frames, oracle_py, orb_oracle, have_xflann, windows=()):
     """The reference's CPU path for the same stages: ORB extraction of every frame (cv2-backed restatement of
     ORBextractor.cpp: the reference itself cannot be linked without OpenCV C++ headers) + FrameMatcher_Flann's
     xflann HKMeans(32,0) build + 16-check k-NN against the previous frame (the reference's own code)."""
@@ -114,14 +123,18 @@ def cpu_reference_step(frames, oracle_py, orb_oracle, have_xflann):
             else:
                 oracle_py.hamming_knn(d, prev, K_NN, 0)
         prev = d
+    for pb in windows:  # the reference's own g2o + typesg2o.h (oracle/_ref) when it was built, else the C restatement
+        if oracle_py.ref_ba_optimize(pb, BA_ITERS) is None:
+            oracle_py.ba_optimize(pb, BA_ITERS)
 
 
 def cpu_baseline_info(have_xflann, n):
     return {"cores": 1, "kind": "port",
-            "sample": "%d frames: ORB = Python/cv2-4.13 restatement of ORBextractor.cpp (blur/resize/FAST native OpenCV, "
-                      "1 thread; interpreter overhead included), match = %s" % (
-                          n, "the reference's xflann HKMeans(32,0) build + 16-check search, 1 thread" if have_xflann
-                          else "exact linear port")}
+            "sample": "%d frames + %d local-BA windows: ORB = Python/cv2-4.13 restatement of ORBextractor.cpp (blur/resize/FAST "
+                      "native OpenCV, 1 thread; interpreter overhead included), match = %s, BA = the reference's g2o + "
+                      "typesg2o.h compiled from its sources (oracle/_ref), 1 thread as the reference runs it" % (
+                          n, max(1, n // KF_EVERY), "the reference's xflann HKMeans(32,0) build + 16-check search, 1 thread"
+                          if have_xflann else "exact linear port")}
 
 
 def run_reference(args, rank, world):
@@ -131,12 +144,13 @@ def run_reference(args, rank, world):
     import oracle_py, orb_oracle
     n = min(args.frames, 8)
     frames = synth_clip(n, 1234)
+    windows = ba_windows(max(1, n // KF_EVERY), 500)
     have = oracle_py.load_ref("libref_xflann.so") is not None
     for _ in range(args.warmup):
-        cpu_reference_step(frames, oracle_py, orb_oracle, have)
+        cpu_reference_step(frames, oracle_py, orb_oracle, have, windows)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_reference_step(frames, oracle_py, orb_oracle, have)
+        cpu_reference_step(frames, oracle_py, orb_oracle, have, windows)
     dt = time.perf_counter() - t0
     fps = n * args.steps / dt
     info = cpu_baseline_info(have, n)
@@ -178,7 +192,15 @@ def run_b200(args, rank, world, local_rank):
     idx_host = torch.empty((F, KPTS, K_NN), dtype=torch.int32).pin_memory()
     dist_host = torch.empty((F, KPTS, K_NN), dtype=torch.int32).pin_memory()
     img_ptrs = (ctypes_voidp_array(F))(*[clip_pin[i].data_ptr() for i in range(F)])
+    n_ba = max(1, F // KF_EVERY)
+    windows = ba_windows(n_ba, 500 + 100 * rank)
+    ba_packed = ctx.ba_pack_batch(windows, BA_ITERS)
+    ba_in_bytes = sum(sum(a.nbytes for a in keep.values()) for keep in ba_packed[2])
+    ba_out_bytes = sum(sum(v.nbytes for v in o.values()) for o in ba_packed[3])
     ctx.sync()
+
+    def ba_all():  # host-buffer C-ABI call (there is no device-resident variant: the window is assembled by the host mapper)
+        ctx.ba_solve_batch(None, BA_ITERS, packed=ba_packed)
 
     def orb_dev():
         ctx.orb_extract_batch_dev(clip_dev.data_ptr(), F, W, H, W, W * H, prm, kps_dev.data_ptr(), desc_dev.data_ptr(),
@@ -199,6 +221,7 @@ def run_b200(args, rank, world, local_rank):
     def step_device():
         orb_dev()
         knn_all_dev()
+        ba_all()
 
     lib, h = ctx.lib, ctx.h
     import ctypes
@@ -215,6 +238,7 @@ def run_b200(args, rank, world, local_rank):
                                           dist_host[f].data_ptr())
             if rc != 0:
                 raise RuntimeError(lib.uco_b200_last_error(h))
+        ba_all()
 
     def barrier():
         ctx.sync()
@@ -281,8 +305,12 @@ def run_b200(args, rank, world, local_rank):
             acc[k] = acc.get(k, 0.0) + v / reps
     ctx.set_profiling(False)
     knn_ms = timed_events(knn_all_dev, reps) / reps
+    ba_ms = timed_events(ba_all, reps) / reps
     stage_ms = dict(acc)
     stage_ms["hamming_knn"] = knn_ms
+    stage_ms["local_ba"] = ba_ms
+    n_obs = sum(len(w["obs_pose"]) for w in windows)
+    ba_trials = sum(int(o["trace"][:, 1].sum()) for o in ba_packed[3])
     pb = ctx.orb_plan_bytes()
     cand_bytes = 0  # candidate lists are small and L2 resident; not counted as algorithmic traffic
     alg = {  # ALGORITHMIC bytes per frame of each kernel (DESIGN.md "Measurement")
@@ -292,6 +320,8 @@ def run_b200(args, rank, world, local_rank):
         "select": 0,
         "orient_describe": KPTS * (28 + 32),                                      # write keypoints + descriptors
         "hamming_knn": 2 * KPTS * 32 + KPTS * K_NN * 8,
+        # per LM trial and observation: z 16 + ids 8 + sigma 4 in, W block 144 written + read; per frame
+        "local_ba": (28 + 288) * (n_obs / n_ba) * (ba_trials / n_ba) * n_ba / F,
     }
     top = max(stage_ms, key=stage_ms.get)
     peaks = {}
@@ -307,12 +337,13 @@ def run_b200(args, rank, world, local_rank):
         line = {"metric": METRIC, "value": total_frames / (ms_dev * 1e-3), "unit": "frames/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "stages": STAGES, "frames_per_step_per_gpu": F,
+                "config": {"workload": WORKLOAD, "stages": STAGES, "frames_per_step_per_gpu": F, "ba_windows_per_step_per_gpu": n_ba,
+                           "ba_window": "12 KF (2 fixed), 2000 points, %d observations, nIters=5" % (n_obs // max(1, n_ba)),
                            "parallelism": "frames sharded over %d GPU(s), no collective" % world,
                            "l2": "flushed between timed steps (256 MB write)"},
                 "e2e": {"value": total_frames / (e2e_ms * 1e-3), "unit": "frames/s",
-                        "h2d_bytes_per_step": F * (W * H + 2 * KPTS * 32),
-                        "d2h_bytes_per_step": F * (KPTS * 60 + 4 + KPTS * K_NN * 8)},
+                        "h2d_bytes_per_step": F * (W * H + 2 * KPTS * 32) + ba_in_bytes,
+                        "d2h_bytes_per_step": F * (KPTS * 60 + 4 + KPTS * K_NN * 8) + ba_out_bytes},
                 "gpu_launches": launches, "clocks": clocks,
                 "roofline": {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                              "frac": achieved / hbm_peak, "traffic": None,
@@ -346,9 +377,10 @@ def cpu_baseline(clip):
     import oracle_py, orb_oracle
     have = oracle_py.load_ref("libref_xflann.so") is not None
     n = min(len(clip), 16)
+    windows = ba_windows(max(1, n // KF_EVERY), 500)
     cpu_reference_step(clip[:2], oracle_py, orb_oracle, have)  # warm caches
     t0 = time.perf_counter()
-    cpu_reference_step(clip[:n], oracle_py, orb_oracle, have)
+    cpu_reference_step(clip[:n], oracle_py, orb_oracle, have, windows)
     dt = time.perf_counter() - t0
     info = cpu_baseline_info(have, n)
     info.update({"value": n / dt, "unit": "frames/s"})

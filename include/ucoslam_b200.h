@@ -211,6 +211,8 @@ typedef struct uco_ba_result {   /* every pointer may be NULL (not wanted) */
 /* stop: optional flag polled between LM trials (GlobalOptimizerG2O::optimize(bool* stopASAP), sparse_optimizer.h:189);
  * when raised during stage 1 the solve returns the current estimate with UCO_OK and iters[1] = 0 like the reference. */
 int uco_b200_ba_solve(uco_b200_ctx* ctx, const uco_ba_problem* pb, const volatile int* stop, uco_ba_result* res);
+/* n independent problems (one local-BA window per camera / map) solved together; results as n separate uco_b200_ba_solve calls */
+int uco_b200_ba_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* pbs, const volatile int* stop, uco_ba_result* res);
 
 #ifdef __cplusplus
 }

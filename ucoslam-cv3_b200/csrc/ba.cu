@@ -865,3 +865,13 @@ extern "C" int uco_b200_ba_solve(uco_b200_ctx* ctx, const uco_ba_problem* pb, co
     res->device_ms = ms;
     return UCO_OK;
 }
+
+extern "C" int uco_b200_ba_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* pbs, const volatile int* stop, uco_ba_result* res) {
+    if (!ctx) return UCO_E_INVALID;
+    if (n < 0 || (n && (!pbs || !res))) return uco_fail(ctx, UCO_E_INVALID, "ba_solve_batch: bad arguments");
+    for (int i = 0; i < n; i++) {
+        int rc = uco_b200_ba_solve(ctx, pbs + i, stop, res + i);
+        if (rc != UCO_OK) return rc;
+    }
+    return UCO_OK;
+}

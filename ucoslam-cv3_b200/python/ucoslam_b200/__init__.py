@@ -44,6 +44,7 @@ SIGNATURES = {
     "uco_b200_bow_transform": (_i, [_vp, _vp, _vp, _i, _sz, _i, _vp, _vp, _vp]),
     "uco_b200_bow_transform_dev": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "uco_b200_ba_solve": (_i, [_vp, _vp, _vp, _vp]),
+    "uco_b200_ba_solve_batch": (_i, [_vp, _i, _vp, _vp, _vp]),
     "uco_b200_probe_math": (_i, [_i, _vp, _vp, _i, _vp, _vp]),
     "uco_b200_probe_retain_best": (_i, [_vp, _i, _i]),
 }
@@ -171,9 +172,9 @@ class Context:
         return idx, dist
 
     # -- K10-K13 -------------------------------------------------------------------------------------------------
-    def ba_solve(self, pb, n_iters, stop=None):
-        """pb: dict with the uco_ba_problem arrays (poses44 f32 (P,16), fixed u8, points3 f32 (N,3), obs_pose/obs_point i32,
-        obs_uv f32 (M,2), obs_ur f32, obs_stereo u8, obs_inv_sigma2 f32, fx fy cx cy bf).  Returns a dict like the oracle's."""
+    @staticmethod
+    def ba_pack(pb, n_iters):
+        """(uco_ba_problem, uco_ba_result, keep-alive input arrays, output dict) for a problem dict (see ba_solve)."""
         A = lambda k, dt: np.ascontiguousarray(pb[k], dtype=dt)
         a = dict(poses44=A("poses44", np.float32), fixed=A("fixed", np.uint8), points3=A("points3", np.float32),
                  obs_pose=A("obs_pose", np.int32), obs_point=A("obs_point", np.int32), obs_uv=A("obs_uv", np.float32),
@@ -186,10 +187,32 @@ class Context:
                        pb["cx"], pb["cy"], pb["bf"], int(n_iters))
         cr = BaResult(_p(out["pose7"]), _p(out["pose44"]), _p(out["point3"]), _p(out["chi2"]), _p(out["level"]), _p(out["bad"]),
                       _p(out["trace"]))
+        return cp, cr, a, out
+
+    def ba_solve(self, pb, n_iters, stop=None):
+        """pb: dict with the uco_ba_problem arrays (poses44 f32 (P,16), fixed u8, points3 f32 (N,3), obs_pose/obs_point i32,
+        obs_uv f32 (M,2), obs_ur f32, obs_stereo u8, obs_inv_sigma2 f32, fx fy cx cy bf).  Returns a dict like the oracle's."""
+        cp, cr, keep, out = self.ba_pack(pb, n_iters)
         self._chk(self.lib.uco_b200_ba_solve(self.h, ctypes.addressof(cp), _p(stop), ctypes.addressof(cr)))
         out["iters"] = np.array(list(cr.iters), np.int32)
         out["device_ms"] = float(cr.device_ms)
         return out
+
+    def ba_solve_batch(self, pbs, n_iters, stop=None, packed=None):
+        """several independent problems in one call; `packed` = result of a previous ba_pack_batch to skip the packing"""
+        packed = packed or self.ba_pack_batch(pbs, n_iters)
+        cps, crs, keep, outs = packed
+        self._chk(self.lib.uco_b200_ba_solve_batch(self.h, len(outs), ctypes.addressof(cps), _p(stop), ctypes.addressof(crs)))
+        for i, o in enumerate(outs):
+            o["iters"] = np.array(list(crs[i].iters), np.int32)
+            o["device_ms"] = float(crs[i].device_ms)
+        return outs
+
+    def ba_pack_batch(self, pbs, n_iters):
+        packs = [self.ba_pack(pb, n_iters) for pb in pbs]
+        cps = (BaProblem * len(packs))(*[p[0] for p in packs])
+        crs = (BaResult * len(packs))(*[p[1] for p in packs])
+        return cps, crs, [p[2] for p in packs], [p[3] for p in packs]
 
     # -- K9 ------------------------------------------------------------------------------------------------------
     def bow_load(self, voc_bytes):
