@@ -213,6 +213,10 @@ typedef struct uco_ba_result {   /* every pointer may be NULL (not wanted) */
 int uco_b200_ba_solve(uco_b200_ctx* ctx, const uco_ba_problem* pb, const volatile int* stop, uco_ba_result* res);
 /* n independent problems (one local-BA window per camera / map) solved together; results as n separate uco_b200_ba_solve calls */
 int uco_b200_ba_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* pbs, const volatile int* stop, uco_ba_result* res);
+/* tuning / test knob.  mode 0 (default): windows with <= 38 free keyframes run cluster-resident (one thread-block cluster per
+ * window, the whole LM loop in one launch), larger ones as streamed kernels; 1: always streamed; 2: always cluster-resident.
+ * cluster_size: CTAs per cluster (power of two <= 16, 0 = 8). */
+int uco_b200_ba_set_mode(uco_b200_ctx* ctx, int mode, int cluster_size);
 
 #ifdef __cplusplus
 }

@@ -13,11 +13,22 @@ from test_ba_oracle import check_ba, GOLD, BA_CASES
 pytestmark = pytest.mark.gpu
 
 
+MODES = {"streamed": (1, 0), "cluster8": (2, 8), "cluster4": (2, 4), "cluster16": (2, 16), "cluster1": (2, 1)}
+
+
+@pytest.fixture(params=list(MODES))
+def bctx(ctx, request):
+    """the context with the BA solver forced into one of its two forms (streamed kernels / cluster-resident kernel)"""
+    ctx.ba_set_mode(*MODES[request.param])
+    yield ctx
+    ctx.ba_set_mode(0, 0)
+
+
 @pytest.mark.parametrize("name", list(BA_CASES))
-def test_ba_matches_reference_golden(ctx, name):
+def test_ba_matches_reference_golden(bctx, name):
     g = np.load(GOLD)
     pb = oracle_py.ba_problem_from_golden(g, name)
-    got = ctx.ba_solve(pb, BA_CASES[name][1])
+    got = bctx.ba_solve(pb, BA_CASES[name][1])
     ref = {k[len(name) + 5:]: g[k] for k in g.files if k.startswith(name + "_out_")}
     check_ba(got, ref)
 
@@ -32,13 +43,33 @@ def test_ba_matches_reference_golden(ctx, name):
 def test_ba_matches_oracle(ctx, kw, iters):
     pb = oracle_py.synth_ba_problem(**kw)
     ref = oracle_py.ref_ba_optimize(pb, iters) or oracle_py.ba_optimize(pb, iters)
-    got = ctx.ba_solve(pb, iters)
-    check_ba(got, ref)
+    for mode in ((1, 0), (0, 0)):  # streamed, then automatic (cluster-resident when the reduced system fits)
+        ctx.ba_set_mode(*mode)
+        got = ctx.ba_solve(pb, iters)
+        ctx.ba_set_mode(0, 0)
+        check_ba(got, ref)
 
 
-def test_ba_is_bitwise_reproducible(ctx):
+def test_ba_batch_equals_single_solves(ctx):
+    """a batch is one launch with one cluster per window; every window gets exactly the result of a single solve"""
+    pbs = [oracle_py.synth_ba_problem(40 + i, n_poses=6 + 2 * i, n_fixed=1 + i % 2, n_points=150 + 60 * i, stereo_frac=0.1 * i)
+           for i in range(5)]
+    singles = [ctx.ba_solve(pb, 5) for pb in pbs]
+    batch = ctx.ba_solve_batch(pbs, 5)
+    for a, b in zip(singles, batch):
+        for k in ("pose7", "pose44", "point3", "chi2", "level", "bad", "trace", "iters"):
+            assert np.array_equal(a[k], b[k]), k
+    with pytest.raises(Exception):
+        ctx.ba_set_mode(2, 8)
+        try:
+            ctx.ba_solve(oracle_py.synth_ba_problem(25, n_poses=45, n_fixed=1, n_points=100), 1)  # 44 free KFs: not cluster-resident
+        finally:
+            ctx.ba_set_mode(0, 0)
+
+
+def test_ba_is_bitwise_reproducible(bctx):
     pb = oracle_py.synth_ba_problem(31, n_poses=10, n_fixed=2, n_points=800, stereo_frac=0.2)
-    a, b = ctx.ba_solve(pb, 5), ctx.ba_solve(pb, 5)
+    a, b = bctx.ba_solve(pb, 5), bctx.ba_solve(pb, 5)
     for k in ("pose7", "point3", "chi2", "trace"):
         assert np.array_equal(a[k], b[k]), k
 
@@ -57,8 +88,9 @@ def test_ba_observation_order_does_not_matter_much(ctx):
     assert np.array_equal(a["level"][perm], b["level"])
 
 
-def test_ba_stop_flag_and_errors(ctx):
+def test_ba_stop_flag_and_errors(bctx):
     import ucoslam_b200
+    ctx = bctx
     pb = oracle_py.synth_ba_problem(33, n_poses=6, n_fixed=1, n_points=200)
     stop = np.ones(1, np.int32)
     out = ctx.ba_solve(pb, 5, stop=stop)

@@ -19,6 +19,7 @@
 // The LM state machine lives on the device (LmState); the host only reads two flags per trial to know what to enqueue next.
 #include "common.cuh"
 #include "ba_math.cuh"
+#include "ba_plan.h"
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -608,7 +609,18 @@ void uco_ba_state_free(uco_b200_ctx* ctx) {
     ctx->ba = nullptr;
 }
 
-extern "C" int uco_b200_ba_solve(uco_b200_ctx* ctx, const uco_ba_problem* pb, const volatile int* stop, uco_ba_result* res) {
+cudaEvent_t* uco_ba_events(uco_b200_ctx* ctx) {
+    if (!ctx->ba) {
+        ctx->ba = new uco_ba_state();
+        cudaEventCreate(&ctx->ba->ev0);
+        cudaEventCreate(&ctx->ba->ev1);
+        cudaDeviceGetAttribute(&ctx->ba->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
+    }
+    return &ctx->ba->ev0;
+}
+
+// streamed form: one kernel per phase, the host enqueues the next trial after reading two flags (any problem size)
+int ba_streamed_solve(uco_b200_ctx* ctx, const uco_ba_problem* pb, const volatile int* stop, uco_ba_result* res) {
     if (!ctx) return UCO_E_INVALID;
     if (!pb || !res) return uco_fail(ctx, UCO_E_INVALID, "ba_solve: null problem / result");
     const int P = pb->n_poses, N = pb->n_points, M = pb->n_obs;
@@ -621,12 +633,7 @@ extern "C" int uco_b200_ba_solve(uco_b200_ctx* ctx, const uco_ba_problem* pb, co
                             pb->obs_pose[i], pb->obs_point[i]);
         if (pb->obs_stereo && pb->obs_stereo[i] && !pb->obs_ur) return uco_fail(ctx, UCO_E_INVALID, "ba_solve: stereo observation without obs_ur");
     }
-    if (!ctx->ba) {
-        ctx->ba = new uco_ba_state();
-        cudaEventCreate(&ctx->ba->ev0);
-        cudaEventCreate(&ctx->ba->ev1);
-        cudaDeviceGetAttribute(&ctx->ba->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
-    }
+    uco_ba_events(ctx);
     // ---- structure (host): free-pose numbering, observations sorted by landmark, per-pose lists, Schur gather lists
     std::vector<int> free_idx(P), free_list;
     for (int i = 0; i < P; i++) {
@@ -866,12 +873,50 @@ extern "C" int uco_b200_ba_solve(uco_b200_ctx* ctx, const uco_ba_problem* pb, co
     return UCO_OK;
 }
 
-extern "C" int uco_b200_ba_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* pbs, const volatile int* stop, uco_ba_result* res) {
+extern "C" {
+
+int uco_b200_ba_set_mode(uco_b200_ctx* ctx, int mode, int cluster_size) {
+    if (!ctx) return UCO_E_INVALID;
+    if (mode < 0 || mode > 2 || cluster_size < 0 || cluster_size > 16 || (cluster_size & (cluster_size - 1)))
+        return uco_fail(ctx, UCO_E_INVALID, "ba_set_mode: mode 0..2, cluster size a power of two <= 16");
+    ctx->ba_mode = mode;
+    ctx->ba_cluster_size = cluster_size;
+    return UCO_OK;
+}
+
+int uco_b200_ba_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* pbs, const volatile int* stop, uco_ba_result* res) {
     if (!ctx) return UCO_E_INVALID;
     if (n < 0 || (n && (!pbs || !res))) return uco_fail(ctx, UCO_E_INVALID, "ba_solve_batch: bad arguments");
+    std::vector<const uco_ba_problem*> cp;
+    std::vector<uco_ba_result*> cr;
     for (int i = 0; i < n; i++) {
-        int rc = uco_b200_ba_solve(ctx, pbs + i, stop, res + i);
+        int rc = ba_validate(ctx, pbs + i);
+        if (rc != UCO_OK) return rc;
+        const bool fits = 6 * ba_free_poses(pbs + i) <= BA_CLUSTER_MAX_N;
+        if (ctx->ba_mode == 2 && !fits)
+            return uco_fail(ctx, UCO_E_INVALID, "ba_solve: %d free poses exceed the cluster-resident solver (%d)", ba_free_poses(pbs + i),
+                            BA_CLUSTER_MAX_N / 6);
+        if (ctx->ba_mode != 1 && fits) {
+            cp.push_back(pbs + i);
+            cr.push_back(res + i);
+        } else {
+            rc = ba_streamed_solve(ctx, pbs + i, stop, res + i);
+            if (rc != UCO_OK) return rc;
+        }
+    }
+    const int per_launch = std::max(1, ctx->sm_count / (ctx->ba_cluster_size > 0 ? ctx->ba_cluster_size : 8));  // co-resident clusters
+    for (size_t k = 0; k < cp.size(); k += per_launch) {
+        int m = (int)std::min(cp.size() - k, (size_t)per_launch);
+        int rc = ba_cluster_solve_batch(ctx, m, cp.data() + k, stop, cr.data() + k);
         if (rc != UCO_OK) return rc;
     }
     return UCO_OK;
 }
+
+int uco_b200_ba_solve(uco_b200_ctx* ctx, const uco_ba_problem* pb, const volatile int* stop, uco_ba_result* res) {
+    if (!ctx) return UCO_E_INVALID;
+    if (!pb || !res) return uco_fail(ctx, UCO_E_INVALID, "ba_solve: null problem / result");
+    return uco_b200_ba_solve_batch(ctx, 1, pb, stop, res);
+}
+
+}  // extern "C"

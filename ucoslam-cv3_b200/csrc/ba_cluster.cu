@@ -1,0 +1,868 @@
+// ba_cluster.cu — K10-K13, cluster-resident form: ONE thread-block cluster per bundle-adjustment window runs the whole
+// two-stage Levenberg-Marquardt solve (every iteration, every trial, the outlier pass between the stages and the result
+// extraction) inside a single kernel launch; a batch of independent windows is one launch with one cluster per window.
+//
+// Why: a local-BA window (10-30 keyframes, a few thousand points, ~15k observations) is far too small to fill a B200 and
+// its LM loop is a chain of ~100 tiny dependent phases.  As separate kernels each phase pays a launch + drain (ba.cu, the
+// streamed form, spends ~300 us per LM trial that way); inside one cluster the phases are separated by barrier.cluster
+// (~0.2 us), the LM state machine is replicated in every CTA's shared memory (each CTA derives the same decision from the
+// same ordered partial sums, so no broadcast is needed), and 18 windows run side by side on the 148 SMs.
+//
+// Phases of one LM trial (S = cluster barrier):  prep (D^-1, Y = W D^-1)  S  Schur gather into per-unit partials  S
+//   CTA 0: assemble the reduced system in shared memory, blocked (6-wide) L D L^T, back-substitution  S
+//   update (landmark back-substitution, backup, oplus)  S  residuals + ordered chi2 partials  S  decide (+ restore).
+// All sums have a fixed order (strided partials, tree within a CTA, rank order across CTAs): results are bitwise
+// reproducible for a given cluster size.  Arithmetic is the same as ba.cu's (ba_math.cuh); the reference code each phase
+// restates is cited there and in include/ucoslam_b200.h.
+#include "common.cuh"
+#include "ba_math.cuh"
+#include "ba_plan.h"
+#include <cooperative_groups.h>
+#include <cfloat>
+#include <cstring>
+#include <vector>
+
+namespace cg = cooperative_groups;
+
+namespace {
+using namespace ba;
+
+constexpr int BS = 512;           // threads per CTA (f64 Jacobian code wants ~128 registers)
+constexpr int TEAMS = BS / 36;    // Schur-gather teams of 36 threads (one 6x6 block element each)
+constexpr int NW = BS / 32;
+
+struct LmLocal {  // replicated per CTA
+    double lambda, ni, currentChi, rho;
+    float prevChi2, curChi2, chi2Diff;
+    int it, qmax, ok, cont_trial, cont_iter, reject, ntrace, stopped;
+};
+
+__device__ __forceinline__ double block_sum(double v, double* red) {  // ordered: xor-tree in the warp, warps in order
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0;
+#pragma unroll
+    for (int w = 0; w < NW; w++) s += red[w];
+    return s;
+}
+__device__ __forceinline__ double block_max(double v, double* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0;
+#pragma unroll
+    for (int w = 0; w < NW; w++) s = fmax(s, red[w]);
+    return s;
+}
+
+__device__ __forceinline__ void obs_weights(const CbDev& B, int i, int robust, double& wo, double* orr) {
+    double w = (double)B.info[i], r1 = 1, r0;
+    if (robust) huber(B.chi2[i], B.stereo[i] ? B.d3 : B.d2, 1.0, r0, r1);
+    wo = r1 * w;
+#pragma unroll
+    for (int d = 0; d < 3; d++) orr[d] = -(w * B.err[3 * i + d]) * r1;
+}
+
+// residuals of every active observation; returns this thread's ordered partial of the (robustified) chi2
+__device__ __forceinline__ double phase_errors(const CbDev& B, int ct, int cn, int robust) {
+    double s = 0;
+    for (int i = ct; i < B.M; i += cn) {
+        if (!B.active[i]) continue;
+        Pose T = load_pose(B.pose + 7 * B.obs_pose[i]);
+        const double* X = B.pt + 3 * B.obs_lm[i];
+        double x[3] = {X[0], X[1], X[2]}, p[3], e[3];
+        se3_map(T, x, p);
+        bool st = B.stereo[i];
+        double z[3] = {(double)B.z[3 * i], (double)B.z[3 * i + 1], (double)B.z[3 * i + 2]};
+        residual(p, z, st, B.cam, e);
+        double info = (double)B.info[i];
+        double c2 = st ? (e[0] * e[0] + e[1] * e[1] + e[2] * e[2]) * info : (e[0] * e[0] + e[1] * e[1]) * info;
+        B.err[3 * i] = e[0]; B.err[3 * i + 1] = e[1]; B.err[3 * i + 2] = e[2];
+        B.chi2[i] = c2;
+        double r0 = c2, r1;
+        if (robust) huber(c2, st ? B.d3 : B.d2, 1.0, r0, r1);
+        s += r0;
+    }
+    return s;
+}
+
+// per observation: W block (6x3) and this observation's terms of Hll / bl
+__device__ __forceinline__ void phase_linearize_obs(const CbDev& B, int ct, int cn, int robust) {
+    for (int i = ct; i < B.M; i += cn) {
+        double* W = B.W + 18 * (size_t)i;
+        double* C = B.lmc + 9 * (size_t)i;
+        if (!B.active[i]) {
+#pragma unroll
+            for (int k = 0; k < 18; k++) W[k] = 0;
+#pragma unroll
+            for (int k = 0; k < 9; k++) C[k] = 0;
+            continue;
+        }
+        const int pi = B.obs_pose[i];
+        Pose T = load_pose(B.pose + 7 * pi);
+        const double* X = B.pt + 3 * B.obs_lm[i];
+        double x[3] = {X[0], X[1], X[2]}, p[3], R[9], JX[9], wo, orr[3];
+        se3_map(T, x, p);
+        quat_to_R(T.q, R);
+        const bool st = B.stereo[i];
+        jac_point(p, R, st, B.cam, JX);
+        obs_weights(B, i, robust, wo, orr);
+        const int D = st ? 3 : 2;
+        {
+            int k = 0;
+#pragma unroll
+            for (int a = 0; a < 3; a++)
+#pragma unroll
+                for (int c = a; c < 3; c++, k++) {
+                    double h = 0;
+                    for (int d = 0; d < D; d++) h += JX[3 * d + a] * wo * JX[3 * d + c];
+                    C[k] = h;
+                }
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                double s = 0;
+                for (int d = 0; d < D; d++) s += JX[3 * d + a] * orr[d];
+                C[6 + a] = s;
+            }
+        }
+        if (B.free_idx[pi] >= 0) {
+            double JT[18];
+            jac_pose(p, st, B.cam, JT);
+#pragma unroll
+            for (int a = 0; a < 6; a++)
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    double h = 0;
+                    for (int d = 0; d < D; d++) h += JT[6 * d + a] * wo * JX[3 * d + c];
+                    W[3 * a + c] = h;
+                }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 18; k++) W[k] = 0;
+        }
+    }
+}
+
+// landmark sums (thread per landmark, observation order) and pose blocks (CTA per free pose); returns max |diagonal| seen
+__device__ __forceinline__ double phase_linearize_sum(const CbDev& B, int ct, int cn, int rank, int CL, int robust, double* red27) {
+    double md = 0;
+    for (int l = ct; l < B.N; l += cn) {
+        double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (int i = B.lm_ptr[l]; i < B.lm_ptr[l + 1]; i++) {
+            const double* C = B.lmc + 9 * (size_t)i;
+#pragma unroll
+            for (int k = 0; k < 9; k++) acc[k] += C[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 6; k++) B.Hll[6 * (size_t)l + k] = acc[k];
+#pragma unroll
+        for (int k = 0; k < 3; k++) B.bl[3 * (size_t)l + k] = acc[6 + k];
+        md = fmax(md, fmax(fabs(acc[0]), fmax(fabs(acc[3]), fabs(acc[5]))));
+    }
+    const int tid = threadIdx.x;
+    for (int f = rank; f < B.Pf; f += CL) {
+        const int pi = B.free_list[f];
+        Pose T = load_pose(B.pose + 7 * pi);
+        double acc[27];
+#pragma unroll
+        for (int k = 0; k < 27; k++) acc[k] = 0;
+        for (int j = B.pose_ptr[f] + tid; j < B.pose_ptr[f + 1]; j += BS) {
+            const int i = B.pose_obs[j];
+            if (!B.active[i]) continue;
+            const double* X = B.pt + 3 * B.obs_lm[i];
+            double x[3] = {X[0], X[1], X[2]}, p[3], JT[18], wo, orr[3];
+            se3_map(T, x, p);
+            const bool st = B.stereo[i];
+            jac_pose(p, st, B.cam, JT);
+            obs_weights(B, i, robust, wo, orr);
+            const int D = st ? 3 : 2;
+            int k = 0;
+#pragma unroll
+            for (int a = 0; a < 6; a++)
+#pragma unroll
+                for (int c = a; c < 6; c++, k++) {
+                    double h = 0;
+                    for (int d = 0; d < D; d++) h += JT[6 * d + a] * wo * JT[6 * d + c];
+                    acc[k] += h;
+                }
+#pragma unroll
+            for (int a = 0; a < 6; a++) {
+                double s = 0;
+                for (int d = 0; d < D; d++) s += JT[6 * d + a] * orr[d];
+                acc[21 + a] += s;
+            }
+        }
+        __syncthreads();  // red27 reuse
+#pragma unroll
+        for (int k = 0; k < 27; k++) {
+            double v = acc[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((tid & 31) == 0) red27[(tid >> 5) * 27 + k] = v;
+        }
+        __syncthreads();
+        if (tid < 27) {
+            double v = 0;
+#pragma unroll
+            for (int w = 0; w < NW; w++) v += red27[w * 27 + tid];
+            red27[NW * 27 + tid] = v;
+        }
+        __syncthreads();
+        if (tid < 36) {
+            int a = tid / 6, c = tid % 6;
+            int lo = a < c ? a : c, hi = a < c ? c : a;
+            int k = lo * 6 - lo * (lo - 1) / 2 + (hi - lo);
+            double v = red27[NW * 27 + k];
+            B.Hpp[36 * (size_t)f + tid] = v;
+            if (a == c) md = fmax(md, fabs(v));
+        }
+        if (tid < 6) B.bp[6 * (size_t)f + tid] = red27[NW * 27 + 21 + tid];
+    }
+    return md;
+}
+
+__device__ __forceinline__ void phase_prep(const CbDev& B, int ct, int cn, double lambda) {
+    for (int i = ct; i < B.M; i += cn) {
+        const int l = B.obs_lm[i];
+        double D[6], I[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) D[k] = B.Hll[6 * (size_t)l + k];
+        D[0] += lambda; D[3] += lambda; D[5] += lambda;
+        inv3_sym(D, I);
+        const double Im[9] = {I[0], I[1], I[2], I[1], I[3], I[4], I[2], I[4], I[5]};
+        if (i == B.lm_ptr[l]) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) B.Dinv[6 * (size_t)l + k] = I[k];
+            double b[3] = {B.bl[3 * (size_t)l], B.bl[3 * (size_t)l + 1], B.bl[3 * (size_t)l + 2]};
+#pragma unroll
+            for (int a = 0; a < 3; a++) B.db[3 * (size_t)l + a] = Im[3 * a] * b[0] + Im[3 * a + 1] * b[1] + Im[3 * a + 2] * b[2];
+        }
+        const double* W = B.W + 18 * (size_t)i;
+        double* Y = B.Y + 18 * (size_t)i;
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+            double w0 = W[3 * a], w1 = W[3 * a + 1], w2 = W[3 * a + 2];
+#pragma unroll
+            for (int c = 0; c < 3; c++) Y[3 * a + c] = w0 * Im[c] + w1 * Im[3 + c] + w2 * Im[6 + c];
+        }
+    }
+}
+
+// Schur gather: teams of 36 threads walk units of <= BA_UNIT contributions of one 6x6 block
+__device__ __forceinline__ void phase_gather(const CbDev& B, int rank, int CL) {
+    const int tid = threadIdx.x, team = tid / 36, e = tid % 36, r = e / 6, c = e % 6;
+    if (team >= TEAMS) return;
+    for (int u = rank * TEAMS + team; u < B.nunits; u += CL * TEAMS) {
+        const int4 un = B.unit[u];  // blk, c0, c1, diag
+        const bool diag = un.w != 0;
+        double s = 0, sb = 0;
+        int k = un.y;
+        for (; k + 1 < un.z; k += 2) {  // two contributions in flight
+            const int2 ab0 = B.con[k], ab1 = B.con[k + 1];
+            const double* Y0 = B.Y + 18 * (size_t)ab0.x + 3 * r;
+            const double* W0 = B.W + 18 * (size_t)ab0.y + 3 * c;
+            const double* Y1 = B.Y + 18 * (size_t)ab1.x + 3 * r;
+            const double* W1 = B.W + 18 * (size_t)ab1.y + 3 * c;
+            double y00 = Y0[0], y01 = Y0[1], y02 = Y0[2], w00 = W0[0], w01 = W0[1], w02 = W0[2];
+            double y10 = Y1[0], y11 = Y1[1], y12 = Y1[2], w10 = W1[0], w11 = W1[1], w12 = W1[2];
+            s += y00 * w00 + y01 * w01 + y02 * w02;
+            s += y10 * w10 + y11 * w11 + y12 * w12;
+            if (diag && c == 0) {
+                const double* Wa0 = B.W + 18 * (size_t)ab0.x + 3 * r;
+                const double* d0 = B.db + 3 * (size_t)B.obs_lm[ab0.x];
+                const double* Wa1 = B.W + 18 * (size_t)ab1.x + 3 * r;
+                const double* d1 = B.db + 3 * (size_t)B.obs_lm[ab1.x];
+                sb += Wa0[0] * d0[0] + Wa0[1] * d0[1] + Wa0[2] * d0[2];
+                sb += Wa1[0] * d1[0] + Wa1[1] * d1[1] + Wa1[2] * d1[2];
+            }
+        }
+        if (k < un.z) {
+            const int2 ab = B.con[k];
+            const double* Y = B.Y + 18 * (size_t)ab.x + 3 * r;
+            const double* W = B.W + 18 * (size_t)ab.y + 3 * c;
+            s += Y[0] * W[0] + Y[1] * W[1] + Y[2] * W[2];
+            if (diag && c == 0) {
+                const double* Wa = B.W + 18 * (size_t)ab.x + 3 * r;
+                const double* d = B.db + 3 * (size_t)B.obs_lm[ab.x];
+                sb += Wa[0] * d[0] + Wa[1] * d[1] + Wa[2] * d[2];
+            }
+        }
+        B.part[36 * (size_t)u + e] = s;
+        if (diag && c == 0) B.partb[6 * (size_t)u + r] = sb;
+    }
+}
+
+// CTA 0: reduced system in shared memory (lower triangle packed by rows, row n = right-hand side), L D L^T in 6-wide block
+// columns (same operation order as the column-by-column elimination), back-substitution by one warp.  Returns 0 on a
+// non-positive pivot.
+__device__ int phase_solve(const CbDev& B, double lambda, double* A, double* aux, int* sflag) {
+    const int tid = threadIdx.x, n = B.n, lane = tid & 31, warp = tid >> 5;
+    const int tot = (n + 1) * (n + 2) / 2;
+    for (int k = tid; k < tot; k += BS) A[k] = 0;
+    if (tid == 0) *sflag = 0;
+    __syncthreads();
+    for (int w = tid; w < B.nblk * 36; w += BS) {
+        const int blk = w / 36, e = w % 36, r = e / 6, c = e % 6;
+        const int2 ij = B.blk_ij[blk];
+        const bool diag = ij.x == ij.y;
+        if (diag && r > c) continue;  // the solver reads the upper triangle (SimplicialLDLT<Upper>)
+        double t = 0;
+        for (int u = B.blk_unit_ptr[blk]; u < B.blk_unit_ptr[blk + 1]; u++) t += B.part[36 * (size_t)u + e];
+        double h = 0;
+        if (diag) {
+            h = B.Hpp[36 * (size_t)ij.x + e];
+            if (r == c) h += lambda;
+        }
+        h -= t;
+        const int row = 6 * ij.y + c, col = 6 * ij.x + r;  // element (col, row) of the upper triangle -> (row, col) of the lower
+        A[row * (row + 1) / 2 + col] = h;
+    }
+    for (int k = tid; k < n; k += BS) {
+        const int f = k / 6, r = k % 6;
+        const int blk = B.diag_blk[f];
+        double t = 0;
+        for (int u = B.blk_unit_ptr[blk]; u < B.blk_unit_ptr[blk + 1]; u++) t += B.partb[6 * (size_t)u + r];
+        A[n * (n + 1) / 2 + k] = B.bp[k] - t;
+    }
+    __syncthreads();
+    double* dinv = aux;        // 6 reciprocal pivots of the current block column
+    double* Ps = aux + 8;      // scaled panel: Ps[(i - c0 - 6) * 6 + j] = A[i][c0 + j] / d_j for the rows below the block
+    for (int kb = 0; kb < B.Pf; kb++) {
+        const int c0 = 6 * kb;
+        if (warp == 0) {  // diagonal 6x6 block, element (i, k) with k <= i on lane
+            int li = 0, lk = 0;
+            if (lane < 21) {
+                int q = lane;
+                while (q > li) { q -= li + 1; li++; }
+                lk = q;
+            }
+            double* a = A + (c0 + li) * (c0 + li + 1) / 2 + c0 + lk;
+            for (int j = 0; j < 6; j++) {
+                const double p = A[(c0 + j) * (c0 + j + 1) / 2 + c0 + j];
+                if (!(p > 0) || !isfinite(p)) {
+                    if (lane == 0) *sflag = 1;
+                    break;
+                }
+                double upd = 0;
+                const bool mine = lane < 21 && lk > j;
+                if (mine) upd = A[(c0 + li) * (c0 + li + 1) / 2 + c0 + j] * A[(c0 + lk) * (c0 + lk + 1) / 2 + c0 + j] * (1.0 / p);
+                __syncwarp();
+                if (mine) *a -= upd;
+                if (lane == 0) dinv[j] = 1.0 / p;
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        if (*sflag) break;
+        // panel rows below the block (including the right-hand-side row n): forward substitution against the block
+        for (int i = c0 + 6 + tid; i <= n; i += BS) {
+            double* row = A + i * (i + 1) / 2 + c0;
+            double v[6];
+#pragma unroll
+            for (int j = 0; j < 6; j++) v[j] = row[j];
+#pragma unroll
+            for (int j = 0; j < 6; j++) {
+                const double lj = v[j] * dinv[j];
+#pragma unroll
+                for (int k = j + 1; k < 6; k++) v[k] -= lj * A[(c0 + k) * (c0 + k + 1) / 2 + c0 + j];
+            }
+#pragma unroll
+            for (int j = 0; j < 6; j++) {
+                row[j] = v[j];
+                Ps[(i - c0 - 6) * 6 + j] = v[j] * dinv[j];
+            }
+        }
+        __syncthreads();
+        // trailing update, one term per eliminated column in column order
+        for (int i = c0 + 6 + warp; i <= n; i += NW) {
+            double* row = A + i * (i + 1) / 2;
+            const double* pi = Ps + (i - c0 - 6) * 6;
+            const double l0 = pi[0], l1 = pi[1], l2 = pi[2], l3 = pi[3], l4 = pi[4], l5 = pi[5];
+            const int kmax = i < n ? i : n - 1;
+            for (int k = c0 + 6 + lane; k <= kmax; k += 32) {
+                const double* ak = A + k * (k + 1) / 2 + c0;
+                double v = row[k];
+                v -= l0 * ak[0]; v -= l1 * ak[1]; v -= l2 * ak[2]; v -= l3 * ak[3]; v -= l4 * ak[4]; v -= l5 * ak[5];
+                row[k] = v;
+            }
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (*sflag) {
+        for (int k = tid; k < n; k += BS) B.xp[k] = 0;
+        return 0;
+    }
+    if (warp == 0) {  // x_j = (w_j - sum_{i>j} A[i][j] x_i) / d_j
+        double* s = aux;  // n entries
+        const double* wrow = A + n * (n + 1) / 2;
+        for (int k = lane; k < n; k += 32) s[k] = wrow[k];
+        __syncwarp();
+        for (int j = n - 1; j >= 0; j--) {
+            const double* row = A + j * (j + 1) / 2;
+            const double xj = s[j] / row[j];
+            __syncwarp();
+            if (lane == 0) s[j] = xj;
+            for (int k = lane; k < j; k += 32) s[k] -= row[k] * xj;
+            __syncwarp();
+        }
+        for (int k = lane; k < n; k += 32) B.xp[k] = s[k];
+    }
+    __syncthreads();
+    return 1;
+}
+
+// landmark back-substitution + backup + update; returns this thread's ordered partial of computeScale
+__device__ __forceinline__ double phase_update(const CbDev& B, int ct, int cn, double lambda, bool apply) {
+    double sc = 0;
+    for (int t = ct; t < B.N + B.Pf; t += cn) {
+        if (t < B.N) {
+            const int l = t;
+            if (B.lm_ptr[l] == B.lm_ptr[l + 1]) continue;  // no edge: not an active vertex
+            double c[3] = {B.bl[3 * (size_t)l], B.bl[3 * (size_t)l + 1], B.bl[3 * (size_t)l + 2]};
+            for (int i = B.lm_ptr[l]; i < B.lm_ptr[l + 1]; i++) {
+                const int f = B.free_idx[B.obs_pose[i]];
+                if (f < 0 || !B.active[i]) continue;
+                const double* W = B.W + 18 * (size_t)i;
+                const double* x = B.xp + 6 * f;
+#pragma unroll
+                for (int b = 0; b < 3; b++) {
+                    double s = 0;
+#pragma unroll
+                    for (int a = 0; a < 6; a++) s += W[3 * a + b] * x[a];
+                    c[b] -= s;
+                }
+            }
+            const double* I = B.Dinv + 6 * (size_t)l;
+            const double xl[3] = {I[0] * c[0] + I[1] * c[1] + I[2] * c[2], I[1] * c[0] + I[3] * c[1] + I[4] * c[2],
+                                  I[2] * c[0] + I[4] * c[1] + I[5] * c[2]};
+            double s = 0;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const double v = B.pt[3 * (size_t)l + k];
+                B.pt_bak[3 * (size_t)l + k] = v;
+                if (apply) B.pt[3 * (size_t)l + k] = v + xl[k];
+                s += xl[k] * (lambda * xl[k] + B.bl[3 * (size_t)l + k]);
+            }
+            sc += s;
+        } else {
+            const int f = t - B.N, pi = B.free_list[f];
+            Pose T = load_pose(B.pose + 7 * pi);
+            store_pose(B.pose_bak + 7 * pi, T);
+            double u[6], s = 0;
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                u[k] = B.xp[6 * f + k];
+                s += u[k] * (lambda * u[k] + B.bp[6 * f + k]);
+            }
+            sc += s;
+            if (apply) {
+                se3_oplus(T, u);
+                store_pose(B.pose + 7 * pi, T);
+            }
+        }
+    }
+    return sc;
+}
+__device__ __forceinline__ void phase_restore(const CbDev& B, int ct, int cn) {  // same thread mapping as phase_update
+    for (int t = ct; t < B.N + B.Pf; t += cn) {
+        if (t < B.N) {
+            if (B.lm_ptr[t] == B.lm_ptr[t + 1]) continue;
+#pragma unroll
+            for (int k = 0; k < 3; k++) B.pt[3 * (size_t)t + k] = B.pt_bak[3 * (size_t)t + k];
+        } else {
+            const int pi = B.free_list[t - B.N];
+#pragma unroll
+            for (int k = 0; k < 7; k++) B.pose[7 * pi + k] = B.pose_bak[7 * pi + k];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(BS, 1) ba_cluster_kernel(const CbDev* __restrict__ probs) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const int prob = blockIdx.x / CL, tid = threadIdx.x, ct = rank * BS + tid, cn = CL * BS;
+    extern __shared__ double sm_dyn[];   // CTA 0: packed reduced system
+    __shared__ CbDev B;
+    __shared__ LmLocal L;
+    __shared__ double red[NW + 1];
+    __shared__ double red27[(NW + 1) * 27];
+    __shared__ double aux[BA_CLUSTER_MAX_N * 6 + 16];
+    __shared__ int sflag;
+    for (int k = tid; k < (int)(sizeof(CbDev) / 4); k += BS) ((int*)&B)[k] = ((const int*)(probs + prob))[k];
+    if (tid == 0) { L.ntrace = 0; L.stopped = 0; }
+    __syncthreads();
+    // vertices: Frame::pose_f2g -> SE3Quat, cv::Point3f -> Vector3d
+    for (int t = ct; t < B.P; t += cn) {
+        Pose T = pose_from_m44f(B.p44_in + 16 * t);
+        store_pose(B.pose + 7 * t, T);
+        store_pose(B.pose_bak + 7 * t, T);
+    }
+    for (int k = ct; k < 3 * B.N; k += cn) B.pt[k] = (double)B.pt_in[k];
+    for (int i = ct; i < B.M; i += cn) {
+        B.active[i] = 1;
+        B.chi2[i] = 0;
+        B.err[3 * i] = B.err[3 * i + 1] = B.err[3 * i + 2] = 0;
+    }
+    cluster.sync();
+    for (int stage = 0; stage < 2; stage++) {
+        const int robust = stage == 0, max_iters = stage == 0 ? B.n_iters : 2 * B.n_iters;
+        if (stage == 1) {  // globaloptimizer_g2o.cpp:432-449
+            for (int i = ct; i < B.M; i += cn) {
+                Pose T = load_pose(B.pose + 7 * B.obs_pose[i]);
+                const double* X = B.pt + 3 * B.obs_lm[i];
+                double x[3] = {X[0], X[1], X[2]}, p[3];
+                se3_map(T, x, p);
+                if (B.chi2[i] > (double)(B.stereo[i] ? B.chi3d : B.chi2d) || !(p[2] > 0.0)) B.active[i] = 0;
+            }
+            __syncthreads();  // active[] is re-read by the same strided owner below; other CTAs see it after the barrier
+            cluster.sync();
+        }
+        {
+            double s = block_sum(phase_errors(B, ct, cn, robust), red);
+            if (tid == 0) B.parts[rank] = s;
+        }
+        if (rank == 0 && tid == 0) B.chol_fail[1] = B.stop ? *(volatile const int*)B.stop : 0;  // one reader: every CTA must see the same value
+        cluster.sync();
+        if (tid == 0) {
+            L.prevChi2 = L.curChi2 = L.chi2Diff = FLT_MAX;
+            L.it = 0;
+            L.ok = 1;
+            const int stop = ((volatile int*)B.chol_fail)[1];
+            L.cont_iter = max_iters > 0 && !stop;
+            if (stop) L.stopped = 1;
+        }
+        while (true) {
+            __syncthreads();
+            if (!L.cont_iter) break;
+            // ---- linearize at the current estimate
+            phase_linearize_obs(B, ct, cn, robust);
+            cluster.sync();
+            {
+                double md = block_max(phase_linearize_sum(B, ct, cn, rank, CL, robust, red27), red);
+                if (tid == 0) B.parts[32 + rank] = md;
+            }
+            cluster.sync();
+            if (tid == 0) {
+                if (L.it == 0) {  // computeLambdaInit, levenberg.cpp:152-166
+                    double s = 0, md = 0;
+                    for (int r = 0; r < CL; r++) { s += B.parts[r]; md = fmax(md, B.parts[32 + r]); }
+                    L.currentChi = s;
+                    L.lambda = 1e-5 * md;
+                    L.ni = 2;
+                }
+                float t = L.prevChi2; L.prevChi2 = L.curChi2; L.curChi2 = t;
+                L.qmax = 0;
+                L.rho = 0;
+                L.cont_trial = 1;
+            }
+            __syncthreads();
+            while (L.cont_trial) {
+                const double lambda = L.lambda;
+                phase_prep(B, ct, cn, lambda);
+                cluster.sync();
+                phase_gather(B, rank, CL);
+                cluster.sync();
+                if (rank == 0) {
+                    int ok = 1;
+                    if (B.Pf) ok = phase_solve(B, lambda, sm_dyn, aux, &sflag);
+                    if (tid == 0) {
+                        B.chol_fail[0] = !ok;
+                        B.chol_fail[1] = B.stop ? *(volatile const int*)B.stop : 0;
+                    }
+                }
+                cluster.sync();
+                const bool fail = *(volatile int*)B.chol_fail != 0;
+                {
+                    double s = block_sum(phase_update(B, ct, cn, lambda, !fail), red);
+                    if (tid == 0) B.parts[64 + rank] = s;
+                }
+                cluster.sync();
+                {
+                    double s = block_sum(phase_errors(B, ct, cn, robust), red);
+                    if (tid == 0) B.parts[rank] = s;
+                }
+                cluster.sync();
+                if (tid == 0) {  // levenberg.cpp:96-150, identical in every CTA
+                    double chi_raw = 0, scale = 0;
+                    for (int r = 0; r < CL; r++) { chi_raw += B.parts[r]; scale += B.parts[64 + r]; }
+                    const int stop = ((volatile int*)B.chol_fail)[1];
+                    double tempChi = fail ? DBL_MAX : chi_raw;
+                    double rho = L.currentChi - tempChi;
+                    scale += 1e-3;
+                    rho /= scale;
+                    int rej = 0, lam_bad = 0;
+                    if (rho > 0 && isfinite(tempChi) && !fail) {
+                        double alpha = 1. - pow((2 * rho - 1), 3.0);
+                        alpha = fmin(alpha, 2. / 3.);
+                        L.lambda *= fmax(1. / 3., alpha);
+                        L.ni = 2;
+                        L.currentChi = tempChi;
+                    } else {
+                        L.lambda *= L.ni;
+                        L.ni *= 2;
+                        rej = 1;
+                        if (!isfinite(L.lambda)) lam_bad = 1;
+                    }
+                    if (!lam_bad) L.qmax++;
+                    L.rho = rho;
+                    L.reject = rej;
+                    const int cont = !lam_bad && rho < 0 && L.qmax < 10 && !stop;
+                    L.cont_trial = cont;
+                    if (stop) L.stopped = 1;
+                    if (!cont) {  // sparse_optimizer.cpp:403-436
+                        if (L.qmax == 10 || rho == 0 || !isfinite(L.lambda)) L.ok = 0;
+                        L.curChi2 = (float)chi_raw;
+                        L.chi2Diff = L.prevChi2 - L.curChi2;
+                        if (rank == 0 && L.ntrace < 64) {
+                            B.res->trace[2 * L.ntrace] = chi_raw;
+                            B.res->trace[2 * L.ntrace + 1] = L.qmax;
+                        }
+                        if (L.ntrace < 64) L.ntrace++;
+                        L.it++;
+                        L.cont_iter = L.it < max_iters && !stop && L.ok && L.chi2Diff > 1.0f;
+                    }
+                }
+                __syncthreads();
+                if (L.reject) phase_restore(B, ct, cn);
+            }
+            cluster.sync();  // estimates settled (accepted or restored) before anyone linearizes or flags outliers
+        }
+        if (tid == 0 && rank == 0) B.res->iters[stage] = L.it;
+        __syncthreads();
+        if (L.stopped) {  // GlobalOptimizerG2O::optimize: no second stage after stopASAP
+            if (stage == 0 && tid == 0 && rank == 0) B.res->iters[1] = 0;
+            break;
+        }
+    }
+    cluster.sync();
+    // ---- getResults
+    if (rank == 0 && tid == 0) B.res->ntrace = L.ntrace;
+    for (int t = ct; t < B.P; t += cn) {
+        float* m = B.p44_out + 16 * t;
+        if (B.free_idx[t] < 0) {
+            for (int k = 0; k < 16; k++) m[k] = B.p44_in[16 * t + k];
+        } else {
+            Pose T = load_pose(B.pose + 7 * t);
+            double R[9];
+            quat_to_R(T.q, R);
+            for (int r = 0; r < 3; r++) {
+                for (int c = 0; c < 3; c++) m[4 * r + c] = (float)R[3 * r + c];
+                m[4 * r + 3] = (float)T.t[r];
+            }
+            m[12] = m[13] = m[14] = 0;
+            m[15] = 1;
+        }
+    }
+    for (int i = ct; i < B.M; i += cn) {
+        const int pi = B.obs_pose[i];
+        Pose T = load_pose(B.pose + 7 * pi);
+        const double* X = B.pt + 3 * B.obs_lm[i];
+        double x[3] = {X[0], X[1], X[2]}, p[3];
+        se3_map(T, x, p);
+        int b = 0;
+        if (B.stereo[i]) {
+            if (B.chi2[i] > (double)B.chi3d || !(p[2] > 0.0)) b = 1;
+        } else if (B.chi2[i] > (double)B.chi2d) b = 1;
+        if (!b) {  // pincam = pose_f2g (f32) * point (f32), z < 0  (:515-518)
+            float m8, m9, m10, m11;
+            if (B.free_idx[pi] < 0) {
+                const float* m = B.p44_in + 16 * pi;
+                m8 = m[8]; m9 = m[9]; m10 = m[10]; m11 = m[11];
+            } else {
+                double R[9];
+                quat_to_R(T.q, R);
+                m8 = (float)R[6]; m9 = (float)R[7]; m10 = (float)R[8]; m11 = (float)T.t[2];
+            }
+            const float zc = m8 * (float)x[0] + m9 * (float)x[1] + m10 * (float)x[2] + m11;
+            if (zc < 0) b = 1;
+        }
+        B.bad[i] = (uint8_t)(b | (B.active[i] ? 0 : 2));  // bit 1: the edge left the problem after stage 1 (level 1)
+    }
+}
+
+}  // namespace
+
+// ---- host side: one launch for a batch of windows ------------------------------------------------------------------------------
+struct BaArena {
+    size_t off = 0;
+    size_t take(size_t bytes) {
+        size_t o = off;
+        off += (bytes + 255) & ~(size_t)255;
+        return o;
+    }
+};
+
+int ba_cluster_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* const* pbs, const volatile int* stop, uco_ba_result* const* res) {
+    if (n <= 0) return UCO_OK;
+    std::vector<BaPlan> plans(n);
+    int max_n = 0;
+    for (int i = 0; i < n; i++) {
+        int rc = ba_plan_build(ctx, *pbs[i], BA_UNIT, plans[i]);
+        if (rc != UCO_OK) return rc;
+        max_n = std::max(max_n, 6 * plans[i].Pf);
+    }
+    if (max_n > BA_CLUSTER_MAX_N) return uco_fail(ctx, UCO_E_INVALID, "ba cluster path: reduced system of %d unknowns", max_n);
+    // layout: [inputs of all windows | CbDev array | stop flag][work][outputs of all windows]
+    struct Off {
+        size_t p44, free_idx, free_list, lm_ptr, obs_pose, obs_lm, pose_ptr, pose_obs, blk_unit_ptr, blk_ij, diag_blk, unit, con, z, info,
+            stereo, pt_in;
+        size_t pose_bak, pt_bak, err, lmc, Hll, bl, W, Y, Dinv, db, Hpp, bp, part, partb, xp, parts, chol_fail, active;
+        size_t pose, p44o, pt, chi2, level_dummy, bad, resd;
+    };
+    std::vector<Off> off(n);
+    BaArena A;
+    for (int i = 0; i < n; i++) {
+        const BaPlan& p = plans[i];
+        Off& o = off[i];
+        o.p44 = A.take(64 * (size_t)p.P); o.free_idx = A.take(4 * (size_t)p.P); o.free_list = A.take(4 * (size_t)(p.Pf + 1));
+        o.lm_ptr = A.take(4 * (size_t)(p.N + 1)); o.obs_pose = A.take(4 * (size_t)(p.M + 1)); o.obs_lm = A.take(4 * (size_t)(p.M + 1));
+        o.pose_ptr = A.take(4 * (size_t)(p.Pf + 1)); o.pose_obs = A.take(4 * (p.pose_obs.size() + 1));
+        o.blk_unit_ptr = A.take(4 * (p.blk_unit_ptr.size() + 1)); o.blk_ij = A.take(8 * (p.blk_ij.size() + 1));
+        o.diag_blk = A.take(4 * (size_t)(p.Pf + 1)); o.unit = A.take(16 * (p.unit.size() + 1)); o.con = A.take(8 * (p.con.size() + 1));
+        o.z = A.take(12 * (size_t)(p.M + 1)); o.info = A.take(4 * (size_t)(p.M + 1)); o.stereo = A.take((size_t)p.M + 1);
+        o.pt_in = A.take(12 * (size_t)(p.N + 1));
+    }
+    const size_t o_probs = A.take(sizeof(CbDev) * (size_t)n);
+    const size_t in_bytes = A.off;
+    for (int i = 0; i < n; i++) {
+        const BaPlan& p = plans[i];
+        Off& o = off[i];
+        const size_t M1 = p.M + 1, N1 = p.N + 1, F1 = p.Pf + 1, U1 = p.unit.size() + 1;
+        o.pose_bak = A.take(56 * (size_t)p.P); o.pt_bak = A.take(24 * N1); o.err = A.take(24 * M1); o.lmc = A.take(72 * M1);
+        o.Hll = A.take(48 * N1); o.bl = A.take(24 * N1); o.W = A.take(144 * M1); o.Y = A.take(144 * M1); o.Dinv = A.take(48 * N1);
+        o.db = A.take(24 * N1); o.Hpp = A.take(288 * F1); o.bp = A.take(48 * F1); o.part = A.take(288 * U1); o.partb = A.take(48 * U1);
+        o.xp = A.take(48 * F1); o.parts = A.take(8 * 96); o.chol_fail = A.take(16); o.active = A.take(M1);
+    }
+    const size_t out_begin = A.off;
+    for (int i = 0; i < n; i++) {
+        const BaPlan& p = plans[i];
+        Off& o = off[i];
+        o.pose = A.take(56 * (size_t)p.P); o.p44o = A.take(64 * (size_t)p.P); o.pt = A.take(24 * (size_t)(p.N + 1));
+        o.chi2 = A.take(8 * (size_t)(p.M + 1)); o.bad = A.take((size_t)p.M + 1); o.resd = A.take(sizeof(CbResult));
+    }
+    const size_t out_bytes = A.off - out_begin;
+    uint8_t* d = (uint8_t*)uco_ws(ctx, WS_BA, A.off);
+    uint8_t* h = (uint8_t*)uco_pinned(ctx, WS_BA, in_bytes);
+    uint8_t* ho = (uint8_t*)uco_pinned(ctx, WS_BA_OUT, out_bytes + 64);
+    if (!d || !h || !ho) return UCO_E_NOMEM;
+    // the stop flag the kernel polls: pinned, mapped (zero-copy) memory owned by the context
+    volatile int* hstop = (volatile int*)uco_pinned(ctx, WS_BA_STOP, 64);
+    if (!hstop) return UCO_E_NOMEM;
+    *hstop = (stop && *stop) ? 1 : 0;
+    int* dstop = nullptr;
+    UCO_CUDA(ctx, cudaHostGetDevicePointer((void**)&dstop, (void*)hstop, 0));
+    CbDev* hp = (CbDev*)(h + o_probs);
+    for (int i = 0; i < n; i++) {
+        const BaPlan& p = plans[i];
+        const uco_ba_problem& pb = *pbs[i];
+        const Off& o = off[i];
+        memcpy(h + o.p44, pb.poses44, 64 * (size_t)p.P);
+        memcpy(h + o.free_idx, p.free_idx.data(), 4 * (size_t)p.P);
+        memcpy(h + o.free_list, p.free_list.data(), 4 * (size_t)p.Pf);
+        memcpy(h + o.lm_ptr, p.lm_ptr.data(), 4 * (size_t)(p.N + 1));
+        memcpy(h + o.obs_pose, p.s_pose.data(), 4 * (size_t)p.M);
+        memcpy(h + o.obs_lm, p.s_lm.data(), 4 * (size_t)p.M);
+        memcpy(h + o.pose_ptr, p.pose_ptr.data(), 4 * (size_t)(p.Pf + 1));
+        memcpy(h + o.pose_obs, p.pose_obs.data(), 4 * p.pose_obs.size());
+        memcpy(h + o.blk_unit_ptr, p.blk_unit_ptr.data(), 4 * p.blk_unit_ptr.size());
+        memcpy(h + o.blk_ij, p.blk_ij.data(), 8 * p.blk_ij.size());
+        memcpy(h + o.diag_blk, p.diag_blk.data(), 4 * (size_t)p.Pf);
+        memcpy(h + o.unit, p.unit.data(), 16 * p.unit.size());
+        memcpy(h + o.con, p.con.data(), 8 * p.con.size());
+        float* z = (float*)(h + o.z);
+        float* info = (float*)(h + o.info);
+        uint8_t* st = h + o.stereo;
+        for (int k = 0; k < p.M; k++) {
+            const int j = p.order[k];
+            const bool s = pb.obs_stereo && pb.obs_stereo[j];
+            z[3 * k] = pb.obs_uv[2 * j]; z[3 * k + 1] = pb.obs_uv[2 * j + 1]; z[3 * k + 2] = s ? pb.obs_ur[j] : 0.f;
+            info[k] = pb.obs_inv_sigma2[j];
+            st[k] = s;
+        }
+        if (p.N) memcpy(h + o.pt_in, pb.points3, 12 * (size_t)p.N);
+        CbDev& B = hp[i];
+        memset(&B, 0, sizeof(B));
+        B.P = p.P; B.N = p.N; B.M = p.M; B.Pf = p.Pf; B.n = 6 * p.Pf; B.nblk = (int)p.blk_ij.size(); B.nunits = (int)p.unit.size();
+        B.n_iters = pb.n_iters;
+        B.p44_in = (const float*)(d + o.p44); B.free_idx = (const int*)(d + o.free_idx); B.free_list = (const int*)(d + o.free_list);
+        B.lm_ptr = (const int*)(d + o.lm_ptr); B.obs_pose = (const int*)(d + o.obs_pose); B.obs_lm = (const int*)(d + o.obs_lm);
+        B.pose_ptr = (const int*)(d + o.pose_ptr); B.pose_obs = (const int*)(d + o.pose_obs);
+        B.blk_unit_ptr = (const int*)(d + o.blk_unit_ptr); B.blk_ij = (const int2*)(d + o.blk_ij); B.diag_blk = (const int*)(d + o.diag_blk);
+        B.unit = (const int4*)(d + o.unit); B.con = (const int2*)(d + o.con); B.z = (const float*)(d + o.z); B.info = (const float*)(d + o.info);
+        B.stereo = d + o.stereo; B.pt_in = (const float*)(d + o.pt_in);
+        B.pose_bak = (double*)(d + o.pose_bak); B.pt_bak = (double*)(d + o.pt_bak); B.err = (double*)(d + o.err); B.lmc = (double*)(d + o.lmc);
+        B.Hll = (double*)(d + o.Hll); B.bl = (double*)(d + o.bl); B.W = (double*)(d + o.W); B.Y = (double*)(d + o.Y);
+        B.Dinv = (double*)(d + o.Dinv); B.db = (double*)(d + o.db); B.Hpp = (double*)(d + o.Hpp); B.bp = (double*)(d + o.bp);
+        B.part = (double*)(d + o.part); B.partb = (double*)(d + o.partb); B.xp = (double*)(d + o.xp); B.parts = (double*)(d + o.parts);
+        B.chol_fail = (int*)(d + o.chol_fail); B.active = d + o.active;
+        B.pose = (double*)(d + o.pose); B.p44_out = (float*)(d + o.p44o); B.pt = (double*)(d + o.pt); B.chi2 = (double*)(d + o.chi2);
+        B.bad = d + o.bad; B.res = (CbResult*)(d + o.resd);
+        B.cam.fx = pb.fx; B.cam.fy = pb.fy; B.cam.cx = pb.cx; B.cam.cy = pb.cy; B.cam.bf = pb.bf; B.cam.bf_f = pb.bf;
+        B.chi2d = 5.99f; B.chi3d = 7.815f;
+        B.d2 = (double)sqrtf(B.chi2d); B.d3 = (double)sqrtf(B.chi3d);
+        B.stop = dstop;
+    }
+    cudaStream_t s = ctx->stream;
+    UCO_CUDA(ctx, cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, s));
+    UCO_CUDA(ctx, cudaMemsetAsync(d + out_begin, 0, out_bytes, s));
+    const size_t smem = 8 * ((size_t)(max_n + 1) * (max_n + 2) / 2);
+    UCO_CUDA(ctx, cudaFuncSetAttribute(ba_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int CL = ctx->ba_cluster_size > 0 ? ctx->ba_cluster_size : 8;
+    if (CL > 8) UCO_CUDA(ctx, cudaFuncSetAttribute(ba_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n * CL));
+    cfg.blockDim = dim3(BS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    UCO_CUDA(ctx, cudaEventRecord(uco_ba_events(ctx)[0], s));
+    UCO_CUDA(ctx, cudaLaunchKernelEx(&cfg, ba_cluster_kernel, (const CbDev*)(d + o_probs)));
+    UCO_LAUNCH_CHECK(ctx);
+    UCO_CUDA(ctx, cudaEventRecord(uco_ba_events(ctx)[1], s));
+    UCO_CUDA(ctx, cudaMemcpyAsync(ho, d + out_begin, out_bytes, cudaMemcpyDeviceToHost, s));
+    if (stop) {  // forward an asynchronous stopASAP to the flag the kernel polls
+        cudaError_t q;
+        while ((q = cudaStreamQuery(s)) == cudaErrorNotReady)
+            if (*stop) *hstop = 1;
+        if (q != cudaSuccess) return uco_fail(ctx, UCO_E_CUDA, "ba cluster kernel -> %s", cudaGetErrorString(q));
+    }
+    UCO_CUDA(ctx, cudaStreamSynchronize(s));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, uco_ba_events(ctx)[0], uco_ba_events(ctx)[1]);
+    for (int i = 0; i < n; i++) {
+        const BaPlan& p = plans[i];
+        const Off& o = off[i];
+        uco_ba_result& r = *res[i];
+        const uint8_t* base = ho - out_begin;
+        if (r.pose7) memcpy(r.pose7, base + o.pose, 56 * (size_t)p.P);
+        if (r.poses44) memcpy(r.poses44, base + o.p44o, 64 * (size_t)p.P);
+        if (r.points3 && p.N) memcpy(r.points3, base + o.pt, 24 * (size_t)p.N);
+        const double* chi = (const double*)(base + o.chi2);
+        const uint8_t* bad = base + o.bad;
+        for (int k = 0; k < p.M; k++) {
+            const int j = p.order[k];
+            if (r.obs_chi2) r.obs_chi2[j] = chi[k];
+            if (r.obs_bad) r.obs_bad[j] = bad[k] & 1;
+            if (r.obs_level) r.obs_level[j] = (bad[k] >> 1) & 1;
+        }
+        const CbResult* cr = (const CbResult*)(base + o.resd);
+        if (r.trace) {
+            memset(r.trace, 0, sizeof(double) * 128);
+            memcpy(r.trace, cr->trace, sizeof(double) * 2 * (size_t)std::min(cr->ntrace, 64));
+        }
+        r.iters[0] = cr->iters[0];
+        r.iters[1] = cr->iters[1];
+        r.device_ms = ms;
+    }
+    return UCO_OK;
+}

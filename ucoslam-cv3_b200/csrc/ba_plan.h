@@ -1,0 +1,160 @@
+// ba_plan.h — host-side structure of one bundle-adjustment window (built once per solve, no arithmetic):
+// free-pose numbering, observations sorted by landmark, per-pose observation lists and the Schur gather lists
+// (for every 6x6 block (i <= j) of the reduced system the (obs_a, obs_b) pairs of the landmarks both poses see, in
+// landmark order, cut into units of <= `unit` contributions).  Mirrors what BlockSolver::buildStructure prepares
+// (3rdparty/g2o/g2o/core/block_solver.hpp:103-312) for the graph GlobalOptimizerG2O::setParams assembles.
+#pragma once
+#include "common.cuh"
+#include "ba_math.cuh"
+#include <vector>
+
+constexpr int BA_UNIT = 48;            // contributions per Schur-gather unit
+constexpr int BA_CLUSTER_MAX_N = 228;  // reduced-system size the cluster kernel holds in shared memory (38 free keyframes)
+
+struct CbResult {
+    int iters[2];
+    int ntrace, pad;
+    double trace[128];
+};
+
+struct CbDev {  // one window as the cluster kernel sees it (device pointers)
+    int P, N, M, Pf, n, nblk, nunits, n_iters;
+    const float *p44_in, *pt_in, *z, *info;
+    const uint8_t* stereo;
+    const int *free_idx, *free_list, *lm_ptr, *obs_pose, *obs_lm, *pose_ptr, *pose_obs, *blk_unit_ptr, *diag_blk;
+    const int2 *blk_ij, *con;
+    const int4* unit;
+    double *pose, *pose_bak, *pt, *pt_bak, *err, *chi2, *lmc, *Hll, *bl, *W, *Y, *Dinv, *db, *Hpp, *bp, *part, *partb, *xp, *parts;
+    int* chol_fail;  // [0] reduced solve failed in this trial, [1] stop flag as latched by CTA 0
+    uint8_t *active, *bad;
+    float* p44_out;
+    CbResult* res;
+    ba::Cam cam;
+    double d2, d3;
+    float chi2d, chi3d;
+    const int* stop;
+};
+
+struct BaPlan {
+    int P = 0, N = 0, M = 0, Pf = 0;
+    std::vector<int> free_idx, free_list, lm_ptr, order, s_pose, s_lm, pose_ptr, pose_obs, blk_unit_ptr, diag_blk;
+    std::vector<int2> blk_ij, con;
+    std::vector<int4> unit;  // (block, first contribution, one past the last, block is diagonal)
+};
+
+inline int ba_validate(uco_b200_ctx* ctx, const uco_ba_problem* pb) {
+    if (!pb) return uco_fail(ctx, UCO_E_INVALID, "ba_solve: null problem");
+    const int P = pb->n_poses, N = pb->n_points, M = pb->n_obs;
+    if (P <= 0 || N < 0 || M < 0 || pb->n_iters < 0) return uco_fail(ctx, UCO_E_INVALID, "ba_solve: bad sizes");
+    if (!pb->poses44 || !pb->fixed || (N && !pb->points3) || (M && (!pb->obs_pose || !pb->obs_point || !pb->obs_uv || !pb->obs_inv_sigma2)))
+        return uco_fail(ctx, UCO_E_INVALID, "ba_solve: null input array");
+    for (int i = 0; i < M; i++) {
+        if ((unsigned)pb->obs_pose[i] >= (unsigned)P || (unsigned)pb->obs_point[i] >= (unsigned)N)
+            return uco_fail(ctx, UCO_E_INVALID, "ba_solve: observation %d references pose %d / point %d out of range", i,
+                            pb->obs_pose[i], pb->obs_point[i]);
+        if (pb->obs_stereo && pb->obs_stereo[i] && !pb->obs_ur)
+            return uco_fail(ctx, UCO_E_INVALID, "ba_solve: stereo observation without obs_ur");
+    }
+    return UCO_OK;
+}
+
+inline int ba_free_poses(const uco_ba_problem* pb) {
+    int f = 0;
+    for (int i = 0; i < pb->n_poses; i++) f += pb->fixed[i] ? 0 : 1;
+    return f;
+}
+
+inline int ba_plan_build(uco_b200_ctx* ctx, const uco_ba_problem& pb, int unit, BaPlan& p) {
+    int rc = ba_validate(ctx, &pb);
+    if (rc != UCO_OK) return rc;
+    const int P = pb.n_poses, N = pb.n_points, M = pb.n_obs;
+    p.P = P; p.N = N; p.M = M;
+    p.free_idx.assign(P, -1);
+    p.free_list.clear();
+    for (int i = 0; i < P; i++)
+        if (!pb.fixed[i]) {
+            p.free_idx[i] = (int)p.free_list.size();
+            p.free_list.push_back(i);
+        }
+    const int Pf = p.Pf = (int)p.free_list.size();
+    p.lm_ptr.assign(N + 1, 0);
+    for (int i = 0; i < M; i++) p.lm_ptr[pb.obs_point[i] + 1]++;
+    for (int l = 0; l < N; l++) p.lm_ptr[l + 1] += p.lm_ptr[l];
+    p.order.resize(M);
+    {
+        std::vector<int> fill(p.lm_ptr.begin(), p.lm_ptr.end() - 1);
+        for (int i = 0; i < M; i++) p.order[fill[pb.obs_point[i]]++] = i;  // sorted position -> caller index (stable)
+    }
+    p.s_pose.resize(M);
+    p.s_lm.resize(M);
+    for (int k = 0; k < M; k++) {
+        p.s_pose[k] = pb.obs_pose[p.order[k]];
+        p.s_lm[k] = pb.obs_point[p.order[k]];
+    }
+    p.pose_ptr.assign(Pf + 1, 0);
+    for (int k = 0; k < M; k++) {
+        int f = p.free_idx[p.s_pose[k]];
+        if (f >= 0) p.pose_ptr[f + 1]++;
+    }
+    for (int f = 0; f < Pf; f++) p.pose_ptr[f + 1] += p.pose_ptr[f];
+    p.pose_obs.resize(p.pose_ptr[Pf]);
+    {
+        std::vector<int> fill(p.pose_ptr.begin(), p.pose_ptr.end() - 1);
+        for (int k = 0; k < M; k++) {
+            int f = p.free_idx[p.s_pose[k]];
+            if (f >= 0) p.pose_obs[fill[f]++] = k;
+        }
+    }
+    // contributions per block (i <= j): count, then fill in landmark order
+    std::vector<int> cnt((size_t)Pf * Pf, 0);
+    for (int l = 0; l < N; l++)
+        for (int a = p.lm_ptr[l]; a < p.lm_ptr[l + 1]; a++) {
+            const int fa = p.free_idx[p.s_pose[a]];
+            if (fa < 0) continue;
+            for (int b = p.lm_ptr[l]; b < p.lm_ptr[l + 1]; b++) {
+                const int fb = p.free_idx[p.s_pose[b]];
+                if (fb < fa || (fb == fa && b != a)) continue;
+                cnt[(size_t)fa * Pf + fb]++;
+            }
+        }
+    std::vector<int> blk_of((size_t)Pf * Pf, -1), blk_ptr(1, 0);
+    p.blk_ij.clear();
+    p.diag_blk.assign(Pf, -1);
+    for (int i = 0; i < Pf; i++)
+        for (int j = i; j < Pf; j++)
+            if (cnt[(size_t)i * Pf + j] || i == j) {  // diagonal blocks always exist (Hpp + lambda I)
+                blk_of[(size_t)i * Pf + j] = (int)p.blk_ij.size();
+                if (i == j) p.diag_blk[i] = (int)p.blk_ij.size();
+                p.blk_ij.push_back(make_int2(i, j));
+                blk_ptr.push_back(blk_ptr.back() + cnt[(size_t)i * Pf + j]);
+            }
+    const int nblk = (int)p.blk_ij.size();
+    p.con.resize(blk_ptr.back());
+    {
+        std::vector<int> fill(blk_ptr.begin(), blk_ptr.end() - 1);
+        for (int l = 0; l < N; l++)
+            for (int a = p.lm_ptr[l]; a < p.lm_ptr[l + 1]; a++) {
+                const int fa = p.free_idx[p.s_pose[a]];
+                if (fa < 0) continue;
+                for (int b = p.lm_ptr[l]; b < p.lm_ptr[l + 1]; b++) {
+                    const int fb = p.free_idx[p.s_pose[b]];
+                    if (fb < fa || (fb == fa && b != a)) continue;
+                    p.con[fill[blk_of[(size_t)fa * Pf + fb]]++] = make_int2(a, b);
+                }
+            }
+    }
+    p.unit.clear();
+    p.blk_unit_ptr.assign(1, 0);
+    for (int k = 0; k < nblk; k++) {
+        for (int c0 = blk_ptr[k]; c0 < blk_ptr[k + 1]; c0 += unit)
+            p.unit.push_back(make_int4(k, c0, std::min(c0 + unit, blk_ptr[k + 1]), p.blk_ij[k].x == p.blk_ij[k].y));
+        p.blk_unit_ptr.push_back((int)p.unit.size());
+    }
+    return UCO_OK;
+}
+
+// ba.cu
+cudaEvent_t* uco_ba_events(uco_b200_ctx* ctx);
+int ba_streamed_solve(uco_b200_ctx* ctx, const uco_ba_problem* pb, const volatile int* stop, uco_ba_result* res);
+// ba_cluster.cu
+int ba_cluster_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* const* pbs, const volatile int* stop, uco_ba_result* const* res);

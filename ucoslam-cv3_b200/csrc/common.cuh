@@ -27,13 +27,15 @@ struct uco_b200_ctx {
     std::vector<uco_dev_buf> pin;
     uco_orb_state* orb = nullptr;
     uco_ba_state* ba = nullptr;
+    int ba_mode = 0;          // 0 auto, 1 streamed kernels (ba.cu), 2 cluster-resident kernel (ba_cluster.cu)
+    int ba_cluster_size = 0;  // CTAs per cluster of the cluster-resident solver (0 = default 8)
 };
 
 enum {  // device workspace slots
     WS_KNN_Q = 0, WS_KNN_T, WS_KNN_IDX, WS_KNN_DIST,
     WS_BOW_DESC, WS_BOW_OUT,
     WS_GENERIC0, WS_GENERIC1, WS_GENERIC2, WS_GENERIC3,
-    WS_BA, WS_BA_OUT,
+    WS_BA, WS_BA_OUT, WS_BA_STOP,
     WS_COUNT
 };
 

@@ -45,6 +45,7 @@ SIGNATURES = {
     "uco_b200_bow_transform_dev": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "uco_b200_ba_solve": (_i, [_vp, _vp, _vp, _vp]),
     "uco_b200_ba_solve_batch": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "uco_b200_ba_set_mode": (_i, [_vp, _i, _i]),
     "uco_b200_probe_math": (_i, [_i, _vp, _vp, _i, _vp, _vp]),
     "uco_b200_probe_retain_best": (_i, [_vp, _i, _i]),
 }
@@ -172,6 +173,9 @@ class Context:
         return idx, dist
 
     # -- K10-K13 -------------------------------------------------------------------------------------------------
+    def ba_set_mode(self, mode=0, cluster_size=0):
+        self._chk(self.lib.uco_b200_ba_set_mode(self.h, mode, cluster_size))
+
     @staticmethod
     def ba_pack(pb, n_iters):
         """(uco_ba_problem, uco_ba_result, keep-alive input arrays, output dict) for a problem dict (see ba_solve)."""
