@@ -206,6 +206,7 @@ typedef struct uco_ba_result {   /* every pointer may be NULL (not wanted) */
     double* trace;               /* 64 x 2        per LM iteration: robust chi2, number of LM trials (both stages, in order) */
     int32_t iters[2];            /* iterations executed by stage 1 / stage 2 (SparseOptimizer::optimize return values) */
     float device_ms;             /* device time of the solve between first and last kernel (CUDA events) */
+    double* profile;             /* 16 doubles, optional: SM cycles CTA 0 of the window's cluster spent per phase (cluster-resident form) */
 } uco_ba_result;
 
 /* stop: optional flag polled between LM trials (GlobalOptimizerG2O::optimize(bool* stopASAP), sparse_optimizer.h:189);
@@ -217,6 +218,9 @@ int uco_b200_ba_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* pbs,
  * window, the whole LM loop in one launch), larger ones as streamed kernels; 1: always streamed; 2: always cluster-resident.
  * cluster_size: CTAs per cluster (power of two <= 16, 0 = 8). */
 int uco_b200_ba_set_mode(uco_b200_ctx* ctx, int mode, int cluster_size);
+/* host-only inspection hook (no GPU needed): builds the window structure the solver uses and reports
+ * {free poses, Schur blocks, gather units, contributions, chunks, pose-list entries, max observations per chunk, landmarks covered} */
+int uco_b200_probe_ba_plan(const uco_ba_problem* pb, int cluster_size, int* out8);
 
 #ifdef __cplusplus
 }

@@ -870,10 +870,28 @@ int ba_streamed_solve(uco_b200_ctx* ctx, const uco_ba_problem* pb, const volatil
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ba->ev0, ctx->ba->ev1);
     res->device_ms = ms;
+    if (res->profile) memset(res->profile, 0, sizeof(double) * 16);
     return UCO_OK;
 }
 
 extern "C" {
+
+// host-only: builds the window structure (no device needed) and reports its sizes; used by the CPU tests and to time the planner
+int uco_b200_probe_ba_plan(const uco_ba_problem* pb, int cluster_size, int* out8) {
+    uco_b200_ctx tmp;
+    BaPlan p;
+    int rc = ba_plan_build(&tmp, *pb, BA_UNIT, p, cluster_size > 0 ? cluster_size : 8, 512);
+    if (rc != UCO_OK) return rc;
+    if (out8) {
+        out8[0] = p.Pf; out8[1] = (int)p.blk_ij.size(); out8[2] = (int)p.unit.size(); out8[3] = p.ncon;
+        out8[4] = (int)p.chunk_lm.size() - 1; out8[5] = (int)p.pose_obs.size();
+        int mx = 0;
+        for (size_t c = 0; c + 1 < p.chunk_lm.size(); c++) mx = std::max(mx, p.lm_ptr[p.chunk_lm[c + 1]] - p.lm_ptr[p.chunk_lm[c]]);
+        out8[6] = mx;
+        out8[7] = p.cta_lm.back();
+    }
+    return UCO_OK;
+}
 
 int uco_b200_ba_set_mode(uco_b200_ctx* ctx, int mode, int cluster_size) {
     if (!ctx) return UCO_E_INVALID;

@@ -20,6 +20,8 @@
 #include <cooperative_groups.h>
 #include <cfloat>
 #include <cstring>
+#include <string>
+#include <thread>
 #include <vector>
 
 namespace cg = cooperative_groups;
@@ -91,79 +93,103 @@ __device__ __forceinline__ double phase_errors(const CbDev& B, int ct, int cn, i
     return s;
 }
 
-// per observation: W block (6x3) and this observation's terms of Hll / bl
-__device__ __forceinline__ void phase_linearize_obs(const CbDev& B, int ct, int cn, int robust) {
-    for (int i = ct; i < B.M; i += cn) {
-        double* W = B.W + 18 * (size_t)i;
-        double* C = B.lmc + 9 * (size_t)i;
-        if (!B.active[i]) {
+// Work is cut along landmarks: CTA `rank` owns the landmark range [cta_lm[rank], cta_lm[rank+1]) and, observations being
+// sorted by landmark, a contiguous range of observations; it walks that range in chunks of whole landmarks with <= BS
+// observations (chunk_lm[]), so everything a landmark needs is inside one CTA and one __syncthreads away.  Per-observation
+// 6x3 blocks live in HBM as 18 contiguous doubles (what the Schur gather wants); a thread never writes its own 144-byte
+// row directly (32 lanes x 8 B scattered over 32 sectors) but stages it in shared memory and the warp copies it out
+// contiguously.
+constexpr int WPAD = 19;  // staged row pitch (doubles): odd-ish pitch keeps the per-lane row writes off the same banks
+
+// linearize: per observation the W block and its Hll / bl terms; per landmark the ordered sums.  Returns max |diag(Hll)|.
+__device__ __forceinline__ double phase_linearize_lm(const CbDev& B, int rank, int robust, double* stage) {
+    const int tid = threadIdx.x;
+    double* sW = stage;                 // [BS][WPAD]
+    double* sC = stage + BS * WPAD;     // [BS][9]
+    double md = 0;
+    for (int ch = B.cta_chunk_ptr[rank]; ch < B.cta_chunk_ptr[rank + 1]; ch++) {
+        const int l0 = B.chunk_lm[ch], l1 = B.chunk_lm[ch + 1], o0 = B.lm_ptr[l0], o1 = B.lm_ptr[l1], nobs = o1 - o0;
+        if (tid < nobs) {
+            const int i = o0 + tid;
+            double* W = sW + tid * WPAD;
+            double* C = sC + tid * 9;
+            if (!B.active[i]) {
 #pragma unroll
-            for (int k = 0; k < 18; k++) W[k] = 0;
+                for (int k = 0; k < 18; k++) W[k] = 0;
 #pragma unroll
-            for (int k = 0; k < 9; k++) C[k] = 0;
-            continue;
-        }
-        const int pi = B.obs_pose[i];
-        Pose T = load_pose(B.pose + 7 * pi);
-        const double* X = B.pt + 3 * B.obs_lm[i];
-        double x[3] = {X[0], X[1], X[2]}, p[3], R[9], JX[9], wo, orr[3];
-        se3_map(T, x, p);
-        quat_to_R(T.q, R);
-        const bool st = B.stereo[i];
-        jac_point(p, R, st, B.cam, JX);
-        obs_weights(B, i, robust, wo, orr);
-        const int D = st ? 3 : 2;
-        {
-            int k = 0;
+                for (int k = 0; k < 9; k++) C[k] = 0;
+            } else {
+                const int pi = B.obs_pose[i];
+                Pose T = load_pose(B.pose + 7 * pi);
+                const double* X = B.pt + 3 * B.obs_lm[i];
+                double x[3] = {X[0], X[1], X[2]}, p[3], R[9], JX[9], JT[18], wo, orr[3];
+                se3_map(T, x, p);
+                quat_to_R(T.q, R);
+                const bool st = B.stereo[i];
+                jac_point(p, R, st, B.cam, JX);   // rows beyond the residual dimension are zero: adding their terms changes nothing
+                obs_weights(B, i, robust, wo, orr);
+                {
+                    int k = 0;
 #pragma unroll
-            for (int a = 0; a < 3; a++)
+                    for (int a = 0; a < 3; a++)
 #pragma unroll
-                for (int c = a; c < 3; c++, k++) {
-                    double h = 0;
-                    for (int d = 0; d < D; d++) h += JX[3 * d + a] * wo * JX[3 * d + c];
-                    C[k] = h;
+                        for (int c = a; c < 3; c++, k++) {
+                            double h = 0;
+#pragma unroll
+                            for (int d = 0; d < 3; d++) h += JX[3 * d + a] * wo * JX[3 * d + c];
+                            C[k] = h;
+                        }
+#pragma unroll
+                    for (int a = 0; a < 3; a++) {
+                        double sacc = 0;
+#pragma unroll
+                        for (int d = 0; d < 3; d++) sacc += JX[3 * d + a] * orr[d];
+                        C[6 + a] = sacc;
+                    }
                 }
+                if (B.free_idx[pi] >= 0) {
+                    jac_pose(p, st, B.cam, JT);
 #pragma unroll
-            for (int a = 0; a < 3; a++) {
-                double s = 0;
-                for (int d = 0; d < D; d++) s += JX[3 * d + a] * orr[d];
-                C[6 + a] = s;
+                    for (int a = 0; a < 6; a++)
+#pragma unroll
+                        for (int c = 0; c < 3; c++) {
+                            double h = 0;
+#pragma unroll
+                            for (int d = 0; d < 3; d++) h += JT[6 * d + a] * wo * JX[3 * d + c];
+                            W[3 * a + c] = h;
+                        }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 18; k++) W[k] = 0;
+                }
             }
         }
-        if (B.free_idx[pi] >= 0) {
-            double JT[18];
-            jac_pose(p, st, B.cam, JT);
-#pragma unroll
-            for (int a = 0; a < 6; a++)
-#pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    double h = 0;
-                    for (int d = 0; d < D; d++) h += JT[6 * d + a] * wo * JX[3 * d + c];
-                    W[3 * a + c] = h;
-                }
-        } else {
-#pragma unroll
-            for (int k = 0; k < 18; k++) W[k] = 0;
+        __syncthreads();
+        {
+            double* Wg = B.W + 18 * (size_t)o0;
+            for (int e = tid; e < 18 * nobs; e += BS) Wg[e] = sW[(e / 18) * WPAD + e % 18];
         }
+        if (tid < l1 - l0) {
+            const int l = l0 + tid;
+            double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            for (int i = B.lm_ptr[l] - o0; i < B.lm_ptr[l + 1] - o0; i++) {
+#pragma unroll
+                for (int k = 0; k < 9; k++) acc[k] += sC[i * 9 + k];
+            }
+#pragma unroll
+            for (int k = 0; k < 6; k++) B.Hll[6 * (size_t)l + k] = acc[k];
+#pragma unroll
+            for (int k = 0; k < 3; k++) B.bl[3 * (size_t)l + k] = acc[6 + k];
+            md = fmax(md, fmax(fabs(acc[0]), fmax(fabs(acc[3]), fabs(acc[5]))));
+        }
+        __syncthreads();
     }
+    return md;
 }
 
-// landmark sums (thread per landmark, observation order) and pose blocks (CTA per free pose); returns max |diagonal| seen
-__device__ __forceinline__ double phase_linearize_sum(const CbDev& B, int ct, int cn, int rank, int CL, int robust, double* red27) {
+// pose blocks Hpp / bp: one CTA per free pose, Jacobian recomputed from the pose's observation list, ordered reduction
+__device__ __forceinline__ double phase_linearize_pose(const CbDev& B, int rank, int CL, int robust, double* red27) {
     double md = 0;
-    for (int l = ct; l < B.N; l += cn) {
-        double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        for (int i = B.lm_ptr[l]; i < B.lm_ptr[l + 1]; i++) {
-            const double* C = B.lmc + 9 * (size_t)i;
-#pragma unroll
-            for (int k = 0; k < 9; k++) acc[k] += C[k];
-        }
-#pragma unroll
-        for (int k = 0; k < 6; k++) B.Hll[6 * (size_t)l + k] = acc[k];
-#pragma unroll
-        for (int k = 0; k < 3; k++) B.bl[3 * (size_t)l + k] = acc[6 + k];
-        md = fmax(md, fmax(fabs(acc[0]), fmax(fabs(acc[3]), fabs(acc[5]))));
-    }
     const int tid = threadIdx.x;
     for (int f = rank; f < B.Pf; f += CL) {
         const int pi = B.free_list[f];
@@ -180,21 +206,22 @@ __device__ __forceinline__ double phase_linearize_sum(const CbDev& B, int ct, in
             const bool st = B.stereo[i];
             jac_pose(p, st, B.cam, JT);
             obs_weights(B, i, robust, wo, orr);
-            const int D = st ? 3 : 2;
             int k = 0;
 #pragma unroll
             for (int a = 0; a < 6; a++)
 #pragma unroll
                 for (int c = a; c < 6; c++, k++) {
                     double h = 0;
-                    for (int d = 0; d < D; d++) h += JT[6 * d + a] * wo * JT[6 * d + c];
+#pragma unroll
+                    for (int d = 0; d < 3; d++) h += JT[6 * d + a] * wo * JT[6 * d + c];
                     acc[k] += h;
                 }
 #pragma unroll
             for (int a = 0; a < 6; a++) {
-                double s = 0;
-                for (int d = 0; d < D; d++) s += JT[6 * d + a] * orr[d];
-                acc[21 + a] += s;
+                double sacc = 0;
+#pragma unroll
+                for (int d = 0; d < 3; d++) sacc += JT[6 * d + a] * orr[d];
+                acc[21 + a] += sacc;
             }
         }
         __syncthreads();  // red27 reuse
@@ -226,74 +253,126 @@ __device__ __forceinline__ double phase_linearize_sum(const CbDev& B, int ct, in
     return md;
 }
 
-__device__ __forceinline__ void phase_prep(const CbDev& B, int ct, int cn, double lambda) {
-    for (int i = ct; i < B.M; i += cn) {
-        const int l = B.obs_lm[i];
-        double D[6], I[6];
+// per trial and chunk: D^-1 of the chunk's landmarks (kept in shared memory and in HBM for the back-substitution), then
+// Y = W D^-1 one 3-wide row per thread (consecutive threads read and write consecutive 24 bytes), two rows in flight
+__device__ __forceinline__ void phase_prep(const CbDev& B, int rank, double lambda, double* stage) {
+    const int tid = threadIdx.x;
+    double* sD = stage;  // [BS][6]
+    for (int ch = B.cta_chunk_ptr[rank]; ch < B.cta_chunk_ptr[rank + 1]; ch++) {
+        const int l0 = B.chunk_lm[ch], l1 = B.chunk_lm[ch + 1], o0 = B.lm_ptr[l0], o1 = B.lm_ptr[l1];
+        if (tid < l1 - l0) {
+            const int l = l0 + tid;
+            double D[6], I[6];
 #pragma unroll
-        for (int k = 0; k < 6; k++) D[k] = B.Hll[6 * (size_t)l + k];
-        D[0] += lambda; D[3] += lambda; D[5] += lambda;
-        inv3_sym(D, I);
-        const double Im[9] = {I[0], I[1], I[2], I[1], I[3], I[4], I[2], I[4], I[5]};
-        if (i == B.lm_ptr[l]) {
+            for (int k = 0; k < 6; k++) D[k] = B.Hll[6 * (size_t)l + k];
+            D[0] += lambda; D[3] += lambda; D[5] += lambda;
+            inv3_sym(D, I);
 #pragma unroll
-            for (int k = 0; k < 6; k++) B.Dinv[6 * (size_t)l + k] = I[k];
-            double b[3] = {B.bl[3 * (size_t)l], B.bl[3 * (size_t)l + 1], B.bl[3 * (size_t)l + 2]};
-#pragma unroll
-            for (int a = 0; a < 3; a++) B.db[3 * (size_t)l + a] = Im[3 * a] * b[0] + Im[3 * a + 1] * b[1] + Im[3 * a + 2] * b[2];
+            for (int k = 0; k < 6; k++) {
+                B.Dinv[6 * (size_t)l + k] = I[k];
+                sD[6 * tid + k] = I[k];
+            }
         }
-        const double* W = B.W + 18 * (size_t)i;
-        double* Y = B.Y + 18 * (size_t)i;
-#pragma unroll
-        for (int a = 0; a < 6; a++) {
-            double w0 = W[3 * a], w1 = W[3 * a + 1], w2 = W[3 * a + 2];
-#pragma unroll
-            for (int c = 0; c < 3; c++) Y[3 * a + c] = w0 * Im[c] + w1 * Im[3 + c] + w2 * Im[6 + c];
+        __syncthreads();
+        const int r0 = 6 * o0, r1 = 6 * o1;
+        for (int row = r0 + tid; row < r1; row += 2 * BS) {
+            const int rowb = row + BS;
+            const bool hb = rowb < r1;
+            const int la = B.obs_lm[row / 6] - l0, lb = hb ? B.obs_lm[rowb / 6] - l0 : 0;
+            const double* Wa = B.W + 3 * (size_t)row;
+            const double* Wb = B.W + 3 * (size_t)(hb ? rowb : row);
+            const double a0 = Wa[0], a1 = Wa[1], a2 = Wa[2], b0 = Wb[0], b1 = Wb[1], b2 = Wb[2];
+            {
+                const double* I = sD + 6 * la;
+                double* Y = B.Y + 3 * (size_t)row;
+                Y[0] = a0 * I[0] + a1 * I[1] + a2 * I[2];
+                Y[1] = a0 * I[1] + a1 * I[3] + a2 * I[4];
+                Y[2] = a0 * I[2] + a1 * I[4] + a2 * I[5];
+            }
+            if (hb) {
+                const double* I = sD + 6 * lb;
+                double* Y = B.Y + 3 * (size_t)rowb;
+                Y[0] = b0 * I[0] + b1 * I[1] + b2 * I[2];
+                Y[1] = b0 * I[1] + b1 * I[3] + b2 * I[4];
+                Y[2] = b0 * I[2] + b1 * I[4] + b2 * I[5];
+            }
         }
+        __syncthreads();
     }
 }
 
-// Schur gather: teams of 36 threads walk units of <= BA_UNIT contributions of one 6x6 block
+// Schur gather on the FP64 tensor pipe: one warp per unit (<= BA_UNIT contributions of one 6x6 block), one
+// mma.m8n8k4.f64 per contribution: A = Y_a (6x3 in an 8x4 tile), B = W_b^T (3x6 in 4x8), accumulated in the warp's 8x8 C.
+// Diagonal units (a == b; con holds (a, landmark)) put bl of the landmark in column 6 of B, so C[:,6] accumulates
+// Y_a bl = W_a D^-1 bl, the Schur right-hand-side term.  Fragment layout (PTX ISA, mma.m8n8k4): A[lane/4][lane%4],
+// B[lane%4][lane/4], C[lane/4][2(lane%4) + {0,1}]; element (row, k) of a 6x3 block sits at 3 row + k.
+__device__ __forceinline__ void mma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+// Instruction diet (the phase is issue-bound, ~16 warps per SM): units are padded on the host to a multiple of four
+// contributions with the all-zero dummy observation M / landmark N, and every lane's operand address is
+// base + stride * index with lane-constant base / stride (lanes outside the 6x3 tiles read a zero double with stride 0),
+// so a contribution costs two shuffles, two address computations, two loads and one DMMA, with no branch.
 __device__ __forceinline__ void phase_gather(const CbDev& B, int rank, int CL) {
-    const int tid = threadIdx.x, team = tid / 36, e = tid % 36, r = e / 6, c = e % 6;
-    if (team >= TEAMS) return;
-    for (int u = rank * TEAMS + team; u < B.nunits; u += CL * TEAMS) {
-        const int4 un = B.unit[u];  // blk, c0, c1, diag
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = lane >> 2, k4 = lane & 3, off = 3 * q + k4;
+    const bool valid = k4 < 3 && q < 6, isbl = k4 < 3 && q == 6;
+    const int stride = CL * NW;
+    int u = rank * NW + warp;
+    if (u >= B.nunits) return;
+    const double* zero = B.W + 18 * (size_t)B.M;  // the dummy observation's (all-zero) block
+    const double* baseA = valid ? B.Y + off : zero;
+    const int strideA = valid ? 18 : 0;
+    int4 un = B.unit[u];
+    int2 i0 = make_int2(B.M, B.M), i1 = i0;
+    if (lane < un.z - un.y) i0 = B.con[un.y + lane];
+    if (lane + 32 < un.z - un.y) i1 = B.con[un.y + 32 + lane];
+    while (true) {
+        const int un_next = u + stride;
+        int4 nn = make_int4(0, 0, 0, 0);
+        int2 n0 = make_int2(B.M, B.M), n1 = n0;
+        if (un_next < B.nunits) {
+            nn = B.unit[un_next];
+            if (lane < nn.z - nn.y) n0 = B.con[nn.y + lane];
+            if (lane + 32 < nn.z - nn.y) n1 = B.con[nn.y + 32 + lane];
+        }
         const bool diag = un.w != 0;
-        double s = 0, sb = 0;
-        int k = un.y;
-        for (; k + 1 < un.z; k += 2) {  // two contributions in flight
-            const int2 ab0 = B.con[k], ab1 = B.con[k + 1];
-            const double* Y0 = B.Y + 18 * (size_t)ab0.x + 3 * r;
-            const double* W0 = B.W + 18 * (size_t)ab0.y + 3 * c;
-            const double* Y1 = B.Y + 18 * (size_t)ab1.x + 3 * r;
-            const double* W1 = B.W + 18 * (size_t)ab1.y + 3 * c;
-            double y00 = Y0[0], y01 = Y0[1], y02 = Y0[2], w00 = W0[0], w01 = W0[1], w02 = W0[2];
-            double y10 = Y1[0], y11 = Y1[1], y12 = Y1[2], w10 = W1[0], w11 = W1[1], w12 = W1[2];
-            s += y00 * w00 + y01 * w01 + y02 * w02;
-            s += y10 * w10 + y11 * w11 + y12 * w12;
-            if (diag && c == 0) {
-                const double* Wa0 = B.W + 18 * (size_t)ab0.x + 3 * r;
-                const double* d0 = B.db + 3 * (size_t)B.obs_lm[ab0.x];
-                const double* Wa1 = B.W + 18 * (size_t)ab1.x + 3 * r;
-                const double* d1 = B.db + 3 * (size_t)B.obs_lm[ab1.x];
-                sb += Wa0[0] * d0[0] + Wa0[1] * d0[1] + Wa0[2] * d0[2];
-                sb += Wa1[0] * d1[0] + Wa1[1] * d1[1] + Wa1[2] * d1[2];
+        const int cnt = un.z - un.y;  // multiple of 4
+        // B operand: W_b (off-diagonal), W_a (diagonal, 6x3 tile lanes), bl of the landmark (diagonal, column 6 lanes)
+        const double* baseB = valid ? B.W + off : (diag && isbl ? B.bl + k4 : zero);
+        const int strideB = valid ? 18 : (diag && isbl ? 3 : 0);
+        const bool b_from_a = diag && valid;
+        double acc0[4] = {0, 0, 0, 0}, acc1[4] = {0, 0, 0, 0}, av[4], bv[4], an[4], bn[4];  // four independent accumulator tiles: the
+                                                                                           // DMMA dependent-issue latency is long
+#define BA_FETCH(k, A_, B_)                                                                        \
+    _Pragma("unroll") for (int j = 0; j < 4; j++) {                                               \
+        const int kk = (k) + j;                                                                    \
+        const int2 src = kk < 32 ? i0 : i1;                                                        \
+        const int a = __shfl_sync(0xffffffffu, src.x, kk & 31), b = __shfl_sync(0xffffffffu, src.y, kk & 31); \
+        A_[j] = baseA[(size_t)(strideA * a)];                                                     \
+        B_[j] = baseB[(size_t)(strideB * (b_from_a ? a : b))];                                     \
+    }
+        BA_FETCH(0, av, bv)
+        for (int k = 0; k < cnt; k += 4) {
+            if (k + 4 < cnt) { BA_FETCH(k + 4, an, bn) }
+#pragma unroll
+            for (int j = 0; j < 4; j++) mma884(acc0[j], acc1[j], av[j], bv[j]);
+#pragma unroll
+            for (int j = 0; j < 4; j++) { av[j] = an[j]; bv[j] = bn[j]; }
+        }
+#undef BA_FETCH
+        const double c0 = (acc0[0] + acc0[1]) + (acc0[2] + acc0[3]), c1 = (acc1[0] + acc1[1]) + (acc1[2] + acc1[3]);
+        if (q < 6) {
+            const int col = 2 * k4;
+            if (col < 6) {
+                B.part[36 * (size_t)u + 6 * q + col] = c0;
+                B.part[36 * (size_t)u + 6 * q + col + 1] = c1;
+            } else if (diag) {
+                B.partb[6 * (size_t)u + q] = c0;
             }
         }
-        if (k < un.z) {
-            const int2 ab = B.con[k];
-            const double* Y = B.Y + 18 * (size_t)ab.x + 3 * r;
-            const double* W = B.W + 18 * (size_t)ab.y + 3 * c;
-            s += Y[0] * W[0] + Y[1] * W[1] + Y[2] * W[2];
-            if (diag && c == 0) {
-                const double* Wa = B.W + 18 * (size_t)ab.x + 3 * r;
-                const double* d = B.db + 3 * (size_t)B.obs_lm[ab.x];
-                sb += Wa[0] * d[0] + Wa[1] * d[1] + Wa[2] * d[2];
-            }
-        }
-        B.part[36 * (size_t)u + e] = s;
-        if (diag && c == 0) B.partb[6 * (size_t)u + r] = sb;
+        if (un_next >= B.nunits) break;
+        u = un_next; un = nn; i0 = n0; i1 = n1;
     }
 }
 
@@ -398,14 +477,17 @@ __device__ int phase_solve(const CbDev& B, double lambda, double* A, double* aux
         for (int k = tid; k < n; k += BS) B.xp[k] = 0;
         return 0;
     }
+    for (int j = tid; j < n; j += BS) aux[256 + j] = 1.0 / A[j * (j + 1) / 2 + j];  // pivots inverted side by side, off the serial chain
+    __syncthreads();
     if (warp == 0) {  // x_j = (w_j - sum_{i>j} A[i][j] x_i) / d_j
         double* s = aux;  // n entries
+        const double* rcp = aux + 256;
         const double* wrow = A + n * (n + 1) / 2;
         for (int k = lane; k < n; k += 32) s[k] = wrow[k];
         __syncwarp();
         for (int j = n - 1; j >= 0; j--) {
             const double* row = A + j * (j + 1) / 2;
-            const double xj = s[j] / row[j];
+            const double xj = s[j] * rcp[j];
             __syncwarp();
             if (lane == 0) s[j] = xj;
             for (int k = lane; k < j; k += 32) s[k] -= row[k] * xj;
@@ -417,69 +499,87 @@ __device__ int phase_solve(const CbDev& B, double lambda, double* A, double* aux
     return 1;
 }
 
-// landmark back-substitution + backup + update; returns this thread's ordered partial of computeScale
-__device__ __forceinline__ double phase_update(const CbDev& B, int ct, int cn, double lambda, bool apply) {
+// landmark back-substitution xl = D^-1 (bl - sum W^T xp) (block_solver.hpp:413-443), backup (push) and update of the points
+// of this CTA's landmark range and of the free poses (spread over the cluster); returns the thread's partial of computeScale.
+// Per chunk: one thread per 3-wide row of W multiplies it by its xp entry (coalesced), one thread per landmark adds the
+// rows up in (observation, row) order.
+__device__ __forceinline__ double phase_update(const CbDev& B, int rank, int ct, int cn, double lambda, bool apply, double* stage) {
+    const int tid = threadIdx.x;
+    double* sx = stage;              // xp, n doubles
+    double* sP = stage + 256;        // [BS * 6][3] products
+    for (int k = tid; k < B.n; k += BS) sx[k] = B.xp[k];
+    __syncthreads();
     double sc = 0;
-    for (int t = ct; t < B.N + B.Pf; t += cn) {
-        if (t < B.N) {
-            const int l = t;
-            if (B.lm_ptr[l] == B.lm_ptr[l + 1]) continue;  // no edge: not an active vertex
-            double c[3] = {B.bl[3 * (size_t)l], B.bl[3 * (size_t)l + 1], B.bl[3 * (size_t)l + 2]};
-            for (int i = B.lm_ptr[l]; i < B.lm_ptr[l + 1]; i++) {
-                const int f = B.free_idx[B.obs_pose[i]];
-                if (f < 0 || !B.active[i]) continue;
-                const double* W = B.W + 18 * (size_t)i;
-                const double* x = B.xp + 6 * f;
+    for (int ch = B.cta_chunk_ptr[rank]; ch < B.cta_chunk_ptr[rank + 1]; ch++) {
+        const int l0 = B.chunk_lm[ch], l1 = B.chunk_lm[ch + 1], o0 = B.lm_ptr[l0], o1 = B.lm_ptr[l1], nrows = 6 * (o1 - o0);
+        for (int rr = tid; rr < nrows; rr += 2 * BS) {  // two rows in flight; W of an inactive / fixed-pose observation is zero
+            const int rb = rr + BS;
+            const bool hb = rb < nrows;
+            const int fa = B.obs_free[o0 + rr / 6], fb = hb ? B.obs_free[o0 + rb / 6] : -1;
+            const double* Wa = B.W + 3 * ((size_t)6 * o0 + rr);
+            const double* Wb = B.W + 3 * ((size_t)6 * o0 + (hb ? rb : rr));
+            const double a0 = Wa[0], a1 = Wa[1], a2 = Wa[2], b0 = Wb[0], b1 = Wb[1], b2 = Wb[2];
+            const double xa = fa >= 0 ? sx[6 * fa + rr % 6] : 0.0;
+            sP[3 * rr] = a0 * xa; sP[3 * rr + 1] = a1 * xa; sP[3 * rr + 2] = a2 * xa;
+            if (hb) {
+                const double xb = fb >= 0 ? sx[6 * fb + rb % 6] : 0.0;
+                sP[3 * rb] = b0 * xb; sP[3 * rb + 1] = b1 * xb; sP[3 * rb + 2] = b2 * xb;
+            }
+        }
+        __syncthreads();
+        if (tid < l1 - l0) {
+            const int l = l0 + tid;
+            if (B.lm_ptr[l] != B.lm_ptr[l + 1]) {  // a point without edges is not an active vertex
+                double c[3] = {B.bl[3 * (size_t)l], B.bl[3 * (size_t)l + 1], B.bl[3 * (size_t)l + 2]};
+                for (int i = B.lm_ptr[l] - o0; i < B.lm_ptr[l + 1] - o0; i++) {
+                    double s0 = 0, s1 = 0, s2 = 0;
 #pragma unroll
-                for (int b = 0; b < 3; b++) {
-                    double s = 0;
-#pragma unroll
-                    for (int a = 0; a < 6; a++) s += W[3 * a + b] * x[a];
-                    c[b] -= s;
+                    for (int a = 0; a < 6; a++) {
+                        s0 += sP[3 * (6 * i + a)]; s1 += sP[3 * (6 * i + a) + 1]; s2 += sP[3 * (6 * i + a) + 2];
+                    }
+                    c[0] -= s0; c[1] -= s1; c[2] -= s2;
                 }
-            }
-            const double* I = B.Dinv + 6 * (size_t)l;
-            const double xl[3] = {I[0] * c[0] + I[1] * c[1] + I[2] * c[2], I[1] * c[0] + I[3] * c[1] + I[4] * c[2],
-                                  I[2] * c[0] + I[4] * c[1] + I[5] * c[2]};
-            double s = 0;
+                const double* I = B.Dinv + 6 * (size_t)l;
+                const double xl[3] = {I[0] * c[0] + I[1] * c[1] + I[2] * c[2], I[1] * c[0] + I[3] * c[1] + I[4] * c[2],
+                                      I[2] * c[0] + I[4] * c[1] + I[5] * c[2]};
+                double sacc = 0;
 #pragma unroll
-            for (int k = 0; k < 3; k++) {
-                const double v = B.pt[3 * (size_t)l + k];
-                B.pt_bak[3 * (size_t)l + k] = v;
-                if (apply) B.pt[3 * (size_t)l + k] = v + xl[k];
-                s += xl[k] * (lambda * xl[k] + B.bl[3 * (size_t)l + k]);
+                for (int k = 0; k < 3; k++) {
+                    const double v = B.pt[3 * (size_t)l + k];
+                    B.pt_bak[3 * (size_t)l + k] = v;
+                    if (apply) B.pt[3 * (size_t)l + k] = v + xl[k];
+                    sacc += xl[k] * (lambda * xl[k] + B.bl[3 * (size_t)l + k]);
+                }
+                sc += sacc;
             }
-            sc += s;
-        } else {
-            const int f = t - B.N, pi = B.free_list[f];
-            Pose T = load_pose(B.pose + 7 * pi);
-            store_pose(B.pose_bak + 7 * pi, T);
-            double u[6], s = 0;
+        }
+        __syncthreads();
+    }
+    for (int f = ct; f < B.Pf; f += cn) {
+        const int pi = B.free_list[f];
+        Pose T = load_pose(B.pose + 7 * pi);
+        store_pose(B.pose_bak + 7 * pi, T);
+        double u[6], sacc = 0;
 #pragma unroll
-            for (int k = 0; k < 6; k++) {
-                u[k] = B.xp[6 * f + k];
-                s += u[k] * (lambda * u[k] + B.bp[6 * f + k]);
-            }
-            sc += s;
-            if (apply) {
-                se3_oplus(T, u);
-                store_pose(B.pose + 7 * pi, T);
-            }
+        for (int k = 0; k < 6; k++) {
+            u[k] = sx[6 * f + k];
+            sacc += u[k] * (lambda * u[k] + B.bp[6 * f + k]);
+        }
+        sc += sacc;
+        if (apply) {
+            se3_oplus(T, u);
+            store_pose(B.pose + 7 * pi, T);
         }
     }
     return sc;
 }
-__device__ __forceinline__ void phase_restore(const CbDev& B, int ct, int cn) {  // same thread mapping as phase_update
-    for (int t = ct; t < B.N + B.Pf; t += cn) {
-        if (t < B.N) {
-            if (B.lm_ptr[t] == B.lm_ptr[t + 1]) continue;
+__device__ __forceinline__ void phase_restore(const CbDev& B, int rank, int ct, int cn) {  // pop: same owners as phase_update
+    const int L0 = B.cta_lm[rank], L1 = B.cta_lm[rank + 1];
+    for (int k = 3 * L0 + threadIdx.x; k < 3 * L1; k += BS) B.pt[k] = B.pt_bak[k];
+    for (int f = ct; f < B.Pf; f += cn) {
+        const int pi = B.free_list[f];
 #pragma unroll
-            for (int k = 0; k < 3; k++) B.pt[3 * (size_t)t + k] = B.pt_bak[3 * (size_t)t + k];
-        } else {
-            const int pi = B.free_list[t - B.N];
-#pragma unroll
-            for (int k = 0; k < 7; k++) B.pose[7 * pi + k] = B.pose_bak[7 * pi + k];
-        }
+        for (int k = 0; k < 7; k++) B.pose[7 * pi + k] = B.pose_bak[7 * pi + k];
     }
 }
 
@@ -487,7 +587,7 @@ __global__ void __launch_bounds__(BS, 1) ba_cluster_kernel(const CbDev* __restri
     cg::cluster_group cluster = cg::this_cluster();
     const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
     const int prob = blockIdx.x / CL, tid = threadIdx.x, ct = rank * BS + tid, cn = CL * BS;
-    extern __shared__ double sm_dyn[];   // CTA 0: packed reduced system
+    extern __shared__ double sm_dyn[];   // staging area of the chunked phases; CTA 0 also holds the packed reduced system here
     __shared__ CbDev B;
     __shared__ LmLocal L;
     __shared__ double red[NW + 1];
@@ -497,19 +597,33 @@ __global__ void __launch_bounds__(BS, 1) ba_cluster_kernel(const CbDev* __restri
     for (int k = tid; k < (int)(sizeof(CbDev) / 4); k += BS) ((int*)&B)[k] = ((const int*)(probs + prob))[k];
     if (tid == 0) { L.ntrace = 0; L.stopped = 0; }
     __syncthreads();
+    // per-phase cycle counters of CTA 0 (read back through uco_ba_result::profile)
+    long long tprev = clock64();
+    const bool timing = rank == 0 && tid == 0;
+#define BA_TICK(slot)                                        \
+    do {                                                     \
+        if (timing) {                                        \
+            long long tnow = clock64();                      \
+            B.res->phase_cycles[slot] += (double)(tnow - tprev); \
+            tprev = tnow;                                    \
+        }                                                    \
+    } while (0)
     // vertices: Frame::pose_f2g -> SE3Quat, cv::Point3f -> Vector3d
     for (int t = ct; t < B.P; t += cn) {
         Pose T = pose_from_m44f(B.p44_in + 16 * t);
         store_pose(B.pose + 7 * t, T);
         store_pose(B.pose_bak + 7 * t, T);
     }
-    for (int k = ct; k < 3 * B.N; k += cn) B.pt[k] = (double)B.pt_in[k];
+    for (int k = ct; k < 3 * B.N; k += cn) B.pt[k] = B.pt_bak[k] = (double)B.pt_in[k];
+    if (ct < 18) B.W[18 * (size_t)B.M + ct] = B.Y[18 * (size_t)B.M + ct] = 0;  // the dummy observation / landmark the padded
+    if (ct < 3) B.bl[3 * (size_t)B.N + ct] = 0;                                  // Schur-gather units point at
     for (int i = ct; i < B.M; i += cn) {
         B.active[i] = 1;
         B.chi2[i] = 0;
         B.err[3 * i] = B.err[3 * i + 1] = B.err[3 * i + 2] = 0;
     }
     cluster.sync();
+    BA_TICK(0);
     for (int stage = 0; stage < 2; stage++) {
         const int robust = stage == 0, max_iters = stage == 0 ? B.n_iters : 2 * B.n_iters;
         if (stage == 1) {  // globaloptimizer_g2o.cpp:432-449
@@ -522,6 +636,7 @@ __global__ void __launch_bounds__(BS, 1) ba_cluster_kernel(const CbDev* __restri
             }
             __syncthreads();  // active[] is re-read by the same strided owner below; other CTAs see it after the barrier
             cluster.sync();
+            BA_TICK(11);
         }
         {
             double s = block_sum(phase_errors(B, ct, cn, robust), red);
@@ -537,14 +652,15 @@ __global__ void __launch_bounds__(BS, 1) ba_cluster_kernel(const CbDev* __restri
             L.cont_iter = max_iters > 0 && !stop;
             if (stop) L.stopped = 1;
         }
+        BA_TICK(1);
         while (true) {
             __syncthreads();
             if (!L.cont_iter) break;
             // ---- linearize at the current estimate
-            phase_linearize_obs(B, ct, cn, robust);
-            cluster.sync();
             {
-                double md = block_max(phase_linearize_sum(B, ct, cn, rank, CL, robust, red27), red);
+                double md = phase_linearize_lm(B, rank, robust, sm_dyn);
+                BA_TICK(2);
+                md = block_max(fmax(md, phase_linearize_pose(B, rank, CL, robust, red27)), red);
                 if (tid == 0) B.parts[32 + rank] = md;
             }
             cluster.sync();
@@ -562,12 +678,15 @@ __global__ void __launch_bounds__(BS, 1) ba_cluster_kernel(const CbDev* __restri
                 L.cont_trial = 1;
             }
             __syncthreads();
+            BA_TICK(3);
             while (L.cont_trial) {
                 const double lambda = L.lambda;
-                phase_prep(B, ct, cn, lambda);
+                phase_prep(B, rank, lambda, sm_dyn);
                 cluster.sync();
+                BA_TICK(4);
                 phase_gather(B, rank, CL);
                 cluster.sync();
+                BA_TICK(5);
                 if (rank == 0) {
                     int ok = 1;
                     if (B.Pf) ok = phase_solve(B, lambda, sm_dyn, aux, &sflag);
@@ -577,17 +696,20 @@ __global__ void __launch_bounds__(BS, 1) ba_cluster_kernel(const CbDev* __restri
                     }
                 }
                 cluster.sync();
+                BA_TICK(6);
                 const bool fail = *(volatile int*)B.chol_fail != 0;
                 {
-                    double s = block_sum(phase_update(B, ct, cn, lambda, !fail), red);
+                    double s = block_sum(phase_update(B, rank, ct, cn, lambda, !fail, sm_dyn), red);
                     if (tid == 0) B.parts[64 + rank] = s;
                 }
                 cluster.sync();
+                BA_TICK(7);
                 {
                     double s = block_sum(phase_errors(B, ct, cn, robust), red);
                     if (tid == 0) B.parts[rank] = s;
                 }
                 cluster.sync();
+                BA_TICK(8);
                 if (tid == 0) {  // levenberg.cpp:96-150, identical in every CTA
                     double chi_raw = 0, scale = 0;
                     for (int r = 0; r < CL; r++) { chi_raw += B.parts[r]; scale += B.parts[64 + r]; }
@@ -629,9 +751,11 @@ __global__ void __launch_bounds__(BS, 1) ba_cluster_kernel(const CbDev* __restri
                     }
                 }
                 __syncthreads();
-                if (L.reject) phase_restore(B, ct, cn);
+                if (L.reject) phase_restore(B, rank, ct, cn);
+                BA_TICK(9);
             }
             cluster.sync();  // estimates settled (accepted or restored) before anyone linearizes or flags outliers
+            BA_TICK(9);
         }
         if (tid == 0 && rank == 0) B.res->iters[stage] = L.it;
         __syncthreads();
@@ -684,6 +808,8 @@ __global__ void __launch_bounds__(BS, 1) ba_cluster_kernel(const CbDev* __restri
         }
         B.bad[i] = (uint8_t)(b | (B.active[i] ? 0 : 2));  // bit 1: the edge left the problem after stage 1 (level 1)
     }
+    BA_TICK(10);
+#undef BA_TICK
 }
 
 }  // namespace
@@ -702,16 +828,31 @@ int ba_cluster_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* const
     if (n <= 0) return UCO_OK;
     std::vector<BaPlan> plans(n);
     int max_n = 0;
-    for (int i = 0; i < n; i++) {
-        int rc = ba_plan_build(ctx, *pbs[i], BA_UNIT, plans[i]);
-        if (rc != UCO_OK) return rc;
-        max_n = std::max(max_n, 6 * plans[i].Pf);
+    const int CL = ctx->ba_cluster_size > 0 ? ctx->ba_cluster_size : 8;
+    {  // the planner is pure host work (~0.5 ms per window): one thread per window
+        std::vector<int> rcs(n, UCO_OK);
+        std::vector<std::string> errs(n);
+        auto job = [&](int i) {
+            uco_b200_ctx tmp;
+            rcs[i] = ba_plan_build(&tmp, *pbs[i], BA_UNIT, plans[i], CL, BS);
+            errs[i] = tmp.err;
+        };
+        if (n == 1) job(0);
+        else {
+            std::vector<std::thread> th;
+            for (int i = 0; i < n; i++) th.emplace_back(job, i);
+            for (auto& t : th) t.join();
+        }
+        for (int i = 0; i < n; i++) {
+            if (rcs[i] != UCO_OK) return uco_fail(ctx, rcs[i], "%s", errs[i].c_str());
+            max_n = std::max(max_n, 6 * plans[i].Pf);
+        }
     }
     if (max_n > BA_CLUSTER_MAX_N) return uco_fail(ctx, UCO_E_INVALID, "ba cluster path: reduced system of %d unknowns", max_n);
     // layout: [inputs of all windows | CbDev array | stop flag][work][outputs of all windows]
     struct Off {
-        size_t p44, free_idx, free_list, lm_ptr, obs_pose, obs_lm, pose_ptr, pose_obs, blk_unit_ptr, blk_ij, diag_blk, unit, con, z, info,
-            stereo, pt_in;
+        size_t p44, free_idx, free_list, lm_ptr, obs_pose, obs_lm, obs_free, pose_ptr, pose_obs, blk_unit_ptr, blk_ij, diag_blk, unit, con, z, info,
+            stereo, pt_in, cta_lm, cta_chunk_ptr, chunk_lm;
         size_t pose_bak, pt_bak, err, lmc, Hll, bl, W, Y, Dinv, db, Hpp, bp, part, partb, xp, parts, chol_fail, active;
         size_t pose, p44o, pt, chi2, level_dummy, bad, resd;
     };
@@ -722,11 +863,13 @@ int ba_cluster_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* const
         Off& o = off[i];
         o.p44 = A.take(64 * (size_t)p.P); o.free_idx = A.take(4 * (size_t)p.P); o.free_list = A.take(4 * (size_t)(p.Pf + 1));
         o.lm_ptr = A.take(4 * (size_t)(p.N + 1)); o.obs_pose = A.take(4 * (size_t)(p.M + 1)); o.obs_lm = A.take(4 * (size_t)(p.M + 1));
+        o.obs_free = A.take(4 * (size_t)(p.M + 1));
         o.pose_ptr = A.take(4 * (size_t)(p.Pf + 1)); o.pose_obs = A.take(4 * (p.pose_obs.size() + 1));
         o.blk_unit_ptr = A.take(4 * (p.blk_unit_ptr.size() + 1)); o.blk_ij = A.take(8 * (p.blk_ij.size() + 1));
         o.diag_blk = A.take(4 * (size_t)(p.Pf + 1)); o.unit = A.take(16 * (p.unit.size() + 1)); o.con = A.take(8 * (p.con.size() + 1));
         o.z = A.take(12 * (size_t)(p.M + 1)); o.info = A.take(4 * (size_t)(p.M + 1)); o.stereo = A.take((size_t)p.M + 1);
         o.pt_in = A.take(12 * (size_t)(p.N + 1));
+        o.cta_lm = A.take(4 * p.cta_lm.size()); o.cta_chunk_ptr = A.take(4 * p.cta_chunk_ptr.size()); o.chunk_lm = A.take(4 * p.chunk_lm.size());
     }
     const size_t o_probs = A.take(sizeof(CbDev) * (size_t)n);
     const size_t in_bytes = A.off;
@@ -758,7 +901,7 @@ int ba_cluster_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* const
     int* dstop = nullptr;
     UCO_CUDA(ctx, cudaHostGetDevicePointer((void**)&dstop, (void*)hstop, 0));
     CbDev* hp = (CbDev*)(h + o_probs);
-    for (int i = 0; i < n; i++) {
+    auto fill = [&](int i) {
         const BaPlan& p = plans[i];
         const uco_ba_problem& pb = *pbs[i];
         const Off& o = off[i];
@@ -768,6 +911,7 @@ int ba_cluster_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* const
         memcpy(h + o.lm_ptr, p.lm_ptr.data(), 4 * (size_t)(p.N + 1));
         memcpy(h + o.obs_pose, p.s_pose.data(), 4 * (size_t)p.M);
         memcpy(h + o.obs_lm, p.s_lm.data(), 4 * (size_t)p.M);
+        memcpy(h + o.obs_free, p.s_free.data(), 4 * (size_t)p.M);
         memcpy(h + o.pose_ptr, p.pose_ptr.data(), 4 * (size_t)(p.Pf + 1));
         memcpy(h + o.pose_obs, p.pose_obs.data(), 4 * p.pose_obs.size());
         memcpy(h + o.blk_unit_ptr, p.blk_unit_ptr.data(), 4 * p.blk_unit_ptr.size());
@@ -786,16 +930,20 @@ int ba_cluster_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* const
             st[k] = s;
         }
         if (p.N) memcpy(h + o.pt_in, pb.points3, 12 * (size_t)p.N);
+        memcpy(h + o.cta_lm, p.cta_lm.data(), 4 * p.cta_lm.size());
+        memcpy(h + o.cta_chunk_ptr, p.cta_chunk_ptr.data(), 4 * p.cta_chunk_ptr.size());
+        memcpy(h + o.chunk_lm, p.chunk_lm.data(), 4 * p.chunk_lm.size());
         CbDev& B = hp[i];
         memset(&B, 0, sizeof(B));
         B.P = p.P; B.N = p.N; B.M = p.M; B.Pf = p.Pf; B.n = 6 * p.Pf; B.nblk = (int)p.blk_ij.size(); B.nunits = (int)p.unit.size();
         B.n_iters = pb.n_iters;
         B.p44_in = (const float*)(d + o.p44); B.free_idx = (const int*)(d + o.free_idx); B.free_list = (const int*)(d + o.free_list);
-        B.lm_ptr = (const int*)(d + o.lm_ptr); B.obs_pose = (const int*)(d + o.obs_pose); B.obs_lm = (const int*)(d + o.obs_lm);
+        B.lm_ptr = (const int*)(d + o.lm_ptr); B.obs_pose = (const int*)(d + o.obs_pose); B.obs_lm = (const int*)(d + o.obs_lm); B.obs_free = (const int*)(d + o.obs_free);
         B.pose_ptr = (const int*)(d + o.pose_ptr); B.pose_obs = (const int*)(d + o.pose_obs);
         B.blk_unit_ptr = (const int*)(d + o.blk_unit_ptr); B.blk_ij = (const int2*)(d + o.blk_ij); B.diag_blk = (const int*)(d + o.diag_blk);
         B.unit = (const int4*)(d + o.unit); B.con = (const int2*)(d + o.con); B.z = (const float*)(d + o.z); B.info = (const float*)(d + o.info);
         B.stereo = d + o.stereo; B.pt_in = (const float*)(d + o.pt_in);
+        B.cta_lm = (const int*)(d + o.cta_lm); B.cta_chunk_ptr = (const int*)(d + o.cta_chunk_ptr); B.chunk_lm = (const int*)(d + o.chunk_lm);
         B.pose_bak = (double*)(d + o.pose_bak); B.pt_bak = (double*)(d + o.pt_bak); B.err = (double*)(d + o.err); B.lmc = (double*)(d + o.lmc);
         B.Hll = (double*)(d + o.Hll); B.bl = (double*)(d + o.bl); B.W = (double*)(d + o.W); B.Y = (double*)(d + o.Y);
         B.Dinv = (double*)(d + o.Dinv); B.db = (double*)(d + o.db); B.Hpp = (double*)(d + o.Hpp); B.bp = (double*)(d + o.bp);
@@ -807,13 +955,18 @@ int ba_cluster_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* const
         B.chi2d = 5.99f; B.chi3d = 7.815f;
         B.d2 = (double)sqrtf(B.chi2d); B.d3 = (double)sqrtf(B.chi3d);
         B.stop = dstop;
+    };
+    if (n == 1) fill(0);
+    else {
+        std::vector<std::thread> th;
+        for (int i = 0; i < n; i++) th.emplace_back(fill, i);
+        for (auto& t : th) t.join();
     }
     cudaStream_t s = ctx->stream;
     UCO_CUDA(ctx, cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, s));
     UCO_CUDA(ctx, cudaMemsetAsync(d + out_begin, 0, out_bytes, s));
-    const size_t smem = 8 * ((size_t)(max_n + 1) * (max_n + 2) / 2);
+    const size_t smem = std::max<size_t>(8 * ((size_t)(max_n + 1) * (max_n + 2) / 2), 8 * (size_t)BS * (WPAD + 9));
     UCO_CUDA(ctx, cudaFuncSetAttribute(ba_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int CL = ctx->ba_cluster_size > 0 ? ctx->ba_cluster_size : 8;
     if (CL > 8) UCO_CUDA(ctx, cudaFuncSetAttribute(ba_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(n * CL));
@@ -863,6 +1016,7 @@ int ba_cluster_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* const
         r.iters[0] = cr->iters[0];
         r.iters[1] = cr->iters[1];
         r.device_ms = ms;
+        if (r.profile) memcpy(r.profile, cr->phase_cycles, sizeof(double) * 16);
     }
     return UCO_OK;
 }

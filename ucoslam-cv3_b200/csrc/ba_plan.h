@@ -8,20 +8,22 @@
 #include "ba_math.cuh"
 #include <vector>
 
-constexpr int BA_UNIT = 48;            // contributions per Schur-gather unit
+constexpr int BA_UNIT = 64;            // contributions per Schur-gather unit (two index registers per lane)
 constexpr int BA_CLUSTER_MAX_N = 228;  // reduced-system size the cluster kernel holds in shared memory (38 free keyframes)
 
 struct CbResult {
     int iters[2];
     int ntrace, pad;
     double trace[128];
+    double phase_cycles[16];
 };
 
 struct CbDev {  // one window as the cluster kernel sees it (device pointers)
     int P, N, M, Pf, n, nblk, nunits, n_iters;
     const float *p44_in, *pt_in, *z, *info;
     const uint8_t* stereo;
-    const int *free_idx, *free_list, *lm_ptr, *obs_pose, *obs_lm, *pose_ptr, *pose_obs, *blk_unit_ptr, *diag_blk;
+    const int *free_idx, *free_list, *lm_ptr, *obs_pose, *obs_lm, *obs_free, *pose_ptr, *pose_obs, *blk_unit_ptr, *diag_blk;
+    const int *cta_lm, *cta_chunk_ptr, *chunk_lm;  // landmark range per CTA, its chunks (whole landmarks, <= CTA-size observations)
     const int2 *blk_ij, *con;
     const int4* unit;
     double *pose, *pose_bak, *pt, *pt_bak, *err, *chi2, *lmc, *Hll, *bl, *W, *Y, *Dinv, *db, *Hpp, *bp, *part, *partb, *xp, *parts;
@@ -36,10 +38,11 @@ struct CbDev {  // one window as the cluster kernel sees it (device pointers)
 };
 
 struct BaPlan {
-    int P = 0, N = 0, M = 0, Pf = 0;
-    std::vector<int> free_idx, free_list, lm_ptr, order, s_pose, s_lm, pose_ptr, pose_obs, blk_unit_ptr, diag_blk;
+    int P = 0, N = 0, M = 0, Pf = 0, ncon = 0;  // ncon: contributions before padding
+    std::vector<int> free_idx, free_list, lm_ptr, order, s_pose, s_lm, s_free, pose_ptr, pose_obs, blk_unit_ptr, diag_blk;
     std::vector<int2> blk_ij, con;
     std::vector<int4> unit;  // (block, first contribution, one past the last, block is diagonal)
+    std::vector<int> cta_lm, cta_chunk_ptr, chunk_lm;
 };
 
 inline int ba_validate(uco_b200_ctx* ctx, const uco_ba_problem* pb) {
@@ -64,7 +67,7 @@ inline int ba_free_poses(const uco_ba_problem* pb) {
     return f;
 }
 
-inline int ba_plan_build(uco_b200_ctx* ctx, const uco_ba_problem& pb, int unit, BaPlan& p) {
+inline int ba_plan_build(uco_b200_ctx* ctx, const uco_ba_problem& pb, int unit, BaPlan& p, int n_cta, int cta_threads) {
     int rc = ba_validate(ctx, &pb);
     if (rc != UCO_OK) return rc;
     const int P = pb.n_poses, N = pb.n_points, M = pb.n_obs;
@@ -105,18 +108,26 @@ inline int ba_plan_build(uco_b200_ctx* ctx, const uco_ba_problem& pb, int unit, 
             if (f >= 0) p.pose_obs[fill[f]++] = k;
         }
     }
-    // contributions per block (i <= j): count, then fill in landmark order
+    // contributions per block (i <= j), in landmark order.  Within a landmark every pose pair appears once (a pose observes
+    // a landmark once), so visiting position pairs a <= b and ordering each by free-pose index gives every block its
+    // contributions sorted by landmark: Y comes from the lower-indexed pose (the block row), W from the higher one.
+    p.s_free.resize(M);
+    for (int k = 0; k < M; k++) p.s_free[k] = p.free_idx[p.s_pose[k]];
     std::vector<int> cnt((size_t)Pf * Pf, 0);
-    for (int l = 0; l < N; l++)
-        for (int a = p.lm_ptr[l]; a < p.lm_ptr[l + 1]; a++) {
-            const int fa = p.free_idx[p.s_pose[a]];
+    const int* sf = p.s_free.data();
+    for (int l = 0; l < N; l++) {
+        const int e0 = p.lm_ptr[l], e1 = p.lm_ptr[l + 1];
+        for (int a = e0; a < e1; a++) {
+            const int fa = sf[a];
             if (fa < 0) continue;
-            for (int b = p.lm_ptr[l]; b < p.lm_ptr[l + 1]; b++) {
-                const int fb = p.free_idx[p.s_pose[b]];
-                if (fb < fa || (fb == fa && b != a)) continue;
-                cnt[(size_t)fa * Pf + fb]++;
+            cnt[(size_t)fa * Pf + fa]++;
+            for (int b = a + 1; b < e1; b++) {
+                const int fb = sf[b];
+                if (fb < 0 || fb == fa) continue;
+                cnt[fa < fb ? (size_t)fa * Pf + fb : (size_t)fb * Pf + fa]++;
             }
         }
+    }
     std::vector<int> blk_of((size_t)Pf * Pf, -1), blk_ptr(1, 0);
     p.blk_ij.clear();
     p.diag_blk.assign(Pf, -1);
@@ -132,23 +143,65 @@ inline int ba_plan_build(uco_b200_ctx* ctx, const uco_ba_problem& pb, int unit, 
     p.con.resize(blk_ptr.back());
     {
         std::vector<int> fill(blk_ptr.begin(), blk_ptr.end() - 1);
-        for (int l = 0; l < N; l++)
-            for (int a = p.lm_ptr[l]; a < p.lm_ptr[l + 1]; a++) {
-                const int fa = p.free_idx[p.s_pose[a]];
+        int2* con = p.con.data();
+        for (int l = 0; l < N; l++) {
+            const int e0 = p.lm_ptr[l], e1 = p.lm_ptr[l + 1];
+            for (int a = e0; a < e1; a++) {
+                const int fa = sf[a];
                 if (fa < 0) continue;
-                for (int b = p.lm_ptr[l]; b < p.lm_ptr[l + 1]; b++) {
-                    const int fb = p.free_idx[p.s_pose[b]];
-                    if (fb < fa || (fb == fa && b != a)) continue;
-                    p.con[fill[blk_of[(size_t)fa * Pf + fb]]++] = make_int2(a, b);
+                con[fill[blk_of[(size_t)fa * Pf + fa]]++] = make_int2(a, l);  // diagonal: (observation, landmark)
+                for (int b = a + 1; b < e1; b++) {
+                    const int fb = sf[b];
+                    if (fb < 0 || fb == fa) continue;
+                    if (fa < fb) con[fill[blk_of[(size_t)fa * Pf + fb]]++] = make_int2(a, b);
+                    else con[fill[blk_of[(size_t)fb * Pf + fa]]++] = make_int2(b, a);
                 }
             }
+        }
     }
-    p.unit.clear();
-    p.blk_unit_ptr.assign(1, 0);
-    for (int k = 0; k < nblk; k++) {
-        for (int c0 = blk_ptr[k]; c0 < blk_ptr[k + 1]; c0 += unit)
-            p.unit.push_back(make_int4(k, c0, std::min(c0 + unit, blk_ptr[k + 1]), p.blk_ij[k].x == p.blk_ij[k].y));
-        p.blk_unit_ptr.push_back((int)p.unit.size());
+    // units of <= `unit` contributions, each padded to a multiple of four with the all-zero dummy observation M (diagonal
+    // blocks: dummy landmark N), so the gather loop needs no bounds checks
+    {
+        std::vector<int2> padded;
+        padded.reserve(p.con.size() + 4 * (size_t)nblk + p.con.size() / unit * 4 + 16);
+        p.unit.clear();
+        p.blk_unit_ptr.assign(1, 0);
+        for (int k = 0; k < nblk; k++) {
+            const bool dg = p.blk_ij[k].x == p.blk_ij[k].y;
+            for (int c0 = blk_ptr[k]; c0 < blk_ptr[k + 1]; c0 += unit) {
+                const int c1 = std::min(c0 + unit, blk_ptr[k + 1]), b0 = (int)padded.size();
+                padded.insert(padded.end(), p.con.begin() + c0, p.con.begin() + c1);
+                while ((padded.size() - b0) & 3) padded.push_back(make_int2(M, dg ? N : M));
+                p.unit.push_back(make_int4(k, b0, (int)padded.size(), dg));
+            }
+            p.blk_unit_ptr.push_back((int)p.unit.size());
+        }
+        p.ncon = (int)p.con.size();
+        p.con.swap(padded);
+    }
+    // landmark ranges per CTA (balanced by observation count), cut into chunks of whole landmarks
+    p.cta_lm.assign(n_cta + 1, N);
+    p.cta_lm[0] = 0;
+    {
+        int l = 0;
+        for (int c = 1; c < n_cta; c++) {
+            const long long target = (long long)M * c / n_cta;
+            while (l < N && p.lm_ptr[l] < target) l++;
+            p.cta_lm[c] = l;
+        }
+    }
+    p.chunk_lm.assign(1, 0);
+    p.cta_chunk_ptr.assign(1, 0);
+    for (int c = 0; c < n_cta; c++) {
+        int l = p.cta_lm[c];
+        while (l < p.cta_lm[c + 1]) {
+            int e = l;
+            while (e < p.cta_lm[c + 1] && e - l < cta_threads && p.lm_ptr[e + 1] - p.lm_ptr[l] <= cta_threads) e++;
+            if (e == l) return uco_fail(ctx, UCO_E_INVALID, "ba_solve: landmark %d has %d observations (> %d per chunk)", l, p.lm_ptr[l + 1] - p.lm_ptr[l], cta_threads);
+            p.chunk_lm.push_back(e);
+            l = e;
+        }
+        p.cta_chunk_ptr.push_back((int)p.chunk_lm.size() - 1);
     }
     return UCO_OK;
 }

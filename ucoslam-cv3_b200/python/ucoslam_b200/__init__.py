@@ -46,6 +46,7 @@ SIGNATURES = {
     "uco_b200_ba_solve": (_i, [_vp, _vp, _vp, _vp]),
     "uco_b200_ba_solve_batch": (_i, [_vp, _i, _vp, _vp, _vp]),
     "uco_b200_ba_set_mode": (_i, [_vp, _i, _i]),
+    "uco_b200_probe_ba_plan": (_i, [_vp, _i, _vp]),
     "uco_b200_probe_math": (_i, [_i, _vp, _vp, _i, _vp, _vp]),
     "uco_b200_probe_retain_best": (_i, [_vp, _i, _i]),
 }
@@ -107,7 +108,7 @@ class BaProblem(ctypes.Structure):  # uco_ba_problem
 
 class BaResult(ctypes.Structure):  # uco_ba_result
     _fields_ = [("pose7", _vp), ("poses44", _vp), ("points3", _vp), ("obs_chi2", _vp), ("obs_level", _vp), ("obs_bad", _vp),
-                ("trace", _vp), ("iters", _c.c_int32 * 2), ("device_ms", _c.c_float)]
+                ("trace", _vp), ("iters", _c.c_int32 * 2), ("device_ms", _c.c_float), ("profile", _vp)]
 
 
 class UcoError(RuntimeError):
@@ -185,12 +186,13 @@ class Context:
                  obs_ur=A("obs_ur", np.float32), obs_stereo=A("obs_stereo", np.uint8), obs_inv_sigma2=A("obs_inv_sigma2", np.float32))
         P, N, M = len(a["fixed"]), len(a["points3"]), len(a["obs_pose"])
         out = dict(pose7=np.zeros((P, 7)), pose44=np.zeros((P, 16), np.float32), point3=np.zeros((N, 3)), chi2=np.zeros(M),
-                   level=np.zeros(M, np.uint8), bad=np.zeros(M, np.uint8), trace=np.zeros((64, 2)))
+                   level=np.zeros(M, np.uint8), bad=np.zeros(M, np.uint8), trace=np.zeros((64, 2)), profile=np.zeros(16))
         cp = BaProblem(P, N, M, _p(a["poses44"]), _p(a["fixed"]), _p(a["points3"]), _p(a["obs_pose"]), _p(a["obs_point"]),
                        _p(a["obs_uv"]), _p(a["obs_ur"]), _p(a["obs_stereo"]), _p(a["obs_inv_sigma2"]), pb["fx"], pb["fy"],
                        pb["cx"], pb["cy"], pb["bf"], int(n_iters))
         cr = BaResult(_p(out["pose7"]), _p(out["pose44"]), _p(out["point3"]), _p(out["chi2"]), _p(out["level"]), _p(out["bad"]),
                       _p(out["trace"]))
+        cr.profile = _p(out["profile"])
         return cp, cr, a, out
 
     def ba_solve(self, pb, n_iters, stop=None):
