@@ -209,11 +209,12 @@ typedef struct uco_ba_result {   /* every pointer may be NULL (not wanted) */
     double* profile;             /* 16 doubles, optional: SM cycles CTA 0 of the window's cluster spent per phase (cluster-resident form) */
 } uco_ba_result;
 
-/* stop: optional flag polled between LM trials (GlobalOptimizerG2O::optimize(bool* stopASAP), sparse_optimizer.h:189);
+/* stop: optional one-byte flag (the reference's bool* stopASAP can be passed as it is) polled between LM trials
+ * (GlobalOptimizerG2O::optimize(bool* stopASAP), sparse_optimizer.h:189);
  * when raised during stage 1 the solve returns the current estimate with UCO_OK and iters[1] = 0 like the reference. */
-int uco_b200_ba_solve(uco_b200_ctx* ctx, const uco_ba_problem* pb, const volatile int* stop, uco_ba_result* res);
+int uco_b200_ba_solve(uco_b200_ctx* ctx, const uco_ba_problem* pb, const volatile unsigned char* stop, uco_ba_result* res);
 /* n independent problems (one local-BA window per camera / map) solved together; results as n separate uco_b200_ba_solve calls */
-int uco_b200_ba_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* pbs, const volatile int* stop, uco_ba_result* res);
+int uco_b200_ba_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* pbs, const volatile unsigned char* stop, uco_ba_result* res);
 /* tuning / test knob.  mode 0 (default): windows with <= 38 free keyframes run cluster-resident (one thread-block cluster per
  * window, the whole LM loop in one launch), larger ones as streamed kernels; 1: always streamed; 2: always cluster-resident.
  * cluster_size: CTAs per cluster (power of two <= 16, 0 = 8). */

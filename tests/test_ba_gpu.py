@@ -92,7 +92,7 @@ def test_ba_stop_flag_and_errors(bctx):
     import ucoslam_b200
     ctx = bctx
     pb = oracle_py.synth_ba_problem(33, n_poses=6, n_fixed=1, n_points=200)
-    stop = np.ones(1, np.int32)
+    stop = np.ones(1, np.uint8)  # the reference's bool stopASAP
     out = ctx.ba_solve(pb, 5, stop=stop)
     assert out["iters"].tolist() == [0, 0]
     assert np.abs(out["pose44"] - pb["poses44"]).max() < 1e-6  # nothing moved

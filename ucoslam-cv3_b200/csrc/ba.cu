@@ -620,7 +620,7 @@ cudaEvent_t* uco_ba_events(uco_b200_ctx* ctx) {
 }
 
 // streamed form: one kernel per phase, the host enqueues the next trial after reading two flags (any problem size)
-int ba_streamed_solve(uco_b200_ctx* ctx, const uco_ba_problem* pb, const volatile int* stop, uco_ba_result* res) {
+int ba_streamed_solve(uco_b200_ctx* ctx, const uco_ba_problem* pb, const volatile unsigned char* stop, uco_ba_result* res) {
     if (!ctx) return UCO_E_INVALID;
     if (!pb || !res) return uco_fail(ctx, UCO_E_INVALID, "ba_solve: null problem / result");
     const int P = pb->n_poses, N = pb->n_points, M = pb->n_obs;
@@ -902,7 +902,7 @@ int uco_b200_ba_set_mode(uco_b200_ctx* ctx, int mode, int cluster_size) {
     return UCO_OK;
 }
 
-int uco_b200_ba_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* pbs, const volatile int* stop, uco_ba_result* res) {
+int uco_b200_ba_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* pbs, const volatile unsigned char* stop, uco_ba_result* res) {
     if (!ctx) return UCO_E_INVALID;
     if (n < 0 || (n && (!pbs || !res))) return uco_fail(ctx, UCO_E_INVALID, "ba_solve_batch: bad arguments");
     std::vector<const uco_ba_problem*> cp;
@@ -931,7 +931,7 @@ int uco_b200_ba_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* pbs,
     return UCO_OK;
 }
 
-int uco_b200_ba_solve(uco_b200_ctx* ctx, const uco_ba_problem* pb, const volatile int* stop, uco_ba_result* res) {
+int uco_b200_ba_solve(uco_b200_ctx* ctx, const uco_ba_problem* pb, const volatile unsigned char* stop, uco_ba_result* res) {
     if (!ctx) return UCO_E_INVALID;
     if (!pb || !res) return uco_fail(ctx, UCO_E_INVALID, "ba_solve: null problem / result");
     return uco_b200_ba_solve_batch(ctx, 1, pb, stop, res);

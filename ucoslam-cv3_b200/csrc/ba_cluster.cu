@@ -824,7 +824,7 @@ struct BaArena {
     }
 };
 
-int ba_cluster_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* const* pbs, const volatile int* stop, uco_ba_result* const* res) {
+int ba_cluster_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* const* pbs, const volatile unsigned char* stop, uco_ba_result* const* res) {
     if (n <= 0) return UCO_OK;
     std::vector<BaPlan> plans(n);
     int max_n = 0;

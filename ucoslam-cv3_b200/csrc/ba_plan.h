@@ -208,6 +208,6 @@ inline int ba_plan_build(uco_b200_ctx* ctx, const uco_ba_problem& pb, int unit, 
 
 // ba.cu
 cudaEvent_t* uco_ba_events(uco_b200_ctx* ctx);
-int ba_streamed_solve(uco_b200_ctx* ctx, const uco_ba_problem* pb, const volatile int* stop, uco_ba_result* res);
+int ba_streamed_solve(uco_b200_ctx* ctx, const uco_ba_problem* pb, const volatile unsigned char* stop, uco_ba_result* res);
 // ba_cluster.cu
-int ba_cluster_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* const* pbs, const volatile int* stop, uco_ba_result* const* res);
+int ba_cluster_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* const* pbs, const volatile unsigned char* stop, uco_ba_result* const* res);

@@ -1,0 +1,161 @@
+// global_optimizer_b200.h — the reference's bundle-adjustment seam: a ucoslam::GlobalOptimizer
+// (src/optimization/globaloptimizer.h:28-68) whose optimize() is uco_b200_ba_solve.  setParams walks the Map with the rules
+// of GlobalOptimizerG2O::setParams (src/optimization/globaloptimizer_g2o.cpp:98-176: used / fixed frames, points with >= 2
+// observations or stereo and not bad, frames that only observe a used point enter as fixed) and flattens it into
+// uco_ba_problem; getResults writes poses, points and the bad-association list back as :466-538 does.  The object keeps
+// its own copy of inputs and results, because the mapper thread calls setParams + optimize WITHOUT the map lock and the
+// tracker thread calls getResults later (src/utils/mapmanager.cpp:11361-11405, :1267-1305); *stopASAP is forwarded.
+// Windows that involve ArUco markers (marker vertices / MarkerEdge, not handled on the device yet) or keyframes taken
+// with different cameras are handed to the reference's own GlobalOptimizerG2O.
+// Selected with Params::global_optimizer = "b200" once registered in GlobalOptimizer::create.
+// Compile inside the reference tree (needs its headers and OpenCV C++; see the note in orb_extractor_b200.h).
+#pragma once
+#include <cstring>
+#include <limits>
+#include <vector>
+#include "optimization/globaloptimizer.h"
+#include "optimization/globaloptimizer_g2o.h"
+#include "uco_b200_cxx.h"
+
+namespace ucoslam {
+
+class GlobalOptimizerB200 : public GlobalOptimizer {
+public:
+    explicit GlobalOptimizerB200(int device = 0) : _ctx(device) {}
+    string getName() const override { return "b200"; }
+
+    void setParams(std::shared_ptr<Map> map, const ParamSet& ps) override {
+        _params = ps;
+        _delegate.reset();
+        const uint32_t INVALID = std::numeric_limits<uint32_t>::max();
+        std::vector<uint32_t> frameSlot(map->keyframes.capacity(), INVALID), pointSlot(map->map_points.capacity(), INVALID);
+        std::vector<char> fixedKind(map->keyframes.capacity(), 0);  // 0 free, 1 fixed without points, 2 fixed with points
+        _frameIds.clear(); _pointIds.clear();
+        auto useFrame = [&](uint32_t f, char kind) {
+            if (frameSlot[f] == INVALID) { frameSlot[f] = (uint32_t)_frameIds.size(); _frameIds.push_back(f); fixedKind[f] = kind; }
+        };
+        if (_params.used_frames.empty()) for (auto& f : map->keyframes) useFrame(f.idx, 0);
+        else for (auto f : _params.used_frames) useFrame(f, 0);
+        if (_params.fixFirstFrame && frameSlot[map->keyframes.front().idx] != INVALID) fixedKind[map->keyframes.front().idx] = 2;
+        for (auto f : _params.fixed_frames) if (frameSlot[f] != INVALID) fixedKind[f] = 2;
+        bool markers = false, mixedCameras = false;
+        const size_t nInitial = _frameIds.size();
+        for (size_t k = 0; k < nInitial; k++) {           // :135-176 (frames added as observers are not walked for points)
+            const uint32_t f = _frameIds[k];
+            for (auto pid : map->keyframes[f].ids) {
+                if (pid == INVALID || pointSlot[pid] != INVALID) continue;
+                MapPoint& mp = map->map_points[pid];
+                if ((mp.frames.size() < 2 && !mp.isStereo()) || mp.isBad()) { pointSlot[pid] = INVALID - 1; continue; }
+                pointSlot[pid] = (uint32_t)_pointIds.size();
+                _pointIds.push_back(pid);
+                for (const auto& fi : mp.frames) useFrame(fi.first, 1);
+            }
+            for (auto& m : map->keyframes[f].markers)
+                if (map->map_markers[m.id].pose_g2m.isValid()) markers = true;
+        }
+        const Frame& f0 = map->keyframes[_frameIds.front()];
+        for (auto f : _frameIds) {
+            const ImageParams& ip = map->keyframes[f].imageParams;
+            if (ip.fx() != f0.imageParams.fx() || ip.fy() != f0.imageParams.fy() || ip.cx() != f0.imageParams.cx() ||
+                ip.cy() != f0.imageParams.cy() || ip.bl != f0.imageParams.bl) mixedCameras = true;
+        }
+        if (markers || mixedCameras) {                     // not on the device yet: the reference's own optimiser takes the window
+            _delegate = std::make_shared<GlobalOptimizerG2O>();
+            _delegate->setParams(map, ps);
+            return;
+        }
+        // ---- flatten (own copy: the map may change before optimize()/getResults())
+        const size_t P = _frameIds.size(), N = _pointIds.size();
+        _poses.resize(16 * P); _fixed.resize(P); _points.resize(3 * N);
+        _obsPose.clear(); _obsPoint.clear(); _obsUV.clear(); _obsUR.clear(); _obsStereo.clear(); _obsInv.clear();
+        std::vector<float> invScale;
+        for (auto s : map->keyframes.front().scaleFactors) invScale.push_back(1. / s);   // :95-96
+        for (size_t k = 0; k < P; k++) {
+            cv::Mat T = map->keyframes[_frameIds[k]].pose_f2g;
+            for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) _poses[16 * k + 4 * r + c] = T.at<float>(r, c);
+            _fixed[k] = fixedKind[_frameIds[k]] != 0;
+        }
+        for (size_t j = 0; j < N; j++) {
+            MapPoint& mp = map->map_points[_pointIds[j]];
+            const cv::Point3f p = mp.getCoordinates();
+            _points[3 * j] = p.x; _points[3 * j + 1] = p.y; _points[3 * j + 2] = p.z;
+            for (const auto& fi : mp.frames) {             // :228-276
+                if (frameSlot[fi.first] == INVALID) continue;
+                const Frame& fr = map->keyframes[fi.first];
+                const cv::KeyPoint& kp = fr.und_kpts[fi.second];
+                const float depth = fr.getDepth(fi.second);
+                _obsPose.push_back((int32_t)frameSlot[fi.first]);
+                _obsPoint.push_back((int32_t)j);
+                _obsUV.push_back(kp.pt.x); _obsUV.push_back(kp.pt.y);
+                const float mbf = fr.imageParams.bl * fr.imageParams.fx();
+                _obsStereo.push_back(depth > 0);
+                _obsUR.push_back(depth > 0 ? kp.pt.x - mbf / depth : 0.f);
+                _obsInv.push_back(invScale[kp.octave]);
+            }
+        }
+        _pb = uco_ba_problem{};
+        _pb.n_poses = (int32_t)P; _pb.n_points = (int32_t)N; _pb.n_obs = (int32_t)_obsPose.size();
+        _pb.poses44 = _poses.data(); _pb.fixed = _fixed.data(); _pb.points3 = _points.data();
+        _pb.obs_pose = _obsPose.data(); _pb.obs_point = _obsPoint.data(); _pb.obs_uv = _obsUV.data(); _pb.obs_ur = _obsUR.data();
+        _pb.obs_stereo = _obsStereo.data(); _pb.obs_inv_sigma2 = _obsInv.data();
+        _pb.fx = f0.imageParams.fx(); _pb.fy = f0.imageParams.fy(); _pb.cx = f0.imageParams.cx(); _pb.cy = f0.imageParams.cy();
+        _pb.bf = f0.imageParams.bl * f0.imageParams.fx();
+        _pb.n_iters = _params.nIters;
+    }
+
+    void optimize(bool* stopASAP = nullptr) override {
+        if (_delegate) { _delegate->optimize(stopASAP); return; }
+        _outPoses.resize(16 * (size_t)_pb.n_poses); _outPoints.resize(3 * (size_t)_pb.n_points); _outBad.resize(_pb.n_obs);
+        uco_ba_result res{};
+        res.poses44 = _outPoses.data(); res.points3 = _outPoints.data(); res.obs_bad = _outBad.data();
+        static_assert(sizeof(bool) == 1, "the ABI polls a one-byte flag");
+        // the mapper may flip *stopASAP from another thread (MapManager::stop, mapmanager.cpp:1614-1625): the solver polls it
+        _ctx.check(uco_b200_ba_solve(_ctx.get(), &_pb, reinterpret_cast<const volatile unsigned char*>(stopASAP), &res));
+    }
+
+    void getResults(std::shared_ptr<Map> map) override {
+        if (_delegate) { _delegate->getResults(map); return; }
+        for (size_t k = 0; k < _frameIds.size(); k++) {   // :483-492
+            if (_fixed[k]) continue;
+            cv::Mat T(4, 4, CV_32F);
+            std::memcpy(T.data, &_outPoses[16 * k], 64);
+            map->keyframes[_frameIds[k]].pose_f2g = T.clone();
+        }
+        _badAssociations.clear();
+        size_t o = 0;
+        for (size_t j = 0; j < _pointIds.size(); j++) {   // :497-523 (observations were pushed point by point)
+            map->map_points[_pointIds[j]].setCoordinates(
+                cv::Point3f((float)_outPoints[3 * j], (float)_outPoints[3 * j + 1], (float)_outPoints[3 * j + 2]));
+            for (; o < _obsPoint.size() && (size_t)_obsPoint[o] == j; o++)
+                if (_outBad[o]) _badAssociations.push_back(std::make_pair(_pointIds[j], _frameIds[_obsPose[o]]));
+        }
+        for (auto pid : _pointIds) map->updatePointNormalAndDistances(pid);   // :533-536
+    }
+
+    void optimize(std::shared_ptr<Map> map, const ParamSet& p = ParamSet()) override {
+        setParams(map, p);
+        optimize();
+        getResults(map);
+    }
+    vector<std::pair<uint32_t, uint32_t>> getBadAssociations() override {
+        return _delegate ? _delegate->getBadAssociations() : _badAssociations;
+    }
+
+protected:
+    void saveToStream_impl(std::ostream&) override {}
+    void readFromStream_impl(std::istream&) override {}
+
+private:
+    uco_b200::Context _ctx;
+    ParamSet _params;
+    std::shared_ptr<GlobalOptimizerG2O> _delegate;
+    uco_ba_problem _pb{};
+    std::vector<uint32_t> _frameIds, _pointIds;
+    std::vector<float> _poses, _points, _obsUV, _obsUR, _obsInv, _outPoses;
+    std::vector<uint8_t> _fixed, _obsStereo, _outBad;
+    std::vector<int32_t> _obsPose, _obsPoint;
+    std::vector<double> _outPoints;
+    vector<std::pair<uint32_t, uint32_t>> _badAssociations;
+};
+
+}  // namespace ucoslam
