@@ -1,0 +1,31 @@
+"""The C++ adapters (ucoslam-cv3_b200/host/) exercised through the reference's OWN classes: xflann::impl::IndexImpl next to
+xflann's Linear index, and the fbow transform next to fbow::Vocabulary::transform on the shipped orb.fbow.  The test program
+(tests/adapters/adapter_test.cpp) is compiled in the build container against /root/reference (`make -C oracle ref`) and
+travels to the GPU box as oracle/_ref/adapter_test."""
+import os, subprocess
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "oracle", "_ref", "adapter_test")
+VOC = os.path.join(ROOT, "oracle", "_ref", "orb.fbow")
+
+
+@pytest.mark.gpu
+def test_adapters_match_reference_classes():
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/adapter_test not built (needs /root/reference at build time)")
+    args = [BIN] + ([VOC] if os.path.exists(VOC) else [])
+    r = subprocess.run(args, capture_output=True, text=True, timeout=300)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ADAPTERS OK" in r.stdout
+
+
+def test_adapter_headers_are_self_contained():
+    """every adapter header names the reference interface it implements and includes only the C ABI + that interface"""
+    host = os.path.join(ROOT, "ucoslam-cv3_b200", "host")
+    for h, iface in (("orb_extractor_b200.h", "Feature2DSerializable"), ("hamming_index_b200.h", "IndexImpl"),
+                     ("bow_b200.h", "fbow::Vocabulary::transform"), ("global_optimizer_b200.h", "GlobalOptimizer")):
+        src = open(os.path.join(host, h)).read()
+        assert iface in src and "uco_b200_cxx.h" in src
+        assert "torch" not in src and "oracle" not in src.replace("oracle/shim", "")
