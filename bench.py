@@ -169,9 +169,9 @@ def run_b200(args, rank, world, local_rank):
     import torch.distributed as dist
     import ucoslam_b200
 
+    from ucoslam_b200 import shard
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    shard.init("nccl", torch.device("cuda", local_rank))
     ctx = ucoslam_b200.Context(local_rank)      # tracker thread's context: ORB extraction + matching
     ctx_ba = ucoslam_b200.Context(local_rank)   # mapper thread's context (own stream): local bundle adjustment
     stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
@@ -179,7 +179,7 @@ def run_b200(args, rank, world, local_rank):
     mapper = ThreadPoolExecutor(1)              # UcoSLAM runs local BA in its mapper thread next to tracking (mapmanager.cpp)
     F = args.frames
     prm = ucoslam_b200.OrbParams(KPTS)
-    clip = synth_clip(F, 1234 + rank)
+    clip = synth_clip(F, shard.unit_seed(1234, rank, 0))   # every rank tracks its own stream of frames (weak scaling)
     clip_pin = torch.from_numpy(clip).pin_memory()
     with torch.cuda.stream(stream):
         clip_dev = clip_pin.to("cuda", non_blocking=True)
@@ -196,7 +196,7 @@ def run_b200(args, rank, world, local_rank):
     dist_host = torch.empty((F, KPTS, K_NN), dtype=torch.int32).pin_memory()
     img_ptrs = (ctypes_voidp_array(F))(*[clip_pin[i].data_ptr() for i in range(F)])
     n_ba = max(1, F // KF_EVERY)
-    windows = ba_windows(n_ba, 500 + 100 * rank)
+    windows = ba_windows(n_ba, shard.unit_seed(500, rank, 0))
     ba_packed = ctx_ba.ba_pack_batch(windows, BA_ITERS)
     ba_in_bytes = sum(sum(a.nbytes for a in keep.values()) for keep in ba_packed[2])
     ba_out_bytes = sum(sum(v.nbytes for v in o.values()) for o in ba_packed[3])
@@ -249,14 +249,10 @@ def run_b200(args, rank, world, local_rank):
         ctx.sync()
         ctx_ba.sync()
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+        shard.barrier()
 
     def reduce_max(v):
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return shard.max_over_ranks(v, "cuda")
 
     def timed_events(fn, reps, flush_l2=True):
         """sum of per-repetition device durations (CUDA events on the context stream), L2 flushed between repetitions"""
@@ -368,8 +364,7 @@ def run_b200(args, rank, world, local_rank):
         print(json.dumps(line))
         sys.stdout.flush()
     barrier()
-    if world > 1:
-        dist.destroy_process_group()
+    shard.finalize()
     # the context (and its stream) outlives every torch object that references the stream; skip interpreter teardown
     sys.stdout.flush()
     sys.stderr.flush()
