@@ -622,6 +622,7 @@ cudaEvent_t* uco_ba_events(uco_b200_ctx* ctx) {
 // streamed form: one kernel per phase, the host enqueues the next trial after reading two flags (any problem size)
 int ba_streamed_solve(uco_b200_ctx* ctx, const uco_ba_problem* pb, const volatile unsigned char* stop, uco_ba_result* res) {
     if (!ctx) return UCO_E_INVALID;
+    cudaSetDevice(ctx->device);  // the calling thread may be a new one (mapper / tracker threads): bind it to the context's GPU
     if (!pb || !res) return uco_fail(ctx, UCO_E_INVALID, "ba_solve: null problem / result");
     const int P = pb->n_poses, N = pb->n_points, M = pb->n_obs;
     if (P <= 0 || N < 0 || M < 0 || pb->n_iters < 0) return uco_fail(ctx, UCO_E_INVALID, "ba_solve: bad sizes");
@@ -895,6 +896,7 @@ int uco_b200_probe_ba_plan(const uco_ba_problem* pb, int cluster_size, int* out8
 
 int uco_b200_ba_set_mode(uco_b200_ctx* ctx, int mode, int cluster_size) {
     if (!ctx) return UCO_E_INVALID;
+    cudaSetDevice(ctx->device);  // the calling thread may be a new one (mapper / tracker threads): bind it to the context's GPU
     if (mode < 0 || mode > 2 || cluster_size < 0 || cluster_size > 16 || (cluster_size & (cluster_size - 1)))
         return uco_fail(ctx, UCO_E_INVALID, "ba_set_mode: mode 0..2, cluster size a power of two <= 16");
     ctx->ba_mode = mode;
@@ -904,6 +906,7 @@ int uco_b200_ba_set_mode(uco_b200_ctx* ctx, int mode, int cluster_size) {
 
 int uco_b200_ba_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* pbs, const volatile unsigned char* stop, uco_ba_result* res) {
     if (!ctx) return UCO_E_INVALID;
+    cudaSetDevice(ctx->device);  // the calling thread may be a new one (mapper / tracker threads): bind it to the context's GPU
     if (n < 0 || (n && (!pbs || !res))) return uco_fail(ctx, UCO_E_INVALID, "ba_solve_batch: bad arguments");
     std::vector<const uco_ba_problem*> cp;
     std::vector<uco_ba_result*> cr;
@@ -933,6 +936,7 @@ int uco_b200_ba_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* pbs,
 
 int uco_b200_ba_solve(uco_b200_ctx* ctx, const uco_ba_problem* pb, const volatile unsigned char* stop, uco_ba_result* res) {
     if (!ctx) return UCO_E_INVALID;
+    cudaSetDevice(ctx->device);  // the calling thread may be a new one (mapper / tracker threads): bind it to the context's GPU
     if (!pb || !res) return uco_fail(ctx, UCO_E_INVALID, "ba_solve: null problem / result");
     return uco_b200_ba_solve_batch(ctx, 1, pb, stop, res);
 }

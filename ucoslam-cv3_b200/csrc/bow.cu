@@ -101,6 +101,7 @@ extern "C" {
 
 int uco_b200_bow_load(uco_b200_ctx* ctx, const void* bytes, size_t n, uco_b200_voc** voc_out) {
     if (!ctx) return UCO_E_INVALID;
+    cudaSetDevice(ctx->device);  // the calling thread may be a new one (mapper / tracker threads): bind it to the context's GPU
     if (!bytes || !voc_out) return uco_fail(ctx, UCO_E_INVALID, "bow_load: null pointer");
     const uint8_t* p = (const uint8_t*)bytes;
     uint64_t sig = 0;
@@ -166,6 +167,7 @@ int uco_b200_bow_info(const uco_b200_voc* voc, uint32_t* k, uint32_t* nblocks, u
 int uco_b200_bow_transform_dev(uco_b200_ctx* ctx, const uco_b200_voc* voc, const uint8_t* desc_dev, int n, int level,
                                uint32_t* word_dev, float* weight_dev, uint32_t* node_dev) {
     if (!ctx) return UCO_E_INVALID;
+    cudaSetDevice(ctx->device);  // the calling thread may be a new one (mapper / tracker threads): bind it to the context's GPU
     if (!voc) return uco_fail(ctx, UCO_E_INVALID, "bow_transform: no vocabulary");
     if (n <= 0) return uco_fail(ctx, UCO_E_INVALID, "Vocabulary::transform No input data");   // fbow.cpp:52
     if (!desc_dev || !word_dev || !weight_dev || !node_dev) return uco_fail(ctx, UCO_E_INVALID, "bow_transform: null pointer");
@@ -185,6 +187,7 @@ int uco_b200_bow_transform_dev(uco_b200_ctx* ctx, const uco_b200_voc* voc, const
 int uco_b200_bow_transform(uco_b200_ctx* ctx, const uco_b200_voc* voc, const uint8_t* desc, int n, size_t stride, int level,
                            uint32_t* word, float* weight, uint32_t* node) {
     if (!ctx) return UCO_E_INVALID;
+    cudaSetDevice(ctx->device);  // the calling thread may be a new one (mapper / tracker threads): bind it to the context's GPU
     if (!voc) return uco_fail(ctx, UCO_E_INVALID, "bow_transform: no vocabulary");
     if (n <= 0) return uco_fail(ctx, UCO_E_INVALID, "Vocabulary::transform No input data");
     if (!desc || !word || !weight || !node) return uco_fail(ctx, UCO_E_INVALID, "bow_transform: null pointer");

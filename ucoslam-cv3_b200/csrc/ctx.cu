@@ -97,6 +97,7 @@ const char* uco_b200_last_error(const uco_b200_ctx* ctx) { return ctx ? ctx->err
 void* uco_b200_stream(uco_b200_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int uco_b200_sync(uco_b200_ctx* ctx) {
     if (!ctx) return UCO_E_INVALID;
+    cudaSetDevice(ctx->device);  // the calling thread may be a new one (mapper / tracker threads): bind it to the context's GPU
     UCO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return UCO_OK;
 }

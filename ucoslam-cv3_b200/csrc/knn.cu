@@ -240,6 +240,7 @@ static int knn_launch(uco_b200_ctx* ctx, const uint8_t* q_dev, int nq, const uin
                       int32_t* idx_dev, int32_t* dist_dev, int n_pairs, const int* nq_dev, const int* nt_dev, size_t q_stride,
                       size_t t_stride) {
     if (!ctx) return UCO_E_INVALID;
+    cudaSetDevice(ctx->device);  // the calling thread may be a new one (mapper / tracker threads): bind it to the context's GPU
     if (nq < 0 || nt < 0 || n_pairs < 0 || k <= 0 || k > UCO_KNN_MAX_K || (order != UCO_KNN_HEAP && order != UCO_KNN_SORTED))
         return uco_fail(ctx, UCO_E_INVALID, "hamming_knn: bad sizes nq=%d nt=%d k=%d order=%d", nq, nt, k, order);
     if (nq == 0 || n_pairs == 0) return UCO_OK;
@@ -280,6 +281,7 @@ extern "C" int uco_b200_hamming_knn_batch_dev(uco_b200_ctx* ctx, int n_pairs, co
 extern "C" int uco_b200_hamming_knn(uco_b200_ctx* ctx, const uint8_t* q, int nq, size_t q_stride, const uint8_t* t,
                                     int nt, size_t t_stride, int k, int order, int32_t* idx, int32_t* dist) {
     if (!ctx) return UCO_E_INVALID;
+    cudaSetDevice(ctx->device);  // the calling thread may be a new one (mapper / tracker threads): bind it to the context's GPU
     if (nq < 0 || nt < 0 || k <= 0 || k > UCO_KNN_MAX_K)
         return uco_fail(ctx, UCO_E_INVALID, "hamming_knn: bad sizes nq=%d nt=%d k=%d", nq, nt, k);
     if (nq == 0) return UCO_OK;

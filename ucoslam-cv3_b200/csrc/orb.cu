@@ -802,6 +802,7 @@ int uco_b200_orb_extract_batch_dev(uco_b200_ctx* ctx, const uint8_t* imgs_dev, i
                                    size_t frame_stride, const uco_orb_params* prm, uco_keypoint* kps_dev,
                                    uint8_t* desc_dev, int* n_out_dev) {
     if (!ctx) return UCO_E_INVALID;
+    cudaSetDevice(ctx->device);  // the calling thread may be a new one (mapper / tracker threads): bind it to the context's GPU
     if (!prm || n_imgs < 0) return uco_fail(ctx, UCO_E_INVALID, "orb: bad arguments");
     if (n_imgs == 0) return UCO_OK;
     if (!imgs_dev || !kps_dev || !desc_dev || !n_out_dev) return uco_fail(ctx, UCO_E_INVALID, "orb: null pointer");
@@ -814,6 +815,7 @@ int uco_b200_orb_extract_batch_dev(uco_b200_ctx* ctx, const uint8_t* imgs_dev, i
 int uco_b200_orb_extract_batch(uco_b200_ctx* ctx, const uint8_t* const* imgs, int n_imgs, int w, int h, size_t stride,
                                const uco_orb_params* prm, uco_keypoint* kps, uint8_t* desc, int capacity, int* n_out) {
     if (!ctx) return UCO_E_INVALID;
+    cudaSetDevice(ctx->device);  // the calling thread may be a new one (mapper / tracker threads): bind it to the context's GPU
     if (!prm || n_imgs < 0) return uco_fail(ctx, UCO_E_INVALID, "orb: bad arguments");
     if (n_imgs == 0) return UCO_OK;
     if (!imgs || !kps || !desc || !n_out) return uco_fail(ctx, UCO_E_INVALID, "orb: null pointer");
