@@ -223,6 +223,46 @@ int uco_b200_ba_set_mode(uco_b200_ctx* ctx, int mode, int cluster_size);
  * {free poses, Schur blocks, gather units, contributions, chunks, pose-list entries, max observations per chunk, landmarks covered} */
 int uco_b200_probe_ba_plan(const uco_ba_problem* pb, int cluster_size, int* out8);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * K14  pose-only optimisation (tracking): 4 rounds x 10 Levenberg-Marquardt iterations on one camera pose
+ *   replaces ucoslam::PnPSolver::solvePnp(frame, map, matches_io, pose_io, currentKeyFrame)
+ *     src/optimization/pnpsolver.cpp:116-408, src/optimization/pnpsolver.h:33   (tracker thread, 2-3 calls per frame)
+ *   i.e. what g2o does for that graph:
+ *     src/optimization/typesg2o.h:590-663, 521-588   EdgeSE3ProjectXYZOnlyPose / EdgeStereoSE3ProjectXYZOnlyPose
+ *     src/optimization/typesg2o.h:82-105             WeightedHubberRobustKernel (weight 0.5 for unstable points, x2 stereo)
+ *     src/optimization/typesg2o.h:414-470            MarkerEdgeOnlyProject (numeric Jacobian, delta 1e-4; base_binary_edge.hpp:167-232)
+ *     3rdparty/g2o/g2o/core/base_unary_edge.hpp:50-80, optimization_algorithm_levenberg.cpp:58-175, sparse_optimizer.cpp:366-436
+ *   The caller flattens the matches as solvePnp walks them (pnpsolver.cpp:200-259): one row per cv::DMatch.
+ *   n_matches == 0 and n_markers == 0 returns n_good = 0 and the input pose, like the reference (:144).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct uco_pnp_problem {
+    int32_t n_matches;
+    const float* pose44;         /* 16            estimatedPose, row-major 4x4 (frame <- global) */
+    const float* points3;        /* n x 3         map_points[trainIdx].getCoordinates() */
+    const float* obs_uv;         /* n x 2         frame.und_kpts[queryIdx].pt */
+    const float* obs_ur;         /* n             kpt.pt.x - mbf/depth of stereo matches (pnpsolver.cpp:226); may be NULL */
+    const uint8_t* obs_stereo;   /* n             frame.getDepth(queryIdx) > 0; may be NULL (all monocular) */
+    const float* obs_inv_sigma2; /* n             1/scaleFactors[kpt.octave] */
+    const uint8_t* stable;       /* n             MapPoint::isStable(); may be NULL (all stable) */
+    float fx, fy, cx, cy, bf;    /* ImageParams; bf = bl * fx */
+    int32_t n_markers;           /* frame markers with a valid map pose seen from the neighbourhood (pnpsolver.cpp:262-281) */
+    const float* marker_pose44;  /* n_markers x 16  Marker::pose_g2m */
+    const float* marker_size;    /* n_markers */
+    const float* marker_corners; /* n_markers x 8   MarkerObservation::und_corners */
+} uco_pnp_problem;
+
+typedef struct uco_pnp_result {
+    float pose44[16];            /* estimatedPose after the call */
+    double pose7[7];             /* the same vertex as qx qy qz qw tx ty tz (f64) */
+    int32_t n_good;              /* return value of solvePnp: matches not flagged as outliers */
+    int32_t iters[4];            /* LM iterations executed by each of the 4 rounds */
+    uint8_t* bad;                /* n_matches, caller-owned, may be NULL: != 0 <-> map_matches[i].imgIdx = -1 */
+} uco_pnp_result;
+
+int uco_b200_pose_only(uco_b200_ctx* ctx, const uco_pnp_problem* pb, uco_pnp_result* res);
+/* n independent problems (frames / cameras) in one launch, one thread block each */
+int uco_b200_pose_only_batch(uco_b200_ctx* ctx, int n, const uco_pnp_problem* pbs, uco_pnp_result* res);
+
 #ifdef __cplusplus
 }
 #endif

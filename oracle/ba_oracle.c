@@ -508,3 +508,296 @@ int oracle_ba_optimize(int n_poses, const float* poses44, const uint8_t* fixed, 
     free(B.err); free(B.chi2); free(B.Hpp); free(B.bp); free(B.Hll); free(B.bl); free(B.Hpl); free(B.lm_ptr); free(B.lm_obs);
     return 0;
 }
+
+/* ======================================================================================================================
+ * Pose-only optimisation — PnPSolver::solvePnp, /root/reference/src/optimization/pnpsolver.cpp:116-408:
+ *   one free SE3 vertex; per match a unary edge EdgeSE3ProjectXYZOnlyPose (typesg2o.h:590-663) or
+ *   EdgeStereoSE3ProjectXYZOnlyPose (:521-588) with WeightedHubberRobustKernel (:82-105: the weight scales rho only);
+ *   per visible map marker a MarkerEdgeOnlyProject (:414-470; float projections, NUMERIC Jacobian with delta = 1e-4f,
+ *   base_binary_edge.hpp:167-232) against a fixed marker vertex; 4 rounds of optimize(10) (minChi2BetweenIter = 0), the
+ *   estimate reset to the initial pose before every round (:358), inliers re-classified after each (:364-374), kernels
+ *   dropped after round index 2, early exit when < 10 inliers and no markers (:383).
+ *   Unary quadratic form: base_unary_edge.hpp:50-80.  Parity pin: oracle/_ref/libref_g2o.so ref_pose_only (the reference's
+ *   own edge classes + g2o), tests/test_pnp_oracle.py and tests/golden/pnp_g2o.npz.
+ * ==================================================================================================================== */
+typedef struct {
+    int n, nm;
+    const float *pts, *uv, *ur, *isig;
+    const uint8_t *stereo;
+    double* w;       /* kernel weight per match */
+    uint8_t* robust; /* per match: kernel still attached */
+    uint8_t* active; /* level 0 */
+    double *err, *chi2;
+    cam_t cam;
+    /* markers */
+    se3* g2m; double* mpts; /* nm x 4 x 3 local corner coordinates */
+    const float* mobs; double wm; uint8_t* mrobust; double *merr, *mchi2;
+    se3 T, Tbak;
+    double H[36], b[6];
+} pnp_t;
+
+static void pnp_edge_error(const pnp_t* P, const se3* T, int i, double* e) {
+    double X[3] = {P->pts[3 * i], P->pts[3 * i + 1], P->pts[3 * i + 2]}, p[3];
+    se3_map(T, X, p);
+    if (!P->stereo[i]) { /* typesg2o.h:640-652 */
+        e[0] = (double)P->uv[2 * i] - ((p[0] / p[2]) * P->cam.fx + P->cam.cx);
+        e[1] = (double)P->uv[2 * i + 1] - ((p[1] / p[2]) * P->cam.fy + P->cam.cy);
+        e[2] = 0;
+    } else { /* :572-580: float 1/z, bf is a double member here */
+        const float invz = 1.0f / p[2];
+        double r0 = p[0] * invz * P->cam.fx + P->cam.cx, r1 = p[1] * invz * P->cam.fy + P->cam.cy;
+        double r2 = r0 - P->cam.bf * invz;
+        e[0] = (double)P->uv[2 * i] - r0; e[1] = (double)P->uv[2 * i + 1] - r1; e[2] = (double)P->ur[i] - r2;
+    }
+}
+static void se3_mul(const se3* A, const se3* B, se3* C) { /* se3quat.h:156-163 */
+    double rt[3];
+    quat_rot(A->q, B->t, rt);
+    se3 R;
+    quat_mul(A->q, B->q, R.q);
+    for (int k = 0; k < 3; k++) R.t[k] = A->t[k] + rt[k];
+    quat_normalize(R.q);
+    *C = R;
+}
+static void pnp_marker_error(const pnp_t* P, const se3* T, int m, double* e) { /* typesg2o.h:440-468 */
+    se3 C2M;
+    se3_mul(T, &P->g2m[m], &C2M);
+    for (int i = 0; i < 4; i++) {
+        double p[3];
+        se3_map(&C2M, P->mpts + 12 * m + 3 * i, p);
+        float projx = (p[0] / p[2]) * P->cam.fx + P->cam.cx;
+        e[2 * i] = (double)P->mobs[8 * m + 2 * i] - projx;
+        float projy = (p[1] / p[2]) * P->cam.fy + P->cam.cy;
+        e[2 * i + 1] = (double)P->mobs[8 * m + 2 * i + 1] - projy;
+    }
+}
+/* computeActiveErrors + activeRobustChi2 */
+static double pnp_errors(pnp_t* P) {
+    double s = 0;
+    for (int i = 0; i < P->n; i++) {
+        if (!P->active[i]) continue;
+        double* e = P->err + 3 * i;
+        pnp_edge_error(P, &P->T, i, e);
+        double c = P->isig[i] * (e[0] * e[0]) + P->isig[i] * (e[1] * e[1]);
+        if (P->stereo[i]) c += P->isig[i] * (e[2] * e[2]);
+        P->chi2[i] = c;
+    }
+    for (int m = 0; m < P->nm; m++) {
+        double* e = P->merr + 8 * m;
+        pnp_marker_error(P, &P->T, m, e);
+        double c = 0;
+        for (int k = 0; k < 8; k++) c += e[k] * e[k];
+        P->mchi2[m] = c;
+    }
+    for (int i = 0; i < P->n; i++) {
+        if (!P->active[i]) continue;
+        if (P->robust[i]) { double r0, r1; huber(P->chi2[i], P->stereo[i] ? sqrtf(7.815f) : sqrtf(5.99f), P->w[i], &r0, &r1); s += r0; }
+        else s += P->chi2[i];
+    }
+    for (int m = 0; m < P->nm; m++) {
+        if (P->mrobust[m]) { double r0, r1; huber(P->mchi2[m], sqrtf(15.507f), P->wm, &r0, &r1); s += r0; }
+        else s += P->mchi2[m];
+    }
+    return s;
+}
+static void pnp_build(pnp_t* P) {
+    memset(P->H, 0, sizeof(P->H)); memset(P->b, 0, sizeof(P->b));
+    for (int i = 0; i < P->n; i++) {
+        if (!P->active[i]) continue;
+        double X[3] = {P->pts[3 * i], P->pts[3 * i + 1], P->pts[3 * i + 2]}, p[3], J[18];
+        se3_map(&P->T, X, p);
+        double x = p[0], y = p[1], invz = 1.0 / p[2], invz_2 = invz * invz, fx = P->cam.fx, fy = P->cam.fy, bf = P->cam.bf;
+        J[0] = x * y * invz_2 * fx; J[1] = -(1 + (x * x * invz_2)) * fx; J[2] = y * invz * fx; J[3] = -invz * fx; J[4] = 0; J[5] = x * invz_2 * fx;
+        J[6] = (1 + y * y * invz_2) * fy; J[7] = -x * y * invz_2 * fy; J[8] = -x * invz * fy; J[9] = 0; J[10] = -invz * fy; J[11] = y * invz_2 * fy;
+        int D = 2;
+        if (P->stereo[i]) {
+            D = 3;
+            J[12] = J[0] - bf * y * invz_2; J[13] = J[1] + bf * x * invz_2; J[14] = J[2]; J[15] = J[3]; J[16] = 0; J[17] = J[5] - bf * invz_2;
+        }
+        double rho1 = 1;
+        if (P->robust[i]) { double r0; huber(P->chi2[i], P->stereo[i] ? sqrtf(7.815f) : sqrtf(5.99f), P->w[i], &r0, &rho1); }
+        const double* e = P->err + 3 * i;
+        double om = P->isig[i];
+        for (int a = 0; a < 6; a++) {
+            double s = 0;
+            for (int d = 0; d < D; d++) s += J[6 * d + a] * (om * e[d]);
+            P->b[a] -= rho1 * s;
+            for (int c = 0; c < 6; c++) {
+                double h = 0;
+                for (int d = 0; d < D; d++) h += J[6 * d + a] * (rho1 * om) * J[6 * d + c];
+                P->H[6 * a + c] += h;
+            }
+        }
+    }
+    for (int m = 0; m < P->nm; m++) { /* numeric Jacobian wrt the camera vertex, base_binary_edge.hpp:200-226 */
+        const double delta = (double)1e-4f, scalar = 1 / (2 * delta);
+        double J[48];
+        for (int d = 0; d < 6; d++) {
+            double u[6] = {0, 0, 0, 0, 0, 0}, e1[8], e2[8];
+            se3 Tp = P->T;
+            u[d] = delta; se3_oplus(&Tp, u); pnp_marker_error(P, &Tp, m, e1);
+            Tp = P->T;
+            u[d] = -delta; se3_oplus(&Tp, u); pnp_marker_error(P, &Tp, m, e2);
+            for (int k = 0; k < 8; k++) J[6 * k + d] = scalar * (e1[k] - e2[k]);
+        }
+        double rho1 = 1;
+        if (P->mrobust[m]) { double r0; huber(P->mchi2[m], sqrtf(15.507f), P->wm, &r0, &rho1); }
+        const double* e = P->merr + 8 * m;
+        for (int a = 0; a < 6; a++) {
+            double s = 0;
+            for (int d = 0; d < 8; d++) s += J[6 * d + a] * e[d];
+            P->b[a] -= rho1 * s;
+            for (int c = 0; c < 6; c++) {
+                double h = 0;
+                for (int d = 0; d < 8; d++) h += J[6 * d + a] * rho1 * J[6 * d + c];
+                P->H[6 * a + c] += h;
+            }
+        }
+    }
+}
+/* SparseOptimizer::optimize(iterations) with minChi2BetweenIter = 0 */
+static int pnp_stage(pnp_t* P, int iterations) {
+    double lambda = 0, ni = 2;
+    float prevChi2 = FLT_MAX, curChi2 = FLT_MAX, Chi2Diff = FLT_MAX;
+    int ok = 1, its = 0;
+    for (int it = 0; it < iterations && ok && Chi2Diff > 0.0f; it++) {
+        { float t = prevChi2; prevChi2 = curChi2; curChi2 = t; }
+        double currentChi = pnp_errors(P), tempChi;
+        pnp_build(P);
+        if (it == 0) {
+            double md = 0;
+            for (int j = 0; j < 6; j++) md = fmax(fabs(P->H[7 * j]), md);
+            lambda = 1e-5 * md;
+            ni = 2;
+        }
+        double rho = 0;
+        int qmax = 0;
+        do {
+            P->Tbak = P->T;
+            double A[36], x[6] = {0, 0, 0, 0, 0, 0};
+            memcpy(A, P->H, sizeof(A));
+            for (int j = 0; j < 6; j++) A[7 * j] += lambda;
+            int ok2 = chol_solve(A, 6, P->b, x);
+            if (ok2) se3_oplus(&P->T, x);
+            tempChi = pnp_errors(P);
+            if (!ok2) tempChi = DBL_MAX;
+            rho = currentChi - tempChi;
+            double scale = 0;
+            for (int k = 0; k < 6; k++) scale += x[k] * (lambda * x[k] + P->b[k]);
+            scale += 1e-3;
+            rho /= scale;
+            if (rho > 0 && isfinite(tempChi)) {
+                double alpha = 1. - pow((2 * rho - 1), 3);
+                alpha = fmin(alpha, 2. / 3.);
+                lambda *= fmax(1. / 3., alpha);
+                ni = 2;
+                currentChi = tempChi;
+            } else {
+                lambda *= ni;
+                ni *= 2;
+                P->T = P->Tbak;
+                if (!isfinite(lambda)) break;
+            }
+            qmax++;
+        } while (rho < 0 && qmax < 10);
+        if (qmax == 10 || rho == 0 || !isfinite(lambda)) ok = 0;
+        double last = 0; /* activeRobustChi2 over the stored (possibly stale) edge errors */
+        for (int i = 0; i < P->n; i++) {
+            if (!P->active[i]) continue;
+            if (P->robust[i]) { double r0, r1; huber(P->chi2[i], P->stereo[i] ? sqrtf(7.815f) : sqrtf(5.99f), P->w[i], &r0, &r1); last += r0; }
+            else last += P->chi2[i];
+        }
+        for (int m = 0; m < P->nm; m++) {
+            if (P->mrobust[m]) { double r0, r1; huber(P->mchi2[m], sqrtf(15.507f), P->wm, &r0, &r1); last += r0; }
+            else last += P->mchi2[m];
+        }
+        curChi2 = (float)last;
+        Chi2Diff = prevChi2 - curChi2;
+        its++;
+    }
+    return its;
+}
+
+/* same signature as oracle/ref_g2o_wrap.cpp: ref_pose_only */
+int oracle_pose_only(const float* pose44, int n, const float* points3, const float* obs_uv, const float* obs_ur,
+                     const uint8_t* obs_stereo, const float* obs_inv_sigma2, const uint8_t* stable, float fx, float fy, float cx,
+                     float cy, float bf, int n_markers, const float* marker_pose44, const float* marker_size,
+                     const float* marker_corners, float* out_pose44, double* out_pose7, uint8_t* bad, int* iters_done) {
+    if (n == 0 && n_markers == 0) return 0;
+    const float Chi2D = 5.99f, Chi3D = 7.815f, Chi8D = 15.507f;
+    pnp_t P;
+    memset(&P, 0, sizeof(P));
+    P.n = n; P.nm = n_markers; P.pts = points3; P.uv = obs_uv; P.ur = obs_ur; P.isig = obs_inv_sigma2; P.stereo = obs_stereo;
+    P.w = malloc(sizeof(double) * (n + 1)); P.robust = malloc(n + 1); P.active = malloc(n + 1);
+    P.err = calloc(3 * n + 1, sizeof(double)); P.chi2 = calloc(n + 1, sizeof(double));
+    P.cam.fx = fx; P.cam.fy = fy; P.cam.cx = cx; P.cam.cy = cy; P.cam.bf = bf;
+    double KpWeightSum = 0;
+    for (int i = 0; i < n; i++) {
+        float ew = 1;
+        if (!stable[i]) ew = 0.5;
+        if (obs_stereo[i]) ew *= 2;
+        P.w[i] = ew; P.robust[i] = 1; P.active[i] = 1;
+        KpWeightSum += ew;
+    }
+    P.g2m = malloc(sizeof(se3) * (n_markers + 1)); P.mpts = malloc(sizeof(double) * 12 * (n_markers + 1));
+    P.mrobust = malloc(n_markers + 1); P.merr = calloc(8 * n_markers + 1, sizeof(double)); P.mchi2 = calloc(n_markers + 1, sizeof(double));
+    P.mobs = marker_corners;
+    {
+        float w_markers = 0.3;
+        int total = n + n_markers;
+        P.wm = ((w_markers * total) / (1. - w_markers)) / (float)KpWeightSum; /* :298-300 */
+    }
+    for (int m = 0; m < n_markers; m++) {
+        se3_from_m44f(marker_pose44 + 16 * m, &P.g2m[m]);
+        float s = marker_size[m]; /* Marker::get3DPointsLocalRefSystem, marker.cpp:58-62: cv::Point3f of size/2. */
+        float h = (float)(s / 2.), mh = (float)(-s / 2.);
+        double c[12] = {mh, h, 0, h, h, 0, h, mh, 0, mh, mh, 0};
+        memcpy(P.mpts + 12 * m, c, sizeof(c));
+        P.mrobust[m] = 1;
+    }
+    se3 T0;
+    se3_from_m44f(pose44, &T0);
+    uint8_t* vbad = calloc(n + 1, 1);
+    for (int it = 0; it < 4; it++) if (iters_done) iters_done[it] = 0;
+    for (int it = 0; it < 4; it++) {
+        P.T = T0;
+        int r = pnp_stage(&P, 10);
+        if (iters_done) iters_done[it] = r;
+        int good = 0;
+        for (int i = 0; i < n; i++) {
+            if (vbad[i]) { /* e->computeError() on an inactive edge */
+                double* e = P.err + 3 * i;
+                pnp_edge_error(&P, &P.T, i, e);
+                double c = P.isig[i] * (e[0] * e[0]) + P.isig[i] * (e[1] * e[1]);
+                if (obs_stereo[i]) c += P.isig[i] * (e[2] * e[2]);
+                P.chi2[i] = c;
+            }
+            vbad[i] = P.chi2[i] > (obs_stereo[i] ? Chi3D : Chi2D);
+            P.active[i] = !vbad[i];
+            if (it >= 2) P.robust[i] = 0;
+            if (!vbad[i]) good++;
+        }
+        for (int m = 0; m < n_markers; m++) {
+            double* e = P.merr + 8 * m;
+            pnp_marker_error(&P, &P.T, m, e);
+            double c = 0;
+            for (int k = 0; k < 8; k++) c += e[k] * e[k];
+            P.mchi2[m] = c;
+            if (c > Chi8D || it >= 2) P.mrobust[m] = 0;
+        }
+        if (good < 10 && n_markers == 0) break;
+    }
+    {
+        double R[9];
+        quat_to_R(P.T.q, R);
+        for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) out_pose44[4 * r + c] = (float)R[3 * r + c]; out_pose44[4 * r + 3] = (float)P.T.t[r]; }
+        out_pose44[12] = out_pose44[13] = out_pose44[14] = 0; out_pose44[15] = 1;
+        for (int k = 0; k < 4; k++) out_pose7[k] = P.T.q[k];
+        for (int k = 0; k < 3; k++) out_pose7[4 + k] = P.T.t[k];
+    }
+    int nbad = 0;
+    for (int i = 0; i < n; i++) { bad[i] = vbad[i]; nbad += vbad[i]; }
+    free(P.w); free(P.robust); free(P.active); free(P.err); free(P.chi2); free(P.g2m); free(P.mpts); free(P.mrobust); free(P.merr);
+    free(P.mchi2); free(vbad);
+    return n - nbad;
+}

@@ -242,3 +242,43 @@ def _ba_call(fn, pb, n_iters):
                         int(n_iters), _p(out["pose7"]), _p(out["pose44"]), _p(out["point3"]), _p(out["chi2"]),
                         _p(out["level"]), _p(out["bad"]), _p(out["iters"]), _p(out["trace"]))
     return out
+
+
+# ---- pose-only optimisation (PnPSolver::solvePnp) ------------------------------------------------------------------------
+from ucoslam_b200.synth import synth_pnp_problem
+
+PNP_INPUT_KEYS = ("pose44", "points3", "obs_uv", "obs_ur", "obs_stereo", "obs_inv_sigma2", "stable", "fx", "fy", "cx", "cy", "bf",
+                  "marker_pose44", "marker_size", "marker_corners")
+
+
+def pnp_problem_from_golden(g, name):
+    pb = {k: g["%s_in_%s" % (name, k)] for k in PNP_INPUT_KEYS}
+    for k in ("fx", "fy", "cx", "cy", "bf"):
+        pb[k] = float(pb[k])
+    return pb
+
+
+def pose_only(pb):
+    """oracle/ba_oracle.c oracle_pose_only (plain-C restatement of pnpsolver.cpp:116-408)."""
+    return _pnp_call(load_oracle().oracle_pose_only, pb)
+
+
+def ref_pose_only(pb):
+    """The reference's own edge classes + g2o (oracle/_ref/libref_g2o.so ref_pose_only)."""
+    lib = load_ref("libref_g2o.so")
+    if lib is None:
+        return None
+    return _pnp_call(lib.ref_pose_only, pb)
+
+
+def _pnp_call(fn, pb):
+    n, nm = len(pb["points3"]), len(pb["marker_size"])
+    out = dict(pose44=np.zeros(16, np.float32), pose7=np.zeros(7), bad=np.zeros(max(n, 1), np.uint8), iters=np.zeros(4, np.int32))
+    f = lambda v: ctypes.c_float(v)
+    fn.restype = ctypes.c_int
+    out["n_good"] = fn(_p(pb["pose44"]), n, _p(pb["points3"]), _p(pb["obs_uv"]), _p(pb["obs_ur"]), _p(pb["obs_stereo"]),
+                       _p(pb["obs_inv_sigma2"]), _p(pb["stable"]), f(pb["fx"]), f(pb["fy"]), f(pb["cx"]), f(pb["cy"]), f(pb["bf"]),
+                       nm, _p(pb["marker_pose44"]), _p(pb["marker_size"]), _p(pb["marker_corners"]),
+                       _p(out["pose44"]), _p(out["pose7"]), _p(out["bad"]), _p(out["iters"]))
+    out["bad"] = out["bad"][:n]
+    return out

@@ -160,4 +160,126 @@ int ref_ba_optimize(int n_poses, const float* poses44, const uint8_t* fixed, int
     }
     return 0;
 }
+
+// PnPSolver::solvePnp (src/optimization/pnpsolver.cpp:116-408) on flat arrays: one free camera vertex, one unary edge per
+// (keypoint, map point) match, optional fixed marker vertices with MarkerEdgeOnlyProject edges, 4 rounds x 10 LM iterations
+// with inlier re-classification.  stable[i] = MapPoint::isStable(); obs_ur[i] = kpt.pt.x - mbf/depth (:226) where stereo[i].
+// Returns the number of inliers (the reference's return value); bad[i] != 0 <-> map_matches[i].imgIdx = -1.
+int ref_pose_only(const float* pose44, int n, const float* points3, const float* obs_uv, const float* obs_ur,
+                  const uint8_t* obs_stereo, const float* obs_inv_sigma2, const uint8_t* stable, float fx, float fy, float cx,
+                  float cy, float bf, int n_markers, const float* marker_pose44, const float* marker_size,
+                  const float* marker_corners /* n_markers x 8 */, float* out_pose44, double* out_pose7, uint8_t* bad,
+                  int* iters_done /* 4 */) {
+    if (n == 0 && n_markers == 0) return 0;  // :144
+    g2o::SparseOptimizer optimizer;
+    std::unique_ptr<g2o::BlockSolver_6_3::LinearSolverType> linearSolver =
+        g2o::make_unique<g2o::LinearSolverEigen<g2o::BlockSolver_6_3::PoseMatrixType>>();
+    auto* solver = new g2o::OptimizationAlgorithmLevenberg(g2o::make_unique<g2o::BlockSolver_6_3>(std::move(linearSolver)));
+    optimizer.setAlgorithm(solver);
+    auto* cam = new VertexSE3Expmap();
+    cam->setEstimate(toSE3Quat(pose44));
+    cam->setId(0);
+    cam->setFixed(false);
+    optimizer.addVertex(cam);
+    const float Chi2D = 5.99, Chi3D = 7.815, Chi8D = 15.507;
+    const float thHuber2D = sqrt(5.99), thHuber3D = sqrt(7.815), thHuber8D = sqrt(15.507);
+    struct edgeinfo { float MaxChi = 0; void* ptr; };
+    std::vector<edgeinfo> edgesInfo(n);
+    std::vector<bool> vBad(n, false);
+    double KpWeightSum = 0;
+    for (int i = 0; i < n; i++) {
+        float edge_weight = 1;
+        if (!stable[i]) edge_weight = 0.5;
+        const float invSigma2 = obs_inv_sigma2[i];
+        if (!obs_stereo[i]) {
+            Eigen::Matrix<double, 2, 1> obs;
+            obs << obs_uv[2 * i], obs_uv[2 * i + 1];
+            auto* e = new EdgeSE3ProjectXYZOnlyPose(points3[3 * i], points3[3 * i + 1], points3[3 * i + 2], fx, fy, cx, cy);
+            e->setVertex(0, dynamic_cast<g2o::OptimizableGraph::Vertex*>(cam));
+            e->setMeasurement(obs);
+            e->setInformation(Eigen::Matrix2d::Identity() * invSigma2);
+            auto* rk = new WeightedHubberRobustKernel;
+            rk->set(thHuber2D, edge_weight);
+            e->setRobustKernel(rk);
+            optimizer.addEdge(e);
+            edgesInfo[i].ptr = (void*)e;
+            edgesInfo[i].MaxChi = Chi2D;
+        } else {
+            Eigen::Matrix<double, 3, 1> obs;
+            obs << obs_uv[2 * i], obs_uv[2 * i + 1], obs_ur[i];
+            auto* e = new EdgeStereoSE3ProjectXYZOnlyPose();
+            e->setVertex(0, dynamic_cast<g2o::OptimizableGraph::Vertex*>(cam));
+            e->setMeasurement(obs);
+            Eigen::Matrix3d Info = Eigen::Matrix3d::Identity() * invSigma2;
+            e->setInformation(Info);
+            edge_weight *= 2;
+            auto* rk = new WeightedHubberRobustKernel;
+            rk->set(thHuber3D, edge_weight);
+            e->setRobustKernel(rk);
+            e->fx = fx; e->fy = fy; e->cx = cx; e->cy = cy; e->bf = bf;
+            e->Xw[0] = points3[3 * i]; e->Xw[1] = points3[3 * i + 1]; e->Xw[2] = points3[3 * i + 2];
+            optimizer.addEdge(e);
+            edgesInfo[i].ptr = (void*)e;
+            edgesInfo[i].MaxChi = Chi3D;
+        }
+        KpWeightSum += edge_weight;
+    }
+    std::vector<MarkerEdgeOnlyProject*> marker_edges;
+    float w_markers = 0.3;
+    int totalNEdges = n + n_markers;
+    double weight_marker = ((w_markers * totalNEdges) / (1. - w_markers)) / float(KpWeightSum);
+    uint32_t vid = 1;
+    for (int m = 0; m < n_markers; m++) {
+        auto* vm = new VertexSE3Expmap();
+        vm->setEstimate(toSE3Quat(marker_pose44 + 16 * m));
+        vm->setFixed(true);
+        vm->setId(vid++);
+        optimizer.addVertex(vm);
+        auto* e = new MarkerEdgeOnlyProject(marker_size[m]);
+        Eigen::Matrix<double, 8, 1> obs;
+        for (int i = 0; i < 8; i++) obs(i) = marker_corners[8 * m + i];
+        e->setMeasurement(obs);
+        e->setVertex(0, dynamic_cast<g2o::OptimizableGraph::Vertex*>(vm));
+        e->setVertex(1, dynamic_cast<g2o::OptimizableGraph::Vertex*>(cam));
+        e->fx = fx; e->fy = fy; e->cx = cx; e->cy = cy;
+        e->setInformation(Eigen::Matrix<double, 8, 8>::Identity());
+        auto* rk = new WeightedHubberRobustKernel;
+        e->setRobustKernel(rk);
+        rk->set(thHuber8D, weight_marker);
+        optimizer.addEdge(e);
+        marker_edges.push_back(e);
+    }
+    for (int it = 0; it < 4; it++) {
+        if (iters_done) iters_done[it] = 0;
+    }
+    for (int it = 0; it < 4; it++) {
+        cam->setEstimate(toSE3Quat(pose44));
+        optimizer.initializeOptimization(0);
+        optimizer.setVerbose(false);
+        int r = optimizer.optimize(10);
+        if (iters_done) iters_done[it] = r;
+        int nGood = 0;
+        for (int i = 0; i < n; i++) {
+            auto* e = (EdgeSE3ProjectXYZOnlyPose*)edgesInfo[i].ptr;
+            if (vBad[i]) e->computeError();
+            vBad[i] = e->chi2() > edgesInfo[i].MaxChi;
+            e->setLevel(vBad[i] ? 1 : 0);
+            if (it >= 2) e->setRobustKernel(nullptr);
+            if (!vBad[i]) nGood++;
+        }
+        for (auto me : marker_edges) {
+            me->computeError();
+            if (me->chi2() > Chi8D || it >= 2) me->setRobustKernel(nullptr);
+        }
+        if (nGood < 10 && n_markers == 0) break;
+    }
+    g2o::SE3Quat q = static_cast<VertexSE3Expmap*>(optimizer.vertex(0))->estimate();
+    Eigen::Matrix<double, 4, 4> M = q.to_homogeneous_matrix();
+    for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) out_pose44[4 * r + c] = (float)M(r, c);
+    out_pose7[0] = q.rotation().x(); out_pose7[1] = q.rotation().y(); out_pose7[2] = q.rotation().z(); out_pose7[3] = q.rotation().w();
+    for (int k = 0; k < 3; k++) out_pose7[4 + k] = q.translation()[k];
+    int nbad = 0;
+    for (int i = 0; i < n; i++) { bad[i] = vBad[i]; nbad += vBad[i]; }
+    return n - nbad;
+}
 }

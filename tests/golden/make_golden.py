@@ -8,6 +8,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "ucoslam-cv3_b200", "python"))
 import oracle_py
 
 
@@ -76,7 +77,34 @@ def ba():
     print("ba golden written", {n: int(out[n + "_out_iters"].sum()) for n in BA_CASES})
 
 
+PNP_CASES = {  # name -> synth_pnp_problem kwargs   (also imported by the tests)
+    "mono": dict(seed=1, n_matches=800),
+    "stereo": dict(seed=2, n_matches=600, stereo_frac=0.5),
+    "markers": dict(seed=3, n_matches=300, n_markers=3),
+    "few": dict(seed=4, n_matches=40, outlier_frac=0.5),
+    "markers_only": dict(seed=5, n_matches=0, n_markers=2),
+    "hopeless": dict(seed=6, n_matches=12, outlier_frac=0.9),            # < 10 inliers after round 0: early exit (:383)
+    "big": dict(seed=7, n_matches=1500, stereo_frac=0.3, n_markers=2, outlier_frac=0.2),
+    "far": dict(seed=8, n_matches=500, pose_noise=(0.15, 6.0), outlier_frac=0.25),   # rejected LM trials
+}
+
+
+def pnp():
+    """PnPSolver::solvePnp's graph + 4-round schedule run by the reference's own g2o / typesg2o.h (oracle/ref_g2o_wrap.cpp)."""
+    oracle_py.build_ref()
+    out = {}
+    for name, kw in PNP_CASES.items():
+        pb = oracle_py.synth_pnp_problem(**kw)
+        r = oracle_py.ref_pose_only(pb)
+        for k in oracle_py.PNP_INPUT_KEYS:
+            out["%s_in_%s" % (name, k)] = np.asarray(pb[k])
+        for k, v in r.items():
+            out["%s_out_%s" % (name, k)] = np.asarray(v)
+    np.savez_compressed(os.path.join(HERE, "pnp_g2o.npz"), **out)
+    print("pnp golden written", {n: (int(out[n + "_out_n_good"]), out[n + "_out_iters"].tolist()) for n in PNP_CASES})
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["knn", "bow", "ba"]
+    which = sys.argv[1:] or ["knn", "bow", "ba", "pnp"]
     for w in which:
         globals()[w]()

@@ -27,22 +27,38 @@ def _stamp(paths):
 
 
 def build(force=False, verbose=False):
+    """Compile every csrc/*.cu (in parallel; an object is reused when neither its source, nor any header, nor the flags changed)
+    and link libucoslam_b200.so."""
+    from concurrent.futures import ThreadPoolExecutor
     os.makedirs(OUT, exist_ok=True)
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
-    deps = srcs + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(HERE, "..", "include", "*.h"))
-    stamp = _stamp(deps)
+    hdrs = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(HERE, "..", "include", "*.h"))
+    stamp = _stamp(srcs + hdrs)
     stamp_file = os.path.join(OUT, "build.stamp")
     if not force and os.path.exists(LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
         return LIB
-    objs = []
-    log = []
-    for s in srcs:
+
+    def compile_one(s):
         o = os.path.join(OUT, os.path.basename(s)[:-3] + ".o")
+        ostamp, olog = o + ".stamp", o + ".log"
+        st = _stamp([s] + hdrs)
+        if not force and os.path.exists(o) and os.path.exists(ostamp) and os.path.exists(olog) and open(ostamp).read() == st:
+            return o, open(olog).read(), 0
         cmd = [NVCC] + FLAGS + ["-c", s, "-o", o]
         r = subprocess.run(cmd, capture_output=True, text=True)
-        log.append("$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
-        if r.returncode != 0:
-            sys.stderr.write(log[-1])
+        text = "$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr
+        if r.returncode == 0:
+            open(ostamp, "w").write(st)
+            open(olog, "w").write(text)
+        return o, text, r.returncode
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        results = list(ex.map(compile_one, srcs))
+    log, objs = [], []
+    for (o, text, rc), s in zip(results, srcs):
+        log.append(text)
+        if rc != 0:
+            sys.stderr.write(text)
             raise RuntimeError("nvcc failed for " + s)
         objs.append(o)
     cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]

@@ -36,6 +36,7 @@ enum {  // device workspace slots
     WS_BOW_DESC, WS_BOW_OUT,
     WS_GENERIC0, WS_GENERIC1, WS_GENERIC2, WS_GENERIC3,
     WS_BA, WS_BA_OUT, WS_BA_STOP,
+    WS_PNP_IN, WS_PNP_OUT, WS_PNP_SCRATCH,
     WS_COUNT
 };
 

@@ -47,6 +47,8 @@ SIGNATURES = {
     "uco_b200_ba_solve_batch": (_i, [_vp, _i, _vp, _vp, _vp]),
     "uco_b200_ba_set_mode": (_i, [_vp, _i, _i]),
     "uco_b200_probe_ba_plan": (_i, [_vp, _i, _vp]),
+    "uco_b200_pose_only": (_i, [_vp, _vp, _vp]),
+    "uco_b200_pose_only_batch": (_i, [_vp, _i, _vp, _vp]),
     "uco_b200_probe_math": (_i, [_i, _vp, _vp, _i, _vp, _vp]),
     "uco_b200_probe_retain_best": (_i, [_vp, _i, _i]),
 }
@@ -109,6 +111,18 @@ class BaProblem(ctypes.Structure):  # uco_ba_problem
 class BaResult(ctypes.Structure):  # uco_ba_result
     _fields_ = [("pose7", _vp), ("poses44", _vp), ("points3", _vp), ("obs_chi2", _vp), ("obs_level", _vp), ("obs_bad", _vp),
                 ("trace", _vp), ("iters", _c.c_int32 * 2), ("device_ms", _c.c_float), ("profile", _vp)]
+
+
+class PnpProblem(ctypes.Structure):  # uco_pnp_problem
+    _fields_ = [("n_matches", _c.c_int32), ("pose44", _vp), ("points3", _vp), ("obs_uv", _vp), ("obs_ur", _vp), ("obs_stereo", _vp),
+                ("obs_inv_sigma2", _vp), ("stable", _vp), ("fx", _c.c_float), ("fy", _c.c_float), ("cx", _c.c_float),
+                ("cy", _c.c_float), ("bf", _c.c_float), ("n_markers", _c.c_int32), ("marker_pose44", _vp), ("marker_size", _vp),
+                ("marker_corners", _vp)]
+
+
+class PnpResult(ctypes.Structure):  # uco_pnp_result
+    _fields_ = [("pose44", _c.c_float * 16), ("pose7", _c.c_double * 7), ("n_good", _c.c_int32), ("iters", _c.c_int32 * 4),
+                ("bad", _vp)]
 
 
 class UcoError(RuntimeError):
@@ -219,6 +233,42 @@ class Context:
         cps = (BaProblem * len(packs))(*[p[0] for p in packs])
         crs = (BaResult * len(packs))(*[p[1] for p in packs])
         return cps, crs, [p[2] for p in packs], [p[3] for p in packs]
+
+    # -- K14 -----------------------------------------------------------------------------------------------------
+    @staticmethod
+    def pnp_pack(pbs):
+        """(uco_pnp_problem[], uco_pnp_result[], keep-alive arrays, bad arrays) for problem dicts (see synth_pnp_problem)."""
+        keep, cps, crs, bads = [], [], [], []
+        for pb in pbs:
+            A = lambda k, dt: np.ascontiguousarray(pb[k], dtype=dt)
+            a = dict(pose44=A("pose44", np.float32), points3=A("points3", np.float32), obs_uv=A("obs_uv", np.float32),
+                     obs_ur=A("obs_ur", np.float32), obs_stereo=A("obs_stereo", np.uint8), obs_inv_sigma2=A("obs_inv_sigma2", np.float32),
+                     stable=A("stable", np.uint8), marker_pose44=A("marker_pose44", np.float32), marker_size=A("marker_size", np.float32),
+                     marker_corners=A("marker_corners", np.float32))
+            n, nm = len(a["points3"]), len(a["marker_size"])
+            bad = np.zeros(max(n, 1), np.uint8)
+            cps.append(PnpProblem(n, _p(a["pose44"]), _p(a["points3"]), _p(a["obs_uv"]), _p(a["obs_ur"]), _p(a["obs_stereo"]),
+                                  _p(a["obs_inv_sigma2"]), _p(a["stable"]), pb["fx"], pb["fy"], pb["cx"], pb["cy"], pb["bf"], nm,
+                                  _p(a["marker_pose44"]), _p(a["marker_size"]), _p(a["marker_corners"])))
+            r = PnpResult()
+            r.bad = _p(bad)
+            crs.append(r)
+            keep.append(a)
+            bads.append(bad[:n])
+        return (PnpProblem * len(cps))(*cps), (PnpResult * len(crs))(*crs), keep, bads
+
+    def pose_only_batch(self, pbs, packed=None):
+        """PnPSolver::solvePnp for several frames in one launch; returns dicts like oracle_py.pose_only."""
+        cps, crs, keep, bads = packed or self.pnp_pack(pbs)
+        self._chk(self.lib.uco_b200_pose_only_batch(self.h, len(bads), ctypes.addressof(cps), ctypes.addressof(crs)))
+        return [dict(pose44=np.array(list(crs[i].pose44), np.float32), pose7=np.array(list(crs[i].pose7)), n_good=int(crs[i].n_good),
+                     iters=np.array(list(crs[i].iters), np.int32), bad=bads[i].copy()) for i in range(len(bads))]
+
+    def pose_only(self, pb):
+        cps, crs, keep, bads = self.pnp_pack([pb])
+        self._chk(self.lib.uco_b200_pose_only(self.h, ctypes.addressof(cps), ctypes.addressof(crs)))
+        return dict(pose44=np.array(list(crs[0].pose44), np.float32), pose7=np.array(list(crs[0].pose7)), n_good=int(crs[0].n_good),
+                    iters=np.array(list(crs[0].iters), np.int32), bad=bads[0].copy())
 
     # -- K9 ------------------------------------------------------------------------------------------------------
     def bow_load(self, voc_bytes):

@@ -65,3 +65,55 @@ def synth_ba_problem(seed, n_poses=12, n_fixed=2, n_points=2000, stereo_frac=0.0
                 obs_stereo=np.array(obs_st, np.uint8), obs_inv_sigma2=np.array(obs_inv, np.float32),
                 fx=float(fx), fy=float(fy), cx=float(cx), cy=float(cy), bf=float(np.float32(bf)),
                 poses_gt=poses_gt, points_gt=pts_gt)
+
+
+def synth_pnp_problem(seed, n_matches=800, stereo_frac=0.0, outlier_frac=0.1, unstable_frac=0.3, n_markers=0, px_sigma=0.5,
+                      pose_noise=(0.03, 1.5), w=640, h=480, f=525.0, bf=0.12 * 525.0):
+    """A seeded pose-only problem as the tracker hands it to PnPSolver::solvePnp (SURVEY.md 8a row a21): one camera, n_matches
+    (keypoint, map point) pairs with octave-scaled pixel noise and gross outliers (wrong associations), optionally stereo
+    observations and ArUco markers with known map pose.  f32 containers as in the reference's data model."""
+    rng = np.random.default_rng(seed)
+    fx = fy = np.float32(f)
+    cx, cy = np.float32(w / 2 - 0.5), np.float32(h / 2 - 0.5)
+    T = np.eye(4)
+    T[:3, :3] = _rodrigues(rng.normal(0, 0.2, 3))
+    T[:3, 3] = rng.normal(0, 0.5, 3)
+    pts, uv, ur, st, inv, stable = [], [], [], [], [], []
+    while len(pts) < n_matches:
+        u, v, z = rng.uniform(20, w - 20), rng.uniform(20, h - 20), rng.uniform(1.0, 8.0)
+        Xc = np.array([(u - cx) / f * z, (v - cy) / f * z, z])
+        X = T[:3, :3].T @ (Xc - T[:3, 3])
+        octave = int(rng.integers(0, 8))
+        s = 1.2 ** octave
+        nu, nv = rng.normal(0, px_sigma * s, 2)
+        if rng.random() < outlier_frac:
+            nu, nv = rng.uniform(-60, 60, 2)
+        is_st = rng.random() < stereo_frac
+        pts.append(X); uv.append((u + nu, v + nv))
+        depth = np.float32(z + (rng.normal(0, 0.01 * z) if is_st else 0))
+        ur.append(np.float32(u + nu) - np.float32(bf) / depth if is_st else 0.0)   # kp_ur = kpt.pt.x - mbf/depth, pnpsolver.cpp:226
+        st.append(1 if is_st else 0)
+        inv.append(np.float32(1.0) / np.float32(np.float32(1.2) ** octave))
+        stable.append(0 if rng.random() < unstable_frac else 1)
+    m_pose, m_size, m_corners = [], [], []
+    for m in range(n_markers):
+        size = np.float32(rng.uniform(0.1, 0.3))
+        Mc = np.eye(4)   # marker -> camera
+        Mc[:3, :3] = _rodrigues(rng.normal(0, 0.3, 3))
+        Mc[:3, 3] = [rng.uniform(-0.8, 0.8), rng.uniform(-0.5, 0.5), rng.uniform(1.0, 3.0)]
+        g2m = np.linalg.inv(T) @ Mc
+        hs = size / 2
+        corners = []
+        for c in ((-hs, hs, 0), (hs, hs, 0), (hs, -hs, 0), (-hs, -hs, 0)):
+            Xc = Mc[:3, :3] @ np.array(c) + Mc[:3, 3]
+            corners += [f * Xc[0] / Xc[2] + cx + rng.normal(0, 0.3), f * Xc[1] / Xc[2] + cy + rng.normal(0, 0.3)]
+        m_pose.append(g2m.reshape(16)); m_size.append(size); m_corners.append(corners)
+    T0 = T.copy()
+    T0[:3, :3] = _rodrigues(rng.normal(0, np.deg2rad(pose_noise[1]), 3)) @ T0[:3, :3]
+    T0[:3, 3] += rng.normal(0, pose_noise[0], 3)
+    return dict(pose44=T0.reshape(16).astype(np.float32), points3=np.array(pts, np.float32).reshape(-1, 3),
+                obs_uv=np.array(uv, np.float32).reshape(-1, 2), obs_ur=np.array(ur, np.float32),
+                obs_stereo=np.array(st, np.uint8), obs_inv_sigma2=np.array(inv, np.float32), stable=np.array(stable, np.uint8),
+                fx=float(fx), fy=float(fy), cx=float(cx), cy=float(cy), bf=float(np.float32(bf)),
+                marker_pose44=np.array(m_pose, np.float32).reshape(-1, 16), marker_size=np.array(m_size, np.float32),
+                marker_corners=np.array(m_corners, np.float32).reshape(-1, 8), pose_gt=T)
