@@ -263,6 +263,49 @@ int uco_b200_pose_only(uco_b200_ctx* ctx, const uco_pnp_problem* pb, uco_pnp_res
 /* n independent problems (frames / cameras) in one launch, one thread block each */
 int uco_b200_pose_only_batch(uco_b200_ctx* ctx, int n, const uco_pnp_problem* pbs, uco_pnp_result* res);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * K8  descriptor matcher between two frames: exact k-NN (K7) + the reference's post-filters, on the device
+ *   replaces FrameMatcher_Flann::setParams + match / matchEpipolar
+ *     src/utils/framematcher.cpp:200-215, 216-322   (k = 10 candidates per query in index order; minDescDist, octave gate,
+ *                                                    optional epipolar gate, second-best ratio test)
+ *     src/basictypes/misc.cpp:153-185, 105-107      filter_ambiguous_train + remove_unused_matches
+ *     src/utils/framematcher.cpp:67-108, 288-316    rotation-consistency histogram (three fullest of 30 bins)
+ *     src/basictypes/misc.h:72-81                   epipolarLineSqDist
+ *   behind _impl::FrameMatcher_impl (src/utils/framematcher.cpp:31-58).  The candidates come from the EXACT linear search
+ *   (K7), not from the reference's 16-check k-means tree, which approximates them.
+ *   q_map / t_map: keypoint index of descriptor row i (FrameMatcher::manageMode :160-198 packs the rows of the requested
+ *   mode); NULL = identity (MODE_ALL).  Output: cv::DMatch records in the reference's order.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct uco_match { /* == cv::DMatch */
+    int32_t queryIdx, trainIdx, imgIdx;
+    float distance;
+} uco_match;
+
+#define UCO_MATCH_MAX_SCALES 32
+typedef struct uco_match_params {
+    float min_desc_dist;       /* _minDescDist */
+    float nn_match_ratio;      /* _nn_match_ratio (0.8 default, 0.6 tracker) */
+    int32_t check_orientation; /* _checkOrientation */
+    int32_t max_octave_diff;   /* _maxOctaveDiff */
+    int32_t use_f12;           /* != 0: epipolar gate with F12 (matchEpipolar with a non-empty FQ2T) */
+    float f12[9];              /* row-major 3x3, computeF12(...) of the caller (src/basictypes/misc.cpp:893-920) */
+    int32_t n_scales;          /* queryFrame.scaleFactors.size() */
+    float scale_factors[UCO_MATCH_MAX_SCALES];
+} uco_match_params;
+
+int uco_b200_frame_match(uco_b200_ctx* ctx, const uint8_t* q_desc, int nq, size_t q_stride, const uco_keypoint* q_kps,
+                         int n_q_kps, const int32_t* q_map, const uint8_t* t_desc, int nt, size_t t_stride,
+                         const uco_keypoint* t_kps, int n_t_kps, const int32_t* t_map, const uco_match_params* prm,
+                         uco_match* out, int capacity, int* n_out);
+/* a clip in one pass, device resident (outputs of uco_b200_orb_extract_batch_dev): pair p matches the descriptors at
+ * q_desc_dev + p*q_pair_stride (bytes; keypoints at q_kps_dev + p*q_kps_pair_stride records) against t_* likewise, all
+ * keypoints used (MODE_ALL); nq_dev / nt_dev: optional per-pair row counts.  Writes out_dev[p*nq_max ..] and n_out_dev[p]. */
+int uco_b200_frame_match_batch_dev(uco_b200_ctx* ctx, int n_pairs, const uint8_t* q_desc_dev, size_t q_pair_stride,
+                                   const uco_keypoint* q_kps_dev, size_t q_kps_pair_stride, int nq_max, const int32_t* nq_dev,
+                                   const uint8_t* t_desc_dev, size_t t_pair_stride, const uco_keypoint* t_kps_dev,
+                                   size_t t_kps_pair_stride, int nt_max, const int32_t* nt_dev, const uco_match_params* prm,
+                                   uco_match* out_dev, int32_t* n_out_dev);
+
 #ifdef __cplusplus
 }
 #endif

@@ -282,3 +282,56 @@ def _pnp_call(fn, pb):
                        _p(out["pose44"]), _p(out["pose7"]), _p(out["bad"]), _p(out["iters"]))
     out["bad"] = out["bad"][:n]
     return out
+
+
+# ---- frame matcher post-filters (FrameMatcher_Flann::matchEpipolar on exact k-NN) -----------------------------------------
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+MATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
+
+
+def synth_match_frames(seed, nt=2000, nq=2000, max_flips=40, rot=25.0, w=640, h=480):
+    """Two synthetic frames' keypoints + descriptors: query keypoint i re-observes train keypoint perm[i] (descriptor with a few
+    bit flips, angle turned by ~rot degrees, octave within +-1, position moved by a small shift); 20 % of the queries are new."""
+    rng = np.random.default_rng(seed)
+    t_desc = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+    t_kps = np.zeros(nt, KP_DTYPE)
+    t_kps["x"], t_kps["y"] = rng.uniform(20, w - 20, nt), rng.uniform(20, h - 20, nt)
+    t_kps["octave"] = rng.integers(0, 8, nt)
+    t_kps["angle"] = rng.uniform(0, 360, nt)
+    t_kps["size"] = 31 * np.float32(1.2) ** t_kps["octave"]
+    t_kps["class_id"] = -1
+    src = rng.integers(0, nt, nq)
+    q_desc = t_desc[src].copy()
+    for i in range(nq):
+        nf = int(rng.integers(0, max_flips + 1))
+        bits = rng.integers(0, 256, nf)
+        for b in bits:
+            q_desc[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    fresh = rng.random(nq) < 0.2
+    q_desc[fresh] = rng.integers(0, 256, (int(fresh.sum()), 32), dtype=np.uint8)
+    q_kps = t_kps[src].copy()
+    q_kps["x"] += rng.normal(3, 1, nq).astype(np.float32)
+    q_kps["y"] += rng.normal(-2, 1, nq).astype(np.float32)
+    q_kps["octave"] = np.clip(q_kps["octave"] + rng.integers(-1, 2, nq) * (rng.random(nq) < 0.3), 0, 7)
+    ang = t_kps["angle"][src] - rot + rng.normal(0, 6, nq) + (rng.random(nq) < 0.1) * rng.uniform(0, 360, nq)
+    q_kps["angle"] = np.mod(ang, 360).astype(np.float32)
+    return q_desc, q_kps, t_desc, t_kps
+
+
+def frame_match(q_desc, q_kps, t_desc, t_kps, min_desc_dist=50.0, ratio=0.8, check_orientation=True, max_octave_diff=1, F12=None,
+                scale_factors=None, q_map=None, t_map=None):
+    """oracle/match_oracle.c on (n,32) uint8 descriptors and KP_DTYPE keypoints -> MATCH_DTYPE records."""
+    lib = load_oracle()
+    q_desc = np.ascontiguousarray(q_desc, np.uint8).reshape(-1, 32)
+    t_desc = np.ascontiguousarray(t_desc, np.uint8).reshape(-1, 32)
+    q_kps, t_kps = np.ascontiguousarray(q_kps, KP_DTYPE), np.ascontiguousarray(t_kps, KP_DTYPE)
+    sf = np.asarray(scale_factors if scale_factors is not None else [np.float32(1.2) ** i for i in range(8)], np.float32)
+    f12 = None if F12 is None else np.ascontiguousarray(F12, np.float32).reshape(9)
+    qm = None if q_map is None else np.ascontiguousarray(q_map, np.int32)
+    tm = None if t_map is None else np.ascontiguousarray(t_map, np.int32)
+    out = np.zeros(max(len(q_desc), 1), MATCH_DTYPE)
+    P = lambda a: None if a is None else _p(a)
+    n = lib.oracle_frame_match(_p(q_desc), len(q_desc), _sz(32), _p(q_kps), P(qm), _p(t_desc), len(t_desc), _sz(32), _p(t_kps), P(tm),
+                               ctypes.c_float(min_desc_dist), ctypes.c_float(ratio), int(check_orientation), int(max_octave_diff),
+                               P(f12), _p(sf), len(sf), _p(out))
+    return out[:n].copy()

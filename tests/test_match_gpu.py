@@ -1,0 +1,88 @@
+"""Parity of the sm_100a frame matcher (uco_b200_frame_match{,_batch_dev}: exact k-NN + FrameMatcher_Flann's post-filters)
+against oracle/match_oracle.c on seeded frames: bit-exact cv::DMatch records (indices, order, distances)."""
+import numpy as np
+import pytest
+import torch
+import oracle_py
+import ucoslam_b200
+
+pytestmark = pytest.mark.gpu
+
+
+def same(a, b):
+    return len(a) == len(b) and all(np.array_equal(a[k], b[k]) for k in ("queryIdx", "trainIdx", "imgIdx", "distance"))
+
+
+F = np.array([[0, -1e-6, 2e-4], [1e-6, 0, -3e-3], [-2e-4, 3.1e-3, 0.01]], np.float32)
+
+
+@pytest.mark.parametrize("seed,nt,nq,kw", [
+    (1, 2000, 2000, dict()),                                                     # config 2: two 2000-keypoint frames
+    (2, 2000, 1777, dict(check_orientation=False)),
+    (3, 1500, 2000, dict(ratio=0.6, max_octave_diff=0)),                         # the tracker's ratio
+    (4, 4000, 4000, dict(min_desc_dist=100.0)),                                  # config 3 size
+    (5, 2000, 2000, dict(F12=F)),                                                # epipolar gate
+    (6, 7, 40, dict(min_desc_dist=300.0)),                                       # fewer train rows than k
+    (7, 1200, 3000, dict(min_desc_dist=60.0, check_orientation=True, max_octave_diff=7)),
+])
+def test_match_equals_oracle(ctx, seed, nt, nq, kw):
+    q, qk, t, tk = oracle_py.synth_match_frames(seed, nt=nt, nq=nq)
+    if seed in (3, 7):
+        t[nt // 2:] = t[:nt - nt // 2]                                           # duplicated rows: ties + ratio test
+    ref = oracle_py.frame_match(q, qk, t, tk, **kw)
+    prm = ucoslam_b200.MatchParams(kw.get("min_desc_dist", 50.0), kw.get("ratio", 0.8), kw.get("check_orientation", True),
+                                   kw.get("max_octave_diff", 1), kw.get("F12"))
+    got = ctx.frame_match(q, qk, t, tk, prm)
+    assert same(got, ref)
+    assert len(ref) > 0
+
+
+def test_match_with_index_maps(ctx):
+    """MODE_ASSIGNED-style subsets: descriptor row i belongs to keypoint map[i] (framematcher.cpp:160-198)"""
+    q, qk, t, tk = oracle_py.synth_match_frames(11, nt=1500, nq=1500)
+    rng = np.random.default_rng(5)
+    qm = np.sort(rng.choice(1500, 900, replace=False)).astype(np.int32)
+    tm = np.sort(rng.choice(1500, 1100, replace=False)).astype(np.int32)
+    ref = oracle_py.frame_match(q[qm], qk, t[tm], tk, q_map=qm, t_map=tm)
+    got = ctx.frame_match(q[qm], qk, t[tm], tk, ucoslam_b200.MatchParams(), q_map=qm, t_map=tm)
+    assert same(got, ref) and len(ref) > 100
+
+
+def test_match_empty(ctx):
+    q, qk, t, tk = oracle_py.synth_match_frames(4, nt=50, nq=20)
+    assert len(ctx.frame_match(q[:0], qk, t, tk, ucoslam_b200.MatchParams())) == 0
+    assert len(ctx.frame_match(q, qk, t[:0], tk, ucoslam_b200.MatchParams())) == 0
+
+
+def test_match_batch_dev_equals_oracle(ctx):
+    """a clip: frame p+1 against frame p for every p, one launch pair, ragged keypoint counts from device arrays"""
+    n, cap = 6, 800
+    frames = [oracle_py.synth_match_frames(20 + i, nt=cap, nq=cap)[2:] for i in range(n)]
+    counts = np.array([800, 640, 800, 1, 333, 800], np.int32)
+    desc = np.zeros((n, cap, 32), np.uint8)
+    kps = np.zeros((n, cap), ucoslam_b200.KP_DTYPE)
+    for i, (d, k) in enumerate(frames):
+        desc[i], kps[i] = d, k
+        if i:  # make frame i a re-observation of frame i-1
+            m = min(counts[i], counts[i - 1])
+            desc[i, :m] = desc[i - 1, :m]
+            desc[i, :m, 3] ^= 0x11
+            kps[i]["angle"][:m] = np.mod(kps[i - 1]["angle"][:m] + 10, 360)
+            kps[i]["octave"][:m] = kps[i - 1]["octave"][:m]
+    d_desc = torch.from_numpy(desc).cuda()
+    d_kps = torch.from_numpy(kps.view(np.uint8).reshape(n, cap * 28)).cuda()
+    d_cnt = torch.from_numpy(counts).cuda()
+    out = torch.zeros((n - 1) * cap * 16, dtype=torch.uint8, device="cuda")
+    nout = torch.zeros(n - 1, dtype=torch.int32, device="cuda")
+    prm = ucoslam_b200.MatchParams()
+    torch.cuda.synchronize()
+    ctx.frame_match_batch_dev(n - 1, d_desc.data_ptr() + cap * 32, cap * 32, d_kps.data_ptr() + cap * 28, cap, cap,
+                              d_cnt.data_ptr() + 4, d_desc.data_ptr(), cap * 32, d_kps.data_ptr(), cap, cap, d_cnt.data_ptr(), prm,
+                              out.data_ptr(), nout.data_ptr())
+    ctx.sync()
+    res = out.cpu().numpy().view(ucoslam_b200.MATCH_DTYPE).reshape(n - 1, cap)
+    cnt = nout.cpu().numpy()
+    for p in range(n - 1):
+        nq, nt = counts[p + 1], counts[p]
+        ref = oracle_py.frame_match(desc[p + 1, :nq], kps[p + 1], desc[p, :nt], kps[p])
+        assert cnt[p] == len(ref) and same(res[p, :cnt[p]], ref), p

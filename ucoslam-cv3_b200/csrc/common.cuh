@@ -37,6 +37,7 @@ enum {  // device workspace slots
     WS_GENERIC0, WS_GENERIC1, WS_GENERIC2, WS_GENERIC3,
     WS_BA, WS_BA_OUT, WS_BA_STOP,
     WS_PNP_IN, WS_PNP_OUT, WS_PNP_SCRATCH,
+    WS_MATCH_KNN, WS_MATCH_SCRATCH, WS_MATCH_IN, WS_MATCH_OUT,
     WS_COUNT
 };
 

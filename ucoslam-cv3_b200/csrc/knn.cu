@@ -265,6 +265,13 @@ static int knn_launch(uco_b200_ctx* ctx, const uint8_t* q_dev, int nq, const uin
     return UCO_OK;
 }
 
+// used by match.cu (K8 = K7 + post-filters)
+int uco_knn_launch_internal(uco_b200_ctx* ctx, const uint8_t* q_dev, int nq, const uint8_t* t_dev, int nt, int k, int order,
+                            int32_t* idx_dev, int32_t* dist_dev, int n_pairs, const int* nq_dev, const int* nt_dev,
+                            size_t q_stride, size_t t_stride) {
+    return knn_launch(ctx, q_dev, nq, t_dev, nt, k, order, idx_dev, dist_dev, n_pairs, nq_dev, nt_dev, q_stride, t_stride);
+}
+
 extern "C" int uco_b200_hamming_knn_dev(uco_b200_ctx* ctx, const uint8_t* q_dev, int nq, const uint8_t* t_dev, int nt,
                                         int k, int order, int32_t* idx_dev, int32_t* dist_dev) {
     return knn_launch(ctx, q_dev, nq, t_dev, nt, k, order, idx_dev, dist_dev, 1, nullptr, nullptr, 0, 0);

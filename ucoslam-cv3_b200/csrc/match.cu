@@ -1,0 +1,265 @@
+// match.cu — K8: frame-to-frame descriptor matcher = exact Hamming k-NN (knn.cu) + the post-filters of
+// FrameMatcher_Flann::matchEpipolar (src/utils/framematcher.cpp:228-322), all on the device.
+//
+// One thread block per frame pair.  The reference's sequential passes are restated as order-independent operations with the
+// same result:
+//   * per query (framematcher.cpp:246-283): the k candidates are scanned in the order the index returned them (the heap
+//     order knn.cu reproduces exactly) — one thread per query;
+//   * filter_ambiguous_train (misc.cpp:153-185) keeps, per train keypoint, the match of least distance and among equals the
+//     one met first: that is the minimum of (distance, query position), taken with a 64-bit atomicMin — integer, so
+//     independent of thread order;
+//   * the rotation histogram (:288-316) needs only bin COUNTS (integer atomics) before the three maxima are chosen;
+//   * remove_unused_matches is a stable compaction: block-wide prefix sums over query order.
+#include "common.cuh"
+#include <float.h>
+
+int uco_knn_launch_internal(uco_b200_ctx* ctx, const uint8_t* q_dev, int nq, const uint8_t* t_dev, int nt, int k, int order,
+                            int32_t* idx_dev, int32_t* dist_dev, int n_pairs, const int* nq_dev, const int* nt_dev,
+                            size_t q_stride, size_t t_stride);
+
+namespace {
+
+constexpr int MT = 1024;  // threads per block
+constexpr int NN = 10;    // framematcher.cpp:122
+constexpr int NBINS = 30;
+
+struct MatchArgs {
+    const int32_t* knn_idx;   // n_pairs x nq_max x NN
+    const int32_t* knn_dist;
+    const uco_keypoint* q_kps; size_t q_kps_stride;
+    const uco_keypoint* t_kps; size_t t_kps_stride;
+    const int32_t* q_map;     // optional (single pair)
+    const int32_t* t_map;
+    int nq_max, nt_max, n_t_kps;   // n_t_kps: size of the `used` table of a pair
+    const int32_t* nq_dev; const int32_t* nt_dev;
+    unsigned long long* used; // n_pairs x n_t_kps
+    int2* cand;               // n_pairs x nq_max : (train keypoint or -1, distance)
+    uco_match* out;           // n_pairs x nq_max
+    int32_t* n_out;
+    uco_match_params prm;
+};
+
+__device__ __forceinline__ float epipolar_sq_dist(const uco_keypoint& kp1, const uco_keypoint& kp2, const float* F) {  // misc.h:72-81
+    const float a = kp1.x * F[0] + kp1.y * F[3] + F[6];
+    const float b = kp1.x * F[1] + kp1.y * F[4] + F[7];
+    const float den = a * a + b * b;
+    if (den == 0) return FLT_MAX;
+    const float c = kp1.x * F[2] + kp1.y * F[5] + F[8];
+    const float num = a * kp2.x + b * kp2.y + c;
+    return num * num / den;
+}
+
+__global__ void __launch_bounds__(MT) match_filter_kernel(MatchArgs A) {
+    __shared__ int hist[NBINS];
+    __shared__ int keep[3];
+    __shared__ int warp_tot[MT / 32];
+    __shared__ int running;
+    const int pair = blockIdx.x, tid = threadIdx.x;
+    const int nq = A.nq_dev ? min(A.nq_max, A.nq_dev[pair]) : A.nq_max;
+    const int nt = A.nt_dev ? min(A.nt_max, A.nt_dev[pair]) : A.nt_max;
+    const int32_t* kidx = A.knn_idx + (size_t)pair * A.nq_max * NN;
+    const int32_t* kdist = A.knn_dist + (size_t)pair * A.nq_max * NN;
+    const uco_keypoint* qk = A.q_kps + (size_t)pair * A.q_kps_stride;
+    const uco_keypoint* tk = A.t_kps + (size_t)pair * A.t_kps_stride;
+    unsigned long long* used = A.used + (size_t)pair * A.n_t_kps;
+    int2* cand = A.cand + (size_t)pair * A.nq_max;
+    uco_match* out = A.out + (size_t)pair * A.nq_max;
+    const uco_match_params& P = A.prm;
+
+    for (int t = tid; t < A.n_t_kps; t += MT) used[t] = ~0ull;
+    if (tid < NBINS) hist[tid] = 0;
+    if (tid == 0) running = 0;
+    __syncthreads();
+    // per query: best / second best among the k candidates (framematcher.cpp:246-283)
+    for (int i = tid; i < nq; i += MT) {
+        float bestDist = P.min_desc_dist, bestDist2 = FLT_MAX;
+        int bestTrain = -1, octaveBest2 = -1;
+        const int queryIndex = A.q_map ? A.q_map[i] : i;
+        const uco_keypoint q = qk[queryIndex];
+        for (int j = 0; j < NN; j++) {
+            const int ti = kidx[i * NN + j];
+            if (ti < 0 || ti >= nt) continue;
+            const float d = (float)kdist[i * NN + j];
+            if (d > P.min_desc_dist) continue;
+            if (d < bestDist2) {
+                const int trainIndex = A.t_map ? A.t_map[ti] : ti;
+                const uco_keypoint t = tk[trainIndex];
+                if (abs(t.octave - q.octave) > P.max_octave_diff) continue;
+                if (P.use_f12) {
+                    const float sf = P.scale_factors[min(max(q.octave, 0), UCO_MATCH_MAX_SCALES - 1)];
+                    if ((double)epipolar_sq_dist(t, q, P.f12) >= 3.84 * (double)(sf * sf)) continue;
+                }
+                if (d < bestDist) { bestDist = d; bestTrain = trainIndex; }
+                else { bestDist2 = d; octaveBest2 = t.octave; }
+            }
+        }
+        if (bestTrain != -1 && (octaveBest2 == q.octave && bestDist > bestDist2 * P.nn_match_ratio)) bestTrain = -1;
+        cand[i] = make_int2(bestTrain, (int)bestDist);
+        if (bestTrain != -1) atomicMin(&used[bestTrain], ((unsigned long long)(unsigned)(int)bestDist << 32) | (unsigned)i);
+    }
+    __syncthreads();
+    // survivors of filter_ambiguous_train and their rotation bin (:292-304); cand.x < 0 marks a dropped query
+    for (int i = tid; i < nq; i += MT) {
+        int2 c = cand[i];
+        if (c.x < 0) continue;
+        if (used[c.x] != (((unsigned long long)(unsigned)c.y << 32) | (unsigned)i)) { cand[i].x = -1; continue; }
+        if (P.check_orientation) {
+            const int queryIndex = A.q_map ? A.q_map[i] : i;
+            float rot = tk[c.x].angle - qk[queryIndex].angle;
+            if (rot < 0.0f) rot += 360.0f;
+            int bin = (int)roundf(rot * (1.0f / (float)NBINS));
+            if (bin == NBINS) bin = 0;
+            atomicAdd(&hist[bin], 1);
+            cand[i].y = c.y | (bin << 16);  // distance <= 256 fits the low half
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {  // ucoslam_FM___computeThreeMaxima, framematcher.cpp:67-108
+        int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < NBINS; i++) {
+            const int s = hist[i];
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+            else if (s > max3) { max3 = s; ind3 = i; }
+        }
+        if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if (max3 < 0.1f * (float)max1) ind3 = -1;
+        keep[0] = ind1; keep[1] = ind2; keep[2] = ind3;
+    }
+    __syncthreads();
+    // stable compaction in query order
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int base = 0; base < nq; base += MT) {
+        const int i = base + tid;
+        bool flag = false;
+        int2 c = make_int2(-1, 0);
+        if (i < nq) {
+            c = cand[i];
+            flag = c.x >= 0;
+            if (flag && P.check_orientation) {
+                const int bin = c.y >> 16;
+                flag = bin == keep[0] || bin == keep[1] || bin == keep[2];
+            }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, flag);
+        if (lane == 0) warp_tot[warp] = __popc(bal);
+        __syncthreads();
+        int before = running;
+        for (int w = 0; w < warp; w++) before += warp_tot[w];
+        if (flag) {
+            uco_match m;
+            m.queryIdx = A.q_map ? A.q_map[i] : i;
+            m.trainIdx = c.x;
+            m.imgIdx = -1;
+            m.distance = (float)(c.y & 0xffff);
+            out[before + __popc(bal & ((1u << lane) - 1))] = m;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int tot = 0;
+            for (int w = 0; w < MT / 32; w++) tot += warp_tot[w];
+            running += tot;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) A.n_out[pair] = running;
+}
+
+int check_params(uco_b200_ctx* ctx, const uco_match_params* prm) {
+    if (!prm) return uco_fail(ctx, UCO_E_INVALID, "frame_match: no parameters");
+    if (prm->n_scales < 0 || prm->n_scales > UCO_MATCH_MAX_SCALES) return uco_fail(ctx, UCO_E_INVALID, "frame_match: n_scales out of range");
+    if (!(prm->min_desc_dist <= 65535.f)) return uco_fail(ctx, UCO_E_INVALID, "frame_match: min_desc_dist out of range");
+    return UCO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int uco_b200_frame_match_batch_dev(uco_b200_ctx* ctx, int n_pairs, const uint8_t* q_desc_dev, size_t q_pair_stride,
+                                   const uco_keypoint* q_kps_dev, size_t q_kps_pair_stride, int nq_max, const int32_t* nq_dev,
+                                   const uint8_t* t_desc_dev, size_t t_pair_stride, const uco_keypoint* t_kps_dev,
+                                   size_t t_kps_pair_stride, int nt_max, const int32_t* nt_dev, const uco_match_params* prm,
+                                   uco_match* out_dev, int32_t* n_out_dev) {
+    if (!ctx) return UCO_E_INVALID;
+    cudaSetDevice(ctx->device);  // the calling thread may be a new one (mapper / tracker threads): bind it to the context's GPU
+    int rc = check_params(ctx, prm);
+    if (rc) return rc;
+    if (n_pairs <= 0 || nq_max <= 0 || nt_max <= 0) return uco_fail(ctx, UCO_E_INVALID, "frame_match: bad sizes");
+    if (!q_desc_dev || !q_kps_dev || !t_desc_dev || !t_kps_dev || !out_dev || !n_out_dev) return uco_fail(ctx, UCO_E_INVALID, "frame_match: null pointer");
+    const size_t knn_elems = (size_t)n_pairs * nq_max * NN;
+    int32_t* knn = (int32_t*)uco_ws(ctx, WS_MATCH_KNN, knn_elems * 8);
+    const size_t used_bytes = (size_t)n_pairs * nt_max * 8, cand_bytes = (size_t)n_pairs * nq_max * 8;
+    uint8_t* scr = (uint8_t*)uco_ws(ctx, WS_MATCH_SCRATCH, used_bytes + cand_bytes);
+    if (!knn || !scr) return UCO_E_NOMEM;
+    rc = uco_knn_launch_internal(ctx, q_desc_dev, nq_max, t_desc_dev, nt_max, NN, UCO_KNN_HEAP, knn, knn + knn_elems, n_pairs, nq_dev,
+                                 nt_dev, q_pair_stride, t_pair_stride);
+    if (rc) return rc;
+    MatchArgs A;
+    A.knn_idx = knn; A.knn_dist = knn + knn_elems;
+    A.q_kps = q_kps_dev; A.q_kps_stride = q_kps_pair_stride; A.t_kps = t_kps_dev; A.t_kps_stride = t_kps_pair_stride;
+    A.q_map = nullptr; A.t_map = nullptr;
+    A.nq_max = nq_max; A.nt_max = nt_max; A.n_t_kps = nt_max; A.nq_dev = nq_dev; A.nt_dev = nt_dev;
+    A.used = (unsigned long long*)scr; A.cand = (int2*)(scr + used_bytes);
+    A.out = out_dev; A.n_out = n_out_dev; A.prm = *prm;
+    match_filter_kernel<<<n_pairs, MT, 0, ctx->stream>>>(A);
+    UCO_LAUNCH_CHECK(ctx);
+    return UCO_OK;
+}
+
+int uco_b200_frame_match(uco_b200_ctx* ctx, const uint8_t* q_desc, int nq, size_t q_stride, const uco_keypoint* q_kps,
+                         int n_q_kps, const int32_t* q_map, const uint8_t* t_desc, int nt, size_t t_stride,
+                         const uco_keypoint* t_kps, int n_t_kps, const int32_t* t_map, const uco_match_params* prm,
+                         uco_match* out, int capacity, int* n_out) {
+    if (!ctx) return UCO_E_INVALID;
+    cudaSetDevice(ctx->device);  // the calling thread may be a new one (mapper / tracker threads): bind it to the context's GPU
+    int rc = check_params(ctx, prm);
+    if (rc) return rc;
+    if (!n_out) return uco_fail(ctx, UCO_E_INVALID, "frame_match: null pointer");
+    *n_out = 0;
+    if (nq < 0 || nt < 0 || n_q_kps < 0 || n_t_kps < 0) return uco_fail(ctx, UCO_E_INVALID, "frame_match: bad sizes");
+    if (nq == 0 || nt == 0) return UCO_OK;  // trainIndex.search fails on an empty index -> {} (framematcher.cpp:239)
+    if (!q_desc || !q_kps || !t_desc || !t_kps || !out) return uco_fail(ctx, UCO_E_INVALID, "frame_match: null pointer");
+    if (q_stride < 32 || t_stride < 32) return uco_fail(ctx, UCO_E_INVALID, "frame_match: row stride below 32 bytes");
+    if (capacity < nq) return uco_fail(ctx, UCO_E_CAPACITY, "frame_match: output capacity %d below the %d query rows", capacity, nq);
+    if ((!q_map && n_q_kps < nq) || (!t_map && n_t_kps < nt)) return uco_fail(ctx, UCO_E_INVALID, "frame_match: fewer keypoints than descriptor rows");
+    for (int i = 0; q_map && i < nq; i++)
+        if (q_map[i] < 0 || q_map[i] >= n_q_kps) return uco_fail(ctx, UCO_E_INVALID, "frame_match: q_map[%d] out of range", i);
+    for (int i = 0; t_map && i < nt; i++)
+        if (t_map[i] < 0 || t_map[i] >= n_t_kps) return uco_fail(ctx, UCO_E_INVALID, "frame_match: t_map[%d] out of range", i);
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t o_qd = 0, o_td = al(o_qd + (size_t)nq * 32), o_qk = al(o_td + (size_t)nt * 32), o_tk = al(o_qk + sizeof(uco_keypoint) * n_q_kps),
+                 o_qm = al(o_tk + sizeof(uco_keypoint) * n_t_kps), o_tm = al(o_qm + 4 * (size_t)nq), in_bytes = al(o_tm + 4 * (size_t)nt);
+    uint8_t* din = (uint8_t*)uco_ws(ctx, WS_MATCH_IN, in_bytes);
+    const size_t knn_elems = (size_t)nq * NN;
+    int32_t* knn = (int32_t*)uco_ws(ctx, WS_MATCH_KNN, knn_elems * 8);
+    const size_t used_bytes = (size_t)n_t_kps * 8, cand_bytes = (size_t)nq * 8;
+    uint8_t* scr = (uint8_t*)uco_ws(ctx, WS_MATCH_SCRATCH, used_bytes + cand_bytes);
+    uint8_t* dout = (uint8_t*)uco_ws(ctx, WS_MATCH_OUT, sizeof(uco_match) * (size_t)nq + 16);
+    if (!din || !knn || !scr || !dout) return UCO_E_NOMEM;
+    UCO_CUDA(ctx, cudaMemcpy2DAsync(din + o_qd, 32, q_desc, q_stride, 32, nq, cudaMemcpyHostToDevice, ctx->stream));
+    UCO_CUDA(ctx, cudaMemcpy2DAsync(din + o_td, 32, t_desc, t_stride, 32, nt, cudaMemcpyHostToDevice, ctx->stream));
+    UCO_CUDA(ctx, cudaMemcpyAsync(din + o_qk, q_kps, sizeof(uco_keypoint) * n_q_kps, cudaMemcpyHostToDevice, ctx->stream));
+    UCO_CUDA(ctx, cudaMemcpyAsync(din + o_tk, t_kps, sizeof(uco_keypoint) * n_t_kps, cudaMemcpyHostToDevice, ctx->stream));
+    if (q_map) UCO_CUDA(ctx, cudaMemcpyAsync(din + o_qm, q_map, 4 * (size_t)nq, cudaMemcpyHostToDevice, ctx->stream));
+    if (t_map) UCO_CUDA(ctx, cudaMemcpyAsync(din + o_tm, t_map, 4 * (size_t)nt, cudaMemcpyHostToDevice, ctx->stream));
+    rc = uco_knn_launch_internal(ctx, din + o_qd, nq, din + o_td, nt, NN, UCO_KNN_HEAP, knn, knn + knn_elems, 1, nullptr, nullptr, 0, 0);
+    if (rc) return rc;
+    MatchArgs A;
+    A.knn_idx = knn; A.knn_dist = knn + knn_elems;
+    A.q_kps = (const uco_keypoint*)(din + o_qk); A.q_kps_stride = 0; A.t_kps = (const uco_keypoint*)(din + o_tk); A.t_kps_stride = 0;
+    A.q_map = q_map ? (const int32_t*)(din + o_qm) : nullptr; A.t_map = t_map ? (const int32_t*)(din + o_tm) : nullptr;
+    A.nq_max = nq; A.nt_max = nt; A.n_t_kps = n_t_kps; A.nq_dev = nullptr; A.nt_dev = nullptr;
+    A.used = (unsigned long long*)scr; A.cand = (int2*)(scr + used_bytes);
+    A.out = (uco_match*)(dout + 16); A.n_out = (int32_t*)dout; A.prm = *prm;
+    match_filter_kernel<<<1, MT, 0, ctx->stream>>>(A);
+    UCO_LAUNCH_CHECK(ctx);
+    int n = 0;
+    UCO_CUDA(ctx, cudaMemcpyAsync(&n, dout, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    UCO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n > 0) UCO_CUDA(ctx, cudaMemcpy(out, dout + 16, sizeof(uco_match) * (size_t)n, cudaMemcpyDeviceToHost));
+    *n_out = n;
+    return UCO_OK;
+}
+
+}  // extern "C"

@@ -48,6 +48,8 @@ SIGNATURES = {
     "uco_b200_ba_set_mode": (_i, [_vp, _i, _i]),
     "uco_b200_probe_ba_plan": (_i, [_vp, _i, _vp]),
     "uco_b200_pose_only": (_i, [_vp, _vp, _vp]),
+    "uco_b200_frame_match": (_i, [_vp, _vp, _i, _sz, _vp, _i, _vp, _vp, _i, _sz, _vp, _i, _vp, _vp, _vp, _i, _vp]),
+    "uco_b200_frame_match_batch_dev": (_i, [_vp, _i, _vp, _sz, _vp, _sz, _i, _vp, _vp, _sz, _vp, _sz, _i, _vp, _vp, _vp, _vp]),
     "uco_b200_pose_only_batch": (_i, [_vp, _i, _vp, _vp]),
     "uco_b200_probe_math": (_i, [_i, _vp, _vp, _i, _vp, _vp]),
     "uco_b200_probe_retain_best": (_i, [_vp, _i, _i]),
@@ -111,6 +113,23 @@ class BaProblem(ctypes.Structure):  # uco_ba_problem
 class BaResult(ctypes.Structure):  # uco_ba_result
     _fields_ = [("pose7", _vp), ("poses44", _vp), ("points3", _vp), ("obs_chi2", _vp), ("obs_level", _vp), ("obs_bad", _vp),
                 ("trace", _vp), ("iters", _c.c_int32 * 2), ("device_ms", _c.c_float), ("profile", _vp)]
+
+
+MATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])  # uco_match == cv::DMatch
+
+
+class MatchParams(ctypes.Structure):  # uco_match_params
+    _fields_ = [("min_desc_dist", _c.c_float), ("nn_match_ratio", _c.c_float), ("check_orientation", _c.c_int32),
+                ("max_octave_diff", _c.c_int32), ("use_f12", _c.c_int32), ("f12", _c.c_float * 9), ("n_scales", _c.c_int32),
+                ("scale_factors", _c.c_float * 32)]
+
+    def __init__(self, min_desc_dist=50.0, ratio=0.8, check_orientation=True, max_octave_diff=1, F12=None, scale_factors=None):
+        super().__init__(min_desc_dist, ratio, int(check_orientation), max_octave_diff, int(F12 is not None))
+        if F12 is not None:
+            self.f12 = (_c.c_float * 9)(*[float(v) for v in np.asarray(F12, np.float32).reshape(9)])
+        sf = np.asarray(scale_factors if scale_factors is not None else [np.float32(1.2) ** i for i in range(8)], np.float32)
+        self.n_scales = len(sf)
+        self.scale_factors = (_c.c_float * 32)(*([float(v) for v in sf] + [1.0] * (32 - len(sf))))
 
 
 class PnpProblem(ctypes.Structure):  # uco_pnp_problem
@@ -233,6 +252,27 @@ class Context:
         cps = (BaProblem * len(packs))(*[p[0] for p in packs])
         crs = (BaResult * len(packs))(*[p[1] for p in packs])
         return cps, crs, [p[2] for p in packs], [p[3] for p in packs]
+
+    # -- K8 ------------------------------------------------------------------------------------------------------
+    def frame_match(self, q_desc, q_kps, t_desc, t_kps, prm, q_map=None, t_map=None):
+        """FrameMatcher_Flann::setParams(train) + matchEpipolar(query): (n,) MATCH_DTYPE records in the reference's order."""
+        q_desc = np.ascontiguousarray(q_desc, np.uint8).reshape(-1, 32)
+        t_desc = np.ascontiguousarray(t_desc, np.uint8).reshape(-1, 32)
+        q_kps, t_kps = np.ascontiguousarray(q_kps, KP_DTYPE), np.ascontiguousarray(t_kps, KP_DTYPE)
+        qm = None if q_map is None else np.ascontiguousarray(q_map, np.int32)
+        tm = None if t_map is None else np.ascontiguousarray(t_map, np.int32)
+        out = np.zeros(max(len(q_desc), 1), MATCH_DTYPE)
+        n = _c.c_int(0)
+        self._chk(self.lib.uco_b200_frame_match(self.h, _p(q_desc), len(q_desc), 32, _p(q_kps), len(q_kps), _p(qm), _p(t_desc),
+                                                len(t_desc), 32, _p(t_kps), len(t_kps), _p(tm), ctypes.addressof(prm), _p(out),
+                                                len(out), ctypes.addressof(n)))
+        return out[:n.value].copy()
+
+    def frame_match_batch_dev(self, n_pairs, q_desc_dev, q_stride, q_kps_dev, q_kps_stride, nq_max, nq_dev, t_desc_dev, t_stride,
+                              t_kps_dev, t_kps_stride, nt_max, nt_dev, prm, out_dev, n_out_dev):
+        self._chk(self.lib.uco_b200_frame_match_batch_dev(self.h, n_pairs, _p(q_desc_dev), q_stride, _p(q_kps_dev), q_kps_stride,
+                                                          nq_max, _p(nq_dev), _p(t_desc_dev), t_stride, _p(t_kps_dev), t_kps_stride,
+                                                          nt_max, _p(nt_dev), ctypes.addressof(prm), _p(out_dev), _p(n_out_dev)))
 
     # -- K14 -----------------------------------------------------------------------------------------------------
     @staticmethod
