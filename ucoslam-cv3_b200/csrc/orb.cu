@@ -165,9 +165,31 @@ __global__ void __launch_bounds__(256) resize_cubic_kernel(const __grid_constant
 
 // ---- K3 + K4a: FAST-9/16 corner score on each grid cell's interior + 3x3 non-maximum suppression clipped to the cell
 // (cv::FAST is called per cell ROI, ORBextractor.cpp:976-986, so neighbours in the adjacent cell never suppress) + ordered
-// compaction (row-major, the order cv::FAST emits) --------------------------------------------------------------------------
+// compaction (row-major, the order cv::FAST emits).
+// The kernel is integer-ALU bound, so the work is arranged to keep every issued instruction useful:
+//   1. decision, four horizontally adjacent pixels per thread in packed bytes: the 16 ring pixels arrive as 21 aligned 32-bit
+//      shared-memory words + funnel shifts, "brighter than v+th" / "darker than v-th" are byte-wise unsigned compares whose
+//      result sits in bit 7 of every byte, and the "9 contiguous of 16" test is 2 x 40 three-input LOPs on those words (a
+//      rotation of the ring is a renaming of registers).  ~65 instructions per pixel, no divergence.
+//   2. only the pixels that passed (a few percent) are appended to a list and scored afterwards by dense warps, on packed
+//      (d, -d) 16-bit pairs so that one VIMNMX3.S16x2 advances the "min over the arc" of both polarities.
+//   3. non-maximum suppression and the ordered output walk the corner bit mask (one thread per 32 pixels).
+__device__ __forceinline__ unsigned gtu4(unsigned a, unsigned b) {  // bit 7 of every byte: a > b (unsigned); other bits undefined
+    unsigned t = (a & 0x7f7f7f7fu) + (~b & 0x7f7f7f7fu);
+    return (a & ~b) | (~(a ^ b) & t);
+}
+__device__ __forceinline__ unsigned arc9(const unsigned (&m)[16]) {  // bit 7 of byte j set iff 9 circularly contiguous m[k] have it
+    unsigned r3[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) r3[k] = m[k] & m[(k + 1) & 15] & m[(k + 2) & 15];
+    unsigned any = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) any |= r3[k] & r3[(k + 3) & 15] & r3[(k + 6) & 15];
+    return any;
+}
+// score = max(th, A, B) - 1 with A = max over the 16 arcs of 9 of min(d), B = max over arcs of min(-d) (cv cornerScore<16>),
+// d = centre - ring.  x[k] packs (d, -d) as s16x2; arcs k..k+8 and k+1..k+9 share the min over k+1..k+8.
 __device__ __forceinline__ int fast_score(const uint8_t* p, int pitch, int th) {
-    // ring offsets of the 16-pixel Bresenham circle, starting at (0,3) going clockwise as OpenCV's makeOffsets
     const int v = p[0];
     int d[16];
     d[0] = v - p[3 * pitch];
@@ -186,45 +208,34 @@ __device__ __forceinline__ int fast_score(const uint8_t* p, int pitch, int th) {
     d[13] = v - p[pitch - 3];
     d[14] = v - p[2 * pitch - 2];
     d[15] = v - p[3 * pitch - 1];
-    unsigned dark = 0, bright = 0;  // ring pixel darker than v - th  /  brighter than v + th
+    unsigned x[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
-        dark |= (unsigned)(d[k] > th) << k;
-        bright |= (unsigned)(d[k] < -th) << k;
+    for (int k = 0; k < 16; k++) x[k] = __byte_perm((unsigned)d[k], (unsigned)(-d[k]), 0x5410);
+    unsigned best = 0xff00ff00u;  // (-256, -256)
+#pragma unroll
+    for (int k = 0; k < 16; k += 2) {
+        unsigned a = __vimin3_s16x2(x[(k + 1) & 15], x[(k + 2) & 15], x[(k + 3) & 15]);
+        a = __vimin3_s16x2(a, x[(k + 4) & 15], x[(k + 5) & 15]);
+        a = __vimin3_s16x2(a, x[(k + 6) & 15], x[(k + 7) & 15]);
+        a = __vmins2(a, x[(k + 8) & 15]);
+        best = __vimax3_s16x2(best, __vmins2(a, x[k]), __vmins2(a, x[(k + 9) & 15]));
     }
-    // 9 contiguous (circular) set bits?
-    unsigned md = dark | (dark << 16), mb = bright | (bright << 16);
-    unsigned rd = md & (md >> 1);
-    rd &= rd >> 2;
-    rd &= rd >> 4;
-    rd &= md >> 8;
-    unsigned rb = mb & (mb >> 1);
-    rb &= rb >> 2;
-    rb &= rb >> 4;
-    rb &= mb >> 8;
-    if (((rd | rb) & 0xffffu) == 0) return 0;
-    // score = max(th, A, B) - 1 with A = max over the 16 arcs of 9 of min(d), B = max over arcs of min(-d) = -min over arcs of
-    // max(d)  (cv cornerScore<16>).  B - 1 is formed as ~x (= -x - 1): ptxas 12.9 for sm_100a was observed to fold
-    // max(a, -b) into VIMNMX3 and LOSE the negation, so no negated value is ever fed to min/max here.
-    int a_best = -256, b_worst = 256;
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-        int mn = d[k], mx = d[k];
-#pragma unroll
-        for (int j = 1; j < 9; j++) {
-            int e = d[(k + j) & 15];
-            mn = min(mn, e);
-            mx = max(mx, e);
-        }
-        a_best = max(a_best, mn);
-        b_worst = min(b_worst, mx);
-    }
-    return max(max(th, a_best) - 1, ~b_worst);
+    const int A = (int)(short)(best & 0xffffu), B = (int)(short)(best >> 16);
+    return max(max(th, A), B) - 1;
+}
+
+// shared-memory geometry of a cell (host and device agree through these)
+__host__ __device__ inline int fc_roi_pitch(int cw) { return (cw + 8) & ~3; }            // ROI column c at byte c + 1; slack for the last group
+__host__ __device__ inline int fc_sc_pitch(int iw) { return ((iw + 3) & ~3) + 8; }       // interior column c at byte c + 4, zero frame around
+__host__ __device__ inline int fc_list_cap(int n) { return (max(512, n / 4) + 1) & ~1; }
+__host__ __device__ inline int fc_smem_bytes(int cw, int ch) {
+    const int iw = cw - 6, ih = ch - 6, n = iw * ih;
+    return ch * fc_roi_pitch(cw) + (ih + 2) * fc_sc_pitch(iw) + 4 * ((n + 31) / 32) + 2 * fc_list_cap(n) + 16;
 }
 
 __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__ PlanDev c_plan, const uint8_t* __restrict__ pyr, const CellDev* __restrict__ cells,
                                                          uint32_t* __restrict__ cand, int* __restrict__ cand_cnt) {
-    extern __shared__ uint8_t smem[];
+    extern __shared__ __align__(16) uint8_t smem[];
     const int ci = blockIdx.x, f = blockIdx.y;
     const CellDev C = cells[ci];
     int* cnt = cand_cnt + ((size_t)f * c_plan.n_cells_total + ci) * 2;
@@ -235,70 +246,152 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
     }
     const LevelDev& L = c_plan.lv[C.level];
     const uint8_t* src = pyr + (size_t)f * c_plan.frame_bytes + L.off + (size_t)(C.y0 + ORB_E) * L.pitch + C.x0 + ORB_E;
-    const int rp = (C.w + 3) & ~3;                 // ROI pitch in shared memory
-    uint8_t* roi = smem;                            // C.h x rp
-    uint8_t* sc = smem + (size_t)rp * C.h;          // ih x iw scores
-    for (int i = threadIdx.x; i < C.h * C.w; i += 256) {
-        int r = i / C.w, c = i - r * C.w;
-        roi[r * rp + c] = src[(size_t)r * L.pitch + c];
-    }
-    __syncthreads();
-    const int min_th = c_plan.min_th, ini_th = c_plan.ini_th;
-    for (int i = threadIdx.x; i < iw * ih; i += 256) {
-        int r = i / iw, c = i - r * iw;
-        sc[i] = (uint8_t)fast_score(roi + (r + 3) * rp + c + 3, rp, min_th);
-    }
-    __syncthreads();
+    const int n = iw * ih, nw = (n + 31) >> 5;
+    const int rp = fc_roi_pitch(C.w), sp = fc_sc_pitch(iw), lcap = fc_list_cap(n);
+    uint8_t* roi = smem;                                       // C.h x rp
+    uint8_t* sc = roi + (size_t)rp * C.h;                      // (ih + 2) x sp scores, zero where there is no corner
+    unsigned* cmask = (unsigned*)(sc + (size_t)sp * (ih + 2)); // nw words: pixel i = r * iw + c passed the min_th segment test
+    unsigned short* list = (unsigned short*)(cmask + nw);      // the same pixels, unordered, for the dense scoring pass
+    __shared__ int nlist;
     __shared__ int wsum[8];
     __shared__ int running, running_ini;
-    if (threadIdx.x == 0) running = running_ini = 0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int r = warp; r < C.h; r += 8)
+        for (int c = lane; c < C.w; c += 32) roi[r * rp + c + 1] = src[(size_t)r * L.pitch + c];
+    for (int i = tid; i < ((sp * (ih + 2)) >> 2) + nw; i += 256) ((unsigned*)sc)[i] = 0;  // sc and cmask are contiguous
+    if (tid == 0) nlist = running = running_ini = 0;
     __syncthreads();
-    uint32_t* out = cand + (size_t)f * c_plan.cand_per_frame + C.cand_off;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int base = 0; base < iw * ih; base += 256) {
-        int i = base + threadIdx.x;
-        int s = 0, r = 0, c = 0;
-        bool keep = false;
-        if (i < iw * ih) {
-            r = i / iw;
-            c = i - r * iw;
-            s = sc[i];
-            if (s >= min_th) {
-                keep = true;
+    const int min_th = c_plan.min_th, ini_th = c_plan.ini_th;
+    // 1. segment test, 4 pixels per thread
+    {
+        const int gpr = (iw + 3) >> 2, G = gpr * ih, rpw = rp >> 2;
+        const unsigned gm = (unsigned)((0x100000000ull + gpr - 1) / (unsigned)gpr);  // g / gpr == umulhi(g, gm) for g < 2^16 ...
+        const bool small = G < 65536;
+        const unsigned th4 = (unsigned)min_th * 0x01010101u;
+        for (int g = tid; g < G; g += 256) {
+            const int r = small ? (int)__umulhi((unsigned)g, gm) : g / gpr;
+            const int c0 = (g - r * gpr) << 2;
+            const unsigned* row = (const unsigned*)(roi + (size_t)(r + 3) * rp) + (c0 >> 2) + 1;
+            unsigned ring[16];
+            const unsigned v4 = row[0];
+            {
+                const unsigned* q = row + 3 * rpw;
+                const unsigned a = q[-1], b = q[0], c = q[1];
+                ring[15] = __funnelshift_r(a, b, 24); ring[0] = b; ring[1] = __funnelshift_r(b, c, 8);
+            }
+            {
+                const unsigned* q = row + 2 * rpw;
+                const unsigned a = q[-1], b = q[0], c = q[1];
+                ring[14] = __funnelshift_r(a, b, 16); ring[2] = __funnelshift_r(b, c, 16);
+            }
+            {
+                const unsigned* q = row + rpw;
+                const unsigned a = q[-1], b = q[0], c = q[1];
+                ring[13] = __funnelshift_r(a, b, 8); ring[3] = __funnelshift_r(b, c, 24);
+            }
+            {
+                const unsigned a = row[-1], c = row[1];
+                ring[12] = __funnelshift_r(a, v4, 8); ring[4] = __funnelshift_r(v4, c, 24);
+            }
+            {
+                const unsigned* q = row - rpw;
+                const unsigned a = q[-1], b = q[0], c = q[1];
+                ring[11] = __funnelshift_r(a, b, 8); ring[5] = __funnelshift_r(b, c, 24);
+            }
+            {
+                const unsigned* q = row - 2 * rpw;
+                const unsigned a = q[-1], b = q[0], c = q[1];
+                ring[10] = __funnelshift_r(a, b, 16); ring[6] = __funnelshift_r(b, c, 16);
+            }
+            {
+                const unsigned* q = row - 3 * rpw;
+                const unsigned a = q[-1], b = q[0], c = q[1];
+                ring[9] = __funnelshift_r(a, b, 24); ring[8] = b; ring[7] = __funnelshift_r(b, c, 8);
+            }
+            const unsigned hi = __vaddus4(v4, th4), lo = __vsubus4(v4, th4);  // saturation = "no pixel can be beyond"
+            unsigned m[16];
 #pragma unroll
-                for (int dy = -1; dy <= 1; dy++)
+            for (int k = 0; k < 16; k++) m[k] = gtu4(ring[k], hi);
+            unsigned res = arc9(m);
 #pragma unroll
-                    for (int dx = -1; dx <= 1; dx++) {
-                        if (dx == 0 && dy == 0) continue;
-                        int rr = r + dy, cc = c + dx;
-                        int nb = (rr >= 0 && rr < ih && cc >= 0 && cc < iw) ? sc[rr * iw + cc] : 0;
-                        keep = keep && (s > nb);
-                    }
+            for (int k = 0; k < 16; k++) m[k] = gtu4(lo, ring[k]);
+            res = (res | arc9(m)) & 0x80808080u;
+            while (res) {
+                const int j = (__ffs(res) - 1) >> 3;
+                res &= res - 1;
+                if (c0 + j < iw) {
+                    const int i = r * iw + c0 + j;
+                    atomicOr(&cmask[i >> 5], 1u << (i & 31));
+                    const int pos = atomicAdd(&nlist, 1);
+                    if (pos < lcap && i < 65536) list[pos] = (unsigned short)i;
+                    else sc[(r + 1) * sp + c0 + j + 4] = (uint8_t)fast_score(roi + (r + 3) * rp + c0 + j + 4, rp, min_th);
+                }
             }
         }
-        unsigned m = __ballot_sync(0xffffffffu, keep);
-        unsigned mi = __ballot_sync(0xffffffffu, keep && s >= ini_th);
-        if (lane == 0) wsum[warp] = __popc(m) | (__popc(mi) << 16);
+    }
+    __syncthreads();
+    // 2. scores of the listed pixels, dense
+    {
+        const int nl = min(nlist, lcap);
+        for (int e = tid; e < nl; e += 256) {
+            const int i = list[e];
+            const int r = i / iw, c = i - r * iw;
+            sc[(r + 1) * sp + c + 4] = (uint8_t)fast_score(roi + (r + 3) * rp + c + 4, rp, min_th);
+        }
+    }
+    __syncthreads();
+    // 3. 3x3 non-maximum suppression (strictly greater than all 8 neighbours; the zero frame stands for the ROI edge) and
+    //    ordered emission: a thread owns the 32 pixels of one mask word, a block scan orders the words
+    uint32_t* out = cand + (size_t)f * c_plan.cand_per_frame + C.cand_off;
+    for (int wbase = 0; wbase < nw; wbase += 256) {
+        const int w = wbase + tid;
+        unsigned bits = w < nw ? cmask[w] : 0u, keep = 0, ini = 0;
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const int i = (w << 5) + b;
+            const int r = i / iw, c = i - r * iw;
+            const uint8_t* q = sc + (r + 1) * sp + c + 4;
+            const int s = q[0];
+            const int nb = max(max(max(q[-sp - 1], q[-sp]), max(q[-sp + 1], q[-1])), max(max(q[1], q[sp - 1]), max(q[sp], q[sp + 1])));
+            if (s > nb) {
+                keep |= 1u << b;
+                if (s >= ini_th) ini |= 1u << b;
+            }
+        }
+        const int mine = __popc(keep) | (__popc(ini) << 16);
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
         __syncthreads();
-        int before = running, tot = 0, tot_ini = 0;
+        int before = running, tot = 0;
         for (int k = 0; k < 8; k++) {
-            int ws = wsum[k];
+            const int ws = wsum[k];
             if (k < warp) before += ws & 0xffff;
-            tot += ws & 0xffff;
-            tot_ini += ws >> 16;
+            tot += ws;
         }
-        if (keep) {
-            int pos = before + __popc(m & ((1u << lane) - 1));
-            if (pos < C.cand_cap) out[pos] = ((uint32_t)s << 24) | ((uint32_t)(C.y0 + 3 + r) << 12) | (uint32_t)(C.x0 + 3 + c);
+        int pos = before + ((incl - mine) & 0xffff);
+        while (keep) {
+            const int b = __ffs(keep) - 1;
+            keep &= keep - 1;
+            const int i = (w << 5) + b;
+            const int r = i / iw, c = i - r * iw;
+            const uint32_t s = sc[(r + 1) * sp + c + 4];
+            if (pos < C.cand_cap) out[pos] = (s << 24) | ((uint32_t)(C.y0 + 3 + r) << 12) | (uint32_t)(C.x0 + 3 + c);
+            pos++;
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            running += tot;
-            running_ini += tot_ini;
+        if (tid == 0) {
+            running += tot & 0xffff;
+            running_ini += tot >> 16;
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         cnt[0] = min(running, C.cand_cap);
         cnt[1] = running_ini;
     }
@@ -685,7 +778,7 @@ static int orb_prepare(uco_b200_ctx* ctx, int w, int h, const uco_orb_params* pr
                 C.cand_off = cand_off;
                 C.cand_cap = ((iw + 1) / 2) * ((ih + 1) / 2) + 1;
                 cand_off += C.cand_cap;
-                int smem = ((C.w + 3) & ~3) * C.h + iw * ih;
+                int smem = valid && iw > 0 && ih > 0 ? fc_smem_bytes(C.w, C.h) : 0;
                 s->max_cell_smem = std::max(s->max_cell_smem, smem);
                 s->cells.push_back(C);
             }
