@@ -87,6 +87,14 @@ int uco_b200_hamming_knn_batch_dev(uco_b200_ctx* ctx, int n_pairs, const uint8_t
                                    const int32_t* nq_dev, const uint8_t* t_dev, size_t t_pair_stride, int nt_max,
                                    const int32_t* nt_dev, int k, int order, int32_t* idx_dev, int32_t* dist_dev);
 
+/* Host-buffer batch of (query set, train set) pairs: one launch, one synchronisation (the host-side twin of the call above, for
+ * callers that hold descriptors in cv::Mat rows).  q[i] / t[i]: nq[i] / nt[i] rows of 32 bytes with row strides q_stride / t_stride
+ * (the same for every pair); idx[i] / dist[i]: nq[i] x k outputs as uco_b200_hamming_knn.  The chain pattern of tracking
+ * (t[i] == q[i-1]) is detected and every descriptor block is uploaded once. */
+int uco_b200_hamming_knn_batch(uco_b200_ctx* ctx, int n_pairs, const uint8_t* const* q, const int32_t* nq, size_t q_stride,
+                               const uint8_t* const* t, const int32_t* nt, size_t t_stride, int k, int order, int32_t* const* idx,
+                               int32_t* const* dist);
+
 /* ------------------------------------------------------------------------------------------------------------
  * K1-K6  ORB pyramid extractor
  *   replaces ucoslam::ORBextractor::detectAndCompute_impl -> compute()

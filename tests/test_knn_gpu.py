@@ -86,3 +86,21 @@ def test_gpu_batch_pairs_with_device_counts(ctx):
         oi, od = oracle_py.hamming_knn(desc[p + 1][:nq], desc[p][:nt], k, 0)
         assert np.array_equal(idx[p][:nq], oi) and np.array_equal(dist[p][:nq], od)
         assert (idx[p][nq:] == -7).all()
+
+
+@pytest.mark.gpu
+def test_host_batch_matches_single_calls(ctx):
+    """uco_b200_hamming_knn_batch (one launch for many host-buffer pairs) == uco_b200_hamming_knn per pair, for the tracking
+    chain (train of pair i is the query of pair i-1, ragged row counts) and for unrelated pairs."""
+    rng = np.random.default_rng(11)
+    sets = [rng.integers(0, 256, (n, 32), dtype=np.uint8) for n in (300, 257, 0, 300, 64, 1)]
+    block = rng.integers(0, 256, (4, 300, 32), dtype=np.uint8)   # contiguous equal-sized blocks: the coalesced-copy path
+    for qs, ts in (([sets[i] for i in range(1, 6)], [sets[i - 1] for i in range(1, 6)]),
+                   ([sets[0], sets[3], sets[4]], [sets[1], sets[4], sets[2]]),
+                   ([block[i] for i in range(4)], [block[i - 1] for i in range(4)])):
+        idx, dist = ctx.hamming_knn_batch(qs, ts, 10)
+        for q, t, i_b, d_b in zip(qs, ts, idx, dist):
+            if len(q) == 0:
+                continue
+            i_s, d_s = ctx.hamming_knn(q, t.reshape(-1, 32), 10)
+            assert np.array_equal(i_b, i_s) and np.array_equal(d_b, d_s)

@@ -23,6 +23,9 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 namespace cg = cooperative_groups;
 
@@ -826,6 +829,9 @@ struct BaArena {
 
 int ba_cluster_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* const* pbs, const volatile unsigned char* stop, uco_ba_result* const* res) {
     if (n <= 0) return UCO_OK;
+    static const bool trace = getenv("UCO_BA_TRACE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto t0 = now();
     std::vector<BaPlan> plans(n);
     int max_n = 0;
     const int CL = ctx->ba_cluster_size > 0 ? ctx->ba_cluster_size : 8;
@@ -890,6 +896,7 @@ int ba_cluster_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* const
         o.chi2 = A.take(8 * (size_t)(p.M + 1)); o.bad = A.take((size_t)p.M + 1); o.resd = A.take(sizeof(CbResult));
     }
     const size_t out_bytes = A.off - out_begin;
+    auto t1 = now();
     uint8_t* d = (uint8_t*)uco_ws(ctx, WS_BA, A.off);
     uint8_t* h = (uint8_t*)uco_pinned(ctx, WS_BA, in_bytes);
     uint8_t* ho = (uint8_t*)uco_pinned(ctx, WS_BA_OUT, out_bytes + 64);
@@ -962,6 +969,7 @@ int ba_cluster_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* const
         for (int i = 0; i < n; i++) th.emplace_back(fill, i);
         for (auto& t : th) t.join();
     }
+    auto t2 = now();
     cudaStream_t s = ctx->stream;
     UCO_CUDA(ctx, cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, s));
     UCO_CUDA(ctx, cudaMemsetAsync(d + out_begin, 0, out_bytes, s));
@@ -990,6 +998,7 @@ int ba_cluster_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* const
         if (q != cudaSuccess) return uco_fail(ctx, UCO_E_CUDA, "ba cluster kernel -> %s", cudaGetErrorString(q));
     }
     UCO_CUDA(ctx, cudaStreamSynchronize(s));
+    auto t3 = now();
     float ms = 0;
     cudaEventElapsedTime(&ms, uco_ba_events(ctx)[0], uco_ba_events(ctx)[1]);
     for (int i = 0; i < n; i++) {
@@ -1017,6 +1026,13 @@ int ba_cluster_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* const
         r.iters[1] = cr->iters[1];
         r.device_ms = ms;
         if (r.profile) memcpy(r.profile, cr->phase_cycles, sizeof(double) * 16);
+    }
+    if (trace) {
+        auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+            return std::chrono::duration<double, std::micro>(b - a).count();
+        };
+        fprintf(stderr, "[ba] n=%d plan %.0f us  fill %.0f us  h2d+kernel+d2h %.0f us (kernel %.0f us, in %zu B, out %zu B)  unpack %.0f us\n", n,
+                us(t0, t1), us(t1, t2), us(t2, t3), ms * 1e3, in_bytes, out_bytes, us(t3, now()));
     }
     return UCO_OK;
 }

@@ -17,6 +17,8 @@
 // is identical, including all tie cases.
 #include "common.cuh"
 #include <climits>
+#include <algorithm>
+#include <cstring>
 
 #define KNN_WARPS 8
 #define KNN_TILE_ROWS 256         // train rows per shared-memory tile (8 KB)
@@ -308,5 +310,95 @@ extern "C" int uco_b200_hamming_knn(uco_b200_ctx* ctx, const uint8_t* q, int nq,
     UCO_CUDA(ctx, cudaMemcpyAsync(idx, di, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, ctx->stream));
     UCO_CUDA(ctx, cudaMemcpyAsync(dist, dd, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, ctx->stream));
     UCO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return UCO_OK;
+}
+
+// Host-buffer batch: n_pairs (query set, train set) pairs in ONE launch and one synchronisation (the per-call fixed cost of
+// uco_b200_hamming_knn, ~60 us of copies + launch + sync, is what a 64-frame clip pays 64 times otherwise).  Copies are
+// coalesced: a run of pairs whose host buffers are contiguous in the device layout is one transfer, and the chain pattern of
+// tracking (the train set of pair i is the query set of pair i-1) is detected so every descriptor block is uploaded once.
+extern "C" int uco_b200_hamming_knn_batch(uco_b200_ctx* ctx, int n_pairs, const uint8_t* const* q, const int32_t* nq,
+                                          size_t q_stride, const uint8_t* const* t, const int32_t* nt, size_t t_stride, int k,
+                                          int order, int32_t* const* idx, int32_t* const* dist) {
+    if (!ctx) return UCO_E_INVALID;
+    cudaSetDevice(ctx->device);
+    if (n_pairs < 0 || k <= 0 || k > UCO_KNN_MAX_K) return uco_fail(ctx, UCO_E_INVALID, "hamming_knn_batch: bad sizes n_pairs=%d k=%d", n_pairs, k);
+    if (n_pairs == 0) return UCO_OK;
+    if (!q || !nq || !t || !nt || !idx || !dist) return uco_fail(ctx, UCO_E_INVALID, "hamming_knn_batch: null pointer");
+    if (q_stride < 32 || t_stride < 32) return uco_fail(ctx, UCO_E_INVALID, "hamming_knn_batch: row stride below 32 bytes");
+    int nq_max = 0, nt_max = 0;
+    for (int i = 0; i < n_pairs; i++) {
+        if (nq[i] < 0 || nt[i] < 0) return uco_fail(ctx, UCO_E_INVALID, "hamming_knn_batch: negative row count in pair %d", i);
+        if ((nq[i] > 0 && (!q[i] || !idx[i] || !dist[i])) || (nt[i] > 0 && !t[i]))
+            return uco_fail(ctx, UCO_E_INVALID, "hamming_knn_batch: null buffer in pair %d", i);
+        nq_max = std::max(nq_max, nq[i]);
+        nt_max = std::max(nt_max, nt[i]);
+    }
+    if (nq_max == 0) return UCO_OK;
+    bool chain = q_stride == t_stride;   // train set of pair i == query set of pair i-1
+    for (int i = 1; i < n_pairs && chain; i++) chain = t[i] == q[i - 1] && nt[i] == nq[i - 1];
+    const int slot_rows = chain ? std::max(nq_max, nt_max) : 0;
+    const size_t qs = (size_t)(chain ? slot_rows : nq_max) * 32, ts = (size_t)(chain ? slot_rows : std::max(nt_max, 1)) * 32;
+    uint8_t *dq, *dt;
+    if (chain) {
+        uint8_t* d = (uint8_t*)uco_ws(ctx, WS_KNN_Q, qs * (size_t)(n_pairs + 1));
+        if (!d) return UCO_E_NOMEM;
+        dt = d;
+        dq = d + qs;
+    } else {
+        dq = (uint8_t*)uco_ws(ctx, WS_KNN_Q, qs * (size_t)n_pairs);
+        dt = (uint8_t*)uco_ws(ctx, WS_KNN_T, ts * (size_t)n_pairs);
+    }
+    const size_t os = (size_t)nq_max * k;  // output entries per pair
+    int32_t* di = (int32_t*)uco_ws(ctx, WS_KNN_IDX, os * 4 * (size_t)n_pairs);
+    int32_t* dd = (int32_t*)uco_ws(ctx, WS_KNN_DIST, os * 4 * (size_t)n_pairs);
+    int32_t* dn = (int32_t*)uco_ws(ctx, WS_KNN_N, 8 * (size_t)n_pairs);
+    int32_t* hn = (int32_t*)uco_pinned(ctx, WS_KNN_N, 8 * (size_t)n_pairs);
+    if (!dq || !dt || !di || !dd || !dn || !hn) return UCO_E_NOMEM;
+    cudaStream_t s = ctx->stream;
+    memcpy(hn, nq, 4 * (size_t)n_pairs);
+    memcpy(hn + n_pairs, nt, 4 * (size_t)n_pairs);
+    UCO_CUDA(ctx, cudaMemcpyAsync(dn, hn, 8 * (size_t)n_pairs, cudaMemcpyHostToDevice, s));
+    // uploads: runs of host blocks that are already laid out like the device slots become one copy
+    auto upload = [&](uint8_t* dbase, size_t slot, const uint8_t* const* hp, const int32_t* rows, size_t stride, int n) -> int {
+        for (int i = 0; i < n;) {
+            if (rows[i] == 0) { i++; continue; }
+            int j = i + 1;
+            if (stride == 32)
+                while (j < n && hp[j] == hp[j - 1] + slot && (size_t)rows[j - 1] * 32 == slot) j++;
+            if (j - i > 1 || stride == 32) {
+                const size_t bytes = slot * (size_t)(j - 1 - i) + (size_t)rows[j - 1] * 32;
+                UCO_CUDA(ctx, cudaMemcpyAsync(dbase + slot * i, hp[i], bytes, cudaMemcpyHostToDevice, s));
+            } else {
+                UCO_CUDA(ctx, cudaMemcpy2DAsync(dbase + slot * i, 32, hp[i], stride, 32, rows[i], cudaMemcpyHostToDevice, s));
+            }
+            i = j;
+        }
+        return UCO_OK;
+    };
+    int rc;
+    if (chain) {
+        if ((rc = upload(dt, qs, t, nt, t_stride, 1)) != UCO_OK) return rc;
+        if ((rc = upload(dq, qs, q, nq, q_stride, n_pairs)) != UCO_OK) return rc;
+    } else {
+        if ((rc = upload(dq, qs, q, nq, q_stride, n_pairs)) != UCO_OK) return rc;
+        if ((rc = upload(dt, ts, t, nt, t_stride, n_pairs)) != UCO_OK) return rc;
+    }
+    rc = knn_launch(ctx, dq, nq_max, dt, nt_max, k, order, di, dd, n_pairs, dn, dn + n_pairs, qs, ts);
+    if (rc != UCO_OK) return rc;
+    auto download = [&](const int32_t* dbase, int32_t* const* hp) -> int {
+        for (int i = 0; i < n_pairs;) {
+            if (nq[i] == 0) { i++; continue; }
+            int j = i + 1;
+            while (j < n_pairs && nq[j - 1] == nq_max && nq[j] > 0 && hp[j] == hp[j - 1] + os) j++;
+            const size_t n_int = os * (size_t)(j - 1 - i) + (size_t)nq[j - 1] * k;
+            UCO_CUDA(ctx, cudaMemcpyAsync(hp[i], dbase + os * i, n_int * 4, cudaMemcpyDeviceToHost, s));
+            i = j;
+        }
+        return UCO_OK;
+    };
+    if ((rc = download(di, idx)) != UCO_OK) return rc;
+    if ((rc = download(dd, dist)) != UCO_OK) return rc;
+    UCO_CUDA(ctx, cudaStreamSynchronize(s));
     return UCO_OK;
 }

@@ -27,6 +27,7 @@ SIGNATURES = {
     "uco_b200_hamming_knn": (_i, [_vp, _vp, _i, _sz, _vp, _i, _sz, _i, _i, _vp, _vp]),
     "uco_b200_hamming_knn_dev": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp]),
     "uco_b200_hamming_knn_batch_dev": (_i, [_vp, _i, _vp, _sz, _i, _vp, _vp, _sz, _i, _vp, _i, _i, _vp, _vp]),
+    "uco_b200_hamming_knn_batch": (_i, [_vp, _i, _vp, _vp, _sz, _vp, _vp, _sz, _i, _i, _vp, _vp]),
     "uco_b200_orb_default_params": (None, [_vp]),
     "uco_b200_orb_extract": (_i, [_vp, _vp, _i, _i, _sz, _vp, _vp, _vp, _i, _vp]),
     "uco_b200_orb_extract_batch": (_i, [_vp, _vp, _i, _i, _i, _sz, _vp, _vp, _vp, _i, _vp]),
@@ -207,6 +208,21 @@ class Context:
         return idx, dist
 
     # -- K10-K13 -------------------------------------------------------------------------------------------------
+    def hamming_knn_batch(self, qs, ts, k, order=UCO_KNN_HEAP):
+        """host-buffer batch: qs[i] against ts[i] for every pair in one launch; returns lists of (idx, dist) arrays"""
+        qs = [np.ascontiguousarray(q, np.uint8).reshape(-1, 32) for q in qs]
+        ts = [t if any(t is q for q in qs) else np.ascontiguousarray(t, np.uint8).reshape(-1, 32) for t in ts]
+        n = len(qs)
+        idx = [np.empty((len(q), k), np.int32) for q in qs]
+        dist = [np.empty((len(q), k), np.int32) for q in qs]
+        VP = ctypes.c_void_p * n
+        nq = np.array([len(q) for q in qs], np.int32)
+        nt = np.array([len(t) for t in ts], np.int32)
+        self._chk(self.lib.uco_b200_hamming_knn_batch(self.h, n, VP(*[q.ctypes.data for q in qs]), _p(nq), 32,
+                                                      VP(*[t.ctypes.data for t in ts]), _p(nt), 32, k, order,
+                                                      VP(*[a.ctypes.data for a in idx]), VP(*[a.ctypes.data for a in dist])))
+        return idx, dist
+
     def ba_set_mode(self, mode=0, cluster_size=0):
         self._chk(self.lib.uco_b200_ba_set_mode(self.h, mode, cluster_size))
 
