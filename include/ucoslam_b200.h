@@ -223,6 +223,27 @@ typedef struct uco_ba_result {   /* every pointer may be NULL (not wanted) */
 int uco_b200_ba_solve(uco_b200_ctx* ctx, const uco_ba_problem* pb, const volatile unsigned char* stop, uco_ba_result* res);
 /* n independent problems (one local-BA window per camera / map) solved together; results as n separate uco_b200_ba_solve calls */
 int uco_b200_ba_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* pbs, const volatile unsigned char* stop, uco_ba_result* res);
+/* ---- multi-GPU (BASELINE config 5: global BA sharded over the GPUs of a node; config 4: row-sharded descriptor map) -------------
+ * One process per GPU.  The process group is the caller's (torch.distributed under torchrun, MPI, ...): rank 0 obtains a 128-byte
+ * id, the caller distributes it, every rank creates its communicator on its own context.  Collectives are NCCL over NVLink /
+ * NVSwitch, issued on the context's stream.  world == 1 needs no id and no NCCL. */
+typedef struct uco_b200_comm uco_b200_comm;
+int uco_b200_comm_unique_id(uint8_t* id128);
+int uco_b200_comm_create(uco_b200_ctx* ctx, const uint8_t* id128, int rank, int world, uco_b200_comm** out);
+void uco_b200_comm_destroy(uco_b200_comm* comm);
+
+/* GlobalOptimizerG2O::optimize on a problem of any size, optionally sharded: every rank passes the SAME complete problem; the
+ * landmarks (with all their observations: the Hll / Hpl columns of block_solver.hpp:329-400) are partitioned over the ranks, each
+ * rank linearizes its part and builds its partial Hpp / bp and partial Schur complement, ONE all-reduce per LM trial sums the
+ * packed reduced Hessian + right-hand side over NVLink, every rank solves the reduced system redundantly (dense Cholesky; above
+ * 170 free keyframes through cuSOLVER's potrf) and back-substitutes its own landmarks.  The LM control sums (chi2, scale) and the
+ * ranks' stop flags are all-reduced too, so every rank takes identical decisions.  Every rank returns the complete result.
+ * comm == NULL: single GPU.  Results equal uco_b200_ba_solve's up to the summation order of the Schur complement. */
+int uco_b200_ba_solve_sharded(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_problem* pb, const volatile unsigned char* stop,
+                              uco_ba_result* res);
+/* host-only inspection hook: landmark ranges of the sharded solver, out[0..world] = boundaries, out[world+1 .. 2 world] = observations per rank */
+int uco_b200_probe_ba_partition(const uco_ba_problem* pb, int world, int* out);
+
 /* tuning / test knob.  mode 0 (default): windows with <= 38 free keyframes run cluster-resident (one thread-block cluster per
  * window, the whole LM loop in one launch), larger ones as streamed kernels; 1: always streamed; 2: always cluster-resident.
  * cluster_size: CTAs per cluster (power of two <= 16, 0 = 8). */

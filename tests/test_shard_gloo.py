@@ -49,3 +49,19 @@ def test_two_gloo_ranks(tmp_path):
     assert not set(outs[0]["seeds"]) & set(outs[1]["seeds"])
     assert outs[0]["max"] == outs[1]["max"] == 11.0
     assert outs[0]["sum"] == outs[1]["sum"] == 37.0
+
+
+def test_ba_landmark_partition_covers_and_balances():
+    """host logic of the sharded global BA (uco_b200_probe_ba_partition): contiguous landmark ranges that tile [0, N) and carry
+    equal shares of the observations; two gloo ranks derive the same boundaries independently (every rank plans the full graph)."""
+    sys.path.insert(0, os.path.join(ROOT, "ucoslam-cv3_b200", "python"))
+    import numpy as np, ucoslam_b200
+    from ucoslam_b200.synth import synth_global_ba
+    pb = synth_global_ba(9, n_kf=50, n_points=4000)
+    M, N = len(pb["obs_pose"]), len(pb["points3"])
+    for world in (1, 2, 3, 8):
+        L, cnt = ucoslam_b200.probe_ba_partition(pb, world)
+        assert L[0] == 0 and L[-1] == N and np.all(np.diff(L) >= 0)
+        assert cnt.sum() == M and cnt.max() - cnt.min() <= 12      # within two landmarks' worth of observations
+        per_lm = np.bincount(pb["obs_point"], minlength=N)
+        assert [int(per_lm[L[r]:L[r + 1]].sum()) for r in range(world)] == cnt.tolist()

@@ -25,6 +25,9 @@
 #include <cmath>
 #include <cstring>
 #include <vector>
+#include <mutex>
+#include <dlfcn.h>
+#include <cusolverDn.h>
 
 namespace {
 using namespace ba;
@@ -235,20 +238,27 @@ __device__ double block_reduce_1024(double v, double* sm) {
 }
 
 // ---- LM control, start of a stage / of an outer iteration (sparse_optimizer.cpp:366-381, levenberg.cpp:58-96,152-166) ----------
-__global__ void __launch_bounds__(1024) ba_iter_begin_kernel(const __grid_constant__ BaDev B, int first_of_stage) {
+// ext (sharded form): the sums over ALL ranks' observations / landmarks, already all-reduced: ext[0] = robust chi2,
+// ext[1] = landmark part of computeScale, ext[2] = max |diagonal|, ext[3] = number of ranks whose stop flag is raised
+__global__ void __launch_bounds__(1024) ba_iter_begin_kernel(const __grid_constant__ BaDev B, int first_of_stage, const double* ext = nullptr) {
     __shared__ double sm[33];
     LmState* st = B.st;
     if (first_of_stage) {
-        double s = 0;
-        for (int i = threadIdx.x; i < B.M; i += 1024) s += B.rho0[i];
-        s = block_reduce_1024<false>(s, sm);
-        double md = 0;  // computeLambdaInit: tau * max |diagonal| over all active vertices
-        for (int k = threadIdx.x; k < 6 * B.Pf; k += 1024) md = fmax(md, fabs(B.Hpp[36 * (size_t)(k / 6) + 7 * (k % 6)]));
-        for (int k = threadIdx.x; k < 3 * B.N; k += 1024) {
-            int l = k / 3, j = k % 3;
-            md = fmax(md, fabs(B.Hll[6 * (size_t)l + (j == 0 ? 0 : (j == 1 ? 3 : 5))]));
+        double s = 0, md = 0;
+        if (ext) {
+            s = ext[0];
+            md = ext[2];
+        } else {
+            for (int i = threadIdx.x; i < B.M; i += 1024) s += B.rho0[i];
+            s = block_reduce_1024<false>(s, sm);
+            // computeLambdaInit: tau * max |diagonal| over all active vertices
+            for (int k = threadIdx.x; k < 6 * B.Pf; k += 1024) md = fmax(md, fabs(B.Hpp[36 * (size_t)(k / 6) + 7 * (k % 6)]));
+            for (int k = threadIdx.x; k < 3 * B.N; k += 1024) {
+                int l = k / 3, j = k % 3;
+                md = fmax(md, fabs(B.Hll[6 * (size_t)l + (j == 0 ? 0 : (j == 1 ? 3 : 5))]));
+            }
+            md = block_reduce_1024<true>(md, sm);
         }
-        md = block_reduce_1024<true>(md, sm);
         if (threadIdx.x == 0) {
             st->currentChi = s;
             st->lambda = 1e-5 * md;
@@ -462,19 +472,22 @@ __global__ void __launch_bounds__(128) ba_update_kernel(const __grid_constant__ 
 }
 
 // ---- LM control, end of a trial (levenberg.cpp:96-150) and, when the trial loop ends, of the iteration (sparse_optimizer.cpp:403-436)
-__global__ void __launch_bounds__(1024) ba_decide_kernel(const __grid_constant__ BaDev B, int stop, int max_iters) {
+__global__ void __launch_bounds__(1024) ba_decide_kernel(const __grid_constant__ BaDev B, int stop, int max_iters, const double* ext = nullptr) {
     __shared__ double sm[33];
     __shared__ int reject;
     LmState* st = B.st;
     double s = 0;
-    for (int i = threadIdx.x; i < B.M; i += 1024) s += B.rho0[i];
-    const double chi_raw = block_reduce_1024<false>(s, sm);
+    if (!ext)
+        for (int i = threadIdx.x; i < B.M; i += 1024) s += B.rho0[i];
+    const double chi_raw = ext ? ext[0] : block_reduce_1024<false>(s, sm);
     double sc = 0;
     for (int f = threadIdx.x; f < B.Pf; f += 1024) sc += B.scale_pose[f];
     const double sc_p = block_reduce_1024<false>(sc, sm);
     sc = 0;
-    for (int l = threadIdx.x; l < B.N; l += 1024) sc += B.scale_lm[l];
-    const double sc_l = block_reduce_1024<false>(sc, sm);
+    if (!ext)
+        for (int l = threadIdx.x; l < B.N; l += 1024) sc += B.scale_lm[l];
+    const double sc_l = ext ? ext[1] : block_reduce_1024<false>(sc, sm);
+    if (ext) stop = ext[3] != 0.0;
     if (threadIdx.x == 0) {
         double tempChi = st->chol_fail ? DBL_MAX : chi_raw;
         double rho = st->currentChi - tempChi;
@@ -584,6 +597,103 @@ __global__ void __launch_bounds__(128) ba_init_poses_kernel(const __grid_constan
     store_pose(B.pose_bak + 7 * t, T);
 }
 
+
+// ---- sharded / large form (BASELINE config 5): the landmarks (with all their observations) are partitioned over the ranks, so
+// every Hll / W / Y block lives on one GPU; each rank builds the partial Hpp / bp of its observations and the partial Schur
+// complement of its landmarks as PACKED blocks (the block list is global: same layout on every rank), one all-reduce per LM
+// trial sums them over NVLink, and every rank assembles and solves the reduced system redundantly (block_solver.hpp:329-400
+// split by landmark; the sum over landmarks is associative up to rounding, see DESIGN.md for the tolerance).
+__global__ void __launch_bounds__(36 * GATHER_CHUNKS) ba_schur_gather_packed_kernel(const __grid_constant__ BaDev B, double* __restrict__ Sp,
+                                                                                    double* __restrict__ bsp) {
+    const int blk = blockIdx.x;
+    const int2 ij = B.blk_ij[blk];
+    const int beg = B.blk_ptr[blk], end = B.blk_ptr[blk + 1];
+    const int e = threadIdx.x % 36, chunk = threadIdx.x / 36, r = e / 6, c = e % 6;
+    const int len = end - beg, per = (len + GATHER_CHUNKS - 1) / GATHER_CHUNKS;
+    const int c0 = beg + chunk * per, c1 = min(end, c0 + per);
+    const bool diag = ij.x == ij.y;
+    double s = 0, sb = 0;
+    for (int k = c0; k < c1; k++) {
+        const int2 ab = B.con[k];
+        const double* Y = B.Y + 18 * (size_t)ab.x + 3 * r;
+        const double* W = B.Hpl + 18 * (size_t)ab.y + 3 * c;
+        s += Y[0] * W[0] + Y[1] * W[1] + Y[2] * W[2];
+        if (diag && c == 0) {
+            const double* Wa = B.Hpl + 18 * (size_t)ab.x + 3 * r;
+            const double* db = B.db + 3 * (size_t)B.obs_lm[ab.x];
+            sb += Wa[0] * db[0] + Wa[1] * db[1] + Wa[2] * db[2];
+        }
+    }
+    __shared__ double red[GATHER_CHUNKS][36], redb[GATHER_CHUNKS][6];
+    red[chunk][e] = s;
+    if (c == 0) redb[chunk][r] = sb;
+    __syncthreads();
+    if (chunk == 0) {
+        double t = 0;
+#pragma unroll
+        for (int k = 0; k < GATHER_CHUNKS; k++) t += red[k][e];
+        Sp[36 * (size_t)blk + e] = t;
+        if (diag && c == 0) {
+            double tb = 0;
+#pragma unroll
+            for (int k = 0; k < GATHER_CHUNKS; k++) tb += redb[k][r];
+            bsp[6 * ij.x + r] = tb;
+        }
+    }
+}
+
+// S = [i == j](Hpp + lambda I) - (sum over all ranks of the packed Schur blocks), bs = bp - (summed right-hand side); S was zeroed
+__global__ void __launch_bounds__(36) ba_assemble_kernel(const __grid_constant__ BaDev B, const double* __restrict__ Sp, const double* __restrict__ bsp) {
+    const int blk = blockIdx.x, e = threadIdx.x, r = e / 6, c = e % 6;
+    const int2 ij = B.blk_ij[blk];
+    const bool diag = ij.x == ij.y;
+    double h = 0;
+    if (diag) {
+        h = B.Hpp[36 * (size_t)ij.x + e];
+        if (r == c) h += B.st->lambda;
+    }
+    h -= Sp[36 * (size_t)blk + e];
+    const int n = B.n;
+    B.S[(size_t)(6 * ij.x + r) * n + 6 * ij.y + c] = h;
+    if (!diag) B.S[(size_t)(6 * ij.y + c) * n + 6 * ij.x + r] = h;
+    if (diag && c == 0) B.bs[6 * ij.x + r] = B.bp[6 * ij.x + r] - bsp[6 * ij.x + r];
+}
+
+// this rank's ordered partial sums for the LM control: buf[0] = sum rho0, buf[1] = sum scale_lm, buf[3] = stop flag;
+// mx[0] = max |diagonal| of (full) Hpp and of the local Hll
+__global__ void __launch_bounds__(1024) ba_partial_sums_kernel(const __grid_constant__ BaDev B, double* __restrict__ buf, double* __restrict__ mx, int stop) {
+    __shared__ double sm[33];
+    double s = 0;
+    for (int i = threadIdx.x; i < B.M; i += 1024) s += B.rho0[i];
+    s = block_reduce_1024<false>(s, sm);
+    double sc = 0;
+    for (int l = threadIdx.x; l < B.N; l += 1024) sc += B.scale_lm[l];
+    sc = block_reduce_1024<false>(sc, sm);
+    double md = 0;
+    if (mx) {
+        for (int k = threadIdx.x; k < 6 * B.Pf; k += 1024) md = fmax(md, fabs(B.Hpp[36 * (size_t)(k / 6) + 7 * (k % 6)]));
+        for (int k = threadIdx.x; k < 3 * B.N; k += 1024) {
+            int l = k / 3, j = k % 3;
+            md = fmax(md, fabs(B.Hll[6 * (size_t)l + (j == 0 ? 0 : (j == 1 ? 3 : 5))]));
+        }
+        md = block_reduce_1024<true>(md, sm);
+    }
+    if (threadIdx.x == 0) {
+        buf[0] = s;
+        buf[1] = sc;
+        buf[2] = 0;
+        buf[3] = stop ? 1.0 : 0.0;
+        if (mx) mx[0] = md;
+    }
+}
+
+// after the library Cholesky of a large reduced system: publish the outcome where the update / decide kernels look for it
+__global__ void ba_solve_finish_kernel(const __grid_constant__ BaDev B, const int* __restrict__ info, const double* __restrict__ x) {
+    const bool fail = info[0] != 0 || info[1] != 0;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < B.n; k += gridDim.x * blockDim.x) B.xp[k] = fail ? 0.0 : x[k];
+    if (blockIdx.x == 0 && threadIdx.x == 0) B.st->chol_fail = fail;
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------------------------
 struct Arena {
     size_t off = 0;
@@ -596,15 +706,67 @@ struct Arena {
 
 }  // namespace
 
+// ---- sharded / large form, host side -----------------------------------------------------------------------------------------------
+namespace {
+// dense Cholesky of a reduced system that does not fit the single-CTA solver: cuSOLVER potrf / potrs (FP64 tensor-core DGEMM
+// inside), bound at run time so that the library has no link-time dependency on it
+struct SolverApi {
+    cusolverStatus_t (*Create)(cusolverDnHandle_t*) = nullptr;
+    cusolverStatus_t (*Destroy)(cusolverDnHandle_t) = nullptr;
+    cusolverStatus_t (*SetStream)(cusolverDnHandle_t, cudaStream_t) = nullptr;
+    cusolverStatus_t (*PotrfBuf)(cusolverDnHandle_t, cublasFillMode_t, int, double*, int, int*) = nullptr;
+    cusolverStatus_t (*Potrf)(cusolverDnHandle_t, cublasFillMode_t, int, double*, int, double*, int, int*) = nullptr;
+    cusolverStatus_t (*Potrs)(cusolverDnHandle_t, cublasFillMode_t, int, int, const double*, int, double*, int, int*) = nullptr;
+    bool ok = false;
+};
+SolverApi& solver_api() {
+    static SolverApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* h = nullptr;
+        for (const char* name : {"libcusolver.so.11", "libcusolver.so.12", "libcusolver.so"}) {
+            h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (h) break;
+        }
+        if (!h) return;
+        bool all = true;
+        auto sym = [&](const char* n) { void* p = dlsym(h, n); all = all && p; return p; };
+        api.Create = (decltype(api.Create))sym("cusolverDnCreate");
+        api.Destroy = (decltype(api.Destroy))sym("cusolverDnDestroy");
+        api.SetStream = (decltype(api.SetStream))sym("cusolverDnSetStream");
+        api.PotrfBuf = (decltype(api.PotrfBuf))sym("cusolverDnDpotrf_bufferSize");
+        api.Potrf = (decltype(api.Potrf))sym("cusolverDnDpotrf");
+        api.Potrs = (decltype(api.Potrs))sym("cusolverDnDpotrs");
+        api.ok = all;
+    });
+    return api;
+}
+
+// landmark range [L[r], L[r+1]) of every rank: contiguous, balanced by observation count (the Schur work follows it)
+void ba_partition_landmarks(const std::vector<int>& lm_ptr, int N, int M, int R, std::vector<int>& L) {
+    L.assign(R + 1, N);
+    L[0] = 0;
+    int l = 0;
+    for (int k = 1; k < R; k++) {
+        const long long target = (long long)M * k / R;
+        while (l < N && lm_ptr[l] < target) l++;
+        L[k] = l;
+    }
+    L[R] = N;
+}
+}  // namespace
+
 struct uco_ba_state {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int smem_optin = 0;
+    cusolverDnHandle_t solver = nullptr;
 };
 
 void uco_ba_state_free(uco_b200_ctx* ctx) {
     if (!ctx->ba) return;
     if (ctx->ba->ev0) cudaEventDestroy(ctx->ba->ev0);
     if (ctx->ba->ev1) cudaEventDestroy(ctx->ba->ev1);
+    if (ctx->ba->solver) solver_api().Destroy(ctx->ba->solver);
     delete ctx->ba;
     ctx->ba = nullptr;
 }
@@ -875,6 +1037,359 @@ int ba_streamed_solve(uco_b200_ctx* ctx, const uco_ba_problem* pb, const volatil
     return UCO_OK;
 }
 
+
+int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_problem* pb, const volatile unsigned char* stop, uco_ba_result* res) {
+    if (!ctx) return UCO_E_INVALID;
+    cudaSetDevice(ctx->device);
+    if (!res) return uco_fail(ctx, UCO_E_INVALID, "ba_solve_sharded: null result");
+    int rc = ba_validate(ctx, pb);
+    if (rc != UCO_OK) return rc;
+    const int R = uco_comm_world(comm), rank = uco_comm_rank(comm);
+    const int P = pb->n_poses, N = pb->n_points, M = pb->n_obs;
+    uco_ba_events(ctx);
+    // ---- global structure (identical on every rank): free-pose numbering, observations sorted by landmark, Schur block list
+    std::vector<int> free_idx(P), free_list;
+    for (int i = 0; i < P; i++) {
+        free_idx[i] = pb->fixed[i] ? -1 : (int)free_list.size();
+        if (!pb->fixed[i]) free_list.push_back(i);
+    }
+    const int Pf = (int)free_list.size(), n = 6 * Pf;
+    std::vector<int> lm_ptr(N + 1, 0), order(M), fill(N, 0);
+    for (int i = 0; i < M; i++) lm_ptr[pb->obs_point[i] + 1]++;
+    for (int l = 0; l < N; l++) lm_ptr[l + 1] += lm_ptr[l];
+    for (int i = 0; i < M; i++) order[lm_ptr[pb->obs_point[i]] + fill[pb->obs_point[i]]++] = i;
+    std::vector<int> g_free(M);  // free index of the pose of the k-th sorted observation
+    for (int k = 0; k < M; k++) g_free[k] = free_idx[pb->obs_pose[order[k]]];
+    std::vector<int> L;
+    ba_partition_landmarks(lm_ptr, N, M, R, L);
+    const int l0 = L[rank], l1 = L[rank + 1], NL = l1 - l0, o0 = lm_ptr[l0], o1 = lm_ptr[l1], ML = o1 - o0;
+    // block list from ALL landmarks (so that the packed layout agrees across ranks), contributions from the local ones
+    std::vector<int> blk_of((size_t)Pf * Pf, -1);
+    {
+        std::vector<uint8_t> present((size_t)Pf * Pf, 0);
+        for (int l = 0; l < N; l++)
+            for (int a = lm_ptr[l]; a < lm_ptr[l + 1]; a++) {
+                const int fa = g_free[a];
+                if (fa < 0) continue;
+                for (int b = lm_ptr[l]; b < lm_ptr[l + 1]; b++) {
+                    const int fb = g_free[b];
+                    if (fb < fa || (fb == fa && b != a)) continue;
+                    present[(size_t)fa * Pf + fb] = 1;
+                }
+            }
+        int nb = 0;
+        for (int i = 0; i < Pf; i++)
+            for (int j = i; j < Pf; j++)
+                if (present[(size_t)i * Pf + j] || i == j) blk_of[(size_t)i * Pf + j] = nb++;
+    }
+    std::vector<int2> blk_ij;
+    for (int i = 0; i < Pf; i++)
+        for (int j = i; j < Pf; j++)
+            if (blk_of[(size_t)i * Pf + j] >= 0) blk_ij.push_back(make_int2(i, j));
+    const int nblk = (int)blk_ij.size();
+    std::vector<int> blk_ptr(nblk + 1, 0);
+    for (int l = l0; l < l1; l++)
+        for (int a = lm_ptr[l]; a < lm_ptr[l + 1]; a++) {
+            const int fa = g_free[a];
+            if (fa < 0) continue;
+            for (int b = lm_ptr[l]; b < lm_ptr[l + 1]; b++) {
+                const int fb = g_free[b];
+                if (fb < fa || (fb == fa && b != a)) continue;
+                blk_ptr[blk_of[(size_t)fa * Pf + fb] + 1]++;
+            }
+        }
+    for (int k = 0; k < nblk; k++) blk_ptr[k + 1] += blk_ptr[k];
+    std::vector<int2> con(blk_ptr[nblk]);
+    {
+        std::vector<int> bf(nblk, 0);
+        for (int l = l0; l < l1; l++)
+            for (int a = lm_ptr[l]; a < lm_ptr[l + 1]; a++) {
+                const int fa = g_free[a];
+                if (fa < 0) continue;
+                for (int b = lm_ptr[l]; b < lm_ptr[l + 1]; b++) {
+                    const int fb = g_free[b];
+                    if (fb < fa || (fb == fa && b != a)) continue;
+                    const int k = blk_of[(size_t)fa * Pf + fb];
+                    con[blk_ptr[k] + bf[k]++] = make_int2(a - o0, b - o0);  // local observation indices
+                }
+            }
+    }
+    // local observation lists
+    std::vector<int> s_pose(ML), s_lm(ML), lm_ptr_loc(NL + 1);
+    for (int k = 0; k < ML; k++) { s_pose[k] = pb->obs_pose[order[o0 + k]]; s_lm[k] = pb->obs_point[order[o0 + k]] - l0; }
+    for (int l = 0; l <= NL; l++) lm_ptr_loc[l] = lm_ptr[l0 + l] - o0;
+    std::vector<int> pose_ptr(Pf + 1, 0), pose_obs;
+    for (int k = 0; k < ML; k++) if (g_free[o0 + k] >= 0) pose_ptr[g_free[o0 + k] + 1]++;
+    for (int f = 0; f < Pf; f++) pose_ptr[f + 1] += pose_ptr[f];
+    pose_obs.resize(pose_ptr[Pf]);
+    {
+        std::vector<int> pf(Pf, 0);
+        for (int k = 0; k < ML; k++) { const int f = g_free[o0 + k]; if (f >= 0) pose_obs[pose_ptr[f] + pf[f]++] = k; }
+    }
+    // ---- arena: [inputs][work][full-size result arrays that are summed over the ranks]
+    Arena A;
+    const size_t o_free_idx = A.take(4 * (size_t)P), o_free_list = A.take(4 * (size_t)(Pf + 1)), o_lm_ptr = A.take(4 * (size_t)(NL + 1)),
+                 o_obs_pose = A.take(4 * (size_t)(ML + 1)), o_obs_lm = A.take(4 * (size_t)(ML + 1)), o_pose_ptr = A.take(4 * (size_t)(Pf + 1)),
+                 o_pose_obs = A.take(4 * (pose_obs.size() + 1)), o_blk_ptr = A.take(4 * (size_t)(nblk + 1)),
+                 o_blk_ij = A.take(8 * (size_t)(nblk + 1)), o_con = A.take(8 * (con.size() + 1)), o_z = A.take(24 * (size_t)(ML + 1)),
+                 o_info = A.take(8 * (size_t)(ML + 1)), o_stereo = A.take((size_t)ML + 1), o_active = A.take((size_t)ML + 1),
+                 o_pt = A.take(24 * (size_t)(NL + 1)), o_p44 = A.take(64 * (size_t)P);
+    const size_t in_bytes = A.off;
+    const size_t n_red = 36 * (size_t)nblk + (size_t)n;  // packed Schur blocks | right-hand side: the per-trial all-reduce payload
+    const size_t o_pose = A.take(56 * (size_t)P), o_pose_bak = A.take(56 * (size_t)P), o_pt_bak = A.take(24 * (size_t)(NL + 1)),
+                 o_err = A.take(24 * (size_t)(ML + 1)), o_chi2 = A.take(8 * (size_t)(ML + 1)), o_rho0 = A.take(8 * (size_t)(ML + 1)),
+                 o_Hll = A.take(48 * (size_t)(NL + 1)), o_bl = A.take(24 * (size_t)(NL + 1)), o_Hpl = A.take(144 * (size_t)(ML + 1)),
+                 o_Y = A.take(144 * (size_t)(ML + 1)), o_Dinv = A.take(48 * (size_t)(NL + 1)), o_db = A.take(24 * (size_t)(NL + 1)),
+                 o_xl = A.take(24 * (size_t)(NL + 1)), o_HppBp = A.take(8 * (42 * (size_t)Pf + 6)),
+                 o_S = A.take(8 * ((size_t)n * n + 1)), o_bs = A.take(8 * (size_t)(n + 1)), o_xp = A.take(8 * (size_t)(n + 1)),
+                 o_scl = A.take(8 * (size_t)(NL + 1)), o_scp = A.take(8 * (size_t)(Pf + 1)), o_st = A.take(sizeof(LmState)),
+                 o_p44o = A.take(64 * (size_t)P), o_bad = A.take((size_t)ML + 1), o_red = A.take(8 * (n_red + 1)), o_sums = A.take(64),
+                 o_info2 = A.take(16);
+    const size_t o_full_pt = A.take(24 * (size_t)(N + 1)), o_full_chi = A.take(8 * (size_t)(M + 1)), o_full_flags = A.take(2 * (size_t)M + 2);
+    const bool big = n > 1023;
+    size_t o_chol = 0, o_work = 0;
+    int lwork = 0;
+    SolverApi& sol = solver_api();
+    if (!ctx->ba->smem_optin) cudaDeviceGetAttribute(&ctx->ba->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
+    uint8_t* d = nullptr;
+    if (big) {
+        if (!sol.ok) return uco_fail(ctx, UCO_E_INVALID, "ba_solve_sharded: %d free poses need the dense library Cholesky and libcusolver could not be loaded", Pf);
+        if (!ctx->ba->solver) {
+            if (sol.Create(&ctx->ba->solver) != CUSOLVER_STATUS_SUCCESS) return uco_fail(ctx, UCO_E_CUDA, "cusolverDnCreate failed");
+            sol.SetStream(ctx->ba->solver, ctx->stream);
+        }
+        if (sol.PotrfBuf(ctx->ba->solver, CUBLAS_FILL_MODE_LOWER, n, nullptr, n, &lwork) != CUSOLVER_STATUS_SUCCESS)
+            return uco_fail(ctx, UCO_E_CUDA, "cusolverDnDpotrf_bufferSize failed");
+        o_work = A.take(8 * (size_t)lwork + 8);
+    } else {
+        o_chol = A.take(8 * ((size_t)(n + 1) * (n + 2) / 2 + 1));
+    }
+    d = (uint8_t*)uco_ws(ctx, WS_BA, A.off);
+    uint8_t* h = (uint8_t*)uco_pinned(ctx, WS_BA, in_bytes + sizeof(LmState) + 64);
+    if (!d || !h) return UCO_E_NOMEM;
+    memcpy(h + o_free_idx, free_idx.data(), 4 * (size_t)P);
+    memcpy(h + o_free_list, free_list.data(), 4 * (size_t)Pf);
+    memcpy(h + o_lm_ptr, lm_ptr_loc.data(), 4 * (size_t)(NL + 1));
+    memcpy(h + o_obs_pose, s_pose.data(), 4 * (size_t)ML);
+    memcpy(h + o_obs_lm, s_lm.data(), 4 * (size_t)ML);
+    memcpy(h + o_pose_ptr, pose_ptr.data(), 4 * (size_t)(Pf + 1));
+    memcpy(h + o_pose_obs, pose_obs.data(), 4 * pose_obs.size());
+    memcpy(h + o_blk_ptr, blk_ptr.data(), 4 * (size_t)(nblk + 1));
+    memcpy(h + o_blk_ij, blk_ij.data(), 8 * (size_t)nblk);
+    memcpy(h + o_con, con.data(), 8 * con.size());
+    {
+        double* z = (double*)(h + o_z);
+        double* info = (double*)(h + o_info);
+        uint8_t* st = h + o_stereo;
+        for (int k = 0; k < ML; k++) {
+            const int i = order[o0 + k];
+            const bool s = pb->obs_stereo && pb->obs_stereo[i];
+            z[3 * k] = pb->obs_uv[2 * i]; z[3 * k + 1] = pb->obs_uv[2 * i + 1]; z[3 * k + 2] = s ? pb->obs_ur[i] : 0.0;
+            info[k] = pb->obs_inv_sigma2[i];
+            st[k] = s;
+        }
+        memset(h + o_active, 1, (size_t)ML);
+        double* pt = (double*)(h + o_pt);
+        for (int k = 0; k < 3 * NL; k++) pt[k] = pb->points3[3 * (size_t)l0 + k];
+        memcpy(h + o_p44, pb->poses44, 64 * (size_t)P);
+    }
+    cudaStream_t s = ctx->stream;
+    UCO_CUDA(ctx, cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, s));
+    UCO_CUDA(ctx, cudaMemsetAsync(d + o_st, 0, sizeof(LmState), s));
+    UCO_CUDA(ctx, cudaMemsetAsync(d + o_err, 0, 24 * (size_t)(ML + 1), s));
+    UCO_CUDA(ctx, cudaMemsetAsync(d + o_chi2, 0, 8 * (size_t)(ML + 1), s));
+    UCO_CUDA(ctx, cudaMemsetAsync(d + o_S, 0, 8 * ((size_t)n * n + 1), s));
+    UCO_CUDA(ctx, cudaMemsetAsync(d + o_red, 0, 8 * (n_red + 1), s));
+    UCO_CUDA(ctx, cudaMemsetAsync(d + o_full_pt, 0, o_full_flags + 2 * (size_t)M + 2 - o_full_pt, s));
+    BaDev B;
+    B.P = P; B.N = NL; B.M = ML; B.Pf = Pf; B.n = n; B.nblk = nblk;
+    B.pose = (double*)(d + o_pose); B.pose_bak = (double*)(d + o_pose_bak); B.pt = (double*)(d + o_pt); B.pt_bak = (double*)(d + o_pt_bak);
+    B.free_idx = (int*)(d + o_free_idx); B.free_list = (int*)(d + o_free_list); B.lm_ptr = (int*)(d + o_lm_ptr);
+    B.obs_pose = (int*)(d + o_obs_pose); B.obs_lm = (int*)(d + o_obs_lm); B.pose_ptr = (int*)(d + o_pose_ptr); B.pose_obs = (int*)(d + o_pose_obs);
+    B.z = (double*)(d + o_z); B.info = (double*)(d + o_info); B.stereo = d + o_stereo; B.active = d + o_active;
+    B.err = (double*)(d + o_err); B.chi2 = (double*)(d + o_chi2); B.rho0 = (double*)(d + o_rho0); B.Hll = (double*)(d + o_Hll);
+    B.bl = (double*)(d + o_bl); B.Hpl = (double*)(d + o_Hpl); B.Y = (double*)(d + o_Y); B.Dinv = (double*)(d + o_Dinv); B.db = (double*)(d + o_db);
+    B.xl = (double*)(d + o_xl);
+    B.Hpp = (double*)(d + o_HppBp); B.bp = B.Hpp + 36 * (size_t)Pf;   // contiguous: one all-reduce per outer iteration
+    B.S = (double*)(d + o_S); B.bs = (double*)(d + o_bs);
+    B.xp = (double*)(d + o_xp); B.scale_lm = (double*)(d + o_scl); B.scale_pose = (double*)(d + o_scp);
+    B.blk_ptr = (int*)(d + o_blk_ptr); B.blk_ij = (int2*)(d + o_blk_ij); B.con = (int2*)(d + o_con);
+    B.st = (LmState*)(d + o_st);
+    B.cam.fx = pb->fx; B.cam.fy = pb->fy; B.cam.cx = pb->cx; B.cam.cy = pb->cy; B.cam.bf = pb->bf; B.cam.bf_f = pb->bf;
+    B.chi2d = 5.99f; B.chi3d = 7.815f;
+    B.d2 = (double)sqrtf(B.chi2d); B.d3 = (double)sqrtf(B.chi3d);
+    double* Sp = (double*)(d + o_red);
+    double* bsp = Sp + 36 * (size_t)nblk;
+    double* sums = (double*)(d + o_sums);      // [0..3] sums, [4] max
+    int* info2 = (int*)(d + o_info2);
+    LmState* hst = (LmState*)(h + in_bytes);
+    double* hsums = (double*)(h + in_bytes + sizeof(LmState));
+    const size_t chol_bytes = 8 * ((size_t)(n + 1) * (n + 2) / 2);
+    const int chol_smem = !big && chol_bytes + 16 * 1024 <= (size_t)ctx->ba->smem_optin;
+    if (chol_smem) UCO_CUDA(ctx, cudaFuncSetAttribute(ba_chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_bytes));
+    const int gM = (ML + 255) / 256, gN = (NL + 127) / 128, gU = (NL + Pf + 127) / 128;
+    auto stop_now = [&] { return stop && *stop ? 1 : 0; };
+    // all-reduce of the LM sums (+ the ranks' stop flags); with first = true also the max |diagonal| for lambda_0
+    auto reduce_sums = [&](bool first) -> int {
+        ba_partial_sums_kernel<<<1, 1024, 0, s>>>(B, sums, first ? sums + 4 : nullptr, stop_now());
+        UCO_LAUNCH_CHECK(ctx);
+        int r2 = uco_comm_allreduce(comm, sums, sums, 4, 0, s);
+        if (r2 != UCO_OK) return r2;
+        if (first) {
+            r2 = uco_comm_allreduce(comm, sums + 4, sums + 2, 1, 1, s);  // max lands in ext[2]
+            if (r2 != UCO_OK) return r2;
+        }
+        return UCO_OK;
+    };
+
+    UCO_CUDA(ctx, cudaEventRecord(ctx->ba->ev0, s));
+    ba_init_poses_kernel<<<(P + 127) / 128, 128, 0, s>>>(B, (const float*)(d + o_p44));
+    UCO_LAUNCH_CHECK(ctx);
+    int iters[2] = {0, 0};
+    bool stopped = false;
+    for (int stage = 0; stage < 2 && !stopped; stage++) {
+        const int robust = stage == 0, max_iters = stage == 0 ? pb->n_iters : 2 * pb->n_iters;
+        if (stage == 1 && ML) {
+            ba_flag_outliers_kernel<<<gM, 256, 0, s>>>(B);
+            UCO_LAUNCH_CHECK(ctx);
+        }
+        if (ML) {
+            ba_errors_kernel<<<gM, 256, 0, s>>>(B, robust);
+            UCO_LAUNCH_CHECK(ctx);
+        }
+        bool cont_iter = max_iters > 0;
+        for (int it = 0; cont_iter; it++) {
+            if (NL) {
+                ba_linearize_lm_kernel<<<gN, 128, 0, s>>>(B, robust);
+                UCO_LAUNCH_CHECK(ctx);
+            }
+            if (Pf) {
+                ba_linearize_pose_kernel<<<Pf, POSE_THREADS, 0, s>>>(B, robust);
+                UCO_LAUNCH_CHECK(ctx);
+                if ((rc = uco_comm_allreduce(comm, B.Hpp, B.Hpp, 42 * (size_t)Pf, 0, s)) != UCO_OK) return rc;
+            }
+            if (it == 0) {
+                if ((rc = reduce_sums(true)) != UCO_OK) return rc;
+                UCO_CUDA(ctx, cudaMemcpyAsync(hsums, sums, 32, cudaMemcpyDeviceToHost, s));
+                UCO_CUDA(ctx, cudaStreamSynchronize(s));
+                if (hsums[3] != 0.0) {  // some rank saw stopASAP before the stage started: every rank leaves together
+                    stopped = true;
+                    break;
+                }
+            }
+            ba_iter_begin_kernel<<<1, 1024, 0, s>>>(B, it == 0, sums);
+            UCO_LAUNCH_CHECK(ctx);
+            bool cont_trial = true;
+            while (cont_trial) {
+                if (NL) {
+                    ba_prep_kernel<<<gN, 128, 0, s>>>(B);
+                    UCO_LAUNCH_CHECK(ctx);
+                }
+                if (Pf) {
+                    ba_schur_gather_packed_kernel<<<nblk, 36 * GATHER_CHUNKS, 0, s>>>(B, Sp, bsp);
+                    UCO_LAUNCH_CHECK(ctx);
+                    if ((rc = uco_comm_allreduce(comm, Sp, Sp, n_red, 0, s)) != UCO_OK) return rc;   // THE exchange step of the path
+                    if (big) UCO_CUDA(ctx, cudaMemsetAsync(B.S, 0, 8 * (size_t)n * n, s));            // potrf factors in place
+                    ba_assemble_kernel<<<nblk, 36, 0, s>>>(B, Sp, bsp);
+                    UCO_LAUNCH_CHECK(ctx);
+                    if (big) {
+                        UCO_CUDA(ctx, cudaMemsetAsync(info2, 0, 8, s));
+                        if (sol.Potrf(ctx->ba->solver, CUBLAS_FILL_MODE_LOWER, n, B.S, n, (double*)(d + o_work), lwork, info2) != CUSOLVER_STATUS_SUCCESS)
+                            return uco_fail(ctx, UCO_E_CUDA, "cusolverDnDpotrf failed");
+                        if (sol.Potrs(ctx->ba->solver, CUBLAS_FILL_MODE_LOWER, n, 1, B.S, n, B.bs, n, info2 + 1) != CUSOLVER_STATUS_SUCCESS)
+                            return uco_fail(ctx, UCO_E_CUDA, "cusolverDnDpotrs failed");
+                        ctx->launches += 2;
+                        ba_solve_finish_kernel<<<8, 256, 0, s>>>(B, info2, B.bs);
+                        UCO_LAUNCH_CHECK(ctx);
+                    } else {
+                        ba_chol_solve_kernel<<<1, CHOL_THREADS, chol_smem ? chol_bytes : 0, s>>>(B, (double*)(d + o_chol), chol_smem);
+                        UCO_LAUNCH_CHECK(ctx);
+                    }
+                }
+                ba_update_kernel<<<gU, 128, 0, s>>>(B);
+                UCO_LAUNCH_CHECK(ctx);
+                if (ML) {
+                    ba_errors_kernel<<<gM, 256, 0, s>>>(B, robust);
+                    UCO_LAUNCH_CHECK(ctx);
+                }
+                if ((rc = reduce_sums(false)) != UCO_OK) return rc;
+                ba_decide_kernel<<<1, 1024, 0, s>>>(B, 0, max_iters, sums);
+                UCO_LAUNCH_CHECK(ctx);
+                UCO_CUDA(ctx, cudaMemcpyAsync(hst, B.st, offsetof(LmState, trace), cudaMemcpyDeviceToHost, s));
+                UCO_CUDA(ctx, cudaMemcpyAsync(hsums, sums, 32, cudaMemcpyDeviceToHost, s));
+                UCO_CUDA(ctx, cudaStreamSynchronize(s));
+                cont_trial = hst->cont_trial != 0;
+            }
+            cont_iter = hst->cont_iter != 0;
+            iters[stage] = hst->it;
+            if (hsums[3] != 0.0) stopped = true;
+        }
+    }
+    // ---- results: poses are replicated; points / per-observation values are written into full-size arrays at this rank's
+    // range and summed over the ranks (every rank returns the complete result)
+    float* p44o = (float*)(d + o_p44o);
+    uint8_t* bad = d + o_bad;
+    ba_results_kernel<<<(P + 255) / 256, 256, 0, s>>>(B, (const float*)(d + o_p44), p44o, bad);
+    UCO_LAUNCH_CHECK(ctx);
+    if (ML) {
+        ba_bad_kernel<<<gM, 256, 0, s>>>(B, p44o, bad);
+        UCO_LAUNCH_CHECK(ctx);
+    }
+    double* full_pt = (double*)(d + o_full_pt);
+    double* full_chi = (double*)(d + o_full_chi);
+    uint8_t* full_flags = d + o_full_flags;  // [0, M): active, [M, 2M): bad
+    if (NL) UCO_CUDA(ctx, cudaMemcpyAsync(full_pt + 3 * (size_t)l0, B.pt, 24 * (size_t)NL, cudaMemcpyDeviceToDevice, s));
+    if (ML) {
+        UCO_CUDA(ctx, cudaMemcpyAsync(full_chi + o0, B.chi2, 8 * (size_t)ML, cudaMemcpyDeviceToDevice, s));
+        UCO_CUDA(ctx, cudaMemcpyAsync(full_flags + o0, B.active, (size_t)ML, cudaMemcpyDeviceToDevice, s));
+        UCO_CUDA(ctx, cudaMemcpyAsync(full_flags + (size_t)M + o0, bad, (size_t)ML, cudaMemcpyDeviceToDevice, s));
+    }
+    if (R > 1) {
+        if ((rc = uco_comm_allreduce(comm, full_pt, full_pt, 3 * (size_t)N, 0, s)) != UCO_OK) return rc;
+        if ((rc = uco_comm_allreduce(comm, full_chi, full_chi, (size_t)M, 0, s)) != UCO_OK) return rc;
+        if ((rc = uco_comm_allreduce(comm, full_flags, full_flags, 2 * (size_t)M, 2, s)) != UCO_OK) return rc;
+    }
+    UCO_CUDA(ctx, cudaEventRecord(ctx->ba->ev1, s));
+    const size_t o_h_pose = 0, o_h_p44 = o_h_pose + 56 * (size_t)P, o_h_pt = o_h_p44 + 64 * (size_t)P, o_h_chi = o_h_pt + 24 * (size_t)N,
+                 o_h_fl = o_h_chi + 8 * (size_t)M, o_h_st = ((o_h_fl + 2 * (size_t)M + 7) & ~(size_t)7), out_bytes = o_h_st + sizeof(LmState);
+    uint8_t* ho = (uint8_t*)uco_pinned(ctx, WS_BA_OUT, out_bytes);
+    if (!ho) return UCO_E_NOMEM;
+    UCO_CUDA(ctx, cudaMemcpyAsync(ho + o_h_pose, B.pose, 56 * (size_t)P, cudaMemcpyDeviceToHost, s));
+    UCO_CUDA(ctx, cudaMemcpyAsync(ho + o_h_p44, p44o, 64 * (size_t)P, cudaMemcpyDeviceToHost, s));
+    if (N) UCO_CUDA(ctx, cudaMemcpyAsync(ho + o_h_pt, full_pt, 24 * (size_t)N, cudaMemcpyDeviceToHost, s));
+    if (M) {
+        UCO_CUDA(ctx, cudaMemcpyAsync(ho + o_h_chi, full_chi, 8 * (size_t)M, cudaMemcpyDeviceToHost, s));
+        UCO_CUDA(ctx, cudaMemcpyAsync(ho + o_h_fl, full_flags, 2 * (size_t)M, cudaMemcpyDeviceToHost, s));
+    }
+    UCO_CUDA(ctx, cudaMemcpyAsync(ho + o_h_st, B.st, sizeof(LmState), cudaMemcpyDeviceToHost, s));
+    UCO_CUDA(ctx, cudaStreamSynchronize(s));
+    if (res->pose7) memcpy(res->pose7, ho + o_h_pose, 56 * (size_t)P);
+    if (res->poses44) memcpy(res->poses44, ho + o_h_p44, 64 * (size_t)P);
+    if (res->points3) memcpy(res->points3, ho + o_h_pt, 24 * (size_t)N);
+    const double* hchi = (const double*)(ho + o_h_chi);
+    for (int k = 0; k < M; k++) {
+        const int i = order[k];
+        if (res->obs_chi2) res->obs_chi2[i] = hchi[k];
+        if (res->obs_level) res->obs_level[i] = !(ho + o_h_fl)[k];
+        if (res->obs_bad) res->obs_bad[i] = (ho + o_h_fl)[(size_t)M + k];
+    }
+    const LmState* fst = (const LmState*)(ho + o_h_st);
+    if (res->trace) {
+        memset(res->trace, 0, sizeof(double) * 128);
+        memcpy(res->trace, fst->trace, sizeof(double) * 2 * (size_t)std::min(fst->ntrace, 64));
+    }
+    res->iters[0] = iters[0];
+    res->iters[1] = iters[1];
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ba->ev0, ctx->ba->ev1);
+    res->device_ms = ms;
+    if (res->profile) {
+        memset(res->profile, 0, sizeof(double) * 16);
+        res->profile[0] = NL; res->profile[1] = ML; res->profile[2] = nblk; res->profile[3] = (double)n_red * 8;  // shard sizes, all-reduce bytes per trial
+    }
+    return UCO_OK;
+}
+
 extern "C" {
 
 // host-only: builds the window structure (no device needed) and reports its sizes; used by the CPU tests and to time the planner
@@ -931,6 +1446,25 @@ int uco_b200_ba_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* pbs,
         int rc = ba_cluster_solve_batch(ctx, m, cp.data() + k, stop, cr.data() + k);
         if (rc != UCO_OK) return rc;
     }
+    return UCO_OK;
+}
+
+int uco_b200_ba_solve_sharded(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_problem* pb, const volatile unsigned char* stop,
+                              uco_ba_result* res) {
+    return ba_sharded_solve(ctx, comm, pb, stop, res);
+}
+
+// host-only: the landmark ranges the sharded solver gives each of `world` ranks: out[0..world] boundaries, out[world+1 ..] observation counts
+int uco_b200_probe_ba_partition(const uco_ba_problem* pb, int world, int* out) {
+    uco_b200_ctx tmp;
+    if (ba_validate(&tmp, pb) != UCO_OK || world < 1 || !out) return UCO_E_INVALID;
+    const int N = pb->n_points, M = pb->n_obs;
+    std::vector<int> lm_ptr(N + 1, 0), L;
+    for (int i = 0; i < M; i++) lm_ptr[pb->obs_point[i] + 1]++;
+    for (int l = 0; l < N; l++) lm_ptr[l + 1] += lm_ptr[l];
+    ba_partition_landmarks(lm_ptr, N, M, world, L);
+    for (int r = 0; r <= world; r++) out[r] = L[r];
+    for (int r = 0; r < world; r++) out[world + 1 + r] = lm_ptr[L[r + 1]] - lm_ptr[L[r]];
     return UCO_OK;
 }
 

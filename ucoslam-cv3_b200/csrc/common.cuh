@@ -47,6 +47,13 @@ int uco_fail(uco_b200_ctx* ctx, int code, const char* fmt, ...);
 void* uco_ws(uco_b200_ctx* ctx, int slot, size_t bytes);
 void* uco_pinned(uco_b200_ctx* ctx, int slot, size_t bytes);
 
+// comm.cu: collectives on a stream; a null communicator (or world 1) degenerates to a local copy
+struct uco_b200_comm;
+int uco_comm_rank(const uco_b200_comm* c);
+int uco_comm_world(const uco_b200_comm* c);
+int uco_comm_allreduce(uco_b200_comm* c, const void* send, void* recv, size_t count, int op /*0 f64 sum, 1 f64 max, 2 u8 sum, 3 i32 sum*/, cudaStream_t s);
+int uco_comm_allgather(uco_b200_comm* c, const void* send, void* recv, size_t bytes, cudaStream_t s);
+
 void uco_orb_state_free(uco_b200_ctx* ctx);
 void uco_ba_state_free(uco_b200_ctx* ctx);
 

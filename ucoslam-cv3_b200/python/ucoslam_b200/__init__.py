@@ -28,6 +28,11 @@ SIGNATURES = {
     "uco_b200_hamming_knn_dev": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp]),
     "uco_b200_hamming_knn_batch_dev": (_i, [_vp, _i, _vp, _sz, _i, _vp, _vp, _sz, _i, _vp, _i, _i, _vp, _vp]),
     "uco_b200_hamming_knn_batch": (_i, [_vp, _i, _vp, _vp, _sz, _vp, _vp, _sz, _i, _i, _vp, _vp]),
+    "uco_b200_comm_unique_id": (_i, [_vp]),
+    "uco_b200_comm_create": (_i, [_vp, _vp, _i, _i, _vp]),
+    "uco_b200_comm_destroy": (None, [_vp]),
+    "uco_b200_ba_solve_sharded": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "uco_b200_probe_ba_partition": (_i, [_vp, _i, _vp]),
     "uco_b200_orb_default_params": (None, [_vp]),
     "uco_b200_orb_extract": (_i, [_vp, _vp, _i, _i, _sz, _vp, _vp, _vp, _i, _vp]),
     "uco_b200_orb_extract_batch": (_i, [_vp, _vp, _i, _i, _i, _sz, _vp, _vp, _vp, _i, _vp]),
@@ -89,6 +94,15 @@ def probe_retain_best(packed, n_points):
 
 
 _lib = None
+
+
+def probe_ba_partition(pb, world):
+    """host-only: (boundaries[world+1], observations per rank[world]) of the sharded solver's landmark partition"""
+    cp, cr, keep, out = Context.ba_pack(pb, 1)
+    o = np.zeros(2 * world + 1, np.int32)
+    if load().uco_b200_probe_ba_partition(ctypes.addressof(cp), world, _p(o)) != 0:
+        raise UcoError("probe_ba_partition failed")
+    return o[:world + 1].copy(), o[world + 1:].copy()
 
 
 def load():
@@ -222,6 +236,32 @@ class Context:
                                                       VP(*[t.ctypes.data for t in ts]), _p(nt), 32, k, order,
                                                       VP(*[a.ctypes.data for a in idx]), VP(*[a.ctypes.data for a in dist])))
         return idx, dist
+
+    # -- multi-GPU ----------------------------------------------------------------------------------------------
+    def comm_create(self, rank=0, world=1, broadcast=None):
+        """communicator of this context; `broadcast(bytes_or_None) -> bytes` distributes rank 0's 128-byte id (see shard.make_comm)"""
+        idb = None
+        if world > 1:
+            buf = (ctypes.c_uint8 * 128)()
+            if rank == 0:
+                if self.lib.uco_b200_comm_unique_id(buf) != 0:
+                    raise UcoError("uco_b200_comm_unique_id failed (NCCL not loadable)")
+            data = broadcast(bytes(buf) if rank == 0 else None)
+            idb = (ctypes.c_uint8 * 128).from_buffer_copy(data)
+        out = ctypes.c_void_p()
+        self._chk(self.lib.uco_b200_comm_create(self.h, idb, rank, world, ctypes.byref(out)))
+        return out
+
+    def comm_destroy(self, comm):
+        self.lib.uco_b200_comm_destroy(comm)
+
+    def ba_solve_sharded(self, pb, n_iters, comm=None, stop=None):
+        """uco_b200_ba_solve_sharded: any problem size; with a communicator the landmarks are sharded over its ranks"""
+        cp, cr, keep, out = self.ba_pack(pb, n_iters)
+        self._chk(self.lib.uco_b200_ba_solve_sharded(self.h, comm, ctypes.addressof(cp), _p(stop), ctypes.addressof(cr)))
+        out["iters"] = np.array(list(cr.iters), np.int32)
+        out["device_ms"] = float(cr.device_ms)
+        return out
 
     def ba_set_mode(self, mode=0, cluster_size=0):
         self._chk(self.lib.uco_b200_ba_set_mode(self.h, mode, cluster_size))

@@ -54,6 +54,23 @@ def sum_over_ranks(value, device="cpu"):
     return float(t.item())
 
 
+def make_comm(ctx, device="cpu"):
+    """NCCL communicator of a library context over the ranks of the initialised process group: rank 0's 128-byte id travels through
+    torch.distributed (the plumbing); the data path then talks NCCL directly from the library (uco_b200_comm_*)."""
+    import torch
+    import torch.distributed as dist
+    rank, world, _ = env_rank_world()
+
+    def bcast(data):
+        t = torch.zeros(128, dtype=torch.uint8, device=device)
+        if rank == 0:
+            t = torch.frombuffer(bytearray(data), dtype=torch.uint8).to(device)
+        dist.broadcast(t, 0)
+        return bytes(t.cpu().numpy().tobytes())
+
+    return ctx.comm_create(rank, world, bcast if world > 1 else None)
+
+
 def finalize():
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():

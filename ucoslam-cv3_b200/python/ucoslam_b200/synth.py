@@ -67,6 +67,65 @@ def synth_ba_problem(seed, n_poses=12, n_fixed=2, n_points=2000, stereo_frac=0.0
                 poses_gt=poses_gt, points_gt=pts_gt)
 
 
+def synth_global_ba(seed, n_kf=500, n_points=50000, obs_per_point=6, n_fixed=2, loop_m=50.0, px_sigma=0.5, pose_noise=(0.01, 0.5),
+                    point_noise=0.02, outlier_frac=0.01, w=640, h=480, f=525.0):
+    """BASELINE config 5: n_kf keyframes on a closed loop of loop_m metres looking outwards, n_points landmarks each
+    seen by obs_per_point consecutive keyframes (the reduced camera system is block-banded plus the loop-closing corner), pixel
+    noise px_sigma, perturbed initial poses / points, the first n_fixed keyframes fixed.  Vectorised; f32 containers."""
+    rng = np.random.default_rng(seed)
+    cx, cy = np.float32(w / 2 - 0.5), np.float32(h / 2 - 0.5)
+    r = loop_m / (2 * np.pi)
+    th = 2 * np.pi * np.arange(n_kf) / n_kf
+    zc = np.stack([np.cos(th), np.zeros(n_kf), np.sin(th)], 1)
+    xc = np.stack([np.sin(th), np.zeros(n_kf), -np.cos(th)], 1)
+    yc = np.tile(np.array([0.0, 1.0, 0.0]), (n_kf, 1))
+    C = r * zc
+    R = np.stack([xc, yc, zc], 1)                      # (n_kf, 3, 3) rows = camera axes in the world
+    t = -np.einsum("kij,kj->ki", R, C)
+    base = rng.integers(0, n_kf, n_points)
+    thm = 2 * np.pi * (base + (obs_per_point - 1) / 2) / n_kf
+    zm = np.stack([np.cos(thm), np.zeros(n_points), np.sin(thm)], 1)
+    xm = np.stack([np.sin(thm), np.zeros(n_points), -np.cos(thm)], 1)
+    depth = rng.uniform(3, 8, n_points)
+    pts_gt = r * zm + depth[:, None] * zm + rng.uniform(-1.5, 1.5, n_points)[:, None] * xm
+    pts_gt[:, 1] += rng.uniform(-1.5, 1.5, n_points)
+    op, ol, ouv, oinv = [], [], [], []
+    for k in range(obs_per_point):
+        kf = (base + k) % n_kf
+        Xc = np.einsum("nij,nj->ni", R[kf], pts_gt) + t[kf]
+        u = f * Xc[:, 0] / Xc[:, 2] + cx
+        v = f * Xc[:, 1] / Xc[:, 2] + cy
+        octave = rng.integers(0, 8, n_points)
+        sc = 1.2 ** octave
+        noise = rng.normal(0, px_sigma, (n_points, 2)) * sc[:, None]
+        out = rng.random(n_points) < outlier_frac
+        noise[out] = rng.uniform(-40, 40, (int(out.sum()), 2))
+        ok = (Xc[:, 2] > 0.5) & (u > 20) & (u < w - 20) & (v > 20) & (v < h - 20)
+        op.append(kf[ok]); ol.append(np.nonzero(ok)[0]); ouv.append(np.stack([u + noise[:, 0], v + noise[:, 1]], 1)[ok])
+        oinv.append((np.float32(1.0) / (np.float32(1.2) ** octave.astype(np.float32)))[ok])
+    obs_pose = np.concatenate(op).astype(np.int32)
+    obs_point = np.concatenate(ol).astype(np.int32)
+    perm = np.argsort(obs_point * n_kf + obs_pose, kind="stable")   # landmark-major like a map walk; any order is accepted
+    poses_gt = np.tile(np.eye(4), (n_kf, 1, 1))
+    poses_gt[:, :3, :3] = R
+    poses_gt[:, :3, 3] = t
+    poses0 = poses_gt.copy()
+    for i in range(n_fixed, n_kf):
+        dR = _rodrigues(rng.normal(0, np.deg2rad(pose_noise[1]), 3))
+        poses0[i][:3, :3] = dR @ poses0[i][:3, :3]
+        poses0[i][:3, 3] += rng.normal(0, pose_noise[0], 3)
+    pts0 = pts_gt + rng.normal(0, point_noise, pts_gt.shape)
+    fixed = np.zeros(n_kf, np.uint8)
+    fixed[:n_fixed] = 1
+    M = len(obs_pose)
+    return dict(poses44=poses0.reshape(n_kf, 16).astype(np.float32), fixed=fixed, points3=pts0.astype(np.float32),
+                obs_pose=obs_pose[perm], obs_point=obs_point[perm], obs_uv=np.concatenate(ouv).astype(np.float32)[perm],
+                obs_ur=np.zeros(M, np.float32), obs_stereo=np.zeros(M, np.uint8),
+                obs_inv_sigma2=np.concatenate(oinv).astype(np.float32)[perm],
+                fx=float(np.float32(f)), fy=float(np.float32(f)), cx=float(cx), cy=float(cy), bf=float(np.float32(0.12 * f)),
+                poses_gt=poses_gt, points_gt=pts_gt)
+
+
 def synth_pnp_problem(seed, n_matches=800, stereo_frac=0.0, outlier_frac=0.1, unstable_frac=0.3, n_markers=0, px_sigma=0.5,
                       pose_noise=(0.03, 1.5), w=640, h=480, f=525.0, bf=0.12 * 525.0):
     """A seeded pose-only problem as the tracker hands it to PnPSolver::solvePnp (SURVEY.md 8a row a21): one camera, n_matches
