@@ -232,6 +232,20 @@ int uco_b200_comm_unique_id(uint8_t* id128);
 int uco_b200_comm_create(uco_b200_ctx* ctx, const uint8_t* id128, int rank, int world, uco_b200_comm** out);
 void uco_b200_comm_destroy(uco_b200_comm* comm);
 
+/* Hamming k-NN over a ROW-SHARDED train set (config 4: a 10^6-descriptor map split over the GPUs): rank r holds rows
+ * [row_base, row_base + nt_shard) of the map, the queries are replicated.  Every rank scans its shard, the per-shard top-k lists
+ * are all-gathered (nq x k 64-bit keys per rank) and merged on every rank.  Output rows are in (distance, row index) order with
+ * the same distance list as xflann's linear scan and the same rows for every distance below the k-th.  Among rows TIED at the
+ * k-th distance xflann keeps whichever its max-heap still holds after later, closer rows evicted the root (resultset.h:64-85) —
+ * a function of the scan order that no partition of the scan can reproduce; the merged lists keep the lowest row indices there.
+ * comm == NULL: one shard.  With few queries a shard is itself scanned in up to 32 row ranges by different CTAs and merged the same
+ * way, so that a single query still streams the map at HBM speed.  Asynchronous on the stream. */
+int uco_b200_hamming_knn_sharded_dev(uco_b200_ctx* ctx, uco_b200_comm* comm, const uint8_t* q_dev, int nq, const uint8_t* t_shard_dev,
+                                     int nt_shard, int row_base, int k, int32_t* idx_dev, int32_t* dist_dev);
+/* the merge step on its own: n_lists (<= 32) lists of nq x k (global row index, distance) with -1 padding, list-major */
+int uco_b200_knn_merge_dev(uco_b200_ctx* ctx, int n_lists, int nq, int k, const int32_t* idx_lists_dev, const int32_t* dist_lists_dev,
+                           int32_t* idx_dev, int32_t* dist_dev);
+
 /* GlobalOptimizerG2O::optimize on a problem of any size, optionally sharded: every rank passes the SAME complete problem; the
  * landmarks (with all their observations: the Hll / Hpl columns of block_solver.hpp:329-400) are partitioned over the ranks, each
  * rank linearizes its part and builds its partial Hpp / bp and partial Schur complement, ONE all-reduce per LM trial sums the

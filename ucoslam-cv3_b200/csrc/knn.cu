@@ -402,3 +402,120 @@ extern "C" int uco_b200_hamming_knn_batch(uco_b200_ctx* ctx, int n_pairs, const 
     UCO_CUDA(ctx, cudaStreamSynchronize(s));
     return UCO_OK;
 }
+
+// ---- row-sharded train set (BASELINE config 4: a 10^6-descriptor map split over the GPUs of a node) ------------------------------
+// Every rank scans its own rows (same kernel), the per-shard top-k lists travel once (all-gather of nq x k 64-bit keys per rank) and
+// every rank merges them.  A key is  distance << 32 | global row index ; the merged rows come out in (distance, index) order with
+// xflann's distance list and xflann's rows below the k-th distance.  Which of the rows TIED at the k-th distance survive in xflann
+// depends on its heap layout when closer rows arrive later (resultset.h:64-85), i.e. on the scan order: per-shard lists cannot
+// reproduce that, so the merge keeps the lowest row indices among those ties (SURVEY.md 8(c)(ii) defines parity on sorted lists).
+namespace {
+// list l (per_list entries each) holds row indices relative to base + l * list_rows
+__global__ void knn_pack_keys_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ dist, int n, int base, int per_list,
+                                     int list_rows, unsigned long long* __restrict__ keys) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int id = idx[i];
+    keys[i] = id < 0 ? ~0ull : ((unsigned long long)(unsigned)dist[i] << 32) | (unsigned)(id + base + (i / per_list) * list_rows);
+}
+// one warp per query: n_lists x k candidate keys (list l of query q at keys[(l * nq + q) * k]), k rounds of warp-wide minimum
+__global__ void __launch_bounds__(256) knn_merge_kernel(const unsigned long long* __restrict__ keys, int n_lists, int nq, int k,
+                                                        int32_t* __restrict__ out_idx, int32_t* __restrict__ out_dist) {
+    const int q = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const int total = n_lists * k;   // <= 32 * 32
+    unsigned long long mine[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        const int e = j * 32 + lane;
+        mine[j] = e < total ? keys[((size_t)(e / k) * nq + q) * k + e % k] : ~0ull;
+    }
+    for (int r = 0; r < k; r++) {
+        unsigned long long m = ~0ull;
+#pragma unroll
+        for (int j = 0; j < 32; j++) m = mine[j] < m ? mine[j] : m;
+        unsigned long long w = m;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long t = __shfl_xor_sync(0xffffffffu, w, o);
+            w = t < w ? t : w;
+        }
+        if (w != ~0ull && m == w) {  // keys are unique (distinct rows): exactly one lane owns the winner
+#pragma unroll
+            for (int j = 0; j < 32; j++)
+                if (mine[j] == w) mine[j] = ~0ull;
+        }
+        if (lane == 0) {
+            out_idx[(size_t)q * k + r] = w == ~0ull ? -1 : (int32_t)(unsigned)w;
+            out_dist[(size_t)q * k + r] = w == ~0ull ? 0 : (int32_t)(w >> 32);
+        }
+    }
+}
+}  // namespace
+
+extern "C" int uco_b200_knn_merge_dev(uco_b200_ctx* ctx, int n_lists, int nq, int k, const int32_t* idx_lists_dev,
+                                      const int32_t* dist_lists_dev, int32_t* idx_dev, int32_t* dist_dev) {
+    if (!ctx) return UCO_E_INVALID;
+    cudaSetDevice(ctx->device);
+    if (n_lists <= 0 || n_lists > 32 || nq < 0 || k <= 0 || k > UCO_KNN_MAX_K || !idx_lists_dev || !dist_lists_dev || !idx_dev || !dist_dev)
+        return uco_fail(ctx, UCO_E_INVALID, "knn_merge: bad arguments");
+    if (nq == 0) return UCO_OK;
+    const size_t n = (size_t)n_lists * nq * k;
+    unsigned long long* keys = (unsigned long long*)uco_ws(ctx, WS_KNN_MERGE, 8 * n);
+    if (!keys) return UCO_E_NOMEM;
+    knn_pack_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(idx_lists_dev, dist_lists_dev, (int)n, 0, (int)n, 0, keys);
+    UCO_LAUNCH_CHECK(ctx);
+    knn_merge_kernel<<<(nq + 7) / 8, 256, 0, ctx->stream>>>(keys, n_lists, nq, k, idx_dev, dist_dev);
+    UCO_LAUNCH_CHECK(ctx);
+    return UCO_OK;
+}
+
+extern "C" int uco_b200_hamming_knn_sharded_dev(uco_b200_ctx* ctx, uco_b200_comm* comm, const uint8_t* q_dev, int nq,
+                                                const uint8_t* t_shard_dev, int nt_shard, int row_base, int k, int32_t* idx_dev,
+                                                int32_t* dist_dev) {
+    if (!ctx) return UCO_E_INVALID;
+    cudaSetDevice(ctx->device);
+    const int R = uco_comm_world(comm), rank = uco_comm_rank(comm);
+    if (R > 32) return uco_fail(ctx, UCO_E_INVALID, "hamming_knn_sharded: more than 32 ranks");
+    if (nq <= 0) return nq == 0 ? UCO_OK : uco_fail(ctx, UCO_E_INVALID, "hamming_knn_sharded: nq < 0");
+    const size_t n = (size_t)nq * k;
+    // few queries against many rows: one CTA per 8 queries would leave the GPU idle, so the shard is itself scanned in S row ranges
+    // (grid.y) and the S lists are merged first — the same step as across ranks
+    int S = 1;
+    const int qcta = (nq + KNN_WARPS - 1) / KNN_WARPS;
+    if (qcta < 2 * ctx->sm_count && nt_shard >= 2 * 8192) S = std::min(std::min(32, nt_shard / 8192), (2 * ctx->sm_count + qcta - 1) / qcta);
+    const int chunk = S > 1 ? (((nt_shard + S - 1) / S + 255) & ~255) : nt_shard;
+    if (S > 1) S = (nt_shard + chunk - 1) / chunk;
+    int32_t* li = (int32_t*)uco_ws(ctx, WS_KNN_IDX, 4 * n * (size_t)S);
+    int32_t* ld = (int32_t*)uco_ws(ctx, WS_KNN_DIST, 4 * n * (size_t)S);
+    unsigned long long* keys = (unsigned long long*)uco_ws(ctx, WS_KNN_MERGE, 8 * n * (size_t)(R + S));
+    if (!li || !ld || !keys) return UCO_E_NOMEM;
+    int rc;
+    if (S == 1) {
+        rc = knn_launch(ctx, q_dev, nq, t_shard_dev, nt_shard, k, UCO_KNN_SORTED, li, ld, 1, nullptr, nullptr, 0, 0);
+        if (rc != UCO_OK) return rc;
+        knn_pack_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(li, ld, (int)n, row_base, (int)n, 0, keys + n * rank);
+        UCO_LAUNCH_CHECK(ctx);
+    } else {
+        int32_t* dn = (int32_t*)uco_ws(ctx, WS_KNN_N, 4 * 32);
+        int32_t* hn = (int32_t*)uco_pinned(ctx, WS_KNN_N, 4 * 32);
+        if (!dn || !hn) return UCO_E_NOMEM;
+        UCO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // hn may still be in flight from the previous call
+        for (int i = 0; i < S; i++) hn[i] = std::min(chunk, nt_shard - i * chunk);
+        UCO_CUDA(ctx, cudaMemcpyAsync(dn, hn, 4 * (size_t)S, cudaMemcpyHostToDevice, ctx->stream));
+        rc = knn_launch(ctx, q_dev, nq, t_shard_dev, chunk, k, UCO_KNN_SORTED, li, ld, S, nullptr, dn, 0, (size_t)chunk * 32);
+        if (rc != UCO_OK) return rc;
+        unsigned long long* part = keys + n * (size_t)R;
+        knn_pack_keys_kernel<<<(unsigned)((n * S + 255) / 256), 256, 0, ctx->stream>>>(li, ld, (int)(n * S), row_base, (int)n, chunk, part);
+        UCO_LAUNCH_CHECK(ctx);
+        // merged shard list -> (idx, dist) -> this rank's slot of the exchange buffer
+        knn_merge_kernel<<<(nq + 7) / 8, 256, 0, ctx->stream>>>(part, S, nq, k, li, ld);
+        UCO_LAUNCH_CHECK(ctx);
+        knn_pack_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(li, ld, (int)n, 0, (int)n, 0, keys + n * rank);
+        UCO_LAUNCH_CHECK(ctx);
+    }
+    if ((rc = uco_comm_allgather(comm, keys + n * rank, keys, 8 * n, ctx->stream)) != UCO_OK) return rc;
+    knn_merge_kernel<<<(nq + 7) / 8, 256, 0, ctx->stream>>>(keys, R, nq, k, idx_dev, dist_dev);
+    UCO_LAUNCH_CHECK(ctx);
+    return UCO_OK;
+}

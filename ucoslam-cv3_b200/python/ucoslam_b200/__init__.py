@@ -28,6 +28,8 @@ SIGNATURES = {
     "uco_b200_hamming_knn_dev": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp]),
     "uco_b200_hamming_knn_batch_dev": (_i, [_vp, _i, _vp, _sz, _i, _vp, _vp, _sz, _i, _vp, _i, _i, _vp, _vp]),
     "uco_b200_hamming_knn_batch": (_i, [_vp, _i, _vp, _vp, _sz, _vp, _vp, _sz, _i, _i, _vp, _vp]),
+    "uco_b200_hamming_knn_sharded_dev": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp]),
+    "uco_b200_knn_merge_dev": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "uco_b200_comm_unique_id": (_i, [_vp]),
     "uco_b200_comm_create": (_i, [_vp, _vp, _i, _i, _vp]),
     "uco_b200_comm_destroy": (None, [_vp]),
@@ -254,6 +256,12 @@ class Context:
 
     def comm_destroy(self, comm):
         self.lib.uco_b200_comm_destroy(comm)
+
+    def hamming_knn_sharded_dev(self, comm, q_dev, nq, t_shard_dev, nt_shard, row_base, k, idx_dev, dist_dev):
+        self._chk(self.lib.uco_b200_hamming_knn_sharded_dev(self.h, comm, q_dev, nq, t_shard_dev, nt_shard, row_base, k, idx_dev, dist_dev))
+
+    def knn_merge_dev(self, n_lists, nq, k, idx_lists_dev, dist_lists_dev, idx_dev, dist_dev):
+        self._chk(self.lib.uco_b200_knn_merge_dev(self.h, n_lists, nq, k, idx_lists_dev, dist_lists_dev, idx_dev, dist_dev))
 
     def ba_solve_sharded(self, pb, n_iters, comm=None, stop=None):
         """uco_b200_ba_solve_sharded: any problem size; with a communicator the landmarks are sharded over its ranks"""
