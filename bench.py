@@ -368,6 +368,16 @@ def run_b200(args, rank, world, local_rank):
         peaks = json.load(open(pk))
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     achieved = alg[top] * F / (stage_ms[top] * 1e-3) / 1e9
+    # DRAM bytes per launch of that kernel from the committed ncu --set full capture of the same step (profiles/r1_traffic.json)
+    traffic = None
+    tk = {"local_ba": "ba_cluster_kernel", "hamming_knn": "hamming_knn_kernel", "fast_cells": "fast_cells_kernel", "blur": "blur7_kernel",
+          "select": "select_kernel", "orient_describe": "orient_describe_kernel"}.get(top)
+    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if tk and os.path.exists(tp) and F == 64:
+        for name, v in json.load(open(tp))["kernels"].items():
+            if tk in name:
+                traffic = v["dram_bytes_per_launch"]
+                break
     orb_total_ms = sum(acc.values())
     orb_alg = W * H + 2 * pb["pyramid_px"] + KPTS * 60                          # 2 328 264 B/frame
     if rank == 0:
@@ -386,7 +396,7 @@ def run_b200(args, rank, world, local_rank):
                         "d2h_bytes_per_step": F * (KPTS * 60 + 4 + KPTS * K_NN * 8) + ba_out_bytes},
                 "gpu_launches": launches, "clocks": clocks,
                 "roofline": {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": achieved / hbm_peak, "traffic": None,
+                             "frac": achieved / hbm_peak, "traffic": traffic,
                              "peak_source": "measured" if peaks else "fallback",
                              "kernel_ms_per_step": stage_ms[top], "algorithmic_bytes_per_frame": alg[top]},
                 "stage_ms_per_step": stage_ms,

@@ -238,11 +238,11 @@ void uco_b200_comm_destroy(uco_b200_comm* comm);
  * the same distance list as xflann's linear scan and the same rows for every distance below the k-th.  Among rows TIED at the
  * k-th distance xflann keeps whichever its max-heap still holds after later, closer rows evicted the root (resultset.h:64-85) —
  * a function of the scan order that no partition of the scan can reproduce; the merged lists keep the lowest row indices there.
- * comm == NULL: one shard.  With few queries a shard is itself scanned in up to 32 row ranges by different CTAs and merged the same
+ * comm == NULL: one shard.  With few queries a shard is itself scanned in up to 128 row ranges by different CTAs and merged the same
  * way, so that a single query still streams the map at HBM speed.  Asynchronous on the stream. */
 int uco_b200_hamming_knn_sharded_dev(uco_b200_ctx* ctx, uco_b200_comm* comm, const uint8_t* q_dev, int nq, const uint8_t* t_shard_dev,
                                      int nt_shard, int row_base, int k, int32_t* idx_dev, int32_t* dist_dev);
-/* the merge step on its own: n_lists (<= 32) lists of nq x k (global row index, distance) with -1 padding, list-major */
+/* the merge step on its own: n_lists (n_lists * k <= 1024) lists of nq x k (global row index, distance) with -1 padding, list-major */
 int uco_b200_knn_merge_dev(uco_b200_ctx* ctx, int n_lists, int nq, int k, const int32_t* idx_lists_dev, const int32_t* dist_lists_dev,
                            int32_t* idx_dev, int32_t* dist_dev);
 

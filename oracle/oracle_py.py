@@ -335,3 +335,112 @@ def frame_match(q_desc, q_kps, t_desc, t_kps, min_desc_dist=50.0, ratio=0.8, che
                                ctypes.c_float(min_desc_dist), ctypes.c_float(ratio), int(check_orientation), int(max_octave_diff),
                                P(f12), _p(sf), len(sf), _p(out))
     return out[:n].copy()
+
+
+# ---- projection matcher (row a12): kd-tree restatement, the reference's own picoflann, Map::matchFrameToMapPoints ------------------
+_stl = None
+
+
+def load_stl():
+    global _stl
+    if _stl is None:
+        p = os.path.join(HERE, "_build", "liboracle_stl.so")
+        if not os.path.exists(p):
+            build_oracle()
+        _stl = ctypes.CDLL(p)
+    return _stl
+
+
+def kdtree_build(xy):
+    """restated picoflann build over (n,2) f32 points -> dict(nodes (k,5) i32 [col,left,right,leaf_begin,leaf_count], div (k,2) f32
+    [divlow, divhigh], div_val (k,) f64, leaf_idx (n,) i32, bbox (4,) f64)"""
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    n = len(xy)
+    cap = 2 * n + 4
+    ni, nf, nd = np.zeros((cap, 5), np.int32), np.zeros((cap, 2), np.float32), np.zeros(cap, np.float64)
+    leaf, bbox = np.zeros(max(n, 1), np.int32), np.zeros(4, np.float64)
+    k = load_stl().oracle_kdtree_build(_p(xy), 2, n, _p(ni), _p(nf), _p(nd), _p(leaf), _p(bbox), cap)
+    assert k >= 0
+    return dict(nodes=ni[:k].copy(), div=nf[:k].copy(), div_val=nd[:k].copy(), leaf_idx=leaf[:n].copy(), bbox=bbox)
+
+
+def kdtree_radius(xy, queries, radii):
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    queries = np.ascontiguousarray(queries, np.float32).reshape(-1, 2)
+    radii = np.ascontiguousarray(radii, np.float32)
+    nq, cap = len(queries), max(1, len(queries) * len(xy))
+    ptr, idx = np.zeros(nq + 1, np.int32), np.zeros(cap, np.int32)
+    tot = load_stl().oracle_kdtree_radius(_p(xy), 2, len(xy), _p(queries), _p(radii), nq, _p(ptr), _p(idx), cap)
+    assert tot >= 0
+    return ptr, idx[:tot].copy()
+
+
+def ref_picoflann_stream(xy):
+    """KdTreeIndex::toStream bytes of the reference's own kd-tree over the points, or None where oracle/_ref was not built"""
+    lib = load_ref("libref_picoflann.so")
+    if lib is None:
+        return None
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    cap = 1024 + 200 * max(1, len(xy))
+    buf = np.zeros(cap, np.uint8)
+    lib.ref_picoflann_stream.restype = ctypes.c_long
+    n = lib.ref_picoflann_stream(_p(xy), len(xy), _p(buf), ctypes.c_long(cap))
+    assert n >= 0
+    return buf[:n].tobytes()
+
+
+def ref_picoflann_radius(xy, queries, radii):
+    lib = load_ref("libref_picoflann.so")
+    if lib is None:
+        return None
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    queries = np.ascontiguousarray(queries, np.float32).reshape(-1, 2)
+    radii = np.ascontiguousarray(radii, np.float32)
+    nq, cap = len(queries), max(1, len(queries) * len(xy))
+    ptr, idx = np.zeros(nq + 1, np.int32), np.zeros(cap, np.int32)
+    tot = lib.ref_picoflann_radius(_p(xy), len(xy), _p(queries), _p(radii), nq, _p(ptr), _p(idx), cap)
+    assert tot >= 0
+    return ptr, idx[:tot].copy()
+
+
+def parse_picoflann_stream(b):
+    """the byte format of picoflann.h:603-660 (Index::toStream / Node::toStream) -> the same dict as kdtree_build"""
+    import struct
+    o = 0
+    dims, nvalues = struct.unpack_from("<ii", b, o); o += 8
+    (nb,) = struct.unpack_from("<Q", b, o); o += 8
+    bbox = np.frombuffer(b, np.float64, 2 * nb, o).copy(); o += 16 * nb
+    (k,) = struct.unpack_from("<Q", b, o); o += 8
+    nodes, div, div_val, leaf = [], [], [], []
+    for _ in range(k):
+        (dv,) = struct.unpack_from("<d", b, o); o += 8
+        (col,) = struct.unpack_from("<H", b, o); o += 2
+        dh, dl = struct.unpack_from("<ff", b, o); o += 8
+        l, r = struct.unpack_from("<qq", b, o); o += 16
+        (s,) = struct.unpack_from("<Q", b, o); o += 8
+        ids = np.frombuffer(b, np.int32, s, o); o += 4 * s
+        nodes.append((col, l, r, len(leaf), s)); div.append((dl, dh)); div_val.append(dv); leaf.extend(ids.tolist())
+    assert o == len(b)
+    return dict(nodes=np.array(nodes, np.int32).reshape(-1, 5), div=np.array(div, np.float32).reshape(-1, 2), div_val=np.array(div_val),
+                leaf_idx=np.array(leaf, np.int32), bbox=bbox, n_values=nvalues)
+
+
+MATCH_DT = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
+
+
+def match_projected(sc, min_desc_dist, max_reproj_dist):
+    """Map::matchFrameToMapPoints on a scene dict (ucoslam_b200.synth.synth_projection_scene): (matches[MATCH_DT], visible u8)"""
+    A = lambda k, dt: np.ascontiguousarray(sc[k], dt)
+    ids, pos, nrm = A("mp_id", np.uint32), A("mp_pos", np.float32), A("mp_normal", np.float32)
+    dmin, dmax, mdesc = A("mp_min_dist", np.float32), A("mp_max_dist", np.float32), A("mp_desc", np.uint8)
+    kxy, koct, kdesc = A("kp_xy", np.float32), A("kp_octave", np.int32), A("kp_desc", np.uint8)
+    sf, pose = A("scale_factors", np.float32), A("pose44", np.float32)
+    mn, mx = A("min_xy", np.float32), A("max_xy", np.float32)
+    m = len(ids)
+    out, vis = np.zeros(max(m, 1), MATCH_DT), np.zeros(max(m, 1), np.uint8)
+    f = load_stl().oracle_match_projected
+    f.argtypes = [ctypes.c_int] + [ctypes.c_void_p] * 6 + [ctypes.c_int] + [ctypes.c_void_p] * 4 + [ctypes.c_int] + [ctypes.c_float] * 4 + \
+                 [ctypes.c_void_p] * 3 + [ctypes.c_float] * 2 + [ctypes.c_void_p] * 2
+    n = f(m, _p(ids), _p(pos), _p(nrm), _p(dmin), _p(dmax), _p(mdesc), len(kxy), _p(kxy), _p(koct), _p(kdesc), _p(sf), len(sf),
+          sc["fx"], sc["fy"], sc["cx"], sc["cy"], _p(mn), _p(mx), _p(pose), min_desc_dist, max_reproj_dist, _p(out), _p(vis))
+    return out[:n].copy(), vis[:m].copy()

@@ -50,7 +50,8 @@ def full(paths):
                 if w in hdr:
                     i = hdr.index(w)
                     print("    %-70s %14s %s" % (w, r[i], units[i]))
-            break  # first captured launch; the others repeat it
+            if "--first" in sys.argv:
+                break  # first captured launch; the others repeat it
         print()
 
 
@@ -58,4 +59,4 @@ if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2])
     else:
-        full(sys.argv[2:])
+        full([a for a in sys.argv[2:] if not a.startswith('--')])

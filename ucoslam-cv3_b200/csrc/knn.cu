@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(256) knn_merge_kernel(const unsigned long long
                                                         int32_t* __restrict__ out_idx, int32_t* __restrict__ out_dist) {
     const int q = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (q >= nq) return;
-    const int total = n_lists * k;   // <= 32 * 32
+    const int total = n_lists * k;   // <= 1024
     unsigned long long mine[32];
 #pragma unroll
     for (int j = 0; j < 32; j++) {
@@ -457,7 +457,7 @@ extern "C" int uco_b200_knn_merge_dev(uco_b200_ctx* ctx, int n_lists, int nq, in
                                       const int32_t* dist_lists_dev, int32_t* idx_dev, int32_t* dist_dev) {
     if (!ctx) return UCO_E_INVALID;
     cudaSetDevice(ctx->device);
-    if (n_lists <= 0 || n_lists > 32 || nq < 0 || k <= 0 || k > UCO_KNN_MAX_K || !idx_lists_dev || !dist_lists_dev || !idx_dev || !dist_dev)
+    if (n_lists <= 0 || n_lists * k > 1024 || nq < 0 || k <= 0 || k > UCO_KNN_MAX_K || !idx_lists_dev || !dist_lists_dev || !idx_dev || !dist_dev)
         return uco_fail(ctx, UCO_E_INVALID, "knn_merge: bad arguments");
     if (nq == 0) return UCO_OK;
     const size_t n = (size_t)n_lists * nq * k;
@@ -483,7 +483,7 @@ extern "C" int uco_b200_hamming_knn_sharded_dev(uco_b200_ctx* ctx, uco_b200_comm
     // (grid.y) and the S lists are merged first — the same step as across ranks
     int S = 1;
     const int qcta = (nq + KNN_WARPS - 1) / KNN_WARPS;
-    if (qcta < 2 * ctx->sm_count && nt_shard >= 2 * 8192) S = std::min(std::min(32, nt_shard / 8192), (2 * ctx->sm_count + qcta - 1) / qcta);
+    if (qcta < 2 * ctx->sm_count && nt_shard >= 2 * 8192) S = std::min(std::min(std::min(128, 1024 / k), nt_shard / 8192), (2 * ctx->sm_count + qcta - 1) / qcta);
     const int chunk = S > 1 ? (((nt_shard + S - 1) / S + 255) & ~255) : nt_shard;
     if (S > 1) S = (nt_shard + chunk - 1) / chunk;
     int32_t* li = (int32_t*)uco_ws(ctx, WS_KNN_IDX, 4 * n * (size_t)S);
@@ -497,8 +497,8 @@ extern "C" int uco_b200_hamming_knn_sharded_dev(uco_b200_ctx* ctx, uco_b200_comm
         knn_pack_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(li, ld, (int)n, row_base, (int)n, 0, keys + n * rank);
         UCO_LAUNCH_CHECK(ctx);
     } else {
-        int32_t* dn = (int32_t*)uco_ws(ctx, WS_KNN_N, 4 * 32);
-        int32_t* hn = (int32_t*)uco_pinned(ctx, WS_KNN_N, 4 * 32);
+        int32_t* dn = (int32_t*)uco_ws(ctx, WS_KNN_N, 4 * 128);
+        int32_t* hn = (int32_t*)uco_pinned(ctx, WS_KNN_N, 4 * 128);
         if (!dn || !hn) return UCO_E_NOMEM;
         UCO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // hn may still be in flight from the previous call
         for (int i = 0; i < S; i++) hn[i] = std::min(chunk, nt_shard - i * chunk);

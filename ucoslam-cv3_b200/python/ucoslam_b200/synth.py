@@ -176,3 +176,62 @@ def synth_pnp_problem(seed, n_matches=800, stereo_frac=0.0, outlier_frac=0.1, un
                 fx=float(fx), fy=float(fy), cx=float(cx), cy=float(cy), bf=float(np.float32(bf)),
                 marker_pose44=np.array(m_pose, np.float32).reshape(-1, 16), marker_size=np.array(m_size, np.float32),
                 marker_corners=np.array(m_corners, np.float32).reshape(-1, 8), pose_gt=T)
+
+
+def synth_projection_scene(seed, n_kp=2000, n_mp=3000, n_levels=8, scale=1.2, w=640, h=480, f=525.0, dup_frac=0.1, clutter=0.3):
+    """A frame (undistorted keypoints with octaves and 256-bit descriptors) and the local map handed to
+    Map::matchFrameToMapPoints (SURVEY.md 8a row a12): most map points project next to a keypoint of a compatible octave and carry
+    that keypoint's descriptor with a few flipped bits; some share their keypoint with another map point (filter_ambiguous_query),
+    some look away, lie behind the camera, outside the image or outside their scale-invariance range; keypoints cluster so that
+    several candidates fall inside a search radius (best / second-best bookkeeping)."""
+    rng = np.random.default_rng(seed)
+    cx, cy = np.float32(w / 2 - 0.5), np.float32(h / 2 - 0.5)
+    sf = np.array([np.float32(scale) ** i for i in range(n_levels)], np.float32)
+    n_clusters = max(1, int(n_kp * clutter / 4))
+    kxy = rng.uniform([20, 20], [w - 20, h - 20], (n_kp, 2))
+    own = rng.integers(0, n_kp - n_clusters * 4, n_clusters)
+    for c in range(n_clusters):   # small clumps of keypoints around some others
+        kxy[n_kp - 4 * c - 4:n_kp - 4 * c] = kxy[own[c]] + rng.normal(0, 2.5, (4, 2))
+    kxy = kxy.astype(np.float32)
+    koct = rng.integers(0, n_levels, n_kp).astype(np.int32)
+    kdesc = rng.integers(0, 256, (n_kp, 32), dtype=np.uint8)
+    T = np.eye(4)
+    T[:3, :3] = _rodrigues(rng.normal(0, 0.3, 3))
+    T[:3, 3] = rng.normal(0, 1.0, 3)
+    pose = T.astype(np.float32)
+    Rm, t = pose[:3, :3].astype(np.float64), pose[:3, 3].astype(np.float64)
+    C = -Rm.T @ t
+    pos, nrm, dmin, dmax, mdesc = [], [], [], [], []
+    for i in range(n_mp):
+        kind = rng.random()
+        kp = int(rng.integers(0, n_kp)) if (i == 0 or rng.random() > dup_frac) else last_kp
+        last_kp = kp
+        z = rng.uniform(1.0, 8.0)
+        u, v = kxy[kp] + rng.normal(0, 1.2, 2)
+        Xc = np.array([(u - cx) / f * z, (v - cy) / f * z, z])
+        if kind < 0.05:
+            Xc[2] = -Xc[2]                                   # behind the camera
+        elif kind < 0.10:
+            Xc[0] += 3 * z                                   # projects outside the image
+        X = Rm.T @ (Xc - t)
+        dist = np.linalg.norm(Xc)
+        n = (C - X) / max(np.linalg.norm(C - X), 1e-9)
+        if kind < 0.18:
+            n = _rodrigues(rng.normal(0, 1.0, 3)) @ n        # looks (more or less) away
+        else:
+            n = _rodrigues(rng.normal(0, 0.15, 3)) @ n
+        octv = int(koct[kp])
+        mx = dist * float(sf[octv]) * rng.uniform(0.92, 1.0)  # predictScale() lands on the keypoint's octave (or the one above)
+        mn = mx / float(sf[-1]) * rng.uniform(0.7, 1.0)
+        if 0.18 <= kind < 0.22:
+            mx *= 0.5                                        # too far for its invariance range
+        d = kdesc[kp].copy()
+        for b in rng.integers(0, 256, int(rng.integers(0, 70))):
+            d[b >> 3] ^= 1 << (b & 7)
+        pos.append(X); nrm.append(n); dmin.append(mn); dmax.append(mx); mdesc.append(d)
+    return dict(kp_xy=kxy, kp_octave=koct, kp_desc=kdesc, mp_id=(np.arange(n_mp) * 3 + 7).astype(np.uint32),
+                mp_pos=np.array(pos, np.float32).reshape(-1, 3), mp_normal=np.array(nrm, np.float32).reshape(-1, 3),
+                mp_min_dist=np.array(dmin, np.float32), mp_max_dist=np.array(dmax, np.float32),
+                mp_desc=np.array(mdesc, np.uint8).reshape(-1, 32), scale_factors=sf, pose44=pose.reshape(16),
+                fx=float(np.float32(f)), fy=float(np.float32(f)), cx=float(cx), cy=float(cy),
+                min_xy=np.array([0, 0], np.float32), max_xy=np.array([w, h], np.float32))
