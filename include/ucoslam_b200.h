@@ -349,6 +349,61 @@ int uco_b200_frame_match_batch_dev(uco_b200_ctx* ctx, int n_pairs, const uint8_t
                                    size_t t_kps_pair_stride, int nt_max, const int32_t* nt_dev, const uco_match_params* prm,
                                    uco_match* out_dev, int32_t* n_out_dev);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * K9  projection matcher: local map points -> keypoints of the current frame
+ *   replaces ucoslam::Map::matchFrameToMapPoints(used_frames, curframe, pose_f2g, minDescDist, maxRepjDist, markVisible, ...)
+ *     src/map.cpp:651-770 (the per-map-point loop from :684 on and filter_ambiguous_query; gathering the map-point list,
+ *     :655-672, is container walking and stays with the caller), src/map_types/frame.cpp:102-115 getKeyPointsInRegion,
+ *     src/map_types/frame.h:129-136 predictScale, src/map_types/mappoint.h:99,146-162, src/basictypes/misc.cpp:117-150
+ *   The reference's best / second-best bookkeeping depends on the ORDER in which Frame::keypoint_kdtree (picoflann) reports the
+ *   keypoints of a region, so the frame's kd-tree is an input: flattened nodes in picoflann's numbering.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct uco_kdnode {   /* one picoflann node (picoflann.h:203-215) */
+    float divlow, divhigh;    /* internal node: the two sides of the cut */
+    int32_t col;              /* internal node: split dimension 0 / 1; leaf: -1 */
+    int32_t left, right;      /* children (node indices), -1 for a leaf */
+    int32_t leaf_begin, leaf_count; /* leaf: its keypoint indices are leaf_idx[leaf_begin .. leaf_begin + leaf_count) */
+} uco_kdnode;
+
+/* host-side: the tree of n 2-d points (first two floats of records stride_bytes apart, e.g. cv::KeyPoint::pt with stride 28),
+ * node for node what picoflann::KdTreeIndex<2>::build gives (mean/variance split, leaf size 10, libstdc++ std::sort for the
+ * degenerate cuts).  nodes: capacity cap_nodes >= 2 n; leaf_idx: n entries; bbox4 = {x.min, x.max, y.min, y.max}. */
+int uco_b200_kdtree_build(const float* xy, size_t stride_bytes, int n, uco_kdnode* nodes, int cap_nodes, int32_t* leaf_idx,
+                          double* bbox4, int* n_nodes);
+/* host-side: the same structure from the bytes KdTreeIndex::toStream writes (picoflann.h:603-660; Frame::toStream embeds them) */
+int uco_b200_kdtree_parse(const void* bytes, size_t n_bytes, uco_kdnode* nodes, int cap_nodes, int32_t* leaf_idx, int cap_leaf,
+                          double* bbox4, int* n_nodes, int* n_leaf);
+
+typedef struct uco_mappoints {      /* the candidate map points in the order of smap_ids (map.cpp:655-672) */
+    int32_t n;
+    const uint32_t* ids;            /* n        MapPoint::id -> DMatch::trainIdx */
+    const float* pos;               /* n x 3    getCoordinates() */
+    const float* normal;            /* n x 3    getNormal() */
+    const float* min_dist;          /* n        getMinDistanceInvariance() */
+    const float* max_dist;          /* n        getMaxDistanceInvariance() */
+    const uint8_t* desc;            /* n x 32   the map point's descriptor */
+} uco_mappoints;
+
+typedef struct uco_frame_view {
+    int32_t n_kp;
+    const uco_keypoint* kps;        /* n_kp     Frame::und_kpts (pt and octave are read) */
+    const uint8_t* desc;            /* n_kp rows of 32 bytes, Frame::desc */
+    size_t desc_stride;             /* bytes between rows (0 = 32) */
+    int32_t n_nodes;                /* Frame::keypoint_kdtree, flattened */
+    const uco_kdnode* nodes;
+    const int32_t* leaf_idx;
+    double bbox[4];
+    int32_t n_levels;               /* Frame::scaleFactors */
+    const float* scale_factors;
+    float fx, fy, cx, cy;           /* Frame::imageParams.CameraMatrix */
+    float min_xy[2], max_xy[2];     /* Frame::minXY / maxXY */
+} uco_frame_view;
+
+/* out: capacity mp->n matches (queryIdx = keypoint, trainIdx = map point id, distance = Hamming), in map-point order like the
+ * reference; visible (optional, mp->n bytes): 1 where the reference calls MapPoint::setVisible() (map.cpp:711). */
+int uco_b200_match_projected(uco_b200_ctx* ctx, const uco_mappoints* mp, const uco_frame_view* fr, const float* pose_f2g,
+                             float min_desc_dist, float max_reproj_dist, uco_match* out, int* n_out, uint8_t* visible);
+
 #ifdef __cplusplus
 }
 #endif

@@ -104,7 +104,29 @@ def pnp():
     print("pnp golden written", {n: (int(out[n + "_out_n_good"]), out[n + "_out_iters"].tolist()) for n in PNP_CASES})
 
 
+def project():
+    """Map::matchFrameToMapPoints: the reference itself cannot be linked here (OpenCV C++), so these vectors come from the restatement
+    oracle/project_oracle.cpp, whose kd-tree part (the only third-party-free, order-defining piece) is checked in the same breath
+    against the reference's own picoflann.h (oracle/_ref/libref_picoflann.so).  Scenes are small so the fixture stays small."""
+    oracle_py.build_ref()
+    from ucoslam_b200.synth import synth_projection_scene
+    out = {}
+    for name, (kw, thr) in {"a": (dict(seed=11, n_kp=1200, n_mp=1500), (50.0, 15.0)), "b": (dict(seed=12, n_kp=600, n_mp=900, dup_frac=0.4), (80.0, 30.0)),
+                            "c": (dict(seed=13, n_kp=800, n_mp=1000, clutter=0.8), (100.0, 40.0))}.items():
+        sc = synth_projection_scene(**kw)
+        ref = oracle_py.parse_picoflann_stream(oracle_py.ref_picoflann_stream(sc["kp_xy"]))
+        mine = oracle_py.kdtree_build(sc["kp_xy"])
+        assert all(np.array_equal(ref[k], mine[k]) for k in ("nodes", "div", "leaf_idx"))
+        m, vis = oracle_py.match_projected(sc, *thr)
+        for k, v in sc.items():
+            out["%s_%s" % (name, k)] = np.asarray(v)
+        out[name + "_out_matches"], out[name + "_out_visible"] = m, vis
+        out[name + "_out_min_desc"], out[name + "_out_max_reproj"] = np.float32(thr[0]), np.float32(thr[1])
+    np.savez_compressed(os.path.join(HERE, "project_match.npz"), **out)
+    print("projection golden written", {n: len(out[n + "_out_matches"]) for n in "abc"})
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["knn", "bow", "ba", "pnp"]
+    which = sys.argv[1:] or ["knn", "bow", "ba", "pnp", "project"]
     for w in which:
         globals()[w]()

@@ -38,7 +38,7 @@ enum {  // device workspace slots
     WS_BA, WS_BA_OUT, WS_BA_STOP,
     WS_PNP_IN, WS_PNP_OUT, WS_PNP_SCRATCH,
     WS_MATCH_KNN, WS_MATCH_SCRATCH, WS_MATCH_IN, WS_MATCH_OUT,
-    WS_KNN_N, WS_KNN_MERGE,
+    WS_KNN_N, WS_KNN_MERGE, WS_PROJ, WS_PROJ_OUT,
     WS_COUNT
 };
 

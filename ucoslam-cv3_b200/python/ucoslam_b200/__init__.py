@@ -30,6 +30,9 @@ SIGNATURES = {
     "uco_b200_hamming_knn_batch": (_i, [_vp, _i, _vp, _vp, _sz, _vp, _vp, _sz, _i, _i, _vp, _vp]),
     "uco_b200_hamming_knn_sharded_dev": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp]),
     "uco_b200_knn_merge_dev": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "uco_b200_kdtree_build": (_i, [_vp, _sz, _i, _vp, _i, _vp, _vp, _vp]),
+    "uco_b200_kdtree_parse": (_i, [_vp, _sz, _vp, _i, _vp, _i, _vp, _vp, _vp]),
+    "uco_b200_match_projected": (_i, [_vp, _vp, _vp, _vp, _c.c_float, _c.c_float, _vp, _vp, _vp]),
     "uco_b200_comm_unique_id": (_i, [_vp]),
     "uco_b200_comm_create": (_i, [_vp, _vp, _i, _i, _vp]),
     "uco_b200_comm_destroy": (None, [_vp]),
@@ -96,6 +99,41 @@ def probe_retain_best(packed, n_points):
 
 
 _lib = None
+
+
+KDNODE_DTYPE = np.dtype([("divlow", "<f4"), ("divhigh", "<f4"), ("col", "<i4"), ("left", "<i4"), ("right", "<i4"),
+                         ("leaf_begin", "<i4"), ("leaf_count", "<i4")])  # uco_kdnode
+
+
+class MapPoints(ctypes.Structure):  # uco_mappoints
+    _fields_ = [("n", _c.c_int32), ("ids", _vp), ("pos", _vp), ("normal", _vp), ("min_dist", _vp), ("max_dist", _vp), ("desc", _vp)]
+
+
+class FrameView(ctypes.Structure):  # uco_frame_view
+    _fields_ = [("n_kp", _c.c_int32), ("kps", _vp), ("desc", _vp), ("desc_stride", _c.c_size_t), ("n_nodes", _c.c_int32), ("nodes", _vp),
+                ("leaf_idx", _vp), ("bbox", _c.c_double * 4), ("n_levels", _c.c_int32), ("scale_factors", _vp), ("fx", _c.c_float),
+                ("fy", _c.c_float), ("cx", _c.c_float), ("cy", _c.c_float), ("min_xy", _c.c_float * 2), ("max_xy", _c.c_float * 2)]
+
+
+def kdtree_build(xy):
+    """host-side uco_b200_kdtree_build over (n,2) f32 points -> (nodes[KDNODE_DTYPE], leaf_idx i32, bbox f64[4])"""
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    n = len(xy)
+    nodes, leaf, bbox, k = np.zeros(2 * n + 2, KDNODE_DTYPE), np.zeros(max(n, 1), np.int32), np.zeros(4), ctypes.c_int(0)
+    if load().uco_b200_kdtree_build(_p(xy), 8, n, _p(nodes), len(nodes), _p(leaf), _p(bbox), ctypes.byref(k)) != 0:
+        raise UcoError("kdtree_build failed")
+    return nodes[:k.value].copy(), leaf[:n].copy(), bbox
+
+
+def kdtree_parse(stream_bytes):
+    """host-side uco_b200_kdtree_parse of KdTreeIndex::toStream bytes -> (nodes, leaf_idx, bbox)"""
+    buf = np.frombuffer(stream_bytes, np.uint8)
+    cap = len(buf) // 4 + 4
+    nodes, leaf, bbox = np.zeros(cap, KDNODE_DTYPE), np.zeros(cap, np.int32), np.zeros(4)
+    k, nl = ctypes.c_int(0), ctypes.c_int(0)
+    if load().uco_b200_kdtree_parse(_p(buf), len(buf), _p(nodes), cap, _p(leaf), cap, _p(bbox), ctypes.byref(k), ctypes.byref(nl)) != 0:
+        raise UcoError("kdtree_parse failed")
+    return nodes[:k.value].copy(), leaf[:nl.value].copy(), bbox
 
 
 def probe_ba_partition(pb, world):
@@ -238,6 +276,28 @@ class Context:
                                                       VP(*[t.ctypes.data for t in ts]), _p(nt), 32, k, order,
                                                       VP(*[a.ctypes.data for a in idx]), VP(*[a.ctypes.data for a in dist])))
         return idx, dist
+
+    # -- K9 ------------------------------------------------------------------------------------------------------
+    def match_projected(self, sc, min_desc_dist, max_reproj_dist, tree=None):
+        """Map::matchFrameToMapPoints on a scene dict (synth.synth_projection_scene keys); tree = (nodes, leaf_idx, bbox) of the frame's
+        kd-tree (default: built here).  Returns (matches[MATCH_DTYPE], visible u8[m])."""
+        A = lambda k, dt: np.ascontiguousarray(sc[k], dt)
+        ids, pos, nrm = A("mp_id", np.uint32), A("mp_pos", np.float32), A("mp_normal", np.float32)
+        dmin, dmax, mdesc = A("mp_min_dist", np.float32), A("mp_max_dist", np.float32), A("mp_desc", np.uint8)
+        kdesc, sf, pose = A("kp_desc", np.uint8), A("scale_factors", np.float32), A("pose44", np.float32)
+        kxy, koct = A("kp_xy", np.float32).reshape(-1, 2), A("kp_octave", np.int32)
+        kps = np.zeros(len(kxy), KP_DTYPE)
+        kps["x"], kps["y"], kps["octave"] = kxy[:, 0], kxy[:, 1], koct
+        nodes, leaf, bbox = tree if tree is not None else kdtree_build(kxy)
+        nodes, leaf = np.ascontiguousarray(nodes), np.ascontiguousarray(leaf, np.int32)
+        mp = MapPoints(len(ids), _p(ids), _p(pos), _p(nrm), _p(dmin), _p(dmax), _p(mdesc))
+        fr = FrameView(len(kps), _p(kps), _p(kdesc), 32, len(nodes), _p(nodes), _p(leaf), (ctypes.c_double * 4)(*bbox), len(sf), _p(sf),
+                       sc["fx"], sc["fy"], sc["cx"], sc["cy"], (ctypes.c_float * 2)(*sc["min_xy"]), (ctypes.c_float * 2)(*sc["max_xy"]))
+        m = len(ids)
+        out, vis, n = np.zeros(max(m, 1), MATCH_DTYPE), np.zeros(max(m, 1), np.uint8), ctypes.c_int(0)
+        self._chk(self.lib.uco_b200_match_projected(self.h, ctypes.addressof(mp), ctypes.addressof(fr), _p(pose), min_desc_dist,
+                                                    max_reproj_dist, _p(out), ctypes.byref(n), _p(vis)))
+        return out[:n.value].copy(), vis[:m].copy()
 
     # -- multi-GPU ----------------------------------------------------------------------------------------------
     def comm_create(self, rank=0, world=1, broadcast=None):
