@@ -1,0 +1,71 @@
+// frame_matcher_b200.h — the reference's descriptor-matcher seam: an _impl::FrameMatcher_impl
+// (src/utils/framematcher.cpp:31-58: setParams(trainFrame, mode, minDescDist, ratio, checkOrientation, maxOctaveDiff), match,
+// matchEpipolar) whose work is uco_b200_frame_match: exact 10-NN + the post-filters of FrameMatcher_Flann::matchEpipolar
+// (:228-322) on the device.  The class is declared inside framematcher.cpp in the reference; paste it next to FrameMatcher_Flann
+// and select it in FrameMatcher::FrameMatcher(Type) (:110-125) with a new Type value.  setParams only records the train frame (there
+// is no index to build); match* are re-entrant per object as long as each calling thread owns its own instance, which is how the
+// OpenMP callers use FrameMatcher (src/utils/mapmanager.cpp:9992-10065, src/utils/system.cpp:5026-5078).
+// Compile inside the reference tree (needs its headers and OpenCV C++).
+#pragma once
+#include <vector>
+#include "uco_b200_cxx.h"
+
+namespace ucoslam { namespace _impl {
+
+class FrameMatcher_B200 : public FrameMatcher_impl {
+public:
+    explicit FrameMatcher_B200(int device = 0) : _ctx(device) {}
+    void setParams(const Frame& trainFrame, FrameMatcher::Mode mode, float minDescDist, float nn_match_ratio, bool checkOrientation,
+                   int maxOctaveDiff) override {
+        _train = &trainFrame;
+        _prm = uco_match_params{};
+        _prm.min_desc_dist = minDescDist; _prm.nn_match_ratio = nn_match_ratio;
+        _prm.check_orientation = checkOrientation; _prm.max_octave_diff = maxOctaveDiff;
+        rows(trainFrame, mode, _tRows, _tDesc);
+    }
+    std::vector<cv::DMatch> match(const Frame& queryFrame, FrameMatcher::Mode mode) override { return run(queryFrame, mode, cv::Mat()); }
+    std::vector<cv::DMatch> matchEpipolar(const Frame& queryFrame, FrameMatcher::Mode mode, const cv::Mat& FQ2T) override {
+        return run(queryFrame, mode, FQ2T);
+    }
+
+private:
+    // FrameMatcher::manageMode (:160-198): the descriptor rows of the requested mode and the keypoint each one belongs to
+    static void rows(const Frame& f, FrameMatcher::Mode mode, std::vector<int32_t>& map, std::vector<uint8_t>& desc) {
+        map.clear();
+        for (size_t i = 0; i < f.ids.size(); i++) {
+            const bool assigned = f.ids[i] != std::numeric_limits<uint32_t>::max();
+            if (f.flags[i].is(Frame::FLAG_NONMAXIMA)) continue;
+            if (mode == FrameMatcher::MODE_ALL || (mode == FrameMatcher::MODE_ASSIGNED && assigned) ||
+                (mode == FrameMatcher::MODE_UNASSIGNED && !assigned))
+                map.push_back((int32_t)i);
+        }
+        desc.resize(32 * map.size());
+        for (size_t r = 0; r < map.size(); r++) memcpy(&desc[32 * r], f.desc.ptr<uchar>(map[r]), 32);
+    }
+    std::vector<cv::DMatch> run(const Frame& q, FrameMatcher::Mode mode, const cv::Mat& F) {
+        static_assert(sizeof(cv::KeyPoint) == sizeof(uco_keypoint) && sizeof(cv::DMatch) == sizeof(uco_match), "layouts");
+        std::vector<int32_t> qRows;
+        std::vector<uint8_t> qDesc;
+        rows(q, mode, qRows, qDesc);
+        uco_match_params prm = _prm;
+        prm.use_f12 = !F.empty();
+        if (prm.use_f12) { cv::Mat f32; F.convertTo(f32, CV_32F); memcpy(prm.f12, f32.ptr<float>(0), 36); }
+        prm.n_scales = (int)q.scaleFactors.size();
+        for (int i = 0; i < prm.n_scales && i < UCO_MATCH_MAX_SCALES; i++) prm.scale_factors[i] = q.scaleFactors[i];
+        std::vector<cv::DMatch> out(qRows.size());
+        int n = 0;
+        _ctx.check(uco_b200_frame_match(_ctx.get(), qDesc.data(), (int)qRows.size(), 32, reinterpret_cast<const uco_keypoint*>(q.und_kpts.data()),
+                                        (int)q.und_kpts.size(), qRows.data(), _tDesc.data(), (int)_tRows.size(), 32,
+                                        reinterpret_cast<const uco_keypoint*>(_train->und_kpts.data()), (int)_train->und_kpts.size(),
+                                        _tRows.data(), &prm, reinterpret_cast<uco_match*>(out.data()), (int)out.size(), &n));
+        out.resize(n);
+        return out;
+    }
+    uco_b200::Context _ctx;
+    const Frame* _train = nullptr;
+    uco_match_params _prm{};
+    std::vector<int32_t> _tRows;
+    std::vector<uint8_t> _tDesc;
+};
+
+}}  // namespace ucoslam::_impl
