@@ -1,5 +1,7 @@
+"""Two config-5 global-BA solves on one GPU (the second one is warm), for an ncu launch list:
+    ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/gba_launches.csv python scripts/gba_one.py"""
 import os, sys
-ROOT = "/root/repo"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "ucoslam-cv3_b200", "python"))
 import ucoslam_b200
 from ucoslam_b200.synth import synth_global_ba
