@@ -28,7 +28,8 @@ STAGES = ["orb_extract", "hamming_knn_match", "local_ba"]
 KF_EVERY = 8          # one keyframe (= one local-BA call, mapmanager.cpp:4005) per KF_EVERY frames
 BA_WINDOW = dict(n_poses=12, n_fixed=2, n_points=2000)   # 10 free KFs + 2 fixed observers, ~15k observations, nIters = 5
 BA_ITERS = 5
-N_MAPPERS = 2
+N_MAPPERS = int(os.environ.get("UCO_BENCH_MAPPERS", "2"))          # mapper contexts alternating between steps
+BA_CLUSTER = int(os.environ.get("UCO_BENCH_BA_CLUSTER", "0"))       # CTAs per BA cluster (0 = library default 8)
 
 
 def parse():
@@ -138,28 +139,60 @@ def cpu_baseline_info(have_xflann, n):
                           if have_xflann else "exact linear port")}
 
 
-def run_reference(args, rank, world):
-    if rank != 0:
-        return
+_REF = {}
+
+
+def _ref_worker_init():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py, orb_oracle
+    try:
+        import cv2
+        cv2.setNumThreads(1)          # one worker per host core: no nested thread pools
+    except Exception:
+        pass
+    _REF["mods"] = (oracle_py, orb_oracle, oracle_py.load_ref("libref_xflann.so") is not None)
+
+
+def _ref_worker_step(job):
+    seed, n = job
+    if "mods" not in _REF:
+        _ref_worker_init()
+    oracle_py, orb_oracle, have = _REF["mods"]
+    key = ("data", seed, n)
+    if key not in _REF:               # every worker tracks its own stream of frames (generated once, outside the timed steps)
+        _REF[key] = (synth_clip(n, seed), ba_windows(max(1, n // KF_EVERY), 500 + seed))
+    frames, windows = _REF[key]
+    cpu_reference_step(frames, oracle_py, orb_oracle, have, windows)
+    return n
+
+
+def run_reference(args, rank, world):
+    """The reference's CPU path on ALL host cores of the box: one worker process per core, each tracking its own stream of frames
+    (the same sharding by independent streams the GPU arm uses); a step = every worker processes its bounded sample."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    workers = max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     n = min(args.frames, 8)
-    frames = synth_clip(n, 1234)
-    windows = ba_windows(max(1, n // KF_EVERY), 500)
+    jobs = [(1234 + 17 * w, n) for w in range(workers)]
+    with mp.get_context("fork").Pool(workers, initializer=_ref_worker_init) as pool:
+        for _ in range(max(1, args.warmup)):
+            pool.map(_ref_worker_step, jobs, chunksize=1)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_ref_worker_step, jobs, chunksize=1)
+        dt = time.perf_counter() - t0
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py
     have = oracle_py.load_ref("libref_xflann.so") is not None
-    for _ in range(args.warmup):
-        cpu_reference_step(frames, oracle_py, orb_oracle, have, windows)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_reference_step(frames, oracle_py, orb_oracle, have, windows)
-    dt = time.perf_counter() - t0
-    fps = n * args.steps / dt
+    fps = workers * n * args.steps / dt
     info = cpu_baseline_info(have, n)
-    info.update({"value": fps, "unit": "frames/s"})
+    info.update({"value": fps, "unit": "frames/s", "cores": workers,
+                 "sample": "%d worker processes (one per host core), each: %s" % (workers, info["sample"])})
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                      "config": {"workload": WORKLOAD, "stages": STAGES, "frames_per_step": n},
+                      "config": {"workload": WORKLOAD, "stages": STAGES, "frames_per_step": n * workers, "host_workers": workers},
                       "cpu_baseline": info,
                       "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
@@ -178,6 +211,9 @@ def run_b200(args, rank, world, local_rank):
     # planner + H2D + cluster-resident kernel + D2H) overlaps the tracking of step i+1, as UcoSLAM's threaded mode lets the
     # mapper lag behind the tracker (mapmanager.cpp:1517); every BA finishes inside the timed region.
     ctx_bas = [ucoslam_b200.Context(local_rank) for _ in range(N_MAPPERS)]
+    if BA_CLUSTER:
+        for c in ctx_bas:
+            c.ba_set_mode(0, BA_CLUSTER)
     stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
     from concurrent.futures import ThreadPoolExecutor
     mapper = ThreadPoolExecutor(N_MAPPERS)      # UcoSLAM runs local BA in its mapper thread next to tracking (mapmanager.cpp)

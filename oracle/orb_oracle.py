@@ -163,6 +163,28 @@ def ic_angle(img, step_img, x, y):
     return f32(cv2.fastAtan2(float(f32(m01)), float(f32(m10))))
 
 
+_DISC = None
+
+
+def ic_angles(img, xs, ys):
+    """IC_Angle for many keypoints at once: the same integer moments (exact, so the order of the sums does not matter) gathered
+    with one fancy index per level instead of a Python loop per keypoint; fastAtan2 stays OpenCV's scalar function."""
+    global _DISC
+    if _DISC is None:
+        dv, du = [], []
+        for v in range(-HALF_PATCH_SIZE, HALF_PATCH_SIZE + 1):
+            d = UMAX[abs(v)] if v != 0 else HALF_PATCH_SIZE
+            for u in range(-d, d + 1):
+                dv.append(v)
+                du.append(u)
+        _DISC = (np.array(dv, np.int64), np.array(du, np.int64))
+    dv, du = _DISC
+    xs, ys = np.asarray(xs, np.int64), np.asarray(ys, np.int64)
+    vals = img[ys[:, None] + dv[None, :], xs[:, None] + du[None, :]].astype(np.int64)
+    m01, m10 = (vals * dv).sum(1), (vals * du).sum(1)
+    return np.array([cv2.fastAtan2(float(f32(a)), float(f32(b))) for a, b in zip(m01, m10)], f32)
+
+
 FACTOR_PI = f32(np.pi / np.float64(f32(180.0)))   # (float)(CV_PI/180.f), ORBextractor.cpp:112
 
 
@@ -271,8 +293,8 @@ def compute_level_keypoints(buf, P, level, cols0, rows0, want_candidates=False):
     kps = np.concatenate(out) if out else np.zeros(0, KP_DTYPE)
     if len(kps) > n_desired:
         kps = retain_best(kps, n_desired)[:n_desired].copy()
-    for n in range(len(kps)):                                                          # computeOrientation :516
-        kps["angle"][n] = ic_angle(buf, None, E + cv_round(kps["x"][n]), E + cv_round(kps["y"][n]))
+    if len(kps):                                                                       # computeOrientation :516
+        kps["angle"] = ic_angles(buf, [E + cv_round(v) for v in kps["x"]], [E + cv_round(v) for v in kps["y"]])
     return (kps, cand, g, ini_x_col, ini_y_row) if want_candidates else kps
 
 

@@ -66,3 +66,15 @@ def test_oracle_extract_invariants():
     assert (np.diff(K["octave"]) >= 0).all()
     assert (K["angle"] >= 0).all() and (K["angle"] < 360).all()
     assert (K["x"] >= 19).all() and (K["x"] <= 640).all()
+
+
+def test_vectorised_orientation_equals_the_per_keypoint_restatement():
+    """oracle/orb_oracle.py: ic_angles (one gather per level, used by extract and by bench.py's CPU baseline) == ic_angle (the
+    line-by-line restatement of IC_Angle, ORBextractor.cpp:79-106) on random patches"""
+    import orb_oracle
+    rng = np.random.default_rng(4)
+    img = rng.integers(0, 256, (120, 160), dtype=np.uint8)
+    xs, ys = rng.integers(20, 140, 200), rng.integers(20, 100, 200)
+    a = orb_oracle.ic_angles(img, xs, ys)
+    b = np.array([orb_oracle.ic_angle(img, None, int(x), int(y)) for x, y in zip(xs, ys)], np.float32)
+    assert np.array_equal(a, b)
