@@ -28,8 +28,8 @@ STAGES = ["orb_extract", "hamming_knn_match", "local_ba"]
 KF_EVERY = 8          # one keyframe (= one local-BA call, mapmanager.cpp:4005) per KF_EVERY frames
 BA_WINDOW = dict(n_poses=12, n_fixed=2, n_points=2000)   # 10 free KFs + 2 fixed observers, ~15k observations, nIters = 5
 BA_ITERS = 5
-N_MAPPERS = int(os.environ.get("UCO_BENCH_MAPPERS", "2"))          # mapper contexts alternating between steps
-BA_CLUSTER = int(os.environ.get("UCO_BENCH_BA_CLUSTER", "0"))       # CTAs per BA cluster (0 = library default 8)
+N_MAPPERS = int(os.environ.get("UCO_BENCH_MAPPERS", "4"))          # mapper contexts alternating between steps
+BA_CLUSTER = int(os.environ.get("UCO_BENCH_BA_CLUSTER", "4"))       # CTAs per BA cluster (0 = library default 8)
 
 
 def parse():
@@ -425,8 +425,9 @@ def run_b200(args, rank, world, local_rank):
                            "ba_window": "12 KF (2 fixed), 2000 points, %d observations, nIters=5" % (n_obs // max(1, n_ba)),
                            "parallelism": "frames sharded over %d GPU(s), no collective" % world,
                            "l2": "flushed between timed steps (256 MB write, inside the timed region)",
-                           "mapper": "%d BA contexts alternate between steps: the local BA of step i overlaps the tracking of step "
-                                     "i+1 (threaded mode); all BA results are back on the host inside the timed region" % N_MAPPERS},
+                           "mapper": "%d BA contexts take turns (clusters of %d CTAs per window): the local BA of a step overlaps the tracking "
+                                     "of the following steps (threaded mode: the mapper lags the tracker); all BA results are back on the "
+                                     "host inside the timed region" % (N_MAPPERS, BA_CLUSTER or 8)},
                 "e2e": {"value": total_frames / (e2e_ms * 1e-3), "unit": "frames/s",
                         "h2d_bytes_per_step": F * (W * H + 2 * KPTS * 32) + ba_in_bytes,
                         "d2h_bytes_per_step": F * (KPTS * 60 + 4 + KPTS * K_NN * 8) + ba_out_bytes},
