@@ -40,7 +40,16 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=64, help="frames per step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--res", default="640x480", choices=["640x480", "1280x720"],
+                    help="640x480 / 2000 keypoints = BASELINE config 2 (the metric's configuration, default); 1280x720 / 4000 keypoints = the "
+                         "mono part of config 3 (north_star asks for both stream sizes)")
+    a = ap.parse_args()
+    if a.res == "1280x720":
+        global W, H, KPTS, METRIC, WORKLOAD
+        W, H, KPTS = 1280, 720, 4000
+        METRIC = "frames/sec (ORB+match+local-BA) 1280x720 mono"
+        WORKLOAD = "config3 (mono part): 1280x720 tracking, 4000 ORB kpts/frame, local-BA window=10 KF"
+    return a
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -85,7 +94,7 @@ def synth_clip(n_frames, seed):
     (SURVEY.md 8(d)); FAST-dense, so every frame yields the full 2000 keypoints."""
     import numpy as np, cv2
     rng = np.random.default_rng(seed)
-    size = 2048
+    size = 2048 if W <= 640 else 4096
     acc = np.zeros((size, size), np.float64)
     amp = 1.0
     for blk in (64, 32, 16, 8, 4):
@@ -211,9 +220,11 @@ def run_b200(args, rank, world, local_rank):
     # planner + H2D + cluster-resident kernel + D2H) overlaps the tracking of step i+1, as UcoSLAM's threaded mode lets the
     # mapper lag behind the tracker (mapmanager.cpp:1517); every BA finishes inside the timed region.
     ctx_bas = [ucoslam_b200.Context(local_rank) for _ in range(N_MAPPERS)]
-    if BA_CLUSTER:
-        for c in ctx_bas:
+    for c in ctx_bas:
+        if BA_CLUSTER:
             c.ba_set_mode(0, BA_CLUSTER)
+        if N_MAPPERS > 1:
+            c.ba_set_host_threads(1)     # N_MAPPERS batches are already planned side by side: one planner thread per call
     stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
     from concurrent.futures import ThreadPoolExecutor
     mapper = ThreadPoolExecutor(N_MAPPERS)      # UcoSLAM runs local BA in its mapper thread next to tracking (mapmanager.cpp)
@@ -409,7 +420,7 @@ def run_b200(args, rank, world, local_rank):
     tk = {"local_ba": "ba_cluster_kernel", "hamming_knn": "hamming_knn_kernel", "fast_cells": "fast_cells_kernel", "blur": "blur7_kernel",
           "select": "select_kernel", "orient_describe": "orient_describe_kernel"}.get(top)
     tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if tk and os.path.exists(tp) and F == 64:
+    if tk and os.path.exists(tp) and F == 64 and W == 640:
         for name, v in json.load(open(tp))["kernels"].items():
             if tk in name:
                 traffic = v["dram_bytes_per_launch"]

@@ -262,6 +262,9 @@ int uco_b200_probe_ba_partition(const uco_ba_problem* pb, int world, int* out);
  * window, the whole LM loop in one launch), larger ones as streamed kernels; 1: always streamed; 2: always cluster-resident.
  * cluster_size: CTAs per cluster (power of two <= 16, 0 = 8). */
 int uco_b200_ba_set_mode(uco_b200_ctx* ctx, int mode, int cluster_size);
+/* worker threads the host-side planner of uco_b200_ba_solve_batch may use per call (0 = automatic: this process's share of the host
+ * cores).  A caller that keeps several batches in flight from several mapper threads wants 1; a single caller wants the default. */
+int uco_b200_ba_set_host_threads(uco_b200_ctx* ctx, int n_threads);
 /* host-only inspection hook (no GPU needed): builds the window structure the solver uses and reports
  * {free poses, Schur blocks, gather units, contributions, chunks, pose-list entries, max observations per chunk, landmarks covered} */
 int uco_b200_probe_ba_plan(const uco_ba_problem* pb, int cluster_size, int* out8);

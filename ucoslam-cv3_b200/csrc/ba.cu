@@ -1419,6 +1419,12 @@ int uco_b200_ba_set_mode(uco_b200_ctx* ctx, int mode, int cluster_size) {
     return UCO_OK;
 }
 
+int uco_b200_ba_set_host_threads(uco_b200_ctx* ctx, int n_threads) {
+    if (!ctx || n_threads < 0 || n_threads > 64) return UCO_E_INVALID;
+    ctx->ba_host_threads = n_threads;
+    return UCO_OK;
+}
+
 int uco_b200_ba_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* pbs, const volatile unsigned char* stop, uco_ba_result* res) {
     if (!ctx) return UCO_E_INVALID;
     cudaSetDevice(ctx->device);  // the calling thread may be a new one (mapper / tracker threads): bind it to the context's GPU

@@ -18,6 +18,7 @@
 #include "ba_math.cuh"
 #include "ba_plan.h"
 #include <cooperative_groups.h>
+#include <algorithm>
 #include <cfloat>
 #include <cstring>
 #include <string>
@@ -827,6 +828,29 @@ struct BaArena {
     }
 };
 
+// host-side planning / staging of a batch: a few worker threads, each taking windows in turn.  The count is bounded by this
+// process's share of the host cores (one process per GPU, several mapper contexts per process): oversubscribing them was measured
+// to stretch the 8-GPU step by 50 %.  uco_b200_ba_set_host_threads / UCO_BA_HOST_THREADS override.
+template <class F>
+static void ba_parallel_for(int n, int want, F&& f) {
+    static const int auto_cap = [] {
+        if (const char* e = getenv("UCO_BA_HOST_THREADS")) return std::max(1, atoi(e));
+        int ndev = 1;
+        cudaGetDeviceCount(&ndev);
+        const int hc = (int)std::thread::hardware_concurrency();
+        return std::max(1, std::min(8, hc / std::max(1, ndev) / 4));
+    }();
+    const int nt = std::min(n, want > 0 ? want : auto_cap);
+    if (nt <= 1) {
+        for (int i = 0; i < n; i++) f(i);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++)
+        th.emplace_back([&, t] { for (int i = t; i < n; i += nt) f(i); });
+    for (auto& t : th) t.join();
+}
+
 int ba_cluster_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* const* pbs, const volatile unsigned char* stop, uco_ba_result* const* res) {
     if (n <= 0) return UCO_OK;
     static const bool trace = getenv("UCO_BA_TRACE") != nullptr;
@@ -843,12 +867,7 @@ int ba_cluster_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* const
             rcs[i] = ba_plan_build(&tmp, *pbs[i], BA_UNIT, plans[i], CL, BS);
             errs[i] = tmp.err;
         };
-        if (n == 1) job(0);
-        else {
-            std::vector<std::thread> th;
-            for (int i = 0; i < n; i++) th.emplace_back(job, i);
-            for (auto& t : th) t.join();
-        }
+        ba_parallel_for(n, ctx->ba_host_threads, job);
         for (int i = 0; i < n; i++) {
             if (rcs[i] != UCO_OK) return uco_fail(ctx, rcs[i], "%s", errs[i].c_str());
             max_n = std::max(max_n, 6 * plans[i].Pf);
@@ -963,12 +982,7 @@ int ba_cluster_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* const
         B.d2 = (double)sqrtf(B.chi2d); B.d3 = (double)sqrtf(B.chi3d);
         B.stop = dstop;
     };
-    if (n == 1) fill(0);
-    else {
-        std::vector<std::thread> th;
-        for (int i = 0; i < n; i++) th.emplace_back(fill, i);
-        for (auto& t : th) t.join();
-    }
+    ba_parallel_for(n, ctx->ba_host_threads, fill);
     auto t2 = now();
     cudaStream_t s = ctx->stream;
     UCO_CUDA(ctx, cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, s));

@@ -29,6 +29,7 @@ struct uco_b200_ctx {
     uco_ba_state* ba = nullptr;
     int ba_mode = 0;          // 0 auto, 1 streamed kernels (ba.cu), 2 cluster-resident kernel (ba_cluster.cu)
     int ba_cluster_size = 0;  // CTAs per cluster of the cluster-resident solver (0 = default 8)
+    int ba_host_threads = 0;  // worker threads of the host-side planner per batch call (0 = this process's share of the cores)
 };
 
 enum {  // device workspace slots

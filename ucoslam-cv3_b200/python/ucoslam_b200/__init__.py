@@ -33,6 +33,7 @@ SIGNATURES = {
     "uco_b200_kdtree_build": (_i, [_vp, _sz, _i, _vp, _i, _vp, _vp, _vp]),
     "uco_b200_kdtree_parse": (_i, [_vp, _sz, _vp, _i, _vp, _i, _vp, _vp, _vp]),
     "uco_b200_match_projected": (_i, [_vp, _vp, _vp, _vp, _c.c_float, _c.c_float, _vp, _vp, _vp]),
+    "uco_b200_ba_set_host_threads": (_i, [_vp, _i]),
     "uco_b200_comm_unique_id": (_i, [_vp]),
     "uco_b200_comm_create": (_i, [_vp, _vp, _i, _i, _vp]),
     "uco_b200_comm_destroy": (None, [_vp]),
@@ -333,6 +334,9 @@ class Context:
 
     def ba_set_mode(self, mode=0, cluster_size=0):
         self._chk(self.lib.uco_b200_ba_set_mode(self.h, mode, cluster_size))
+
+    def ba_set_host_threads(self, n):
+        self._chk(self.lib.uco_b200_ba_set_host_threads(self.h, n))
 
     @staticmethod
     def ba_pack(pb, n_iters):
