@@ -155,33 +155,53 @@ hamming_knn_kernel(const uint4* __restrict__ q, int nq, const uint4* __restrict_
         const int s = tl % KNN_STAGES;
         mbar_wait(&full[s], (tl / KNN_STAGES) & 1);
         const int rows = min(KNN_TILE_ROWS, nt - tl * KNN_TILE_ROWS);
-        const uint4* tp = tile[s];
-#pragma unroll 2
-        for (int c = 0; c < rows; c += 32) {
-            const int r = c + lane;
-            const bool valid = r < rows;
-            const int rr = valid ? r : 0;
-            uint4 ta = tp[rr * 2 + swap], tb = tp[rr * 2 + (swap ^ 1)];
-            int d = __popc(ta.x ^ qa.x) + __popc(ta.y ^ qa.y) + __popc(ta.z ^ qa.z) + __popc(ta.w ^ qa.w) +
-                    __popc(tb.x ^ qb.x) + __popc(tb.y ^ qb.y) + __popc(tb.z ^ qb.z) + __popc(tb.w ^ qb.w);
-            const int base = tl * KNN_TILE_ROWS + c;
-            unsigned m = __ballot_sync(0xffffffffu, valid && d < worst);
-            while (m) {  // candidates in train-index order, exactly the order of the reference's scalar loop
-                int b = __ffs(m) - 1;
-                m &= m - 1;
-                int db = __shfl_sync(0xffffffffu, d, b);
-                if (db < worst) {  // worst only shrinks: re-test against the current value (warp-uniform)
-                    uint32_t v = ((uint32_t)db << 23) | (uint32_t)(base + b);
-                    if (n < K) {
-                        push_fill<K, 0>(h, n, v);
-                        n++;
-                    } else {
-                        push_full<K>(h, v);
-                    }
-                    if (n >= K) worst = (int)HD(h[0]);  // once full the reference tests val.dist < distances[0]
-                }
-            }
+        // this lane's row of every 32-row chunk: one address add per chunk; lanes with (lane>>2)&1 read the halves swapped
+        const uint4* lp = tile[s] + lane * 2;
+        const int base_t = tl * KNN_TILE_ROWS;
+#define KNN_DIST(c, valid_)                                                                                              \
+    ({                                                                                                                   \
+        const uint4 ta = lp[(valid_) ? (c) * 2 + swap : swap - lane * 2], tb = lp[(valid_) ? (c) * 2 + (swap ^ 1) : (swap ^ 1) - lane * 2]; \
+        __popc(ta.x ^ qa.x) + __popc(ta.y ^ qa.y) + __popc(ta.z ^ qa.z) + __popc(ta.w ^ qa.w) + __popc(tb.x ^ qb.x) +  \
+            __popc(tb.y ^ qb.y) + __popc(tb.z ^ qb.z) + __popc(tb.w ^ qb.w);                                           \
+    })
+        // candidates of one chunk (mask m, distances d) enter the heap in train-index order, exactly the order of the reference's
+        // scalar loop; `worst` only shrinks, so every candidate is re-tested against the current value (warp-uniform)
+#define KNN_INSERT(m_, d_, c_)                                                                                           \
+    {                                                                                                                    \
+        unsigned m = (m_);                                                                                               \
+        while (m) {                                                                                                      \
+            const int b = __ffs(m) - 1;                                                                                  \
+            m &= m - 1;                                                                                                  \
+            const int db = __shfl_sync(0xffffffffu, (d_), b);                                                            \
+            if (db < worst) {                                                                                            \
+                const uint32_t v = ((uint32_t)db << 23) | (uint32_t)(base_t + (c_) + b);                                \
+                if (n < K) {                                                                                             \
+                    push_fill<K, 0>(h, n, v);                                                                            \
+                    n++;                                                                                                 \
+                } else {                                                                                                 \
+                    push_full<K>(h, v);                                                                                  \
+                }                                                                                                        \
+                if (n >= K) worst = (int)HD(h[0]); /* once full the reference tests val.dist < distances[0] */          \
+            }                                                                                                            \
+        }                                                                                                                \
+    }
+        const int rows64 = rows & ~63;
+        int c = 0;
+        for (; c < rows64; c += 64) {   // two chunks per round: two independent popc chains, one test for the common "nothing enters" case
+            const int d0 = KNN_DIST(c, true), d1 = KNN_DIST(c + 32, true);
+            const unsigned m0 = __ballot_sync(0xffffffffu, d0 < worst), m1 = __ballot_sync(0xffffffffu, d1 < worst);
+            if ((m0 | m1) == 0) continue;
+            KNN_INSERT(m0, d0, c)
+            KNN_INSERT(m1 & __ballot_sync(0xffffffffu, d1 < worst), d1, c + 32)
         }
+        for (; c < rows; c += 32) {   // ragged tail of the last tile
+            const bool valid = c + lane < rows;
+            const int d = KNN_DIST(c, valid);
+            const unsigned m0 = __ballot_sync(0xffffffffu, valid && d < worst);
+            KNN_INSERT(m0, d, c)
+        }
+#undef KNN_DIST
+#undef KNN_INSERT
         __syncthreads();  // every warp is done reading tile[s]
         if (threadIdx.x == 0 && tl + KNN_STAGES < ntiles) {
             int nx = tl + KNN_STAGES;
