@@ -42,7 +42,7 @@ def test_orb_1280x720_4000(ctx):
 
 
 @pytest.mark.parametrize("w,h,nf,nl,sf", [(752, 480, 1000, 8, 1.2), (641, 479, 1500, 6, 1.3), (320, 240, 500, 4, 1.5),
-                                            (1241, 376, 2000, 8, 1.2)])
+                                            (1241, 376, 2000, 8, 1.2), (640, 480, 800, 4, 2.0), (800, 600, 900, 4, 1.7)])
 def test_orb_odd_shapes(ctx, w, h, nf, nl, sf):
     _check_frame(ctx, oo.synth_frame(2, w, h), dict(max_features=nf, n_levels=nl, scale_factor=sf))
 

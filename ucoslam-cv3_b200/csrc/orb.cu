@@ -126,41 +126,69 @@ __global__ void __launch_bounds__(256) blur7_kernel(const __grid_constant__ Plan
 
 // ---- K2: cv::resize INTER_CUBIC, 8U: integer horizontal pass (11-bit coefficients), vertical pass in float for
 // x < vec_limit (OpenCV's SSE VResizeCubicVec_32s8u) and in 22-bit fixed point for the row tail ---------------------------
+// Separable form: a CTA owns a 32 x 32 tile of the destination level.  Pass 1 runs the horizontal filter once per (source row the
+// tile needs, destination column) into shared memory (the 4 source rows of vertically adjacent outputs overlap: ~1.3 filtered
+// rows per output row instead of 4), pass 2 combines 4 of those rows per output pixel.  Same integers as the per-pixel form.
+#define RS_T 32
+#define RS_ROWS 72   // source rows a tile can need: 31 * scale + 4 with scale <= 2 (checked in orb_prepare)
 __global__ void __launch_bounds__(256) resize_cubic_kernel(const __grid_constant__ PlanDev c_plan, uint8_t* __restrict__ pyr, int level,
                                                            const int* __restrict__ tab_ofs,
                                                            const short4* __restrict__ tab_coef) {
     const LevelDev& D = c_plan.lv[level];
     const LevelDev& S = c_plan.lv[level - 1];
-    const int dx = blockIdx.x * 32 + threadIdx.x, dy = blockIdx.y * 8 + threadIdx.y;
-    if (dx >= D.w || dy >= D.h) return;
+    __shared__ int sr[RS_ROWS][RS_T + 1];
+    __shared__ int s_sx[RS_T];
+    __shared__ short4 s_a[RS_T];
+    const int x0 = blockIdx.x * RS_T, y0 = blockIdx.y * RS_T, tid = threadIdx.x;
     uint8_t* frame = pyr + (size_t)blockIdx.z * c_plan.frame_bytes;
     const uint8_t* src = frame + S.off + (size_t)ORB_E * S.pitch + ORB_E;
-    const int sx = tab_ofs[D.tab_x + dx], sy = tab_ofs[D.tab_y + dy];
-    const short4 a = tab_coef[D.tab_x + dx], b = tab_coef[D.tab_y + dy];
-    const int c0 = min(max(sx - 1, 0), S.w - 1), c1 = min(max(sx, 0), S.w - 1), c2 = min(max(sx + 1, 0), S.w - 1),
-              c3 = min(max(sx + 2, 0), S.w - 1);
-    int Sr[4];
+    const int ny = min(RS_T, D.h - y0), nx = min(RS_T, D.w - x0);
+    // clamped source row range of the tile
+    const int r_lo = min(max(tab_ofs[D.tab_y + y0] - 1, 0), S.h - 1);
+    const int r_hi = min(max(tab_ofs[D.tab_y + y0 + ny - 1] + 2, 0), S.h - 1);
+    const int nr = r_hi - r_lo + 1;
+    if (tid < RS_T) {
+        const int dx = min(x0 + tid, D.w - 1);
+        s_sx[tid] = tab_ofs[D.tab_x + dx];
+        s_a[tid] = tab_coef[D.tab_x + dx];
+    }
+    __syncthreads();
+    for (int i = tid; i < nr * RS_T; i += 256) {   // pass 1: horizontal, 11-bit coefficients
+        const int r = i >> 5, x = i & 31;
+        const int sx = s_sx[x];
+        const short4 a = s_a[x];
+        const uint8_t* p = src + (size_t)(r_lo + r) * S.pitch;
+        const int c0 = min(max(sx - 1, 0), S.w - 1), c1 = min(max(sx, 0), S.w - 1), c2 = min(max(sx + 1, 0), S.w - 1),
+                  c3 = min(max(sx + 2, 0), S.w - 1);
+        sr[r][x] = p[c0] * a.x + p[c1] * a.y + p[c2] * a.z + p[c3] * a.w;
+    }
+    __syncthreads();
+    for (int i = tid; i < RS_T * RS_T; i += 256) {  // pass 2: vertical (float for x < vec_limit as OpenCV's SIMD path, else 22-bit fixed point)
+        const int y = i >> 5, x = i & 31;
+        const int dx = x0 + x, dy = y0 + y;
+        if (x >= nx || y >= ny) continue;
+        const int sy = tab_ofs[D.tab_y + dy];
+        const short4 b = tab_coef[D.tab_y + dy];
+        int Sr[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const uint8_t* p = src + (size_t)min(max(sy - 1 + k, 0), S.h - 1) * S.pitch;
-        Sr[k] = p[c0] * a.x + p[c1] * a.y + p[c2] * a.z + p[c3] * a.w;
+        for (int k = 0; k < 4; k++) Sr[k] = sr[min(max(sy - 1 + k, 0), S.h - 1) - r_lo][x];
+        int v;
+        if (dx < D.vec_limit) {
+            const float scale = 1.f / (2048.f * 2048.f);
+            float b0 = __fmul_rn((float)b.x, scale), b1 = __fmul_rn((float)b.y, scale), b2 = __fmul_rn((float)b.z, scale),
+                  b3 = __fmul_rn((float)b.w, scale);
+            float t = __fmul_rn((float)Sr[3], b3);
+            t = __fadd_rn(__fmul_rn((float)Sr[2], b2), t);
+            t = __fadd_rn(__fmul_rn((float)Sr[1], b1), t);
+            t = __fadd_rn(__fmul_rn((float)Sr[0], b0), t);
+            v = __float2int_rn(t);
+        } else {
+            int acc = Sr[0] * b.x + Sr[1] * b.y + Sr[2] * b.z + Sr[3] * b.w;
+            v = (acc + (1 << 21)) >> 22;
+        }
+        v = min(max(v, 0), 255);
+        store_with_border(frame + D.off, D.pitch, D.w, D.h, dx, dy, (uint8_t)v);
     }
-    int v;
-    if (dx < D.vec_limit) {
-        const float scale = 1.f / (2048.f * 2048.f);
-        float b0 = __fmul_rn((float)b.x, scale), b1 = __fmul_rn((float)b.y, scale), b2 = __fmul_rn((float)b.z, scale),
-              b3 = __fmul_rn((float)b.w, scale);
-        float t = __fmul_rn((float)Sr[3], b3);
-        t = __fadd_rn(__fmul_rn((float)Sr[2], b2), t);
-        t = __fadd_rn(__fmul_rn((float)Sr[1], b1), t);
-        t = __fadd_rn(__fmul_rn((float)Sr[0], b0), t);
-        v = __float2int_rn(t);
-    } else {
-        int acc = Sr[0] * b.x + Sr[1] * b.y + Sr[2] * b.z + Sr[3] * b.w;
-        v = (acc + (1 << 21)) >> 22;
-    }
-    v = min(max(v, 0), 255);
-    store_with_border(frame + D.off, D.pitch, D.w, D.h, dx, dy, (uint8_t)v);
 }
 
 // ---- K3 + K4a: FAST-9/16 corner score on each grid cell's interior + 3x3 non-maximum suppression clipped to the cell
@@ -671,6 +699,7 @@ static int orb_prepare(uco_b200_ctx* ctx, int w, int h, const uco_orb_params* pr
     if (w > 4096 || h > 4096 || w < 64 || h < 64) return uco_fail(ctx, UCO_E_INVALID, "orb: image size %dx%d unsupported", w, h);
     if (prm->n_levels < 1 || prm->n_levels > ORB_MAXL || prm->max_features < 1 || !(prm->scale_factor > 1.f))
         return uco_fail(ctx, UCO_E_INVALID, "orb: bad parameters");
+    if (prm->scale_factor > 2.f) return uco_fail(ctx, UCO_E_INVALID, "orb: scale factor %g above 2 is not supported", prm->scale_factor);
     UCO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     orb_free_buffers(s);
     s->batch_cap = 0;
@@ -859,8 +888,8 @@ static int orb_run_dev(uco_b200_ctx* ctx, const uint8_t* in_dev, size_t in_pitch
     UCO_LAUNCH_CHECK(ctx);
     if (prof) cudaEventRecord(s->ev[1], st);
     for (int l = 1; l < P.n_levels; l++) {
-        dim3 g((P.lv[l].w + 31) / 32, (P.lv[l].h + 7) / 8, n);
-        resize_cubic_kernel<<<g, dim3(32, 8), 0, st>>>(P, s->d_pyr, l, s->d_tab_ofs, s->d_tab_coef);
+        dim3 g((P.lv[l].w + RS_T - 1) / RS_T, (P.lv[l].h + RS_T - 1) / RS_T, n);
+        resize_cubic_kernel<<<g, 256, 0, st>>>(P, s->d_pyr, l, s->d_tab_ofs, s->d_tab_coef);
         UCO_LAUNCH_CHECK(ctx);
     }
     if (prof) cudaEventRecord(s->ev[2], st);
