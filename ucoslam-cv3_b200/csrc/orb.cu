@@ -284,8 +284,31 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
     __shared__ int wsum[8];
     __shared__ int running, running_ini;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int r = warp; r < C.h; r += 8)
-        for (int c = lane; c < C.w; c += 32) roi[r * rp + c + 1] = src[(size_t)r * L.pitch + c];
+    if (C.w <= 128) {  // two ROI rows per round, all their loads issued before the first store (the load latency was 23 % of the stall samples)
+        for (int r = warp; r < C.h; r += 16) {
+            const int r2 = r + 8;
+            const bool has2 = r2 < C.h;
+            const uint8_t *p0 = src + (size_t)r * L.pitch, *p1 = src + (size_t)(has2 ? r2 : r) * L.pitch;
+            uint8_t v0[4], v1[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int c = lane + 32 * k;
+                v0[k] = c < C.w ? p0[c] : 0;
+                v1[k] = c < C.w ? p1[c] : 0;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int c = lane + 32 * k;
+                if (c < C.w) {
+                    roi[r * rp + c + 1] = v0[k];
+                    if (has2) roi[r2 * rp + c + 1] = v1[k];
+                }
+            }
+        }
+    } else {
+        for (int r = warp; r < C.h; r += 8)
+            for (int c = lane; c < C.w; c += 32) roi[r * rp + c + 1] = src[(size_t)r * L.pitch + c];
+    }
     for (int i = tid; i < ((sp * (ih + 2)) >> 2) + nw; i += 256) ((unsigned*)sc)[i] = 0;  // sc and cmask are contiguous
     if (tid == 0) nlist = running = running_ini = 0;
     __syncthreads();
@@ -537,6 +560,9 @@ __global__ void __launch_bounds__(256) orient_describe_kernel(const __grid_const
                                                               uint8_t* __restrict__ desc, int* __restrict__ n_out,
                                                               int capacity) {
     __shared__ float pat[UCO_ORB_NPTS * 2];
+    // the 39 x 39 window around the keypoint (orientation disc radius 15, rotated pattern radius <= 18.4 -> +-19 = EDGE_THRESHOLD),
+    // staged per warp with row-coalesced loads: the 709 disc reads and 512 pattern gathers then hit shared memory, not L1 sectors
+    __shared__ uint8_t patch_all[8][39][40];
     for (int i = threadIdx.x; i < UCO_ORB_NPTS * 2; i += blockDim.x) pat[(i & 31) * 32 + (i >> 5)] = (float)c_pattern[i];
     __syncthreads();
     const int f = blockIdx.y, lane = threadIdx.x & 31;
@@ -557,12 +583,22 @@ __global__ void __launch_bounds__(256) orient_describe_kernel(const __grid_const
     const uint32_t e = sel[(size_t)f * c_plan.sel_per_frame + L.sel_off + (slot - first)];
     const int x = e & 0xfff, y = (e >> 12) & 0xfff, score = e >> 24;
     const uint8_t* center = pyr + (size_t)f * c_plan.frame_bytes + L.off + (size_t)(y + ORB_E) * L.pitch + x + ORB_E;
+    uint8_t (*patch)[40] = patch_all[threadIdx.x >> 5];
+    {
+        const uint8_t* p = center - 19 * L.pitch - 19;
+#pragma unroll 3
+        for (int r = 0; r < 39; r++, p += L.pitch) {
+            patch[r][lane] = p[lane];
+            if (lane < 7) patch[r][32 + lane] = p[32 + lane];
+        }
+    }
+    __syncwarp();
     // IC_Angle: lane v+15 sums image row v of the radius-15 disc
     int m10 = 0, m01 = 0;
     if (lane < 31) {
         const int v = lane - 15;
         const int d = c_umax[v < 0 ? -v : v];
-        const uint8_t* row = center + v * L.pitch;
+        const uint8_t* row = &patch[19 + v][19];
         int su = 0, s1 = 0;
         for (int u = -d; u <= d; u++) {
             int val = row[u];
@@ -588,7 +624,7 @@ __global__ void __launch_bounds__(256) orient_describe_kernel(const __grid_const
         int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
         int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
         int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-        int t0 = center[r0 * L.pitch + c0], t1 = center[r1 * L.pitch + c1];
+        int t0 = patch[19 + r0][19 + c0], t1 = patch[19 + r1][19 + c1];
         byte |= (unsigned)(t0 < t1) << t;
     }
     const size_t o = (size_t)f * capacity + slot;
