@@ -352,6 +352,22 @@ int uco_b200_frame_match_batch_dev(uco_b200_ctx* ctx, int n_pairs, const uint8_t
                                    size_t t_kps_pair_stride, int nt_max, const int32_t* nt_dev, const uco_match_params* prm,
                                    uco_match* out_dev, int32_t* n_out_dev);
 
+/* FrameMatcher_BoW::matchEpipolar (src/utils/framematcher.cpp:407-541): candidates of a query keypoint are the train keypoints under
+ * the same level-3 vocabulary node (Frame::bowvector_level, what uco_b200_bow_transform reports as level_node), then the same
+ * filters as above.  A frame's fBow2 is passed flattened in std::map order. */
+typedef struct uco_bow_index {
+    int32_t n_nodes;
+    const uint32_t* node_id;   /* n_nodes, ascending (std::map<uint32_t, std::vector<uint32_t>> iteration order) */
+    const int32_t* ptr;        /* n_nodes + 1: the keypoint indices of node i are kp[ptr[i] .. ptr[i+1]) in the vector's order */
+    const int32_t* kp;
+} uco_bow_index;
+/* q_desc / t_desc: one 32-byte row per KEYPOINT (Frame::desc); q_usable / t_usable: isUsed(frame, keypoint, mode) per keypoint or NULL;
+ * out: capacity >= number of query entries (q_bow->ptr[n_nodes]); matches in the reference's order (node by node). */
+int uco_b200_frame_match_bow(uco_b200_ctx* ctx, const uint8_t* q_desc, size_t q_stride, const uco_keypoint* q_kps, int n_q_kps,
+                             const uint8_t* q_usable, const uco_bow_index* q_bow, const uint8_t* t_desc, size_t t_stride,
+                             const uco_keypoint* t_kps, int n_t_kps, const uint8_t* t_usable, const uco_bow_index* t_bow,
+                             const uco_match_params* prm, uco_match* out, int capacity, int* n_out);
+
 /* ------------------------------------------------------------------------------------------------------------
  * K9  projection matcher: local map points -> keypoints of the current frame
  *   replaces ucoslam::Map::matchFrameToMapPoints(used_frames, curframe, pose_f2g, minDescDist, maxRepjDist, markVisible, ...)

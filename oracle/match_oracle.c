@@ -48,48 +48,9 @@ static int remove_unused(dmatch_t* m, int n) { /* misc.cpp:105-107 */
     return o;
 }
 
-/* q_map / t_map: keypoint index of descriptor row i (FrameMatcher::manageMode, framematcher.cpp:160-198); NULL = identity.
- * F12: 9 floats or NULL.  Returns the number of matches written to out (capacity >= nq). */
-int oracle_frame_match(const uint8_t* q_desc, int nq, size_t q_stride, const kp_t* q_kps, const int32_t* q_map,
-                       const uint8_t* t_desc, int nt, size_t t_stride, const kp_t* t_kps, const int32_t* t_map,
-                       float minDescDist, float nn_match_ratio, int checkOrientation, int maxOctaveDiff, const float* F12,
-                       const float* scaleFactors, int nScale, dmatch_t* out) {
-    const int nn = 10;
-    if (nq <= 0 || nt <= 0) return 0;
-    int32_t* indices = malloc(sizeof(int32_t) * nq * nn);
-    int32_t* idist = malloc(sizeof(int32_t) * nq * nn);
-    oracle_hamming_knn(q_desc, nq, q_stride, t_desc, nt, t_stride, nn, 0, indices, idist);
-    float* sf2 = malloc(sizeof(float) * (nScale + 1));
-    for (int i = 0; i < nScale; i++) sf2[i] = scaleFactors[i] * scaleFactors[i];
-    int n = 0;
-    for (int i = 0; i < nq; i++) {
-        float bestDist = minDescDist, bestDist2 = FLT_MAX;
-        int64_t bestQuery = -1, bestTrain = -1;
-        int octaveBest2 = -1;
-        int queryIndex = q_map ? q_map[i] : i;
-        const kp_t* qk = &q_kps[queryIndex];
-        for (int j = 0; j < nn; j++) {
-            if (indices[i * nn + j] < 0) continue; /* fewer than k train rows (the reference would index out of range) */
-            float d = (float)idist[i * nn + j];
-            if (d > minDescDist) continue;
-            if (d < bestDist2) {
-                int trainIndex = t_map ? t_map[indices[i * nn + j]] : indices[i * nn + j];
-                const kp_t* tk = &t_kps[trainIndex];
-                if (abs(tk->octave - qk->octave) > maxOctaveDiff) continue;
-                if (F12)
-                    if (epipolarLineSqDist(&tk->x, &qk->x, F12) >= 3.84 * sf2[qk->octave]) continue;
-                if (d < bestDist) { bestDist = d; bestQuery = queryIndex; bestTrain = trainIndex; }
-                else { bestDist2 = d; octaveBest2 = tk->octave; }
-            }
-        }
-        if (bestQuery != -1) {
-            if (!(octaveBest2 == q_kps[bestQuery].octave && bestDist > bestDist2 * nn_match_ratio)) {
-                out[n].queryIdx = (int32_t)bestQuery; out[n].trainIdx = (int32_t)bestTrain; out[n].imgIdx = -1; out[n].distance = bestDist;
-                n++;
-            }
-        }
-    }
-    free(indices); free(idist); free(sf2);
+/* what both matchers do with their raw matches: filter_ambiguous_train (misc.cpp:153-185) and the rotation-consistency
+ * histogram (framematcher.cpp:288-316 and, identically, :497-528) */
+static int match_tail(dmatch_t* out, int n, const kp_t* q_kps, const kp_t* t_kps, int checkOrientation) {
     /* filter_ambiguous_train, misc.cpp:153-185 */
     if (n) {
         int maxT = -1;
@@ -140,4 +101,107 @@ int oracle_frame_match(const uint8_t* q_desc, int nq, size_t q_stride, const kp_
         n = remove_unused(out, n);
     }
     return n;
+}
+
+/* q_map / t_map: keypoint index of descriptor row i (FrameMatcher::manageMode, framematcher.cpp:160-198); NULL = identity.
+ * F12: 9 floats or NULL.  Returns the number of matches written to out (capacity >= nq). */
+int oracle_frame_match(const uint8_t* q_desc, int nq, size_t q_stride, const kp_t* q_kps, const int32_t* q_map,
+                       const uint8_t* t_desc, int nt, size_t t_stride, const kp_t* t_kps, const int32_t* t_map,
+                       float minDescDist, float nn_match_ratio, int checkOrientation, int maxOctaveDiff, const float* F12,
+                       const float* scaleFactors, int nScale, dmatch_t* out) {
+    const int nn = 10;
+    if (nq <= 0 || nt <= 0) return 0;
+    int32_t* indices = malloc(sizeof(int32_t) * nq * nn);
+    int32_t* idist = malloc(sizeof(int32_t) * nq * nn);
+    oracle_hamming_knn(q_desc, nq, q_stride, t_desc, nt, t_stride, nn, 0, indices, idist);
+    float* sf2 = malloc(sizeof(float) * (nScale + 1));
+    for (int i = 0; i < nScale; i++) sf2[i] = scaleFactors[i] * scaleFactors[i];
+    int n = 0;
+    for (int i = 0; i < nq; i++) {
+        float bestDist = minDescDist, bestDist2 = FLT_MAX;
+        int64_t bestQuery = -1, bestTrain = -1;
+        int octaveBest2 = -1;
+        int queryIndex = q_map ? q_map[i] : i;
+        const kp_t* qk = &q_kps[queryIndex];
+        for (int j = 0; j < nn; j++) {
+            if (indices[i * nn + j] < 0) continue; /* fewer than k train rows (the reference would index out of range) */
+            float d = (float)idist[i * nn + j];
+            if (d > minDescDist) continue;
+            if (d < bestDist2) {
+                int trainIndex = t_map ? t_map[indices[i * nn + j]] : indices[i * nn + j];
+                const kp_t* tk = &t_kps[trainIndex];
+                if (abs(tk->octave - qk->octave) > maxOctaveDiff) continue;
+                if (F12)
+                    if (epipolarLineSqDist(&tk->x, &qk->x, F12) >= 3.84 * sf2[qk->octave]) continue;
+                if (d < bestDist) { bestDist = d; bestQuery = queryIndex; bestTrain = trainIndex; }
+                else { bestDist2 = d; octaveBest2 = tk->octave; }
+            }
+        }
+        if (bestQuery != -1) {
+            if (!(octaveBest2 == q_kps[bestQuery].octave && bestDist > bestDist2 * nn_match_ratio)) {
+                out[n].queryIdx = (int32_t)bestQuery; out[n].trainIdx = (int32_t)bestTrain; out[n].imgIdx = -1; out[n].distance = bestDist;
+                n++;
+            }
+        }
+    }
+    free(indices); free(idist); free(sf2);
+    return match_tail(out, n, q_kps, t_kps, checkOrientation);
+}
+
+
+/* FrameMatcher_BoW::matchEpipolar, /root/reference/src/utils/framematcher.cpp:407-541: the two frames' fBow2 (level-3 node id ->
+ * keypoint indices, std::map order = ascending node id) are walked in step; inside a common node every usable query keypoint
+ * looks for its best train keypoint (octave window, optional epipolar gate, Hamming distance below minDescDist); ANY later
+ * candidate that is not a new best overwrites the runner-up (:453-460), and the ratio test applies only when that runner-up lies
+ * in the query keypoint's octave.  Then the same tail as the Flann matcher.  *_usable: isUsed(frame, idx, mode) per keypoint, or NULL.
+ * PARITY UNPINNED (needs OpenCV C++ / Frame): restated statement by statement. */
+int oracle_frame_match_bow(const uint8_t* q_desc, const kp_t* q_kps, const uint8_t* q_usable, int q_nodes, const uint32_t* q_node_id,
+                           const int32_t* q_ptr, const int32_t* q_kp, const uint8_t* t_desc, const kp_t* t_kps, const uint8_t* t_usable,
+                           int t_nodes, const uint32_t* t_node_id, const int32_t* t_ptr, const int32_t* t_kp, float minDescDist,
+                           float nn_match_ratio, int checkOrientation, int maxOctaveDiff, const float* F12, const float* scaleFactors,
+                           int nScale, dmatch_t* out) {
+    float* sf2 = malloc(sizeof(float) * (nScale + 1));
+    for (int i = 0; i < nScale; i++) sf2[i] = scaleFactors[i] * scaleFactors[i];
+    int n = 0, qi = 0, ti = 0;
+    while (qi < q_nodes && ti < t_nodes) {
+        if (q_node_id[qi] == t_node_id[ti]) {
+            for (int a = q_ptr[qi]; a < q_ptr[qi + 1]; a++) {
+                const int qidx = q_kp[a];
+                if (q_usable && !q_usable[qidx]) continue;
+                const kp_t* qk = &q_kps[qidx];
+                float bestDist = minDescDist, bestDist2 = FLT_MAX;
+                int64_t bestQuery = -1, bestTrain = -1;
+                int octaveBest2 = -1;
+                for (int b = t_ptr[ti]; b < t_ptr[ti + 1]; b++) {
+                    const int tidx = t_kp[b];
+                    if (t_usable && !t_usable[tidx]) continue;
+                    const kp_t* tk = &t_kps[tidx];
+                    if (abs(tk->octave - qk->octave) > maxOctaveDiff) continue;
+                    if (F12)
+                        if (epipolarLineSqDist(&tk->x, &qk->x, F12) >= 3.84 * sf2[qk->octave]) continue;
+                    int pc = 0;
+                    const uint64_t* x = (const uint64_t*)(t_desc + 32 * (size_t)tidx);
+                    const uint64_t* y = (const uint64_t*)(q_desc + 32 * (size_t)qidx);
+                    for (int w = 0; w < 4; w++) pc += __builtin_popcountll(x[w] ^ y[w]);
+                    const float dist = (float)pc;
+                    if (dist < bestDist) { bestDist = dist; bestQuery = qidx; bestTrain = tidx; }
+                    else { bestDist2 = dist; octaveBest2 = tk->octave; }
+                }
+                if (bestQuery != -1) {
+                    if (!(octaveBest2 == q_kps[bestQuery].octave && bestDist > bestDist2 * nn_match_ratio)) {
+                        out[n].queryIdx = (int32_t)bestQuery; out[n].trainIdx = (int32_t)bestTrain; out[n].imgIdx = -1; out[n].distance = bestDist;
+                        n++;
+                    }
+                }
+            }
+            ++qi;
+            ++ti;
+        } else if (q_node_id[qi] < t_node_id[ti]) {
+            while (qi < q_nodes && q_node_id[qi] < t_node_id[ti]) ++qi;
+        } else {
+            while (ti < t_nodes && t_node_id[ti] < q_node_id[qi]) ++ti;
+        }
+    }
+    free(sf2);
+    return match_tail(out, n, q_kps, t_kps, checkOrientation);
 }

@@ -337,6 +337,94 @@ def frame_match(q_desc, q_kps, t_desc, t_kps, min_desc_dist=50.0, ratio=0.8, che
     return out[:n].copy()
 
 
+def frame_match_bow(q_desc, q_kps, q_bow, t_desc, t_kps, t_bow, min_desc_dist=50.0, ratio=0.8, check_orientation=True, max_octave_diff=1,
+                    F12=None, scale_factors=None, q_usable=None, t_usable=None):
+    """oracle/match_oracle.c oracle_frame_match_bow; q_bow / t_bow = (node_id u32 ascending, ptr i32, kp i32)"""
+    lib = load_oracle()
+    q_desc = np.ascontiguousarray(q_desc, np.uint8).reshape(-1, 32)
+    t_desc = np.ascontiguousarray(t_desc, np.uint8).reshape(-1, 32)
+    q_kps, t_kps = np.ascontiguousarray(q_kps, KP_DTYPE), np.ascontiguousarray(t_kps, KP_DTYPE)
+    sf = np.asarray(scale_factors if scale_factors is not None else [np.float32(1.2) ** i for i in range(8)], np.float32)
+    f12 = None if F12 is None else np.ascontiguousarray(F12, np.float32).reshape(9)
+    qb = [np.ascontiguousarray(q_bow[0], np.uint32), np.ascontiguousarray(q_bow[1], np.int32), np.ascontiguousarray(q_bow[2], np.int32)]
+    tb = [np.ascontiguousarray(t_bow[0], np.uint32), np.ascontiguousarray(t_bow[1], np.int32), np.ascontiguousarray(t_bow[2], np.int32)]
+    qu = None if q_usable is None else np.ascontiguousarray(q_usable, np.uint8)
+    tu = None if t_usable is None else np.ascontiguousarray(t_usable, np.uint8)
+    out = np.zeros(max(len(qb[2]), 1), MATCH_DTYPE)
+    P = lambda a: None if a is None else _p(a)
+    n = lib.oracle_frame_match_bow(_p(q_desc), _p(q_kps), P(qu), len(qb[0]), _p(qb[0]), _p(qb[1]), _p(qb[2]), _p(t_desc), _p(t_kps), P(tu),
+                                   len(tb[0]), _p(tb[0]), _p(tb[1]), _p(tb[2]), ctypes.c_float(min_desc_dist), ctypes.c_float(ratio),
+                                   int(check_orientation), int(max_octave_diff), P(f12), _p(sf), len(sf), _p(out))
+    return out[:n].copy()
+
+
+def frame_match_bow_py(q_desc, q_kps, q_bow, t_desc, t_kps, t_bow, min_desc_dist=50.0, ratio=0.8, check_orientation=True, max_octave_diff=1,
+                       q_usable=None, t_usable=None):
+    """independent pure-Python restatement of FrameMatcher_BoW::matchEpipolar (no epipolar gate) used to cross-check the C oracle"""
+    tnode = {int(n): i for i, n in enumerate(t_bow[0])}
+    matches = []
+    for qi, node in enumerate(q_bow[0]):
+        ti = tnode.get(int(node))
+        if ti is None:
+            continue
+        for qidx in q_bow[2][q_bow[1][qi]:q_bow[1][qi + 1]]:
+            if q_usable is not None and not q_usable[qidx]:
+                continue
+            best, best2, bt, o2 = np.float32(min_desc_dist), np.float32(3.4e38), -1, -1
+            for tidx in t_bow[2][t_bow[1][ti]:t_bow[1][ti + 1]]:
+                if t_usable is not None and not t_usable[tidx]:
+                    continue
+                if abs(int(t_kps["octave"][tidx]) - int(q_kps["octave"][qidx])) > max_octave_diff:
+                    continue
+                d = np.float32(int(np.unpackbits(q_desc[qidx] ^ t_desc[tidx]).sum()))
+                if d < best:
+                    best, bt = d, int(tidx)
+                else:
+                    best2, o2 = d, int(t_kps["octave"][tidx])
+            if bt >= 0 and not (o2 == int(q_kps["octave"][qidx]) and best > np.float32(best2 * np.float32(ratio))):
+                matches.append([int(qidx), bt, -1, float(best)])
+    # filter_ambiguous_train
+    used = {}
+    for i, m in enumerate(matches):
+        j = used.get(m[1])
+        if j is None:
+            used[m[1]] = i
+        elif matches[j][3] > m[3]:
+            matches[j][1] = -1
+            used[m[1]] = i
+        else:
+            m[1] = -1
+    matches = [m for m in matches if m[1] != -1]
+    if check_orientation:
+        bins = []
+        for m in matches:
+            rot = np.float32(t_kps["angle"][m[1]]) - np.float32(q_kps["angle"][m[0]])
+            if rot < 0:
+                rot = np.float32(rot + np.float32(360.0))
+            b = int(np.floor(np.float32(rot * np.float32(1.0 / 30.0)) + np.float32(0.5)))   # roundf for non-negative values
+            bins.append(0 if b == 30 else b)
+        cnt = np.bincount(bins, minlength=30) if bins else np.zeros(30, int)
+        max1 = max2 = max3 = 0
+        i1 = i2 = i3 = -1
+        for i in range(30):
+            s_ = int(cnt[i])
+            if s_ > max1:
+                max3, max2, max1, i3, i2, i1 = max2, max1, s_, i2, i1, i
+            elif s_ > max2:
+                max3, max2, i3, i2 = max2, s_, i2, i
+            elif s_ > max3:
+                max3, i3 = s_, i
+        if max2 < np.float32(0.1) * np.float32(max1):
+            i2 = i3 = -1
+        elif max3 < np.float32(0.1) * np.float32(max1):
+            i3 = -1
+        matches = [m for m, b in zip(matches, bins) if b in (i1, i2, i3)]
+    out = np.zeros(len(matches), MATCH_DTYPE)
+    for i, m in enumerate(matches):
+        out[i] = tuple(m)
+    return out
+
+
 # ---- projection matcher (row a12): kd-tree restatement, the reference's own picoflann, Map::matchFrameToMapPoints ------------------
 _stl = None
 

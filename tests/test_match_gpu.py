@@ -86,3 +86,35 @@ def test_match_batch_dev_equals_oracle(ctx):
         nq, nt = counts[p + 1], counts[p]
         ref = oracle_py.frame_match(desc[p + 1, :nq], kps[p + 1], desc[p, :nt], kps[p])
         assert cnt[p] == len(ref) and same(res[p, :cnt[p]], ref), p
+
+
+@pytest.mark.parametrize("seed,nt,nq,bits,kw", [
+    (11, 2000, 2000, 9, dict()),
+    (12, 2000, 1777, 10, dict(check_orientation=False)),
+    (13, 1500, 2000, 6, dict(ratio=0.6, max_octave_diff=0)),          # few, crowded nodes: long candidate lists, many ties
+    (14, 4000, 4000, 10, dict(min_desc_dist=100.0)),
+    (15, 2000, 2000, 8, dict(F12=F)),
+    (16, 30, 40, 2, dict(min_desc_dist=300.0)),
+])
+def test_bow_match_equals_oracle(ctx, seed, nt, nq, bits, kw):
+    """uco_b200_frame_match_bow against the restatement of FrameMatcher_BoW::matchEpipolar, with usable masks (matcher modes)"""
+    from test_match_oracle import _bow_frames
+    q, qk, qb, t, tk, tb = _bow_frames(seed, nt, nq, bits)
+    rng = np.random.default_rng(seed)
+    qu, tu = (rng.random(nq) > 0.15).astype(np.uint8), (rng.random(nt) > 0.15).astype(np.uint8)
+    prm = ucoslam_b200.MatchParams(kw.get("min_desc_dist", 50.0), kw.get("ratio", 0.8), kw.get("check_orientation", True),
+                                   kw.get("max_octave_diff", 1), kw.get("F12"))
+    for masks in ((None, None), (qu, tu)):
+        ref = oracle_py.frame_match_bow(q, qk, qb, t, tk, tb, q_usable=masks[0], t_usable=masks[1], **kw)
+        got = ctx.frame_match_bow(q, qk, qb, t, tk, tb, prm, q_usable=masks[0], t_usable=masks[1])
+        assert same(got, ref)
+        assert len(ref) > 0
+
+
+def test_bow_match_disjoint_vocabulary_nodes(ctx):
+    """no common node -> no match; empty inputs -> no match"""
+    from test_match_oracle import _bow_frames
+    q, qk, qb, t, tk, tb = _bow_frames(17, 300, 300, 6)
+    tb2 = (tb[0] + np.uint32(1), tb[1], tb[2])
+    assert len(ctx.frame_match_bow(q, qk, qb, t, tk, tb2, ucoslam_b200.MatchParams())) == 0
+    assert len(oracle_py.frame_match_bow(q, qk, qb, t, tk, tb2)) == 0

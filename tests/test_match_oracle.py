@@ -93,3 +93,25 @@ def test_empty_inputs():
     q, qk, t, tk = oracle_py.synth_match_frames(4, nt=50, nq=20)
     assert len(oracle_py.frame_match(q[:0], qk, t, tk)) == 0
     assert len(oracle_py.frame_match(q, qk, t[:0], tk)) == 0
+
+
+def _bow_frames(seed, nt, nq, bits=9):
+    """two frames whose keypoints are filed under synthetic level-3 nodes: node id = the first `bits` bits of the descriptor, so
+    re-observed keypoints usually (not always: flipped bits) share a node, as with a real vocabulary"""
+    import ucoslam_b200
+    q, qk, t, tk = oracle_py.synth_match_frames(seed, nt=nt, nq=nq)
+    node = lambda d: ((d[:, 0].astype(np.uint32) << 8 | d[:, 1]) >> (16 - bits)).astype(np.uint32) * 16 + 3
+    return q, qk, ucoslam_b200.bow_index(node(q)), t, tk, ucoslam_b200.bow_index(node(t))
+
+
+def test_bow_matcher_oracle_equals_python_restatement():
+    """oracle_frame_match_bow (C) against an independent pure-Python restatement of FrameMatcher_BoW::matchEpipolar"""
+    for seed, nt, nq, kw in ((1, 700, 700, {}), (2, 500, 650, dict(ratio=0.6, max_octave_diff=0)), (3, 600, 400, dict(check_orientation=False, min_desc_dist=80.0))):
+        q, qk, qb, t, tk, tb = _bow_frames(seed, nt, nq, bits=6)
+        rng = np.random.default_rng(seed)
+        qu, tu = (rng.random(nq) > 0.1).astype(np.uint8), (rng.random(nt) > 0.1).astype(np.uint8)
+        a = oracle_py.frame_match_bow(q, qk, qb, t, tk, tb, q_usable=qu, t_usable=tu, **kw)
+        b = oracle_py.frame_match_bow_py(q, qk, qb, t, tk, tb, q_usable=qu, t_usable=tu, **kw)
+        assert len(a) > 20 and len(a) == len(b)
+        for k in ("queryIdx", "trainIdx", "imgIdx", "distance"):
+            assert np.array_equal(a[k], b[k]), k

@@ -1,5 +1,6 @@
 // match.cu — K8: frame-to-frame descriptor matcher = exact Hamming k-NN (knn.cu) + the post-filters of
-// FrameMatcher_Flann::matchEpipolar (src/utils/framematcher.cpp:228-322), all on the device.
+// FrameMatcher_Flann::matchEpipolar (src/utils/framematcher.cpp:228-322), all on the device; and its BoW-guided twin
+// FrameMatcher_BoW::matchEpipolar (:407-541), whose candidates are the keypoints sharing a level-3 vocabulary node.
 //
 // One thread block per frame pair.  The reference's sequential passes are restated as order-independent operations with the
 // same result:
@@ -12,6 +13,7 @@
 //   * remove_unused_matches is a stable compaction: block-wide prefix sums over query order.
 #include "common.cuh"
 #include <float.h>
+#include <vector>
 
 int uco_knn_launch_internal(uco_b200_ctx* ctx, const uint8_t* q_dev, int nq, const uint8_t* t_dev, int nt, int k, int order,
                             int32_t* idx_dev, int32_t* dist_dev, int n_pairs, const int* nq_dev, const int* nt_dev,
@@ -37,6 +39,14 @@ struct MatchArgs {
     uco_match* out;           // n_pairs x nq_max
     int32_t* n_out;
     uco_match_params prm;
+    // BoW-guided candidates (FrameMatcher_BoW): entry i = i-th keypoint reference of the query's fBow2 in node order; q_map = the
+    // keypoint of an entry.  Null bow_entry_node selects the k-NN candidates above.
+    const int32_t* bow_entry_node;   // nq_max: query node of the entry
+    const int32_t* bow_t_node;       // per query node: index of the train node with the same id, or -1
+    const int32_t* bow_t_ptr;        // train node -> range in bow_t_kp
+    const int32_t* bow_t_kp;
+    const uint8_t *q_usable, *t_usable;   // optional isUsed(frame, keypoint, mode)
+    const uint32_t *q_desc, *t_desc;      // descriptors by KEYPOINT index, 8 words each
 };
 
 __device__ __forceinline__ float epipolar_sq_dist(const uco_keypoint& kp1, const uco_keypoint& kp2, const float* F) {  // misc.h:72-81
@@ -71,7 +81,7 @@ __global__ void __launch_bounds__(MT) match_filter_kernel(MatchArgs A) {
     if (tid == 0) running = 0;
     __syncthreads();
     // per query: best / second best among the k candidates (framematcher.cpp:246-283)
-    for (int i = tid; i < nq; i += MT) {
+    for (int i = tid; i < nq && !A.bow_entry_node; i += MT) {
         float bestDist = P.min_desc_dist, bestDist2 = FLT_MAX;
         int bestTrain = -1, octaveBest2 = -1;
         const int queryIndex = A.q_map ? A.q_map[i] : i;
@@ -90,6 +100,40 @@ __global__ void __launch_bounds__(MT) match_filter_kernel(MatchArgs A) {
                     if ((double)epipolar_sq_dist(t, q, P.f12) >= 3.84 * (double)(sf * sf)) continue;
                 }
                 if (d < bestDist) { bestDist = d; bestTrain = trainIndex; }
+                else { bestDist2 = d; octaveBest2 = t.octave; }
+            }
+        }
+        if (bestTrain != -1 && (octaveBest2 == q.octave && bestDist > bestDist2 * P.nn_match_ratio)) bestTrain = -1;
+        cand[i] = make_int2(bestTrain, (int)bestDist);
+        if (bestTrain != -1) atomicMin(&used[bestTrain], ((unsigned long long)(unsigned)(int)bestDist << 32) | (unsigned)i);
+    }
+    // FrameMatcher_BoW::matchEpipolar (framematcher.cpp:433-480): the candidates of a query keypoint are the train keypoints of the
+    // same level-3 vocabulary node, in the node's list order; any candidate that is not a new best overwrites the runner-up
+    for (int i = tid; i < nq && A.bow_entry_node; i += MT) {
+        const int qidx = A.q_map[i];
+        int bestTrain = -1;
+        float bestDist = P.min_desc_dist, bestDist2 = FLT_MAX;
+        int octaveBest2 = -1;
+        const int tn = A.bow_t_node[A.bow_entry_node[i]];
+        const uco_keypoint q = qk[qidx];
+        if (tn >= 0 && (!A.q_usable || A.q_usable[qidx])) {
+            uint32_t qd[8];
+#pragma unroll
+            for (int w = 0; w < 8; w++) qd[w] = A.q_desc[8 * (size_t)qidx + w];
+            for (int j = A.bow_t_ptr[tn]; j < A.bow_t_ptr[tn + 1]; j++) {
+                const int tidx = A.bow_t_kp[j];
+                if (A.t_usable && !A.t_usable[tidx]) continue;
+                const uco_keypoint t = tk[tidx];
+                if (abs(t.octave - q.octave) > P.max_octave_diff) continue;
+                if (P.use_f12) {
+                    const float sf = P.scale_factors[min(max(q.octave, 0), UCO_MATCH_MAX_SCALES - 1)];
+                    if ((double)epipolar_sq_dist(t, q, P.f12) >= 3.84 * (double)(sf * sf)) continue;
+                }
+                int pc = 0;
+#pragma unroll
+                for (int w = 0; w < 8; w++) pc += __popc(qd[w] ^ A.t_desc[8 * (size_t)tidx + w]);
+                const float d = (float)pc;
+                if (d < bestDist) { bestDist = d; bestTrain = tidx; }
                 else { bestDist2 = d; octaveBest2 = t.octave; }
             }
         }
@@ -202,6 +246,7 @@ int uco_b200_frame_match_batch_dev(uco_b200_ctx* ctx, int n_pairs, const uint8_t
     A.nq_max = nq_max; A.nt_max = nt_max; A.n_t_kps = nt_max; A.nq_dev = nq_dev; A.nt_dev = nt_dev;
     A.used = (unsigned long long*)scr; A.cand = (int2*)(scr + used_bytes);
     A.out = out_dev; A.n_out = n_out_dev; A.prm = *prm;
+    A.bow_entry_node = nullptr; A.bow_t_node = nullptr; A.bow_t_ptr = nullptr; A.bow_t_kp = nullptr; A.q_usable = A.t_usable = nullptr; A.q_desc = A.t_desc = nullptr;
     match_filter_kernel<<<n_pairs, MT, 0, ctx->stream>>>(A);
     UCO_LAUNCH_CHECK(ctx);
     return UCO_OK;
@@ -252,11 +297,89 @@ int uco_b200_frame_match(uco_b200_ctx* ctx, const uint8_t* q_desc, int nq, size_
     A.nq_max = nq; A.nt_max = nt; A.n_t_kps = n_t_kps; A.nq_dev = nullptr; A.nt_dev = nullptr;
     A.used = (unsigned long long*)scr; A.cand = (int2*)(scr + used_bytes);
     A.out = (uco_match*)(dout + 16); A.n_out = (int32_t*)dout; A.prm = *prm;
+    A.bow_entry_node = nullptr; A.bow_t_node = nullptr; A.bow_t_ptr = nullptr; A.bow_t_kp = nullptr; A.q_usable = A.t_usable = nullptr; A.q_desc = A.t_desc = nullptr;
     match_filter_kernel<<<1, MT, 0, ctx->stream>>>(A);
     UCO_LAUNCH_CHECK(ctx);
     int n = 0;
     UCO_CUDA(ctx, cudaMemcpyAsync(&n, dout, 4, cudaMemcpyDeviceToHost, ctx->stream));
     UCO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n > 0) UCO_CUDA(ctx, cudaMemcpy(out, dout + 16, sizeof(uco_match) * (size_t)n, cudaMemcpyDeviceToHost));
+    *n_out = n;
+    return UCO_OK;
+}
+
+int uco_b200_frame_match_bow(uco_b200_ctx* ctx, const uint8_t* q_desc, size_t q_stride, const uco_keypoint* q_kps, int n_q_kps,
+                             const uint8_t* q_usable, const uco_bow_index* q_bow, const uint8_t* t_desc, size_t t_stride,
+                             const uco_keypoint* t_kps, int n_t_kps, const uint8_t* t_usable, const uco_bow_index* t_bow,
+                             const uco_match_params* prm, uco_match* out, int capacity, int* n_out) {
+    if (!ctx) return UCO_E_INVALID;
+    cudaSetDevice(ctx->device);
+    int rc = check_params(ctx, prm);
+    if (rc) return rc;
+    if (!n_out || !q_bow || !t_bow) return uco_fail(ctx, UCO_E_INVALID, "frame_match_bow: null pointer");
+    *n_out = 0;
+    if (n_q_kps < 0 || n_t_kps < 0 || q_bow->n_nodes < 0 || t_bow->n_nodes < 0) return uco_fail(ctx, UCO_E_INVALID, "frame_match_bow: bad sizes");
+    if (n_q_kps == 0 || n_t_kps == 0 || q_bow->n_nodes == 0 || t_bow->n_nodes == 0) return UCO_OK;
+    if (!q_desc || !q_kps || !t_desc || !t_kps || !out || !q_bow->node_id || !q_bow->ptr || !q_bow->kp || !t_bow->node_id || !t_bow->ptr || !t_bow->kp)
+        return uco_fail(ctx, UCO_E_INVALID, "frame_match_bow: null pointer");
+    if (q_stride < 32 || t_stride < 32) return uco_fail(ctx, UCO_E_INVALID, "frame_match_bow: row stride below 32 bytes");
+    const int ne = q_bow->ptr[q_bow->n_nodes], nte = t_bow->ptr[t_bow->n_nodes];
+    if (capacity < ne) return uco_fail(ctx, UCO_E_CAPACITY, "frame_match_bow: output capacity %d below the %d query entries", capacity, ne);
+    for (int i = 0; i < ne; i++)
+        if ((unsigned)q_bow->kp[i] >= (unsigned)n_q_kps) return uco_fail(ctx, UCO_E_INVALID, "frame_match_bow: query keypoint %d out of range", q_bow->kp[i]);
+    for (int i = 0; i < nte; i++)
+        if ((unsigned)t_bow->kp[i] >= (unsigned)n_t_kps) return uco_fail(ctx, UCO_E_INVALID, "frame_match_bow: train keypoint %d out of range", t_bow->kp[i]);
+    if (ne == 0 || nte == 0) return UCO_OK;
+    // the in-step walk of the two std::maps (framematcher.cpp:426-431, 482-491): which train node carries the id of a query node
+    std::vector<int32_t> t_of_q(q_bow->n_nodes, -1), entry_node(ne);
+    for (int qi = 0, ti = 0; qi < q_bow->n_nodes && ti < t_bow->n_nodes;) {
+        if (q_bow->node_id[qi] == t_bow->node_id[ti]) t_of_q[qi++] = ti++;
+        else if (q_bow->node_id[qi] < t_bow->node_id[ti]) qi++;
+        else ti++;
+    }
+    for (int qn = 0; qn < q_bow->n_nodes; qn++)
+        for (int e = q_bow->ptr[qn]; e < q_bow->ptr[qn + 1]; e++) entry_node[e] = qn;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t off = 0;
+    auto take = [&](size_t b) { size_t o = off; off = al(off + b); return o; };
+    const size_t o_qd = take((size_t)n_q_kps * 32), o_td = take((size_t)n_t_kps * 32), o_qk = take(sizeof(uco_keypoint) * (size_t)n_q_kps),
+                 o_tk = take(sizeof(uco_keypoint) * (size_t)n_t_kps), o_qe = take(4 * (size_t)ne), o_en = take(4 * (size_t)ne),
+                 o_tq = take(4 * (size_t)q_bow->n_nodes), o_tp = take(4 * (size_t)(t_bow->n_nodes + 1)), o_te = take(4 * (size_t)nte),
+                 o_qu = take((size_t)n_q_kps), o_tu = take((size_t)n_t_kps);
+    uint8_t* din = (uint8_t*)uco_ws(ctx, WS_MATCH_IN, off);
+    const size_t used_bytes = (size_t)n_t_kps * 8, cand_bytes = (size_t)ne * 8;
+    uint8_t* scr = (uint8_t*)uco_ws(ctx, WS_MATCH_SCRATCH, used_bytes + cand_bytes);
+    uint8_t* dout = (uint8_t*)uco_ws(ctx, WS_MATCH_OUT, sizeof(uco_match) * (size_t)ne + 16);
+    if (!din || !scr || !dout) return UCO_E_NOMEM;
+    cudaStream_t st = ctx->stream;
+    UCO_CUDA(ctx, cudaMemcpy2DAsync(din + o_qd, 32, q_desc, q_stride, 32, n_q_kps, cudaMemcpyHostToDevice, st));
+    UCO_CUDA(ctx, cudaMemcpy2DAsync(din + o_td, 32, t_desc, t_stride, 32, n_t_kps, cudaMemcpyHostToDevice, st));
+    UCO_CUDA(ctx, cudaMemcpyAsync(din + o_qk, q_kps, sizeof(uco_keypoint) * (size_t)n_q_kps, cudaMemcpyHostToDevice, st));
+    UCO_CUDA(ctx, cudaMemcpyAsync(din + o_tk, t_kps, sizeof(uco_keypoint) * (size_t)n_t_kps, cudaMemcpyHostToDevice, st));
+    UCO_CUDA(ctx, cudaMemcpyAsync(din + o_qe, q_bow->kp, 4 * (size_t)ne, cudaMemcpyHostToDevice, st));
+    UCO_CUDA(ctx, cudaMemcpyAsync(din + o_en, entry_node.data(), 4 * (size_t)ne, cudaMemcpyHostToDevice, st));
+    UCO_CUDA(ctx, cudaMemcpyAsync(din + o_tq, t_of_q.data(), 4 * (size_t)q_bow->n_nodes, cudaMemcpyHostToDevice, st));
+    UCO_CUDA(ctx, cudaMemcpyAsync(din + o_tp, t_bow->ptr, 4 * (size_t)(t_bow->n_nodes + 1), cudaMemcpyHostToDevice, st));
+    UCO_CUDA(ctx, cudaMemcpyAsync(din + o_te, t_bow->kp, 4 * (size_t)nte, cudaMemcpyHostToDevice, st));
+    if (q_usable) UCO_CUDA(ctx, cudaMemcpyAsync(din + o_qu, q_usable, (size_t)n_q_kps, cudaMemcpyHostToDevice, st));
+    if (t_usable) UCO_CUDA(ctx, cudaMemcpyAsync(din + o_tu, t_usable, (size_t)n_t_kps, cudaMemcpyHostToDevice, st));
+    UCO_CUDA(ctx, cudaStreamSynchronize(st));   // entry_node / t_of_q are stack-lifetime host vectors
+    MatchArgs A;
+    A.knn_idx = nullptr; A.knn_dist = nullptr;
+    A.q_kps = (const uco_keypoint*)(din + o_qk); A.q_kps_stride = 0; A.t_kps = (const uco_keypoint*)(din + o_tk); A.t_kps_stride = 0;
+    A.q_map = (const int32_t*)(din + o_qe); A.t_map = nullptr;
+    A.nq_max = ne; A.nt_max = n_t_kps; A.n_t_kps = n_t_kps; A.nq_dev = nullptr; A.nt_dev = nullptr;
+    A.used = (unsigned long long*)scr; A.cand = (int2*)(scr + used_bytes);
+    A.out = (uco_match*)(dout + 16); A.n_out = (int32_t*)dout; A.prm = *prm;
+    A.bow_entry_node = (const int32_t*)(din + o_en); A.bow_t_node = (const int32_t*)(din + o_tq); A.bow_t_ptr = (const int32_t*)(din + o_tp);
+    A.bow_t_kp = (const int32_t*)(din + o_te);
+    A.q_usable = q_usable ? din + o_qu : nullptr; A.t_usable = t_usable ? din + o_tu : nullptr;
+    A.q_desc = (const uint32_t*)(din + o_qd); A.t_desc = (const uint32_t*)(din + o_td);
+    match_filter_kernel<<<1, MT, 0, st>>>(A);
+    UCO_LAUNCH_CHECK(ctx);
+    int n = 0;
+    UCO_CUDA(ctx, cudaMemcpyAsync(&n, dout, 4, cudaMemcpyDeviceToHost, st));
+    UCO_CUDA(ctx, cudaStreamSynchronize(st));
     if (n > 0) UCO_CUDA(ctx, cudaMemcpy(out, dout + 16, sizeof(uco_match) * (size_t)n, cudaMemcpyDeviceToHost));
     *n_out = n;
     return UCO_OK;

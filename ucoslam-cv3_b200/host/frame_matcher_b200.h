@@ -61,6 +61,45 @@ private:
         out.resize(n);
         return out;
     }
+public:
+    // FrameMatcher_BoW::matchEpipolar (:407-541) on the same object: candidates from the frames' bowvector_level (fBow2)
+    std::vector<cv::DMatch> matchEpipolarBoW(const Frame& q, FrameMatcher::Mode qMode, FrameMatcher::Mode tMode, const cv::Mat& F12) {
+        struct Flat { std::vector<uint32_t> id; std::vector<int32_t> ptr, kp; std::vector<uint8_t> usable; };
+        auto flatten = [](const Frame& f, FrameMatcher::Mode mode) {
+            Flat o;
+            o.ptr.push_back(0);
+            for (const auto& kv : *f.bowvector_level) {            // std::map: ascending node id
+                o.id.push_back(kv.first);
+                for (auto k : kv.second) o.kp.push_back((int32_t)k);
+                o.ptr.push_back((int32_t)o.kp.size());
+            }
+            o.usable.resize(f.und_kpts.size());
+            for (size_t i = 0; i < f.und_kpts.size(); i++) {       // isUsed(frame, idx, mode), framematcher.cpp:543-556
+                const bool assigned = f.ids[i] != std::numeric_limits<uint32_t>::max();
+                o.usable[i] = !f.flags[i].is(Frame::FLAG_NONMAXIMA) &&
+                              (mode == FrameMatcher::MODE_ALL || (mode == FrameMatcher::MODE_ASSIGNED) == assigned);
+            }
+            return o;
+        };
+        const Flat fq = flatten(q, qMode), ft = flatten(*_train, tMode);
+        uco_bow_index qb{(int32_t)fq.id.size(), fq.id.data(), fq.ptr.data(), fq.kp.data()};
+        uco_bow_index tb{(int32_t)ft.id.size(), ft.id.data(), ft.ptr.data(), ft.kp.data()};
+        uco_match_params prm = _prm;
+        prm.use_f12 = !F12.empty();
+        if (prm.use_f12) { cv::Mat f32; F12.convertTo(f32, CV_32F); memcpy(prm.f12, f32.ptr<float>(0), 36); }
+        prm.n_scales = (int)q.scaleFactors.size();
+        for (int i = 0; i < prm.n_scales && i < UCO_MATCH_MAX_SCALES; i++) prm.scale_factors[i] = q.scaleFactors[i];
+        std::vector<cv::DMatch> out(fq.kp.size());
+        int n = 0;
+        _ctx.check(uco_b200_frame_match_bow(_ctx.get(), q.desc.ptr<uchar>(0), q.desc.step[0], reinterpret_cast<const uco_keypoint*>(q.und_kpts.data()),
+                                            (int)q.und_kpts.size(), fq.usable.data(), &qb, _train->desc.ptr<uchar>(0), _train->desc.step[0],
+                                            reinterpret_cast<const uco_keypoint*>(_train->und_kpts.data()), (int)_train->und_kpts.size(),
+                                            ft.usable.data(), &tb, &prm, reinterpret_cast<uco_match*>(out.data()), (int)out.size(), &n));
+        out.resize(n);
+        return out;
+    }
+
+private:
     uco_b200::Context _ctx;
     const Frame* _train = nullptr;
     uco_match_params _prm{};

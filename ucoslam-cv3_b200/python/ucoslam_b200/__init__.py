@@ -30,6 +30,7 @@ SIGNATURES = {
     "uco_b200_hamming_knn_batch": (_i, [_vp, _i, _vp, _vp, _sz, _vp, _vp, _sz, _i, _i, _vp, _vp]),
     "uco_b200_hamming_knn_sharded_dev": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp]),
     "uco_b200_knn_merge_dev": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "uco_b200_frame_match_bow": (_i, [_vp, _vp, _sz, _vp, _i, _vp, _vp, _vp, _sz, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "uco_b200_kdtree_build": (_i, [_vp, _sz, _i, _vp, _i, _vp, _vp, _vp]),
     "uco_b200_kdtree_parse": (_i, [_vp, _sz, _vp, _i, _vp, _i, _vp, _vp, _vp]),
     "uco_b200_match_projected": (_i, [_vp, _vp, _vp, _vp, _c.c_float, _c.c_float, _vp, _vp, _vp]),
@@ -186,6 +187,20 @@ class MatchParams(ctypes.Structure):  # uco_match_params
         sf = np.asarray(scale_factors if scale_factors is not None else [np.float32(1.2) ** i for i in range(8)], np.float32)
         self.n_scales = len(sf)
         self.scale_factors = (_c.c_float * 32)(*([float(v) for v in sf] + [1.0] * (32 - len(sf))))
+
+
+class BowIndex(ctypes.Structure):  # uco_bow_index
+    _fields_ = [("n_nodes", _c.c_int32), ("node_id", _vp), ("ptr", _vp), ("kp", _vp)]
+
+
+def bow_index(level_node, usable=None):
+    """a frame's fBow2 flattened in std::map order from the per-keypoint level-3 node ids (what uco_b200_bow_transform reports):
+    (node_id u32 ascending, ptr i32, kp i32 in keypoint order inside a node)"""
+    level_node = np.asarray(level_node, np.uint32)
+    order = np.argsort(level_node, kind="stable").astype(np.int32)
+    ids, counts = np.unique(level_node, return_counts=True)
+    ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    return ids.astype(np.uint32), ptr, order
 
 
 class PnpProblem(ctypes.Structure):  # uco_pnp_problem
@@ -394,6 +409,23 @@ class Context:
         self._chk(self.lib.uco_b200_frame_match(self.h, _p(q_desc), len(q_desc), 32, _p(q_kps), len(q_kps), _p(qm), _p(t_desc),
                                                 len(t_desc), 32, _p(t_kps), len(t_kps), _p(tm), ctypes.addressof(prm), _p(out),
                                                 len(out), ctypes.addressof(n)))
+        return out[:n.value].copy()
+
+    def frame_match_bow(self, q_desc, q_kps, q_bow, t_desc, t_kps, t_bow, prm, q_usable=None, t_usable=None):
+        """FrameMatcher_BoW::matchEpipolar; q_bow / t_bow = (node_id, ptr, kp) as bow_index() gives"""
+        q_desc = np.ascontiguousarray(q_desc, np.uint8).reshape(-1, 32)
+        t_desc = np.ascontiguousarray(t_desc, np.uint8).reshape(-1, 32)
+        q_kps, t_kps = np.ascontiguousarray(q_kps, KP_DTYPE), np.ascontiguousarray(t_kps, KP_DTYPE)
+        keep = [np.ascontiguousarray(a) for a in (*q_bow, *t_bow)]
+        qb = BowIndex(len(keep[0]), _p(keep[0]), _p(keep[1]), _p(keep[2]))
+        tb = BowIndex(len(keep[3]), _p(keep[3]), _p(keep[4]), _p(keep[5]))
+        qu = None if q_usable is None else np.ascontiguousarray(q_usable, np.uint8)
+        tu = None if t_usable is None else np.ascontiguousarray(t_usable, np.uint8)
+        out = np.zeros(max(len(keep[2]), 1), MATCH_DTYPE)
+        n = _c.c_int(0)
+        self._chk(self.lib.uco_b200_frame_match_bow(self.h, _p(q_desc), 32, _p(q_kps), len(q_kps), _p(qu), ctypes.addressof(qb), _p(t_desc), 32,
+                                                    _p(t_kps), len(t_kps), _p(tu), ctypes.addressof(tb), ctypes.addressof(prm), _p(out), len(out),
+                                                    ctypes.addressof(n)))
         return out[:n.value].copy()
 
     def frame_match_batch_dev(self, n_pairs, q_desc_dev, q_stride, q_kps_dev, q_kps_stride, nq_max, nq_dev, t_desc_dev, t_stride,
