@@ -1011,7 +1011,7 @@ int ba_cluster_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* const
             if (*stop) *hstop = 1;
         if (q != cudaSuccess) return uco_fail(ctx, UCO_E_CUDA, "ba cluster kernel -> %s", cudaGetErrorString(q));
     }
-    UCO_CUDA(ctx, cudaStreamSynchronize(s));
+    UCO_CUDA(ctx, uco_sleep_sync(ctx));   // milliseconds of device work: sleep, do not spin
     auto t3 = now();
     float ms = 0;
     cudaEventElapsedTime(&ms, uco_ba_events(ctx)[0], uco_ba_events(ctx)[1]);

@@ -19,6 +19,7 @@ struct uco_b200_ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    cudaEvent_t sleep_event = nullptr;  // blocking-sync event: long waits (a BA batch) sleep instead of spinning a host core
     std::string err;
     uint64_t launches = 0;
     int profiling = 0;  // record per-stage CUDA events
@@ -47,6 +48,9 @@ int uco_fail(uco_b200_ctx* ctx, int code, const char* fmt, ...);
 // returns device pointer with at least `bytes` capacity for the slot (grow-only), nullptr on failure (error set)
 void* uco_ws(uco_b200_ctx* ctx, int slot, size_t bytes);
 void* uco_pinned(uco_b200_ctx* ctx, int slot, size_t bytes);
+// wait for everything queued on the context stream with the calling thread ASLEEP (for waits of milliseconds: several mapper
+// threads spinning in cudaStreamSynchronize starve the tracker thread on a host with few cores per GPU)
+cudaError_t uco_sleep_sync(uco_b200_ctx* ctx);
 
 // comm.cu: collectives on a stream; a null communicator (or world 1) degenerates to a local copy
 struct uco_b200_comm;

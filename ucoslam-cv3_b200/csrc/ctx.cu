@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <new>
 
 int uco_fail(uco_b200_ctx* ctx, int code, const char* fmt, ...) {
@@ -58,6 +59,14 @@ void* uco_pinned(uco_b200_ctx* ctx, int slot, size_t bytes) {
     return b.p;
 }
 
+cudaError_t uco_sleep_sync(uco_b200_ctx* ctx) {
+    static const bool spin = getenv("UCO_SPIN_SYNC") != nullptr;   // A/B switch for measurements
+    if (!ctx->sleep_event || spin) return cudaStreamSynchronize(ctx->stream);
+    cudaError_t e = cudaEventRecord(ctx->sleep_event, ctx->stream);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(ctx->sleep_event);
+}
+
 extern "C" {
 
 uco_b200_ctx* uco_b200_create(int device, int flags) {
@@ -74,6 +83,7 @@ uco_b200_ctx* uco_b200_create(int device, int flags) {
         delete ctx;
         return nullptr;
     }
+    cudaEventCreateWithFlags(&ctx->sleep_event, cudaEventBlockingSync | cudaEventDisableTiming);
     ctx->dev.resize(WS_COUNT);
     ctx->pin.resize(WS_COUNT);
     return ctx;
@@ -89,6 +99,7 @@ void uco_b200_destroy(uco_b200_ctx* ctx) {
         if (b.p) cudaFree(b.p);
     for (auto& b : ctx->pin)
         if (b.p) cudaFreeHost(b.p);
+    if (ctx->sleep_event) cudaEventDestroy(ctx->sleep_event);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
