@@ -227,7 +227,28 @@ def ref_ba_optimize(pb, n_iters):
     lib = load_ref("libref_g2o.so")
     if lib is None:
         return None
+    if len(pb.get("marker_size", ())):
+        return _ba_call_markers(lib.ref_ba_optimize_markers, pb, n_iters)
     return _ba_call(lib.ref_ba_optimize, pb, n_iters)
+
+
+def _ba_call_markers(fn, pb, n_iters):
+    """ref_ba_optimize_markers: the reference's g2o + its own MarkerEdge class on a problem with ArUco markers"""
+    P, N, M = len(pb["fixed"]), len(pb["points3"]), len(pb["obs_pose"])
+    nm, nmo = len(pb["marker_size"]), len(pb["mobs_marker"])
+    out = dict(pose7=np.zeros((P, 7)), pose44=np.zeros((P, 16), np.float32), point3=np.zeros((N, 3)), chi2=np.zeros(M),
+               level=np.zeros(M, np.uint8), bad=np.zeros(M, np.uint8), iters=np.zeros(2, np.int32), trace=np.zeros((64, 2)),
+               marker_pose7=np.zeros((nm, 7)), marker_pose44=np.zeros((nm, 16), np.float32), mobs_chi2=np.zeros(nmo))
+    f = lambda v: ctypes.c_float(v)
+    A = lambda k, dt: np.ascontiguousarray(pb[k], dt)
+    keep = [A("marker_pose44", np.float32), A("marker_size", np.float32), A("mobs_marker", np.int32), A("mobs_pose", np.int32),
+            A("mobs_corners", np.float32), A("mobs_weight", np.float32)]
+    fn(P, _p(pb["poses44"]), _p(pb["fixed"]), N, _p(pb["points3"]), M, _p(pb["obs_pose"]), _p(pb["obs_point"]), _p(pb["obs_uv"]),
+       _p(pb["obs_ur"]), _p(pb["obs_stereo"]), _p(pb["obs_inv_sigma2"]), f(pb["fx"]), f(pb["fy"]), f(pb["cx"]), f(pb["cy"]), f(pb["bf"]),
+       int(n_iters), _p(out["pose7"]), _p(out["pose44"]), _p(out["point3"]), _p(out["chi2"]), _p(out["level"]), _p(out["bad"]),
+       _p(out["iters"]), _p(out["trace"]), nm, _p(keep[0]), _p(keep[1]), nmo, _p(keep[2]), _p(keep[3]), _p(keep[4]), _p(keep[5]),
+       _p(out["marker_pose7"]), _p(out["marker_pose44"]), _p(out["mobs_chi2"]))
+    return out
 
 
 def _ba_call(fn, pb, n_iters):

@@ -27,11 +27,37 @@ extern "C" {
 // obs_ur[i] is used when obs_stereo[i] != 0.  out_pose7: qx qy qz qw tx ty tz (f64); out_pose44: what getResults stores
 // (CV_32F 4x4); out_chi2 / out_level / out_depth_pos: per observation state after optimize(); out_bad: the
 // getBadAssociations() predicate (:506-521).  trace (optional, 64 doubles): chi2 after each outer iteration.
+// Markers (globaloptimizer_g2o.cpp:157-170, 304-350): one free VertexSE3Expmap per map marker (pose_g2m) and one MarkerEdge (the
+// reference's own class, typesg2o.h:108-167: 8 residuals, numeric Jacobian with delta 1e-4) per (marker, keyframe) observation with
+// information = I8 * mobs_weight (frame_MarkerWeight, :276-297, computed by the caller); no robust kernel; they stay at level 0 in both
+// stages (:447-451).  The InPlaneMarkers extension (:360-401) is not covered.
+int ref_ba_optimize_markers(int n_poses, const float* poses44, const uint8_t* fixed, int n_points, const float* points3, int n_obs,
+                    const int32_t* obs_pose, const int32_t* obs_point, const float* obs_uv, const float* obs_ur,
+                    const uint8_t* obs_stereo, const float* obs_inv_sigma2, float fx, float fy, float cx, float cy, float bf,
+                    int n_iters, double* out_pose7, float* out_pose44, double* out_point3, double* out_chi2,
+                    uint8_t* out_level, uint8_t* out_bad, int* iters_done, double* trace,
+                    int n_markers, const float* marker_pose44, const float* marker_size, int n_mobs, const int32_t* mobs_marker,
+                    const int32_t* mobs_pose, const float* mobs_corners, const float* mobs_weight, double* out_marker_pose7,
+                    float* out_marker_pose44, double* out_mobs_chi2);
+
 int ref_ba_optimize(int n_poses, const float* poses44, const uint8_t* fixed, int n_points, const float* points3, int n_obs,
                     const int32_t* obs_pose, const int32_t* obs_point, const float* obs_uv, const float* obs_ur,
                     const uint8_t* obs_stereo, const float* obs_inv_sigma2, float fx, float fy, float cx, float cy, float bf,
                     int n_iters, double* out_pose7, float* out_pose44, double* out_point3, double* out_chi2,
                     uint8_t* out_level, uint8_t* out_bad, int* iters_done, double* trace /* optional: per outer iteration {chi2, LM trials}, 2 x 64 */) {
+    return ref_ba_optimize_markers(n_poses, poses44, fixed, n_points, points3, n_obs, obs_pose, obs_point, obs_uv, obs_ur, obs_stereo, obs_inv_sigma2,
+                                   fx, fy, cx, cy, bf, n_iters, out_pose7, out_pose44, out_point3, out_chi2, out_level, out_bad, iters_done, trace,
+                                   0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+int ref_ba_optimize_markers(int n_poses, const float* poses44, const uint8_t* fixed, int n_points, const float* points3, int n_obs,
+                    const int32_t* obs_pose, const int32_t* obs_point, const float* obs_uv, const float* obs_ur,
+                    const uint8_t* obs_stereo, const float* obs_inv_sigma2, float fx, float fy, float cx, float cy, float bf,
+                    int n_iters, double* out_pose7, float* out_pose44, double* out_point3, double* out_chi2,
+                    uint8_t* out_level, uint8_t* out_bad, int* iters_done, double* trace,
+                    int n_markers, const float* marker_pose44, const float* marker_size, int n_mobs, const int32_t* mobs_marker,
+                    const int32_t* mobs_pose, const float* mobs_corners, const float* mobs_weight, double* out_marker_pose7,
+                    float* out_marker_pose44, double* out_mobs_chi2) {
     const float Chi2D = 5.99f, Chi3D = 7.815f;
     const float thHuber2D = sqrt(Chi2D), thHuber3D = sqrt(Chi3D);
     auto Optimizer = std::make_shared<g2o::SparseOptimizer>();
@@ -91,6 +117,25 @@ int ref_ba_optimize(int n_poses, const float* poses44, const uint8_t* fixed, int
             edges[i] = e;
         }
     }
+    std::vector<MarkerEdge*> marker_edges;
+    for (int m = 0; m < n_markers; m++) {   // :304-313
+        auto* v = new VertexSE3Expmap();
+        v->setEstimate(toSE3Quat(marker_pose44 + 16 * m));
+        v->setId(n_poses + n_points + m);
+        Optimizer->addVertex(v);
+    }
+    for (int k = 0; k < n_mobs; k++) {      // :317-347
+        auto* e = new MarkerEdge(marker_size[mobs_marker[k]], mobs_marker[k], mobs_pose[k]);
+        Eigen::Matrix<double, 8, 1> obs;
+        for (int i = 0; i < 8; i++) obs(i) = mobs_corners[8 * k + i];
+        e->setMeasurement(obs);
+        e->setVertex(0, dynamic_cast<g2o::OptimizableGraph::Vertex*>(Optimizer->vertex(n_poses + n_points + mobs_marker[k])));
+        e->setVertex(1, dynamic_cast<g2o::OptimizableGraph::Vertex*>(Optimizer->vertex(mobs_pose[k])));
+        e->fx = fx; e->fy = fy; e->cx = cx; e->cy = cy;
+        e->setInformation(Eigen::Matrix<double, 8, 8>::Identity() * double(mobs_weight[k]));
+        Optimizer->addEdge(e);
+        marker_edges.push_back(e);
+    }
     // optimize(), :418-463
     Optimizer->initializeOptimization();
     Optimizer->setVerbose(false);
@@ -115,6 +160,10 @@ int ref_ba_optimize(int n_poses, const float* poses44, const uint8_t* fixed, int
             e->setRobustKernel(0);
         }
     }
+    for (auto* me : marker_edges) {   // :447-451
+        if (me->chi2() > 15.507) me->setLevel(0);
+        me->setRobustKernel(0);
+    }
     Optimizer->initializeOptimization();
     int it2 = Optimizer->optimize(n_iters * 2, 1);
     dump(it2);
@@ -134,6 +183,15 @@ int ref_ba_optimize(int n_poses, const float* poses44, const uint8_t* fixed, int
         auto* v = static_cast<VertexSBAPointXYZ*>(Optimizer->vertex(n_poses + p));
         for (int k = 0; k < 3; k++) out_point3[3 * p + k] = v->estimate()(k);
     }
+    for (int m = 0; m < n_markers; m++) {   // :526-527
+        g2o::SE3Quat q = static_cast<VertexSE3Expmap*>(Optimizer->vertex(n_poses + n_points + m))->estimate();
+        out_marker_pose7[7 * m + 0] = q.rotation().x(); out_marker_pose7[7 * m + 1] = q.rotation().y(); out_marker_pose7[7 * m + 2] = q.rotation().z();
+        out_marker_pose7[7 * m + 3] = q.rotation().w();
+        for (int k = 0; k < 3; k++) out_marker_pose7[7 * m + 4 + k] = q.translation()[k];
+        Eigen::Matrix<double, 4, 4> M = q.to_homogeneous_matrix();
+        for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) out_marker_pose44[16 * m + 4 * r + c] = (float)M(r, c);
+    }
+    for (int k = 0; k < n_mobs && out_mobs_chi2; k++) out_mobs_chi2[k] = marker_edges[k]->chi2();
     for (int i = 0; i < n_obs; i++) {
         bool bad = false;
         double c2;

@@ -67,6 +67,54 @@ def synth_ba_problem(seed, n_poses=12, n_fixed=2, n_points=2000, stereo_frac=0.0
                 poses_gt=poses_gt, points_gt=pts_gt)
 
 
+def add_markers(pb, seed, n_markers=4, size=0.25, corner_sigma=0.3, pose_noise=(0.02, 1.0), opt_weight=0.5, min_markers=5, w=640, h=480):
+    """ArUco markers for a BA problem made by synth_ba_problem / synth_global_ba: marker poses (global <- marker) in front of the
+    cameras, an observation (4 undistorted corners) in every keyframe that sees all four, perturbed initial marker poses, and the
+    per-observation weight the reference derives per keyframe (globaloptimizer_g2o.cpp:276-297: markersOptWeight share of the frame's
+    keypoint weight spread over its markers' 8 residuals).  Adds marker_pose44, marker_size, mobs_marker / _pose / _corners / _weight."""
+    rng = np.random.default_rng(seed)
+    T = pb["poses_gt"]
+    P = len(T)
+    f, cx, cy = pb["fx"], pb["cx"], pb["cy"]
+    hs = size / 2
+    local = np.array([[-hs, hs, 0], [hs, hs, 0], [hs, -hs, 0], [-hs, -hs, 0]])
+    g2m_gt, mm, mp, mc = [], [], [], []
+    for m in range(n_markers):
+        cam = T[int(rng.integers(0, P))]
+        Mc = np.eye(4)   # marker -> that camera
+        Mc[:3, :3] = _rodrigues(rng.normal(0, 0.3, 3))
+        Mc[:3, 3] = [rng.uniform(-0.6, 0.6), rng.uniform(-0.4, 0.4), rng.uniform(1.5, 3.5)]
+        G = np.linalg.inv(cam) @ Mc
+        g2m_gt.append(G)
+        for i in range(P):
+            Xc = (T[i] @ G @ np.c_[local, np.ones(4)].T).T[:, :3]
+            if (Xc[:, 2] < 0.3).any():
+                continue
+            uv = np.c_[f * Xc[:, 0] / Xc[:, 2] + cx, f * Xc[:, 1] / Xc[:, 2] + cy]
+            if ((uv[:, 0] < 5) | (uv[:, 0] > w - 5) | (uv[:, 1] < 5) | (uv[:, 1] > h - 5)).any():
+                continue
+            mm.append(m); mp.append(i); mc.append((uv + rng.normal(0, corner_sigma, (4, 2))).reshape(8))
+    mm, mp = np.array(mm, np.int32), np.array(mp, np.int32)
+    kpw = np.zeros(P)
+    np.add.at(kpw, pb["obs_pose"], np.where(pb["obs_stereo"] != 0, 3.0, 2.0) * pb["obs_inv_sigma2"].astype(np.float64))
+    n_in_frame = np.bincount(mp, minlength=P)
+    wgt = np.ones(len(mm))
+    for k in range(len(mm)):
+        fr = mp[k]
+        if kpw[fr] > 40 and n_in_frame[fr] > 0:
+            wgt[k] = opt_weight * min(1.0, n_in_frame[fr] / min_markers) * kpw[fr] / (n_in_frame[fr] * 8)
+    g0 = []
+    for G in g2m_gt:
+        G0 = G.copy()
+        G0[:3, :3] = _rodrigues(rng.normal(0, np.deg2rad(pose_noise[1]), 3)) @ G0[:3, :3]
+        G0[:3, 3] += rng.normal(0, pose_noise[0], 3)
+        g0.append(G0.reshape(16))
+    out = dict(pb)
+    out.update(marker_pose44=np.array(g0, np.float32).reshape(-1, 16), marker_size=np.full(n_markers, size, np.float32), mobs_marker=mm, mobs_pose=mp,
+               mobs_corners=np.array(mc, np.float32).reshape(-1, 8), mobs_weight=wgt.astype(np.float32), marker_gt=np.array(g2m_gt))
+    return out
+
+
 def synth_global_ba(seed, n_kf=500, n_points=50000, obs_per_point=6, n_fixed=2, loop_m=50.0, px_sigma=0.5, pose_noise=(0.01, 0.5),
                     point_noise=0.02, outlier_frac=0.01, w=640, h=480, f=525.0):
     """BASELINE config 5: n_kf keyframes on a closed loop of loop_m metres looking outwards, n_points landmarks each
