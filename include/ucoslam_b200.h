@@ -202,6 +202,18 @@ typedef struct uco_ba_problem {
     const float* obs_inv_sigma2; /* n_obs         _InvScaleFactors[kp.octave] */
     float fx, fy, cx, cy, bf;    /* ImageParams; bf = baseline * fx */
     int32_t n_iters;             /* ParamSet::nIters: stage 1 runs n_iters LM iterations, stage 2 runs 2 * n_iters */
+    /* ArUco markers (globaloptimizer_g2o.cpp:157-170, 304-350; zero / NULL when there are none): one free SE3 vertex per map marker
+     * with a valid pose and one MarkerEdge (typesg2o.h:108-167: the 4 corners reprojected through camera * marker, 8 residuals, numeric
+     * Jacobian with delta 1e-4, no robust kernel) per (marker, keyframe) observation.  The InPlaneMarkers extension (:360-401) is not
+     * covered.  Problems with markers are solved by the streamed / sharded solver. */
+    int32_t n_markers;
+    const float* marker_pose44;  /* n_markers x 16   Marker::pose_g2m (global <- marker), row-major 4x4 */
+    const float* marker_size;    /* n_markers        Marker::size */
+    int32_t n_marker_obs;
+    const int32_t* mobs_marker;  /* n_marker_obs     index into the markers */
+    const int32_t* mobs_pose;    /* n_marker_obs     index into poses */
+    const float* mobs_corners;   /* n_marker_obs x 8 MarkerObservation::und_corners */
+    const float* mobs_weight;    /* n_marker_obs     frame_MarkerWeight[frame] (:276-297): information = I8 * weight */
 } uco_ba_problem;
 
 typedef struct uco_ba_result {   /* every pointer may be NULL (not wanted) */
@@ -215,6 +227,9 @@ typedef struct uco_ba_result {   /* every pointer may be NULL (not wanted) */
     int32_t iters[2];            /* iterations executed by stage 1 / stage 2 (SparseOptimizer::optimize return values) */
     float device_ms;             /* device time of the solve between first and last kernel (CUDA events) */
     double* profile;             /* 16 doubles, optional: SM cycles CTA 0 of the window's cluster spent per phase (cluster-resident form) */
+    float* marker_poses44;       /* n_markers x 16   optimised Marker::pose_g2m (getResults :526-527); may be NULL */
+    double* marker_pose7;        /* n_markers x 7    the same vertices as qx qy qz qw tx ty tz (f64); may be NULL */
+    double* mobs_chi2;           /* n_marker_obs     chi2 of each marker edge at the end; may be NULL */
 } uco_ba_result;
 
 /* stop: optional one-byte flag (the reference's bool* stopASAP can be passed as it is) polled between LM trials

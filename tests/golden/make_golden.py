@@ -77,6 +77,30 @@ def ba():
     print("ba golden written", {n: int(out[n + "_out_iters"].sum()) for n in BA_CASES})
 
 
+BA_MARKER_CASES = {  # name -> (synth_ba_problem kwargs, add_markers kwargs, n_iters)   (also imported by the tests)
+    "mk_mono": (dict(seed=61, n_poses=8, n_fixed=1, n_points=250), dict(seed=5, n_markers=3), 5),
+    "mk_stereo": (dict(seed=62, n_poses=6, n_fixed=2, n_points=200, stereo_frac=0.4), dict(seed=6, n_markers=2, size=0.15), 5),
+    "mk_many": (dict(seed=63, n_poses=10, n_fixed=1, n_points=150, outlier_frac=0.08), dict(seed=7, n_markers=8, corner_sigma=0.6), 10),
+}
+BA_MARKER_KEYS = ("marker_pose44", "marker_size", "mobs_marker", "mobs_pose", "mobs_corners", "mobs_weight")
+
+
+def ba_markers():
+    """the same graph with ArUco markers: the reference's g2o + its OWN MarkerEdge class (typesg2o.h:108-167), numeric Jacobians"""
+    oracle_py.build_ref()
+    from ucoslam_b200.synth import add_markers
+    out = {}
+    for name, (kw, mkw, iters) in BA_MARKER_CASES.items():
+        pb = add_markers(oracle_py.synth_ba_problem(**kw), **mkw)
+        r = oracle_py.ref_ba_optimize(pb, iters)
+        for k in oracle_py.BA_INPUT_KEYS + BA_MARKER_KEYS:
+            out["%s_in_%s" % (name, k)] = np.asarray(pb[k])
+        for k, v in r.items():
+            out["%s_out_%s" % (name, k)] = v
+    np.savez_compressed(os.path.join(HERE, "ba_markers_g2o.npz"), **out)
+    print("ba marker golden written", {n: (int(out[n + "_out_iters"].sum()), len(out[n + "_in_mobs_marker"])) for n in BA_MARKER_CASES})
+
+
 PNP_CASES = {  # name -> synth_pnp_problem kwargs   (also imported by the tests)
     "mono": dict(seed=1, n_matches=800),
     "stereo": dict(seed=2, n_matches=600, stereo_frac=0.5),
@@ -127,6 +151,6 @@ def project():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["knn", "bow", "ba", "pnp", "project"]
+    which = sys.argv[1:] or ["knn", "bow", "ba", "ba_markers", "pnp", "project"]
     for w in which:
         globals()[w]()

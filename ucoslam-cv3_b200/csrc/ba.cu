@@ -45,7 +45,21 @@ struct LmState {
     double trace[128];
 };
 
+struct MkDev {  // ArUco markers: free SE3 vertices appended after the free keyframes (replicated on every rank), binary MarkerEdges
+    int Nm = 0, Ne = 0;
+    double *pose = nullptr, *pose_bak = nullptr;              // Nm x 7, global <- marker
+    const float* size = nullptr;                              // Nm
+    const int *e_marker = nullptr, *e_pose = nullptr;         // Ne
+    const float *e_corners = nullptr, *e_weight = nullptr;    // Ne x 8, Ne
+    double* e_chi2 = nullptr;                                 // Ne
+    double* e_blk = nullptr;                                  // Ne x 120: Hcc(36) Hmm(36) Hcm(36) bc(6) bm(6)
+    const int *cam_ptr = nullptr, *cam_edges = nullptr;       // free keyframe -> its marker edges (edge order)
+    const int *mk_ptr = nullptr, *mk_edges = nullptr;         // marker -> its edges
+    const int* blk_edge = nullptr;                            // Schur block -> marker edge whose Hcm fills it, or -1
+};
+
 struct BaDev {
+    MkDev mk;
     int P, N, M, Pf, n, nblk;
     double *pose, *pose_bak, *pt, *pt_bak;
     const int *free_idx, *free_list, *lm_ptr, *obs_pose, *obs_lm, *pose_ptr, *pose_obs;
@@ -481,7 +495,7 @@ __global__ void __launch_bounds__(1024) ba_decide_kernel(const __grid_constant__
         for (int i = threadIdx.x; i < B.M; i += 1024) s += B.rho0[i];
     const double chi_raw = ext ? ext[0] : block_reduce_1024<false>(s, sm);
     double sc = 0;
-    for (int f = threadIdx.x; f < B.Pf; f += 1024) sc += B.scale_pose[f];
+    for (int f = threadIdx.x; f < B.Pf + B.mk.Nm; f += 1024) sc += B.scale_pose[f];
     const double sc_p = block_reduce_1024<false>(sc, sm);
     sc = 0;
     if (!ext)
@@ -534,6 +548,7 @@ __global__ void __launch_bounds__(1024) ba_decide_kernel(const __grid_constant__
             int pi = B.free_list[k / 7];
             B.pose[7 * pi + k % 7] = B.pose_bak[7 * pi + k % 7];
         }
+        for (int k = threadIdx.x; k < 7 * B.mk.Nm; k += 1024) B.mk.pose[k] = B.mk.pose_bak[k];
     }
 }
 
@@ -653,25 +668,177 @@ __global__ void __launch_bounds__(36) ba_assemble_kernel(const __grid_constant__
         if (r == c) h += B.st->lambda;
     }
     h -= Sp[36 * (size_t)blk + e];
+    if (B.mk.blk_edge) {  // (keyframe, marker) block: J_c^T Omega J_m of that marker edge
+        const int ed = B.mk.blk_edge[blk];
+        if (ed >= 0) h += B.mk.e_blk[120 * (size_t)ed + 72 + e];
+    }
     const int n = B.n;
     B.S[(size_t)(6 * ij.x + r) * n + 6 * ij.y + c] = h;
     if (!diag) B.S[(size_t)(6 * ij.y + c) * n + 6 * ij.x + r] = h;
     if (diag && c == 0) B.bs[6 * ij.x + r] = B.bp[6 * ij.x + r] - bsp[6 * ij.x + r];
 }
 
+
+// ---- ArUco markers (globaloptimizer_g2o.cpp:304-350; typesg2o.h:108-167 MarkerEdge) ----------------------------------------------
+__device__ __forceinline__ Pose pose_compose(const Pose& a, const Pose& b) {  // SE3Quat::operator*, se3quat.h:156-163
+    Pose r;
+    double rt[3];
+    quat_rot(a.q, b.t, rt);
+    const double *x = a.q, *y = b.q;
+    r.q[3] = x[3] * y[3] - x[0] * y[0] - x[1] * y[1] - x[2] * y[2];
+    r.q[0] = x[3] * y[0] + x[0] * y[3] + x[1] * y[2] - x[2] * y[1];
+    r.q[1] = x[3] * y[1] + x[1] * y[3] + x[2] * y[0] - x[0] * y[2];
+    r.q[2] = x[3] * y[2] + x[2] * y[3] + x[0] * y[1] - x[1] * y[0];
+    r.t[0] = a.t[0] + rt[0]; r.t[1] = a.t[1] + rt[1]; r.t[2] = a.t[2] + rt[2];
+    quat_normalize(r.q);
+    return r;
+}
+// MarkerEdge::computeError: corners of the marker through camera * marker, projections narrowed to float (typesg2o.h:133-165)
+__device__ void marker_edge_error(const Pose& c2g, const Pose& g2m, float size, const float* obs, const Cam& cam, double* e) {
+    const Pose c2m = pose_compose(c2g, g2m);
+    const float hp = (float)(size / 2.), hn = (float)(-size / 2.);  // Marker::get3DPointsLocalRefSystem, marker.cpp:58-62
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        double c[3] = {(double)((i == 0 || i == 3) ? hn : hp), (double)((i < 2) ? hp : hn), 0.0}, p[3];
+        se3_map(c2m, c, p);
+        const float projx = (float)((p[0] / p[2]) * cam.fx + cam.cx);
+        const float projy = (float)((p[1] / p[2]) * cam.fy + cam.cy);
+        e[2 * i] = (double)obs[2 * i] - (double)projx;
+        e[2 * i + 1] = (double)obs[2 * i + 1] - (double)projy;
+    }
+}
+// one thread per marker edge: chi2 = w |e|^2; with `linearize` also the numeric Jacobians (central differences, delta 1e-4,
+// base_binary_edge.hpp:165-230) of both vertices and the edge's quadratic-form blocks (base_binary_edge.hpp:83-155, no robust kernel)
+__global__ void __launch_bounds__(64) ba_marker_kernel(const __grid_constant__ BaDev B, int linearize) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= B.mk.Ne) return;
+    const int m = B.mk.e_marker[k], pi = B.mk.e_pose[k];
+    const Pose T = load_pose(B.pose + 7 * pi), G = load_pose(B.mk.pose + 7 * m);
+    const float size = B.mk.size[m];
+    const float* obs = B.mk.e_corners + 8 * k;
+    const double w = (double)B.mk.e_weight[k];
+    double e0[8];
+    marker_edge_error(T, G, size, obs, B.cam, e0);
+    double c2 = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) c2 += e0[i] * w * e0[i];
+    B.mk.e_chi2[k] = c2;
+    if (!linearize) return;
+    const double delta = 1e-4, scalar = 1 / (2 * delta);
+    const bool cam_free = B.free_idx[pi] >= 0;
+    double Jm[48], Jc[48];  // [row * 6 + d]
+    for (int d = 0; d < 6; d++) {
+        double u[6] = {0, 0, 0, 0, 0, 0}, ea[8], eb[8];
+        Pose Gp = G, Gn = G;
+        u[d] = delta; se3_oplus(Gp, u);
+        u[d] = -delta; se3_oplus(Gn, u);
+        marker_edge_error(T, Gp, size, obs, B.cam, ea);
+        marker_edge_error(T, Gn, size, obs, B.cam, eb);
+        for (int i = 0; i < 8; i++) Jm[i * 6 + d] = scalar * (ea[i] - eb[i]);
+        if (cam_free) {
+            Pose Tp = T, Tn = T;
+            u[d] = delta; se3_oplus(Tp, u);
+            u[d] = -delta; se3_oplus(Tn, u);
+            marker_edge_error(Tp, G, size, obs, B.cam, ea);
+            marker_edge_error(Tn, G, size, obs, B.cam, eb);
+            for (int i = 0; i < 8; i++) Jc[i * 6 + d] = scalar * (ea[i] - eb[i]);
+        } else {
+            for (int i = 0; i < 8; i++) Jc[i * 6 + d] = 0;
+        }
+    }
+    double* o = B.mk.e_blk + 120 * (size_t)k;
+    for (int a = 0; a < 6; a++) {
+        for (int c = 0; c < 6; c++) {
+            double hcc = 0, hmm = 0, hcm = 0;
+            for (int i = 0; i < 8; i++) {
+                hcc += Jc[i * 6 + a] * w * Jc[i * 6 + c];
+                hmm += Jm[i * 6 + a] * w * Jm[i * 6 + c];
+                hcm += Jc[i * 6 + a] * w * Jm[i * 6 + c];
+            }
+            o[6 * a + c] = hcc;
+            o[36 + 6 * a + c] = hmm;
+            o[72 + 6 * a + c] = hcm;
+        }
+        double bc = 0, bm = 0;
+        for (int i = 0; i < 8; i++) {
+            bc += Jc[i * 6 + a] * (-(w * e0[i]));
+            bm += Jm[i * 6 + a] * (-(w * e0[i]));
+        }
+        o[108 + a] = bc;
+        o[114 + a] = bm;
+    }
+}
+// ordered accumulation of the marker edges' diagonal blocks: keyframe f gets += sum Hcc / bc of its edges (after the all-reduce of the
+// keypoint part: the markers are replicated, not sharded), marker m gets its Hmm / bm
+__global__ void __launch_bounds__(128) ba_marker_accumulate_kernel(const __grid_constant__ BaDev B) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B.Pf + B.mk.Nm) return;
+    const bool is_cam = t < B.Pf;
+    const int* ptr = is_cam ? B.mk.cam_ptr : B.mk.mk_ptr;
+    const int* lst = is_cam ? B.mk.cam_edges : B.mk.mk_edges;
+    const int i = is_cam ? t : t - B.Pf;
+    double H[36], b[6];
+    for (int k = 0; k < 36; k++) H[k] = is_cam ? B.Hpp[36 * (size_t)t + k] : 0.0;
+    for (int k = 0; k < 6; k++) b[k] = is_cam ? B.bp[6 * (size_t)t + k] : 0.0;
+    for (int j = ptr[i]; j < ptr[i + 1]; j++) {
+        const double* o = B.mk.e_blk + 120 * (size_t)lst[j];
+        for (int k = 0; k < 36; k++) H[k] += o[(is_cam ? 0 : 36) + k];
+        for (int k = 0; k < 6; k++) b[k] += o[(is_cam ? 108 : 114) + k];
+    }
+    for (int k = 0; k < 36; k++) B.Hpp[36 * (size_t)t + k] = H[k];
+    for (int k = 0; k < 6; k++) B.bp[6 * (size_t)t + k] = b[k];
+}
+// marker part of the update (push + oplus + computeScale terms); xp / bp / scale_pose entries Pf .. Pf + Nm - 1 belong to the markers
+__global__ void __launch_bounds__(128) ba_marker_update_kernel(const __grid_constant__ BaDev B) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= B.mk.Nm) return;
+    const LmState* st = B.st;
+    const bool apply = !st->chol_fail;
+    const double lambda = st->lambda;
+    Pose G = load_pose(B.mk.pose + 7 * m);
+    store_pose(B.mk.pose_bak + 7 * m, G);
+    double u[6], sc = 0;
+    for (int k = 0; k < 6; k++) {
+        u[k] = B.xp[6 * (B.Pf + m) + k];
+        sc += u[k] * (lambda * u[k] + B.bp[6 * (size_t)(B.Pf + m) + k]);
+    }
+    B.scale_pose[B.Pf + m] = sc;
+    if (apply) {
+        se3_oplus(G, u);
+        store_pose(B.mk.pose + 7 * m, G);
+    }
+}
+__global__ void ba_marker_results_kernel(const __grid_constant__ BaDev B, float* __restrict__ m44) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= B.mk.Nm) return;
+    const Pose G = load_pose(B.mk.pose + 7 * m);
+    double R[9];
+    quat_to_R(G.q, R);
+    float* o = m44 + 16 * m;
+    for (int r = 0; r < 3; r++) {
+        for (int c = 0; c < 3; c++) o[4 * r + c] = (float)R[3 * r + c];
+        o[4 * r + 3] = (float)G.t[r];
+    }
+    o[12] = o[13] = o[14] = 0;
+    o[15] = 1;
+}
+
 // this rank's ordered partial sums for the LM control: buf[0] = sum rho0, buf[1] = sum scale_lm, buf[3] = stop flag;
 // mx[0] = max |diagonal| of (full) Hpp and of the local Hll
-__global__ void __launch_bounds__(1024) ba_partial_sums_kernel(const __grid_constant__ BaDev B, double* __restrict__ buf, double* __restrict__ mx, int stop) {
+__global__ void __launch_bounds__(1024) ba_partial_sums_kernel(const __grid_constant__ BaDev B, double* __restrict__ buf, double* __restrict__ mx, int stop,
+                                                               int add_markers) {
     __shared__ double sm[33];
     double s = 0;
     for (int i = threadIdx.x; i < B.M; i += 1024) s += B.rho0[i];
+    if (add_markers)  // the marker edges are replicated: only one rank contributes their chi2 to the all-reduced sum
+        for (int k = threadIdx.x; k < B.mk.Ne; k += 1024) s += B.mk.e_chi2[k];
     s = block_reduce_1024<false>(s, sm);
     double sc = 0;
     for (int l = threadIdx.x; l < B.N; l += 1024) sc += B.scale_lm[l];
     sc = block_reduce_1024<false>(sc, sm);
     double md = 0;
     if (mx) {
-        for (int k = threadIdx.x; k < 6 * B.Pf; k += 1024) md = fmax(md, fabs(B.Hpp[36 * (size_t)(k / 6) + 7 * (k % 6)]));
+        for (int k = threadIdx.x; k < 6 * (B.Pf + B.mk.Nm); k += 1024) md = fmax(md, fabs(B.Hpp[36 * (size_t)(k / 6) + 7 * (k % 6)]));
         for (int k = threadIdx.x; k < 3 * B.N; k += 1024) {
             int l = k / 3, j = k % 3;
             md = fmax(md, fabs(B.Hll[6 * (size_t)l + (j == 0 ? 0 : (j == 1 ? 3 : 5))]));
@@ -1046,6 +1213,12 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
     if (rc != UCO_OK) return rc;
     const int R = uco_comm_world(comm), rank = uco_comm_rank(comm);
     const int P = pb->n_poses, N = pb->n_points, M = pb->n_obs;
+    const int Nm = pb->n_markers, Ne = pb->n_marker_obs;
+    if (Nm < 0 || Ne < 0 || (Nm && (!pb->marker_pose44 || !pb->marker_size)) || (Ne && (!Nm || !pb->mobs_marker || !pb->mobs_pose || !pb->mobs_corners || !pb->mobs_weight)))
+        return uco_fail(ctx, UCO_E_INVALID, "ba_solve: malformed marker arrays");
+    for (int k = 0; k < Ne; k++)
+        if ((unsigned)pb->mobs_marker[k] >= (unsigned)Nm || (unsigned)pb->mobs_pose[k] >= (unsigned)P)
+            return uco_fail(ctx, UCO_E_INVALID, "ba_solve: marker observation %d references marker %d / pose %d out of range", k, pb->mobs_marker[k], pb->mobs_pose[k]);
     uco_ba_events(ctx);
     // ---- global structure (identical on every rank): free-pose numbering, observations sorted by landmark, Schur block list
     std::vector<int> free_idx(P), free_list;
@@ -1053,7 +1226,7 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
         free_idx[i] = pb->fixed[i] ? -1 : (int)free_list.size();
         if (!pb->fixed[i]) free_list.push_back(i);
     }
-    const int Pf = (int)free_list.size(), n = 6 * Pf;
+    const int Pf = (int)free_list.size(), PT = Pf + Nm, n = 6 * PT;   // unknowns: free keyframes, then markers
     std::vector<int> lm_ptr(N + 1, 0), order(M), fill(N, 0);
     for (int i = 0; i < M; i++) lm_ptr[pb->obs_point[i] + 1]++;
     for (int l = 0; l < N; l++) lm_ptr[l + 1] += lm_ptr[l];
@@ -1064,9 +1237,13 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
     ba_partition_landmarks(lm_ptr, N, M, R, L);
     const int l0 = L[rank], l1 = L[rank + 1], NL = l1 - l0, o0 = lm_ptr[l0], o1 = lm_ptr[l1], ML = o1 - o0;
     // block list from ALL landmarks (so that the packed layout agrees across ranks), contributions from the local ones
-    std::vector<int> blk_of((size_t)Pf * Pf, -1);
+    std::vector<int> blk_of((size_t)PT * PT, -1);
     {
-        std::vector<uint8_t> present((size_t)Pf * Pf, 0);
+        std::vector<uint8_t> present((size_t)PT * PT, 0);
+        for (int k = 0; k < Ne; k++) {  // (keyframe, marker) blocks of the marker edges; marker diagonals exist like every diagonal
+            const int fc = free_idx[pb->mobs_pose[k]];
+            if (fc >= 0) present[(size_t)fc * PT + Pf + pb->mobs_marker[k]] = 1;
+        }
         for (int l = 0; l < N; l++)
             for (int a = lm_ptr[l]; a < lm_ptr[l + 1]; a++) {
                 const int fa = g_free[a];
@@ -1074,18 +1251,18 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
                 for (int b = lm_ptr[l]; b < lm_ptr[l + 1]; b++) {
                     const int fb = g_free[b];
                     if (fb < fa || (fb == fa && b != a)) continue;
-                    present[(size_t)fa * Pf + fb] = 1;
+                    present[(size_t)fa * PT + fb] = 1;
                 }
             }
         int nb = 0;
-        for (int i = 0; i < Pf; i++)
-            for (int j = i; j < Pf; j++)
-                if (present[(size_t)i * Pf + j] || i == j) blk_of[(size_t)i * Pf + j] = nb++;
+        for (int i = 0; i < PT; i++)
+            for (int j = i; j < PT; j++)
+                if (present[(size_t)i * PT + j] || i == j) blk_of[(size_t)i * PT + j] = nb++;
     }
     std::vector<int2> blk_ij;
-    for (int i = 0; i < Pf; i++)
-        for (int j = i; j < Pf; j++)
-            if (blk_of[(size_t)i * Pf + j] >= 0) blk_ij.push_back(make_int2(i, j));
+    for (int i = 0; i < PT; i++)
+        for (int j = i; j < PT; j++)
+            if (blk_of[(size_t)i * PT + j] >= 0) blk_ij.push_back(make_int2(i, j));
     const int nblk = (int)blk_ij.size();
     std::vector<int> blk_ptr(nblk + 1, 0);
     for (int l = l0; l < l1; l++)
@@ -1095,7 +1272,7 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
             for (int b = lm_ptr[l]; b < lm_ptr[l + 1]; b++) {
                 const int fb = g_free[b];
                 if (fb < fa || (fb == fa && b != a)) continue;
-                blk_ptr[blk_of[(size_t)fa * Pf + fb] + 1]++;
+                blk_ptr[blk_of[(size_t)fa * PT + fb] + 1]++;
             }
         }
     for (int k = 0; k < nblk; k++) blk_ptr[k + 1] += blk_ptr[k];
@@ -1109,7 +1286,7 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
                 for (int b = lm_ptr[l]; b < lm_ptr[l + 1]; b++) {
                     const int fb = g_free[b];
                     if (fb < fa || (fb == fa && b != a)) continue;
-                    const int k = blk_of[(size_t)fa * Pf + fb];
+                    const int k = blk_of[(size_t)fa * PT + fb];
                     con[blk_ptr[k] + bf[k]++] = make_int2(a - o0, b - o0);  // local observation indices
                 }
             }
@@ -1126,6 +1303,29 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
         std::vector<int> pf(Pf, 0);
         for (int k = 0; k < ML; k++) { const int f = g_free[o0 + k]; if (f >= 0) pose_obs[pose_ptr[f] + pf[f]++] = k; }
     }
+    // markers: per free keyframe / per marker the list of marker edges (edge order), per block the edge that fills it
+    std::vector<int> cam_ptr(Pf + 1, 0), cam_edges, mk_ptr(Nm + 1, 0), mk_edges(Ne), blk_edge(nblk, -1);
+    for (int k = 0; k < Ne; k++) {
+        const int fc = free_idx[pb->mobs_pose[k]];
+        if (fc >= 0) {
+            cam_ptr[fc + 1]++;
+            int& be = blk_edge[blk_of[(size_t)fc * PT + Pf + pb->mobs_marker[k]]];
+            if (be >= 0) return uco_fail(ctx, UCO_E_INVALID, "ba_solve: marker %d is observed twice by pose %d", pb->mobs_marker[k], pb->mobs_pose[k]);
+            be = k;
+        }
+        mk_ptr[pb->mobs_marker[k] + 1]++;
+    }
+    for (int i = 0; i < Pf; i++) cam_ptr[i + 1] += cam_ptr[i];
+    for (int i = 0; i < Nm; i++) mk_ptr[i + 1] += mk_ptr[i];
+    cam_edges.resize(cam_ptr[Pf]);
+    {
+        std::vector<int> cf(cam_ptr.begin(), cam_ptr.end() - 1), mf(mk_ptr.begin(), mk_ptr.end() - 1);
+        for (int k = 0; k < Ne; k++) {
+            const int fc = free_idx[pb->mobs_pose[k]];
+            if (fc >= 0) cam_edges[cf[fc]++] = k;
+            mk_edges[mf[pb->mobs_marker[k]]++] = k;
+        }
+    }
     // ---- arena: [inputs][work][full-size result arrays that are summed over the ranks]
     Arena A;
     const size_t o_free_idx = A.take(4 * (size_t)P), o_free_list = A.take(4 * (size_t)(Pf + 1)), o_lm_ptr = A.take(4 * (size_t)(NL + 1)),
@@ -1134,15 +1334,20 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
                  o_blk_ij = A.take(8 * (size_t)(nblk + 1)), o_con = A.take(8 * (con.size() + 1)), o_z = A.take(24 * (size_t)(ML + 1)),
                  o_info = A.take(8 * (size_t)(ML + 1)), o_stereo = A.take((size_t)ML + 1), o_active = A.take((size_t)ML + 1),
                  o_pt = A.take(24 * (size_t)(NL + 1)), o_p44 = A.take(64 * (size_t)P);
+    const size_t o_mk44 = A.take(64 * (size_t)(Nm + 1)), o_mksz = A.take(4 * (size_t)(Nm + 1)), o_em = A.take(4 * (size_t)(Ne + 1)), o_ep = A.take(4 * (size_t)(Ne + 1)),
+                 o_ec = A.take(32 * (size_t)(Ne + 1)), o_ew = A.take(4 * (size_t)(Ne + 1)), o_cptr = A.take(4 * (size_t)(Pf + 2)), o_cedg = A.take(4 * (cam_edges.size() + 1)),
+                 o_mptr = A.take(4 * (size_t)(Nm + 2)), o_medg = A.take(4 * (size_t)(Ne + 1)), o_bedg = A.take(4 * (size_t)(nblk + 1));
     const size_t in_bytes = A.off;
+    const size_t o_mkpose = A.take(56 * (size_t)(Nm + 1)), o_mkbak = A.take(56 * (size_t)(Nm + 1)), o_echi = A.take(8 * (size_t)(Ne + 1)), o_eblk = A.take(960 * (size_t)(Ne + 1)),
+                 o_mk44o = A.take(64 * (size_t)(Nm + 1));
     const size_t n_red = 36 * (size_t)nblk + (size_t)n;  // packed Schur blocks | right-hand side: the per-trial all-reduce payload
     const size_t o_pose = A.take(56 * (size_t)P), o_pose_bak = A.take(56 * (size_t)P), o_pt_bak = A.take(24 * (size_t)(NL + 1)),
                  o_err = A.take(24 * (size_t)(ML + 1)), o_chi2 = A.take(8 * (size_t)(ML + 1)), o_rho0 = A.take(8 * (size_t)(ML + 1)),
                  o_Hll = A.take(48 * (size_t)(NL + 1)), o_bl = A.take(24 * (size_t)(NL + 1)), o_Hpl = A.take(144 * (size_t)(ML + 1)),
                  o_Y = A.take(144 * (size_t)(ML + 1)), o_Dinv = A.take(48 * (size_t)(NL + 1)), o_db = A.take(24 * (size_t)(NL + 1)),
-                 o_xl = A.take(24 * (size_t)(NL + 1)), o_HppBp = A.take(8 * (42 * (size_t)Pf + 6)),
+                 o_xl = A.take(24 * (size_t)(NL + 1)), o_HppBp = A.take(8 * (42 * (size_t)PT + 6)),
                  o_S = A.take(8 * ((size_t)n * n + 1)), o_bs = A.take(8 * (size_t)(n + 1)), o_xp = A.take(8 * (size_t)(n + 1)),
-                 o_scl = A.take(8 * (size_t)(NL + 1)), o_scp = A.take(8 * (size_t)(Pf + 1)), o_st = A.take(sizeof(LmState)),
+                 o_scl = A.take(8 * (size_t)(NL + 1)), o_scp = A.take(8 * (size_t)(PT + 1)), o_st = A.take(sizeof(LmState)),
                  o_p44o = A.take(64 * (size_t)P), o_bad = A.take((size_t)ML + 1), o_red = A.take(8 * (n_red + 1)), o_sums = A.take(64),
                  o_info2 = A.take(16);
     const size_t o_full_pt = A.take(24 * (size_t)(N + 1)), o_full_chi = A.take(8 * (size_t)(M + 1)), o_full_flags = A.take(2 * (size_t)M + 2);
@@ -1193,6 +1398,21 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
         for (int k = 0; k < 3 * NL; k++) pt[k] = pb->points3[3 * (size_t)l0 + k];
         memcpy(h + o_p44, pb->poses44, 64 * (size_t)P);
     }
+    if (Nm) {
+        memcpy(h + o_mk44, pb->marker_pose44, 64 * (size_t)Nm);
+        memcpy(h + o_mksz, pb->marker_size, 4 * (size_t)Nm);
+    }
+    if (Ne) {
+        memcpy(h + o_em, pb->mobs_marker, 4 * (size_t)Ne);
+        memcpy(h + o_ep, pb->mobs_pose, 4 * (size_t)Ne);
+        memcpy(h + o_ec, pb->mobs_corners, 32 * (size_t)Ne);
+        memcpy(h + o_ew, pb->mobs_weight, 4 * (size_t)Ne);
+        memcpy(h + o_medg, mk_edges.data(), 4 * (size_t)Ne);
+        if (!cam_edges.empty()) memcpy(h + o_cedg, cam_edges.data(), 4 * cam_edges.size());
+    }
+    memcpy(h + o_cptr, cam_ptr.data(), 4 * (size_t)(Pf + 1));
+    memcpy(h + o_mptr, mk_ptr.data(), 4 * (size_t)(Nm + 1));
+    if (nblk) memcpy(h + o_bedg, blk_edge.data(), 4 * (size_t)nblk);
     cudaStream_t s = ctx->stream;
     UCO_CUDA(ctx, cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, s));
     UCO_CUDA(ctx, cudaMemsetAsync(d + o_st, 0, sizeof(LmState), s));
@@ -1210,7 +1430,13 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
     B.err = (double*)(d + o_err); B.chi2 = (double*)(d + o_chi2); B.rho0 = (double*)(d + o_rho0); B.Hll = (double*)(d + o_Hll);
     B.bl = (double*)(d + o_bl); B.Hpl = (double*)(d + o_Hpl); B.Y = (double*)(d + o_Y); B.Dinv = (double*)(d + o_Dinv); B.db = (double*)(d + o_db);
     B.xl = (double*)(d + o_xl);
-    B.Hpp = (double*)(d + o_HppBp); B.bp = B.Hpp + 36 * (size_t)Pf;   // contiguous: one all-reduce per outer iteration
+    B.Hpp = (double*)(d + o_HppBp); B.bp = B.Hpp + 36 * (size_t)PT;   // contiguous: one all-reduce per outer iteration
+    B.mk.Nm = Nm; B.mk.Ne = Ne;
+    B.mk.pose = (double*)(d + o_mkpose); B.mk.pose_bak = (double*)(d + o_mkbak); B.mk.size = (const float*)(d + o_mksz);
+    B.mk.e_marker = (const int*)(d + o_em); B.mk.e_pose = (const int*)(d + o_ep); B.mk.e_corners = (const float*)(d + o_ec);
+    B.mk.e_weight = (const float*)(d + o_ew); B.mk.e_chi2 = (double*)(d + o_echi); B.mk.e_blk = (double*)(d + o_eblk);
+    B.mk.cam_ptr = (const int*)(d + o_cptr); B.mk.cam_edges = (const int*)(d + o_cedg); B.mk.mk_ptr = (const int*)(d + o_mptr);
+    B.mk.mk_edges = (const int*)(d + o_medg); B.mk.blk_edge = Ne ? (const int*)(d + o_bedg) : nullptr;
     B.S = (double*)(d + o_S); B.bs = (double*)(d + o_bs);
     B.xp = (double*)(d + o_xp); B.scale_lm = (double*)(d + o_scl); B.scale_pose = (double*)(d + o_scp);
     B.blk_ptr = (int*)(d + o_blk_ptr); B.blk_ij = (int2*)(d + o_blk_ij); B.con = (int2*)(d + o_con);
@@ -1231,7 +1457,7 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
     auto stop_now = [&] { return stop && *stop ? 1 : 0; };
     // all-reduce of the LM sums (+ the ranks' stop flags); with first = true also the max |diagonal| for lambda_0
     auto reduce_sums = [&](bool first) -> int {
-        ba_partial_sums_kernel<<<1, 1024, 0, s>>>(B, sums, first ? sums + 4 : nullptr, stop_now());
+        ba_partial_sums_kernel<<<1, 1024, 0, s>>>(B, sums, first ? sums + 4 : nullptr, stop_now(), rank == 0);
         UCO_LAUNCH_CHECK(ctx);
         int r2 = uco_comm_allreduce(comm, sums, sums, 4, 0, s);
         if (r2 != UCO_OK) return r2;
@@ -1245,6 +1471,13 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
     UCO_CUDA(ctx, cudaEventRecord(ctx->ba->ev0, s));
     ba_init_poses_kernel<<<(P + 127) / 128, 128, 0, s>>>(B, (const float*)(d + o_p44));
     UCO_LAUNCH_CHECK(ctx);
+    if (Nm) {  // marker vertices: Marker::pose_g2m -> SE3Quat, like the keyframes
+        BaDev Bm = B;
+        Bm.P = Nm; Bm.pose = B.mk.pose; Bm.pose_bak = B.mk.pose_bak;
+        ba_init_poses_kernel<<<(Nm + 127) / 128, 128, 0, s>>>(Bm, (const float*)(d + o_mk44));
+        UCO_LAUNCH_CHECK(ctx);
+    }
+    const int gE = (Ne + 63) / 64, gPT = (PT + 127) / 128;
     int iters[2] = {0, 0};
     bool stopped = false;
     for (int stage = 0; stage < 2 && !stopped; stage++) {
@@ -1266,7 +1499,19 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
             if (Pf) {
                 ba_linearize_pose_kernel<<<Pf, POSE_THREADS, 0, s>>>(B, robust);
                 UCO_LAUNCH_CHECK(ctx);
-                if ((rc = uco_comm_allreduce(comm, B.Hpp, B.Hpp, 42 * (size_t)Pf, 0, s)) != UCO_OK) return rc;
+            }
+            if (PT) {
+                if (Nm) {  // marker rows of Hpp | bp hold no keypoint terms: cleared so that the all-reduce leaves them zero
+                    UCO_CUDA(ctx, cudaMemsetAsync(B.Hpp + 36 * (size_t)Pf, 0, 8 * 36 * (size_t)Nm, s));
+                    UCO_CUDA(ctx, cudaMemsetAsync(B.bp + 6 * (size_t)Pf, 0, 8 * 6 * (size_t)Nm, s));
+                }
+                if ((rc = uco_comm_allreduce(comm, B.Hpp, B.Hpp, 42 * (size_t)PT, 0, s)) != UCO_OK) return rc;
+                if (Ne) {  // marker edges: replicated on every rank, added after the exchange
+                    ba_marker_kernel<<<gE, 64, 0, s>>>(B, 1);
+                    UCO_LAUNCH_CHECK(ctx);
+                    ba_marker_accumulate_kernel<<<gPT, 128, 0, s>>>(B);
+                    UCO_LAUNCH_CHECK(ctx);
+                }
             }
             if (it == 0) {
                 if ((rc = reduce_sums(true)) != UCO_OK) return rc;
@@ -1285,7 +1530,7 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
                     ba_prep_kernel<<<gN, 128, 0, s>>>(B);
                     UCO_LAUNCH_CHECK(ctx);
                 }
-                if (Pf) {
+                if (PT) {
                     ba_schur_gather_packed_kernel<<<nblk, 36 * GATHER_CHUNKS, 0, s>>>(B, Sp, bsp);
                     UCO_LAUNCH_CHECK(ctx);
                     if ((rc = uco_comm_allreduce(comm, Sp, Sp, n_red, 0, s)) != UCO_OK) return rc;   // THE exchange step of the path
@@ -1308,8 +1553,16 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
                 }
                 ba_update_kernel<<<gU, 128, 0, s>>>(B);
                 UCO_LAUNCH_CHECK(ctx);
+                if (Nm) {
+                    ba_marker_update_kernel<<<(Nm + 127) / 128, 128, 0, s>>>(B);
+                    UCO_LAUNCH_CHECK(ctx);
+                }
                 if (ML) {
                     ba_errors_kernel<<<gM, 256, 0, s>>>(B, robust);
+                    UCO_LAUNCH_CHECK(ctx);
+                }
+                if (Ne) {
+                    ba_marker_kernel<<<gE, 64, 0, s>>>(B, 0);
                     UCO_LAUNCH_CHECK(ctx);
                 }
                 if ((rc = reduce_sums(false)) != UCO_OK) return rc;
@@ -1335,6 +1588,10 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
         ba_bad_kernel<<<gM, 256, 0, s>>>(B, p44o, bad);
         UCO_LAUNCH_CHECK(ctx);
     }
+    if (Nm) {
+        ba_marker_results_kernel<<<(Nm + 127) / 128, 128, 0, s>>>(B, (float*)(d + o_mk44o));
+        UCO_LAUNCH_CHECK(ctx);
+    }
     double* full_pt = (double*)(d + o_full_pt);
     double* full_chi = (double*)(d + o_full_chi);
     uint8_t* full_flags = d + o_full_flags;  // [0, M): active, [M, 2M): bad
@@ -1351,7 +1608,8 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
     }
     UCO_CUDA(ctx, cudaEventRecord(ctx->ba->ev1, s));
     const size_t o_h_pose = 0, o_h_p44 = o_h_pose + 56 * (size_t)P, o_h_pt = o_h_p44 + 64 * (size_t)P, o_h_chi = o_h_pt + 24 * (size_t)N,
-                 o_h_fl = o_h_chi + 8 * (size_t)M, o_h_st = ((o_h_fl + 2 * (size_t)M + 7) & ~(size_t)7), out_bytes = o_h_st + sizeof(LmState);
+                 o_h_fl = o_h_chi + 8 * (size_t)M, o_h_st = ((o_h_fl + 2 * (size_t)M + 7) & ~(size_t)7), o_h_mk7 = o_h_st + ((sizeof(LmState) + 7) & ~(size_t)7),
+                 o_h_mk44 = o_h_mk7 + 56 * (size_t)Nm, o_h_echi = o_h_mk44 + 64 * (size_t)Nm, out_bytes = o_h_echi + 8 * (size_t)Ne + 8;
     uint8_t* ho = (uint8_t*)uco_pinned(ctx, WS_BA_OUT, out_bytes);
     if (!ho) return UCO_E_NOMEM;
     UCO_CUDA(ctx, cudaMemcpyAsync(ho + o_h_pose, B.pose, 56 * (size_t)P, cudaMemcpyDeviceToHost, s));
@@ -1362,7 +1620,15 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
         UCO_CUDA(ctx, cudaMemcpyAsync(ho + o_h_fl, full_flags, 2 * (size_t)M, cudaMemcpyDeviceToHost, s));
     }
     UCO_CUDA(ctx, cudaMemcpyAsync(ho + o_h_st, B.st, sizeof(LmState), cudaMemcpyDeviceToHost, s));
+    if (Nm) {
+        UCO_CUDA(ctx, cudaMemcpyAsync(ho + o_h_mk7, B.mk.pose, 56 * (size_t)Nm, cudaMemcpyDeviceToHost, s));
+        UCO_CUDA(ctx, cudaMemcpyAsync(ho + o_h_mk44, d + o_mk44o, 64 * (size_t)Nm, cudaMemcpyDeviceToHost, s));
+    }
+    if (Ne) UCO_CUDA(ctx, cudaMemcpyAsync(ho + o_h_echi, B.mk.e_chi2, 8 * (size_t)Ne, cudaMemcpyDeviceToHost, s));
     UCO_CUDA(ctx, cudaStreamSynchronize(s));
+    if (res->marker_pose7 && Nm) memcpy(res->marker_pose7, ho + o_h_mk7, 56 * (size_t)Nm);
+    if (res->marker_poses44 && Nm) memcpy(res->marker_poses44, ho + o_h_mk44, 64 * (size_t)Nm);
+    if (res->mobs_chi2 && Ne) memcpy(res->mobs_chi2, ho + o_h_echi, 8 * (size_t)Ne);
     if (res->pose7) memcpy(res->pose7, ho + o_h_pose, 56 * (size_t)P);
     if (res->poses44) memcpy(res->poses44, ho + o_h_p44, 64 * (size_t)P);
     if (res->points3) memcpy(res->points3, ho + o_h_pt, 24 * (size_t)N);
@@ -1434,6 +1700,11 @@ int uco_b200_ba_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* pbs,
     for (int i = 0; i < n; i++) {
         int rc = ba_validate(ctx, pbs + i);
         if (rc != UCO_OK) return rc;
+        if (pbs[i].n_markers > 0) {  // ArUco markers: the streamed / sharded solver handles the marker vertices and edges
+            rc = ba_sharded_solve(ctx, nullptr, pbs + i, stop, res + i);
+            if (rc != UCO_OK) return rc;
+            continue;
+        }
         const bool fits = 6 * ba_free_poses(pbs + i) <= BA_CLUSTER_MAX_N;
         if (ctx->ba_mode == 2 && !fits)
             return uco_fail(ctx, UCO_E_INVALID, "ba_solve: %d free poses exceed the cluster-resident solver (%d)", ba_free_poses(pbs + i),

@@ -5,8 +5,9 @@
 // uco_ba_problem; getResults writes poses, points and the bad-association list back as :466-538 does.  The object keeps
 // its own copy of inputs and results, because the mapper thread calls setParams + optimize WITHOUT the map lock and the
 // tracker thread calls getResults later (src/utils/mapmanager.cpp:11361-11405, :1267-1305); *stopASAP is forwarded.
-// Windows that involve ArUco markers (marker vertices / MarkerEdge, not handled on the device yet) or keyframes taken
-// with different cameras are handed to the reference's own GlobalOptimizerG2O.
+// Windows that involve ArUco markers or keyframes taken with different cameras are handed to the reference's own
+// GlobalOptimizerG2O by this adapter (TODO: flatten Map::map_markers / frame_MarkerWeight into uco_ba_problem::marker_* — the C ABI
+// solves marker vertices / MarkerEdges since round 1, see include/ucoslam_b200.h).
 // Selected with Params::global_optimizer = "b200" once registered in GlobalOptimizer::create.
 // Compile inside the reference tree (needs its headers and OpenCV C++; see the note in orb_extractor_b200.h).
 #pragma once

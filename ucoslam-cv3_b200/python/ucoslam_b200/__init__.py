@@ -164,12 +164,14 @@ class BaProblem(ctypes.Structure):  # uco_ba_problem
     _fields_ = [("n_poses", _c.c_int32), ("n_points", _c.c_int32), ("n_obs", _c.c_int32), ("poses44", _vp), ("fixed", _vp),
                 ("points3", _vp), ("obs_pose", _vp), ("obs_point", _vp), ("obs_uv", _vp), ("obs_ur", _vp), ("obs_stereo", _vp),
                 ("obs_inv_sigma2", _vp), ("fx", _c.c_float), ("fy", _c.c_float), ("cx", _c.c_float), ("cy", _c.c_float),
-                ("bf", _c.c_float), ("n_iters", _c.c_int32)]
+                ("bf", _c.c_float), ("n_iters", _c.c_int32), ("n_markers", _c.c_int32), ("marker_pose44", _vp), ("marker_size", _vp),
+                ("n_marker_obs", _c.c_int32), ("mobs_marker", _vp), ("mobs_pose", _vp), ("mobs_corners", _vp), ("mobs_weight", _vp)]
 
 
 class BaResult(ctypes.Structure):  # uco_ba_result
     _fields_ = [("pose7", _vp), ("poses44", _vp), ("points3", _vp), ("obs_chi2", _vp), ("obs_level", _vp), ("obs_bad", _vp),
-                ("trace", _vp), ("iters", _c.c_int32 * 2), ("device_ms", _c.c_float), ("profile", _vp)]
+                ("trace", _vp), ("iters", _c.c_int32 * 2), ("device_ms", _c.c_float), ("profile", _vp), ("marker_poses44", _vp),
+                ("marker_pose7", _vp), ("mobs_chi2", _vp)]
 
 
 MATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])  # uco_match == cv::DMatch
@@ -369,6 +371,15 @@ class Context:
         cr = BaResult(_p(out["pose7"]), _p(out["pose44"]), _p(out["point3"]), _p(out["chi2"]), _p(out["level"]), _p(out["bad"]),
                       _p(out["trace"]))
         cr.profile = _p(out["profile"])
+        if len(pb.get("marker_size", ())):   # ArUco markers
+            a.update(marker_pose44=A("marker_pose44", np.float32), marker_size=A("marker_size", np.float32), mobs_marker=A("mobs_marker", np.int32),
+                     mobs_pose=A("mobs_pose", np.int32), mobs_corners=A("mobs_corners", np.float32), mobs_weight=A("mobs_weight", np.float32))
+            nm, nmo = len(a["marker_size"]), len(a["mobs_marker"])
+            cp.n_markers, cp.marker_pose44, cp.marker_size = nm, _p(a["marker_pose44"]), _p(a["marker_size"])
+            cp.n_marker_obs, cp.mobs_marker, cp.mobs_pose = nmo, _p(a["mobs_marker"]), _p(a["mobs_pose"])
+            cp.mobs_corners, cp.mobs_weight = _p(a["mobs_corners"]), _p(a["mobs_weight"])
+            out.update(marker_pose44=np.zeros((nm, 16), np.float32), marker_pose7=np.zeros((nm, 7)), mobs_chi2=np.zeros(nmo))
+            cr.marker_poses44, cr.marker_pose7, cr.mobs_chi2 = _p(out["marker_pose44"]), _p(out["marker_pose7"]), _p(out["mobs_chi2"])
         return cp, cr, a, out
 
     def ba_solve(self, pb, n_iters, stop=None):
