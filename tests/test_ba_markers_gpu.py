@@ -33,8 +33,8 @@ def check_markers(got, ref, slack=1.0):
     assert np.abs(got["marker_pose44"] - ref["marker_pose44"]).max() < 6e-3 * slack
     print("marker edge chi2: sum", got["mobs_chi2"].sum(), ref["mobs_chi2"].sum(), "max |d|", np.abs(got["mobs_chi2"] - ref["mobs_chi2"]).max(),
           "max", ref["mobs_chi2"].max())
-    assert abs(got["mobs_chi2"].sum() - ref["mobs_chi2"].sum()) < 2e-3 * ref["mobs_chi2"].sum() + 1e-3
-    assert np.allclose(got["mobs_chi2"], ref["mobs_chi2"], rtol=5e-2, atol=2e-2)
+    assert abs(got["mobs_chi2"].sum() - ref["mobs_chi2"].sum()) < 2e-3 * min(slack, 10.0) * ref["mobs_chi2"].sum() + 1e-3
+    assert np.allclose(got["mobs_chi2"], ref["mobs_chi2"], rtol=5e-2 * min(slack, 4.0), atol=2e-2 * min(slack, 4.0))
     near_gate = np.minimum(np.abs(ref["chi2"] - 5.99), np.abs(ref["chi2"] - 7.815)) < 0.05
     assert np.allclose(got["chi2"][~near_gate], ref["chi2"][~near_gate], rtol=2e-2, atol=1e-3)
     assert np.array_equal(got["level"][~near_gate], ref["level"][~near_gate])
