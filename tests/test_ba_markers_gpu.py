@@ -60,8 +60,15 @@ def test_markers_on_a_loop_graph_match_live_reference(ctx):
     if ref is None:
         pytest.skip("oracle/_ref/libref_g2o.so not built")
     got = ctx.ba_solve_sharded(pb, 5)
-    check_markers(got, ref, slack=100.0)   # a 40-keyframe loop held by two fixed keyframes: the same chi2 at every iteration (checked to
-                                            # 5e-5), but centimetre-level play along the loop between equally good solutions
+    # a 40-keyframe loop held by two fixed keyframes: the two optimisers must agree on chi2 at EVERY iteration and on the iteration /
+    # LM-trial counts; between equally good solutions there is centimetre-level play along the loop, so states are compared loosely
+    assert np.array_equal(got["iters"], ref["iters"])
+    n = int(ref["iters"].sum())
+    assert np.array_equal(got["trace"][:n, 1], ref["trace"][:n, 1])
+    assert np.allclose(got["trace"][:n, 0], ref["trace"][:n, 0], rtol=5e-5)
+    assert np.abs(got["pose7"] - ref["pose7"]).max() < 2e-2 and np.abs(got["marker_pose7"] - ref["marker_pose7"]).max() < 5e-2
+    assert abs(got["mobs_chi2"].sum() - ref["mobs_chi2"].sum()) < 0.05 * ref["mobs_chi2"].sum()
+    assert (got["level"] != ref["level"]).mean() < 0.01
     err0 = np.abs(pb["marker_pose44"].reshape(-1, 4, 4)[:, :3, 3] - pb["marker_gt"][:, :3, 3]).max()
     err1 = np.abs(got["marker_pose44"].reshape(-1, 4, 4)[:, :3, 3] - pb["marker_gt"][:, :3, 3]).max()
     assert err1 < err0
