@@ -128,57 +128,59 @@ inline int ba_plan_build(uco_b200_ctx* ctx, const uco_ba_problem& pb, int unit, 
             }
         }
     }
-    std::vector<int> blk_of((size_t)Pf * Pf, -1), blk_ptr(1, 0);
+    // Blocks in (i, j >= i) order.  A block's contributions are written straight into the PADDED layout the gather kernel reads:
+    // units of <= `unit` contributions (unit is a multiple of four), the last unit of a block padded to a multiple of four with the
+    // all-zero dummy observation M (diagonal blocks: dummy landmark N), so the gather loop needs no bounds checks.
+    std::vector<int> pos((size_t)Pf * Pf, -1), blk_ptr(1, 0);   // pos: next write position of block (i, j) in the padded array
     p.blk_ij.clear();
     p.diag_blk.assign(Pf, -1);
+    p.unit.clear();
+    p.blk_unit_ptr.assign(1, 0);
+    int padded_total = 0, ncon = 0;
     for (int i = 0; i < Pf; i++)
-        for (int j = i; j < Pf; j++)
-            if (cnt[(size_t)i * Pf + j] || i == j) {  // diagonal blocks always exist (Hpp + lambda I)
-                blk_of[(size_t)i * Pf + j] = (int)p.blk_ij.size();
-                if (i == j) p.diag_blk[i] = (int)p.blk_ij.size();
-                p.blk_ij.push_back(make_int2(i, j));
-                blk_ptr.push_back(blk_ptr.back() + cnt[(size_t)i * Pf + j]);
+        for (int j = i; j < Pf; j++) {
+            const int c = cnt[(size_t)i * Pf + j];
+            if (!c && i != j) continue;   // diagonal blocks always exist (Hpp + lambda I)
+            const int k = (int)p.blk_ij.size();
+            if (i == j) p.diag_blk[i] = k;
+            p.blk_ij.push_back(make_int2(i, j));
+            pos[(size_t)i * Pf + j] = padded_total;
+            for (int c0 = 0; c0 < c; c0 += unit) {
+                const int c1 = std::min(c0 + unit, c);
+                p.unit.push_back(make_int4(k, padded_total + c0, padded_total + ((c1 + 3) & ~3), i == j));
             }
+            p.blk_unit_ptr.push_back((int)p.unit.size());
+            ncon += c;
+            padded_total += (c + 3) & ~3;
+            blk_ptr.push_back(padded_total);
+        }
     const int nblk = (int)p.blk_ij.size();
-    p.con.resize(blk_ptr.back());
+    (void)nblk;
+    p.con.resize(padded_total);
     {
-        std::vector<int> fill(blk_ptr.begin(), blk_ptr.end() - 1);
         int2* con = p.con.data();
+        int* ps = pos.data();
         for (int l = 0; l < N; l++) {
             const int e0 = p.lm_ptr[l], e1 = p.lm_ptr[l + 1];
             for (int a = e0; a < e1; a++) {
                 const int fa = sf[a];
                 if (fa < 0) continue;
-                con[fill[blk_of[(size_t)fa * Pf + fa]]++] = make_int2(a, l);  // diagonal: (observation, landmark)
+                con[ps[(size_t)fa * Pf + fa]++] = make_int2(a, l);  // diagonal: (observation, landmark)
                 for (int b = a + 1; b < e1; b++) {
                     const int fb = sf[b];
                     if (fb < 0 || fb == fa) continue;
-                    if (fa < fb) con[fill[blk_of[(size_t)fa * Pf + fb]]++] = make_int2(a, b);
-                    else con[fill[blk_of[(size_t)fb * Pf + fa]]++] = make_int2(b, a);
+                    if (fa < fb) con[ps[(size_t)fa * Pf + fb]++] = make_int2(a, b);
+                    else con[ps[(size_t)fb * Pf + fa]++] = make_int2(b, a);
                 }
             }
         }
-    }
-    // units of <= `unit` contributions, each padded to a multiple of four with the all-zero dummy observation M (diagonal
-    // blocks: dummy landmark N), so the gather loop needs no bounds checks
-    {
-        std::vector<int2> padded;
-        padded.reserve(p.con.size() + 4 * (size_t)nblk + p.con.size() / unit * 4 + 16);
-        p.unit.clear();
-        p.blk_unit_ptr.assign(1, 0);
-        for (int k = 0; k < nblk; k++) {
-            const bool dg = p.blk_ij[k].x == p.blk_ij[k].y;
-            for (int c0 = blk_ptr[k]; c0 < blk_ptr[k + 1]; c0 += unit) {
-                const int c1 = std::min(c0 + unit, blk_ptr[k + 1]), b0 = (int)padded.size();
-                padded.insert(padded.end(), p.con.begin() + c0, p.con.begin() + c1);
-                while ((padded.size() - b0) & 3) padded.push_back(make_int2(M, dg ? N : M));
-                p.unit.push_back(make_int4(k, b0, (int)padded.size(), dg));
-            }
-            p.blk_unit_ptr.push_back((int)p.unit.size());
+        for (size_t k = 0; k < p.blk_ij.size(); k++) {   // the padding of each block's last unit
+            const int2 ij = p.blk_ij[k];
+            const bool dg = ij.x == ij.y;
+            for (int q = ps[(size_t)ij.x * Pf + ij.y]; q < blk_ptr[k + 1]; q++) con[q] = make_int2(M, dg ? N : M);
         }
-        p.ncon = (int)p.con.size();
-        p.con.swap(padded);
     }
+    p.ncon = ncon;
     // landmark ranges per CTA (balanced by observation count), cut into chunks of whole landmarks
     p.cta_lm.assign(n_cta + 1, N);
     p.cta_lm[0] = 0;
