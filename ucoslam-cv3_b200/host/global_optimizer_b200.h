@@ -5,14 +5,14 @@
 // uco_ba_problem; getResults writes poses, points and the bad-association list back as :466-538 does.  The object keeps
 // its own copy of inputs and results, because the mapper thread calls setParams + optimize WITHOUT the map lock and the
 // tracker thread calls getResults later (src/utils/mapmanager.cpp:11361-11405, :1267-1305); *stopASAP is forwarded.
-// Windows that involve ArUco markers or keyframes taken with different cameras are handed to the reference's own
-// GlobalOptimizerG2O by this adapter (TODO: flatten Map::map_markers / frame_MarkerWeight into uco_ba_problem::marker_* — the C ABI
-// solves marker vertices / MarkerEdges since round 1, see include/ucoslam_b200.h).
+// ArUco markers travel too (marker vertices, MarkerEdges, the per-keyframe marker weights of :276-297).  Windows whose keyframes were
+// taken with different cameras, or that use the InPlaneMarkers option, are handed to the reference's own GlobalOptimizerG2O.
 // Selected with Params::global_optimizer = "b200" once registered in GlobalOptimizer::create.
 // Compile inside the reference tree (needs its headers and OpenCV C++; see the note in orb_extractor_b200.h).
 #pragma once
 #include <cstring>
 #include <limits>
+#include <map>
 #include <vector>
 #include "optimization/globaloptimizer.h"
 #include "optimization/globaloptimizer_g2o.h"
@@ -40,6 +40,8 @@ public:
         if (_params.fixFirstFrame && frameSlot[map->keyframes.front().idx] != INVALID) fixedKind[map->keyframes.front().idx] = 2;
         for (auto f : _params.fixed_frames) if (frameSlot[f] != INVALID) fixedKind[f] = 2;
         bool markers = false, mixedCameras = false;
+        std::map<uint32_t, uint32_t> markerSlot;
+        _markerIds.clear();
         const size_t nInitial = _frameIds.size();
         for (size_t k = 0; k < nInitial; k++) {           // :135-176 (frames added as observers are not walked for points)
             const uint32_t f = _frameIds[k];
@@ -51,8 +53,13 @@ public:
                 _pointIds.push_back(pid);
                 for (const auto& fi : mp.frames) useFrame(fi.first, 1);
             }
-            for (auto& m : map->keyframes[f].markers)
-                if (map->map_markers[m.id].pose_g2m.isValid()) markers = true;
+            for (auto& m : map->keyframes[f].markers) {    // :157-170: valid map markers, all their frames join as fixed observers
+                if (markerSlot.count(m.id) || !map->map_markers[m.id].pose_g2m.isValid()) continue;
+                markerSlot[m.id] = (uint32_t)_markerIds.size();
+                _markerIds.push_back(m.id);
+                for (auto fid : map->map_markers[m.id].frames) useFrame(fid, 1);
+                markers = true;
+            }
         }
         const Frame& f0 = map->keyframes[_frameIds.front()];
         for (auto f : _frameIds) {
@@ -60,7 +67,7 @@ public:
             if (ip.fx() != f0.imageParams.fx() || ip.fy() != f0.imageParams.fy() || ip.cx() != f0.imageParams.cx() ||
                 ip.cy() != f0.imageParams.cy() || ip.bl != f0.imageParams.bl) mixedCameras = true;
         }
-        if (markers || mixedCameras) {                     // not on the device yet: the reference's own optimiser takes the window
+        if (mixedCameras || (markers && _params.InPlaneMarkers)) {   // not covered by the C ABI: the reference's own optimiser takes the window
             _delegate = std::make_shared<GlobalOptimizerG2O>();
             _delegate->setParams(map, ps);
             return;
@@ -94,7 +101,34 @@ public:
                 _obsInv.push_back(invScale[kp.octave]);
             }
         }
+        // markers (:304-350) and the per-keyframe weight of their 8 residuals (:276-297)
+        _mkPose.clear(); _mkSize.clear(); _moMarker.clear(); _moPose.clear(); _moCorners.clear(); _moWeight.clear();
+        if (markers) {
+            std::vector<double> kpw(P, 0.0);
+            for (size_t o = 0; o < _obsPose.size(); o++) kpw[_obsPose[o]] += (_obsStereo[o] ? 3 : 2) * _obsInv[o];
+            for (auto mid : _markerIds) {
+                const Marker& mk = map->map_markers[mid];
+                const float* g = mk.pose_g2m.ptr<float>(0);
+                _mkPose.insert(_mkPose.end(), g, g + 16);
+                _mkSize.push_back(mk.size);
+                for (auto fid : mk.frames) {
+                    const Frame& fr = map->keyframes[fid];
+                    const uint32_t slot = frameSlot[fid];
+                    double w = 1;
+                    if (kpw[slot] > 40 && fr.markers.size() > 0)
+                        w = _params.markersOptWeight * std::min(1., double(fr.markers.size()) / _params.minMarkersForMaxWeight) * kpw[slot] /
+                            double(fr.markers.size() * 8);
+                    _moMarker.push_back((int32_t)markerSlot[mid]);
+                    _moPose.push_back((int32_t)slot);
+                    for (const auto& c : fr.getMarker(mid).und_corners) { _moCorners.push_back(c.x); _moCorners.push_back(c.y); }
+                    _moWeight.push_back((float)w);
+                }
+            }
+        }
         _pb = uco_ba_problem{};
+        _pb.n_markers = (int32_t)_mkSize.size(); _pb.marker_pose44 = _mkPose.data(); _pb.marker_size = _mkSize.data();
+        _pb.n_marker_obs = (int32_t)_moMarker.size(); _pb.mobs_marker = _moMarker.data(); _pb.mobs_pose = _moPose.data();
+        _pb.mobs_corners = _moCorners.data(); _pb.mobs_weight = _moWeight.data();
         _pb.n_poses = (int32_t)P; _pb.n_points = (int32_t)N; _pb.n_obs = (int32_t)_obsPose.size();
         _pb.poses44 = _poses.data(); _pb.fixed = _fixed.data(); _pb.points3 = _points.data();
         _pb.obs_pose = _obsPose.data(); _pb.obs_point = _obsPoint.data(); _pb.obs_uv = _obsUV.data(); _pb.obs_ur = _obsUR.data();
@@ -109,6 +143,8 @@ public:
         _outPoses.resize(16 * (size_t)_pb.n_poses); _outPoints.resize(3 * (size_t)_pb.n_points); _outBad.resize(_pb.n_obs);
         uco_ba_result res{};
         res.poses44 = _outPoses.data(); res.points3 = _outPoints.data(); res.obs_bad = _outBad.data();
+        _outMarkers.resize(16 * (size_t)_pb.n_markers);
+        res.marker_poses44 = _outMarkers.data();
         static_assert(sizeof(bool) == 1, "the ABI polls a one-byte flag");
         // the mapper may flip *stopASAP from another thread (MapManager::stop, mapmanager.cpp:1614-1625): the solver polls it
         _ctx.check(uco_b200_ba_solve(_ctx.get(), &_pb, reinterpret_cast<const volatile unsigned char*>(stopASAP), &res));
@@ -129,6 +165,11 @@ public:
                 cv::Point3f((float)_outPoints[3 * j], (float)_outPoints[3 * j + 1], (float)_outPoints[3 * j + 2]));
             for (; o < _obsPoint.size() && (size_t)_obsPoint[o] == j; o++)
                 if (_outBad[o]) _badAssociations.push_back(std::make_pair(_pointIds[j], _frameIds[_obsPose[o]]));
+        }
+        for (size_t m = 0; m < _markerIds.size(); m++) {  // :526-527
+            cv::Mat T(4, 4, CV_32F);
+            std::memcpy(T.data, &_outMarkers[16 * m], 64);
+            map->map_markers[_markerIds[m]].pose_g2m = T.clone();
         }
         for (auto pid : _pointIds) map->updatePointNormalAndDistances(pid);   // :533-536
     }
@@ -151,8 +192,9 @@ private:
     ParamSet _params;
     std::shared_ptr<GlobalOptimizerG2O> _delegate;
     uco_ba_problem _pb{};
-    std::vector<uint32_t> _frameIds, _pointIds;
-    std::vector<float> _poses, _points, _obsUV, _obsUR, _obsInv, _outPoses;
+    std::vector<uint32_t> _frameIds, _pointIds, _markerIds;
+    std::vector<float> _poses, _points, _obsUV, _obsUR, _obsInv, _outPoses, _mkPose, _mkSize, _moCorners, _moWeight, _outMarkers;
+    std::vector<int32_t> _moMarker, _moPose;
     std::vector<uint8_t> _fixed, _obsStereo, _outBad;
     std::vector<int32_t> _obsPose, _obsPoint;
     std::vector<double> _outPoints;
