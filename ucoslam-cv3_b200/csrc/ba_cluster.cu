@@ -385,6 +385,15 @@ __device__ __forceinline__ void phase_gather(const CbDev& B, int rank, int CL) {
 // non-positive pivot.
 __device__ int phase_solve(const CbDev& B, double lambda, double* A, double* aux, int* sflag) {
     const int tid = threadIdx.x, n = B.n, lane = tid & 31, warp = tid >> 5;
+    long long ts = clock64();
+#define SOLVE_TICK(slot)                                          \
+    do {                                                          \
+        if (tid == 0) {                                           \
+            const long long tn = clock64();                       \
+            B.res->phase_cycles[slot] += (double)(tn - ts);       \
+            ts = tn;                                              \
+        }                                                         \
+    } while (0)
     const int tot = (n + 1) * (n + 2) / 2;
     for (int k = tid; k < tot; k += BS) A[k] = 0;
     if (tid == 0) *sflag = 0;
@@ -413,6 +422,7 @@ __device__ int phase_solve(const CbDev& B, double lambda, double* A, double* aux
         A[n * (n + 1) / 2 + k] = B.bp[k] - t;
     }
     __syncthreads();
+    SOLVE_TICK(12);
     double* dinv = aux;        // 6 reciprocal pivots of the current block column
     double* Ps = aux + 8;      // scaled panel: Ps[(i - c0 - 6) * 6 + j] = A[i][c0 + j] / d_j for the rows below the block
     for (int kb = 0; kb < B.Pf; kb++) {
@@ -481,6 +491,7 @@ __device__ int phase_solve(const CbDev& B, double lambda, double* A, double* aux
         for (int k = tid; k < n; k += BS) B.xp[k] = 0;
         return 0;
     }
+    SOLVE_TICK(13);
     for (int j = tid; j < n; j += BS) aux[256 + j] = 1.0 / A[j * (j + 1) / 2 + j];  // pivots inverted side by side, off the serial chain
     __syncthreads();
     if (warp == 0) {  // x_j = (w_j - sum_{i>j} A[i][j] x_i) / d_j
@@ -500,6 +511,8 @@ __device__ int phase_solve(const CbDev& B, double lambda, double* A, double* aux
         for (int k = lane; k < n; k += 32) B.xp[k] = s[k];
     }
     __syncthreads();
+    SOLVE_TICK(14);
+#undef SOLVE_TICK
     return 1;
 }
 
