@@ -438,6 +438,41 @@ typedef struct uco_frame_view {
 int uco_b200_match_projected(uco_b200_ctx* ctx, const uco_mappoints* mp, const uco_frame_view* fr, const float* pose_f2g,
                              float min_desc_dist, float max_reproj_dist, uco_match* out, int* n_out, uint8_t* visible);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * K11  keyframe database: relocalisation / loop-closure candidates by bag of words (BASELINE config 4)
+ *   replaces ucoslam::KeyFrameDataBase (KPFrameDataBase) add / del / clear / size / isId / relocalizationCandidates
+ *     src/map_types/keyframedatabase.h:31-52, src/map_types/keyframedatabase.cpp:136-171 (add/del/clear),
+ *     :195-233 (votes per frame over the inverted word index, maxCommonWords, minCommonWords = max*0.8f, fbow::fBow::score
+ *     3rdparty/fbow/fbow/fbow.cpp:192-243 of the frames above it, kept if > minScore), :236-275 (covisibility accumulation over
+ *     the 10 best neighbours, 0.75*best gate, optional sort by decreasing accumulated score -> uco_b200_kfdb_rank, host only).
+ *   A frame's bag of words is passed as its fBow in map order: `words` strictly ascending, `weights` the float values
+ *   (what uco_b200_bow_transform + the host fold produce).  The database is device resident (one context's device).
+ *   query: out_* hold the scored frames (the reference's frame_score map) in ascending frame id, capacity `cap`
+ *   (UCO_E_CAPACITY with *n_out = needed otherwise); scores are bit-identical doubles; out_common (optional) = votes of
+ *   each returned frame; max_common (optional) = maxCommonWords.  excluded = the reference's excludedFrames (unknown ids ignored).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct uco_b200_kfdb uco_b200_kfdb;
+int uco_b200_kfdb_create(uco_b200_ctx* ctx, uco_b200_kfdb** out);
+void uco_b200_kfdb_free(uco_b200_ctx* ctx, uco_b200_kfdb* db);
+int uco_b200_kfdb_clear(uco_b200_ctx* ctx, uco_b200_kfdb* db);
+int uco_b200_kfdb_size(const uco_b200_kfdb* db, uint32_t* n_frames, uint64_t* n_words);
+int uco_b200_kfdb_has(const uco_b200_kfdb* db, uint32_t frame_id); /* KeyFrameDataBase::isId */
+int uco_b200_kfdb_add(uco_b200_ctx* ctx, uco_b200_kfdb* db, uint32_t frame_id, const uint32_t* words, const float* weights, int n);
+/* several frames in one call: counts[f] words each, concatenated in `words` / `weights` */
+int uco_b200_kfdb_add_batch(uco_b200_ctx* ctx, uco_b200_kfdb* db, int n_frames, const uint32_t* frame_ids, const int32_t* counts,
+                            const uint32_t* words, const float* weights);
+int uco_b200_kfdb_del(uco_b200_ctx* ctx, uco_b200_kfdb* db, uint32_t frame_id);
+int uco_b200_kfdb_query(uco_b200_ctx* ctx, uco_b200_kfdb* db, const uint32_t* words, const float* weights, int n,
+                        const uint32_t* excluded, int n_excluded, float min_score, uint32_t* out_frame, double* out_score,
+                        uint32_t* out_common, int cap, int* n_out, uint32_t* max_common);
+/* device time (ms) of the vote scan [0] and the scoring pass [1] of the LAST query (context profiling on) */
+int uco_b200_kfdb_last_ms(const uco_b200_kfdb* db, float* out2);
+/* steps 3-4 on the scored frames (ascending ids, as uco_b200_kfdb_query returns them).  nbr_off[n+1] / nbr: for scored frame i
+ * the neighbour ids CovisGraph::getNeighborsWeights(frame[i], true) returns (decreasing weight; the first 10 are used).
+ * out: capacity n. */
+int uco_b200_kfdb_rank(const uint32_t* frame, const double* score, int n, const int32_t* nbr_off, const uint32_t* nbr, int sorted,
+                       float min_score, uint32_t* out, int* n_out);
+
 #ifdef __cplusplus
 }
 #endif

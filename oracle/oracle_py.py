@@ -92,7 +92,7 @@ def ref_voc_bytes():
     return np.fromfile(REF_VOC_PATH, dtype=np.uint8)
 
 
-def synth_vocabulary(seed, k=10, depth=4, desc_size=32, leaf_prob=0.08, partial_prob=0.1):
+def synth_vocabulary(seed, k=10, depth=4, desc_size=32, leaf_prob=0.08, partial_prob=0.1, weight_scale=1.0):
     """A seeded vocabulary file image in fbow's stream format (fbow.cpp:160-190, fbow.h:125-194): a k-ary tree of
     `depth` levels of internal blocks, with some early leaves and some blocks holding fewer than k nodes."""
     rng = np.random.default_rng(seed)
@@ -112,7 +112,7 @@ def synth_vocabulary(seed, k=10, depth=4, desc_size=32, leaf_prob=0.08, partial_
         for c in range(n):
             if level == depth - 1 or rng.random() < leaf_prob:
                 blk["ids"][c] = 0x80000000 | words[0]
-                blk["w"][c] = float(np.float32(rng.random() * 3 + 0.01))
+                blk["w"][c] = float(np.float32(np.float32(rng.random() * 3 + 0.01) * np.float32(weight_scale)))
                 words[0] += 1
             else:
                 blk["ids"][c] = make_block(level + 1, b)
@@ -553,3 +553,153 @@ def match_projected(sc, min_desc_dist, max_reproj_dist):
     n = f(m, _p(ids), _p(pos), _p(nrm), _p(dmin), _p(dmax), _p(mdesc), len(kxy), _p(kxy), _p(koct), _p(kdesc), _p(sf), len(sf),
           sc["fx"], sc["fy"], sc["cx"], sc["cy"], _p(mn), _p(mx), _p(pose), min_desc_dist, max_reproj_dist, _p(out), _p(vis))
     return out[:n].copy(), vis[:m].copy()
+
+
+# ---- keyframe database: relocalisation / loop-closure candidates ------------------------------------------------
+def synth_places(seed, n_places=12, views_per_place=5, n_desc=400, flip_bits=6, replace_frac=0.25):
+    """Seeded descriptor sets of keyframes that revisit a few places: every place has n_desc base descriptors, a view flips up to
+    flip_bits bits in each and replaces replace_frac of them by fresh random rows.  Returns (list of (n_desc,32) u8, place of each)."""
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, 256, (n_places, n_desc, 32), dtype=np.uint8)
+    frames, place = [], []
+    for v in range(views_per_place):
+        for p in range(n_places):
+            d = base[p].copy()
+            bits = np.unpackbits(d, axis=1)
+            for r in range(n_desc):
+                nf = int(rng.integers(0, flip_bits + 1))
+                if nf:
+                    bits[r, rng.choice(256, nf, replace=False)] ^= 1
+            d = np.packbits(bits, axis=1)
+            rep = rng.random(n_desc) < replace_frac
+            d[rep] = rng.integers(0, 256, (int(rep.sum()), 32), dtype=np.uint8)
+            frames.append(d)
+            place.append(p)
+    return frames, np.array(place)
+
+
+def synth_covis(seed, frame_ids, place, extra=0.1):
+    """Seeded covisibility edges: views of one place are connected (integer-valued float weights with ties), plus a few random
+    edges.  Returns (edge_a, edge_b, edge_w)."""
+    rng = np.random.default_rng(seed)
+    ea, eb, ew = [], [], []
+    n = len(frame_ids)
+    for i in range(n):
+        for j in range(i + 1, n):
+            if place[i] == place[j] or rng.random() < extra:
+                ea.append(frame_ids[i]); eb.append(frame_ids[j]); ew.append(float(rng.integers(20, 26)))
+    return np.array(ea, np.uint32), np.array(eb, np.uint32), np.array(ew, np.float32)
+
+
+def bow_score(ids1, w1, ids2, w2):
+    """oracle/kfdb_oracle.cpp: fBow::score restated."""
+    lib = load_stl()
+    lib.oracle_bow_score.restype = ctypes.c_double
+    ids1 = np.ascontiguousarray(ids1, np.uint32); w1 = np.ascontiguousarray(w1, np.float32)
+    ids2 = np.ascontiguousarray(ids2, np.uint32); w2 = np.ascontiguousarray(w2, np.float32)
+    return lib.oracle_bow_score(_p(ids1), _p(w1), len(ids1), _p(ids2), _p(w2), len(ids2))
+
+
+def _csr(bows):
+    off = np.zeros(len(bows) + 1, np.int64)
+    for i, (ids, w) in enumerate(bows):
+        off[i + 1] = off[i] + len(ids)
+    words = np.concatenate([np.asarray(b[0], np.uint32) for b in bows]) if bows else np.zeros(0, np.uint32)
+    weights = np.concatenate([np.asarray(b[1], np.float32) for b in bows]) if bows else np.zeros(0, np.float32)
+    return off, np.ascontiguousarray(words, np.uint32), np.ascontiguousarray(weights, np.float32)
+
+
+def kfdb_candidates(frame_ids, bows, q_bow, excluded=(), min_score=0.0, sorted_=True, edges=None):
+    """oracle/kfdb_oracle.cpp: KPFrameDataBase::relocalizationCandidates restated.  bows: list of (ids, weights) per database
+    frame; q_bow: (ids, weights); edges: (edge_a, edge_b, edge_w) of the covisibility graph.
+    Returns dict(scored_frame, scored_score, scored_common, max_common, candidates)."""
+    lib = load_stl()
+    frame_ids = np.ascontiguousarray(frame_ids, np.uint32)
+    off, words, weights = _csr(bows)
+    qw = np.ascontiguousarray(q_bow[0], np.uint32); qf = np.ascontiguousarray(q_bow[1], np.float32)
+    exc = np.ascontiguousarray(list(excluded), np.uint32)
+    ea, eb, ew = edges if edges is not None else (np.zeros(0, np.uint32), np.zeros(0, np.uint32), np.zeros(0, np.float32))
+    n = len(frame_ids)
+    sf = np.zeros(max(n, 1), np.uint32); ss = np.zeros(max(n, 1), np.float64); sc = np.zeros(max(n, 1), np.uint32)
+    cand = np.zeros(max(n, 1), np.uint32)
+    ns, nc, mc = ctypes.c_int(), ctypes.c_int(), ctypes.c_uint32()
+    lib.oracle_kfdb_candidates(n, _p(frame_ids), _p(off), _p(words), _p(weights), _p(qw), _p(qf), len(qw), _p(exc), len(exc),
+                               ctypes.c_float(min_score), int(bool(sorted_)), len(ea), _p(ea), _p(eb), _p(ew), _p(sf), _p(ss), _p(sc),
+                               ctypes.byref(ns), ctypes.byref(mc), _p(cand), ctypes.byref(nc))
+    return dict(scored_frame=sf[:ns.value].copy(), scored_score=ss[:ns.value].copy(), scored_common=sc[:ns.value].copy(),
+                max_common=int(mc.value), candidates=cand[:nc.value].copy())
+
+
+def covis_neighbors(edges, idx, cap=4096):
+    """CovisGraph::getNeighborsWeights(idx, true) restated: neighbour ids by decreasing weight."""
+    lib = load_stl()
+    ea, eb, ew = edges
+    out = np.zeros(cap, np.uint32)
+    n = lib.oracle_covis_neighbors(len(ea), _p(ea), _p(eb), _p(ew), ctypes.c_uint32(int(idx)), _p(out), cap)
+    return out[:min(n, cap)].copy()
+
+
+class RefKeyFrameDataBase:
+    """The reference's own KeyFrameDataBase + CovisGraph + fbow (oracle/_ref/libref_kfdb.so) fed with descriptors."""
+
+    def __init__(self, voc_path):
+        self.lib = load_ref("libref_kfdb.so")
+        if self.lib is None:
+            raise RuntimeError("oracle/_ref/libref_kfdb.so not built")
+        self.lib.ref_kfdb_create.restype = ctypes.c_void_p
+        self.lib.ref_kfdb_score.restype = ctypes.c_float
+        self.h = self.lib.ref_kfdb_create(voc_path.encode())
+        if not self.h:
+            raise RuntimeError("the reference rejected the vocabulary file")
+
+    def add(self, idx, desc):
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        ids = np.empty(len(desc), np.uint32); w = np.empty(len(desc), np.float32); nb = ctypes.c_int()
+        rc = self.lib.ref_kfdb_add(ctypes.c_void_p(self.h), ctypes.c_uint32(int(idx)), _p(desc), len(desc), _p(ids), _p(w),
+                                   ctypes.byref(nb))
+        if rc != 0:
+            raise RuntimeError("ref_kfdb_add rc=%d" % rc)
+        return ids[:nb.value].copy(), w[:nb.value].copy()
+
+    def delete(self, idx):
+        rc = self.lib.ref_kfdb_del(ctypes.c_void_p(self.h), ctypes.c_uint32(int(idx)))
+        if rc != 0:
+            raise RuntimeError("ref_kfdb_del rc=%d" % rc)
+
+    def covis_edge(self, a, b, w):
+        self.lib.ref_kfdb_covis_edge(ctypes.c_void_p(self.h), ctypes.c_uint32(int(a)), ctypes.c_uint32(int(b)), ctypes.c_float(w))
+
+    def query(self, desc, sorted_=True, min_score=0.0, excluded=()):
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        exc = np.ascontiguousarray(list(excluded), np.uint32)
+        out = np.zeros(65536, np.uint32)
+        ids = np.empty(len(desc), np.uint32); w = np.empty(len(desc), np.float32); nb = ctypes.c_int()
+        n = self.lib.ref_kfdb_query(ctypes.c_void_p(self.h), _p(desc), len(desc), int(bool(sorted_)), ctypes.c_float(min_score),
+                                    _p(exc), len(exc), _p(out), len(out), _p(ids), _p(w), ctypes.byref(nb))
+        if n < 0:
+            raise RuntimeError("ref_kfdb_query rc=%d" % n)
+        return out[:n].copy(), (ids[:nb.value].copy(), w[:nb.value].copy())
+
+    def add_bow(self, idx, ids, w):
+        ids = np.ascontiguousarray(ids, np.uint32); w = np.ascontiguousarray(w, np.float32)
+        rc = self.lib.ref_kfdb_add_bow(ctypes.c_void_p(self.h), ctypes.c_uint32(int(idx)), _p(ids), _p(w), len(ids))
+        if rc != 0:
+            raise RuntimeError("ref_kfdb_add_bow rc=%d" % rc)
+
+    def query_bow(self, ids, w, sorted_=True, min_score=0.0, excluded=()):
+        ids = np.ascontiguousarray(ids, np.uint32); w = np.ascontiguousarray(w, np.float32)
+        exc = np.ascontiguousarray(list(excluded), np.uint32)
+        out = np.zeros(65536, np.uint32)
+        n = self.lib.ref_kfdb_query_bow(ctypes.c_void_p(self.h), _p(ids), _p(w), len(ids), int(bool(sorted_)), ctypes.c_float(min_score),
+                                        _p(exc), len(exc), _p(out), len(out))
+        if n < 0:
+            raise RuntimeError("ref_kfdb_query_bow rc=%d" % n)
+        return out[:n].copy()
+
+    def score(self, a, b):
+        return float(self.lib.ref_kfdb_score(ctypes.c_void_p(self.h), ctypes.c_uint32(int(a)), ctypes.c_uint32(int(b))))
+
+    def close(self):
+        if self.h:
+            self.lib.ref_kfdb_free(ctypes.c_void_p(self.h))
+            self.h = None

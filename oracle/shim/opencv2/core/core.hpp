@@ -14,7 +14,13 @@
 #define CV_32FC1 5
 #define CV_32F 5
 #include <memory>
+#include <algorithm>   // the real OpenCV headers pull these in; the reference relies on that (keyframedatabase.cpp:263-266)
+typedef unsigned char uchar;
 namespace cv {
+struct Point2f {
+    float x, y;
+    Point2f(float a = 0, float b = 0) : x(a), y(b) {}
+};
 struct Point3f {
     float x, y, z;
     Point3f(float a = 0, float b = 0, float c = 0) : x(a), y(b), z(c) {}
@@ -43,6 +49,8 @@ public:
     template <typename T> T* ptr(int r = 0) { return (T*)(_data + (size_t)r * _step); }
     template <typename T> const T* ptr(int r = 0) const { return (const T*)(_data + (size_t)r * _step); }
     bool empty() const { return rows == 0 || cols == 0; }
+    size_t total() const { return (size_t)rows * cols; }
+    bool isContinuous() const { return _step == (size_t)cols * elemSize(); }
 private:
     int _type = 0;
     unsigned char* _data = nullptr;

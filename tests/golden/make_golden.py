@@ -150,7 +150,68 @@ def project():
     print("projection golden written", {n: len(out[n + "_out_matches"]) for n in "abc"})
 
 
+KFDB_CASES = {  # name -> (vocabulary kwargs or None = the shipped orb.fbow, synth_places kwargs)
+    "s": (dict(seed=5, k=10, depth=4, weight_scale=0.02), dict(seed=1, n_places=12, views_per_place=5, n_desc=400)),
+    "t": (dict(seed=6, k=8, depth=5, leaf_prob=0.02, weight_scale=0.004), dict(seed=2, n_places=5, views_per_place=8, n_desc=700, replace_frac=0.5)),
+    "orb": (None, dict(seed=3, n_places=6, views_per_place=4, n_desc=300)),
+}
+
+
+def kfdb():
+    """KeyFrameDataBase::relocalizationCandidates of the reference (its own keyframedatabase.cpp + covisgraph.cpp + fbow compiled
+    unchanged, oracle/_ref/libref_kfdb.so) on seeded keyframes that revisit a few places."""
+    import tempfile
+    oracle_py.build_ref()
+    out = {}
+    for name, (vkw, pkw) in KFDB_CASES.items():
+        if vkw is None:
+            path = oracle_py.REF_VOC_PATH
+        else:
+            path = os.path.join(tempfile.mkdtemp(), "v.fbow")
+            oracle_py.synth_vocabulary(**vkw).tofile(path)
+        ref = oracle_py.RefKeyFrameDataBase(path)
+        frames, place = oracle_py.synth_places(**pkw)
+        ids = (np.arange(len(frames)) * 3 + 7).astype(np.uint32)
+        ids[::7] += 1000          # insertion order is not id order
+        bows = [ref.add(i, d) for i, d in zip(ids, frames)]
+        ea, eb, ew = oracle_py.synth_covis(pkw["seed"] + 100, ids, place)
+        for a, b, w in zip(ea, eb, ew):
+            ref.covis_edge(a, b, w)
+        off, words, weights = oracle_py._csr(bows)
+        out[name + "_ids"], out[name + "_off"], out[name + "_words"], out[name + "_weights"] = ids, off, words, weights
+        out[name + "_ea"], out[name + "_eb"], out[name + "_ew"] = ea, eb, ew
+        qkw = dict(pkw); qkw["seed"] += 50; qkw["views_per_place"] = 1
+        qframes, _ = oracle_py.synth_places(**qkw)
+        nq = 0
+        deleted = []
+        for phase in range(2):
+            for qi, qd in enumerate(qframes[:4]):
+                for sorted_ in (1, 0):
+                    for ms, exc in ((0.0, []), (0.05, [int(ids[2]), int(ids[9]), 123456])):
+                        cand, qbow = ref.query(qd, sorted_, ms, exc)
+                        k = "%s_q%d" % (name, nq)
+                        out[k + "_words"], out[k + "_weights"] = qbow
+                        out[k + "_prm"] = np.array([sorted_, ms, phase], np.float64)
+                        out[k + "_exc"] = np.array(exc, np.uint32)
+                        out[k + "_cand"] = cand
+                        nq += 1
+            if phase == 0:      # the second phase queries after deletions
+                deleted = [int(x) for x in ids[1::4]]
+                for d in deleted:
+                    ref.delete(d)
+        out[name + "_deleted"] = np.array(deleted, np.uint32)
+        out[name + "_nq"] = np.int32(nq)
+        # KeyFrameDataBase::score (float) of a few pairs still in the database
+        alive = [int(x) for x in ids if int(x) not in deleted]
+        pairs = [(alive[i], alive[(i * 5 + 3) % len(alive)]) for i in range(12)]
+        out[name + "_pairs"] = np.array(pairs, np.uint32)
+        out[name + "_pair_score"] = np.array([ref.score(a, b) for a, b in pairs], np.float32)
+        ref.close()
+    np.savez_compressed(os.path.join(HERE, "kfdb_ref.npz"), **out)
+    print("kfdb golden written", len(out), {n: int(out[n + "_nq"]) for n in KFDB_CASES})
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["knn", "bow", "ba", "ba_markers", "pnp", "project"]
+    which = sys.argv[1:] or ["knn", "bow", "ba", "ba_markers", "pnp", "project", "kfdb"]
     for w in which:
         globals()[w]()

@@ -66,6 +66,17 @@ SIGNATURES = {
     "uco_b200_pose_only_batch": (_i, [_vp, _i, _vp, _vp]),
     "uco_b200_probe_math": (_i, [_i, _vp, _vp, _i, _vp, _vp]),
     "uco_b200_probe_retain_best": (_i, [_vp, _i, _i]),
+    "uco_b200_kfdb_create": (_i, [_vp, _vp]),
+    "uco_b200_kfdb_free": (None, [_vp, _vp]),
+    "uco_b200_kfdb_clear": (_i, [_vp, _vp]),
+    "uco_b200_kfdb_size": (_i, [_vp, _vp, _vp]),
+    "uco_b200_kfdb_has": (_i, [_vp, _c.c_uint32]),
+    "uco_b200_kfdb_add": (_i, [_vp, _vp, _c.c_uint32, _vp, _vp, _i]),
+    "uco_b200_kfdb_add_batch": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "uco_b200_kfdb_del": (_i, [_vp, _vp, _c.c_uint32]),
+    "uco_b200_kfdb_query": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _c.c_float, _vp, _vp, _vp, _i, _vp, _vp]),
+    "uco_b200_kfdb_last_ms": (_i, [_vp, _vp]),
+    "uco_b200_kfdb_rank": (_i, [_vp, _vp, _i, _vp, _vp, _i, _c.c_float, _vp, _vp]),
 }
 
 KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
@@ -575,3 +586,85 @@ class Context:
     def hamming_knn_dev(self, q_dev, nq, t_dev, nt, k, order, idx_dev, dist_dev):
         """Device pointers (ints, e.g. torch.Tensor.data_ptr()); asynchronous on the context stream."""
         self._chk(self.lib.uco_b200_hamming_knn_dev(self.h, q_dev, nq, t_dev, nt, k, order, idx_dev, dist_dev))
+
+
+class KeyFrameDataBase:
+    """Host-side mirror of ucoslam::KeyFrameDataBase (src/map_types/keyframedatabase.h:31-52) over the device-resident database:
+    add / delete / clear / size / is_id / relocalization_candidates with the reference's argument meaning.  A frame is passed as its
+    bag of words (ids ascending, float weights): what Vocabulary::transform + the host fold produce.  `neighbors(frame_id)` stands
+    for CovisGraph::getNeighborsWeights(frame_id, true): neighbour ids by decreasing weight."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.h = ctypes.c_void_p()
+        ctx._chk(ctx.lib.uco_b200_kfdb_create(ctx.h, ctypes.addressof(self.h)))
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.uco_b200_kfdb_free(self.ctx.h, self.h)
+            self.h = None
+
+    def add(self, frame_id, words, weights):
+        words = np.ascontiguousarray(words, np.uint32); weights = np.ascontiguousarray(weights, np.float32)
+        self.ctx._chk(self.ctx.lib.uco_b200_kfdb_add(self.ctx.h, self.h, int(frame_id), _p(words), _p(weights), len(words)))
+
+    def add_batch(self, frame_ids, bows):
+        frame_ids = np.ascontiguousarray(frame_ids, np.uint32)
+        counts = np.array([len(b[0]) for b in bows], np.int32)
+        words = np.ascontiguousarray(np.concatenate([np.asarray(b[0], np.uint32) for b in bows]) if len(bows) else np.zeros(0, np.uint32))
+        weights = np.ascontiguousarray(np.concatenate([np.asarray(b[1], np.float32) for b in bows]) if len(bows) else np.zeros(0, np.float32))
+        self.ctx._chk(self.ctx.lib.uco_b200_kfdb_add_batch(self.ctx.h, self.h, len(frame_ids), _p(frame_ids), _p(counts), _p(words),
+                                                           _p(weights)))
+
+    def delete(self, frame_id):
+        self.ctx._chk(self.ctx.lib.uco_b200_kfdb_del(self.ctx.h, self.h, int(frame_id)))
+
+    def clear(self):
+        self.ctx._chk(self.ctx.lib.uco_b200_kfdb_clear(self.ctx.h, self.h))
+
+    def size(self):
+        n, w = ctypes.c_uint32(), ctypes.c_uint64()
+        self.ctx.lib.uco_b200_kfdb_size(self.h, ctypes.addressof(n), ctypes.addressof(w))
+        return int(n.value), int(w.value)
+
+    def is_id(self, frame_id):
+        return bool(self.ctx.lib.uco_b200_kfdb_has(self.h, int(frame_id)))
+
+    def query(self, words, weights, excluded=(), min_score=0.0):
+        """steps 1-2: dict(frame, score, common, max_common) of the scored frames, ascending frame id"""
+        words = np.ascontiguousarray(words, np.uint32); weights = np.ascontiguousarray(weights, np.float32)
+        exc = np.ascontiguousarray(list(excluded), np.uint32)
+        cap = max(self.size()[0], 1)
+        fr = np.zeros(cap, np.uint32); sc = np.zeros(cap, np.float64); cm = np.zeros(cap, np.uint32)
+        n, mc = ctypes.c_int(), ctypes.c_uint32()
+        self.ctx._chk(self.ctx.lib.uco_b200_kfdb_query(self.ctx.h, self.h, _p(words), _p(weights), len(words), _p(exc), len(exc),
+                                                       float(min_score), _p(fr), _p(sc), _p(cm), cap, ctypes.addressof(n),
+                                                       ctypes.addressof(mc)))
+        return dict(frame=fr[:n.value].copy(), score=sc[:n.value].copy(), common=cm[:n.value].copy(), max_common=int(mc.value))
+
+    def last_ms(self):
+        out = np.zeros(2, np.float32)
+        self.ctx.lib.uco_b200_kfdb_last_ms(self.h, _p(out))
+        return out
+
+    def relocalization_candidates(self, words, weights, neighbors, sorted_=True, min_score=0.0, excluded=()):
+        q = self.query(words, weights, excluded, min_score)
+        return rank_candidates(q["frame"], q["score"], neighbors, sorted_, min_score)
+
+
+def rank_candidates(frame, score, neighbors, sorted_=True, min_score=0.0):
+    """uco_b200_kfdb_rank: covisibility accumulation, 0.75*best gate, optional sort (keyframedatabase.cpp:236-275)."""
+    frame = np.ascontiguousarray(frame, np.uint32); score = np.ascontiguousarray(score, np.float64)
+    n = len(frame)
+    lists = [np.asarray(neighbors(int(f)), np.uint32) for f in frame] if n > 1 else [np.zeros(0, np.uint32)] * n
+    off = np.zeros(n + 1, np.int32)
+    for i, l in enumerate(lists):
+        off[i + 1] = off[i] + len(l)
+    nbr = np.ascontiguousarray(np.concatenate(lists) if n else np.zeros(0, np.uint32), np.uint32)
+    out = np.zeros(max(n, 1), np.uint32)
+    no = ctypes.c_int()
+    rc = load().uco_b200_kfdb_rank(_p(frame), _p(score), n, _p(off), _p(nbr), int(bool(sorted_)), float(min_score), _p(out),
+                                   ctypes.addressof(no))
+    if rc != 0:
+        raise UcoError("uco_b200_kfdb_rank rc=%d" % rc)
+    return out[:no.value].copy()
