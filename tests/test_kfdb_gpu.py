@@ -56,17 +56,17 @@ def random_bows(rng, n_frames, n_words, vocab, n_places=40, scale=0.01):
     return bows, places
 
 
-def test_large_database_batch_add_and_edge_cases(ctx):
+@pytest.mark.parametrize("vocab,n_frames", [(1_000_000, 3000), (6_000_000, 1200)])   # shared-memory bitmap / global bitmap scan
+def test_large_database_batch_add_and_edge_cases(ctx, vocab, n_frames):
     rng = np.random.default_rng(17)
-    vocab = 1_000_000
-    bows, places = random_bows(rng, 3000, 600, vocab)
+    bows, places = random_bows(rng, n_frames, 600, vocab)
     bows[5] = (np.zeros(0, np.uint32), np.zeros(0, np.float32))                    # a frame without words
     bows[6] = (np.array([0, vocab - 1], np.uint32), np.array([0.5, 0.25], np.float32))
     ids = (rng.permutation(len(bows)) * 2 + 1).astype(np.uint32)
     db = ucoslam_b200.KeyFrameDataBase(ctx)
-    db.add_batch(ids[:2000], bows[:2000])
-    db.add_batch(ids[2000:], bows[2000:])
-    assert db.size()[0] == 3000
+    db.add_batch(ids[:n_frames // 2], bows[:n_frames // 2])
+    db.add_batch(ids[n_frames // 2:], bows[n_frames // 2:])
+    assert db.size()[0] == n_frames
     empty = (np.zeros(0, np.uint32), np.zeros(0, np.float32))
     assert len(db.query(*empty)["frame"]) == 0
     for t in range(6):

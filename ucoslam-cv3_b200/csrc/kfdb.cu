@@ -100,52 +100,153 @@ __global__ void __launch_bounds__(256) kfdb_count_kernel(const uint4* __restrict
     if (lane == 0 && local_max) atomicMax(d_max, local_max);
 }
 
-// step 2 (keyframedatabase.cpp:221-233): fBow::score of the frames with more than 0.8*max votes
-__global__ void __launch_bounds__(256) kfdb_score_kernel(const uint32_t* __restrict__ words, const float* __restrict__ weights,
-                                                         const uint2* __restrict__ slots, const uint32_t* __restrict__ frame,
-                                                         const uint32_t* __restrict__ nobs, int n_slots,
-                                                         const uint32_t* __restrict__ bitmap, uint32_t max_word,
-                                                         const uint32_t* __restrict__ qwords, const float* __restrict__ qweights, int nq,
-                                                         const uint32_t* __restrict__ d_max, float min_score, KfHit* __restrict__ out,
-                                                         int cap, uint32_t* __restrict__ n_out) {
+// the same scan with the query bitmap staged in shared memory (vocabularies up to KFDB_SMEM_BITMAP_BYTES * 8 words: the shipped
+// 10^6-word vocabulary needs 122 KB): one persistent CTA of 32 warps per SM, warps take keyframes from a global ticket counter.
+// Through L1 every word test is its own 32-byte sector request (ncu on the kernel above: 37.7 M sector requests per query against
+// 4.7 M for the word stream itself, warps waiting in lg_throttle); in shared memory it is a bank-conflicted 4-byte read.
+#define KFDB_SMEM_BITMAP_BYTES (200 * 1024)
+__device__ __forceinline__ unsigned kf_test_s(uint32_t w, const uint32_t* bm, uint32_t max_word) {
+    return (w <= max_word) ? ((bm[w >> 5] >> (w & 31)) & 1u) : 0u;
+}
+__device__ __forceinline__ unsigned kf_test4_s(const uint4 a, const uint32_t* bm, uint32_t max_word) {
+    return kf_test_s(a.x, bm, max_word) + kf_test_s(a.y, bm, max_word) + kf_test_s(a.z, bm, max_word) + kf_test_s(a.w, bm, max_word);
+}
+__global__ void __launch_bounds__(1024, 1) kfdb_count_smem_kernel(const uint4* __restrict__ words4, const uint2* __restrict__ slots,
+                                                                  const uint8_t* __restrict__ excl, int n_slots,
+                                                                  const uint32_t* __restrict__ bitmap, uint32_t max_word,
+                                                                  uint32_t* __restrict__ nobs, uint32_t* __restrict__ d_max,
+                                                                  uint32_t* __restrict__ ticket) {
+    extern __shared__ uint4 bm4[];
+    const uint32_t* bm = (const uint32_t*)bm4;
+    const int bm16 = (int)(((max_word >> 5) + 4) >> 2);          // bitmap length in 16-byte units (the workspace is padded)
+    for (int i = threadIdx.x; i < bm16; i += blockDim.x) bm4[i] = __ldg((const uint4*)bitmap + i);
+    __syncthreads();
     const int lane = threadIdx.x & 31;
-    const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (slot >= n_slots) return;
+    uint32_t local_max = 0;
+    for (;;) {
+        int slot = 0;
+        if (lane == 0) slot = (int)atomicAdd(ticket, 1u);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (slot >= n_slots) break;
+        const uint2 s = slots[slot];
+        uint32_t cnt = 0;
+        if (s.y != 0 && !excl[slot]) {
+            const uint4* p = words4 + s.x;
+            const int n4 = (int)((s.y + 3) >> 2);
+            int i = lane;
+            for (; i + 96 < n4; i += 128) {   // four 16-byte loads in flight per lane
+                const uint4 a = __ldcs(p + i), b = __ldcs(p + i + 32), c = __ldcs(p + i + 64), d = __ldcs(p + i + 96);
+                cnt += kf_test4_s(a, bm, max_word) + kf_test4_s(b, bm, max_word) + kf_test4_s(c, bm, max_word) + kf_test4_s(d, bm, max_word);
+            }
+            uint4 t[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) t[k] = (i + 32 * k < n4) ? __ldcs(p + i + 32 * k) : make_uint4(~0u, ~0u, ~0u, ~0u);
+#pragma unroll
+            for (int k = 0; k < 3; k++) cnt += kf_test4_s(t[k], bm, max_word);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        }
+        if (lane == 0) nobs[slot] = cnt;
+        local_max = max(local_max, cnt);
+    }
+    if (lane == 0 && local_max) atomicMax(d_max, local_max);
+}
+
+// step 2a (keyframedatabase.cpp:222-226): the frames with more than 0.8*max votes, as a work list
+__global__ void __launch_bounds__(256) kfdb_select_kernel(const uint32_t* __restrict__ nobs, int n_slots, const uint32_t* __restrict__ d_max,
+                                                          uint32_t* __restrict__ sel, uint32_t* __restrict__ n_sel) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t max_common = *d_max;
     const uint32_t min_common = __float2uint_rz(__fmul_rn(__uint2float_rn(max_common), 0.8f));   // uint32_t = maxCommonWords*0.8f
-    const uint32_t common = nobs[slot];
-    if (max_common == 0 || !(common > min_common)) return;
-    const uint2 s = slots[slot];
-    const uint32_t* w = words + (size_t)s.x * 4;
-    const float* wt = weights + (size_t)s.x * 4;
-    double score = 0.0;
-    for (uint32_t base = 0; base < s.y; base += 32) {
-        const uint32_t i = base + lane;
-        float prod = 0.f;
-        bool hit = false;
-        if (i < s.y) {
-            const uint32_t wi = w[i];
-            if (kf_test(wi, bitmap, max_word)) {
-                int lo = 0, hi = nq - 1;   // the word is in the query: find its weight
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (__ldg(qwords + mid) < wi) lo = mid + 1; else hi = mid;
+    const bool take = slot < n_slots && max_common != 0 && nobs[slot] > min_common;
+    const unsigned m = __ballot_sync(0xffffffffu, take);
+    if (!m) return;
+    const int lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(n_sel, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (take) sel[base + __popc(m & ((1u << lane) - 1))] = (uint32_t)slot;
+}
+
+// step 2b (keyframedatabase.cpp:227-232): fBow::score of the listed frames.  One CTA per frame: all threads find the common words
+// and their float products in parallel and park them IN WORD ORDER in shared memory (ballot + block scan), then one thread adds them
+// into the double one by one -- the only part of fbow.cpp:209 whose order matters.
+#define KFDB_SCORE_THREADS 256
+#define KFDB_SCORE_CAP 4096
+__global__ void __launch_bounds__(KFDB_SCORE_THREADS) kfdb_score_kernel(const uint32_t* __restrict__ words, const float* __restrict__ weights,
+                                                         const uint2* __restrict__ slots, const uint32_t* __restrict__ frame,
+                                                         const uint32_t* __restrict__ nobs,
+                                                         const uint32_t* __restrict__ bitmap, uint32_t max_word,
+                                                         const uint32_t* __restrict__ qwords, const float* __restrict__ qweights, int nq,
+                                                         const uint32_t* __restrict__ sel, const uint32_t* __restrict__ n_sel,
+                                                         float min_score, KfHit* __restrict__ out, int cap, uint32_t* __restrict__ n_out) {
+    __shared__ float prod[KFDB_SCORE_CAP];
+    __shared__ uint32_t warp_cnt[KFDB_SCORE_THREADS / 32];
+    __shared__ uint32_t fill;
+    __shared__ double acc;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t total = *n_sel;
+    for (uint32_t it = blockIdx.x; it < total; it += gridDim.x) {
+        const uint32_t slot = sel[it];
+        const uint2 s = slots[slot];
+        const uint32_t* w = words + (size_t)s.x * 4;
+        const float* wt = weights + (size_t)s.x * 4;
+        if (threadIdx.x == 0) { fill = 0; acc = 0.0; }
+        __syncthreads();
+        for (uint32_t base = 0; base < s.y; base += KFDB_SCORE_THREADS) {
+            const uint32_t i = base + threadIdx.x;
+            float p = 0.f;
+            bool hit = false;
+            if (i < s.y) {
+                const uint32_t wi = w[i];
+                if (kf_test(wi, bitmap, max_word)) {
+                    int lo = 0, hi = nq - 1;   // the word is in the query: find its weight
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (__ldg(qwords + mid) < wi) lo = mid + 1; else hi = mid;
+                    }
+                    p = __fmul_rn(__ldg(qweights + lo), wt[i]);   // float product (fBow values are floats), fbow.cpp:209
+                    hit = true;
                 }
-                prod = __fmul_rn(__ldg(qweights + lo), wt[i]);   // float product (fBow values are floats), fbow.cpp:209
-                hit = true;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (lane == 0) warp_cnt[warp] = __popc(m);
+            __syncthreads();
+            uint32_t before = 0, tile = 0;
+#pragma unroll
+            for (int k = 0; k < KFDB_SCORE_THREADS / 32; k++) {
+                const uint32_t c = warp_cnt[k];
+                before += (k < warp) ? c : 0u;
+                tile += c;
+            }
+            const uint32_t start = fill;
+            if (start + tile > KFDB_SCORE_CAP) {   // flush what is parked (uniform branch: every thread sees the same counters)
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    double a = acc;
+                    for (uint32_t k = 0; k < start; k++) a = __dadd_rn(a, (double)prod[k]);
+                    acc = a;
+                    fill = 0;
+                }
+                __syncthreads();
+            }
+            const uint32_t at = (start + tile > KFDB_SCORE_CAP) ? 0u : start;
+            if (hit) prod[at + before + __popc(m & ((1u << lane) - 1))] = p;
+            __syncthreads();
+            if (threadIdx.x == 0) fill = at + tile;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            double score = acc;
+            const uint32_t n = fill;
+            for (uint32_t k = 0; k < n; k++) score = __dadd_rn(score, (double)prod[k]);   // ascending word order, like the two map iterators
+            const double si = (score >= 1.0) ? 1.0 : 1.0 - sqrt(1.0 - score);             // fbow.cpp:237-240
+            if (si > (double)min_score) {
+                const uint32_t k = atomicAdd(n_out, 1u);
+                if (k < (uint32_t)cap) out[k] = KfHit{frame[slot], nobs[slot], si};
             }
         }
-        unsigned m = __ballot_sync(0xffffffffu, hit);
-        while (m) {   // ascending word order, like the two map iterators
-            const int b = __ffs(m) - 1;
-            m &= m - 1;
-            score = __dadd_rn(score, (double)__shfl_sync(0xffffffffu, prod, b));
-        }
-    }
-    const double si = (score >= 1.0) ? 1.0 : 1.0 - sqrt(1.0 - score);   // fbow.cpp:237-240
-    if (lane == 0 && si > (double)min_score) {
-        const uint32_t k = atomicAdd(n_out, 1u);
-        if (k < (uint32_t)cap) out[k] = KfHit{frame[slot], common, si};
+        __syncthreads();
     }
 }
 
@@ -398,7 +499,7 @@ int uco_b200_kfdb_query(uco_b200_ctx* ctx, uco_b200_kfdb* db, const uint32_t* wo
     const int n_slots = (int)db->slots.size();
     if (n == 0 || n_slots == 0 || db->live == 0) return UCO_OK;   // frame_nobs.size()==0 -> {}  (keyframedatabase.cpp:221)
     const uint32_t max_word = words[n - 1];
-    const size_t bm_words = (size_t)(max_word >> 5) + 1;
+    const size_t bm_words = (((size_t)(max_word >> 5) + 1) + 3) & ~(size_t)3;   // whole 16-byte units (the scan copies it as uint4)
     std::vector<uint32_t> excl_slots;
     for (int i = 0; i < n_excluded; i++) {
         auto it = db->slot_of.find(excluded[i]);
@@ -413,15 +514,18 @@ int uco_b200_kfdb_query(uco_b200_ctx* ctx, uco_b200_kfdb* db, const uint32_t* wo
     const int hit_cap = n_slots;
     uint8_t* dout = (uint8_t*)uco_ws(ctx, WS_KFDB_OUT, 16 + (size_t)hit_cap * sizeof(KfHit));
     uint8_t* hout = (uint8_t*)uco_pinned(ctx, WS_KFDB_OUT, 16 + (size_t)hit_cap * sizeof(KfHit));
-    if (!hq || !dq || !bitmap || !dout || !hout) return UCO_E_NOMEM;
+    uint32_t* d_sel = (uint32_t*)uco_ws(ctx, WS_KFDB_STAGE, (size_t)n_slots * 4);
+    if (!hq || !dq || !bitmap || !dout || !hout || !d_sel) return UCO_E_NOMEM;
     memcpy(hq, words, (size_t)n * 4);
     memcpy(hq + (size_t)n * 4, weights, (size_t)n * 4);
     if (ne) memcpy(hq + (size_t)n * 8, excl_slots.data(), (size_t)ne * 4);
     const uint32_t* d_qw = (const uint32_t*)dq;
     const float* d_qf = (const float*)(dq + (size_t)n * 4);
     const uint32_t* d_ex = (const uint32_t*)(dq + (size_t)n * 8);
-    uint32_t* d_max = (uint32_t*)dout;          // [0] max votes, [1] number of hits
+    uint32_t* d_max = (uint32_t*)dout;          // [0] max votes, [1] number of hits, [2] scan ticket, [3] number of selected frames
     uint32_t* d_nhit = d_max + 1;
+    uint32_t* d_ticket = d_max + 2;
+    uint32_t* d_nsel = d_max + 3;
     KfHit* d_hits = (KfHit*)(dout + 16);
     cudaEvent_t ev[3] = {};
     const bool prof = ctx->profiling != 0;
@@ -435,14 +539,27 @@ int uco_b200_kfdb_query(uco_b200_ctx* ctx, uco_b200_kfdb* db, const uint32_t* wo
     kfdb_mark_kernel<<<(nm + 255) / 256, 256, 0, ctx->stream>>>(d_qw, n, bitmap, d_ex, ne, db->d_excl);
     UCO_LAUNCH_CHECK(ctx);
     if (prof) cudaEventRecord(ev[0], ctx->stream);
-    const int blocks = std::min((n_slots + 7) / 8, ctx->sm_count * 8);
-    kfdb_count_kernel<<<blocks, 256, 0, ctx->stream>>>((const uint4*)db->d_words, db->d_slots, db->d_excl, n_slots, bitmap, max_word,
-                                                       db->d_nobs, d_max);
+    if (bm_words * 4 <= KFDB_SMEM_BITMAP_BYTES) {
+        static bool attr_set = false;   // per process; the attribute is per function and device-wide
+        if (!attr_set) {
+            UCO_CUDA(ctx, cudaFuncSetAttribute(kfdb_count_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KFDB_SMEM_BITMAP_BYTES));
+            attr_set = true;
+        }
+        const int blocks = std::min((n_slots + 31) / 32, ctx->sm_count);
+        kfdb_count_smem_kernel<<<blocks, 1024, bm_words * 4, ctx->stream>>>((const uint4*)db->d_words, db->d_slots, db->d_excl, n_slots,
+                                                                           bitmap, max_word, db->d_nobs, d_max, d_ticket);
+    } else {
+        const int blocks = std::min((n_slots + 7) / 8, ctx->sm_count * 8);
+        kfdb_count_kernel<<<blocks, 256, 0, ctx->stream>>>((const uint4*)db->d_words, db->d_slots, db->d_excl, n_slots, bitmap, max_word,
+                                                           db->d_nobs, d_max);
+    }
     UCO_LAUNCH_CHECK(ctx);
     if (prof) cudaEventRecord(ev[1], ctx->stream);
-    kfdb_score_kernel<<<(n_slots + 7) / 8, 256, 0, ctx->stream>>>(db->d_words, db->d_weights, db->d_slots, db->d_frame, db->d_nobs,
-                                                                  n_slots, bitmap, max_word, d_qw, d_qf, n, d_max, min_score, d_hits,
-                                                                  hit_cap, d_nhit);
+    kfdb_select_kernel<<<(n_slots + 255) / 256, 256, 0, ctx->stream>>>(db->d_nobs, n_slots, d_max, d_sel, d_nsel);
+    UCO_LAUNCH_CHECK(ctx);
+    kfdb_score_kernel<<<std::min(n_slots, ctx->sm_count * 4), KFDB_SCORE_THREADS, 0, ctx->stream>>>(
+        db->d_words, db->d_weights, db->d_slots, db->d_frame, db->d_nobs, bitmap, max_word, d_qw, d_qf, n, d_sel, d_nsel, min_score,
+        d_hits, hit_cap, d_nhit);
     UCO_LAUNCH_CHECK(ctx);
     if (prof) cudaEventRecord(ev[2], ctx->stream);
     // the common case returns a handful of frames: fetch the counters and the first hits in one transfer, the rest if needed
