@@ -473,6 +473,30 @@ int uco_b200_kfdb_last_ms(const uco_b200_kfdb* db, float* out2);
 int uco_b200_kfdb_rank(const uint32_t* frame, const double* score, int n, const int32_t* nbr_off, const uint32_t* nbr, int sorted,
                        float min_score, uint32_t* out, int* n_out);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * K12  stereo depth association of a rectified pair (BASELINE config 3)
+ *   replaces the association loop of ucoslam::FrameExtractor::processStereo
+ *     src/utils/frameextractor.cpp:1410-2634 (macro-obfuscated; see csrc/stereo.cu for the de-obfuscated statement list):
+ *     right keypoints bucketed by round(y); per left keypoint the first candidate of least Hamming distance among those not to its
+ *     right, at most one octave apart and closer than Params::maxDescDistance; 6x6 SAD over offsets -7..7, parabola refinement,
+ *     depth = bl*fx / disparity (Frame::depth, 0 = none).
+ *   img_l / img_r: the two grey images the keypoints were extracted from (w x h); kps_l = the left frame's UNDISTORTED keypoints
+ *   (Frame::und_kpts), kps_r = the right image's raw detections; desc_*: 32-byte rows.
+ *   depth: n_l floats; match_r (optional): index of the associated right keypoint or -1 (also set when the SAD stage then rejects
+ *   the pair); n_with_depth (optional): number of keypoints that received a depth.
+ *   Where the reference would throw (cv::Mat ROI outside the right image: a matched right keypoint within 10 px of the border,
+ *   impossible for ORB keypoints) the call fails with UCO_E_INVALID.
+ *   _dev: device pointers, dense 32-byte descriptor rows, asynchronous; counters_dev = 2 int32 (keypoints with depth, error flag).
+ * ---------------------------------------------------------------------------------------------------------- */
+int uco_b200_stereo_depth(uco_b200_ctx* ctx, const uint8_t* img_l, size_t stride_l, const uint8_t* img_r, size_t stride_r, int w, int h,
+                          const uco_keypoint* kps_l, const uint8_t* desc_l, size_t desc_l_stride, int n_l, const uco_keypoint* kps_r,
+                          const uint8_t* desc_r, size_t desc_r_stride, int n_r, float max_desc_dist, float bl, float fx, float* depth,
+                          int32_t* match_r, int* n_with_depth);
+int uco_b200_stereo_depth_dev(uco_b200_ctx* ctx, const uint8_t* img_l_dev, size_t pitch_l, const uint8_t* img_r_dev, size_t pitch_r,
+                              int w, int h, const uco_keypoint* kps_l_dev, const uint8_t* desc_l_dev, int n_l,
+                              const uco_keypoint* kps_r_dev, const uint8_t* desc_r_dev, int n_r, float max_desc_dist, float bl, float fx,
+                              float* depth_dev, int32_t* match_dev, int32_t* counters_dev);
+
 #ifdef __cplusplus
 }
 #endif

@@ -703,3 +703,70 @@ class RefKeyFrameDataBase:
         if self.h:
             self.lib.ref_kfdb_free(ctypes.c_void_p(self.h))
             self.h = None
+
+
+# ---- stereo depth association ----------------------------------------------------------------------------------
+def stereo_depth(sc, max_desc_dist=50.0):
+    """oracle/stereo_oracle.c on a synth_stereo scene -> (depth f32 (n_l,), match i32 (n_l,), n_with_depth)"""
+    lib = load_oracle()
+    il, ir = np.ascontiguousarray(sc["img_l"]), np.ascontiguousarray(sc["img_r"])
+    h, w = il.shape
+    kl, kr = np.ascontiguousarray(sc["kps_l"]), np.ascontiguousarray(sc["kps_r"])
+    dl, dr = np.ascontiguousarray(sc["desc_l"]), np.ascontiguousarray(sc["desc_r"])
+    depth = np.zeros(len(kl), np.float32); match = np.full(len(kl), -1, np.int32)
+    n = lib.oracle_stereo_depth(_p(il), _sz(il.strides[0]), _p(ir), _sz(ir.strides[0]), w, h, _p(kl), _p(dl), len(kl), _p(kr), _p(dr),
+                                len(kr), ctypes.c_float(max_desc_dist), ctypes.c_float(sc["bl"]), ctypes.c_float(sc["fx"]), _p(depth),
+                                _p(match))
+    return depth, match, n
+
+
+def stereo_depth_py(sc, max_desc_dist=50.0):
+    """Independent restatement of the same loop in numpy, with the loop's two OpenCV calls (cv::absdiff, cv::sum) made through cv2."""
+    import cv2
+    il, ir = sc["img_l"], sc["img_r"]
+    rows, cols = il.shape
+    kl, kr, dl, dr = sc["kps_l"], sc["kps_r"], sc["desc_l"], sc["desc_r"]
+    rnd = lambda v: int(np.floor(abs(float(v)) + 0.5) * (1 if v >= 0 else -1))      # std::round: half away from zero
+    buckets = [[] for _ in range(rows)]
+    for j in range(len(kr)):
+        y = rnd(np.float64(kr["y"][j]))
+        for yy in range(max(0, y), min(rows - 1, y) + 1):
+            buckets[yy].append(j)
+    depth = np.zeros(len(kl), np.float32); match = np.full(len(kl), -1, np.int32)
+    pc = np.array([bin(i).count("1") for i in range(256)], np.int32)
+    md = np.float32(max_desc_dist)
+    nm = 0
+    for i in range(len(kl)):
+        y = rnd(kl["y"][i])
+        if not (0 <= y < rows):
+            continue
+        best, bj = None, -1
+        for j in buckets[y]:
+            if kr["x"][j] > kl["x"][i] or abs(int(kr["octave"][j]) - int(kl["octave"][i])) > 1:
+                continue
+            d = np.float32(pc[dl[i] ^ dr[j]].sum())
+            if d < md and (best is None or d < best):
+                best, bj = d, j
+        if bj < 0:
+            continue
+        match[i] = bj
+        xl, yl, xr, yr = rnd(kl["x"][i]), rnd(kl["y"][i]), rnd(kr["x"][bj]), rnd(kr["y"][bj])
+        if xl < 3 or xl + 3 >= cols or yl < 3 or yl + 3 >= rows or xr < 3 or xr + 3 >= cols or yr < 3 or yr + 3 >= rows:
+            continue
+        lo, hi = max(-7, -xr), min(7, cols - 1 - xr)
+        pl = il[yl - 3:yl + 3, xl - 3:xl + 3]
+        sads = {}
+        for inc in range(lo, hi + 1):
+            xc = xr + inc
+            if xc - 3 < 0 or xc + 3 > cols:
+                return None
+            sads[inc + 7] = float(cv2.sumElems(cv2.absdiff(np.ascontiguousarray(pl), np.ascontiguousarray(ir[yr - 3:yr + 3, xc - 3:xc + 3])))[0])
+        b = min(sads, key=lambda k: (sads[k], k))
+        if lo + 7 < b < hi + 7:
+            d1, d2, d3 = np.float64(sads[b - 1]), np.float64(sads[b]), np.float64(sads[b + 1])
+            with np.errstate(all="ignore"):
+                off = np.float64(0.5) * (d1 - d3) / (d1 + d3 - 2 * d2) + b - 7
+                xs = np.float64(kr["x"][bj]) + off
+                depth[i] = np.float32(np.float64(np.float32(sc["bl"]) * np.float32(sc["fx"])) / (np.float64(kl["x"][i]) - xs))
+            nm += 1
+    return depth, match, nm

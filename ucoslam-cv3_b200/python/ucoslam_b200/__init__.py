@@ -66,6 +66,10 @@ SIGNATURES = {
     "uco_b200_pose_only_batch": (_i, [_vp, _i, _vp, _vp]),
     "uco_b200_probe_math": (_i, [_i, _vp, _vp, _i, _vp, _vp]),
     "uco_b200_probe_retain_best": (_i, [_vp, _i, _i]),
+    "uco_b200_stereo_depth": (_i, [_vp, _vp, _sz, _vp, _sz, _i, _i, _vp, _vp, _sz, _i, _vp, _vp, _sz, _i, _c.c_float, _c.c_float,
+                                   _c.c_float, _vp, _vp, _vp]),
+    "uco_b200_stereo_depth_dev": (_i, [_vp, _vp, _sz, _vp, _sz, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _c.c_float, _c.c_float, _c.c_float,
+                                       _vp, _vp, _vp]),
     "uco_b200_kfdb_create": (_i, [_vp, _vp]),
     "uco_b200_kfdb_free": (None, [_vp, _vp]),
     "uco_b200_kfdb_clear": (_i, [_vp, _vp]),
@@ -273,6 +277,21 @@ class Context:
 
     def launch_count(self):
         return int(self.lib.uco_b200_launch_count(self.h))
+
+    # -- K12 -----------------------------------------------------------------------------------------------------
+    def stereo_depth(self, sc, max_desc_dist=50.0):
+        """sc: dict(img_l, img_r, kps_l, desc_l, kps_r, desc_r, bl, fx) -> (depth f32 (n_l,), match i32 (n_l,), n_with_depth)"""
+        il, ir = np.asarray(sc["img_l"]), np.asarray(sc["img_r"])
+        h, w = il.shape
+        kl, kr = np.ascontiguousarray(sc["kps_l"]), np.ascontiguousarray(sc["kps_r"])
+        dl, dr = np.asarray(sc["desc_l"]), np.asarray(sc["desc_r"])
+        depth = np.zeros(len(kl), np.float32); match = np.full(len(kl), -1, np.int32)
+        n = ctypes.c_int()
+        self._chk(self.lib.uco_b200_stereo_depth(self.h, _p(il), il.strides[0], _p(ir), ir.strides[0], w, h, _p(kl), _p(dl),
+                                                 dl.strides[0] if len(dl) else 32, len(kl), _p(kr), _p(dr),
+                                                 dr.strides[0] if len(dr) else 32, len(kr), float(max_desc_dist), float(sc["bl"]),
+                                                 float(sc["fx"]), _p(depth), _p(match), ctypes.addressof(n)))
+        return depth, match, int(n.value)
 
     # -- K7 ------------------------------------------------------------------------------------------------------
     def hamming_knn(self, q, t, k, order=UCO_KNN_HEAP):

@@ -283,3 +283,64 @@ def synth_projection_scene(seed, n_kp=2000, n_mp=3000, n_levels=8, scale=1.2, w=
                 mp_desc=np.array(mdesc, np.uint8).reshape(-1, 32), scale_factors=sf, pose44=pose.reshape(16),
                 fx=float(np.float32(f)), fy=float(np.float32(f)), cx=float(cx), cy=float(cy),
                 min_xy=np.array([0, 0], np.float32), max_xy=np.array([w, h], np.float32))
+
+
+def synth_stereo(seed, w=640, h=480, n=1500, max_disp=48.0, outlier_frac=0.2, tie_frac=0.05):
+    """A seeded rectified stereo pair as FrameExtractor::processStereo sees it (SURVEY.md 8f rank 3): block-noise images where the
+    right image is the left one shifted by a smoothly varying sub-pixel disparity, left keypoints with octaves and 256-bit
+    descriptors, and right detections = most left keypoints moved by the disparity (pixel noise, octave changes, descriptor bit
+    flips) plus unrelated ones; some keypoints sit exactly on .5 rows / columns and some right descriptors are duplicated so that
+    distance ties and rounding edges are exercised.  Returns dict(img_l, img_r, kps_l, desc_l, kps_r, desc_r, bl, fx)."""
+    from . import KP_DTYPE
+    rng = np.random.default_rng(seed)
+    coarse = np.kron(rng.integers(0, 256, (h // 8 + 2, (w + 64) // 8 + 2)), np.ones((8, 8)))[:h, :w + 64]
+    left_wide = np.clip(0.6 * coarse + 0.4 * rng.integers(0, 256, (h, w + 64)), 0, 255)
+    img_l = left_wide[:, :w].astype(np.uint8)
+    disp_row = 8.0 + (max_disp - 8.0) * (0.5 + 0.5 * np.sin(np.arange(h) / h * 2 * np.pi))   # disparity per row
+    img_r = np.empty((h, w), np.uint8)
+    xs = np.arange(w)
+    for y in range(h):
+        src = xs + disp_row[y]                 # right(x) = left(x + d)
+        x0 = np.floor(src).astype(int); a = src - x0
+        img_r[y] = np.clip((1 - a) * left_wide[y, x0] + a * left_wide[y, x0 + 1] + 0.5, 0, 255).astype(np.uint8)
+    kps_l = np.zeros(n, KP_DTYPE)
+    kps_l["x"] = rng.uniform(16, w - 17, n).astype(np.float32)
+    kps_l["y"] = rng.uniform(16, h - 17, n).astype(np.float32)
+    half = rng.random(n) < 0.1
+    kps_l["y"][half] = np.floor(kps_l["y"][half]) + 0.5
+    kps_l["x"][half[::-1]] = np.floor(kps_l["x"][half[::-1]]) + 0.5
+    kps_l["octave"] = rng.integers(0, 8, n)
+    kps_l["size"] = 31.0; kps_l["angle"] = rng.uniform(0, 360, n); kps_l["response"] = rng.integers(20, 200, n); kps_l["class_id"] = -1
+    desc_l = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    keep = np.nonzero(rng.random(n) > outlier_frac)[0]
+    m = len(keep)
+    kps_r = np.zeros(m, KP_DTYPE)
+    yl = kps_l["y"][keep]
+    d = disp_row[np.clip(np.round(yl).astype(int), 0, h - 1)]
+    xerr = np.where(rng.random(m) < 0.15, rng.uniform(-10, 10, m), rng.uniform(-1.5, 1.5, m))   # some minima fall on the search border
+    kps_r["x"] = (kps_l["x"][keep] - d + xerr).astype(np.float32)
+    kps_r["y"] = (yl + rng.choice([0.0, 0.0, 0.0, 0.3, -0.3, 0.6, -0.6], m)).astype(np.float32)
+    kps_r["octave"] = kps_l["octave"][keep] + rng.choice([0, 0, 0, 1, -1, 2], m)
+    kps_r["size"] = 31.0; kps_r["angle"] = kps_l["angle"][keep]; kps_r["response"] = kps_l["response"][keep]; kps_r["class_id"] = -1
+    bits = np.unpackbits(desc_l[keep], axis=1)
+    for r in range(m):
+        nf = int(rng.integers(0, 70))
+        if nf:
+            bits[r, rng.choice(256, nf, replace=False)] ^= 1
+    desc_r = np.packbits(bits, axis=1)
+    # unrelated right detections + duplicated rows (ties) appended, then everything shuffled
+    extra = int(n * outlier_frac)
+    kx = np.zeros(extra, KP_DTYPE)
+    kx["x"] = rng.uniform(16, w - 17, extra).astype(np.float32); kx["y"] = rng.uniform(16, h - 17, extra).astype(np.float32)
+    kx["octave"] = rng.integers(0, 8, extra); kx["size"] = 31.0; kx["class_id"] = -1
+    dx = rng.integers(0, 256, (extra, 32), dtype=np.uint8)
+    nt = int(m * tie_frac)
+    dup = rng.integers(0, m, nt)
+    kt = kps_r[dup].copy()
+    kt["x"] -= rng.uniform(0.0, 3.0, nt).astype(np.float32)
+    kps_r = np.concatenate([kps_r, kx, kt]); desc_r = np.concatenate([desc_r, dx, desc_r[dup]])
+    ok = (kps_r["x"] >= 16) & (kps_r["x"] <= w - 17)      # ORB keypoints stay 16 px inside the image
+    kps_r, desc_r = kps_r[ok], desc_r[ok]
+    perm = rng.permutation(len(kps_r))
+    return dict(img_l=np.ascontiguousarray(img_l), img_r=np.ascontiguousarray(img_r), kps_l=kps_l, desc_l=np.ascontiguousarray(desc_l),
+                kps_r=np.ascontiguousarray(kps_r[perm]), desc_r=np.ascontiguousarray(desc_r[perm]), bl=np.float32(0.12), fx=np.float32(525.0))
