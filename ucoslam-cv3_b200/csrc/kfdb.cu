@@ -105,11 +105,12 @@ __global__ void __launch_bounds__(256) kfdb_count_kernel(const uint4* __restrict
 // Through L1 every word test is its own 32-byte sector request (ncu on the kernel above: 37.7 M sector requests per query against
 // 4.7 M for the word stream itself, warps waiting in lg_throttle); in shared memory it is a bank-conflicted 4-byte read.
 #define KFDB_SMEM_BITMAP_BYTES (200 * 1024)
-__device__ __forceinline__ unsigned kf_test_s(uint32_t w, const uint32_t* bm, uint32_t max_word) {
-    return (w <= max_word) ? ((bm[w >> 5] >> (w & 31)) & 1u) : 0u;
+// word -> bit; indices past the bitmap (the 0xFFFFFFFF padding, words above the query's largest) are clamped onto a zero word
+__device__ __forceinline__ unsigned kf_test_s(uint32_t w, const uint32_t* bm, uint32_t zero_idx) {
+    return (bm[min(w >> 5, zero_idx)] >> (w & 31)) & 1u;
 }
-__device__ __forceinline__ unsigned kf_test4_s(const uint4 a, const uint32_t* bm, uint32_t max_word) {
-    return kf_test_s(a.x, bm, max_word) + kf_test_s(a.y, bm, max_word) + kf_test_s(a.z, bm, max_word) + kf_test_s(a.w, bm, max_word);
+__device__ __forceinline__ unsigned kf_test4_s(const uint4 a, const uint32_t* bm, uint32_t zero_idx) {
+    return kf_test_s(a.x, bm, zero_idx) + kf_test_s(a.y, bm, zero_idx) + kf_test_s(a.z, bm, zero_idx) + kf_test_s(a.w, bm, zero_idx);
 }
 __global__ void __launch_bounds__(1024, 1) kfdb_count_smem_kernel(const uint4* __restrict__ words4, const uint2* __restrict__ slots,
                                                                   const uint8_t* __restrict__ excl, int n_slots,
@@ -119,35 +120,50 @@ __global__ void __launch_bounds__(1024, 1) kfdb_count_smem_kernel(const uint4* _
     extern __shared__ uint4 bm4[];
     const uint32_t* bm = (const uint32_t*)bm4;
     const int bm16 = (int)(((max_word >> 5) + 4) >> 2);          // bitmap length in 16-byte units (the workspace is padded)
-    for (int i = threadIdx.x; i < bm16; i += blockDim.x) bm4[i] = __ldg((const uint4*)bitmap + i);
-    __syncthreads();
+    const uint32_t zero_idx = (uint32_t)bm16 * 4;                // one more 16-byte unit of zeros behind it
+    for (int i = threadIdx.x; i <= bm16; i += blockDim.x) bm4[i] = (i < bm16) ? __ldg((const uint4*)bitmap + i) : make_uint4(0, 0, 0, 0);
     const int lane = threadIdx.x & 31;
+    const uint4 pad = make_uint4(~0u, ~0u, ~0u, ~0u);
+    // software pipeline over keyframes: the ticket and the header of the NEXT keyframe are fetched while this one streams
+    int slot = 0;
+    if (lane == 0) slot = (int)atomicAdd(ticket, 1u);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    uint2 s = make_uint2(0, 0);
+    if (slot < n_slots) {
+        s = slots[slot];
+        if (excl[slot]) s.y = 0;
+    }
+    __syncthreads();
     uint32_t local_max = 0;
-    for (;;) {
-        int slot = 0;
-        if (lane == 0) slot = (int)atomicAdd(ticket, 1u);
-        slot = __shfl_sync(0xffffffffu, slot, 0);
-        if (slot >= n_slots) break;
-        const uint2 s = slots[slot];
-        uint32_t cnt = 0;
-        if (s.y != 0 && !excl[slot]) {
-            const uint4* p = words4 + s.x;
-            const int n4 = (int)((s.y + 3) >> 2);
-            int i = lane;
-            for (; i + 96 < n4; i += 128) {   // four 16-byte loads in flight per lane
-                const uint4 a = __ldcs(p + i), b = __ldcs(p + i + 32), c = __ldcs(p + i + 64), d = __ldcs(p + i + 96);
-                cnt += kf_test4_s(a, bm, max_word) + kf_test4_s(b, bm, max_word) + kf_test4_s(c, bm, max_word) + kf_test4_s(d, bm, max_word);
-            }
-            uint4 t[3];
+    while (slot < n_slots) {
+        int nslot = 0;
+        if (lane == 0) nslot = (int)atomicAdd(ticket, 1u);
+        const uint4* p = words4 + s.x;
+        const int n4 = (int)((s.y + 3) >> 2);
+        uint4 v[8];
 #pragma unroll
-            for (int k = 0; k < 3; k++) t[k] = (i + 32 * k < n4) ? __ldcs(p + i + 32 * k) : make_uint4(~0u, ~0u, ~0u, ~0u);
-#pragma unroll
-            for (int k = 0; k < 3; k++) cnt += kf_test4_s(t[k], bm, max_word);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        for (int k = 0; k < 8; k++) v[k] = (lane + 32 * k < n4) ? __ldcs(p + lane + 32 * k) : pad;   // eight 16-byte loads in flight per lane
+        nslot = __shfl_sync(0xffffffffu, nslot, 0);
+        uint2 ns = make_uint2(0, 0);
+        if (nslot < n_slots) {
+            ns = slots[nslot];
+            if (excl[nslot]) ns.y = 0;
         }
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) cnt += kf_test4_s(v[k], bm, zero_idx);
+        for (int base = 256; base < n4; base += 256) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = (base + lane + 32 * k < n4) ? __ldcs(p + base + lane + 32 * k) : pad;
+#pragma unroll
+            for (int k = 0; k < 8; k++) cnt += kf_test4_s(v[k], bm, zero_idx);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
         if (lane == 0) nobs[slot] = cnt;
         local_max = max(local_max, cnt);
+        slot = nslot;
+        s = ns;
     }
     if (lane == 0 && local_max) atomicMax(d_max, local_max);
 }
@@ -171,7 +187,20 @@ __global__ void __launch_bounds__(256) kfdb_select_kernel(const uint32_t* __rest
 // step 2b (keyframedatabase.cpp:227-232): fBow::score of the listed frames.  One CTA per frame: all threads find the common words
 // and their float products in parallel and park them IN WORD ORDER in shared memory (ballot + block scan), then one thread adds them
 // into the double one by one -- the only part of fbow.cpp:209 whose order matters.
-#define KFDB_SCORE_THREADS 256
+#define KFDB_SCORE_THREADS 1024
+// a + p[0] + p[1] + ... one rounded double addition at a time, in index order; the loads run ahead of the dependent add chain
+__device__ __forceinline__ double kf_ordered_sum(double a, const float* p, uint32_t n) {
+    uint32_t k = 0;
+    for (; k + 8 <= n; k += 8) {
+        float t[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) t[j] = p[k + j];
+#pragma unroll
+        for (int j = 0; j < 8; j++) a = __dadd_rn(a, (double)t[j]);
+    }
+    for (; k < n; k++) a = __dadd_rn(a, (double)p[k]);
+    return a;
+}
 #define KFDB_SCORE_CAP 4096
 __global__ void __launch_bounds__(KFDB_SCORE_THREADS) kfdb_score_kernel(const uint32_t* __restrict__ words, const float* __restrict__ weights,
                                                          const uint2* __restrict__ slots, const uint32_t* __restrict__ frame,
@@ -223,9 +252,7 @@ __global__ void __launch_bounds__(KFDB_SCORE_THREADS) kfdb_score_kernel(const ui
             if (start + tile > KFDB_SCORE_CAP) {   // flush what is parked (uniform branch: every thread sees the same counters)
                 __syncthreads();
                 if (threadIdx.x == 0) {
-                    double a = acc;
-                    for (uint32_t k = 0; k < start; k++) a = __dadd_rn(a, (double)prod[k]);
-                    acc = a;
+                    acc = kf_ordered_sum(acc, prod, start);
                     fill = 0;
                 }
                 __syncthreads();
@@ -237,9 +264,7 @@ __global__ void __launch_bounds__(KFDB_SCORE_THREADS) kfdb_score_kernel(const ui
             __syncthreads();
         }
         if (threadIdx.x == 0) {
-            double score = acc;
-            const uint32_t n = fill;
-            for (uint32_t k = 0; k < n; k++) score = __dadd_rn(score, (double)prod[k]);   // ascending word order, like the two map iterators
+            const double score = kf_ordered_sum(acc, prod, fill);                         // ascending word order, like the two map iterators
             const double si = (score >= 1.0) ? 1.0 : 1.0 - sqrt(1.0 - score);             // fbow.cpp:237-240
             if (si > (double)min_score) {
                 const uint32_t k = atomicAdd(n_out, 1u);
@@ -539,14 +564,14 @@ int uco_b200_kfdb_query(uco_b200_ctx* ctx, uco_b200_kfdb* db, const uint32_t* wo
     kfdb_mark_kernel<<<(nm + 255) / 256, 256, 0, ctx->stream>>>(d_qw, n, bitmap, d_ex, ne, db->d_excl);
     UCO_LAUNCH_CHECK(ctx);
     if (prof) cudaEventRecord(ev[0], ctx->stream);
-    if (bm_words * 4 <= KFDB_SMEM_BITMAP_BYTES) {
+    if (bm_words * 4 + 16 <= KFDB_SMEM_BITMAP_BYTES) {
         static bool attr_set = false;   // per process; the attribute is per function and device-wide
         if (!attr_set) {
             UCO_CUDA(ctx, cudaFuncSetAttribute(kfdb_count_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KFDB_SMEM_BITMAP_BYTES));
             attr_set = true;
         }
         const int blocks = std::min((n_slots + 31) / 32, ctx->sm_count);
-        kfdb_count_smem_kernel<<<blocks, 1024, bm_words * 4, ctx->stream>>>((const uint4*)db->d_words, db->d_slots, db->d_excl, n_slots,
+        kfdb_count_smem_kernel<<<blocks, 1024, bm_words * 4 + 16, ctx->stream>>>((const uint4*)db->d_words, db->d_slots, db->d_excl, n_slots,
                                                                            bitmap, max_word, db->d_nobs, d_max, d_ticket);
     } else {
         const int blocks = std::min((n_slots + 7) / 8, ctx->sm_count * 8);
@@ -557,7 +582,7 @@ int uco_b200_kfdb_query(uco_b200_ctx* ctx, uco_b200_kfdb* db, const uint32_t* wo
     if (prof) cudaEventRecord(ev[1], ctx->stream);
     kfdb_select_kernel<<<(n_slots + 255) / 256, 256, 0, ctx->stream>>>(db->d_nobs, n_slots, d_max, d_sel, d_nsel);
     UCO_LAUNCH_CHECK(ctx);
-    kfdb_score_kernel<<<std::min(n_slots, ctx->sm_count * 4), KFDB_SCORE_THREADS, 0, ctx->stream>>>(
+    kfdb_score_kernel<<<std::min(n_slots, ctx->sm_count * 2), KFDB_SCORE_THREADS, 0, ctx->stream>>>(
         db->d_words, db->d_weights, db->d_slots, db->d_frame, db->d_nobs, bitmap, max_word, d_qw, d_qf, n, d_sel, d_nsel, min_score,
         d_hits, hit_cap, d_nhit);
     UCO_LAUNCH_CHECK(ctx);

@@ -293,8 +293,9 @@ def synth_stereo(seed, w=640, h=480, n=1500, max_disp=48.0, outlier_frac=0.2, ti
     distance ties and rounding edges are exercised.  Returns dict(img_l, img_r, kps_l, desc_l, kps_r, desc_r, bl, fx)."""
     from . import KP_DTYPE
     rng = np.random.default_rng(seed)
-    coarse = np.kron(rng.integers(0, 256, (h // 8 + 2, (w + 64) // 8 + 2)), np.ones((8, 8)))[:h, :w + 64]
-    left_wide = np.clip(0.6 * coarse + 0.4 * rng.integers(0, 256, (h, w + 64)), 0, 255)
+    margin = max(64, int(max_disp) + 2)
+    coarse = np.kron(rng.integers(0, 256, (h // 8 + 2, (w + margin) // 8 + 2)), np.ones((8, 8)))[:h, :w + margin]
+    left_wide = np.clip(0.6 * coarse + 0.4 * rng.integers(0, 256, (h, w + margin)), 0, 255)
     img_l = left_wide[:, :w].astype(np.uint8)
     disp_row = 8.0 + (max_disp - 8.0) * (0.5 + 0.5 * np.sin(np.arange(h) / h * 2 * np.pi))   # disparity per row
     img_r = np.empty((h, w), np.uint8)
