@@ -497,6 +497,28 @@ int uco_b200_stereo_depth_dev(uco_b200_ctx* ctx, const uint8_t* img_l_dev, size_
                               const uco_keypoint* kps_r_dev, const uint8_t* desc_r_dev, int n_r, float max_desc_dist, float bl, float fx,
                               float* depth_dev, int32_t* match_dev, int32_t* counters_dev);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * K13  two-view triangulation with the reference's acceptance gates (new-map-point creation)
+ *   replaces ucoslam::Triangulate(Train, Query, RT_Q2T, matches, maxChi2)   src/basictypes/misc.cpp:921-1040
+ *   (and the body of triangulate_ :1042-1160), called from src/utils/mapmanager.cpp:10093 and mapinitializer.cpp:1574.
+ *   kps_train / kps_query: Frame::und_kpts of the two frames; matches: cv::DMatch records (trainIdx -> camera 1 = K_train [I|0],
+ *   queryIdx -> camera 2 = K_query [R|t] with RT = the 4x4 row-major transform camera 1 -> camera 2);
+ *   scale_factors_*: Frame::scaleFactors.  xyz: 3 floats per match in camera-1 coordinates, NaN NaN NaN where the reference
+ *   rejects (parallax cosine outside [0, 0.9998], w == 0, non-finite, behind either camera, reprojection chi2 > max_chi2).
+ *   Floating point: the reference takes the null vector from OpenCV's float SVD; here it is computed in double, so points agree
+ *   to float-SVD accuracy (tolerance stated in tests/test_triangulate_gpu.py), not bit for bit.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct uco_triangulate_params {
+    float K_train[4];             /* fx fy cx cy */
+    float K_query[4];
+    float RT[16];
+    int32_t n_levels_train; const float* scale_factors_train;
+    int32_t n_levels_query; const float* scale_factors_query;
+    float max_chi2;               /* 5.998 default, misc.h:65 */
+} uco_triangulate_params;
+int uco_b200_triangulate(uco_b200_ctx* ctx, const uco_keypoint* kps_train, int n_train, const uco_keypoint* kps_query, int n_query,
+                         const uco_match* matches, int n_matches, const uco_triangulate_params* prm, float* xyz, int* n_good);
+
 #ifdef __cplusplus
 }
 #endif

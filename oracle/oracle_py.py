@@ -770,3 +770,68 @@ def stereo_depth_py(sc, max_desc_dist=50.0):
                 depth[i] = np.float32(np.float64(np.float32(sc["bl"]) * np.float32(sc["fx"])) / (np.float64(kl["x"][i]) - xs))
             nm += 1
     return depth, match, nm
+
+
+# ---- two-view triangulation ------------------------------------------------------------------------------------
+def triangulate_py(sc, max_chi2=5.998):
+    """ucoslam::Triangulate (src/basictypes/misc.cpp:921-1040) restated on numpy float32 with OpenCV's own float SVD through cv2
+    (cv2.SVDecomp with MODIFY_A | FULL_UV, the call of :931).  Returns (xyz f32 (n,3) NaN = rejected, n_good, margin (n,)): margin is
+    the distance of the closest gate to its threshold (relative), so that tests can leave out matches a float rounding could flip."""
+    import cv2
+    f32 = np.float32
+    k1, k2, m = sc["kps_train"], sc["kps_query"], sc["matches"]
+    fx1, fy1, cx1, cy1 = [f32(x) for x in sc["K_train"]]
+    fx2, fy2, cx2, cy2 = [f32(x) for x in sc["K_query"]]
+    RT = np.asarray(sc["RT"], f32)
+    R, t = RT[:3, :3], RT[:3, 3]
+    inv1 = [f32(1) / (f32(s) * f32(s)) for s in sc["sf_train"]]
+    inv2 = [f32(1) / (f32(s) * f32(s)) for s in sc["sf_query"]]
+    P1 = np.zeros((3, 4), f32); P1[0, 0], P1[1, 1], P1[0, 2], P1[1, 2], P1[2, 2] = fx1, fy1, cx1, cy1, 1
+    K2 = np.array([[fx2, 0, cx2], [0, fy2, cy2], [0, 0, 1]], f32)
+    P2 = (K2.astype(np.float64) @ np.c_[R, t].astype(np.float64)).astype(f32)
+    n = len(m)
+    out = np.full((n, 3), np.nan, f32)
+    margin = np.full(n, np.inf)
+    good = 0
+    for i in range(n):
+        a, b = k1[m["trainIdx"][i]], k2[m["queryIdx"][i]]
+        x1 = np.array([(a["x"] - cx1) * (f32(1) / fx1), (a["y"] - cy1) * (f32(1) / fy1), 1], f32)
+        x2 = np.array([(b["x"] - cx2) * (f32(1) / fx2), (b["y"] - cy2) * (f32(1) / fy2), 1], f32)
+        r1 = (x1 * f32(1.0 / np.linalg.norm(x1.astype(np.float64)))).astype(f32)
+        r2 = (R.T.astype(np.float64) @ (x2 * f32(1.0 / np.linalg.norm(x2.astype(np.float64)))).astype(np.float64)).astype(f32)
+        cosp = float(r1.astype(np.float64) @ r2.astype(np.float64))
+        margin[i] = min(abs(cosp - 0.9998) / 1e-4, abs(cosp) / 1e-4 if cosp < 0.1 else np.inf)
+        if cosp < 0 or cosp > 0.9998:
+            continue
+        A = np.empty((4, 4), f32)
+        A[0] = a["x"] * P1[2] - P1[0]; A[1] = a["y"] * P1[2] - P1[1]
+        A[2] = b["x"] * P2[2] - P2[0]; A[3] = b["y"] * P2[2] - P2[1]
+        w_, u_, vt = cv2.SVDecomp(A, flags=cv2.SVD_MODIFY_A | cv2.SVD_FULL_UV)
+        x = vt[3].astype(f32)
+        if x[3] == 0:
+            continue
+        p = (x[:3] / x[3]).astype(f32)
+        if not np.isfinite(p).all():
+            continue
+        margin[i] = min(margin[i], abs(float(p[2])) / 1e-3)
+        if p[2] <= 0:
+            continue
+        p2 = ((R.astype(np.float64) @ p.astype(np.float64)).astype(f32) + t).astype(f32)
+        margin[i] = min(margin[i], abs(float(p2[2])) / 1e-3)
+        if p2[2] <= 0:
+            continue
+        iz = f32(1) / p[2]
+        px, py = fx1 * p[0] * iz + cx1, fy1 * p[1] * iz + cy1
+        chi = inv1[a["octave"]] * ((px - a["x"]) * (px - a["x"]) + (py - a["y"]) * (py - a["y"]))
+        margin[i] = min(margin[i], abs(float(chi) - max_chi2) / (0.02 * max_chi2))
+        if chi > f32(max_chi2):
+            continue
+        iz2 = f32(1) / p2[2]
+        qx, qy = fx2 * p2[0] * iz2 + cx2, fy2 * p2[1] * iz2 + cy2
+        chi = inv2[b["octave"]] * ((qx - b["x"]) * (qx - b["x"]) + (qy - b["y"]) * (qy - b["y"]))
+        margin[i] = min(margin[i], abs(float(chi) - max_chi2) / (0.02 * max_chi2))
+        if chi > f32(max_chi2):
+            continue
+        out[i] = p
+        good += 1
+    return out, good, margin

@@ -70,6 +70,7 @@ SIGNATURES = {
                                    _c.c_float, _vp, _vp, _vp]),
     "uco_b200_stereo_depth_dev": (_i, [_vp, _vp, _sz, _vp, _sz, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _c.c_float, _c.c_float, _c.c_float,
                                        _vp, _vp, _vp]),
+    "uco_b200_triangulate": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp]),
     "uco_b200_kfdb_create": (_i, [_vp, _vp]),
     "uco_b200_kfdb_free": (None, [_vp, _vp]),
     "uco_b200_kfdb_clear": (_i, [_vp, _vp]),
@@ -232,6 +233,11 @@ class PnpResult(ctypes.Structure):  # uco_pnp_result
                 ("bad", _vp)]
 
 
+class TriangulateParams(ctypes.Structure):  # uco_triangulate_params
+    _fields_ = [("K_train", _c.c_float * 4), ("K_query", _c.c_float * 4), ("RT", _c.c_float * 16), ("n_levels_train", _c.c_int32),
+                ("scale_factors_train", _vp), ("n_levels_query", _c.c_int32), ("scale_factors_query", _vp), ("max_chi2", _c.c_float)]
+
+
 class UcoError(RuntimeError):
     pass
 
@@ -277,6 +283,25 @@ class Context:
 
     def launch_count(self):
         return int(self.lib.uco_b200_launch_count(self.h))
+
+    # -- K13 -----------------------------------------------------------------------------------------------------
+    def triangulate(self, sc, max_chi2=5.998):
+        """sc: dict(kps_train, kps_query, matches (MATCH_DTYPE), K_train, K_query (fx fy cx cy), RT (4,4), sf_train, sf_query)
+        -> (xyz f32 (n,3) with NaN rows where rejected, n_good)"""
+        k1, k2 = np.ascontiguousarray(sc["kps_train"]), np.ascontiguousarray(sc["kps_query"])
+        m = np.ascontiguousarray(sc["matches"])
+        s1, s2 = np.ascontiguousarray(sc["sf_train"], np.float32), np.ascontiguousarray(sc["sf_query"], np.float32)
+        prm = TriangulateParams()
+        prm.K_train[:] = [float(x) for x in sc["K_train"]]; prm.K_query[:] = [float(x) for x in sc["K_query"]]
+        prm.RT[:] = [float(x) for x in np.asarray(sc["RT"], np.float32).reshape(-1)]
+        prm.n_levels_train, prm.scale_factors_train = len(s1), _p(s1)
+        prm.n_levels_query, prm.scale_factors_query = len(s2), _p(s2)
+        prm.max_chi2 = max_chi2
+        xyz = np.zeros((len(m), 3), np.float32)
+        n = ctypes.c_int()
+        self._chk(self.lib.uco_b200_triangulate(self.h, _p(k1), len(k1), _p(k2), len(k2), _p(m), len(m), ctypes.addressof(prm), _p(xyz),
+                                                ctypes.addressof(n)))
+        return xyz, int(n.value)
 
     # -- K12 -----------------------------------------------------------------------------------------------------
     def stereo_depth(self, sc, max_desc_dist=50.0):

@@ -345,3 +345,39 @@ def synth_stereo(seed, w=640, h=480, n=1500, max_disp=48.0, outlier_frac=0.2, ti
     perm = rng.permutation(len(kps_r))
     return dict(img_l=np.ascontiguousarray(img_l), img_r=np.ascontiguousarray(img_r), kps_l=kps_l, desc_l=np.ascontiguousarray(desc_l),
                 kps_r=np.ascontiguousarray(kps_r[perm]), desc_r=np.ascontiguousarray(desc_r[perm]), bl=np.float32(0.12), fx=np.float32(525.0))
+
+
+def synth_two_view(seed, n=1500, w=640, h=480, f=525.0, baseline=0.25, px_sigma=0.6, outlier_frac=0.15, far_frac=0.15):
+    """Two keyframes and their matches as the mapper hands them to ucoslam::Triangulate (SURVEY.md 8f rank 2): 3-D points in front of
+    camera 1 (some far away: parallax below the reference's gate), camera 2 displaced by `baseline` and slightly rotated, pixel noise
+    scaled by octave, a share of wrong matches.  Returns dict(kps_train, kps_query, matches, K_train, K_query, RT, sf_train, sf_query,
+    xyz_gt (n,3) with NaN for wrong matches)."""
+    from . import KP_DTYPE, MATCH_DTYPE
+    rng = np.random.default_rng(seed)
+    sf = (1.2 ** np.arange(8)).astype(np.float32)
+    K = np.array([f, f, w / 2 - 0.5, h / 2 - 0.5], np.float32)
+    Rm = _rodrigues(np.array([0.01, -0.04, 0.02]))
+    t = np.array([-baseline, 0.02, 0.03])
+    RT = np.eye(4, dtype=np.float32); RT[:3, :3] = Rm; RT[:3, 3] = t
+    far = rng.random(n) < far_frac
+    Z = np.where(far, rng.uniform(60, 400, n), rng.uniform(1.0, 8.0, n))
+    u = rng.uniform(30, w - 30, n); v = rng.uniform(30, h - 30, n)
+    X = np.c_[(u - K[2]) / f * Z, (v - K[3]) / f * Z, Z]
+    X2 = X @ Rm.T + t
+    oct1 = rng.integers(0, 8, n); oct2 = np.clip(oct1 + rng.integers(-1, 2, n), 0, 7)
+    k1 = np.zeros(n, KP_DTYPE); k2 = np.zeros(n, KP_DTYPE)
+    k1["x"] = u + rng.normal(0, px_sigma, n) * sf[oct1]; k1["y"] = v + rng.normal(0, px_sigma, n) * sf[oct1]; k1["octave"] = oct1
+    with np.errstate(all="ignore"):
+        k2["x"] = f * X2[:, 0] / X2[:, 2] + K[2] + rng.normal(0, px_sigma, n) * sf[oct2]
+        k2["y"] = f * X2[:, 1] / X2[:, 2] + K[3] + rng.normal(0, px_sigma, n) * sf[oct2]
+    k2["octave"] = oct2
+    wrong = rng.random(n) < outlier_frac
+    k2["x"][wrong] = rng.uniform(0, w, int(wrong.sum())); k2["y"][wrong] = rng.uniform(0, h, int(wrong.sum()))
+    perm = rng.permutation(n)                       # query keypoints are stored in another order than train keypoints
+    k2s = np.zeros(n, KP_DTYPE); k2s[perm] = k2
+    m = np.zeros(n, MATCH_DTYPE)
+    m["trainIdx"] = np.arange(n); m["queryIdx"] = perm; m["distance"] = rng.integers(0, 60, n)
+    m = m[rng.permutation(n)]
+    gt = X.astype(np.float32); gt[wrong] = np.nan
+    return dict(kps_train=k1, kps_query=k2s, matches=np.ascontiguousarray(m), K_train=K, K_query=K.copy(), RT=RT, sf_train=sf,
+                sf_query=sf.copy(), xyz_gt=gt)
