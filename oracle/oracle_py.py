@@ -800,7 +800,7 @@ def triangulate_py(sc, max_chi2=5.998):
         r1 = (x1 * f32(1.0 / np.linalg.norm(x1.astype(np.float64)))).astype(f32)
         r2 = (R.T.astype(np.float64) @ (x2 * f32(1.0 / np.linalg.norm(x2.astype(np.float64)))).astype(np.float64)).astype(f32)
         cosp = float(r1.astype(np.float64) @ r2.astype(np.float64))
-        margin[i] = min(abs(cosp - 0.9998) / 1e-4, abs(cosp) / 1e-4 if cosp < 0.1 else np.inf)
+        margin[i] = min(abs(cosp - 0.9998) / 2e-6, abs(cosp) / 2e-6)
         if cosp < 0 or cosp > 0.9998:
             continue
         A = np.empty((4, 4), f32)
@@ -813,23 +813,23 @@ def triangulate_py(sc, max_chi2=5.998):
         p = (x[:3] / x[3]).astype(f32)
         if not np.isfinite(p).all():
             continue
-        margin[i] = min(margin[i], abs(float(p[2])) / 1e-3)
+        margin[i] = min(margin[i], abs(float(p[2])) / 1e-4)
         if p[2] <= 0:
             continue
         p2 = ((R.astype(np.float64) @ p.astype(np.float64)).astype(f32) + t).astype(f32)
-        margin[i] = min(margin[i], abs(float(p2[2])) / 1e-3)
+        margin[i] = min(margin[i], abs(float(p2[2])) / 1e-4)
         if p2[2] <= 0:
             continue
         iz = f32(1) / p[2]
         px, py = fx1 * p[0] * iz + cx1, fy1 * p[1] * iz + cy1
         chi = inv1[a["octave"]] * ((px - a["x"]) * (px - a["x"]) + (py - a["y"]) * (py - a["y"]))
-        margin[i] = min(margin[i], abs(float(chi) - max_chi2) / (0.02 * max_chi2))
+        margin[i] = min(margin[i], abs(float(chi) - max_chi2) / (0.005 * max_chi2))
         if chi > f32(max_chi2):
             continue
         iz2 = f32(1) / p2[2]
         qx, qy = fx2 * p2[0] * iz2 + cx2, fy2 * p2[1] * iz2 + cy2
         chi = inv2[b["octave"]] * ((qx - b["x"]) * (qx - b["x"]) + (qy - b["y"]) * (qy - b["y"]))
-        margin[i] = min(margin[i], abs(float(chi) - max_chi2) / (0.02 * max_chi2))
+        margin[i] = min(margin[i], abs(float(chi) - max_chi2) / (0.005 * max_chi2))
         if chi > f32(max_chi2):
             continue
         out[i] = p

@@ -19,7 +19,7 @@ def test_matches_restatement(ctx, name):
     got, n = ctx.triangulate(sc)
     a, b = ~np.isnan(want[:, 0]), ~np.isnan(got[:, 0])
     clear = margin >= 1.0
-    assert clear.mean() > 0.9
+    assert clear.mean() > 0.95
     assert np.array_equal(a[clear], b[clear])
     assert abs(n - good) <= (~clear).sum() and n == b.sum()
     both = a & b

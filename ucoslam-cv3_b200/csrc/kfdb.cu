@@ -44,6 +44,7 @@ struct uco_b200_kfdb {
     std::unordered_map<uint32_t, uint32_t> slot_of;
     uint32_t live = 0;
     float last_ms[2] = {0, 0};
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -415,6 +416,8 @@ void uco_b200_kfdb_free(uco_b200_ctx* ctx, uco_b200_kfdb* db) {
     }
     cudaFree(db->d_words); cudaFree(db->d_weights); cudaFree(db->d_slots); cudaFree(db->d_frame); cudaFree(db->d_nobs);
     cudaFree(db->d_excl);
+    for (auto& e : db->ev)
+        if (e) cudaEventDestroy(e);
     delete db;
 }
 
@@ -581,10 +584,10 @@ int uco_b200_kfdb_query(uco_b200_ctx* ctx, uco_b200_kfdb* db, const uint32_t* wo
     uint32_t* d_ticket = d_max + 2;
     uint32_t* d_nsel = d_max + 3;
     KfHit* d_hits = (KfHit*)(dout + 16);
-    cudaEvent_t ev[3] = {};
     const bool prof = ctx->profiling != 0;
-    if (prof)
-        for (auto& e : ev) cudaEventCreate(&e);
+    cudaEvent_t* ev = db->ev;   // owned by the database (created once): no leak on the error returns below
+    if (prof && !ev[0])
+        for (int k = 0; k < 3; k++) cudaEventCreate(&ev[k]);
     UCO_CUDA(ctx, cudaMemcpyAsync(dq, hq, qbytes, cudaMemcpyHostToDevice, ctx->stream));
     UCO_CUDA(ctx, cudaMemsetAsync(bitmap, 0, bm_words * 4, ctx->stream));
     UCO_CUDA(ctx, cudaMemsetAsync(db->d_excl, 0, n_slots, ctx->stream));
@@ -594,11 +597,8 @@ int uco_b200_kfdb_query(uco_b200_ctx* ctx, uco_b200_kfdb* db, const uint32_t* wo
     UCO_LAUNCH_CHECK(ctx);
     if (prof) cudaEventRecord(ev[0], ctx->stream);
     if (bm_words * 4 + 16 <= KFDB_SMEM_BITMAP_BYTES) {
-        static bool attr_set = false;   // per process; the attribute is per function and device-wide
-        if (!attr_set) {
-            UCO_CUDA(ctx, cudaFuncSetAttribute(kfdb_count_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KFDB_SMEM_BITMAP_BYTES));
-            attr_set = true;
-        }
+        // per device (a process may drive several GPUs), so set on every call: it is a host-side table update
+        UCO_CUDA(ctx, cudaFuncSetAttribute(kfdb_count_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KFDB_SMEM_BITMAP_BYTES));
         const int blocks = std::min((n_slots + KFDB_SCAN_THREADS / 32 - 1) / (KFDB_SCAN_THREADS / 32), ctx->sm_count);
         const int n_warps = blocks * (KFDB_SCAN_THREADS / 32);
         // three quarters of the keyframes are dealt round-robin, the tail is ticketed (measured on B200, 20 k keyframes: all tickets
@@ -635,7 +635,6 @@ int uco_b200_kfdb_query(uco_b200_ctx* ctx, uco_b200_kfdb* db, const uint32_t* wo
     if (prof) {
         cudaEventElapsedTime(&db->last_ms[0], ev[0], ev[1]);
         cudaEventElapsedTime(&db->last_ms[1], ev[1], ev[2]);
-        for (auto& e : ev) cudaEventDestroy(e);
     }
     *n_out = (int)nhit;
     if ((int)nhit > cap) return uco_fail(ctx, UCO_E_CAPACITY, "kfdb_query: %u frames scored, capacity %d", nhit, cap);
