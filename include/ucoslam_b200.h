@@ -519,6 +519,24 @@ typedef struct uco_triangulate_params {
 int uco_b200_triangulate(uco_b200_ctx* ctx, const uco_keypoint* kps_train, int n_train, const uco_keypoint* kps_query, int n_query,
                          const uco_match* matches, int n_matches, const uco_triangulate_params* prm, float* xyz, int* n_good);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * K14  RANSAC pose from 2D-3D matches (relocalisation / loop-closure candidate scoring)
+ *   replaces ucoslam::PnPSolver::solvePnPRansac(frame, map, matches_io, posef2g_io, maxIters)
+ *     src/optimization/pnpsolver.cpp:36-114 (4-match samples, cv::solvePnP P3P hypothesis, float reprojection test < 5.99 px^2,
+ *     MapPoint::getViewCos >= 0.5, first iteration with the most inliers wins, fewer than 4 inliers -> false).
+ *   Per match j: p3d = MapPoint::getCoordinates(), normals = MapPoint::getNormal(), p2d = frame.und_kpts[queryIdx].pt;
+ *   cam = fx fy cx cy of the frame.  samples: max_iters x 4 match indices (the caller's random stream), or NULL to draw them from
+ *   the counter-based generator seeded with `seed` (the reference's std::random_shuffle / rand() stream is not reproduced).
+ *   Result: *n_inliers = 0 means `false` (pose untouched); otherwise pose44 = the winning float 4x4 (world -> camera, what
+ *   Se3Transform(rv,tv) holds), inliers = indices of the matches to keep (ascending), best_iter / counts (optional, max_iters;
+ *   -1 where P3P had no solution) for inspection.
+ *   uco_b200_probe_p3p: host-only, one hypothesis from 4 correspondences exactly as the kernel forms it (returns 1 / 0).
+ * ---------------------------------------------------------------------------------------------------------- */
+int uco_b200_pnp_ransac(uco_b200_ctx* ctx, const float* p3d, const float* p2d, const float* normals, int n, const float* cam_fxfycxcy,
+                        int max_iters, const int32_t* samples, uint64_t seed, float* pose44, int32_t* inliers, int* n_inliers,
+                        int32_t* counts, int* best_iter);
+int uco_b200_probe_p3p(const double* X4x3, const double* px4x2, const double* K_fxfycxcy, double* R9, double* t3);
+
 #ifdef __cplusplus
 }
 #endif

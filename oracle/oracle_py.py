@@ -835,3 +835,50 @@ def triangulate_py(sc, max_chi2=5.998):
         out[i] = p
         good += 1
     return out, good, margin
+
+
+# ---- RANSAC P3P pose -------------------------------------------------------------------------------------------
+def pnp_ransac_py(sc, samples):
+    """PnPSolver::solvePnPRansac (src/optimization/pnpsolver.cpp:36-114) restated with the reference's own OpenCV call
+    (cv2.solvePnP, SOLVEPNP_P3P, 4 points) on GIVEN 4-match samples (the reference draws them with std::random_shuffle) and its float
+    inlier test.  Returns dict(ok, pose44 f32, inliers, counts (per iteration, -1 = no P3P solution), best_iter,
+    borderline (per iteration: matches whose test is within rounding of a threshold))."""
+    import cv2
+    f32 = np.float32
+    p3 = np.asarray(sc["p3d"], f32); p2 = np.asarray(sc["p2d"], f32); nr = np.asarray(sc["normals"], f32)
+    fx, fy, cx, cy = [f32(x) for x in sc["cam"]]
+    Km = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], f32)
+    n = len(p3)
+    counts = np.full(len(samples), -1, np.int32); border = np.zeros(len(samples), np.int32)
+    best, best_inl, best_pose, best_it = -1, None, None, -1
+    p3d64, p2d64 = p3.astype(np.float64), p2.astype(np.float64)
+    for it, smp in enumerate(samples):
+        ok, rv, tv = cv2.solvePnP(p3d64[smp].reshape(-1, 1, 3), p2d64[smp].reshape(-1, 1, 2), Km, np.zeros((1, 5), f32),
+                                  flags=cv2.SOLVEPNP_P3P)
+        if not ok or rv.size != 3 or tv.size != 3:
+            continue
+        M = np.eye(4, dtype=f32)
+        M[:3, :3] = cv2.Rodrigues(rv.astype(f32).reshape(3, 1))[0].astype(f32)      # Se3Transform(rv, tv): float 4x4
+        M[:3, 3] = tv.astype(f32).ravel()
+        x = M[0, 0] * p3[:, 0] + M[0, 1] * p3[:, 1] + M[0, 2] * p3[:, 2] + M[0, 3]
+        y = M[1, 0] * p3[:, 0] + M[1, 1] * p3[:, 1] + M[1, 2] * p3[:, 2] + M[1, 3]
+        z = M[2, 0] * p3[:, 0] + M[2, 1] * p3[:, 1] + M[2, 2] * p3[:, 2] + M[2, 3]
+        with np.errstate(all="ignore"):
+            z = (1.0 / z.astype(np.float64)).astype(f32)
+            rx = (((fx * x) * z) + cx).astype(np.float64); ry = (((fy * y) * z) + cy).astype(np.float64)
+            dx = (p2d64[:, 0] - rx).astype(f32); dy = (p2d64[:, 1] - ry).astype(f32)
+            d2 = dx * dx + dy * dy
+            c = -np.array([M[0, 3] * M[0, 0] + M[1, 3] * M[1, 0] + M[2, 3] * M[2, 0], M[0, 3] * M[0, 1] + M[1, 3] * M[1, 1] + M[2, 3] * M[2, 1],
+                           M[0, 3] * M[0, 2] + M[1, 3] * M[1, 2] + M[2, 3] * M[2, 2]], f32)
+            v = (c[None, :] - p3).astype(f32)
+            inv = 1.0 / np.sqrt((v.astype(np.float64) ** 2).sum(axis=1))
+            v = (v.astype(np.float64) * inv[:, None]).astype(f32)
+            vc = v[:, 0] * nr[:, 0] + v[:, 1] * nr[:, 1] + v[:, 2] * nr[:, 2]
+        inl = (d2 < f32(5.99)) & ~(vc < f32(0.5))
+        counts[it] = int(inl.sum())
+        border[it] = int(((np.abs(d2 - 5.99) < 0.02) | ((d2 < 5.99) & (np.abs(vc - 0.5) < 1e-4))).sum())
+        if counts[it] > best:
+            best, best_inl, best_pose, best_it = counts[it], np.nonzero(inl)[0].astype(np.int32), M, it
+    ok = best >= 4
+    return dict(ok=ok, pose44=best_pose if ok else None, inliers=best_inl if ok else np.zeros(0, np.int32), counts=counts,
+                best_iter=best_it if ok else -1, borderline=border)

@@ -44,6 +44,7 @@ enum {  // device workspace slots
     WS_KFDB_STAGE, WS_KFDB_Q, WS_KFDB_BITMAP, WS_KFDB_OUT,
     WS_STEREO_SOA, WS_STEREO_IN, WS_STEREO_OUT,
     WS_TRI_IN, WS_TRI_OUT,
+    WS_RANSAC_IN, WS_RANSAC_OUT,
     WS_COUNT
 };
 

@@ -71,6 +71,8 @@ SIGNATURES = {
     "uco_b200_stereo_depth_dev": (_i, [_vp, _vp, _sz, _vp, _sz, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _c.c_float, _c.c_float, _c.c_float,
                                        _vp, _vp, _vp]),
     "uco_b200_triangulate": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp]),
+    "uco_b200_pnp_ransac": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _u64, _vp, _vp, _vp, _vp, _vp]),
+    "uco_b200_probe_p3p": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "uco_b200_kfdb_create": (_i, [_vp, _vp]),
     "uco_b200_kfdb_free": (None, [_vp, _vp]),
     "uco_b200_kfdb_clear": (_i, [_vp, _vp]),
@@ -108,6 +110,14 @@ def probe_sincos(a):
     s = np.empty_like(a); c = np.empty_like(a)
     assert load().uco_b200_probe_math(1, _p(a), None, len(a), _p(s), _p(c)) == 0
     return s, c
+
+
+def probe_p3p(X4, px4, K):
+    """host-only: (R (3,3), t (3,)) of the hypothesis the RANSAC kernel forms from 4 correspondences, or None"""
+    X4 = np.ascontiguousarray(X4, np.float64); px4 = np.ascontiguousarray(px4, np.float64); K = np.ascontiguousarray(K, np.float64)
+    R = np.zeros(9, np.float64); t = np.zeros(3, np.float64)
+    ok = load().uco_b200_probe_p3p(_p(X4), _p(px4), _p(K), _p(R), _p(t))
+    return (R.reshape(3, 3), t) if ok else None
 
 
 def probe_retain_best(packed, n_points):
@@ -283,6 +293,19 @@ class Context:
 
     def launch_count(self):
         return int(self.lib.uco_b200_launch_count(self.h))
+
+    # -- K14 -----------------------------------------------------------------------------------------------------
+    def pnp_ransac(self, sc, max_iters, samples=None, seed=0):
+        """sc: dict(p3d (n,3) f32, p2d (n,2) f32, normals (n,3) f32, cam (fx fy cx cy)).  Returns dict(ok, pose44, inliers, counts, best_iter)"""
+        p3 = np.ascontiguousarray(sc["p3d"], np.float32); p2 = np.ascontiguousarray(sc["p2d"], np.float32)
+        nr = np.ascontiguousarray(sc["normals"], np.float32); cam = np.ascontiguousarray(sc["cam"], np.float32)
+        n = len(p3)
+        smp = None if samples is None else np.ascontiguousarray(samples, np.int32)
+        pose = np.zeros((4, 4), np.float32); inl = np.zeros(max(n, 1), np.int32); counts = np.zeros(max(max_iters, 1), np.int32)
+        ni, bi = ctypes.c_int(), ctypes.c_int()
+        self._chk(self.lib.uco_b200_pnp_ransac(self.h, _p(p3), _p(p2), _p(nr), n, _p(cam), int(max_iters), _p(smp), int(seed), _p(pose),
+                                               _p(inl), ctypes.addressof(ni), _p(counts), ctypes.addressof(bi)))
+        return dict(ok=ni.value > 0, pose44=pose, inliers=inl[:ni.value].copy(), counts=counts[:max_iters].copy(), best_iter=int(bi.value))
 
     # -- K13 -----------------------------------------------------------------------------------------------------
     def triangulate(self, sc, max_chi2=5.998):

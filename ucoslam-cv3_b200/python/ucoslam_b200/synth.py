@@ -381,3 +381,30 @@ def synth_two_view(seed, n=1500, w=640, h=480, f=525.0, baseline=0.25, px_sigma=
     gt = X.astype(np.float32); gt[wrong] = np.nan
     return dict(kps_train=k1, kps_query=k2s, matches=np.ascontiguousarray(m), K_train=K, K_query=K.copy(), RT=RT, sf_train=sf,
                 sf_query=sf.copy(), xyz_gt=gt)
+
+
+def synth_reloc_matches(seed, n=400, outlier_frac=0.4, px_sigma=0.8, w=640, h=480, f=525.0, backface_frac=0.1):
+    """2D-3D matches as the relocaliser hands them to PnPSolver::solvePnPRansac (SURVEY.md 8f rank 1): map points in front of a
+    camera with a known pose, their pixels with noise, a share of wrong matches, and map-point normals (most facing the camera,
+    some seen from behind so that the viewing-angle test rejects them).  Returns dict(p3d, p2d, normals, cam, pose_gt (4,4))."""
+    rng = np.random.default_rng(seed)
+    R = _rodrigues(rng.uniform(-0.4, 0.4, 3)); t = rng.uniform(-0.5, 0.5, 3) + np.array([0, 0, 0.5])
+    cam = np.array([f, f, w / 2 - 0.5, h / 2 - 0.5], np.float32)
+    Z = rng.uniform(2.0, 9.0, n)
+    u = rng.uniform(20, w - 20, n); v = rng.uniform(20, h - 20, n)
+    Xc = np.c_[(u - cam[2]) / f * Z, (v - cam[3]) / f * Z, Z]
+    Xw = (Xc - t) @ R                      # Xc = R Xw + t
+    p3d = Xw.astype(np.float32)
+    Xc = p3d.astype(np.float64) @ R.T + t
+    p2d = np.c_[f * Xc[:, 0] / Xc[:, 2] + cam[2], f * Xc[:, 1] / Xc[:, 2] + cam[3]] + rng.normal(0, px_sigma, (n, 2))
+    wrong = rng.random(n) < outlier_frac
+    p2d[wrong] = np.c_[rng.uniform(0, w, int(wrong.sum())), rng.uniform(0, h, int(wrong.sum()))]
+    centre = -R.T @ t
+    to_cam = centre - Xw
+    to_cam /= np.linalg.norm(to_cam, axis=1)[:, None]
+    normals = to_cam + rng.normal(0, 0.35, (n, 3))
+    normals /= np.linalg.norm(normals, axis=1)[:, None]
+    back = rng.random(n) < backface_frac
+    normals[back] *= -1
+    pose = np.eye(4); pose[:3, :3] = R; pose[:3, 3] = t
+    return dict(p3d=p3d, p2d=p2d.astype(np.float32), normals=normals.astype(np.float32), cam=cam, pose_gt=pose)
