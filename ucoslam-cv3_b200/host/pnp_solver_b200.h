@@ -62,4 +62,37 @@ inline int solvePnp_b200(uco_b200::Context& ctx, const Frame& frame, std::shared
     return res.n_good;
 }
 
+// PnPSolver::solvePnPRansac (src/optimization/pnpsolver.h, pnpsolver.cpp:36-114): same signature and effects (false -> arguments
+// untouched; true -> posef2g_io = winning hypothesis, matches_io = its inliers).  All maxIters hypotheses run side by side in
+// uco_b200_pnp_ransac; the 4-match samples come from its counter-based generator seeded per call (the reference consumes the
+// process-wide rand() stream through std::random_shuffle, which a parallel sampler cannot replay).
+inline bool solvePnPRansac_b200(uco_b200::Context& ctx, const Frame& frame, std::shared_ptr<Map> map, std::vector<cv::DMatch>& matches_io,
+                                se3& posef2g_io, int maxIters, uint64_t seed = 0) {
+    if (matches_io.size() < 4) return false;                                             // :39
+    const int n = (int)matches_io.size();
+    std::vector<float> p3(3 * (size_t)n), p2(2 * (size_t)n), nr(3 * (size_t)n);
+    for (int i = 0; i < n; i++) {
+        const MapPoint& mp = map->map_points[matches_io[i].trainIdx];
+        const cv::Point3f p = mp.getCoordinates(), nn = mp.getNormal();
+        const cv::Point2f k = frame.und_kpts[matches_io[i].queryIdx].pt;
+        p3[3 * i] = p.x; p3[3 * i + 1] = p.y; p3[3 * i + 2] = p.z;
+        nr[3 * i] = nn.x; nr[3 * i + 1] = nn.y; nr[3 * i + 2] = nn.z;
+        p2[2 * i] = k.x; p2[2 * i + 1] = k.y;
+    }
+    const float* cam = frame.imageParams.CameraMatrix.ptr<float>(0);
+    const float K[4] = {cam[0], cam[4], cam[2], cam[5]};
+    cv::Mat pose(4, 4, CV_32F);
+    std::vector<int32_t> inl(n);
+    int ni = 0;
+    ctx.check(uco_b200_pnp_ransac(ctx.get(), p3.data(), p2.data(), nr.data(), n, K, maxIters, nullptr, seed, pose.ptr<float>(0), inl.data(),
+                                  &ni, nullptr, nullptr));
+    if (ni < 4) return false;                                                            // :103
+    std::vector<cv::DMatch> kept;
+    kept.reserve(ni);
+    for (int i = 0; i < ni; i++) kept.push_back(matches_io[inl[i]]);
+    matches_io = kept;
+    posef2g_io = pose;
+    return true;
+}
+
 }  // namespace ucoslam
