@@ -515,6 +515,15 @@ typedef struct uco_triangulate_params {
     int32_t n_levels_train; const float* scale_factors_train;
     int32_t n_levels_query; const float* scale_factors_query;
     float max_chi2;               /* 5.998 default, misc.h:65 */
+    /* the mapper's scale-consistency test on the surviving points (new-map-point creation, src/utils/mapmanager.cpp:9772-10788,
+     * de-obfuscated): ratioDist = |P - C_train| / |P - C_query|, ratioOctave = sf_train[oct] / sf_query[oct]; rejected if
+     * ratioDist * f < ratioOctave or ratioDist > ratioOctave * f with f = 1.5f * Params::scaleFactor, or if a distance is 0.
+     * 0 = test off (plain ucoslam::Triangulate). */
+    float scale_ratio_factor;
+    /* when non-zero the accepted points are returned as g2f_train * p (the mapper's `pose_f2g.inv() * p`, Se3Transform float
+     * arithmetic) instead of camera-1 coordinates */
+    int32_t to_global;
+    float g2f_train[16];
 } uco_triangulate_params;
 int uco_b200_triangulate(uco_b200_ctx* ctx, const uco_keypoint* kps_train, int n_train, const uco_keypoint* kps_query, int n_query,
                          const uco_match* matches, int n_matches, const uco_triangulate_params* prm, float* xyz, int* n_good);

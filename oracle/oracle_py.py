@@ -773,7 +773,7 @@ def stereo_depth_py(sc, max_desc_dist=50.0):
 
 
 # ---- two-view triangulation ------------------------------------------------------------------------------------
-def triangulate_py(sc, max_chi2=5.998):
+def triangulate_py(sc, max_chi2=5.998, scale_ratio_factor=0.0, g2f_train=None):
     """ucoslam::Triangulate (src/basictypes/misc.cpp:921-1040) restated on numpy float32 with OpenCV's own float SVD through cv2
     (cv2.SVDecomp with MODIFY_A | FULL_UV, the call of :931).  Returns (xyz f32 (n,3) NaN = rejected, n_good, margin (n,)): margin is
     the distance of the closest gate to its threshold (relative), so that tests can leave out matches a float rounding could flip."""
@@ -832,6 +832,25 @@ def triangulate_py(sc, max_chi2=5.998):
         margin[i] = min(margin[i], abs(float(chi) - max_chi2) / (0.005 * max_chi2))
         if chi > f32(max_chi2):
             continue
+        if scale_ratio_factor:      # the mapper's scale-consistency test (mapmanager.cpp new-point creation), in global coordinates
+            G = np.asarray(np.eye(4) if g2f_train is None else g2f_train, f32)
+            Pg = np.array([G[r, 0] * p[0] + G[r, 1] * p[1] + G[r, 2] * p[2] + G[r, 3] for r in range(3)], f32)
+            c1 = G[:3, 3]                                            # train camera centre
+            Rq, tq = RT[:3, :3], RT[:3, 3]
+            cq_train = -(Rq.T.astype(np.float64) @ tq.astype(np.float64)).astype(f32)   # query centre in train coordinates
+            c2 = np.array([G[r, 0] * cq_train[0] + G[r, 1] * cq_train[1] + G[r, 2] * cq_train[2] + G[r, 3] for r in range(3)], f32)
+            d1 = f32(np.sqrt(((Pg - c1).astype(np.float64) ** 2).sum())); d2 = f32(np.sqrt(((Pg - c2).astype(np.float64) ** 2).sum()))
+            if d1 == 0 or d2 == 0:
+                continue
+            rd = d1 / d2
+            ro = f32(sc["sf_train"][a["octave"]]) / f32(sc["sf_query"][b["octave"]])
+            fct = f32(scale_ratio_factor)
+            margin[i] = min(margin[i], abs(float(rd * fct) - float(ro)) / (1e-4 * float(ro)), abs(float(rd) - float(ro * fct)) / (1e-4 * float(ro * fct)))
+            if rd * fct < ro or rd > ro * fct:
+                continue
+        if g2f_train is not None:
+            G = np.asarray(g2f_train, f32)
+            p = np.array([G[r, 0] * p[0] + G[r, 1] * p[1] + G[r, 2] * p[2] + G[r, 3] for r in range(3)], f32)
         out[i] = p
         good += 1
     return out, good, margin

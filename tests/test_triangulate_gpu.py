@@ -28,6 +28,28 @@ def test_matches_restatement(ctx, name):
     assert np.isnan(got[~b]).all()
 
 
+def test_scale_consistency_and_global_frame(ctx):
+    """the mapper's follow-up to Triangulate (new-map-point creation): distance-ratio vs octave-ratio gate, points in global coordinates"""
+    from ucoslam_b200.synth import _rodrigues
+    sc = synth_two_view(1)
+    G = np.eye(4); G[:3, :3] = _rodrigues(np.array([0.3, -0.2, 0.1])); G[:3, 3] = [1.0, -2.0, 0.5]
+    plain, n_plain = ctx.triangulate(sc)
+    for factor in (1.8, 1.15):                      # 1.5 * scaleFactor = 1.8 for the default pyramid; a tight one that rejects
+        want, good, margin = oracle_py.triangulate_py(sc, 5.998, factor, G)
+        got, n = ctx.triangulate(sc, 5.998, factor, G)
+        a, b = ~np.isnan(want[:, 0]), ~np.isnan(got[:, 0])
+        clear = margin >= 1.0
+        assert clear.mean() > 0.95 and np.array_equal(a[clear], b[clear]) and n == b.sum()
+        both = a & b
+        rel = np.linalg.norm(got[both].astype(np.float64) - want[both], axis=1) / np.linalg.norm(want[both].astype(np.float64), axis=1)
+        assert rel.max() < REL_TOL
+        assert n <= n_plain
+    assert n < 0.8 * n_plain                        # the tight factor does reject
+    loose, n_loose = ctx.triangulate(sc, 5.998, 1.8, G)
+    back = (loose[~np.isnan(loose[:, 0])].astype(np.float64) - G[:3, 3]) @ G[:3, :3]
+    assert np.abs(back - plain[~np.isnan(loose[:, 0])]).max() < 1e-4
+
+
 def test_edges(ctx):
     sc = synth_two_view(7, n=64)
     empty = dict(sc, matches=sc["matches"][:0])

@@ -9,6 +9,8 @@
 //     homogeneous DLT: the 4x4 system of misc.cpp:923-929, null vector = last row of V^T of its SVD (:931-933), w == 0 rejects;
 //     finite, in front of both cameras (:996-1009); reprojection chi2 in both images, scaled by 1/scaleFactor[octave]^2, <= maxChi2;
 //   a rejected match yields (NaN, NaN, NaN).
+// Optionally followed by the mapper's scale-consistency test on the survivors and the transform to global coordinates
+// (src/utils/mapmanager.cpp:9772-10788, de-obfuscated: the statements after the Triangulate call of new-map-point creation).
 //
 // The reference runs OpenCV's float SVD per match (LAPACK sgesdd or OpenCV's Jacobi, depending on the build: not reproducible bit for
 // bit across builds).  Here one thread per match forms the same float system, converts it to double and takes the eigenvector of the
@@ -29,7 +31,8 @@ struct TriArgs {
     float R[9], t[3];         // camera 1 -> camera 2
     const float* inv_sf1; int nl1;   // 1 / scaleFactor^2 per octave
     const float* inv_sf2; int nl2;
-    float max_chi2;
+    const float* sf1; const float* sf2;   // the scale factors themselves
+    float max_chi2, ratio_factor; int to_global; float G[12];
     float* xyz; int32_t* counters;   // [0] accepted, [1] bad index flag
 };
 
@@ -152,8 +155,23 @@ __global__ void __launch_bounds__(128) triangulate_kernel(const __grid_constant_
                                 const float qx = fx2 * X2 * iz2 + cx2, qy = fy2 * Y2 * iz2 + cy2;
                                 const float chi2 = A.inv_sf2[k2.octave] * ((qx - k2.x) * (qx - k2.x) + (qy - k2.y) * (qy - k2.y));
                                 ok = !(chi2 > A.max_chi2);
+                                if (ok && A.ratio_factor != 0.f) {   // mapper's scale consistency (distances are pose invariant)
+                                    const float d1 = (float)sqrt((double)X * X + (double)Y * Y + (double)Z * Z);
+                                    const float d2 = (float)sqrt((double)X2 * X2 + (double)Y2 * Y2 + (double)Z2 * Z2);
+                                    ok = !(d1 == 0.f || d2 == 0.f);
+                                    if (ok) {
+                                        const float rd = d1 / d2, ro = A.sf1[k1.octave] / A.sf2[k2.octave];
+                                        ok = !(rd * A.ratio_factor < ro || rd > ro * A.ratio_factor);
+                                    }
+                                }
                                 if (ok) {
-                                    out[0] = X; out[1] = Y; out[2] = Z;
+                                    if (A.to_global) {               // Se3Transform::operator*(Point3f)
+                                        out[0] = A.G[0] * X + A.G[1] * Y + A.G[2] * Z + A.G[3];
+                                        out[1] = A.G[4] * X + A.G[5] * Y + A.G[6] * Z + A.G[7];
+                                        out[2] = A.G[8] * X + A.G[9] * Y + A.G[10] * Z + A.G[11];
+                                    } else {
+                                        out[0] = X; out[1] = Y; out[2] = Z;
+                                    }
                                     atomicAdd(A.counters, 1);
                                 }
                             }
@@ -186,7 +204,7 @@ int uco_b200_triangulate(uco_b200_ctx* ctx, const uco_keypoint* kps_train, int n
     const size_t b1 = (size_t)n_train * sizeof(uco_keypoint), b2 = (size_t)n_query * sizeof(uco_keypoint);
     const size_t bm = (size_t)n_matches * sizeof(uco_match);
     const size_t o2 = (b1 + 15) & ~(size_t)15, om = o2 + ((b2 + 15) & ~(size_t)15), os = om + ((bm + 15) & ~(size_t)15);
-    const size_t total = os + 2 * UCO_MATCH_MAX_SCALES * sizeof(float);
+    const size_t total = os + 4 * UCO_MATCH_MAX_SCALES * sizeof(float);
     uint8_t* h_in = (uint8_t*)uco_pinned(ctx, WS_TRI_IN, total);
     uint8_t* d_in = (uint8_t*)uco_ws(ctx, WS_TRI_IN, total);
     const size_t out_bytes = 16 + (size_t)n_matches * 12;
@@ -201,9 +219,14 @@ int uco_b200_triangulate(uco_b200_ctx* ctx, const uco_keypoint* kps_train, int n
     for (int l = 0; l < prm->n_levels_train; l++) sf[l] = 1.f / (prm->scale_factors_train[l] * prm->scale_factors_train[l]);
     for (int l = 0; l < prm->n_levels_query; l++)
         sf[UCO_MATCH_MAX_SCALES + l] = 1.f / (prm->scale_factors_query[l] * prm->scale_factors_query[l]);
+    for (int l = 0; l < prm->n_levels_train; l++) sf[2 * UCO_MATCH_MAX_SCALES + l] = prm->scale_factors_train[l];
+    for (int l = 0; l < prm->n_levels_query; l++) sf[3 * UCO_MATCH_MAX_SCALES + l] = prm->scale_factors_query[l];
     UCO_CUDA(ctx, cudaMemcpyAsync(d_in, h_in, total, cudaMemcpyHostToDevice, ctx->stream));
     UCO_CUDA(ctx, cudaMemsetAsync(d_out, 0, 16, ctx->stream));
     TriArgs A;
+    A.ratio_factor = prm->scale_ratio_factor;
+    A.to_global = prm->to_global;
+    memcpy(A.G, prm->g2f_train, sizeof A.G);
     A.kp1 = (const uco_keypoint*)d_in; A.n1 = n_train;
     A.kp2 = (const uco_keypoint*)(d_in + o2); A.n2 = n_query;
     A.matches = (const uco_match*)(d_in + om); A.n = n_matches;
@@ -215,6 +238,7 @@ int uco_b200_triangulate(uco_b200_ctx* ctx, const uco_keypoint* kps_train, int n
     }
     A.inv_sf1 = (const float*)(d_in + os); A.nl1 = prm->n_levels_train;
     A.inv_sf2 = A.inv_sf1 + UCO_MATCH_MAX_SCALES; A.nl2 = prm->n_levels_query;
+    A.sf1 = A.inv_sf1 + 2 * UCO_MATCH_MAX_SCALES; A.sf2 = A.inv_sf1 + 3 * UCO_MATCH_MAX_SCALES;
     A.max_chi2 = prm->max_chi2;
     A.counters = (int32_t*)d_out;
     A.xyz = (float*)(d_out + 16);

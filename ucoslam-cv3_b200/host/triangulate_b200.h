@@ -26,7 +26,7 @@ inline std::vector<cv::Point3f> Triangulate_b200(uco_b200::Context& ctx, const F
         for (int c = 0; c < 4; c++) p.RT[4 * r + c] = RT.at<float>(r, c);
     p.n_levels_train = (int)Train.scaleFactors.size(); p.scale_factors_train = Train.scaleFactors.data();
     p.n_levels_query = (int)Query.scaleFactors.size(); p.scale_factors_query = Query.scaleFactors.data();
-    p.max_chi2 = maxChi2;
+    p.max_chi2 = maxChi2;   // scale_ratio_factor / to_global stay 0: plain ucoslam::Triangulate
     ctx.check(uco_b200_triangulate(ctx.get(), reinterpret_cast<const uco_keypoint*>(Train.und_kpts.data()), (int)Train.und_kpts.size(),
                                    reinterpret_cast<const uco_keypoint*>(Query.und_kpts.data()), (int)Query.und_kpts.size(),
                                    reinterpret_cast<const uco_match*>(matches.data()), (int)matches.size(), &p,

@@ -245,7 +245,8 @@ class PnpResult(ctypes.Structure):  # uco_pnp_result
 
 class TriangulateParams(ctypes.Structure):  # uco_triangulate_params
     _fields_ = [("K_train", _c.c_float * 4), ("K_query", _c.c_float * 4), ("RT", _c.c_float * 16), ("n_levels_train", _c.c_int32),
-                ("scale_factors_train", _vp), ("n_levels_query", _c.c_int32), ("scale_factors_query", _vp), ("max_chi2", _c.c_float)]
+                ("scale_factors_train", _vp), ("n_levels_query", _c.c_int32), ("scale_factors_query", _vp), ("max_chi2", _c.c_float),
+                ("scale_ratio_factor", _c.c_float), ("to_global", _c.c_int32), ("g2f_train", _c.c_float * 16)]
 
 
 class UcoError(RuntimeError):
@@ -308,7 +309,7 @@ class Context:
         return dict(ok=ni.value > 0, pose44=pose, inliers=inl[:ni.value].copy(), counts=counts[:max_iters].copy(), best_iter=int(bi.value))
 
     # -- K13 -----------------------------------------------------------------------------------------------------
-    def triangulate(self, sc, max_chi2=5.998):
+    def triangulate(self, sc, max_chi2=5.998, scale_ratio_factor=0.0, g2f_train=None):
         """sc: dict(kps_train, kps_query, matches (MATCH_DTYPE), K_train, K_query (fx fy cx cy), RT (4,4), sf_train, sf_query)
         -> (xyz f32 (n,3) with NaN rows where rejected, n_good)"""
         k1, k2 = np.ascontiguousarray(sc["kps_train"]), np.ascontiguousarray(sc["kps_query"])
@@ -320,6 +321,9 @@ class Context:
         prm.n_levels_train, prm.scale_factors_train = len(s1), _p(s1)
         prm.n_levels_query, prm.scale_factors_query = len(s2), _p(s2)
         prm.max_chi2 = max_chi2
+        prm.scale_ratio_factor = scale_ratio_factor
+        prm.to_global = int(g2f_train is not None)
+        prm.g2f_train[:] = [float(x) for x in np.asarray(np.eye(4) if g2f_train is None else g2f_train, np.float32).reshape(-1)]
         xyz = np.zeros((len(m), 3), np.float32)
         n = ctypes.c_int()
         self._chk(self.lib.uco_b200_triangulate(self.h, _p(k1), len(k1), _p(k2), len(k2), _p(m), len(m), ctypes.addressof(prm), _p(xyz),
