@@ -35,7 +35,7 @@ BA_CLUSTER = int(os.environ.get("UCO_BENCH_BA_CLUSTER", "4"))       # CTAs per B
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=64, help="frames per step per GPU")
