@@ -706,7 +706,10 @@ class KeyFrameDataBase:
         words = np.ascontiguousarray(words, np.uint32); weights = np.ascontiguousarray(weights, np.float32)
         exc = np.ascontiguousarray(list(excluded), np.uint32)
         cap = max(self.size()[0], 1)
-        fr = np.zeros(cap, np.uint32); sc = np.zeros(cap, np.float64); cm = np.zeros(cap, np.uint32)
+        if getattr(self, "_cap", 0) < cap:      # output buffers are kept between queries (a caller's std::vector would be too)
+            self._cap = cap
+            self._out = (np.zeros(cap, np.uint32), np.zeros(cap, np.float64), np.zeros(cap, np.uint32))
+        fr, sc, cm = self._out
         n, mc = ctypes.c_int(), ctypes.c_uint32()
         self.ctx._chk(self.ctx.lib.uco_b200_kfdb_query(self.ctx.h, self.h, _p(words), _p(weights), len(words), _p(exc), len(exc),
                                                        float(min_score), _p(fr), _p(sc), _p(cm), cap, ctypes.addressof(n),
