@@ -546,6 +546,21 @@ int uco_b200_pnp_ransac(uco_b200_ctx* ctx, const float* p3d, const float* p2d, c
                         int32_t* counts, int* best_iter);
 int uco_b200_probe_p3p(const double* X4x3, const double* px4x2, const double* K_fxfycxcy, double* R9, double* t3);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * K15  point undistortion when a Frame is built (Frame::und_kpts, marker corners, image bounds)
+ *   replaces ucoslam::undistortPoints(points_io, ImageParams)   src/basictypes/misc.cpp:269-292
+ *   (cv::undistortPoints with its default 5 iterations, then x*fx+cx in float).
+ *   pts / out: n points of two floats, `stride` bytes apart (8 for cv::Point2f arrays, 28 for the pt field of cv::KeyPoint
+ *   arrays -- in place is allowed); K = fx fy cx cy; dist: the n_dist (0..12; 14 with zero tilt terms) coefficients of
+ *   ImageParams::Distorsion (k1 k2 p1 p2 [k3 [k4 k5 k6 [s1 s2 s3 s4]]]).
+ *   uco_b200_probe_undistort: host-only, the same arithmetic compiled for the host (dense points).
+ * ---------------------------------------------------------------------------------------------------------- */
+int uco_b200_undistort_points(uco_b200_ctx* ctx, const float* pts, size_t in_stride, int n, const float* K_fxfycxcy, const float* dist,
+                              int n_dist, float* out, size_t out_stride);
+int uco_b200_undistort_points_dev(uco_b200_ctx* ctx, const float* pts_dev, size_t in_stride, int n, const float* K_fxfycxcy, const float* dist,
+                                  int n_dist, float* out_dev, size_t out_stride);
+int uco_b200_probe_undistort(const float* pts, int n, const float* K_fxfycxcy, const float* dist, int n_dist, float* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -901,3 +901,18 @@ def pnp_ransac_py(sc, samples):
     ok = best >= 4
     return dict(ok=ok, pose44=best_pose if ok else None, inliers=best_inl if ok else np.zeros(0, np.int32), counts=counts,
                 best_iter=best_it if ok else -1, borderline=border)
+
+
+# ---- point undistortion ----------------------------------------------------------------------------------------
+def undistort_points_py(pts, K, dist):
+    """ucoslam::undistortPoints (src/basictypes/misc.cpp:269-292) with the reference's own OpenCV call made through cv2:
+    cv2.undistortPoints (default termination), then x*fx+cx in float.  pts (n,2) f32, K = fx fy cx cy, dist = coefficients."""
+    import cv2
+    pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+    K = np.asarray(K, np.float32)
+    Km = np.array([[K[0], 0, K[2]], [0, K[1], K[3]], [0, 0, 1]], np.float32)
+    d = np.asarray(dist, np.float32).reshape(-1)
+    if len(pts) == 0:
+        return pts.copy()
+    n = cv2.undistortPoints(pts.reshape(-1, 1, 2), Km, d if len(d) else None).reshape(-1, 2).astype(np.float32)
+    return np.c_[n[:, 0] * K[0] + K[2], n[:, 1] * K[1] + K[3]].astype(np.float32)

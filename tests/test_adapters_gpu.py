@@ -27,7 +27,7 @@ def test_adapter_headers_are_self_contained():
     for h, iface in (("orb_extractor_b200.h", "Feature2DSerializable"), ("hamming_index_b200.h", "IndexImpl"),
                      ("bow_b200.h", "fbow::Vocabulary::transform"), ("global_optimizer_b200.h", "GlobalOptimizer"),
                      ("keyframe_database_b200.h", "KFDataBaseVirtual"), ("stereo_depth_b200.h", "processStereo"),
-                     ("triangulate_b200.h", "ucoslam::Triangulate")):
+                     ("triangulate_b200.h", "ucoslam::Triangulate"), ("undistort_b200.h", "ucoslam::undistortPoints")):
         src = open(os.path.join(host, h)).read()
         assert iface in src and "uco_b200_cxx.h" in src
         assert "torch" not in src and "oracle" not in src.replace("oracle/shim", "")

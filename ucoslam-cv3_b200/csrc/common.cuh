@@ -45,6 +45,7 @@ enum {  // device workspace slots
     WS_STEREO_SOA, WS_STEREO_IN, WS_STEREO_OUT,
     WS_TRI_IN, WS_TRI_OUT,
     WS_RANSAC_IN, WS_RANSAC_OUT,
+    WS_UNDISTORT,
     WS_COUNT
 };
 

@@ -73,6 +73,9 @@ SIGNATURES = {
     "uco_b200_triangulate": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp]),
     "uco_b200_pnp_ransac": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _u64, _vp, _vp, _vp, _vp, _vp]),
     "uco_b200_probe_p3p": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "uco_b200_undistort_points": (_i, [_vp, _vp, _sz, _i, _vp, _vp, _i, _vp, _sz]),
+    "uco_b200_undistort_points_dev": (_i, [_vp, _vp, _sz, _i, _vp, _vp, _i, _vp, _sz]),
+    "uco_b200_probe_undistort": (_i, [_vp, _i, _vp, _vp, _i, _vp]),
     "uco_b200_kfdb_create": (_i, [_vp, _vp]),
     "uco_b200_kfdb_free": (None, [_vp, _vp]),
     "uco_b200_kfdb_clear": (_i, [_vp, _vp]),
@@ -110,6 +113,16 @@ def probe_sincos(a):
     s = np.empty_like(a); c = np.empty_like(a)
     assert load().uco_b200_probe_math(1, _p(a), None, len(a), _p(s), _p(c)) == 0
     return s, c
+
+
+def probe_undistort(pts, K, dist):
+    """host-only: ucoslam::undistortPoints on (n,2) f32 pixel coordinates as the kernel computes it"""
+    pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2); K = np.ascontiguousarray(K, np.float32)
+    dist = np.ascontiguousarray(dist, np.float32).reshape(-1)
+    out = np.empty_like(pts)
+    if load().uco_b200_probe_undistort(_p(pts), len(pts), _p(K), _p(dist), len(dist), _p(out)) != 0:
+        raise UcoError("probe_undistort failed")
+    return out
 
 
 def probe_p3p(X4, px4, K):
@@ -294,6 +307,23 @@ class Context:
 
     def launch_count(self):
         return int(self.lib.uco_b200_launch_count(self.h))
+
+    # -- K15 -----------------------------------------------------------------------------------------------------
+    def undistort_points(self, pts, K, dist):
+        """(n,2) f32 pixel coordinates -> undistorted pixel coordinates (ucoslam::undistortPoints)"""
+        pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2); K = np.ascontiguousarray(K, np.float32)
+        dist = np.ascontiguousarray(dist, np.float32).reshape(-1)
+        out = np.empty_like(pts)
+        self._chk(self.lib.uco_b200_undistort_points(self.h, _p(pts), 8, len(pts), _p(K), _p(dist), len(dist), _p(out), 8))
+        return out
+
+    def undistort_keypoints(self, kps, K, dist):
+        """Frame::und_kpts from the extracted keypoints: a copy of kps with pt undistorted (the other fields untouched)"""
+        und = np.ascontiguousarray(kps).copy()
+        K = np.ascontiguousarray(K, np.float32); dist = np.ascontiguousarray(dist, np.float32).reshape(-1)
+        self._chk(self.lib.uco_b200_undistort_points(self.h, _p(und), und.dtype.itemsize, len(und), _p(K), _p(dist), len(dist), _p(und),
+                                                     und.dtype.itemsize))
+        return und
 
     # -- K14 -----------------------------------------------------------------------------------------------------
     def pnp_ransac(self, sc, max_iters, samples=None, seed=0):
