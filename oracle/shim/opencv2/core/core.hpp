@@ -21,6 +21,24 @@ struct Point2f {
     float x, y;
     Point2f(float a = 0, float b = 0) : x(a), y(b) {}
 };
+struct KeyPoint {                 // opencv2/core/types.hpp: 28 bytes
+    Point2f pt;
+    float size = 0, angle = -1, response = 0;
+    int octave = 0, class_id = -1;
+};
+struct DMatch {                   // 16 bytes
+    int queryIdx = -1, trainIdx = -1, imgIdx = -1;
+    float distance = 0;
+};
+struct Size {
+    int width = 0, height = 0;
+    bool operator==(const Size& o) const { return width == o.width && height == o.height; }
+    bool operator!=(const Size& o) const { return !(*this == o); }
+};
+struct MatStep {
+    size_t p[2] = {0, 0};
+    size_t operator[](int i) const { return p[i]; }
+};
 struct Point3f {
     float x, y, z;
     Point3f(float a = 0, float b = 0, float c = 0) : x(a), y(b), z(c) {}
@@ -29,8 +47,10 @@ class Mat {
 public:
     int rows = 0, cols = 0;
     Mat() {}
+    MatStep step;
     Mat(int r, int c, int type) : rows(r), cols(c), _type(type) {   // owning (typesg2o.h: cv::Mat cvMat(4,4,CV_32F))
         _step = (size_t)c * elemSize();
+        step.p[0] = _step; step.p[1] = elemSize();
         _own = std::shared_ptr<unsigned char>(new unsigned char[_step * r](), std::default_delete<unsigned char[]>());
         _data = _own.get();
     }
@@ -42,6 +62,23 @@ public:
     template <typename T> T& at(int r, int c) { return *(T*)(_data + (size_t)r * _step + (size_t)c * sizeof(T)); }
     Mat(int r, int c, int type, void* data, size_t step = 0) : rows(r), cols(c), _type(type), _data((unsigned char*)data) {
         _step = step ? step : (size_t)c * elemSize();
+        this->step.p[0] = _step; this->step.p[1] = elemSize();
+    }
+    Size size() const { Size s; s.width = cols; s.height = rows; return s; }
+    template <typename T> const T& at(int r, int c) const { return *(const T*)(_data + (size_t)r * _step + (size_t)c * sizeof(T)); }
+    void convertTo(Mat& m, int type) const {                       // 8U / 32F only, enough for the adapters' syntax check
+        Mat o(rows, cols, type);
+        for (int r = 0; r < rows; r++)
+            for (int c = 0; c < cols; c++) {
+                const double v = _type == CV_32FC1 ? (double)*(const float*)(_data + r * _step + c * 4) : (double)_data[r * _step + c];
+                if (type == CV_32FC1) *(float*)(o._data + r * o._step + c * 4) = (float)v; else o._data[r * o._step + c] = (unsigned char)v;
+            }
+        m = o;
+    }
+    Mat reshape(int /*cn*/, int new_rows) const {                   // continuous matrices only
+        Mat o = *this;
+        if (new_rows > 0 && total()) { o.cols = (int)(total() / new_rows); o.rows = new_rows; o._step = (size_t)o.cols * elemSize(); o.step.p[0] = o._step; }
+        return o;
     }
     int type() const { return _type; }
     size_t elemSize() const { return _type == CV_32FC1 ? 4 : 1; }

@@ -21,6 +21,18 @@ def test_adapters_match_reference_classes():
     assert "ADAPTERS OK" in r.stdout
 
 
+@pytest.mark.gpu
+def test_frame_level_adapters_compile_and_run():
+    """stereo_depth_b200.h / triangulate_b200.h / undistort_b200.h compiled against the container shims (tests/adapters/adapter_syntax.cpp)
+    and driven once each"""
+    exe = os.path.join(ROOT, "oracle", "_ref", "adapter_syntax")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/adapter_syntax not built (needs /root/reference at build time)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0 and "ADAPTER SYNTAX OK" in r.stdout, r.stdout + r.stderr
+
+
 def test_adapter_headers_are_self_contained():
     """every adapter header names the reference interface it implements and includes only the C ABI + that interface"""
     host = os.path.join(ROOT, "ucoslam-cv3_b200", "host")
