@@ -103,3 +103,37 @@ def test_host_rank_step_matches_reference_golden(name):
         got = ucoslam_b200.rank_candidates(r["scored_frame"], r["scored_score"], lambda f: oracle_py.covis_neighbors(edges, f),
                                            q["sorted"], q["min_score"])
         assert np.array_equal(got, q["cand"])
+
+
+def test_host_rank_step_fuzz():
+    """uco_b200_kfdb_rank against a direct restatement of keyframedatabase.cpp:236-275 on random scored frames / neighbour lists
+    (distinct accumulated scores, so the order does not depend on std::sort's treatment of ties)"""
+    import ucoslam_b200
+    rng = np.random.default_rng(8)
+    for trial in range(200):
+        n = int(rng.integers(0, 40))
+        frame = np.sort(rng.choice(500, n, replace=False)).astype(np.uint32)
+        score = rng.uniform(0.01, 1.0, n)
+        nbrs = {int(f): rng.permutation(rng.choice(500, int(rng.integers(0, 25)), replace=False)).astype(np.uint32) for f in frame}
+        sorted_, ms = bool(trial % 2), float(rng.choice([0.0, 0.3]))
+        got = ucoslam_b200.rank_candidates(frame, score, lambda f: nbrs[f], sorted_, ms)
+        # restatement
+        if n == 0:
+            want = []
+        elif n == 1:
+            want = [int(frame[0])]
+        else:
+            sc = {int(f): float(s) for f, s in zip(frame, score)}
+            acc, best = [], np.float64(np.float32(ms))
+            for f in frame:
+                a = sc[int(f)]
+                for nb in nbrs[int(f)][:10]:
+                    if int(nb) in sc:
+                        a += sc[int(nb)]
+                acc.append((int(f), a))
+                best = max(best, a)
+            keep = [(f, a) for f, a in acc if not a < np.float64(np.float32(0.75)) * best]
+            if sorted_:
+                keep.sort(key=lambda fa: -fa[1])
+            want = [f for f, _ in keep]
+        assert got.tolist() == want
