@@ -137,3 +137,34 @@ def test_host_rank_step_fuzz():
                 keep.sort(key=lambda fa: -fa[1])
             want = [f for f, _ in keep]
         assert got.tolist() == want
+
+
+def test_edge_cases_against_live_reference():
+    """empty database, disjoint words, a single scored frame (returned whatever its score), a minScore above every score,
+    every frame excluded -- the reference's early exits (keyframedatabase.cpp:221,236,237)"""
+    if oracle_py.load_ref("libref_kfdb.so") is None or not os.path.exists(oracle_py.REF_VOC_PATH):
+        pytest.skip("oracle/_ref not built")
+    ref = oracle_py.RefKeyFrameDataBase(oracle_py.REF_VOC_PATH)
+    q = (np.array([5, 9, 100, 2000], np.uint32), np.array([0.1, 0.2, 0.05, 0.3], np.float32))
+    bows, ids = [], []
+
+    def both(excluded=(), min_score=0.0):
+        a = ref.query_bow(q[0], q[1], True, min_score, excluded)
+        b = oracle_py.kfdb_candidates(np.array(ids, np.uint32), bows, q, excluded, min_score, True, None)["candidates"]
+        assert np.array_equal(a, b)
+        return a
+
+    assert len(both()) == 0                                             # empty database
+    for i, (w, f) in enumerate([([1, 2, 3], [0.5, 0.5, 0.5]), ([7, 8], [0.1, 0.1])]):
+        ids.append(10 + i); bows.append((np.array(w, np.uint32), np.array(f, np.float32))); ref.add_bow(ids[-1], *bows[-1])
+    assert len(both()) == 0                                             # no common word
+    ids.append(20); bows.append((np.array([5, 9, 77], np.uint32), np.array([0.2, 0.1, 0.4], np.float32))); ref.add_bow(20, *bows[-1])
+    assert both().tolist() == [20]                                      # one scored frame
+    assert len(both(min_score=0.9)) == 0                                # nothing above minScore
+    ids.append(21); bows.append((np.array([5, 9, 100], np.uint32), np.array([0.3, 0.3, 0.3], np.float32))); ref.add_bow(21, *bows[-1])
+    ids.append(22); bows.append((np.array([9, 100, 2000], np.uint32), np.array([0.01, 0.01, 0.01], np.float32))); ref.add_bow(22, *bows[-1])
+    r = both()
+    assert 21 in r.tolist()
+    assert both(excluded=[21]).tolist() != r.tolist()
+    assert len(both(excluded=[20, 21, 22, 10, 11])) == 0                # everything excluded
+    ref.close()
