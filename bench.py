@@ -466,11 +466,21 @@ def run_b200(args, rank, world, local_rank):
         print(json.dumps(line))
         sys.stdout.flush()
     barrier()
+    # orderly teardown (the driver's exit hook records the loaded libraries, so the interpreter must exit normally): every torch
+    # object that refers to the tracker context's stream goes first, then the mapper pool, then the contexts, then the process group
+    mapper.shutdown(wait=True)
+    del stream, clip_dev, kps_dev, desc_dev, nout_dev, idx_dev, dist_dev, flush, clip_pin, desc_host, idx_host, dist_host, ev_a, ev_b
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()       # the caching allocators record events on the streams their blocks were used on: drop the blocks
+    torch._C._host_emptyCache() if hasattr(torch._C, "_host_emptyCache") else None
+    for c in ctx_bas:
+        c.close()
+    ctx.close()
     shard.finalize()
-    # the context (and its stream) outlives every torch object that references the stream; skip interpreter teardown
     sys.stdout.flush()
     sys.stderr.flush()
-    os._exit(0)
 
 
 def ctypes_voidp_array(n):

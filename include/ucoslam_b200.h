@@ -408,6 +408,21 @@ int uco_b200_kdtree_build(const float* xy, size_t stride_bytes, int n, uco_kdnod
 int uco_b200_kdtree_parse(const void* bytes, size_t n_bytes, uco_kdnode* nodes, int cap_nodes, int32_t* leaf_idx, int cap_leaf,
                           double* bbox4, int* n_nodes, int* n_leaf);
 
+/* device-side build of the same tree (K16, kdtree.cu): one thread block per frame, node for node what uco_b200_kdtree_build and
+ * picoflann::KdTreeIndex::build give (Frame::create_kdtree, src/map_types/frame.h:124-127).  *_batch_dev: everything device
+ * resident — keypoints of frame f at kps_dev + f * kps_frame_stride (records; pt is read), n_kp_dev[f] <= cap of them; writes
+ * nodes_dev + f * node_cap (node_cap >= 2 * (cap / 5) + 2), leaf_idx_dev + f * cap, bbox_dev + 4 f, n_nodes_dev[f].
+ * cap <= UCO_KDTREE_DEV_MAX_POINTS (the build lives in shared memory).  _dev: host buffers in and out (one tree). */
+#define UCO_KDTREE_DEV_MAX_POINTS 4096
+int uco_b200_kdtree_build_batch_dev(uco_b200_ctx* ctx, int n_frames, const uco_keypoint* kps_dev, size_t kps_frame_stride,
+                                    const int32_t* n_kp_dev, int cap, uco_kdnode* nodes_dev, int node_cap, int32_t* leaf_idx_dev,
+                                    double* bbox_dev, int32_t* n_nodes_dev);
+int uco_b200_kdtree_build_dev(uco_b200_ctx* ctx, const float* xy, size_t stride_bytes, int n, uco_kdnode* nodes, int cap_nodes,
+                              int32_t* leaf_idx, double* bbox4, int* n_nodes);
+/* host-side probe: the libstdc++ std::sort replay the device build uses for degenerate cuts (csrc/sort_exact.h), on indices keyed
+ * by keys[idx] */
+int uco_b200_probe_sort_indices(uint32_t* idx, int n, const float* keys);
+
 typedef struct uco_mappoints {      /* the candidate map points in the order of smap_ids (map.cpp:655-672) */
     int32_t n;
     const uint32_t* ids;            /* n        MapPoint::id -> DMatch::trainIdx */
@@ -437,6 +452,73 @@ typedef struct uco_frame_view {
  * reference; visible (optional, mp->n bytes): 1 where the reference calls MapPoint::setVisible() (map.cpp:711). */
 int uco_b200_match_projected(uco_b200_ctx* ctx, const uco_mappoints* mp, const uco_frame_view* fr, const float* pose_f2g,
                              float min_desc_dist, float max_reproj_dist, uco_match* out, int* n_out, uint8_t* visible);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K17  the tracker's per-frame sequence (track.cu)
+ *   uco_b200_track_projected: the search by projection from the PREVIOUS frame, System::_11946837405316294395
+ *     (src/utils/system.cpp:5921-6456, macro-obfuscated; called first thing in tracking, :6559): every previous-frame keypoint with a
+ *     valid, non-bad map point (prev_mp_row[i] >= 0 = row of that point in `mp`) is projected with the current pose guess
+ *     (Frame::project(p, true, true), src/map_types/frame.h:140-161); current keypoints of the SAME octave within
+ *     proj_dist_thr * scaleFactors[octave] in kd-tree visit order; best / second best (a new best does not demote the old one);
+ *     accepted when best < 0.7 * second; filter_ambiguous_query.  dist_thr = maxDescDistance*1.5 at the reference's call site.
+ *     out: capacity n_prev (queryIdx = current keypoint, trainIdx = map point id, distance = Hamming), previous-keypoint order.
+ *   uco_b200_track_batch[_dev]: the tracker's main branch (System::_11166622111371682966, system.cpp:6460-6960) for n_frames INDEPENDENT
+ *     frames (cameras / streams) in eight launches: kd-trees -> that search (maxDescDistance*1.5) -> solvePnp when > 30 matches
+ *     -> (> 30 inliers: pose taken, matched points marked seen, radius 4; else matches dropped, radius projDistThr)
+ *     -> Map::matchFrameToMapPoints over the rows flagged mp_local that were not seen (maxDescDistance*2) -> append,
+ *     filter_ambiguous_query -> solvePnp.  Frame f's arrays start at f * kp_cap / prev_cap / map_cap records.  The keypoints are
+ *     the frame's und_kpts (undistort first: uco_b200_undistort_points_dev).  status[f]: bit 0 = the first search found <= 30
+ *     matches (the reference then tries FrameMatcher against the reference keyframe, :6600-6700: the caller's), bit 1 = the
+ *     first solvePnp kept <= 30 inliers.  matches[f]: imgIdx = 1 inlier / -1 outlier of the final solvePnp (pnpsolver.cpp:398-404).
+ *     Markers are not part of the batch (frames with markers go through uco_b200_pose_only).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct uco_track_params {
+    float max_desc_dist;        /* Params::maxDescDistance (50 for ORB, ORBextractor.h:105) */
+    float proj_dist_thr;        /* Params::projDistThr (15, ucoslamtypes.cpp:49) */
+    float fx, fy, cx, cy, bf;   /* ImageParams; bf = bl * fx (stereo only) */
+    float min_xy[2], max_xy[2]; /* Frame::minXY / maxXY */
+    int32_t n_levels;
+    float scale_factors[UCO_MATCH_MAX_SCALES];
+} uco_track_params;
+
+#define UCO_TRACK_NO_SYNC 1     /* _dev only: return after queueing the launches (errors of this call surface with the next sync) */
+typedef struct uco_track_batch {
+    int32_t n_frames, kp_cap, prev_cap, map_cap, flags;
+    const uco_keypoint* kps;    /* n_frames x kp_cap   current frames' und_kpts (pt, octave) */
+    const uint8_t* desc;        /* n_frames x kp_cap x 32 */
+    const int32_t* n_kp;        /* n_frames */
+    const float* depth;         /* n_frames x kp_cap   Frame::depth, NULL = monocular */
+    const uco_keypoint* prev_kps;   /* n_frames x prev_cap  previous frames' und_kpts (octave) */
+    const uint8_t* prev_desc;       /* n_frames x prev_cap x 32 */
+    const int32_t* prev_n_kp;       /* n_frames */
+    const int32_t* prev_mp_row;     /* n_frames x prev_cap  row of the keypoint's map point in the frame's map block, -1 = none / bad */
+    const int32_t* map_n;           /* n_frames             rows used in each map block */
+    const uint32_t* mp_id;          /* n_frames x map_cap */
+    const float* mp_pos;            /* x 3 */
+    const float* mp_normal;         /* x 3 */
+    const float* mp_min_dist;
+    const float* mp_max_dist;
+    const uint8_t* mp_desc;         /* x 32 */
+    const uint8_t* mp_stable;       /* MapPoint::isStable(), NULL = all stable */
+    const uint8_t* mp_local;        /* 1 = belongs to the local map searched by matchFrameToMapPoints, NULL = all */
+    const float* pose_prior;        /* n_frames x 16        the pose guess (frame <- global) */
+} uco_track_batch;
+
+typedef struct uco_track_out {
+    uco_match* matches;             /* n_frames x kp_cap */
+    int32_t* n_matches;             /* n_frames */
+    float* pose;                    /* n_frames x 16 */
+    int32_t* n_good;                /* n_frames   return value of the final solvePnp */
+    int32_t* status;                /* n_frames */
+    int32_t* n_tbp;                 /* n_frames   matches of the first search */
+    uint8_t* visible;               /* n_frames x map_cap, optional: MapPoint::setVisible() of map.cpp:711 */
+} uco_track_out;
+
+int uco_b200_track_batch_dev(uco_b200_ctx* ctx, const uco_track_batch* in_dev, const uco_track_params* prm, const uco_track_out* out_dev);
+int uco_b200_track_batch(uco_b200_ctx* ctx, const uco_track_batch* in_host, const uco_track_params* prm, const uco_track_out* out_host);
+int uco_b200_track_projected(uco_b200_ctx* ctx, int n_prev, const uco_keypoint* prev_kps, const uint8_t* prev_desc,
+                             const int32_t* prev_mp_row, const uco_mappoints* mp, const uco_frame_view* fr, const float* pose_f2g,
+                             float dist_thr, float proj_dist_thr, uco_match* out, int* n_out);
 
 /* ------------------------------------------------------------------------------------------------------------
  * K11  keyframe database: relocalisation / loop-closure candidates by bag of words (BASELINE config 4)

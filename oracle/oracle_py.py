@@ -555,6 +555,92 @@ def match_projected(sc, min_desc_dist, max_reproj_dist):
     return out[:n].copy(), vis[:m].copy()
 
 
+def track_projected(sc, dist_thr, proj_dist_thr):
+    """System::_11946837405316294395 (search by projection from the previous frame, src/utils/system.cpp:5921-6456) on a scene dict
+    (ucoslam_b200.synth.synth_track_scene) -> matches[MATCH_DT]"""
+    A = lambda k, dt: np.ascontiguousarray(sc[k], dt)
+    ids, pos = A("mp_id", np.uint32), A("mp_pos", np.float32)
+    kxy, koct, kdesc = A("kp_xy", np.float32), A("kp_octave", np.int32), A("kp_desc", np.uint8)
+    poct, pdesc, prow = A("prev_octave", np.int32), A("prev_desc", np.uint8), A("prev_mp_row", np.int32)
+    sf, pose = A("scale_factors", np.float32), A("pose44", np.float32)
+    mn, mx = A("min_xy", np.float32), A("max_xy", np.float32)
+    out = np.zeros(max(len(poct), 1), MATCH_DT)
+    f = load_stl().oracle_track_projected
+    f.argtypes = [ctypes.c_int] + [ctypes.c_void_p] * 5 + [ctypes.c_int] + [ctypes.c_void_p] * 4 + [ctypes.c_int] + [ctypes.c_float] * 4 + \
+                 [ctypes.c_void_p] * 3 + [ctypes.c_float] * 2 + [ctypes.c_void_p]
+    n = f(len(poct), _p(poct), _p(pdesc), _p(prow), _p(ids), _p(pos), len(kxy), _p(kxy), _p(koct), _p(kdesc), _p(sf), len(sf),
+          sc["fx"], sc["fy"], sc["cx"], sc["cy"], _p(mn), _p(mx), _p(pose), dist_thr, proj_dist_thr, _p(out))
+    return out[:n].copy()
+
+
+def filter_ambiguous_query(matches):
+    m = np.ascontiguousarray(matches, MATCH_DT).copy()
+    n = load_stl().oracle_filter_ambiguous_query(_p(m), len(m))
+    return m[:n].copy()
+
+
+def track_frame(sc, max_desc_dist=50.0, proj_dist_thr=15.0, pnp=None):
+    """The tracker's main branch (System::_11166622111371682966, src/utils/system.cpp:6460-6960) on one scene dict, assembled from the
+    stage oracles exactly as the reference sequences them: search by projection (maxDescDistance*1.5) -> solvePnp when > 30 matches
+    -> on > 30 inliers take the pose, mark the matched points seen, radius 4, else drop the matches, radius projDistThr ->
+    matchFrameToMapPoints over the local, unseen points (maxDescDistance*2) -> append -> filter_ambiguous_query -> solvePnp.
+    pnp: the pose-only solver to use (default: the plain-C restatement; bench's CPU arm passes the reference's g2o)."""
+    pnp = pnp or pose_only
+    f32 = np.float32
+    sf = np.asarray(sc["scale_factors"], f32)
+    kxy, koct = np.asarray(sc["kp_xy"], f32).reshape(-1, 2), np.asarray(sc["kp_octave"], np.int32)
+    id2row = {int(v): i for i, v in enumerate(sc["mp_id"])}
+    stable = np.asarray(sc.get("mp_stable", np.ones(len(sc["mp_id"]), np.uint8)), np.uint8)
+    local = np.asarray(sc.get("mp_local", np.ones(len(sc["mp_id"]), np.uint8)), np.uint8)
+
+    def solve(matches, pose):
+        rows = np.array([id2row[int(t)] for t in matches["trainIdx"]], np.int64)
+        q = matches["queryIdx"]
+        inv = (1.0 / sf[koct[q]].astype(np.float64)).astype(f32)
+        pb = dict(pose44=np.asarray(pose, f32).reshape(16).copy(), points3=np.asarray(sc["mp_pos"], f32)[rows], obs_uv=kxy[q],
+                  obs_ur=np.zeros(len(q), f32), obs_stereo=np.zeros(len(q), np.uint8), obs_inv_sigma2=inv, stable=stable[rows],
+                  fx=sc["fx"], fy=sc["fy"], cx=sc["cx"], cy=sc["cy"], bf=float(sc.get("bf", 0.0)),
+                  marker_pose44=np.zeros((0, 16), f32), marker_size=np.zeros(0, f32), marker_corners=np.zeros((0, 8), f32))
+        return pnp(pb)
+
+    thr1 = float(f32(float(f32(max_desc_dist)) * 1.5))
+    thr2 = float(f32(max_desc_dist) * f32(2))
+    pose = np.asarray(sc["pose44"], f32).reshape(16).copy()
+    m1 = track_projected(sc, thr1, proj_dist_thr)
+    n_tbp, status, n_in1 = len(m1), 0, 0
+    if len(m1) > 30:
+        r1 = solve(m1, pose)
+        n_in1 = int(r1["n_good"])
+        if n_in1 > 30:
+            pose = np.asarray(r1["pose44"], f32).reshape(16).copy()
+            m1["imgIdx"] = np.where(r1["bad"] != 0, -1, 1)
+        else:
+            status |= 2
+    else:
+        status |= 1
+    reproj = 4.0 if n_in1 > 30 else proj_dist_thr
+    keep = local.astype(bool).copy()
+    if n_in1 > 30:
+        for t in m1["trainIdx"]:
+            keep[id2row[int(t)]] = False        # lastFIdxSeen == fseq_idx, map.cpp:659-667
+    else:
+        m1 = m1[:0]
+    rows2 = np.nonzero(keep)[0]
+    sc2 = dict(sc, pose44=pose)
+    for k in ("mp_id", "mp_pos", "mp_normal", "mp_min_dist", "mp_max_dist", "mp_desc"):
+        sc2[k] = np.asarray(sc[k])[rows2]
+    m2, vis2 = match_projected(sc2, thr2, reproj)
+    visible = np.zeros(len(sc["mp_id"]), np.uint8)
+    visible[rows2] = vis2
+    allm = filter_ambiguous_query(np.concatenate([m1, m2]))
+    out = dict(matches=allm, pose44=pose, n_good=0, status=status, n_tbp=n_tbp, visible=visible)
+    if len(allm):
+        r2 = solve(allm, pose)
+        allm["imgIdx"] = np.where(r2["bad"] != 0, -1, 1)
+        out.update(pose44=np.asarray(r2["pose44"], f32).reshape(16), n_good=int(r2["n_good"]), iters=r2["iters"])
+    return out
+
+
 # ---- keyframe database (SURVEY 8f rank 1): relocalisation / loop-closure candidates ------------------------------------------------
 def synth_places(seed, n_places=12, views_per_place=5, n_desc=400, flip_bits=6, replace_frac=0.25):
     """Seeded descriptor sets of keyframes that revisit a few places: every place has n_desc base descriptors, a view flips up to

@@ -332,4 +332,81 @@ int oracle_match_projected(int m, const uint32_t* ids, const float* pos, const f
     return n;
 }
 
+// filter_ambiguous_query + remove_unused_matches (misc.cpp:105-150) on a match list, in place; returns the new count
+int oracle_filter_ambiguous_query(OracleMatch* m, int n) {
+    if (n == 0) return 0;
+    int maxq = -1;
+    for (int i = 0; i < n; i++) maxq = std::max(maxq, m[i].queryIdx);
+    std::vector<int> used(maxq + 1, -1);
+    for (int i = 0; i < n; i++) {
+        OracleMatch& mm = m[i];
+        if (used[mm.queryIdx] == -1) used[mm.queryIdx] = i;
+        else if (m[used[mm.queryIdx]].distance > mm.distance) {
+            m[used[mm.queryIdx]].queryIdx = -1;
+            used[mm.queryIdx] = i;
+        } else mm.queryIdx = -1;
+    }
+    int k = 0;
+    for (int i = 0; i < n; i++)
+        if (m[i].queryIdx != -1 && m[i].trainIdx != -1) m[k++] = m[i];
+    return k;
+}
+
+// The tracker's search by projection from the previous frame, System::_11946837405316294395 (src/utils/system.cpp:5921-6456, macro-obfuscated;
+// called first thing in tracking, :6559, with dist_thr = maxDescDistance*1.5 and proj_dist_thr = Params::projDistThr):
+// every keypoint of the PREVIOUS frame that carries a valid, non-bad map point (prev_row[i] >= 0: row of that point in ids/pos) is
+// projected with the current frame's pose guess (Frame::project(p, true, true), frame.h:140-161), the current frame's keypoints of
+// the SAME octave within proj_dist_thr * scaleFactors[octave] are scanned in kd-tree visit order with the order-dependent best /
+// second-best bookkeeping of the reference (a new best does not demote the old one), accepted when best < 0.7 * second, then
+// filter_ambiguous_query.  queryIdx = current keypoint, trainIdx = map point id, distance = Hamming.
+int oracle_track_projected(int n_prev, const int32_t* prev_octave, const uint8_t* prev_desc, const int32_t* prev_row, const uint32_t* ids,
+                           const float* pos, int n_kp, const float* kp_xy, const int32_t* kp_octave, const uint8_t* kp_desc,
+                           const float* scale_factors, int n_levels, float fx, float fy, float cx, float cy, const float* min_xy,
+                           const float* max_xy, const float* pose, float dist_thr, float proj_dist_thr, OracleMatch* out) {
+    (void)n_levels;
+    Tree T;
+    build(T, kp_xy, 2, n_kp);
+    std::vector<OracleMatch> matches;
+    std::vector<int> region;
+    const float nanv = std::numeric_limits<float>::quiet_NaN();
+    for (int i = 0; i < n_prev; i++) {
+        const int row = prev_row[i];
+        if (row < 0) continue;
+        const float* P = pos + 3 * (size_t)row;
+        // Frame::project(p3d, setNanIfDepthNegative = true, setNanIfDoNotProjectInImage = true)
+        float p2[2];
+        {
+            float rz = P[0] * pose[8] + P[1] * pose[9] + P[2] * pose[10] + pose[11];
+            if (rz < 0) p2[0] = p2[1] = nanv;
+            else {
+                const float rx = P[0] * pose[0] + P[1] * pose[1] + P[2] * pose[2] + pose[3];
+                const float ry = P[0] * pose[4] + P[1] * pose[5] + P[2] * pose[6] + pose[7];
+                rz = (float)(1. / rz);
+                p2[0] = ((fx * rx) * rz) + cx;
+                p2[1] = ((fy * ry) * rz) + cy;
+                if (!(p2[0] >= min_xy[0] && p2[1] >= min_xy[1] && p2[0] < max_xy[0] && p2[1] < max_xy[1])) p2[0] = p2[1] = nanv;
+            }
+        }
+        if (std::isnan(p2[0])) continue;
+        const int oct = prev_octave[i];
+        const float scale = scale_factors[oct];
+        radius_search(T, p2, proj_dist_thr * scale, region);
+        float best = (float)(dist_thr + 0.01), best2 = std::numeric_limits<float>::max();
+        int best_kp = -1;
+        for (int kp : region) {
+            if (kp_octave[kp] != oct) continue;   // getKeyPointsInRegion(.., oct, oct) and the explicit test are the same condition
+            const float d = hamming32(prev_desc + 32 * (size_t)i, kp_desc + 32 * (size_t)kp);
+            if (d < best) {
+                best = d;
+                best_kp = kp;
+            } else if (d < best2) best2 = d;
+        }
+        if (best_kp != -1 && best < 0.7 * best2) matches.push_back({best_kp, (int32_t)ids[row], 0, best});
+    }
+    int n = (int)matches.size();
+    n = oracle_filter_ambiguous_query(matches.data(), n);
+    for (int i = 0; i < n; i++) out[i] = matches[i];
+    return n;
+}
+
 }  // extern "C"

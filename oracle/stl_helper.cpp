@@ -25,6 +25,11 @@ int stl_retain_best(KP* kps, int count, int n_points) {
     }
     return count;
 }
+// std::sort of indices by keys[idx] with the host C++ runtime's own algorithm (what picoflann's kd-tree build calls for degenerate
+// cuts, /root/reference/src/basictypes/picoflann.h:310-318): the unstable introsort decides the order of equal keys
+void stl_sort_indices(uint32_t* idx, int n, const float* keys) {
+    std::sort(idx, idx + n, [keys](const uint32_t& a, const uint32_t& b) { return keys[a] < keys[b]; });
+}
 float stl_cosf(float x) { return std::cos(x); }
 float stl_sinf(float x) { return std::sin(x); }
 void stl_sincosf_array(const float* x, int n, float* c, float* s) {

@@ -30,6 +30,7 @@ struct uco_b200_ctx {
     uco_ba_state* ba = nullptr;
     int ba_mode = 0;          // 0 auto, 1 streamed kernels (ba.cu), 2 cluster-resident kernel (ba_cluster.cu)
     int ba_cluster_size = 0;  // CTAs per cluster of the cluster-resident solver (0 = default 8)
+    void* track_err_dev = nullptr;  // error words of the last track_batch_dev launch sequence (track.cu)
     int ba_host_threads = 0;  // worker threads of the host-side planner per batch call (0 = this process's share of the cores)
 };
 
@@ -46,6 +47,8 @@ enum {  // device workspace slots
     WS_TRI_IN, WS_TRI_OUT,
     WS_RANSAC_IN, WS_RANSAC_OUT,
     WS_UNDISTORT,
+    WS_KDTREE, WS_KDTREE_ERR,
+    WS_TRACK, WS_TRACK_ERR, WS_TRACK_IN, WS_TRACK_OUT,
     WS_COUNT
 };
 

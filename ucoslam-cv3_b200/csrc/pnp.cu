@@ -15,6 +15,7 @@
 // the classification after each round needs the values of the LAST evaluation (stale after a rejected trial, as in g2o).
 #include "common.cuh"
 #include "ba_math.cuh"
+#include "pnp_dev.cuh"
 #include <float.h>
 #include <math.h>
 #include <string.h>
@@ -26,34 +27,6 @@ constexpr int PNP_WARPS = PNP_THREADS / 32;
 constexpr int PNP_GROUP = 16;  // lanes cooperating on one marker edge
 constexpr int PNP_GROUPS = PNP_THREADS / PNP_GROUP;
 constexpr int NACC = 28;       // 21 (upper triangle of H) + 6 (b) + 1 (robust chi2)
-
-struct PnpHead {
-    int n, nm, off, moff;  // matches / markers of this problem and their offsets in the concatenated arrays
-    float pose44[16];
-    double fx, fy, cx, cy, bf, wm;  // wm = WeightedHubber weight of the marker edges (pnpsolver.cpp:298-300)
-};
-struct PnpOut {
-    float pose44[16];
-    double pose7[7];
-    int n_good;
-    int iters[4];
-    int pad;
-};
-struct PnpArrays {
-    const float* pts;    // 3 per match
-    const float* uv;     // 2 per match
-    const float* ur;     // 1
-    const float* isig;   // 1
-    const uint8_t* flg;  // bit 0 stereo, bit 1 stable
-    const float* mpose;  // 16 per marker
-    const float* msize;  // 1
-    const float* mobs;   // 8
-    double* chi2;        // scratch, per match
-    uint8_t* active;     // scratch, per match (level 0)
-    double* mchi2;       // scratch, per marker
-    uint8_t* mrobust;    // scratch, per marker
-    uint8_t* bad;        // out, per match
-};
 
 struct PnpShared {
     ba::Pose T, Tbak, T0;
@@ -462,6 +435,13 @@ __global__ void __launch_bounds__(PNP_THREADS) pose_only_kernel(const PnpHead* h
 inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace
+
+// device-resident launch shared with track.cu: n problems described by heads / arrays already in device memory
+int uco_pnp_launch_dev(uco_b200_ctx* ctx, int n, const PnpHead* heads_dev, const PnpArrays& A, PnpOut* outs_dev) {
+    pose_only_kernel<<<n, PNP_THREADS, 0, ctx->stream>>>(heads_dev, A, outs_dev);
+    UCO_LAUNCH_CHECK(ctx);
+    return UCO_OK;
+}
 
 extern "C" {
 

@@ -14,6 +14,7 @@
 // that only hold keypoints.  Arithmetic follows the reference expression by expression (f32 without FMA, the three double-precision
 // spots of cv::norm / 1./z / the kd-tree distances), see the comments.
 #include "common.cuh"
+#include "kdwalk.cuh"
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -199,9 +200,8 @@ struct ProjDev {
     float* best_dist;              // m
     uint8_t* visible;              // m
     unsigned long long* kp_owner;  // n_kp: min over map points of (distance << 32 | map point index)
+    int* err;                      // set when a walk overflowed its stack
 };
-
-constexpr int KD_STACK = 48;
 
 __global__ void __launch_bounds__(128) project_match_kernel(const __grid_constant__ ProjDev D) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -244,79 +244,30 @@ __global__ void __launch_bounds__(128) project_match_kernel(const __grid_constan
     if (view_cos < 0.98) radius_scale = (float)(radius_scale * 1.6);
     const double radius = (double)(radius_scale * D.max_reproj_dist);
     if (D.n_nodes == 0 || !(radius > 0)) return;
-    const double r2 = radius * radius;
     uint32_t md[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) md[k] = D.mp_desc[8 * (size_t)i + k];
-    // generalSearch / computeInitialDistances (picoflann.h:435-463): float accumulator of double terms
-    double d0 = 0, d1 = 0;
-    float distsq = 0;
-    {
-        const double e0 = q[0], e1 = q[1];
-        if (e0 < D.bbox[0]) { const double d = e0 - D.bbox[0]; d0 = d * d; distsq = (float)(distsq + d0); }
-        if (e0 > D.bbox[1]) { const double d = e0 - D.bbox[1]; d0 = d * d; distsq = (float)(distsq + d0); }
-        if (e1 < D.bbox[2]) { const double d = e1 - D.bbox[2]; d1 = d * d; distsq = (float)(distsq + d1); }
-        if (e1 > D.bbox[3]) { const double d = e1 - D.bbox[3]; d1 = d * d; distsq = (float)(distsq + d1); }
-    }
-    int st_node[KD_STACK];
-    double st_min[KD_STACK], st_d0[KD_STACK], st_d1[KD_STACK];
-    int sp = 0;
-    st_node[0] = 0; st_min[0] = (double)distsq; st_d0[0] = d0; st_d1[0] = d1; sp = 1;
     int best_kp = -1, best_level = 0, best_level2 = -1;
     float best = FLT_MAX, best2 = FLT_MAX;
-    while (sp > 0) {
-        sp--;
-        int node = st_node[sp];
-        const double mind = st_min[sp];
-        double e0 = st_d0[sp], e1 = st_d1[sp];
-        for (;;) {  // searchExactLevel (picoflann.h:556-600): nearest child first, the other one is deferred on the stack
-            const uco_kdnode N = D.nodes[node];
-            if (N.col < 0) {
-                for (int t = 0; t < N.leaf_count; t++) {
-                    const int kp = D.leaf_idx[N.leaf_begin + t];
-                    const uco_keypoint K = D.kps[kp];
-                    double dd = (double)(q[0] - K.x);   // L2::compute_distance: float difference, double square
-                    double sqd = dd * dd;
-                    if (!(sqd > r2)) {
-                        dd = (double)(q[1] - K.y);
-                        sqd += dd * dd;
-                    }
-                    if (!(sqd < r2)) continue;
-                    if (!(K.octave >= octave - 1 && K.octave <= octave)) continue;  // getKeyPointsInRegion's scale window
-                    const uint32_t* kd = D.kp_desc + 8 * (size_t)kp;
-                    int pc = 0;
+    const bool walked = kd_radius_walk(D.nodes, D.leaf_idx, D.bbox, D.kps, q, radius, [&](int kp, const uco_keypoint& K) {
+        if (!(K.octave >= octave - 1 && K.octave <= octave)) return;  // getKeyPointsInRegion's scale window
+        const uint32_t* kd = D.kp_desc + 8 * (size_t)kp;
+        int pc = 0;
 #pragma unroll
-                    for (int w = 0; w < 8; w++) pc += __popc(md[w] ^ kd[w]);
-                    const float dsc = (float)pc;
-                    if (dsc < D.min_desc_dist) {   // map.cpp:722-737, order dependent on purpose
-                        if (dsc < best) {
-                            best = dsc;
-                            best_kp = kp;
-                            best_level = K.octave;
-                        } else if (dsc < best2) {
-                            best2 = dsc;
-                            best_level2 = K.octave;
-                        }
-                    }
-                }
-                break;
+        for (int w = 0; w < 8; w++) pc += __popc(md[w] ^ kd[w]);
+        const float dsc = (float)pc;
+        if (dsc < D.min_desc_dist) {   // map.cpp:722-737, order dependent on purpose
+            if (dsc < best) {
+                best = dsc;
+                best_kp = kp;
+                best_level = K.octave;
+            } else if (dsc < best2) {
+                best2 = dsc;
+                best_level2 = K.octave;
             }
-            const double val = (double)q[N.col];
-            const double diff1 = val - (double)N.divlow, diff2 = val - (double)N.divhigh;
-            int bestc, other;
-            double cut;
-            if (diff1 + diff2 < 0) { bestc = N.left; other = N.right; cut = diff2 * diff2; }
-            else { bestc = N.right; other = N.left; cut = diff1 * diff1; }
-            const float dst = (float)(N.col == 0 ? e0 : e1);
-            const double mind2 = mind + cut - (double)dst;
-            if (mind2 <= r2 && sp < KD_STACK) {
-                st_node[sp] = other; st_min[sp] = mind2;
-                st_d0[sp] = N.col == 0 ? cut : e0; st_d1[sp] = N.col == 0 ? e1 : cut;
-                sp++;
-            }
-            node = bestc;   // mindistsq and dists are passed on unchanged to the nearer child
         }
-    }
+    });
+    if (!walked) atomicExch(D.err, 1);
     if (best_kp < 0) return;
     if (best_level2 == best_level && (double)best > 0.8 * (double)best2) return;
     D.best_kp[i] = best_kp;
@@ -386,7 +337,7 @@ extern "C" int uco_b200_match_projected(uco_b200_ctx* ctx, const uco_mappoints* 
     for (int i = 0; i < fr->n_nodes; i++) {
         const uco_kdnode& N = fr->nodes[i];
         if (N.col < 0) n_leaf = std::max(n_leaf, N.leaf_begin + N.leaf_count);
-        else if ((unsigned)N.left >= (unsigned)fr->n_nodes || (unsigned)N.right >= (unsigned)fr->n_nodes || N.col > 1)
+        else if ((unsigned)N.left >= (unsigned)fr->n_nodes || (unsigned)N.right >= (unsigned)fr->n_nodes || N.col > 1 || N.left <= i || N.right <= i)  // children follow their parent in picoflann's numbering: rules out cycles
             return uco_fail(ctx, UCO_E_INVALID, "match_projected: kd-tree node %d is malformed", i);
     }
     for (int i = 0; i < n_leaf; i++)
@@ -433,6 +384,8 @@ extern "C" int uco_b200_match_projected(uco_b200_ctx* ctx, const uco_mappoints* 
     memcpy(D.pose, pose_f2g, 64);
     D.min_desc_dist = min_desc_dist; D.max_reproj_dist = max_reproj_dist;
     D.best_kp = (int*)(d + o_bkp); D.best_dist = (float*)(d + o_bd); D.visible = d + o_vis; D.kp_owner = (unsigned long long*)(d + o_own);
+    D.err = (int*)(d + o_n) + 1;
+    UCO_CUDA(ctx, cudaMemsetAsync(d + o_n, 0, 8, s));
     project_match_kernel<<<(m + 127) / 128, 128, 0, s>>>(D);
     UCO_LAUNCH_CHECK(ctx);
     project_compact_kernel<<<1, 1024, 0, s>>>(D, (const uint32_t*)(d + o_ids), (uco_match*)(d + o_out), (int*)(d + o_n));
@@ -440,8 +393,9 @@ extern "C" int uco_b200_match_projected(uco_b200_ctx* ctx, const uco_mappoints* 
     int* hn = (int*)(ho + sizeof(uco_match) * (size_t)m + (((size_t)m + 15) & ~(size_t)15));
     UCO_CUDA(ctx, cudaMemcpyAsync(ho, d + o_out, sizeof(uco_match) * (size_t)m, cudaMemcpyDeviceToHost, s));
     UCO_CUDA(ctx, cudaMemcpyAsync(ho + sizeof(uco_match) * (size_t)m, d + o_vis, (size_t)m, cudaMemcpyDeviceToHost, s));
-    UCO_CUDA(ctx, cudaMemcpyAsync(hn, d + o_n, 4, cudaMemcpyDeviceToHost, s));
+    UCO_CUDA(ctx, cudaMemcpyAsync(hn, d + o_n, 8, cudaMemcpyDeviceToHost, s));
     UCO_CUDA(ctx, cudaStreamSynchronize(s));
+    if (hn[1]) return uco_fail(ctx, UCO_E_CAPACITY, "match_projected: the kd-tree is deeper than the %d deferred branches the device walk keeps", KD_STACK);
     *n_out = *hn;
     memcpy(out, ho, sizeof(uco_match) * (size_t)*hn);
     if (visible) memcpy(visible, ho + sizeof(uco_match) * (size_t)m, (size_t)m);

@@ -12,6 +12,7 @@ PKG_ROOT = os.path.abspath(os.path.join(_HERE, "..", ".."))
 LIB_PATH = os.path.join(PKG_ROOT, "lib", "libucoslam_b200.so")
 
 UCO_KNN_HEAP, UCO_KNN_SORTED = 0, 1
+UCO_KDTREE_DEV_MAX_POINTS = 4096
 _c = ctypes
 _vp, _i, _sz, _u64 = _c.c_void_p, _c.c_int, _c.c_size_t, _c.c_uint64
 
@@ -34,6 +35,12 @@ SIGNATURES = {
     "uco_b200_kdtree_build": (_i, [_vp, _sz, _i, _vp, _i, _vp, _vp, _vp]),
     "uco_b200_kdtree_parse": (_i, [_vp, _sz, _vp, _i, _vp, _i, _vp, _vp, _vp]),
     "uco_b200_match_projected": (_i, [_vp, _vp, _vp, _vp, _c.c_float, _c.c_float, _vp, _vp, _vp]),
+    "uco_b200_kdtree_build_batch_dev": (_i, [_vp, _i, _vp, _sz, _vp, _i, _vp, _i, _vp, _vp, _vp]),
+    "uco_b200_kdtree_build_dev": (_i, [_vp, _vp, _sz, _i, _vp, _i, _vp, _vp, _vp]),
+    "uco_b200_probe_sort_indices": (_i, [_vp, _i, _vp]),
+    "uco_b200_track_batch_dev": (_i, [_vp, _vp, _vp, _vp]),
+    "uco_b200_track_batch": (_i, [_vp, _vp, _vp, _vp]),
+    "uco_b200_track_projected": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _c.c_float, _c.c_float, _vp, _vp]),
     "uco_b200_ba_set_host_threads": (_i, [_vp, _i]),
     "uco_b200_comm_unique_id": (_i, [_vp]),
     "uco_b200_comm_create": (_i, [_vp, _vp, _i, _i, _vp]),
@@ -164,6 +171,44 @@ def kdtree_build(xy):
     if load().uco_b200_kdtree_build(_p(xy), 8, n, _p(nodes), len(nodes), _p(leaf), _p(bbox), ctypes.byref(k)) != 0:
         raise UcoError("kdtree_build failed")
     return nodes[:k.value].copy(), leaf[:n].copy(), bbox
+
+
+def probe_sort_indices(keys):
+    """libstdc++ std::sort replay (csrc/sort_exact.h) of the indices 0..n-1 by keys[idx]"""
+    keys = np.ascontiguousarray(keys, np.float32)
+    idx = np.arange(len(keys), dtype=np.uint32)
+    rc = load().uco_b200_probe_sort_indices(_p(idx), len(keys), _p(keys))
+    assert rc == 0
+    return idx
+
+
+class TrackParams(ctypes.Structure):  # uco_track_params
+    _fields_ = [("max_desc_dist", ctypes.c_float), ("proj_dist_thr", ctypes.c_float), ("fx", ctypes.c_float), ("fy", ctypes.c_float),
+                ("cx", ctypes.c_float), ("cy", ctypes.c_float), ("bf", ctypes.c_float), ("min_xy", ctypes.c_float * 2),
+                ("max_xy", ctypes.c_float * 2), ("n_levels", ctypes.c_int32), ("scale_factors", ctypes.c_float * 32)]
+
+    def __init__(self, sc=None, max_desc_dist=50.0, proj_dist_thr=15.0):
+        super().__init__()
+        self.max_desc_dist, self.proj_dist_thr = max_desc_dist, proj_dist_thr
+        if sc is not None:
+            self.fx, self.fy, self.cx, self.cy, self.bf = sc["fx"], sc["fy"], sc["cx"], sc["cy"], sc.get("bf", 0.0)
+            self.min_xy[:] = [float(v) for v in sc["min_xy"]]
+            self.max_xy[:] = [float(v) for v in sc["max_xy"]]
+            sf = np.asarray(sc["scale_factors"], np.float32)
+            self.n_levels = len(sf)
+            for i, v in enumerate(sf):
+                self.scale_factors[i] = float(v)
+
+
+class TrackBatch(ctypes.Structure):  # uco_track_batch
+    _fields_ = [("n_frames", ctypes.c_int32), ("kp_cap", ctypes.c_int32), ("prev_cap", ctypes.c_int32), ("map_cap", ctypes.c_int32),
+                ("flags", ctypes.c_int32)] + [(k, ctypes.c_void_p) for k in (
+                    "kps", "desc", "n_kp", "depth", "prev_kps", "prev_desc", "prev_n_kp", "prev_mp_row", "map_n", "mp_id", "mp_pos",
+                    "mp_normal", "mp_min_dist", "mp_max_dist", "mp_desc", "mp_stable", "mp_local", "pose_prior")]
+
+
+class TrackOut(ctypes.Structure):  # uco_track_out
+    _fields_ = [(k, ctypes.c_void_p) for k in ("matches", "n_matches", "pose", "n_good", "status", "n_tbp", "visible")]
 
 
 def kdtree_parse(stream_bytes):
@@ -428,6 +473,78 @@ class Context:
         self._chk(self.lib.uco_b200_match_projected(self.h, ctypes.addressof(mp), ctypes.addressof(fr), _p(pose), min_desc_dist,
                                                     max_reproj_dist, _p(out), ctypes.byref(n), _p(vis)))
         return out[:n.value].copy(), vis[:m].copy()
+
+    # -- K16 / K17 ----------------------------------------------------------------------------------------------
+    def kdtree_build_dev(self, xy):
+        """the frame's kd-tree built on the device: (nodes[KDNODE_DTYPE], leaf_idx i32, bbox f64[4]) like kdtree_build"""
+        xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+        n = len(xy)
+        cap = 2 * n + 4
+        nodes, leaf, bbox, k = np.zeros(cap, KDNODE_DTYPE), np.zeros(max(n, 1), np.int32), np.zeros(4), ctypes.c_int(0)
+        self._chk(self.lib.uco_b200_kdtree_build_dev(self.h, _p(xy), 8, n, _p(nodes), cap, _p(leaf), _p(bbox), ctypes.byref(k)))
+        return nodes[:k.value].copy(), leaf[:n].copy(), bbox
+
+    def track_projected(self, sc, dist_thr, proj_dist_thr, tree=None):
+        """System's search by projection from the previous frame on a scene dict (synth.synth_track_scene keys) -> matches"""
+        A = lambda k, dt: np.ascontiguousarray(sc[k], dt)
+        ids, pos = A("mp_id", np.uint32), A("mp_pos", np.float32)
+        kdesc, sf, pose = A("kp_desc", np.uint8), A("scale_factors", np.float32), A("pose44", np.float32)
+        kxy, koct = A("kp_xy", np.float32).reshape(-1, 2), A("kp_octave", np.int32)
+        kps = np.zeros(len(kxy), KP_DTYPE)
+        kps["x"], kps["y"], kps["octave"] = kxy[:, 0], kxy[:, 1], koct
+        pkps = np.zeros(len(sc["prev_octave"]), KP_DTYPE)
+        pkps["octave"] = sc["prev_octave"]
+        pdesc, prow = A("prev_desc", np.uint8), A("prev_mp_row", np.int32)
+        nodes, leaf, bbox = tree if tree is not None else kdtree_build(kxy)
+        nodes, leaf = np.ascontiguousarray(nodes), np.ascontiguousarray(leaf, np.int32)
+        mp = MapPoints(len(ids), _p(ids), _p(pos), None, None, None, None)
+        fr = FrameView(len(kps), _p(kps), _p(kdesc), 32, len(nodes), _p(nodes), _p(leaf), (ctypes.c_double * 4)(*bbox), len(sf), _p(sf),
+                       sc["fx"], sc["fy"], sc["cx"], sc["cy"], (ctypes.c_float * 2)(*sc["min_xy"]), (ctypes.c_float * 2)(*sc["max_xy"]))
+        out, n = np.zeros(max(len(pkps), 1), MATCH_DTYPE), ctypes.c_int(0)
+        self._chk(self.lib.uco_b200_track_projected(self.h, len(pkps), _p(pkps), _p(pdesc), _p(prow), ctypes.addressof(mp),
+                                                    ctypes.addressof(fr), _p(pose), dist_thr, proj_dist_thr, _p(out), ctypes.byref(n)))
+        return out[:n.value].copy()
+
+    @staticmethod
+    def track_pack(scs):
+        """flatten scene dicts (synth.synth_track_scene) into the fixed-stride arrays of uco_track_batch"""
+        F = len(scs)
+        kc = max(len(s["kp_octave"]) for s in scs)
+        pc = max(len(s["prev_octave"]) for s in scs)
+        mc = max(len(s["mp_id"]) for s in scs)
+        a = dict(kps=np.zeros((F, kc), KP_DTYPE), desc=np.zeros((F, kc, 32), np.uint8), n_kp=np.zeros(F, np.int32),
+                 prev_kps=np.zeros((F, pc), KP_DTYPE), prev_desc=np.zeros((F, pc, 32), np.uint8), prev_n_kp=np.zeros(F, np.int32),
+                 prev_mp_row=np.full((F, pc), -1, np.int32), map_n=np.zeros(F, np.int32), mp_id=np.zeros((F, mc), np.uint32),
+                 mp_pos=np.zeros((F, mc, 3), np.float32), mp_normal=np.zeros((F, mc, 3), np.float32), mp_min_dist=np.zeros((F, mc), np.float32),
+                 mp_max_dist=np.zeros((F, mc), np.float32), mp_desc=np.zeros((F, mc, 32), np.uint8), mp_stable=np.ones((F, mc), np.uint8),
+                 mp_local=np.ones((F, mc), np.uint8), pose_prior=np.zeros((F, 16), np.float32))
+        for f, s in enumerate(scs):
+            nk, npv, nm = len(s["kp_octave"]), len(s["prev_octave"]), len(s["mp_id"])
+            xy = np.asarray(s["kp_xy"], np.float32).reshape(-1, 2)
+            a["kps"][f, :nk]["x"], a["kps"][f, :nk]["y"], a["kps"][f, :nk]["octave"] = xy[:, 0], xy[:, 1], s["kp_octave"]
+            a["desc"][f, :nk] = s["kp_desc"]; a["n_kp"][f] = nk
+            a["prev_kps"][f, :npv]["octave"] = s["prev_octave"]; a["prev_desc"][f, :npv] = s["prev_desc"]; a["prev_n_kp"][f] = npv
+            a["prev_mp_row"][f, :npv] = s["prev_mp_row"]; a["map_n"][f] = nm; a["mp_id"][f, :nm] = s["mp_id"]
+            a["mp_pos"][f, :nm] = s["mp_pos"]; a["mp_normal"][f, :nm] = s["mp_normal"]; a["mp_min_dist"][f, :nm] = s["mp_min_dist"]
+            a["mp_max_dist"][f, :nm] = s["mp_max_dist"]; a["mp_desc"][f, :nm] = s["mp_desc"]
+            if "mp_stable" in s: a["mp_stable"][f, :nm] = s["mp_stable"]
+            if "mp_local" in s: a["mp_local"][f, :nm] = s["mp_local"]
+            a["pose_prior"][f] = np.asarray(s["pose44"], np.float32).reshape(16)
+        return a, (F, kc, pc, mc)
+
+    def track_batch(self, scs, prm=None, packed=None):
+        """the tracker's main branch for a batch of independent frames (host buffers) -> list of dicts(matches, pose44, n_good, status, n_tbp, visible)"""
+        a, (F, kc, pc, mc) = packed or self.track_pack(scs)
+        prm = prm or TrackParams(scs[0])
+        tb = TrackBatch(F, kc, pc, mc, 0, *[_p(a[k]) if k in a else None for k in (
+            "kps", "desc", "n_kp", "depth", "prev_kps", "prev_desc", "prev_n_kp", "prev_mp_row", "map_n", "mp_id", "mp_pos", "mp_normal",
+            "mp_min_dist", "mp_max_dist", "mp_desc", "mp_stable", "mp_local", "pose_prior")])
+        o = dict(matches=np.zeros((F, kc), MATCH_DTYPE), n_matches=np.zeros(F, np.int32), pose=np.zeros((F, 16), np.float32),
+                 n_good=np.zeros(F, np.int32), status=np.zeros(F, np.int32), n_tbp=np.zeros(F, np.int32), visible=np.zeros((F, mc), np.uint8))
+        to = TrackOut(*[_p(o[k]) for k in ("matches", "n_matches", "pose", "n_good", "status", "n_tbp", "visible")])
+        self._chk(self.lib.uco_b200_track_batch(self.h, ctypes.addressof(tb), ctypes.addressof(prm), ctypes.addressof(to)))
+        return [dict(matches=o["matches"][f, :o["n_matches"][f]].copy(), pose44=o["pose"][f].copy(), n_good=int(o["n_good"][f]),
+                     status=int(o["status"][f]), n_tbp=int(o["n_tbp"][f]), visible=o["visible"][f, :a["map_n"][f]].copy()) for f in range(F)]
 
     # -- multi-GPU ----------------------------------------------------------------------------------------------
     def comm_create(self, rank=0, world=1, broadcast=None):

@@ -285,6 +285,48 @@ def synth_projection_scene(seed, n_kp=2000, n_mp=3000, n_levels=8, scale=1.2, w=
                 min_xy=np.array([0, 0], np.float32), max_xy=np.array([w, h], np.float32))
 
 
+def synth_track_scene(seed, n_kp=2000, n_mp=3000, n_prev=1800, prior_noise=(0.004, 0.01), **kw):
+    """A tracking problem as the tracker's main branch sees it (System::_11166622111371682966, src/utils/system.cpp:6460-6960): the
+    projection scene of synth_projection_scene (current frame + map, consistent with a true pose up to ~1 px) plus a PREVIOUS frame
+    whose keypoints carry map points (prev_mp_row, some -1, a few shared), descriptors a few bits off the map point's and mostly
+    the octave of the keypoint the point lands on, and a pose prior a few pixels off the true pose."""
+    sc = synth_projection_scene(seed, n_kp=n_kp, n_mp=n_mp, **kw)
+    rng = np.random.default_rng(seed + 77)
+    n_mp = len(sc["mp_id"])
+    T = sc["pose44"].reshape(4, 4).astype(np.float64)
+    # which current keypoint each map point lands next to (nearest projection), to give the previous keypoint a plausible octave
+    X = sc["mp_pos"].astype(np.float64)
+    Xc = X @ T[:3, :3].T + T[:3, 3]
+    z = np.where(np.abs(Xc[:, 2]) < 1e-9, 1e-9, Xc[:, 2])
+    uv = np.stack([Xc[:, 0] / z * sc["fx"] + sc["cx"], Xc[:, 1] / z * sc["fy"] + sc["cy"]], 1)
+    kxy = sc["kp_xy"].astype(np.float64)
+    rows = rng.integers(0, n_mp, n_prev).astype(np.int32)
+    rows[rng.random(n_prev) < 0.15] = -1
+    poct = np.zeros(n_prev, np.int32)
+    pdesc = np.zeros((n_prev, 32), np.uint8)
+    n_levels = len(sc["scale_factors"])
+    for i in range(n_prev):
+        r = rows[i]
+        if r < 0:
+            poct[i] = rng.integers(0, n_levels)
+            pdesc[i] = rng.integers(0, 256, 32)
+            continue
+        j = int(np.argmin(((kxy - uv[r]) ** 2).sum(1)))
+        poct[i] = sc["kp_octave"][j] if rng.random() > 0.08 else rng.integers(0, n_levels)
+        d = sc["kp_desc"][j].copy() if rng.random() > 0.2 else sc["mp_desc"][r].copy()
+        for b in rng.integers(0, 256, int(rng.integers(0, 50))):
+            d[b >> 3] ^= 1 << (b & 7)
+        pdesc[i] = d
+    dT = np.eye(4)
+    dT[:3, :3] = _rodrigues(rng.normal(0, prior_noise[0], 3))
+    dT[:3, 3] = rng.normal(0, prior_noise[1], 3)
+    sc["pose_true44"] = sc["pose44"].copy()
+    sc["pose44"] = (dT @ T).astype(np.float32).reshape(16)
+    sc.update(prev_octave=poct, prev_desc=pdesc, prev_mp_row=rows, mp_stable=(rng.random(n_mp) > 0.2).astype(np.uint8),
+              mp_local=(rng.random(n_mp) > 0.1).astype(np.uint8), bf=0.0)
+    return sc
+
+
 def synth_stereo(seed, w=640, h=480, n=1500, max_disp=48.0, outlier_frac=0.2, tie_frac=0.05):
     """A seeded rectified stereo pair as FrameExtractor::processStereo sees it (SURVEY.md 8f rank 3): block-noise images where the
     right image is the left one shifted by a smoothly varying sub-pixel disparity, left keypoints with octaves and 256-bit
