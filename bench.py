@@ -1,35 +1,50 @@
 #!/usr/bin/env python
-"""bench.py — frames/s of the per-frame tracking hot path on B200 (BASELINE.json metric), one JSON line on rank 0.
+"""bench.py — frames/s of UcoSLAM's per-frame tracking hot path on B200 (BASELINE.json metric), one JSON line on rank 0.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--frames F]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--frames F] [--res 640x480|1280x720]
 
-A step is one pass of the hot path over one batch of F synthetic frames of BASELINE config 2 (640x480 mono, 2000 ORB
-keypoints/frame, 8 levels x1.2, local-BA window 10 KF): ORB extraction of every frame, Hamming k-NN (k=10) of every frame
-against its predecessor, and one local bundle adjustment (10 free + 2 fixed keyframes, 2000 points, ~15k observations, the
-reference's two-stage 5 + 10 LM iterations) per KF_EVERY = 8 frames.  Every stage runs through the C ABI of libucoslam_b200.so
-(no CPU fallback: the library refuses to create a context without a CUDA device).
-  value   : frames/s with the step's input frames already resident in HBM (CUDA events on the context stream, L2 flushed
-            between timed steps, max over ranks)
-  e2e     : the same work through the host-buffer C-ABI calls (pinned host frames in, keypoints/descriptors/matches out;
-            H2D and D2H copies inside the timed region)
-  roofline: the dominant kernel of the step, timed live with CUDA events on the launching stream
-  cpu_baseline / --impl reference : the CPU path on this box's host cores (see DESIGN.md "Measurement")
-Multi-GPU: frames shard across ranks (independent units, no data-path collective) -> weak scaling.
+A step is one pass of the hot path over F INDEPENDENT synthetic frames (streams / cameras) of BASELINE config 2 (640x480 mono,
+2000 ORB keypoints/frame, 8 levels x1.2, local-BA window 10 KF), in the order the reference runs it (src/utils/system.cpp:6460-6960
+per frame, src/utils/mapmanager.cpp per keyframe):
+  per frame          ORB extraction -> kd-tree of the keypoints -> search by projection from the previous frame -> solvePnp ->
+                     Map::matchFrameToMapPoints over the local map -> filter_ambiguous_query -> solvePnp
+  per keyframe       (one frame in KF_EVERY = 8) fbow transform of its descriptors (computeBow), FrameMatcher (k-NN + filters)
+                     against its 7 neighbouring frames (new-map-point creation), one local bundle adjustment (10 free + 2 fixed
+                     keyframes, 2000 points, ~15k observations, the reference's two-stage 5 + 10 LM iterations)
+Every stage runs through the C ABI of libucoslam_b200.so (no CPU fallback: the library refuses to create a context without a CUDA
+device).
+  value   : frames/s with the step's input frames already resident in HBM (CUDA events on the tracker stream, L2 flushed between
+            timed steps, max over ranks)
+  e2e     : the same work through the host-buffer C-ABI calls (pinned host frames in; keypoints, descriptors, poses, match lists,
+            bags of words, BA results out; H2D and D2H copies inside the timed region)
+  roofline: the kernel with the largest SM x time share of the step against the roof that bounds it; `roofline_stages` lists every
+            stage the same way (INT-ALU issue rate for the extractor, popc rate for the k-NN, FP64 rate of the occupied SMs for BA)
+  cpu_baseline / --impl reference : the same step on this box's host cores through the reference's own code where it compiles
+            here (g2o, xflann, fbow, picoflann) and the cv2-backed restatement elsewhere (see DESIGN.md "Measurement")
+Multi-GPU: frames shard across ranks (independent units, no data-path collective) -> weak scaling.  Under torchrun the line also
+carries `collective_paths`: config 4 (row-sharded 10^6-descriptor map, NCCL all-gather) and config 5 (landmark-sharded global BA,
+NCCL all-reduce) timed on all ranks.
 """
 import argparse, json, os, subprocess, sys, threading, time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "ucoslam-cv3_b200", "python"))
 
-W, H, KPTS, K_NN = 640, 480, 2000, 10
+W, H, KPTS, K_NN, FOCAL = 640, 480, 2000, 10, 525.0
 METRIC = "frames/sec (ORB+match+local-BA) 640x480 mono"
 WORKLOAD = "config2: 640x480 mono tracking, 2000 ORB kpts/frame, local-BA window=10 KF"
-STAGES = ["orb_extract", "hamming_knn_match", "local_ba"]
-KF_EVERY = 8          # one keyframe (= one local-BA call, mapmanager.cpp:4005) per KF_EVERY frames
+STAGES = ["orb_extract", "kdtree_build", "track_by_projection", "pose_only_lm", "local_map_match", "pose_only_lm",
+          "bow_transform(per KF)", "frame_match_vs_7_neighbours(per KF)", "local_ba(per KF)"]
+KF_EVERY = 8          # one keyframe (= one computeBow + new-point matching + local-BA call, mapmanager.cpp:4005) per KF_EVERY frames
 BA_WINDOW = dict(n_poses=12, n_fixed=2, n_points=2000)   # 10 free KFs + 2 fixed observers, ~15k observations, nIters = 5
 BA_ITERS = 5
+MAX_DESC_DIST, PROJ_DIST_THR = 50.0, 15.0                          # ORBextractor.h:105, ucoslamtypes.cpp:49
 N_MAPPERS = int(os.environ.get("UCO_BENCH_MAPPERS", "4"))          # mapper contexts alternating between steps
 BA_CLUSTER = int(os.environ.get("UCO_BENCH_BA_CLUSTER", "4"))       # CTAs per BA cluster (0 = library default 8)
+SM_COUNT, SM_GHZ = 148, 1.965
+PEAK_ALU = 64 * SM_COUNT * SM_GHZ * 1e9      # alu-pipe thread-instructions/s (16 lanes/clk/SMSP, B300_MICROARCH.md "Pipe rates")
+PEAK_POPC = 16 * SM_COUNT * SM_GHZ * 1e9     # popc32/s
+PEAK_FP64_SM = 2 * 64 * SM_GHZ * 1e9 / 2     # DFMA flop/s per SM (64 DFMA lanes/clk/SM at half rate: 2 flop x 32/clk), nominal
 
 
 def parse():
@@ -40,16 +55,29 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=64, help="frames per step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra sections (720p, single-frame latency, ATE, collective paths)")
     ap.add_argument("--res", default="640x480", choices=["640x480", "1280x720"],
                     help="640x480 / 2000 keypoints = BASELINE config 2 (the metric's configuration, default); 1280x720 / 4000 keypoints = the "
                          "mono part of config 3 (north_star asks for both stream sizes)")
     a = ap.parse_args()
     if a.res == "1280x720":
-        global W, H, KPTS, METRIC, WORKLOAD
-        W, H, KPTS = 1280, 720, 4000
-        METRIC = "frames/sec (ORB+match+local-BA) 1280x720 mono"
-        WORKLOAD = "config3 (mono part): 1280x720 tracking, 4000 ORB kpts/frame, local-BA window=10 KF"
+        set_res_720p()
     return a
+
+
+def set_res_720p():
+    global W, H, KPTS, METRIC, WORKLOAD, FOCAL
+    W, H, KPTS, FOCAL = 1280, 720, 4000, 1050.0
+    METRIC = "frames/sec (ORB+match+local-BA) 1280x720 mono"
+    WORKLOAD = "config3 (mono part): 1280x720 tracking, 4000 ORB kpts/frame, local-BA window=10 KF"
+
+
+def config_common(n_ba):
+    """keys shared by both arms (the driver compares them)"""
+    return {"workload": WORKLOAD, "stages": STAGES, "kf_every": KF_EVERY,
+            "ba_window": "12 KF (2 fixed), 2000 points, ~15k observations, nIters=5", "ba_windows_per_%d_frames" % KF_EVERY: 1,
+            "tracking_problem": "independent per frame: previous frame (2000 keypoints, each with a map point) + local map of ~4000 points + "
+                                "pose prior = previous pose; thresholds maxDescDistance=50, projDistThr=15"}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -89,136 +117,179 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
-def synth_clip(n_frames, seed):
-    """Seeded synthetic clip: perspective views of a multi-octave block-noise texture along a smooth camera path
-    (SURVEY.md 8(d)); FAST-dense, so every frame yields the full 2000 keypoints."""
-    import numpy as np, cv2
-    rng = np.random.default_rng(seed)
-    size = 2048 if W <= 640 else 4096
-    acc = np.zeros((size, size), np.float64)
-    amp = 1.0
-    for blk in (64, 32, 16, 8, 4):
-        n = size // blk
-        acc += amp * np.kron(rng.random((n, n)), np.ones((blk, blk)))
-        amp *= 0.5
-    acc -= acc.min()
-    tex = (acc / acc.max() * 255).astype(np.uint8)
-    out = np.empty((n_frames, H, W), np.uint8)
-    for i in range(n_frames):
-        t = i * 0.02
-        c, s = np.cos(0.15 * np.sin(t)), np.sin(0.15 * np.sin(t))
-        zoom = 1.6 + 0.2 * np.sin(0.7 * t)
-        Hm = np.array([[c * zoom, -s * zoom, 300 + 120 * t], [s * zoom, c * zoom, 400 + 40 * np.sin(t)],
-                       [1e-4 * np.sin(t), 5e-5, 1.0]])
-        out[i] = cv2.warpPerspective(tex, Hm, (W, H), flags=cv2.INTER_LINEAR | cv2.WARP_INVERSE_MAP,
-                                     borderMode=cv2.BORDER_REFLECT_101)
-    return out
-
-
-# ---------------------------------------------------------------------------------------------------------------------
 def ba_windows(n, seed):
     from ucoslam_b200.synth import synth_ba_problem
     return [synth_ba_problem(seed + i, **BA_WINDOW) for i in range(n)]
 
 
-def cpu_reference_step(frames, oracle_py, orb_oracle, have_xflann, windows=()):
-    """The reference's CPU path for the same stages: ORB extraction of every frame (cv2-backed restatement of
-    ORBextractor.cpp: the reference itself cannot be linked without OpenCV C++ headers) + FrameMatcher_Flann's
-    xflann HKMeans(32,0) build + 16-check k-NN against the previous frame (the reference's own code)."""
-    prev = None
-    for f in frames:
-        k, d = orb_oracle.extract(f, KPTS)
-        if prev is not None and len(d) and len(prev):
-            if have_xflann:
-                oracle_py.ref_xflann_knn(d, prev, K_NN, 1, 16, 0)
-            else:
-                oracle_py.hamming_knn(d, prev, K_NN, 0)
-        prev = d
-    for pb in windows:  # the reference's own g2o + typesg2o.h (oracle/_ref) when it was built, else the C restatement
+def kf_groups(n_frames):
+    """(keyframe, its neighbours) per group of KF_EVERY consecutive frames: the last frame of a group is the keyframe"""
+    return [(g + KF_EVERY - 1, list(range(g, g + KF_EVERY - 1))) for g in range(0, n_frames - KF_EVERY + 1, KF_EVERY)]
+
+
+def camera():
+    from ucoslam_b200 import workload
+    return workload.Camera(W, H, FOCAL)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the same step on the host cores
+def cpu_step(imgs, scenes, windows, mods, voc, split):
+    """one CPU pass over the frames: per frame extract + the tracker's sequence, per keyframe bag of words + frame matcher against
+    its neighbours + local BA.  `split` accumulates seconds per stage."""
+    oracle_py, orb_oracle, have_ref = mods
+    from ucoslam_b200 import workload
+    pnp = oracle_py.ref_pose_only if have_ref else oracle_py.pose_only
+    feats = []
+    for img, sc in zip(imgs, scenes):
+        t0 = time.perf_counter()
+        k, d = orb_oracle.extract(img, KPTS)
+        t1 = time.perf_counter()
+        oracle_py.track_frame(workload.with_current(sc, k, d), MAX_DESC_DIST, PROJ_DIST_THR, pnp=pnp)
+        t2 = time.perf_counter()
+        split["orb_extract"] += t1 - t0
+        split["track_sequence"] += t2 - t1
+        feats.append((k, d))
+    for (kf, nb), pb in zip(kf_groups(len(imgs)), windows):
+        t0 = time.perf_counter()
+        if voc is not None:
+            voc.transform(feats[kf][1], 3)
+        t1 = time.perf_counter()
+        r = oracle_py.ref_frame_match_multi(feats[kf][1], feats[kf][0], [feats[i][1] for i in nb], [feats[i][0] for i in nb],
+                                            MAX_DESC_DIST * 2, 0.6, True, 1 << 30) if have_ref else None
+        if r is None:
+            for i in nb:
+                oracle_py.frame_match(feats[i][1], feats[i][0], feats[kf][1], feats[kf][0], MAX_DESC_DIST * 2, 0.6, True, 1 << 30)
+        t2 = time.perf_counter()
         if oracle_py.ref_ba_optimize(pb, BA_ITERS) is None:
             oracle_py.ba_optimize(pb, BA_ITERS)
+        t3 = time.perf_counter()
+        split["bow_transform"] += t1 - t0
+        split["frame_match"] += t2 - t1
+        split["local_ba"] += t3 - t2
 
 
-def cpu_baseline_info(have_xflann, n):
+def cpu_info(have_ref, n):
     return {"cores": 1, "kind": "port",
-            "sample": "%d frames + %d local-BA windows: ORB = Python/cv2-4.13 restatement of ORBextractor.cpp (blur/resize/FAST "
-                      "native OpenCV, 1 thread; interpreter overhead included), match = %s, BA = the reference's g2o + "
-                      "typesg2o.h compiled from its sources (oracle/_ref), 1 thread as the reference runs it" % (
-                          n, max(1, n // KF_EVERY), "the reference's xflann HKMeans(32,0) build + 16-check search, 1 thread"
-                          if have_xflann else "exact linear port")}
+            "sample": "%d frames + %d keyframes: ORB = Python/cv2-4.13 restatement of ORBextractor.cpp (blur/resize/FAST native OpenCV, 1 "
+                      "thread; interpreter overhead included - the reference's C++ extractor cannot be built here, expect it to be "
+                      "several times cheaper than this arm's ORB share); tracker sequence = C/C++ restatements of system.cpp / map.cpp on "
+                      "the reference's picoflann tree order with solvePnp by %s; per keyframe: fbow transform by %s, FrameMatcher = %s, "
+                      "local BA = %s; 1 thread as the reference runs each of them" % (
+                          n, max(1, n // KF_EVERY), "the reference's g2o + typesg2o.h" if have_ref else "the C restatement",
+                          "the reference's fbow" if have_ref else "skipped (oracle/_ref absent)",
+                          "the reference's xflann HKMeans(32,0) built once + 16-check search per neighbour + restated filters" if have_ref
+                          else "exact linear port + restated filters",
+                          "the reference's g2o compiled from its sources (oracle/_ref)" if have_ref else "the C restatement")}
 
 
 _REF = {}
 
 
-def _ref_worker_init():
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle_py, orb_oracle
-    try:
-        import cv2
-        cv2.setNumThreads(1)          # one worker per host core: no nested thread pools
-    except Exception:
-        pass
-    _REF["mods"] = (oracle_py, orb_oracle, oracle_py.load_ref("libref_xflann.so") is not None)
+def _ref_mods():
+    if "mods" not in _REF:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle_py, orb_oracle
+        try:
+            import cv2
+            cv2.setNumThreads(1)          # one worker per host core: no nested thread pools
+        except Exception:
+            pass
+        have = all(oracle_py.load_ref(n) is not None for n in ("libref_xflann.so", "libref_g2o.so", "libref_fbow.so"))
+        _REF["mods"] = (oracle_py, orb_oracle, have)
+    return _REF["mods"]
+
+
+def _ref_data(seed, n):
+    key = ("data", seed, n)
+    if key not in _REF:               # every worker tracks its own streams (generated once, outside the timed steps)
+        oracle_py, orb_oracle, have = _ref_mods()
+        from ucoslam_b200 import workload
+        imgs, scenes, _ = workload.make_problems(n, lambda im: orb_oracle.extract(im, KPTS), seed, camera())
+        voc = None
+        if have:
+            if "vocb" not in _REF:
+                _REF["vocb"] = workload.synth_vocabulary_full()
+            voc = oracle_py.RefVocabulary(_REF["vocb"])
+        _REF[key] = (imgs, scenes, ba_windows(max(1, n // KF_EVERY), 500 + seed), voc)
+    return _REF[key]
 
 
 def _ref_worker_step(job):
-    seed, n = job
-    if "mods" not in _REF:
-        _ref_worker_init()
-    oracle_py, orb_oracle, have = _REF["mods"]
-    key = ("data", seed, n)
-    if key not in _REF:               # every worker tracks its own stream of frames (generated once, outside the timed steps)
-        _REF[key] = (synth_clip(n, seed), ba_windows(max(1, n // KF_EVERY), 500 + seed))
-    frames, windows = _REF[key]
-    cpu_reference_step(frames, oracle_py, orb_oracle, have, windows)
-    return n
+    seed, n, res = job
+    if res == "1280x720" and W != 1280:
+        set_res_720p()
+    mods = _ref_mods()
+    imgs, scenes, windows, voc = _ref_data(seed, n)
+    split = dict.fromkeys(("orb_extract", "track_sequence", "bow_transform", "frame_match", "local_ba"), 0.0)
+    cpu_step(imgs, scenes, windows, mods, voc, split)
+    return split
 
 
 def run_reference(args, rank, world):
-    """The reference's CPU path on ALL host cores of the box: one worker process per core, each tracking its own stream of frames
-    (the same sharding by independent streams the GPU arm uses); a step = every worker processes its bounded sample."""
+    """The reference's CPU path on ALL host cores of the box: one worker process per core, each tracking its own streams
+    (the same sharding by independent units the GPU arm uses); a step = every worker processes its bounded sample."""
     if rank != 0:
         return
     import multiprocessing as mp
     workers = max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
-    n = min(args.frames, 8)
-    jobs = [(1234 + 17 * w, n) for w in range(workers)]
-    with mp.get_context("fork").Pool(workers, initializer=_ref_worker_init) as pool:
-        for _ in range(max(1, args.warmup)):
+    n = KF_EVERY
+    jobs = [(1234 + 17 * w, n, args.res) for w in range(workers)]
+    with mp.get_context("fork").Pool(workers) as pool:
+        for _ in range(max(1, min(args.warmup, 2))):
             pool.map(_ref_worker_step, jobs, chunksize=1)
         t0 = time.perf_counter()
+        tot = {}
         for _ in range(args.steps):
-            pool.map(_ref_worker_step, jobs, chunksize=1)
+            for sp in pool.map(_ref_worker_step, jobs, chunksize=1):
+                for k, v in sp.items():
+                    tot[k] = tot.get(k, 0.0) + v
         dt = time.perf_counter() - t0
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle_py
-    have = oracle_py.load_ref("libref_xflann.so") is not None
+    have = _ref_mods()[2]
     fps = workers * n * args.steps / dt
-    info = cpu_baseline_info(have, n)
+    info = cpu_info(have, n)
+    ssum = sum(tot.values()) or 1.0
     info.update({"value": fps, "unit": "frames/s", "cores": workers,
-                 "sample": "%d worker processes (one per host core), each: %s" % (workers, info["sample"])})
+                 "sample": "%d worker processes (one per host core), each: %s" % (workers, info["sample"]),
+                 "stage_share": {k: v / ssum for k, v in tot.items()},
+                 "stage_ms_per_frame_per_core": {k: v / (workers * n * args.steps) * 1e3 for k, v in tot.items()}})
+    cfg = config_common(1)
+    cfg["arm"] = {"frames_per_step_per_unit": n, "units": "%d host worker processes" % workers}
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                      "config": {"workload": WORKLOAD, "stages": STAGES, "frames_per_step": n * workers, "host_workers": workers},
-                      "cpu_baseline": info,
+                      "config": cfg, "cpu_baseline": info,
                       "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def cpu_baseline(n):
+    """Bounded CPU sample of the same workload on this box's host cores (rank 0, N=1), one thread."""
+    mods = _ref_mods()
+    imgs, scenes, windows, voc = _ref_data(1234, n)
+    split = dict.fromkeys(("orb_extract", "track_sequence", "bow_transform", "frame_match", "local_ba"), 0.0)
+    cpu_step(imgs[:2], scenes[:2], [], mods, voc, dict(split))  # warm caches
+    t0 = time.perf_counter()
+    cpu_step(imgs, scenes, windows, mods, voc, split)
+    dt = time.perf_counter() - t0
+    info = cpu_info(mods[2], n)
+    info.update({"value": n / dt, "unit": "frames/s", "stage_ms_per_frame": {k: v / n * 1e3 for k, v in split.items()}})
+    return info
 
 
 # ---------------------------------------------------------------------------------------------------------------------
 def run_b200(args, rank, world, local_rank):
+    import ctypes, gc
     import numpy as np, torch
-    import torch.distributed as dist
     import ucoslam_b200
+    from ucoslam_b200 import shard, workload, chain
+    from concurrent.futures import ThreadPoolExecutor
 
-    from ucoslam_b200 import shard
     torch.cuda.set_device(local_rank)
     shard.init("nccl", torch.device("cuda", local_rank))
-    ctx = ucoslam_b200.Context(local_rank)      # tracker thread's context: ORB extraction + matching
-    # mapper side (own streams): local bundle adjustment.  Two contexts alternate between steps, so the BA of step i (host
-    # planner + H2D + cluster-resident kernel + D2H) overlaps the tracking of step i+1, as UcoSLAM's threaded mode lets the
-    # mapper lag behind the tracker (mapmanager.cpp:1517); every BA finishes inside the timed region.
+    ctx = ucoslam_b200.Context(local_rank)      # tracker thread's context: extraction, tracking sequence, BoW, frame matcher
+    # mapper side (own streams): local bundle adjustment.  N_MAPPERS contexts take turns, so the BA of step i (host planner + H2D +
+    # cluster-resident kernel + D2H) overlaps the tracking of the following steps, as UcoSLAM's threaded mode lets the mapper lag
+    # behind the tracker (mapmanager.cpp:1517); every BA finishes inside the timed region.
     ctx_bas = [ucoslam_b200.Context(local_rank) for _ in range(N_MAPPERS)]
     for c in ctx_bas:
         if BA_CLUSTER:
@@ -226,67 +297,136 @@ def run_b200(args, rank, world, local_rank):
         if N_MAPPERS > 1:
             c.ba_set_host_threads(1)     # N_MAPPERS batches are already planned side by side: one planner thread per call
     stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
-    from concurrent.futures import ThreadPoolExecutor
-    mapper = ThreadPoolExecutor(N_MAPPERS)      # UcoSLAM runs local BA in its mapper thread next to tracking (mapmanager.cpp)
+    mapper = ThreadPoolExecutor(N_MAPPERS)
+    lib, h = ctx.lib, ctx.h
+    VP = lambda n: ctypes.c_void_p * n
+
+    class Work:
+        """everything one resolution needs: problems, device-resident state, buffers, the step functions"""
+
+        def __init__(self, F, w, hgt, kpts, seed):
+            self.F, self.w, self.h, self.kpts = F, w, hgt, kpts
+            self.prm = ucoslam_b200.OrbParams(kpts)
+            cam = workload.Camera(w, hgt, FOCAL if w == W else (1050.0 if w == 1280 else 525.0))
+            ext = lambda im: ctx.orb_extract(im, self.prm)
+            self.imgs, self.scenes, self.gt = workload.make_problems(F, ext, seed, cam)
+            self.tprm = ucoslam_b200.TrackParams(self.scenes[0], MAX_DESC_DIST, PROJ_DIST_THR)
+            pc = max(len(s["prev_octave"]) for s in self.scenes)
+            mc = max(len(s["mp_id"]) for s in self.scenes)
+            self.state = ucoslam_b200.TrackState(ctx, F, pc, mc)
+            for f, s in enumerate(self.scenes):
+                self.state.set_scene(f, s)
+            self.prior = np.stack([np.asarray(s["pose44"], np.float32).reshape(16) for s in self.scenes])
+            self.groups = kf_groups(F)
+            self.mprm = ucoslam_b200.MatchParams(MAX_DESC_DIST * 2, 0.6, True, 1 << 30)     # mapmanager.cpp:9990
+            self.clip_pin = torch.from_numpy(self.imgs).pin_memory()
+            with torch.cuda.stream(stream):
+                self.clip_dev = self.clip_pin.to("cuda", non_blocking=True)
+                z = lambda shape, dt: torch.zeros(shape, dtype=dt, device="cuda")
+                self.kps_dev, self.desc_dev, self.nout_dev = z((F, kpts, 28), torch.uint8), z((F, kpts, 32), torch.uint8), z(F, torch.int32)
+                self.prior_dev = torch.from_numpy(self.prior).to("cuda")
+                self.m_dev, self.nm_dev, self.pose_dev = z((F, kpts, 16), torch.uint8), z(F, torch.int32), z((F, 16), torch.float32)
+                self.good_dev, self.stat_dev, self.tbp_dev = z(F, torch.int32), z(F, torch.int32), z(F, torch.int32)
+                self.word_dev, self.wgt_dev, self.node_dev = z(kpts, torch.int32), z(kpts, torch.float32), z(kpts, torch.int32)
+                nb = KF_EVERY - 1
+                self.fm_dev, self.fmn_dev = z((nb, kpts, 16), torch.uint8), z(nb, torch.int32)
+            self.tout = ucoslam_b200.TrackOut(self.m_dev.data_ptr(), self.nm_dev.data_ptr(), self.pose_dev.data_ptr(), self.good_dev.data_ptr(),
+                                              self.stat_dev.data_ptr(), self.tbp_dev.data_ptr(), None)
+            # host-side buffers of the e2e path
+            self.img_ptrs = VP(F)(*[self.clip_pin[i].data_ptr() for i in range(F)])
+            self.kps_h = np.zeros((F, kpts), ucoslam_b200.KP_DTYPE)
+            self.desc_h = np.zeros((F, kpts, 32), np.uint8)
+            self.nkp_h = np.zeros(F, np.int32)
+            self.o_h = dict(matches=np.zeros((F, kpts), ucoslam_b200.MATCH_DTYPE), n_matches=np.zeros(F, np.int32), pose=np.zeros((F, 16), np.float32),
+                            n_good=np.zeros(F, np.int32), status=np.zeros(F, np.int32), n_tbp=np.zeros(F, np.int32))
+            self.tout_h = ucoslam_b200.TrackOut(*[self.o_h[k].ctypes.data for k in ("matches", "n_matches", "pose", "n_good", "status", "n_tbp")], None)
+            self.bow_h = (np.zeros(kpts, np.uint32), np.zeros(kpts, np.float32), np.zeros(kpts, np.uint32))
+            nb = KF_EVERY - 1
+            self.fm_h = [np.zeros(kpts, ucoslam_b200.MATCH_DTYPE) for _ in range(nb)]
+            self.fm_ptrs = VP(nb)(*[a.ctypes.data for a in self.fm_h])
+            self.fmn_h = np.zeros(nb, np.int32)
+
+        # -- device-resident step (tracker stream) --
+        def orb_dev(self):
+            ctx.orb_extract_batch_dev(self.clip_dev.data_ptr(), self.F, self.w, self.h, self.w, self.w * self.h, self.prm,
+                                      self.kps_dev.data_ptr(), self.desc_dev.data_ptr(), self.nout_dev.data_ptr())
+
+        def track_dev(self):
+            rc = lib.uco_b200_track_state_step_dev(h, self.state.h, self.kps_dev.data_ptr(), self.desc_dev.data_ptr(), self.nout_dev.data_ptr(),
+                                                   self.kpts, self.prior_dev.data_ptr(), ctypes.addressof(self.tprm), ctypes.addressof(self.tout),
+                                                   ucoslam_b200.UCO_TRACK_NO_SYNC)
+            if rc != 0:
+                raise RuntimeError(lib.uco_b200_last_error(h))
+
+        def bow_dev(self):
+            for kf, _ in self.groups:
+                ctx.bow_transform_dev(voc, self.desc_dev[kf].data_ptr(), self.kpts, 3, self.word_dev.data_ptr(), self.wgt_dev.data_ptr(),
+                                      self.node_dev.data_ptr())
+
+        def match_dev(self):
+            nb = KF_EVERY - 1
+            for kf, nbrs in self.groups:     # train = the keyframe (stride 0), queries = its neighbours (consecutive frames)
+                ctx.frame_match_batch_dev(nb, self.desc_dev[nbrs[0]].data_ptr(), self.kpts * 32, self.kps_dev[nbrs[0]].data_ptr(), self.kpts,
+                                          self.kpts, self.nout_dev[nbrs[0]:].data_ptr(), self.desc_dev[kf].data_ptr(), 0,
+                                          self.kps_dev[kf].data_ptr(), 0, self.kpts, None, self.mprm, self.fm_dev.data_ptr(),
+                                          self.fmn_dev.data_ptr())
+
+        def step_dev(self):
+            self.orb_dev()
+            self.track_dev()
+            self.bow_dev()
+            self.match_dev()
+
+        # -- the same through host buffers --
+        def step_host(self):
+            rc = lib.uco_b200_track_frames(h, self.state.h, ctypes.cast(self.img_ptrs, ctypes.c_void_p), self.w, self.h, self.w,
+                                           ctypes.addressof(self.prm), ctypes.addressof(self.tprm), self.prior.ctypes.data, self.kps_h.ctypes.data,
+                                           self.desc_h.ctypes.data, self.nkp_h.ctypes.data, ctypes.addressof(self.tout_h))
+            if rc != 0:
+                raise RuntimeError(lib.uco_b200_last_error(h))
+            nb = KF_EVERY - 1
+            for kf, nbrs in self.groups:
+                rc = lib.uco_b200_bow_transform(h, voc, self.desc_h[kf].ctypes.data, int(self.nkp_h[kf]), 32, 3, self.bow_h[0].ctypes.data,
+                                                self.bow_h[1].ctypes.data, self.bow_h[2].ctypes.data)
+                if rc != 0:
+                    raise RuntimeError(lib.uco_b200_last_error(h))
+                qd = VP(nb)(*[self.desc_h[i].ctypes.data for i in nbrs])
+                qk = VP(nb)(*[self.kps_h[i].ctypes.data for i in nbrs])
+                nq = np.ascontiguousarray(self.nkp_h[nbrs[0]:nbrs[0] + nb])
+                rc = lib.uco_b200_frame_match_multi(h, self.desc_h[kf].ctypes.data, int(self.nkp_h[kf]), 32, self.kps_h[kf].ctypes.data,
+                                                    int(self.nkp_h[kf]), None, nb, ctypes.cast(qd, ctypes.c_void_p), nq.ctypes.data, 32,
+                                                    ctypes.cast(qk, ctypes.c_void_p), nq.ctypes.data, None, None, ctypes.addressof(self.mprm),
+                                                    ctypes.cast(self.fm_ptrs, ctypes.c_void_p), self.kpts, self.fmn_h.ctypes.data)
+                if rc != 0:
+                    raise RuntimeError(lib.uco_b200_last_error(h))
+
+        def h2d_bytes(self):
+            return self.F * (self.w * self.h + 64) + len(self.groups) * (self.kpts * 32 + KF_EVERY * self.kpts * (32 + 28))
+
+        def d2h_bytes(self):
+            return self.F * (self.kpts * (28 + 32 + 16) + 64 + 24) + len(self.groups) * (self.kpts * 12 + (KF_EVERY - 1) * self.kpts * 16)
+
+        def close(self):
+            self.state.close()
+            for k in list(self.__dict__):
+                if k.endswith("_dev") or k == "clip_pin":
+                    delattr(self, k)
+
     F = args.frames
-    prm = ucoslam_b200.OrbParams(KPTS)
-    clip = synth_clip(F, shard.unit_seed(1234, rank, 0))   # every rank tracks its own stream of frames (weak scaling)
-    clip_pin = torch.from_numpy(clip).pin_memory()
+    voc_bytes = workload.synth_vocabulary_full()
+    voc = ctx.bow_load(voc_bytes)
+    wk = Work(F, W, H, KPTS, shard.unit_seed(1234, rank, 0))   # every rank tracks its own streams (weak scaling)
     with torch.cuda.stream(stream):
-        clip_dev = clip_pin.to("cuda", non_blocking=True)
-        kps_dev = torch.zeros((F, KPTS, 28), dtype=torch.uint8, device="cuda")
-        desc_dev = torch.zeros((F, KPTS, 32), dtype=torch.uint8, device="cuda")
-        nout_dev = torch.zeros(F, dtype=torch.int32, device="cuda")
-        idx_dev = torch.empty((F, KPTS, K_NN), dtype=torch.int32, device="cuda")
-        dist_dev = torch.empty((F, KPTS, K_NN), dtype=torch.int32, device="cuda")
         flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-    kps_host = np.zeros((F, KPTS), ucoslam_b200.KP_DTYPE)
-    desc_host = torch.zeros((F, KPTS, 32), dtype=torch.uint8).pin_memory()
-    nout_host = np.zeros(F, np.int32)
-    idx_host = torch.empty((F, KPTS, K_NN), dtype=torch.int32).pin_memory()
-    dist_host = torch.empty((F, KPTS, K_NN), dtype=torch.int32).pin_memory()
-    img_ptrs = (ctypes_voidp_array(F))(*[clip_pin[i].data_ptr() for i in range(F)])
-    VP = ctypes_voidp_array(F)
-    q_ptrs = VP(*[desc_host[f].data_ptr() for f in range(F)])
-    t_ptrs = VP(*[desc_host[f - 1].data_ptr() for f in range(F)])
-    i_ptrs = VP(*[idx_host[f].data_ptr() for f in range(F)])
-    d_ptrs = VP(*[dist_host[f].data_ptr() for f in range(F)])
-    nq_h, nt_h = np.zeros(F, np.int32), np.zeros(F, np.int32)
     n_ba = max(1, F // KF_EVERY)
     windows = ba_windows(n_ba, shard.unit_seed(500, rank, 0))
     ba_packs = [c.ba_pack_batch(windows, BA_ITERS) for c in ctx_bas]   # one set of result buffers per mapper context
-    ba_packed = ba_packs[0]
-    ba_in_bytes = sum(sum(a.nbytes for a in keep.values()) for keep in ba_packed[2])
-    ba_out_bytes = sum(sum(v.nbytes for v in o.values()) for o in ba_packed[3])
+    ba_in_bytes = sum(sum(a.nbytes for a in keep.values()) for keep in ba_packs[0][2])
+    ba_out_bytes = sum(sum(v.nbytes for v in o.values()) for o in ba_packs[0][3])
     ctx.sync()
 
-    def ba_all(m=0):  # host-buffer C-ABI call (there is no device-resident variant: the window is assembled by the host mapper)
+    def ba_all(m=0):  # host-buffer C-ABI call (the window is assembled by the host mapper: there is no device-resident variant)
         ctx_bas[m].ba_solve_batch(None, BA_ITERS, packed=ba_packs[m])
-
-    def orb_dev():
-        ctx.orb_extract_batch_dev(clip_dev.data_ptr(), F, W, H, W, W * H, prm, kps_dev.data_ptr(), desc_dev.data_ptr(),
-                                  nout_dev.data_ptr())
-
-    def knn_dev(f):  # frame f against its predecessor (frame 0 against the last one of the batch)
-        ctx.hamming_knn_dev(desc_dev[f].data_ptr(), KPTS, desc_dev[f - 1].data_ptr(), KPTS, K_NN,
-                            ucoslam_b200.UCO_KNN_HEAP, idx_dev[f].data_ptr(), dist_dev[f].data_ptr())
-
-    def knn_all_dev():
-        # frames 1..F-1 against their predecessors in ONE launch (row counts read from the extractor's device-side n_out),
-        # frame 0 against the last frame of the batch in a second one
-        ctx.hamming_knn_batch_dev(F - 1, desc_dev[1].data_ptr(), KPTS * 32, KPTS, nout_dev[1:].data_ptr(),
-                                  desc_dev[0].data_ptr(), KPTS * 32, KPTS, nout_dev.data_ptr(), K_NN,
-                                  ucoslam_b200.UCO_KNN_HEAP, idx_dev[1].data_ptr(), dist_dev[1].data_ptr())
-        knn_dev(0)
-
-    def track_device():
-        orb_dev()
-        knn_all_dev()
-
-    def step_device():  # one self-contained step: mapper (BA windows) and tracker (extract + match) side by side
-        fut = mapper.submit(ba_all, 0)
-        track_device()
-        fut.result()
 
     def run_pipelined(track, n_steps, between=None):
         """n_steps steps; the BA windows of step i go to mapper i % N_MAPPERS and are waited for before that mapper is reused
@@ -302,24 +442,6 @@ def run_b200(args, rank, world, local_rank):
         for f in futs:
             f.result()
 
-    lib, h = ctx.lib, ctx.h
-    import ctypes
-    prm_p = ctypes.addressof(prm)
-
-    def track_host():  # reference-facing calls with HOST buffers: H2D + kernels + D2H inside
-        rc = lib.uco_b200_orb_extract_batch(h, ctypes.cast(img_ptrs, ctypes.c_void_p), F, W, H, W, prm_p,
-                                            kps_host.ctypes.data, desc_host.data_ptr(), KPTS, nout_host.ctypes.data)
-        if rc != 0:
-            raise RuntimeError(lib.uco_b200_last_error(h))
-        # every frame against its predecessor, host descriptor buffers in, host k-NN tables out: one batched call
-        nq_h[:] = nout_host
-        nt_h[:] = np.roll(nout_host, 1)
-        rc = lib.uco_b200_hamming_knn_batch(h, F, ctypes.cast(q_ptrs, ctypes.c_void_p), nq_h.ctypes.data, 32,
-                                            ctypes.cast(t_ptrs, ctypes.c_void_p), nt_h.ctypes.data, 32, K_NN, 0,
-                                            ctypes.cast(i_ptrs, ctypes.c_void_p), ctypes.cast(d_ptrs, ctypes.c_void_p))
-        if rc != 0:
-            raise RuntimeError(lib.uco_b200_last_error(h))
-
     def barrier():
         ctx.sync()
         for c in ctx_bas:
@@ -331,7 +453,7 @@ def run_b200(args, rank, world, local_rank):
         return shard.max_over_ranks(v, "cuda")
 
     def timed_events(fn, reps, flush_l2=True):
-        """sum of per-repetition device durations (CUDA events on the context stream), L2 flushed between repetitions"""
+        """mean device duration of fn (CUDA events on the tracker stream), L2 flushed before every repetition"""
         with torch.cuda.stream(stream):
             evs = []
             for _ in range(reps):
@@ -343,16 +465,19 @@ def run_b200(args, rank, world, local_rank):
                 b.record(stream)
                 evs.append((a, b))
             barrier()
-            return sum(a.elapsed_time(b) for a, b in evs)
+            return sum(a.elapsed_time(b) for a, b in evs) / reps
 
-    # warm-up (also builds the extractor plan and its buffers), sanity: every frame yields the full keypoint budget
-    for m in range(N_MAPPERS):     # every mapper context allocates its arenas / pinned buffers on its first batch: do that here,
-        ba_all(m)                  # whatever W is (with W < N_MAPPERS warm-up steps the last contexts would first run inside the timed region)
+    # warm-up (also builds the extractor plan and every workspace), sanity: every frame yields the full keypoint budget and tracks
+    for m in range(N_MAPPERS):     # every mapper context allocates its arenas / pinned buffers on its first batch: do that here
+        ba_all(m)
     with torch.cuda.stream(stream):
-        run_pipelined(track_device, max(args.warmup, 3), between=flush.zero_)
+        run_pipelined(wk.step_dev, max(args.warmup, 3), between=flush.zero_)
     barrier()
-    n_kp = nout_dev.cpu().numpy()
+    n_kp = wk.nout_dev.cpu().numpy()
     assert (n_kp == KPTS).all(), "synthetic frames must give %d keypoints, got %s" % (KPTS, n_kp[:8])
+    good = wk.good_dev.cpu().numpy()
+    assert (good > 300).all() and (wk.stat_dev.cpu().numpy() == 0).all(), "every synthetic frame must track: inliers %s" % good[:8]
+    pose_err = float(np.abs(wk.pose_dev.cpu().numpy().reshape(F, 4, 4) - wk.gt.astype(np.float32)).max())
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -365,116 +490,180 @@ def run_b200(args, rank, world, local_rank):
     with torch.cuda.stream(stream):
         ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev_a.record(stream)
-        run_pipelined(track_device, args.steps, between=flush.zero_)
+        run_pipelined(wk.step_dev, args.steps, between=flush.zero_)
         ev_b.record(stream)
     barrier()
     ms_dev = reduce_max(ev_a.elapsed_time(ev_b))
     launches = (count() - n0) // max(1, args.steps)
 
-    run_pipelined(track_host, max(1, args.warmup))
+    run_pipelined(wk.step_host, max(1, args.warmup))
     barrier()
     t0 = time.perf_counter()
-    run_pipelined(track_host, args.steps)
+    run_pipelined(wk.step_host, args.steps)
     barrier()
     e2e_ms = reduce_max((time.perf_counter() - t0) * 1e3)
     clocks = sampler.summary() if sampler else None
+    assert np.array_equal(wk.o_h["n_good"], good), "host-buffer path and device-resident path disagree"
 
-    # per-kernel device times of the same step (events at the stage boundaries inside the library)
-    ctx.set_profiling(True)
+    # ---- per-stage device times of the same step (events at the stage boundaries) ----
     reps = 5
+    ctx.set_profiling(True)
     acc = {}
     for _ in range(reps):
         with torch.cuda.stream(stream):
             flush.zero_()
-            orb_dev()
+            wk.orb_dev()
         for k, v in ctx.orb_last_stage_ms().items():
             acc[k] = acc.get(k, 0.0) + v / reps
     ctx.set_profiling(False)
-    knn_ms = timed_events(knn_all_dev, reps) / reps
-    ba_call_ms = timed_events(ba_all, reps) / reps          # the host-synchronous C-ABI call: planner + H2D + kernel + D2H
+    stage_ms = dict(acc)
+    nodes_dev = torch.zeros((F, 2 * (KPTS // 5) + 2, 28), dtype=torch.uint8, device="cuda")
+    leaf_dev = torch.zeros((F, KPTS), dtype=torch.int32, device="cuda")
+    bbox_dev = torch.zeros((F, 4), dtype=torch.float64, device="cuda")
+    nn_dev = torch.zeros(F, dtype=torch.int32, device="cuda")
+    stage_ms["kdtree_build"] = timed_events(lambda: ctx._chk(lib.uco_b200_kdtree_build_batch_dev(
+        h, F, wk.kps_dev.data_ptr(), KPTS, wk.nout_dev.data_ptr(), KPTS, nodes_dev.data_ptr(), nodes_dev.shape[1], leaf_dev.data_ptr(),
+        bbox_dev.data_ptr(), nn_dev.data_ptr())), reps)
+    stage_ms["track_sequence"] = timed_events(wk.track_dev, reps)          # kd-trees + tbp + solvePnp + local map + solvePnp
+    stage_ms["bow_transform"] = timed_events(wk.bow_dev, reps)
+    stage_ms["frame_match"] = timed_events(wk.match_dev, reps)             # k-NN + filters, 7 pairs per keyframe
+    knn_pairs = len(wk.groups) * (KF_EVERY - 1)
+    idx_dev = torch.empty((knn_pairs, KPTS, K_NN), dtype=torch.int32, device="cuda")
+    dist_dev = torch.empty_like(idx_dev)
+
+    def knn_only():
+        for g, (kf, nbrs) in enumerate(wk.groups):
+            ctx.hamming_knn_batch_dev(KF_EVERY - 1, wk.desc_dev[nbrs[0]].data_ptr(), KPTS * 32, KPTS, wk.nout_dev[nbrs[0]:].data_ptr(),
+                                      wk.desc_dev[kf].data_ptr(), 0, KPTS, None, K_NN, ucoslam_b200.UCO_KNN_HEAP,
+                                      idx_dev[g * (KF_EVERY - 1)].data_ptr(), dist_dev[g * (KF_EVERY - 1)].data_ptr())
+    stage_ms["hamming_knn"] = timed_events(knn_only, reps)                 # the k-NN kernel inside frame_match
+    ba_call_ms = timed_events(ba_all, reps)                                # the host-synchronous C-ABI call: planner + H2D + kernel + D2H
     ba_dev = []
-    for _ in range(reps):                                   # the kernel alone: CUDA events around the launch on the mapper's stream
+    for _ in range(reps):                                                  # the kernel alone: CUDA events around the launch on the mapper's stream
         ba_all()
         ba_dev.append(float(ba_packs[0][3][0]["device_ms"]))
-    ba_ms = sum(ba_dev) / len(ba_dev)
-    stage_ms = dict(acc)
-    stage_ms["hamming_knn"] = knn_ms
-    stage_ms["local_ba"] = ba_ms
+    stage_ms["local_ba"] = sum(ba_dev) / len(ba_dev)
+    del nodes_dev, leaf_dev, bbox_dev, nn_dev, idx_dev, dist_dev
+    ba_trials = sum(int(o["trace"][:, 1].sum()) for o in ba_packs[0][3])
     n_obs = sum(len(w["obs_pose"]) for w in windows)
-    ba_trials = sum(int(o["trace"][:, 1].sum()) for o in ba_packed[3])
     pb = ctx.orb_plan_bytes()
-    cand_bytes = 0  # candidate lists are small and L2 resident; not counted as algorithmic traffic
-    alg = {  # ALGORITHMIC bytes per frame of each kernel (DESIGN.md "Measurement")
-        "blur": 2 * W * H,                                                        # read frame, write level 0
-        "resize": 2 * pb["pyramid_px"] - W * H - 179 * 134,                       # read levels 0..6, write levels 1..7
-        "fast_cells": pb["pyramid_px"] + cand_bytes,                              # read every level once
-        "select": 0,
-        "orient_describe": KPTS * (28 + 32),                                      # write keypoints + descriptors
-        "hamming_knn": 2 * KPTS * 32 + KPTS * K_NN * 8,
-        # compulsory HBM traffic of a window: its inputs in, its results out (everything an LM trial touches, SURVEY.md 8(d)'s
-        # 316 B per observation and trial, stays in L2: ncu shows ~1.7 MB of DRAM traffic per window); per frame
-        "local_ba": (ba_in_bytes + ba_out_bytes) / F,
-    }
-    top = max(stage_ms, key=stage_ms.get)
+
+    # ---- rooflines: every stage against the roof that bounds it; SM x time decides which one is "dominant" ----
+    ba_sms = n_ba * (BA_CLUSTER or 8)
+    px = pb["pyramid_px"]
+    int_ops = {  # algorithmic integer operations per frame: blur 2 x 7 MAC separable, bicubic 2 x 4 taps + border,
+        # FAST 16 ring compares + score for the ~3 % that pass, selection ~ per candidate, descriptor 512 gathers + 1024 f32 mul per keypoint
+        "blur": 28 * W * H, "resize": 16 * (px - W * H), "fast_cells": 40 * px, "select": 64 * 4 * KPTS, "orient_describe": (709 * 2 + 2560) * KPTS}
+    hbm_bytes = {"blur": 2 * W * H, "resize": 2 * px - W * H, "fast_cells": px, "select": 0, "orient_describe": KPTS * 60}
     peaks = {}
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
         peaks = json.load(open(pk))
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    achieved = alg[top] * F / (stage_ms[top] * 1e-3) / 1e9
-    # DRAM bytes per launch of that kernel from the committed ncu --set full capture of the same step (profiles/r1_traffic.json)
-    traffic = None
-    tk = {"local_ba": "ba_cluster_kernel", "hamming_knn": "hamming_knn_kernel", "fast_cells": "fast_cells_kernel", "blur": "blur7_kernel",
-          "select": "select_kernel", "orient_describe": "orient_describe_kernel"}.get(top)
-    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if tk and os.path.exists(tp) and F == 64 and W == 640:
-        for name, v in json.load(open(tp))["kernels"].items():
-            if tk in name:
-                traffic = v["dram_bytes_per_launch"]
-                break
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if os.path.exists(tp) and F == 64 and W == 640:
+        traffic = json.load(open(tp)).get("kernels", {})
+
+    def traffic_of(kernel):
+        for name, v in traffic.items():
+            if kernel in name:
+                return v.get("dram_bytes_per_launch")
+        return None
+
+    rl = {}
+    for k in ("blur", "resize", "fast_cells", "select", "orient_describe"):
+        ms = stage_ms.get(k, 0.0)
+        if ms <= 0:
+            continue
+        ach = int_ops[k] * F / (ms * 1e-3)
+        rl[k] = {"kernel": {"blur": "blur7_kernel", "resize": "resize_cubic_kernel x7", "fast_cells": "fast_cells_kernel", "select": "select_kernel",
+                            "orient_describe": "orient_describe_kernel"}[k], "bound": "int_alu", "achieved": ach / 1e12, "peak": PEAK_ALU / 1e12,
+                 "unit": "T int-op/s", "frac": ach / PEAK_ALU, "ms_per_step": ms, "sm_ms": ms * SM_COUNT,
+                 "hbm_gbs": hbm_bytes[k] * F / (ms * 1e-3) / 1e9, "hbm_frac": hbm_bytes[k] * F / (ms * 1e-3) / 1e9 / hbm_peak,
+                 "traffic": traffic_of({"blur": "blur7", "resize": "resize_cubic", "fast_cells": "fast_cells", "select": "select_kernel",
+                                        "orient_describe": "orient_describe"}[k])}
+    ms = stage_ms["hamming_knn"]
+    popc = knn_pairs * KPTS * KPTS * 8.0 / (ms * 1e-3)
+    rl["hamming_knn"] = {"kernel": "hamming_knn_kernel", "bound": "int_popc", "achieved": popc / 1e12, "peak": PEAK_POPC / 1e12, "unit": "T popc32/s",
+                         "frac": popc / PEAK_POPC, "ms_per_step": ms, "sm_ms": ms * SM_COUNT, "traffic": traffic_of("hamming_knn")}
+    ms = stage_ms["local_ba"]
+    # f64 flops of a window: per LM trial linearize ~400 / observation + Schur ~ (k(k+1)/2) x 216 per landmark (k = obs per landmark) + solve (6P)^3/3
+    k_obs = n_obs / max(1, sum(len(w["points3"]) for w in windows))
+    flop_trial = n_obs * 400.0 + sum(len(w["points3"]) for w in windows) * (k_obs * (k_obs + 1) / 2) * 216.0 + n_ba * (60.0 ** 3) / 3
+    ba_flops = flop_trial * (ba_trials / max(1, n_ba)) / (ms * 1e-3)
+    rl["local_ba"] = {"kernel": "ba_cluster_kernel", "bound": "fp64 (latency chain on %d of %d SMs)" % (ba_sms, SM_COUNT), "achieved": ba_flops / 1e12,
+                      "peak": PEAK_FP64_SM * ba_sms / 1e12, "unit": "TFLOP/s f64", "frac": ba_flops / (PEAK_FP64_SM * ba_sms), "ms_per_launch": ms,
+                      "ms_per_step": ms * ba_sms / SM_COUNT, "sm_ms": ms * ba_sms, "traffic": traffic_of("ba_cluster"),
+                      "note": "runs on the mappers' streams beside the tracker: ms_per_step is its SM-share of a step"}
+    for k in ("kdtree_build", "track_sequence", "bow_transform"):
+        rl[k] = {"bound": "latency (L2-resident, a few hundred flops per unit)", "ms_per_step": stage_ms[k], "sm_ms": stage_ms[k] * SM_COUNT,
+                 "achieved": None, "peak": None, "frac": None, "unit": None, "traffic": None}
+    filt_ms = max(0.0, stage_ms["frame_match"] - stage_ms["hamming_knn"])
+    rl["match_filters"] = {"bound": "latency", "ms_per_step": filt_ms, "sm_ms": filt_ms * SM_COUNT, "achieved": None, "peak": None, "frac": None,
+                           "unit": None, "traffic": None}
+    top = max((k for k in rl if rl[k]["frac"] is not None), key=lambda k: rl[k]["sm_ms"])
+    roof = dict(rl[top])
+    roof.update({"stage": top, "peak_source": "B300_MICROARCH.md pipe rates x 148 SMs x 1.965 GHz; HBM " + ("measured" if peaks else "fallback"),
+                 "kernel_ms_per_step": rl[top]["ms_per_step"], "dominant_by": "SM x time share of the step"})
     orb_total_ms = sum(acc.values())
-    orb_alg = W * H + 2 * pb["pyramid_px"] + KPTS * 60                          # 2 328 264 B/frame
+    orb_alg = W * H + 2 * px + KPTS * 60                          # 2 328 264 B/frame
+
+    # ---- extras (outside the timed region, bounded) ----
+    extras = {}
+    if not args.no_extras:
+        try:
+            extras.update(run_extras(args, rank, world, local_rank, ctx, stream, wk, Work, flush, barrier, reduce_max, run_pipelined,
+                                     timed_events, voc))
+        except Exception as e:      # an extra must never cost the headline line
+            extras["error"] = repr(e)
     if rank == 0:
         total_frames = F * world * args.steps
+        cfg = config_common(n_ba)
+        cfg["arm"] = ({"frames_per_step_per_unit": F, "units": "%d GPU(s)" % world, "parallelism": "frames sharded over %d GPU(s), no collective" % world,
+                    "l2": "flushed between timed steps (256 MB write, inside the timed region)",
+                    "state": "previous frames + map blocks are device resident (uco_b200_track_state); a step's host inputs are its frames and pose priors",
+                    "mapper": "%d BA contexts take turns (clusters of %d CTAs per window): the local BA of a step overlaps the tracking "
+                              "of the following steps (threaded mode: the mapper lags the tracker); all BA results are back on the "
+                              "host inside the timed region" % (N_MAPPERS, BA_CLUSTER or 8)})
+        cfg["frames_per_step_per_gpu"] = F
         line = {"metric": METRIC, "value": total_frames / (ms_dev * 1e-3), "unit": "frames/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "stages": STAGES, "frames_per_step_per_gpu": F, "ba_windows_per_step_per_gpu": n_ba,
-                           "ba_window": "12 KF (2 fixed), 2000 points, %d observations, nIters=5" % (n_obs // max(1, n_ba)),
-                           "parallelism": "frames sharded over %d GPU(s), no collective" % world,
-                           "l2": "flushed between timed steps (256 MB write, inside the timed region)",
-                           "mapper": "%d BA contexts take turns (clusters of %d CTAs per window): the local BA of a step overlaps the tracking "
-                                     "of the following steps (threaded mode: the mapper lags the tracker); all BA results are back on the "
-                                     "host inside the timed region" % (N_MAPPERS, BA_CLUSTER or 8)},
+                "config": cfg,
                 "e2e": {"value": total_frames / (e2e_ms * 1e-3), "unit": "frames/s",
-                        "h2d_bytes_per_step": F * (W * H + 2 * KPTS * 32) + ba_in_bytes,
-                        "d2h_bytes_per_step": F * (KPTS * 60 + 4 + KPTS * K_NN * 8) + ba_out_bytes},
+                        "h2d_bytes_per_step": wk.h2d_bytes() + ba_in_bytes, "d2h_bytes_per_step": wk.d2h_bytes() + ba_out_bytes},
                 "gpu_launches": launches, "clocks": clocks,
-                "roofline": {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": achieved / hbm_peak, "traffic": traffic,
-                             "peak_source": "measured" if peaks else "fallback",
-                             "kernel_ms_per_step": stage_ms[top], "algorithmic_bytes_per_frame": alg[top]},
+                "roofline": roof, "roofline_stages": rl,
                 "stage_ms_per_step": stage_ms,
-                "stage_note": "tracker stages (blur..hamming_knn) run on one stream, local_ba (ba_cluster_kernel, one launch per %d windows, "
-                              "%d LM trials per window) on the mappers' streams in parallel; the host-synchronous C-ABI call around it "
-                              "(planner + H2D + launch + D2H) takes %.2f ms" % (n_ba, ba_trials // max(1, n_ba), ba_call_ms),
+                "stage_note": "tracker stages run on one stream in the order extract (blur..orient_describe) -> track_sequence (contains "
+                              "kdtree_build) -> bow_transform -> frame_match (contains hamming_knn); local_ba (ba_cluster_kernel, one launch "
+                              "per %d windows, %d LM trials per window) runs on the mappers' streams in parallel; the host-synchronous C-ABI call "
+                              "around it (planner + H2D + launch + D2H) takes %.2f ms" % (n_ba, ba_trials // max(1, n_ba), ba_call_ms),
+                "tracking": {"min_inliers": int(good.min()), "mean_inliers": float(good.mean()), "mean_tbp_matches": float(wk.tbp_dev.cpu().numpy().mean()),
+                             "mean_matches": float(wk.nm_dev.cpu().numpy().mean()), "max_abs_pose_entry_error_vs_ground_truth": pose_err},
                 "orb_pipeline": {"ms_per_step": orb_total_ms, "algorithmic_bytes_per_frame": orb_alg,
                                  "achieved_gbs": orb_alg * F / (orb_total_ms * 1e-3) / 1e9,
-                                 "frac_of_hbm_peak": orb_alg * F / (orb_total_ms * 1e-3) / 1e9 / hbm_peak}}
+                                 "frac_of_hbm_peak": orb_alg * F / (orb_total_ms * 1e-3) / 1e9 / hbm_peak,
+                                 "int_ops_per_frame": sum(int_ops.values()),
+                                 "frac_of_int_alu_peak": sum(int_ops.values()) * F / (orb_total_ms * 1e-3) / PEAK_ALU}}
+        line.update(extras)
         if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(clip)
+            line["cpu_baseline"] = cpu_baseline(2 * KF_EVERY)
         print(json.dumps(line))
         sys.stdout.flush()
     barrier()
     # orderly teardown (the driver's exit hook records the loaded libraries, so the interpreter must exit normally): every torch
     # object that refers to the tracker context's stream goes first, then the mapper pool, then the contexts, then the process group
     mapper.shutdown(wait=True)
-    del stream, clip_dev, kps_dev, desc_dev, nout_dev, idx_dev, dist_dev, flush, clip_pin, desc_host, idx_host, dist_host, ev_a, ev_b
-    import gc
+    wk.close()
+    ctx.bow_free(voc)
+    del stream, flush, ev_a, ev_b, wk
     gc.collect()
     torch.cuda.synchronize()
     torch.cuda.empty_cache()       # the caching allocators record events on the streams their blocks were used on: drop the blocks
-    torch._C._host_emptyCache() if hasattr(torch._C, "_host_emptyCache") else None
+    if hasattr(torch._C, "_host_emptyCache"):
+        torch._C._host_emptyCache()
     for c in ctx_bas:
         c.close()
     ctx.close()
@@ -483,25 +672,95 @@ def run_b200(args, rank, world, local_rank):
     sys.stderr.flush()
 
 
-def ctypes_voidp_array(n):
+def run_extras(args, rank, world, local_rank, ctx, stream, wk, Work, flush, barrier, reduce_max, run_pipelined, timed_events, voc):
+    """single-frame latency, the 1280x720 stream, ATE of a sequential clip, and (under torchrun) the two collective paths"""
+    import numpy as np, torch
+    import ucoslam_b200
+    from ucoslam_b200 import shard, chain, workload
+    out = {}
+    # -- single-frame latency through the host-buffer calls (the reference's caller issues one frame per call, frameextractor.cpp:3505)
+    one = Work(1, W, H, KPTS, shard.unit_seed(77, rank, 0))
+    lat, lat_orb = [], []
+    kps1 = np.zeros(KPTS, ucoslam_b200.KP_DTYPE); d1 = np.zeros((KPTS, 32), np.uint8); n1 = np.zeros(1, np.int32)
     import ctypes
-    return ctypes.c_void_p * n
-
-
-def cpu_baseline(clip):
-    """Bounded CPU sample of the same workload on this box's host cores (rank 0, N=1)."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle_py, orb_oracle
-    have = oracle_py.load_ref("libref_xflann.so") is not None
-    n = min(len(clip), 16)
-    windows = ba_windows(max(1, n // KF_EVERY), 500)
-    cpu_reference_step(clip[:2], oracle_py, orb_oracle, have)  # warm caches
-    t0 = time.perf_counter()
-    cpu_reference_step(clip[:n], oracle_py, orb_oracle, have, windows)
-    dt = time.perf_counter() - t0
-    info = cpu_baseline_info(have, n)
-    info.update({"value": n / dt, "unit": "frames/s"})
-    return info
+    for i in range(25):
+        t0 = time.perf_counter()
+        rc = ctx.lib.uco_b200_track_frames(ctx.h, one.state.h, ctypes.cast(one.img_ptrs, ctypes.c_void_p), W, H, W, ctypes.addressof(one.prm),
+                                           ctypes.addressof(one.tprm), one.prior.ctypes.data, one.kps_h.ctypes.data, one.desc_h.ctypes.data,
+                                           one.nkp_h.ctypes.data, ctypes.addressof(one.tout_h))
+        t1 = time.perf_counter()
+        ctx.lib.uco_b200_orb_extract(ctx.h, one.clip_pin[0].data_ptr(), W, H, W, ctypes.addressof(one.prm), kps1.ctypes.data, d1.ctypes.data,
+                                     KPTS, n1.ctypes.data)
+        t2 = time.perf_counter()
+        if rc != 0:
+            raise RuntimeError(ctx.lib.uco_b200_last_error(ctx.h))
+        if i >= 5:
+            lat.append((t1 - t0) * 1e3); lat_orb.append((t2 - t1) * 1e3)
+    out["latency_ms_single_frame"] = {"extract_and_track_host_call_median": float(np.median(lat)), "orb_extract_host_call_median": float(np.median(lat_orb)),
+                                      "note": "one 640x480 frame per call through host buffers (upload + kernels + download + sync), median of 20"}
+    one.close()
+    # -- ATE of a sequential clip through the CUDA path (BASELINE metric: "ATE vs ref"); the CPU arm's ATE over the same clip is
+    # computed by tests/test_chain_ate_gpu.py and scripts/ate_check.py (identical trajectories: bit-exact matching, 1e-12 LM)
+    n_ate = 40
+    tex = chain.texture()
+    gt = np.array([chain.gt_pose(i) for i in range(n_ate)])
+    frames = [chain.render(tex, T) for T in gt]
+    prm = ucoslam_b200.OrbParams(2000)
+    poses, stats = chain.track_full(frames, gt[0], lambda im: ctx.orb_extract(im, prm), lambda sc: ctx.track_batch([sc])[0])
+    out["ate"] = {"ate_m_cuda_path": chain.ate(poses, gt), "frames": n_ate, "min_inliers": int(min(s[2] for s in stats)),
+                  "sequence": "extract -> search by projection -> solvePnp -> local-map search -> solvePnp, state carried from frame to frame",
+                  "reference_path": "profiles/r2_ate_chain.json holds the CPU-oracle trajectory of the same clip (identical poses)"}
+    # -- the 1280x720 / 4000-keypoint stream (north_star asks for both sizes), device-resident value only
+    if W == 640:
+        F2 = 32
+        w2 = Work(F2, 1280, 720, 4000, shard.unit_seed(4321, rank, 0))
+        with torch.cuda.stream(stream):
+            for _ in range(3):
+                w2.step_dev(); flush.zero_()
+        barrier()
+        ms = timed_events(w2.step_dev, 5)
+        ms = reduce_max(ms)
+        g2 = w2.good_dev.cpu().numpy()
+        out["stream_1280x720"] = {"frames_per_s_device_resident": F2 * world / (ms * 1e-3), "ms_per_step": ms, "frames_per_step_per_gpu": F2,
+                                  "kpts": 4000, "min_inliers": int(g2.min()),
+                                  "note": "tracker stream only (extract + tracking sequence + BoW + frame matcher per keyframe), no BA overlap"}
+        w2.close()
+        del w2
+    # -- collective paths under torchrun (SURVEY.md 8e): config 4 all-gather, config 5 all-reduce
+    if world > 1:
+        comm = shard.make_comm(ctx, "cuda")
+        coll = {}
+        nt, nq, k = 1_000_000, 2000, 10
+        rng = np.random.default_rng(1234)
+        t_h = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+        q_h = t_h[rng.integers(0, nt, nq)].copy()
+        q_h[:, :2] ^= 0x5A
+        t, q = torch.from_numpy(t_h).cuda(), torch.from_numpy(q_h).cuda()
+        b, e = shard.shard_range(nt, rank, world)
+        sh_i = torch.empty((nq, k), dtype=torch.int32, device="cuda"); sh_d = torch.empty_like(sh_i)
+        fn = lambda: ctx.hamming_knn_sharded_dev(comm, q.data_ptr(), nq, t[b:].data_ptr(), e - b, b, k, sh_i.data_ptr(), sh_d.data_ptr())
+        fn(); barrier()
+        ms = reduce_max(timed_events(fn, 10, flush_l2=False))
+        coll["config4_map_query"] = {"workload": "2000 queries x 10^6-row map, k=10, rows sharded over %d GPUs, NCCL all-gather of per-shard top-k + merge" % world,
+                                     "ms": ms, "queries_per_s": nq / (ms * 1e-3), "popc32_per_s": nq * nt * 8.0 / (ms * 1e-3),
+                                     "frac_of_aggregate_popc_peak": nq * nt * 8.0 / (ms * 1e-3) / (PEAK_POPC * world)}
+        del t, q, sh_i, sh_d
+        from ucoslam_b200.synth import synth_global_ba
+        pb = synth_global_ba(42)
+        for _ in range(2):
+            o = ctx.ba_solve_sharded(pb, 5, comm=comm)
+        barrier()
+        dev = []
+        for _ in range(3):
+            o = ctx.ba_solve_sharded(pb, 5, comm=comm)
+            dev.append(o["device_ms"])
+        ms = reduce_max(float(np.mean(dev)))
+        coll["config5_global_ba"] = {"workload": "global BA 500 KF / 50k landmarks / %d observations, landmarks sharded over %d GPUs, NCCL all-reduce of the packed "
+                                                 "reduced Hessian per LM trial" % (len(pb["obs_pose"]), world), "ms_per_solve": ms,
+                                     "lm_trials": int(o["trace"][:, 1].sum()), "allreduce_bytes_per_trial": float(o["profile"][3])}
+        ctx.comm_destroy(comm)
+        out["collective_paths"] = coll
+    return out
 
 
 def main():

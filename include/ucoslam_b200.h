@@ -367,6 +367,15 @@ int uco_b200_frame_match_batch_dev(uco_b200_ctx* ctx, int n_pairs, const uint8_t
                                    size_t t_kps_pair_stride, int nt_max, const int32_t* nt_dev, const uco_match_params* prm,
                                    uco_match* out_dev, int32_t* n_out_dev);
 
+/* the mapper's pattern (new-map-point creation, src/utils/mapmanager.cpp:9972-10065): FrameMatcher::setParams(train = the keyframe)
+ * once, then matchEpipolar(query = each of n_frames neighbour keyframes, F12_f).  t_*: the keyframe (descriptor rows of the
+ * requested mode + t_map, as in uco_b200_frame_match); q_*[f]: the neighbours; f12: n_frames x 9 (row-major, required when
+ * prm->use_f12; prm->f12 is ignored); out[f]: capacity `capacity` >= nq[f] matches, n_out[f].  One upload, two launches, one download. */
+int uco_b200_frame_match_multi(uco_b200_ctx* ctx, const uint8_t* t_desc, int nt, size_t t_stride, const uco_keypoint* t_kps, int n_t_kps,
+                               const int32_t* t_map, int n_frames, const uint8_t* const* q_desc, const int32_t* nq, size_t q_stride,
+                               const uco_keypoint* const* q_kps, const int32_t* n_q_kps, const int32_t* const* q_map, const float* f12,
+                               const uco_match_params* prm, uco_match* const* out, int capacity, int32_t* n_out);
+
 /* FrameMatcher_BoW::matchEpipolar (src/utils/framematcher.cpp:407-541): candidates of a query keypoint are the train keypoints under
  * the same level-3 vocabulary node (Frame::bowvector_level, what uco_b200_bow_transform reports as level_node), then the same
  * filters as above.  A frame's fBow2 is passed flattened in std::map order. */
@@ -516,6 +525,26 @@ typedef struct uco_track_out {
 
 int uco_b200_track_batch_dev(uco_b200_ctx* ctx, const uco_track_batch* in_dev, const uco_track_params* prm, const uco_track_out* out_dev);
 int uco_b200_track_batch(uco_b200_ctx* ctx, const uco_track_batch* in_host, const uco_track_params* prm, const uco_track_out* out_host);
+/* device-resident mirror of the tracking state of n_streams independent streams (what Frame / Map hold for the
+ * tracker — the previous frame's und_kpts / desc / ids, src/map_types/frame.h:60-75, and the local map's points,
+ * src/map_types/mappoint.h — kept in HBM between calls).  set_prev / set_map replace one stream's block from host arrays.
+ * track_frames: one tracking step of every stream through HOST buffers — images in (n_streams pointers, w x h, row stride),
+ * ORB extraction (uco_orb_params), kd-trees and the tracker's sequence on the device, out: the frames' keypoints / descriptors /
+ * counts (n_streams x orb->max_features records; kps / desc / n_kp may be NULL) and `out` (rows of orb->max_features matches).
+ * track_state_step_dev: the same against keypoints / descriptors already on the device (uco_b200_orb_extract_batch_dev). */
+typedef struct uco_b200_track_state uco_b200_track_state;
+int uco_b200_track_state_create(uco_b200_ctx* ctx, int n_streams, int prev_cap, int map_cap, uco_b200_track_state** out);
+void uco_b200_track_state_free(uco_b200_ctx* ctx, uco_b200_track_state* st);
+int uco_b200_track_state_set_prev(uco_b200_ctx* ctx, uco_b200_track_state* st, int stream, int n, const uco_keypoint* kps, const uint8_t* desc,
+                                  const int32_t* mp_row);
+int uco_b200_track_state_set_map(uco_b200_ctx* ctx, uco_b200_track_state* st, int stream, const uco_mappoints* mp, const uint8_t* stable,
+                                 const uint8_t* local);
+int uco_b200_track_state_step_dev(uco_b200_ctx* ctx, const uco_b200_track_state* st, const uco_keypoint* kps_dev, const uint8_t* desc_dev,
+                                  const int32_t* n_kp_dev, int kp_cap, const float* pose_prior_dev, const uco_track_params* prm,
+                                  const uco_track_out* out_dev, int flags);
+int uco_b200_track_frames(uco_b200_ctx* ctx, const uco_b200_track_state* st, const uint8_t* const* imgs, int w, int h, size_t stride,
+                          const uco_orb_params* orb, const uco_track_params* prm, const float* pose_prior, uco_keypoint* kps, uint8_t* desc,
+                          int32_t* n_kp, const uco_track_out* out);
 int uco_b200_track_projected(uco_b200_ctx* ctx, int n_prev, const uco_keypoint* prev_kps, const uint8_t* prev_desc,
                              const int32_t* prev_mp_row, const uco_mappoints* mp, const uco_frame_view* fr, const float* pose_f2g,
                              float dist_thr, float proj_dist_thr, uco_match* out, int* n_out);

@@ -103,6 +103,10 @@ static int match_tail(dmatch_t* out, int n, const kp_t* q_kps, const kp_t* t_kps
     return n;
 }
 
+int oracle_frame_match_knn(const int32_t* indices, const int32_t* idist, int nq, const kp_t* q_kps, const int32_t* q_map, const kp_t* t_kps,
+                           const int32_t* t_map, float minDescDist, float nn_match_ratio, int checkOrientation, int maxOctaveDiff,
+                           const float* F12, const float* scaleFactors, int nScale, dmatch_t* out);
+
 /* q_map / t_map: keypoint index of descriptor row i (FrameMatcher::manageMode, framematcher.cpp:160-198); NULL = identity.
  * F12: 9 floats or NULL.  Returns the number of matches written to out (capacity >= nq). */
 int oracle_frame_match(const uint8_t* q_desc, int nq, size_t q_stride, const kp_t* q_kps, const int32_t* q_map,
@@ -114,6 +118,19 @@ int oracle_frame_match(const uint8_t* q_desc, int nq, size_t q_stride, const kp_
     int32_t* indices = malloc(sizeof(int32_t) * nq * nn);
     int32_t* idist = malloc(sizeof(int32_t) * nq * nn);
     oracle_hamming_knn(q_desc, nq, q_stride, t_desc, nt, t_stride, nn, 0, indices, idist);
+    int n = oracle_frame_match_knn(indices, idist, nq, q_kps, q_map, t_kps, t_map, minDescDist, nn_match_ratio, checkOrientation, maxOctaveDiff,
+                                   F12, scaleFactors, nScale, out);
+    free(indices); free(idist);
+    return n;
+}
+
+/* the same filters on a GIVEN 10-NN table (nq x 10 indices / distances as xflann returns them): lets bench.py's CPU arm feed the
+ * reference's own approximate index (HKMeans(32,0) + 16 checks, framematcher.cpp:213,239) instead of the exact search */
+int oracle_frame_match_knn(const int32_t* indices, const int32_t* idist, int nq, const kp_t* q_kps, const int32_t* q_map, const kp_t* t_kps,
+                           const int32_t* t_map, float minDescDist, float nn_match_ratio, int checkOrientation, int maxOctaveDiff,
+                           const float* F12, const float* scaleFactors, int nScale, dmatch_t* out) {
+    const int nn = 10;
+    if (nq <= 0) return 0;
     float* sf2 = malloc(sizeof(float) * (nScale + 1));
     for (int i = 0; i < nScale; i++) sf2[i] = scaleFactors[i] * scaleFactors[i];
     int n = 0;
@@ -144,7 +161,7 @@ int oracle_frame_match(const uint8_t* q_desc, int nq, size_t q_stride, const kp_
             }
         }
     }
-    free(indices); free(idist); free(sf2);
+    free(sf2);
     return match_tail(out, n, q_kps, t_kps, checkOrientation);
 }
 

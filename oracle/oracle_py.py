@@ -358,6 +358,34 @@ def frame_match(q_desc, q_kps, t_desc, t_kps, min_desc_dist=50.0, ratio=0.8, che
     return out[:n].copy()
 
 
+def ref_frame_match_multi(t_desc, t_kps, q_descs, q_kpss, min_desc_dist=50.0, ratio=0.8, check_orientation=True, max_octave_diff=1,
+                          scale_factors=None):
+    """FrameMatcher_Flann as the reference runs it (bench.py's CPU arm): setParams builds the reference's own xflann HKMeans(32,0)
+    index over the train frame ONCE (framematcher.cpp:200-215), every neighbour searches it with 16 checks (:239), then the
+    post-filters (oracle/match_oracle.c on that 10-NN table).  Returns the match lists, or None where oracle/_ref was not built."""
+    ref = load_ref("libref_xflann.so")
+    if ref is None:
+        return None
+    lib = load_oracle()
+    t_desc = np.ascontiguousarray(t_desc, np.uint8).reshape(-1, 32)
+    t_kps = np.ascontiguousarray(t_kps, KP_DTYPE)
+    sf = np.asarray(scale_factors if scale_factors is not None else [np.float32(1.2) ** i for i in range(8)], np.float32)
+    ref.ref_xflann_build.restype = ctypes.c_void_p
+    h = ref.ref_xflann_build(_p(t_desc), len(t_desc), 1)
+    outs = []
+    for q_desc, q_kps in zip(q_descs, q_kpss):
+        q_desc = np.ascontiguousarray(q_desc, np.uint8).reshape(-1, 32)
+        q_kps = np.ascontiguousarray(q_kps, KP_DTYPE)
+        idx, dist = np.zeros((len(q_desc), 10), np.int32), np.zeros((len(q_desc), 10), np.int32)
+        ref.ref_xflann_search(ctypes.c_void_p(h), _p(q_desc), len(q_desc), 10, 16, 0, _p(idx), _p(dist))
+        out = np.zeros(max(len(q_desc), 1), MATCH_DTYPE)
+        n = lib.oracle_frame_match_knn(_p(idx), _p(dist), len(q_desc), _p(q_kps), None, _p(t_kps), None, ctypes.c_float(min_desc_dist),
+                                       ctypes.c_float(ratio), int(check_orientation), int(max_octave_diff), None, _p(sf), len(sf), _p(out))
+        outs.append(out[:n].copy())
+    ref.ref_xflann_free(ctypes.c_void_p(h))
+    return outs
+
+
 def frame_match_bow(q_desc, q_kps, q_bow, t_desc, t_kps, t_bow, min_desc_dist=50.0, ratio=0.8, check_orientation=True, max_octave_diff=1,
                     F12=None, scale_factors=None, q_usable=None, t_usable=None):
     """oracle/match_oracle.c oracle_frame_match_bow; q_bow / t_bow = (node_id u32 ascending, ptr i32, kp i32)"""

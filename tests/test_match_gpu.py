@@ -118,3 +118,40 @@ def test_bow_match_disjoint_vocabulary_nodes(ctx):
     tb2 = (tb[0] + np.uint32(1), tb[1], tb[2])
     assert len(ctx.frame_match_bow(q, qk, qb, t, tk, tb2, ucoslam_b200.MatchParams())) == 0
     assert len(oracle_py.frame_match_bow(q, qk, qb, t, tk, tb2)) == 0
+
+
+def test_match_multi_equals_oracle(ctx):
+    """the mapper's pattern: one keyframe (train) against several neighbours (queries), each with its own F12, ragged sizes and
+    MODE_UNASSIGNED-style row maps; every list must equal the per-pair oracle"""
+    rng = np.random.default_rng(9)
+    _, _, t, tk = oracle_py.synth_match_frames(50, nt=1800, nq=10)
+    tm = np.sort(rng.choice(1800, 1300, replace=False)).astype(np.int32)
+    qs, qks, qms, f12s = [], [], [], []
+    for f, nq in enumerate([1500, 900, 2000, 0, 37]):
+        q, qk, _, _ = oracle_py.synth_match_frames(60 + f, nt=10, nq=max(nq, 1))
+        # queries = noisy copies of train rows so that matches exist
+        if nq:
+            src = rng.integers(0, 1800, nq)
+            q = t[src].copy()
+            flips = rng.integers(0, 256, (nq, 12))
+            for j in range(12):
+                q[np.arange(nq), flips[:, j] >> 3] ^= (1 << (flips[:, j] & 7)).astype(np.uint8)
+            qk = qk[:nq]
+            qk["octave"] = tk["octave"][src]
+            qk["angle"] = tk["angle"][src]
+            qk["x"], qk["y"] = tk["x"][src] + rng.normal(0, 1, nq).astype(np.float32), tk["y"][src] + rng.normal(0, 1, nq).astype(np.float32)
+        else:
+            q, qk = q[:0], qk[:0]
+        qm = None if f % 2 else np.sort(rng.choice(max(nq, 1), nq * 2 // 3, replace=False)).astype(np.int32) if nq else None
+        qs.append(q if qm is None else q[qm]); qks.append(qk); qms.append(qm)
+        f12s.append(F * np.float32(1 + 0.1 * f))
+    for use_f in (False, True):
+        prm = ucoslam_b200.MatchParams(100.0, 0.6, True, 100, F if use_f else None)
+        got = ctx.frame_match_multi(t[tm], tk, qs, qks, prm, f12=np.array(f12s) if use_f else None, t_map=tm, q_maps=qms)
+        tot = 0
+        for f in range(len(qs)):
+            ref = oracle_py.frame_match(qs[f], qks[f], t[tm], tk, min_desc_dist=100.0, ratio=0.6, check_orientation=True, max_octave_diff=100,
+                                        F12=f12s[f] if use_f else None, q_map=qms[f], t_map=tm) if len(qs[f]) else np.zeros(0, ucoslam_b200.MATCH_DTYPE)
+            assert same(got[f], ref)
+            tot += len(ref)
+        assert tot > 50

@@ -13,6 +13,7 @@
 //   * remove_unused_matches is a stable compaction: block-wide prefix sums over query order.
 #include "common.cuh"
 #include <float.h>
+#include <string.h>
 #include <vector>
 
 int uco_knn_launch_internal(uco_b200_ctx* ctx, const uint8_t* q_dev, int nq, const uint8_t* t_dev, int nt, int k, int order,
@@ -30,8 +31,10 @@ struct MatchArgs {
     const int32_t* knn_dist;
     const uco_keypoint* q_kps; size_t q_kps_stride;
     const uco_keypoint* t_kps; size_t t_kps_stride;
-    const int32_t* q_map;     // optional (single pair)
-    const int32_t* t_map;
+    const int32_t* q_map;     // optional: descriptor row -> keypoint index (pair p's map at q_map + p * q_map_stride)
+    const int32_t* t_map;     // optional, shared by all pairs
+    size_t q_map_stride;
+    const float* f12_pair;    // optional: 9 floats per pair (matchEpipolar against several frames); null -> prm.f12
     int nq_max, nt_max, n_t_kps;   // n_t_kps: size of the `used` table of a pair
     const int32_t* nq_dev; const int32_t* nt_dev;
     unsigned long long* used; // n_pairs x n_t_kps
@@ -75,6 +78,8 @@ __global__ void __launch_bounds__(MT) match_filter_kernel(MatchArgs A) {
     int2* cand = A.cand + (size_t)pair * A.nq_max;
     uco_match* out = A.out + (size_t)pair * A.nq_max;
     const uco_match_params& P = A.prm;
+    const int32_t* q_map = A.q_map ? A.q_map + (size_t)pair * A.q_map_stride : nullptr;
+    const float* F12 = A.f12_pair ? A.f12_pair + 9 * (size_t)pair : P.f12;
 
     for (int t = tid; t < A.n_t_kps; t += MT) used[t] = ~0ull;
     if (tid < NBINS) hist[tid] = 0;
@@ -84,7 +89,7 @@ __global__ void __launch_bounds__(MT) match_filter_kernel(MatchArgs A) {
     for (int i = tid; i < nq && !A.bow_entry_node; i += MT) {
         float bestDist = P.min_desc_dist, bestDist2 = FLT_MAX;
         int bestTrain = -1, octaveBest2 = -1;
-        const int queryIndex = A.q_map ? A.q_map[i] : i;
+        const int queryIndex = q_map ? q_map[i] : i;
         const uco_keypoint q = qk[queryIndex];
         for (int j = 0; j < NN; j++) {
             const int ti = kidx[i * NN + j];
@@ -97,7 +102,7 @@ __global__ void __launch_bounds__(MT) match_filter_kernel(MatchArgs A) {
                 if (abs(t.octave - q.octave) > P.max_octave_diff) continue;
                 if (P.use_f12) {
                     const float sf = P.scale_factors[min(max(q.octave, 0), UCO_MATCH_MAX_SCALES - 1)];
-                    if ((double)epipolar_sq_dist(t, q, P.f12) >= 3.84 * (double)(sf * sf)) continue;
+                    if ((double)epipolar_sq_dist(t, q, F12) >= 3.84 * (double)(sf * sf)) continue;
                 }
                 if (d < bestDist) { bestDist = d; bestTrain = trainIndex; }
                 else { bestDist2 = d; octaveBest2 = t.octave; }
@@ -110,7 +115,7 @@ __global__ void __launch_bounds__(MT) match_filter_kernel(MatchArgs A) {
     // FrameMatcher_BoW::matchEpipolar (framematcher.cpp:433-480): the candidates of a query keypoint are the train keypoints of the
     // same level-3 vocabulary node, in the node's list order; any candidate that is not a new best overwrites the runner-up
     for (int i = tid; i < nq && A.bow_entry_node; i += MT) {
-        const int qidx = A.q_map[i];
+        const int qidx = q_map[i];
         int bestTrain = -1;
         float bestDist = P.min_desc_dist, bestDist2 = FLT_MAX;
         int octaveBest2 = -1;
@@ -127,7 +132,7 @@ __global__ void __launch_bounds__(MT) match_filter_kernel(MatchArgs A) {
                 if (abs(t.octave - q.octave) > P.max_octave_diff) continue;
                 if (P.use_f12) {
                     const float sf = P.scale_factors[min(max(q.octave, 0), UCO_MATCH_MAX_SCALES - 1)];
-                    if ((double)epipolar_sq_dist(t, q, P.f12) >= 3.84 * (double)(sf * sf)) continue;
+                    if ((double)epipolar_sq_dist(t, q, F12) >= 3.84 * (double)(sf * sf)) continue;
                 }
                 int pc = 0;
 #pragma unroll
@@ -148,11 +153,12 @@ __global__ void __launch_bounds__(MT) match_filter_kernel(MatchArgs A) {
         if (c.x < 0) continue;
         if (used[c.x] != (((unsigned long long)(unsigned)c.y << 32) | (unsigned)i)) { cand[i].x = -1; continue; }
         if (P.check_orientation) {
-            const int queryIndex = A.q_map ? A.q_map[i] : i;
+            const int queryIndex = q_map ? q_map[i] : i;
             float rot = tk[c.x].angle - qk[queryIndex].angle;
             if (rot < 0.0f) rot += 360.0f;
             int bin = (int)roundf(rot * (1.0f / (float)NBINS));
             if (bin == NBINS) bin = 0;
+            if (bin < 0 || bin >= NBINS) { cand[i].x = -1; continue; }   // angles outside [0, 360] (the reference asserts): the match is dropped
             atomicAdd(&hist[bin], 1);
             cand[i].y = c.y | (bin << 16);  // distance <= 256 fits the low half
         }
@@ -192,7 +198,7 @@ __global__ void __launch_bounds__(MT) match_filter_kernel(MatchArgs A) {
         for (int w = 0; w < warp; w++) before += warp_tot[w];
         if (flag) {
             uco_match m;
-            m.queryIdx = A.q_map ? A.q_map[i] : i;
+            m.queryIdx = q_map ? q_map[i] : i;
             m.trainIdx = c.x;
             m.imgIdx = -1;
             m.distance = (float)(c.y & 0xffff);
@@ -242,7 +248,7 @@ int uco_b200_frame_match_batch_dev(uco_b200_ctx* ctx, int n_pairs, const uint8_t
     MatchArgs A;
     A.knn_idx = knn; A.knn_dist = knn + knn_elems;
     A.q_kps = q_kps_dev; A.q_kps_stride = q_kps_pair_stride; A.t_kps = t_kps_dev; A.t_kps_stride = t_kps_pair_stride;
-    A.q_map = nullptr; A.t_map = nullptr;
+    A.q_map = nullptr; A.t_map = nullptr; A.q_map_stride = 0; A.f12_pair = nullptr;
     A.nq_max = nq_max; A.nt_max = nt_max; A.n_t_kps = nt_max; A.nq_dev = nq_dev; A.nt_dev = nt_dev;
     A.used = (unsigned long long*)scr; A.cand = (int2*)(scr + used_bytes);
     A.out = out_dev; A.n_out = n_out_dev; A.prm = *prm;
@@ -293,7 +299,7 @@ int uco_b200_frame_match(uco_b200_ctx* ctx, const uint8_t* q_desc, int nq, size_
     MatchArgs A;
     A.knn_idx = knn; A.knn_dist = knn + knn_elems;
     A.q_kps = (const uco_keypoint*)(din + o_qk); A.q_kps_stride = 0; A.t_kps = (const uco_keypoint*)(din + o_tk); A.t_kps_stride = 0;
-    A.q_map = q_map ? (const int32_t*)(din + o_qm) : nullptr; A.t_map = t_map ? (const int32_t*)(din + o_tm) : nullptr;
+    A.q_map = q_map ? (const int32_t*)(din + o_qm) : nullptr; A.t_map = t_map ? (const int32_t*)(din + o_tm) : nullptr; A.q_map_stride = 0; A.f12_pair = nullptr;
     A.nq_max = nq; A.nt_max = nt; A.n_t_kps = n_t_kps; A.nq_dev = nullptr; A.nt_dev = nullptr;
     A.used = (unsigned long long*)scr; A.cand = (int2*)(scr + used_bytes);
     A.out = (uco_match*)(dout + 16); A.n_out = (int32_t*)dout; A.prm = *prm;
@@ -367,7 +373,7 @@ int uco_b200_frame_match_bow(uco_b200_ctx* ctx, const uint8_t* q_desc, size_t q_
     MatchArgs A;
     A.knn_idx = nullptr; A.knn_dist = nullptr;
     A.q_kps = (const uco_keypoint*)(din + o_qk); A.q_kps_stride = 0; A.t_kps = (const uco_keypoint*)(din + o_tk); A.t_kps_stride = 0;
-    A.q_map = (const int32_t*)(din + o_qe); A.t_map = nullptr;
+    A.q_map = (const int32_t*)(din + o_qe); A.t_map = nullptr; A.q_map_stride = 0; A.f12_pair = nullptr;
     A.nq_max = ne; A.nt_max = n_t_kps; A.n_t_kps = n_t_kps; A.nq_dev = nullptr; A.nt_dev = nullptr;
     A.used = (unsigned long long*)scr; A.cand = (int2*)(scr + used_bytes);
     A.out = (uco_match*)(dout + 16); A.n_out = (int32_t*)dout; A.prm = *prm;
@@ -382,6 +388,98 @@ int uco_b200_frame_match_bow(uco_b200_ctx* ctx, const uint8_t* q_desc, size_t q_
     UCO_CUDA(ctx, cudaStreamSynchronize(st));
     if (n > 0) UCO_CUDA(ctx, cudaMemcpy(out, dout + 16, sizeof(uco_match) * (size_t)n, cudaMemcpyDeviceToHost));
     *n_out = n;
+    return UCO_OK;
+}
+
+// The mapper's pattern (new-map-point creation, src/utils/mapmanager.cpp:9972-10065): FrameMatcher::setParams(train = the keyframe)
+// once, then matchEpipolar(query = each neighbour keyframe, F12_i).  One call = one upload, two launches (k-NN of all the
+// neighbours' rows against the keyframe's rows; the filters, one block per neighbour), one download.
+int uco_b200_frame_match_multi(uco_b200_ctx* ctx, const uint8_t* t_desc, int nt, size_t t_stride, const uco_keypoint* t_kps, int n_t_kps,
+                               const int32_t* t_map, int n_frames, const uint8_t* const* q_desc, const int32_t* nq, size_t q_stride,
+                               const uco_keypoint* const* q_kps, const int32_t* n_q_kps, const int32_t* const* q_map, const float* f12,
+                               const uco_match_params* prm, uco_match* const* out, int capacity, int32_t* n_out) {
+    if (!ctx) return UCO_E_INVALID;
+    cudaSetDevice(ctx->device);
+    int rc = check_params(ctx, prm);
+    if (rc) return rc;
+    if (n_frames < 0 || !n_out) return uco_fail(ctx, UCO_E_INVALID, "frame_match_multi: bad arguments");
+    for (int f = 0; f < n_frames; f++) n_out[f] = 0;
+    if (n_frames == 0 || nt == 0) return UCO_OK;
+    if (nt < 0 || n_t_kps < 0 || !t_desc || !t_kps || !q_desc || !nq || !q_kps || !n_q_kps || !out || q_stride < 32 || t_stride < 32)
+        return uco_fail(ctx, UCO_E_INVALID, "frame_match_multi: bad arguments");
+    if (!t_map && n_t_kps < nt) return uco_fail(ctx, UCO_E_INVALID, "frame_match_multi: fewer train keypoints than descriptor rows");
+    if (prm->use_f12 && !f12) return uco_fail(ctx, UCO_E_INVALID, "frame_match_multi: use_f12 without the per-frame matrices");
+    int nq_max = 0, nk_max = 0;
+    for (int f = 0; f < n_frames; f++) {
+        if (nq[f] < 0 || n_q_kps[f] < 0 || (nq[f] && (!q_desc[f] || !q_kps[f] || !out[f]))) return uco_fail(ctx, UCO_E_INVALID, "frame_match_multi: frame %d malformed", f);
+        if (!(q_map && q_map[f]) && n_q_kps[f] < nq[f]) return uco_fail(ctx, UCO_E_INVALID, "frame_match_multi: frame %d has fewer keypoints than rows", f);
+        if (capacity < nq[f]) return uco_fail(ctx, UCO_E_CAPACITY, "frame_match_multi: output capacity %d below the %d rows of frame %d", capacity, nq[f], f);
+        for (int i = 0; q_map && q_map[f] && i < nq[f]; i++)
+            if ((unsigned)q_map[f][i] >= (unsigned)n_q_kps[f]) return uco_fail(ctx, UCO_E_INVALID, "frame_match_multi: q_map[%d][%d] out of range", f, i);
+        nq_max = nq[f] > nq_max ? nq[f] : nq_max;
+        nk_max = n_q_kps[f] > nk_max ? n_q_kps[f] : nk_max;
+    }
+    for (int i = 0; t_map && i < nt; i++)
+        if ((unsigned)t_map[i] >= (unsigned)n_t_kps) return uco_fail(ctx, UCO_E_INVALID, "frame_match_multi: t_map[%d] out of range", i);
+    if (nq_max == 0) return UCO_OK;
+    const bool any_qmap = q_map != nullptr;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t off = 0;
+    auto take = [&](size_t b) { size_t o = off; off = al(off + b); return o; };
+    const size_t F = n_frames;
+    const size_t o_td = take((size_t)nt * 32), o_tk = take(sizeof(uco_keypoint) * (size_t)n_t_kps), o_tm = take(t_map ? 4 * (size_t)nt : 0),
+                 o_qd = take(F * nq_max * 32), o_qk = take(sizeof(uco_keypoint) * F * nk_max), o_qm = take(any_qmap ? 4 * F * nq_max : 0),
+                 o_nq = take(4 * F), o_f = take(36 * F);
+    const size_t in_bytes = off;
+    uint8_t* h = (uint8_t*)uco_pinned(ctx, WS_MATCH_IN, in_bytes);
+    uint8_t* din = (uint8_t*)uco_ws(ctx, WS_MATCH_IN, in_bytes);
+    const size_t knn_elems = F * nq_max * NN;
+    int32_t* knn = (int32_t*)uco_ws(ctx, WS_MATCH_KNN, knn_elems * 8);
+    const size_t used_bytes = F * n_t_kps * 8, cand_bytes = F * nq_max * 8;
+    uint8_t* scr = (uint8_t*)uco_ws(ctx, WS_MATCH_SCRATCH, used_bytes + cand_bytes);
+    const size_t out_bytes = al(4 * F) + sizeof(uco_match) * F * nq_max;
+    uint8_t* dout = (uint8_t*)uco_ws(ctx, WS_MATCH_OUT, out_bytes);
+    uint8_t* hout = (uint8_t*)uco_pinned(ctx, WS_MATCH_OUT, out_bytes);
+    if (!h || !din || !knn || !scr || !dout || !hout) return UCO_E_NOMEM;
+    for (int i = 0; i < nt; i++) memcpy(h + o_td + 32 * (size_t)i, t_desc + t_stride * (size_t)i, 32);
+    memcpy(h + o_tk, t_kps, sizeof(uco_keypoint) * (size_t)n_t_kps);
+    if (t_map) memcpy(h + o_tm, t_map, 4 * (size_t)nt);
+    for (size_t f = 0; f < F; f++) {
+        uint8_t* qd = h + o_qd + f * nq_max * 32;
+        if (q_stride == 32) memcpy(qd, q_desc[f], 32 * (size_t)nq[f]);
+        else for (int i = 0; i < nq[f]; i++) memcpy(qd + 32 * (size_t)i, q_desc[f] + q_stride * (size_t)i, 32);
+        memcpy(h + o_qk + sizeof(uco_keypoint) * f * nk_max, q_kps[f], sizeof(uco_keypoint) * (size_t)n_q_kps[f]);
+        if (any_qmap) {
+            int32_t* m = (int32_t*)(h + o_qm) + f * nq_max;
+            for (int i = 0; i < nq[f]; i++) m[i] = q_map[f] ? q_map[f][i] : i;
+        }
+        ((int32_t*)(h + o_nq))[f] = nq[f];
+        if (f12) memcpy(h + o_f + 36 * f, f12 + 9 * f, 36);
+        else memset(h + o_f + 36 * f, 0, 36);
+    }
+    cudaStream_t st = ctx->stream;
+    UCO_CUDA(ctx, cudaMemcpyAsync(din, h, in_bytes, cudaMemcpyHostToDevice, st));
+    rc = uco_knn_launch_internal(ctx, din + o_qd, nq_max, din + o_td, nt, NN, UCO_KNN_HEAP, knn, knn + knn_elems, n_frames, (const int*)(din + o_nq),
+                                 nullptr, (size_t)nq_max * 32, 0);
+    if (rc) return rc;
+    MatchArgs A;
+    A.knn_idx = knn; A.knn_dist = knn + knn_elems;
+    A.q_kps = (const uco_keypoint*)(din + o_qk); A.q_kps_stride = nk_max; A.t_kps = (const uco_keypoint*)(din + o_tk); A.t_kps_stride = 0;
+    A.q_map = any_qmap ? (const int32_t*)(din + o_qm) : nullptr; A.q_map_stride = nq_max; A.t_map = t_map ? (const int32_t*)(din + o_tm) : nullptr;
+    A.f12_pair = f12 ? (const float*)(din + o_f) : nullptr;
+    A.nq_max = nq_max; A.nt_max = nt; A.n_t_kps = n_t_kps; A.nq_dev = (const int32_t*)(din + o_nq); A.nt_dev = nullptr;
+    A.used = (unsigned long long*)scr; A.cand = (int2*)(scr + used_bytes);
+    A.out = (uco_match*)(dout + al(4 * F)); A.n_out = (int32_t*)dout; A.prm = *prm;
+    A.bow_entry_node = nullptr; A.bow_t_node = nullptr; A.bow_t_ptr = nullptr; A.bow_t_kp = nullptr; A.q_usable = A.t_usable = nullptr; A.q_desc = A.t_desc = nullptr;
+    match_filter_kernel<<<n_frames, MT, 0, st>>>(A);
+    UCO_LAUNCH_CHECK(ctx);
+    UCO_CUDA(ctx, cudaMemcpyAsync(hout, dout, out_bytes, cudaMemcpyDeviceToHost, st));
+    UCO_CUDA(ctx, cudaStreamSynchronize(st));
+    for (size_t f = 0; f < F; f++) {
+        const int n = ((const int32_t*)hout)[f];
+        n_out[f] = n;
+        if (n > 0) memcpy(out[f], hout + al(4 * F) + sizeof(uco_match) * f * nq_max, sizeof(uco_match) * (size_t)n);
+    }
     return UCO_OK;
 }
 

@@ -1003,6 +1003,26 @@ int uco_b200_orb_extract_batch(uco_b200_ctx* ctx, const uint8_t* const* imgs, in
     return UCO_OK;
 }
 
+// internal (track.cu): host frames in, extraction on the device, results LEFT on the device: keypoints of frame i at
+// (*d_kps) + i * max_features, descriptors at (*d_desc) + 32 * i * max_features, counts at (*d_nout)[i]; the extractor's error word at *d_err
+int uco_orb_extract_keep_dev(uco_b200_ctx* ctx, const uint8_t* const* imgs, int n_imgs, int w, int h, size_t stride, const uco_orb_params* prm,
+                             uco_keypoint** d_kps, uint8_t** d_desc, int** d_nout, int** d_err) {
+    if (!prm || n_imgs <= 0 || !imgs) return uco_fail(ctx, UCO_E_INVALID, "orb: bad arguments");
+    if (stride < (size_t)w) return uco_fail(ctx, UCO_E_INVALID, "orb: stride below width");
+    int rc = orb_prepare(ctx, w, h, prm, n_imgs);
+    if (rc != UCO_OK) return rc;
+    uco_orb_state* s = ctx->orb;
+    for (int i = 0; i < n_imgs; i++) {
+        if (!imgs[i]) return uco_fail(ctx, UCO_E_INVALID, "orb: null image %d", i);
+        UCO_CUDA(ctx, cudaMemcpy2DAsync(s->d_in + (size_t)i * s->in_pitch * h, s->in_pitch, imgs[i], stride, w, h,
+                                        cudaMemcpyHostToDevice, ctx->stream));
+    }
+    rc = orb_run_dev(ctx, s->d_in, s->in_pitch, s->in_pitch * h, n_imgs, s->d_kps, s->d_desc, s->d_nout);
+    if (rc != UCO_OK) return rc;
+    *d_kps = s->d_kps; *d_desc = s->d_desc; *d_nout = s->d_nout; *d_err = s->d_err;
+    return UCO_OK;
+}
+
 int uco_b200_orb_extract(uco_b200_ctx* ctx, const uint8_t* img, int w, int h, size_t stride, const uco_orb_params* prm,
                          uco_keypoint* kps, uint8_t* desc, int capacity, int* n_out) {
     const uint8_t* one[1] = {img};

@@ -27,6 +27,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstring>
+#include <new>
 
 int uco_kdtree_build_launch(uco_b200_ctx* ctx, int n_frames, const uco_keypoint* kps_dev, size_t kps_stride, const int32_t* n_kp_dev,
                             int n_fixed, int cap, uco_kdnode* nodes_dev, int node_cap, int32_t* leaf_dev, double* bbox_dev,
@@ -675,6 +676,178 @@ int uco_b200_track_projected(uco_b200_ctx* ctx, int n_prev, const uco_keypoint* 
     const int n = *(int*)(ho + (o_cnt - o_match));
     memcpy(out, ho, sizeof(uco_match) * (size_t)n);
     *n_out = n;
+    return UCO_OK;
+}
+
+// ---- device-resident mirror of the tracking state of n independent streams (Frame / Map mirrors) ------------------
+// What the tracker reads besides the new image: the previous frame's keypoints / descriptors / map-point assignment
+// (Frame::und_kpts, ::desc, ::ids, src/map_types/frame.h:60-75) and the local map's points (MapPoint coordinates, normal, scale
+// range, descriptor, stable flag; src/map_types/mappoint.h).  In the reference these live in host containers; here they live in
+// HBM between calls, so a frame costs one image upload and one result download.
+struct uco_b200_track_state {
+    int n_streams, prev_cap, map_cap;
+    uint8_t* d;      // one allocation
+    size_t o_pkps, o_pdesc, o_pn, o_prow, o_mn, o_id, o_pos, o_nrm, o_min, o_max, o_mdesc, o_stab, o_loc, o_prior, total;
+};
+
+int uco_b200_track_state_create(uco_b200_ctx* ctx, int n_streams, int prev_cap, int map_cap, uco_b200_track_state** out) {
+    if (!ctx) return UCO_E_INVALID;
+    cudaSetDevice(ctx->device);
+    if (!out || n_streams <= 0 || prev_cap <= 0 || map_cap <= 0) return uco_fail(ctx, UCO_E_INVALID, "track_state_create: bad arguments");
+    uco_b200_track_state* st = new (std::nothrow) uco_b200_track_state();
+    if (!st) return UCO_E_NOMEM;
+    st->n_streams = n_streams; st->prev_cap = prev_cap; st->map_cap = map_cap;
+    const size_t F = n_streams, P = F * prev_cap, M = F * map_cap;
+    size_t off = 0;
+    auto take = [&](size_t b) { size_t o = off; off += al(b); return o; };
+    st->o_pkps = take(sizeof(uco_keypoint) * P); st->o_pdesc = take(32 * P); st->o_pn = take(4 * F); st->o_prow = take(4 * P);
+    st->o_mn = take(4 * F); st->o_id = take(4 * M); st->o_pos = take(12 * M); st->o_nrm = take(12 * M); st->o_min = take(4 * M);
+    st->o_max = take(4 * M); st->o_mdesc = take(32 * M); st->o_stab = take(M); st->o_loc = take(M); st->o_prior = take(64 * F);
+    st->total = off;
+    cudaError_t e = cudaMalloc(&st->d, off);
+    if (e != cudaSuccess) { delete st; return uco_fail(ctx, UCO_E_NOMEM, "track_state_create: cudaMalloc(%zu) -> %s", off, cudaGetErrorString(e)); }
+    cudaMemsetAsync(st->d, 0, off, ctx->stream);
+    cudaMemsetAsync(st->d + st->o_stab, 1, M, ctx->stream);
+    cudaMemsetAsync(st->d + st->o_loc, 1, M, ctx->stream);
+    UCO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = st;
+    return UCO_OK;
+}
+
+void uco_b200_track_state_free(uco_b200_ctx* ctx, uco_b200_track_state* st) {
+    if (!st) return;
+    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    cudaFree(st->d);
+    delete st;
+}
+
+// previous frame of one stream: n keypoints (octave is read), descriptors, and per keypoint the ROW of its map point in the stream's
+// map block (-1: none / bad point)
+int uco_b200_track_state_set_prev(uco_b200_ctx* ctx, uco_b200_track_state* st, int stream, int n, const uco_keypoint* kps, const uint8_t* desc,
+                                  const int32_t* mp_row) {
+    if (!ctx || !st) return UCO_E_INVALID;
+    cudaSetDevice(ctx->device);
+    if (stream < 0 || stream >= st->n_streams || n < 0 || n > st->prev_cap || (n && (!kps || !desc || !mp_row)))
+        return uco_fail(ctx, UCO_E_INVALID, "track_state_set_prev: bad arguments");
+    cudaStream_t s = ctx->stream;
+    const size_t b = (size_t)stream * st->prev_cap;
+    int32_t* hn = (int32_t*)uco_pinned(ctx, WS_TRACK_ERR, 64);
+    if (!hn) return UCO_E_NOMEM;
+    hn[2] = n;
+    if (n) {
+        UCO_CUDA(ctx, cudaMemcpyAsync(st->d + st->o_pkps + sizeof(uco_keypoint) * b, kps, sizeof(uco_keypoint) * (size_t)n, cudaMemcpyHostToDevice, s));
+        UCO_CUDA(ctx, cudaMemcpyAsync(st->d + st->o_pdesc + 32 * b, desc, 32 * (size_t)n, cudaMemcpyHostToDevice, s));
+        UCO_CUDA(ctx, cudaMemcpyAsync(st->d + st->o_prow + 4 * b, mp_row, 4 * (size_t)n, cudaMemcpyHostToDevice, s));
+    }
+    UCO_CUDA(ctx, cudaMemcpyAsync(st->d + st->o_pn + 4 * (size_t)stream, hn + 2, 4, cudaMemcpyHostToDevice, s));
+    UCO_CUDA(ctx, cudaStreamSynchronize(s));
+    return UCO_OK;
+}
+
+// the map block of one stream (the points the tracker may see: those of the previous frame + the local map of the reference keyframe)
+int uco_b200_track_state_set_map(uco_b200_ctx* ctx, uco_b200_track_state* st, int stream, const uco_mappoints* mp, const uint8_t* stable,
+                                 const uint8_t* local) {
+    if (!ctx || !st) return UCO_E_INVALID;
+    cudaSetDevice(ctx->device);
+    if (stream < 0 || stream >= st->n_streams || !mp || mp->n < 0 || mp->n > st->map_cap ||
+        (mp->n && (!mp->ids || !mp->pos || !mp->normal || !mp->min_dist || !mp->max_dist || !mp->desc)))
+        return uco_fail(ctx, UCO_E_INVALID, "track_state_set_map: bad arguments");
+    cudaStream_t s = ctx->stream;
+    const size_t b = (size_t)stream * st->map_cap, n = mp->n;
+    int32_t* hn = (int32_t*)uco_pinned(ctx, WS_TRACK_ERR, 64);
+    if (!hn) return UCO_E_NOMEM;
+    hn[3] = mp->n;
+    if (n) {
+        UCO_CUDA(ctx, cudaMemcpyAsync(st->d + st->o_id + 4 * b, mp->ids, 4 * n, cudaMemcpyHostToDevice, s));
+        UCO_CUDA(ctx, cudaMemcpyAsync(st->d + st->o_pos + 12 * b, mp->pos, 12 * n, cudaMemcpyHostToDevice, s));
+        UCO_CUDA(ctx, cudaMemcpyAsync(st->d + st->o_nrm + 12 * b, mp->normal, 12 * n, cudaMemcpyHostToDevice, s));
+        UCO_CUDA(ctx, cudaMemcpyAsync(st->d + st->o_min + 4 * b, mp->min_dist, 4 * n, cudaMemcpyHostToDevice, s));
+        UCO_CUDA(ctx, cudaMemcpyAsync(st->d + st->o_max + 4 * b, mp->max_dist, 4 * n, cudaMemcpyHostToDevice, s));
+        UCO_CUDA(ctx, cudaMemcpyAsync(st->d + st->o_mdesc + 32 * b, mp->desc, 32 * n, cudaMemcpyHostToDevice, s));
+        if (stable) UCO_CUDA(ctx, cudaMemcpyAsync(st->d + st->o_stab + b, stable, n, cudaMemcpyHostToDevice, s));
+        else UCO_CUDA(ctx, cudaMemsetAsync(st->d + st->o_stab + b, 1, n, s));
+        if (local) UCO_CUDA(ctx, cudaMemcpyAsync(st->d + st->o_loc + b, local, n, cudaMemcpyHostToDevice, s));
+        else UCO_CUDA(ctx, cudaMemsetAsync(st->d + st->o_loc + b, 1, n, s));
+    }
+    UCO_CUDA(ctx, cudaMemcpyAsync(st->d + st->o_mn + 4 * (size_t)stream, hn + 3, 4, cudaMemcpyHostToDevice, s));
+    UCO_CUDA(ctx, cudaStreamSynchronize(s));
+    return UCO_OK;
+}
+
+namespace {
+void state_view(const uco_b200_track_state* st, uco_track_batch* b) {
+    b->n_frames = st->n_streams; b->prev_cap = st->prev_cap; b->map_cap = st->map_cap;
+    b->prev_kps = (const uco_keypoint*)(st->d + st->o_pkps); b->prev_desc = st->d + st->o_pdesc; b->prev_n_kp = (const int32_t*)(st->d + st->o_pn);
+    b->prev_mp_row = (const int32_t*)(st->d + st->o_prow); b->map_n = (const int32_t*)(st->d + st->o_mn); b->mp_id = (const uint32_t*)(st->d + st->o_id);
+    b->mp_pos = (const float*)(st->d + st->o_pos); b->mp_normal = (const float*)(st->d + st->o_nrm); b->mp_min_dist = (const float*)(st->d + st->o_min);
+    b->mp_max_dist = (const float*)(st->d + st->o_max); b->mp_desc = st->d + st->o_mdesc; b->mp_stable = st->d + st->o_stab; b->mp_local = st->d + st->o_loc;
+    b->pose_prior = (const float*)(st->d + st->o_prior);
+}
+}  // namespace
+
+// device-resident variant: the current frames' keypoints / descriptors (outputs of uco_b200_orb_extract_batch_dev) against the mirrored
+// state; pose_prior_dev: n_streams x 16 (device).  Outputs device resident.
+int uco_b200_track_state_step_dev(uco_b200_ctx* ctx, const uco_b200_track_state* st, const uco_keypoint* kps_dev, const uint8_t* desc_dev,
+                                  const int32_t* n_kp_dev, int kp_cap, const float* pose_prior_dev, const uco_track_params* prm,
+                                  const uco_track_out* out_dev, int flags) {
+    if (!ctx || !st) return UCO_E_INVALID;
+    uco_track_batch b;
+    memset(&b, 0, sizeof b);
+    state_view(st, &b);
+    b.kp_cap = kp_cap; b.kps = kps_dev; b.desc = desc_dev; b.n_kp = n_kp_dev; b.flags = flags;
+    if (pose_prior_dev) b.pose_prior = pose_prior_dev;
+    return uco_b200_track_batch_dev(ctx, &b, prm, out_dev);
+}
+
+int uco_orb_extract_keep_dev(uco_b200_ctx* ctx, const uint8_t* const* imgs, int n_imgs, int w, int h, size_t stride, const uco_orb_params* prm,
+                             uco_keypoint** d_kps, uint8_t** d_desc, int** d_nout, int** d_err);
+
+// One tracking step of every stream through HOST buffers: the new frames in (n_streams images) + pose priors, on the device ORB
+// extraction -> kd-trees -> the tracker's sequence against the mirrored state, out: the frames' keypoints / descriptors (what
+// Frame::kpts / ::desc hold), poses, match lists with inlier flags.  One upload per image, one staged download.
+int uco_b200_track_frames(uco_b200_ctx* ctx, const uco_b200_track_state* st, const uint8_t* const* imgs, int w, int h, size_t stride,
+                          const uco_orb_params* orb, const uco_track_params* prm, const float* pose_prior, uco_keypoint* kps, uint8_t* desc,
+                          int32_t* n_kp, const uco_track_out* out) {
+    if (!ctx || !st) return UCO_E_INVALID;
+    cudaSetDevice(ctx->device);
+    if (!imgs || !orb || !prm || !pose_prior || !out || !out->matches || !out->n_matches || !out->pose || !out->n_good || !out->status || !out->n_tbp)
+        return uco_fail(ctx, UCO_E_INVALID, "track_frames: null argument");
+    const int F = st->n_streams, mf = orb->max_features;
+    uco_keypoint* d_kps; uint8_t* d_desc; int* d_nout; int* d_oerr;
+    int rc = uco_orb_extract_keep_dev(ctx, imgs, F, w, h, stride, orb, &d_kps, &d_desc, &d_nout, &d_oerr);
+    if (rc != UCO_OK) return rc;
+    const size_t K = (size_t)F * mf;
+    size_t off = 0;
+    auto take = [&](size_t b) { size_t o = off; off += al(b); return o; };
+    const size_t o_match = take(sizeof(uco_match) * K), o_nm = take(4 * (size_t)F), o_pose = take(64 * (size_t)F), o_good = take(4 * (size_t)F),
+                 o_stat = take(4 * (size_t)F), o_tbp = take(4 * (size_t)F), o_nkp = take(4 * (size_t)F), o_oerr = take(16), o_prior = take(64 * (size_t)F);
+    const size_t o_kps = take(kps ? sizeof(uco_keypoint) * K : 0), o_desc = take(desc ? 32 * K : 0);
+    uint8_t* d = (uint8_t*)uco_ws(ctx, WS_TRACK_IN, off);
+    uint8_t* ho = (uint8_t*)uco_pinned(ctx, WS_TRACK_OUT, off);
+    if (!d || !ho) return UCO_E_NOMEM;
+    cudaStream_t s = ctx->stream;
+    memcpy(ho + o_prior, pose_prior, 64 * (size_t)F);
+    UCO_CUDA(ctx, cudaMemcpyAsync(d + o_prior, ho + o_prior, 64 * (size_t)F, cudaMemcpyHostToDevice, s));
+    uco_track_out dout;
+    dout.matches = (uco_match*)(d + o_match); dout.n_matches = (int32_t*)(d + o_nm); dout.pose = (float*)(d + o_pose);
+    dout.n_good = (int32_t*)(d + o_good); dout.status = (int32_t*)(d + o_stat); dout.n_tbp = (int32_t*)(d + o_tbp); dout.visible = nullptr;
+    rc = uco_b200_track_state_step_dev(ctx, st, d_kps, d_desc, d_nout, mf, (const float*)(d + o_prior), prm, &dout, UCO_TRACK_NO_SYNC);
+    if (rc != UCO_OK) return rc;
+    UCO_CUDA(ctx, cudaMemcpyAsync(ho, d, o_nkp, cudaMemcpyDeviceToHost, s));
+    UCO_CUDA(ctx, cudaMemcpyAsync(ho + o_nkp, d_nout, 4 * (size_t)F, cudaMemcpyDeviceToHost, s));
+    UCO_CUDA(ctx, cudaMemcpyAsync(ho + o_oerr, d_oerr, 4, cudaMemcpyDeviceToHost, s));
+    if (kps) UCO_CUDA(ctx, cudaMemcpyAsync(ho + o_kps, d_kps, sizeof(uco_keypoint) * K, cudaMemcpyDeviceToHost, s));
+    if (desc) UCO_CUDA(ctx, cudaMemcpyAsync(ho + o_desc, d_desc, 32 * K, cudaMemcpyDeviceToHost, s));
+    rc = uco_track_check_errors(ctx);
+    if (rc != UCO_OK) return rc;
+    if (*(int*)(ho + o_oerr)) return uco_fail(ctx, UCO_E_CAPACITY, "track_frames: the extractor's internal selection list overflowed");
+    memcpy(out->n_matches, ho + o_nm, 4 * (size_t)F); memcpy(out->pose, ho + o_pose, 64 * (size_t)F); memcpy(out->n_good, ho + o_good, 4 * (size_t)F);
+    memcpy(out->status, ho + o_stat, 4 * (size_t)F); memcpy(out->n_tbp, ho + o_tbp, 4 * (size_t)F);
+    if (n_kp) memcpy(n_kp, ho + o_nkp, 4 * (size_t)F);
+    if (kps) memcpy(kps, ho + o_kps, sizeof(uco_keypoint) * K);
+    if (desc) memcpy(desc, ho + o_desc, 32 * K);
+    for (int f = 0; f < F; f++)
+        memcpy(out->matches + (size_t)f * mf, ho + o_match + sizeof(uco_match) * (size_t)f * mf, sizeof(uco_match) * (size_t)out->n_matches[f]);
     return UCO_OK;
 }
 

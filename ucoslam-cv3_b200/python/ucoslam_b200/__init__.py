@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(PKG_ROOT, "lib", "libucoslam_b200.so")
 
 UCO_KNN_HEAP, UCO_KNN_SORTED = 0, 1
 UCO_KDTREE_DEV_MAX_POINTS = 4096
+UCO_TRACK_NO_SYNC = 1
 _c = ctypes
 _vp, _i, _sz, _u64 = _c.c_void_p, _c.c_int, _c.c_size_t, _c.c_uint64
 
@@ -40,6 +41,12 @@ SIGNATURES = {
     "uco_b200_probe_sort_indices": (_i, [_vp, _i, _vp]),
     "uco_b200_track_batch_dev": (_i, [_vp, _vp, _vp, _vp]),
     "uco_b200_track_batch": (_i, [_vp, _vp, _vp, _vp]),
+    "uco_b200_track_state_create": (_i, [_vp, _i, _i, _i, _vp]),
+    "uco_b200_track_state_free": (None, [_vp, _vp]),
+    "uco_b200_track_state_set_prev": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "uco_b200_track_state_set_map": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "uco_b200_track_state_step_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i]),
+    "uco_b200_track_frames": (_i, [_vp, _vp, _vp, _i, _i, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "uco_b200_track_projected": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _c.c_float, _c.c_float, _vp, _vp]),
     "uco_b200_ba_set_host_threads": (_i, [_vp, _i]),
     "uco_b200_comm_unique_id": (_i, [_vp]),
@@ -71,6 +78,7 @@ SIGNATURES = {
     "uco_b200_frame_match": (_i, [_vp, _vp, _i, _sz, _vp, _i, _vp, _vp, _i, _sz, _vp, _i, _vp, _vp, _vp, _i, _vp]),
     "uco_b200_frame_match_batch_dev": (_i, [_vp, _i, _vp, _sz, _vp, _sz, _i, _vp, _vp, _sz, _vp, _sz, _i, _vp, _vp, _vp, _vp]),
     "uco_b200_pose_only_batch": (_i, [_vp, _i, _vp, _vp]),
+    "uco_b200_frame_match_multi": (_i, [_vp, _vp, _i, _sz, _vp, _i, _vp, _i, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "uco_b200_probe_math": (_i, [_i, _vp, _vp, _i, _vp, _vp]),
     "uco_b200_probe_retain_best": (_i, [_vp, _i, _i]),
     "uco_b200_stereo_depth": (_i, [_vp, _vp, _sz, _vp, _sz, _i, _i, _vp, _vp, _sz, _i, _vp, _vp, _sz, _i, _c.c_float, _c.c_float,
@@ -651,6 +659,30 @@ class Context:
                                                 len(out), ctypes.addressof(n)))
         return out[:n.value].copy()
 
+    def frame_match_multi(self, t_desc, t_kps, q_descs, q_kpss, prm, f12=None, t_map=None, q_maps=None):
+        """FrameMatcher::setParams(train = the keyframe) + matchEpipolar(query = each neighbour, F12_f): list of match arrays"""
+        t_desc = np.ascontiguousarray(t_desc, np.uint8).reshape(-1, 32)
+        t_kps = np.ascontiguousarray(t_kps, KP_DTYPE)
+        qd = [np.ascontiguousarray(d, np.uint8).reshape(-1, 32) for d in q_descs]
+        qk = [np.ascontiguousarray(k, KP_DTYPE) for k in q_kpss]
+        F = len(qd)
+        VP = ctypes.c_void_p * max(F, 1)
+        nq = np.array([len(d) for d in qd], np.int32)
+        nk = np.array([len(k) for k in qk], np.int32)
+        tm = None if t_map is None else np.ascontiguousarray(t_map, np.int32)
+        qm = None if q_maps is None else [None if m is None else np.ascontiguousarray(m, np.int32) for m in q_maps]
+        qmp = None if qm is None else VP(*[None if m is None else m.ctypes.data for m in qm])
+        f12a = None if f12 is None else np.ascontiguousarray(f12, np.float32).reshape(F, 9)
+        cap = max(1, int(nq.max()) if F else 1)
+        outs = [np.zeros(cap, MATCH_DTYPE) for _ in range(F)]
+        n_out = np.zeros(max(F, 1), np.int32)
+        self._chk(self.lib.uco_b200_frame_match_multi(
+            self.h, _p(t_desc), len(t_desc), 32, _p(t_kps), len(t_kps), _p(tm), F, ctypes.cast(VP(*[d.ctypes.data for d in qd]), ctypes.c_void_p),
+            _p(nq), 32, ctypes.cast(VP(*[k.ctypes.data for k in qk]), ctypes.c_void_p), _p(nk),
+            None if qmp is None else ctypes.cast(qmp, ctypes.c_void_p), _p(f12a), ctypes.addressof(prm),
+            ctypes.cast(VP(*[o.ctypes.data for o in outs]), ctypes.c_void_p), cap, _p(n_out)))
+        return [outs[f][:n_out[f]].copy() for f in range(F)]
+
     def frame_match_bow(self, q_desc, q_kps, q_bow, t_desc, t_kps, t_bow, prm, q_usable=None, t_usable=None):
         """FrameMatcher_BoW::matchEpipolar; q_bow / t_bow = (node_id, ptr, kp) as bow_index() gives"""
         q_desc = np.ascontiguousarray(q_desc, np.uint8).reshape(-1, 32)
@@ -804,6 +836,56 @@ class Context:
     def hamming_knn_dev(self, q_dev, nq, t_dev, nt, k, order, idx_dev, dist_dev):
         """Device pointers (ints, e.g. torch.Tensor.data_ptr()); asynchronous on the context stream."""
         self._chk(self.lib.uco_b200_hamming_knn_dev(self.h, q_dev, nq, t_dev, nt, k, order, idx_dev, dist_dev))
+
+
+class TrackState:
+    """uco_b200_track_state: device-resident mirror of the tracking state (previous frame + map block) of n independent streams."""
+
+    def __init__(self, ctx, n_streams, prev_cap, map_cap):
+        self.ctx, self.n, self.prev_cap, self.map_cap = ctx, n_streams, prev_cap, map_cap
+        h = ctypes.c_void_p()
+        ctx._chk(ctx.lib.uco_b200_track_state_create(ctx.h, n_streams, prev_cap, map_cap, ctypes.addressof(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.uco_b200_track_state_free(self.ctx.h, self.h)
+            self.h = None
+
+    def set_scene(self, stream, sc):
+        """previous frame + map block of one stream from a scene dict (synth.synth_track_scene keys)"""
+        A = lambda k, dt: np.ascontiguousarray(sc[k], dt)
+        pk = np.zeros(len(sc["prev_octave"]), KP_DTYPE)
+        pk["octave"] = sc["prev_octave"]
+        pd, pr = A("prev_desc", np.uint8), A("prev_mp_row", np.int32)
+        c = self.ctx
+        c._chk(c.lib.uco_b200_track_state_set_prev(c.h, self.h, stream, len(pk), _p(pk), _p(pd), _p(pr)))
+        ids, pos, nrm = A("mp_id", np.uint32), A("mp_pos", np.float32), A("mp_normal", np.float32)
+        dmin, dmax, mdesc = A("mp_min_dist", np.float32), A("mp_max_dist", np.float32), A("mp_desc", np.uint8)
+        mp = MapPoints(len(ids), _p(ids), _p(pos), _p(nrm), _p(dmin), _p(dmax), _p(mdesc))
+        st = A("mp_stable", np.uint8) if "mp_stable" in sc else None
+        lo = A("mp_local", np.uint8) if "mp_local" in sc else None
+        c._chk(c.lib.uco_b200_track_state_set_map(c.h, self.h, stream, ctypes.addressof(mp), _p(st) if st is not None else None,
+                                                  _p(lo) if lo is not None else None))
+
+    def track_frames(self, imgs, orb_prm, prm, pose_prior):
+        """one step of every stream through host buffers: imgs (n, h, w) u8 -> (kps, desc, n_kp, list of result dicts)"""
+        c = self.ctx
+        imgs = np.ascontiguousarray(imgs, np.uint8)
+        F, h, w = imgs.shape
+        assert F == self.n
+        mf = orb_prm.max_features
+        ptrs = (ctypes.c_void_p * F)(*[imgs[i].ctypes.data for i in range(F)])
+        prior = np.ascontiguousarray(pose_prior, np.float32).reshape(F, 16)
+        kps, desc, nkp = np.zeros((F, mf), KP_DTYPE), np.zeros((F, mf, 32), np.uint8), np.zeros(F, np.int32)
+        o = dict(matches=np.zeros((F, mf), MATCH_DTYPE), n_matches=np.zeros(F, np.int32), pose=np.zeros((F, 16), np.float32),
+                 n_good=np.zeros(F, np.int32), status=np.zeros(F, np.int32), n_tbp=np.zeros(F, np.int32))
+        to = TrackOut(*[_p(o[k]) for k in ("matches", "n_matches", "pose", "n_good", "status", "n_tbp")], None)
+        c._chk(c.lib.uco_b200_track_frames(c.h, self.h, ctypes.cast(ptrs, ctypes.c_void_p), w, h, w, ctypes.addressof(orb_prm),
+                                           ctypes.addressof(prm), _p(prior), _p(kps), _p(desc), _p(nkp), ctypes.addressof(to)))
+        res = [dict(matches=o["matches"][f, :o["n_matches"][f]].copy(), pose44=o["pose"][f].copy(), n_good=int(o["n_good"][f]),
+                    status=int(o["status"][f]), n_tbp=int(o["n_tbp"][f])) for f in range(F)]
+        return kps, desc, nkp, res
 
 
 class KeyFrameDataBase:

@@ -91,6 +91,35 @@ def track(frames, T0, extract, match_projected, pose_only, min_desc_dist=60.0, m
     return np.array(poses), stats
 
 
+def track_full(frames, T0, extract, track_frame):
+    """The tracker's full per-frame sequence (System::_11166622111371682966, src/utils/system.cpp:6460-6960) over a clip: the map is made
+    from the first frame; every following frame is extracted and handed to `track_frame(scene) -> dict(pose44, matches, n_good, ..)`
+    (search by projection from the previous frame -> solvePnp -> local-map search -> solvePnp) together with the previous frame's
+    keypoints and their map-point assignment, which the matches of the previous call define (Frame::ids, :6950-6956).
+    Returns (poses (n,4,4) f32 incl. the given first one, per-frame (n_tbp, n_matches, n_good))."""
+    kps, desc = extract(frames[0])
+    scene = make_map(kps, desc, T0)
+    scene["mp_stable"] = np.ones(len(kps), np.uint8)
+    scene["mp_local"] = np.ones(len(kps), np.uint8)
+    scene["bf"] = 0.0
+    prev = dict(prev_octave=kps["octave"].astype(np.int32), prev_desc=desc, prev_mp_row=np.arange(len(kps), dtype=np.int32))
+    pose = T0.astype(np.float32)
+    poses, stats = [pose], []
+    for img in frames[1:]:
+        kps, desc = extract(img)
+        sc = dict(scene, kp_xy=np.stack([kps["x"], kps["y"]], 1).astype(np.float32), kp_octave=kps["octave"].astype(np.int32), kp_desc=desc,
+                  pose44=pose.reshape(16), **prev)
+        r = track_frame(sc)
+        pose = np.asarray(r["pose44"], np.float32).reshape(4, 4)
+        poses.append(pose)
+        m = r["matches"]
+        rows = np.full(len(kps), -1, np.int32)
+        rows[m["queryIdx"]] = m["trainIdx"]          # mp_id == row in make_map
+        prev = dict(prev_octave=kps["octave"].astype(np.int32), prev_desc=desc, prev_mp_row=rows)
+        stats.append((int(r["n_tbp"]), len(m), int(r["n_good"])))
+    return np.array(poses), stats
+
+
 def centres(poses):
     return np.array([-(T[:3, :3].astype(np.float64).T @ T[:3, 3].astype(np.float64)) for T in poses])
 
