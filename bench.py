@@ -327,24 +327,27 @@ def run_b200(args, rank, world, local_rank):
                 self.prior_dev = torch.from_numpy(self.prior).to("cuda")
                 self.m_dev, self.nm_dev, self.pose_dev = z((F, kpts, 16), torch.uint8), z(F, torch.int32), z((F, 16), torch.float32)
                 self.good_dev, self.stat_dev, self.tbp_dev = z(F, torch.int32), z(F, torch.int32), z(F, torch.int32)
-                self.word_dev, self.wgt_dev, self.node_dev = z(kpts, torch.int32), z(kpts, torch.float32), z(kpts, torch.int32)
-                nb = KF_EVERY - 1
-                self.fm_dev, self.fmn_dev = z((nb, kpts, 16), torch.uint8), z(nb, torch.int32)
+                nkf, npairs = len(self.groups), sum(len(g[1]) for g in self.groups)
+                self.word_dev, self.wgt_dev, self.node_dev = z((nkf, kpts), torch.int32), z((nkf, kpts), torch.float32), z((nkf, kpts), torch.int32)
+                self.fm_dev, self.fmn_dev = z((npairs, kpts, 16), torch.uint8), z(npairs, torch.int32)
             self.tout = ucoslam_b200.TrackOut(self.m_dev.data_ptr(), self.nm_dev.data_ptr(), self.pose_dev.data_ptr(), self.good_dev.data_ptr(),
                                               self.stat_dev.data_ptr(), self.tbp_dev.data_ptr(), None)
             # host-side buffers of the e2e path
             self.img_ptrs = VP(F)(*[self.clip_pin[i].data_ptr() for i in range(F)])
-            self.kps_h = np.zeros((F, kpts), ucoslam_b200.KP_DTYPE)
-            self.desc_h = np.zeros((F, kpts, 32), np.uint8)
+            self.kps_pin = torch.zeros((F, kpts, 28), dtype=torch.uint8).pin_memory()      # page-locked result buffers: direct D2H
+            self.desc_pin = torch.zeros((F, kpts, 32), dtype=torch.uint8).pin_memory()
+            self.kps_h = self.kps_pin.numpy().view(ucoslam_b200.KP_DTYPE).reshape(F, kpts)
+            self.desc_h = self.desc_pin.numpy()
             self.nkp_h = np.zeros(F, np.int32)
             self.o_h = dict(matches=np.zeros((F, kpts), ucoslam_b200.MATCH_DTYPE), n_matches=np.zeros(F, np.int32), pose=np.zeros((F, 16), np.float32),
                             n_good=np.zeros(F, np.int32), status=np.zeros(F, np.int32), n_tbp=np.zeros(F, np.int32))
             self.tout_h = ucoslam_b200.TrackOut(*[self.o_h[k].ctypes.data for k in ("matches", "n_matches", "pose", "n_good", "status", "n_tbp")], None)
-            self.bow_h = (np.zeros(kpts, np.uint32), np.zeros(kpts, np.float32), np.zeros(kpts, np.uint32))
-            nb = KF_EVERY - 1
-            self.fm_h = [np.zeros(kpts, ucoslam_b200.MATCH_DTYPE) for _ in range(nb)]
-            self.fm_ptrs = VP(nb)(*[a.ctypes.data for a in self.fm_h])
-            self.fmn_h = np.zeros(nb, np.int32)
+            self.kf_idx = np.array([g[0] for g in self.groups], np.int32)
+            self.nb_ptr = np.zeros(nkf + 1, np.int32)
+            self.nb_ptr[1:] = np.cumsum([len(g[1]) for g in self.groups])
+            self.nb_idx = np.array([f for g in self.groups for f in g[1]], np.int32)
+            self.bow_h = (np.zeros((nkf, kpts), np.uint32), np.zeros((nkf, kpts), np.float32), np.zeros((nkf, kpts), np.uint32))
+            self.fm_h, self.fmn_h = np.zeros((npairs, kpts), ucoslam_b200.MATCH_DTYPE), np.zeros(npairs, np.int32)
 
         # -- device-resident step (tracker stream) --
         def orb_dev(self):
@@ -358,24 +361,20 @@ def run_b200(args, rank, world, local_rank):
             if rc != 0:
                 raise RuntimeError(lib.uco_b200_last_error(h))
 
-        def bow_dev(self):
-            for kf, _ in self.groups:
-                ctx.bow_transform_dev(voc, self.desc_dev[kf].data_ptr(), self.kpts, 3, self.word_dev.data_ptr(), self.wgt_dev.data_ptr(),
-                                      self.node_dev.data_ptr())
-
-        def match_dev(self):
-            nb = KF_EVERY - 1
-            for kf, nbrs in self.groups:     # train = the keyframe (stride 0), queries = its neighbours (consecutive frames)
-                ctx.frame_match_batch_dev(nb, self.desc_dev[nbrs[0]].data_ptr(), self.kpts * 32, self.kps_dev[nbrs[0]].data_ptr(), self.kpts,
-                                          self.kpts, self.nout_dev[nbrs[0]:].data_ptr(), self.desc_dev[kf].data_ptr(), 0,
-                                          self.kps_dev[kf].data_ptr(), 0, self.kpts, None, self.mprm, self.fm_dev.data_ptr(),
-                                          self.fmn_dev.data_ptr())
+        def keyframes_dev(self, with_voc=True, with_match=True):
+            """per keyframe: bag of words + FrameMatcher against its neighbours, on the resident frames: three launches"""
+            rc = lib.uco_b200_keyframes_batch_dev(h, voc if with_voc else None, 3, self.kps_dev.data_ptr(), self.kpts, self.desc_dev.data_ptr(),
+                                                  self.kpts * 32, self.nout_dev.data_ptr(), self.kpts, self.F, len(self.groups),
+                                                  self.kf_idx.ctypes.data, (self.nb_ptr if with_match else np.zeros_like(self.nb_ptr)).ctypes.data,
+                                                  self.nb_idx.ctypes.data, None, ctypes.addressof(self.mprm), self.word_dev.data_ptr(),
+                                                  self.wgt_dev.data_ptr(), self.node_dev.data_ptr(), self.fm_dev.data_ptr(), self.fmn_dev.data_ptr())
+            if rc != 0:
+                raise RuntimeError(lib.uco_b200_last_error(h))
 
         def step_dev(self):
             self.orb_dev()
             self.track_dev()
-            self.bow_dev()
-            self.match_dev()
+            self.keyframes_dev()
 
         # -- the same through host buffers --
         def step_host(self):
@@ -384,32 +383,22 @@ def run_b200(args, rank, world, local_rank):
                                            self.desc_h.ctypes.data, self.nkp_h.ctypes.data, ctypes.addressof(self.tout_h))
             if rc != 0:
                 raise RuntimeError(lib.uco_b200_last_error(h))
-            nb = KF_EVERY - 1
-            for kf, nbrs in self.groups:
-                rc = lib.uco_b200_bow_transform(h, voc, self.desc_h[kf].ctypes.data, int(self.nkp_h[kf]), 32, 3, self.bow_h[0].ctypes.data,
-                                                self.bow_h[1].ctypes.data, self.bow_h[2].ctypes.data)
-                if rc != 0:
-                    raise RuntimeError(lib.uco_b200_last_error(h))
-                qd = VP(nb)(*[self.desc_h[i].ctypes.data for i in nbrs])
-                qk = VP(nb)(*[self.kps_h[i].ctypes.data for i in nbrs])
-                nq = np.ascontiguousarray(self.nkp_h[nbrs[0]:nbrs[0] + nb])
-                rc = lib.uco_b200_frame_match_multi(h, self.desc_h[kf].ctypes.data, int(self.nkp_h[kf]), 32, self.kps_h[kf].ctypes.data,
-                                                    int(self.nkp_h[kf]), None, nb, ctypes.cast(qd, ctypes.c_void_p), nq.ctypes.data, 32,
-                                                    ctypes.cast(qk, ctypes.c_void_p), nq.ctypes.data, None, None, ctypes.addressof(self.mprm),
-                                                    ctypes.cast(self.fm_ptrs, ctypes.c_void_p), self.kpts, self.fmn_h.ctypes.data)
-                if rc != 0:
-                    raise RuntimeError(lib.uco_b200_last_error(h))
+            rc = lib.uco_b200_keyframes_batch(h, voc, 3, len(self.groups), self.kf_idx.ctypes.data, self.nb_ptr.ctypes.data, self.nb_idx.ctypes.data,
+                                              None, ctypes.addressof(self.mprm), self.bow_h[0].ctypes.data, self.bow_h[1].ctypes.data,
+                                              self.bow_h[2].ctypes.data, self.fm_h.ctypes.data, self.fmn_h.ctypes.data)
+            if rc != 0:
+                raise RuntimeError(lib.uco_b200_last_error(h))
 
         def h2d_bytes(self):
-            return self.F * (self.w * self.h + 64) + len(self.groups) * (self.kpts * 32 + KF_EVERY * self.kpts * (32 + 28))
+            return self.F * (self.w * self.h + 64) + 8 * (len(self.groups) + len(self.nb_idx))
 
         def d2h_bytes(self):
-            return self.F * (self.kpts * (28 + 32 + 16) + 64 + 24) + len(self.groups) * (self.kpts * 12 + (KF_EVERY - 1) * self.kpts * 16)
+            return self.F * (self.kpts * (28 + 32 + 16) + 64 + 24) + len(self.groups) * self.kpts * 12 + len(self.nb_idx) * (self.kpts * 16 + 4)
 
         def close(self):
             self.state.close()
             for k in list(self.__dict__):
-                if k.endswith("_dev") or k == "clip_pin":
+                if k.endswith("_dev") or k.endswith("_pin") or k in ("kps_h", "desc_h"):
                     delattr(self, k)
 
     F = args.frames
@@ -525,17 +514,15 @@ def run_b200(args, rank, world, local_rank):
         h, F, wk.kps_dev.data_ptr(), KPTS, wk.nout_dev.data_ptr(), KPTS, nodes_dev.data_ptr(), nodes_dev.shape[1], leaf_dev.data_ptr(),
         bbox_dev.data_ptr(), nn_dev.data_ptr())), reps)
     stage_ms["track_sequence"] = timed_events(wk.track_dev, reps)          # kd-trees + tbp + solvePnp + local map + solvePnp
-    stage_ms["bow_transform"] = timed_events(wk.bow_dev, reps)
-    stage_ms["frame_match"] = timed_events(wk.match_dev, reps)             # k-NN + filters, 7 pairs per keyframe
+    stage_ms["bow_transform"] = timed_events(lambda: wk.keyframes_dev(True, False), reps)
+    stage_ms["frame_match"] = timed_events(lambda: wk.keyframes_dev(False, True), reps)   # k-NN + filters, 7 pairs per keyframe, one launch each
     knn_pairs = len(wk.groups) * (KF_EVERY - 1)
     idx_dev = torch.empty((knn_pairs, KPTS, K_NN), dtype=torch.int32, device="cuda")
     dist_dev = torch.empty_like(idx_dev)
 
-    def knn_only():
-        for g, (kf, nbrs) in enumerate(wk.groups):
-            ctx.hamming_knn_batch_dev(KF_EVERY - 1, wk.desc_dev[nbrs[0]].data_ptr(), KPTS * 32, KPTS, wk.nout_dev[nbrs[0]:].data_ptr(),
-                                      wk.desc_dev[kf].data_ptr(), 0, KPTS, None, K_NN, ucoslam_b200.UCO_KNN_HEAP,
-                                      idx_dev[g * (KF_EVERY - 1)].data_ptr(), dist_dev[g * (KF_EVERY - 1)].data_ptr())
+    def knn_only():      # the same number of 2000 x 2000 pairs in one launch (every frame against its successor)
+        ctx.hamming_knn_batch_dev(knn_pairs, wk.desc_dev[0].data_ptr(), KPTS * 32, KPTS, wk.nout_dev.data_ptr(), wk.desc_dev[1].data_ptr(), KPTS * 32,
+                                  KPTS, wk.nout_dev[1:].data_ptr(), K_NN, ucoslam_b200.UCO_KNN_HEAP, idx_dev.data_ptr(), dist_dev.data_ptr())
     stage_ms["hamming_knn"] = timed_events(knn_only, reps)                 # the k-NN kernel inside frame_match
     ba_call_ms = timed_events(ba_all, reps)                                # the host-synchronous C-ABI call: planner + H2D + kernel + D2H
     ba_dev = []
@@ -585,7 +572,7 @@ def run_b200(args, rank, world, local_rank):
                                         "orient_describe": "orient_describe"}[k])}
     ms = stage_ms["hamming_knn"]
     popc = knn_pairs * KPTS * KPTS * 8.0 / (ms * 1e-3)
-    rl["hamming_knn"] = {"kernel": "hamming_knn_kernel", "bound": "int_popc", "achieved": popc / 1e12, "peak": PEAK_POPC / 1e12, "unit": "T popc32/s",
+    rl["hamming_knn"] = {"kernel": "hamming_knn_lq_kernel", "bound": "int_popc", "achieved": popc / 1e12, "peak": PEAK_POPC / 1e12, "unit": "T popc32/s",
                          "frac": popc / PEAK_POPC, "ms_per_step": ms, "sm_ms": ms * SM_COUNT, "traffic": traffic_of("hamming_knn")}
     ms = stage_ms["local_ba"]
     # f64 flops of a window: per LM trial linearize ~400 / observation + Schur ~ (k(k+1)/2) x 216 per landmark (k = obs per landmark) + solve (6P)^3/3

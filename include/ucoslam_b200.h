@@ -376,6 +376,22 @@ int uco_b200_frame_match_multi(uco_b200_ctx* ctx, const uint8_t* t_desc, int nt,
                                const uco_keypoint* const* q_kps, const int32_t* n_q_kps, const int32_t* const* q_map, const float* f12,
                                const uco_match_params* prm, uco_match* const* out, int capacity, int32_t* n_out);
 
+/* per-keyframe work of the mapper on DEVICE-RESIDENT frames (rows of a frame-strided buffer: the extractor's batch output):
+ * the bag of words of each keyframe (KPFrameDataBase::computeBow, src/map_types/keyframedatabase.cpp:310-321: fbow transform at
+ * `bow_level`; voc may be NULL to skip it) and FrameMatcher::setParams(train = keyframe) + matchEpipolar(query = each neighbour)
+ * (src/utils/mapmanager.cpp:9972-10065).  kf_frame[n_kf], nb_ptr[n_kf+1], nb_frame[nb_ptr[n_kf]] and f12 (pairs x 9, required
+ * when prm->use_f12) are HOST arrays; three launches for the whole batch.  _dev: outputs stay on the device (words / weights /
+ * nodes of keyframe j at [j * kp_cap ..), matches of pair e at [e * kp_cap ..), n_match[e]).  The host variant works on the frames
+ * of this context's last extraction call (uco_b200_track_frames / uco_b200_orb_extract_batch) with kp_cap = max_features. */
+int uco_b200_keyframes_batch_dev(uco_b200_ctx* ctx, const uco_b200_voc* voc, int bow_level, const uco_keypoint* kps_dev, size_t kps_frame_stride,
+                                 const uint8_t* desc_dev, size_t desc_frame_stride, const int32_t* n_kp_dev, int kp_cap, int n_frames,
+                                 int n_kf, const int32_t* kf_frame, const int32_t* nb_ptr, const int32_t* nb_frame, const float* f12,
+                                 const uco_match_params* prm, uint32_t* word_dev, float* weight_dev, uint32_t* node_dev,
+                                 uco_match* match_dev, int32_t* n_match_dev);
+int uco_b200_keyframes_batch(uco_b200_ctx* ctx, const uco_b200_voc* voc, int bow_level, int n_kf, const int32_t* kf_frame, const int32_t* nb_ptr,
+                             const int32_t* nb_frame, const float* f12, const uco_match_params* prm, uint32_t* word, float* weight, uint32_t* node,
+                             uco_match* matches, int32_t* n_matches);
+
 /* FrameMatcher_BoW::matchEpipolar (src/utils/framematcher.cpp:407-541): candidates of a query keypoint are the train keypoints under
  * the same level-3 vocabulary node (Frame::bowvector_level, what uco_b200_bow_transform reports as level_node), then the same
  * filters as above.  A frame's fBow2 is passed flattened in std::map order. */

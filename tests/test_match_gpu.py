@@ -155,3 +155,28 @@ def test_match_multi_equals_oracle(ctx):
             assert same(got[f], ref)
             tot += len(ref)
         assert tot > 50
+
+
+def test_keyframes_batch_on_resident_frames(ctx):
+    """the mapper's per-keyframe work on the frames of the last extraction call: bags of words equal uco_b200_bow_transform of the
+    downloaded descriptors, match lists equal the per-pair oracle (train = keyframe, query = neighbour)"""
+    from ucoslam_b200 import workload
+    rng = np.random.default_rng(3)
+    tex = workload.texture(5, 1024)
+    cam = workload.Camera()
+    imgs = np.stack([workload.render(cam, tex, workload.gt_pose(i, 0.3)) for i in range(6)])
+    prm = ucoslam_b200.OrbParams(1000)
+    kps, desc, n = ctx.orb_extract_batch(list(imgs), prm)
+    voc_bytes = oracle_py.synth_vocabulary(3, k=10, depth=4)
+    voc = ctx.bow_load(voc_bytes)
+    groups = [(5, [0, 1, 2, 3, 4]), (2, [0, 1]), (3, [])]
+    mprm = ucoslam_b200.MatchParams(100.0, 0.6, True, 1 << 30)
+    bows, matches = ctx.keyframes_batch(voc, groups, mprm, 1000)
+    for j, (kf, nbs) in enumerate(groups):
+        w, wt, nd = ctx.bow_transform(voc, desc[kf][:n[kf]], 3)
+        assert np.array_equal(bows[j][0][:n[kf]], w) and np.array_equal(bows[j][1][:n[kf]], wt) and np.array_equal(bows[j][2][:n[kf]], nd)
+        for e, f in enumerate(nbs):
+            ref = oracle_py.frame_match(desc[f][:n[f]], kps[f][:n[f]], desc[kf][:n[kf]], kps[kf][:n[kf]], min_desc_dist=100.0, ratio=0.6,
+                                        check_orientation=True, max_octave_diff=1 << 30)
+            assert same(matches[j][e], ref) and len(ref) > 20
+    ctx.bow_free(voc)

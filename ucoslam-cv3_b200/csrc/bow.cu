@@ -39,15 +39,24 @@ struct VocDev {
 __global__ void __launch_bounds__(256) bow_transform_kernel(const __grid_constant__ VocDev V, const uint2* __restrict__ desc,
                                                             int n, int store_level, uint32_t* __restrict__ word,
                                                             float* __restrict__ weight, uint32_t* __restrict__ node,
-                                                            int* __restrict__ err) {
+                                                            int* __restrict__ err, const int* __restrict__ seg_sel, int seg_rows,
+                                                            size_t seg_stride8, const int* __restrict__ seg_n) {
     const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / BOW_GROUP;
     const int c = threadIdx.x & (BOW_GROUP - 1);
     const unsigned gmask = 0xFFFFu << (threadIdx.x & 16);   // the two 16-lane groups of a warp leave the loop independently
-    const bool active = gid < n;
-    const int f = active ? gid : n - 1;   // inactive groups shadow the last descriptor so that shuffles stay convergent
+    // plain form: descriptor gid of a dense array.  Segmented form (seg_sel): output slot gid = (segment gid / seg_rows, row
+    // gid % seg_rows); the segment's descriptors are those of frame seg_sel[segment] in a frame-strided buffer, seg_n[frame] of them
+    bool active = gid < n;
+    const int f = gid < n ? gid : n - 1;   // inactive groups shadow the last descriptor so that shuffles stay convergent
+    const uint2* src = desc + (size_t)f * 4;
+    if (seg_sel) {
+        const int fr = seg_sel[f / seg_rows], r = f % seg_rows, nr = seg_n ? min(seg_n[fr], seg_rows) : seg_rows;
+        active = active && r < nr;
+        src = desc + (size_t)fr * seg_stride8 + (size_t)(r < nr ? r : 0) * 4;
+    }
     uint2 q[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) q[i] = desc[(size_t)f * 4 + i];
+    for (int i = 0; i < 4; i++) q[i] = src[i];
     uint32_t block = 0, level = 0, cur_node = 0, best_idx = 0;
     uint32_t out_word = 0xFFFFFFFFu, out_node = 0xFFFFFFFFu;
     float out_w = 0.f;
@@ -179,10 +188,29 @@ int uco_b200_bow_transform_dev(uco_b200_ctx* ctx, const uco_b200_voc* voc, const
              (unsigned)voc->desc_size_wp, voc->k, voc->nblocks, voc->nbits};
     const int groups_per_block = 256 / BOW_GROUP;
     bow_transform_kernel<<<(n + groups_per_block - 1) / groups_per_block, 256, 0, ctx->stream>>>(
-        V, (const uint2*)desc_dev, n, level, word_dev, weight_dev, node_dev, err);
+        V, (const uint2*)desc_dev, n, level, word_dev, weight_dev, node_dev, err, nullptr, 0, 0, nullptr);
     UCO_LAUNCH_CHECK(ctx);
     return UCO_OK;
 }
+}  // extern "C"
+
+// internal (match.cu, keyframes batch): the descriptors of n_seg selected frames of a frame-strided device buffer in ONE launch;
+// outputs at [segment * seg_rows + row]; the error word is the caller's
+int uco_bow_transform_segments(uco_b200_ctx* ctx, const uco_b200_voc* voc, const uint8_t* desc_dev, size_t frame_stride_bytes, const int* n_dev,
+                               const int* seg_sel_dev, int n_seg, int seg_rows, int level, uint32_t* word_dev, float* weight_dev,
+                               uint32_t* node_dev, int* err_dev) {
+    if (!voc) return uco_fail(ctx, UCO_E_INVALID, "bow_transform: no vocabulary");
+    if ((uintptr_t)desc_dev & 7 || frame_stride_bytes & 7) return uco_fail(ctx, UCO_E_INVALID, "bow_transform: descriptors must be 8-byte aligned");
+    VocDev V{voc->d_data, (unsigned)voc->block_size, (unsigned)voc->feature_off, (unsigned)voc->child_off,
+             (unsigned)voc->desc_size_wp, voc->k, voc->nblocks, voc->nbits};
+    const int n = n_seg * seg_rows, groups_per_block = 256 / BOW_GROUP;
+    bow_transform_kernel<<<(n + groups_per_block - 1) / groups_per_block, 256, 0, ctx->stream>>>(
+        V, (const uint2*)desc_dev, n, level, word_dev, weight_dev, node_dev, err_dev, seg_sel_dev, seg_rows, frame_stride_bytes / 8, n_dev);
+    UCO_LAUNCH_CHECK(ctx);
+    return UCO_OK;
+}
+
+extern "C" {
 
 int uco_b200_bow_transform(uco_b200_ctx* ctx, const uco_b200_voc* voc, const uint8_t* desc, int n, size_t stride, int level,
                            uint32_t* word, float* weight, uint32_t* node) {

@@ -30,7 +30,9 @@ struct uco_b200_ctx {
     uco_ba_state* ba = nullptr;
     int ba_mode = 0;          // 0 auto, 1 streamed kernels (ba.cu), 2 cluster-resident kernel (ba_cluster.cu)
     int ba_cluster_size = 0;  // CTAs per cluster of the cluster-resident solver (0 = default 8)
-    void* track_err_dev = nullptr;  // error words of the last track_batch_dev launch sequence (track.cu)
+    void* track_err_dev = nullptr;
+    int* kf_err_dev = nullptr;          // error word of the last keyframes_batch_dev launch sequence (match.cu)
+    cudaEvent_t stage_event = nullptr;  // recorded after an un-synchronised upload from a pinned staging buffer: the next writer waits on it  // error words of the last track_batch_dev launch sequence (track.cu)
     int ba_host_threads = 0;  // worker threads of the host-side planner per batch call (0 = this process's share of the cores)
 };
 

@@ -100,6 +100,7 @@ void uco_b200_destroy(uco_b200_ctx* ctx) {
     for (auto& b : ctx->pin)
         if (b.p) cudaFreeHost(b.p);
     if (ctx->sleep_event) cudaEventDestroy(ctx->sleep_event);
+    if (ctx->stage_event) cudaEventDestroy(ctx->stage_event);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

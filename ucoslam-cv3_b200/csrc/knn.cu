@@ -19,6 +19,7 @@
 #include <climits>
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
 
 #define KNN_WARPS 8
 #define KNN_TILE_ROWS 256         // train rows per shared-memory tile (8 KB)
@@ -30,6 +31,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -98,21 +102,42 @@ __device__ __forceinline__ void push_full(uint32_t (&h)[K], uint32_t v) {
     sift_to_root<K, K - 1>(h);
 }
 
+// 256-bit population count of x[0..7] with FEWER POPC instructions (Harley-Seal): bitwise carry-save adders (a full adder is two
+// LOP3s) compress words into a ones plane and carry planes of weight two.  POPC is quarter rate (8 cycles per warp instruction
+// on its own pipe), LOP3 runs on the ALU pipe (2 cycles): three adders leave 5 POPC + 14 LOP3 per distance — 40 POPC cycles
+// against ~34 ALU cycles, the balance point (the full tree, 4 POPC + 22 LOP3, is ALU bound: measured 71 % ALU pipe, 0.559 ms;
+// 8 plain POPCs are POPC bound: 0.648 ms).  Exact integer arithmetic either way.
+__device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t& sum, uint32_t& carry) {
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(sum) : "r"(a), "r"(b), "r"(c));     // a ^ b ^ c
+    asm("lop3.b32 %0, %1, %2, %3, 0xe8;" : "=r"(carry) : "r"(a), "r"(b), "r"(c));   // majority
+}
+__device__ __forceinline__ int popc256_xor(const uint4& ta, const uint4& tb, const uint4& qa, const uint4& qb) {
+    const uint32_t x0 = ta.x ^ qa.x, x1 = ta.y ^ qa.y, x2 = ta.z ^ qa.z, x3 = ta.w ^ qa.w, x4 = tb.x ^ qb.x, x5 = tb.y ^ qb.y, x6 = tb.z ^ qb.z,
+                   x7 = tb.w ^ qb.w;
+    uint32_t s1, c1, s2, c2, s3, c3;
+    csa(x0, x1, x2, s1, c1);
+    csa(x3, x4, x5, s2, c2);
+    csa(s1, s2, x6, s3, c3);
+    return __popc(s3) + __popc(x7) + 2 * (__popc(c1) + __popc(c2) + __popc(c3));
+}
+
 template <int K>
 __global__ void __launch_bounds__(KNN_WARPS * 32)
 hamming_knn_kernel(const uint4* __restrict__ q, int nq, const uint4* __restrict__ t, int nt, int order,
                    int32_t* __restrict__ out_idx, int32_t* __restrict__ out_dist, const int* __restrict__ nq_dev,
-                   const int* __restrict__ nt_dev, size_t q_stride16, size_t t_stride16, size_t out_stride) {
+                   const int* __restrict__ nt_dev, size_t q_stride16, size_t t_stride16, size_t out_stride,
+                   const int* __restrict__ q_sel, const int* __restrict__ t_sel) {
     // blockIdx.y = (query set, train set) pair of a batch; per-pair row counts may live on the device (e.g. the
     // extractor's n_out), so a whole clip is matched without a host round trip
     {
         const int pair = blockIdx.y;
-        q += pair * q_stride16;
-        t += pair * t_stride16;
+        const int qp = q_sel ? q_sel[pair] : pair, tp_ = t_sel ? t_sel[pair] : pair;   // optional frame selection: pair p = (frame q_sel[p], frame t_sel[p])
+        q += qp * q_stride16;
+        t += tp_ * t_stride16;
         out_idx += pair * out_stride;
         out_dist += pair * out_stride;
-        if (nq_dev) nq = min(nq, nq_dev[pair]);
-        if (nt_dev) nt = min(nt, nt_dev[pair]);
+        if (nq_dev) nq = min(nq, nq_dev[qp]);
+        if (nt_dev) nt = min(nt, nt_dev[tp_]);
         if ((int)(blockIdx.x * KNN_WARPS) >= nq) return;
     }
     __shared__ __align__(128) uint4 tile[KNN_STAGES][KNN_TILE_ROWS * 2];
@@ -161,8 +186,7 @@ hamming_knn_kernel(const uint4* __restrict__ q, int nq, const uint4* __restrict_
 #define KNN_DIST(c, valid_)                                                                                              \
     ({                                                                                                                   \
         const uint4 ta = lp[(valid_) ? (c) * 2 + swap : swap - lane * 2], tb = lp[(valid_) ? (c) * 2 + (swap ^ 1) : (swap ^ 1) - lane * 2]; \
-        __popc(ta.x ^ qa.x) + __popc(ta.y ^ qa.y) + __popc(ta.z ^ qa.z) + __popc(ta.w ^ qa.w) + __popc(tb.x ^ qb.x) +  \
-            __popc(tb.y ^ qb.y) + __popc(tb.z ^ qb.z) + __popc(tb.w ^ qb.w);                                           \
+        popc256_xor(ta, tb, qa, qb);                                                                                     \
     })
         // candidates of one chunk (mask m, distances d) enter the heap in train-index order, exactly the order of the reference's
         // scalar loop; `worst` only shrinks, so every candidate is re-tested against the current value (warp-uniform)
@@ -242,25 +266,169 @@ hamming_knn_kernel(const uint4* __restrict__ q, int nq, const uint4* __restrict_
     }
 }
 
+
+// ---- lane-per-query form (the default when a launch holds enough queries to fill the machine) ------------------------------------
+// Profile of the kernel above at the tracking shape (2000 x 2000): of 113 issued instructions per 32 distances only 47 score;
+// the rest replays the reference's heap, once per accepted row (~53 per query) and redundantly in all 32 lanes of the query's
+// warp, which makes the kernel issue-bound at ~52 % of the popc roof.  The replay is inherent — the final ARRAY ORDER is a
+// function of every accepted push — but 32 heaps can advance per instruction instead of one:
+//   * a LANE owns a query (8 registers) and its heap (K registers); a warp scans the train rows of the shared-memory tile one
+//     row at a time (two broadcast LDS.128), every lane scoring the row against its own query: ~27 instructions per 32
+//     distances, below the 64 cycles the popc pipe needs for them;
+//   * rows with d < bound (the lane's heap root at the start of the current 32-row window: stale values are only LARGER, so this
+//     is a superset of what the reference accepts) are appended, in train order, to a lane-private ring in shared memory
+//     (ring[pos][thread]: the bank is the lane, no conflicts);
+//   * at the end of every window the warp replays the rings in lockstep — round r handles the r-th entry of every lane with the
+//     exact test d < worst — so one instruction stream serves up to 32 pushes; late windows need 0-2 rounds.
+// Identical output to the kernel above (and to xflann's linear index) by construction: every query sees its candidate rows in
+// train-index order and every row the reference would accept is in its ring.
+#define KLQ_WARPS 4
+#define KLQ_WINDOW 32
+#define KLQ_TILE_ROWS 128         // 4 KB tiles x 3 stages + the 16 KB ring = 28 KB per CTA: 7 CTAs per SM, so a clip's launch
+#define KLQ_STAGES 3              // (16 CTAs per 2000-query frame pair) is resident in one wave
+
+template <int K>
+__global__ void __launch_bounds__((KLQ_WARPS + 1) * 32)
+hamming_knn_lq_kernel(const uint4* __restrict__ q, int nq, const uint4* __restrict__ t, int nt, int order,
+                      int32_t* __restrict__ out_idx, int32_t* __restrict__ out_dist, const int* __restrict__ nq_dev,
+                      const int* __restrict__ nt_dev, size_t q_stride16, size_t t_stride16, size_t out_stride,
+                   const int* __restrict__ q_sel, const int* __restrict__ t_sel) {
+    {
+        const int pair = blockIdx.y;
+        const int qp = q_sel ? q_sel[pair] : pair, tp_ = t_sel ? t_sel[pair] : pair;   // optional frame selection: pair p = (frame q_sel[p], frame t_sel[p])
+        q += qp * q_stride16;
+        t += tp_ * t_stride16;
+        out_idx += pair * out_stride;
+        out_dist += pair * out_stride;
+        if (nq_dev) nq = min(nq, nq_dev[qp]);
+        if (nt_dev) nt = min(nt, nt_dev[tp_]);
+        if ((int)(blockIdx.x * KLQ_WARPS * 32) >= nq) return;
+    }
+    __shared__ __align__(128) uint4 tile[KLQ_STAGES][KLQ_TILE_ROWS * 2];
+    __shared__ __align__(8) uint64_t full[KLQ_STAGES], empty[KLQ_STAGES];
+    __shared__ uint32_t ring[KLQ_WINDOW][KLQ_WARPS * 32];
+
+    const int ntiles = (nt + KLQ_TILE_ROWS - 1) / KLQ_TILE_ROWS;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < KLQ_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], KLQ_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x >= KLQ_WARPS * 32) {
+        // producer warp: one thread streams the train tiles through the ring; a stage is refilled as soon as all scanning warps
+        // have released it (empty[s]), so the scanning warps never wait for each other, only for data
+        if (threadIdx.x == KLQ_WARPS * 32) {
+            for (int tl = 0; tl < ntiles; tl++) {
+                const int s = tl % KLQ_STAGES;
+                if (tl >= KLQ_STAGES) mbar_wait(&empty[s], ((tl / KLQ_STAGES) - 1) & 1);
+                const int rows = min(KLQ_TILE_ROWS, nt - tl * KLQ_TILE_ROWS);
+                mbar_expect_tx(&full[s], rows * 32);
+                tma_bulk_g2s(tile[s], t + (size_t)tl * KLQ_TILE_ROWS * 2, rows * 32, &full[s]);
+            }
+        }
+        return;
+    }
+    const int qi = blockIdx.x * KLQ_WARPS * 32 + threadIdx.x;
+    uint4 qa, qb;
+    {
+        const int qq = min(qi, nq - 1);
+        qa = q[(size_t)qq * 2];
+        qb = q[(size_t)qq * 2 + 1];
+    }
+    uint32_t h[K];
+#pragma unroll
+    for (int i = 0; i < K; i++) h[i] = 0;
+    int n = 0, worst = INT_MAX;
+    uint32_t* my_ring = &ring[0][threadIdx.x];
+
+    for (int tl = 0; tl < ntiles; tl++) {
+        const int s = tl % KLQ_STAGES;
+        mbar_wait(&full[s], (tl / KLQ_STAGES) & 1);
+        const int rows = min(KLQ_TILE_ROWS, nt - tl * KLQ_TILE_ROWS);
+        const int base_t = tl * KLQ_TILE_ROWS;
+        for (int w0 = 0; w0 < rows; w0 += KLQ_WINDOW) {
+            const int wr = min(KLQ_WINDOW, rows - w0);
+            const uint4* tp = tile[s] + w0 * 2;
+            const int bound = worst;
+            int cnt = 0;
+#pragma unroll 8
+            for (int r = 0; r < wr; r++) {
+                const uint4 ta = tp[2 * r], tb = tp[2 * r + 1];   // the whole warp reads the same row: broadcast
+                const int d = popc256_xor(ta, tb, qa, qb);
+                // branch-free append: the slot is always written, the counter only advances for a candidate (cnt <= r < 32)
+                my_ring[cnt * (KLQ_WARPS * 32)] = ((uint32_t)d << 23) | (uint32_t)(base_t + w0 + r);
+                cnt += d < bound ? 1 : 0;
+            }
+            const int rounds = __reduce_max_sync(0xffffffffu, cnt);
+            for (int r = 0; r < rounds; r++) {
+                if (r < cnt) {
+                    const uint32_t v = my_ring[r * (KLQ_WARPS * 32)];
+                    if ((int)HD(v) < worst) {
+                        if (n < K) {
+                            push_fill<K, 0>(h, n, v);
+                            n++;
+                        } else {
+                            push_full<K>(h, v);
+                        }
+                        if (n >= K) worst = (int)HD(h[0]);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[s]);   // this warp is done reading tile[s]
+    }
+    if (qi >= nq) return;
+    int od[K], oi[K];
+#pragma unroll
+    for (int i = 0; i < K; i++) {
+        od[i] = i < n ? (int)HD(h[i]) : 0;
+        oi[i] = i < n ? (int)(h[i] & 0x7fffffu) : -1;
+    }
+    if (order == UCO_KNN_SORTED) {  // index.h:119-133
+#pragma unroll
+        for (int i = 0; i < K - 1; i++) {
+#pragma unroll
+            for (int j = i + 1; j < K; j++) {
+                if (oi[i] != -1 && od[i] > od[j]) {
+                    int tmp = od[i]; od[i] = od[j]; od[j] = tmp;
+                    tmp = oi[i]; oi[i] = oi[j]; oi[j] = tmp;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < K; i++) {
+        out_idx[(size_t)qi * K + i] = oi[i];
+        out_dist[(size_t)qi * K + i] = od[i];
+    }
+}
+
 typedef void (*knn_fn)(const uint4*, int, const uint4*, int, int, int32_t*, int32_t*, const int*, const int*, size_t, size_t,
-                       size_t);
+                       size_t, const int*, const int*);
 template <int K>
 struct KnnTable {
-    static void fill(knn_fn* f) {
+    static void fill(knn_fn* f, knn_fn* w) {
         f[K] = hamming_knn_kernel<K>;
-        KnnTable<K - 1>::fill(f);
+        if constexpr (K <= 16) w[K] = hamming_knn_lq_kernel<K>;
+        else w[K] = nullptr;
+        KnnTable<K - 1>::fill(f, w);
     }
 };
 template <>
 struct KnnTable<0> {
-    static void fill(knn_fn*) {}
+    static void fill(knn_fn*, knn_fn*) {}
+};
+struct KnnTables {
+    knn_fn warp_per_query[UCO_KNN_MAX_K + 1], specialised[UCO_KNN_MAX_K + 1];
+    KnnTables() { KnnTable<UCO_KNN_MAX_K>::fill(warp_per_query, specialised); }
 };
 
 }  // namespace
 
 static int knn_launch(uco_b200_ctx* ctx, const uint8_t* q_dev, int nq, const uint8_t* t_dev, int nt, int k, int order,
                       int32_t* idx_dev, int32_t* dist_dev, int n_pairs, const int* nq_dev, const int* nt_dev, size_t q_stride,
-                      size_t t_stride) {
+                      size_t t_stride, const int* q_sel = nullptr, const int* t_sel = nullptr) {
     if (!ctx) return UCO_E_INVALID;
     cudaSetDevice(ctx->device);  // the calling thread may be a new one (mapper / tracker threads): bind it to the context's GPU
     if (nq < 0 || nt < 0 || n_pairs < 0 || k <= 0 || k > UCO_KNN_MAX_K || (order != UCO_KNN_HEAP && order != UCO_KNN_SORTED))
@@ -273,16 +441,19 @@ static int knn_launch(uco_b200_ctx* ctx, const uint8_t* q_dev, int nq, const uin
     if (nt >= (1 << 23))
         return uco_fail(ctx, UCO_E_INVALID, "hamming_knn: train set above %d rows, shard it", (1 << 23) - 1);
     if (n_pairs > 65535) return uco_fail(ctx, UCO_E_INVALID, "hamming_knn: more than 65535 pairs in one call");
-    static knn_fn table[UCO_KNN_MAX_K + 1];
-    static bool init = false;
-    if (!init) {
-        KnnTable<UCO_KNN_MAX_K>::fill(table);
-        init = true;
+    static const KnnTables tables;   // thread-safe initialisation (C++11 magic static): contexts on several threads may race here
+    static const bool force_old = getenv("UCO_KNN_WARP_PER_QUERY") != nullptr;   // A/B switch for measurements
+    // lane-per-query needs 32 queries per warp: only when the launch still fills the machine that way (a clip's frame pairs);
+    // a single 2000-query scan of a large map keeps the warp-per-query form (8x more warps)
+    if ((size_t)n_pairs * ((nq + 31) / 32) >= (size_t)ctx->sm_count * 8 && tables.specialised[k] && !force_old) {
+        dim3 grid((nq + KLQ_WARPS * 32 - 1) / (KLQ_WARPS * 32), n_pairs);
+        tables.specialised[k]<<<grid, (KLQ_WARPS + 1) * 32, 0, ctx->stream>>>((const uint4*)q_dev, nq, (const uint4*)t_dev, nt, order, idx_dev, dist_dev,
+                                                                      nq_dev, nt_dev, q_stride / 16, t_stride / 16, (size_t)nq * k, q_sel, t_sel);
+    } else {
+        dim3 grid((nq + KNN_WARPS - 1) / KNN_WARPS, n_pairs);
+        tables.warp_per_query[k]<<<grid, KNN_WARPS * 32, 0, ctx->stream>>>((const uint4*)q_dev, nq, (const uint4*)t_dev, nt, order, idx_dev,
+                                                                            dist_dev, nq_dev, nt_dev, q_stride / 16, t_stride / 16, (size_t)nq * k, q_sel, t_sel);
     }
-    dim3 grid((nq + KNN_WARPS - 1) / KNN_WARPS, n_pairs);
-    table[k]<<<grid, KNN_WARPS * 32, 0, ctx->stream>>>((const uint4*)q_dev, nq, (const uint4*)t_dev, nt, order, idx_dev,
-                                                       dist_dev, nq_dev, nt_dev, q_stride / 16, t_stride / 16,
-                                                       (size_t)nq * k);
     UCO_LAUNCH_CHECK(ctx);
     return UCO_OK;
 }
@@ -292,6 +463,12 @@ int uco_knn_launch_internal(uco_b200_ctx* ctx, const uint8_t* q_dev, int nq, con
                             int32_t* idx_dev, int32_t* dist_dev, int n_pairs, const int* nq_dev, const int* nt_dev,
                             size_t q_stride, size_t t_stride) {
     return knn_launch(ctx, q_dev, nq, t_dev, nt, k, order, idx_dev, dist_dev, n_pairs, nq_dev, nt_dev, q_stride, t_stride);
+}
+// pair p = (query frame q_sel[p], train frame t_sel[p]) of a frame-strided buffer; nq_dev / nt_dev are indexed by FRAME
+int uco_knn_launch_selected(uco_b200_ctx* ctx, const uint8_t* q_dev, int nq, const uint8_t* t_dev, int nt, int k, int order,
+                            int32_t* idx_dev, int32_t* dist_dev, int n_pairs, const int* nq_dev, const int* nt_dev,
+                            size_t q_stride, size_t t_stride, const int* q_sel, const int* t_sel) {
+    return knn_launch(ctx, q_dev, nq, t_dev, nt, k, order, idx_dev, dist_dev, n_pairs, nq_dev, nt_dev, q_stride, t_stride, q_sel, t_sel);
 }
 
 extern "C" int uco_b200_hamming_knn_dev(uco_b200_ctx* ctx, const uint8_t* q_dev, int nq, const uint8_t* t_dev, int nt,

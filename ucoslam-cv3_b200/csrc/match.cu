@@ -34,6 +34,7 @@ struct MatchArgs {
     const int32_t* q_map;     // optional: descriptor row -> keypoint index (pair p's map at q_map + p * q_map_stride)
     const int32_t* t_map;     // optional, shared by all pairs
     size_t q_map_stride;
+    const int32_t *q_sel, *t_sel;   // optional frame selection of pair p (kps strides and nq_dev / nt_dev are then per FRAME)
     const float* f12_pair;    // optional: 9 floats per pair (matchEpipolar against several frames); null -> prm.f12
     int nq_max, nt_max, n_t_kps;   // n_t_kps: size of the `used` table of a pair
     const int32_t* nq_dev; const int32_t* nt_dev;
@@ -68,12 +69,13 @@ __global__ void __launch_bounds__(MT) match_filter_kernel(MatchArgs A) {
     __shared__ int warp_tot[MT / 32];
     __shared__ int running;
     const int pair = blockIdx.x, tid = threadIdx.x;
-    const int nq = A.nq_dev ? min(A.nq_max, A.nq_dev[pair]) : A.nq_max;
-    const int nt = A.nt_dev ? min(A.nt_max, A.nt_dev[pair]) : A.nt_max;
+    const int qf = A.q_sel ? A.q_sel[pair] : pair, tf = A.t_sel ? A.t_sel[pair] : pair;
+    const int nq = A.nq_dev ? min(A.nq_max, A.nq_dev[qf]) : A.nq_max;
+    const int nt = A.nt_dev ? min(A.nt_max, A.nt_dev[tf]) : A.nt_max;
     const int32_t* kidx = A.knn_idx + (size_t)pair * A.nq_max * NN;
     const int32_t* kdist = A.knn_dist + (size_t)pair * A.nq_max * NN;
-    const uco_keypoint* qk = A.q_kps + (size_t)pair * A.q_kps_stride;
-    const uco_keypoint* tk = A.t_kps + (size_t)pair * A.t_kps_stride;
+    const uco_keypoint* qk = A.q_kps + (size_t)qf * A.q_kps_stride;
+    const uco_keypoint* tk = A.t_kps + (size_t)tf * A.t_kps_stride;
     unsigned long long* used = A.used + (size_t)pair * A.n_t_kps;
     int2* cand = A.cand + (size_t)pair * A.nq_max;
     uco_match* out = A.out + (size_t)pair * A.nq_max;
@@ -248,7 +250,7 @@ int uco_b200_frame_match_batch_dev(uco_b200_ctx* ctx, int n_pairs, const uint8_t
     MatchArgs A;
     A.knn_idx = knn; A.knn_dist = knn + knn_elems;
     A.q_kps = q_kps_dev; A.q_kps_stride = q_kps_pair_stride; A.t_kps = t_kps_dev; A.t_kps_stride = t_kps_pair_stride;
-    A.q_map = nullptr; A.t_map = nullptr; A.q_map_stride = 0; A.f12_pair = nullptr;
+    A.q_map = nullptr; A.t_map = nullptr; A.q_map_stride = 0; A.f12_pair = nullptr; A.q_sel = A.t_sel = nullptr;
     A.nq_max = nq_max; A.nt_max = nt_max; A.n_t_kps = nt_max; A.nq_dev = nq_dev; A.nt_dev = nt_dev;
     A.used = (unsigned long long*)scr; A.cand = (int2*)(scr + used_bytes);
     A.out = out_dev; A.n_out = n_out_dev; A.prm = *prm;
@@ -299,7 +301,7 @@ int uco_b200_frame_match(uco_b200_ctx* ctx, const uint8_t* q_desc, int nq, size_
     MatchArgs A;
     A.knn_idx = knn; A.knn_dist = knn + knn_elems;
     A.q_kps = (const uco_keypoint*)(din + o_qk); A.q_kps_stride = 0; A.t_kps = (const uco_keypoint*)(din + o_tk); A.t_kps_stride = 0;
-    A.q_map = q_map ? (const int32_t*)(din + o_qm) : nullptr; A.t_map = t_map ? (const int32_t*)(din + o_tm) : nullptr; A.q_map_stride = 0; A.f12_pair = nullptr;
+    A.q_map = q_map ? (const int32_t*)(din + o_qm) : nullptr; A.t_map = t_map ? (const int32_t*)(din + o_tm) : nullptr; A.q_map_stride = 0; A.f12_pair = nullptr; A.q_sel = A.t_sel = nullptr;
     A.nq_max = nq; A.nt_max = nt; A.n_t_kps = n_t_kps; A.nq_dev = nullptr; A.nt_dev = nullptr;
     A.used = (unsigned long long*)scr; A.cand = (int2*)(scr + used_bytes);
     A.out = (uco_match*)(dout + 16); A.n_out = (int32_t*)dout; A.prm = *prm;
@@ -373,7 +375,7 @@ int uco_b200_frame_match_bow(uco_b200_ctx* ctx, const uint8_t* q_desc, size_t q_
     MatchArgs A;
     A.knn_idx = nullptr; A.knn_dist = nullptr;
     A.q_kps = (const uco_keypoint*)(din + o_qk); A.q_kps_stride = 0; A.t_kps = (const uco_keypoint*)(din + o_tk); A.t_kps_stride = 0;
-    A.q_map = (const int32_t*)(din + o_qe); A.t_map = nullptr; A.q_map_stride = 0; A.f12_pair = nullptr;
+    A.q_map = (const int32_t*)(din + o_qe); A.t_map = nullptr; A.q_map_stride = 0; A.f12_pair = nullptr; A.q_sel = A.t_sel = nullptr;
     A.nq_max = ne; A.nt_max = n_t_kps; A.n_t_kps = n_t_kps; A.nq_dev = nullptr; A.nt_dev = nullptr;
     A.used = (unsigned long long*)scr; A.cand = (int2*)(scr + used_bytes);
     A.out = (uco_match*)(dout + 16); A.n_out = (int32_t*)dout; A.prm = *prm;
@@ -465,7 +467,7 @@ int uco_b200_frame_match_multi(uco_b200_ctx* ctx, const uint8_t* t_desc, int nt,
     MatchArgs A;
     A.knn_idx = knn; A.knn_dist = knn + knn_elems;
     A.q_kps = (const uco_keypoint*)(din + o_qk); A.q_kps_stride = nk_max; A.t_kps = (const uco_keypoint*)(din + o_tk); A.t_kps_stride = 0;
-    A.q_map = any_qmap ? (const int32_t*)(din + o_qm) : nullptr; A.q_map_stride = nq_max; A.t_map = t_map ? (const int32_t*)(din + o_tm) : nullptr;
+    A.q_map = any_qmap ? (const int32_t*)(din + o_qm) : nullptr; A.q_map_stride = nq_max; A.q_sel = A.t_sel = nullptr; A.t_map = t_map ? (const int32_t*)(din + o_tm) : nullptr;
     A.f12_pair = f12 ? (const float*)(din + o_f) : nullptr;
     A.nq_max = nq_max; A.nt_max = nt; A.n_t_kps = n_t_kps; A.nq_dev = (const int32_t*)(din + o_nq); A.nt_dev = nullptr;
     A.used = (unsigned long long*)scr; A.cand = (int2*)(scr + used_bytes);
@@ -479,6 +481,136 @@ int uco_b200_frame_match_multi(uco_b200_ctx* ctx, const uint8_t* t_desc, int nt,
         const int n = ((const int32_t*)hout)[f];
         n_out[f] = n;
         if (n > 0) memcpy(out[f], hout + al(4 * F) + sizeof(uco_match) * f * nq_max, sizeof(uco_match) * (size_t)n);
+    }
+    return UCO_OK;
+}
+
+}  // extern "C"
+
+// ---- per-keyframe work of the mapper on DEVICE-RESIDENT frames ------------------------------------------------------------------------
+// What UcoSLAM's mapper does with a new keyframe before local BA (src/utils/mapmanager.cpp): its bag of words
+// (KPFrameDataBase::computeBow, src/map_types/keyframedatabase.cpp:310-321 -> fbow transform at level 3) and, for new-map-point
+// creation (:9972-10065), FrameMatcher::setParams(train = the keyframe) + matchEpipolar(query = each neighbour keyframe, F12).
+// The frames are rows of a frame-strided device buffer (the extractor's batch output): n_kf keyframes, keyframe j has the
+// neighbours nb_frame[nb_ptr[j] .. nb_ptr[j+1]).  Three launches for the whole batch: one fbow walk over all keyframes'
+// descriptors, one k-NN over all (neighbour, keyframe) pairs, one filter pass.  Index arrays and f12 are HOST arrays.
+int uco_knn_launch_selected(uco_b200_ctx* ctx, const uint8_t* q_dev, int nq, const uint8_t* t_dev, int nt, int k, int order,
+                            int32_t* idx_dev, int32_t* dist_dev, int n_pairs, const int* nq_dev, const int* nt_dev,
+                            size_t q_stride, size_t t_stride, const int* q_sel, const int* t_sel);
+struct uco_b200_voc;
+int uco_bow_transform_segments(uco_b200_ctx* ctx, const uco_b200_voc* voc, const uint8_t* desc_dev, size_t frame_stride_bytes, const int* n_dev,
+                               const int* seg_sel_dev, int n_seg, int seg_rows, int level, uint32_t* word_dev, float* weight_dev,
+                               uint32_t* node_dev, int* err_dev);
+extern "C" int uco_orb_resident(uco_b200_ctx* ctx, const uco_keypoint** d_kps, const uint8_t** d_desc, const int** d_nout, int* max_features, int* n_frames);
+
+extern "C" {
+
+int uco_b200_keyframes_batch_dev(uco_b200_ctx* ctx, const uco_b200_voc* voc, int bow_level, const uco_keypoint* kps_dev, size_t kps_frame_stride,
+                                 const uint8_t* desc_dev, size_t desc_frame_stride, const int32_t* n_kp_dev, int kp_cap, int n_frames,
+                                 int n_kf, const int32_t* kf_frame, const int32_t* nb_ptr, const int32_t* nb_frame, const float* f12,
+                                 const uco_match_params* prm, uint32_t* word_dev, float* weight_dev, uint32_t* node_dev,
+                                 uco_match* match_dev, int32_t* n_match_dev) {
+    if (!ctx) return UCO_E_INVALID;
+    cudaSetDevice(ctx->device);
+    int rc = check_params(ctx, prm);
+    if (rc) return rc;
+    if (n_kf <= 0 || kp_cap <= 0 || n_frames <= 0 || !kps_dev || !desc_dev || !n_kp_dev || !kf_frame || !nb_ptr || (nb_ptr[n_kf] > 0 && !nb_frame))
+        return uco_fail(ctx, UCO_E_INVALID, "keyframes_batch: bad arguments");
+    const int n_pairs = nb_ptr[n_kf];
+    if (n_pairs < 0 || (n_pairs > 0 && (!match_dev || !n_match_dev))) return uco_fail(ctx, UCO_E_INVALID, "keyframes_batch: bad arguments");
+    if (voc && (!word_dev || !weight_dev || !node_dev)) return uco_fail(ctx, UCO_E_INVALID, "keyframes_batch: null bag-of-words output");
+    if (prm->use_f12 && n_pairs > 0 && !f12) return uco_fail(ctx, UCO_E_INVALID, "keyframes_batch: use_f12 without the per-pair matrices");
+    for (int j = 0; j < n_kf; j++) {
+        if ((unsigned)kf_frame[j] >= (unsigned)n_frames || nb_ptr[j + 1] < nb_ptr[j]) return uco_fail(ctx, UCO_E_INVALID, "keyframes_batch: keyframe %d malformed", j);
+        for (int e = nb_ptr[j]; e < nb_ptr[j + 1]; e++)
+            if ((unsigned)nb_frame[e] >= (unsigned)n_frames) return uco_fail(ctx, UCO_E_INVALID, "keyframes_batch: neighbour frame %d out of range", nb_frame[e]);
+    }
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t off = 0;
+    auto take = [&](size_t b) { size_t o = off; off = al(off + b); return o; };
+    const size_t o_kf = take(4 * (size_t)n_kf), o_q = take(4 * (size_t)n_pairs), o_t = take(4 * (size_t)n_pairs), o_f = take(36 * (size_t)n_pairs), o_err = take(16);
+    uint8_t* h = (uint8_t*)uco_pinned(ctx, WS_MATCH_IN, off);
+    uint8_t* d = (uint8_t*)uco_ws(ctx, WS_MATCH_IN, off);
+    if (!h || !d) return UCO_E_NOMEM;
+    if (!ctx->stage_event) UCO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->stage_event, cudaEventDisableTiming));
+    else UCO_CUDA(ctx, cudaEventSynchronize(ctx->stage_event));   // the previous call's upload has left the staging buffer
+    memcpy(h + o_kf, kf_frame, 4 * (size_t)n_kf);
+    for (int j = 0; j < n_kf; j++)
+        for (int e = nb_ptr[j]; e < nb_ptr[j + 1]; e++) {
+            ((int32_t*)(h + o_q))[e] = nb_frame[e];      // query = the neighbour
+            ((int32_t*)(h + o_t))[e] = kf_frame[j];      // train = the keyframe
+        }
+    if (f12 && n_pairs) memcpy(h + o_f, f12, 36 * (size_t)n_pairs);
+    memset(h + o_err, 0, 16);
+    cudaStream_t st = ctx->stream;
+    UCO_CUDA(ctx, cudaMemcpyAsync(d, h, off, cudaMemcpyHostToDevice, st));
+    UCO_CUDA(ctx, cudaEventRecord(ctx->stage_event, st));
+    ctx->kf_err_dev = (int*)(d + o_err);
+    if (voc) {
+        rc = uco_bow_transform_segments(ctx, voc, desc_dev, desc_frame_stride, n_kp_dev, (const int*)(d + o_kf), n_kf, kp_cap, bow_level, word_dev,
+                                        weight_dev, node_dev, (int*)(d + o_err));
+        if (rc) return rc;
+    }
+    if (n_pairs == 0) return UCO_OK;
+    const size_t knn_elems = (size_t)n_pairs * kp_cap * NN;
+    int32_t* knn = (int32_t*)uco_ws(ctx, WS_MATCH_KNN, knn_elems * 8);
+    const size_t used_bytes = (size_t)n_pairs * kp_cap * 8, cand_bytes = (size_t)n_pairs * kp_cap * 8;
+    uint8_t* scr = (uint8_t*)uco_ws(ctx, WS_MATCH_SCRATCH, used_bytes + cand_bytes);
+    if (!knn || !scr) return UCO_E_NOMEM;
+    rc = uco_knn_launch_selected(ctx, desc_dev, kp_cap, desc_dev, kp_cap, NN, UCO_KNN_HEAP, knn, knn + knn_elems, n_pairs, n_kp_dev, n_kp_dev,
+                                 desc_frame_stride, desc_frame_stride, (const int*)(d + o_q), (const int*)(d + o_t));
+    if (rc) return rc;
+    MatchArgs A;
+    A.knn_idx = knn; A.knn_dist = knn + knn_elems;
+    A.q_kps = kps_dev; A.q_kps_stride = kps_frame_stride; A.t_kps = kps_dev; A.t_kps_stride = kps_frame_stride;
+    A.q_map = nullptr; A.t_map = nullptr; A.q_map_stride = 0; A.q_sel = (const int32_t*)(d + o_q); A.t_sel = (const int32_t*)(d + o_t);
+    A.f12_pair = (f12 && prm->use_f12) ? (const float*)(d + o_f) : nullptr;
+    A.nq_max = kp_cap; A.nt_max = kp_cap; A.n_t_kps = kp_cap; A.nq_dev = n_kp_dev; A.nt_dev = n_kp_dev;
+    A.used = (unsigned long long*)scr; A.cand = (int2*)(scr + used_bytes);
+    A.out = match_dev; A.n_out = n_match_dev; A.prm = *prm;
+    A.bow_entry_node = nullptr; A.bow_t_node = nullptr; A.bow_t_ptr = nullptr; A.bow_t_kp = nullptr; A.q_usable = A.t_usable = nullptr; A.q_desc = A.t_desc = nullptr;
+    match_filter_kernel<<<n_pairs, MT, 0, st>>>(A);
+    UCO_LAUNCH_CHECK(ctx);
+    return UCO_OK;
+}
+
+// the same on the frames of this context's LAST extraction call (uco_b200_track_frames / uco_b200_orb_extract_batch): host index arrays
+// in, host results out — words / weights / level nodes of keyframe j at [j * max_features ..), matches of pair e at
+// [e * max_features ..) with n_matches[e]; one small upload, three launches, one staged download
+int uco_b200_keyframes_batch(uco_b200_ctx* ctx, const uco_b200_voc* voc, int bow_level, int n_kf, const int32_t* kf_frame, const int32_t* nb_ptr,
+                             const int32_t* nb_frame, const float* f12, const uco_match_params* prm, uint32_t* word, float* weight, uint32_t* node,
+                             uco_match* matches, int32_t* n_matches) {
+    if (!ctx) return UCO_E_INVALID;
+    cudaSetDevice(ctx->device);
+    const uco_keypoint* d_kps; const uint8_t* d_desc; const int* d_nout; int mf, nfr;
+    int rc = uco_orb_resident(ctx, &d_kps, &d_desc, &d_nout, &mf, &nfr);
+    if (rc) return rc;
+    if (n_kf <= 0 || !nb_ptr) return uco_fail(ctx, UCO_E_INVALID, "keyframes_batch: bad arguments");
+    const int n_pairs = nb_ptr[n_kf];
+    if (n_pairs < 0 || (voc && (!word || !weight || !node)) || (n_pairs > 0 && (!matches || !n_matches))) return uco_fail(ctx, UCO_E_INVALID, "keyframes_batch: null output");
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t K = (size_t)n_kf * mf, P = (size_t)n_pairs * mf;
+    size_t off = 0;
+    auto take = [&](size_t b) { size_t o = off; off = al(off + b); return o; };
+    const size_t o_w = take(voc ? 4 * K : 0), o_wt = take(voc ? 4 * K : 0), o_n = take(voc ? 4 * K : 0), o_nm = take(4 * (size_t)n_pairs + 16), o_m = take(sizeof(uco_match) * P);
+    uint8_t* d = (uint8_t*)uco_ws(ctx, WS_MATCH_OUT, off);
+    uint8_t* ho = (uint8_t*)uco_pinned(ctx, WS_MATCH_OUT, off);
+    if (!d || !ho) return UCO_E_NOMEM;
+    rc = uco_b200_keyframes_batch_dev(ctx, voc, bow_level, d_kps, (size_t)mf, d_desc, (size_t)32 * mf, d_nout, mf, nfr, n_kf, kf_frame, nb_ptr, nb_frame, f12,
+                                      prm, (uint32_t*)(d + o_w), (float*)(d + o_wt), (uint32_t*)(d + o_n), (uco_match*)(d + o_m), (int32_t*)(d + o_nm));
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    UCO_CUDA(ctx, cudaMemcpyAsync(ho, d, off, cudaMemcpyDeviceToHost, st));
+    int* herr = (int*)uco_pinned(ctx, WS_GENERIC0, 16);
+    if (!herr) return UCO_E_NOMEM;
+    UCO_CUDA(ctx, cudaMemcpyAsync(herr, ctx->kf_err_dev, 4, cudaMemcpyDeviceToHost, st));
+    UCO_CUDA(ctx, cudaStreamSynchronize(st));
+    if (*herr) return uco_fail(ctx, UCO_E_FORMAT, "keyframes_batch: malformed vocabulary (cycle or block index out of range)");
+    if (voc) { memcpy(word, ho + o_w, 4 * K); memcpy(weight, ho + o_wt, 4 * K); memcpy(node, ho + o_n, 4 * K); }
+    for (int e = 0; e < n_pairs; e++) {
+        const int n = ((const int32_t*)(ho + o_nm))[e];
+        n_matches[e] = n;
+        if (n > 0) memcpy(matches + (size_t)e * mf, ho + o_m + sizeof(uco_match) * (size_t)e * mf, sizeof(uco_match) * (size_t)n);
     }
     return UCO_OK;
 }

@@ -672,6 +672,7 @@ struct uco_orb_state {
     uco_keypoint* d_kps = nullptr;
     uint8_t* d_desc = nullptr;
     int* d_nout = nullptr;
+    int last_n = 0, last_max_features = 0;   // frames / row capacity of the last extraction (its results stay resident)
     int* h_nout = nullptr;         // pinned
     int* h_err = nullptr;          // pinned
     cudaEvent_t ev[6] = {};        // stage boundaries when ctx->profiling is set
@@ -990,6 +991,7 @@ int uco_b200_orb_extract_batch(uco_b200_ctx* ctx, const uint8_t* const* imgs, in
     }
     rc = orb_run_dev(ctx, s->d_in, s->in_pitch, s->in_pitch * h, n_imgs, s->d_kps, s->d_desc, s->d_nout);
     if (rc != UCO_OK) return rc;
+    s->last_n = n_imgs; s->last_max_features = prm->max_features;
     const int mf = prm->max_features;
     UCO_CUDA(ctx, cudaMemcpyAsync(s->h_nout, s->d_nout, sizeof(int) * n_imgs, cudaMemcpyDeviceToHost, ctx->stream));
     UCO_CUDA(ctx, cudaMemcpyAsync(s->h_err, s->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1000,6 +1002,14 @@ int uco_b200_orb_extract_batch(uco_b200_ctx* ctx, const uint8_t* const* imgs, in
     UCO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (*s->h_err) return uco_fail(ctx, UCO_E_CAPACITY, "orb: internal selection list overflow");
     for (int i = 0; i < n_imgs; i++) n_out[i] = s->h_nout[i];
+    return UCO_OK;
+}
+
+// internal (match.cu): the frames of the LAST extraction call, still resident in the context's buffers
+int uco_orb_resident(uco_b200_ctx* ctx, const uco_keypoint** d_kps, const uint8_t** d_desc, const int** d_nout, int* max_features, int* n_frames) {
+    if (!ctx->orb || !ctx->orb->batch_cap || !ctx->orb->last_n) return uco_fail(ctx, UCO_E_INVALID, "no extraction result is resident in this context");
+    *d_kps = ctx->orb->d_kps; *d_desc = ctx->orb->d_desc; *d_nout = ctx->orb->d_nout;
+    *max_features = ctx->orb->last_max_features; *n_frames = ctx->orb->last_n;
     return UCO_OK;
 }
 
@@ -1019,6 +1029,7 @@ int uco_orb_extract_keep_dev(uco_b200_ctx* ctx, const uint8_t* const* imgs, int 
     }
     rc = orb_run_dev(ctx, s->d_in, s->in_pitch, s->in_pitch * h, n_imgs, s->d_kps, s->d_desc, s->d_nout);
     if (rc != UCO_OK) return rc;
+    s->last_n = n_imgs; s->last_max_features = prm->max_features;
     *d_kps = s->d_kps; *d_desc = s->d_desc; *d_nout = s->d_nout; *d_err = s->d_err;
     return UCO_OK;
 }

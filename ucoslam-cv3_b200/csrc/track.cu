@@ -821,7 +821,15 @@ int uco_b200_track_frames(uco_b200_ctx* ctx, const uco_b200_track_state* st, con
     auto take = [&](size_t b) { size_t o = off; off += al(b); return o; };
     const size_t o_match = take(sizeof(uco_match) * K), o_nm = take(4 * (size_t)F), o_pose = take(64 * (size_t)F), o_good = take(4 * (size_t)F),
                  o_stat = take(4 * (size_t)F), o_tbp = take(4 * (size_t)F), o_nkp = take(4 * (size_t)F), o_oerr = take(16), o_prior = take(64 * (size_t)F);
-    const size_t o_kps = take(kps ? sizeof(uco_keypoint) * K : 0), o_desc = take(desc ? 32 * K : 0);
+    // page-locked caller buffers (cudaHostAlloc / cudaHostRegister'ed, e.g. a pinned cv::Mat allocator) receive the keypoints and
+    // descriptors directly; pageable ones go through the context's pinned staging buffer + a host copy
+    auto pinned = [](const void* p) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return a.type == cudaMemoryTypeHost;
+    };
+    const bool kps_direct = kps && pinned(kps), desc_direct = desc && pinned(desc);
+    const size_t o_kps = take(kps && !kps_direct ? sizeof(uco_keypoint) * K : 0), o_desc = take(desc && !desc_direct ? 32 * K : 0);
     uint8_t* d = (uint8_t*)uco_ws(ctx, WS_TRACK_IN, off);
     uint8_t* ho = (uint8_t*)uco_pinned(ctx, WS_TRACK_OUT, off);
     if (!d || !ho) return UCO_E_NOMEM;
@@ -836,16 +844,16 @@ int uco_b200_track_frames(uco_b200_ctx* ctx, const uco_b200_track_state* st, con
     UCO_CUDA(ctx, cudaMemcpyAsync(ho, d, o_nkp, cudaMemcpyDeviceToHost, s));
     UCO_CUDA(ctx, cudaMemcpyAsync(ho + o_nkp, d_nout, 4 * (size_t)F, cudaMemcpyDeviceToHost, s));
     UCO_CUDA(ctx, cudaMemcpyAsync(ho + o_oerr, d_oerr, 4, cudaMemcpyDeviceToHost, s));
-    if (kps) UCO_CUDA(ctx, cudaMemcpyAsync(ho + o_kps, d_kps, sizeof(uco_keypoint) * K, cudaMemcpyDeviceToHost, s));
-    if (desc) UCO_CUDA(ctx, cudaMemcpyAsync(ho + o_desc, d_desc, 32 * K, cudaMemcpyDeviceToHost, s));
+    if (kps) UCO_CUDA(ctx, cudaMemcpyAsync(kps_direct ? (void*)kps : (void*)(ho + o_kps), d_kps, sizeof(uco_keypoint) * K, cudaMemcpyDeviceToHost, s));
+    if (desc) UCO_CUDA(ctx, cudaMemcpyAsync(desc_direct ? (void*)desc : (void*)(ho + o_desc), d_desc, 32 * K, cudaMemcpyDeviceToHost, s));
     rc = uco_track_check_errors(ctx);
     if (rc != UCO_OK) return rc;
     if (*(int*)(ho + o_oerr)) return uco_fail(ctx, UCO_E_CAPACITY, "track_frames: the extractor's internal selection list overflowed");
     memcpy(out->n_matches, ho + o_nm, 4 * (size_t)F); memcpy(out->pose, ho + o_pose, 64 * (size_t)F); memcpy(out->n_good, ho + o_good, 4 * (size_t)F);
     memcpy(out->status, ho + o_stat, 4 * (size_t)F); memcpy(out->n_tbp, ho + o_tbp, 4 * (size_t)F);
     if (n_kp) memcpy(n_kp, ho + o_nkp, 4 * (size_t)F);
-    if (kps) memcpy(kps, ho + o_kps, sizeof(uco_keypoint) * K);
-    if (desc) memcpy(desc, ho + o_desc, 32 * K);
+    if (kps && !kps_direct) memcpy(kps, ho + o_kps, sizeof(uco_keypoint) * K);
+    if (desc && !desc_direct) memcpy(desc, ho + o_desc, 32 * K);
     for (int f = 0; f < F; f++)
         memcpy(out->matches + (size_t)f * mf, ho + o_match + sizeof(uco_match) * (size_t)f * mf, sizeof(uco_match) * (size_t)out->n_matches[f]);
     return UCO_OK;

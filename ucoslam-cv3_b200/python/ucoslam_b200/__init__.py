@@ -78,6 +78,8 @@ SIGNATURES = {
     "uco_b200_frame_match": (_i, [_vp, _vp, _i, _sz, _vp, _i, _vp, _vp, _i, _sz, _vp, _i, _vp, _vp, _vp, _i, _vp]),
     "uco_b200_frame_match_batch_dev": (_i, [_vp, _i, _vp, _sz, _vp, _sz, _i, _vp, _vp, _sz, _vp, _sz, _i, _vp, _vp, _vp, _vp]),
     "uco_b200_pose_only_batch": (_i, [_vp, _i, _vp, _vp]),
+    "uco_b200_keyframes_batch_dev": (_i, [_vp, _vp, _i, _vp, _sz, _vp, _sz, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "uco_b200_keyframes_batch": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "uco_b200_frame_match_multi": (_i, [_vp, _vp, _i, _sz, _vp, _i, _vp, _i, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "uco_b200_probe_math": (_i, [_i, _vp, _vp, _i, _vp, _vp]),
     "uco_b200_probe_retain_best": (_i, [_vp, _i, _i]),
@@ -244,7 +246,7 @@ def load():
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise RuntimeError("libucoslam_b200.so not built: run python ucoslam-cv3_b200/build.py (%s)" % LIB_PATH)
-        lib = ctypes.CDLL(LIB_PATH)
+        lib = ctypes.CDLL(os.environ.get("UCO_B200_LIB", LIB_PATH))   # the override loads a build variant for A/B measurements
         for name, (res, args) in SIGNATURES.items():
             f = getattr(lib, name)
             f.restype, f.argtypes = res, args
@@ -682,6 +684,23 @@ class Context:
             None if qmp is None else ctypes.cast(qmp, ctypes.c_void_p), _p(f12a), ctypes.addressof(prm),
             ctypes.cast(VP(*[o.ctypes.data for o in outs]), ctypes.c_void_p), cap, _p(n_out)))
         return [outs[f][:n_out[f]].copy() for f in range(F)]
+
+    def keyframes_batch(self, voc, groups, prm, max_features, f12=None, level=3):
+        """per-keyframe work on the frames of this context's last extraction call: groups = [(kf_frame, [neighbour frames])];
+        -> (list of (word, weight, node) per keyframe, list of lists of match arrays per keyframe)"""
+        kf = np.array([g[0] for g in groups], np.int32)
+        ptr = np.zeros(len(groups) + 1, np.int32)
+        ptr[1:] = np.cumsum([len(g[1]) for g in groups])
+        nb = np.array([f for g in groups for f in g[1]], np.int32) if ptr[-1] else np.zeros(1, np.int32)
+        npairs, mf = int(ptr[-1]), max_features
+        word, wgt, node = (np.zeros((len(groups), mf), np.uint32), np.zeros((len(groups), mf), np.float32), np.zeros((len(groups), mf), np.uint32))
+        m, nm = np.zeros((max(npairs, 1), mf), MATCH_DTYPE), np.zeros(max(npairs, 1), np.int32)
+        f12a = None if f12 is None else np.ascontiguousarray(f12, np.float32).reshape(npairs, 9)
+        self._chk(self.lib.uco_b200_keyframes_batch(self.h, voc, level, len(groups), _p(kf), _p(ptr), _p(nb), _p(f12a), ctypes.addressof(prm),
+                                                    _p(word), _p(wgt), _p(node), _p(m), _p(nm)))
+        bows = [(word[j], wgt[j], node[j]) for j in range(len(groups))]
+        matches = [[m[e, :nm[e]].copy() for e in range(ptr[j], ptr[j + 1])] for j in range(len(groups))]
+        return bows, matches
 
     def frame_match_bow(self, q_desc, q_kps, q_bow, t_desc, t_kps, t_bow, prm, q_usable=None, t_usable=None):
         """FrameMatcher_BoW::matchEpipolar; q_bow / t_bow = (node_id, ptr, kp) as bow_index() gives"""
