@@ -601,6 +601,88 @@ def track_projected(sc, dist_thr, proj_dist_thr):
     return out[:n].copy()
 
 
+def ref_match_projected(sc, min_desc_dist, max_reproj_dist):
+    """The REFERENCE's own Map::matchFrameToMapPoints (oracle/_ref/libref_project.so: src/map.cpp:651-770 and the helpers it calls,
+    compiled from the reference's statements against container stand-ins); map point ids are the row numbers.  None where
+    oracle/_ref was not built."""
+    lib = load_ref("libref_project.so")
+    if lib is None:
+        return None
+    A = lambda k, dt: np.ascontiguousarray(sc[k], dt)
+    pos, nrm = A("mp_pos", np.float32), A("mp_normal", np.float32)
+    dmin, dmax, mdesc = A("mp_min_dist", np.float32), A("mp_max_dist", np.float32), A("mp_desc", np.uint8)
+    kxy, koct, kdesc = A("kp_xy", np.float32), A("kp_octave", np.int32), A("kp_desc", np.uint8)
+    sf, pose = A("scale_factors", np.float32), A("pose44", np.float32)
+    mn, mx = A("min_xy", np.float32), A("max_xy", np.float32)
+    m = len(pos)
+    out, vis = np.zeros(max(m, 1), MATCH_DT), np.zeros(max(m, 1), np.uint8)
+    f = lib.ref_match_projected
+    f.argtypes = [ctypes.c_int] + [ctypes.c_void_p] * 5 + [ctypes.c_int] + [ctypes.c_void_p] * 4 + [ctypes.c_int] + [ctypes.c_float] * 4 + \
+                 [ctypes.c_void_p] * 3 + [ctypes.c_float] * 2 + [ctypes.c_void_p] * 2
+    n = f(m, _p(pos), _p(nrm), _p(dmin), _p(dmax), _p(mdesc), len(kxy), _p(kxy), _p(koct), _p(kdesc), _p(sf), len(sf),
+          sc["fx"], sc["fy"], sc["cx"], sc["cy"], _p(mn), _p(mx), _p(pose), min_desc_dist, max_reproj_dist, _p(out), _p(vis))
+    assert n >= 0
+    return out[:n].copy(), vis[:m].copy()
+
+
+def ref_track_projected(sc, dist_thr, proj_dist_thr):
+    """The REFERENCE's own search by projection from the previous frame (System::_11946837405316294395, src/utils/system.cpp:5921-6456,
+    de-obfuscated with the C preprocessor and compiled into oracle/_ref/libref_project.so).  None where oracle/_ref was not built."""
+    lib = load_ref("libref_project.so")
+    if lib is None:
+        return None
+    A = lambda k, dt: np.ascontiguousarray(sc[k], dt)
+    ids, pos = A("mp_id", np.uint32), A("mp_pos", np.float32)
+    kxy, koct, kdesc = A("kp_xy", np.float32), A("kp_octave", np.int32), A("kp_desc", np.uint8)
+    poct, pdesc, prow = A("prev_octave", np.int32), A("prev_desc", np.uint8), A("prev_mp_row", np.int32)
+    sf, pose = A("scale_factors", np.float32), A("pose44", np.float32)
+    mn, mx = A("min_xy", np.float32), A("max_xy", np.float32)
+    out = np.zeros(max(len(poct), 1), MATCH_DT)
+    f = lib.ref_track_projected
+    f.argtypes = [ctypes.c_int] + [ctypes.c_void_p] * 3 + [ctypes.c_int] + [ctypes.c_void_p] * 2 + [ctypes.c_int] + [ctypes.c_void_p] * 4 + \
+                 [ctypes.c_int] + [ctypes.c_float] * 4 + [ctypes.c_void_p] * 3 + [ctypes.c_float] * 2 + [ctypes.c_void_p]
+    n = f(len(poct), _p(poct), _p(pdesc), _p(prow), len(ids), _p(ids), _p(pos), len(kxy), _p(kxy), _p(koct), _p(kdesc), _p(sf), len(sf),
+          sc["fx"], sc["fy"], sc["cx"], sc["cy"], _p(mn), _p(mx), _p(pose), dist_thr, proj_dist_thr, _p(out))
+    assert n >= 0
+    return out[:n].copy()
+
+
+def ref_frame_match(q_desc, q_kps, t_desc, t_kps, min_desc_dist=50.0, ratio=0.8, check_orientation=True, max_octave_diff=1, F12=None,
+                    scale_factors=None, kind="flann", q_bow=None, t_bow=None, q_ids=None, t_ids=None, q_flags=None, t_flags=None, q_mode=0, t_mode=0):
+    """The REFERENCE's own FrameMatcher (oracle/_ref/libref_match.so: src/utils/framematcher.cpp compiled unchanged, with its index
+    type swapped to xflann's exact LinearParams so that the post-filters see the product's candidates; kind="bow": FrameMatcher_BoW
+    as is).  q_bow / t_bow = (node_id, ptr, kp).  None where oracle/_ref was not built."""
+    lib = load_ref("libref_match.so")
+    if lib is None:
+        return None
+    q_desc = np.ascontiguousarray(q_desc, np.uint8).reshape(-1, 32)
+    t_desc = np.ascontiguousarray(t_desc, np.uint8).reshape(-1, 32)
+    q_kps, t_kps = np.ascontiguousarray(q_kps, KP_DTYPE), np.ascontiguousarray(t_kps, KP_DTYPE)
+    sf = np.asarray(scale_factors if scale_factors is not None else [np.float32(1.2) ** i for i in range(8)], np.float32)
+    f12 = None if F12 is None else np.ascontiguousarray(F12, np.float32).reshape(9)
+    P = lambda a, dt=None: None if a is None else _p(np.ascontiguousarray(a, dt))
+    keep = []
+
+    def bow(b):
+        if b is None:
+            return 0, None, None, None
+        arrs = [np.ascontiguousarray(b[0], np.uint32), np.ascontiguousarray(b[1], np.int32), np.ascontiguousarray(b[2], np.int32)]
+        keep.extend(arrs)
+        return len(arrs[0]), _p(arrs[0]), _p(arrs[1]), _p(arrs[2])
+    tb, qb = bow(t_bow), bow(q_bow)
+    opt = [None if a is None else np.ascontiguousarray(a, dt) for a, dt in ((t_ids, np.uint32), (t_flags, np.uint8), (q_ids, np.uint32), (q_flags, np.uint8))]
+    out = np.zeros(max(len(q_kps), 1), MATCH_DTYPE)
+    fn = lib.ref_frame_match
+    fn.argtypes = [ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 4 + [ctypes.c_int] * 2 + [ctypes.c_void_p] * 3 + [ctypes.c_int] + [ctypes.c_void_p] * 4 + \
+                  [ctypes.c_int] * 2 + [ctypes.c_void_p] * 3 + [ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_int,
+                                                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    n = fn(1 if kind == "flann" else 2, len(t_kps), _p(t_kps), _p(t_desc), P(opt[0]), P(opt[1]), t_mode, *tb,
+           len(q_kps), _p(q_kps), _p(q_desc), P(opt[2]), P(opt[3]), q_mode, *qb, _p(sf), len(sf), min_desc_dist, ratio, int(check_orientation),
+           int(max_octave_diff), P(f12), _p(out), len(out))
+    assert n >= 0
+    return out[:n].copy()
+
+
 def filter_ambiguous_query(matches):
     m = np.ascontiguousarray(matches, MATCH_DT).copy()
     n = load_stl().oracle_filter_ambiguous_query(_p(m), len(m))

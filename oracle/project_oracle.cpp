@@ -308,7 +308,7 @@ int oracle_match_projected(int m, const uint32_t* ids, const float* pos, const f
         if (best_kp != -1) {
             bool valid = true;
             if (best_level2 == best_level && best > 0.8 * best2) valid = false;
-            if (valid) matches.push_back({best_kp, (int32_t)ids[i], 0, best});
+            if (valid) matches.push_back({best_kp, (int32_t)ids[i], -1, best});   // cv::DMatch() leaves imgIdx = -1
         }
     }
     // filter_ambiguous_query, misc.cpp:117-150
@@ -401,7 +401,7 @@ int oracle_track_projected(int n_prev, const int32_t* prev_octave, const uint8_t
                 best_kp = kp;
             } else if (d < best2) best2 = d;
         }
-        if (best_kp != -1 && best < 0.7 * best2) matches.push_back({best_kp, (int32_t)ids[row], 0, best});
+        if (best_kp != -1 && best < 0.7 * best2) matches.push_back({best_kp, (int32_t)ids[row], -1, best});
     }
     int n = (int)matches.size();
     n = oracle_filter_ambiguous_query(matches.data(), n);

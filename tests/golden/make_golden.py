@@ -129,25 +129,85 @@ def pnp():
 
 
 def project():
-    """Map::matchFrameToMapPoints: the reference itself cannot be linked here (OpenCV C++), so these vectors come from the restatement
-    oracle/project_oracle.cpp, whose kd-tree part (the only third-party-free, order-defining piece) is checked in the same breath
-    against the reference's own picoflann.h (oracle/_ref/libref_picoflann.so).  Scenes are small so the fixture stays small."""
+    """Map::matchFrameToMapPoints and the tracker's search by projection from the previous frame, BY THE REFERENCE ITSELF: its own
+    statements (src/map.cpp:651-770, src/utils/system.cpp:5921-6456, the Frame / MapPoint / Se3Transform helpers they call, picoflann)
+    compiled into oracle/_ref/libref_project.so (oracle/ref_project_wrap.cpp, oracle/gen_ref_extract.py).  The restatement
+    oracle/project_oracle.cpp is checked against it in the same breath.  Scenes are small so the fixture stays small."""
     oracle_py.build_ref()
-    from ucoslam_b200.synth import synth_projection_scene
+    from ucoslam_b200.synth import synth_projection_scene, synth_track_scene
     out = {}
     for name, (kw, thr) in {"a": (dict(seed=11, n_kp=1200, n_mp=1500), (50.0, 15.0)), "b": (dict(seed=12, n_kp=600, n_mp=900, dup_frac=0.4), (80.0, 30.0)),
                             "c": (dict(seed=13, n_kp=800, n_mp=1000, clutter=0.8), (100.0, 40.0))}.items():
         sc = synth_projection_scene(**kw)
+        sc["mp_id"] = np.arange(len(sc["mp_id"]), dtype=np.uint32)      # the reference wrapper names the points by their row
         ref = oracle_py.parse_picoflann_stream(oracle_py.ref_picoflann_stream(sc["kp_xy"]))
         mine = oracle_py.kdtree_build(sc["kp_xy"])
         assert all(np.array_equal(ref[k], mine[k]) for k in ("nodes", "div", "leaf_idx"))
-        m, vis = oracle_py.match_projected(sc, *thr)
+        m, vis = oracle_py.ref_match_projected(sc, *thr)
+        m2, vis2 = oracle_py.match_projected(sc, *thr)
+        assert np.array_equal(m, m2) and np.array_equal(vis, vis2), "restatement differs from the reference"
         for k, v in sc.items():
             out["%s_%s" % (name, k)] = np.asarray(v)
         out[name + "_out_matches"], out[name + "_out_visible"] = m, vis
         out[name + "_out_min_desc"], out[name + "_out_max_reproj"] = np.float32(thr[0]), np.float32(thr[1])
     np.savez_compressed(os.path.join(HERE, "project_match.npz"), **out)
-    print("projection golden written", {n: len(out[n + "_out_matches"]) for n in "abc"})
+    print("projection golden written (reference-compiled)", {n: len(out[n + "_out_matches"]) for n in "abc"})
+    out = {}
+    for name, (kw, thr) in {"a": (dict(seed=21, n_kp=1200, n_mp=1500, n_prev=1000), (75.0, 15.0)),
+                            "b": (dict(seed=22, n_kp=500, n_mp=900, n_prev=800, dup_frac=0.4), (120.0, 30.0)),
+                            "c": (dict(seed=23, n_kp=800, n_mp=1000, n_prev=700, clutter=0.8), (40.0, 4.0))}.items():
+        sc = synth_track_scene(**kw)
+        m = oracle_py.ref_track_projected(sc, *thr)
+        assert np.array_equal(m, oracle_py.track_projected(sc, *thr)), "restatement differs from the reference"
+        for k, v in sc.items():
+            out["%s_%s" % (name, k)] = np.asarray(v)
+        out[name + "_out_matches"] = m
+        out[name + "_out_dist_thr"], out[name + "_out_proj_thr"] = np.float32(thr[0]), np.float32(thr[1])
+    np.savez_compressed(os.path.join(HERE, "track_projected.npz"), **out)
+    print("search-by-projection golden written (reference-compiled)", {n: len(out[n + "_out_matches"]) for n in "abc"})
+
+
+def match():
+    """FrameMatcher_Flann (on xflann's exact index, see oracle/ref_match_wrap.cpp) and FrameMatcher_BoW BY THE REFERENCE ITSELF:
+    src/utils/framematcher.cpp compiled unchanged into oracle/_ref/libref_match.so with the reference's own match filters."""
+    oracle_py.build_ref()
+    import ucoslam_b200
+    F = np.array([[0, -1e-6, 2e-4], [1e-6, 0, -3e-3], [-2e-4, 3.1e-3, 0.01]], np.float32)
+    out = {}
+    for name, (seed, nt, nq, kw) in {"a": (1, 1200, 1200, {}), "b": (3, 900, 1100, dict(ratio=0.6, max_octave_diff=0)),
+                                     "c": (5, 1000, 1000, dict(F12=F)), "d": (7, 700, 1500, dict(min_desc_dist=60.0, max_octave_diff=7)),
+                                     "e": (9, 800, 800, dict(check_orientation=False, min_desc_dist=90.0))}.items():
+        q, qk, t, tk = oracle_py.synth_match_frames(seed, nt=nt, nq=nq)
+        if name in "bd":
+            t[nt // 2:] = t[:nt - nt // 2]                          # duplicated rows: ties + ratio test
+        m = oracle_py.ref_frame_match(q, qk, t, tk, **kw)
+        assert np.array_equal(m, oracle_py.frame_match(q, qk, t, tk, **kw)), "restatement differs from the reference"
+        out.update({name + "_q": q, name + "_qk": qk, name + "_t": t, name + "_tk": tk, name + "_out": m})
+        for k, v in dict(min_desc_dist=50.0, ratio=0.8, check_orientation=True, max_octave_diff=1).items():
+            out["%s_%s" % (name, k)] = np.float32(kw.get(k, v))
+        if "F12" in kw:
+            out[name + "_F12"] = kw["F12"]
+    node = lambda d, bits: ((d[:, 0].astype(np.uint32) << 8 | d[:, 1]) >> (16 - bits)).astype(np.uint32) * 16 + 3
+    for name, (seed, nt, nq, kw) in {"p": (1, 700, 700, {}), "q": (2, 500, 650, dict(ratio=0.6, max_octave_diff=0)),
+                                     "r": (3, 600, 400, dict(check_orientation=False, min_desc_dist=80.0)), "s": (4, 600, 600, dict(F12=F))}.items():
+        q, qk, t, tk = oracle_py.synth_match_frames(seed, nt=nt, nq=nq)
+        qb, tb = ucoslam_b200.bow_index(node(q, 6)), ucoslam_b200.bow_index(node(t, 6))
+        rng = np.random.default_rng(seed)
+        qflags, tflags = (rng.random(nq) < 0.1).astype(np.uint8), (rng.random(nt) < 0.1).astype(np.uint8)   # FLAG_NONMAXIMA
+        m = oracle_py.ref_frame_match(q, qk, t, tk, kind="bow", q_bow=qb, t_bow=tb, q_flags=qflags, t_flags=tflags, **kw)
+        m2 = oracle_py.frame_match_bow(q, qk, qb, t, tk, tb, q_usable=1 - qflags, t_usable=1 - tflags, **kw)
+        assert np.array_equal(m, m2), "BoW restatement differs from the reference"
+        out.update({name + "_q": q, name + "_qk": qk, name + "_t": t, name + "_tk": tk, name + "_out": m, name + "_qflags": qflags, name + "_tflags": tflags})
+        for i, a in enumerate(qb):
+            out["%s_qb%d" % (name, i)] = np.asarray(a)
+        for i, a in enumerate(tb):
+            out["%s_tb%d" % (name, i)] = np.asarray(a)
+        for k, v in dict(min_desc_dist=50.0, ratio=0.8, check_orientation=True, max_octave_diff=1).items():
+            out["%s_%s" % (name, k)] = np.float32(kw.get(k, v))
+        if "F12" in kw:
+            out[name + "_F12"] = kw["F12"]
+    np.savez_compressed(os.path.join(HERE, "match_ref.npz"), **out)
+    print("frame-matcher golden written (reference-compiled)", {n: len(out[n + "_out"]) for n in "abcdepqrs"})
 
 
 KFDB_CASES = {  # name -> (vocabulary kwargs or None = the shipped orb.fbow, synth_places kwargs)
@@ -212,6 +272,6 @@ def kfdb():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["knn", "bow", "ba", "ba_markers", "pnp", "project", "kfdb"]
+    which = sys.argv[1:] or ["knn", "bow", "ba", "ba_markers", "pnp", "project", "match", "kfdb"]
     for w in which:
         globals()[w]()

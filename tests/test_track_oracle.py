@@ -72,7 +72,7 @@ def _tbp_numpy(sc, dist_thr, proj):
             elif d < best2:
                 best2 = d
         if bk >= 0 and np.float64(best) < 0.7 * np.float64(best2):
-            out.append((bk, int(sc["mp_id"][sc["prev_mp_row"][i]]), 0, best))
+            out.append((bk, int(sc["mp_id"][sc["prev_mp_row"][i]]), -1, best))
     m = np.array(out, oracle_py.MATCH_DT)
     # filter_ambiguous_query: per keypoint the smallest distance, the earlier entry on ties; order kept
     keep = np.ones(len(m), bool)

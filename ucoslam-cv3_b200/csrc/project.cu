@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(1024) project_compact_kernel(const __grid_cons
             uco_match mt;
             mt.queryIdx = kp;
             mt.trainIdx = (int32_t)ids[i];
-            mt.imgIdx = 0;
+            mt.imgIdx = -1;   // cv::DMatch() leaves imgIdx = -1 and the reference never sets it here
             mt.distance = D.best_dist[i];
             out[before + __popc(bal & ((1u << lane) - 1))] = mt;
         }

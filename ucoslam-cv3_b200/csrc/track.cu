@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(1024) tbp_compact_kernel(const __grid_constant
             const int slot = running + r;
             const int row = D.prev_row[gi];
             uco_match mt;
-            mt.queryIdx = kp; mt.trainIdx = (int32_t)D.mp_id[(size_t)f * D.map_cap + row]; mt.imgIdx = 0; mt.distance = D.best_d1[gi];
+            mt.queryIdx = kp; mt.trainIdx = (int32_t)D.mp_id[(size_t)f * D.map_cap + row]; mt.imgIdx = -1; mt.distance = D.best_d1[gi];
             D.m1[(size_t)f * D.kp_cap + slot] = mt;
             D.row1[(size_t)f * D.kp_cap + slot] = row;
             D.seen[(size_t)f * D.map_cap + row] = 1;
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(1024) merge_kernel(const __grid_constant__ Tra
         if (kp >= 0) {
             const int slot = running + r;
             uco_match mt;
-            mt.queryIdx = kp; mt.trainIdx = (int32_t)D.mp_id[gi]; mt.imgIdx = 0; mt.distance = D.best_d2[gi];
+            mt.queryIdx = kp; mt.trainIdx = (int32_t)D.mp_id[gi]; mt.imgIdx = -1; mt.distance = D.best_d2[gi];
             D.matches[(size_t)f * D.kp_cap + slot] = mt;
             write_edge(D, f, slot, kp, i);
         }
