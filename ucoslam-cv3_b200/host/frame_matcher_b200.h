@@ -5,7 +5,7 @@
 // and select it in FrameMatcher::FrameMatcher(Type) (:110-125) with a new Type value.  setParams only records the train frame (there
 // is no index to build); match* are re-entrant per object as long as each calling thread owns its own instance, which is how the
 // OpenMP callers use FrameMatcher (src/utils/mapmanager.cpp:9992-10065, src/utils/system.cpp:5026-5078).
-// Compile inside the reference tree (needs its headers and OpenCV C++).
+// Compiled and driven next to the reference's own code by tests/adapters/adapter_world_test.cpp (oracle/shim2 stand-ins).
 #pragma once
 #include <vector>
 #include "uco_b200_cxx.h"
@@ -34,9 +34,9 @@ private:
         map.clear();
         for (size_t i = 0; i < f.ids.size(); i++) {
             const bool assigned = f.ids[i] != std::numeric_limits<uint32_t>::max();
-            if (f.flags[i].is(Frame::FLAG_NONMAXIMA)) continue;
-            if (mode == FrameMatcher::MODE_ALL || (mode == FrameMatcher::MODE_ASSIGNED && assigned) ||
-                (mode == FrameMatcher::MODE_UNASSIGNED && !assigned))
+            // MODE_ALL takes every keypoint (:168-173); the two selective modes also drop FLAG_NONMAXIMA keypoints (:174-196)
+            if (mode == FrameMatcher::MODE_ALL ||
+                (!f.flags[i].is(Frame::FLAG_NONMAXIMA) && ((mode == FrameMatcher::MODE_ASSIGNED && assigned) || (mode == FrameMatcher::MODE_UNASSIGNED && !assigned))))
                 map.push_back((int32_t)i);
         }
         desc.resize(32 * map.size());

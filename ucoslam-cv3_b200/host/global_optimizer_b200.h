@@ -6,16 +6,18 @@
 // its own copy of inputs and results, because the mapper thread calls setParams + optimize WITHOUT the map lock and the
 // tracker thread calls getResults later (src/utils/mapmanager.cpp:11361-11405, :1267-1305); *stopASAP is forwarded.
 // ArUco markers travel too (marker vertices, MarkerEdges, the per-keyframe marker weights of :276-297).  Windows whose keyframes were
-// taken with different cameras, or that use the InPlaneMarkers option, are handed to the reference's own GlobalOptimizerG2O.
+// taken with different cameras, or that use the InPlaneMarkers option (MarkerEdgeX, :360-401), are NOT covered by the C ABI: setParams
+// throws std::runtime_error for them, like every other error path of the reference's plugins (there is no CPU fallback).
 // Selected with Params::global_optimizer = "b200" once registered in GlobalOptimizer::create.
-// Compile inside the reference tree (needs its headers and OpenCV C++; see the note in orb_extractor_b200.h).
+// Compiled and driven against the reference's own globaloptimizer.h by tests/adapters/adapter_world_test.cpp (container stand-ins for
+// Map / Frame / OpenCV, oracle/shim2); inside the reference tree it compiles against the real headers.
 #pragma once
+#include <algorithm>
 #include <cstring>
 #include <limits>
 #include <map>
 #include <vector>
 #include "optimization/globaloptimizer.h"
-#include "optimization/globaloptimizer_g2o.h"
 #include "uco_b200_cxx.h"
 
 namespace ucoslam {
@@ -27,7 +29,6 @@ public:
 
     void setParams(std::shared_ptr<Map> map, const ParamSet& ps) override {
         _params = ps;
-        _delegate.reset();
         const uint32_t INVALID = std::numeric_limits<uint32_t>::max();
         std::vector<uint32_t> frameSlot(map->keyframes.capacity(), INVALID), pointSlot(map->map_points.capacity(), INVALID);
         std::vector<char> fixedKind(map->keyframes.capacity(), 0);  // 0 free, 1 fixed without points, 2 fixed with points
@@ -67,11 +68,11 @@ public:
             if (ip.fx() != f0.imageParams.fx() || ip.fy() != f0.imageParams.fy() || ip.cx() != f0.imageParams.cx() ||
                 ip.cy() != f0.imageParams.cy() || ip.bl != f0.imageParams.bl) mixedCameras = true;
         }
-        if (mixedCameras || (markers && _params.InPlaneMarkers)) {   // not covered by the C ABI: the reference's own optimiser takes the window
-            _delegate = std::make_shared<GlobalOptimizerG2O>();
-            _delegate->setParams(map, ps);
-            return;
-        }
+        if (mixedCameras) throw std::runtime_error("GlobalOptimizerB200: keyframes taken with different cameras in one window are not supported");
+        if (markers && _params.InPlaneMarkers) throw std::runtime_error("GlobalOptimizerB200: the InPlaneMarkers option is not supported");
+        // the reference emits marker vertices / edges in ascending marker id (std::map, globaloptimizer_g2o.cpp:306-348)
+        std::sort(_markerIds.begin(), _markerIds.end());
+        for (size_t i = 0; i < _markerIds.size(); i++) markerSlot[_markerIds[i]] = (uint32_t)i;
         // ---- flatten (own copy: the map may change before optimize()/getResults())
         const size_t P = _frameIds.size(), N = _pointIds.size();
         _poses.resize(16 * P); _fixed.resize(P); _points.resize(3 * N);
@@ -139,7 +140,6 @@ public:
     }
 
     void optimize(bool* stopASAP = nullptr) override {
-        if (_delegate) { _delegate->optimize(stopASAP); return; }
         _outPoses.resize(16 * (size_t)_pb.n_poses); _outPoints.resize(3 * (size_t)_pb.n_points); _outBad.resize(_pb.n_obs);
         uco_ba_result res{};
         res.poses44 = _outPoses.data(); res.points3 = _outPoints.data(); res.obs_bad = _outBad.data();
@@ -151,7 +151,6 @@ public:
     }
 
     void getResults(std::shared_ptr<Map> map) override {
-        if (_delegate) { _delegate->getResults(map); return; }
         for (size_t k = 0; k < _frameIds.size(); k++) {   // :483-492
             if (_fixed[k]) continue;
             cv::Mat T(4, 4, CV_32F);
@@ -180,8 +179,10 @@ public:
         getResults(map);
     }
     vector<std::pair<uint32_t, uint32_t>> getBadAssociations() override {
-        return _delegate ? _delegate->getBadAssociations() : _badAssociations;
+        return _badAssociations;
     }
+
+    const uco_ba_problem& problem() const { return _pb; }   // the flattened window (tests compare it with the reference's g2o)
 
 protected:
     void saveToStream_impl(std::ostream&) override {}
@@ -190,7 +191,6 @@ protected:
 private:
     uco_b200::Context _ctx;
     ParamSet _params;
-    std::shared_ptr<GlobalOptimizerG2O> _delegate;
     uco_ba_problem _pb{};
     std::vector<uint32_t> _frameIds, _pointIds, _markerIds;
     std::vector<float> _poses, _points, _obsUV, _obsUR, _obsInv, _outPoses, _mkPose, _mkSize, _moCorners, _moWeight, _outMarkers;

@@ -3,8 +3,8 @@
 // ucoslam::ORBextractor answers (src/featureextractors/ORBextractor.h:86-116): F2D_ORB, DESC_ORB, min descriptor distance
 // 50, FeatParams streamed as the raw struct (ORBextractor.cpp:417-423), sensitivity -> FAST thresholds
 // (ORBextractor.cpp:457-466).  Registered in Feature2DSerializable::create / fromStream.
-// Compile inside the reference tree (needs its headers and OpenCV C++; neither exists in the build container of this
-// repository, so this header is exercised by the maintainers' build, the C ABI beneath it by tests/test_orb_gpu.py).
+// Compiled and driven through the reference's own Feature2DSerializable (its real header + member definitions) by
+// tests/adapters/adapter_world_test.cpp against container stand-ins for OpenCV (oracle/shim2).
 #pragma once
 #include <cstring>
 #include <vector>

@@ -4,7 +4,7 @@
 // flattened exactly as solvePnp walks them (:200-259): und_kpts[queryIdx], map point coordinates, stability weight, stereo
 // observations from Frame::getDepth, markers with a valid map pose seen from the neighbourhood of currentKeyFrame (:262-281).
 // The tracker calls it 2-3 times per frame from one thread (src/utils/system.cpp); use one context per calling thread.
-// Compile inside the reference tree (needs its headers and OpenCV C++).
+// Compiled and driven next to the reference's own code by tests/adapters/adapter_world_test.cpp (oracle/shim2 stand-ins).
 #pragma once
 #include <vector>
 #include "map.h"

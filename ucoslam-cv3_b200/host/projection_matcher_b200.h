@@ -4,7 +4,7 @@
 // walking) and hands it to ucoslam::matchFrameToMapPoints_b200, which flattens it, calls uco_b200_match_projected and applies
 // MapPoint::setVisible() where the reference does (:711).  The frame's kd-tree travels as the bytes KdTreeIndex::toStream writes
 // (picoflann.h:603-660), so the device walks exactly the tree the reference built in Frame (frame.h:125).
-// Compile inside the reference tree (needs its headers and OpenCV C++; see the note in orb_extractor_b200.h).
+// Compiled and driven next to the reference's own statements by tests/adapters/adapter_world_test.cpp (oracle/shim2 stand-ins).
 #pragma once
 #include <sstream>
 #include <vector>
