@@ -40,7 +40,7 @@ def test_loop_graph_matches_oracle(ctx):
 
 
 def test_large_reduced_system_matches_reference_g2o(ctx):
-    """240 keyframes -> 1428 unknowns: beyond the single-CTA solver, solved with the dense library Cholesky"""
+    """240 keyframes -> 1428 unknowns: beyond the single-CTA dense solver, solved with the block-envelope Cholesky (ba_band.cu)"""
     pb = synth_global_ba(5, n_kf=240, n_points=20000)
     ref = oracle_py.ref_ba_optimize(pb, 5)
     if ref is None:

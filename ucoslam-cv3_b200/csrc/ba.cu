@@ -27,7 +27,6 @@
 #include <vector>
 #include <mutex>
 #include <dlfcn.h>
-#include <cusolverDn.h>
 
 namespace {
 using namespace ba;
@@ -874,41 +873,20 @@ struct Arena {
 }  // namespace
 
 // ---- sharded / large form, host side -----------------------------------------------------------------------------------------------
-namespace {
-// dense Cholesky of a reduced system that does not fit the single-CTA solver: cuSOLVER potrf / potrs (FP64 tensor-core DGEMM
-// inside), bound at run time so that the library has no link-time dependency on it
-struct SolverApi {
-    cusolverStatus_t (*Create)(cusolverDnHandle_t*) = nullptr;
-    cusolverStatus_t (*Destroy)(cusolverDnHandle_t) = nullptr;
-    cusolverStatus_t (*SetStream)(cusolverDnHandle_t, cudaStream_t) = nullptr;
-    cusolverStatus_t (*PotrfBuf)(cusolverDnHandle_t, cublasFillMode_t, int, double*, int, int*) = nullptr;
-    cusolverStatus_t (*Potrf)(cusolverDnHandle_t, cublasFillMode_t, int, double*, int, double*, int, int*) = nullptr;
-    cusolverStatus_t (*Potrs)(cusolverDnHandle_t, cublasFillMode_t, int, int, const double*, int, double*, int, int*) = nullptr;
-    bool ok = false;
+// reduced systems beyond the single-CTA dense solver: block-envelope Cholesky (ba_band.cu)
+struct uco_band_plan {
+    int nb = 0, bmax = 0;
+    size_t n_env = 0;
+    std::vector<int> perm, fcol, rowptr;
 };
-SolverApi& solver_api() {
-    static SolverApi api;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        void* h = nullptr;
-        for (const char* name : {"libcusolver.so.11", "libcusolver.so.12", "libcusolver.so"}) {
-            h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
-            if (h) break;
-        }
-        if (!h) return;
-        bool all = true;
-        auto sym = [&](const char* n) { void* p = dlsym(h, n); all = all && p; return p; };
-        api.Create = (decltype(api.Create))sym("cusolverDnCreate");
-        api.Destroy = (decltype(api.Destroy))sym("cusolverDnDestroy");
-        api.SetStream = (decltype(api.SetStream))sym("cusolverDnSetStream");
-        api.PotrfBuf = (decltype(api.PotrfBuf))sym("cusolverDnDpotrf_bufferSize");
-        api.Potrf = (decltype(api.Potrf))sym("cusolverDnDpotrf");
-        api.Potrs = (decltype(api.Potrs))sym("cusolverDnDpotrs");
-        api.ok = all;
-    });
-    return api;
-}
-
+void uco_band_make_plan(int nb, int nblk, const int2* blk_ij, uco_band_plan& P);
+int uco_band_assemble_launch(uco_b200_ctx* ctx, int nb, int W, const int* perm_dev, const int* fcol_dev, const int* rowptr_dev, double* E, size_t n_env,
+                             double* rhs, int nblk, const int2* blk_ij_dev, const double* Hpp, const double* lambda_dev, const double* Sp,
+                             const double* bp, const double* bsp, const int* mk_blk_edge, const double* mk_e_blk);
+size_t uco_band_scratch_bytes(int nb, int W, int smem_optin);
+int uco_band_solve_launch(uco_b200_ctx* ctx, int nb, int W, const int* perm_dev, const int* fcol_dev, const int* rowptr_dev, double* E, double* rhs,
+                          double* xp, int* fail_dev, double* wglobal, int smem_optin);
+namespace {
 // landmark range [L[r], L[r+1]) of every rank: contiguous, balanced by observation count (the Schur work follows it)
 void ba_partition_landmarks(const std::vector<int>& lm_ptr, int N, int M, int R, std::vector<int>& L) {
     L.assign(R + 1, N);
@@ -926,14 +904,12 @@ void ba_partition_landmarks(const std::vector<int>& lm_ptr, int N, int M, int R,
 struct uco_ba_state {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int smem_optin = 0;
-    cusolverDnHandle_t solver = nullptr;
 };
 
 void uco_ba_state_free(uco_b200_ctx* ctx) {
     if (!ctx->ba) return;
     if (ctx->ba->ev0) cudaEventDestroy(ctx->ba->ev0);
     if (ctx->ba->ev1) cudaEventDestroy(ctx->ba->ev1);
-    if (ctx->ba->solver) solver_api().Destroy(ctx->ba->solver);
     delete ctx->ba;
     ctx->ba = nullptr;
 }
@@ -1346,26 +1322,22 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
                  o_Hll = A.take(48 * (size_t)(NL + 1)), o_bl = A.take(24 * (size_t)(NL + 1)), o_Hpl = A.take(144 * (size_t)(ML + 1)),
                  o_Y = A.take(144 * (size_t)(ML + 1)), o_Dinv = A.take(48 * (size_t)(NL + 1)), o_db = A.take(24 * (size_t)(NL + 1)),
                  o_xl = A.take(24 * (size_t)(NL + 1)), o_HppBp = A.take(8 * (42 * (size_t)PT + 6)),
-                 o_S = A.take(8 * ((size_t)n * n + 1)), o_bs = A.take(8 * (size_t)(n + 1)), o_xp = A.take(8 * (size_t)(n + 1)),
+                 o_S = A.take(8 * ((n > 1023 ? 0 : (size_t)n * n) + 1)), o_bs = A.take(8 * (size_t)(n + 1)), o_xp = A.take(8 * (size_t)(n + 1)),
                  o_scl = A.take(8 * (size_t)(NL + 1)), o_scp = A.take(8 * (size_t)(PT + 1)), o_st = A.take(sizeof(LmState)),
                  o_p44o = A.take(64 * (size_t)P), o_bad = A.take((size_t)ML + 1), o_red = A.take(8 * (n_red + 1)), o_sums = A.take(64),
                  o_info2 = A.take(16);
     const size_t o_full_pt = A.take(24 * (size_t)(N + 1)), o_full_chi = A.take(8 * (size_t)(M + 1)), o_full_flags = A.take(2 * (size_t)M + 2);
-    const bool big = n > 1023;
-    size_t o_chol = 0, o_work = 0;
-    int lwork = 0;
-    SolverApi& sol = solver_api();
+    const bool big = n > 1023;   // beyond the single-CTA dense solver: block-envelope Cholesky over the RCM-ordered block graph (ba_band.cu)
+    size_t o_chol = 0, o_bperm = 0, o_bE = 0, o_brhs = 0, o_bwin = 0;
+    uco_band_plan band;
     if (!ctx->ba->smem_optin) cudaDeviceGetAttribute(&ctx->ba->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
     uint8_t* d = nullptr;
     if (big) {
-        if (!sol.ok) return uco_fail(ctx, UCO_E_INVALID, "ba_solve_sharded: %d free poses need the dense library Cholesky and libcusolver could not be loaded", Pf);
-        if (!ctx->ba->solver) {
-            if (sol.Create(&ctx->ba->solver) != CUSOLVER_STATUS_SUCCESS) return uco_fail(ctx, UCO_E_CUDA, "cusolverDnCreate failed");
-            sol.SetStream(ctx->ba->solver, ctx->stream);
-        }
-        if (sol.PotrfBuf(ctx->ba->solver, CUBLAS_FILL_MODE_LOWER, n, nullptr, n, &lwork) != CUSOLVER_STATUS_SUCCESS)
-            return uco_fail(ctx, UCO_E_CUDA, "cusolverDnDpotrf_bufferSize failed");
-        o_work = A.take(8 * (size_t)lwork + 8);
+        uco_band_make_plan(n / 6, nblk, blk_ij.data(), band);
+        o_bperm = A.take(4 * (3 * (size_t)band.nb + 2));
+        o_bE = A.take(8 * 36 * band.n_env + 8);
+        o_brhs = A.take(8 * 6 * (size_t)band.nb + 8);
+        o_bwin = A.take(uco_band_scratch_bytes(band.nb, band.bmax + 1, ctx->ba->smem_optin) + 8);
     } else {
         o_chol = A.take(8 * ((size_t)(n + 1) * (n + 2) / 2 + 1));
     }
@@ -1418,7 +1390,7 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
     UCO_CUDA(ctx, cudaMemsetAsync(d + o_st, 0, sizeof(LmState), s));
     UCO_CUDA(ctx, cudaMemsetAsync(d + o_err, 0, 24 * (size_t)(ML + 1), s));
     UCO_CUDA(ctx, cudaMemsetAsync(d + o_chi2, 0, 8 * (size_t)(ML + 1), s));
-    UCO_CUDA(ctx, cudaMemsetAsync(d + o_S, 0, 8 * ((size_t)n * n + 1), s));
+    if (!big) UCO_CUDA(ctx, cudaMemsetAsync(d + o_S, 0, 8 * ((size_t)n * n + 1), s));
     UCO_CUDA(ctx, cudaMemsetAsync(d + o_red, 0, 8 * (n_red + 1), s));
     UCO_CUDA(ctx, cudaMemsetAsync(d + o_full_pt, 0, o_full_flags + 2 * (size_t)M + 2 - o_full_pt, s));
     BaDev B;
@@ -1448,6 +1420,15 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
     double* bsp = Sp + 36 * (size_t)nblk;
     double* sums = (double*)(d + o_sums);      // [0..3] sums, [4] max
     int* info2 = (int*)(d + o_info2);
+    (void)info2;
+    const int* bperm = (const int*)(d + o_bperm);
+    double* bwin = (double*)(d + o_bwin);
+    if (big) {   // the ordering and the envelope of the reduced system: perm | fcol | rowptr
+        UCO_CUDA(ctx, cudaMemcpyAsync(d + o_bperm, band.perm.data(), 4 * (size_t)band.nb, cudaMemcpyHostToDevice, ctx->stream));
+        UCO_CUDA(ctx, cudaMemcpyAsync(d + o_bperm + 4 * (size_t)band.nb, band.fcol.data(), 4 * (size_t)band.nb, cudaMemcpyHostToDevice, ctx->stream));
+        UCO_CUDA(ctx, cudaMemcpyAsync(d + o_bperm + 8 * (size_t)band.nb, band.rowptr.data(), 4 * (size_t)band.nb + 4, cudaMemcpyHostToDevice, ctx->stream));
+        UCO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     LmState* hst = (LmState*)(h + in_bytes);
     double* hsums = (double*)(h + in_bytes + sizeof(LmState));
     const size_t chol_bytes = 8 * ((size_t)(n + 1) * (n + 2) / 2);
@@ -1534,19 +1515,15 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
                     ba_schur_gather_packed_kernel<<<nblk, 36 * GATHER_CHUNKS, 0, s>>>(B, Sp, bsp);
                     UCO_LAUNCH_CHECK(ctx);
                     if ((rc = uco_comm_allreduce(comm, Sp, Sp, n_red, 0, s)) != UCO_OK) return rc;   // THE exchange step of the path
-                    if (big) UCO_CUDA(ctx, cudaMemsetAsync(B.S, 0, 8 * (size_t)n * n, s));            // potrf factors in place
-                    ba_assemble_kernel<<<nblk, 36, 0, s>>>(B, Sp, bsp);
-                    UCO_LAUNCH_CHECK(ctx);
-                    if (big) {
-                        UCO_CUDA(ctx, cudaMemsetAsync(info2, 0, 8, s));
-                        if (sol.Potrf(ctx->ba->solver, CUBLAS_FILL_MODE_LOWER, n, B.S, n, (double*)(d + o_work), lwork, info2) != CUSOLVER_STATUS_SUCCESS)
-                            return uco_fail(ctx, UCO_E_CUDA, "cusolverDnDpotrf failed");
-                        if (sol.Potrs(ctx->ba->solver, CUBLAS_FILL_MODE_LOWER, n, 1, B.S, n, B.bs, n, info2 + 1) != CUSOLVER_STATUS_SUCCESS)
-                            return uco_fail(ctx, UCO_E_CUDA, "cusolverDnDpotrs failed");
-                        ctx->launches += 2;
-                        ba_solve_finish_kernel<<<8, 256, 0, s>>>(B, info2, B.bs);
-                        UCO_LAUNCH_CHECK(ctx);
+                    if (big) {   // block-envelope Cholesky: assemble straight into the envelope, factor + solve in one launch
+                        if ((rc = uco_band_assemble_launch(ctx, band.nb, band.bmax + 1, bperm, bperm + band.nb, bperm + 2 * band.nb, (double*)(d + o_bE), band.n_env,
+                                                           (double*)(d + o_brhs), nblk, B.blk_ij, B.Hpp, &B.st->lambda, Sp, B.bp, bsp, B.mk.blk_edge,
+                                                           B.mk.e_blk)) != UCO_OK) return rc;
+                        if ((rc = uco_band_solve_launch(ctx, band.nb, band.bmax + 1, bperm, bperm + band.nb, bperm + 2 * band.nb, (double*)(d + o_bE),
+                                                        (double*)(d + o_brhs), B.xp, &B.st->chol_fail, bwin, ctx->ba->smem_optin)) != UCO_OK) return rc;
                     } else {
+                        ba_assemble_kernel<<<nblk, 36, 0, s>>>(B, Sp, bsp);
+                        UCO_LAUNCH_CHECK(ctx);
                         ba_chol_solve_kernel<<<1, CHOL_THREADS, chol_smem ? chol_bytes : 0, s>>>(B, (double*)(d + o_chol), chol_smem);
                         UCO_LAUNCH_CHECK(ctx);
                     }
