@@ -265,13 +265,32 @@ int uco_b200_knn_merge_dev(uco_b200_ctx* ctx, int n_lists, int nq, int k, const 
  * landmarks (with all their observations: the Hll / Hpl columns of block_solver.hpp:329-400) are partitioned over the ranks, each
  * rank linearizes its part and builds its partial Hpp / bp and partial Schur complement, ONE all-reduce per LM trial sums the
  * packed reduced Hessian + right-hand side over NVLink, every rank solves the reduced system redundantly (dense Cholesky; above
- * 170 free keyframes through cuSOLVER's potrf) and back-substitutes its own landmarks.  The LM control sums (chi2, scale) and the
+ * 170 free keyframes the two-level block-envelope Cholesky of uco_b200_block_solve) and back-substitutes its own landmarks.  The LM control sums (chi2, scale) and the
  * ranks' stop flags are all-reduced too, so every rank takes identical decisions.  Every rank returns the complete result.
  * comm == NULL: single GPU.  Results equal uco_b200_ba_solve's up to the summation order of the Schur complement. */
 int uco_b200_ba_solve_sharded(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_problem* pb, const volatile unsigned char* stop,
                               uco_ba_result* res);
 /* host-only inspection hook: landmark ranges of the sharded solver, out[0..world] = boundaries, out[world+1 .. 2 world] = observations per rank */
 int uco_b200_probe_ba_partition(const uco_ba_problem* pb, int world, int* out);
+
+/* The linear-solver seam on its own (3rdparty/g2o/g2o/core/linear_solver.h:44-90, LinearSolver<MatrixType>::solve(A, x, b); the
+ * reference plugs LinearSolverEigen into it, solvers/eigen/linear_solver_eigen.h:92-123): S x = b for a symmetric positive definite
+ * block-sparse S of nb x nb blocks of 6 x 6, given by nblk blocks of its UPPER block triangle (blk_ij[2 b] <= blk_ij[2 b + 1], every
+ * diagonal block present, blocks row-major, host buffers).  This is the solver uco_b200_ba_solve_sharded runs on reduced systems of
+ * more than 170 free keyframes: a two-level block-envelope Cholesky (csrc/ba_band.cu) — separator levels of the block graph's
+ * breadth-first level structure, the pieces between them factored by one thread block each, the separator system by one more.
+ * force_k < 0: number of separator levels chosen by the cost model; >= 0: forced (0 = plain envelope Cholesky in one thread block).
+ * info8 (optional): {fronts, separator levels, root rows, root window, longest interior front, widest interior window, widest
+ * border, 1 if a pivot was not positive (x = 0 then)}. */
+int uco_b200_block_solve(uco_b200_ctx* ctx, int nb, int nblk, const int* blk_ij, const double* blocks, const double* rhs, int force_k, double* x,
+                         int* info8);
+/* device time (ms) of the solver's launches (assemble + fronts + root + back substitution) in the LAST uco_b200_block_solve of the
+ * calling thread, measured on a second pass with CUDA events when context profiling is on */
+int uco_b200_block_solve_profile(uco_b200_ctx* ctx, float* ms);
+/* host-only inspection hook of its planner (no GPU needed): same ordering, fronts and storage map, the same algebra executed by plain
+ * host loops.  smem_optin <= 0: 227 KB.  info8[7] = doubles of factor storage.  Returns 0, 1 (a pivot was not positive), < 0 (bad input). */
+int uco_b200_probe_block_solve(int nb, int nblk, const int* blk_ij, const double* blocks, const double* rhs, int smem_optin, int force_k, double* x,
+                               int* info8);
 
 /* tuning / test knob.  mode 0 (default): windows with <= 38 free keyframes run cluster-resident (one thread-block cluster per
  * window, the whole LM loop in one launch), larger ones as streamed kernels; 1: always streamed; 2: always cluster-resident.

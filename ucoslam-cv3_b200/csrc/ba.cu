@@ -26,7 +26,7 @@
 #include <cstring>
 #include <vector>
 #include <mutex>
-#include <dlfcn.h>
+#include "ba_band.h"
 
 namespace {
 using namespace ba;
@@ -873,19 +873,7 @@ struct Arena {
 }  // namespace
 
 // ---- sharded / large form, host side -----------------------------------------------------------------------------------------------
-// reduced systems beyond the single-CTA dense solver: block-envelope Cholesky (ba_band.cu)
-struct uco_band_plan {
-    int nb = 0, bmax = 0;
-    size_t n_env = 0;
-    std::vector<int> perm, fcol, rowptr;
-};
-void uco_band_make_plan(int nb, int nblk, const int2* blk_ij, uco_band_plan& P);
-int uco_band_assemble_launch(uco_b200_ctx* ctx, int nb, int W, const int* perm_dev, const int* fcol_dev, const int* rowptr_dev, double* E, size_t n_env,
-                             double* rhs, int nblk, const int2* blk_ij_dev, const double* Hpp, const double* lambda_dev, const double* Sp,
-                             const double* bp, const double* bsp, const int* mk_blk_edge, const double* mk_e_blk);
-size_t uco_band_scratch_bytes(int nb, int W, int smem_optin);
-int uco_band_solve_launch(uco_b200_ctx* ctx, int nb, int W, const int* perm_dev, const int* fcol_dev, const int* rowptr_dev, double* E, double* rhs,
-                          double* xp, int* fail_dev, double* wglobal, int smem_optin);
+// reduced systems beyond the single-CTA dense solver: two-level block-envelope Cholesky (ba_band.cu)
 namespace {
 // landmark range [L[r], L[r+1]) of every rank: contiguous, balanced by observation count (the Schur work follows it)
 void ba_partition_landmarks(const std::vector<int>& lm_ptr, int N, int M, int R, std::vector<int>& L) {
@@ -1328,16 +1316,15 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
                  o_info2 = A.take(16);
     const size_t o_full_pt = A.take(24 * (size_t)(N + 1)), o_full_chi = A.take(8 * (size_t)(M + 1)), o_full_flags = A.take(2 * (size_t)M + 2);
     const bool big = n > 1023;   // beyond the single-CTA dense solver: block-envelope Cholesky over the RCM-ordered block graph (ba_band.cu)
-    size_t o_chol = 0, o_bperm = 0, o_bE = 0, o_brhs = 0, o_bwin = 0;
+    size_t o_chol = 0, o_bblob = 0, o_bZ = 0, o_bwin = 0;
     uco_band_plan band;
     if (!ctx->ba->smem_optin) cudaDeviceGetAttribute(&ctx->ba->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
     uint8_t* d = nullptr;
     if (big) {
-        uco_band_make_plan(n / 6, nblk, blk_ij.data(), band);
-        o_bperm = A.take(4 * (3 * (size_t)band.nb + 2));
-        o_bE = A.take(8 * 36 * band.n_env + 8);
-        o_brhs = A.take(8 * 6 * (size_t)band.nb + 8);
-        o_bwin = A.take(uco_band_scratch_bytes(band.nb, band.bmax + 1, ctx->ba->smem_optin) + 8);
+        uco_band_make_plan(n / 6, nblk, blk_ij.data(), ctx->ba->smem_optin, -1, band);
+        o_bblob = A.take(band.blob.size() + 16);
+        o_bZ = A.take(8 * (size_t)band.z_doubles + 16);
+        o_bwin = A.take(8 * band.scratch_doubles + 16);
     } else {
         o_chol = A.take(8 * ((size_t)(n + 1) * (n + 2) / 2 + 1));
     }
@@ -1421,12 +1408,8 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
     double* sums = (double*)(d + o_sums);      // [0..3] sums, [4] max
     int* info2 = (int*)(d + o_info2);
     (void)info2;
-    const int* bperm = (const int*)(d + o_bperm);
-    double* bwin = (double*)(d + o_bwin);
-    if (big) {   // the ordering and the envelope of the reduced system: perm | fcol | rowptr
-        UCO_CUDA(ctx, cudaMemcpyAsync(d + o_bperm, band.perm.data(), 4 * (size_t)band.nb, cudaMemcpyHostToDevice, ctx->stream));
-        UCO_CUDA(ctx, cudaMemcpyAsync(d + o_bperm + 4 * (size_t)band.nb, band.fcol.data(), 4 * (size_t)band.nb, cudaMemcpyHostToDevice, ctx->stream));
-        UCO_CUDA(ctx, cudaMemcpyAsync(d + o_bperm + 8 * (size_t)band.nb, band.rowptr.data(), 4 * (size_t)band.nb + 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (big) {   // the ordering, the fronts and the storage map of the reduced system
+        UCO_CUDA(ctx, cudaMemcpyAsync(d + o_bblob, band.blob.data(), band.blob.size(), cudaMemcpyHostToDevice, ctx->stream));
         UCO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     LmState* hst = (LmState*)(h + in_bytes);
@@ -1515,12 +1498,10 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
                     ba_schur_gather_packed_kernel<<<nblk, 36 * GATHER_CHUNKS, 0, s>>>(B, Sp, bsp);
                     UCO_LAUNCH_CHECK(ctx);
                     if ((rc = uco_comm_allreduce(comm, Sp, Sp, n_red, 0, s)) != UCO_OK) return rc;   // THE exchange step of the path
-                    if (big) {   // block-envelope Cholesky: assemble straight into the envelope, factor + solve in one launch
-                        if ((rc = uco_band_assemble_launch(ctx, band.nb, band.bmax + 1, bperm, bperm + band.nb, bperm + 2 * band.nb, (double*)(d + o_bE), band.n_env,
-                                                           (double*)(d + o_brhs), nblk, B.blk_ij, B.Hpp, &B.st->lambda, Sp, B.bp, bsp, B.mk.blk_edge,
-                                                           B.mk.e_blk)) != UCO_OK) return rc;
-                        if ((rc = uco_band_solve_launch(ctx, band.nb, band.bmax + 1, bperm, bperm + band.nb, bperm + 2 * band.nb, (double*)(d + o_bE),
-                                                        (double*)(d + o_brhs), B.xp, &B.st->chol_fail, bwin, ctx->ba->smem_optin)) != UCO_OK) return rc;
+                    if (big) {   // two-level block-envelope Cholesky: assemble straight into the fronts, factor, solve (4 launches)
+                        if ((rc = uco_band_solve_launch(ctx, band, d + o_bblob, (double*)(d + o_bZ), band.scratch_doubles ? (double*)(d + o_bwin) : nullptr,
+                                                        B.blk_ij, B.Hpp, &B.st->lambda, Sp, B.bp, bsp, B.mk.blk_edge, B.mk.e_blk, B.xp, &B.st->chol_fail,
+                                                        ctx->ba->smem_optin)) != UCO_OK) return rc;
                     } else {
                         ba_assemble_kernel<<<nblk, 36, 0, s>>>(B, Sp, bsp);
                         UCO_LAUNCH_CHECK(ctx);

@@ -54,6 +54,9 @@ SIGNATURES = {
     "uco_b200_comm_destroy": (None, [_vp]),
     "uco_b200_ba_solve_sharded": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "uco_b200_probe_ba_partition": (_i, [_vp, _i, _vp]),
+    "uco_b200_block_solve": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
+    "uco_b200_block_solve_profile": (_i, [_vp, _vp]),
+    "uco_b200_probe_block_solve": (_i, [_i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "uco_b200_orb_default_params": (None, [_vp]),
     "uco_b200_orb_extract": (_i, [_vp, _vp, _i, _i, _sz, _vp, _vp, _vp, _i, _vp]),
     "uco_b200_orb_extract_batch": (_i, [_vp, _vp, _i, _i, _i, _sz, _vp, _vp, _vp, _i, _vp]),
@@ -230,6 +233,19 @@ def kdtree_parse(stream_bytes):
     if load().uco_b200_kdtree_parse(_p(buf), len(buf), _p(nodes), cap, _p(leaf), cap, _p(bbox), ctypes.byref(k), ctypes.byref(nl)) != 0:
         raise UcoError("kdtree_parse failed")
     return nodes[:k.value].copy(), leaf[:nl.value].copy(), bbox
+
+
+def probe_block_solve(nb, blk_ij, blocks, rhs, force_k=-1, smem_optin=0, solve=True):
+    """host-only: planner + plain host execution of the two-level block-envelope Cholesky; returns (x or None, info8)"""
+    blk_ij = np.ascontiguousarray(blk_ij, np.int32).reshape(-1, 2)
+    blocks = np.ascontiguousarray(blocks, np.float64).reshape(-1, 36)
+    rhs = np.ascontiguousarray(rhs, np.float64).reshape(-1)
+    x = np.zeros(6 * nb)
+    info = np.zeros(8, np.int32)
+    rc = load().uco_b200_probe_block_solve(nb, len(blk_ij), _p(blk_ij), _p(blocks), _p(rhs), smem_optin, force_k, _p(x) if solve else None, _p(info))
+    if rc < 0:
+        raise UcoError("probe_block_solve: bad input (%d)" % rc)
+    return (x if solve and rc == 0 else None), info
 
 
 def probe_ba_partition(pb, world):
@@ -579,6 +595,21 @@ class Context:
 
     def knn_merge_dev(self, n_lists, nq, k, idx_lists_dev, dist_lists_dev, idx_dev, dist_dev):
         self._chk(self.lib.uco_b200_knn_merge_dev(self.h, n_lists, nq, k, idx_lists_dev, dist_lists_dev, idx_dev, dist_dev))
+
+    def block_solve(self, nb, blk_ij, blocks, rhs, force_k=-1):
+        """S x = b, S symmetric positive definite block sparse (upper block triangle given); returns (x, info8)"""
+        blk_ij = np.ascontiguousarray(blk_ij, np.int32).reshape(-1, 2)
+        blocks = np.ascontiguousarray(blocks, np.float64).reshape(-1, 36)
+        rhs = np.ascontiguousarray(rhs, np.float64).reshape(-1)
+        x = np.zeros(6 * nb)
+        info = np.zeros(8, np.int32)
+        self._chk(self.lib.uco_b200_block_solve(self.h, nb, len(blk_ij), _p(blk_ij), _p(blocks), _p(rhs), force_k, _p(x), _p(info)))
+        return x, info
+
+    def block_solve_ms(self):
+        ms = np.zeros(1, np.float32)
+        self._chk(self.lib.uco_b200_block_solve_profile(self.h, _p(ms)))
+        return float(ms[0])
 
     def ba_solve_sharded(self, pb, n_iters, comm=None, stop=None):
         """uco_b200_ba_solve_sharded: any problem size; with a communicator the landmarks are sharded over its ranks"""
