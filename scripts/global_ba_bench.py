@@ -37,6 +37,7 @@ if rank == 0:
     line = {"workload": "config5: global BA 500 KF / 50k landmarks / %d observations, nIters=5 (5 + <=10 LM iterations)" % len(pb["obs_pose"]),
             "n_gpus": world, "ms_per_solve_wall": wall, "ms_per_solve_device": dev_ms, "lm_iterations": out["iters"].tolist(), "lm_trials": trials,
             "ms_per_trial": dev_ms / max(1, trials), "allreduce_bytes_per_trial": float(out["profile"][3]), "schur_blocks": int(out["profile"][2]),
+            "host_ms": {"structure_plan_upload": float(out["profile"][4]), "lm_loop_wall": float(out["profile"][5]), "download_scatter": float(out["profile"][6])},
             "landmarks_per_rank": int(out["profile"][0]), "observations_per_rank": int(out["profile"][1]),
             "final_chi2": float(out["trace"][int(out["iters"].sum()) - 1, 0])}
     if "--ref" in sys.argv:

@@ -25,6 +25,7 @@
 #include <cmath>
 #include <cstring>
 #include <vector>
+#include <chrono>
 #include <mutex>
 #include "ba_band.h"
 
@@ -1171,6 +1172,7 @@ int ba_streamed_solve(uco_b200_ctx* ctx, const uco_ba_problem* pb, const volatil
 
 int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_problem* pb, const volatile unsigned char* stop, uco_ba_result* res) {
     if (!ctx) return UCO_E_INVALID;
+    const auto t_enter = std::chrono::steady_clock::now();
     cudaSetDevice(ctx->device);
     if (!res) return uco_fail(ctx, UCO_E_INVALID, "ba_solve_sharded: null result");
     int rc = ba_validate(ctx, pb);
@@ -1432,6 +1434,7 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
         return UCO_OK;
     };
 
+    const auto t_prep = std::chrono::steady_clock::now();
     UCO_CUDA(ctx, cudaEventRecord(ctx->ba->ev0, s));
     ba_init_poses_kernel<<<(P + 127) / 128, 128, 0, s>>>(B, (const float*)(d + o_p44));
     UCO_LAUNCH_CHECK(ctx);
@@ -1565,6 +1568,7 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
         if ((rc = uco_comm_allreduce(comm, full_flags, full_flags, 2 * (size_t)M, 2, s)) != UCO_OK) return rc;
     }
     UCO_CUDA(ctx, cudaEventRecord(ctx->ba->ev1, s));
+    const auto t_loop = std::chrono::steady_clock::now();
     const size_t o_h_pose = 0, o_h_p44 = o_h_pose + 56 * (size_t)P, o_h_pt = o_h_p44 + 64 * (size_t)P, o_h_chi = o_h_pt + 24 * (size_t)N,
                  o_h_fl = o_h_chi + 8 * (size_t)M, o_h_st = ((o_h_fl + 2 * (size_t)M + 7) & ~(size_t)7), o_h_mk7 = o_h_st + ((sizeof(LmState) + 7) & ~(size_t)7),
                  o_h_mk44 = o_h_mk7 + 56 * (size_t)Nm, o_h_echi = o_h_mk44 + 64 * (size_t)Nm, out_bytes = o_h_echi + 8 * (size_t)Ne + 8;
@@ -1610,6 +1614,10 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
     if (res->profile) {
         memset(res->profile, 0, sizeof(double) * 16);
         res->profile[0] = NL; res->profile[1] = ML; res->profile[2] = nblk; res->profile[3] = (double)n_red * 8;  // shard sizes, all-reduce bytes per trial
+        auto ms_between = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        res->profile[4] = ms_between(t_enter, t_prep);   // host: structure, solver plan, staging, upload
+        res->profile[5] = ms_between(t_prep, t_loop);    // host wall time of the LM loop (kernel launches + one synchronisation per trial)
+        res->profile[6] = ms_between(t_loop, std::chrono::steady_clock::now());   // download + scatter
     }
     return UCO_OK;
 }

@@ -45,7 +45,7 @@ size_t front_smem_fixed(int n, int W, int nbr) {   // doubles: y | bv | Lkk + sd
     return 8 * (6 * (size_t)n + 6 * (size_t)nbr + 56 + 36 * (size_t)(B + nbr) + 36 * (size_t)W * nbr + 36 * (size_t)nbr * nbr) +
            4 * (2 * (size_t)n + npairs + 4);
 }
-size_t front_smem_window(int W) { return 8 * 36 * (size_t)W * W; }
+size_t front_smem_window(int W) { return 8 * 36 * (size_t)std::max(W * W, 5 * W); }   // the back substitution's row ring reuses lcol + window: (4 + 1) W blocks
 
 using Adj = std::vector<std::vector<int>>;
 
@@ -175,32 +175,57 @@ void uco_band_make_plan(int nb, int nblk, const int2* blk_ij, int smem_optin, in
     // cost of a cut: the chain of dependent pivots (longest interior front, then the separators) — and everything has to fit shared memory
     int bestK = 0, best_style = 0;
     {
-        double best = 1e300;
+        struct Cand { double cost; int K, style; };
+        std::vector<Cand> cands;
         std::vector<int> m;
         std::vector<Piece> pcs;
         const int Kmax = std::min(48, (L - 1) / 3);
         for (int K = 0; K <= Kmax; K++)
             for (int style = 0; style < (K == 0 ? 1 : 2); style++) {
+                if (force_k < 0 && K > 8 && (K & (K > 16 ? 3 : 1))) continue;   // beyond 8 levels the cost curve is flat: every 2nd, then every 4th
                 if (force_k >= 0 && (K != std::min(force_k % 100, Kmax) || (force_k >= 100 && style != 1))) continue;
                 cut(K, style, m);
-                pieces_of(m, pcs);
-                if ((int)pcs.size() > 256) continue;
-                size_t longest = 0, nsep = 0;
-                bool fits = true;
-                for (const Piece& pc : pcs) {
-                    longest = std::max(longest, pc.nodes.size());
-                    const int w = local_W(pc.nodes);
-                    if (K > 0 && front_smem_fixed((int)pc.nodes.size(), w, (int)pc.border.size()) + front_smem_window(w) > (size_t)smem_optin) fits = false;
+                // sizes of the pieces only (one sweep); the orderings are built for the winner
+                size_t longest = 0, nsep = 0, npieces = 0;
+                std::vector<char> seen(nb, 0);
+                std::vector<int> stack;
+                for (int s0 = 0; s0 < nb; s0++) {
+                    if (m[s0] == 1) { nsep++; continue; }
+                    if (seen[s0]) continue;
+                    size_t sz = 0;
+                    stack.assign(1, s0);
+                    seen[s0] = 1;
+                    while (!stack.empty()) {
+                        const int u = stack.back();
+                        stack.pop_back();
+                        sz++;
+                        for (int v : adj[u])
+                            if (m[v] == 0 && !seen[v]) { seen[v] = 1; stack.push_back(v); }
+                    }
+                    longest = std::max(longest, sz);
+                    npieces++;
                 }
-                for (int v = 0; v < nb; v++) nsep += m[v];
-                if (!fits) continue;
-                const double cost = K == 0 ? 1.5 * (double)longest : 1.5 * (double)longest + 2.5 * (double)nsep + 8.0;   // forward + back steps; the root's band is about twice as wide
-                if (cost < best) {
-                    best = cost;
-                    bestK = K;
-                    best_style = style;
+                if (npieces > 256) continue;
+                // forward + back steps; the root's band is about twice as wide
+                cands.push_back({K == 0 ? 1.5 * (double)longest : 1.5 * (double)longest + 2.5 * (double)nsep + 8.0, K, style});
+            }
+        std::stable_sort(cands.begin(), cands.end(), [](const Cand& x, const Cand& y) { return x.cost < y.cost; });
+        for (const Cand& cd : cands) {   // the cheapest cut whose fronts fit shared memory
+            bool fits = true;
+            if (cd.K > 0) {
+                cut(cd.K, cd.style, m);
+                pieces_of(m, pcs);
+                for (const Piece& pc : pcs) {
+                    const int w = local_W(pc.nodes);
+                    if (front_smem_fixed((int)pc.nodes.size(), w, (int)pc.border.size()) + front_smem_window(w) > (size_t)smem_optin) fits = false;
                 }
             }
+            if (fits) {
+                bestK = cd.K;
+                best_style = cd.style;
+                break;
+            }
+        }
     }
     if (force_k >= 0 && bestK != std::min(force_k % 100, std::min(48, (L - 1) / 3))) {   // the forced cut does not fit shared memory: choose freely
         uco_band_make_plan(nb, nblk, blk_ij, smem_optin, -1, P);
@@ -575,6 +600,56 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory"); }
 
+// back substitution L^T x = y over a front's envelope factor (diagonal slots hold the INVERSE of L_kk), column-oriented: once x_k is
+// known, y_j -= L_kj^T x_k for the blocks of ROW k — which the row envelope stores contiguously.  No reduction: every participating
+// thread computes x_k itself (21 FMA) and owns one entry of one y_j; one named barrier per step.  Rows arrive through a cp.async ring
+// BACK_DEPTH steps ahead, so no L2 latency is on the chain.  Needs 18 W <= BAND_THREADS and (BACK_DEPTH + 1) 36 W doubles of ring.
+constexpr int BACK_DEPTH = 4;
+__device__ void band_back_substitute_ring(const double* __restrict__ E, const int* fcol, const int* rowptr, int n, int W, double* y, double* ring) {
+    const int tid = threadIdx.x, B = W - 1;
+    const int nthr = (18 * W + 31) / 32 * 32;         // whole warps: they copy the rows; the first 6 B threads also compute
+    if (tid >= nthr || n <= 0) return;                // the others wait at the caller's next __syncthreads
+    const int jj = tid / 6, c = tid % 6;
+    auto issue = [&](int i) {                         // row i -> slot i % (BACK_DEPTH + 1); one commit group per row (empty below row 0)
+        if (i >= 0 && tid < 18 * (i - fcol[i] + 1)) cp_async16(ring + 36 * W * (i % (BACK_DEPTH + 1)) + 2 * tid, E + 36 * (size_t)rowptr[i] + 2 * tid);
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+    for (int i = n - 1; i > n - 1 - BACK_DEPTH; i--) issue(i);
+    double xprev = 0;
+    for (int k = n - 1; k >= 0; k--) {
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(BACK_DEPTH - 1) : "memory");
+        asm volatile("bar.sync 1, %0;\n" ::"r"(nthr) : "memory");   // row k has landed for everyone; the y updates of step k + 1 are visible
+        if (tid < 6 && k + 1 < n) y[6 * (k + 1) + tid] = xprev;       // y_(k+1) is not read any more: it becomes x_(k+1)
+        issue(k - BACK_DEPTH);                         // into the slot row k + 1 has just left
+        const double* row = ring + 36 * W * (k % (BACK_DEPTH + 1));
+        const int f = fcol[k];
+        const double* Linv = row + 36 * (k - f);
+        double yk[6], x[6];
+#pragma unroll
+        for (int r = 0; r < 6; r++) yk[r] = y[6 * k + r];
+#pragma unroll
+        for (int cc = 0; cc < 6; cc++) {
+            double v = 0;
+#pragma unroll
+            for (int r = 0; r < 6; r++) if (r >= cc) v = fma(Linv[6 * r + cc], yk[r], v);
+            x[cc] = v;
+        }
+        const int j = k - 1 - jj;
+        if (jj < B && j >= f) {
+            const double* Lb = row + 36 * (j - f);
+            double v = 0;
+#pragma unroll
+            for (int r = 0; r < 6; r++) v = fma(Lb[6 * r + c], x[r], v);
+            y[6 * j + c] -= v;
+        }
+        if (tid < 6) {
+#pragma unroll
+            for (int r = 0; r < 6; r++) if (r == tid) xprev = x[r];
+        }
+    }
+    if (tid < 6) y[tid] = xprev;
+}
+
 // back substitution L^T x = y over a front's envelope factor (diagonal slots hold the INVERSE of L_kk): x_k = Linv_k^T (y_k - sum_{i > k}
 // L_ik^T x_i).  Thread (ii, c) owns column c of block (k + 1 + ii, k), streamed from L2 one step ahead; warp 0 folds the partial sums.
 __device__ void band_back_substitute(const double* __restrict__ E, const int* fcol, const int* rowptr, int n, int B, double* y, double* part) {
@@ -676,7 +751,7 @@ __global__ void __launch_bounds__(BAND_THREADS) band_front_kernel(BandDev D, int
     double* Sbb = bwin + 36 * (size_t)W * nbr;        // nbr x nbr blocks: Schur complement of the border (lower block triangle)
     double* after = Sbb + 36 * (size_t)nbr * nbr;
     double* win = win_in_smem ? after : D.wglobal;    // W x W blocks, circular: block (i, j) at ((i % W) * W + (j % W)) * 36 (template: shared loads when in smem)
-    int* fcol = (int*)(win_in_smem ? after + 36 * (size_t)W * W : after);
+    int* fcol = (int*)(win_in_smem ? after + 36 * (size_t)max(W * W, 5 * W) : after);
     int* rowptr = fcol + n;
     int* ptab = rowptr + n;                           // slot pairs a >= b, a << 16 | b
     __shared__ int s_fail;
@@ -914,7 +989,9 @@ __global__ void __launch_bounds__(BAND_THREADS) band_front_kernel(BandDev D, int
         for (int t = tid; t < 6 * n; t += BAND_THREADS) D.Z[F.oY + t] = y[t];
         return;
     }
-    band_back_substitute(E, fcol, rowptr, n, B, y, lcol);
+    if (win_in_smem && 18 * W <= BAND_THREADS) band_back_substitute_ring(E, fcol, rowptr, n, W, y, lcol);   // the ring takes over lcol + window
+    else band_back_substitute(E, fcol, rowptr, n, B, y, lcol);
+    __syncthreads();
     for (int t = tid; t < 6 * n; t += BAND_THREADS) {
         D.xp[6 * D.node[F.row0 + t / 6] + t % 6] = y[t];
         D.Z[F.oY + t] = y[t];                         // the root's solution in root order: the interior fronts' borders read it
@@ -935,7 +1012,8 @@ __global__ void __launch_bounds__(BAND_THREADS) band_back_kernel(BandDev D) {
     double* y = sm;
     double* xb = y + 6 * (size_t)n;
     double* part = xb + 6 * (size_t)nbr;
-    int* fcol = (int*)(part + 6 * (size_t)max(B, 1));
+    double* ring = part + 6 * (size_t)max(B, 1);
+    int* fcol = (int*)(ring + 36 * (size_t)(BACK_DEPTH + 1) * F.W);
     int* rowptr = fcol + n;
     const uco_band_front R = D.fr[D.nfronts - 1];
     for (int t = tid; t < n; t += BAND_THREADS) { fcol[t] = D.fcol[F.row0 + t]; rowptr[t] = D.rowptr[F.row0 + t]; }
@@ -951,11 +1029,15 @@ __global__ void __launch_bounds__(BAND_THREADS) band_back_kernel(BandDev D) {
         y[t] = v;
     }
     __syncthreads();
-    band_back_substitute(D.Z + F.oE, fcol, rowptr, n, B, y, part);
+    if (18 * F.W <= BAND_THREADS) band_back_substitute_ring(D.Z + F.oE, fcol, rowptr, n, F.W, y, ring);
+    else band_back_substitute(D.Z + F.oE, fcol, rowptr, n, B, y, part);
+    __syncthreads();
     for (int t = tid; t < 6 * n; t += BAND_THREADS) D.xp[6 * D.node[F.row0 + t / 6] + t % 6] = y[t];
 }
 
-size_t back_smem(int n, int W, int nbr) { return 8 * (6 * (size_t)n + 6 * (size_t)nbr + 6 * (size_t)std::max(W - 1, 1)) + 8 * (size_t)n + 16; }
+size_t back_smem(int n, int W, int nbr) {
+    return 8 * (6 * (size_t)n + 6 * (size_t)nbr + 6 * (size_t)std::max(W - 1, 1) + 36 * (size_t)(BACK_DEPTH + 1) * W) + 8 * (size_t)n + 16;
+}
 
 BandDev band_dev(const uco_band_plan& P, const unsigned char* blob_dev, double* Z, double* xp, int* fail_dev, double* wglobal) {
     BandDev D;
