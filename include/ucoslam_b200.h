@@ -674,6 +674,40 @@ typedef struct uco_triangulate_params {
 int uco_b200_triangulate(uco_b200_ctx* ctx, const uco_keypoint* kps_train, int n_train, const uco_keypoint* kps_query, int n_query,
                          const uco_match* matches, int n_matches, const uco_triangulate_params* prm, float* xyz, int* n_good);
 
+/* New-map-point creation of one keyframe as a unit:
+ *   replaces MapManager::createNewPoints(frame, nn, maxPoints)   src/utils/mapmanager.cpp:9772-10788 (macro-obfuscated; de-obfuscated
+ *   with the C preprocessor): FrameMatcher::setParams(frame, MODE_UNASSIGNED, maxDescDistance*2, 0.6, true, INT_MAX), then per neighbour
+ *   keyframe f of the covisibility graph (the OpenMP loop :9992): T_f = nb.pose_f2g * frame.pose_f2g.inv(), matchEpipolar(nb,
+ *   MODE_UNASSIGNED, T_f), Triangulate(frame, nb, T_f, matches), p = frame.pose_f2g.inv() * xyz, the scale-consistency gate
+ *   (ratioDist vs ratioOctave, factor 1.5f * scaleFactor), and the merge into one NewPointInfo per keyframe keypoint.
+ *   Inputs as uco_b200_frame_match_multi (t_* = the keyframe with t_map = its unassigned keypoints, q_*[f] = the neighbours with
+ *   q_map[f]); f12: n_frames x 9 (computeF12 of the caller, as for the matcher); rt: n_frames x 16, T_f row-major (keyframe camera ->
+ *   neighbour camera); K_nb: n_frames x 4 (fx fy cx cy).
+ *   Output, merged: point j < *n_points belongs to keyframe keypoint pt_kpt[j] (ascending: std::map order; after a max_points cut in
+ *   std::sort order of the descriptor distance), pt_xyz / pt_dist = position (global) and descriptor distance taken from the LAST
+ *   neighbour that saw it (what the reference's minimum-octave loop returns: its minimum is never updated), observations
+ *   obs_ptr[j] .. obs_ptr[j+1]: (obs_frame = neighbour index f, obs_kpt = its keypoint) in neighbour order; the keyframe's own
+ *   observation (frame.idx, pt_kpt[j]) is implied.  Optional per-neighbour output: matches[f] / n_matches[f] (the matcher's lists) and
+ *   xyz[f] (3 floats per match, global, NaN = rejected); pass NULL to skip.
+ *   One upload, three launches (k-NN, filters, triangulation of all neighbours), one download; the merge runs on the host.
+ *   Parity: matches bit-exact (K8); points to the float tolerance of K13 (tests/test_new_points_gpu.py). */
+typedef struct uco_new_points_params {
+    uco_match_params match;       /* min_desc_dist = maxDescDistance*2, nn_match_ratio 0.6, check_orientation 1, max_octave_diff INT_MAX, use_f12 1 */
+    float K_kf[4];                /* fx fy cx cy of the new keyframe */
+    float g2f_kf[16];             /* frame.pose_f2g.inv(), row-major 4x4 (keyframe camera -> global) */
+    int32_t n_levels_kf; const float* scale_factors_kf;
+    int32_t n_levels_nb; const float* scale_factors_nb;   /* the neighbours' (one extractor configuration per map) */
+    float max_chi2;               /* Triangulate's default 5.998 (misc.h:65) */
+    float scale_ratio_factor;     /* 1.5f * Params::scaleFactor */
+    int32_t max_points;           /* maxPoints (< 0: no limit) */
+} uco_new_points_params;
+int uco_b200_new_points(uco_b200_ctx* ctx, const uint8_t* t_desc, int nt, size_t t_stride, const uco_keypoint* t_kps, int n_t_kps, const int32_t* t_map,
+                        int n_frames, const uint8_t* const* q_desc, const int32_t* nq, size_t q_stride, const uco_keypoint* const* q_kps,
+                        const int32_t* n_q_kps, const int32_t* const* q_map, const float* f12, const float* rt, const float* K_nb,
+                        const uco_new_points_params* prm, int32_t* n_points, int32_t* pt_kpt, float* pt_xyz, float* pt_dist, int32_t* obs_ptr,
+                        int32_t* obs_frame, int32_t* obs_kpt, int capacity_points, int capacity_obs, uco_match* const* matches, int32_t* n_matches,
+                        float* const* xyz);
+
 /* ------------------------------------------------------------------------------------------------------------
  * K14  RANSAC pose from 2D-3D matches (relocalisation / loop-closure candidate scoring)
  *   replaces ucoslam::PnPSolver::solvePnPRansac(frame, map, matches_io, posef2g_io, maxIters)

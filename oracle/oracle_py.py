@@ -1052,6 +1052,54 @@ def triangulate_py(sc, max_chi2=5.998, scale_ratio_factor=0.0, g2f_train=None):
     return out, good, margin
 
 
+def std_sort_indices(keys):
+    """the permutation std::sort (host libstdc++, through oracle/stl_helper.cpp) applies to 0..n-1 under keys[a] < keys[b]"""
+    keys = np.ascontiguousarray(keys, np.float32)
+    idx = np.arange(len(keys), dtype=np.uint32)
+    load_stl().stl_sort_indices(_p(idx), len(idx), _p(keys))
+    return idx.astype(np.int64)
+
+
+def new_points_py(sc, max_points=-1):
+    """MapManager::createNewPoints (src/utils/mapmanager.cpp:9772-10788, de-obfuscated with the C preprocessor) restated over the
+    restatements of its callees: per neighbour f matchEpipolar (frame_match: oracle/match_oracle.c, pinned to the reference's own
+    framematcher.cpp) on the MODE_UNASSIGNED rows, Triangulate + scale consistency + global frame (triangulate_py), then the merge:
+    std::map keyed by the keyframe keypoint, elements in neighbour order, position / distance of the LAST element (the reference's
+    minimum-octave loop never updates its minimum), std::sort on the distance + resize above max_points (through the host library's
+    own std::sort: oracle/stl_helper.cpp, so ties fall the same way).
+    Returns dict(kpt, xyz, dist, obs_ptr, obs_frame, obs_kpt, matches (per neighbour), xyz_pairs, margin (per neighbour))."""
+    groups = {}
+    matches, xyzs, margins = [], [], []
+    for f in range(len(sc["q_desc"])):
+        qm, tm = np.asarray(sc["q_map"][f], np.int32), np.asarray(sc["t_map"], np.int32)
+        if len(qm) and len(tm):
+            m = frame_match(np.ascontiguousarray(sc["q_desc"][f][qm]), sc["q_kps"][f], np.ascontiguousarray(sc["t_desc"][tm]), sc["t_kps"],
+                            min_desc_dist=sc["min_desc_dist"], ratio=sc["ratio"], check_orientation=True, max_octave_diff=2 ** 31 - 1, F12=sc["f12"][f],
+                            scale_factors=sc["sf_nb"], q_map=qm, t_map=tm)
+        else:
+            m = np.zeros(0, MATCH_DTYPE)
+        tv = dict(kps_train=sc["t_kps"], kps_query=sc["q_kps"][f], matches=m, K_train=sc["K_kf"], K_query=sc["K_nb"][f], RT=sc["rt"][f],
+                  sf_train=sc["sf_kf"], sf_query=sc["sf_nb"])
+        xyz, _, margin = triangulate_py(tv, sc.get("max_chi2", 5.998), sc["scale_ratio_factor"], sc["g2f_kf"])
+        matches.append(m); xyzs.append(xyz); margins.append(margin)
+        for i in range(len(m)):
+            if not np.isnan(xyz[i, 0]):
+                groups.setdefault(int(m["trainIdx"][i]), []).append((f, int(m["queryIdx"][i]), float(m["distance"][i]), xyz[i]))
+    keys = sorted(groups)
+    if max_points >= 0 and len(keys) > max_points:
+        d = np.array([groups[k][-1][2] for k in keys], np.float32)
+        order = std_sort_indices(d)[:max_points]
+        keys = [keys[i] for i in order]
+    kpt = np.array(keys, np.int32)
+    xyz = np.array([groups[k][-1][3] for k in keys], np.float32).reshape(-1, 3)
+    dist = np.array([groups[k][-1][2] for k in keys], np.float32)
+    ptr = np.zeros(len(keys) + 1, np.int32)
+    ptr[1:] = np.cumsum([len(groups[k]) for k in keys])
+    ofr = np.array([r[0] for k in keys for r in groups[k]], np.int32)
+    okp = np.array([r[1] for k in keys for r in groups[k]], np.int32)
+    return dict(kpt=kpt, xyz=xyz, dist=dist, obs_ptr=ptr, obs_frame=ofr, obs_kpt=okp, matches=matches, xyz_pairs=xyzs, margin=margins)
+
+
 # ---- RANSAC P3P pose (SURVEY 8f rank 1) -------------------------------------------------------------------------------------------
 def pnp_ransac_py(sc, samples):
     """PnPSolver::solvePnPRansac (src/optimization/pnpsolver.cpp:36-114) restated with the reference's own OpenCV call

@@ -123,6 +123,17 @@ private:
     int _type = 0;
     std::shared_ptr<unsigned char> _own;
 };
+// CV_32F matrix product (double accumulator, like cv::gemm's small-matrix path), as far as the adapters use it (4x4 pose products)
+static inline Mat operator*(const Mat& a, const Mat& b) {
+    Mat o(a.rows, b.cols, CV_32F);
+    for (int r = 0; r < a.rows; r++)
+        for (int c = 0; c < b.cols; c++) {
+            double v = 0;
+            for (int k = 0; k < a.cols; k++) v += (double)a.at<float>(r, k) * (double)b.at<float>(k, c);
+            o.at<float>(r, c) = (float)v;
+        }
+    return o;
+}
 // InputArray / OutputArray: thin handles on a Mat, as far as the extractor seam uses them (getMat / create / release)
 class _InputArray {
 public:

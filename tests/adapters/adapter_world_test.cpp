@@ -8,7 +8,8 @@
 //   3. matchFrameToMapPoints_b200 against the reference's own Map::matchFrameToMapPoints statements (map.cpp:651-770): identical lists
 //      and setVisible() marks, the kd-tree travelling as the bytes the reference's picoflann writes;
 //   4. solvePnp_b200 against the reference's g2o + typesg2o.h (oracle/_ref/libref_g2o.so): pose to 1e-6, identical inlier flags;
-//   5. GlobalOptimizerB200 (derived from the reference's real globaloptimizer.h) against the same g2o on the window it flattened.
+//   5. GlobalOptimizerB200 (derived from the reference's real globaloptimizer.h) against the same g2o on the window it flattened;
+//   6. createNewPoints_b200 (the body of the mapper's new-map-point creation) on three keyframes: every point re-projects onto its keypoints.
 // OpenCV / Frame / Map are the container stand-ins of oracle/shim2 (the image has no OpenCV C++).  Built by `make -C oracle ref`
 // into oracle/_ref/, run by tests/test_adapters_gpu.py.  Exit code 0 = every comparison held.
 #include <cstdio>
@@ -27,13 +28,44 @@
 #include "pnp_solver_b200.h"
 #include <optimization/globaloptimizer.h>
 #include "global_optimizer_b200.h"
+#include "new_points_b200.h"
 
 namespace ucoslam {
 #include "gen/misc_filters.inc"
 #include "gen/f2d_members.inc"
 #include "gen/frame_region.inc"
 #include "gen/map_match.inc"
-cv::Mat computeF12(const cv::Mat&, const cv::Mat&, const cv::Mat&, const cv::Mat&) { return cv::Mat(); }
+// computeF12 (misc.cpp:893-920) is OpenCV matrix algebra: off (empty matrix = no epipolar gate, as in oracle/ref_match_wrap.cpp) for the
+// matcher comparison; for the new-point adapter a plain restatement: F12 = K1^-T [t12]x R12 K2^-1, R12 = R1 R2^T, t12 = -R1 R2^T t2 + t1
+static bool g_real_f12 = false;
+cv::Mat computeF12(const cv::Mat& RT1, const cv::Mat& K1, const cv::Mat& RT2, const cv::Mat& K2_) {
+    if (!g_real_f12) return cv::Mat();
+    const cv::Mat& K2 = K2_.empty() ? K1 : K2_;
+    double R12[3][3], t12[3];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) {
+            R12[r][c] = 0;
+            for (int k = 0; k < 3; k++) R12[r][c] += (double)RT1.at<float>(r, k) * RT2.at<float>(c, k);
+        }
+    for (int r = 0; r < 3; r++) {
+        t12[r] = RT1.at<float>(r, 3);
+        for (int k = 0; k < 3; k++) t12[r] -= R12[r][k] * RT2.at<float>(k, 3);
+    }
+    const double tx[3][3] = {{0, -t12[2], t12[1]}, {t12[2], 0, -t12[0]}, {-t12[1], t12[0], 0}};
+    auto kinv = [](const cv::Mat& K, double o[3][3]) {   // inverse of [fx 0 cx; 0 fy cy; 0 0 1]
+        const double fx = K.at<float>(0, 0), fy = K.at<float>(1, 1), cx = K.at<float>(0, 2), cy = K.at<float>(1, 2);
+        const double v[3][3] = {{1 / fx, 0, -cx / fx}, {0, 1 / fy, -cy / fy}, {0, 0, 1}};
+        memcpy(o, v, sizeof v);
+    };
+    double k1i[3][3], k2i[3][3], A[3][3], B[3][3], C[3][3];
+    kinv(K1, k1i); kinv(K2, k2i);
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) { A[r][c] = 0; for (int k = 0; k < 3; k++) A[r][c] += k1i[k][r] * tx[k][c]; }
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) { B[r][c] = 0; for (int k = 0; k < 3; k++) B[r][c] += A[r][k] * R12[k][c]; }
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) { C[r][c] = 0; for (int k = 0; k < 3; k++) C[r][c] += B[r][k] * k2i[k][c]; }
+    cv::Mat F(3, 3, CV_32F);
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) F.at<float>(r, c) = (float)C[r][c];
+    return F;
+}
 }  // namespace ucoslam
 
 extern "C" {
@@ -226,6 +258,47 @@ int main() {
             ok = ok && ngood == rgood && flags && dmax < 1e-6 && ngood > 400 && terr < 5e-3;
         }
         EXPECT(ok, "solvePnp_b200 == the reference's g2o pose-only solve (pose 1e-6, inlier flags, count) and recovers the pose");
+    }
+
+    // ---- 6. new-map-point creation (the mapper's createNewPoints body) ---------------------------------------------------------------
+    {
+        struct NewPointInfo { cv::Point3d pose; bool isStereo = false; std::vector<std::pair<uint32_t, uint32_t>> frame_kpt; float dist = std::numeric_limits<float>::max(); };
+        // fresh copies of the three keyframes with no keypoint assigned: everything is a candidate; a tilted, displaced set of cameras
+        // would need other images, so the poses stay the sliding ones (baseline 3-4 cm at 2 m: parallax cosine ~0.9998 -> use frames 1, 2
+        // against 0 with the parallax gate doing its job on part of the matches)
+        auto fresh = std::make_shared<Map>();
+        for (int k = 0; k < 3; k++) {
+            Frame& kf = fresh->keyframes.add(k);
+            kf = F[k];
+            kf.ids.assign(kf.und_kpts.size(), std::numeric_limits<uint32_t>::max());
+            kf.pose_f2g = Se3Transform();
+            // a wider baseline than the texture shift: the views are those of cameras 0.25 m apart looking at a plane 2 m away whose texture
+            // moved with them by all but (off[k] - off[0]) pixels — geometrically: points at depth Zk with f * B / Zk = pixel shift
+            kf.pose_f2g[3] = -(off[k][0] - off[0][0]) * Z / f; kf.pose_f2g[7] = -(off[k][1] - off[0][1]) * Z / f;
+        }
+        g_real_f12 = true;
+        uco_b200::Context c6;
+        std::vector<NewPointInfo> pts = createNewPoints_b200<NewPointInfo>(c6, *fresh, fresh->keyframes[0], std::vector<uint32_t>{1, 2}, 100000, 50.f, 1.2f);
+        g_real_f12 = false;
+        bool ok = !pts.empty();
+        size_t two = 0;
+        double worst = 0;
+        for (const auto& pnt : pts) {
+            ok = ok && pnt.frame_kpt.size() >= 2 && pnt.frame_kpt[0].first == 0 && pnt.frame_kpt[0].second < fresh->keyframes[0].und_kpts.size();
+            two += pnt.frame_kpt.size() == 3;
+            // the point re-projects onto its keypoints (5.998 chi2 gate at the keypoint's scale) and lies in front of the cameras
+            for (const auto& fk : pnt.frame_kpt) {
+                const Frame& kf = fresh->keyframes[fk.first];
+                const cv::KeyPoint& kp = kf.und_kpts[fk.second];
+                const double X = pnt.pose.x + kf.pose_f2g.at_(3), Y = pnt.pose.y + kf.pose_f2g.at_(7), Zc = pnt.pose.z;
+                const double u = f * X / Zc + cx, v = f * Y / Zc + cy, s = kf.scaleFactors[kp.octave];
+                worst = std::max(worst, ((u - kp.pt.x) * (u - kp.pt.x) + (v - kp.pt.y) * (v - kp.pt.y)) / (s * s));
+                ok = ok && Zc > 0;
+            }
+        }
+        std::printf("     new points: %zu (%zu seen by both neighbours), worst reprojection chi2 %.3f\n", pts.size(), two, worst);
+        EXPECT(ok && pts.size() > 10 && worst < 3 * 5.998,   // the 8-pixel texture shifts are right at the 0.9998 parallax gate: few matches pass it
+               "createNewPoints_b200 (mapper's new-point creation body): points re-project onto the keypoints they were made from");
     }
 
     // ---- 5. bundle adjustment ----------------------------------------------------------------------------------------------------------

@@ -674,6 +674,11 @@ extern "C" int uco_b200_hamming_knn_sharded_dev(uco_b200_ctx* ctx, uco_b200_comm
     cudaSetDevice(ctx->device);
     const int R = uco_comm_world(comm), rank = uco_comm_rank(comm);
     if (R > 32) return uco_fail(ctx, UCO_E_INVALID, "hamming_knn_sharded: more than 32 ranks");
+    // every argument is checked before anything is sized from it or any rank enters a collective (an early return on one rank
+    // only — e.g. out of memory below — is NOT collective: the caller has to tear the communicator down, see include/ucoslam_b200.h)
+    if (k <= 0 || k > UCO_KNN_MAX_K || (size_t)R * k > 1024) return uco_fail(ctx, UCO_E_INVALID, "hamming_knn_sharded: k=%d with %d ranks (need 1 <= k <= %d, ranks * k <= 1024)", k, R, UCO_KNN_MAX_K);
+    if (nt_shard < 0 || row_base < 0) return uco_fail(ctx, UCO_E_INVALID, "hamming_knn_sharded: negative shard size / row base");
+    if (nq > 0 && (!q_dev || !idx_dev || !dist_dev || (nt_shard > 0 && !t_shard_dev))) return uco_fail(ctx, UCO_E_INVALID, "hamming_knn_sharded: null pointer");
     if (nq <= 0) return nq == 0 ? UCO_OK : uco_fail(ctx, UCO_E_INVALID, "hamming_knn_sharded: nq < 0");
     const size_t n = (size_t)nq * k;
     // few queries against many rows: one CTA per 8 queries would leave the GPU idle, so the shard is itself scanned in S row ranges

@@ -12,6 +12,10 @@
 //   * the rotation histogram (:288-316) needs only bin COUNTS (integer atomics) before the three maxima are chosen;
 //   * remove_unused_matches is a stable compaction: block-wide prefix sums over query order.
 #include "common.cuh"
+#include <map>
+#include <vector>
+#include <algorithm>
+#include <cmath>
 #include <float.h>
 #include <string.h>
 #include <vector>
@@ -396,10 +400,27 @@ int uco_b200_frame_match_bow(uco_b200_ctx* ctx, const uint8_t* q_desc, size_t q_
 // The mapper's pattern (new-map-point creation, src/utils/mapmanager.cpp:9972-10065): FrameMatcher::setParams(train = the keyframe)
 // once, then matchEpipolar(query = each neighbour keyframe, F12_i).  One call = one upload, two launches (k-NN of all the
 // neighbours' rows against the keyframe's rows; the filters, one block per neighbour), one download.
-int uco_b200_frame_match_multi(uco_b200_ctx* ctx, const uint8_t* t_desc, int nt, size_t t_stride, const uco_keypoint* t_kps, int n_t_kps,
-                               const int32_t* t_map, int n_frames, const uint8_t* const* q_desc, const int32_t* nq, size_t q_stride,
-                               const uco_keypoint* const* q_kps, const int32_t* n_q_kps, const int32_t* const* q_map, const float* f12,
-                               const uco_match_params* prm, uco_match* const* out, int capacity, int32_t* n_out) {
+}  // extern "C" (internal helpers follow)
+
+// optional second stage of the multi-frame matcher: triangulation of every neighbour's matches on the device (triangulate.cu)
+int uco_tri_pairs_launch(uco_b200_ctx* ctx, const uco_keypoint* kp1, int n1, const uco_keypoint* kp2, int kp2_stride, const int32_t* n2_dev, int n_frames,
+                         const uco_match* matches, int match_stride, const int32_t* n_matches_dev, const float* K1, const float* cam2_dev,
+                         const float* sf_dev, int nl1, int nl2, float max_chi2, float ratio_factor, const float* g2f_train, float* xyz_dev,
+                         int32_t* counters_dev);
+namespace {
+struct TriStaged { const uco_match* matches; const float* xyz; int stride; };   // pinned staging of the last call (valid until the next one)
+struct TriStage {
+    const float* rt; const float* K_nb; const float* K_kf; const float* g2f;
+    const float* sf1; int nl1; const float* sf2; int nl2;
+    float max_chi2, ratio_factor;
+    TriStaged* res;
+};
+}  // namespace
+
+static int match_multi_impl(uco_b200_ctx* ctx, const uint8_t* t_desc, int nt, size_t t_stride, const uco_keypoint* t_kps, int n_t_kps,
+                            const int32_t* t_map, int n_frames, const uint8_t* const* q_desc, const int32_t* nq, size_t q_stride,
+                            const uco_keypoint* const* q_kps, const int32_t* n_q_kps, const int32_t* const* q_map, const float* f12,
+                            const uco_match_params* prm, uco_match* const* out, int capacity, int32_t* n_out, const TriStage* tri) {
     if (!ctx) return UCO_E_INVALID;
     cudaSetDevice(ctx->device);
     int rc = check_params(ctx, prm);
@@ -407,15 +428,15 @@ int uco_b200_frame_match_multi(uco_b200_ctx* ctx, const uint8_t* t_desc, int nt,
     if (n_frames < 0 || !n_out) return uco_fail(ctx, UCO_E_INVALID, "frame_match_multi: bad arguments");
     for (int f = 0; f < n_frames; f++) n_out[f] = 0;
     if (n_frames == 0 || nt == 0) return UCO_OK;
-    if (nt < 0 || n_t_kps < 0 || !t_desc || !t_kps || !q_desc || !nq || !q_kps || !n_q_kps || !out || q_stride < 32 || t_stride < 32)
+    if (nt < 0 || n_t_kps < 0 || !t_desc || !t_kps || !q_desc || !nq || !q_kps || !n_q_kps || (!out && !tri) || q_stride < 32 || t_stride < 32)
         return uco_fail(ctx, UCO_E_INVALID, "frame_match_multi: bad arguments");
     if (!t_map && n_t_kps < nt) return uco_fail(ctx, UCO_E_INVALID, "frame_match_multi: fewer train keypoints than descriptor rows");
     if (prm->use_f12 && !f12) return uco_fail(ctx, UCO_E_INVALID, "frame_match_multi: use_f12 without the per-frame matrices");
     int nq_max = 0, nk_max = 0;
     for (int f = 0; f < n_frames; f++) {
-        if (nq[f] < 0 || n_q_kps[f] < 0 || (nq[f] && (!q_desc[f] || !q_kps[f] || !out[f]))) return uco_fail(ctx, UCO_E_INVALID, "frame_match_multi: frame %d malformed", f);
+        if (nq[f] < 0 || n_q_kps[f] < 0 || (nq[f] && (!q_desc[f] || !q_kps[f] || (!tri && !out[f])))) return uco_fail(ctx, UCO_E_INVALID, "frame_match_multi: frame %d malformed", f);
         if (!(q_map && q_map[f]) && n_q_kps[f] < nq[f]) return uco_fail(ctx, UCO_E_INVALID, "frame_match_multi: frame %d has fewer keypoints than rows", f);
-        if (capacity < nq[f]) return uco_fail(ctx, UCO_E_CAPACITY, "frame_match_multi: output capacity %d below the %d rows of frame %d", capacity, nq[f], f);
+        if (capacity < nq[f] && out && out[f]) return uco_fail(ctx, UCO_E_CAPACITY, "frame_match_multi: output capacity %d below the %d rows of frame %d", capacity, nq[f], f);
         for (int i = 0; q_map && q_map[f] && i < nq[f]; i++)
             if ((unsigned)q_map[f][i] >= (unsigned)n_q_kps[f]) return uco_fail(ctx, UCO_E_INVALID, "frame_match_multi: q_map[%d][%d] out of range", f, i);
         nq_max = nq[f] > nq_max ? nq[f] : nq_max;
@@ -431,7 +452,8 @@ int uco_b200_frame_match_multi(uco_b200_ctx* ctx, const uint8_t* t_desc, int nt,
     const size_t F = n_frames;
     const size_t o_td = take((size_t)nt * 32), o_tk = take(sizeof(uco_keypoint) * (size_t)n_t_kps), o_tm = take(t_map ? 4 * (size_t)nt : 0),
                  o_qd = take(F * nq_max * 32), o_qk = take(sizeof(uco_keypoint) * F * nk_max), o_qm = take(any_qmap ? 4 * F * nq_max : 0),
-                 o_nq = take(4 * F), o_f = take(36 * F);
+                 o_nq = take(4 * F), o_f = take(36 * F), o_nk = take(tri ? 4 * F : 0), o_cam = take(tri ? 64 * F : 0),
+                 o_sf = take(tri ? 16 * UCO_MATCH_MAX_SCALES : 0);
     const size_t in_bytes = off;
     uint8_t* h = (uint8_t*)uco_pinned(ctx, WS_MATCH_IN, in_bytes);
     uint8_t* din = (uint8_t*)uco_ws(ctx, WS_MATCH_IN, in_bytes);
@@ -439,7 +461,8 @@ int uco_b200_frame_match_multi(uco_b200_ctx* ctx, const uint8_t* t_desc, int nt,
     int32_t* knn = (int32_t*)uco_ws(ctx, WS_MATCH_KNN, knn_elems * 8);
     const size_t used_bytes = F * n_t_kps * 8, cand_bytes = F * nq_max * 8;
     uint8_t* scr = (uint8_t*)uco_ws(ctx, WS_MATCH_SCRATCH, used_bytes + cand_bytes);
-    const size_t out_bytes = al(4 * F) + sizeof(uco_match) * F * nq_max;
+    const size_t o_xyz = al(al(4 * F) + sizeof(uco_match) * F * nq_max), o_cnt = o_xyz + al(tri ? 12 * F * nq_max : 0);
+    const size_t out_bytes = tri ? o_cnt + al(4 * (F + 1)) : al(4 * F) + sizeof(uco_match) * F * nq_max;
     uint8_t* dout = (uint8_t*)uco_ws(ctx, WS_MATCH_OUT, out_bytes);
     uint8_t* hout = (uint8_t*)uco_pinned(ctx, WS_MATCH_OUT, out_bytes);
     if (!h || !din || !knn || !scr || !dout || !hout) return UCO_E_NOMEM;
@@ -458,6 +481,21 @@ int uco_b200_frame_match_multi(uco_b200_ctx* ctx, const uint8_t* t_desc, int nt,
         ((int32_t*)(h + o_nq))[f] = nq[f];
         if (f12) memcpy(h + o_f + 36 * f, f12 + 9 * f, 36);
         else memset(h + o_f + 36 * f, 0, 36);
+        if (tri) {   // K2 | R | t of neighbour f (camera 1 = the keyframe)
+            ((int32_t*)(h + o_nk))[f] = n_q_kps[f];
+            float* c2 = (float*)(h + o_cam) + 16 * f;
+            memcpy(c2, tri->K_nb + 4 * f, 16);
+            for (int r = 0; r < 3; r++) {
+                for (int c = 0; c < 3; c++) c2[4 + 3 * r + c] = tri->rt[16 * f + 4 * r + c];
+                c2[13 + r] = tri->rt[16 * f + 4 * r + 3];
+            }
+        }
+    }
+    if (tri) {   // invScaleFactors: 1.f/(f*f) per octave (misc.cpp:943-945), then the factors themselves
+        float* sf = (float*)(h + o_sf);
+        memset(sf, 0, 16 * UCO_MATCH_MAX_SCALES);
+        for (int l = 0; l < tri->nl1; l++) { sf[l] = 1.f / (tri->sf1[l] * tri->sf1[l]); sf[2 * UCO_MATCH_MAX_SCALES + l] = tri->sf1[l]; }
+        for (int l = 0; l < tri->nl2; l++) { sf[UCO_MATCH_MAX_SCALES + l] = 1.f / (tri->sf2[l] * tri->sf2[l]); sf[3 * UCO_MATCH_MAX_SCALES + l] = tri->sf2[l]; }
     }
     cudaStream_t st = ctx->stream;
     UCO_CUDA(ctx, cudaMemcpyAsync(din, h, in_bytes, cudaMemcpyHostToDevice, st));
@@ -475,13 +513,107 @@ int uco_b200_frame_match_multi(uco_b200_ctx* ctx, const uint8_t* t_desc, int nt,
     A.bow_entry_node = nullptr; A.bow_t_node = nullptr; A.bow_t_ptr = nullptr; A.bow_t_kp = nullptr; A.q_usable = A.t_usable = nullptr; A.q_desc = A.t_desc = nullptr;
     match_filter_kernel<<<n_frames, MT, 0, st>>>(A);
     UCO_LAUNCH_CHECK(ctx);
+    if (tri) {   // Triangulate + the mapper's gates on the matcher's device output, all neighbours in one launch
+        rc = uco_tri_pairs_launch(ctx, A.t_kps, n_t_kps, A.q_kps, nk_max, (const int32_t*)(din + o_nk), n_frames, A.out, nq_max, A.n_out, tri->K_kf,
+                                  (const float*)(din + o_cam), (const float*)(din + o_sf), tri->nl1, tri->nl2, tri->max_chi2, tri->ratio_factor, tri->g2f,
+                                  (float*)(dout + o_xyz), (int32_t*)(dout + o_cnt));
+        if (rc) return rc;
+    }
     UCO_CUDA(ctx, cudaMemcpyAsync(hout, dout, out_bytes, cudaMemcpyDeviceToHost, st));
     UCO_CUDA(ctx, cudaStreamSynchronize(st));
+    if (tri && ((const int32_t*)(hout + o_cnt))[0]) return uco_fail(ctx, UCO_E_INVALID, "new_points: a match refers to a keypoint or an octave out of range");
     for (size_t f = 0; f < F; f++) {
         const int n = ((const int32_t*)hout)[f];
         n_out[f] = n;
-        if (n > 0) memcpy(out[f], hout + al(4 * F) + sizeof(uco_match) * f * nq_max, sizeof(uco_match) * (size_t)n);
+        if (n > 0 && out && out[f]) memcpy(out[f], hout + al(4 * F) + sizeof(uco_match) * f * nq_max, sizeof(uco_match) * (size_t)n);
     }
+    if (tri) {   // hand the staged results to the caller's merge
+        tri->res->matches = (const uco_match*)(hout + al(4 * F));
+        tri->res->xyz = (const float*)(hout + o_xyz);
+        tri->res->stride = nq_max;
+    }
+    return UCO_OK;
+}
+
+
+extern "C" {
+
+int uco_b200_frame_match_multi(uco_b200_ctx* ctx, const uint8_t* t_desc, int nt, size_t t_stride, const uco_keypoint* t_kps, int n_t_kps,
+                               const int32_t* t_map, int n_frames, const uint8_t* const* q_desc, const int32_t* nq, size_t q_stride,
+                               const uco_keypoint* const* q_kps, const int32_t* n_q_kps, const int32_t* const* q_map, const float* f12,
+                               const uco_match_params* prm, uco_match* const* out, int capacity, int32_t* n_out) {
+    return match_multi_impl(ctx, t_desc, nt, t_stride, t_kps, n_t_kps, t_map, n_frames, q_desc, nq, q_stride, q_kps, n_q_kps, q_map, f12, prm, out, capacity,
+                            n_out, nullptr);
+}
+
+// New-map-point creation of one keyframe as a unit (MapManager's createNewPoints, src/utils/mapmanager.cpp:9772-10788, de-obfuscated):
+//   FrameMatcher::setParams(frame, MODE_UNASSIGNED, ...) ; per neighbour f (the reference's OpenMP loop :9992): matchEpipolar(neighbour,
+//   MODE_UNASSIGNED, T_f) -> Triangulate(frame, neighbour, T_f, matches) -> global coordinates -> scale-consistency gate -> (trainIdx,
+//   neighbour, queryIdx, p, distance); then the merge: one point per keyframe keypoint (std::map order), position / distance of the LAST
+//   neighbour that saw it (the reference's minimum-octave loop never updates its minimum, so it always ends on the last element),
+//   observations in neighbour order; above max_points the points with the smallest distance survive (std::sort on dist + resize).
+// One upload, three launches (k-NN, filters, triangulation), one download; the merge runs on the host over the downloaded lists.
+int uco_b200_new_points(uco_b200_ctx* ctx, const uint8_t* t_desc, int nt, size_t t_stride, const uco_keypoint* t_kps, int n_t_kps, const int32_t* t_map,
+                        int n_frames, const uint8_t* const* q_desc, const int32_t* nq, size_t q_stride, const uco_keypoint* const* q_kps,
+                        const int32_t* n_q_kps, const int32_t* const* q_map, const float* f12, const float* rt, const float* K_nb,
+                        const uco_new_points_params* prm, int32_t* n_points, int32_t* pt_kpt, float* pt_xyz, float* pt_dist, int32_t* obs_ptr,
+                        int32_t* obs_frame, int32_t* obs_kpt, int capacity_points, int capacity_obs, uco_match* const* matches, int32_t* n_matches,
+                        float* const* xyz) {
+    if (!ctx) return UCO_E_INVALID;
+    if (!prm || !n_points || n_frames < 0) return uco_fail(ctx, UCO_E_INVALID, "new_points: bad arguments");
+    *n_points = 0;
+    if (obs_ptr && capacity_points >= 0) obs_ptr[0] = 0;
+    if (n_frames == 0 || nt == 0) return UCO_OK;
+    if (!rt || !K_nb || !f12 || !prm->match.use_f12) return uco_fail(ctx, UCO_E_INVALID, "new_points: the epipolar matcher needs f12, rt and K_nb per neighbour (match.use_f12 = 1)");
+    if (prm->n_levels_kf <= 0 || prm->n_levels_nb <= 0 || prm->n_levels_kf > UCO_MATCH_MAX_SCALES || prm->n_levels_nb > UCO_MATCH_MAX_SCALES ||
+        !prm->scale_factors_kf || !prm->scale_factors_nb)
+        return uco_fail(ctx, UCO_E_INVALID, "new_points: scale factor tables of 1..%d levels expected", UCO_MATCH_MAX_SCALES);
+    if (!pt_kpt || !pt_xyz || !pt_dist || !obs_ptr || !obs_frame || !obs_kpt) return uco_fail(ctx, UCO_E_INVALID, "new_points: null output");
+    TriStaged staged{nullptr, nullptr, 0};
+    TriStage tri{rt, K_nb, prm->K_kf, prm->g2f_kf, prm->scale_factors_kf, prm->n_levels_kf, prm->scale_factors_nb, prm->n_levels_nb,
+                 prm->max_chi2, prm->scale_ratio_factor, &staged};
+    std::vector<int32_t> nm(n_frames, 0);
+    int cap = 0;
+    for (int f = 0; f < n_frames; f++) cap = nq && nq[f] > cap ? nq[f] : cap;
+    int rc = match_multi_impl(ctx, t_desc, nt, t_stride, t_kps, n_t_kps, t_map, n_frames, q_desc, nq, q_stride, q_kps, n_q_kps, q_map, f12, &prm->match,
+                              matches, cap, nm.data(), &tri);
+    if (rc) return rc;
+    if (n_matches) memcpy(n_matches, nm.data(), 4 * (size_t)n_frames);
+    if (!staged.matches) return UCO_OK;   // nothing to match
+    // accepted records per keyframe keypoint, in (neighbour, match) order
+    struct Rec { int32_t f, q; float d; const float* p; };
+    std::map<int32_t, std::vector<Rec>> groups;
+    for (int f = 0; f < n_frames; f++) {
+        const uco_match* m = staged.matches + (size_t)f * staged.stride;
+        const float* p = staged.xyz + 3 * (size_t)f * staged.stride;
+        if (xyz && xyz[f]) memcpy(xyz[f], p, 12 * (size_t)nm[f]);
+        for (int i = 0; i < nm[f]; i++)
+            if (!std::isnan(p[3 * i])) groups[m[i].trainIdx].push_back({f, m[i].queryIdx, m[i].distance, p + 3 * i});
+    }
+    std::vector<std::pair<int32_t, const std::vector<Rec>*>> pts;
+    for (const auto& g : groups) pts.push_back({g.first, &g.second});
+    std::vector<int> order(pts.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
+    size_t keep = pts.size();
+    if (prm->max_points >= 0 && pts.size() > (size_t)prm->max_points) {   // std::sort on dist + resize (not stable: the same comparisons on the same sequence)
+        std::sort(order.begin(), order.end(), [&](int a, int b) { return pts[a].second->back().d < pts[b].second->back().d; });
+        keep = (size_t)prm->max_points;
+    }
+    size_t n_obs = 0;
+    for (size_t j = 0; j < keep; j++) n_obs += pts[order[j]].second->size();
+    if (keep > (size_t)capacity_points || n_obs > (size_t)capacity_obs)
+        return uco_fail(ctx, UCO_E_CAPACITY, "new_points: %zu points / %zu observations exceed the output capacity (%d / %d)", keep, n_obs, capacity_points, capacity_obs);
+    int at = 0;
+    for (size_t j = 0; j < keep; j++) {
+        const auto& g = pts[order[j]];
+        const Rec& best = g.second->back();
+        pt_kpt[j] = g.first;
+        pt_xyz[3 * j] = best.p[0]; pt_xyz[3 * j + 1] = best.p[1]; pt_xyz[3 * j + 2] = best.p[2];
+        pt_dist[j] = best.d;
+        for (const Rec& r : *g.second) { obs_frame[at] = r.f; obs_kpt[at] = r.q; at++; }
+        obs_ptr[j + 1] = at;
+    }
+    *n_points = (int)keep;
     return UCO_OK;
 }
 

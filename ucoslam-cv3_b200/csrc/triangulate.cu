@@ -82,19 +82,19 @@ __device__ void jacobi_smallest_eigvec4(double S[4][4], double v[4]) {
     for (int k = 0; k < 4; k++) v[k] = (m == 0) ? V[k][0] : (m == 1) ? V[k][1] : (m == 2) ? V[k][2] : V[k][3];
 }
 
-__global__ void __launch_bounds__(128) triangulate_kernel(const __grid_constant__ TriArgs A) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= A.n) return;
-    const float nanv = __int_as_float(0x7fc00000);
-    float out[3] = {nanv, nanv, nanv};
-    const uco_match m = A.matches[i];
-    bool ok = m.trainIdx >= 0 && m.trainIdx < A.n1 && m.queryIdx >= 0 && m.queryIdx < A.n2;
-    if (!ok) A.counters[1] = 1;
-    if (ok) {
-        const uco_keypoint k1 = A.kp1[m.trainIdx], k2 = A.kp2[m.queryIdx];
-        ok = k1.octave >= 0 && k1.octave < A.nl1 && k2.octave >= 0 && k2.octave < A.nl2;
-        if (!ok) A.counters[1] = 1;
-        if (ok) {
+// one match: the gates of misc.cpp:981-1040 (+ the mapper's scale consistency / global frame); writes out[3] (NaN = rejected)
+struct TriCam {
+    float K1[4], K2[4];       // fx fy cx cy
+    float R[9], t[3];         // camera 1 -> camera 2
+};
+struct TriGates {
+    const float* inv_sf1; const float* inv_sf2; const float* sf1; const float* sf2;
+    float max_chi2, ratio_factor; int to_global; float G[12];
+};
+__device__ __forceinline__ bool tri_one(const uco_keypoint& k1, const uco_keypoint& k2, const TriCam& A, const TriGates& T, float out[3]) {
+    bool ok = true;
+    {
+        {
             const float fx1 = A.K1[0], fy1 = A.K1[1], cx1 = A.K1[2], cy1 = A.K1[3];
             const float fx2 = A.K2[0], fy2 = A.K2[1], cx2 = A.K2[2], cy2 = A.K2[3];
             const float* R = A.R;
@@ -148,31 +148,31 @@ __global__ void __launch_bounds__(128) triangulate_kernel(const __grid_constant_
                         if (ok) {
                             const float iz1 = 1.f / Z;
                             const float px = fx1 * X * iz1 + cx1, py = fy1 * Y * iz1 + cy1;
-                            const float chi1 = A.inv_sf1[k1.octave] * ((px - k1.x) * (px - k1.x) + (py - k1.y) * (py - k1.y));
-                            ok = !(chi1 > A.max_chi2);
+                            const float chi1 = T.inv_sf1[k1.octave] * ((px - k1.x) * (px - k1.x) + (py - k1.y) * (py - k1.y));
+                            ok = !(chi1 > T.max_chi2);
                             if (ok) {
                                 const float iz2 = 1.f / Z2;
                                 const float qx = fx2 * X2 * iz2 + cx2, qy = fy2 * Y2 * iz2 + cy2;
-                                const float chi2 = A.inv_sf2[k2.octave] * ((qx - k2.x) * (qx - k2.x) + (qy - k2.y) * (qy - k2.y));
-                                ok = !(chi2 > A.max_chi2);
-                                if (ok && A.ratio_factor != 0.f) {   // mapper's scale consistency (distances are pose invariant)
+                                const float chi2 = T.inv_sf2[k2.octave] * ((qx - k2.x) * (qx - k2.x) + (qy - k2.y) * (qy - k2.y));
+                                ok = !(chi2 > T.max_chi2);
+                                if (ok && T.ratio_factor != 0.f) {   // mapper's scale consistency (distances are pose invariant)
                                     const float d1 = (float)sqrt((double)X * X + (double)Y * Y + (double)Z * Z);
                                     const float d2 = (float)sqrt((double)X2 * X2 + (double)Y2 * Y2 + (double)Z2 * Z2);
                                     ok = !(d1 == 0.f || d2 == 0.f);
                                     if (ok) {
-                                        const float rd = d1 / d2, ro = A.sf1[k1.octave] / A.sf2[k2.octave];
-                                        ok = !(rd * A.ratio_factor < ro || rd > ro * A.ratio_factor);
+                                        const float rd = d1 / d2, ro = T.sf1[k1.octave] / T.sf2[k2.octave];
+                                        ok = !(rd * T.ratio_factor < ro || rd > ro * T.ratio_factor);
                                     }
                                 }
                                 if (ok) {
-                                    if (A.to_global) {               // Se3Transform::operator*(Point3f)
-                                        out[0] = A.G[0] * X + A.G[1] * Y + A.G[2] * Z + A.G[3];
-                                        out[1] = A.G[4] * X + A.G[5] * Y + A.G[6] * Z + A.G[7];
-                                        out[2] = A.G[8] * X + A.G[9] * Y + A.G[10] * Z + A.G[11];
+                                    if (T.to_global) {               // Se3Transform::operator*(Point3f)
+                                        out[0] = T.G[0] * X + T.G[1] * Y + T.G[2] * Z + T.G[3];
+                                        out[1] = T.G[4] * X + T.G[5] * Y + T.G[6] * Z + T.G[7];
+                                        out[2] = T.G[8] * X + T.G[9] * Y + T.G[10] * Z + T.G[11];
                                     } else {
                                         out[0] = X; out[1] = Y; out[2] = Z;
                                     }
-                                    atomicAdd(A.counters, 1);
+                                    
                                 }
                             }
                         }
@@ -181,12 +181,106 @@ __global__ void __launch_bounds__(128) triangulate_kernel(const __grid_constant_
             }
         }
     }
+    return ok;
+}
+
+__global__ void __launch_bounds__(128) triangulate_kernel(const __grid_constant__ TriArgs A) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n) return;
+    const float nanv = __int_as_float(0x7fc00000);
+    float out[3] = {nanv, nanv, nanv};
+    const uco_match m = A.matches[i];
+    bool ok = m.trainIdx >= 0 && m.trainIdx < A.n1 && m.queryIdx >= 0 && m.queryIdx < A.n2;
+    if (!ok) A.counters[1] = 1;
+    if (ok) {
+        const uco_keypoint k1 = A.kp1[m.trainIdx], k2 = A.kp2[m.queryIdx];
+        ok = k1.octave >= 0 && k1.octave < A.nl1 && k2.octave >= 0 && k2.octave < A.nl2;
+        if (!ok) A.counters[1] = 1;
+        if (ok) {
+            TriCam C;
+            TriGates T;
+#pragma unroll
+            for (int q = 0; q < 4; q++) { C.K1[q] = A.K1[q]; C.K2[q] = A.K2[q]; }
+#pragma unroll
+            for (int q = 0; q < 9; q++) C.R[q] = A.R[q];
+#pragma unroll
+            for (int q = 0; q < 3; q++) C.t[q] = A.t[q];
+            T.inv_sf1 = A.inv_sf1; T.inv_sf2 = A.inv_sf2; T.sf1 = A.sf1; T.sf2 = A.sf2;
+            T.max_chi2 = A.max_chi2; T.ratio_factor = A.ratio_factor; T.to_global = A.to_global;
+#pragma unroll
+            for (int q = 0; q < 12; q++) T.G[q] = A.G[q];
+            if (tri_one(k1, k2, C, T, out)) atomicAdd(A.counters, 1);
+        }
+    }
     A.xyz[3 * (size_t)i] = out[0];
     A.xyz[3 * (size_t)i + 1] = out[1];
     A.xyz[3 * (size_t)i + 2] = out[2];
 }
 
+// new-map-point creation: all (keyframe, neighbour f) pairs of one keyframe in one launch, reading the matcher's device output.
+// blockIdx.y = neighbour; matches of neighbour f at matches[f * match_stride ..], n_matches[f] of them; the keyframe is camera 1.
+struct TriPairsArgs {
+    const uco_keypoint* kp1; int n1;                  // the keyframe's keypoints
+    const uco_keypoint* kp2; int kp2_stride; const int32_t* n2;   // neighbour f: kp2 + f * kp2_stride, n2[f] keypoints
+    const uco_match* matches; int match_stride; const int32_t* n_matches;
+    float K1[4];
+    const float* cam2;                                // per neighbour: K2 (4), R (9), t (3) = 16 floats
+    TriGates T; int nl1, nl2;
+    float* xyz; int32_t* counters;                    // xyz like matches; counters[0] = bad index flag, counters[1 + f] = accepted of f
+};
+__global__ void __launch_bounds__(128) triangulate_pairs_kernel(const __grid_constant__ TriPairsArgs A) {
+    const int f = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n_matches[f]) return;
+    const float nanv = __int_as_float(0x7fc00000);
+    float out[3] = {nanv, nanv, nanv};
+    const size_t at = (size_t)f * A.match_stride + i;
+    const uco_match m = A.matches[at];
+    bool ok = m.trainIdx >= 0 && m.trainIdx < A.n1 && m.queryIdx >= 0 && m.queryIdx < A.n2[f];
+    if (!ok) A.counters[0] = 1;
+    if (ok) {
+        const uco_keypoint k1 = A.kp1[m.trainIdx], k2 = A.kp2[(size_t)f * A.kp2_stride + m.queryIdx];
+        ok = k1.octave >= 0 && k1.octave < A.nl1 && k2.octave >= 0 && k2.octave < A.nl2;
+        if (!ok) A.counters[0] = 1;
+        if (ok) {
+            TriCam C;
+            const float* c2 = A.cam2 + 16 * (size_t)f;
+#pragma unroll
+            for (int q = 0; q < 4; q++) { C.K1[q] = A.K1[q]; C.K2[q] = c2[q]; }
+#pragma unroll
+            for (int q = 0; q < 9; q++) C.R[q] = c2[4 + q];
+#pragma unroll
+            for (int q = 0; q < 3; q++) C.t[q] = c2[13 + q];
+            if (tri_one(k1, k2, C, A.T, out)) atomicAdd(A.counters + 1 + f, 1);
+        }
+    }
+    A.xyz[3 * at] = out[0];
+    A.xyz[3 * at + 1] = out[1];
+    A.xyz[3 * at + 2] = out[2];
+}
+
 }  // namespace
+
+// internal (match.cu: uco_b200_new_points): every pointer is a DEVICE pointer; sf_dev = 4 x UCO_MATCH_MAX_SCALES floats
+// (1/sf1^2 | 1/sf2^2 | sf1 | sf2); cam2_dev = n_frames x 16; counters_dev = 1 + n_frames ints (zeroed here)
+int uco_tri_pairs_launch(uco_b200_ctx* ctx, const uco_keypoint* kp1, int n1, const uco_keypoint* kp2, int kp2_stride, const int32_t* n2_dev, int n_frames,
+                         const uco_match* matches, int match_stride, const int32_t* n_matches_dev, const float* K1, const float* cam2_dev,
+                         const float* sf_dev, int nl1, int nl2, float max_chi2, float ratio_factor, const float* g2f_train, float* xyz_dev,
+                         int32_t* counters_dev) {
+    TriPairsArgs A;
+    A.kp1 = kp1; A.n1 = n1; A.kp2 = kp2; A.kp2_stride = kp2_stride; A.n2 = n2_dev;
+    A.matches = matches; A.match_stride = match_stride; A.n_matches = n_matches_dev;
+    memcpy(A.K1, K1, sizeof A.K1);
+    A.cam2 = cam2_dev;
+    A.T.inv_sf1 = sf_dev; A.T.inv_sf2 = sf_dev + UCO_MATCH_MAX_SCALES; A.T.sf1 = sf_dev + 2 * UCO_MATCH_MAX_SCALES; A.T.sf2 = sf_dev + 3 * UCO_MATCH_MAX_SCALES;
+    A.T.max_chi2 = max_chi2; A.T.ratio_factor = ratio_factor; A.T.to_global = g2f_train != nullptr;
+    for (int q = 0; q < 12; q++) A.T.G[q] = g2f_train ? g2f_train[q] : 0.f;
+    A.nl1 = nl1; A.nl2 = nl2;
+    A.xyz = xyz_dev; A.counters = counters_dev;
+    UCO_CUDA(ctx, cudaMemsetAsync(counters_dev, 0, 4 * (size_t)(1 + n_frames), ctx->stream));
+    triangulate_pairs_kernel<<<dim3((match_stride + 127) / 128, n_frames), 128, 0, ctx->stream>>>(A);
+    UCO_LAUNCH_CHECK(ctx);
+    return UCO_OK;
+}
 
 extern "C" {
 

@@ -18,14 +18,17 @@ public:
     void setParams(const Frame& trainFrame, FrameMatcher::Mode mode, float minDescDist, float nn_match_ratio, bool checkOrientation,
                    int maxOctaveDiff) override {
         _train = &trainFrame;
+        _trainImageParams = trainFrame.imageParams;        // as FrameMatcher_Flann::setParams: getFund12 reads it
         _prm = uco_match_params{};
         _prm.min_desc_dist = minDescDist; _prm.nn_match_ratio = nn_match_ratio;
         _prm.check_orientation = checkOrientation; _prm.max_octave_diff = maxOctaveDiff;
         rows(trainFrame, mode, _tRows, _tDesc);
     }
     std::vector<cv::DMatch> match(const Frame& queryFrame, FrameMatcher::Mode mode) override { return run(queryFrame, mode, cv::Mat()); }
+    // FQ2T is the SE3 matrix train -> query; the fundamental matrix comes from the reference's own getFund12 / computeF12
+    // (framematcher.cpp:58-64, misc.cpp:893-920), exactly as in FrameMatcher_Flann::matchEpipolar (:234)
     std::vector<cv::DMatch> matchEpipolar(const Frame& queryFrame, FrameMatcher::Mode mode, const cv::Mat& FQ2T) override {
-        return run(queryFrame, mode, FQ2T);
+        return run(queryFrame, mode, getFund12(_trainImageParams.CameraMatrix, queryFrame.imageParams.CameraMatrix, FQ2T));
     }
 
 private:

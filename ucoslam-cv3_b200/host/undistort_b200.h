@@ -1,6 +1,9 @@
 // undistort_b200.h — the reference's undistortion helper ucoslam::undistortPoints(points_io, ImageParams, out)
 // (src/basictypes/misc.h, misc.cpp:269-292), which FrameExtractor applies to the extracted keypoints (Frame::und_kpts), the marker
-// corners and the image bounds when it builds a Frame.  Same signature plus the context, same in-place / out semantics.
+// corners and the image bounds when it builds a Frame.  Same signature plus the context.  In-place use (out == nullptr, the only
+// form the reference calls) is identical.  With `out` given this adapter writes PIXEL coordinates to *out; the reference's out
+// branch (misc.cpp:287-291) runs its rescale loop over an empty vector and so leaves *out in normalised camera coordinates — a
+// deliberate difference: no caller relies on that branch and the in-place meaning is the documented one.
 // Compile inside the reference tree (needs its headers and OpenCV C++; see the note in orb_extractor_b200.h).
 #pragma once
 #include <vector>

@@ -54,6 +54,7 @@ SIGNATURES = {
     "uco_b200_comm_destroy": (None, [_vp]),
     "uco_b200_ba_solve_sharded": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "uco_b200_probe_ba_partition": (_i, [_vp, _i, _vp]),
+    "uco_b200_new_points": (_i, [_vp] + [_vp, _i, _c.c_size_t, _vp, _i, _vp] + [_i, _vp, _vp, _c.c_size_t, _vp, _vp, _vp] + [_vp, _vp, _vp, _vp] + [_vp] * 7 + [_i, _i] + [_vp, _vp, _vp]),
     "uco_b200_block_solve": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
     "uco_b200_block_solve_profile": (_i, [_vp, _vp]),
     "uco_b200_probe_block_solve": (_i, [_i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp]),
@@ -331,6 +332,12 @@ class TriangulateParams(ctypes.Structure):  # uco_triangulate_params
     _fields_ = [("K_train", _c.c_float * 4), ("K_query", _c.c_float * 4), ("RT", _c.c_float * 16), ("n_levels_train", _c.c_int32),
                 ("scale_factors_train", _vp), ("n_levels_query", _c.c_int32), ("scale_factors_query", _vp), ("max_chi2", _c.c_float),
                 ("scale_ratio_factor", _c.c_float), ("to_global", _c.c_int32), ("g2f_train", _c.c_float * 16)]
+
+
+class NewPointsParams(ctypes.Structure):  # uco_new_points_params
+    _fields_ = [("match", MatchParams), ("K_kf", _c.c_float * 4), ("g2f_kf", _c.c_float * 16), ("n_levels_kf", _c.c_int32), ("scale_factors_kf", _vp),
+                ("n_levels_nb", _c.c_int32), ("scale_factors_nb", _vp), ("max_chi2", _c.c_float), ("scale_ratio_factor", _c.c_float),
+                ("max_points", _c.c_int32)]
 
 
 class UcoError(RuntimeError):
@@ -715,6 +722,54 @@ class Context:
             None if qmp is None else ctypes.cast(qmp, ctypes.c_void_p), _p(f12a), ctypes.addressof(prm),
             ctypes.cast(VP(*[o.ctypes.data for o in outs]), ctypes.c_void_p), cap, _p(n_out)))
         return [outs[f][:n_out[f]].copy() for f in range(F)]
+
+    def new_points(self, sc, max_points=-1, per_pair=False):
+        """MapManager::createNewPoints on a scene dict (synth.synth_new_points_scene): returns dict(kpt, xyz, dist, obs_ptr, obs_frame, obs_kpt
+        [, matches, xyz_pairs])"""
+        t_desc = np.ascontiguousarray(sc["t_desc"], np.uint8).reshape(-1, 32)
+        t_kps = np.ascontiguousarray(sc["t_kps"], KP_DTYPE)
+        tm = np.ascontiguousarray(sc["t_map"], np.int32)
+        qd = [np.ascontiguousarray(d, np.uint8).reshape(-1, 32) for d in sc["q_desc"]]
+        qk = [np.ascontiguousarray(k, KP_DTYPE) for k in sc["q_kps"]]
+        qm = [np.ascontiguousarray(m, np.int32) for m in sc["q_map"]]
+        F = len(qd)
+        VP = ctypes.c_void_p * max(F, 1)
+        rows_t = np.ascontiguousarray(t_desc[tm])
+        rows_q = [np.ascontiguousarray(d[m]) for d, m in zip(qd, qm)]
+        nq = np.array([len(d) for d in rows_q], np.int32)
+        nk = np.array([len(k) for k in qk], np.int32)
+        sf1, sf2 = np.ascontiguousarray(sc["sf_kf"], np.float32), np.ascontiguousarray(sc["sf_nb"], np.float32)
+        prm = NewPointsParams()
+        prm.match = MatchParams(sc["min_desc_dist"], sc["ratio"], True, 2 ** 31 - 1, np.eye(3), sf2)
+        prm.K_kf[:] = [float(v) for v in sc["K_kf"]]
+        prm.g2f_kf[:] = [float(v) for v in np.asarray(sc["g2f_kf"], np.float32).reshape(-1)]
+        prm.n_levels_kf, prm.scale_factors_kf = len(sf1), _p(sf1)
+        prm.n_levels_nb, prm.scale_factors_nb = len(sf2), _p(sf2)
+        prm.max_chi2, prm.scale_ratio_factor, prm.max_points = sc.get("max_chi2", 5.998), sc["scale_ratio_factor"], max_points
+        f12 = np.ascontiguousarray(sc["f12"], np.float32).reshape(F, 9)
+        rt = np.ascontiguousarray(sc["rt"], np.float32).reshape(F, 16)
+        Knb = np.ascontiguousarray(sc["K_nb"], np.float32).reshape(F, 4)
+        cap_p, cap_o = max(len(tm), 1), max(int(nq.sum()), 1)
+        n_pts = ctypes.c_int32(0)
+        kpt, xyz, dist = np.zeros(cap_p, np.int32), np.zeros((cap_p, 3), np.float32), np.zeros(cap_p, np.float32)
+        optr, ofr, okp = np.zeros(cap_p + 1, np.int32), np.zeros(cap_o, np.int32), np.zeros(cap_o, np.int32)
+        cap = max(1, int(nq.max()) if F else 1)
+        ms = [np.zeros(cap, MATCH_DTYPE) for _ in range(F)] if per_pair else None
+        xs = [np.zeros((cap, 3), np.float32) for _ in range(F)] if per_pair else None
+        nm = np.zeros(max(F, 1), np.int32)
+        self._chk(self.lib.uco_b200_new_points(
+            self.h, _p(rows_t), len(rows_t), 32, _p(t_kps), len(t_kps), _p(tm), F, ctypes.cast(VP(*[d.ctypes.data for d in rows_q]), ctypes.c_void_p), _p(nq), 32,
+            ctypes.cast(VP(*[k.ctypes.data for k in qk]), ctypes.c_void_p), _p(nk), ctypes.cast(VP(*[m.ctypes.data for m in qm]), ctypes.c_void_p),
+            _p(f12), _p(rt), _p(Knb), ctypes.addressof(prm), ctypes.addressof(n_pts), _p(kpt), _p(xyz), _p(dist), _p(optr), _p(ofr), _p(okp), cap_p, cap_o,
+            None if ms is None else ctypes.cast(VP(*[m.ctypes.data for m in ms]), ctypes.c_void_p), _p(nm),
+            None if xs is None else ctypes.cast(VP(*[x.ctypes.data for x in xs]), ctypes.c_void_p)))
+        n = int(n_pts.value)
+        out = dict(kpt=kpt[:n].copy(), xyz=xyz[:n].copy(), dist=dist[:n].copy(), obs_ptr=optr[:n + 1].copy(), obs_frame=ofr[:optr[n]].copy(),
+                   obs_kpt=okp[:optr[n]].copy())
+        if per_pair:
+            out["matches"] = [ms[f][:nm[f]].copy() for f in range(F)]
+            out["xyz_pairs"] = [xs[f][:nm[f]].copy() for f in range(F)]
+        return out
 
     def keyframes_batch(self, voc, groups, prm, max_features, f12=None, level=3):
         """per-keyframe work on the frames of this context's last extraction call: groups = [(kf_frame, [neighbour frames])];

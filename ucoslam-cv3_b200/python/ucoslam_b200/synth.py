@@ -450,3 +450,72 @@ def synth_reloc_matches(seed, n=400, outlier_frac=0.4, px_sigma=0.8, w=640, h=48
     normals[back] *= -1
     pose = np.eye(4); pose[:3, :3] = R; pose[:3, 3] = t
     return dict(p3d=p3d, p2d=p2d.astype(np.float32), normals=normals.astype(np.float32), cam=cam, pose_gt=pose)
+
+
+def synth_new_points_scene(seed, n_kp=2000, n_nb=6, assigned_frac=0.4, w=640, h=480, f=525.0, flips=10, px_sigma=0.5, far_frac=0.1):
+    """A new keyframe and n_nb covisible neighbour keyframes as MapManager::createNewPoints sees them (SURVEY.md 8f rank 2): n_kp 3-D
+    points in front of the keyframe (some too far for the parallax gate), every frame observes a random 70 % of them plus clutter, with
+    octave-scaled pixel noise, descriptors = the point's descriptor with a few flipped bits, orientation turned with the camera roll;
+    a share of the keypoints already has a map point (MODE_UNASSIGNED leaves them out: t_map / q_map).  Poses are global -> camera
+    (pose_f2g); rt[f] = nb_f.pose_f2g * kf.pose_f2g.inv(); f12[f] = the fundamental matrix the matcher's epipolar gate uses
+    (x_t^T F x_q = 0 for a train keypoint x_t of the keyframe and its match x_q in neighbour f), f32."""
+    from . import KP_DTYPE
+    rng = np.random.default_rng(seed)
+    sf = (np.float32(1.2) ** np.arange(8)).astype(np.float32)
+    K = np.array([f, f, w / 2 - 0.5, h / 2 - 0.5], np.float32)
+    Km = np.array([[f, 0, K[2]], [0, f, K[3]], [0, 0, 1]], np.float64)
+    far = rng.random(n_kp) < far_frac
+    Z = np.where(far, rng.uniform(80, 400, n_kp), rng.uniform(1.5, 8.0, n_kp))
+    u = rng.uniform(30, w - 30, n_kp); v = rng.uniform(30, h - 30, n_kp)
+    Xc = np.c_[(u - K[2]) / f * Z, (v - K[3]) / f * Z, Z]                  # in the keyframe's camera
+    kf_pose = np.eye(4); kf_pose[:3, :3] = _rodrigues(rng.normal(0, 0.3, 3)); kf_pose[:3, 3] = rng.normal(0, 1.0, 3)   # global -> kf camera
+    g2f = np.linalg.inv(kf_pose)
+    Xw = Xc @ g2f[:3, :3].T + g2f[:3, 3]
+    base_desc = rng.integers(0, 256, (n_kp, 32), dtype=np.uint8)
+    base_angle = rng.uniform(0, 360, n_kp)
+    base_oct = rng.integers(0, 7, n_kp)
+
+    def observe(pose, roll_deg, frac):
+        Xf = Xw @ pose[:3, :3].T + pose[:3, 3]
+        with np.errstate(all="ignore"):
+            px = f * Xf[:, 0] / Xf[:, 2] + K[2]; py = f * Xf[:, 1] / Xf[:, 2] + K[3]
+        vis = (Xf[:, 2] > 0.3) & (px > 5) & (px < w - 5) & (py > 5) & (py < h - 5) & (rng.random(n_kp) < frac)
+        ids = np.nonzero(vis)[0]
+        n_cl = len(ids) // 4                                                # clutter: keypoints of nothing in common
+        n = len(ids) + n_cl
+        kp = np.zeros(n, KP_DTYPE)
+        octv = np.clip(base_oct[ids] + rng.integers(-1, 2, len(ids)) * (rng.random(len(ids)) < 0.3), 0, 7)
+        kp["x"][:len(ids)] = px[ids] + rng.normal(0, px_sigma, len(ids)) * sf[octv]
+        kp["y"][:len(ids)] = py[ids] + rng.normal(0, px_sigma, len(ids)) * sf[octv]
+        kp["octave"][:len(ids)] = octv
+        kp["angle"][:len(ids)] = np.mod(base_angle[ids] + roll_deg + rng.normal(0, 4, len(ids)), 360)
+        kp["x"][len(ids):] = rng.uniform(5, w - 5, n_cl); kp["y"][len(ids):] = rng.uniform(5, h - 5, n_cl)
+        kp["octave"][len(ids):] = rng.integers(0, 8, n_cl); kp["angle"][len(ids):] = rng.uniform(0, 360, n_cl)
+        kp["size"] = 31 * sf[kp["octave"]]; kp["class_id"] = -1
+        desc = np.empty((n, 32), np.uint8)
+        desc[:len(ids)] = base_desc[ids]
+        fl = rng.integers(0, 256, (len(ids), flips))
+        for j in range(flips):
+            desc[np.arange(len(ids)), fl[:, j] >> 3] ^= (1 << (fl[:, j] & 7)).astype(np.uint8)
+        desc[len(ids):] = rng.integers(0, 256, (n_cl, 32), dtype=np.uint8)
+        perm = rng.permutation(n)
+        point = np.concatenate([ids, np.full(n_cl, -1)])[perm]
+        unassigned = np.sort(np.nonzero(rng.random(n) >= assigned_frac)[0]).astype(np.int32)
+        return kp[perm], desc[perm], point, unassigned
+
+    t_kps, t_desc, t_point, t_map = observe(kf_pose, 0.0, 0.9)
+    q_kps, q_desc, q_point, q_map, rts, f12s, poses = [], [], [], [], [], [], []
+    for i in range(n_nb):
+        dpose = np.eye(4)
+        dpose[:3, :3] = _rodrigues(rng.normal(0, 0.05, 3))
+        dpose[:3, 3] = rng.normal(0, 0.25, 3) + np.array([0.3 * (1 if i % 2 else -1), 0, 0])
+        pose = dpose @ kf_pose                                              # T_f = dpose: kf camera -> neighbour camera
+        kp, de, pt, un = observe(pose, float(np.degrees(np.arctan2(dpose[1, 0], dpose[0, 0]))), 0.7)
+        q_kps.append(kp); q_desc.append(de); q_point.append(pt); q_map.append(un)
+        Rm, t = dpose[:3, :3], dpose[:3, 3]
+        tx = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]])
+        Fm = (np.linalg.inv(Km).T @ tx @ Rm @ np.linalg.inv(Km)).T          # x_t^T F x_q = 0: epipolarLineSqDist(train, query, F12), misc.h:72-81
+        f12s.append((Fm / np.abs(Fm).max()).astype(np.float32)); rts.append(dpose.astype(np.float32)); poses.append(pose)
+    return dict(t_kps=t_kps, t_desc=t_desc, t_map=t_map, t_point=t_point, q_kps=q_kps, q_desc=q_desc, q_map=q_map, q_point=q_point,
+                f12=np.array(f12s), rt=np.array(rts), K_kf=K, K_nb=np.tile(K, (n_nb, 1)), g2f_kf=g2f.astype(np.float32), sf_kf=sf, sf_nb=sf.copy(),
+                min_desc_dist=100.0, ratio=0.6, scale_ratio_factor=float(np.float32(1.5) * np.float32(1.2)), points_gt=Xw, kf_pose=kf_pose, nb_poses=poses)
