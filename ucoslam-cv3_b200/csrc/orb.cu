@@ -450,16 +450,106 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
 
 // ---- K4b: per (frame, level) keypoint selection: threshold fallback, quota redistribution, per-cell retainBest, level-wide
 // retainBest — ComputeKeyPoints_thread, ORBextractor.cpp:980-1073, replayed exactly ------------------------------------------
+// Block-cooperative EXACT replay of libstdc++'s introselect (select_exact.h) on a list in shared memory.  The costly part of the serial
+// form is __unguarded_partition: two pointers walk towards each other, each step a dependent load.  Its result is a pure function of the
+// input, though: the left pointer stops at the elements whose score is <= the pivot's, in ascending position; the right pointer at the
+// elements whose score is >= the pivot's, in descending position; stop k of the one is swapped with stop k of the other as long as the
+// left one is still left of the right one, and no position takes part in two swaps.  So: positions of both kinds by a block scan, the
+// number of swaps by a count of the (monotone) predicate, the swaps in parallel, the returned cut = the first stop of the left pointer
+// after the last swap.  median-of-3, the depth limit (heap-select fallback, serial) and the final insertion sort stay as they are.
+__device__ int par_unguarded_partition(uint32_t* v, int lo, int hi, uint32_t ps, int* Lpos, int* Rpos, int* sh) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    const int per = (hi - lo + nt - 1) / nt, b = min(hi, lo + tid * per), e = min(hi, b + per);
+    int cl = 0, cr = 0;
+    for (int i = b; i < e; i++) {
+        const uint32_t sc = v[i] >> 24;
+        cl += sc <= ps;
+        cr += sc >= ps;
+    }
+    int il = cl, ir = cr;                                // inclusive scans: warp, then across warps
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int a = __shfl_up_sync(0xffffffffu, il, o), c = __shfl_up_sync(0xffffffffu, ir, o);
+        if (lane >= o) { il += a; ir += c; }
+    }
+    if (lane == 31) { sh[warp] = il; sh[32 + warp] = ir; }
+    __syncthreads();
+    int bl = 0, br = 0, nL = 0, nR = 0;
+    for (int w = 0; w < nw; w++) {
+        if (w < warp) { bl += sh[w]; br += sh[32 + w]; }
+        nL += sh[w]; nR += sh[32 + w];
+    }
+    int pl = bl + il - cl, pr = br + ir - cr;            // stops before this thread's chunk
+    for (int i = b; i < e; i++) {
+        const uint32_t sc = v[i] >> 24;
+        if (sc <= ps) Lpos[pl++] = i;
+        if (sc >= ps) Rpos[nR - 1 - pr++] = i;            // descending position
+    }
+    __syncthreads();
+    const int m = min(nL, nR);
+    int cnt = 0;
+    for (int k = tid; k < m; k += nt) cnt += Lpos[k] < Rpos[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) sh[64 + warp] = cnt;
+    __syncthreads();
+    int ks = 0;
+    for (int w = 0; w < nw; w++) ks += sh[64 + w];
+    for (int k = tid; k < ks; k += nt) {
+        const int a = Lpos[k], c = Rpos[k];
+        const uint32_t t = v[a]; v[a] = v[c]; v[c] = t;
+    }
+    const int cut = min(ks < nL ? Lpos[ks] : hi, ks > 0 ? Rpos[ks - 1] : hi);
+    __syncthreads();
+    return cut;
+}
+// retainBest(v, n) + resize(n) by the whole block; v, Lpos, Rpos in shared memory (Lpos / Rpos: count entries each); returns the new count
+__device__ int par_retain_best_truncate(uint32_t* v, int count, int n, int* Lpos, int* Rpos, int* sh) {
+    if (!(n >= 0 && count > n)) return count;
+    if (n == 0) return 0;
+    const int nth = n - 1;
+    int first = 0, last = count, depth = uco_sel::lg2(count) * 2;
+    while (last - first > 3) {
+        if (depth == 0) {                                // never seen on FAST scores; kept for exactness
+            if (threadIdx.x == 0) {
+                uco_sel::heap_select(v + first, v + nth + 1, v + last);
+                uco_sel::iswap(v + first, v + nth);
+            }
+            __syncthreads();
+            return n;
+        }
+        --depth;
+        if (threadIdx.x == 0) uco_sel::move_median_to_first(v + first, v + first + 1, v + first + (last - first) / 2, v + last - 1);
+        __syncthreads();
+        const int cut = par_unguarded_partition(v, first + 1, last, v[first] >> 24, Lpos, Rpos, sh);
+        if (cut <= nth) first = cut;
+        else last = cut;
+    }
+    if (threadIdx.x == 0) uco_sel::insertion_sort(v + first, v + last);
+    __syncthreads();
+    return n;
+}
+
+// All of a level's lists live in SHARED memory while they are permuted: the per-cell retainBest (one thread per cell) and the level's
+// final retainBest (one thread) are serial introselect replays whose every dependent access would otherwise be an L2 round trip
+// (~0.3 us each: the kernel used to spend 146 us per clip that way).  Dynamic shared memory: cand_budget entries for the cells'
+// candidate lists (packed back to back by a prefix sum of the counts) + list_entries for the concatenated level list; a level that
+// exceeds either works in global memory as before.
 __global__ void __launch_bounds__(256) select_kernel(const __grid_constant__ PlanDev c_plan, const CellDev* __restrict__ cells, uint32_t* __restrict__ cand,
                                                      const int* __restrict__ cand_cnt, uint32_t* __restrict__ sel,
-                                                     int* __restrict__ sel_cnt, int* __restrict__ err_flag) {
+                                                     int* __restrict__ sel_cnt, int* __restrict__ err_flag, int cand_budget, int list_entries) {
     const int level = blockIdx.x, f = blockIdx.y;
     const LevelDev& L = c_plan.lv[level];
     __shared__ int n_total[ORB_MAX_CELLS_PER_LEVEL];
     __shared__ short n_retain[ORB_MAX_CELLS_PER_LEVEL];
     __shared__ short th_used[ORB_MAX_CELLS_PER_LEVEL];
     __shared__ int offs[ORB_MAX_CELLS_PER_LEVEL];
-    __shared__ int total_s;
+    __shared__ int coff[ORB_MAX_CELLS_PER_LEVEL];        // start of the cell's staged candidate list
+    __shared__ unsigned char valid_s[ORB_MAX_CELLS_PER_LEVEL];
+    __shared__ int total_s, cand_total_s;
+    extern __shared__ uint32_t s_dyn[];
+    uint32_t* s_cand = s_dyn;
+    uint32_t* s_list = s_dyn + cand_budget;
     const int nc = L.n_cells;
     const int* cnt = cand_cnt + ((size_t)f * c_plan.n_cells_total + L.cell_begin) * 2;
     for (int c = threadIdx.x; c < nc; c += blockDim.x) {
@@ -467,6 +557,25 @@ __global__ void __launch_bounds__(256) select_kernel(const __grid_constant__ Pla
         bool use_min = n_ini <= 3;                       // :982-987 (second FAST call with minThFAST)
         n_total[c] = use_min ? n_all : n_ini;
         th_used[c] = (short)(use_min ? c_plan.min_th : c_plan.ini_th);
+        const bool v = cells[L.cell_begin + c].valid != 0;
+        valid_s[c] = v;
+        offs[c] = v ? n_all : 0;                         // entries to stage (scratch use of offs until the quotas are dealt)
+    }
+    __syncthreads();
+    if (threadIdx.x == 32) {                             // staging offsets (a second thread: thread 0 deals the quotas meanwhile)
+        int run = 0;
+        for (int c = 0; c < nc; c++) { coff[c] = run; run += offs[c]; }
+        cand_total_s = run;
+    }
+    __syncthreads();
+    const bool staged_c = cand_total_s <= cand_budget;
+    if (staged_c) {                                      // a warp copies a cell's list: coalesced
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        for (int c = warp; c < nc; c += nw) {
+            const uint32_t* src = cand + (size_t)f * c_plan.cand_per_frame + cells[L.cell_begin + c].cand_off;
+            const int n = offs[c];
+            for (int i = lane; i < n; i += 32) s_cand[coff[c] + i] = src[i];
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {                              // :988-1039, serial exactly as the reference
@@ -474,8 +583,7 @@ __global__ void __launch_bounds__(256) select_kernel(const __grid_constant__ Pla
         int n_no_more = 0, n_dist = 0;
         // 0 = may take more, 1 = bNoMore.  Cells the reference skips with `continue` keep bNoMore=false, nTotal=0.
         for (int c = 0; c < nc; c++) {
-            const CellDev& C = cells[L.cell_begin + c];
-            if (!C.valid) {
+            if (!valid_s[c]) {
                 n_retain[c] = 0;
                 offs[c] = 0;
                 continue;
@@ -510,10 +618,8 @@ __global__ void __launch_bounds__(256) select_kernel(const __grid_constant__ Pla
     }
     __syncthreads();
     // per-cell: keep candidates with score >= the threshold in force (stable), then retainBest + truncate, in place
-    for (int c = threadIdx.x; c < nc; c += blockDim.x) {
-        const CellDev& C = cells[L.cell_begin + c];
-        uint32_t* lst = cand + (size_t)f * c_plan.cand_per_frame + C.cand_off;
-        int n_all = C.valid ? cnt[c * 2] : 0;
+    auto cell_select = [&](uint32_t* lst, int c) {
+        int n_all = valid_s[c] ? cnt[c * 2] : 0;
         int n = 0;
         const uint32_t th = (uint32_t)th_used[c];
         if (th == (uint32_t)c_plan.min_th) n = n_all;
@@ -523,7 +629,11 @@ __global__ void __launch_bounds__(256) select_kernel(const __grid_constant__ Pla
                 if ((e >> 24) >= th) lst[n++] = e;
             }
         n_total[c] = uco_sel::retain_best_truncate(lst, n, n_retain[c]);
-    }
+    };
+    if (staged_c)
+        for (int c = threadIdx.x; c < nc; c += blockDim.x) cell_select(s_cand + coff[c], c);   // shared-memory loads
+    else
+        for (int c = threadIdx.x; c < nc; c += blockDim.x) cell_select(cand + (size_t)f * c_plan.cand_per_frame + cells[L.cell_begin + c].cand_off, c);
     __syncthreads();
     if (threadIdx.x == 0) {
         int run = 0;
@@ -539,9 +649,23 @@ __global__ void __launch_bounds__(256) select_kernel(const __grid_constant__ Pla
     }
     __syncthreads();
     uint32_t* out = sel + (size_t)f * c_plan.sel_per_frame + L.sel_off;
-    for (int c = 0; c < nc; c++) {                       // concatenation in cell (row-major) order, :1046-1066
-        const CellDev& C = cells[L.cell_begin + c];
-        const uint32_t* lst = cand + (size_t)f * c_plan.cand_per_frame + C.cand_off;
+    const bool staged = staged_c && L.sel_cap <= list_entries && 2 * L.sel_cap <= cand_budget;
+    __shared__ int scan_s[96];
+    if (staged) {
+        for (int c = 0; c < nc; c++) {                   // concatenation in cell (row-major) order, :1046-1066
+            const uint32_t* lst = s_cand + coff[c];
+            for (int i = threadIdx.x; i < n_total[c]; i += blockDim.x)
+                if (offs[c] + i < L.sel_cap) s_list[offs[c] + i] = lst[i];
+        }
+        __syncthreads();
+        // :1069-1073 by the whole block; the candidate area is dead and holds the stop positions
+        const int n = par_retain_best_truncate(s_list, total_s, L.n_desired, (int*)s_cand, (int*)s_cand + L.sel_cap, scan_s);
+        if (threadIdx.x == 0) sel_cnt[f * ORB_MAXL + level] = n;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = s_list[i];
+        return;
+    }
+    for (int c = 0; c < nc; c++) {
+        const uint32_t* lst = staged_c ? s_cand + coff[c] : cand + (size_t)f * c_plan.cand_per_frame + cells[L.cell_begin + c].cand_off;
         for (int i = threadIdx.x; i < n_total[c]; i += blockDim.x)
             if (offs[c] + i < L.sel_cap) out[offs[c] + i] = lst[i];
     }
@@ -933,7 +1057,19 @@ static int orb_run_dev(uco_b200_ctx* ctx, const uint8_t* in_dev, size_t in_pitch
     fast_cells_kernel<<<dim3(P.n_cells_total, n), 256, s->max_cell_smem, st>>>(P, s->d_pyr, s->d_cells, s->d_cand, s->d_cand_cnt);
     UCO_LAUNCH_CHECK(ctx);
     if (prof) cudaEventRecord(s->ev[3], st);
-    select_kernel<<<dim3(P.n_levels, n), 256, 0, st>>>(P, s->d_cells, s->d_cand, s->d_cand_cnt, s->d_sel, s->d_sel_cnt, s->d_err);
+    int sel_entries = 0;   // largest level list; staged in shared memory next to the cells' candidate lists (static shared memory holds the per-cell tables)
+    for (int l = 0; l < P.n_levels; l++) sel_entries = std::max(sel_entries, P.lv[l].sel_cap);
+    if (sel_entries > 8192) sel_entries = 0;
+    const int cand_budget = 10240;   // 40 KB (three CTAs per SM): a 640x480 level 0 holds a few thousand candidates; a level above the budget works in global memory
+    const size_t sel_smem = 4 * (size_t)(cand_budget + sel_entries);
+    {
+        static size_t configured = 0;   // grow-only attribute (same value from every thread)
+        if (sel_smem > configured) {
+            UCO_CUDA(ctx, cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
+            configured = sel_smem;
+        }
+    }
+    select_kernel<<<dim3(P.n_levels, n), 256, sel_smem, st>>>(P, s->d_cells, s->d_cand, s->d_cand_cnt, s->d_sel, s->d_sel_cnt, s->d_err, cand_budget, sel_entries);
     UCO_LAUNCH_CHECK(ctx);
     if (prof) cudaEventRecord(s->ev[4], st);
     orient_describe_kernel<<<dim3((P.max_features + 7) / 8, n), 256, 0, st>>>(P, s->d_pyr, s->d_sel, s->d_sel_cnt, kps_dev,
