@@ -709,6 +709,69 @@ int uco_b200_new_points(uco_b200_ctx* ctx, const uint8_t* t_desc, int nt, size_t
                         float* const* xyz);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Frame streams and the device-resident Frame mirror
+ *   replaces / reads Frame::toStream / fromStream   src/map_types/frame.cpp:260-341 — the unit of .map / .slm files (Map::toStream,
+ *   src/map.cpp:316-352, writes its keyframes with it; System::saveToFile wraps that) and of the tracker -> mapper queue — together
+ *   with the streams of its members: cv::Mat, std::vector (src/basictypes/io_utils.{h,cpp}), MarkerObservation / MarkerPosesIPPE
+ *   (src/map_types/marker.cpp:94-113, frame.cpp:372-386), Se3Transform (se3transform.h:178-188), fbow::fBow / fBow2
+ *   (3rdparty/fbow/fbow/fbow.cpp:261-303), ImageParams (src/imageparams.cpp:68-84), picoflann::KdTreeIndex (picoflann.h:603-660).
+ *   uco_b200_frame_stream_parse gives a VIEW into the caller's bytes (nothing is copied; variable-size members stay opaque byte
+ *   ranges: markers, bow_level, kdtree); uco_b200_frame_stream_write produces byte for byte what the reference's toStream writes
+ *   for the same field values (out == NULL: size only); uco_b200_kdtree_serialize writes the tree member from a flattened tree.
+ *   uco_b200_frame_upload puts what the *_dev entry points consume on the device in one allocation (keypoints, descriptors, map-point
+ *   ids, flags, depth, pose, scale factors, the kd-tree flattened as uco_kdnode) so that matcher / tracker / mapper kernels chain on a
+ *   keyframe of a loaded map without host vectors in between; uco_b200_frame_dev exposes the device pointers.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct uco_mat_view { int32_t rows, cols, type; const uint8_t* data; } uco_mat_view;   /* OpenCV type code; rows without padding */
+typedef struct uco_frame_stream {
+    uint32_t idx, fseq_idx; uint8_t frame_flags; int8_t kp_desc_type;        /* DescriptorTypes::Type : int8 (1 = ORB) */
+    uco_mat_view desc;
+    uint32_t n_und_kpts; const uco_keypoint* und_kpts;
+    uint32_t n_kpts; const float* kpts;                                       /* cv::Point2f */
+    uint32_t n_depth; const float* depth;
+    uint32_t n_ids; const uint32_t* ids;
+    uint32_t n_flags; const uint8_t* flags;
+    uint32_t n_markers; const uint8_t* markers; uint64_t markers_bytes;       /* the MarkerObservation records as streamed */
+    float pose_f2g[16];
+    uint32_t n_bow; const uint8_t* bow;                                       /* (uint32 word, float weight) pairs */
+    uint32_t n_bow_level; const uint8_t* bow_level; uint64_t bow_level_bytes; /* (uint32 node, uint32 count, count x uint32 keypoint) records */
+    uint32_t n_scale_factors; const float* scale_factors;
+    uco_mat_view camera_matrix, distortion; int32_t cam_size[2]; float bl, rgb_depthscale;
+    uco_mat_view image;
+    const uint8_t* kdtree; uint64_t kdtree_bytes;                             /* KdTreeIndex::toStream bytes (uco_b200_kdtree_parse reads them) */
+    int32_t min_xy[2], max_xy[2];                                             /* cv::Point */
+} uco_frame_stream;
+int uco_b200_frame_stream_parse(const uint8_t* bytes, size_t len, uco_frame_stream* view, size_t* consumed);
+int uco_b200_frame_stream_write(const uco_frame_stream* view, uint8_t* out, size_t cap, size_t* written);
+int uco_b200_kdtree_serialize(const uco_kdnode* nodes, int n_nodes, const int32_t* leaf_idx, const double* bbox4, int n_values, const double* div_val,
+                              uint8_t* out, size_t cap, size_t* written);
+/* MapPoint::toStream / fromStream (src/map_types/mappoint.cpp:117-175), the other record type of a map file: a view and its writer.
+ * The position / normal / distance range / descriptor of the view are what uco_mappoints (K9, K17) holds per row. */
+typedef struct uco_mappoint_stream {
+    uint32_t id; float pos3d[3];
+    uco_mat_view desc;                       /* 1 x 32 bytes for ORB */
+    uint32_t n_frames; const uint32_t* frames;   /* (keyframe idx, keypoint index) pairs in std::map order */
+    float normal[3];
+    uint16_t n_times_seen, n_times_visible; uint8_t flags;
+    float max_distance, min_distance;
+    uint64_t kf_since_addition; uint32_t last_fidx_seen;
+} uco_mappoint_stream;
+int uco_b200_mappoint_stream_parse(const uint8_t* bytes, size_t len, uco_mappoint_stream* view, size_t* consumed);
+int uco_b200_mappoint_stream_write(const uco_mappoint_stream* view, uint8_t* out, size_t cap, size_t* written);
+typedef struct uco_frame_dev {   /* DEVICE pointers (one allocation, owned by the uco_b200_frame) + the small host-side members */
+    uint32_t idx, fseq_idx; int32_t n_kp;
+    const uco_keypoint* kps; const uint8_t* desc; const uint32_t* ids; const uint8_t* flags; const float* depth;   /* depth: NULL without depth */
+    int32_t n_nodes; const uco_kdnode* nodes; int32_t n_leaf; const int32_t* leaf_idx; const double* bbox;
+    int32_t n_scale_factors; const float* scale_factors; const float* pose_f2g;
+    double bbox_host[4]; float pose_host[16]; float K[4]; int32_t min_xy[2], max_xy[2];
+} uco_frame_dev;
+typedef struct uco_b200_frame uco_b200_frame;
+int uco_b200_frame_upload(uco_b200_ctx* ctx, const uco_frame_stream* view, uco_b200_frame** out);
+const uco_frame_dev* uco_b200_frame_dev(const uco_b200_frame* frame);
+int uco_b200_frame_download(uco_b200_ctx* ctx, const uco_b200_frame* frame, uco_keypoint* kps, uint8_t* desc, uint32_t* ids, uint8_t* flags, float* depth);
+void uco_b200_frame_free(uco_b200_frame* frame);
+
+/* ------------------------------------------------------------------------------------------------------------
  * K14  RANSAC pose from 2D-3D matches (relocalisation / loop-closure candidate scoring)
  *   replaces ucoslam::PnPSolver::solvePnPRansac(frame, map, matches_io, posef2g_io, maxIters)
  *     src/optimization/pnpsolver.cpp:36-114 (4-match samples, cv::solvePnP P3P hypothesis, float reprojection test < 5.99 px^2,

@@ -1,0 +1,272 @@
+"""Frame streams: csrc/frame_stream.cu against the reference's OWN Frame::toStream / fromStream statements
+(/root/reference/src/map_types/frame.cpp:260-341 and the streams of its members), compiled by oracle/Makefile into
+oracle/_ref/libref_frame.so on container stand-ins, and against the committed golden stream tests/golden/frame_stream.bin written
+by that library (tests/golden/make_frame_golden.py).  Bit-exact: these are bytes."""
+import ctypes, os
+import numpy as np
+import pytest
+import ucoslam_b200
+from ucoslam_b200 import frame_stream_parse, frame_stream_write, view_array, KP_DTYPE
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+REF = os.path.join(ROOT, "oracle", "_ref", "libref_frame.so")
+
+
+def make_fields(seed, n_kp=300, n_markers=2, img=(12, 16), depth=True):
+    rng = np.random.default_rng(seed)
+    kp = np.zeros(n_kp, KP_DTYPE)
+    kp["x"], kp["y"] = rng.uniform(0, 640, n_kp), rng.uniform(0, 480, n_kp)
+    kp["size"], kp["angle"], kp["response"] = 31, rng.uniform(0, 360, n_kp), rng.integers(5, 200, n_kp)
+    kp["octave"], kp["class_id"] = rng.integers(0, 8, n_kp), -1
+    ids = np.where(rng.random(n_kp) < 0.4, rng.integers(0, 5000, n_kp), 0xFFFFFFFF).astype(np.uint32)
+    node_kp = rng.permutation(n_kp).astype(np.uint32)
+    cuts = np.sort(rng.choice(np.arange(1, max(n_kp, 2)), min(9, max(n_kp - 1, 0)), replace=False)) if n_kp > 1 else np.zeros(0, int)
+    node_ptr = np.concatenate([[0], cuts, [n_kp]]).astype(np.int32)
+    pose = np.eye(4, dtype=np.float32); pose[:3, 3] = rng.normal(0, 1, 3)
+    return dict(idx=7, fseq_idx=123, frame_flags=4, kp=kp, desc=rng.integers(0, 256, (n_kp, 32), dtype=np.uint8),
+                kpts=np.c_[kp["x"], kp["y"]].astype(np.float32) + np.float32(0.25), depth=rng.uniform(0.5, 5, n_kp if depth else 0).astype(np.float32),
+                ids=ids, flags=rng.integers(0, 4, n_kp).astype(np.uint8), marker_id=rng.integers(0, 250, n_markers).astype(np.int32),
+                marker_f=rng.uniform(0, 400, (n_markers, 17)).astype(np.float32), marker_d=rng.normal(0, 1, (n_markers, 19)),
+                pose=pose, bow_word=np.sort(rng.choice(100000, 60, replace=False)).astype(np.uint32), bow_weight=rng.random(60).astype(np.float32),
+                node_id=np.sort(rng.choice(1000, len(node_ptr) - 1, replace=False)).astype(np.uint32), node_ptr=node_ptr, node_kp=node_kp,
+                sf=(np.float32(1.2) ** np.arange(8)).astype(np.float32), K=np.array([[525, 0, 319.5], [0, 525, 239.5], [0, 0, 1]], np.float32),
+                dist=rng.normal(0, 0.01, 5).astype(np.float32), cam=(640, 480), bl=0.12, depthscale=0.001,
+                img=rng.integers(0, 256, img, dtype=np.uint8), min_xy=(-3, -2), max_xy=(644, 483))
+
+
+def ref_stream(fd, build_tree=True):
+    lib = ctypes.CDLL(REF)
+    lib.ref_frame_to_stream.restype = ctypes.c_long
+    P = lambda a: np.ascontiguousarray(a).ctypes.data_as(ctypes.c_void_p)
+    out = np.zeros(4 << 20, np.uint8)
+    keep = [np.ascontiguousarray(fd[k]) for k in ("kp", "desc", "kpts", "depth", "ids", "flags", "marker_id", "marker_f", "marker_d", "pose", "bow_word",
+                                                    "bow_weight", "node_id", "node_ptr", "node_kp", "sf", "K", "dist", "img")]
+    A = [ctypes.c_void_p(a.ctypes.data) for a in keep]
+    n = lib.ref_frame_to_stream(ctypes.c_uint32(fd["idx"]), ctypes.c_uint32(fd["fseq_idx"]), ctypes.c_ubyte(fd["frame_flags"]), len(fd["kp"]), A[0], A[1], A[2],
+                                len(fd["depth"]), A[3], A[4], A[5], len(fd["marker_id"]), A[6], A[7], A[8], A[9], len(fd["bow_word"]), A[10], A[11],
+                                len(fd["node_id"]), A[12], A[13], A[14], len(fd["sf"]), A[15], A[16], len(fd["dist"]), A[17], fd["cam"][0], fd["cam"][1],
+                                ctypes.c_float(fd["bl"]), ctypes.c_float(fd["depthscale"]), fd["img"].shape[0], fd["img"].shape[1], A[18], int(build_tree),
+                                fd["min_xy"][0], fd["min_xy"][1], fd["max_xy"][0], fd["max_xy"][1], ctypes.c_void_p(out.ctypes.data), ctypes.c_long(len(out)))
+    assert n > 0
+    return out[:n].copy()
+
+
+def ref_roundtrip(buf):
+    lib = ctypes.CDLL(REF)
+    lib.ref_frame_roundtrip.restype = ctypes.c_long
+    out = np.zeros(len(buf) + 1024, np.uint8)
+    n = lib.ref_frame_roundtrip(ctypes.c_void_p(buf.ctypes.data), ctypes.c_long(len(buf)), ctypes.c_void_p(out.ctypes.data), ctypes.c_long(len(out)))
+    return None if n < 0 else out[:n].copy()
+
+
+def check_view(v, fd):
+    n = len(fd["kp"])
+    assert (v.idx, v.fseq_idx, v.frame_flags, v.kp_desc_type) == (fd["idx"], fd["fseq_idx"], fd["frame_flags"], 1)
+    assert (v.desc.rows, v.desc.cols, v.desc.type) == ((n, 32, 0) if n else (0, 0, 0))
+    assert np.array_equal(view_array(v.desc.data, 32 * n, np.uint8).reshape(n, 32), fd["desc"])
+    assert v.n_und_kpts == n and view_array(v.und_kpts, n, KP_DTYPE).tobytes() == fd["kp"].tobytes()
+    assert np.array_equal(view_array(v.kpts, 2 * v.n_kpts, np.float32).reshape(-1, 2), fd["kpts"])
+    assert np.array_equal(view_array(v.depth, v.n_depth, np.float32), fd["depth"])
+    assert np.array_equal(view_array(v.ids, v.n_ids, np.uint32), fd["ids"])
+    assert np.array_equal(view_array(v.flags, v.n_flags, np.uint8), fd["flags"])
+    assert v.n_markers == len(fd["marker_id"])
+    assert np.array_equal(np.array(v.pose_f2g[:], np.float32).reshape(4, 4), fd["pose"])
+    bow = view_array(v.bow, v.n_bow, np.dtype([("w", "<u4"), ("v", "<f4")]))
+    assert np.array_equal(bow["w"], fd["bow_word"]) and np.array_equal(bow["v"], fd["bow_weight"])
+    assert v.n_bow_level == len(fd["node_id"])
+    lv = view_array(v.bow_level, v.bow_level_bytes // 4, np.uint32)
+    at = 0
+    for k in range(v.n_bow_level):
+        cnt = int(lv[at + 1])
+        assert lv[at] == fd["node_id"][k] and np.array_equal(lv[at + 2:at + 2 + cnt], fd["node_kp"][fd["node_ptr"][k]:fd["node_ptr"][k + 1]])
+        at += 2 + cnt
+    assert np.array_equal(view_array(v.scale_factors, v.n_scale_factors, np.float32), fd["sf"])
+    assert np.array_equal(view_array(v.camera_matrix.data, 9, np.float32).reshape(3, 3), fd["K"])
+    assert np.array_equal(view_array(v.distortion.data, v.distortion.cols, np.float32), fd["dist"])
+    assert tuple(v.cam_size[:]) == fd["cam"] and v.bl == np.float32(fd["bl"]) and v.rgb_depthscale == np.float32(fd["depthscale"])
+    assert (v.image.rows, v.image.cols) == fd["img"].shape and np.array_equal(view_array(v.image.data, fd["img"].size, np.uint8).reshape(fd["img"].shape), fd["img"])
+    assert tuple(v.min_xy[:]) == fd["min_xy"] and tuple(v.max_xy[:]) == fd["max_xy"]
+
+
+needs_ref = pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/libref_frame.so not built (python __graft_entry__.py where /root/reference exists)")
+
+
+@needs_ref
+@pytest.mark.parametrize("kw", [dict(seed=1), dict(seed=2, n_kp=2000, n_markers=0, img=(0, 0)), dict(seed=3, n_kp=1, n_markers=5), dict(seed=4, n_kp=0, depth=False),
+                                dict(seed=5, n_kp=700, depth=False)])
+def test_parse_and_write_against_the_reference_statements(kw):
+    fd = make_fields(**kw)
+    ref = ref_stream(fd)
+    v, used = frame_stream_parse(ref)
+    assert used == len(ref)
+    check_view(v, fd)
+    assert np.array_equal(frame_stream_write(v), ref)                       # byte for byte what the reference wrote
+    # the kd-tree member parses with the projection matcher's reader and agrees with the library's own build of the same points
+    if len(fd["kp"]) > 10:
+        lib = ucoslam_b200.load()
+        n = len(fd["kp"])
+        nodes, leaf, bbox = np.zeros((2 * n + 4, 7), np.int32), np.zeros(n + 1, np.int32), np.zeros(4)
+        nn, nl = ctypes.c_int(), ctypes.c_int()
+        assert lib.uco_b200_kdtree_parse(v.kdtree, v.kdtree_bytes, nodes.ctypes.data, len(nodes), leaf.ctypes.data, len(leaf), bbox.ctypes.data,
+                                         ctypes.addressof(nn), ctypes.addressof(nl)) == 0
+        nodes2, leaf2, bbox2, n2 = np.zeros_like(nodes), np.zeros_like(leaf), np.zeros(4), ctypes.c_int()
+        xy = np.ascontiguousarray(np.c_[fd["kp"]["x"], fd["kp"]["y"]], np.float32)
+        assert lib.uco_b200_kdtree_build(xy.ctypes.data, 8, n, nodes2.ctypes.data, len(nodes2), leaf2.ctypes.data, bbox2.ctypes.data, ctypes.addressof(n2)) == 0
+        k = nn.value
+        assert k == n2.value and nl.value == n and np.array_equal(nodes[:k, :5], nodes2[:k, :5]) and np.array_equal(nodes[:k, 6], nodes2[:k, 6])
+        for a, b in zip(nodes[:k], nodes2[:k]):      # the two flatten the leaves' index lists in different orders; the lists agree
+            assert np.array_equal(leaf[a[5]:a[5] + a[6]], leaf2[b[5]:b[5] + b[6]])
+        assert np.array_equal(bbox, bbox2)
+        # ... and serialises back to a stream the reader takes to the same tree
+        cap = int(v.kdtree_bytes) + 64
+        out, wn = np.zeros(cap, np.uint8), ctypes.c_size_t()
+        assert lib.uco_b200_kdtree_serialize(nodes.ctypes.data, nn.value, leaf.ctypes.data, bbox.ctypes.data, n, None, out.ctypes.data, cap, ctypes.addressof(wn)) == 0
+        assert wn.value == v.kdtree_bytes
+        nodes3, leaf3, bbox3 = np.zeros_like(nodes), np.zeros_like(leaf), np.zeros(4)
+        assert lib.uco_b200_kdtree_parse(out.ctypes.data, wn.value, nodes3.ctypes.data, len(nodes3), leaf3.ctypes.data, len(leaf3), bbox3.ctypes.data,
+                                         ctypes.addressof(nn), ctypes.addressof(nl)) == 0
+        assert np.array_equal(nodes3, nodes) and np.array_equal(leaf3, leaf) and np.array_equal(bbox3, bbox)
+
+
+@needs_ref
+def test_the_reference_reads_what_the_codec_writes():
+    """fields changed through the view (new map-point ids, a new pose, no image: what a mapper does to a keyframe) -> the reference's
+    fromStream accepts the bytes and its toStream gives them back unchanged"""
+    fd = make_fields(6, n_kp=400)
+    v, _ = frame_stream_parse(ref_stream(fd))
+    ids = (np.arange(400, dtype=np.uint32) * 3)
+    v.ids = ids.ctypes.data
+    pose = np.eye(4, dtype=np.float32); pose[0, 3] = 2.5
+    v.pose_f2g = (ctypes.c_float * 16)(*pose.reshape(-1))
+    v.image.data = None
+    mine = frame_stream_write(v)
+    back = ref_roundtrip(mine)
+    assert back is not None and np.array_equal(back, mine)
+    fd2 = dict(fd, ids=ids, pose=pose, img=np.zeros((0, 0), np.uint8))
+    assert np.array_equal(ref_stream(fd2), mine)
+
+
+def test_golden_stream():
+    """the committed stream (written by the reference's statements, tests/golden/make_frame_golden.py) parses to the committed fields
+    and is reproduced byte for byte — runs where /root/reference does not exist"""
+    ref = np.fromfile(os.path.join(GOLD, "frame_stream.bin"), np.uint8)
+    fd = make_fields(1)
+    v, used = frame_stream_parse(ref)
+    assert used == len(ref)
+    check_view(v, fd)
+    assert np.array_equal(frame_stream_write(v), ref)
+
+
+def test_malformed_streams_are_rejected():
+    ref = np.fromfile(os.path.join(GOLD, "frame_stream.bin"), np.uint8)
+    for cut in (0, 3, 17, 200, len(ref) - 1):
+        with pytest.raises(ucoslam_b200.UcoError):
+            frame_stream_parse(ref[:cut].copy() if cut else np.zeros(4, np.uint8))
+    bad = ref.copy(); bad[0] ^= 1
+    with pytest.raises(ucoslam_b200.UcoError):
+        frame_stream_parse(bad)
+    bad = ref.copy(); bad[-1] ^= 1                                            # closing magic
+    with pytest.raises(ucoslam_b200.UcoError):
+        frame_stream_parse(bad)
+
+
+@pytest.mark.gpu
+def test_device_mirror_chains_into_the_matcher():
+    """two keyframes loaded from streams live on the device; the device-pointer matcher on the mirrors gives what the host-buffer
+    matcher gives on the same frames; per-keypoint arrays come back unchanged"""
+    import torch
+    ctx = ucoslam_b200.Context(0)
+    ref = np.fromfile(os.path.join(GOLD, "frame_stream.bin"), np.uint8)
+    fd = make_fields(1)
+    va, _ = frame_stream_parse(ref)
+    # second frame: the same keypoints seen again (descriptor noise, small motion) through the writer
+    rng = np.random.default_rng(9)
+    kp2 = fd["kp"].copy(); kp2["x"] += rng.normal(0, 1, len(kp2)).astype(np.float32); kp2["y"] += rng.normal(0, 1, len(kp2)).astype(np.float32)
+    d2 = fd["desc"].copy(); fl = rng.integers(0, 256, (len(kp2), 8))
+    for j in range(8):
+        d2[np.arange(len(kp2)), fl[:, j] >> 3] ^= (1 << (fl[:, j] & 7)).astype(np.uint8)
+    vb, _ = frame_stream_parse(ref)
+    vb.und_kpts, vb.desc.data, vb.kdtree, vb.kdtree_bytes = kp2.ctypes.data, d2.ctypes.data, None, 0
+    ha, da = ctx.frame_upload(va)
+    hb, db = ctx.frame_upload(vb)
+    n = len(kp2)
+    assert da.n_kp == n and db.n_kp == n and da.n_nodes > 0 and db.n_nodes == 0
+    kps, desc, ids, flags, depth = ctx.frame_download(ha, n)
+    assert kps.tobytes() == fd["kp"].tobytes() and np.array_equal(desc, fd["desc"]) and np.array_equal(ids, fd["ids"]) and np.array_equal(flags, fd["flags"])
+    assert np.array_equal(depth, fd["depth"])
+    prm = ucoslam_b200.MatchParams(80.0, 0.8, True, 1)
+    want = ctx.frame_match(d2, kp2, fd["desc"], fd["kp"], prm)
+    out = torch.zeros((n, 16), dtype=torch.uint8, device="cuda"); n_out = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ctx.frame_match_batch_dev(1, db.desc, 0, db.kps, 0, n, None, da.desc, 0, da.kps, 0, n, None, prm, out.data_ptr(), n_out.data_ptr())
+    ctx.sync()
+    got = out.cpu().numpy().view(ucoslam_b200.MATCH_DTYPE).reshape(-1)[:int(n_out.item())]
+    assert len(want) > n // 2 and got.tobytes() == want.tobytes()
+    ctx.frame_free(ha); ctx.frame_free(hb)
+    ctx.close()
+
+
+# ---- MapPoint streams (the other record type of a map file) ---------------------------------------------------------------------------
+def _mp_fields(seed, n_frames=5, with_desc=True):
+    rng = np.random.default_rng(seed)
+    fr = np.sort(rng.choice(500, n_frames, replace=False)).astype(np.uint32)
+    return dict(id=int(rng.integers(0, 1 << 20)), pos=rng.normal(0, 2, 3).astype(np.float32), desc=rng.integers(0, 256, 32, dtype=np.uint8) if with_desc else None,
+                frames=np.c_[fr, rng.integers(0, 2000, n_frames)].astype(np.uint32), normal=rng.normal(0, 1, 3).astype(np.float32), seen=int(rng.integers(0, 60000)),
+                visible=int(rng.integers(0, 60000)), flags=int(rng.integers(0, 8)), maxd=float(np.float32(rng.uniform(1, 9))), mind=float(np.float32(rng.uniform(0.1, 1))),
+                kf_since=int(rng.integers(0, 1 << 40)), last_seen=int(rng.integers(0, 1 << 30)))
+
+
+def _ref_mappoint(fd):
+    lib = ctypes.CDLL(REF)
+    lib.ref_mappoint_to_stream.restype = ctypes.c_long
+    out = np.zeros(4096, np.uint8)
+    fr = np.ascontiguousarray(fd["frames"])
+    n = lib.ref_mappoint_to_stream(ctypes.c_uint32(fd["id"]), ctypes.c_void_p(fd["pos"].ctypes.data), None if fd["desc"] is None else ctypes.c_void_p(fd["desc"].ctypes.data),
+                                   len(fr), ctypes.c_void_p(fr.ctypes.data), ctypes.c_void_p(fd["normal"].ctypes.data), fd["seen"], fd["visible"],
+                                   ctypes.c_ubyte(fd["flags"]), ctypes.c_float(fd["maxd"]), ctypes.c_float(fd["mind"]), ctypes.c_ulonglong(fd["kf_since"]),
+                                   ctypes.c_uint32(fd["last_seen"]), ctypes.c_void_p(out.ctypes.data), ctypes.c_long(len(out)))
+    assert n > 0
+    return out[:n].copy()
+
+
+@needs_ref
+@pytest.mark.parametrize("kw", [dict(seed=1), dict(seed=2, n_frames=0), dict(seed=3, n_frames=40, with_desc=False)])
+def test_mappoint_stream_against_the_reference_statements(kw):
+    fd = _mp_fields(**kw)
+    ref = _ref_mappoint(fd)
+    lib = ucoslam_b200.load()
+    v, used = ucoslam_b200.MapPointStream(), ctypes.c_size_t()
+    assert lib.uco_b200_mappoint_stream_parse(ref.ctypes.data, len(ref), ctypes.addressof(v), ctypes.addressof(used)) == 0 and used.value == len(ref)
+    assert v.id == fd["id"] and np.array_equal(np.array(v.pos3d[:], np.float32), fd["pos"]) and np.array_equal(np.array(v.normal[:], np.float32), fd["normal"])
+    assert np.array_equal(view_array(v.frames, 2 * v.n_frames, np.uint32).reshape(-1, 2), fd["frames"])
+    if fd["desc"] is not None:
+        assert (v.desc.rows, v.desc.cols, v.desc.type) == (1, 32, 0) and np.array_equal(view_array(v.desc.data, 32, np.uint8), fd["desc"])
+    else:
+        assert v.desc.rows == 0 and not v.desc.data
+    assert (v.n_times_seen, v.n_times_visible, v.flags, v.kf_since_addition, v.last_fidx_seen) == (fd["seen"], fd["visible"], fd["flags"], fd["kf_since"], fd["last_seen"])
+    assert v.max_distance == np.float32(fd["maxd"]) and v.min_distance == np.float32(fd["mind"])
+    out, n = np.zeros(len(ref) + 8, np.uint8), ctypes.c_size_t()
+    assert lib.uco_b200_mappoint_stream_write(ctypes.addressof(v), out.ctypes.data, len(out), ctypes.addressof(n)) == 0
+    assert np.array_equal(out[:n.value], ref)
+    # a moved point written by the codec is read back by the reference unchanged
+    v.pos3d = (ctypes.c_float * 3)(1.5, -2.0, 0.25)
+    assert lib.uco_b200_mappoint_stream_write(ctypes.addressof(v), out.ctypes.data, len(out), ctypes.addressof(n)) == 0
+    rlib = ctypes.CDLL(REF); rlib.ref_mappoint_roundtrip.restype = ctypes.c_long
+    back = np.zeros(len(out) + 64, np.uint8)
+    m = rlib.ref_mappoint_roundtrip(ctypes.c_void_p(out.ctypes.data), ctypes.c_long(n.value), ctypes.c_void_p(back.ctypes.data), ctypes.c_long(len(back)))
+    assert m == n.value and np.array_equal(back[:m], out[:m])
+    assert np.array_equal(_ref_mappoint(dict(fd, pos=np.array([1.5, -2.0, 0.25], np.float32))), out[:m])
+
+
+def test_mappoint_golden_and_malformed():
+    ref = np.fromfile(os.path.join(GOLD, "mappoint_stream.bin"), np.uint8)
+    fd = _mp_fields(1)
+    lib = ucoslam_b200.load()
+    v, used = ucoslam_b200.MapPointStream(), ctypes.c_size_t()
+    assert lib.uco_b200_mappoint_stream_parse(ref.ctypes.data, len(ref), ctypes.addressof(v), ctypes.addressof(used)) == 0 and used.value == len(ref)
+    assert v.id == fd["id"] and np.array_equal(view_array(v.frames, 2 * v.n_frames, np.uint32).reshape(-1, 2), fd["frames"])
+    out, n = np.zeros(len(ref), np.uint8), ctypes.c_size_t()
+    assert lib.uco_b200_mappoint_stream_write(ctypes.addressof(v), out.ctypes.data, len(out), ctypes.addressof(n)) == 0 and np.array_equal(out, ref)
+    assert lib.uco_b200_mappoint_stream_parse(ref.ctypes.data, len(ref) - 3, ctypes.addressof(v), None) != 0
+    bad = ref.copy(); bad[0] ^= 1
+    assert lib.uco_b200_mappoint_stream_parse(bad.ctypes.data, len(bad), ctypes.addressof(v), None) != 0

@@ -54,6 +54,15 @@ SIGNATURES = {
     "uco_b200_comm_destroy": (None, [_vp]),
     "uco_b200_ba_solve_sharded": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "uco_b200_probe_ba_partition": (_i, [_vp, _i, _vp]),
+    "uco_b200_frame_stream_parse": (_i, [_vp, _c.c_size_t, _vp, _vp]),
+    "uco_b200_frame_stream_write": (_i, [_vp, _vp, _c.c_size_t, _vp]),
+    "uco_b200_mappoint_stream_parse": (_i, [_vp, _c.c_size_t, _vp, _vp]),
+    "uco_b200_mappoint_stream_write": (_i, [_vp, _vp, _c.c_size_t, _vp]),
+    "uco_b200_kdtree_serialize": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _c.c_size_t, _vp]),
+    "uco_b200_frame_upload": (_i, [_vp, _vp, _vp]),
+    "uco_b200_frame_dev": (_vp, [_vp]),
+    "uco_b200_frame_download": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "uco_b200_frame_free": (None, [_vp]),
     "uco_b200_new_points": (_i, [_vp] + [_vp, _i, _c.c_size_t, _vp, _i, _vp] + [_i, _vp, _vp, _c.c_size_t, _vp, _vp, _vp] + [_vp, _vp, _vp, _vp] + [_vp] * 7 + [_i, _i] + [_vp, _vp, _vp]),
     "uco_b200_block_solve": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
     "uco_b200_block_solve_profile": (_i, [_vp, _vp]),
@@ -332,6 +341,63 @@ class TriangulateParams(ctypes.Structure):  # uco_triangulate_params
     _fields_ = [("K_train", _c.c_float * 4), ("K_query", _c.c_float * 4), ("RT", _c.c_float * 16), ("n_levels_train", _c.c_int32),
                 ("scale_factors_train", _vp), ("n_levels_query", _c.c_int32), ("scale_factors_query", _vp), ("max_chi2", _c.c_float),
                 ("scale_ratio_factor", _c.c_float), ("to_global", _c.c_int32), ("g2f_train", _c.c_float * 16)]
+
+
+class MatView(ctypes.Structure):  # uco_mat_view
+    _fields_ = [("rows", _c.c_int32), ("cols", _c.c_int32), ("type", _c.c_int32), ("data", _vp)]
+
+
+class FrameStream(ctypes.Structure):  # uco_frame_stream: a view into a Frame::toStream byte range
+    _fields_ = [("idx", _c.c_uint32), ("fseq_idx", _c.c_uint32), ("frame_flags", _c.c_uint8), ("kp_desc_type", _c.c_int8), ("desc", MatView),
+                ("n_und_kpts", _c.c_uint32), ("und_kpts", _vp), ("n_kpts", _c.c_uint32), ("kpts", _vp), ("n_depth", _c.c_uint32), ("depth", _vp),
+                ("n_ids", _c.c_uint32), ("ids", _vp), ("n_flags", _c.c_uint32), ("flags", _vp), ("n_markers", _c.c_uint32), ("markers", _vp),
+                ("markers_bytes", _c.c_uint64), ("pose_f2g", _c.c_float * 16), ("n_bow", _c.c_uint32), ("bow", _vp), ("n_bow_level", _c.c_uint32),
+                ("bow_level", _vp), ("bow_level_bytes", _c.c_uint64), ("n_scale_factors", _c.c_uint32), ("scale_factors", _vp),
+                ("camera_matrix", MatView), ("distortion", MatView), ("cam_size", _c.c_int32 * 2), ("bl", _c.c_float), ("rgb_depthscale", _c.c_float),
+                ("image", MatView), ("kdtree", _vp), ("kdtree_bytes", _c.c_uint64), ("min_xy", _c.c_int32 * 2), ("max_xy", _c.c_int32 * 2)]
+
+
+class MapPointStream(ctypes.Structure):  # uco_mappoint_stream
+    _fields_ = [("id", _c.c_uint32), ("pos3d", _c.c_float * 3), ("desc", MatView), ("n_frames", _c.c_uint32), ("frames", _vp),
+                ("normal", _c.c_float * 3), ("n_times_seen", _c.c_uint16), ("n_times_visible", _c.c_uint16), ("flags", _c.c_uint8),
+                ("max_distance", _c.c_float), ("min_distance", _c.c_float), ("kf_since_addition", _c.c_uint64), ("last_fidx_seen", _c.c_uint32)]
+
+
+class FrameDev(ctypes.Structure):  # uco_frame_dev
+    _fields_ = [("idx", _c.c_uint32), ("fseq_idx", _c.c_uint32), ("n_kp", _c.c_int32), ("kps", _vp), ("desc", _vp), ("ids", _vp), ("flags", _vp),
+                ("depth", _vp), ("n_nodes", _c.c_int32), ("nodes", _vp), ("n_leaf", _c.c_int32), ("leaf_idx", _vp), ("bbox", _vp),
+                ("n_scale_factors", _c.c_int32), ("scale_factors", _vp), ("pose_f2g", _vp), ("bbox_host", _c.c_double * 4),
+                ("pose_host", _c.c_float * 16), ("K", _c.c_float * 4), ("min_xy", _c.c_int32 * 2), ("max_xy", _c.c_int32 * 2)]
+
+
+def frame_stream_parse(buf):
+    """view of the Frame::toStream bytes at the start of `buf` (uint8 array; it must outlive the view) -> (FrameStream, consumed)"""
+    buf = np.ascontiguousarray(buf, np.uint8)
+    v = FrameStream()
+    n = _c.c_size_t(0)
+    if load().uco_b200_frame_stream_parse(_p(buf), len(buf), ctypes.addressof(v), ctypes.addressof(n)) != 0:
+        raise UcoError("frame_stream_parse: not a Frame stream")
+    v._keep = buf
+    return v, int(n.value)
+
+
+def frame_stream_write(view):
+    n = _c.c_size_t(0)
+    lib = load()
+    if lib.uco_b200_frame_stream_write(ctypes.addressof(view), None, 0, ctypes.addressof(n)) != 0:
+        raise UcoError("frame_stream_write failed")
+    out = np.zeros(n.value, np.uint8)
+    if lib.uco_b200_frame_stream_write(ctypes.addressof(view), _p(out), len(out), ctypes.addressof(n)) != 0:
+        raise UcoError("frame_stream_write failed")
+    return out
+
+
+def view_array(ptr, count, dtype):
+    """numpy view of `count` elements of `dtype` at address `ptr` (a field of a FrameStream)"""
+    if not ptr or count == 0:
+        return np.zeros(0, dtype)
+    dt = np.dtype(dtype)
+    return np.frombuffer((ctypes.c_uint8 * (count * dt.itemsize)).from_address(ptr), dt, count)
 
 
 class NewPointsParams(ctypes.Structure):  # uco_new_points_params
@@ -722,6 +788,22 @@ class Context:
             None if qmp is None else ctypes.cast(qmp, ctypes.c_void_p), _p(f12a), ctypes.addressof(prm),
             ctypes.cast(VP(*[o.ctypes.data for o in outs]), ctypes.c_void_p), cap, _p(n_out)))
         return [outs[f][:n_out[f]].copy() for f in range(F)]
+
+    def frame_upload(self, view):
+        """device-resident mirror of a parsed Frame stream -> (handle, FrameDev with DEVICE pointers); free with frame_free"""
+        hnd = ctypes.c_void_p()
+        self._chk(self.lib.uco_b200_frame_upload(self.h, ctypes.addressof(view), ctypes.addressof(hnd)))
+        dev = FrameDev.from_address(self.lib.uco_b200_frame_dev(hnd))
+        return hnd, dev
+
+    def frame_download(self, hnd, n):
+        kps, desc = np.zeros(n, KP_DTYPE), np.zeros((n, 32), np.uint8)
+        ids, flags, depth = np.zeros(n, np.uint32), np.zeros(n, np.uint8), np.zeros(n, np.float32)
+        self._chk(self.lib.uco_b200_frame_download(self.h, hnd, _p(kps), _p(desc), _p(ids), _p(flags), _p(depth)))
+        return kps, desc, ids, flags, depth
+
+    def frame_free(self, hnd):
+        self.lib.uco_b200_frame_free(hnd)
 
     def new_points(self, sc, max_points=-1, per_pair=False):
         """MapManager::createNewPoints on a scene dict (synth.synth_new_points_scene): returns dict(kpt, xyz, dist, obs_ptr, obs_frame, obs_kpt
