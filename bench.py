@@ -53,7 +53,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=64, help="frames per step per GPU")
+    ap.add_argument("--frames", type=int, default=128, help="frames per step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra sections (720p, single-frame latency, ATE, collective paths)")
     ap.add_argument("--res", default="640x480", choices=["640x480", "1280x720"],
@@ -304,7 +304,9 @@ def run_b200(args, rank, world, local_rank):
     class Work:
         """everything one resolution needs: problems, device-resident state, buffers, the step functions"""
 
-        def __init__(self, F, w, hgt, kpts, seed):
+        def __init__(self, F, w, hgt, kpts, seed, c=None):
+            c = c or ctx
+            self.c, self.lib, self.hc = c, c.lib, c.h                      # the tracker context this work runs on
             self.F, self.w, self.h, self.kpts = F, w, hgt, kpts
             self.prm = ucoslam_b200.OrbParams(kpts)
             cam = workload.Camera(w, hgt, FOCAL if w == W else (1050.0 if w == 1280 else 525.0))
@@ -313,7 +315,7 @@ def run_b200(args, rank, world, local_rank):
             self.tprm = ucoslam_b200.TrackParams(self.scenes[0], MAX_DESC_DIST, PROJ_DIST_THR)
             pc = max(len(s["prev_octave"]) for s in self.scenes)
             mc = max(len(s["mp_id"]) for s in self.scenes)
-            self.state = ucoslam_b200.TrackState(ctx, F, pc, mc)
+            self.state = ucoslam_b200.TrackState(c, F, pc, mc)
             for f, s in enumerate(self.scenes):
                 self.state.set_scene(f, s)
             self.prior = np.stack([np.asarray(s["pose44"], np.float32).reshape(16) for s in self.scenes])
@@ -351,25 +353,25 @@ def run_b200(args, rank, world, local_rank):
 
         # -- device-resident step (tracker stream) --
         def orb_dev(self):
-            ctx.orb_extract_batch_dev(self.clip_dev.data_ptr(), self.F, self.w, self.h, self.w, self.w * self.h, self.prm,
+            self.c.orb_extract_batch_dev(self.clip_dev.data_ptr(), self.F, self.w, self.h, self.w, self.w * self.h, self.prm,
                                       self.kps_dev.data_ptr(), self.desc_dev.data_ptr(), self.nout_dev.data_ptr())
 
         def track_dev(self):
-            rc = lib.uco_b200_track_state_step_dev(h, self.state.h, self.kps_dev.data_ptr(), self.desc_dev.data_ptr(), self.nout_dev.data_ptr(),
+            rc = self.lib.uco_b200_track_state_step_dev(self.hc, self.state.h, self.kps_dev.data_ptr(), self.desc_dev.data_ptr(), self.nout_dev.data_ptr(),
                                                    self.kpts, self.prior_dev.data_ptr(), ctypes.addressof(self.tprm), ctypes.addressof(self.tout),
                                                    ucoslam_b200.UCO_TRACK_NO_SYNC)
             if rc != 0:
-                raise RuntimeError(lib.uco_b200_last_error(h))
+                raise RuntimeError(self.lib.uco_b200_last_error(self.hc))
 
         def keyframes_dev(self, with_voc=True, with_match=True):
             """per keyframe: bag of words + FrameMatcher against its neighbours, on the resident frames: three launches"""
-            rc = lib.uco_b200_keyframes_batch_dev(h, voc if with_voc else None, 3, self.kps_dev.data_ptr(), self.kpts, self.desc_dev.data_ptr(),
+            rc = self.lib.uco_b200_keyframes_batch_dev(self.hc, voc if with_voc else None, 3, self.kps_dev.data_ptr(), self.kpts, self.desc_dev.data_ptr(),
                                                   self.kpts * 32, self.nout_dev.data_ptr(), self.kpts, self.F, len(self.groups),
                                                   self.kf_idx.ctypes.data, (self.nb_ptr if with_match else np.zeros_like(self.nb_ptr)).ctypes.data,
                                                   self.nb_idx.ctypes.data, None, ctypes.addressof(self.mprm), self.word_dev.data_ptr(),
                                                   self.wgt_dev.data_ptr(), self.node_dev.data_ptr(), self.fm_dev.data_ptr(), self.fmn_dev.data_ptr())
             if rc != 0:
-                raise RuntimeError(lib.uco_b200_last_error(h))
+                raise RuntimeError(self.lib.uco_b200_last_error(self.hc))
 
         def step_dev(self):
             self.orb_dev()
@@ -378,16 +380,16 @@ def run_b200(args, rank, world, local_rank):
 
         # -- the same through host buffers --
         def step_host(self):
-            rc = lib.uco_b200_track_frames(h, self.state.h, ctypes.cast(self.img_ptrs, ctypes.c_void_p), self.w, self.h, self.w,
+            rc = self.lib.uco_b200_track_frames(self.hc, self.state.h, ctypes.cast(self.img_ptrs, ctypes.c_void_p), self.w, self.h, self.w,
                                            ctypes.addressof(self.prm), ctypes.addressof(self.tprm), self.prior.ctypes.data, self.kps_h.ctypes.data,
                                            self.desc_h.ctypes.data, self.nkp_h.ctypes.data, ctypes.addressof(self.tout_h))
             if rc != 0:
-                raise RuntimeError(lib.uco_b200_last_error(h))
-            rc = lib.uco_b200_keyframes_batch(h, voc, 3, len(self.groups), self.kf_idx.ctypes.data, self.nb_ptr.ctypes.data, self.nb_idx.ctypes.data,
+                raise RuntimeError(self.lib.uco_b200_last_error(self.hc))
+            rc = self.lib.uco_b200_keyframes_batch(self.hc, voc, 3, len(self.groups), self.kf_idx.ctypes.data, self.nb_ptr.ctypes.data, self.nb_idx.ctypes.data,
                                               None, ctypes.addressof(self.mprm), self.bow_h[0].ctypes.data, self.bow_h[1].ctypes.data,
                                               self.bow_h[2].ctypes.data, self.fm_h.ctypes.data, self.fmn_h.ctypes.data)
             if rc != 0:
-                raise RuntimeError(lib.uco_b200_last_error(h))
+                raise RuntimeError(self.lib.uco_b200_last_error(self.hc))
 
         def h2d_bytes(self):
             return self.F * (self.w * self.h + 64) + 8 * (len(self.groups) + len(self.nb_idx))
@@ -416,6 +418,41 @@ def run_b200(args, rank, world, local_rank):
 
     def ba_all(m=0):  # host-buffer C-ABI call (the window is assembled by the host mapper: there is no device-resident variant)
         ctx_bas[m].ba_solve_batch(None, BA_ITERS, packed=ba_packs[m])
+
+    # end-to-end path: TWO tracker contexts take turns (a second camera stream's worth of state), so that the uploads / downloads of
+    # one step overlap the kernels of the other; every step still uploads its own frames and downloads its own results
+    ctx2 = ucoslam_b200.Context(local_rank)
+    wk2 = Work(F, W, H, KPTS, shard.unit_seed(1234, rank, 0), ctx2)
+    trackers = ThreadPoolExecutor(2)
+
+    def run_e2e(n_steps):
+        futs, tf, wks = [], [None, None], [wk, wk2]
+        for i in range(n_steps):
+            if len(futs) >= N_MAPPERS:
+                futs.pop(0).result()
+            futs.append(mapper.submit(ba_all, i % N_MAPPERS))
+            if tf[i % 2] is not None:
+                tf[i % 2].result()
+            tf[i % 2] = trackers.submit(wks[i % 2].step_host)
+        for f in tf + futs:
+            if f is not None:
+                f.result()
+
+    stream2 = torch.cuda.ExternalStream(ctx2.stream, device=local_rank)
+
+    def run_two_streams(n_steps):
+        """device-resident steps alternate between the two tracker contexts' streams (the small per-frame kernels of one step overlap
+        the wide ones of the other); the L2 flush follows every step on its own stream; BA batches as in run_pipelined"""
+        futs, wks, sts = [], [wk, wk2], [stream, stream2]
+        for i in range(n_steps):
+            if len(futs) >= N_MAPPERS:
+                futs.pop(0).result()
+            futs.append(mapper.submit(ba_all, i % N_MAPPERS))
+            with torch.cuda.stream(sts[i % 2]):
+                wks[i % 2].step_dev()
+                flush.zero_()
+        for f in futs:
+            f.result()
 
     def run_pipelined(track, n_steps, between=None):
         """n_steps steps; the BA windows of step i go to mapper i % N_MAPPERS and are waited for before that mapper is reused
@@ -462,6 +499,9 @@ def run_b200(args, rank, world, local_rank):
     with torch.cuda.stream(stream):
         run_pipelined(wk.step_dev, max(args.warmup, 3), between=flush.zero_)
     barrier()
+    run_two_streams(max(args.warmup, 3))
+    barrier()
+    ctx2.sync()
     n_kp = wk.nout_dev.cpu().numpy()
     assert (n_kp == KPTS).all(), "synthetic frames must give %d keypoints, got %s" % (KPTS, n_kp[:8])
     good = wk.good_dev.cpu().numpy()
@@ -471,28 +511,34 @@ def run_b200(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    count = lambda: ctx.launch_count() + sum(c.launch_count() for c in ctx_bas)
+    count = lambda: ctx.launch_count() + ctx2.launch_count() + sum(c.launch_count() for c in ctx_bas)
     n0 = count()
     # EXACTLY args.steps steps between two events on the tracker stream (the second one recorded after the last BA batch has
     # returned its results to the host), barrier + synchronize on both sides, L2 flushed between steps inside the region
     barrier()
-    with torch.cuda.stream(stream):
-        ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev_a.record(stream)
-        run_pipelined(wk.step_dev, args.steps, between=flush.zero_)
-        ev_b.record(stream)
+    ev_a, ev_b, ev_j = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event()
+    ev_a.record(stream)
+    stream2.wait_event(ev_a)                 # the second tracker stream starts inside the region ...
+    run_two_streams(args.steps)
+    ev_j.record(stream2)
+    stream.wait_event(ev_j)                  # ... and has finished before the closing event
+    ev_b.record(stream)
     barrier()
+    ctx2.sync()
     ms_dev = reduce_max(ev_a.elapsed_time(ev_b))
     launches = (count() - n0) // max(1, args.steps)
 
-    run_pipelined(wk.step_host, max(1, args.warmup))
+    run_e2e(max(2, args.warmup))
     barrier()
+    ctx2.sync()
     t0 = time.perf_counter()
-    run_pipelined(wk.step_host, args.steps)
+    run_e2e(args.steps)
     barrier()
+    ctx2.sync()
     e2e_ms = reduce_max((time.perf_counter() - t0) * 1e3)
     clocks = sampler.summary() if sampler else None
     assert np.array_equal(wk.o_h["n_good"], good), "host-buffer path and device-resident path disagree"
+    assert args.steps < 2 or np.array_equal(wk2.o_h["n_good"], good), "the second tracker context disagrees"
 
     # ---- per-stage device times of the same step (events at the stage boundaries) ----
     reps = 5
@@ -609,7 +655,9 @@ def run_b200(args, rank, world, local_rank):
         cfg = config_common(n_ba)
         cfg["arm"] = ({"frames_per_step_per_unit": F, "units": "%d GPU(s)" % world, "parallelism": "frames sharded over %d GPU(s), no collective" % world,
                     "l2": "flushed between timed steps (256 MB write, inside the timed region)",
+                    "streams": "two tracker contexts (streams) take alternate steps, the mappers run beside them",
                     "state": "previous frames + map blocks are device resident (uco_b200_track_state); a step's host inputs are its frames and pose priors",
+                    "e2e": "two tracker contexts take turns through the host-buffer calls, so one step's copies overlap the other's kernels; every step uploads its frames and downloads its results",
                     "mapper": "%d BA contexts take turns (clusters of %d CTAs per window): the local BA of a step overlaps the tracking "
                               "of the following steps (threaded mode: the mapper lags the tracker); all BA results are back on the "
                               "host inside the timed region" % (N_MAPPERS, BA_CLUSTER or 8)})
@@ -643,9 +691,12 @@ def run_b200(args, rank, world, local_rank):
     # orderly teardown (the driver's exit hook records the loaded libraries, so the interpreter must exit normally): every torch
     # object that refers to the tracker context's stream goes first, then the mapper pool, then the contexts, then the process group
     mapper.shutdown(wait=True)
+    trackers.shutdown(wait=True)
+    wk2.close()
+    del wk2
     wk.close()
     ctx.bow_free(voc)
-    del stream, flush, ev_a, ev_b, wk
+    del stream, stream2, flush, ev_a, ev_b, ev_j, wk
     gc.collect()
     torch.cuda.synchronize()
     torch.cuda.empty_cache()       # the caching allocators record events on the streams their blocks were used on: drop the blocks
@@ -653,6 +704,7 @@ def run_b200(args, rank, world, local_rank):
         torch._C._host_emptyCache()
     for c in ctx_bas:
         c.close()
+    ctx2.close()
     ctx.close()
     shard.finalize()
     sys.stdout.flush()
