@@ -31,5 +31,5 @@ for kw in (dict(seed=21, n_poses=12, n_fixed=2, n_points=2000), dict(seed=23, n_
                 name, nb, wall * 1e3, out["device_ms"], wall * 1e3 / nb, out["iters"], int(out["trace"][:, 1].sum())))
             if nb == 1 and out["profile"].sum() > 0:
                 names = ["init", "err0", "lin_obs", "lin_sum", "prep", "gather", "solve", "update", "errors", "decide", "results", "flag",
-                         "solve:assemble", "solve:factor", "solve:backsub"]
+                         "solve:assemble", "solve:factor", "solve:backsub", "gather:warp0"]
                 print("      phase us (CTA 0 @1.965 GHz): " + "  ".join("%s %.0f" % (n, c / 1965.0) for n, c in zip(names, out["profile"])))

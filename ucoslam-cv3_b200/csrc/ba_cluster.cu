@@ -380,10 +380,132 @@ __device__ __forceinline__ void phase_gather(const CbDev& B, int rank, int CL) {
     }
 }
 
+// Fused prep + Schur gather (windows of <= BA_GSLOTS blocks per warp).  The gather above streams every contribution's two 6x3 operands from
+// L2 (144 B each, every block re-reading the landmarks it shares with the others) and leaves one partial block per 64 contributions in
+// HBM.  Here a CTA walks its landmarks chunk by chunk: the chunk's W rows come in once (coalesced), Y = W D^-1 is formed in shared
+// memory and never written out, and every warp runs the chunk's contributions of the blocks it OWNS from shared memory into register
+// accumulators that live across the chunks (BA_GSLOTS slots x one m8n8k4 C tile).  One partial per (CTA, block) goes to HBM at the end; CTA 0
+// adds them in rank order.  Fixed order throughout: bitwise reproducible for a given cluster size.
+constexpr int PG_W = 0, PG_Y = (BS + 1) * 18, PG_D = 2 * (BS + 1) * 18, PG_BL = PG_D + BS * 6, PG_DOUBLES = PG_BL + (BS + 1) * 3 + 1;
+__device__ __forceinline__ void phase_prep_gather(const CbDev& B, int rank, double lambda, double* stage) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* sW = stage + PG_W;
+    double* sY = stage + PG_Y;
+    double* sD = stage + PG_D;
+    double* sbl = stage + PG_BL;
+    const int q = lane >> 2, k4 = lane & 3, off = 3 * q + k4;
+    const bool valid = k4 < 3 && q < 6, isbl = k4 < 3 && q == 6;
+    double acc[BA_GSLOTS][2];
+#pragma unroll
+    for (int sl = 0; sl < BA_GSLOTS; sl++) acc[sl][0] = acc[sl][1] = 0;
+    for (int ch = B.cta_chunk_ptr[rank]; ch < B.cta_chunk_ptr[rank + 1]; ch++) {
+        const int l0 = B.chunk_lm[ch], l1 = B.chunk_lm[ch + 1], o0 = B.lm_ptr[l0], nobs = B.lm_ptr[l1] - o0, nl = l1 - l0;
+        const long long tc0 = clock64();
+        // the first segment's header and entries are requested now and arrive while the operands are staged
+        int sg = B.gw_ptr[ch * NW + warp];
+        const int sg_end = B.gw_ptr[ch * NW + warp + 1];
+        int4 seg = make_int4(0, 0, 0, 0);
+        uint32_t mine = 0;
+        if (sg < sg_end) {
+            seg = B.gseg[sg];
+            mine = B.gcon[seg.y + lane];                                     // the entry array is padded by 32 at its end
+        }
+        if (tid < nl) {
+            const int l = l0 + tid;
+            double D[6], I[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) D[k] = B.Hll[6 * (size_t)l + k];
+            D[0] += lambda; D[3] += lambda; D[5] += lambda;
+            inv3_sym(D, I);
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                B.Dinv[6 * (size_t)l + k] = I[k];
+                sD[6 * tid + k] = I[k];
+            }
+#pragma unroll
+            for (int k = 0; k < 3; k++) sbl[3 * tid + k] = B.bl[3 * (size_t)l + k];
+        }
+        if (tid < 3) sbl[3 * nl + tid] = 0;                                  // the dummy landmark / observation of the padding
+        if (tid >= 32 && tid < 50) sW[18 * nobs + tid - 32] = sY[18 * nobs + tid - 32] = 0;
+        __syncthreads();
+        for (int row = tid; row < 6 * nobs; row += BS) {
+            const double* Wg = B.W + 3 * ((size_t)6 * o0 + row);
+            const double a0 = Wg[0], a1 = Wg[1], a2 = Wg[2];
+            const double* I = sD + 6 * (B.obs_lm[o0 + row / 6] - l0);
+            sW[3 * row] = a0; sW[3 * row + 1] = a1; sW[3 * row + 2] = a2;
+            sY[3 * row] = a0 * I[0] + a1 * I[1] + a2 * I[2];
+            sY[3 * row + 1] = a0 * I[1] + a1 * I[3] + a2 * I[4];
+            sY[3 * row + 2] = a0 * I[2] + a1 * I[4] + a2 * I[5];
+        }
+        __syncthreads();
+        const long long tc1 = clock64();
+        const double* zero = sW + 18 * nobs;
+        const double* baseA = valid ? sY + off : zero;
+        const int strideA = valid ? 18 : 0;
+        while (sg < sg_end) {
+            int4 nseg = make_int4(0, 0, 0, 0);
+            uint32_t nmine = 0;
+            if (sg + 1 < sg_end) {                                           // the next segment's header and first entries: in flight during this one
+                nseg = B.gseg[sg + 1];
+                nmine = B.gcon[nseg.y + lane];
+            }
+            const int slot = (seg.x >> 16) & 0xff;
+            const bool diag = (seg.x >> 24) != 0;
+            const double* baseB = valid ? sW + off : (diag && isbl ? sbl + k4 : zero);
+            const int strideB = valid ? 18 : (diag && isbl ? 3 : 0);
+            const bool b_from_a = diag && valid;
+            // four independent accumulator tiles cover the DMMA dependent-issue latency; more do not help: at one m8n8k4 per
+            // contribution (256 FMA issued for the 126 the 6x3 . 3x7 product needs) the phase is bound by the FP64 pipe of the SM
+            double a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0};
+            for (int base = seg.y; base < seg.z; base += 32) {
+                const int nb = min(32, seg.z - base);                      // a multiple of four
+                if (base != seg.y) mine = B.gcon[base + lane];
+                for (int k = 0; k < nb; k += 4) {
+                    double av[4], bv[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t e = __shfl_sync(0xffffffffu, mine, k + j);
+                        const int ia = (int)(e & 0xffffu), ib = (int)(e >> 16);
+                        av[j] = baseA[strideA * ia];
+                        bv[j] = baseB[strideB * (b_from_a ? ia : ib)];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; j++) mma884(a0[j], a1[j], av[j], bv[j]);
+                }
+            }
+            const double c0 = (a0[0] + a0[1]) + (a0[2] + a0[3]), c1 = (a1[0] + a1[1]) + (a1[2] + a1[3]);
+#pragma unroll
+            for (int sl = 0; sl < BA_GSLOTS; sl++)
+                if (sl == slot) { acc[sl][0] += c0; acc[sl][1] += c1; }
+            seg = nseg; mine = nmine; sg++;
+        }
+        const long long tc2 = clock64();
+        __syncthreads();                                                     // the next chunk overwrites the staged operands
+        if (rank == 0 && tid == 0) {                                         // profile slots 4 / 15: staging, this warp's own gather (the barrier wait is the rest of slot 5)
+            B.res->phase_cycles[4] += (double)(tc1 - tc0);
+            B.res->phase_cycles[15] += (double)(tc2 - tc1);
+        }
+    }
+    // one partial per (CTA, block)
+#pragma unroll
+    for (int sl = 0; sl < BA_GSLOTS; sl++) {
+        const int blk = B.wblk[warp * BA_GSLOTS + sl];
+        if (blk < 0 || q >= 6) continue;
+        const size_t at = (size_t)rank * B.nblk + blk;
+        const int col = 2 * k4;
+        if (col < 6) {
+            B.part[36 * at + 6 * q + col] = acc[sl][0];
+            B.part[36 * at + 6 * q + col + 1] = acc[sl][1];
+        } else {
+            B.partb[6 * at + q] = acc[sl][0];                                 // column 6 of a diagonal block's tile: Y_a bl (zero for the others)
+        }
+    }
+}
+
 // CTA 0: reduced system in shared memory (lower triangle packed by rows, row n = right-hand side), L D L^T in 6-wide block
 // columns (same operation order as the column-by-column elimination), back-substitution by one warp.  Returns 0 on a
 // non-positive pivot.
-__device__ int phase_solve(const CbDev& B, double lambda, double* A, double* aux, int* sflag) {
+__device__ int phase_solve(const CbDev& B, double lambda, double* A, double* aux, int* sflag, int CL) {
     const int tid = threadIdx.x, n = B.n, lane = tid & 31, warp = tid >> 5;
     long long ts = clock64();
 #define SOLVE_TICK(slot)                                          \
@@ -404,7 +526,10 @@ __device__ int phase_solve(const CbDev& B, double lambda, double* A, double* aux
         const bool diag = ij.x == ij.y;
         if (diag && r > c) continue;  // the solver reads the upper triangle (SimplicialLDLT<Upper>)
         double t = 0;
-        for (int u = B.blk_unit_ptr[blk]; u < B.blk_unit_ptr[blk + 1]; u++) t += B.part[36 * (size_t)u + e];
+        if (B.fused)
+            for (int r = 0; r < CL; r++) t += B.part[36 * ((size_t)r * B.nblk + blk) + e];
+        else
+            for (int u = B.blk_unit_ptr[blk]; u < B.blk_unit_ptr[blk + 1]; u++) t += B.part[36 * (size_t)u + e];
         double h = 0;
         if (diag) {
             h = B.Hpp[36 * (size_t)ij.x + e];
@@ -418,7 +543,10 @@ __device__ int phase_solve(const CbDev& B, double lambda, double* A, double* aux
         const int f = k / 6, r = k % 6;
         const int blk = B.diag_blk[f];
         double t = 0;
-        for (int u = B.blk_unit_ptr[blk]; u < B.blk_unit_ptr[blk + 1]; u++) t += B.partb[6 * (size_t)u + r];
+        if (B.fused)
+            for (int rr = 0; rr < CL; rr++) t += B.partb[6 * ((size_t)rr * B.nblk + blk) + r];
+        else
+            for (int u = B.blk_unit_ptr[blk]; u < B.blk_unit_ptr[blk + 1]; u++) t += B.partb[6 * (size_t)u + r];
         A[n * (n + 1) / 2 + k] = B.bp[k] - t;
     }
     __syncthreads();
@@ -698,15 +826,21 @@ __global__ void __launch_bounds__(BS, 1) ba_cluster_kernel(const CbDev* __restri
             BA_TICK(3);
             while (L.cont_trial) {
                 const double lambda = L.lambda;
-                phase_prep(B, rank, lambda, sm_dyn);
-                cluster.sync();
-                BA_TICK(4);
-                phase_gather(B, rank, CL);
-                cluster.sync();
-                BA_TICK(5);
+                if (B.fused) {
+                    phase_prep_gather(B, rank, lambda, sm_dyn);
+                    cluster.sync();
+                    BA_TICK(5);
+                } else {
+                    phase_prep(B, rank, lambda, sm_dyn);
+                    cluster.sync();
+                    BA_TICK(4);
+                    phase_gather(B, rank, CL);
+                    cluster.sync();
+                    BA_TICK(5);
+                }
                 if (rank == 0) {
                     int ok = 1;
-                    if (B.Pf) ok = phase_solve(B, lambda, sm_dyn, aux, &sflag);
+                    if (B.Pf) ok = phase_solve(B, lambda, sm_dyn, aux, &sflag, CL);
                     if (tid == 0) {
                         B.chol_fail[0] = !ok;
                         B.chol_fail[1] = B.stop ? *(volatile const int*)B.stop : 0;
@@ -877,7 +1011,7 @@ int ba_cluster_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* const
         std::vector<std::string> errs(n);
         auto job = [&](int i) {
             uco_b200_ctx tmp;
-            rcs[i] = ba_plan_build(&tmp, *pbs[i], BA_UNIT, plans[i], CL, BS);
+            rcs[i] = ba_plan_build(&tmp, *pbs[i], BA_UNIT, plans[i], CL, BS, NW);
             errs[i] = tmp.err;
         };
         ba_parallel_for(n, ctx->ba_host_threads, job);
@@ -890,7 +1024,7 @@ int ba_cluster_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* const
     // layout: [inputs of all windows | CbDev array | stop flag][work][outputs of all windows]
     struct Off {
         size_t p44, free_idx, free_list, lm_ptr, obs_pose, obs_lm, obs_free, pose_ptr, pose_obs, blk_unit_ptr, blk_ij, diag_blk, unit, con, z, info,
-            stereo, pt_in, cta_lm, cta_chunk_ptr, chunk_lm;
+            stereo, pt_in, cta_lm, cta_chunk_ptr, chunk_lm, gw_ptr, gseg, gcon, wblk;
         size_t pose_bak, pt_bak, err, lmc, Hll, bl, W, Y, Dinv, db, Hpp, bp, part, partb, xp, parts, chol_fail, active;
         size_t pose, p44o, pt, chi2, level_dummy, bad, resd;
     };
@@ -908,13 +1042,15 @@ int ba_cluster_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* const
         o.z = A.take(12 * (size_t)(p.M + 1)); o.info = A.take(4 * (size_t)(p.M + 1)); o.stereo = A.take((size_t)p.M + 1);
         o.pt_in = A.take(12 * (size_t)(p.N + 1));
         o.cta_lm = A.take(4 * p.cta_lm.size()); o.cta_chunk_ptr = A.take(4 * p.cta_chunk_ptr.size()); o.chunk_lm = A.take(4 * p.chunk_lm.size());
+        o.gw_ptr = A.take(4 * (p.gw_ptr.size() + 1)); o.gseg = A.take(16 * (p.gseg.size() + 1)); o.gcon = A.take(4 * (p.gcon.size() + 1));
+        o.wblk = A.take(4 * (p.wblk.size() + 1));
     }
     const size_t o_probs = A.take(sizeof(CbDev) * (size_t)n);
     const size_t in_bytes = A.off;
     for (int i = 0; i < n; i++) {
         const BaPlan& p = plans[i];
         Off& o = off[i];
-        const size_t M1 = p.M + 1, N1 = p.N + 1, F1 = p.Pf + 1, U1 = p.unit.size() + 1;
+        const size_t M1 = p.M + 1, N1 = p.N + 1, F1 = p.Pf + 1, U1 = std::max(p.unit.size(), (size_t)CL * p.blk_ij.size()) + 1;
         o.pose_bak = A.take(56 * (size_t)p.P); o.pt_bak = A.take(24 * N1); o.err = A.take(24 * M1); o.lmc = A.take(72 * M1);
         o.Hll = A.take(48 * N1); o.bl = A.take(24 * N1); o.W = A.take(144 * M1); o.Y = A.take(144 * M1); o.Dinv = A.take(48 * N1);
         o.db = A.take(24 * N1); o.Hpp = A.take(288 * F1); o.bp = A.take(48 * F1); o.part = A.take(288 * U1); o.partb = A.take(48 * U1);
@@ -972,6 +1108,12 @@ int ba_cluster_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* const
         memcpy(h + o.cta_lm, p.cta_lm.data(), 4 * p.cta_lm.size());
         memcpy(h + o.cta_chunk_ptr, p.cta_chunk_ptr.data(), 4 * p.cta_chunk_ptr.size());
         memcpy(h + o.chunk_lm, p.chunk_lm.data(), 4 * p.chunk_lm.size());
+        if (p.fused) {
+            memcpy(h + o.gw_ptr, p.gw_ptr.data(), 4 * p.gw_ptr.size());
+            memcpy(h + o.gseg, p.gseg.data(), 16 * p.gseg.size());
+            memcpy(h + o.gcon, p.gcon.data(), 4 * p.gcon.size());
+            memcpy(h + o.wblk, p.wblk.data(), 4 * p.wblk.size());
+        }
         CbDev& B = hp[i];
         memset(&B, 0, sizeof(B));
         B.P = p.P; B.N = p.N; B.M = p.M; B.Pf = p.Pf; B.n = 6 * p.Pf; B.nblk = (int)p.blk_ij.size(); B.nunits = (int)p.unit.size();
@@ -983,6 +1125,8 @@ int ba_cluster_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* const
         B.unit = (const int4*)(d + o.unit); B.con = (const int2*)(d + o.con); B.z = (const float*)(d + o.z); B.info = (const float*)(d + o.info);
         B.stereo = d + o.stereo; B.pt_in = (const float*)(d + o.pt_in);
         B.cta_lm = (const int*)(d + o.cta_lm); B.cta_chunk_ptr = (const int*)(d + o.cta_chunk_ptr); B.chunk_lm = (const int*)(d + o.chunk_lm);
+        B.fused = p.fused; B.n_chunks = (int)p.chunk_lm.size() - 1;
+        B.gw_ptr = (const int*)(d + o.gw_ptr); B.gseg = (const int4*)(d + o.gseg); B.gcon = (const uint32_t*)(d + o.gcon); B.wblk = (const int*)(d + o.wblk);
         B.pose_bak = (double*)(d + o.pose_bak); B.pt_bak = (double*)(d + o.pt_bak); B.err = (double*)(d + o.err); B.lmc = (double*)(d + o.lmc);
         B.Hll = (double*)(d + o.Hll); B.bl = (double*)(d + o.bl); B.W = (double*)(d + o.W); B.Y = (double*)(d + o.Y);
         B.Dinv = (double*)(d + o.Dinv); B.db = (double*)(d + o.db); B.Hpp = (double*)(d + o.Hpp); B.bp = (double*)(d + o.bp);
@@ -1000,7 +1144,9 @@ int ba_cluster_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* const
     cudaStream_t s = ctx->stream;
     UCO_CUDA(ctx, cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, s));
     UCO_CUDA(ctx, cudaMemsetAsync(d + out_begin, 0, out_bytes, s));
-    const size_t smem = std::max<size_t>(8 * ((size_t)(max_n + 1) * (max_n + 2) / 2), 8 * (size_t)BS * (WPAD + 9));
+    bool any_fused = false;
+    for (int i = 0; i < n; i++) any_fused = any_fused || plans[i].fused;
+    const size_t smem = std::max<size_t>(std::max<size_t>(8 * ((size_t)(max_n + 1) * (max_n + 2) / 2), 8 * (size_t)BS * (WPAD + 9)), any_fused ? 8 * (size_t)PG_DOUBLES : 0);
     UCO_CUDA(ctx, cudaFuncSetAttribute(ba_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (CL > 8) UCO_CUDA(ctx, cudaFuncSetAttribute(ba_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};

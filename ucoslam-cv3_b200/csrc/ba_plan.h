@@ -4,6 +4,7 @@
 // landmark order, cut into units of <= `unit` contributions).  Mirrors what BlockSolver::buildStructure prepares
 // (3rdparty/g2o/g2o/core/block_solver.hpp:103-312) for the graph GlobalOptimizerG2O::setParams assembles.
 #pragma once
+#include <algorithm>
 #include "common.cuh"
 #include "ba_math.cuh"
 #include <vector>
@@ -18,6 +19,7 @@ struct CbResult {
     double phase_cycles[16];
 };
 
+constexpr int BA_GSLOTS = 8;   // blocks a warp owns in the fused prep + gather phase (register accumulators)
 struct CbDev {  // one window as the cluster kernel sees it (device pointers)
     int P, N, M, Pf, n, nblk, nunits, n_iters;
     const float *p44_in, *pt_in, *z, *info;
@@ -26,6 +28,13 @@ struct CbDev {  // one window as the cluster kernel sees it (device pointers)
     const int *cta_lm, *cta_chunk_ptr, *chunk_lm;  // landmark range per CTA, its chunks (whole landmarks, <= CTA-size observations)
     const int2 *blk_ij, *con;
     const int4* unit;
+    // fused prep + Schur gather (windows of <= BA_GSLOTS blocks per warp): per (chunk, warp) the segments (block | slot << 16 | diag << 24,
+    // first entry, one past the last (padded to 4)) and their entries (chunk-local observation a | b << 16; diagonal: a | landmark << 16)
+    int fused, n_chunks;
+    const int* gw_ptr;
+    const int4* gseg;
+    const uint32_t* gcon;
+    const int* wblk;       // [warp * BA_GSLOTS + slot] -> block (or -1)
     double *pose, *pose_bak, *pt, *pt_bak, *err, *chi2, *lmc, *Hll, *bl, *W, *Y, *Dinv, *db, *Hpp, *bp, *part, *partb, *xp, *parts;
     int* chol_fail;  // [0] reduced solve failed in this trial, [1] stop flag as latched by CTA 0
     uint8_t *active, *bad;
@@ -43,6 +52,10 @@ struct BaPlan {
     std::vector<int2> blk_ij, con;
     std::vector<int4> unit;  // (block, first contribution, one past the last, block is diagonal)
     std::vector<int> cta_lm, cta_chunk_ptr, chunk_lm;
+    bool fused = false;                       // fused prep + gather lists instead of con / unit
+    std::vector<int> gw_ptr, wblk;
+    std::vector<int4> gseg;
+    std::vector<uint32_t> gcon;
 };
 
 inline int ba_validate(uco_b200_ctx* ctx, const uco_ba_problem* pb) {
@@ -67,7 +80,9 @@ inline int ba_free_poses(const uco_ba_problem* pb) {
     return f;
 }
 
-inline int ba_plan_build(uco_b200_ctx* ctx, const uco_ba_problem& pb, int unit, BaPlan& p, int n_cta, int cta_threads) {
+// nwarps > 0: the cluster kernel's warp count; windows with <= BA_GSLOTS blocks per warp get the lists of the fused prep + gather phase
+// (per-chunk, per-owner-warp segments over chunk-local indices) INSTEAD of the per-block contribution list `con`
+inline int ba_plan_build(uco_b200_ctx* ctx, const uco_ba_problem& pb, int unit, BaPlan& p, int n_cta, int cta_threads, int nwarps = 0) {
     int rc = ba_validate(ctx, &pb);
     if (rc != UCO_OK) return rc;
     const int P = pb.n_poses, N = pb.n_points, M = pb.n_obs;
@@ -155,9 +170,9 @@ inline int ba_plan_build(uco_b200_ctx* ctx, const uco_ba_problem& pb, int unit, 
             blk_ptr.push_back(padded_total);
         }
     const int nblk = (int)p.blk_ij.size();
-    (void)nblk;
-    p.con.resize(padded_total);
-    {
+    p.fused = nwarps > 0 && nblk <= BA_GSLOTS * nwarps && cta_threads < 65535;
+    p.con.resize(p.fused ? 0 : padded_total);
+    if (!p.fused) {
         int2* con = p.con.data();
         int* ps = pos.data();
         for (int l = 0; l < N; l++) {
@@ -204,6 +219,76 @@ inline int ba_plan_build(uco_b200_ctx* ctx, const uco_ba_problem& pb, int unit, 
             l = e;
         }
         p.cta_chunk_ptr.push_back((int)p.chunk_lm.size() - 1);
+    }
+    p.gw_ptr.clear(); p.gseg.clear(); p.gcon.clear(); p.wblk.clear();
+    if (p.fused) {
+        // block ownership: heaviest block first to the least loaded warp that still has a free slot (same for every CTA)
+        std::vector<int> ord(nblk), load(nwarps, 0), nslot(nwarps, 0), bcnt(nblk), blk_at((size_t)Pf * Pf, -1);
+        for (int k = 0; k < nblk; k++) {
+            ord[k] = k;
+            bcnt[k] = cnt[(size_t)p.blk_ij[k].x * Pf + p.blk_ij[k].y];
+            blk_at[(size_t)p.blk_ij[k].x * Pf + p.blk_ij[k].y] = k;
+        }
+        std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return bcnt[a] > bcnt[b]; });
+        p.wblk.assign((size_t)nwarps * BA_GSLOTS, -1);
+        std::vector<int> slot_of(nblk, 0), owner(nblk, 0);
+        for (int k : ord) {
+            int w = -1;
+            for (int c = 0; c < nwarps; c++)
+                if (nslot[c] < BA_GSLOTS && (w < 0 || load[c] < load[w])) w = c;
+            owner[k] = w; slot_of[k] = nslot[w];
+            p.wblk[(size_t)w * BA_GSLOTS + nslot[w]++] = k;
+            load[w] += bcnt[k] + 8;
+        }
+        const int n_chunks = (int)p.chunk_lm.size() - 1;
+        p.gw_ptr.assign((size_t)n_chunks * nwarps + 1, 0);
+        std::vector<int> cb(nblk), at(nblk);
+        const int* ba = blk_at.data();
+        for (int ch = 0; ch < n_chunks; ch++) {
+            const int l0 = p.chunk_lm[ch], l1 = p.chunk_lm[ch + 1], o0 = p.lm_ptr[l0], nobs = p.lm_ptr[l1] - o0, nl = l1 - l0;
+            std::fill(cb.begin(), cb.end(), 0);
+            for (int l = l0; l < l1; l++) {
+                const int e0 = p.lm_ptr[l], e1 = p.lm_ptr[l + 1];
+                for (int a = e0; a < e1; a++) {
+                    const int fa = sf[a];
+                    if (fa < 0) continue;
+                    cb[ba[(size_t)fa * Pf + fa]]++;
+                    for (int b = a + 1; b < e1; b++) {
+                        const int fb = sf[b];
+                        if (fb < 0 || fb == fa) continue;
+                        cb[ba[fa < fb ? (size_t)fa * Pf + fb : (size_t)fb * Pf + fa]]++;
+                    }
+                }
+            }
+            for (int w = 0; w < nwarps; w++) {
+                p.gw_ptr[(size_t)ch * nwarps + w] = (int)p.gseg.size();
+                for (int sl = 0; sl < BA_GSLOTS; sl++) {
+                    const int k = p.wblk[(size_t)w * BA_GSLOTS + sl];
+                    if (k < 0 || !cb[k]) continue;
+                    const bool dg = p.blk_ij[k].x == p.blk_ij[k].y;
+                    const int st = (int)p.gcon.size(), padded = (cb[k] + 3) & ~3;
+                    at[k] = st;
+                    p.gseg.push_back(make_int4(k | sl << 16 | (dg ? 1 << 24 : 0), st, st + padded, 0));
+                    p.gcon.resize((size_t)st + padded, (uint32_t)nobs | (uint32_t)(dg ? nl : nobs) << 16);   // the padding: all-zero dummy observation / landmark
+                }
+            }
+            for (int l = l0; l < l1; l++) {
+                const int e0 = p.lm_ptr[l], e1 = p.lm_ptr[l + 1];
+                for (int a = e0; a < e1; a++) {
+                    const int fa = sf[a];
+                    if (fa < 0) continue;
+                    p.gcon[at[ba[(size_t)fa * Pf + fa]]++] = (uint32_t)(a - o0) | (uint32_t)(l - l0) << 16;
+                    for (int b = a + 1; b < e1; b++) {
+                        const int fb = sf[b];
+                        if (fb < 0 || fb == fa) continue;
+                        if (fa < fb) p.gcon[at[ba[(size_t)fa * Pf + fb]]++] = (uint32_t)(a - o0) | (uint32_t)(b - o0) << 16;
+                        else p.gcon[at[ba[(size_t)fb * Pf + fa]]++] = (uint32_t)(b - o0) | (uint32_t)(a - o0) << 16;
+                    }
+                }
+            }
+        }
+        p.gw_ptr[(size_t)n_chunks * nwarps] = (int)p.gseg.size();
+        p.gcon.resize(p.gcon.size() + 32, 0u);   // a warp reads 32 entries at a segment's start whatever its length
     }
     return UCO_OK;
 }
