@@ -18,6 +18,7 @@
 // orient_describe.  No host round trip: the selection that the reference does with std::nth_element runs on the
 // device as an exact replay (select_exact.h).
 #include "common.cuh"
+#include <cuda.h>          // CUtensorMap + the cuTensorMapEncodeTiled prototype (resolved at run time through cudaGetDriverEntryPoint: no libcuda link)
 #include "orb_math.h"
 #include "orb_pattern.h"
 #include "select_exact.h"
@@ -677,16 +678,46 @@ __global__ void __launch_bounds__(256) select_kernel(const __grid_constant__ Pla
     }
 }
 
+// ---- TMA: one tiled tensor map per pyramid level over (bordered column, bordered row, frame) ---------------------------------
+struct OrbTmaps {
+    CUtensorMap m[ORB_MAXL];
+};
+#define ORB_WIN_COLS 64   // the box of a keypoint's window: the inner START has to be a multiple of 16 bytes (measured: scripts/microbench/tma_window.cu;
+                          // any other x raises an illegal-instruction fault), so the box starts at x & ~15 and is 15 + 39 <= 64 columns wide
+#define ORB_WIN_ROWS 39
+__device__ __forceinline__ uint32_t orb_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void orb_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(orb_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
 // ---- K5 + K6: intensity-centroid orientation + steered rBRIEF, one warp per keypoint ------------------------------------
-__global__ void __launch_bounds__(256) orient_describe_kernel(const __grid_constant__ PlanDev c_plan, const uint8_t* __restrict__ pyr,
-                                                              const uint32_t* __restrict__ sel,
+template <bool TMA>
+__global__ void __launch_bounds__(256) orient_describe_kernel(const __grid_constant__ PlanDev c_plan, const CUtensorMap* __restrict__ tmaps,
+                                                              const uint8_t* __restrict__ pyr, const uint32_t* __restrict__ sel,
                                                               const int* __restrict__ sel_cnt, uco_keypoint* __restrict__ kps,
                                                               uint8_t* __restrict__ desc, int* __restrict__ n_out,
                                                               int capacity) {
     __shared__ float pat[UCO_ORB_NPTS * 2];
     // the 39 x 39 window around the keypoint (orientation disc radius 15, rotated pattern radius <= 18.4 -> +-19 = EDGE_THRESHOLD),
-    // staged per warp with row-coalesced loads: the 709 disc reads and 512 pattern gathers then hit shared memory, not L1 sectors
-    __shared__ uint8_t patch_all[8][39][40];
+    // staged per warp — by ONE 2-D TMA tile load (cp.async.bulk.tensor: the box is addressed by element coordinates, so the
+    // unaligned window origin costs nothing and no lane computes an address), or by row-coalesced lane loads when the driver cannot
+    // encode tensor maps: the 709 disc reads and 512 pattern gathers then hit shared memory, not L1 sectors
+    __shared__ __align__(128) uint8_t patch_all[8][ORB_WIN_ROWS + 1][ORB_WIN_COLS];   // 2560 B per warp: a multiple of 128
+    __shared__ __align__(8) uint64_t bars[8];
+    if (TMA) {
+        if ((threadIdx.x & 31) == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(orb_smem_u32(&bars[threadIdx.x >> 5])), "r"(1) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
     for (int i = threadIdx.x; i < UCO_ORB_NPTS * 2; i += blockDim.x) pat[(i & 31) * 32 + (i >> 5)] = (float)c_pattern[i];
     __syncthreads();
     const int f = blockIdx.y, lane = threadIdx.x & 31;
@@ -707,22 +738,33 @@ __global__ void __launch_bounds__(256) orient_describe_kernel(const __grid_const
     const uint32_t e = sel[(size_t)f * c_plan.sel_per_frame + L.sel_off + (slot - first)];
     const int x = e & 0xfff, y = (e >> 12) & 0xfff, score = e >> 24;
     const uint8_t* center = pyr + (size_t)f * c_plan.frame_bytes + L.off + (size_t)(y + ORB_E) * L.pitch + x + ORB_E;
-    uint8_t (*patch)[40] = patch_all[threadIdx.x >> 5];
-    {
+    uint8_t (*patch)[ORB_WIN_COLS] = patch_all[threadIdx.x >> 5];
+    const int dx = TMA ? (x & 15) : 0;           // column of the window's first pixel inside the staged rows
+    if (TMA) {
+        uint64_t* bar = &bars[threadIdx.x >> 5];
+        if (lane == 0) {   // box origin in bordered coordinates: (x + ORB_E - 19, y + ORB_E - 19) = (x, y), x rounded down to 16
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(orb_smem_u32(bar)), "r"(ORB_WIN_COLS * ORB_WIN_ROWS) : "memory");
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                             orb_smem_u32(&patch[0][0])),
+                         "l"(tmaps + level), "r"(x & ~15), "r"(y), "r"(f), "r"(orb_smem_u32(bar))
+                         : "memory");
+        }
+        orb_mbar_wait(bar, 0);
+    } else {
         const uint8_t* p = center - 19 * L.pitch - 19;
 #pragma unroll 3
         for (int r = 0; r < 39; r++, p += L.pitch) {
             patch[r][lane] = p[lane];
             if (lane < 7) patch[r][32 + lane] = p[32 + lane];
         }
+        __syncwarp();
     }
-    __syncwarp();
     // IC_Angle: lane v+15 sums image row v of the radius-15 disc
     int m10 = 0, m01 = 0;
     if (lane < 31) {
         const int v = lane - 15;
         const int d = c_umax[v < 0 ? -v : v];
-        const uint8_t* row = &patch[19 + v][19];
+        const uint8_t* row = &patch[19 + v][19 + dx];
         int su = 0, s1 = 0;
         for (int u = -d; u <= d; u++) {
             int val = row[u];
@@ -748,7 +790,7 @@ __global__ void __launch_bounds__(256) orient_describe_kernel(const __grid_const
         int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
         int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
         int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-        int t0 = patch[19 + r0][19 + c0], t1 = patch[19 + r1][19 + c1];
+        int t0 = patch[19 + r0][19 + dx + c0], t1 = patch[19 + r1][19 + dx + c1];
         byte |= (unsigned)(t0 < t1) << t;
     }
     const size_t o = (size_t)f * capacity + slot;
@@ -783,6 +825,9 @@ struct uco_orb_state {
     std::vector<CellDev> cells;
     int max_cell_smem = 0;
     uint8_t* d_pyr = nullptr;
+    OrbTmaps tmaps{};              // per-level tensor maps over d_pyr (orient_describe stages keypoint windows with them)
+    CUtensorMap* d_tmaps = nullptr; // ... in global memory: the kernel indexes them by level
+    bool use_tma = false;
     uint8_t* d_in = nullptr;       // staging for host images
     size_t in_pitch = 0;
     CellDev* d_cells = nullptr;
@@ -804,7 +849,7 @@ struct uco_orb_state {
 };
 
 static void orb_free_buffers(uco_orb_state* s) {
-    cudaFree(s->d_pyr); cudaFree(s->d_in); cudaFree(s->d_cells); cudaFree(s->d_tab_ofs); cudaFree(s->d_tab_coef);
+    cudaFree(s->d_pyr); cudaFree(s->d_tmaps); cudaFree(s->d_in); cudaFree(s->d_cells); cudaFree(s->d_tab_ofs); cudaFree(s->d_tab_coef);
     cudaFree(s->d_cand); cudaFree(s->d_cand_cnt); cudaFree(s->d_sel); cudaFree(s->d_sel_cnt); cudaFree(s->d_err);
     cudaFree(s->d_kps); cudaFree(s->d_desc); cudaFree(s->d_nout);
     if (s->h_nout) cudaFreeHost(s->h_nout);
@@ -812,7 +857,7 @@ static void orb_free_buffers(uco_orb_state* s) {
     for (auto& e : s->ev)
         if (e) { cudaEventDestroy(e); e = nullptr; }
     s->ev_valid = false;
-    s->d_pyr = s->d_in = nullptr; s->d_cells = nullptr; s->d_tab_ofs = nullptr; s->d_tab_coef = nullptr;
+    s->d_tmaps = nullptr; s->d_pyr = s->d_in = nullptr; s->d_cells = nullptr; s->d_tab_ofs = nullptr; s->d_tab_coef = nullptr;
     s->d_cand = nullptr; s->d_cand_cnt = nullptr; s->d_sel = nullptr; s->d_sel_cnt = nullptr; s->d_err = nullptr;
     s->d_kps = nullptr; s->d_desc = nullptr; s->d_nout = nullptr; s->h_nout = nullptr; s->h_err = nullptr;
 }
@@ -988,6 +1033,26 @@ static int orb_prepare(uco_b200_ctx* ctx, int w, int h, const uco_orb_params* pr
     const int B = std::max(batch, 1);
     s->in_pitch = (size_t)((w + 255) & ~255);
     UCO_CUDA(ctx, cudaMalloc(&s->d_pyr, (size_t)P.frame_bytes * B));
+    {   // tensor maps: level l as a (pitch, h + 2 * ORB_E, frames) u8 tensor inside the pyramid blocks, box = one keypoint window
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        s->use_tma = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn && qres == cudaDriverEntryPointSuccess &&
+                     P.frame_bytes % 16 == 0 && !getenv("UCO_ORB_NO_TMA");
+        for (int l = 0; s->use_tma && l < P.n_levels; l++) {
+            const LevelDev& L = P.lv[l];
+            const cuuint64_t dims[3] = {(cuuint64_t)L.pitch, (cuuint64_t)(L.h + 2 * ORB_E), (cuuint64_t)B};
+            const cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)P.frame_bytes};
+            const cuuint32_t box[3] = {ORB_WIN_COLS, ORB_WIN_ROWS, 1}, estr[3] = {1, 1, 1};
+            if (L.off % 16 || L.pitch % 16 ||
+                ((EncodeFn)fn)(&s->tmaps.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, s->d_pyr + L.off, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                s->use_tma = false;
+        }
+        UCO_CUDA(ctx, cudaMalloc(&s->d_tmaps, sizeof(OrbTmaps)));
+        UCO_CUDA(ctx, cudaMemcpy(s->d_tmaps, &s->tmaps, sizeof(OrbTmaps), cudaMemcpyHostToDevice));
+    }
     UCO_CUDA(ctx, cudaMalloc(&s->d_in, s->in_pitch * h * B));
     UCO_CUDA(ctx, cudaMalloc(&s->d_cells, sizeof(CellDev) * s->cells.size()));
     UCO_CUDA(ctx, cudaMalloc(&s->d_tab_ofs, sizeof(int) * std::max<size_t>(tab_ofs.size(), 1)));
@@ -1072,8 +1137,12 @@ static int orb_run_dev(uco_b200_ctx* ctx, const uint8_t* in_dev, size_t in_pitch
     select_kernel<<<dim3(P.n_levels, n), 256, sel_smem, st>>>(P, s->d_cells, s->d_cand, s->d_cand_cnt, s->d_sel, s->d_sel_cnt, s->d_err, cand_budget, sel_entries);
     UCO_LAUNCH_CHECK(ctx);
     if (prof) cudaEventRecord(s->ev[4], st);
-    orient_describe_kernel<<<dim3((P.max_features + 7) / 8, n), 256, 0, st>>>(P, s->d_pyr, s->d_sel, s->d_sel_cnt, kps_dev,
-                                                                            desc_dev, nout_dev, P.max_features);
+    if (s->use_tma)
+        orient_describe_kernel<true><<<dim3((P.max_features + 7) / 8, n), 256, 0, st>>>(P, s->d_tmaps, s->d_pyr, s->d_sel, s->d_sel_cnt, kps_dev,
+                                                                                      desc_dev, nout_dev, P.max_features);
+    else
+        orient_describe_kernel<false><<<dim3((P.max_features + 7) / 8, n), 256, 0, st>>>(P, s->d_tmaps, s->d_pyr, s->d_sel, s->d_sel_cnt, kps_dev,
+                                                                                       desc_dev, nout_dev, P.max_features);
     UCO_LAUNCH_CHECK(ctx);
     if (prof) {
         cudaEventRecord(s->ev[5], st);
