@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=128, help="frames per step per GPU")
+    ap.add_argument("--profile-step", action="store_true", help="after the warm-up run ONE step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra sections (720p, single-frame latency, ATE, collective paths)")
     ap.add_argument("--res", default="640x480", choices=["640x480", "1280x720"],
@@ -493,6 +494,32 @@ def run_b200(args, rank, world, local_rank):
             barrier()
             return sum(a.elapsed_time(b) for a, b in evs) / reps
 
+    evs = {}
+
+    def finish():
+        nonlocal stream, stream2, flush, wk, wk2
+        # orderly teardown (the driver's exit hook records the loaded libraries, so the interpreter must exit normally): every torch
+        # object that refers to the tracker context's stream goes first, then the mapper pool, then the contexts, then the process group
+        mapper.shutdown(wait=True)
+        trackers.shutdown(wait=True)
+        wk2.close()
+        wk.close()
+        ctx.bow_free(voc)
+        evs.clear()
+        stream = stream2 = flush = wk = wk2 = None
+        gc.collect()
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()       # the caching allocators record events on the streams their blocks were used on: drop the blocks
+        if hasattr(torch._C, "_host_emptyCache"):
+            torch._C._host_emptyCache()
+        for c in ctx_bas:
+            c.close()
+        ctx2.close()
+        ctx.close()
+        shard.finalize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+
     # warm-up (also builds the extractor plan and every workspace), sanity: every frame yields the full keypoint budget and tracks
     for m in range(N_MAPPERS):     # every mapper context allocates its arenas / pinned buffers on its first batch: do that here
         ba_all(m)
@@ -508,6 +535,17 @@ def run_b200(args, rank, world, local_rank):
     assert (good > 300).all() and (wk.stat_dev.cpu().numpy() == 0).all(), "every synthetic frame must track: inliers %s" % good[:8]
     pose_err = float(np.abs(wk.pose_dev.cpu().numpy().reshape(F, 4, 4) - wk.gt.astype(np.float32)).max())
 
+    if args.profile_step:      # ncu --profile-from-start off: one step of every stage (tracker stream + one BA batch), nothing else
+        torch.cuda.cudart().cudaProfilerStart()
+        with torch.cuda.stream(stream):
+            wk.step_dev()
+        ba_all(0)
+        barrier()
+        torch.cuda.cudart().cudaProfilerStop()
+        if rank == 0:
+            print(json.dumps({"profile_step": True, "frames": F, "ba_windows": n_ba}))
+        finish()
+        return
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -517,6 +555,7 @@ def run_b200(args, rank, world, local_rank):
     # returned its results to the host), barrier + synchronize on both sides, L2 flushed between steps inside the region
     barrier()
     ev_a, ev_b, ev_j = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event()
+    evs.update(a=ev_a, b=ev_b, j=ev_j)
     ev_a.record(stream)
     stream2.wait_event(ev_a)                 # the second tracker stream starts inside the region ...
     run_two_streams(args.steps)
@@ -526,6 +565,7 @@ def run_b200(args, rank, world, local_rank):
     barrier()
     ctx2.sync()
     ms_dev = reduce_max(ev_a.elapsed_time(ev_b))
+    del ev_a, ev_b, ev_j
     launches = (count() - n0) // max(1, args.steps)
 
     run_e2e(max(2, args.warmup))
@@ -595,7 +635,7 @@ def run_b200(args, rank, world, local_rank):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     traffic = {}
     tp = os.path.join(ROOT, "profiles", "r2_traffic.json")
-    if os.path.exists(tp) and F == 64 and W == 640:
+    if os.path.exists(tp) and F == 128 and W == 640:
         traffic = json.load(open(tp)).get("kernels", {})
 
     def traffic_of(kernel):
@@ -688,27 +728,7 @@ def run_b200(args, rank, world, local_rank):
         print(json.dumps(line))
         sys.stdout.flush()
     barrier()
-    # orderly teardown (the driver's exit hook records the loaded libraries, so the interpreter must exit normally): every torch
-    # object that refers to the tracker context's stream goes first, then the mapper pool, then the contexts, then the process group
-    mapper.shutdown(wait=True)
-    trackers.shutdown(wait=True)
-    wk2.close()
-    del wk2
-    wk.close()
-    ctx.bow_free(voc)
-    del stream, stream2, flush, ev_a, ev_b, ev_j, wk
-    gc.collect()
-    torch.cuda.synchronize()
-    torch.cuda.empty_cache()       # the caching allocators record events on the streams their blocks were used on: drop the blocks
-    if hasattr(torch._C, "_host_emptyCache"):
-        torch._C._host_emptyCache()
-    for c in ctx_bas:
-        c.close()
-    ctx2.close()
-    ctx.close()
-    shard.finalize()
-    sys.stdout.flush()
-    sys.stderr.flush()
+    finish()
 
 
 def run_extras(args, rank, world, local_rank, ctx, stream, wk, Work, flush, barrier, reduce_max, run_pipelined, timed_events, voc):
