@@ -300,7 +300,8 @@ int uco_b200_ba_set_mode(uco_b200_ctx* ctx, int mode, int cluster_size);
  * cores).  A caller that keeps several batches in flight from several mapper threads wants 1; a single caller wants the default. */
 int uco_b200_ba_set_host_threads(uco_b200_ctx* ctx, int n_threads);
 /* host-only inspection hook (no GPU needed): builds the window structure the solver uses and reports
- * {free poses, Schur blocks, gather units, contributions, chunks, pose-list entries, max observations per chunk, landmarks covered} */
+ * {free poses, Schur blocks, gather units, contributions, chunks, pose-list entries, max observations per chunk, landmarks covered}.
+ * cluster_size >= 1000: the plan the cluster-resident kernel gets for a cluster of (cluster_size - 1000) CTAs (fused lists for small windows) */
 int uco_b200_probe_ba_plan(const uco_ba_problem* pb, int cluster_size, int* out8);
 
 /* ------------------------------------------------------------------------------------------------------------

@@ -1628,7 +1628,9 @@ extern "C" {
 int uco_b200_probe_ba_plan(const uco_ba_problem* pb, int cluster_size, int* out8) {
     uco_b200_ctx tmp;
     BaPlan p;
-    int rc = ba_plan_build(&tmp, *pb, BA_UNIT, p, cluster_size > 0 ? cluster_size : 8, 512);
+    const bool as_cluster = cluster_size >= 1000;   // 1000 + c: exactly the plan the cluster kernel gets (16 warps: fused prep + gather lists for small windows)
+    if (as_cluster) cluster_size -= 1000;
+    int rc = ba_plan_build(&tmp, *pb, BA_UNIT, p, cluster_size > 0 ? cluster_size : 8, 512, as_cluster ? 16 : 0);
     if (rc != UCO_OK) return rc;
     if (out8) {
         out8[0] = p.Pf; out8[1] = (int)p.blk_ij.size(); out8[2] = (int)p.unit.size(); out8[3] = p.ncon;

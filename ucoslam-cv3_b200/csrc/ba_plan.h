@@ -128,20 +128,55 @@ inline int ba_plan_build(uco_b200_ctx* ctx, const uco_ba_problem& pb, int unit, 
     // contributions sorted by landmark: Y comes from the lower-indexed pose (the block row), W from the higher one.
     p.s_free.resize(M);
     for (int k = 0; k < M; k++) p.s_free[k] = p.free_idx[p.s_pose[k]];
+    // landmark ranges per CTA (balanced by observation count), cut into chunks of whole landmarks
+    p.cta_lm.assign(n_cta + 1, N);
+    p.cta_lm[0] = 0;
+    {
+        int l = 0;
+        for (int c = 1; c < n_cta; c++) {
+            const long long target = (long long)M * c / n_cta;
+            while (l < N && p.lm_ptr[l] < target) l++;
+            p.cta_lm[c] = l;
+        }
+    }
+    p.chunk_lm.assign(1, 0);
+    p.cta_chunk_ptr.assign(1, 0);
+    for (int c = 0; c < n_cta; c++) {
+        int l = p.cta_lm[c];
+        while (l < p.cta_lm[c + 1]) {
+            int e = l;
+            while (e < p.cta_lm[c + 1] && e - l < cta_threads && p.lm_ptr[e + 1] - p.lm_ptr[l] <= cta_threads) e++;
+            if (e == l) return uco_fail(ctx, UCO_E_INVALID, "ba_solve: landmark %d has %d observations (> %d per chunk)", l, p.lm_ptr[l + 1] - p.lm_ptr[l], cta_threads);
+            p.chunk_lm.push_back(e);
+            l = e;
+        }
+        p.cta_chunk_ptr.push_back((int)p.chunk_lm.size() - 1);
+    }
     std::vector<int> cnt((size_t)Pf * Pf, 0);
     const int* sf = p.s_free.data();
-    for (int l = 0; l < N; l++) {
-        const int e0 = p.lm_ptr[l], e1 = p.lm_ptr[l + 1];
-        for (int a = e0; a < e1; a++) {
-            const int fa = sf[a];
-            if (fa < 0) continue;
-            cnt[(size_t)fa * Pf + fa]++;
-            for (int b = a + 1; b < e1; b++) {
-                const int fb = sf[b];
-                if (fb < 0 || fb == fa) continue;
-                cnt[fa < fb ? (size_t)fa * Pf + fb : (size_t)fb * Pf + fa]++;
+    // When the fused lists may be built (at most BA_GSLOTS blocks per warp even if every pose pair is covisible) the contributions are
+    // counted per (chunk, pose pair) in ONE pass: the sums give the blocks, the per-chunk counts the segment sizes of the fused lists.
+    const int n_chunks_all = (int)p.chunk_lm.size() - 1;
+    const bool may_fuse = nwarps > 0 && Pf * (Pf + 1) / 2 <= BA_GSLOTS * nwarps && cta_threads < 65535;
+    std::vector<int> ccnt(may_fuse ? (size_t)n_chunks_all * Pf * Pf : 0, 0);
+    for (int ch = 0; ch < (may_fuse ? n_chunks_all : 1); ch++) {
+        int* cc = may_fuse ? ccnt.data() + (size_t)ch * Pf * Pf : cnt.data();
+        const int lb = may_fuse ? p.chunk_lm[ch] : 0, le = may_fuse ? p.chunk_lm[ch + 1] : N;
+        for (int l = lb; l < le; l++) {
+            const int e0 = p.lm_ptr[l], e1 = p.lm_ptr[l + 1];
+            for (int a = e0; a < e1; a++) {
+                const int fa = sf[a];
+                if (fa < 0) continue;
+                cc[(size_t)fa * Pf + fa]++;
+                for (int b = a + 1; b < e1; b++) {
+                    const int fb = sf[b];
+                    if (fb < 0 || fb == fa) continue;
+                    cc[fa < fb ? (size_t)fa * Pf + fb : (size_t)fb * Pf + fa]++;
+                }
             }
         }
+        if (may_fuse)
+            for (int k = 0; k < Pf * Pf; k++) cnt[k] += cc[k];
     }
     // Blocks in (i, j >= i) order.  A block's contributions are written straight into the PADDED layout the gather kernel reads:
     // units of <= `unit` contributions (unit is a multiple of four), the last unit of a block padded to a multiple of four with the
@@ -170,7 +205,7 @@ inline int ba_plan_build(uco_b200_ctx* ctx, const uco_ba_problem& pb, int unit, 
             blk_ptr.push_back(padded_total);
         }
     const int nblk = (int)p.blk_ij.size();
-    p.fused = nwarps > 0 && nblk <= BA_GSLOTS * nwarps && cta_threads < 65535;
+    p.fused = may_fuse;   // nblk <= Pf (Pf + 1) / 2 <= BA_GSLOTS * nwarps
     p.con.resize(p.fused ? 0 : padded_total);
     if (!p.fused) {
         int2* con = p.con.data();
@@ -196,30 +231,6 @@ inline int ba_plan_build(uco_b200_ctx* ctx, const uco_ba_problem& pb, int unit, 
         }
     }
     p.ncon = ncon;
-    // landmark ranges per CTA (balanced by observation count), cut into chunks of whole landmarks
-    p.cta_lm.assign(n_cta + 1, N);
-    p.cta_lm[0] = 0;
-    {
-        int l = 0;
-        for (int c = 1; c < n_cta; c++) {
-            const long long target = (long long)M * c / n_cta;
-            while (l < N && p.lm_ptr[l] < target) l++;
-            p.cta_lm[c] = l;
-        }
-    }
-    p.chunk_lm.assign(1, 0);
-    p.cta_chunk_ptr.assign(1, 0);
-    for (int c = 0; c < n_cta; c++) {
-        int l = p.cta_lm[c];
-        while (l < p.cta_lm[c + 1]) {
-            int e = l;
-            while (e < p.cta_lm[c + 1] && e - l < cta_threads && p.lm_ptr[e + 1] - p.lm_ptr[l] <= cta_threads) e++;
-            if (e == l) return uco_fail(ctx, UCO_E_INVALID, "ba_solve: landmark %d has %d observations (> %d per chunk)", l, p.lm_ptr[l + 1] - p.lm_ptr[l], cta_threads);
-            p.chunk_lm.push_back(e);
-            l = e;
-        }
-        p.cta_chunk_ptr.push_back((int)p.chunk_lm.size() - 1);
-    }
     p.gw_ptr.clear(); p.gseg.clear(); p.gcon.clear(); p.wblk.clear();
     if (p.fused) {
         // block ownership: heaviest block first to the least loaded warp that still has a free slot (same for every CTA)
@@ -246,20 +257,7 @@ inline int ba_plan_build(uco_b200_ctx* ctx, const uco_ba_problem& pb, int unit, 
         const int* ba = blk_at.data();
         for (int ch = 0; ch < n_chunks; ch++) {
             const int l0 = p.chunk_lm[ch], l1 = p.chunk_lm[ch + 1], o0 = p.lm_ptr[l0], nobs = p.lm_ptr[l1] - o0, nl = l1 - l0;
-            std::fill(cb.begin(), cb.end(), 0);
-            for (int l = l0; l < l1; l++) {
-                const int e0 = p.lm_ptr[l], e1 = p.lm_ptr[l + 1];
-                for (int a = e0; a < e1; a++) {
-                    const int fa = sf[a];
-                    if (fa < 0) continue;
-                    cb[ba[(size_t)fa * Pf + fa]]++;
-                    for (int b = a + 1; b < e1; b++) {
-                        const int fb = sf[b];
-                        if (fb < 0 || fb == fa) continue;
-                        cb[ba[fa < fb ? (size_t)fa * Pf + fb : (size_t)fb * Pf + fa]]++;
-                    }
-                }
-            }
+            for (int k = 0; k < nblk; k++) cb[k] = ccnt[(size_t)ch * Pf * Pf + (size_t)p.blk_ij[k].x * Pf + p.blk_ij[k].y];
             for (int w = 0; w < nwarps; w++) {
                 p.gw_ptr[(size_t)ch * nwarps + w] = (int)p.gseg.size();
                 for (int sl = 0; sl < BA_GSLOTS; sl++) {

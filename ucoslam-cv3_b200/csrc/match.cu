@@ -736,7 +736,8 @@ int uco_b200_keyframes_batch(uco_b200_ctx* ctx, const uco_b200_voc* voc, int bow
     int* herr = (int*)uco_pinned(ctx, WS_GENERIC0, 16);
     if (!herr) return UCO_E_NOMEM;
     UCO_CUDA(ctx, cudaMemcpyAsync(herr, ctx->kf_err_dev, 4, cudaMemcpyDeviceToHost, st));
-    UCO_CUDA(ctx, cudaStreamSynchronize(st));
+    if (n_pairs >= 16) UCO_CUDA(ctx, uco_sleep_sync(ctx));   // milliseconds of work: sleep instead of spinning (see uco_track_check_errors)
+    else UCO_CUDA(ctx, cudaStreamSynchronize(st));
     if (*herr) return uco_fail(ctx, UCO_E_FORMAT, "keyframes_batch: malformed vocabulary (cycle or block index out of range)");
     if (voc) { memcpy(word, ho + o_w, 4 * K); memcpy(weight, ho + o_wt, 4 * K); memcpy(node, ho + o_n, 4 * K); }
     for (int e = 0; e < n_pairs; e++) {

@@ -461,11 +461,14 @@ void fill_params(TrackDev& D, const uco_track_params* p) {
 int node_cap_for(int kp_cap) { return 2 * (kp_cap / 5) + 2; }
 
 // after the launches of a track_batch_dev(NO_SYNC) call: wait and turn the device error words into a status
-int uco_track_check_errors(uco_b200_ctx* ctx) {
+// long_wait: the stream holds milliseconds of work (a batch of frames): the calling thread sleeps on an event instead of spinning, so
+// that the tracker threads of several processes per host (one per GPU) do not burn the cores the mappers' planners need
+int uco_track_check_errors(uco_b200_ctx* ctx, bool long_wait = false) {
     int32_t* herr = (int32_t*)uco_pinned(ctx, WS_TRACK_ERR, 16);
     if (!herr || !ctx->track_err_dev) return UCO_E_NOMEM;
     UCO_CUDA(ctx, cudaMemcpyAsync(herr, ctx->track_err_dev, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    UCO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (long_wait) UCO_CUDA(ctx, uco_sleep_sync(ctx));
+    else UCO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (herr[1]) return uco_fail(ctx, UCO_E_CAPACITY, "track_batch: kd-tree build failed (code %d)", herr[1]);
     if (herr[0]) return uco_fail(ctx, UCO_E_CAPACITY, "track_batch: a kd-tree is deeper than the %d deferred branches the device walk keeps", KD_STACK);
     return UCO_OK;
@@ -846,7 +849,7 @@ int uco_b200_track_frames(uco_b200_ctx* ctx, const uco_b200_track_state* st, con
     UCO_CUDA(ctx, cudaMemcpyAsync(ho + o_oerr, d_oerr, 4, cudaMemcpyDeviceToHost, s));
     if (kps) UCO_CUDA(ctx, cudaMemcpyAsync(kps_direct ? (void*)kps : (void*)(ho + o_kps), d_kps, sizeof(uco_keypoint) * K, cudaMemcpyDeviceToHost, s));
     if (desc) UCO_CUDA(ctx, cudaMemcpyAsync(desc_direct ? (void*)desc : (void*)(ho + o_desc), d_desc, 32 * K, cudaMemcpyDeviceToHost, s));
-    rc = uco_track_check_errors(ctx);
+    rc = uco_track_check_errors(ctx, F >= 16);
     if (rc != UCO_OK) return rc;
     if (*(int*)(ho + o_oerr)) return uco_fail(ctx, UCO_E_CAPACITY, "track_frames: the extractor's internal selection list overflowed");
     memcpy(out->n_matches, ho + o_nm, 4 * (size_t)F); memcpy(out->pose, ho + o_pose, 64 * (size_t)F); memcpy(out->n_good, ho + o_good, 4 * (size_t)F);
