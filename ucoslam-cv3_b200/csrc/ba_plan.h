@@ -159,19 +159,28 @@ inline int ba_plan_build(uco_b200_ctx* ctx, const uco_ba_problem& pb, int unit, 
     const int n_chunks_all = (int)p.chunk_lm.size() - 1;
     const bool may_fuse = nwarps > 0 && Pf * (Pf + 1) / 2 <= BA_GSLOTS * nwarps && cta_threads < 65535;
     std::vector<int> ccnt(may_fuse ? (size_t)n_chunks_all * Pf * Pf : 0, 0);
+    // free observations in landmark order, compacted (fixed-pose observations contribute nothing): position -> sorted observation, free pose
+    std::vector<int> fo_ptr(N + 1, 0), fo_obs, fo_free;
+    fo_obs.reserve(M); fo_free.reserve(M);
+    for (int l = 0; l < N; l++) {
+        for (int a = p.lm_ptr[l]; a < p.lm_ptr[l + 1]; a++)
+            if (sf[a] >= 0) { fo_obs.push_back(a); fo_free.push_back(sf[a]); }
+        fo_ptr[l + 1] = (int)fo_obs.size();
+    }
+    const int* fof = fo_free.data();
     for (int ch = 0; ch < (may_fuse ? n_chunks_all : 1); ch++) {
         int* cc = may_fuse ? ccnt.data() + (size_t)ch * Pf * Pf : cnt.data();
         const int lb = may_fuse ? p.chunk_lm[ch] : 0, le = may_fuse ? p.chunk_lm[ch + 1] : N;
         for (int l = lb; l < le; l++) {
-            const int e0 = p.lm_ptr[l], e1 = p.lm_ptr[l + 1];
+            const int e0 = fo_ptr[l], e1 = fo_ptr[l + 1];
             for (int a = e0; a < e1; a++) {
-                const int fa = sf[a];
-                if (fa < 0) continue;
-                cc[(size_t)fa * Pf + fa]++;
+                const int fa = fof[a];
+                cc[fa * Pf + fa]++;
                 for (int b = a + 1; b < e1; b++) {
-                    const int fb = sf[b];
-                    if (fb < 0 || fb == fa) continue;
-                    cc[fa < fb ? (size_t)fa * Pf + fb : (size_t)fb * Pf + fa]++;
+                    const int fb = fof[b];
+                    if (fb == fa) continue;                       // a pose listed twice for a landmark: never in a valid map
+                    const int lo = fa < fb ? fa : fb, hi = fa < fb ? fb : fa;
+                    cc[lo * Pf + hi]++;
                 }
             }
         }
@@ -253,6 +262,8 @@ inline int ba_plan_build(uco_b200_ctx* ctx, const uco_ba_problem& pb, int unit, 
         }
         const int n_chunks = (int)p.chunk_lm.size() - 1;
         p.gw_ptr.assign((size_t)n_chunks * nwarps + 1, 0);
+        p.gseg.reserve((size_t)n_chunks * nblk);
+        p.gcon.reserve((size_t)ncon + 4 * (size_t)n_chunks * nblk + 32);
         std::vector<int> cb(nblk), at(nblk);
         const int* ba = blk_at.data();
         for (int ch = 0; ch < n_chunks; ch++) {
@@ -270,17 +281,20 @@ inline int ba_plan_build(uco_b200_ctx* ctx, const uco_ba_problem& pb, int unit, 
                     p.gcon.resize((size_t)st + padded, (uint32_t)nobs | (uint32_t)(dg ? nl : nobs) << 16);   // the padding: all-zero dummy observation / landmark
                 }
             }
+            uint32_t* gc = p.gcon.data();
             for (int l = l0; l < l1; l++) {
-                const int e0 = p.lm_ptr[l], e1 = p.lm_ptr[l + 1];
+                const int e0 = fo_ptr[l], e1 = fo_ptr[l + 1];
+                const uint32_t ll = (uint32_t)(l - l0) << 16;
                 for (int a = e0; a < e1; a++) {
-                    const int fa = sf[a];
-                    if (fa < 0) continue;
-                    p.gcon[at[ba[(size_t)fa * Pf + fa]]++] = (uint32_t)(a - o0) | (uint32_t)(l - l0) << 16;
+                    const int fa = fof[a];
+                    const uint32_t oa = (uint32_t)(fo_obs[a] - o0);
+                    gc[at[ba[fa * Pf + fa]]++] = oa | ll;
                     for (int b = a + 1; b < e1; b++) {
-                        const int fb = sf[b];
-                        if (fb < 0 || fb == fa) continue;
-                        if (fa < fb) p.gcon[at[ba[(size_t)fa * Pf + fb]]++] = (uint32_t)(a - o0) | (uint32_t)(b - o0) << 16;
-                        else p.gcon[at[ba[(size_t)fb * Pf + fa]]++] = (uint32_t)(b - o0) | (uint32_t)(a - o0) << 16;
+                        const int fb = fof[b];
+                        if (fb == fa) continue;
+                        const uint32_t ob = (uint32_t)(fo_obs[b] - o0);
+                        if (fa < fb) gc[at[ba[fa * Pf + fb]]++] = oa | ob << 16;
+                        else gc[at[ba[fb * Pf + fa]]++] = ob | oa << 16;
                     }
                 }
             }
