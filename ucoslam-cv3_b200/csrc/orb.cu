@@ -192,6 +192,170 @@ __global__ void __launch_bounds__(256) resize_cubic_kernel(const __grid_constant
     }
 }
 
+// ---- K1 / K2, strip forms (the ones launched; the per-pixel forms above stay as the A/B reference under UCO_ORB_PYRAMID_V1=1) ---------
+// Both kernels treat the BORDERED level (w + 38 columns) as their output domain: destination word kd holds columns 4kd..4kd+3 of the
+// bordered buffer = level pixels reflect101(4kd - 19 + j).  For the blur that is exact because the filter is symmetric and its own
+// border rule is the same reflection (blur of the reflected extension at -x = blur at x, the same products in another order, integer
+// adds); for the resize the coefficient tables are simply read at the reflected pixel.  So the left / right borders cost no special
+// stores, every store is one aligned 32-bit word, and the top / bottom borders are the same word stored a second time.
+__device__ __forceinline__ void store_word_rows(uint8_t* dst, int pitch, int h, int y, uint32_t word) {  // dst: column already applied, row 0 of the bordered buffer
+    *(uint32_t*)(dst + (size_t)(y + ORB_E) * pitch) = word;
+    if (y >= 1 && y <= ORB_E) *(uint32_t*)(dst + (size_t)(ORB_E - y) * pitch) = word;
+    if (y <= h - 2 && y >= h - 1 - ORB_E) *(uint32_t*)(dst + (size_t)(2 * (h - 1) - y + ORB_E) * pitch) = word;
+}
+
+// Blur: a thread owns one destination word (4 pixels) and walks down BS_R rows.  Per input row it reads three aligned words of the
+// staged tile (10 of their 12 bytes are the taps of its 4 pixels), runs the horizontal filter on packed u16x2 pairs (a lane never
+// exceeds 256 * 255, so one IMAD serves two pixels) and keeps the last 7 rows of horizontal results in registers (the window rotates
+// by unrolling 7 steps); the vertical filter reads that window.  The tile is staged once per CTA: interior words are copied as words,
+// the reflected edge bytes (and every byte of an unaligned source) one by one.
+#define BS_R 29                      // output rows per CTA
+#define BS_STEPS (BS_R + 6)          // input rows per CTA = 5 x 7
+#define BS_MAXW 256                  // destination words per CTA, at most
+template <bool DO_BLUR>
+__global__ void __launch_bounds__(256) blur7_strip_kernel(const __grid_constant__ PlanDev c_plan, const uint8_t* __restrict__ in, size_t in_pitch, size_t in_frame,
+                                                          uint8_t* __restrict__ pyr, int wpt, int aligned) {
+    const LevelDev& L = c_plan.lv[0];
+    const int w = L.w, h = L.h;
+    const int nwords = (w + 2 * ORB_E + 3) >> 2;
+    const int k0 = blockIdx.x * wpt, nk = min(wpt, nwords - k0);
+    const int y0 = blockIdx.y * BS_R;
+    const int spw = wpt + 2;
+    __shared__ uint32_t tile[BS_STEPS * (BS_MAXW + 2)];
+    const uint8_t* src = in + (size_t)blockIdx.z * in_frame;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int vb0 = 4 * (k0 - 6);                                        // level pixel (virtual: before reflection) of byte 0 of a tile row
+    int s_lo = nk + 2, s_hi = nk + 2;                                    // slots [s_lo, s_hi) are whole words inside the image
+    if (aligned) {
+        s_lo = min(max(0, 6 - k0), nk + 2);
+        s_hi = max(s_lo, min(nk + 2, ((w - 4 - vb0) >> 2) + 1));
+    }
+    const int n_left = 4 * s_lo, n_edge = n_left + 4 * (nk + 2 - s_hi);
+    for (int r = warp; r < BS_STEPS; r += nwarps) {
+        const uint8_t* row = src + (size_t)reflect101(y0 - 3 + r, h) * in_pitch;
+        uint32_t* trow = tile + r * spw;
+        for (int s = s_lo + lane; s < s_hi; s += 32) trow[s] = *(const uint32_t*)(row + vb0 + 4 * s);
+        for (int e = lane; e < n_edge; e += 32) {
+            const int bi = e < n_left ? e : 4 * s_hi + (e - n_left);
+            ((uint8_t*)trow)[bi] = row[reflect101(vb0 + bi, w)];
+        }
+    }
+    __syncthreads();
+    if (tid >= nk) return;
+    uint8_t* dst = pyr + (size_t)blockIdx.z * c_plan.frame_bytes + L.off + 4 * (k0 + tid);
+    const uint32_t* tp = tile + tid;
+    if (!DO_BLUR) {
+        for (int r = 0; r < BS_R && y0 + r < h; r++)
+            store_word_rows(dst, L.pitch, h, y0 + r, __funnelshift_r(tp[(r + 3) * spw + 1], tp[(r + 3) * spw + 2], 8));
+        return;
+    }
+    uint32_t hw[7][4];
+#pragma unroll
+    for (int u = 0; u < 7; u++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) hw[u][j] = 0;
+#pragma unroll 1
+    for (int g = 0; g < BS_STEPS / 7; g++) {
+#pragma unroll
+        for (int u = 0; u < 7; u++) {
+            const int step = g * 7 + u;
+            const uint32_t W0 = tp[step * spw], W1 = tp[step * spw + 1], W2 = tp[step * spw + 2];
+            // pair s = (byte s, byte s + 1) of the 12 staged bytes as u16x2; pixel j of the word is centred on byte 5 + j
+            const uint32_t p2 = __byte_perm(W0, 0, 0x4342), p3 = __byte_perm(W0, W1, 0x0403) & 0x00ff00ffu, p4 = __byte_perm(W1, 0, 0x4140),
+                           p5 = __byte_perm(W1, 0, 0x4241), p6 = __byte_perm(W1, 0, 0x4342), p7 = __byte_perm(W1, W2, 0x0403) & 0x00ff00ffu,
+                           p8 = __byte_perm(W2, 0, 0x4140), p9 = __byte_perm(W2, 0, 0x4241), p10 = __byte_perm(W2, 0, 0x4342);
+            const uint32_t A = 18u * (p2 + p8) + 34u * (p3 + p7) + 48u * (p4 + p6) + 56u * p5;
+            const uint32_t B = 18u * (p4 + p10) + 34u * (p5 + p9) + 48u * (p6 + p8) + 56u * p7;
+            hw[u][0] = A & 0xffffu; hw[u][1] = A >> 16; hw[u][2] = B & 0xffffu; hw[u][3] = B >> 16;
+            const int yo = y0 + step - 6;                                // window = tile rows step-6 .. step; row step-6+k sits in slot (u+1+k) % 7
+            if ((g > 0 || u == 6) && yo < h) {
+                uint32_t v[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    v[j] = 18u * (hw[(u + 1) % 7][j] + hw[u][j]) + 34u * (hw[(u + 2) % 7][j] + hw[(u + 6) % 7][j]) +
+                           48u * (hw[(u + 3) % 7][j] + hw[(u + 5) % 7][j]) + 56u * hw[(u + 4) % 7][j] + 32768u;   // < 2^24: the result is byte 2
+                store_word_rows(dst, L.pitch, h, yo, __byte_perm(__byte_perm(v[0], v[1], 0x0062), __byte_perm(v[2], v[3], 0x0062), 0x5410));
+            }
+        }
+    }
+}
+
+// Resize: a CTA owns 64 bordered destination columns x 32 level rows.  Pass 1: a thread keeps ONE destination column (its source
+// offsets and 11-bit coefficients in registers) and filters the source rows the tile needs into shared memory; pass 2: a thread makes
+// 4 adjacent pixels of one row from four 128-bit shared-memory reads (the row weights are converted once for the 4 pixels).  Same
+// integers / floats per pixel as resize_cubic_kernel.
+#define RS2_TW 64
+#define RS2_TH 32
+__global__ void __launch_bounds__(256) resize_cubic_strip_kernel(const __grid_constant__ PlanDev c_plan, uint8_t* __restrict__ pyr, int level,
+                                                                 const int* __restrict__ tab_ofs, const short4* __restrict__ tab_coef) {
+    const LevelDev& D = c_plan.lv[level];
+    const LevelDev& S = c_plan.lv[level - 1];
+    __shared__ __align__(16) int sr[RS_ROWS][RS2_TW + 4];
+    __shared__ __align__(4) uint8_t s_fix[RS2_TW];
+    const int c0 = blockIdx.x * RS2_TW, y0 = blockIdx.y * RS2_TH, tid = threadIdx.x;
+    const int wext = (D.w + 2 * ORB_E + 3) & ~3;                         // bordered columns, whole words
+    uint8_t* frame = pyr + (size_t)blockIdx.z * c_plan.frame_bytes;
+    const uint8_t* src = frame + S.off + (size_t)ORB_E * S.pitch + ORB_E;
+    const int ny = min(RS2_TH, D.h - y0);
+    const int r_lo = min(max(tab_ofs[D.tab_y + y0] - 1, 0), S.h - 1);
+    const int r_hi = min(max(tab_ofs[D.tab_y + y0 + ny - 1] + 2, 0), S.h - 1);
+    const int nr = r_hi - r_lo + 1;
+    {   // pass 1: horizontal, 11-bit coefficients
+        const int x = tid & (RS2_TW - 1), c = c0 + x;
+        if (c < wext) {
+            const int px = reflect101(c - ORB_E, D.w);
+            const int sx = tab_ofs[D.tab_x + px];
+            const short4 a = tab_coef[D.tab_x + px];
+            const int o0 = min(max(sx - 1, 0), S.w - 1), o1 = min(max(sx, 0), S.w - 1), o2 = min(max(sx + 1, 0), S.w - 1), o3 = min(max(sx + 2, 0), S.w - 1);
+            if (tid < RS2_TW) s_fix[x] = px >= D.vec_limit;
+            unsigned ro = (unsigned)(r_lo + (tid >> 6)) * (unsigned)S.pitch;
+            const unsigned rstep = 4u * (unsigned)S.pitch;
+            for (int r = tid >> 6; r < nr; r += 4, ro += rstep) {
+                const uint8_t* p = src + ro;
+                sr[r][x] = p[o0] * a.x + p[o1] * a.y + p[o2] * a.z + p[o3] * a.w;
+            }
+        } else if (tid < RS2_TW)
+            s_fix[x] = 0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < (RS2_TW / 4) * RS2_TH / 256; it++) {           // pass 2: vertical, one destination word per thread and round
+        const int i = tid + it * 256, y = i >> 4, gx = i & 15;
+        if (y >= ny || c0 + 4 * gx >= wext) continue;
+        const int dy = y0 + y;
+        const int sy = tab_ofs[D.tab_y + dy];
+        const short4 b = tab_coef[D.tab_y + dy];
+        int4 R[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) R[k] = *(const int4*)&sr[min(max(sy - 1 + k, 0), S.h - 1) - r_lo][4 * gx];
+        const uint32_t fix4 = *(const uint32_t*)&s_fix[4 * gx];
+        const float scale = 1.f / (2048.f * 2048.f);
+        const float b0 = __fmul_rn((float)b.x, scale), b1 = __fmul_rn((float)b.y, scale), b2 = __fmul_rn((float)b.z, scale), b3 = __fmul_rn((float)b.w, scale);
+        int v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int S0 = (&R[0].x)[j], S1 = (&R[1].x)[j], S2 = (&R[2].x)[j], S3 = (&R[3].x)[j];
+            float t = __fmul_rn((float)S3, b3);
+            t = __fadd_rn(__fmul_rn((float)S2, b2), t);
+            t = __fadd_rn(__fmul_rn((float)S1, b1), t);
+            t = __fadd_rn(__fmul_rn((float)S0, b0), t);
+            v[j] = __float2int_rn(t);
+        }
+        if (fix4) {                                                       // columns past OpenCV's SIMD width: 22-bit fixed point
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if ((fix4 >> (8 * j)) & 0xffu) {
+                    const int acc = (&R[0].x)[j] * b.x + (&R[1].x)[j] * b.y + (&R[2].x)[j] * b.z + (&R[3].x)[j] * b.w;
+                    v[j] = (acc + (1 << 21)) >> 22;
+                }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[j] = min(max(v[j], 0), 255);
+        const uint32_t word = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
+        store_word_rows(frame + D.off + c0 + 4 * gx, D.pitch, D.h, dy, word);
+    }
+}
+
 // ---- K3 + K4a: FAST-9/16 corner score on each grid cell's interior + 3x3 non-maximum suppression clipped to the cell
 // (cv::FAST is called per cell ROI, ORBextractor.cpp:976-986, so neighbours in the adjacent cell never suppress) + ordered
 // compaction (row-major, the order cv::FAST emits).
@@ -828,6 +992,7 @@ struct uco_orb_state {
     OrbTmaps tmaps{};              // per-level tensor maps over d_pyr (orient_describe stages keypoint windows with them)
     CUtensorMap* d_tmaps = nullptr; // ... in global memory: the kernel indexes them by level
     bool use_tma = false;
+    bool pyramid_v1 = false;       // UCO_ORB_PYRAMID_V1=1: launch the per-pixel blur / resize kernels instead of the strip forms (A/B checks)
     uint8_t* d_in = nullptr;       // staging for host images
     size_t in_pitch = 0;
     CellDev* d_cells = nullptr;
@@ -914,6 +1079,7 @@ static int orb_prepare(uco_b200_ctx* ctx, int w, int h, const uco_orb_params* pr
     s->h = h;
     s->cells.clear();
     s->max_cell_smem = 0;
+    s->pyramid_v1 = getenv("UCO_ORB_PYRAMID_V1") != nullptr;
     PlanDev& P = s->plan;
     memset(&P, 0, sizeof P);
     const int NL = prm->n_levels;
@@ -1109,13 +1275,26 @@ static int orb_run_dev(uco_b200_ctx* ctx, const uint8_t* in_dev, size_t in_pitch
     if (prof && !s->ev[0])
         for (auto& e : s->ev) UCO_CUDA(ctx, cudaEventCreate(&e));
     if (prof) cudaEventRecord(s->ev[0], st);
-    dim3 g0((P.lv[0].w + BL_TW - 1) / BL_TW, (P.lv[0].h + BL_TH - 1) / BL_TH, n);
-    blur7_kernel<<<g0, 256, 0, st>>>(P, in_dev, in_pitch, in_frame, s->d_pyr, s->prm.blur_first);
+    if (s->pyramid_v1) {   // per-pixel forms (A/B reference)
+        dim3 g0((P.lv[0].w + BL_TW - 1) / BL_TW, (P.lv[0].h + BL_TH - 1) / BL_TH, n);
+        blur7_kernel<<<g0, 256, 0, st>>>(P, in_dev, in_pitch, in_frame, s->d_pyr, s->prm.blur_first);
+    } else {
+        const int nwords = (P.lv[0].w + 2 * ORB_E + 3) >> 2, ntx = (nwords + BS_MAXW - 1) / BS_MAXW, wpt = (nwords + ntx - 1) / ntx;
+        const int aligned = (((uintptr_t)in_dev | in_pitch | in_frame) & 3) == 0;
+        dim3 g0(ntx, (P.lv[0].h + BS_R - 1) / BS_R, n);
+        if (s->prm.blur_first) blur7_strip_kernel<true><<<g0, (wpt + 31) & ~31, 0, st>>>(P, in_dev, in_pitch, in_frame, s->d_pyr, wpt, aligned);
+        else blur7_strip_kernel<false><<<g0, (wpt + 31) & ~31, 0, st>>>(P, in_dev, in_pitch, in_frame, s->d_pyr, wpt, aligned);
+    }
     UCO_LAUNCH_CHECK(ctx);
     if (prof) cudaEventRecord(s->ev[1], st);
     for (int l = 1; l < P.n_levels; l++) {
-        dim3 g((P.lv[l].w + RS_T - 1) / RS_T, (P.lv[l].h + RS_T - 1) / RS_T, n);
-        resize_cubic_kernel<<<g, 256, 0, st>>>(P, s->d_pyr, l, s->d_tab_ofs, s->d_tab_coef);
+        if (s->pyramid_v1) {
+            dim3 g((P.lv[l].w + RS_T - 1) / RS_T, (P.lv[l].h + RS_T - 1) / RS_T, n);
+            resize_cubic_kernel<<<g, 256, 0, st>>>(P, s->d_pyr, l, s->d_tab_ofs, s->d_tab_coef);
+        } else {
+            dim3 g((P.lv[l].w + 2 * ORB_E + RS2_TW - 1) / RS2_TW, (P.lv[l].h + RS2_TH - 1) / RS2_TH, n);
+            resize_cubic_strip_kernel<<<g, 256, 0, st>>>(P, s->d_pyr, l, s->d_tab_ofs, s->d_tab_coef);
+        }
         UCO_LAUNCH_CHECK(ctx);
     }
     if (prof) cudaEventRecord(s->ev[2], st);
