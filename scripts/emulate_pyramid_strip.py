@@ -146,17 +146,31 @@ def resize_strip(srcb, sw, sh, dw, dh):
             assert nr <= 72
             sr = np.zeros((72, RS2_TW + 4), np.int64)
             fix = np.zeros(RS2_TW, np.uint8)
+            cl = min(c0 + RS2_TW, wext) - 1
+            pa, pb = reflect101(c0 - E, dw), reflect101(cl - E, dw)
+            pmin, pmax = min(pa, pb), max(pa, pb)
+            if c0 <= E <= cl:
+                pmin = 0
+            if c0 <= dw - 1 + E <= cl:
+                pmax = dw - 1
+            xlo, xhi = min(max(ox[pmin] - 1, 0), sw - 1), min(max(ox[pmax] + 2, 0), sw - 1)
+            a0 = (xlo + E) & ~3
+            nw = ((xhi + E - a0) >> 2) + 1
+            assert nw <= 36
+            s_src = np.full((72, 144), -1, np.int64)
+            for r in range(nr):
+                s_src[r, :4 * nw] = srcb[r_lo + E + r, a0:a0 + 4 * nw]
             for x in range(RS2_TW):
                 c = c0 + x
                 if c >= wext:
                     continue
                 px = reflect101(c - E, dw)
                 sx, a = ox[px], cx[px]
-                o = [min(max(sx - 1 + k, 0), sw - 1) for k in range(4)]
+                q = [min(max(sx - 1 + k, 0), sw - 1) + E - a0 for k in range(4)]
+                assert min(q) >= 0 and max(q) < 4 * nw
                 fix[x] = px >= vec_limit
                 for r in range(nr):
-                    p = src[r_lo + r]
-                    sr[r, x] = sum(int(p[o[k]]) * a[k] for k in range(4))
+                    sr[r, x] = sum(int(s_src[r, q[k]]) * a[k] for k in range(4))
             for i in range(16 * RS2_TH):
                 y, gx = i >> 4, i & 15
                 if y >= ny or c0 + 4 * gx >= wext:

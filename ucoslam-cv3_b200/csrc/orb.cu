@@ -280,68 +280,113 @@ __global__ void __launch_bounds__(256) blur7_strip_kernel(const __grid_constant_
     }
 }
 
-// Resize: a CTA owns 64 bordered destination columns x 32 level rows.  Pass 1: a thread keeps ONE destination column (its source
-// offsets and 11-bit coefficients in registers) and filters the source rows the tile needs into shared memory; pass 2: a thread makes
-// 4 adjacent pixels of one row from four 128-bit shared-memory reads (the row weights are converted once for the 4 pixels).  Same
-// integers / floats per pixel as resize_cubic_kernel.
+__device__ __forceinline__ int reflect_once(int p, int len) {  // reflect101 for -len < p < 2 * len - 1 (one fold), branch free
+    p = p < 0 ? -p : p;
+    return p >= len ? 2 * (len - 1) - p : p;
+}
+
+// Resize: a CTA owns 64 bordered destination columns x 32 level rows.  The source pixels the tile needs are staged in shared memory as
+// aligned words (the gathers of pass 1 then cost one LDS.U8 with an immediate row offset each, no 64-bit address arithmetic), the
+// per-row source indices and float weights are made once per tile row.  Pass 1: a thread keeps ONE destination column (its 4 source
+// offsets and 11-bit coefficients in registers) and filters the staged rows into shared memory; pass 2: a thread makes 4 adjacent
+// pixels of one row from four 128-bit shared-memory reads.  Same integers / floats per pixel as resize_cubic_kernel.
 #define RS2_TW 64
 #define RS2_TH 32
+#define RS2_SP 144                   // staged bytes per source row: 63 * 2 + 5 source columns at scale 2, + 3 of alignment, rounded to 16
 __global__ void __launch_bounds__(256) resize_cubic_strip_kernel(const __grid_constant__ PlanDev c_plan, uint8_t* __restrict__ pyr, int level,
                                                                  const int* __restrict__ tab_ofs, const short4* __restrict__ tab_coef) {
     const LevelDev& D = c_plan.lv[level];
     const LevelDev& S = c_plan.lv[level - 1];
     __shared__ __align__(16) int sr[RS_ROWS][RS2_TW + 4];
+    __shared__ __align__(16) uint8_t s_src[RS_ROWS][RS2_SP];
+    __shared__ __align__(16) float4 s_bw[RS2_TH];
+    __shared__ short4 s_b[RS2_TH];
+    __shared__ uint32_t s_ri[RS2_TH];
     __shared__ __align__(4) uint8_t s_fix[RS2_TW];
-    const int c0 = blockIdx.x * RS2_TW, y0 = blockIdx.y * RS2_TH, tid = threadIdx.x;
+    const int c0 = blockIdx.x * RS2_TW, y0 = blockIdx.y * RS2_TH, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wext = (D.w + 2 * ORB_E + 3) & ~3;                         // bordered columns, whole words
     uint8_t* frame = pyr + (size_t)blockIdx.z * c_plan.frame_bytes;
-    const uint8_t* src = frame + S.off + (size_t)ORB_E * S.pitch + ORB_E;
     const int ny = min(RS2_TH, D.h - y0);
     const int r_lo = min(max(tab_ofs[D.tab_y + y0] - 1, 0), S.h - 1);
     const int r_hi = min(max(tab_ofs[D.tab_y + y0 + ny - 1] + 2, 0), S.h - 1);
     const int nr = r_hi - r_lo + 1;
-    {   // pass 1: horizontal, 11-bit coefficients
-        const int x = tid & (RS2_TW - 1), c = c0 + x;
-        if (c < wext) {
-            const int px = reflect101(c - ORB_E, D.w);
-            const int sx = tab_ofs[D.tab_x + px];
-            const short4 a = tab_coef[D.tab_x + px];
-            const int o0 = min(max(sx - 1, 0), S.w - 1), o1 = min(max(sx, 0), S.w - 1), o2 = min(max(sx + 1, 0), S.w - 1), o3 = min(max(sx + 2, 0), S.w - 1);
-            if (tid < RS2_TW) s_fix[x] = px >= D.vec_limit;
-            unsigned ro = (unsigned)(r_lo + (tid >> 6)) * (unsigned)S.pitch;
-            const unsigned rstep = 4u * (unsigned)S.pitch;
-            for (int r = tid >> 6; r < nr; r += 4, ro += rstep) {
-                const uint8_t* p = src + ro;
-                sr[r][x] = p[o0] * a.x + p[o1] * a.y + p[o2] * a.z + p[o3] * a.w;
-            }
-        } else if (tid < RS2_TW)
-            s_fix[x] = 0;
+    // source columns of the tile: the level pixels of its columns are reflect101(c - 19), piecewise linear in c, and the source offset grows with the pixel
+    const int cl = min(c0 + RS2_TW, wext) - 1;
+    int pa = reflect_once(c0 - ORB_E, D.w), pb = reflect_once(cl - ORB_E, D.w);   // D.w >= 46: the 19 + 3 columns beyond an edge fold once
+    int pmin = min(pa, pb), pmax = max(pa, pb);
+    if (c0 <= ORB_E && ORB_E <= cl) pmin = 0;
+    if (c0 <= D.w - 1 + ORB_E && D.w - 1 + ORB_E <= cl) pmax = D.w - 1;
+    const int xlo = min(max(tab_ofs[D.tab_x + pmin] - 1, 0), S.w - 1), xhi = min(max(tab_ofs[D.tab_x + pmax] + 2, 0), S.w - 1);
+    const int a0 = (xlo + ORB_E) & ~3, nw = min(((xhi + ORB_E - a0) >> 2) + 1, RS2_SP / 4);   // bordered source column of staged byte 0, staged words per row (<= RS2_SP / 4)
+    if (tid < RS2_TH) {                                                  // per destination row: its 4 source rows (relative to r_lo) and weights
+        const int dy = min(y0 + tid, D.h - 1);
+        const int sy = tab_ofs[D.tab_y + dy];
+        const short4 b = tab_coef[D.tab_y + dy];
+        uint32_t ri = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) ri |= (uint32_t)(min(max(sy - 1 + k, 0), S.h - 1) - r_lo) << (8 * k);
+        const float scale = 1.f / (2048.f * 2048.f);
+        s_ri[tid] = ri;
+        s_b[tid] = b;
+        s_bw[tid] = make_float4(__fmul_rn((float)b.x, scale), __fmul_rn((float)b.y, scale), __fmul_rn((float)b.z, scale), __fmul_rn((float)b.w, scale));
+    }
+    {   // stage: a warp per source row, a lane per word (nw <= 36: lanes 0..3 take a second word at scale factors near 2); 4 rows in flight
+        const uint8_t* sb = frame + S.off + (size_t)(r_lo + ORB_E) * S.pitch + a0 + 4 * lane;
+        uint8_t* ss = &s_src[0][0] + 4 * lane;
+        const unsigned sp = (unsigned)S.pitch;
+        for (int r0 = warp; r0 < nr; r0 += 32) {
+            uint32_t v[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) v[j] = (r0 + 8 * j < nr && lane < nw) ? *(const uint32_t*)(sb + (unsigned)(r0 + 8 * j) * sp) : 0u;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (r0 + 8 * j < nr && lane < nw) *(uint32_t*)(ss + (r0 + 8 * j) * RS2_SP) = v[j];
+        }
+        if (nw > 32 && lane + 32 < nw)
+            for (int r = warp; r < nr; r += 8) *(uint32_t*)(ss + r * RS2_SP + 128) = *(const uint32_t*)(sb + (unsigned)r * sp + 128);
+    }
+    const int x = tid & (RS2_TW - 1), c = c0 + x;
+    int q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+    short4 a = make_short4(0, 0, 0, 0);
+    if (c < wext) {
+        const int px = reflect_once(c - ORB_E, D.w);
+        const int sx = tab_ofs[D.tab_x + px];
+        a = tab_coef[D.tab_x + px];
+        const int sh = ORB_E - a0;
+        q0 = min(max(sx - 1, 0), S.w - 1) + sh; q1 = min(max(sx, 0), S.w - 1) + sh; q2 = min(max(sx + 1, 0), S.w - 1) + sh; q3 = min(max(sx + 2, 0), S.w - 1) + sh;
+        if (tid < RS2_TW) s_fix[x] = px >= D.vec_limit;
+    } else if (tid < RS2_TW)
+        s_fix[x] = 0;
+    __syncthreads();
+    if (c < wext) {                                                      // pass 1: horizontal, 11-bit coefficients
+        const uint8_t* p = &s_src[tid >> 6][0];
+        int* o = &sr[tid >> 6][x];
+#pragma unroll 4
+        for (int r = tid >> 6; r < nr; r += 4, p += 4 * RS2_SP, o += 4 * (RS2_TW + 4)) *o = p[q0] * a.x + p[q1] * a.y + p[q2] * a.z + p[q3] * a.w;
     }
     __syncthreads();
 #pragma unroll
     for (int it = 0; it < (RS2_TW / 4) * RS2_TH / 256; it++) {           // pass 2: vertical, one destination word per thread and round
         const int i = tid + it * 256, y = i >> 4, gx = i & 15;
         if (y >= ny || c0 + 4 * gx >= wext) continue;
-        const int dy = y0 + y;
-        const int sy = tab_ofs[D.tab_y + dy];
-        const short4 b = tab_coef[D.tab_y + dy];
+        const uint32_t ri = s_ri[y];
+        const float4 bw = s_bw[y];
         int4 R[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) R[k] = *(const int4*)&sr[min(max(sy - 1 + k, 0), S.h - 1) - r_lo][4 * gx];
+        for (int k = 0; k < 4; k++) R[k] = *(const int4*)&sr[(ri >> (8 * k)) & 0xffu][4 * gx];
         const uint32_t fix4 = *(const uint32_t*)&s_fix[4 * gx];
-        const float scale = 1.f / (2048.f * 2048.f);
-        const float b0 = __fmul_rn((float)b.x, scale), b1 = __fmul_rn((float)b.y, scale), b2 = __fmul_rn((float)b.z, scale), b3 = __fmul_rn((float)b.w, scale);
         int v[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const int S0 = (&R[0].x)[j], S1 = (&R[1].x)[j], S2 = (&R[2].x)[j], S3 = (&R[3].x)[j];
-            float t = __fmul_rn((float)S3, b3);
-            t = __fadd_rn(__fmul_rn((float)S2, b2), t);
-            t = __fadd_rn(__fmul_rn((float)S1, b1), t);
-            t = __fadd_rn(__fmul_rn((float)S0, b0), t);
+            float t = __fmul_rn((float)S3, bw.w);
+            t = __fadd_rn(__fmul_rn((float)S2, bw.z), t);
+            t = __fadd_rn(__fmul_rn((float)S1, bw.y), t);
+            t = __fadd_rn(__fmul_rn((float)S0, bw.x), t);
             v[j] = __float2int_rn(t);
         }
         if (fix4) {                                                       // columns past OpenCV's SIMD width: 22-bit fixed point
+            const short4 b = s_b[y];
 #pragma unroll
             for (int j = 0; j < 4; j++)
                 if ((fix4 >> (8 * j)) & 0xffu) {
@@ -352,7 +397,7 @@ __global__ void __launch_bounds__(256) resize_cubic_strip_kernel(const __grid_co
 #pragma unroll
         for (int j = 0; j < 4; j++) v[j] = min(max(v[j], 0), 255);
         const uint32_t word = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
-        store_word_rows(frame + D.off + c0 + 4 * gx, D.pitch, D.h, dy, word);
+        store_word_rows(frame + D.off + c0 + 4 * gx, D.pitch, D.h, y0 + y, word);
     }
 }
 
