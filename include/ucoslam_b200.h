@@ -187,7 +187,7 @@ int uco_b200_bow_transform_dev(uco_b200_ctx* ctx, const uco_b200_voc* voc, const
  *   The caller (the C++ adapter GlobalOptimizerB200, ucoslam-cv3_b200/host/) flattens the Map into this structure exactly
  *   as setParams walks it: one row per keyframe vertex, per map point vertex and per (map point, keyframe) observation.
  *   All arithmetic is f64 on the device; inputs are the reference's f32 containers (cv::Mat CV_32F pose, cv::Point3f,
- *   cv::KeyPoint::pt, vector<float> _InvScaleFactors).  Marker edges (ArUco) are not handled yet.
+ *   cv::KeyPoint::pt, vector<float> _InvScaleFactors).
  * ---------------------------------------------------------------------------------------------------------- */
 typedef struct uco_ba_problem {
     int32_t n_poses, n_points, n_obs;
@@ -214,6 +214,10 @@ typedef struct uco_ba_problem {
     const int32_t* mobs_pose;    /* n_marker_obs     index into poses */
     const float* mobs_corners;   /* n_marker_obs x 8 MarkerObservation::und_corners */
     const float* mobs_weight;    /* n_marker_obs     frame_MarkerWeight[frame] (:276-297): information = I8 * weight */
+    /* Keyframes taken with different cameras in one window (a map built with one camera and extended with another): every edge carries
+     * the ImageParams of ITS keyframe (globaloptimizer_g2o.cpp:233-236, :262-266, :335-338).  NULL: all keyframes use fx..bf above.
+     * Problems with this table are solved by the sharded solver (one rank when no communicator is given). */
+    const float* pose_cam;       /* n_poses x 5      fx fy cx cy bf (= bl * fx) of each keyframe, or NULL */
 } uco_ba_problem;
 
 typedef struct uco_ba_result {   /* every pointer may be NULL (not wanted) */

@@ -227,6 +227,8 @@ def ref_ba_optimize(pb, n_iters):
     lib = load_ref("libref_g2o.so")
     if lib is None:
         return None
+    if pb.get("pose_cam") is not None:   # one camera per keyframe: the per-edge ImageParams of globaloptimizer_g2o.cpp:233-236, :262-266, :335-338
+        return _ba_call_markers(lib.ref_ba_optimize_cams, pb, n_iters)
     if len(pb.get("marker_size", ())):
         return _ba_call_markers(lib.ref_ba_optimize_markers, pb, n_iters)
     return _ba_call(lib.ref_ba_optimize, pb, n_iters)
@@ -235,6 +237,9 @@ def ref_ba_optimize(pb, n_iters):
 def _ba_call_markers(fn, pb, n_iters):
     """ref_ba_optimize_markers: the reference's g2o + its own MarkerEdge class on a problem with ArUco markers"""
     P, N, M = len(pb["fixed"]), len(pb["points3"]), len(pb["obs_pose"])
+    if not len(pb.get("marker_size", ())):
+        pb = dict(pb, marker_pose44=np.zeros((0, 16), np.float32), marker_size=np.zeros(0, np.float32), mobs_marker=np.zeros(0, np.int32),
+                  mobs_pose=np.zeros(0, np.int32), mobs_corners=np.zeros((0, 8), np.float32), mobs_weight=np.zeros(0, np.float32))
     nm, nmo = len(pb["marker_size"]), len(pb["mobs_marker"])
     out = dict(pose7=np.zeros((P, 7)), pose44=np.zeros((P, 16), np.float32), point3=np.zeros((N, 3)), chi2=np.zeros(M),
                level=np.zeros(M, np.uint8), bad=np.zeros(M, np.uint8), iters=np.zeros(2, np.int32), trace=np.zeros((64, 2)),
@@ -247,7 +252,8 @@ def _ba_call_markers(fn, pb, n_iters):
        _p(pb["obs_ur"]), _p(pb["obs_stereo"]), _p(pb["obs_inv_sigma2"]), f(pb["fx"]), f(pb["fy"]), f(pb["cx"]), f(pb["cy"]), f(pb["bf"]),
        int(n_iters), _p(out["pose7"]), _p(out["pose44"]), _p(out["point3"]), _p(out["chi2"]), _p(out["level"]), _p(out["bad"]),
        _p(out["iters"]), _p(out["trace"]), nm, _p(keep[0]), _p(keep[1]), nmo, _p(keep[2]), _p(keep[3]), _p(keep[4]), _p(keep[5]),
-       _p(out["marker_pose7"]), _p(out["marker_pose44"]), _p(out["mobs_chi2"]))
+       _p(out["marker_pose7"]), _p(out["marker_pose44"]), _p(out["mobs_chi2"]),
+       *([_p(np.ascontiguousarray(pb["pose_cam"], np.float32))] if pb.get("pose_cam") is not None else []))
     return out
 
 

@@ -31,23 +31,27 @@ extern "C" {
 // reference's own class, typesg2o.h:108-167: 8 residuals, numeric Jacobian with delta 1e-4) per (marker, keyframe) observation with
 // information = I8 * mobs_weight (frame_MarkerWeight, :276-297, computed by the caller); no robust kernel; they stay at level 0 in both
 // stages (:447-451).  The InPlaneMarkers extension (:360-401) is not covered.
-int ref_ba_optimize_markers(int n_poses, const float* poses44, const uint8_t* fixed, int n_points, const float* points3, int n_obs,
+}  // extern "C" (the shared body has C++ linkage)
+static int ba_optimize_impl(int n_poses, const float* poses44, const uint8_t* fixed, int n_points, const float* points3, int n_obs,
                     const int32_t* obs_pose, const int32_t* obs_point, const float* obs_uv, const float* obs_ur,
                     const uint8_t* obs_stereo, const float* obs_inv_sigma2, float fx, float fy, float cx, float cy, float bf,
                     int n_iters, double* out_pose7, float* out_pose44, double* out_point3, double* out_chi2,
                     uint8_t* out_level, uint8_t* out_bad, int* iters_done, double* trace,
                     int n_markers, const float* marker_pose44, const float* marker_size, int n_mobs, const int32_t* mobs_marker,
                     const int32_t* mobs_pose, const float* mobs_corners, const float* mobs_weight, double* out_marker_pose7,
-                    float* out_marker_pose44, double* out_mobs_chi2);
+                    float* out_marker_pose44, double* out_mobs_chi2,
+                    const float* pose_cam /* n_poses x 5 (fx fy cx cy bf of each keyframe's ImageParams, :233-236, :262-266) or NULL */);
+extern "C" {
+
 
 int ref_ba_optimize(int n_poses, const float* poses44, const uint8_t* fixed, int n_points, const float* points3, int n_obs,
                     const int32_t* obs_pose, const int32_t* obs_point, const float* obs_uv, const float* obs_ur,
                     const uint8_t* obs_stereo, const float* obs_inv_sigma2, float fx, float fy, float cx, float cy, float bf,
                     int n_iters, double* out_pose7, float* out_pose44, double* out_point3, double* out_chi2,
                     uint8_t* out_level, uint8_t* out_bad, int* iters_done, double* trace /* optional: per outer iteration {chi2, LM trials}, 2 x 64 */) {
-    return ref_ba_optimize_markers(n_poses, poses44, fixed, n_points, points3, n_obs, obs_pose, obs_point, obs_uv, obs_ur, obs_stereo, obs_inv_sigma2,
-                                   fx, fy, cx, cy, bf, n_iters, out_pose7, out_pose44, out_point3, out_chi2, out_level, out_bad, iters_done, trace,
-                                   0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    return ba_optimize_impl(n_poses, poses44, fixed, n_points, points3, n_obs, obs_pose, obs_point, obs_uv, obs_ur, obs_stereo, obs_inv_sigma2,
+                            fx, fy, cx, cy, bf, n_iters, out_pose7, out_pose44, out_point3, out_chi2, out_level, out_bad, iters_done, trace,
+                            0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
 }
 
 int ref_ba_optimize_markers(int n_poses, const float* poses44, const uint8_t* fixed, int n_points, const float* points3, int n_obs,
@@ -58,6 +62,35 @@ int ref_ba_optimize_markers(int n_poses, const float* poses44, const uint8_t* fi
                     int n_markers, const float* marker_pose44, const float* marker_size, int n_mobs, const int32_t* mobs_marker,
                     const int32_t* mobs_pose, const float* mobs_corners, const float* mobs_weight, double* out_marker_pose7,
                     float* out_marker_pose44, double* out_mobs_chi2) {
+    return ba_optimize_impl(n_poses, poses44, fixed, n_points, points3, n_obs, obs_pose, obs_point, obs_uv, obs_ur, obs_stereo, obs_inv_sigma2,
+                            fx, fy, cx, cy, bf, n_iters, out_pose7, out_pose44, out_point3, out_chi2, out_level, out_bad, iters_done, trace,
+                            n_markers, marker_pose44, marker_size, n_mobs, mobs_marker, mobs_pose, mobs_corners, mobs_weight, out_marker_pose7,
+                            out_marker_pose44, out_mobs_chi2, nullptr);
+}
+// keyframes taken with different cameras in one window: every edge carries the ImageParams of ITS keyframe (:233-236, :262-266, :335-338)
+int ref_ba_optimize_cams(int n_poses, const float* poses44, const uint8_t* fixed, int n_points, const float* points3, int n_obs,
+                    const int32_t* obs_pose, const int32_t* obs_point, const float* obs_uv, const float* obs_ur,
+                    const uint8_t* obs_stereo, const float* obs_inv_sigma2, float fx, float fy, float cx, float cy, float bf,
+                    int n_iters, double* out_pose7, float* out_pose44, double* out_point3, double* out_chi2,
+                    uint8_t* out_level, uint8_t* out_bad, int* iters_done, double* trace,
+                    int n_markers, const float* marker_pose44, const float* marker_size, int n_mobs, const int32_t* mobs_marker,
+                    const int32_t* mobs_pose, const float* mobs_corners, const float* mobs_weight, double* out_marker_pose7,
+                    float* out_marker_pose44, double* out_mobs_chi2, const float* pose_cam) {
+    return ba_optimize_impl(n_poses, poses44, fixed, n_points, points3, n_obs, obs_pose, obs_point, obs_uv, obs_ur, obs_stereo, obs_inv_sigma2,
+                            fx, fy, cx, cy, bf, n_iters, out_pose7, out_pose44, out_point3, out_chi2, out_level, out_bad, iters_done, trace,
+                            n_markers, marker_pose44, marker_size, n_mobs, mobs_marker, mobs_pose, mobs_corners, mobs_weight, out_marker_pose7,
+                            out_marker_pose44, out_mobs_chi2, pose_cam);
+}
+}  // extern "C"
+
+static int ba_optimize_impl(int n_poses, const float* poses44, const uint8_t* fixed, int n_points, const float* points3, int n_obs,
+                    const int32_t* obs_pose, const int32_t* obs_point, const float* obs_uv, const float* obs_ur,
+                    const uint8_t* obs_stereo, const float* obs_inv_sigma2, float fx, float fy, float cx, float cy, float bf,
+                    int n_iters, double* out_pose7, float* out_pose44, double* out_point3, double* out_chi2,
+                    uint8_t* out_level, uint8_t* out_bad, int* iters_done, double* trace,
+                    int n_markers, const float* marker_pose44, const float* marker_size, int n_mobs, const int32_t* mobs_marker,
+                    const int32_t* mobs_pose, const float* mobs_corners, const float* mobs_weight, double* out_marker_pose7,
+                    float* out_marker_pose44, double* out_mobs_chi2, const float* pose_cam) {
     const float Chi2D = 5.99f, Chi3D = 7.815f;
     const float thHuber2D = sqrt(Chi2D), thHuber3D = sqrt(Chi3D);
     auto Optimizer = std::make_shared<g2o::SparseOptimizer>();
@@ -91,7 +124,8 @@ int ref_ba_optimize_markers(int n_poses, const float* poses44, const uint8_t* fi
             Eigen::Matrix<double, 2, 1> obs;
             obs << obs_uv[2 * i], obs_uv[2 * i + 1];
             auto* e = new EdgeSE3ProjectXYZ();
-            e->fx = fx; e->fy = fy; e->cx = cx; e->cy = cy;
+            const float* pc = pose_cam ? pose_cam + 5 * obs_pose[i] : nullptr;
+            e->fx = pc ? pc[0] : fx; e->fy = pc ? pc[1] : fy; e->cx = pc ? pc[2] : cx; e->cy = pc ? pc[3] : cy;
             e->setVertex(0, vp);
             e->setVertex(1, vf);
             e->setMeasurement(obs);
@@ -112,7 +146,8 @@ int ref_ba_optimize_markers(int n_poses, const float* poses44, const uint8_t* fi
             auto* rk = new g2o::RobustKernelHuber();
             rk->setDelta(thHuber3D);
             e->setRobustKernel(rk);
-            e->fx = fx; e->fy = fy; e->cx = cx; e->cy = cy; e->bf = bf;
+            const float* pc = pose_cam ? pose_cam + 5 * obs_pose[i] : nullptr;
+            e->fx = pc ? pc[0] : fx; e->fy = pc ? pc[1] : fy; e->cx = pc ? pc[2] : cx; e->cy = pc ? pc[3] : cy; e->bf = pc ? pc[4] : bf;
             Optimizer->addEdge(e);
             edges[i] = e;
         }
@@ -131,7 +166,8 @@ int ref_ba_optimize_markers(int n_poses, const float* poses44, const uint8_t* fi
         e->setMeasurement(obs);
         e->setVertex(0, dynamic_cast<g2o::OptimizableGraph::Vertex*>(Optimizer->vertex(n_poses + n_points + mobs_marker[k])));
         e->setVertex(1, dynamic_cast<g2o::OptimizableGraph::Vertex*>(Optimizer->vertex(mobs_pose[k])));
-        e->fx = fx; e->fy = fy; e->cx = cx; e->cy = cy;
+        const float* pc = pose_cam ? pose_cam + 5 * mobs_pose[k] : nullptr;
+        e->fx = pc ? pc[0] : fx; e->fy = pc ? pc[1] : fy; e->cx = pc ? pc[2] : cx; e->cy = pc ? pc[3] : cy;
         e->setInformation(Eigen::Matrix<double, 8, 8>::Identity() * double(mobs_weight[k]));
         Optimizer->addEdge(e);
         marker_edges.push_back(e);
@@ -218,6 +254,8 @@ int ref_ba_optimize_markers(int n_poses, const float* poses44, const uint8_t* fi
     }
     return 0;
 }
+
+extern "C" {
 
 // PnPSolver::solvePnp (src/optimization/pnpsolver.cpp:116-408) on flat arrays: one free camera vertex, one unary edge per
 // (keypoint, map point) match, optional fixed marker vertices with MarkerEdgeOnlyProject edges, 4 rounds x 10 LM iterations

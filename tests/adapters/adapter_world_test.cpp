@@ -8,7 +8,8 @@
 //   3. matchFrameToMapPoints_b200 against the reference's own Map::matchFrameToMapPoints statements (map.cpp:651-770): identical lists
 //      and setVisible() marks, the kd-tree travelling as the bytes the reference's picoflann writes;
 //   4. solvePnp_b200 against the reference's g2o + typesg2o.h (oracle/_ref/libref_g2o.so): pose to 1e-6, identical inlier flags;
-//   5. GlobalOptimizerB200 (derived from the reference's real globaloptimizer.h) against the same g2o on the window it flattened;
+//   5. GlobalOptimizerB200 (derived from the reference's real globaloptimizer.h) against the same g2o on the window it flattened, with one
+//      camera and with keyframes taken with two cameras;
 //   6. createNewPoints_b200 (the body of the mapper's new-map-point creation) on three keyframes: every point re-projects onto its keypoints.
 // OpenCV / Frame / Map are the container stand-ins of oracle/shim2 (the image has no OpenCV C++).  Built by `make -C oracle ref`
 // into oracle/_ref/, run by tests/test_adapters_gpu.py.  Exit code 0 = every comparison held.
@@ -77,6 +78,12 @@ int ref_ba_optimize(int n_poses, const float* poses44, const uint8_t* fixed, int
                     const int32_t* obs_point, const float* obs_uv, const float* obs_ur, const uint8_t* obs_stereo, const float* obs_inv_sigma2, float fx,
                     float fy, float cx, float cy, float bf, int n_iters, double* out_pose7, float* out_pose44, double* out_point3, double* out_chi2,
                     uint8_t* out_level, uint8_t* out_bad, int* iters_done, double* trace);
+int ref_ba_optimize_cams(int n_poses, const float* poses44, const uint8_t* fixed, int n_points, const float* points3, int n_obs, const int32_t* obs_pose,
+                         const int32_t* obs_point, const float* obs_uv, const float* obs_ur, const uint8_t* obs_stereo, const float* obs_inv_sigma2, float fx,
+                         float fy, float cx, float cy, float bf, int n_iters, double* out_pose7, float* out_pose44, double* out_point3, double* out_chi2,
+                         uint8_t* out_level, uint8_t* out_bad, int* iters_done, double* trace, int n_markers, const float* marker_pose44,
+                         const float* marker_size, int n_mobs, const int32_t* mobs_marker, const int32_t* mobs_pose, const float* mobs_corners,
+                         const float* mobs_weight, double* out_marker_pose7, float* out_marker_pose44, double* out_mobs_chi2, const float* pose_cam);
 }
 
 static int fails = 0;
@@ -340,12 +347,51 @@ int main() {
         EXPECT(pb.n_poses == 3 && pb.n_points > 500 && pb.n_obs > 1500 && dmax < 1e-5 && opt->getBadAssociations().size() == nbad &&
                    map->nNormalUpdates == pb.n_points && opt->getName() == "b200",
                "GlobalOptimizerB200 (reference's GlobalOptimizer interface) == the reference's g2o on the flattened window (poses 1e-5, bad associations)");
+        // keyframe 1 taken with another camera: the adapter flattens one fx fy cx cy bf row per keyframe and the solve still equals the
+        // reference's g2o with the per-edge ImageParams of globaloptimizer_g2o.cpp:233-236
+        map->keyframes[1].imageParams.CameraMatrix.at<float>(0, 0) *= 1.002f;
+        map->keyframes[1].imageParams.CameraMatrix.at<float>(1, 1) *= 1.003f;
+        map->keyframes[1].imageParams.CameraMatrix.at<float>(0, 2) += 0.5f;
+        map->nNormalUpdates = 0;
+        opt->setParams(map, ps);
+        const uco_ba_problem& pc = static_cast<GlobalOptimizerB200*>(opt.get())->problem();
+        EXPECT(pc.pose_cam != nullptr && pc.pose_cam[5] != pc.pose_cam[0] && pc.pose_cam[10] == pc.pose_cam[0], "mixed-camera window: one camera row per keyframe");
+        if (pc.pose_cam) {
+            std::vector<double> c7(7 * pc.n_poses), c3(3 * pc.n_points), cchi(pc.n_obs);
+            std::vector<float> c44(16 * pc.n_poses);
+            std::vector<uint8_t> clev(pc.n_obs), cbad(pc.n_obs);
+            ref_ba_optimize_cams(pc.n_poses, pc.poses44, pc.fixed, pc.n_points, pc.points3, pc.n_obs, pc.obs_pose, pc.obs_point, pc.obs_uv, pc.obs_ur, pc.obs_stereo,
+                                 pc.obs_inv_sigma2, pc.fx, pc.fy, pc.cx, pc.cy, pc.bf, 5, c7.data(), c44.data(), c3.data(), cchi.data(), clev.data(), cbad.data(), its,
+                                 trace.data(), 0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, pc.pose_cam);
+            opt->optimize(&stop);
+            opt->getResults(map);
+            double cmax = 0;
+            for (int k = 0; k < pc.n_poses; k++) {
+                if (pc.fixed[k]) continue;
+                for (int e = 0; e < 12; e++) cmax = std::max(cmax, (double)std::fabs(map->keyframes[k].pose_f2g.at_(e) - c44[16 * k + e]));
+            }
+            size_t cb = 0;
+            for (auto b : cbad) cb += b;
+            EXPECT(cmax < 1e-5 && opt->getBadAssociations().size() == cb,
+                   "GlobalOptimizerB200 on a window taken with two cameras == the reference's g2o with per-edge ImageParams (poses 1e-5, bad associations)");
+        }
+        // InPlaneMarkers (MarkerEdgeX, :360-401) is the one option left out: a window with a marker throws, there is no CPU solver to fall back to
         GlobalOptimizer::ParamSet bad_ps;
+        bad_ps.nIters = 5;
         bad_ps.InPlaneMarkers = true;
-        map->map_markers[4].id = 4;
+        {
+            Marker mk;
+            mk.id = 4; mk.size = 0.2f;
+            mk.pose_g2m = map->keyframes[0].pose_f2g;   // any valid pose
+            mk.frames.insert(0);
+            map->map_markers[4] = mk;
+            ucoslam::MarkerObservation mo;
+            mo.id = 4;
+            map->keyframes[0].markers.push_back(mo);
+        }
         bool threw = false;
-        try { map->keyframes[1].imageParams.CameraMatrix.at<float>(0, 0) = 400; opt->setParams(map, bad_ps); } catch (std::runtime_error&) { threw = true; }
-        EXPECT(threw, "unsupported windows (mixed cameras) throw std::runtime_error instead of falling back to a CPU solver");
+        try { opt->setParams(map, bad_ps); } catch (std::runtime_error&) { threw = true; }
+        EXPECT(threw, "the InPlaneMarkers option throws std::runtime_error instead of falling back to a CPU solver");
     }
     std::printf("%s\n", fails ? "ADAPTER WORLD FAILED" : "ADAPTER WORLD OK");
     return fails ? 1 : 0;

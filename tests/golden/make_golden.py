@@ -101,6 +101,33 @@ def ba_markers():
     print("ba marker golden written", {n: (int(out[n + "_out_iters"].sum()), len(out[n + "_in_mobs_marker"])) for n in BA_MARKER_CASES})
 
 
+BA_CAM_CASES = {  # name -> (synth_ba_problem kwargs, add_markers kwargs or None, mix_cameras kwargs, n_iters)   (also imported by the tests)
+    "cam_mono": (dict(seed=71, n_poses=8, n_fixed=1, n_points=250), None, dict(seed=3), 5),
+    "cam_stereo": (dict(seed=72, n_poses=7, n_fixed=2, n_points=220, stereo_frac=0.4, outlier_frac=0.06), None, dict(seed=4, frac=0.4), 5),
+    "cam_markers": (dict(seed=73, n_poses=8, n_fixed=1, n_points=250), dict(seed=5, n_markers=3), dict(seed=5), 5),
+}
+
+
+def ba_cams():
+    """windows whose keyframes were taken with two cameras: every edge carries the ImageParams of its keyframe (globaloptimizer_g2o.cpp:
+    233-236, :262-266, :335-338); the reference's g2o + its own edge classes through ref_ba_optimize_cams"""
+    oracle_py.build_ref()
+    from ucoslam_b200.synth import add_markers, mix_cameras
+    out = {}
+    for name, (kw, mkw, ckw, iters) in BA_CAM_CASES.items():
+        pb = oracle_py.synth_ba_problem(**kw)
+        if mkw:
+            pb = add_markers(pb, **mkw)
+        pb = mix_cameras(pb, **ckw)
+        r = oracle_py.ref_ba_optimize(pb, iters)
+        for k in oracle_py.BA_INPUT_KEYS + ("pose_cam",) + (BA_MARKER_KEYS if mkw else ()):
+            out["%s_in_%s" % (name, k)] = np.asarray(pb[k])
+        for k, v in r.items():
+            out["%s_out_%s" % (name, k)] = v
+    np.savez_compressed(os.path.join(HERE, "ba_cams_g2o.npz"), **out)
+    print("ba mixed-camera golden written", {n: int(out[n + "_out_iters"].sum()) for n in BA_CAM_CASES})
+
+
 PNP_CASES = {  # name -> synth_pnp_problem kwargs   (also imported by the tests)
     "mono": dict(seed=1, n_matches=800),
     "stereo": dict(seed=2, n_matches=600, stereo_frac=0.5),
@@ -272,6 +299,6 @@ def kfdb():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["knn", "bow", "ba", "ba_markers", "pnp", "project", "match", "kfdb"]
+    which = sys.argv[1:] or ["knn", "bow", "ba", "ba_markers", "ba_cams", "pnp", "project", "match", "kfdb"]
     for w in which:
         globals()[w]()

@@ -52,3 +52,26 @@ def test_oracle_matches_live_reference():
                       (dict(seed=12, n_poses=7, n_fixed=1, n_points=300, outlier_frac=0.1, pose_noise=(0.05, 2.0)), 10)):
         pb = oracle_py.synth_ba_problem(**kw)
         check_ba(oracle_py.ba_optimize(pb, iters), oracle_py.ref_ba_optimize(pb, iters))
+
+
+def test_mixed_camera_goldens_are_reproduced_by_the_live_reference():
+    """tests/golden/ba_cams_g2o.npz (keyframes taken with two cameras, one fx fy cx cy bf row per keyframe) against the reference's g2o
+    compiled here; the table changes the solution (the same observations under one camera end elsewhere)"""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_golden import BA_CAM_CASES, BA_MARKER_KEYS
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ba_cams_g2o.npz"))
+    for name, (kw, mkw, ckw, iters) in BA_CAM_CASES.items():
+        pb = {k: g["%s_in_%s" % (name, k)] for k in oracle_py.BA_INPUT_KEYS + ("pose_cam",) + (BA_MARKER_KEYS if mkw else ())}
+        for k in ("fx", "fy", "cx", "cy", "bf"):
+            pb[k] = float(pb[k])
+        assert pb["pose_cam"].shape == (len(pb["fixed"]), 5) and len(np.unique(pb["pose_cam"][:, 0])) == 2
+        ref = oracle_py.ref_ba_optimize(pb, iters)
+        if ref is None:
+            pytest.skip("oracle/_ref not built")
+        assert np.array_equal(ref["iters"], g[name + "_out_iters"])
+        assert np.abs(ref["pose7"] - g[name + "_out_pose7"]).max() < 1e-9
+        if not mkw:
+            one = dict(pb)
+            one.pop("pose_cam")
+            assert np.abs(oracle_py.ref_ba_optimize(one, iters)["pose7"] - ref["pose7"]).max() > 1e-3

@@ -71,9 +71,13 @@ struct BaDev {
     const int2 *blk_ij, *con;
     LmState* st;
     Cam cam;
+    const Cam* cams = nullptr;   // per keyframe (uco_ba_problem::pose_cam: a window whose keyframes were taken with different cameras), else cam
     double d2, d3;      // Huber deltas sqrt(5.99f), sqrt(7.815f) (globaloptimizer_g2o.h:112-117)
     float chi2d, chi3d;
 };
+
+// every edge carries the ImageParams of ITS keyframe (globaloptimizer_g2o.cpp:233-236, :262-266, :335-338)
+__device__ __forceinline__ const Cam& cam_of(const BaDev& B, int pi) { return B.cams ? B.cams[pi] : B.cam; }
 
 // ---- K10 residuals: computeActiveErrors + the per-edge terms of activeRobustChi2 (sparse_optimizer.cpp:102-116) -------------
 __global__ void __launch_bounds__(256) ba_errors_kernel(const __grid_constant__ BaDev B, int robust) {
@@ -89,7 +93,7 @@ __global__ void __launch_bounds__(256) ba_errors_kernel(const __grid_constant__ 
     se3_map(T, x, p);
     bool st = B.stereo[i];
     double z[3] = {B.z[3 * i], B.z[3 * i + 1], B.z[3 * i + 2]};
-    residual(p, z, st, B.cam, e);
+    residual(p, z, st, cam_of(B, B.obs_pose[i]), e);
     double c2 = st ? (e[0] * e[0] + e[1] * e[1] + e[2] * e[2]) * B.info[i] : (e[0] * e[0] + e[1] * e[1]) * B.info[i];
     B.err[3 * i] = e[0]; B.err[3 * i + 1] = e[1]; B.err[3 * i + 2] = e[2];
     B.chi2[i] = c2;
@@ -126,7 +130,7 @@ __global__ void __launch_bounds__(128) ba_linearize_lm_kernel(const __grid_const
         se3_map(T, x, p);
         quat_to_R(T.q, R);
         bool st = B.stereo[i];
-        jac_point(p, R, st, B.cam, JX);
+        jac_point(p, R, st, cam_of(B, pi), JX);
         obs_weights(B, i, robust, wo, orr);
         const int D = st ? 3 : 2;
 #pragma unroll
@@ -147,7 +151,7 @@ __global__ void __launch_bounds__(128) ba_linearize_lm_kernel(const __grid_const
                 }
         }
         if (B.free_idx[pi] >= 0) {
-            jac_pose(p, st, B.cam, JT);
+            jac_pose(p, st, cam_of(B, pi), JT);
 #pragma unroll
             for (int a = 0; a < 6; a++)
 #pragma unroll
@@ -183,7 +187,7 @@ __global__ void __launch_bounds__(POSE_THREADS) ba_linearize_pose_kernel(const _
         double x[3] = {X[0], X[1], X[2]}, p[3], JT[18], wo, orr[3];
         se3_map(T, x, p);
         bool st = B.stereo[i];
-        jac_pose(p, st, B.cam, JT);
+        jac_pose(p, st, cam_of(B, pi), JT);
         obs_weights(B, i, robust, wo, orr);
         const int D = st ? 3 : 2;
         int k = 0;
@@ -717,8 +721,9 @@ __global__ void __launch_bounds__(64) ba_marker_kernel(const __grid_constant__ B
     const float size = B.mk.size[m];
     const float* obs = B.mk.e_corners + 8 * k;
     const double w = (double)B.mk.e_weight[k];
+    const Cam& cam = cam_of(B, pi);
     double e0[8];
-    marker_edge_error(T, G, size, obs, B.cam, e0);
+    marker_edge_error(T, G, size, obs, cam, e0);
     double c2 = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) c2 += e0[i] * w * e0[i];
@@ -732,15 +737,15 @@ __global__ void __launch_bounds__(64) ba_marker_kernel(const __grid_constant__ B
         Pose Gp = G, Gn = G;
         u[d] = delta; se3_oplus(Gp, u);
         u[d] = -delta; se3_oplus(Gn, u);
-        marker_edge_error(T, Gp, size, obs, B.cam, ea);
-        marker_edge_error(T, Gn, size, obs, B.cam, eb);
+        marker_edge_error(T, Gp, size, obs, cam, ea);
+        marker_edge_error(T, Gn, size, obs, cam, eb);
         for (int i = 0; i < 8; i++) Jm[i * 6 + d] = scalar * (ea[i] - eb[i]);
         if (cam_free) {
             Pose Tp = T, Tn = T;
             u[d] = delta; se3_oplus(Tp, u);
             u[d] = -delta; se3_oplus(Tn, u);
-            marker_edge_error(Tp, G, size, obs, B.cam, ea);
-            marker_edge_error(Tn, G, size, obs, B.cam, eb);
+            marker_edge_error(Tp, G, size, obs, cam, ea);
+            marker_edge_error(Tn, G, size, obs, cam, eb);
             for (int i = 0; i < 8; i++) Jc[i * 6 + d] = scalar * (ea[i] - eb[i]);
         } else {
             for (int i = 0; i < 8; i++) Jc[i * 6 + d] = 0;
@@ -914,10 +919,12 @@ cudaEvent_t* uco_ba_events(uco_b200_ctx* ctx) {
 }
 
 // streamed form: one kernel per phase, the host enqueues the next trial after reading two flags (any problem size)
+int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_problem* pb, const volatile unsigned char* stop, uco_ba_result* res);
 int ba_streamed_solve(uco_b200_ctx* ctx, const uco_ba_problem* pb, const volatile unsigned char* stop, uco_ba_result* res) {
     if (!ctx) return UCO_E_INVALID;
     cudaSetDevice(ctx->device);  // the calling thread may be a new one (mapper / tracker threads): bind it to the context's GPU
     if (!pb || !res) return uco_fail(ctx, UCO_E_INVALID, "ba_solve: null problem / result");
+    if (pb->pose_cam) return ba_sharded_solve(ctx, nullptr, pb, stop, res);   // one camera per keyframe: only the sharded solver's kernels read the per-pose table
     const int P = pb->n_poses, N = pb->n_points, M = pb->n_obs;
     if (P <= 0 || N < 0 || M < 0 || pb->n_iters < 0) return uco_fail(ctx, UCO_E_INVALID, "ba_solve: bad sizes");
     if (!pb->poses44 || !pb->fixed || (N && !pb->points3) || (M && (!pb->obs_pose || !pb->obs_point || !pb->obs_uv || !pb->obs_inv_sigma2)))
@@ -1303,6 +1310,7 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
     const size_t o_mk44 = A.take(64 * (size_t)(Nm + 1)), o_mksz = A.take(4 * (size_t)(Nm + 1)), o_em = A.take(4 * (size_t)(Ne + 1)), o_ep = A.take(4 * (size_t)(Ne + 1)),
                  o_ec = A.take(32 * (size_t)(Ne + 1)), o_ew = A.take(4 * (size_t)(Ne + 1)), o_cptr = A.take(4 * (size_t)(Pf + 2)), o_cedg = A.take(4 * (cam_edges.size() + 1)),
                  o_mptr = A.take(4 * (size_t)(Nm + 2)), o_medg = A.take(4 * (size_t)(Ne + 1)), o_bedg = A.take(4 * (size_t)(nblk + 1));
+    const size_t o_cams = A.take(pb->pose_cam ? sizeof(Cam) * (size_t)P : 0);   // one camera per keyframe (mixed-camera windows)
     const size_t in_bytes = A.off;
     const size_t o_mkpose = A.take(56 * (size_t)(Nm + 1)), o_mkbak = A.take(56 * (size_t)(Nm + 1)), o_echi = A.take(8 * (size_t)(Ne + 1)), o_eblk = A.take(960 * (size_t)(Ne + 1)),
                  o_mk44o = A.take(64 * (size_t)(Nm + 1));
@@ -1333,6 +1341,13 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
     d = (uint8_t*)uco_ws(ctx, WS_BA, A.off);
     uint8_t* h = (uint8_t*)uco_pinned(ctx, WS_BA, in_bytes + sizeof(LmState) + 64);
     if (!d || !h) return UCO_E_NOMEM;
+    if (pb->pose_cam)
+        for (int p = 0; p < P; p++) {
+            const float* c = pb->pose_cam + 5 * (size_t)p;
+            Cam k;
+            k.fx = c[0]; k.fy = c[1]; k.cx = c[2]; k.cy = c[3]; k.bf = c[4]; k.bf_f = c[4];
+            memcpy(h + o_cams + sizeof(Cam) * (size_t)p, &k, sizeof(Cam));
+        }
     memcpy(h + o_free_idx, free_idx.data(), 4 * (size_t)P);
     memcpy(h + o_free_list, free_list.data(), 4 * (size_t)Pf);
     memcpy(h + o_lm_ptr, lm_ptr_loc.data(), 4 * (size_t)(NL + 1));
@@ -1403,6 +1418,7 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
     B.blk_ptr = (int*)(d + o_blk_ptr); B.blk_ij = (int2*)(d + o_blk_ij); B.con = (int2*)(d + o_con);
     B.st = (LmState*)(d + o_st);
     B.cam.fx = pb->fx; B.cam.fy = pb->fy; B.cam.cx = pb->cx; B.cam.cy = pb->cy; B.cam.bf = pb->bf; B.cam.bf_f = pb->bf;
+    if (pb->pose_cam) B.cams = (const Cam*)(d + o_cams);
     B.chi2d = 5.99f; B.chi3d = 7.815f;
     B.d2 = (double)sqrtf(B.chi2d); B.d3 = (double)sqrtf(B.chi3d);
     double* Sp = (double*)(d + o_red);
@@ -1668,7 +1684,7 @@ int uco_b200_ba_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* pbs,
     for (int i = 0; i < n; i++) {
         int rc = ba_validate(ctx, pbs + i);
         if (rc != UCO_OK) return rc;
-        if (pbs[i].n_markers > 0) {  // ArUco markers: the streamed / sharded solver handles the marker vertices and edges
+        if (pbs[i].n_markers > 0 || pbs[i].pose_cam) {  // ArUco markers / one camera per keyframe: the sharded solver (any size, one rank) handles them
             rc = ba_sharded_solve(ctx, nullptr, pbs + i, stop, res + i);
             if (rc != UCO_OK) return rc;
             continue;

@@ -1000,6 +1000,9 @@ static void ba_parallel_for(int n, int want, F&& f) {
 
 int ba_cluster_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* const* pbs, const volatile unsigned char* stop, uco_ba_result* const* res) {
     if (n <= 0) return UCO_OK;
+    for (int i = 0; i < n; i++)
+        if (pbs[i]->pose_cam || pbs[i]->n_markers > 0)   // the callers route these to the sharded solver
+            return uco_fail(ctx, UCO_E_INVALID, "ba_solve: markers / per-keyframe cameras are not handled by the cluster-resident solver");
     static const bool trace = getenv("UCO_BA_TRACE") != nullptr;
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto t0 = now();

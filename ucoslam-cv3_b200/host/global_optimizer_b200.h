@@ -5,9 +5,11 @@
 // uco_ba_problem; getResults writes poses, points and the bad-association list back as :466-538 does.  The object keeps
 // its own copy of inputs and results, because the mapper thread calls setParams + optimize WITHOUT the map lock and the
 // tracker thread calls getResults later (src/utils/mapmanager.cpp:11361-11405, :1267-1305); *stopASAP is forwarded.
-// ArUco markers travel too (marker vertices, MarkerEdges, the per-keyframe marker weights of :276-297).  Windows whose keyframes were
-// taken with different cameras, or that use the InPlaneMarkers option (MarkerEdgeX, :360-401), are NOT covered by the C ABI: setParams
-// throws std::runtime_error for them, like every other error path of the reference's plugins (there is no CPU fallback).
+// ArUco markers travel too (marker vertices, MarkerEdges, the per-keyframe marker weights of :276-297), and so do windows whose keyframes
+// were taken with different cameras (one fx fy cx cy bf row per keyframe: uco_ba_problem::pose_cam).  The InPlaneMarkers option
+// (MarkerEdgeX, :360-401: marker-to-marker edges differentiated numerically with g2o's default delta of 1e-9, whose result depends on
+// the last bits of Eigen's 4x4 inverse) is NOT covered by the C ABI: setParams throws std::runtime_error for it, like every other error
+// path of the reference's plugins (there is no CPU fallback).
 // Selected with Params::global_optimizer = "b200" once registered in GlobalOptimizer::create.
 // Compiled and driven against the reference's own globaloptimizer.h by tests/adapters/adapter_world_test.cpp (container stand-ins for
 // Map / Frame / OpenCV, oracle/shim2); inside the reference tree it compiles against the real headers.
@@ -68,7 +70,6 @@ public:
             if (ip.fx() != f0.imageParams.fx() || ip.fy() != f0.imageParams.fy() || ip.cx() != f0.imageParams.cx() ||
                 ip.cy() != f0.imageParams.cy() || ip.bl != f0.imageParams.bl) mixedCameras = true;
         }
-        if (mixedCameras) throw std::runtime_error("GlobalOptimizerB200: keyframes taken with different cameras in one window are not supported");
         if (markers && _params.InPlaneMarkers) throw std::runtime_error("GlobalOptimizerB200: the InPlaneMarkers option is not supported");
         // the reference emits marker vertices / edges in ascending marker id (std::map, globaloptimizer_g2o.cpp:306-348)
         std::sort(_markerIds.begin(), _markerIds.end());
@@ -136,6 +137,15 @@ public:
         _pb.obs_stereo = _obsStereo.data(); _pb.obs_inv_sigma2 = _obsInv.data();
         _pb.fx = f0.imageParams.fx(); _pb.fy = f0.imageParams.fy(); _pb.cx = f0.imageParams.cx(); _pb.cy = f0.imageParams.cy();
         _pb.bf = f0.imageParams.bl * f0.imageParams.fx();
+        _poseCam.clear();
+        if (mixedCameras) {   // every edge carries the ImageParams of its keyframe (:233-236, :262-266, :335-338)
+            for (auto f : _frameIds) {
+                const ImageParams& ip = map->keyframes[f].imageParams;
+                const float c[5] = {ip.fx(), ip.fy(), ip.cx(), ip.cy(), ip.bl * ip.fx()};
+                _poseCam.insert(_poseCam.end(), c, c + 5);
+            }
+            _pb.pose_cam = _poseCam.data();
+        }
         _pb.n_iters = _params.nIters;
     }
 
@@ -193,7 +203,7 @@ private:
     ParamSet _params;
     uco_ba_problem _pb{};
     std::vector<uint32_t> _frameIds, _pointIds, _markerIds;
-    std::vector<float> _poses, _points, _obsUV, _obsUR, _obsInv, _outPoses, _mkPose, _mkSize, _moCorners, _moWeight, _outMarkers;
+    std::vector<float> _poses, _points, _obsUV, _obsUR, _obsInv, _outPoses, _mkPose, _mkSize, _moCorners, _moWeight, _outMarkers, _poseCam;
     std::vector<int32_t> _moMarker, _moPose;
     std::vector<uint8_t> _fixed, _obsStereo, _outBad;
     std::vector<int32_t> _obsPose, _obsPoint;

@@ -285,7 +285,8 @@ class BaProblem(ctypes.Structure):  # uco_ba_problem
                 ("points3", _vp), ("obs_pose", _vp), ("obs_point", _vp), ("obs_uv", _vp), ("obs_ur", _vp), ("obs_stereo", _vp),
                 ("obs_inv_sigma2", _vp), ("fx", _c.c_float), ("fy", _c.c_float), ("cx", _c.c_float), ("cy", _c.c_float),
                 ("bf", _c.c_float), ("n_iters", _c.c_int32), ("n_markers", _c.c_int32), ("marker_pose44", _vp), ("marker_size", _vp),
-                ("n_marker_obs", _c.c_int32), ("mobs_marker", _vp), ("mobs_pose", _vp), ("mobs_corners", _vp), ("mobs_weight", _vp)]
+                ("n_marker_obs", _c.c_int32), ("mobs_marker", _vp), ("mobs_pose", _vp), ("mobs_corners", _vp), ("mobs_weight", _vp),
+                ("pose_cam", _vp)]
 
 
 class BaResult(ctypes.Structure):  # uco_ba_result
@@ -723,6 +724,10 @@ class Context:
             cp.mobs_corners, cp.mobs_weight = _p(a["mobs_corners"]), _p(a["mobs_weight"])
             out.update(marker_pose44=np.zeros((nm, 16), np.float32), marker_pose7=np.zeros((nm, 7)), mobs_chi2=np.zeros(nmo))
             cr.marker_poses44, cr.marker_pose7, cr.mobs_chi2 = _p(out["marker_pose44"]), _p(out["marker_pose7"]), _p(out["mobs_chi2"])
+        if pb.get("pose_cam") is not None:   # one camera per keyframe (fx fy cx cy bf)
+            a["pose_cam"] = A("pose_cam", np.float32)
+            assert a["pose_cam"].shape == (P, 5)
+            cp.pose_cam = _p(a["pose_cam"])
         return cp, cr, a, out
 
     def ba_solve(self, pb, n_iters, stop=None):

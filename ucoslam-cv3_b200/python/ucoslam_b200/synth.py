@@ -115,6 +115,40 @@ def add_markers(pb, seed, n_markers=4, size=0.25, corner_sigma=0.3, pose_noise=(
     return out
 
 
+def mix_cameras(pb, seed, frac=0.5, scale=(1.6, 1.45), shift=(37.0, -21.0), bl_scale=1.3):
+    """Turn a single-camera BA problem (synth_ba_problem / synth_global_ba, optionally with add_markers) into a window whose keyframes were
+    taken with two cameras: about `frac` of the keyframes get a second camera (fx, fy scaled, principal point shifted, another stereo
+    baseline) and their observations are re-projected through it (same rays, the pixel noise scales with the focal length).  Adds pose_cam
+    (n_poses x 5: fx fy cx cy bf per keyframe) - the table uco_ba_problem::pose_cam / GlobalOptimizerG2O's per-edge ImageParams stand for."""
+    rng = np.random.default_rng(seed)
+    P = len(pb["fixed"])
+    second = rng.random(P) < frac
+    second[0], second[-1] = False, True                      # both cameras are present
+    c1 = np.array([pb["fx"], pb["fy"], pb["cx"], pb["cy"], pb["bf"]], np.float64)
+    c2 = np.array([c1[0] * scale[0], c1[1] * scale[1], c1[2] + shift[0], c1[3] + shift[1], c1[4] * scale[0] * bl_scale])
+    out = dict(pb)
+    cam = np.where(second[:, None], c2[None, :], c1[None, :])
+    uv = np.array(pb["obs_uv"], np.float64).reshape(-1, 2)
+    ur = np.array(pb["obs_ur"], np.float64).reshape(-1)
+    st = np.asarray(pb["obs_stereo"]).astype(bool)
+    sel = second[np.asarray(pb["obs_pose"])]
+    disp = uv[:, 0] - ur                                      # bf / depth
+    uv2 = uv.copy()
+    uv2[sel, 0] = (uv[sel, 0] - c1[2]) / c1[0] * c2[0] + c2[2]
+    uv2[sel, 1] = (uv[sel, 1] - c1[3]) / c1[1] * c2[1] + c2[3]
+    ur2 = ur.copy()
+    both = sel & st
+    ur2[both] = uv2[both, 0] - disp[both] / c1[4] * c2[4] if c1[4] else ur[both]
+    out.update(obs_uv=uv2.astype(np.float32), obs_ur=ur2.astype(np.float32), pose_cam=cam.astype(np.float32))
+    if len(pb.get("marker_size", ())):
+        mc = np.array(pb["mobs_corners"], np.float64).reshape(-1, 4, 2)
+        msel = second[np.asarray(pb["mobs_pose"])]
+        mc[msel, :, 0] = (mc[msel, :, 0] - c1[2]) / c1[0] * c2[0] + c2[2]
+        mc[msel, :, 1] = (mc[msel, :, 1] - c1[3]) / c1[1] * c2[1] + c2[3]
+        out["mobs_corners"] = mc.reshape(-1, 8).astype(np.float32)
+    return out
+
+
 def synth_global_ba(seed, n_kf=500, n_points=50000, obs_per_point=6, n_fixed=2, loop_m=50.0, px_sigma=0.5, pose_noise=(0.01, 0.5),
                     point_noise=0.02, outlier_frac=0.01, w=640, h=480, f=525.0):
     """BASELINE config 5: n_kf keyframes on a closed loop of loop_m metres looking outwards, n_points landmarks each
