@@ -44,7 +44,8 @@ BA_CLUSTER = int(os.environ.get("UCO_BENCH_BA_CLUSTER", "4"))       # CTAs per B
 SM_COUNT, SM_GHZ = 148, 1.965
 PEAK_ALU = 64 * SM_COUNT * SM_GHZ * 1e9      # alu-pipe thread-instructions/s (16 lanes/clk/SMSP, B300_MICROARCH.md "Pipe rates")
 PEAK_POPC = 16 * SM_COUNT * SM_GHZ * 1e9     # popc32/s
-PEAK_FP64_SM = 2 * 64 * SM_GHZ * 1e9 / 2     # DFMA flop/s per SM (64 DFMA lanes/clk/SM at half rate: 2 flop x 32/clk), nominal
+PEAK_FP64_SM = 2 * 61.6 * SM_GHZ * 1e9       # DFMA flop/s per SM, MEASURED on this B200: 512 threads x 8 independent DFMA chains issue 61.6 DFMA/clk/SM
+                                             # (profiles/r2_fp64_latency_microbench.txt: 66.5 cycles per 8 DFMA per thread); B200 keeps the full-rate FP64 pipe
 
 
 def parse():
@@ -677,7 +678,7 @@ def run_b200(args, rank, world, local_rank):
                            "unit": None, "traffic": None}
     top = max((k for k in rl if rl[k]["frac"] is not None), key=lambda k: rl[k]["sm_ms"])
     roof = dict(rl[top])
-    roof.update({"stage": top, "peak_source": "B300_MICROARCH.md pipe rates x 148 SMs x 1.965 GHz; HBM " + ("measured" if peaks else "fallback"),
+    roof.update({"stage": top, "peak_source": "INT / popc: B300_MICROARCH.md pipe rates x 148 SMs x 1.965 GHz; FP64: DFMA rate measured on this B200 (profiles/r2_fp64_latency_microbench.txt); HBM " + ("measured" if peaks else "fallback"),
                  "kernel_ms_per_step": rl[top]["ms_per_step"], "dominant_by": "SM x time share of the step"})
     orb_total_ms = sum(acc.values())
     orb_alg = W * H + 2 * px + KPTS * 60                          # 2 328 264 B/frame

@@ -968,20 +968,24 @@ __global__ void __launch_bounds__(256) orient_describe_kernel(const __grid_const
         }
         __syncwarp();
     }
-    // IC_Angle: lane v+15 sums image row v of the radius-15 disc
+    // IC_Angle: lane u+15 sums image COLUMN u of the radius-15 disc.  The disc is symmetric under transposition (the umax table is built
+    // that way, ORBextractor.cpp:436-451: |u| <= umax[|v|] <=> |v| <= umax[|u|]) and the moments are integer sums, so the order is free;
+    // with a lane per column the 32 lanes of every step read one row (8 consecutive words), where a lane per row had them 64 bytes
+    // apart - 16 lanes on each of two banks (the kernel's top stall was the shared-memory queue)
     int m10 = 0, m01 = 0;
     if (lane < 31) {
-        const int v = lane - 15;
-        const int d = c_umax[v < 0 ? -v : v];
-        const uint8_t* row = &patch[19 + v][19 + dx];
-        int su = 0, s1 = 0;
-        for (int u = -d; u <= d; u++) {
-            int val = row[u];
-            su += u * val;
+        const int u = lane - 15;
+        const int d = c_umax[u < 0 ? -u : u];
+        const uint8_t* col = &patch[19][19 + dx + u];
+        int sv = 0, s1 = 0;
+#pragma unroll
+        for (int v = -15; v <= 15; v++) {
+            const int val = (v >= -d && v <= d) ? col[v * ORB_WIN_COLS] : 0;
+            sv += v * val;
             s1 += val;
         }
-        m10 = su;
-        m01 = v * s1;
+        m10 = u * s1;
+        m01 = sv;
     }
     m10 = __reduce_add_sync(0xffffffffu, m10);
     m01 = __reduce_add_sync(0xffffffffu, m01);
