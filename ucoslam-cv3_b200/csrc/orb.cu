@@ -471,7 +471,7 @@ __host__ __device__ inline int fc_smem_bytes(int cw, int ch) {
     return ch * fc_roi_pitch(cw) + (ih + 2) * fc_sc_pitch(iw) + 4 * ((n + 31) / 32) + 2 * fc_list_cap(n) + 16;
 }
 
-__global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__ PlanDev c_plan, const uint8_t* __restrict__ pyr, const CellDev* __restrict__ cells,
+__global__ void __launch_bounds__(256, 5) fast_cells_kernel(const __grid_constant__ PlanDev c_plan, const uint8_t* __restrict__ pyr, const CellDev* __restrict__ cells,
                                                          uint32_t* __restrict__ cand, int* __restrict__ cand_cnt) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int ci = blockIdx.x, f = blockIdx.y;
@@ -494,30 +494,32 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
     __shared__ int wsum[8];
     __shared__ int running, running_ini;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (C.w <= 128) {  // two ROI rows per round, all their loads issued before the first store (the load latency was 23 % of the stall samples)
-        for (int r = warp; r < C.h; r += 16) {
-            const int r2 = r + 8;
-            const bool has2 = r2 < C.h;
-            const uint8_t *p0 = src + (size_t)r * L.pitch, *p1 = src + (size_t)(has2 ? r2 : r) * L.pitch;
-            uint8_t v0[4], v1[4];
+    {   // ROI -> shared memory as 32-bit words: the byte phase of a row start, (x0 + 19) & 3, is the same for every row (level offsets
+        // and pitches are multiples of 64), so destination word k of a row (ROI columns 4k-1 .. 4k+2) is one funnel shift of two aligned
+        // source words; 4 words in flight per thread.  Bytes past the ROI's last column are whatever the image holds there (inside the
+        // bordered row: x0 + w + 8 <= level width + 38); the segment test masks those columns.
+        const int nwr = rp >> 2, total = nwr * C.h;
+        const unsigned wm = (unsigned)((0x100000000ull + nwr - 1) / (unsigned)nwr);   // i / nwr == umulhi(i, wm) for i < 2^16
+        const int phi = (int)((size_t)src & 3);
+        const uint8_t* base = src - phi;
+        for (int i0 = tid; i0 < total; i0 += 4 * 256) {
+            unsigned lo[4], hi[4];
+            int so[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int c = lane + 32 * k;
-                v0[k] = c < C.w ? p0[c] : 0;
-                v1[k] = c < C.w ? p1[c] : 0;
+            for (int j = 0; j < 4; j++) {
+                const int i = i0 + 256 * j;
+                const int r = total < 65536 ? (int)__umulhi((unsigned)i, wm) : i / nwr, k = i - r * nwr;
+                const int o = 4 * k - 1 + phi;                              // byte offset from the aligned row start, >= -1
+                const unsigned* q = (const unsigned*)(base + (size_t)r * L.pitch) + (o >> 2);
+                so[j] = r * rp + 4 * k;
+                lo[j] = hi[j] = 0;
+                if (i < total) { lo[j] = q[0]; hi[j] = q[1]; }
+                lo[j] = __funnelshift_r(lo[j], hi[j], 8 * (o & 3));
             }
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int c = lane + 32 * k;
-                if (c < C.w) {
-                    roi[r * rp + c + 1] = v0[k];
-                    if (has2) roi[r2 * rp + c + 1] = v1[k];
-                }
-            }
+            for (int j = 0; j < 4; j++)
+                if (i0 + 256 * j < total) *(unsigned*)(roi + so[j]) = lo[j];
         }
-    } else {
-        for (int r = warp; r < C.h; r += 8)
-            for (int c = lane; c < C.w; c += 32) roi[r * rp + c + 1] = src[(size_t)r * L.pitch + c];
     }
     for (int i = tid; i < ((sp * (ih + 2)) >> 2) + nw; i += 256) ((unsigned*)sc)[i] = 0;  // sc and cmask are contiguous
     if (tid == 0) nlist = running = running_ini = 0;
