@@ -525,11 +525,13 @@ __global__ void __launch_bounds__(256, 5) fast_cells_kernel(const __grid_constan
     if (tid == 0) nlist = running = running_ini = 0;
     __syncthreads();
     const int min_th = c_plan.min_th, ini_th = c_plan.ini_th;
+    const unsigned iwm = (unsigned)((0x100000000ull + iw - 1) / (unsigned)iw);   // i / iw == umulhi(i, iwm) for i < 2^16 (iw = 1 would wrap the constant)
+    const bool fastdiv = n < 65536 && iw > 1;
     // 1. segment test, 4 pixels per thread
     {
         const int gpr = (iw + 3) >> 2, G = gpr * ih, rpw = rp >> 2;
         const unsigned gm = (unsigned)((0x100000000ull + gpr - 1) / (unsigned)gpr);  // g / gpr == umulhi(g, gm) for g < 2^16 ...
-        const bool small = G < 65536;
+        const bool small = G < 65536 && gpr > 1;
         const unsigned th4 = (unsigned)min_th * 0x01010101u;
         for (int g = tid; g < G; g += 256) {
             const int r = small ? (int)__umulhi((unsigned)g, gm) : g / gpr;
@@ -598,7 +600,7 @@ __global__ void __launch_bounds__(256, 5) fast_cells_kernel(const __grid_constan
         const int nl = min(nlist, lcap);
         for (int e = tid; e < nl; e += 256) {
             const int i = list[e];
-            const int r = i / iw, c = i - r * iw;
+            const int r = fastdiv ? (int)__umulhi((unsigned)i, iwm) : i / iw, c = i - r * iw;
             sc[(r + 1) * sp + c + 4] = (uint8_t)fast_score(roi + (r + 3) * rp + c + 4, rp, min_th);
         }
     }
@@ -613,7 +615,7 @@ __global__ void __launch_bounds__(256, 5) fast_cells_kernel(const __grid_constan
             const int b = __ffs(bits) - 1;
             bits &= bits - 1;
             const int i = (w << 5) + b;
-            const int r = i / iw, c = i - r * iw;
+            const int r = fastdiv ? (int)__umulhi((unsigned)i, iwm) : i / iw, c = i - r * iw;
             const uint8_t* q = sc + (r + 1) * sp + c + 4;
             const int s = q[0];
             const int nb = max(max(max(q[-sp - 1], q[-sp]), max(q[-sp + 1], q[-1])), max(max(q[1], q[sp - 1]), max(q[sp], q[sp + 1])));
@@ -642,7 +644,7 @@ __global__ void __launch_bounds__(256, 5) fast_cells_kernel(const __grid_constan
             const int b = __ffs(keep) - 1;
             keep &= keep - 1;
             const int i = (w << 5) + b;
-            const int r = i / iw, c = i - r * iw;
+            const int r = fastdiv ? (int)__umulhi((unsigned)i, iwm) : i / iw, c = i - r * iw;
             const uint32_t s = sc[(r + 1) * sp + c + 4];
             if (pos < C.cand_cap) out[pos] = (s << 24) | ((uint32_t)(C.y0 + 3 + r) << 12) | (uint32_t)(C.x0 + 3 + c);
             pos++;
