@@ -204,8 +204,8 @@ typedef struct uco_ba_problem {
     int32_t n_iters;             /* ParamSet::nIters: stage 1 runs n_iters LM iterations, stage 2 runs 2 * n_iters */
     /* ArUco markers (globaloptimizer_g2o.cpp:157-170, 304-350; zero / NULL when there are none): one free SE3 vertex per map marker
      * with a valid pose and one MarkerEdge (typesg2o.h:108-167: the 4 corners reprojected through camera * marker, 8 residuals, numeric
-     * Jacobian with delta 1e-4, no robust kernel) per (marker, keyframe) observation.  The InPlaneMarkers extension (:360-401) is not
-     * covered.  Problems with markers are solved by the streamed / sharded solver. */
+     * Jacobian with delta 1e-4, no robust kernel) per (marker, keyframe) observation.  Problems with markers are solved by the sharded
+     * solver (one rank when no communicator is given). */
     int32_t n_markers;
     const float* marker_pose44;  /* n_markers x 16   Marker::pose_g2m (global <- marker), row-major 4x4 */
     const float* marker_size;    /* n_markers        Marker::size */
@@ -218,6 +218,16 @@ typedef struct uco_ba_problem {
      * the ImageParams of ITS keyframe (globaloptimizer_g2o.cpp:233-236, :262-266, :335-338).  NULL: all keyframes use fx..bf above.
      * Problems with this table are solved by the sharded solver (one rank when no communicator is given). */
     const float* pose_cam;       /* n_poses x 5      fx fy cx cy bf (= bl * fx) of each keyframe, or NULL */
+    /* The InPlaneMarkers option (globaloptimizer_g2o.cpp:356-401; n_plane = 0: off): the map's reference marker (the valid marker seen by
+     * most keyframes, :362-368) is tied to every OTHER marker vertex of the window by one MarkerEdgeX (:37-66: with M = inverse(ref) * other,
+     * residuals 10 * (M(0,2), M(1,2), 1 - M(2,2), M(2,3)); g2o's numeric Jacobian, delta 1e-9f; information = I4 * plane_weight, no kernel).
+     * plane_ref is the reference's index among the markers above, or -1 when it is not a vertex of this window: it then enters as a FIXED
+     * vertex with the pose in plane_ref_pose44 (:371-379). */
+    int32_t n_plane;             /* planar edges = markers of the window other than the reference */
+    int32_t plane_ref;
+    const float* plane_ref_pose44; /* 16             Marker::pose_g2m of the reference marker when plane_ref < 0 */
+    const int32_t* plane_other;  /* n_plane          index into the markers */
+    double plane_weight;         /* 0.33 * (sum of marker weights x 8 + sum of keypoint weights) / (4 * n_plane)   (:381-382) */
 } uco_ba_problem;
 
 typedef struct uco_ba_result {   /* every pointer may be NULL (not wanted) */

@@ -227,6 +227,8 @@ def ref_ba_optimize(pb, n_iters):
     lib = load_ref("libref_g2o.so")
     if lib is None:
         return None
+    if len(pb.get("plane_other", ())):   # InPlaneMarkers: MarkerEdgeX restated on the reference's g2o (ref_g2o_wrap.cpp PlanarMarkerEdge)
+        return _ba_call_markers(lib.ref_ba_optimize_planar, pb, n_iters)
     if pb.get("pose_cam") is not None:   # one camera per keyframe: the per-edge ImageParams of globaloptimizer_g2o.cpp:233-236, :262-266, :335-338
         return _ba_call_markers(lib.ref_ba_optimize_cams, pb, n_iters)
     if len(pb.get("marker_size", ())):
@@ -253,7 +255,10 @@ def _ba_call_markers(fn, pb, n_iters):
        int(n_iters), _p(out["pose7"]), _p(out["pose44"]), _p(out["point3"]), _p(out["chi2"]), _p(out["level"]), _p(out["bad"]),
        _p(out["iters"]), _p(out["trace"]), nm, _p(keep[0]), _p(keep[1]), nmo, _p(keep[2]), _p(keep[3]), _p(keep[4]), _p(keep[5]),
        _p(out["marker_pose7"]), _p(out["marker_pose44"]), _p(out["mobs_chi2"]),
-       *([_p(np.ascontiguousarray(pb["pose_cam"], np.float32))] if pb.get("pose_cam") is not None else []))
+       *([_p(np.ascontiguousarray(pb["pose_cam"], np.float32))] if pb.get("pose_cam") is not None else ([None] if len(pb.get("plane_other", ())) else [])),
+       *([len(pb["plane_other"]), int(pb["plane_ref"]),
+          _p(np.ascontiguousarray(pb["plane_ref_pose44"], np.float32)) if int(pb["plane_ref"]) < 0 else None,
+          _p(np.ascontiguousarray(pb["plane_other"], np.int32)), ctypes.c_double(float(pb["plane_weight"]))] if len(pb.get("plane_other", ())) else []))
     return out
 
 

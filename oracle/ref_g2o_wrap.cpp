@@ -22,6 +22,27 @@ static g2o::SE3Quat toSE3Quat(const float* m) {  // globaloptimizer_g2o.cpp:80-9
     return g2o::SE3Quat(R, t);
 }
 
+// The reference defines this edge inside globaloptimizer_g2o.cpp (:37-66), not in a header, so it is restated here: a binary edge between
+// two marker vertices (reference marker, other marker) whose 4 residuals say "both markers lie in one plane with the same normal":
+// with M = inverse(ref) * other as 4x4 matrices, 10 * (M(0,2), M(1,2), 1 - M(2,2), M(2,3)).  No linearizeOplus override: g2o
+// differentiates it numerically (base_binary_edge.hpp:165-233, delta = 1e-9f).
+class PlanarMarkerEdge : public g2o::BaseBinaryEdge<4, Eigen::Matrix<double, 8, 1>, VertexSE3Expmap, VertexSE3Expmap> {
+public:
+    EIGEN_MAKE_ALIGNED_OPERATOR_NEW
+    bool read(std::istream&) { return false; }
+    bool write(std::ostream&) const { return false; }
+    void computeError() {
+        const auto* a = static_cast<const VertexSE3Expmap*>(_vertices[0]);
+        const auto* b = static_cast<const VertexSE3Expmap*>(_vertices[1]);
+        const Eigen::Matrix<double, 4, 4> M = a->estimate().to_homogeneous_matrix().inverse() * b->estimate().to_homogeneous_matrix();
+        _error.resize(4);
+        _error(0) = 10. * M(0, 2);
+        _error(1) = 10. * M(1, 2);
+        _error(2) = 10. * (1 - M(2, 2));
+        _error(3) = 10. * M(2, 3);
+    }
+};
+
 extern "C" {
 
 // obs_ur[i] is used when obs_stereo[i] != 0.  out_pose7: qx qy qz qw tx ty tz (f64); out_pose44: what getResults stores
@@ -40,7 +61,8 @@ static int ba_optimize_impl(int n_poses, const float* poses44, const uint8_t* fi
                     int n_markers, const float* marker_pose44, const float* marker_size, int n_mobs, const int32_t* mobs_marker,
                     const int32_t* mobs_pose, const float* mobs_corners, const float* mobs_weight, double* out_marker_pose7,
                     float* out_marker_pose44, double* out_mobs_chi2,
-                    const float* pose_cam /* n_poses x 5 (fx fy cx cy bf of each keyframe's ImageParams, :233-236, :262-266) or NULL */);
+                    const float* pose_cam /* n_poses x 5 (fx fy cx cy bf of each keyframe's ImageParams, :233-236, :262-266) or NULL */,
+                    int n_plane = 0, int plane_ref = -1, const float* plane_ref_pose44 = nullptr, const int32_t* plane_other = nullptr, double plane_weight = 0);
 extern "C" {
 
 
@@ -81,6 +103,21 @@ int ref_ba_optimize_cams(int n_poses, const float* poses44, const uint8_t* fixed
                             n_markers, marker_pose44, marker_size, n_mobs, mobs_marker, mobs_pose, mobs_corners, mobs_weight, out_marker_pose7,
                             out_marker_pose44, out_mobs_chi2, pose_cam);
 }
+// + the InPlaneMarkers edges: plane_ref = marker index of the reference marker, or -1 with its pose in plane_ref_pose44 (fixed vertex)
+int ref_ba_optimize_planar(int n_poses, const float* poses44, const uint8_t* fixed, int n_points, const float* points3, int n_obs,
+                    const int32_t* obs_pose, const int32_t* obs_point, const float* obs_uv, const float* obs_ur,
+                    const uint8_t* obs_stereo, const float* obs_inv_sigma2, float fx, float fy, float cx, float cy, float bf,
+                    int n_iters, double* out_pose7, float* out_pose44, double* out_point3, double* out_chi2,
+                    uint8_t* out_level, uint8_t* out_bad, int* iters_done, double* trace,
+                    int n_markers, const float* marker_pose44, const float* marker_size, int n_mobs, const int32_t* mobs_marker,
+                    const int32_t* mobs_pose, const float* mobs_corners, const float* mobs_weight, double* out_marker_pose7,
+                    float* out_marker_pose44, double* out_mobs_chi2, const float* pose_cam, int n_plane, int plane_ref, const float* plane_ref_pose44,
+                    const int32_t* plane_other, double plane_weight) {
+    return ba_optimize_impl(n_poses, poses44, fixed, n_points, points3, n_obs, obs_pose, obs_point, obs_uv, obs_ur, obs_stereo, obs_inv_sigma2,
+                            fx, fy, cx, cy, bf, n_iters, out_pose7, out_pose44, out_point3, out_chi2, out_level, out_bad, iters_done, trace,
+                            n_markers, marker_pose44, marker_size, n_mobs, mobs_marker, mobs_pose, mobs_corners, mobs_weight, out_marker_pose7,
+                            out_marker_pose44, out_mobs_chi2, pose_cam, n_plane, plane_ref, plane_ref_pose44, plane_other, plane_weight);
+}
 }  // extern "C"
 
 static int ba_optimize_impl(int n_poses, const float* poses44, const uint8_t* fixed, int n_points, const float* points3, int n_obs,
@@ -90,7 +127,8 @@ static int ba_optimize_impl(int n_poses, const float* poses44, const uint8_t* fi
                     uint8_t* out_level, uint8_t* out_bad, int* iters_done, double* trace,
                     int n_markers, const float* marker_pose44, const float* marker_size, int n_mobs, const int32_t* mobs_marker,
                     const int32_t* mobs_pose, const float* mobs_corners, const float* mobs_weight, double* out_marker_pose7,
-                    float* out_marker_pose44, double* out_mobs_chi2, const float* pose_cam) {
+                    float* out_marker_pose44, double* out_mobs_chi2, const float* pose_cam, int n_plane, int plane_ref, const float* plane_ref_pose44,
+                    const int32_t* plane_other, double plane_weight) {
     const float Chi2D = 5.99f, Chi3D = 7.815f;
     const float thHuber2D = sqrt(Chi2D), thHuber3D = sqrt(Chi3D);
     auto Optimizer = std::make_shared<g2o::SparseOptimizer>();
@@ -171,6 +209,27 @@ static int ba_optimize_impl(int n_poses, const float* poses44, const uint8_t* fi
         e->setInformation(Eigen::Matrix<double, 8, 8>::Identity() * double(mobs_weight[k]));
         Optimizer->addEdge(e);
         marker_edges.push_back(e);
+    }
+    // InPlaneMarkers (:356-401): the reference marker (a free vertex of this window, or a fixed extra vertex when the window does not hold it)
+    // is tied to every other marker by one planar edge of information plane_weight * I4 (:384-392); the edges keep level 0 and no kernel
+    if (n_plane > 0) {
+        g2o::OptimizableGraph::Vertex* vref = nullptr;
+        if (plane_ref >= 0) vref = dynamic_cast<g2o::OptimizableGraph::Vertex*>(Optimizer->vertex(n_poses + n_points + plane_ref));
+        else {
+            auto* v = new VertexSE3Expmap();
+            v->setEstimate(toSE3Quat(plane_ref_pose44));
+            v->setId(std::numeric_limits<int>::max());
+            v->setFixed(true);
+            Optimizer->addVertex(v);
+            vref = v;
+        }
+        for (int k = 0; k < n_plane; k++) {
+            auto* e = new PlanarMarkerEdge();
+            e->setVertex(0, vref);
+            e->setVertex(1, dynamic_cast<g2o::OptimizableGraph::Vertex*>(Optimizer->vertex(n_poses + n_points + plane_other[k])));
+            e->setInformation(plane_weight * Eigen::Matrix<double, 4, 4>::Identity());
+            Optimizer->addEdge(e);
+        }
     }
     // optimize(), :418-463
     Optimizer->initializeOptimization();

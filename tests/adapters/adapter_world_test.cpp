@@ -84,6 +84,13 @@ int ref_ba_optimize_cams(int n_poses, const float* poses44, const uint8_t* fixed
                          uint8_t* out_level, uint8_t* out_bad, int* iters_done, double* trace, int n_markers, const float* marker_pose44,
                          const float* marker_size, int n_mobs, const int32_t* mobs_marker, const int32_t* mobs_pose, const float* mobs_corners,
                          const float* mobs_weight, double* out_marker_pose7, float* out_marker_pose44, double* out_mobs_chi2, const float* pose_cam);
+int ref_ba_optimize_planar(int n_poses, const float* poses44, const uint8_t* fixed, int n_points, const float* points3, int n_obs, const int32_t* obs_pose,
+                           const int32_t* obs_point, const float* obs_uv, const float* obs_ur, const uint8_t* obs_stereo, const float* obs_inv_sigma2, float fx,
+                           float fy, float cx, float cy, float bf, int n_iters, double* out_pose7, float* out_pose44, double* out_point3, double* out_chi2,
+                           uint8_t* out_level, uint8_t* out_bad, int* iters_done, double* trace, int n_markers, const float* marker_pose44,
+                           const float* marker_size, int n_mobs, const int32_t* mobs_marker, const int32_t* mobs_pose, const float* mobs_corners,
+                           const float* mobs_weight, double* out_marker_pose7, float* out_marker_pose44, double* out_mobs_chi2, const float* pose_cam,
+                           int n_plane, int plane_ref, const float* plane_ref_pose44, const int32_t* plane_other, double plane_weight);
 }
 
 static int fails = 0;
@@ -375,23 +382,68 @@ int main() {
             EXPECT(cmax < 1e-5 && opt->getBadAssociations().size() == cb,
                    "GlobalOptimizerB200 on a window taken with two cameras == the reference's g2o with per-edge ImageParams (poses 1e-5, bad associations)");
         }
-        // InPlaneMarkers (MarkerEdgeX, :360-401) is the one option left out: a window with a marker throws, there is no CPU solver to fall back to
-        GlobalOptimizer::ParamSet bad_ps;
-        bad_ps.nIters = 5;
-        bad_ps.InPlaneMarkers = true;
+        // InPlaneMarkers (:356-401): two coplanar markers, each seen by all three keyframes; the adapter picks the reference marker, ties the other one to
+        // it and the solve equals the reference's g2o with MarkerEdgeX (restated in ref_g2o_wrap.cpp) on the window the adapter flattened
         {
-            Marker mk;
-            mk.id = 4; mk.size = 0.2f;
-            mk.pose_g2m = map->keyframes[0].pose_f2g;   // any valid pose
-            mk.frames.insert(0);
-            map->map_markers[4] = mk;
-            ucoslam::MarkerObservation mo;
-            mo.id = 4;
-            map->keyframes[0].markers.push_back(mo);
+            GlobalOptimizer::ParamSet pps;
+            pps.nIters = 5;
+            pps.fixFirstFrame = true;
+            pps.InPlaneMarkers = true;
+            const float msz = 0.2f;
+            for (uint32_t id = 4; id <= 5; id++) {
+                Marker mk;
+                mk.id = id; mk.size = msz;
+                Se3Transform G;                                  // identity rotation: both markers in the plane z = 2.0 in front of keyframe 0's camera
+                G = map->keyframes[0].pose_f2g.inv();
+                cv::Mat S = cv::Mat::eye(4, 4, CV_32F);
+                S.at<float>(0, 3) = id == 4 ? -0.35f : 0.3f; S.at<float>(1, 3) = id == 4 ? 0.1f : -0.15f; S.at<float>(2, 3) = 2.0f;
+                Se3Transform Gm;
+                for (int r = 0; r < 4; r++)
+                    for (int c = 0; c < 4; c++) {
+                        float v = 0;
+                        for (int k = 0; k < 4; k++) v += G.at<float>(r, k) * S.at<float>(k, c);
+                        Gm.at<float>(r, c) = v;
+                    }
+                mk.pose_g2m = Gm;
+                for (int k = 0; k < 3; k++) {
+                    const Frame& fr = map->keyframes[k];
+                    ucoslam::MarkerObservation mo;
+                    mo.id = id;
+                    for (const auto& pl : Marker::get3DPointsLocalRefSystem(msz)) {
+                        float g[3], c[3];
+                        for (int r = 0; r < 3; r++) g[r] = Gm.at<float>(r, 0) * pl.x + Gm.at<float>(r, 1) * pl.y + Gm.at<float>(r, 2) * pl.z + Gm.at<float>(r, 3);
+                        for (int r = 0; r < 3; r++) c[r] = fr.pose_f2g.at<float>(r, 0) * g[0] + fr.pose_f2g.at<float>(r, 1) * g[1] + fr.pose_f2g.at<float>(r, 2) * g[2] + fr.pose_f2g.at<float>(r, 3);
+                        mo.und_corners.push_back(cv::Point2f(fr.imageParams.fx() * c[0] / c[2] + fr.imageParams.cx() + 0.3f * (id - 4), fr.imageParams.fy() * c[1] / c[2] + fr.imageParams.cy() - 0.2f * k));
+                    }
+                    map->keyframes[k].markers.push_back(mo);
+                    mk.frames.insert(k);
+                }
+                mk.pose_g2m[3] += 0.01f * (id - 3); mk.pose_g2m[11] -= 0.015f;   // start away from the observations
+                map->map_markers[id] = mk;
+            }
+            opt->setParams(map, pps);
+            const uco_ba_problem& pq = static_cast<GlobalOptimizerB200*>(opt.get())->problem();
+            EXPECT(pq.n_markers == 2 && pq.n_marker_obs == 6 && pq.n_plane == 1 && pq.plane_ref == 0 && pq.plane_other[0] == 1 && pq.plane_weight > 0,
+                   "InPlaneMarkers: reference marker = the first of the two equally seen ones, one planar edge to the other, weight per :381-382");
+            std::vector<double> q7(7 * pq.n_poses), q3(3 * pq.n_points), qchi(pq.n_obs), m7(7 * 2), mchi(6);
+            std::vector<float> q44(16 * pq.n_poses), m44(16 * 2);
+            std::vector<uint8_t> qlev(pq.n_obs), qbad(pq.n_obs);
+            ref_ba_optimize_planar(pq.n_poses, pq.poses44, pq.fixed, pq.n_points, pq.points3, pq.n_obs, pq.obs_pose, pq.obs_point, pq.obs_uv, pq.obs_ur, pq.obs_stereo,
+                                   pq.obs_inv_sigma2, pq.fx, pq.fy, pq.cx, pq.cy, pq.bf, 5, q7.data(), q44.data(), q3.data(), qchi.data(), qlev.data(), qbad.data(), its,
+                                   trace.data(), pq.n_markers, pq.marker_pose44, pq.marker_size, pq.n_marker_obs, pq.mobs_marker, pq.mobs_pose, pq.mobs_corners,
+                                   pq.mobs_weight, m7.data(), m44.data(), mchi.data(), pq.pose_cam, pq.n_plane, pq.plane_ref, pq.plane_ref_pose44, pq.plane_other,
+                                   pq.plane_weight);
+            opt->optimize(&stop);
+            opt->getResults(map);
+            double pmax = 0, mmax = 0;
+            for (int k = 0; k < pq.n_poses; k++) {
+                if (pq.fixed[k]) continue;
+                for (int e = 0; e < 12; e++) pmax = std::max(pmax, (double)std::fabs(map->keyframes[k].pose_f2g.at_(e) - q44[16 * k + e]));
+            }
+            for (int m = 0; m < 2; m++)
+                for (int e = 0; e < 12; e++) mmax = std::max(mmax, (double)std::fabs(map->map_markers[4 + m].pose_g2m.at_(e) - m44[16 * m + e]));
+            EXPECT(pmax < 1e-4 && mmax < 6e-3, "GlobalOptimizerB200 with InPlaneMarkers == the reference's g2o with planar marker edges (keyframes 1e-4, markers 6e-3)");
         }
-        bool threw = false;
-        try { opt->setParams(map, bad_ps); } catch (std::runtime_error&) { threw = true; }
-        EXPECT(threw, "the InPlaneMarkers option throws std::runtime_error instead of falling back to a CPU solver");
     }
     std::printf("%s\n", fails ? "ADAPTER WORLD FAILED" : "ADAPTER WORLD OK");
     return fails ? 1 : 0;

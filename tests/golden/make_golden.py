@@ -128,6 +128,32 @@ def ba_cams():
     print("ba mixed-camera golden written", {n: int(out[n + "_out_iters"].sum()) for n in BA_CAM_CASES})
 
 
+BA_PLANE_CASES = {  # name -> (synth_ba_problem kwargs, add_markers kwargs, reference marker inside the window?, n_iters)   (also imported by the tests)
+    "plane_in": (dict(seed=81, n_poses=8, n_fixed=1, n_points=250), dict(seed=5, n_markers=4, coplanar=True), True, 5),
+    "plane_out": (dict(seed=82, n_poses=8, n_fixed=1, n_points=250), dict(seed=6, n_markers=5, coplanar=True), False, 5),
+    "plane_stereo": (dict(seed=83, n_poses=6, n_fixed=2, n_points=200, stereo_frac=0.4), dict(seed=7, n_markers=3, size=0.15, coplanar=True), True, 5),
+}
+BA_PLANE_KEYS = ("plane_ref", "plane_other", "plane_weight", "plane_ref_pose44")
+
+
+def ba_planar():
+    """the InPlaneMarkers option (globaloptimizer_g2o.cpp:356-401): MarkerEdgeX restated on the reference's g2o (ref_g2o_wrap.cpp), g2o's
+    own numeric Jacobians; reference marker inside / outside the window"""
+    oracle_py.build_ref()
+    from ucoslam_b200.synth import add_markers, add_plane_edges
+    out = {}
+    for name, (kw, mkw, inw, iters) in BA_PLANE_CASES.items():
+        pb = add_plane_edges(add_markers(oracle_py.synth_ba_problem(**kw), **mkw), inw)
+        r = oracle_py.ref_ba_optimize(pb, iters)
+        for k in oracle_py.BA_INPUT_KEYS + BA_MARKER_KEYS + BA_PLANE_KEYS:
+            if k in pb:
+                out["%s_in_%s" % (name, k)] = np.asarray(pb[k])
+        for k, v in r.items():
+            out["%s_out_%s" % (name, k)] = v
+    np.savez_compressed(os.path.join(HERE, "ba_planar_g2o.npz"), **out)
+    print("ba planar golden written", {n: int(out[n + "_out_iters"].sum()) for n in BA_PLANE_CASES})
+
+
 PNP_CASES = {  # name -> synth_pnp_problem kwargs   (also imported by the tests)
     "mono": dict(seed=1, n_matches=800),
     "stereo": dict(seed=2, n_matches=600, stereo_frac=0.5),
@@ -299,6 +325,6 @@ def kfdb():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["knn", "bow", "ba", "ba_markers", "ba_cams", "pnp", "project", "match", "kfdb"]
+    which = sys.argv[1:] or ["knn", "bow", "ba", "ba_markers", "ba_cams", "ba_planar", "pnp", "project", "match", "kfdb"]
     for w in which:
         globals()[w]()

@@ -56,6 +56,12 @@ struct MkDev {  // ArUco markers: free SE3 vertices appended after the free keyf
     const int *cam_ptr = nullptr, *cam_edges = nullptr;       // free keyframe -> its marker edges (edge order)
     const int *mk_ptr = nullptr, *mk_edges = nullptr;         // marker -> its edges
     const int* blk_edge = nullptr;                            // Schur block -> marker edge whose Hcm fills it, or -1
+    // InPlaneMarkers (globaloptimizer_g2o.cpp:356-401): Nx planar edges (reference marker, other marker) stored after the Ne marker edges in
+    // e_chi2 / e_blk; x_ref < 0: the reference marker is a fixed vertex outside this window (its pose sits in slot Nm of `pose`).  In an edge's block record the "c"
+    // slots belong to the marker with the smaller index, the "m" slots to the other one; a marker's edge list holds ~index for its "c" role.
+    int Nx = 0, x_ref = -1;
+    const int* x_other = nullptr;                             // Nx
+    double x_w = 0;                                           // information = I4 * x_w
 };
 
 struct BaDev {
@@ -713,9 +719,81 @@ __device__ void marker_edge_error(const Pose& c2g, const Pose& g2m, float size, 
 }
 // one thread per marker edge: chi2 = w |e|^2; with `linearize` also the numeric Jacobians (central differences, delta 1e-4,
 // base_binary_edge.hpp:165-230) of both vertices and the edge's quadratic-form blocks (base_binary_edge.hpp:83-155, no robust kernel)
+// MarkerEdgeX::computeError (globaloptimizer_g2o.cpp:52-63): with M = inverse(ref) * other as 4x4 matrices, 10 * (M(0,2), M(1,2), 1 - M(2,2), M(2,3));
+// in closed form M(i,2) = column i of R_ref . column 2 of R_other, M(2,3) = column 2 of R_ref . (t_other - t_ref)
+__device__ void planar_edge_error(const Pose& A, const Pose& O, double* e) {
+    double Ra[9], Ro[9];
+    quat_to_R(A.q, Ra);
+    quat_to_R(O.q, Ro);
+    const double d0 = O.t[0] - A.t[0], d1 = O.t[1] - A.t[1], d2 = O.t[2] - A.t[2];
+    e[0] = 10. * (Ra[0] * Ro[2] + Ra[3] * Ro[5] + Ra[6] * Ro[8]);
+    e[1] = 10. * (Ra[1] * Ro[2] + Ra[4] * Ro[5] + Ra[7] * Ro[8]);
+    e[2] = 10. * (1 - (Ra[2] * Ro[2] + Ra[5] * Ro[5] + Ra[8] * Ro[8]));
+    e[3] = 10. * (Ra[2] * d0 + Ra[5] * d1 + Ra[8] * d2);
+}
+// one planar edge: chi2, and with `linearize` g2o's own numeric Jacobians (base_binary_edge.hpp:165-233: central differences with
+// delta = 1e-9f on every free vertex) and the quadratic-form blocks, stored so that the "c" slots are the lower-numbered marker's
+__device__ void planar_edge(const BaDev& B, int x, int linearize) {
+    const int ro = B.mk.x_other[x], rr = B.mk.x_ref;
+    const Pose O = load_pose(B.mk.pose + 7 * ro), A = load_pose(B.mk.pose + 7 * (rr >= 0 ? rr : B.mk.Nm));
+    const double w = B.mk.x_w;
+    double e0[4];
+    planar_edge_error(A, O, e0);
+    B.mk.e_chi2[B.mk.Ne + x] = e0[0] * w * e0[0] + e0[1] * w * e0[1] + e0[2] * w * e0[2] + e0[3] * w * e0[3];
+    if (!linearize) return;
+    const double delta = (double)1e-9f, scalar = 1 / (2 * delta);
+    double Ja[24], Jo[24];  // [row * 6 + d]
+    for (int d = 0; d < 6; d++) {
+        double u[6] = {0, 0, 0, 0, 0, 0}, ea[4], eb[4];
+        Pose Op = O, On = O;
+        u[d] = delta; se3_oplus(Op, u);
+        u[d] = -delta; se3_oplus(On, u);
+        planar_edge_error(A, Op, ea);
+        planar_edge_error(A, On, eb);
+        for (int i = 0; i < 4; i++) Jo[i * 6 + d] = scalar * (ea[i] - eb[i]);
+        if (rr >= 0) {
+            Pose Ap = A, An = A;
+            u[d] = delta; se3_oplus(Ap, u);
+            u[d] = -delta; se3_oplus(An, u);
+            planar_edge_error(Ap, O, ea);
+            planar_edge_error(An, O, eb);
+            for (int i = 0; i < 4; i++) Ja[i * 6 + d] = scalar * (ea[i] - eb[i]);
+        } else {
+            for (int i = 0; i < 4; i++) Ja[i * 6 + d] = 0;
+        }
+    }
+    const bool ref_first = rr >= 0 && rr < ro;          // which marker owns the "c" slots
+    const double* Jc = ref_first ? Ja : Jo;
+    const double* Jm = ref_first ? Jo : Ja;
+    double* o = B.mk.e_blk + 120 * (size_t)(B.mk.Ne + x);
+    if (rr < 0) { Jc = Ja; Jm = Jo; }                   // fixed reference: only the "m" (other) slots are read
+    for (int a = 0; a < 6; a++) {
+        for (int c = 0; c < 6; c++) {
+            double hcc = 0, hmm = 0, hcm = 0;
+            for (int i = 0; i < 4; i++) {
+                hcc += Jc[i * 6 + a] * w * Jc[i * 6 + c];
+                hmm += Jm[i * 6 + a] * w * Jm[i * 6 + c];
+                hcm += Jc[i * 6 + a] * w * Jm[i * 6 + c];
+            }
+            o[6 * a + c] = hcc;
+            o[36 + 6 * a + c] = hmm;
+            o[72 + 6 * a + c] = hcm;
+        }
+        double bc = 0, bm = 0;
+        for (int i = 0; i < 4; i++) {
+            bc += Jc[i * 6 + a] * (-(w * e0[i]));
+            bm += Jm[i * 6 + a] * (-(w * e0[i]));
+        }
+        o[108 + a] = bc;
+        o[114 + a] = bm;
+    }
+}
 __global__ void __launch_bounds__(64) ba_marker_kernel(const __grid_constant__ BaDev B, int linearize) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= B.mk.Ne) return;
+    if (k >= B.mk.Ne) {
+        if (k < B.mk.Ne + B.mk.Nx) planar_edge(B, k - B.mk.Ne, linearize);
+        return;
+    }
     const int m = B.mk.e_marker[k], pi = B.mk.e_pose[k];
     const Pose T = load_pose(B.pose + 7 * pi), G = load_pose(B.mk.pose + 7 * m);
     const float size = B.mk.size[m];
@@ -786,9 +864,11 @@ __global__ void __launch_bounds__(128) ba_marker_accumulate_kernel(const __grid_
     for (int k = 0; k < 36; k++) H[k] = is_cam ? B.Hpp[36 * (size_t)t + k] : 0.0;
     for (int k = 0; k < 6; k++) b[k] = is_cam ? B.bp[6 * (size_t)t + k] : 0.0;
     for (int j = ptr[i]; j < ptr[i + 1]; j++) {
-        const double* o = B.mk.e_blk + 120 * (size_t)lst[j];
-        for (int k = 0; k < 36; k++) H[k] += o[(is_cam ? 0 : 36) + k];
-        for (int k = 0; k < 6; k++) b[k] += o[(is_cam ? 108 : 114) + k];
+        const int ed = lst[j];
+        const bool c_role = is_cam || ed < 0;          // ~index: this marker owns the "c" slots of a planar edge
+        const double* o = B.mk.e_blk + 120 * (size_t)(ed < 0 ? ~ed : ed);
+        for (int k = 0; k < 36; k++) H[k] += o[(c_role ? 0 : 36) + k];
+        for (int k = 0; k < 6; k++) b[k] += o[(c_role ? 108 : 114) + k];
     }
     for (int k = 0; k < 36; k++) B.Hpp[36 * (size_t)t + k] = H[k];
     for (int k = 0; k < 6; k++) B.bp[6 * (size_t)t + k] = b[k];
@@ -836,7 +916,7 @@ __global__ void __launch_bounds__(1024) ba_partial_sums_kernel(const __grid_cons
     double s = 0;
     for (int i = threadIdx.x; i < B.M; i += 1024) s += B.rho0[i];
     if (add_markers)  // the marker edges are replicated: only one rank contributes their chi2 to the all-reduced sum
-        for (int k = threadIdx.x; k < B.mk.Ne; k += 1024) s += B.mk.e_chi2[k];
+        for (int k = threadIdx.x; k < B.mk.Ne + B.mk.Nx; k += 1024) s += B.mk.e_chi2[k];
     s = block_reduce_1024<false>(s, sm);
     double sc = 0;
     for (int l = threadIdx.x; l < B.N; l += 1024) sc += B.scale_lm[l];
@@ -1192,6 +1272,12 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
     for (int k = 0; k < Ne; k++)
         if ((unsigned)pb->mobs_marker[k] >= (unsigned)Nm || (unsigned)pb->mobs_pose[k] >= (unsigned)P)
             return uco_fail(ctx, UCO_E_INVALID, "ba_solve: marker observation %d references marker %d / pose %d out of range", k, pb->mobs_marker[k], pb->mobs_pose[k]);
+    const int Nx = pb->n_plane, xref = pb->plane_ref;
+    if (Nx < 0 || (Nx && (!Nm || !pb->plane_other || xref >= Nm || (xref < 0 && !pb->plane_ref_pose44) || !(pb->plane_weight >= 0))))
+        return uco_fail(ctx, UCO_E_INVALID, "ba_solve: malformed planar-marker arrays");
+    for (int x = 0; x < Nx; x++)
+        if ((unsigned)pb->plane_other[x] >= (unsigned)Nm || pb->plane_other[x] == xref)
+            return uco_fail(ctx, UCO_E_INVALID, "ba_solve: planar edge %d references marker %d", x, pb->plane_other[x]);
     uco_ba_events(ctx);
     // ---- global structure (identical on every rank): free-pose numbering, observations sorted by landmark, Schur block list
     std::vector<int> free_idx(P), free_list;
@@ -1217,6 +1303,8 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
             const int fc = free_idx[pb->mobs_pose[k]];
             if (fc >= 0) present[(size_t)fc * PT + Pf + pb->mobs_marker[k]] = 1;
         }
+        for (int x = 0; x < Nx && xref >= 0; x++)   // (reference marker, other marker) blocks of the planar edges
+            present[(size_t)(Pf + std::min(xref, pb->plane_other[x])) * PT + Pf + std::max(xref, pb->plane_other[x])] = 1;
         for (int l = 0; l < N; l++)
             for (int a = lm_ptr[l]; a < lm_ptr[l + 1]; a++) {
                 const int fa = g_free[a];
@@ -1277,7 +1365,8 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
         for (int k = 0; k < ML; k++) { const int f = g_free[o0 + k]; if (f >= 0) pose_obs[pose_ptr[f] + pf[f]++] = k; }
     }
     // markers: per free keyframe / per marker the list of marker edges (edge order), per block the edge that fills it
-    std::vector<int> cam_ptr(Pf + 1, 0), cam_edges, mk_ptr(Nm + 1, 0), mk_edges(Ne), blk_edge(nblk, -1);
+    const int n_mk_entries = Ne + Nx + (xref >= 0 ? Nx : 0);   // a planar edge sits in the list of each of its free markers
+    std::vector<int> cam_ptr(Pf + 1, 0), cam_edges, mk_ptr(Nm + 1, 0), mk_edges(n_mk_entries), blk_edge(nblk, -1);
     for (int k = 0; k < Ne; k++) {
         const int fc = free_idx[pb->mobs_pose[k]];
         if (fc >= 0) {
@@ -1287,6 +1376,16 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
             be = k;
         }
         mk_ptr[pb->mobs_marker[k] + 1]++;
+    }
+    for (int x = 0; x < Nx; x++) {
+        const int o = pb->plane_other[x];
+        mk_ptr[o + 1]++;
+        if (xref >= 0) {
+            mk_ptr[xref + 1]++;
+            int& be = blk_edge[blk_of[(size_t)(Pf + std::min(xref, o)) * PT + Pf + std::max(xref, o)]];
+            if (be >= 0) return uco_fail(ctx, UCO_E_INVALID, "ba_solve: marker %d has two planar edges", o);
+            be = Ne + x;
+        }
     }
     for (int i = 0; i < Pf; i++) cam_ptr[i + 1] += cam_ptr[i];
     for (int i = 0; i < Nm; i++) mk_ptr[i + 1] += mk_ptr[i];
@@ -1298,6 +1397,14 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
             if (fc >= 0) cam_edges[cf[fc]++] = k;
             mk_edges[mf[pb->mobs_marker[k]]++] = k;
         }
+        for (int x = 0; x < Nx; x++) {    // after the marker edges, as the reference adds them; ~index = the marker owns the "c" slots
+            const int o = pb->plane_other[x];
+            if (xref < 0) mk_edges[mf[o]++] = Ne + x;
+            else {
+                mk_edges[mf[std::min(xref, o)]++] = ~(Ne + x);
+                mk_edges[mf[std::max(xref, o)]++] = Ne + x;
+            }
+        }
     }
     // ---- arena: [inputs][work][full-size result arrays that are summed over the ranks]
     Arena A;
@@ -1307,12 +1414,13 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
                  o_blk_ij = A.take(8 * (size_t)(nblk + 1)), o_con = A.take(8 * (con.size() + 1)), o_z = A.take(24 * (size_t)(ML + 1)),
                  o_info = A.take(8 * (size_t)(ML + 1)), o_stereo = A.take((size_t)ML + 1), o_active = A.take((size_t)ML + 1),
                  o_pt = A.take(24 * (size_t)(NL + 1)), o_p44 = A.take(64 * (size_t)P);
-    const size_t o_mk44 = A.take(64 * (size_t)(Nm + 1)), o_mksz = A.take(4 * (size_t)(Nm + 1)), o_em = A.take(4 * (size_t)(Ne + 1)), o_ep = A.take(4 * (size_t)(Ne + 1)),
+    const size_t o_mk44 = A.take(64 * (size_t)(Nm + 2)), o_mksz = A.take(4 * (size_t)(Nm + 1)), o_em = A.take(4 * (size_t)(Ne + 1)), o_ep = A.take(4 * (size_t)(Ne + 1)),
                  o_ec = A.take(32 * (size_t)(Ne + 1)), o_ew = A.take(4 * (size_t)(Ne + 1)), o_cptr = A.take(4 * (size_t)(Pf + 2)), o_cedg = A.take(4 * (cam_edges.size() + 1)),
-                 o_mptr = A.take(4 * (size_t)(Nm + 2)), o_medg = A.take(4 * (size_t)(Ne + 1)), o_bedg = A.take(4 * (size_t)(nblk + 1));
+                 o_mptr = A.take(4 * (size_t)(Nm + 2)), o_medg = A.take(4 * (size_t)(n_mk_entries + 1)), o_bedg = A.take(4 * (size_t)(nblk + 1));
+    const size_t o_xoth = A.take(4 * (size_t)(Nx + 1));
     const size_t o_cams = A.take(pb->pose_cam ? sizeof(Cam) * (size_t)P : 0);   // one camera per keyframe (mixed-camera windows)
     const size_t in_bytes = A.off;
-    const size_t o_mkpose = A.take(56 * (size_t)(Nm + 1)), o_mkbak = A.take(56 * (size_t)(Nm + 1)), o_echi = A.take(8 * (size_t)(Ne + 1)), o_eblk = A.take(960 * (size_t)(Ne + 1)),
+    const size_t o_mkpose = A.take(56 * (size_t)(Nm + 2)), o_mkbak = A.take(56 * (size_t)(Nm + 2)), o_echi = A.take(8 * (size_t)(Ne + Nx + 1)), o_eblk = A.take(960 * (size_t)(Ne + Nx + 1)),
                  o_mk44o = A.take(64 * (size_t)(Nm + 1));
     const size_t n_red = 36 * (size_t)nblk + (size_t)n;  // packed Schur blocks | right-hand side: the per-trial all-reduce payload
     const size_t o_pose = A.take(56 * (size_t)P), o_pose_bak = A.take(56 * (size_t)P), o_pt_bak = A.take(24 * (size_t)(NL + 1)),
@@ -1378,12 +1486,16 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
         memcpy(h + o_mk44, pb->marker_pose44, 64 * (size_t)Nm);
         memcpy(h + o_mksz, pb->marker_size, 4 * (size_t)Nm);
     }
+    if (Nx) {
+        memcpy(h + o_xoth, pb->plane_other, 4 * (size_t)Nx);
+        if (xref < 0) memcpy(h + o_mk44 + 64 * (size_t)Nm, pb->plane_ref_pose44, 64);   // the fixed reference marker: slot Nm, never updated
+    }
+    if (n_mk_entries) memcpy(h + o_medg, mk_edges.data(), 4 * (size_t)n_mk_entries);
     if (Ne) {
         memcpy(h + o_em, pb->mobs_marker, 4 * (size_t)Ne);
         memcpy(h + o_ep, pb->mobs_pose, 4 * (size_t)Ne);
         memcpy(h + o_ec, pb->mobs_corners, 32 * (size_t)Ne);
         memcpy(h + o_ew, pb->mobs_weight, 4 * (size_t)Ne);
-        memcpy(h + o_medg, mk_edges.data(), 4 * (size_t)Ne);
         if (!cam_edges.empty()) memcpy(h + o_cedg, cam_edges.data(), 4 * cam_edges.size());
     }
     memcpy(h + o_cptr, cam_ptr.data(), 4 * (size_t)(Pf + 1));
@@ -1408,11 +1520,12 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
     B.xl = (double*)(d + o_xl);
     B.Hpp = (double*)(d + o_HppBp); B.bp = B.Hpp + 36 * (size_t)PT;   // contiguous: one all-reduce per outer iteration
     B.mk.Nm = Nm; B.mk.Ne = Ne;
+    B.mk.Nx = Nx; B.mk.x_ref = xref; B.mk.x_other = (const int*)(d + o_xoth); B.mk.x_w = pb->plane_weight;
     B.mk.pose = (double*)(d + o_mkpose); B.mk.pose_bak = (double*)(d + o_mkbak); B.mk.size = (const float*)(d + o_mksz);
     B.mk.e_marker = (const int*)(d + o_em); B.mk.e_pose = (const int*)(d + o_ep); B.mk.e_corners = (const float*)(d + o_ec);
     B.mk.e_weight = (const float*)(d + o_ew); B.mk.e_chi2 = (double*)(d + o_echi); B.mk.e_blk = (double*)(d + o_eblk);
     B.mk.cam_ptr = (const int*)(d + o_cptr); B.mk.cam_edges = (const int*)(d + o_cedg); B.mk.mk_ptr = (const int*)(d + o_mptr);
-    B.mk.mk_edges = (const int*)(d + o_medg); B.mk.blk_edge = Ne ? (const int*)(d + o_bedg) : nullptr;
+    B.mk.mk_edges = (const int*)(d + o_medg); B.mk.blk_edge = Ne + Nx ? (const int*)(d + o_bedg) : nullptr;
     B.S = (double*)(d + o_S); B.bs = (double*)(d + o_bs);
     B.xp = (double*)(d + o_xp); B.scale_lm = (double*)(d + o_scl); B.scale_pose = (double*)(d + o_scp);
     B.blk_ptr = (int*)(d + o_blk_ptr); B.blk_ij = (int2*)(d + o_blk_ij); B.con = (int2*)(d + o_con);
@@ -1456,11 +1569,11 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
     UCO_LAUNCH_CHECK(ctx);
     if (Nm) {  // marker vertices: Marker::pose_g2m -> SE3Quat, like the keyframes
         BaDev Bm = B;
-        Bm.P = Nm; Bm.pose = B.mk.pose; Bm.pose_bak = B.mk.pose_bak;
-        ba_init_poses_kernel<<<(Nm + 127) / 128, 128, 0, s>>>(Bm, (const float*)(d + o_mk44));
+        Bm.P = Nm + (Nx && xref < 0 ? 1 : 0); Bm.pose = B.mk.pose; Bm.pose_bak = B.mk.pose_bak;
+        ba_init_poses_kernel<<<(Bm.P + 127) / 128, 128, 0, s>>>(Bm, (const float*)(d + o_mk44));
         UCO_LAUNCH_CHECK(ctx);
     }
-    const int gE = (Ne + 63) / 64, gPT = (PT + 127) / 128;
+    const int gE = (Ne + Nx + 63) / 64, gPT = (PT + 127) / 128;
     int iters[2] = {0, 0};
     bool stopped = false;
     for (int stage = 0; stage < 2 && !stopped; stage++) {
@@ -1489,7 +1602,7 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
                     UCO_CUDA(ctx, cudaMemsetAsync(B.bp + 6 * (size_t)Pf, 0, 8 * 6 * (size_t)Nm, s));
                 }
                 if ((rc = uco_comm_allreduce(comm, B.Hpp, B.Hpp, 42 * (size_t)PT, 0, s)) != UCO_OK) return rc;
-                if (Ne) {  // marker edges: replicated on every rank, added after the exchange
+                if (Ne + Nx) {  // marker edges: replicated on every rank, added after the exchange
                     ba_marker_kernel<<<gE, 64, 0, s>>>(B, 1);
                     UCO_LAUNCH_CHECK(ctx);
                     ba_marker_accumulate_kernel<<<gPT, 128, 0, s>>>(B);
@@ -1538,7 +1651,7 @@ int ba_sharded_solve(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_proble
                     ba_errors_kernel<<<gM, 256, 0, s>>>(B, robust);
                     UCO_LAUNCH_CHECK(ctx);
                 }
-                if (Ne) {
+                if (Ne + Nx) {
                     ba_marker_kernel<<<gE, 64, 0, s>>>(B, 0);
                     UCO_LAUNCH_CHECK(ctx);
                 }

@@ -5,11 +5,10 @@
 // uco_ba_problem; getResults writes poses, points and the bad-association list back as :466-538 does.  The object keeps
 // its own copy of inputs and results, because the mapper thread calls setParams + optimize WITHOUT the map lock and the
 // tracker thread calls getResults later (src/utils/mapmanager.cpp:11361-11405, :1267-1305); *stopASAP is forwarded.
-// ArUco markers travel too (marker vertices, MarkerEdges, the per-keyframe marker weights of :276-297), and so do windows whose keyframes
-// were taken with different cameras (one fx fy cx cy bf row per keyframe: uco_ba_problem::pose_cam).  The InPlaneMarkers option
-// (MarkerEdgeX, :360-401: marker-to-marker edges differentiated numerically with g2o's default delta of 1e-9, whose result depends on
-// the last bits of Eigen's 4x4 inverse) is NOT covered by the C ABI: setParams throws std::runtime_error for it, like every other error
-// path of the reference's plugins (there is no CPU fallback).
+// ArUco markers travel too (marker vertices, MarkerEdges, the per-keyframe marker weights of :276-297), so do windows whose keyframes
+// were taken with different cameras (one fx fy cx cy bf row per keyframe: uco_ba_problem::pose_cam) and the InPlaneMarkers option
+// (:356-401: reference marker choice, planar edges, their weight).  There is no CPU fallback: errors of the C ABI become
+// std::runtime_error, like every other error path of the reference's plugins.
 // Selected with Params::global_optimizer = "b200" once registered in GlobalOptimizer::create.
 // Compiled and driven against the reference's own globaloptimizer.h by tests/adapters/adapter_world_test.cpp (container stand-ins for
 // Map / Frame / OpenCV, oracle/shim2); inside the reference tree it compiles against the real headers.
@@ -70,7 +69,6 @@ public:
             if (ip.fx() != f0.imageParams.fx() || ip.fy() != f0.imageParams.fy() || ip.cx() != f0.imageParams.cx() ||
                 ip.cy() != f0.imageParams.cy() || ip.bl != f0.imageParams.bl) mixedCameras = true;
         }
-        if (markers && _params.InPlaneMarkers) throw std::runtime_error("GlobalOptimizerB200: the InPlaneMarkers option is not supported");
         // the reference emits marker vertices / edges in ascending marker id (std::map, globaloptimizer_g2o.cpp:306-348)
         std::sort(_markerIds.begin(), _markerIds.end());
         for (size_t i = 0; i < _markerIds.size(); i++) markerSlot[_markerIds[i]] = (uint32_t)i;
@@ -105,6 +103,7 @@ public:
         }
         // markers (:304-350) and the per-keyframe weight of their 8 residuals (:276-297)
         _mkPose.clear(); _mkSize.clear(); _moMarker.clear(); _moPose.clear(); _moCorners.clear(); _moWeight.clear();
+        double totalMarkerWeight = 0;
         if (markers) {
             std::vector<double> kpw(P, 0.0);
             for (size_t o = 0; o < _obsPose.size(); o++) kpw[_obsPose[o]] += (_obsStereo[o] ? 3 : 2) * _obsInv[o];
@@ -124,6 +123,39 @@ public:
                     _moPose.push_back((int32_t)slot);
                     for (const auto& c : fr.getMarker(mid).und_corners) { _moCorners.push_back(c.x); _moCorners.push_back(c.y); }
                     _moWeight.push_back((float)w);
+                    totalMarkerWeight += w * 8;
+                }
+            }
+        }
+        // InPlaneMarkers (:356-401): the valid map marker seen by most keyframes is the reference (first one in id order on a tie); every
+        // OTHER marker vertex of the window gets one planar edge; a reference outside the window enters as a fixed vertex
+        _planeOther.clear(); _planeRef44.clear();
+        int planeRef = -1;
+        double planeWeight = 0;
+        {
+            int nValid = 0;
+            for (const auto& m : map->map_markers) if (m.second.pose_g2m.isValid()) nValid++;
+            if (_params.InPlaneMarkers && nValid >= 2) {
+                std::pair<uint32_t, uint32_t> best(INVALID, 0);
+                for (const auto& m : map->map_markers)
+                    if (m.second.pose_g2m.isValid() && m.second.frames.size() > best.second) best = {m.first, (uint32_t)m.second.frames.size()};
+                if (best.first != INVALID) {
+                    size_t nInfo = _markerIds.size();
+                    if (markerSlot.count(best.first) && std::binary_search(_markerIds.begin(), _markerIds.end(), best.first)) planeRef = (int)markerSlot[best.first];
+                    else {
+                        nInfo++;
+                        const float* g = map->map_markers[best.first].pose_g2m.ptr<float>(0);
+                        _planeRef44.assign(g, g + 16);
+                    }
+                    for (size_t i = 0; i < _markerIds.size(); i++)
+                        if (_markerIds[i] != best.first) _planeOther.push_back((int32_t)i);
+                    double totalKpWeight = 0;
+                    {
+                        std::vector<double> kpw(P, 0.0);
+                        for (size_t o = 0; o < _obsPose.size(); o++) kpw[_obsPose[o]] += (_obsStereo[o] ? 3 : 2) * _obsInv[o];
+                        for (double v : kpw) totalKpWeight += v;
+                    }
+                    if (nInfo > 1) planeWeight = 0.33 * (totalMarkerWeight + totalKpWeight) / double(4 * (nInfo - 1));   // :381-382
                 }
             }
         }
@@ -131,6 +163,10 @@ public:
         _pb.n_markers = (int32_t)_mkSize.size(); _pb.marker_pose44 = _mkPose.data(); _pb.marker_size = _mkSize.data();
         _pb.n_marker_obs = (int32_t)_moMarker.size(); _pb.mobs_marker = _moMarker.data(); _pb.mobs_pose = _moPose.data();
         _pb.mobs_corners = _moCorners.data(); _pb.mobs_weight = _moWeight.data();
+        if (!_planeOther.empty()) {
+            _pb.n_plane = (int32_t)_planeOther.size(); _pb.plane_other = _planeOther.data(); _pb.plane_ref = planeRef;
+            _pb.plane_ref_pose44 = planeRef < 0 ? _planeRef44.data() : nullptr; _pb.plane_weight = planeWeight;
+        }
         _pb.n_poses = (int32_t)P; _pb.n_points = (int32_t)N; _pb.n_obs = (int32_t)_obsPose.size();
         _pb.poses44 = _poses.data(); _pb.fixed = _fixed.data(); _pb.points3 = _points.data();
         _pb.obs_pose = _obsPose.data(); _pb.obs_point = _obsPoint.data(); _pb.obs_uv = _obsUV.data(); _pb.obs_ur = _obsUR.data();
@@ -204,7 +240,8 @@ private:
     uco_ba_problem _pb{};
     std::vector<uint32_t> _frameIds, _pointIds, _markerIds;
     std::vector<float> _poses, _points, _obsUV, _obsUR, _obsInv, _outPoses, _mkPose, _mkSize, _moCorners, _moWeight, _outMarkers, _poseCam;
-    std::vector<int32_t> _moMarker, _moPose;
+    std::vector<int32_t> _moMarker, _moPose, _planeOther;
+    std::vector<float> _planeRef44;
     std::vector<uint8_t> _fixed, _obsStereo, _outBad;
     std::vector<int32_t> _obsPose, _obsPoint;
     std::vector<double> _outPoints;

@@ -286,7 +286,8 @@ class BaProblem(ctypes.Structure):  # uco_ba_problem
                 ("obs_inv_sigma2", _vp), ("fx", _c.c_float), ("fy", _c.c_float), ("cx", _c.c_float), ("cy", _c.c_float),
                 ("bf", _c.c_float), ("n_iters", _c.c_int32), ("n_markers", _c.c_int32), ("marker_pose44", _vp), ("marker_size", _vp),
                 ("n_marker_obs", _c.c_int32), ("mobs_marker", _vp), ("mobs_pose", _vp), ("mobs_corners", _vp), ("mobs_weight", _vp),
-                ("pose_cam", _vp)]
+                ("pose_cam", _vp), ("n_plane", _c.c_int32), ("plane_ref", _c.c_int32), ("plane_ref_pose44", _vp), ("plane_other", _vp),
+                ("plane_weight", _c.c_double)]
 
 
 class BaResult(ctypes.Structure):  # uco_ba_result
@@ -724,6 +725,12 @@ class Context:
             cp.mobs_corners, cp.mobs_weight = _p(a["mobs_corners"]), _p(a["mobs_weight"])
             out.update(marker_pose44=np.zeros((nm, 16), np.float32), marker_pose7=np.zeros((nm, 7)), mobs_chi2=np.zeros(nmo))
             cr.marker_poses44, cr.marker_pose7, cr.mobs_chi2 = _p(out["marker_pose44"]), _p(out["marker_pose7"]), _p(out["mobs_chi2"])
+        if len(pb.get("plane_other", ())):   # InPlaneMarkers: reference marker (index, or -1 + its fixed pose) tied to the other markers
+            a["plane_other"] = A("plane_other", np.int32)
+            cp.n_plane, cp.plane_ref, cp.plane_other, cp.plane_weight = len(a["plane_other"]), int(pb["plane_ref"]), _p(a["plane_other"]), float(pb["plane_weight"])
+            if int(pb["plane_ref"]) < 0:
+                a["plane_ref_pose44"] = A("plane_ref_pose44", np.float32)
+                cp.plane_ref_pose44 = _p(a["plane_ref_pose44"])
         if pb.get("pose_cam") is not None:   # one camera per keyframe (fx fy cx cy bf)
             a["pose_cam"] = A("pose_cam", np.float32)
             assert a["pose_cam"].shape == (P, 5)

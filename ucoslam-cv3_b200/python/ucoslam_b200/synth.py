@@ -67,7 +67,7 @@ def synth_ba_problem(seed, n_poses=12, n_fixed=2, n_points=2000, stereo_frac=0.0
                 poses_gt=poses_gt, points_gt=pts_gt)
 
 
-def add_markers(pb, seed, n_markers=4, size=0.25, corner_sigma=0.3, pose_noise=(0.02, 1.0), opt_weight=0.5, min_markers=5, w=640, h=480):
+def add_markers(pb, seed, n_markers=4, size=0.25, corner_sigma=0.3, pose_noise=(0.02, 1.0), opt_weight=0.5, min_markers=5, w=640, h=480, coplanar=False):
     """ArUco markers for a BA problem made by synth_ba_problem / synth_global_ba: marker poses (global <- marker) in front of the
     cameras, an observation (4 undistorted corners) in every keyframe that sees all four, perturbed initial marker poses, and the
     per-observation weight the reference derives per keyframe (globaloptimizer_g2o.cpp:276-297: markersOptWeight share of the frame's
@@ -85,6 +85,11 @@ def add_markers(pb, seed, n_markers=4, size=0.25, corner_sigma=0.3, pose_noise=(
         Mc[:3, :3] = _rodrigues(rng.normal(0, 0.3, 3))
         Mc[:3, 3] = [rng.uniform(-0.6, 0.6), rng.uniform(-0.4, 0.4), rng.uniform(1.5, 3.5)]
         G = np.linalg.inv(cam) @ Mc
+        if coplanar and g2m_gt:      # the InPlaneMarkers scene: every marker lies in the first one's plane with the same normal (in-plane shift + turn)
+            S = np.eye(4)
+            S[:3, :3] = _rodrigues(np.array([0, 0, rng.uniform(-0.5, 0.5)]))
+            S[:3, 3] = [rng.uniform(-1.2, 1.2), rng.uniform(-0.8, 0.8), 0.0]
+            G = g2m_gt[0] @ S
         g2m_gt.append(G)
         for i in range(P):
             Xc = (T[i] @ G @ np.c_[local, np.ones(4)].T).T[:, :3]
@@ -146,6 +151,32 @@ def mix_cameras(pb, seed, frac=0.5, scale=(1.6, 1.45), shift=(37.0, -21.0), bl_s
         mc[msel, :, 0] = (mc[msel, :, 0] - c1[2]) / c1[0] * c2[0] + c2[2]
         mc[msel, :, 1] = (mc[msel, :, 1] - c1[3]) / c1[1] * c2[1] + c2[3]
         out["mobs_corners"] = mc.reshape(-1, 8).astype(np.float32)
+    return out
+
+
+def add_plane_edges(pb, ref_in_window=True):
+    """The InPlaneMarkers option for a problem made by add_markers(coplanar=True): the reference marker is the one with most observations
+    (globaloptimizer_g2o.cpp:362-368); every other marker gets one planar edge of weight 0.33 * (sum of marker weights x 8 + sum of the
+    keyframes' keypoint weights) / (4 * (markers - 1)) (:381-382).  ref_in_window=False takes the reference OUT of the window (its
+    vertex, observations and weights go; its pose stays as the fixed plane_ref_pose44) - the case of :371-379."""
+    out = dict(pb)
+    nm = len(pb["marker_size"])
+    counts = np.bincount(pb["mobs_marker"], minlength=nm)
+    ref = int(np.argmax(counts))
+    kpw = np.zeros(len(pb["fixed"]))
+    np.add.at(kpw, pb["obs_pose"], np.where(np.asarray(pb["obs_stereo"]) != 0, 3.0, 2.0) * np.asarray(pb["obs_inv_sigma2"], np.float64))
+    if not ref_in_window:
+        keep = np.asarray(pb["mobs_marker"]) != ref
+        remap = np.cumsum(np.arange(nm) != ref) - 1
+        out.update(plane_ref_pose44=np.asarray(pb["marker_gt"][ref], np.float32).reshape(16), marker_pose44=np.delete(pb["marker_pose44"], ref, 0),
+                   marker_size=np.delete(pb["marker_size"], ref, 0), mobs_marker=remap[np.asarray(pb["mobs_marker"])[keep]].astype(np.int32),
+                   mobs_pose=np.asarray(pb["mobs_pose"])[keep], mobs_corners=np.asarray(pb["mobs_corners"])[keep], mobs_weight=np.asarray(pb["mobs_weight"])[keep],
+                   marker_gt=np.delete(pb["marker_gt"], ref, 0), plane_ref=-1, plane_other=np.arange(nm - 1, dtype=np.int32))
+    else:
+        out.update(plane_ref=ref, plane_other=np.array([m for m in range(nm) if m != ref], np.int32))
+    total = 8.0 * np.asarray(out["mobs_weight"], np.float64).sum() + kpw.sum()
+    n_info = len(out["marker_size"]) + (0 if ref_in_window else 1)          # marker_info.size(): the window's markers + the added reference
+    out["plane_weight"] = 0.33 * total / (4.0 * (n_info - 1))
     return out
 
 
