@@ -651,7 +651,7 @@ def run_b200(args, rank, world, local_rank):
         if ms <= 0:
             continue
         ach = int_ops[k] * F / (ms * 1e-3)
-        rl[k] = {"kernel": {"blur": "blur7_kernel", "resize": "resize_cubic_kernel x7", "fast_cells": "fast_cells_kernel", "select": "select_kernel",
+        rl[k] = {"kernel": {"blur": "blur7_strip_kernel", "resize": "resize_cubic_strip_kernel x7", "fast_cells": "fast_cells_kernel", "select": "select_kernel",
                             "orient_describe": "orient_describe_kernel"}[k], "bound": "int_alu", "achieved": ach / 1e12, "peak": PEAK_ALU / 1e12,
                  "unit": "T int-op/s", "frac": ach / PEAK_ALU, "ms_per_step": ms, "sm_ms": ms * SM_COUNT,
                  "hbm_gbs": hbm_bytes[k] * F / (ms * 1e-3) / 1e9, "hbm_frac": hbm_bytes[k] * F / (ms * 1e-3) / 1e9 / hbm_peak,

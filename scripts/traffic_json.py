@@ -24,7 +24,7 @@ for r in rows[2:]:
     k = kern.setdefault(key, {"launches": 0, "dram_bytes": 0.0, "ncu_duration_ns": 0.0})
     k["launches"] += 1
     k["dram_bytes"] += b
-    k["ncu_duration_ns"] += f("gpu__time_duration.sum")
+    k["ncu_duration_ns"] += f("gpu__time_duration.sum") * {"ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9}.get(rows[1][ix["gpu__time_duration.sum"]], 1.0)
 res = {"source": "ncu --set full --clock-control none over `bench.py --profile-step` (128 frames + 16 BA windows); per-launch averages",
        "kernels": {k: {"launches": v["launches"], "dram_bytes_per_launch": v["dram_bytes"] / v["launches"],
                        "ncu_duration_s": v["ncu_duration_ns"] / v["launches"] * 1e-9} for k, v in kern.items()}}
