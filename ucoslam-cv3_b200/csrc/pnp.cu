@@ -243,10 +243,23 @@ __device__ void pass_linearize(const PnpArrays& A, const PnpHead& h, PnpShared& 
             __syncwarp(gmask);
         }
     }
+    {   // the 28 warp sums as ONE transposing butterfly: at offset o a lane keeps the half of its values whose index has that bit equal to
+        // its own and hands the other half to its partner, so after 5 rounds lane L holds the warp total of accumulator L.  31 exchanges
+        // instead of 28 x 5, and the same additions in the same tree as warp_sum (xor 16, 8, 4, 2, 1): bit-identical sums
+        double a[32];
 #pragma unroll
-    for (int k = 0; k < NACC; k++) {
-        double v = warp_sum(acc[k]);
-        if ((threadIdx.x & 31) == 0) S.red[threadIdx.x >> 5][k] = v;
+        for (int k = 0; k < 32; k++) a[k] = k < NACC ? acc[k] : 0.0;
+        const int lane = threadIdx.x & 31;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const bool up = lane & o;
+#pragma unroll
+            for (int j = 0; j < o; j++) {
+                const double send = up ? a[j] : a[j + o], keep = up ? a[j + o] : a[j];
+                a[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
+        }
+        if (lane < NACC) S.red[threadIdx.x >> 5][lane] = a[0];
     }
     __syncthreads();
     if (threadIdx.x < NACC) {
