@@ -773,6 +773,23 @@ typedef struct uco_mappoint_stream {
 } uco_mappoint_stream;
 int uco_b200_mappoint_stream_parse(const uint8_t* bytes, size_t len, uco_mappoint_stream* view, size_t* consumed);
 int uco_b200_mappoint_stream_write(const uco_mappoint_stream* view, uint8_t* out, size_t cap, size_t* written);
+/* The map-point SECTION of a map file: ReusableContainer<MapPoint>::toStream (src/basictypes/reusablecontainer.h:276-291) over
+ * ExpansibleContainer<Pair>::toStream (expansiblecontainer.h:115-129), as Map::toStream writes it (src/map.cpp:316-325).  walk: one pass over the
+ * section; slot_offset[i] = byte offset of slot i's MapPoint stream (uco_b200_mappoint_stream_parse reads it), slot_valid[i] = its valid flag
+ * (either may be NULL; cap = their length; UCO_E_CAPACITY when the section has more slots, the header is filled anyway).
+ * from_container: the valid points as the flat rows of uco_mappoints / uco_b200_track_state_set_map (a device-resident map from a map file without
+ * building MapPoint objects).  write: the inverse of walk (n_slots a multiple of 200; unused slots: uco_b200_mappoint_stream_default). */
+typedef struct uco_mappoint_container {
+    uint32_t n_slots, n_used, n_valid;            /* capacity (chunks x 200), ExpansibleContainer::size(), slots whose flag is set */
+    uint32_t n_free; const uint32_t* free_slots;  /* _emptySpaces, in the order the slots were freed (insert() reuses the last one) */
+} uco_mappoint_container;
+int uco_b200_mappoint_container_walk(const uint8_t* bytes, size_t len, uco_mappoint_container* c, size_t* slot_offset, uint8_t* slot_valid, uint32_t cap,
+                                     size_t* consumed);
+int uco_b200_mappoints_from_container(const uint8_t* bytes, size_t len, uint32_t cap, uint32_t* ids, float* pos, float* normal, float* min_dist, float* max_dist,
+                                      uint8_t* desc, uint8_t* flags, uint32_t* n_out, size_t* consumed);
+int uco_b200_mappoint_container_write(const uco_mappoint_container* c, const uco_mappoint_stream* points, const uint8_t* valid, uint8_t* out, size_t cap,
+                                      size_t* written);
+void uco_b200_mappoint_stream_default(uco_mappoint_stream* v);
 typedef struct uco_frame_dev {   /* DEVICE pointers (one allocation, owned by the uco_b200_frame) + the small host-side members */
     uint32_t idx, fseq_idx; int32_t n_kp;
     const uco_keypoint* kps; const uint8_t* desc; const uint32_t* ids; const uint8_t* flags; const float* depth;   /* depth: NULL without depth */

@@ -97,6 +97,8 @@ public:
 #include "gen/mappoint_streams.inc"
 }  // namespace ucoslam
 
+#include "basictypes/reusablecontainer.h"   // the reference's own header (and expansiblecontainer.h), unchanged
+
 extern "C" {
 // builds a Frame from flat arrays, lets the reference write it.  markers: n_markers records of (id, ssize, 8 corner floats, 8
 // undistorted corner floats, 16 doubles sols[0] as 4x4 CV_64F, errs[2], err_ratio) = 2 + 16 floats and 19 doubles each, dict "ARUCO_MIP_36h12".
@@ -177,6 +179,47 @@ long ref_mappoint_roundtrip(const unsigned char* in, long len, unsigned char* ou
         p.fromStream(is);
         std::stringstream ss;
         p.toStream(ss);
+        const std::string b = ss.str();
+        if ((long)b.size() > cap) return -1;
+        memcpy(out, b.data(), b.size());
+        return (long)b.size();
+    } catch (std::exception&) { return -2; }
+}
+// The map-point section of a map file (Map::toStream, map.cpp:316-325: map_points.toStream): the reference's OWN ReusableContainer /
+// ExpansibleContainer headers, unchanged, over the MapPoint above.  The container is driven the way Map drives it: `n` points inserted in
+// order (each read from its own stream by the reference's fromStream), the slots in `erase` erased in that order, then `n_again` more points
+// inserted (they take the freed slots, last freed first); the reference writes the container.
+long ref_mappoint_container(const unsigned char* streams, const long* lens, int n, const uint32_t* erase, int n_erase, int n_again, unsigned char* out, long cap) {
+    try {
+        ucoslam::ReusableContainer<ucoslam::MapPoint> c;
+        const unsigned char* p = streams;
+        auto next = [&](int i) {
+            std::stringstream is(std::string((const char*)p, (size_t)lens[i]));
+            p += lens[i];
+            ucoslam::MapPoint mp;
+            mp.fromStream(is);
+            return mp;
+        };
+        for (int i = 0; i < n; i++) c.insert(next(i));
+        for (int i = 0; i < n_erase; i++) c.erase(erase[i]);
+        for (int i = 0; i < n_again; i++) c.insert(next(n + i));
+        std::stringstream ss;
+        c.toStream(ss);
+        const std::string b = ss.str();
+        if ((long)b.size() > cap) return -1;
+        memcpy(out, b.data(), b.size());
+        return (long)b.size();
+    } catch (std::exception&) { return -2; }
+}
+// the reference reads a container stream and writes it again; *n_valid = its size() (valid elements)
+long ref_mappoint_container_roundtrip(const unsigned char* in, long len, unsigned char* out, long cap, long* n_valid) {
+    try {
+        std::stringstream is(std::string((const char*)in, (size_t)len));
+        ucoslam::ReusableContainer<ucoslam::MapPoint> c;
+        c.fromStream(is);
+        if (n_valid) *n_valid = (long)c.size();
+        std::stringstream ss;
+        c.toStream(ss);
         const std::string b = ss.str();
         if ((long)b.size() > cap) return -1;
         memcpy(out, b.data(), b.size());

@@ -9,3 +9,6 @@ print("written")
 from test_frame_stream import _mp_fields, _ref_mappoint
 _ref_mappoint(_mp_fields(1)).tofile(os.path.join(ROOT, "tests", "golden", "mappoint_stream.bin"))
 print("written mappoint")
+from test_frame_stream import _ref_container
+_ref_container([dict(_mp_fields(50 + i, n_frames=i), id=i) for i in range(6)], erase=[2]).tofile(os.path.join(ROOT, "tests", "golden", "mappoint_container.bin"))
+print("written mappoint container")

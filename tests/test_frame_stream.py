@@ -270,3 +270,110 @@ def test_mappoint_golden_and_malformed():
     assert lib.uco_b200_mappoint_stream_parse(ref.ctypes.data, len(ref) - 3, ctypes.addressof(v), None) != 0
     bad = ref.copy(); bad[0] ^= 1
     assert lib.uco_b200_mappoint_stream_parse(bad.ctypes.data, len(bad), ctypes.addressof(v), None) != 0
+
+
+# ---- the map-point SECTION of a map file: ReusableContainer<MapPoint> (Map::toStream, map.cpp:316-325) ------------------------------------
+def _ref_container(points, erase=(), again=()):
+    """the reference's own ReusableContainer / ExpansibleContainer headers (unchanged) driven as Map drives them: insert all of `points`, erase the slots
+    in `erase` (in that order), insert `again` (they take the freed slots, last freed first); returns the bytes the reference writes"""
+    lib = ctypes.CDLL(REF)
+    lib.ref_mappoint_container.restype = ctypes.c_long
+    streams = [_ref_mappoint(fd) for fd in list(points) + list(again)]
+    blob = np.concatenate(streams)
+    lens = np.array([len(s) for s in streams], np.int64)
+    er = np.array(list(erase), np.uint32)
+    out = np.zeros(len(blob) + 400 * 200 + 4096, np.uint8)
+    n = lib.ref_mappoint_container(ctypes.c_void_p(blob.ctypes.data), ctypes.c_void_p(lens.ctypes.data), len(points), ctypes.c_void_p(er.ctypes.data), len(er),
+                                   len(again), ctypes.c_void_p(out.ctypes.data), ctypes.c_long(len(out)))
+    assert n > 0
+    return out[:n].copy()
+
+
+def _container_case():
+    pts = [dict(_mp_fields(100 + i, n_frames=i % 7), id=i) for i in range(450)]      # three chunks of 200 slots, the last one half used
+    erase = [7, 399, 0, 211, 449]
+    again = [dict(_mp_fields(900 + i), id=1000 + i) for i in range(2)]               # reuse slots 449 and 211 (last freed first)
+    return pts, erase, again
+
+
+@needs_ref
+def test_mappoint_container_against_the_reference_headers():
+    from ucoslam_b200 import mappoint_container_walk, mappoints_from_container, MapPointStream, MapPointContainer
+    pts, erase, again = _container_case()
+    ref = _ref_container(pts, erase, again)
+    lib = ucoslam_b200.load()
+    c, off, valid, used = mappoint_container_walk(ref)
+    assert used == len(ref) and (c.n_slots, c.n_used, c.n_valid, c.n_free) == (600, 450, 447, 3)
+    assert list(np.ctypeslib.as_array(ctypes.cast(c.free_slots, ctypes.POINTER(ctypes.c_uint32)), (3,))) == [7, 399, 0]
+    expect = {i: p for i, p in enumerate(pts)}
+    expect[449], expect[211] = again[0], again[1]
+    views = (MapPointStream * c.n_slots)()
+    for i in range(c.n_slots):
+        u = ctypes.c_size_t()
+        assert lib.uco_b200_mappoint_stream_parse(ref.ctypes.data + int(off[i]), len(ref) - int(off[i]), ctypes.addressof(views[i]), ctypes.addressof(u)) == 0
+        assert bool(valid[i]) == (i < 450 and i not in (7, 399, 0))
+        if i < 450:
+            assert views[i].id == expect[i]["id"] and np.allclose(list(views[i].pos3d), expect[i]["pos"])
+        else:                                       # never used: what a default-constructed MapPoint streams as
+            d = MapPointStream()
+            lib.uco_b200_mappoint_stream_default(ctypes.addressof(d))
+            assert (views[i].id, views[i].n_frames, views[i].max_distance, views[i].min_distance, views[i].last_fidx_seen) == \
+                   (d.id, 0, d.max_distance, d.min_distance, d.last_fidx_seen) and views[i].desc.rows == 0
+    # the valid points as flat rows, in slot order
+    mp = mappoints_from_container(ref)
+    order = [i for i in range(450) if i not in (7, 399, 0)]
+    assert list(mp["ids"]) == [expect[i]["id"] for i in order]
+    assert np.array_equal(mp["pos"], np.array([expect[i]["pos"] for i in order])) and np.array_equal(mp["desc"], np.array([expect[i]["desc"] for i in order]))
+    assert np.array_equal(mp["normal"], np.array([expect[i]["normal"] for i in order]))
+    assert np.array_equal(mp["max_dist"], np.array([expect[i]["maxd"] for i in order], np.float32)) and list(mp["flags"]) == [expect[i]["flags"] for i in order]
+    # the writer reproduces the reference's bytes, and the reference reads them back
+    out, n = np.zeros(len(ref) + 64, np.uint8), ctypes.c_size_t()
+    assert lib.uco_b200_mappoint_container_write(ctypes.addressof(c), ctypes.addressof(views), valid.ctypes.data, out.ctypes.data, len(out), ctypes.addressof(n)) == 0
+    assert n.value == len(ref) and np.array_equal(out[:n.value], ref)
+    assert lib.uco_b200_mappoint_container_write(ctypes.addressof(c), ctypes.addressof(views), valid.ctypes.data, out.ctypes.data, 100, ctypes.addressof(n)) == -4
+    rlib = ctypes.CDLL(REF)
+    rlib.ref_mappoint_container_roundtrip.restype = ctypes.c_long
+    back, nv = np.zeros(len(ref) + 64, np.uint8), ctypes.c_long()
+    m = rlib.ref_mappoint_container_roundtrip(ctypes.c_void_p(out.ctypes.data), ctypes.c_long(len(ref)), ctypes.c_void_p(back.ctypes.data), ctypes.c_long(len(back)),
+                                              ctypes.byref(nv))
+    assert m == len(ref) and np.array_equal(back[:m], ref) and nv.value == 447
+
+
+@needs_ref
+@pytest.mark.parametrize("n", [0, 1, 200, 201, 400])
+def test_mappoint_container_chunk_edges(n):
+    """0 points, exactly one / two full chunks, one past a full chunk: curBuffer / curElm as ExpansibleContainer::push_back leaves them"""
+    from ucoslam_b200 import mappoint_container_walk, MapPointStream
+    pts = [dict(_mp_fields(300 + i, n_frames=1), id=i) for i in range(n)]
+    if n == 0:
+        lib = ctypes.CDLL(REF); lib.ref_mappoint_container.restype = ctypes.c_long
+        out = np.zeros(200 * 80 + 256, np.uint8)
+        k = lib.ref_mappoint_container(None, None, 0, None, 0, 0, ctypes.c_void_p(out.ctypes.data), ctypes.c_long(len(out)))
+        ref = out[:k].copy()
+    else:
+        ref = _ref_container(pts)
+    c, off, valid, used = mappoint_container_walk(ref)
+    assert used == len(ref) and c.n_used == n and c.n_valid == n and c.n_slots == 200 * max(1, (n + 199) // 200) and int(valid.sum()) == n
+    lib = ucoslam_b200.load()
+    views = (MapPointStream * c.n_slots)()
+    for i in range(c.n_slots):
+        assert lib.uco_b200_mappoint_stream_parse(ref.ctypes.data + int(off[i]), len(ref) - int(off[i]), ctypes.addressof(views[i]), None) == 0
+    out, w = np.zeros(len(ref), np.uint8), ctypes.c_size_t()
+    assert lib.uco_b200_mappoint_container_write(ctypes.addressof(c), ctypes.addressof(views), valid.ctypes.data, out.ctypes.data, len(out), ctypes.addressof(w)) == 0
+    assert np.array_equal(out, ref)
+
+
+def test_mappoint_container_golden_and_malformed():
+    from ucoslam_b200 import mappoint_container_walk, mappoints_from_container
+    ref = np.fromfile(os.path.join(GOLD, "mappoint_container.bin"), np.uint8)
+    c, off, valid, used = mappoint_container_walk(ref)
+    assert used == len(ref) and (c.n_slots, c.n_used, c.n_valid, c.n_free) == (200, 6, 5, 1)
+    mp = mappoints_from_container(ref)
+    assert list(mp["ids"]) == [0, 1, 3, 4, 5] and mp["desc"].shape == (5, 32)
+    for bad in (ref[:-5], ref[:40], np.concatenate([np.zeros(8, np.uint8), ref[8:]])):
+        with pytest.raises(ucoslam_b200.UcoError):
+            mappoint_container_walk(np.ascontiguousarray(bad))
+    worse = ref.copy()
+    worse[8 + 4 + 4 + 8] = 77          # the chunk count
+    with pytest.raises(ucoslam_b200.UcoError):
+        mappoint_container_walk(worse)

@@ -71,3 +71,41 @@ def test_edge_cases(ctx):
     leaf = leaf.copy(); leaf[0] = 10 ** 6
     with pytest.raises(ucoslam_b200.UcoError):
         ctx.match_projected(bad, 50.0, 15.0, (nodes, leaf, bbox))
+
+
+def test_map_points_from_a_map_file_section(ctx):
+    """the candidate map points of the projection matcher taken from the map-point SECTION of a map file (ReusableContainer<MapPoint>,
+    Map::toStream) without building MapPoint objects: the scene's points are written as a container with erased slots in between, read back as flat
+    rows (uco_b200_mappoints_from_container) and matched; same matches as from the scene's own arrays"""
+    import ctypes
+    from ucoslam_b200 import MapPointStream, MapPointContainer, MatView, mappoints_from_container
+    lib = ucoslam_b200.load()
+    sc = synth_projection_scene(11, n_kp=1200, n_mp=900)
+    m = len(sc["mp_id"])
+    n_slots = 200 * ((m + 60 + 199) // 200)
+    rng = np.random.default_rng(1)
+    slots = np.sort(rng.choice(m + 60, m, replace=False))            # the live points sit in these slots, erased ones in between
+    views, valid = (MapPointStream * n_slots)(), np.zeros(n_slots, np.uint8)
+    for i in range(n_slots):
+        lib.uco_b200_mappoint_stream_default(ctypes.addressof(views[i]))
+    desc = np.ascontiguousarray(sc["mp_desc"], np.uint8)
+    for k, s in enumerate(slots):
+        v = views[int(s)]
+        v.id = int(sc["mp_id"][k])
+        for a in range(3):
+            v.pos3d[a], v.normal[a] = float(sc["mp_pos"][k][a]), float(sc["mp_normal"][k][a])
+        v.min_distance, v.max_distance = float(sc["mp_min_dist"][k]), float(sc["mp_max_dist"][k])
+        v.desc = MatView(1, 32, 0, desc[k].ctypes.data)
+        valid[int(s)] = 1
+    free = np.array([i for i in range(m + 60) if not valid[i]], np.uint32)
+    c = MapPointContainer(n_slots, m + 60, m, len(free), free.ctypes.data)
+    need = ctypes.c_size_t()
+    assert lib.uco_b200_mappoint_container_write(ctypes.addressof(c), ctypes.addressof(views), valid.ctypes.data, None, 0, ctypes.addressof(need)) == 0
+    buf = np.zeros(need.value, np.uint8)
+    assert lib.uco_b200_mappoint_container_write(ctypes.addressof(c), ctypes.addressof(views), valid.ctypes.data, buf.ctypes.data, len(buf), ctypes.addressof(need)) == 0
+    mp = mappoints_from_container(buf)
+    assert len(mp["ids"]) == m and np.array_equal(mp["ids"], np.asarray(sc["mp_id"], np.uint32)) and np.array_equal(mp["desc"], desc)
+    sc2 = dict(sc, mp_id=mp["ids"], mp_pos=mp["pos"], mp_normal=mp["normal"], mp_min_dist=mp["min_dist"], mp_max_dist=mp["max_dist"], mp_desc=mp["desc"])
+    a, va = ctx.match_projected(sc, 50.0, 15.0)
+    b, vb = ctx.match_projected(sc2, 50.0, 15.0)
+    assert len(a) > 100 and a.tobytes() == b.tobytes() and np.array_equal(va, vb)

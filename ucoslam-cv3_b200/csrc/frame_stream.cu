@@ -175,6 +175,109 @@ int uco_b200_mappoint_stream_write(const uco_mappoint_stream* v, uint8_t* out, s
     return UCO_OK;
 }
 
+/* The map-point section of a map file: Map::toStream writes `map_points.toStream(str)` (src/map.cpp:316-325), a ReusableContainer<MapPoint>
+ * (src/basictypes/reusablecontainer.h:276-291): int64 magic 123299999, u32 count + the indices of the free slots (in the order they were freed;
+ * insert() reuses the LAST one), then ExpansibleContainer<Pair>::toStream (expansiblecontainer.h:115-129): u64 signature 13218888, u64 number
+ * of chunks, every slot of every chunk (chunks hold 200 slots: the container's default, which its reader also assumes) as {bool valid,
+ * MapPoint stream}, then int curBuffer, curElm, chunk size.  Slots past size() = curBuffer * chunk + curElm hold default-constructed points. */
+enum { MP_CHUNK = 200 };
+int uco_b200_mappoint_container_walk(const uint8_t* bytes, size_t len, uco_mappoint_container* c, size_t* slot_offset, uint8_t* slot_valid, uint32_t cap,
+                                     size_t* consumed) {
+    if (!bytes || !c) return UCO_E_INVALID;
+    memset(c, 0, sizeof *c);
+    Reader R{bytes, bytes + len};
+    if (R.get<int64_t>() != 123299999) return UCO_E_INVALID;
+    c->n_free = R.get<uint32_t>();
+    c->free_slots = (const uint32_t*)R.skip(4 * (size_t)c->n_free);
+    if (!R.ok || R.get<uint64_t>() != 13218888) return UCO_E_INVALID;
+    const uint64_t chunks = R.get<uint64_t>();
+    if (!R.ok || chunks > (uint64_t)(len / MP_CHUNK) + 1) return UCO_E_INVALID;   // every slot takes more than one byte
+    c->n_slots = (uint32_t)(chunks * MP_CHUNK);
+    uint32_t n_valid = 0;
+    for (uint32_t i = 0; i < c->n_slots; i++) {
+        const uint8_t valid = R.get<uint8_t>();
+        if (!R.ok) return UCO_E_INVALID;
+        uco_mappoint_stream v;
+        size_t used = 0;
+        if (uco_b200_mappoint_stream_parse(R.p, (size_t)(R.end - R.p), &v, &used) != UCO_OK) return UCO_E_INVALID;
+        if (i < cap) {
+            if (slot_offset) slot_offset[i] = (size_t)(R.p - bytes);
+            if (slot_valid) slot_valid[i] = valid;
+        }
+        n_valid += valid != 0;
+        R.skip(used);
+    }
+    const int32_t cur_buffer = R.get<int32_t>(), cur_elm = R.get<int32_t>(), chunk = R.get<int32_t>();
+    if (!R.ok || chunk != MP_CHUNK || cur_buffer < 0 || cur_elm < 0 || cur_elm > MP_CHUNK || (uint64_t)cur_buffer >= chunks) return UCO_E_INVALID;
+    c->n_used = (uint32_t)cur_buffer * MP_CHUNK + (uint32_t)cur_elm;
+    c->n_valid = n_valid;
+    if (consumed) *consumed = (size_t)(R.p - bytes);
+    return c->n_slots > cap && (slot_offset || slot_valid) ? UCO_E_CAPACITY : UCO_OK;
+}
+/* the valid points of the section as the flat rows uco_mappoints / uco_b200_track_state_set_map take (ids = MapPoint::id); every output may be NULL */
+int uco_b200_mappoints_from_container(const uint8_t* bytes, size_t len, uint32_t cap, uint32_t* ids, float* pos, float* normal, float* min_dist, float* max_dist,
+                                      uint8_t* desc, uint8_t* flags, uint32_t* n_out, size_t* consumed) {
+    if (!bytes || !n_out) return UCO_E_INVALID;
+    uco_mappoint_container c;
+    int rc = uco_b200_mappoint_container_walk(bytes, len, &c, nullptr, nullptr, 0, consumed);
+    if (rc != UCO_OK) return rc;
+    *n_out = c.n_valid;
+    if (c.n_valid > cap) return UCO_E_CAPACITY;
+    const uint8_t* p = bytes + 8 + 4 + 4 * (size_t)c.n_free + 16;
+    uint32_t k = 0;
+    for (uint32_t i = 0; i < c.n_slots; i++) {
+        const uint8_t valid = *p++;
+        uco_mappoint_stream v;
+        size_t used = 0;
+        uco_b200_mappoint_stream_parse(p, (size_t)(bytes + len - p), &v, &used);
+        p += used;
+        if (!valid) continue;
+        if (desc && (v.desc.rows != 1 || (size_t)v.desc.cols * elem_size(v.desc.type) != 32)) return UCO_E_INVALID;   // ORB rows only
+        if (ids) ids[k] = v.id;
+        if (pos) memcpy(pos + 3 * (size_t)k, v.pos3d, 12);
+        if (normal) memcpy(normal + 3 * (size_t)k, v.normal, 12);
+        if (min_dist) min_dist[k] = v.min_distance;
+        if (max_dist) max_dist[k] = v.max_distance;
+        if (desc) memcpy(desc + 32 * (size_t)k, v.desc.data, 32);
+        if (flags) flags[k] = v.flags;
+        k++;
+    }
+    return UCO_OK;
+}
+/* the writer: n_slots must be a multiple of 200; slot i is written as {valid[i], points[i]} (the caller passes default points for unused slots:
+ * uco_b200_mappoint_stream_default) */
+int uco_b200_mappoint_container_write(const uco_mappoint_container* c, const uco_mappoint_stream* points, const uint8_t* valid, uint8_t* out, size_t cap,
+                                      size_t* written) {
+    if (!c || !written || c->n_slots % MP_CHUNK || c->n_slots == 0 || c->n_used > c->n_slots || (c->n_slots && (!points || !valid)) || (c->n_free && !c->free_slots))
+        return UCO_E_INVALID;
+    Writer W{out, cap};
+    W.val<int64_t>(123299999);
+    W.val(c->n_free); W.put(c->free_slots, 4 * (size_t)c->n_free);
+    W.val<uint64_t>(13218888); W.val<uint64_t>(c->n_slots / MP_CHUNK);
+    for (uint32_t i = 0; i < c->n_slots; i++) {
+        W.val<uint8_t>(valid[i] ? 1 : 0);
+        size_t n = 0;
+        int rc = uco_b200_mappoint_stream_write(points + i, out && W.n <= cap ? out + W.n : nullptr, out && W.n <= cap ? cap - W.n : 0, &n);
+        if (rc != UCO_OK && rc != UCO_E_CAPACITY) return rc;
+        W.n += n;
+    }
+    // ExpansibleContainer::push_back (expansiblecontainer.h:44-52): after k >= 1 pushes curBuffer = (k - 1) / chunk, curElm = (k - 1) % chunk + 1
+    W.val<int32_t>(c->n_used ? (int32_t)((c->n_used - 1) / MP_CHUNK) : 0);
+    W.val<int32_t>(c->n_used ? (int32_t)((c->n_used - 1) % MP_CHUNK) + 1 : 0);
+    W.val<int32_t>(MP_CHUNK);
+    *written = W.n;
+    if (out && W.n > cap) return UCO_E_CAPACITY;
+    return UCO_OK;
+}
+/* what a default-constructed MapPoint streams as (mappoint.h:111-131 member initialisers): the content of never-used slots */
+void uco_b200_mappoint_stream_default(uco_mappoint_stream* v) {
+    memset(v, 0, sizeof *v);
+    v->id = 0xffffffffu;
+    v->last_fidx_seen = 0xffffffffu;
+    v->max_distance = 1.17549435e-38f;   // std::numeric_limits<float>::min()
+    v->min_distance = 3.40282347e+38f;   // std::numeric_limits<float>::max()
+}
+
 /* KdTreeIndex::toStream bytes from the flattened tree (the inverse of uco_b200_kdtree_parse): what a frame whose tree was built on
  * the device (uco_b200_kdtree_build_batch_dev) writes into its stream.  div_val: the node's split value (picoflann keeps it as a
  * double next to the two float sides); pass NULL to write (divlow + divhigh) / 2. */

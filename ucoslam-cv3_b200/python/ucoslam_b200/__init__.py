@@ -58,6 +58,10 @@ SIGNATURES = {
     "uco_b200_frame_stream_write": (_i, [_vp, _vp, _c.c_size_t, _vp]),
     "uco_b200_mappoint_stream_parse": (_i, [_vp, _c.c_size_t, _vp, _vp]),
     "uco_b200_mappoint_stream_write": (_i, [_vp, _vp, _c.c_size_t, _vp]),
+    "uco_b200_mappoint_container_walk": (_i, [_vp, _c.c_size_t, _vp, _vp, _vp, _c.c_uint32, _vp]),
+    "uco_b200_mappoints_from_container": (_i, [_vp, _c.c_size_t, _c.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "uco_b200_mappoint_container_write": (_i, [_vp, _vp, _vp, _vp, _c.c_size_t, _vp]),
+    "uco_b200_mappoint_stream_default": (None, [_vp]),
     "uco_b200_kdtree_serialize": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _c.c_size_t, _vp]),
     "uco_b200_frame_upload": (_i, [_vp, _vp, _vp]),
     "uco_b200_frame_dev": (_vp, [_vp]),
@@ -363,6 +367,41 @@ class MapPointStream(ctypes.Structure):  # uco_mappoint_stream
     _fields_ = [("id", _c.c_uint32), ("pos3d", _c.c_float * 3), ("desc", MatView), ("n_frames", _c.c_uint32), ("frames", _vp),
                 ("normal", _c.c_float * 3), ("n_times_seen", _c.c_uint16), ("n_times_visible", _c.c_uint16), ("flags", _c.c_uint8),
                 ("max_distance", _c.c_float), ("min_distance", _c.c_float), ("kf_since_addition", _c.c_uint64), ("last_fidx_seen", _c.c_uint32)]
+
+
+class MapPointContainer(ctypes.Structure):  # uco_mappoint_container
+    _fields_ = [("n_slots", _c.c_uint32), ("n_used", _c.c_uint32), ("n_valid", _c.c_uint32), ("n_free", _c.c_uint32), ("free_slots", _vp)]
+
+
+def mappoint_container_walk(buf):
+    """(header, slot offsets, slot valid flags, bytes consumed) of the map-point section at the start of `buf` (uint8 array)"""
+    lib = load()
+    c, used = MapPointContainer(), ctypes.c_size_t()
+    rc = lib.uco_b200_mappoint_container_walk(buf.ctypes.data, len(buf), ctypes.addressof(c), None, None, 0, ctypes.addressof(used))
+    if rc != 0:
+        raise UcoError("mappoint_container_walk: malformed section (%d)" % rc)
+    off, valid = np.zeros(c.n_slots, np.uint64), np.zeros(c.n_slots, np.uint8)
+    rc = lib.uco_b200_mappoint_container_walk(buf.ctypes.data, len(buf), ctypes.addressof(c), _p(off), _p(valid), c.n_slots, ctypes.addressof(used))
+    if rc != 0:
+        raise UcoError("mappoint_container_walk failed (%d)" % rc)
+    return c, off, valid, used.value
+
+
+def mappoints_from_container(buf):
+    """the valid map points of the section as the arrays of uco_mappoints (+ flags): dict(ids, pos, normal, min_dist, max_dist, desc, flags)"""
+    lib = load()
+    n = ctypes.c_uint32()
+    rc = lib.uco_b200_mappoints_from_container(buf.ctypes.data, len(buf), 0, None, None, None, None, None, None, None, ctypes.addressof(n), None)
+    if rc not in (0, -4) and n.value == 0:
+        raise UcoError("mappoints_from_container: malformed section (%d)" % rc)
+    k = n.value
+    out = dict(ids=np.zeros(k, np.uint32), pos=np.zeros((k, 3), np.float32), normal=np.zeros((k, 3), np.float32), min_dist=np.zeros(k, np.float32),
+               max_dist=np.zeros(k, np.float32), desc=np.zeros((k, 32), np.uint8), flags=np.zeros(k, np.uint8))
+    rc = lib.uco_b200_mappoints_from_container(buf.ctypes.data, len(buf), k, _p(out["ids"]), _p(out["pos"]), _p(out["normal"]), _p(out["min_dist"]),
+                                               _p(out["max_dist"]), _p(out["desc"]), _p(out["flags"]), ctypes.addressof(n), None)
+    if rc != 0:
+        raise UcoError("mappoints_from_container failed (%d)" % rc)
+    return out
 
 
 class FrameDev(ctypes.Structure):  # uco_frame_dev
