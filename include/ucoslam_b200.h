@@ -785,6 +785,9 @@ typedef struct uco_mappoint_container {
 } uco_mappoint_container;
 int uco_b200_mappoint_container_walk(const uint8_t* bytes, size_t len, uco_mappoint_container* c, size_t* slot_offset, uint8_t* slot_valid, uint32_t cap,
                                      size_t* consumed);
+/* the keyframe section: FrameSet::toStream (src/map_types/frame.cpp:350-355) = int magic 88888 + the same container over Frame streams */
+int uco_b200_frame_container_walk(const uint8_t* bytes, size_t len, uco_mappoint_container* c, size_t* slot_offset, uint8_t* slot_valid, uint32_t cap,
+                                  size_t* consumed);
 int uco_b200_mappoints_from_container(const uint8_t* bytes, size_t len, uint32_t cap, uint32_t* ids, float* pos, float* normal, float* min_dist, float* max_dist,
                                       uint8_t* desc, uint8_t* flags, uint32_t* n_out, size_t* consumed);
 int uco_b200_mappoint_container_write(const uco_mappoint_container* c, const uco_mappoint_stream* points, const uint8_t* valid, uint8_t* out, size_t cap,

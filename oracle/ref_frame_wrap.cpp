@@ -211,6 +211,32 @@ long ref_mappoint_container(const unsigned char* streams, const long* lens, int 
         return (long)b.size();
     } catch (std::exception&) { return -2; }
 }
+// The keyframe section: FrameSet::toStream (frame.cpp:350-355) is `int magic = 88888` followed by ReusableContainer<Frame>::toStream; the Frame
+// here carries the reference's own toStream / fromStream statements.  Same driving as above.
+long ref_frame_container(const unsigned char* streams, const long* lens, int n, const uint32_t* erase, int n_erase, int n_again, unsigned char* out, long cap) {
+    try {
+        ucoslam::ReusableContainer<ucoslam::Frame> c;
+        const unsigned char* p = streams;
+        auto next = [&](int i) {
+            std::stringstream is(std::string((const char*)p, (size_t)lens[i]));
+            p += lens[i];
+            ucoslam::Frame f;
+            f.fromStream(is);
+            return f;
+        };
+        for (int i = 0; i < n; i++) c.insert(next(i));
+        for (int i = 0; i < n_erase; i++) c.erase(erase[i]);
+        for (int i = 0; i < n_again; i++) c.insert(next(n + i));
+        std::stringstream ss;
+        int magic = 88888;
+        ss.write((char*)&magic, sizeof(magic));
+        c.toStream(ss);
+        const std::string b = ss.str();
+        if ((long)b.size() > cap) return -1;
+        memcpy(out, b.data(), b.size());
+        return (long)b.size();
+    } catch (std::exception&) { return -2; }
+}
 // the reference reads a container stream and writes it again; *n_valid = its size() (valid elements)
 long ref_mappoint_container_roundtrip(const unsigned char* in, long len, unsigned char* out, long cap, long* n_valid) {
     try {

@@ -377,3 +377,40 @@ def test_mappoint_container_golden_and_malformed():
     worse[8 + 4 + 4 + 8] = 77          # the chunk count
     with pytest.raises(ucoslam_b200.UcoError):
         mappoint_container_walk(worse)
+
+
+# ---- the keyframe SECTION of a map file: FrameSet (int 88888 + ReusableContainer<Frame>) -----------------------------------------------------
+def _ref_frame_container(fields, erase=(), again=()):
+    lib = ctypes.CDLL(REF)
+    lib.ref_frame_container.restype = ctypes.c_long
+    streams = [ref_stream(fd) for fd in list(fields) + list(again)]
+    blob = np.concatenate(streams)
+    lens = np.array([len(s) for s in streams], np.int64)
+    er = np.array(list(erase), np.uint32)
+    out = np.zeros(len(blob) + (4 << 20), np.uint8)
+    n = lib.ref_frame_container(ctypes.c_void_p(blob.ctypes.data), ctypes.c_void_p(lens.ctypes.data), len(fields), ctypes.c_void_p(er.ctypes.data), len(er),
+                                len(again), ctypes.c_void_p(out.ctypes.data), ctypes.c_long(len(out)))
+    assert n > 0
+    return out[:n].copy(), streams
+
+
+@needs_ref
+def test_keyframe_container_against_the_reference_headers():
+    """four keyframes inserted, one erased, one more inserted into the freed slot: every slot's Frame stream is found (the 196 never-used slots hold
+    default-constructed Frames, which must parse too) and the live slots carry, byte for byte, the streams that went in"""
+    from ucoslam_b200 import mappoint_container_walk
+    fields = [dict(make_fields(20 + i, n_kp=60 + 10 * i, n_markers=i % 2), idx=i) for i in range(4)]
+    again = [dict(make_fields(30, n_kp=45, n_markers=0), idx=9)]
+    ref, streams = _ref_frame_container(fields, erase=[1], again=again)
+    c, off, valid, used = mappoint_container_walk(ref, frames=True)
+    assert used == len(ref) and (c.n_slots, c.n_used, c.n_valid, c.n_free) == (200, 4, 4, 0) and list(valid[:5]) == [1, 1, 1, 1, 0]
+    want = [streams[0], streams[4], streams[2], streams[3]]
+    for i in range(4):
+        v, n = frame_stream_parse(ref[int(off[i]):])
+        assert n == len(want[i]) and np.array_equal(ref[int(off[i]):int(off[i]) + n], want[i]) and v.idx == (9 if i == 1 else i)
+    v, n = frame_stream_parse(ref[int(off[150]):])             # a default-constructed Frame
+    assert v.n_und_kpts == 0 and v.n_ids == 0 and v.desc.rows == 0
+    with pytest.raises(ucoslam_b200.UcoError):
+        mappoint_container_walk(ref, frames=False)              # a keyframe section is not a map-point section
+    with pytest.raises(ucoslam_b200.UcoError):
+        mappoint_container_walk(np.ascontiguousarray(ref[:-7]), frames=True)

@@ -181,11 +181,12 @@ int uco_b200_mappoint_stream_write(const uco_mappoint_stream* v, uint8_t* out, s
  * of chunks, every slot of every chunk (chunks hold 200 slots: the container's default, which its reader also assumes) as {bool valid,
  * MapPoint stream}, then int curBuffer, curElm, chunk size.  Slots past size() = curBuffer * chunk + curElm hold default-constructed points. */
 enum { MP_CHUNK = 200 };
-int uco_b200_mappoint_container_walk(const uint8_t* bytes, size_t len, uco_mappoint_container* c, size_t* slot_offset, uint8_t* slot_valid, uint32_t cap,
-                                     size_t* consumed) {
+static int container_walk(const uint8_t* bytes, size_t len, bool frames, uco_mappoint_container* c, size_t* slot_offset, uint8_t* slot_valid, uint32_t cap,
+                          size_t* consumed) {
     if (!bytes || !c) return UCO_E_INVALID;
     memset(c, 0, sizeof *c);
     Reader R{bytes, bytes + len};
+    if (frames && R.get<int32_t>() != 88888) return UCO_E_INVALID;   // FrameSet::toStream, frame.cpp:350-355
     if (R.get<int64_t>() != 123299999) return UCO_E_INVALID;
     c->n_free = R.get<uint32_t>();
     c->free_slots = (const uint32_t*)R.skip(4 * (size_t)c->n_free);
@@ -197,9 +198,14 @@ int uco_b200_mappoint_container_walk(const uint8_t* bytes, size_t len, uco_mappo
     for (uint32_t i = 0; i < c->n_slots; i++) {
         const uint8_t valid = R.get<uint8_t>();
         if (!R.ok) return UCO_E_INVALID;
-        uco_mappoint_stream v;
         size_t used = 0;
-        if (uco_b200_mappoint_stream_parse(R.p, (size_t)(R.end - R.p), &v, &used) != UCO_OK) return UCO_E_INVALID;
+        if (frames) {
+            uco_frame_stream v;
+            if (uco_b200_frame_stream_parse(R.p, (size_t)(R.end - R.p), &v, &used) != UCO_OK) return UCO_E_INVALID;
+        } else {
+            uco_mappoint_stream v;
+            if (uco_b200_mappoint_stream_parse(R.p, (size_t)(R.end - R.p), &v, &used) != UCO_OK) return UCO_E_INVALID;
+        }
         if (i < cap) {
             if (slot_offset) slot_offset[i] = (size_t)(R.p - bytes);
             if (slot_valid) slot_valid[i] = valid;
@@ -213,6 +219,16 @@ int uco_b200_mappoint_container_walk(const uint8_t* bytes, size_t len, uco_mappo
     c->n_valid = n_valid;
     if (consumed) *consumed = (size_t)(R.p - bytes);
     return c->n_slots > cap && (slot_offset || slot_valid) ? UCO_E_CAPACITY : UCO_OK;
+}
+int uco_b200_mappoint_container_walk(const uint8_t* bytes, size_t len, uco_mappoint_container* c, size_t* slot_offset, uint8_t* slot_valid, uint32_t cap,
+                                     size_t* consumed) {
+    return container_walk(bytes, len, false, c, slot_offset, slot_valid, cap, consumed);
+}
+/* The keyframe section of a map file: FrameSet::toStream (src/map_types/frame.cpp:350-355) = int magic 88888 + the same container over Frame
+ * streams; slot_offset[i] is where uco_b200_frame_stream_parse (and from there uco_b200_frame_upload) reads keyframe slot i. */
+int uco_b200_frame_container_walk(const uint8_t* bytes, size_t len, uco_mappoint_container* c, size_t* slot_offset, uint8_t* slot_valid, uint32_t cap,
+                                  size_t* consumed) {
+    return container_walk(bytes, len, true, c, slot_offset, slot_valid, cap, consumed);
 }
 /* the valid points of the section as the flat rows uco_mappoints / uco_b200_track_state_set_map take (ids = MapPoint::id); every output may be NULL */
 int uco_b200_mappoints_from_container(const uint8_t* bytes, size_t len, uint32_t cap, uint32_t* ids, float* pos, float* normal, float* min_dist, float* max_dist,

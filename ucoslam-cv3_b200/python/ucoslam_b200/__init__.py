@@ -59,6 +59,7 @@ SIGNATURES = {
     "uco_b200_mappoint_stream_parse": (_i, [_vp, _c.c_size_t, _vp, _vp]),
     "uco_b200_mappoint_stream_write": (_i, [_vp, _vp, _c.c_size_t, _vp]),
     "uco_b200_mappoint_container_walk": (_i, [_vp, _c.c_size_t, _vp, _vp, _vp, _c.c_uint32, _vp]),
+    "uco_b200_frame_container_walk": (_i, [_vp, _c.c_size_t, _vp, _vp, _vp, _c.c_uint32, _vp]),
     "uco_b200_mappoints_from_container": (_i, [_vp, _c.c_size_t, _c.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "uco_b200_mappoint_container_write": (_i, [_vp, _vp, _vp, _vp, _c.c_size_t, _vp]),
     "uco_b200_mappoint_stream_default": (None, [_vp]),
@@ -373,15 +374,17 @@ class MapPointContainer(ctypes.Structure):  # uco_mappoint_container
     _fields_ = [("n_slots", _c.c_uint32), ("n_used", _c.c_uint32), ("n_valid", _c.c_uint32), ("n_free", _c.c_uint32), ("free_slots", _vp)]
 
 
-def mappoint_container_walk(buf):
-    """(header, slot offsets, slot valid flags, bytes consumed) of the map-point section at the start of `buf` (uint8 array)"""
+def mappoint_container_walk(buf, frames=False):
+    """(header, slot offsets, slot valid flags, bytes consumed) of the map-point section (frames=True: the keyframe section, FrameSet) at the start of
+    `buf` (uint8 array)"""
     lib = load()
     c, used = MapPointContainer(), ctypes.c_size_t()
-    rc = lib.uco_b200_mappoint_container_walk(buf.ctypes.data, len(buf), ctypes.addressof(c), None, None, 0, ctypes.addressof(used))
+    walk = lib.uco_b200_frame_container_walk if frames else lib.uco_b200_mappoint_container_walk
+    rc = walk(buf.ctypes.data, len(buf), ctypes.addressof(c), None, None, 0, ctypes.addressof(used))
     if rc != 0:
         raise UcoError("mappoint_container_walk: malformed section (%d)" % rc)
     off, valid = np.zeros(c.n_slots, np.uint64), np.zeros(c.n_slots, np.uint8)
-    rc = lib.uco_b200_mappoint_container_walk(buf.ctypes.data, len(buf), ctypes.addressof(c), _p(off), _p(valid), c.n_slots, ctypes.addressof(used))
+    rc = walk(buf.ctypes.data, len(buf), ctypes.addressof(c), _p(off), _p(valid), c.n_slots, ctypes.addressof(used))
     if rc != 0:
         raise UcoError("mappoint_container_walk failed (%d)" % rc)
     return c, off, valid, used.value
