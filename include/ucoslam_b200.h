@@ -793,6 +793,41 @@ int uco_b200_mappoints_from_container(const uint8_t* bytes, size_t len, uint32_t
 int uco_b200_mappoint_container_write(const uco_mappoint_container* c, const uco_mappoint_stream* points, const uint8_t* valid, uint8_t* out, size_t cap,
                                       size_t* written);
 void uco_b200_mappoint_stream_default(uco_mappoint_stream* v);
+/* The remaining sections of Map::toStream (src/map.cpp:316-325) and the whole stream.  Views: pointers and offsets into the caller's buffer.
+ *   keyframe database  KeyFrameDataBase::toStream (keyframedatabase.cpp:335-340, :278-287, :122-124; vocabulary: fbow.cpp:171-178)
+ *   markers            toStream__kv_complex over std::map<u32, Marker> (io_utils.h:113-121; Marker::toStream, marker.cpp:41-47)
+ *   covisibility graph CovisGraph::toStream (covisgraph.cpp:308-333) */
+typedef struct uco_kfdb_stream {
+    int32_t type;                              /* 0 DummyDataBase, 1 KPFrameDataBase */
+    size_t voc_off, voc_len;                   /* the fbow vocabulary stream (what uco_b200_bow_load takes); 0 / 0 for type 0 */
+    uint32_t n_words; size_t words_off;        /* inverted index: n_words records {u32 word, u32 count, count x u32 frame} from words_off */
+    uint64_t n_word_frames;                    /* total (word, frame) entries */
+    uint32_t n_frames; const uint32_t* frames; /* the database's frame ids, ascending */
+} uco_kfdb_stream;
+typedef struct uco_marker_stream {
+    uint32_t key, id; float pose_g2m[16]; float size;
+    uint32_t n_frames; const uint32_t* frames;
+    uint32_t dict_len; const char* dict;       /* not NUL-terminated */
+} uco_marker_stream;
+typedef struct uco_covis_stream {
+    uint32_t n_nodes; const uint32_t* nodes;
+    uint32_t n_adj; size_t adj_off;            /* n_adj records {u32 node, u32 count, count x u32 neighbour} from adj_off */
+    uint64_t n_neighbours;
+    uint32_t n_weights; const uint8_t* weights; /* n_weights packed records {u64 key = join(a, b), float weight}, 12 bytes each */
+} uco_covis_stream;
+typedef struct uco_map_sections {              /* byte ranges of the five sections, in stream order */
+    size_t kfdb_off, kfdb_len; uco_kfdb_stream kfdb;
+    size_t points_off, points_len; uco_mappoint_container points;
+    size_t markers_off, markers_len; uint32_t n_markers;
+    size_t frames_off, frames_len; uco_mappoint_container frames;
+    size_t covis_off, covis_len; uco_covis_stream covis;
+    size_t total_len;
+} uco_map_sections;
+int uco_b200_kfdb_stream_walk(const uint8_t* bytes, size_t len, uco_kfdb_stream* out, size_t* consumed);
+int uco_b200_marker_map_walk(const uint8_t* bytes, size_t len, uint32_t cap, uco_marker_stream* out, uint32_t* n_out, size_t* consumed);
+int uco_b200_covis_stream_walk(const uint8_t* bytes, size_t len, uco_covis_stream* out, size_t* consumed);
+/* has_file_magic: the buffer is a map FILE (Map::saveToFile, map.cpp:339-345: u64 225237123 first); section offsets are from the buffer start */
+int uco_b200_map_stream_walk(const uint8_t* bytes, size_t len, int has_file_magic, uco_map_sections* out);
 typedef struct uco_frame_dev {   /* DEVICE pointers (one allocation, owned by the uco_b200_frame) + the small host-side members */
     uint32_t idx, fseq_idx; int32_t n_kp;
     const uco_keypoint* kps; const uint8_t* desc; const uint32_t* ids; const uint8_t* flags; const float* depth;   /* depth: NULL without depth */

@@ -93,8 +93,19 @@ public:
     void toStream(std::ostream& str) const;
     void fromStream(std::istream& str);
 };
+class Marker {     // marker.h:33-53: the members Marker::toStream touches
+public:
+    uint32_t id = 0;
+    Se3Transform pose_g2m;
+    float size = 0;
+    std::set<uint32_t> frames;
+    std::string dict_info;
+    void toStream(std::ostream& str) const;
+    void fromStream(std::istream& str);
+};
 #include "gen/frame_streams.inc"
 #include "gen/mappoint_streams.inc"
+#include "gen/marker_streams.inc"
 }  // namespace ucoslam
 
 #include "basictypes/reusablecontainer.h"   // the reference's own header (and expansiblecontainer.h), unchanged
@@ -231,6 +242,27 @@ long ref_frame_container(const unsigned char* streams, const long* lens, int n, 
         int magic = 88888;
         ss.write((char*)&magic, sizeof(magic));
         c.toStream(ss);
+        const std::string b = ss.str();
+        if ((long)b.size() > cap) return -1;
+        memcpy(out, b.data(), b.size());
+        return (long)b.size();
+    } catch (std::exception&) { return -2; }
+}
+// The marker section of a map file: Map::toStream writes toStream__kv_complex(map_markers, str) (map.cpp:321; io_utils.h:113-121, the
+// reference's own template) over std::map<uint32_t, Marker> (SafeMap is a std::map) with the reference's Marker::toStream statements.
+// markers: n records of (id, size, 16 pose floats), frames: n_frames[i] keyframe ids each, dict "ARUCO_MIP_36h12"
+long ref_marker_map_to_stream(int n, const uint32_t* ids, const float* size, const float* pose16, const int* n_frames, const uint32_t* frames, unsigned char* out, long cap) {
+    try {
+        std::map<uint32_t, ucoslam::Marker> mm;
+        for (int i = 0; i < n; i++) {
+            ucoslam::Marker m;
+            m.id = ids[i]; m.size = size[i]; m.dict_info = "ARUCO_MIP_36h12";
+            memcpy(m.pose_g2m.ptr<float>(0), pose16 + 16 * i, 64);
+            for (int k = 0; k < n_frames[i]; k++) m.frames.insert(*frames++);
+            mm[ids[i]] = m;
+        }
+        std::stringstream ss;
+        ucoslam::toStream__kv_complex(mm, ss);
         const std::string b = ss.str();
         if ((long)b.size() > cap) return -1;
         memcpy(out, b.data(), b.size());

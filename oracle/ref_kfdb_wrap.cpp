@@ -9,6 +9,7 @@
 #include <cstdint>
 #include <cstring>
 #include <set>
+#include <sstream>
 #include <vector>
 
 namespace {
@@ -30,6 +31,28 @@ void* ref_kfdb_create(const char* voc_path) {
     try { auto* h = new RefDb(); h->db.loadFromFile(voc_path); return h; } catch (std::exception&) { return nullptr; }
 }
 void ref_kfdb_free(void* h) { delete (RefDb*)h; }
+// the sections Map::toStream writes for these two members (map.cpp:316-325): KeyFrameDataBase::toStream (keyframedatabase.cpp:335-340 over
+// KPFrameDataBase::toStream_, :278-287: vocabulary, inverted word index, frame ids) and CovisGraph::toStream (covisgraph.cpp:308-333)
+long ref_kfdb_to_stream(void* h, unsigned char* out, long cap) {
+    try {
+        std::stringstream ss;
+        ((RefDb*)h)->db.toStream(ss);
+        const std::string b = ss.str();
+        if ((long)b.size() > cap) return -(long)b.size();
+        memcpy(out, b.data(), b.size());
+        return (long)b.size();
+    } catch (std::exception&) { return 0; }
+}
+long ref_covis_to_stream(void* h, unsigned char* out, long cap) {
+    try {
+        std::stringstream ss;
+        ((RefDb*)h)->covis.toStream(ss);
+        const std::string b = ss.str();
+        if ((long)b.size() > cap) return -(long)b.size();
+        memcpy(out, b.data(), b.size());
+        return (long)b.size();
+    } catch (std::exception&) { return 0; }
+}
 // KeyFrameDataBase::add (keyframedatabase.cpp:150-160); returns the frame's bag of words (map order) for the caller
 int ref_kfdb_add(void* h, uint32_t idx, const uint8_t* desc, int n, uint32_t* bow_ids, float* bow_w, int* n_bow) {
     try {

@@ -414,3 +414,106 @@ def test_keyframe_container_against_the_reference_headers():
         mappoint_container_walk(ref, frames=False)              # a keyframe section is not a map-point section
     with pytest.raises(ucoslam_b200.UcoError):
         mappoint_container_walk(np.ascontiguousarray(ref[:-7]), frames=True)
+
+
+# ---- the other sections of Map::toStream and the whole stream --------------------------------------------------------------------------------
+def _ref_bytes(fn, h):
+    out = np.zeros(8 << 20, np.uint8)
+    fn.restype = ctypes.c_long
+    n = fn(ctypes.c_void_p(h), ctypes.c_void_p(out.ctypes.data), ctypes.c_long(len(out)))
+    assert n > 0
+    return out[:n].copy()
+
+
+def _ref_sections(tmp_path):
+    """keyframe-database and covisibility-graph sections written by the reference's own keyframedatabase.cpp / covisgraph.cpp (compiled unchanged,
+    libref_kfdb.so) on a small synthetic vocabulary, the marker section by its Marker::toStream statements under its own toStream__kv_complex"""
+    import oracle_py
+    from ucoslam_b200 import workload
+    voc = workload.synth_vocabulary_full(seed=4, k=6, depth=3)
+    vp = os.path.join(str(tmp_path), "voc.fbow")
+    with open(vp, "wb") as f:
+        f.write(voc)
+    db = oracle_py.RefKeyFrameDataBase(vp)
+    rng = np.random.default_rng(3)
+    n_words = 0
+    for idx in (0, 1, 2, 5, 9):
+        ids, w = db.add(idx, rng.integers(0, 256, (300, 32), dtype=np.uint8))
+        n_words += len(ids)
+    db.delete(2)
+    for a, b, w in ((0, 1, 31.0), (1, 5, 12.0), (5, 9, 40.0), (0, 9, 7.0)):
+        db.covis_edge(a, b, w)
+    kf = _ref_bytes(db.lib.ref_kfdb_to_stream, db.h)
+    cv = _ref_bytes(db.lib.ref_covis_to_stream, db.h)
+    lib = ctypes.CDLL(REF)
+    lib.ref_marker_map_to_stream.restype = ctypes.c_long
+    ids = np.array([17, 3, 250], np.uint32); size = np.array([0.2, 0.15, 0.3], np.float32)
+    pose = rng.normal(0, 1, (3, 16)).astype(np.float32); nfr = np.array([2, 0, 3], np.int32); fr = np.array([0, 5, 1, 5, 9], np.uint32)
+    out = np.zeros(4096, np.uint8)
+    n = lib.ref_marker_map_to_stream(3, ctypes.c_void_p(ids.ctypes.data), ctypes.c_void_p(size.ctypes.data), ctypes.c_void_p(pose.ctypes.data),
+                                     ctypes.c_void_p(nfr.ctypes.data), ctypes.c_void_p(fr.ctypes.data), ctypes.c_void_p(out.ctypes.data), ctypes.c_long(len(out)))
+    assert n > 0
+    return dict(kfdb=kf, covis=cv, markers=out[:n].copy(), voc=np.frombuffer(voc, np.uint8), marker_in=(ids, size, pose, nfr, fr))
+
+
+@needs_ref
+def test_map_sections_against_the_reference(tmp_path):
+    from ucoslam_b200 import KfdbStream, CovisStream, MarkerStream, map_stream_walk
+    lib = ucoslam_b200.load()
+    S = _ref_sections(tmp_path)
+    used = ctypes.c_size_t()
+    # keyframe database: type 1, the vocabulary stream is the vocabulary file, frame ids of the frames still in the database
+    k = KfdbStream()
+    assert lib.uco_b200_kfdb_stream_walk(S["kfdb"].ctypes.data, len(S["kfdb"]), ctypes.addressof(k), ctypes.addressof(used)) == 0 and used.value == len(S["kfdb"])
+    assert k.type == 1 and np.array_equal(S["kfdb"][k.voc_off:k.voc_off + k.voc_len], S["voc"])
+    assert list(np.ctypeslib.as_array(ctypes.cast(k.frames, ctypes.POINTER(ctypes.c_uint32)), (k.n_frames,))) == [0, 1, 5, 9]
+    assert k.n_words > 0 and k.n_word_frames >= k.n_words
+    # covisibility graph
+    c = CovisStream()
+    assert lib.uco_b200_covis_stream_walk(S["covis"].ctypes.data, len(S["covis"]), ctypes.addressof(c), ctypes.addressof(used)) == 0 and used.value == len(S["covis"])
+    assert list(np.ctypeslib.as_array(ctypes.cast(c.nodes, ctypes.POINTER(ctypes.c_uint32)), (c.n_nodes,))) == [0, 1, 5, 9]
+    assert c.n_adj == 4 and c.n_neighbours == 8 and c.n_weights == 4
+    w = np.frombuffer(ctypes.string_at(c.weights, 12 * c.n_weights), np.dtype([("key", "<u8"), ("w", "<f4")]))
+    assert sorted(w["w"].tolist()) == [7.0, 12.0, 31.0, 40.0]
+    # markers: std::map order (ascending key), every field
+    ids, size, pose, nfr, fr = S["marker_in"]
+    mk, n = (MarkerStream * 3)(), ctypes.c_uint32()
+    assert lib.uco_b200_marker_map_walk(S["markers"].ctypes.data, len(S["markers"]), 3, ctypes.addressof(mk), ctypes.addressof(n), ctypes.addressof(used)) == 0
+    assert n.value == 3 and used.value == len(S["markers"]) and [m.key for m in mk] == [3, 17, 250] and [m.id for m in mk] == [3, 17, 250]
+    order = [1, 0, 2]
+    starts = np.concatenate([[0], np.cumsum(nfr)])
+    for m, i in zip(mk, order):
+        assert m.size == size[i] and np.array_equal(np.array(list(m.pose_g2m), np.float32), pose[i]) and m.n_frames == nfr[i]
+        assert sorted(fr[starts[i]:starts[i + 1]].tolist()) == list(np.ctypeslib.as_array(ctypes.cast(m.frames, ctypes.POINTER(ctypes.c_uint32)), (m.n_frames,))) if m.n_frames else True
+        assert ctypes.string_at(m.dict, m.dict_len) == b"ARUCO_MIP_36h12"
+    # the whole stream in the order of Map::toStream (map.cpp:316-325), as a file (Map::saveToFile's magic in front)
+    pts = _ref_container([dict(_mp_fields(70 + i, n_frames=2), id=i) for i in range(5)], erase=[3])
+    frs, _ = _ref_frame_container([dict(make_fields(40 + i, n_kp=50, n_markers=1), idx=i) for i in range(3)])
+    blob = np.concatenate([np.frombuffer(np.uint64(225237123).tobytes(), np.uint8), S["kfdb"], pts, S["markers"], frs, S["covis"]])
+    o = map_stream_walk(blob, has_file_magic=True)
+    assert (o.kfdb_off, o.kfdb_len) == (8, len(S["kfdb"])) and (o.points_off, o.points_len) == (8 + len(S["kfdb"]), len(pts))
+    assert (o.markers_len, o.frames_len, o.covis_len, o.total_len) == (len(S["markers"]), len(frs), len(S["covis"]), len(blob))
+    assert (o.points.n_used, o.points.n_valid, o.frames.n_valid, o.n_markers, o.kfdb.n_frames, o.covis.n_weights) == (5, 4, 3, 3, 4, 4)
+    o2 = map_stream_walk(np.ascontiguousarray(blob[8:]))
+    assert o2.total_len == len(blob) - 8 and o2.frames_off == o.frames_off - 8
+    for bad in (blob[:-3], blob[:len(blob) // 2], np.concatenate([blob[:8], blob[12:]])):
+        with pytest.raises(ucoslam_b200.UcoError):
+            map_stream_walk(np.ascontiguousarray(bad), has_file_magic=True)
+
+
+def test_map_file_golden():
+    """tests/golden/map_file.bin: a complete small map file whose five sections were written by the reference's own code (make_frame_golden.py)"""
+    from ucoslam_b200 import map_stream_walk, mappoint_container_walk, mappoints_from_container
+    blob = np.fromfile(os.path.join(GOLD, "map_file.bin"), np.uint8)
+    o = map_stream_walk(blob, has_file_magic=True)
+    assert o.total_len == len(blob) and o.kfdb.type == 1 and o.kfdb.n_frames == 4 and o.n_markers == 3
+    assert (o.points.n_slots, o.points.n_used, o.points.n_valid, o.points.n_free) == (200, 5, 4, 1) and (o.frames.n_used, o.frames.n_valid) == (3, 3)
+    assert (o.covis.n_nodes, o.covis.n_weights) == (4, 4)
+    mp = mappoints_from_container(blob[o.points_off:o.points_off + o.points_len])
+    assert list(mp["ids"]) == [0, 1, 2, 4]
+    c, off, valid, used = mappoint_container_walk(blob[o.frames_off:o.frames_off + o.frames_len], frames=True)
+    v, n = frame_stream_parse(blob[o.frames_off + int(off[1]):])
+    assert v.idx == 1 and v.n_und_kpts == 50
+    # the vocabulary section loads as a vocabulary (host-side header check: signature, block geometry)
+    voc = blob[o.kfdb_off + o.kfdb.voc_off:o.kfdb_off + o.kfdb.voc_off + o.kfdb.voc_len]
+    assert int(np.frombuffer(voc[:8].tobytes(), np.uint64)[0]) == 55824124

@@ -294,6 +294,127 @@ void uco_b200_mappoint_stream_default(uco_mappoint_stream* v) {
     v->min_distance = 3.40282347e+38f;   // std::numeric_limits<float>::max()
 }
 
+/* ---- the other sections of Map::toStream (src/map.cpp:316-325), and the whole stream ------------------------------------------------------------
+ * keyframe database: KeyFrameDataBase::toStream (keyframedatabase.cpp:335-340) = int type, then for type 1 KPFrameDataBase::toStream_ (:278-287): the
+ *   fbow vocabulary (fbow.cpp:171-178: u64 55824124, the 120-byte params block, _total_size bytes), u32 count + per word {u32 word, set<u32> of frames},
+ *   set<u32> of frame ids; for type 0 (DummyDataBase, :122-124) the set of frame ids alone.  A set<u32> is u32 count + the values (io_utils.h:52-58).
+ * markers: toStream__kv_complex over std::map<u32, Marker> (io_utils.h:113-121): u32 count + per marker {u32 key, Marker::toStream (marker.cpp:41-47):
+ *   u32 id, Se3Transform (u32 928511272 + 16 floats), float size, set<u32> frames, string (u32 length + bytes)}.
+ * covisibility graph: CovisGraph::toStream (covisgraph.cpp:308-333): set<u32> nodes, u32 count + per node {u32 id, set<u32> neighbours}, u32 count +
+ *   per edge {u64 key, float weight}. */
+static bool skip_set(Reader& R, uint32_t* n = nullptr, const uint32_t** v = nullptr) {
+    const uint32_t k = R.get<uint32_t>();
+    const uint8_t* p = R.skip(4 * (size_t)k);
+    if (n) *n = k;
+    if (v) *v = (const uint32_t*)p;
+    return R.ok;
+}
+int uco_b200_kfdb_stream_walk(const uint8_t* bytes, size_t len, uco_kfdb_stream* o, size_t* consumed) {
+    if (!bytes || !o) return UCO_E_INVALID;
+    memset(o, 0, sizeof *o);
+    Reader R{bytes, bytes + len};
+    o->type = R.get<int32_t>();
+    if (!R.ok || (o->type != 0 && o->type != 1)) return UCO_E_INVALID;
+    if (o->type == 1) {
+        o->voc_off = (size_t)(R.p - bytes);
+        if (R.get<uint64_t>() != 55824124ull) return UCO_E_INVALID;
+        const uint8_t* prm = R.skip(120);
+        if (!R.ok) return UCO_E_INVALID;
+        uint64_t total = 0;
+        memcpy(&total, prm + 96, 8);
+        R.skip((size_t)total);
+        if (!R.ok) return UCO_E_INVALID;
+        o->voc_len = (size_t)(R.p - bytes) - o->voc_off;
+        o->n_words = R.get<uint32_t>();
+        o->words_off = (size_t)(R.p - bytes);
+        for (uint32_t w = 0; w < o->n_words && R.ok; w++) {
+            R.get<uint32_t>();
+            uint32_t k = 0;
+            skip_set(R, &k);
+            o->n_word_frames += k;
+        }
+    }
+    if (!skip_set(R, &o->n_frames, &o->frames)) return UCO_E_INVALID;
+    if (consumed) *consumed = (size_t)(R.p - bytes);
+    return UCO_OK;
+}
+int uco_b200_marker_map_walk(const uint8_t* bytes, size_t len, uint32_t cap, uco_marker_stream* out, uint32_t* n_out, size_t* consumed) {
+    if (!bytes || !n_out) return UCO_E_INVALID;
+    Reader R{bytes, bytes + len};
+    const uint32_t n = R.get<uint32_t>();
+    if (!R.ok || n > len / 80) return UCO_E_INVALID;     // a marker record takes at least 4 + 4 + 68 + 4 + 4 + 4 bytes
+    *n_out = n;
+    for (uint32_t i = 0; i < n; i++) {
+        uco_marker_stream m;
+        memset(&m, 0, sizeof m);
+        m.key = R.get<uint32_t>();
+        m.id = R.get<uint32_t>();
+        if (R.get<uint32_t>() != 928511272u) return UCO_E_INVALID;
+        const uint8_t* pose = R.skip(64);
+        if (!R.ok) return UCO_E_INVALID;
+        memcpy(m.pose_g2m, pose, 64);
+        m.size = R.get<float>();
+        skip_set(R, &m.n_frames, &m.frames);
+        m.dict_len = R.get<uint32_t>();
+        m.dict = (const char*)R.skip(m.dict_len);
+        if (!R.ok) return UCO_E_INVALID;
+        if (out && i < cap) out[i] = m;
+    }
+    if (consumed) *consumed = (size_t)(R.p - bytes);
+    return out && n > cap ? UCO_E_CAPACITY : UCO_OK;
+}
+int uco_b200_covis_stream_walk(const uint8_t* bytes, size_t len, uco_covis_stream* o, size_t* consumed) {
+    if (!bytes || !o) return UCO_E_INVALID;
+    memset(o, 0, sizeof *o);
+    Reader R{bytes, bytes + len};
+    if (!skip_set(R, &o->n_nodes, &o->nodes)) return UCO_E_INVALID;
+    o->n_adj = R.get<uint32_t>();
+    o->adj_off = (size_t)(R.p - bytes);
+    for (uint32_t i = 0; i < o->n_adj && R.ok; i++) {
+        R.get<uint32_t>();
+        uint32_t k = 0;
+        skip_set(R, &k);
+        o->n_neighbours += k;
+    }
+    o->n_weights = R.get<uint32_t>();
+    o->weights = R.skip(12 * (size_t)o->n_weights);     // packed {u64 key, float weight} records (12 bytes each, unaligned)
+    if (!R.ok) return UCO_E_INVALID;
+    if (consumed) *consumed = (size_t)(R.p - bytes);
+    return UCO_OK;
+}
+/* Map::toStream (src/map.cpp:316-325): keyframe database, map points, markers, keyframes, covisibility graph - in that order; a map FILE
+ * (Map::saveToFile, :339-345) puts the u64 magic 225237123 in front (has_file_magic != 0). */
+int uco_b200_map_stream_walk(const uint8_t* bytes, size_t len, int has_file_magic, uco_map_sections* o) {
+    if (!bytes || !o) return UCO_E_INVALID;
+    memset(o, 0, sizeof *o);
+    size_t at = 0, used = 0;
+    if (has_file_magic) {
+        uint64_t sig = 0;
+        if (len < 8) return UCO_E_INVALID;
+        memcpy(&sig, bytes, 8);
+        if (sig != 225237123ull) return UCO_E_INVALID;
+        at = 8;
+    }
+    int rc;
+    o->kfdb_off = at;
+    if ((rc = uco_b200_kfdb_stream_walk(bytes + at, len - at, &o->kfdb, &used)) != UCO_OK) return rc;
+    at += used; o->kfdb_len = used;
+    o->points_off = at;
+    if ((rc = uco_b200_mappoint_container_walk(bytes + at, len - at, &o->points, nullptr, nullptr, 0, &used)) != UCO_OK) return rc;
+    at += used; o->points_len = used;
+    o->markers_off = at;
+    if ((rc = uco_b200_marker_map_walk(bytes + at, len - at, 0, nullptr, &o->n_markers, &used)) != UCO_OK) return rc;
+    at += used; o->markers_len = used;
+    o->frames_off = at;
+    if ((rc = uco_b200_frame_container_walk(bytes + at, len - at, &o->frames, nullptr, nullptr, 0, &used)) != UCO_OK) return rc;
+    at += used; o->frames_len = used;
+    o->covis_off = at;
+    if ((rc = uco_b200_covis_stream_walk(bytes + at, len - at, &o->covis, &used)) != UCO_OK) return rc;
+    at += used; o->covis_len = used;
+    o->total_len = at;
+    return UCO_OK;
+}
+
 /* KdTreeIndex::toStream bytes from the flattened tree (the inverse of uco_b200_kdtree_parse): what a frame whose tree was built on
  * the device (uco_b200_kdtree_build_batch_dev) writes into its stream.  div_val: the node's split value (picoflann keeps it as a
  * double next to the two float sides); pass NULL to write (divlow + divhigh) / 2. */

@@ -60,6 +60,10 @@ SIGNATURES = {
     "uco_b200_mappoint_stream_write": (_i, [_vp, _vp, _c.c_size_t, _vp]),
     "uco_b200_mappoint_container_walk": (_i, [_vp, _c.c_size_t, _vp, _vp, _vp, _c.c_uint32, _vp]),
     "uco_b200_frame_container_walk": (_i, [_vp, _c.c_size_t, _vp, _vp, _vp, _c.c_uint32, _vp]),
+    "uco_b200_kfdb_stream_walk": (_i, [_vp, _c.c_size_t, _vp, _vp]),
+    "uco_b200_marker_map_walk": (_i, [_vp, _c.c_size_t, _c.c_uint32, _vp, _vp, _vp]),
+    "uco_b200_covis_stream_walk": (_i, [_vp, _c.c_size_t, _vp, _vp]),
+    "uco_b200_map_stream_walk": (_i, [_vp, _c.c_size_t, _i, _vp]),
     "uco_b200_mappoints_from_container": (_i, [_vp, _c.c_size_t, _c.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "uco_b200_mappoint_container_write": (_i, [_vp, _vp, _vp, _vp, _c.c_size_t, _vp]),
     "uco_b200_mappoint_stream_default": (None, [_vp]),
@@ -372,6 +376,37 @@ class MapPointStream(ctypes.Structure):  # uco_mappoint_stream
 
 class MapPointContainer(ctypes.Structure):  # uco_mappoint_container
     _fields_ = [("n_slots", _c.c_uint32), ("n_used", _c.c_uint32), ("n_valid", _c.c_uint32), ("n_free", _c.c_uint32), ("free_slots", _vp)]
+
+
+class KfdbStream(ctypes.Structure):  # uco_kfdb_stream
+    _fields_ = [("type", _c.c_int32), ("voc_off", _c.c_size_t), ("voc_len", _c.c_size_t), ("n_words", _c.c_uint32), ("words_off", _c.c_size_t),
+                ("n_word_frames", _c.c_uint64), ("n_frames", _c.c_uint32), ("frames", _vp)]
+
+
+class MarkerStream(ctypes.Structure):  # uco_marker_stream
+    _fields_ = [("key", _c.c_uint32), ("id", _c.c_uint32), ("pose_g2m", _c.c_float * 16), ("size", _c.c_float), ("n_frames", _c.c_uint32), ("frames", _vp),
+                ("dict_len", _c.c_uint32), ("dict", _vp)]
+
+
+class CovisStream(ctypes.Structure):  # uco_covis_stream
+    _fields_ = [("n_nodes", _c.c_uint32), ("nodes", _vp), ("n_adj", _c.c_uint32), ("adj_off", _c.c_size_t), ("n_neighbours", _c.c_uint64),
+                ("n_weights", _c.c_uint32), ("weights", _vp)]
+
+
+class MapSections(ctypes.Structure):  # uco_map_sections
+    _fields_ = [("kfdb_off", _c.c_size_t), ("kfdb_len", _c.c_size_t), ("kfdb", KfdbStream), ("points_off", _c.c_size_t), ("points_len", _c.c_size_t),
+                ("points", MapPointContainer), ("markers_off", _c.c_size_t), ("markers_len", _c.c_size_t), ("n_markers", _c.c_uint32),
+                ("frames_off", _c.c_size_t), ("frames_len", _c.c_size_t), ("frames", MapPointContainer), ("covis_off", _c.c_size_t), ("covis_len", _c.c_size_t),
+                ("covis", CovisStream), ("total_len", _c.c_size_t)]
+
+
+def map_stream_walk(buf, has_file_magic=False):
+    """uco_map_sections of a Map::toStream byte range (has_file_magic: a map file written by Map::saveToFile)"""
+    o = MapSections()
+    rc = load().uco_b200_map_stream_walk(buf.ctypes.data, len(buf), int(has_file_magic), ctypes.addressof(o))
+    if rc != 0:
+        raise UcoError("map_stream_walk: malformed stream (%d)" % rc)
+    return o
 
 
 def mappoint_container_walk(buf, frames=False):
