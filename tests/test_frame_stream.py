@@ -517,3 +517,39 @@ def test_map_file_golden():
     # the vocabulary section loads as a vocabulary (host-side header check: signature, block geometry)
     voc = blob[o.kfdb_off + o.kfdb.voc_off:o.kfdb_off + o.kfdb.voc_off + o.kfdb.voc_len]
     assert int(np.frombuffer(voc[:8].tobytes(), np.uint64)[0]) == 55824124
+
+
+@pytest.mark.gpu
+def test_map_file_becomes_device_resident_state():
+    """the reading side of SURVEY 8(f)4 end to end on the GPU: from the bytes of a map file (tests/golden/map_file.bin, sections written by the
+    reference's own code) the vocabulary is loaded into the device BoW transform, every keyframe becomes a device mirror and the map points become the
+    rows the projection matcher takes - no Frame / MapPoint / Vocabulary object is built on the way"""
+    from ucoslam_b200 import map_stream_walk, mappoint_container_walk, mappoints_from_container, workload
+    ctx = ucoslam_b200.Context(0)
+    blob = np.fromfile(os.path.join(GOLD, "map_file.bin"), np.uint8)
+    o = map_stream_walk(blob, has_file_magic=True)
+    # vocabulary: the same words / weights as the vocabulary the database was created with
+    vb = blob[o.kfdb_off + o.kfdb.voc_off:o.kfdb_off + o.kfdb.voc_off + o.kfdb.voc_len]
+    v1, v2 = ctx.bow_load(vb), ctx.bow_load(np.frombuffer(workload.synth_vocabulary_full(seed=4, k=6, depth=3), np.uint8))
+    desc = np.random.default_rng(2).integers(0, 256, (500, 32), dtype=np.uint8)
+    a, b = ctx.bow_transform(v1, desc, 2), ctx.bow_transform(v2, desc, 2)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b)) and len(np.unique(a[0])) > 20
+    # keyframes: every valid slot -> device mirror -> the per-keypoint arrays come back as the fields that were written
+    sec = blob[o.frames_off:o.frames_off + o.frames_len]
+    c, off, valid, _ = mappoint_container_walk(sec, frames=True)
+    handles = []
+    for i in np.nonzero(valid)[0]:
+        view, _ = frame_stream_parse(sec[int(off[i]):])
+        h, d = ctx.frame_upload(view)
+        fd = make_fields(40 + int(i), n_kp=50, n_markers=1)
+        kps, dsc, ids, flags, depth = ctx.frame_download(h, d.n_kp)
+        assert d.idx == i and d.n_kp == 50 and kps.tobytes() == fd["kp"].tobytes() and np.array_equal(dsc, fd["desc"]) and np.array_equal(ids, fd["ids"])
+        handles.append(h)
+    assert len(handles) == 3
+    # map points: the valid slots as matcher rows
+    mp = mappoints_from_container(blob[o.points_off:o.points_off + o.points_len])
+    assert list(mp["ids"]) == [0, 1, 2, 4] and mp["pos"].shape == (4, 3)
+    for h in handles:
+        ctx.frame_free(h)
+    ctx.bow_free(v1); ctx.bow_free(v2)
+    ctx.close()
