@@ -788,6 +788,10 @@ int uco_b200_mappoint_container_walk(const uint8_t* bytes, size_t len, uco_mappo
 /* the keyframe section: FrameSet::toStream (src/map_types/frame.cpp:350-355) = int magic 88888 + the same container over Frame streams */
 int uco_b200_frame_container_walk(const uint8_t* bytes, size_t len, uco_mappoint_container* c, size_t* slot_offset, uint8_t* slot_valid, uint32_t cap,
                                   size_t* consumed);
+/* the keyframe section from already-serialised Frame streams; unused slots take the stream of a default-constructed Frame (copy one from any
+ * reference-written keyframe section) */
+int uco_b200_frame_container_write(const uco_mappoint_container* c, const uint8_t* const* slot_bytes, const size_t* slot_len, const uint8_t* valid, uint8_t* out,
+                                   size_t cap, size_t* written);
 int uco_b200_mappoints_from_container(const uint8_t* bytes, size_t len, uint32_t cap, uint32_t* ids, float* pos, float* normal, float* min_dist, float* max_dist,
                                       uint8_t* desc, uint8_t* flags, uint32_t* n_out, size_t* consumed);
 int uco_b200_mappoint_container_write(const uco_mappoint_container* c, const uco_mappoint_stream* points, const uint8_t* valid, uint8_t* out, size_t cap,
@@ -826,6 +830,16 @@ typedef struct uco_map_sections {              /* byte ranges of the five sectio
 int uco_b200_kfdb_stream_walk(const uint8_t* bytes, size_t len, uco_kfdb_stream* out, size_t* consumed);
 int uco_b200_marker_map_walk(const uint8_t* bytes, size_t len, uint32_t cap, uco_marker_stream* out, uint32_t* n_out, size_t* consumed);
 int uco_b200_covis_stream_walk(const uint8_t* bytes, size_t len, uco_covis_stream* out, size_t* consumed);
+/* writers / unpackers of the three sections (keyed lists in CSR form: key[i] owns values[ptr[i] .. ptr[i+1]); ptr has n + 1 entries); with the Frame,
+ * MapPoint and container writers a whole map file can be written: u64 225237123, then the five sections in the order above */
+int uco_b200_marker_map_write(const uco_marker_stream* markers /* ascending key */, uint32_t n, uint8_t* out, size_t cap, size_t* written);
+int uco_b200_covis_stream_unpack(const uint8_t* bytes, size_t len, const uco_covis_stream* view, uint32_t* adj_node, uint32_t* adj_ptr, uint32_t* adj_idx,
+                                 uint64_t* w_key, float* w);
+int uco_b200_covis_stream_write(uint32_t n_nodes, const uint32_t* nodes, uint32_t n_adj, const uint32_t* adj_node, const uint32_t* adj_ptr, const uint32_t* adj_idx,
+                                uint32_t n_weights, const uint64_t* w_key, const float* w, uint8_t* out, size_t cap, size_t* written);
+int uco_b200_kfdb_stream_unpack(const uint8_t* bytes, size_t len, const uco_kfdb_stream* view, uint32_t* word, uint32_t* word_ptr, uint32_t* word_frames);
+int uco_b200_kfdb_stream_write(int32_t type, const uint8_t* voc, size_t voc_len, uint32_t n_words, const uint32_t* word, const uint32_t* word_ptr,
+                               const uint32_t* word_frames, uint32_t n_frames, const uint32_t* frames, uint8_t* out, size_t cap, size_t* written);
 /* has_file_magic: the buffer is a map FILE (Map::saveToFile, map.cpp:339-345: u64 225237123 first); section offsets are from the buffer start */
 int uco_b200_map_stream_walk(const uint8_t* bytes, size_t len, int has_file_magic, uco_map_sections* out);
 typedef struct uco_frame_dev {   /* DEVICE pointers (one allocation, owned by the uco_b200_frame) + the small host-side members */

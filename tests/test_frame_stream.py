@@ -410,6 +410,14 @@ def test_keyframe_container_against_the_reference_headers():
         assert n == len(want[i]) and np.array_equal(ref[int(off[i]):int(off[i]) + n], want[i]) and v.idx == (9 if i == 1 else i)
     v, n = frame_stream_parse(ref[int(off[150]):])             # a default-constructed Frame
     assert v.n_und_kpts == 0 and v.n_ids == 0 and v.desc.rows == 0
+    # the writer rebuilds the section from the slots' byte ranges (a changed keyframe would go in as frame_stream_write output)
+    lib = ucoslam_b200.load()
+    ends = list(off[1:] - 1) + [used - 12]                       # a slot ends where the next flag byte starts; the last one before curBuffer / curElm / chunk
+    lens = np.array([int(e) - int(o) for o, e in zip(off, ends)], np.uint64)
+    ptrs = (ctypes.c_void_p * c.n_slots)(*[ref.ctypes.data + int(o) for o in off])
+    out, n = np.zeros(len(ref), np.uint8), ctypes.c_size_t()
+    assert lib.uco_b200_frame_container_write(ctypes.addressof(c), ctypes.addressof(ptrs), lens.ctypes.data, valid.ctypes.data, out.ctypes.data, len(out),
+                                              ctypes.addressof(n)) == 0 and n.value == len(ref) and np.array_equal(out, ref)
     with pytest.raises(ucoslam_b200.UcoError):
         mappoint_container_walk(ref, frames=False)              # a keyframe section is not a map-point section
     with pytest.raises(ucoslam_b200.UcoError):
@@ -553,3 +561,43 @@ def test_map_file_becomes_device_resident_state():
         ctx.frame_free(h)
     ctx.bow_free(v1); ctx.bow_free(v2)
     ctx.close()
+
+
+@needs_ref
+def test_map_section_writers_reproduce_the_reference_bytes(tmp_path):
+    """marker map, covisibility graph and keyframe database: unpack the reference-written section, write it again from the unpacked arrays -> the
+    same bytes (so a map file can be written here section by section)"""
+    from ucoslam_b200 import KfdbStream, CovisStream, MarkerStream
+    lib = ucoslam_b200.load()
+    S = _ref_sections(tmp_path)
+    n, used = ctypes.c_size_t(), ctypes.c_size_t()
+    P = lambda a: a.ctypes.data
+    # markers
+    mk, cnt = (MarkerStream * 3)(), ctypes.c_uint32()
+    assert lib.uco_b200_marker_map_walk(P(S["markers"]), len(S["markers"]), 3, ctypes.addressof(mk), ctypes.addressof(cnt), None) == 0
+    out = np.zeros(len(S["markers"]), np.uint8)
+    assert lib.uco_b200_marker_map_write(ctypes.addressof(mk), 3, P(out), len(out), ctypes.addressof(n)) == 0 and np.array_equal(out, S["markers"])
+    mk[1].key = 1                                               # not ascending any more: std::map could not have produced it
+    assert lib.uco_b200_marker_map_write(ctypes.addressof(mk), 3, P(out), len(out), ctypes.addressof(n)) != 0
+    # covisibility graph
+    c = CovisStream()
+    assert lib.uco_b200_covis_stream_walk(P(S["covis"]), len(S["covis"]), ctypes.addressof(c), None) == 0
+    an, ap, ai = np.zeros(c.n_adj, np.uint32), np.zeros(c.n_adj + 1, np.uint32), np.zeros(c.n_neighbours, np.uint32)
+    wk, ww = np.zeros(c.n_weights, np.uint64), np.zeros(c.n_weights, np.float32)
+    assert lib.uco_b200_covis_stream_unpack(P(S["covis"]), len(S["covis"]), ctypes.addressof(c), P(an), P(ap), P(ai), P(wk), P(ww)) == 0
+    assert list(an) == [0, 1, 5, 9] and list(ai[ap[0]:ap[1]]) == [1, 9] and sorted(ww.tolist()) == [7.0, 12.0, 31.0, 40.0]
+    nodes = np.ctypeslib.as_array(ctypes.cast(c.nodes, ctypes.POINTER(ctypes.c_uint32)), (c.n_nodes,)).copy()
+    out = np.zeros(len(S["covis"]), np.uint8)
+    assert lib.uco_b200_covis_stream_write(c.n_nodes, P(nodes), c.n_adj, P(an), P(ap), P(ai), c.n_weights, P(wk), P(ww), P(out), len(out), ctypes.addressof(n)) == 0
+    assert n.value == len(out) and np.array_equal(out, S["covis"])
+    # keyframe database
+    k = KfdbStream()
+    assert lib.uco_b200_kfdb_stream_walk(P(S["kfdb"]), len(S["kfdb"]), ctypes.addressof(k), None) == 0
+    wd, wp, wf = np.zeros(k.n_words, np.uint32), np.zeros(k.n_words + 1, np.uint32), np.zeros(k.n_word_frames, np.uint32)
+    assert lib.uco_b200_kfdb_stream_unpack(P(S["kfdb"]), len(S["kfdb"]), ctypes.addressof(k), P(wd), P(wp), P(wf)) == 0
+    assert (np.diff(wd.astype(np.int64)) > 0).all() and set(wf.tolist()) <= {0, 1, 5, 9}
+    frames = np.ctypeslib.as_array(ctypes.cast(k.frames, ctypes.POINTER(ctypes.c_uint32)), (k.n_frames,)).copy()
+    voc = np.ascontiguousarray(S["kfdb"][k.voc_off:k.voc_off + k.voc_len])
+    out = np.zeros(len(S["kfdb"]), np.uint8)
+    assert lib.uco_b200_kfdb_stream_write(1, P(voc), len(voc), k.n_words, P(wd), P(wp), P(wf), k.n_frames, P(frames), P(out), len(out), ctypes.addressof(n)) == 0
+    assert n.value == len(out) and np.array_equal(out, S["kfdb"])

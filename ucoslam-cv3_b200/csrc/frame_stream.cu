@@ -285,6 +285,29 @@ int uco_b200_mappoint_container_write(const uco_mappoint_container* c, const uco
     if (out && W.n > cap) return UCO_E_CAPACITY;
     return UCO_OK;
 }
+/* the keyframe section from already-serialised Frame streams (uco_b200_frame_stream_write output, or ranges of another map file): int 88888 + the
+ * container framing around slot_bytes[i] (slot_len[i] bytes each).  Unused slots need the stream of a default-constructed Frame: copy one from any
+ * reference-written keyframe section (its slots past n_used). */
+int uco_b200_frame_container_write(const uco_mappoint_container* c, const uint8_t* const* slot_bytes, const size_t* slot_len, const uint8_t* valid, uint8_t* out,
+                                   size_t cap, size_t* written) {
+    if (!c || !written || c->n_slots % MP_CHUNK || c->n_slots == 0 || c->n_used > c->n_slots || !slot_bytes || !slot_len || !valid || (c->n_free && !c->free_slots))
+        return UCO_E_INVALID;
+    Writer W{out, cap};
+    W.val<int32_t>(88888);
+    W.val<int64_t>(123299999);
+    W.val(c->n_free); W.put(c->free_slots, 4 * (size_t)c->n_free);
+    W.val<uint64_t>(13218888); W.val<uint64_t>(c->n_slots / MP_CHUNK);
+    for (uint32_t i = 0; i < c->n_slots; i++) {
+        if (!slot_bytes[i]) return UCO_E_INVALID;
+        W.val<uint8_t>(valid[i] ? 1 : 0);
+        W.put(slot_bytes[i], slot_len[i]);
+    }
+    W.val<int32_t>(c->n_used ? (int32_t)((c->n_used - 1) / MP_CHUNK) : 0);
+    W.val<int32_t>(c->n_used ? (int32_t)((c->n_used - 1) % MP_CHUNK) + 1 : 0);
+    W.val<int32_t>(MP_CHUNK);
+    *written = W.n;
+    return out && W.n > cap ? UCO_E_CAPACITY : UCO_OK;
+}
 /* what a default-constructed MapPoint streams as (mappoint.h:111-131 member initialisers): the content of never-used slots */
 void uco_b200_mappoint_stream_default(uco_mappoint_stream* v) {
     memset(v, 0, sizeof *v);
@@ -382,6 +405,86 @@ int uco_b200_covis_stream_walk(const uint8_t* bytes, size_t len, uco_covis_strea
     if (consumed) *consumed = (size_t)(R.p - bytes);
     return UCO_OK;
 }
+/* ---- writers / unpackers of those three sections: with the Frame, MapPoint and container writers above a whole map file can be written here ------ */
+int uco_b200_marker_map_write(const uco_marker_stream* m, uint32_t n, uint8_t* out, size_t cap, size_t* written) {
+    if (!written || (n && !m)) return UCO_E_INVALID;
+    Writer W{out, cap};
+    W.val(n);
+    for (uint32_t i = 0; i < n; i++) {                       // the caller passes the markers in ascending key order (std::map iteration)
+        if (i && m[i].key <= m[i - 1].key) return UCO_E_INVALID;
+        W.val(m[i].key); W.val(m[i].id);
+        W.val<uint32_t>(928511272u); W.put(m[i].pose_g2m, 64);
+        W.val(m[i].size);
+        W.val(m[i].n_frames); W.put(m[i].frames, 4 * (size_t)m[i].n_frames);
+        W.val(m[i].dict_len); W.put(m[i].dict, m[i].dict_len);
+    }
+    *written = W.n;
+    return out && W.n > cap ? UCO_E_CAPACITY : UCO_OK;
+}
+/* lists in CSR form: rec_key[i] owns values[ptr[i] .. ptr[i+1]) */
+static void write_keyed_sets(Writer& W, uint32_t n, const uint32_t* key, const uint32_t* ptr, const uint32_t* values) {
+    W.val(n);
+    for (uint32_t i = 0; i < n; i++) {
+        W.val(key[i]);
+        W.val<uint32_t>(ptr[i + 1] - ptr[i]);
+        W.put(values + ptr[i], 4 * (size_t)(ptr[i + 1] - ptr[i]));
+    }
+}
+static bool read_keyed_sets(const uint8_t* p, const uint8_t* end, uint32_t n, uint32_t* key, uint32_t* ptr, uint32_t* values) {
+    Reader R{p, end};
+    uint32_t at = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t k = R.get<uint32_t>(), c = R.get<uint32_t>();
+        const uint8_t* v = R.skip(4 * (size_t)c);
+        if (!R.ok) return false;
+        if (key) key[i] = k;
+        if (ptr) ptr[i] = at;
+        if (values) memcpy(values + at, v, 4 * (size_t)c);
+        at += c;
+    }
+    if (ptr) ptr[n] = at;
+    return true;
+}
+int uco_b200_covis_stream_unpack(const uint8_t* bytes, size_t len, const uco_covis_stream* v, uint32_t* adj_node, uint32_t* adj_ptr, uint32_t* adj_idx,
+                                 uint64_t* w_key, float* w) {
+    if (!bytes || !v || v->adj_off > len) return UCO_E_INVALID;
+    if (!read_keyed_sets(bytes + v->adj_off, bytes + len, v->n_adj, adj_node, adj_ptr, adj_idx)) return UCO_E_INVALID;
+    for (uint32_t i = 0; i < v->n_weights; i++) {
+        if (w_key) memcpy(w_key + i, v->weights + 12 * (size_t)i, 8);
+        if (w) memcpy(w + i, v->weights + 12 * (size_t)i + 8, 4);
+    }
+    return UCO_OK;
+}
+int uco_b200_covis_stream_write(uint32_t n_nodes, const uint32_t* nodes, uint32_t n_adj, const uint32_t* adj_node, const uint32_t* adj_ptr, const uint32_t* adj_idx,
+                                uint32_t n_weights, const uint64_t* w_key, const float* w, uint8_t* out, size_t cap, size_t* written) {
+    if (!written || (n_nodes && !nodes) || (n_adj && (!adj_node || !adj_ptr || !adj_idx)) || (n_weights && (!w_key || !w))) return UCO_E_INVALID;
+    Writer W{out, cap};
+    W.val(n_nodes); W.put(nodes, 4 * (size_t)n_nodes);
+    write_keyed_sets(W, n_adj, adj_node, adj_ptr, adj_idx);
+    W.val(n_weights);
+    for (uint32_t i = 0; i < n_weights; i++) { W.val(w_key[i]); W.val(w[i]); }
+    *written = W.n;
+    return out && W.n > cap ? UCO_E_CAPACITY : UCO_OK;
+}
+int uco_b200_kfdb_stream_unpack(const uint8_t* bytes, size_t len, const uco_kfdb_stream* v, uint32_t* word, uint32_t* word_ptr, uint32_t* word_frames) {
+    if (!bytes || !v || v->words_off > len) return UCO_E_INVALID;
+    return read_keyed_sets(bytes + v->words_off, bytes + len, v->n_words, word, word_ptr, word_frames) ? UCO_OK : UCO_E_INVALID;
+}
+int uco_b200_kfdb_stream_write(int32_t type, const uint8_t* voc, size_t voc_len, uint32_t n_words, const uint32_t* word, const uint32_t* word_ptr,
+                               const uint32_t* word_frames, uint32_t n_frames, const uint32_t* frames, uint8_t* out, size_t cap, size_t* written) {
+    if (!written || (type != 0 && type != 1) || (type == 1 && (!voc || voc_len < 128)) || (n_words && (!word || !word_ptr || !word_frames)) || (n_frames && !frames))
+        return UCO_E_INVALID;
+    Writer W{out, cap};
+    W.val(type);
+    if (type == 1) {
+        W.put(voc, voc_len);
+        write_keyed_sets(W, n_words, word, word_ptr, word_frames);
+    }
+    W.val(n_frames); W.put(frames, 4 * (size_t)n_frames);
+    *written = W.n;
+    return out && W.n > cap ? UCO_E_CAPACITY : UCO_OK;
+}
+
 /* Map::toStream (src/map.cpp:316-325): keyframe database, map points, markers, keyframes, covisibility graph - in that order; a map FILE
  * (Map::saveToFile, :339-345) puts the u64 magic 225237123 in front (has_file_magic != 0). */
 int uco_b200_map_stream_walk(const uint8_t* bytes, size_t len, int has_file_magic, uco_map_sections* o) {

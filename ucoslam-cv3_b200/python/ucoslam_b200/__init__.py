@@ -64,6 +64,12 @@ SIGNATURES = {
     "uco_b200_marker_map_walk": (_i, [_vp, _c.c_size_t, _c.c_uint32, _vp, _vp, _vp]),
     "uco_b200_covis_stream_walk": (_i, [_vp, _c.c_size_t, _vp, _vp]),
     "uco_b200_map_stream_walk": (_i, [_vp, _c.c_size_t, _i, _vp]),
+    "uco_b200_frame_container_write": (_i, [_vp, _vp, _vp, _vp, _vp, _c.c_size_t, _vp]),
+    "uco_b200_marker_map_write": (_i, [_vp, _c.c_uint32, _vp, _c.c_size_t, _vp]),
+    "uco_b200_covis_stream_unpack": (_i, [_vp, _c.c_size_t, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "uco_b200_covis_stream_write": (_i, [_c.c_uint32, _vp, _c.c_uint32, _vp, _vp, _vp, _c.c_uint32, _vp, _vp, _vp, _c.c_size_t, _vp]),
+    "uco_b200_kfdb_stream_unpack": (_i, [_vp, _c.c_size_t, _vp, _vp, _vp, _vp]),
+    "uco_b200_kfdb_stream_write": (_i, [_c.c_int32, _vp, _c.c_size_t, _c.c_uint32, _vp, _vp, _vp, _c.c_uint32, _vp, _vp, _c.c_size_t, _vp]),
     "uco_b200_mappoints_from_container": (_i, [_vp, _c.c_size_t, _c.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "uco_b200_mappoint_container_write": (_i, [_vp, _vp, _vp, _vp, _c.c_size_t, _vp]),
     "uco_b200_mappoint_stream_default": (None, [_vp]),
