@@ -601,3 +601,31 @@ def test_map_section_writers_reproduce_the_reference_bytes(tmp_path):
     out = np.zeros(len(S["kfdb"]), np.uint8)
     assert lib.uco_b200_kfdb_stream_write(1, P(voc), len(voc), k.n_words, P(wd), P(wp), P(wf), k.n_frames, P(frames), P(out), len(out), ctypes.addressof(n)) == 0
     assert n.value == len(out) and np.array_equal(out, S["kfdb"])
+
+
+def test_map_file_walkers_survive_damage():
+    """truncations and byte flips of the golden map file: every walker answers OK or an error, never reads outside the buffer it was given
+    (the buffer is copied to its exact size, so an overrun shows under the allocator / sanitizer rather than by luck)"""
+    from ucoslam_b200 import MapSections, MapPointContainer
+    lib = ucoslam_b200.load()
+    blob = np.fromfile(os.path.join(GOLD, "map_file.bin"), np.uint8)
+    rng = np.random.default_rng(12)
+    o = MapSections()
+    n_ok = 0
+    for t in range(400):
+        b = blob.copy()
+        if t % 2:
+            b = np.ascontiguousarray(b[:int(rng.integers(0, len(b)))])
+        else:
+            for _ in range(int(rng.integers(1, 4))):
+                b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+        if len(b) == 0:
+            continue
+        rc = lib.uco_b200_map_stream_walk(b.ctypes.data, len(b), 1, ctypes.addressof(o))
+        assert rc in (0, -1, -2, -3, -4, -5, -6)
+        if rc == 0:
+            n_ok += 1
+            assert o.total_len <= len(b)
+            n = ctypes.c_uint32()
+            lib.uco_b200_mappoints_from_container(b.ctypes.data + o.points_off, o.points_len, 0, None, None, None, None, None, None, None, ctypes.addressof(n), None)
+    assert n_ok > 20        # flips inside payload bytes (descriptors, poses, weights) leave a well-formed file
