@@ -279,6 +279,31 @@ def cpu_baseline(n):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local_rank, world):
+    """Multi-GPU runs on one host: keep a rank's threads (and with them its first-touched pinned buffers) on the NUMA node its GPU hangs off, so that
+    the 72 MB of copies per step do not cross the socket link.  Returns a note for the bench line; does nothing when the topology is not exposed."""
+    if world < 2 or os.environ.get("UCO_BENCH_NO_NUMA"):
+        return "not bound (single rank)" if world < 2 else "not bound (UCO_BENCH_NO_NUMA)"
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return "not bound (numa_node of %s is -1)" % bus
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "not bound (node %d has no allowed cpu)" % node
+        os.sched_setaffinity(0, cpus)
+        return "rank threads bound to NUMA node %d of GPU %s (%d cpus)" % (node, bus, len(cpus))
+    except Exception as e:      # the benchmark must run wherever the topology files are missing
+        return "not bound (%s)" % type(e).__name__
+
+
 def run_b200(args, rank, world, local_rank):
     import ctypes, gc
     import numpy as np, torch
@@ -286,6 +311,7 @@ def run_b200(args, rank, world, local_rank):
     from ucoslam_b200 import shard, workload, chain
     from concurrent.futures import ThreadPoolExecutor
 
+    numa_note = bind_to_gpu_numa_node(local_rank, world)
     torch.cuda.set_device(local_rank)
     shard.init("nccl", torch.device("cuda", local_rank))
     ctx = ucoslam_b200.Context(local_rank)      # tracker thread's context: extraction, tracking sequence, BoW, frame matcher
@@ -703,6 +729,7 @@ def run_b200(args, rank, world, local_rank):
                               "of the following steps (threaded mode: the mapper lags the tracker); all BA results are back on the "
                               "host inside the timed region" % (N_MAPPERS, BA_CLUSTER or 8)})
         arm["frames_per_step_per_gpu"] = F
+        arm["numa"] = numa_note
         line = {"arm": arm, "metric": METRIC, "value": total_frames / (ms_dev * 1e-3), "unit": "frames/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
