@@ -78,3 +78,15 @@ def test_vectorised_orientation_equals_the_per_keypoint_restatement():
     a = orb_oracle.ic_angles(img, xs, ys)
     b = np.array([orb_oracle.ic_angle(img, None, int(x), int(y)) for x, y in zip(xs, ys)], np.float32)
     assert np.array_equal(a, b)
+
+
+def test_strip_kernel_index_arithmetic_matches_opencv():
+    """scripts/emulate_pyramid_strip.py: the index arithmetic of blur7_strip_kernel / resize_cubic_strip_kernel (bordered output domain, reflected
+    coordinates, packed u16x2 horizontal blur, 7-row register window, staged source tile, byte-permute selectors) emulated statement by statement
+    against cv2.GaussianBlur / cv2.resize / cv2.copyMakeBorder on small images, aligned and unaligned sources, scale factors 1.2 ... 2.0"""
+    import importlib.util, os
+    p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "emulate_pyramid_strip.py")
+    spec = importlib.util.spec_from_file_location("emulate_pyramid_strip", p)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    assert m.main() == 0
