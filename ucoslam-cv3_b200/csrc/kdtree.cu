@@ -148,18 +148,31 @@ __global__ void __launch_bounds__(KDB_THREADS, 1) kdtree_build_kernel(const KdBu
     for (;;) {
         if (threadIdx.x == 0) n_internal_lvl = 0;
         __syncthreads();
-        // A. per node: leaf or sampled mean / variance -> split dimension and cut (picoflann.h:372-400)
-        for (int k = lb + threadIdx.x; k < le; k += KDB_THREADS) {
+        // A. per node: leaf or sampled mean / variance -> split dimension and cut (picoflann.h:372-400).  One node per WARP: the lanes fetch 32
+        // samples side by side (two dependent shared-memory reads each: the serial form spent ~100 cycles per sample on them, one thread per
+        // node while the rest of the CTA waited), then every lane accumulates them in the reference's own order (sample after sample, doubles of
+        // float terms, the squares formed in float) - the same additions in the same order, without the load latency on the chain
+        for (int k = lb + (threadIdx.x >> 5); k < le; k += KDB_THREADS / 32) {
             NodeW& N = nd[k];
-            const int count = N.e - N.s;
-            if (count <= 10) { N.col = -1; N.left = -1; continue; }
+            const int lane = threadIdx.x & 31;
+            const int count = N.e - N.s, first = N.s;
+            if (count <= 10) {
+                __syncwarp();
+                if (lane == 0) { N.col = -1; N.left = -1; }
+                continue;
+            }
             double mean[2] = {0, 0}, sq[2] = {0, 0};
             const int inc = count >= 200 ? count / 100 : 1;
-            int cnt = 0;
-            for (int i = N.s; i < N.e; i += inc, cnt++) {
-                const float2 v = xy[all[i]];
-                mean[0] += v.x; sq[0] += v.x * v.x;   // the product is formed in float
-                mean[1] += v.y; sq[1] += v.y * v.y;
+            const int cnt = (count + inc - 1) / inc;
+            for (int c0 = 0; c0 < cnt; c0 += 32) {
+                float2 v = make_float2(0.f, 0.f);
+                if (c0 + lane < cnt) v = xy[all[first + (c0 + lane) * inc]];
+                const int m = min(32, cnt - c0);
+                for (int t = 0; t < m; t++) {
+                    const float x = __shfl_sync(0xffffffffu, v.x, t), y = __shfl_sync(0xffffffffu, v.y, t);
+                    mean[0] += x; sq[0] += x * x;   // the product is formed in float
+                    mean[1] += y; sq[1] += y * y;
+                }
             }
             const double ic = 1. / double(cnt);
             double var[2];
@@ -169,10 +182,13 @@ __global__ void __launch_bounds__(KDB_THREADS, 1) kdtree_build_kernel(const KdBu
                 var[d] = sq[d] * ic - mean[d] * mean[d];
             }
             const int col = var[1] > var[0] ? 1 : 0;
-            N.col = col;
-            N.div = mean[col];
-            N.cutf = (float)mean[col];
-            atomicAdd(&n_internal_lvl, 1);
+            __syncwarp();
+            if (lane == 0) {
+                N.col = col;
+                N.div = mean[col];
+                N.cutf = (float)mean[col];
+                atomicAdd(&n_internal_lvl, 1);
+            }
         }
         __syncthreads();
         if (n_internal_lvl == 0) break;
@@ -236,8 +252,11 @@ __global__ void __launch_bounds__(KDB_THREADS, 1) kdtree_build_kernel(const KdBu
             }
             __syncthreads();
         }
-        // D. split rule (+ the std::sort fallback), children
-        for (int k = lb + threadIdx.x; k < le; k += KDB_THREADS) {
+        // D. split rule (+ the std::sort fallback), children.  One node per WARP, lane 0 works: the serial std::sort replays of neighbouring
+        // nodes (every node of 11 .. 19 points takes one) used to sit in the lanes of ONE warp and ran one after the other (41 % of the kernel
+        // was the barrier below)
+        for (int k = lb + (threadIdx.x >> 5); k < le; k += KDB_THREADS / 32) {
+            if (threadIdx.x & 31) continue;
             NodeW& N = nd[k];
             if (N.col < 0) continue;
             const int count = N.e - N.s, half = count / 2, lim1 = N.lim1, lim2 = N.lim2;
