@@ -61,7 +61,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(text)
             raise RuntimeError("nvcc failed for " + s)
         objs.append(o)
-    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]   # -ldl: NVTX v3 loads its injection library lazily
     r = subprocess.run(cmd, capture_output=True, text=True)
     log.append("$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
     if r.returncode != 0:

@@ -1789,6 +1789,7 @@ int uco_b200_ba_set_host_threads(uco_b200_ctx* ctx, int n_threads) {
 }
 
 int uco_b200_ba_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* pbs, const volatile unsigned char* stop, uco_ba_result* res) {
+    UCO_RANGE();
     if (!ctx) return UCO_E_INVALID;
     cudaSetDevice(ctx->device);  // the calling thread may be a new one (mapper / tracker threads): bind it to the context's GPU
     if (n < 0 || (n && (!pbs || !res))) return uco_fail(ctx, UCO_E_INVALID, "ba_solve_batch: bad arguments");
@@ -1825,6 +1826,7 @@ int uco_b200_ba_solve_batch(uco_b200_ctx* ctx, int n, const uco_ba_problem* pbs,
 
 int uco_b200_ba_solve_sharded(uco_b200_ctx* ctx, uco_b200_comm* comm, const uco_ba_problem* pb, const volatile unsigned char* stop,
                               uco_ba_result* res) {
+    UCO_RANGE();
     return ba_sharded_solve(ctx, comm, pb, stop, res);
 }
 

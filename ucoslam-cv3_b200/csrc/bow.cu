@@ -175,6 +175,7 @@ int uco_b200_bow_info(const uco_b200_voc* voc, uint32_t* k, uint32_t* nblocks, u
 
 int uco_b200_bow_transform_dev(uco_b200_ctx* ctx, const uco_b200_voc* voc, const uint8_t* desc_dev, int n, int level,
                                uint32_t* word_dev, float* weight_dev, uint32_t* node_dev) {
+    UCO_RANGE();
     if (!ctx) return UCO_E_INVALID;
     cudaSetDevice(ctx->device);  // the calling thread may be a new one (mapper / tracker threads): bind it to the context's GPU
     if (!voc) return uco_fail(ctx, UCO_E_INVALID, "bow_transform: no vocabulary");
@@ -214,6 +215,7 @@ extern "C" {
 
 int uco_b200_bow_transform(uco_b200_ctx* ctx, const uco_b200_voc* voc, const uint8_t* desc, int n, size_t stride, int level,
                            uint32_t* word, float* weight, uint32_t* node) {
+    UCO_RANGE();
     if (!ctx) return UCO_E_INVALID;
     cudaSetDevice(ctx->device);  // the calling thread may be a new one (mapper / tracker threads): bind it to the context's GPU
     if (!voc) return uco_fail(ctx, UCO_E_INVALID, "bow_transform: no vocabulary");

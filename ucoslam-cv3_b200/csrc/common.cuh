@@ -6,6 +6,16 @@
 #include <string>
 #include <vector>
 #include "../../include/ucoslam_b200.h"
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: a no-op unless a tool (nsys / ncu --nvtx) injects itself
+// NVTX range named after the C-ABI entry point for the duration of the call (the reference marks the same boundaries with its
+// __UCOSLAM_ADDTIMER__ / __UCOSLAM_TIMER_EVENT__ debug timers, e.g. globaloptimizer_g2o.cpp:411-417, system.cpp's per-frame events)
+struct UcoRange {
+    explicit UcoRange(const char* name) { nvtxRangePushA(name); }
+    ~UcoRange() { nvtxRangePop(); }
+    UcoRange(const UcoRange&) = delete;
+    UcoRange& operator=(const UcoRange&) = delete;
+};
+#define UCO_RANGE() UcoRange uco_range_(__func__)
 
 struct uco_dev_buf {
     void* p = nullptr;

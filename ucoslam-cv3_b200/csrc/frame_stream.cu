@@ -558,6 +558,7 @@ struct uco_b200_frame {
 extern "C" {
 
 int uco_b200_frame_upload(uco_b200_ctx* ctx, const uco_frame_stream* v, uco_b200_frame** out) {
+    UCO_RANGE();
     if (!ctx) return UCO_E_INVALID;
     cudaSetDevice(ctx->device);
     if (!v || !out) return uco_fail(ctx, UCO_E_INVALID, "frame_upload: null argument");

@@ -541,6 +541,7 @@ int uco_b200_kfdb_del(uco_b200_ctx* ctx, uco_b200_kfdb* db, uint32_t frame_id) {
 int uco_b200_kfdb_query(uco_b200_ctx* ctx, uco_b200_kfdb* db, const uint32_t* words, const float* weights, int n,
                         const uint32_t* excluded, int n_excluded, float min_score, uint32_t* out_frame, double* out_score,
                         uint32_t* out_common, int cap, int* n_out, uint32_t* max_common) {
+    UCO_RANGE();
     if (!ctx) return UCO_E_INVALID;
     cudaSetDevice(ctx->device);
     if (!db || !n_out || n < 0 || n_excluded < 0 || cap < 0) return uco_fail(ctx, UCO_E_INVALID, "kfdb_query: bad argument");

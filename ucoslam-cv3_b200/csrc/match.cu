@@ -237,6 +237,7 @@ int uco_b200_frame_match_batch_dev(uco_b200_ctx* ctx, int n_pairs, const uint8_t
                                    const uint8_t* t_desc_dev, size_t t_pair_stride, const uco_keypoint* t_kps_dev,
                                    size_t t_kps_pair_stride, int nt_max, const int32_t* nt_dev, const uco_match_params* prm,
                                    uco_match* out_dev, int32_t* n_out_dev) {
+    UCO_RANGE();
     if (!ctx) return UCO_E_INVALID;
     cudaSetDevice(ctx->device);  // the calling thread may be a new one (mapper / tracker threads): bind it to the context's GPU
     int rc = check_params(ctx, prm);
@@ -268,6 +269,7 @@ int uco_b200_frame_match(uco_b200_ctx* ctx, const uint8_t* q_desc, int nq, size_
                          int n_q_kps, const int32_t* q_map, const uint8_t* t_desc, int nt, size_t t_stride,
                          const uco_keypoint* t_kps, int n_t_kps, const int32_t* t_map, const uco_match_params* prm,
                          uco_match* out, int capacity, int* n_out) {
+    UCO_RANGE();
     if (!ctx) return UCO_E_INVALID;
     cudaSetDevice(ctx->device);  // the calling thread may be a new one (mapper / tracker threads): bind it to the context's GPU
     int rc = check_params(ctx, prm);
@@ -559,6 +561,7 @@ int uco_b200_new_points(uco_b200_ctx* ctx, const uint8_t* t_desc, int nt, size_t
                         const uco_new_points_params* prm, int32_t* n_points, int32_t* pt_kpt, float* pt_xyz, float* pt_dist, int32_t* obs_ptr,
                         int32_t* obs_frame, int32_t* obs_kpt, int capacity_points, int capacity_obs, uco_match* const* matches, int32_t* n_matches,
                         float* const* xyz) {
+    UCO_RANGE();
     if (!ctx) return UCO_E_INVALID;
     if (!prm || !n_points || n_frames < 0) return uco_fail(ctx, UCO_E_INVALID, "new_points: bad arguments");
     *n_points = 0;
@@ -712,6 +715,7 @@ int uco_b200_keyframes_batch_dev(uco_b200_ctx* ctx, const uco_b200_voc* voc, int
 int uco_b200_keyframes_batch(uco_b200_ctx* ctx, const uco_b200_voc* voc, int bow_level, int n_kf, const int32_t* kf_frame, const int32_t* nb_ptr,
                              const int32_t* nb_frame, const float* f12, const uco_match_params* prm, uint32_t* word, float* weight, uint32_t* node,
                              uco_match* matches, int32_t* n_matches) {
+    UCO_RANGE();
     if (!ctx) return UCO_E_INVALID;
     cudaSetDevice(ctx->device);
     const uco_keypoint* d_kps; const uint8_t* d_desc; const int* d_nout; int mf, nfr;

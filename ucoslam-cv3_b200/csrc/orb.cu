@@ -1397,6 +1397,7 @@ void uco_b200_orb_default_params(uco_orb_params* p) {
 int uco_b200_orb_extract_batch_dev(uco_b200_ctx* ctx, const uint8_t* imgs_dev, int n_imgs, int w, int h, size_t pitch,
                                    size_t frame_stride, const uco_orb_params* prm, uco_keypoint* kps_dev,
                                    uint8_t* desc_dev, int* n_out_dev) {
+    UCO_RANGE();
     if (!ctx) return UCO_E_INVALID;
     cudaSetDevice(ctx->device);  // the calling thread may be a new one (mapper / tracker threads): bind it to the context's GPU
     if (!prm || n_imgs < 0) return uco_fail(ctx, UCO_E_INVALID, "orb: bad arguments");
@@ -1410,6 +1411,7 @@ int uco_b200_orb_extract_batch_dev(uco_b200_ctx* ctx, const uint8_t* imgs_dev, i
 
 int uco_b200_orb_extract_batch(uco_b200_ctx* ctx, const uint8_t* const* imgs, int n_imgs, int w, int h, size_t stride,
                                const uco_orb_params* prm, uco_keypoint* kps, uint8_t* desc, int capacity, int* n_out) {
+    UCO_RANGE();
     if (!ctx) return UCO_E_INVALID;
     cudaSetDevice(ctx->device);  // the calling thread may be a new one (mapper / tracker threads): bind it to the context's GPU
     if (!prm || n_imgs < 0) return uco_fail(ctx, UCO_E_INVALID, "orb: bad arguments");

@@ -459,6 +459,7 @@ int uco_pnp_launch_dev(uco_b200_ctx* ctx, int n, const PnpHead* heads_dev, const
 extern "C" {
 
 int uco_b200_pose_only_batch(uco_b200_ctx* ctx, int n, const uco_pnp_problem* pbs, uco_pnp_result* res) {
+    UCO_RANGE();
     if (!ctx) return UCO_E_INVALID;
     cudaSetDevice(ctx->device);  // the calling thread may be a new one (mapper / tracker threads): bind it to the context's GPU
     if (n <= 0 || !pbs || !res) return uco_fail(ctx, UCO_E_INVALID, "pose_only: bad arguments");

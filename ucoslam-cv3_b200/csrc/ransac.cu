@@ -126,6 +126,7 @@ extern "C" {
 int uco_b200_pnp_ransac(uco_b200_ctx* ctx, const float* p3d, const float* p2d, const float* normals, int n, const float* cam_fxfycxcy,
                         int max_iters, const int32_t* samples, uint64_t seed, float* pose44, int32_t* inliers, int* n_inliers,
                         int32_t* counts, int* best_iter) {
+    UCO_RANGE();
     if (!ctx) return UCO_E_INVALID;
     cudaSetDevice(ctx->device);
     if (!n_inliers || n < 0 || max_iters < 0 || !cam_fxfycxcy) return uco_fail(ctx, UCO_E_INVALID, "pnp_ransac: bad argument");

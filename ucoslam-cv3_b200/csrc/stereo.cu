@@ -172,6 +172,7 @@ int uco_b200_stereo_depth(uco_b200_ctx* ctx, const uint8_t* img_l, size_t stride
                           const uco_keypoint* kps_l, const uint8_t* desc_l, size_t desc_l_stride, int n_l, const uco_keypoint* kps_r,
                           const uint8_t* desc_r, size_t desc_r_stride, int n_r, float max_desc_dist, float bl, float fx, float* depth,
                           int32_t* match_r, int* n_with_depth) {
+    UCO_RANGE();
     if (!ctx) return UCO_E_INVALID;
     cudaSetDevice(ctx->device);
     if (w <= 0 || h <= 0 || n_l < 0 || n_r < 0) return uco_fail(ctx, UCO_E_INVALID, "stereo_depth: bad size");

@@ -479,6 +479,7 @@ int uco_track_check_errors(uco_b200_ctx* ctx, bool long_wait = false) {
 extern "C" {
 
 int uco_b200_track_batch_dev(uco_b200_ctx* ctx, const uco_track_batch* in, const uco_track_params* prm, const uco_track_out* out) {
+    UCO_RANGE();
     if (!ctx) return UCO_E_INVALID;
     cudaSetDevice(ctx->device);
     int rc = check_params(ctx, prm);
@@ -531,6 +532,7 @@ int uco_b200_track_batch_dev(uco_b200_ctx* ctx, const uco_track_batch* in, const
 
 // host buffers in, host buffers out: one staged upload, the device sequence, one download
 int uco_b200_track_batch(uco_b200_ctx* ctx, const uco_track_batch* in, const uco_track_params* prm, const uco_track_out* out) {
+    UCO_RANGE();
     if (!ctx) return UCO_E_INVALID;
     cudaSetDevice(ctx->device);
     int rc = check_params(ctx, prm);
@@ -811,6 +813,7 @@ int uco_orb_extract_keep_dev(uco_b200_ctx* ctx, const uint8_t* const* imgs, int 
 int uco_b200_track_frames(uco_b200_ctx* ctx, const uco_b200_track_state* st, const uint8_t* const* imgs, int w, int h, size_t stride,
                           const uco_orb_params* orb, const uco_track_params* prm, const float* pose_prior, uco_keypoint* kps, uint8_t* desc,
                           int32_t* n_kp, const uco_track_out* out) {
+    UCO_RANGE();
     if (!ctx || !st) return UCO_E_INVALID;
     cudaSetDevice(ctx->device);
     if (!imgs || !orb || !prm || !pose_prior || !out || !out->matches || !out->n_matches || !out->pose || !out->n_good || !out->status || !out->n_tbp)

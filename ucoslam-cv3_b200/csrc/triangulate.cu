@@ -286,6 +286,7 @@ extern "C" {
 
 int uco_b200_triangulate(uco_b200_ctx* ctx, const uco_keypoint* kps_train, int n_train, const uco_keypoint* kps_query, int n_query,
                          const uco_match* matches, int n_matches, const uco_triangulate_params* prm, float* xyz, int* n_good) {
+    UCO_RANGE();
     if (!ctx) return UCO_E_INVALID;
     cudaSetDevice(ctx->device);
     if (n_train < 0 || n_query < 0 || n_matches < 0 || !prm) return uco_fail(ctx, UCO_E_INVALID, "triangulate: bad argument");
